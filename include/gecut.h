@@ -1,0 +1,201 @@
+/* gecut.h -- C ABI of the B200-native cutting-and-integration library (libgecut.so).
+ *
+ * Drop-in boundary for the hot path of gridap/GridapEmbedded.jl v0.9.11
+ *     cut(LevelSetCutter(), bgmodel, geo)  +  Triangulation(cutgeo,PHYSICAL) / EmbeddedBoundary(cutgeo) / Measure
+ * on Cartesian (optionally simplexified) background models.  A Julia `Cutter` subtype
+ * (`src/Interfaces/Cutters.jl:22-60`) reaches the GPU only through `ccall`s of the entry points below
+ * (see INTEGRATION.md for the shim); the Python mirror in gridapembedded.jl_b200/ binds the same symbols with ctypes.
+ *
+ * Conventions
+ *   - every function returns an int status (GECUT_OK == 0); no exception, callback or C++ type crosses the ABI;
+ *     `gecut_last_error(ctx)` gives the message of the last failure on that context;
+ *   - calls are blocking: outputs are complete when the call returns (the work itself runs on the context's stream);
+ *   - one context per host thread / per GPU; results, selections belong to the context that made them;
+ *   - all ids in the returned layout are 1-based Int32 and states are Int8 exactly as in the reference structs
+ *     (`SubCellData` src/Interfaces/SubCellTriangulations.jl:2-7, `SubFacetData` src/Interfaces/SubFacetTriangulations.jl:2-8,
+ *     `EmbeddedDiscretization` src/Interfaces/EmbeddedDiscretizations.jl:36-45); coordinates are Float64, AoS (D per point);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with GECUT_ERR_CUDA.
+ */
+#ifndef GECUT_H
+#define GECUT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes -------------------------------------------------------------------------------------------- */
+#define GECUT_OK 0
+#define GECUT_ERR_INVALID 1        /* bad argument (NULL pointer, bad dimension, bad program ...)                    */
+#define GECUT_ERR_NOTIMPLEMENTED 2 /* mirrors @notimplementedif of the reference (CutTriangulations.jl:495-503,538) */
+#define GECUT_ERR_CUDA 3           /* CUDA runtime failure (message in gecut_last_error)                             */
+#define GECUT_ERR_OOM 4            /* device allocation failed                                                        */
+#define GECUT_ERR_OVERFLOW 5       /* an Int32 id of the reference layout would overflow                             */
+
+/* ---- states (src/Interfaces/Interfaces.jl:70-73) ----------------------------------------------------------------- */
+#define GECUT_IN (-1)
+#define GECUT_OUT 1
+#define GECUT_CUT 0
+#define GECUT_INTERFACE 0
+
+/* ---- leaf kinds = the "bytecode" of AnalyticalGeometry leaves (src/LevelSetCutters/AnalyticalGeometries.jl) -------- */
+#define GECUT_LEAF_SPHERE 0   /* _sphere   :146-150  (w.w - R^2), also `disk` in 2-D                                 */
+#define GECUT_LEAF_CYLINDER 1 /* _cylinder :176-182  (v already normalised by the constructor, :165)                  */
+#define GECUT_LEAF_PLANE 2    /* _plane    :194-198  ((x-x0).v, v raw)                                              */
+#define GECUT_LEAF_DOUGHNUT 3 /* _doughnut_fun :75-78                                                               */
+#define GECUT_LEAF_NODAL 4    /* values given per background node: DiscreteGeometry (DiscreteGeometries.jl:81-98),     */
+                              /* arbitrary closures and popcorn                                                        */
+#define GECUT_MAX_LEVELSETS 16
+
+/* ---- postfix boolean program over level-set rows (replaces the recursive compute_inoutcut / compute_inoutboundary,
+ *      src/Interfaces/EmbeddedDiscretizations.jl:107-245): token >= 0 pushes row `token`, negative tokens are operators */
+#define GECUT_OP_UNION (-1)
+#define GECUT_OP_INTERSECT (-2)
+#define GECUT_OP_SETDIFF (-3)
+#define GECUT_OP_COMPLEMENT (-4)
+#define GECUT_MAX_PROGRAM 64
+
+typedef struct gecut_ctx gecut_ctx;             /* device, stream, scratch                                            */
+typedef struct gecut_result gecut_result;       /* device-resident EmbeddedDiscretization                             */
+typedef struct gecut_selection gecut_selection; /* device-resident Triangulation(cut,...) / EmbeddedBoundary(cut,...)   */
+
+/* CartesianDiscreteModel(pmin,pmax,partition) [simplexify(...)]; `slab_begin/slab_end` restrict the cut to the n-cubes
+ * whose index in the LAST direction lies in [slab_begin, slab_end) (0,0 = whole model) -- the z-slab partition that
+ * mirrors src/Distributed/DistributedDiscretizations.jl:29-40.  Node coordinates always use the GLOBAL indices so a
+ * slab is bit-identical to the same cells of the whole model; cell ids in the result are local to the slab
+ * (global id = local id + gecut_sizes.cell_offset). */
+typedef struct {
+  int32_t D;            /* 2 or 3                                                                                 */
+  int32_t simplexified; /* 0: QUAD/HEX cells, 1: TRI/TET cells of simplexify(model)                                 */
+  double pmin[3];
+  double pmax[3];
+  int32_t partition[3];
+  int32_t slab_begin;
+  int32_t slab_end;
+  int32_t pad;
+} gecut_grid;
+
+/* One unique leaf of the CSG tree, in `_find_unique_leaves` order (DiscreteGeometries.jl:65-74). */
+typedef struct {
+  int32_t kind;
+  int32_t pad;
+  double x0[3];
+  double v[3];
+  double R;
+  double r;
+} gecut_leaf;
+
+typedef struct {
+  int64_t num_bgcells;          /* Nc  (cells of the slab)                                                         */
+  int64_t num_bgnodes;          /* Nn  (nodes of the slab incl. its upper plane)                                    */
+  int64_t num_cutcells;         /* Ncut: bg cells CUT by at least one level set                                     */
+  int64_t num_subcells;         /* Nsc                                                                             */
+  int64_t num_subcell_points;   /* Nscp                                                                            */
+  int64_t num_subfacets;        /* Nsf                                                                             */
+  int64_t num_subfacet_points;  /* Nsfp                                                                            */
+  int64_t cell_offset;          /* global bg cell id = local id + cell_offset                                      */
+  int64_t node_offset;          /* global node id = local id + node_offset                                          */
+  int32_t num_levelsets;        /* L                                                                               */
+  int32_t D;
+  int32_t num_vertices_per_bgcell; /* nv                                                                           */
+  int32_t pad;
+} gecut_sizes;
+
+/* Pointers to the arrays of the layout.  Used both to hand out device pointers (gecut_result_device_ptrs) and to name
+ * caller-allocated HOST destinations (gecut_result_copy; NULL entries are skipped).  Row r of an L x N Int8 array
+ * starts at base + r*pitch with pitch = N for host copies and gecut_buffers.state_pitch_* for device pointers. */
+typedef struct {
+  int8_t* ls_to_bgcell_to_inoutcut;   /* L x Nc                                                                    */
+  int32_t* cutcell_to_cell;           /* Ncut, ascending, 1-based                                                   */
+  int32_t* sc_cell_to_points;         /* Nsc*(D+1)   Table.data (ptrs are 1:(D+1):...)                              */
+  int32_t* sc_cell_to_bgcell;         /* Nsc                                                                       */
+  double* sc_point_to_coords;         /* Nscp*D                                                                    */
+  double* sc_point_to_rcoords;        /* Nscp*D                                                                    */
+  int8_t* ls_to_subcell_to_inout;     /* L x Nsc                                                                   */
+  int32_t* sf_facet_to_points;        /* Nsf*D                                                                     */
+  int32_t* sf_facet_to_bgcell;        /* Nsf                                                                       */
+  double* sf_facet_to_normal;         /* Nsf*D                                                                     */
+  double* sf_point_to_coords;         /* Nsfp*D                                                                    */
+  double* sf_point_to_rcoords;        /* Nsfp*D                                                                    */
+  int8_t* ls_to_subfacet_to_inout;    /* L x Nsf                                                                   */
+  int64_t state_pitch_bgcell;         /* device row pitches (bytes), filled by gecut_result_device_ptrs            */
+  int64_t state_pitch_subcell;
+  int64_t state_pitch_subfacet;
+} gecut_buffers;
+
+/* ---- context ------------------------------------------------------------------------------------------------- */
+/* `cuda_stream` is a cudaStream_t (NULL = the legacy default stream).  Replaces nothing in the reference (it has no
+ * device); needed by every other call. */
+int gecut_create(int device, void* cuda_stream, gecut_ctx** ctx);
+int gecut_destroy(gecut_ctx* ctx);
+int gecut_set_stream(gecut_ctx* ctx, void* cuda_stream);
+const char* gecut_last_error(const gecut_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's `gpu_launches`). */
+int64_t gecut_launch_count(const gecut_ctx* ctx);
+
+/* ---- cut ------------------------------------------------------------------------------------------------------ */
+/* cut(::LevelSetCutter, bgmodel, geo)  (src/LevelSetCutters/LevelSetCutters.jl:79-105 -> CutTriangulations.jl:443-460,
+ * 309-343): evaluates the L unique leaves at the nodes, classifies every bg cell per level set, extracts + simplexifies
+ * the cut cells and cuts them sequentially by every level set (ls = L..1), producing subcells, boundary subfacets with
+ * normals, and the IN/OUT rows.  `nodal_values[ls]` is read only for NODAL leaves: Nn doubles (whole model, node ids
+ * lexicographic x fastest), resident on the device if `nodal_on_device` else on the host. */
+int gecut_cut(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* leaves, int num_leaves,
+              const double* const* nodal_values, int nodal_on_device, gecut_result** out);
+/* compute_bgcell_to_inoutcut(::LevelSetCutter, bgmodel, geo) (LevelSetCutters.jl:154-157,175-205): classification only
+ * (result has no subcells / subfacets). */
+int gecut_classify(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* leaves, int num_leaves,
+                   const double* const* nodal_values, int nodal_on_device, gecut_result** out);
+/* discretize(geo, model) (src/LevelSetCutters/DiscreteGeometries.jl:48-63): leaf `leaf` at every node of the model into
+ * `values` (Nn doubles, device pointer if on_device else host). */
+int gecut_eval_leaf_at_nodes(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* leaf, double* values,
+                             int on_device);
+int gecut_result_free(gecut_result* res);
+int gecut_result_sizes(const gecut_result* res, gecut_sizes* sizes);
+int gecut_result_device_ptrs(const gecut_result* res, gecut_buffers* dev);
+int gecut_result_copy(const gecut_result* res, const gecut_buffers* host);
+
+/* ---- selectors -------------------------------------------------------------------------------------------------- */
+/* compute_bgcell_to_inoutcut(cut, geo) (src/Interfaces/EmbeddedDiscretizations.jl:91-105) -> Nc Int8 on the host */
+int gecut_bgcell_to_inoutcut(const gecut_result* res, const int32_t* program, int len, int8_t* host_out);
+/* compute_subcell_to_inout(cut, geo) (EmbeddedDiscretizations.jl:325-339) -> Nsc Int8 on the host */
+int gecut_subcell_to_inout(const gecut_result* res, const int32_t* program, int len, int8_t* host_out);
+
+#define GECUT_SEL_PHYSICAL 0 /* Triangulation(cut,(CutInOrOut(side),side),geo)  (:297-317)                           */
+#define GECUT_SEL_ACTIVE 1   /* Triangulation(cut,ActiveInOrOut(side),geo)      (:319-323)                           */
+#define GECUT_SEL_BOUNDARY 2 /* EmbeddedBoundary(cut,geo1[,geo2])               (:417-463)                           */
+#define GECUT_SEL_CUTONLY 3  /* Triangulation(cut,CutInOrOut(side),geo)         (:303-311) subcells only             */
+#define GECUT_SEL_BGONLY 4   /* Triangulation(cut,side::Integer,geo)            (:313-317) bg cells only             */
+/* side = GECUT_IN or GECUT_OUT.  PHYSICAL: sub-entities = subcells with bg state CUT and subcell state == side,
+ * bg entities = bg cells with state == side.  ACTIVE: bg cells with state CUT or side. */
+int gecut_select_cells(const gecut_result* res, int kind, const int32_t* program, int len, int side,
+                       gecut_selection** out);
+/* program2 == NULL: EmbeddedBoundary(cut,geo1); else the two-geometry form. */
+int gecut_select_boundary(const gecut_result* res, const int32_t* program1, int len1, const int32_t* program2,
+                          int len2, gecut_selection** out);
+int gecut_selection_free(gecut_selection* sel);
+/* n_sub: selected subcells / subfacets, n_bg: selected bg cells */
+int gecut_selection_sizes(const gecut_selection* sel, int64_t* n_sub, int64_t* n_bg);
+/* host copies (NULL skipped): 1-based ids of the selected sub-entities (SubCellData(st,ids) / SubFacetData(st,ids,o),
+ * SubCellTriangulations.jl:9-17, SubFacetTriangulations.jl:10-21), boundary orientation (+-1), selected bg cell ids */
+int gecut_selection_copy(const gecut_selection* sel, int32_t* sub_ids, int8_t* orientation, int32_t* bg_ids);
+/* re-indexed tables of the selection on the host (NULL skipped): connectivity rows, bgcell, oriented normals */
+int gecut_selection_gather(const gecut_selection* sel, int32_t* to_points, int32_t* to_bgcell, double* normals);
+
+/* ---- integration (Gridap Measure(trian,2) semantics) ---------------------------------------- */
+/* sum(∫(1)dΩ) resp. sum(∫(1)dΓ): `values` (host, NULL skipped) gets one value per selected sub-entity; *total also
+ * includes the selected uncut bg cells (tensor Gauss / simplex rule per cell). */
+int gecut_integrate_measure(const gecut_selection* sel, double* values, double* total);
+/* ∫(∇v·∇u)dΩ element matrices of the bg shape functions (Q1 on QUAD/HEX, P1 on TRI/TET), contributions of the selected
+ * subcells accumulated per cut bg cell in subcell order (move_contributions, SubCellTriangulations.jl:63-72):
+ * `K_cut` (host, NULL skipped) is Ncut x nv x nv, row k belongs to cutcell_to_cell[k] (zero if the cell has no selected
+ * subcell); `K_bg` (host, NULL skipped) is ntypes x nv x nv for the uncut cells (ntypes = 1 for n-cubes, 2/6 for
+ * simplexified models, type = (cell-1) mod ntypes). */
+int gecut_integrate_laplacian(const gecut_selection* sel, double* K_cut, double* K_bg);
+/* device pointer to the Ncut x nv x nv matrices of the last gecut_integrate_laplacian on this selection */
+int gecut_selection_device_laplacian(const gecut_selection* sel, double** K_cut_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GECUT_H */
