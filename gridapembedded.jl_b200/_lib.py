@@ -59,7 +59,7 @@ class Buffers(C.Structure):
 
 SOURCES = ["gecut_api.cu", "gecut_classify.cu", "gecut_cutcells.cu", "gecut_select.cu", "gecut_integrate.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xcompiler", "-ffp-contract=off"]
 
 
 def _needs_build() -> bool:

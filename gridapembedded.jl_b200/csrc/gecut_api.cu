@@ -1,0 +1,660 @@
+// gecut_api.cu -- the C ABI (include/gecut.h): contexts, orchestration of the kernels, host<->device copies.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "gecut_internal.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// memory: stream-ordered pool allocations so that repeated cuts reuse memory without cudaMalloc round trips
+// ------------------------------------------------------------------------------------------------
+int gc_malloc(gecut_ctx* ctx, void** p, size_t bytes) {
+  *p = nullptr;
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    char buf[128];
+    snprintf(buf, sizeof(buf), "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    ctx->err = buf;
+    return e == cudaErrorMemoryAllocation ? GECUT_ERR_OOM : GECUT_ERR_CUDA;
+  }
+  return GECUT_OK;
+}
+
+void gc_free(gecut_ctx* ctx, void* p) {
+  if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+int gc_launch_check(gecut_ctx* ctx, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
+    return GECUT_ERR_CUDA;
+  }
+  return GECUT_OK;
+}
+
+static inline int64_t pad_pitch(int64_t n) { return ((n + 255) / 256) * 256; }
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+int make_grid(gecut_ctx* ctx, const gecut_grid* in, GcGrid* g) {
+  if (!in) {
+    ctx->err = "grid is NULL";
+    return GECUT_ERR_INVALID;
+  }
+  if (in->D != 2 && in->D != 3) {
+    ctx->err = "only 2-D and 3-D background models are implemented";
+    return GECUT_ERR_NOTIMPLEMENTED;
+  }
+  memset(g, 0, sizeof(*g));
+  const int D = in->D;
+  g->D = D;
+  g->simplexified = in->simplexified ? 1 : 0;
+  for (int d = 0; d < 3; ++d) {
+    if (d < D) {
+      if (in->partition[d] <= 0 || !(in->pmax[d] > in->pmin[d])) {
+        ctx->err = "invalid Cartesian descriptor (partition <= 0 or pmax <= pmin)";
+        return GECUT_ERR_INVALID;
+      }
+      g->n[d] = in->partition[d];
+      g->nn[d] = in->partition[d] + 1;
+      g->pmin[d] = in->pmin[d];
+      g->dx[d] = (in->pmax[d] - in->pmin[d]) / (double)in->partition[d];  // CartesianDescriptor sizes
+    } else {
+      g->n[d] = 1;
+      g->nn[d] = 1;
+      g->pmin[d] = 0.0;
+      g->dx[d] = 0.0;
+    }
+  }
+  g->k0 = 0;
+  g->k1 = g->n[D - 1];
+  if (!(in->slab_begin == 0 && in->slab_end == 0)) {
+    if (in->slab_begin < 0 || in->slab_end > g->n[D - 1] || in->slab_begin >= in->slab_end) {
+      ctx->err = "invalid slab range";
+      return GECUT_ERR_INVALID;
+    }
+    g->k0 = in->slab_begin;
+    g->k1 = in->slab_end;
+  }
+  g->nt = D == 2 ? 2 : 6;
+  g->cpc = g->simplexified ? g->nt : 1;
+  g->nt0 = g->simplexified ? 1 : g->nt;
+  g->nv = g->simplexified ? D + 1 : (1 << D);
+  g->layer_cubes = D == 3 ? (int64_t)g->n[0] * g->n[1] : (int64_t)g->n[0];
+  g->layer_nodes = D == 3 ? (int64_t)g->nn[0] * g->nn[1] : (int64_t)g->nn[0];
+  g->num_cubes = g->layer_cubes * (g->k1 - g->k0);
+  g->num_cells = g->num_cubes * g->cpc;
+  g->num_nodes = g->layer_nodes * (g->k1 - g->k0 + 1);
+  if (g->num_cells >= 2147483647ll || g->layer_nodes * (int64_t)g->nn[D - 1] >= 2147483647ll) {
+    ctx->err = "background model too large for the Int32 ids of the reference layout";
+    return GECUT_ERR_OVERFLOW;
+  }
+  return GECUT_OK;
+}
+
+void free_result_arrays(gecut_result* r) {
+  gecut_ctx* ctx = r->ctx;
+  GcLayout& l = r->lay;
+  gc_free(ctx, l.bg_state);
+  gc_free(ctx, l.cutcells);
+  gc_free(ctx, l.sc_c2p);
+  gc_free(ctx, l.sc_c2bg);
+  gc_free(ctx, l.sc_X);
+  gc_free(ctx, l.sc_R);
+  gc_free(ctx, l.sc_state);
+  gc_free(ctx, l.sf_c2p);
+  gc_free(ctx, l.sf_c2bg);
+  gc_free(ctx, l.sf_N);
+  gc_free(ctx, l.sf_X);
+  gc_free(ctx, l.sf_R);
+  gc_free(ctx, l.sf_state);
+  gc_free(ctx, r->cutmask);
+  for (int i = 0; i < GC_LMAX; ++i)
+    if (r->owns_nodal[i]) gc_free(ctx, r->nodal_dev[i]);
+  l = GcLayout{};
+  r->cutmask = nullptr;
+}
+
+int do_cut(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* leaves, int L, const double* const* nodal_values,
+           int nodal_on_device, bool classify_only, gecut_result** out) {
+  if (!ctx) return GECUT_ERR_INVALID;
+  if (!out || !leaves) {
+    ctx->err = "NULL argument";
+    return GECUT_ERR_INVALID;
+  }
+  *out = nullptr;
+  if (L < 1 || L > GC_LMAX) {
+    ctx->err = "number of level sets must be in 1..GECUT_MAX_LEVELSETS";
+    return L < 1 ? GECUT_ERR_INVALID : GECUT_ERR_NOTIMPLEMENTED;
+  }
+  DeviceGuard guard(ctx->device);
+  gecut_result* r = new (std::nothrow) gecut_result();
+  if (!r) return GECUT_ERR_OOM;
+  r->ctx = ctx;
+  r->L = L;
+  int st = make_grid(ctx, grid, &r->grid);
+  if (st != GECUT_OK) {
+    delete r;
+    return st;
+  }
+  const GcGrid& g = r->grid;
+  auto fail = [&](int code) {
+    free_result_arrays(r);
+    cudaStreamSynchronize(ctx->stream);
+    delete r;
+    return code;
+  };
+  // leaves
+  r->leaves.L = L;
+  const int64_t nn_total = g.layer_nodes * g.nn[g.D - 1];
+  for (int i = 0; i < L; ++i) {
+    r->leaves.leaf[i] = leaves[i];
+    r->leaves.nodal[i] = nullptr;
+    const int kind = leaves[i].kind;
+    if (kind < GECUT_LEAF_SPHERE || kind > GECUT_LEAF_NODAL) {
+      ctx->err = "unknown leaf kind";
+      return fail(GECUT_ERR_INVALID);
+    }
+    if (kind == GECUT_LEAF_DOUGHNUT && g.D != 3) {
+      ctx->err = "doughnut leaves need a 3-D model";
+      return fail(GECUT_ERR_INVALID);
+    }
+    if (kind == GECUT_LEAF_NODAL) {
+      if (!nodal_values || !nodal_values[i]) {
+        ctx->err = "NODAL leaf without nodal values";
+        return fail(GECUT_ERR_INVALID);
+      }
+      if (nodal_on_device) {
+        r->leaves.nodal[i] = nodal_values[i];
+      } else {
+        double* d = nullptr;
+        st = gc_malloc(ctx, (void**)&d, sizeof(double) * nn_total);
+        if (st != GECUT_OK) return fail(st);
+        r->nodal_dev[i] = d;
+        r->owns_nodal[i] = true;
+        cudaError_t e = cudaMemcpyAsync(d, nodal_values[i], sizeof(double) * nn_total, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) {
+          ctx->err = std::string("H2D copy of nodal values: ") + cudaGetErrorString(e);
+          return fail(GECUT_ERR_CUDA);
+        }
+        r->leaves.nodal[i] = d;
+      }
+    }
+  }
+  // sizes
+  gecut_sizes& sz = r->sizes;
+  memset(&sz, 0, sizeof(sz));
+  sz.num_bgcells = g.num_cells;
+  sz.num_bgnodes = g.num_nodes;
+  sz.cell_offset = (int64_t)g.k0 * g.layer_cubes * g.cpc;
+  sz.node_offset = (int64_t)g.k0 * g.layer_nodes;
+  sz.num_levelsets = L;
+  sz.D = g.D;
+  sz.num_vertices_per_bgcell = g.nv;
+  // classification
+  r->lay.bg_pitch = pad_pitch(g.num_cells);
+  st = gc_malloc(ctx, (void**)&r->lay.bg_state, (size_t)r->lay.bg_pitch * L);
+  if (st != GECUT_OK) return fail(st);
+  const int wxtot = (g.n[0] + 31) / 32;
+  const int64_t rows = (g.D == 3) ? (int64_t)(g.k1 - g.k0) * g.n[1] : (int64_t)(g.k1 - g.k0);
+  const size_t mask_bytes = sizeof(uint32_t) * rows * wxtot * g.cpc;
+  st = gc_malloc(ctx, (void**)&r->cutmask, mask_bytes);
+  if (st != GECUT_OK) return fail(st);
+  if (L > 1) {
+    cudaError_t e = cudaMemsetAsync(r->cutmask, 0, mask_bytes, ctx->stream);
+    if (e != cudaSuccess) {
+      ctx->err = std::string("memset: ") + cudaGetErrorString(e);
+      return fail(GECUT_ERR_CUDA);
+    }
+  }
+  st = gc_classify(ctx, r);
+  if (st != GECUT_OK) return fail(st);
+  st = gc_compact_cutcells(ctx, r);
+  if (st != GECUT_OK) return fail(st);
+  if (!classify_only) {
+    st = gc_cut_cells(ctx, r);
+    if (st != GECUT_OK) return fail(st);
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    ctx->err = std::string("cut: ") + cudaGetErrorString(e);
+    return fail(GECUT_ERR_CUDA);
+  }
+  *out = r;
+  return GECUT_OK;
+}
+
+int make_program(gecut_ctx* ctx, const int32_t* program, int len, int L, GcProgram* p) {
+  if (!program || len <= 0 || len > GECUT_MAX_PROGRAM) {
+    ctx->err = "invalid boolean program";
+    return GECUT_ERR_INVALID;
+  }
+  int depth = 0;
+  for (int i = 0; i < len; ++i) {
+    int t = program[i];
+    if (t >= 0) {
+      if (t >= L) {
+        ctx->err = "program refers to a level set that does not exist";
+        return GECUT_ERR_INVALID;
+      }
+      depth++;
+    } else if (t == GECUT_OP_COMPLEMENT) {
+      if (depth < 1) goto bad;
+    } else if (t >= GECUT_OP_SETDIFF) {
+      if (depth < 2) goto bad;
+      depth--;
+    } else {
+      goto bad;
+    }
+    p->tok[i] = (int8_t)t;
+  }
+  if (depth != 1) goto bad;
+  p->len = len;
+  return GECUT_OK;
+bad:
+  ctx->err = "malformed boolean program";
+  return GECUT_ERR_INVALID;
+}
+
+int copy_rows_to_host(gecut_ctx* ctx, int8_t* host, const int8_t* dev, int64_t pitch, int64_t n, int L) {
+  if (!host || n == 0) return GECUT_OK;
+  GC_CUDA(cudaMemcpy2DAsync(host, (size_t)n, dev, (size_t)pitch, (size_t)n, (size_t)L, cudaMemcpyDeviceToHost, ctx->stream));
+  return GECUT_OK;
+}
+
+template <class T>
+int copy_to_host(gecut_ctx* ctx, T* host, const T* dev, int64_t count) {
+  if (!host || count == 0 || !dev) return GECUT_OK;
+  GC_CUDA(cudaMemcpyAsync(host, dev, sizeof(T) * count, cudaMemcpyDeviceToHost, ctx->stream));
+  return GECUT_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int gecut_create(int device, void* cuda_stream, gecut_ctx** out) {
+  if (!out) return GECUT_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    (void)cudaGetLastError();
+    return GECUT_ERR_CUDA;  // no CUDA device: there is no CPU fallback
+  }
+  gecut_ctx* ctx = new (std::nothrow) gecut_ctx();
+  if (!ctx) return GECUT_ERR_OOM;
+  ctx->device = device;
+  ctx->stream = (cudaStream_t)cuda_stream;
+  DeviceGuard guard(device);
+  // keep freed blocks in the pool: repeated cuts then reuse memory without touching the driver
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  bool ok = cudaMalloc((void**)&ctx->d_tables, sizeof(GC_SIMPLEX_TABLES)) == cudaSuccess &&
+            cudaMalloc((void**)&ctx->d_simplexify_raw, sizeof(GC_SIMPLEXIFY_RAW)) == cudaSuccess &&
+            cudaMalloc((void**)&ctx->d_simplexify_pos, sizeof(GC_SIMPLEXIFY_POS)) == cudaSuccess &&
+            cudaMemcpy(ctx->d_tables, GC_SIMPLEX_TABLES, sizeof(GC_SIMPLEX_TABLES), cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaMemcpy(ctx->d_simplexify_raw, GC_SIMPLEXIFY_RAW, sizeof(GC_SIMPLEXIFY_RAW), cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaMemcpy(ctx->d_simplexify_pos, GC_SIMPLEXIFY_POS, sizeof(GC_SIMPLEXIFY_POS), cudaMemcpyHostToDevice) == cudaSuccess;
+  ctx->h_pinned_bytes = 4096;
+  ok = ok && cudaMallocHost(&ctx->h_pinned, ctx->h_pinned_bytes) == cudaSuccess;
+  if (!ok) {
+    (void)cudaGetLastError();
+    gecut_destroy(ctx);
+    return GECUT_ERR_CUDA;
+  }
+  *out = ctx;
+  return GECUT_OK;
+}
+
+int gecut_destroy(gecut_ctx* ctx) {
+  if (!ctx) return GECUT_OK;
+  DeviceGuard guard(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->d_tables);
+  cudaFree(ctx->d_simplexify_raw);
+  cudaFree(ctx->d_simplexify_pos);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  delete ctx;
+  return GECUT_OK;
+}
+
+int gecut_set_stream(gecut_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return GECUT_ERR_INVALID;
+  DeviceGuard guard(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->stream = (cudaStream_t)cuda_stream;
+  return GECUT_OK;
+}
+
+const char* gecut_last_error(const gecut_ctx* ctx) { return ctx ? ctx->err.c_str() : "NULL context"; }
+
+int64_t gecut_launch_count(const gecut_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int gecut_cut(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* leaves, int num_leaves,
+              const double* const* nodal_values, int nodal_on_device, gecut_result** out) {
+  return do_cut(ctx, grid, leaves, num_leaves, nodal_values, nodal_on_device, false, out);
+}
+
+int gecut_classify(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* leaves, int num_leaves,
+                   const double* const* nodal_values, int nodal_on_device, gecut_result** out) {
+  return do_cut(ctx, grid, leaves, num_leaves, nodal_values, nodal_on_device, true, out);
+}
+
+int gecut_eval_leaf_at_nodes(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* leaf, double* values,
+                             int on_device) {
+  if (!ctx) return GECUT_ERR_INVALID;
+  if (!leaf || !values) {
+    ctx->err = "NULL argument";
+    return GECUT_ERR_INVALID;
+  }
+  if (leaf->kind < GECUT_LEAF_SPHERE || leaf->kind >= GECUT_LEAF_NODAL) {
+    ctx->err = "only closed-form leaves can be evaluated on the device";
+    return GECUT_ERR_INVALID;
+  }
+  DeviceGuard guard(ctx->device);
+  GcGrid g;
+  gecut_grid gg = *grid;
+  gg.slab_begin = gg.slab_end = 0;
+  GC_CHECK(make_grid(ctx, &gg, &g));
+  const int64_t nn = g.layer_nodes * g.nn[g.D - 1];
+  double* d = values;
+  if (!on_device) GC_CHECK(gc_malloc(ctx, (void**)&d, sizeof(double) * nn));
+  int st = gc_eval_leaf_nodes(ctx, g, *leaf, d);
+  if (st == GECUT_OK && !on_device) {
+    cudaError_t e = cudaMemcpyAsync(values, d, sizeof(double) * nn, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e != cudaSuccess) {
+      ctx->err = cudaGetErrorString(e);
+      st = GECUT_ERR_CUDA;
+    }
+  }
+  if (!on_device) gc_free(ctx, d);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (st == GECUT_OK && e != cudaSuccess) {
+    ctx->err = cudaGetErrorString(e);
+    st = GECUT_ERR_CUDA;
+  }
+  return st;
+}
+
+int gecut_result_free(gecut_result* res) {
+  if (!res) return GECUT_OK;
+  DeviceGuard guard(res->ctx->device);
+  free_result_arrays(res);
+  delete res;
+  return GECUT_OK;
+}
+
+int gecut_result_sizes(const gecut_result* res, gecut_sizes* sizes) {
+  if (!res || !sizes) return GECUT_ERR_INVALID;
+  *sizes = res->sizes;
+  return GECUT_OK;
+}
+
+int gecut_result_device_ptrs(const gecut_result* res, gecut_buffers* dev) {
+  if (!res || !dev) return GECUT_ERR_INVALID;
+  const GcLayout& l = res->lay;
+  dev->ls_to_bgcell_to_inoutcut = l.bg_state;
+  dev->cutcell_to_cell = l.cutcells;
+  dev->sc_cell_to_points = l.sc_c2p;
+  dev->sc_cell_to_bgcell = l.sc_c2bg;
+  dev->sc_point_to_coords = l.sc_X;
+  dev->sc_point_to_rcoords = l.sc_R;
+  dev->ls_to_subcell_to_inout = l.sc_state;
+  dev->sf_facet_to_points = l.sf_c2p;
+  dev->sf_facet_to_bgcell = l.sf_c2bg;
+  dev->sf_facet_to_normal = l.sf_N;
+  dev->sf_point_to_coords = l.sf_X;
+  dev->sf_point_to_rcoords = l.sf_R;
+  dev->ls_to_subfacet_to_inout = l.sf_state;
+  dev->state_pitch_bgcell = l.bg_pitch;
+  dev->state_pitch_subcell = l.sc_pitch;
+  dev->state_pitch_subfacet = l.sf_pitch;
+  return GECUT_OK;
+}
+
+int gecut_result_copy(const gecut_result* res, const gecut_buffers* host) {
+  if (!res || !host) return GECUT_ERR_INVALID;
+  gecut_ctx* ctx = res->ctx;
+  DeviceGuard guard(ctx->device);
+  const GcLayout& l = res->lay;
+  const gecut_sizes& s = res->sizes;
+  const int D = s.D, L = s.num_levelsets;
+  GC_CHECK(copy_rows_to_host(ctx, host->ls_to_bgcell_to_inoutcut, l.bg_state, l.bg_pitch, s.num_bgcells, L));
+  GC_CHECK(copy_to_host(ctx, host->cutcell_to_cell, l.cutcells, s.num_cutcells));
+  GC_CHECK(copy_to_host(ctx, host->sc_cell_to_points, l.sc_c2p, s.num_subcells * (D + 1)));
+  GC_CHECK(copy_to_host(ctx, host->sc_cell_to_bgcell, l.sc_c2bg, s.num_subcells));
+  GC_CHECK(copy_to_host(ctx, host->sc_point_to_coords, l.sc_X, s.num_subcell_points * D));
+  GC_CHECK(copy_to_host(ctx, host->sc_point_to_rcoords, l.sc_R, s.num_subcell_points * D));
+  if (l.sc_state) GC_CHECK(copy_rows_to_host(ctx, host->ls_to_subcell_to_inout, l.sc_state, l.sc_pitch, s.num_subcells, L));
+  GC_CHECK(copy_to_host(ctx, host->sf_facet_to_points, l.sf_c2p, s.num_subfacets * D));
+  GC_CHECK(copy_to_host(ctx, host->sf_facet_to_bgcell, l.sf_c2bg, s.num_subfacets));
+  GC_CHECK(copy_to_host(ctx, host->sf_facet_to_normal, l.sf_N, s.num_subfacets * D));
+  GC_CHECK(copy_to_host(ctx, host->sf_point_to_coords, l.sf_X, s.num_subfacet_points * D));
+  GC_CHECK(copy_to_host(ctx, host->sf_point_to_rcoords, l.sf_R, s.num_subfacet_points * D));
+  if (l.sf_state) GC_CHECK(copy_rows_to_host(ctx, host->ls_to_subfacet_to_inout, l.sf_state, l.sf_pitch, s.num_subfacets, L));
+  GC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GECUT_OK;
+}
+
+static int eval_rows_to_host(const gecut_result* res, const int32_t* program, int len, const int8_t* rows, int64_t pitch,
+                             int64_t n, int8_t* host_out) {
+  if (!res) return GECUT_ERR_INVALID;
+  gecut_ctx* ctx = res->ctx;
+  if (!host_out) {
+    ctx->err = "NULL output";
+    return GECUT_ERR_INVALID;
+  }
+  DeviceGuard guard(ctx->device);
+  GcProgram p{};
+  GC_CHECK(make_program(ctx, program, len, res->L, &p));
+  if (n == 0) return GECUT_OK;
+  int8_t* d = nullptr;
+  GC_CHECK(gc_malloc(ctx, (void**)&d, (size_t)n));
+  int st = gc_eval_rows(ctx, rows, pitch, n, p, d);
+  if (st == GECUT_OK) {
+    cudaError_t e = cudaMemcpyAsync(host_out, d, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      ctx->err = cudaGetErrorString(e);
+      st = GECUT_ERR_CUDA;
+    }
+  }
+  gc_free(ctx, d);
+  return st;
+}
+
+int gecut_bgcell_to_inoutcut(const gecut_result* res, const int32_t* program, int len, int8_t* host_out) {
+  if (!res) return GECUT_ERR_INVALID;
+  return eval_rows_to_host(res, program, len, res->lay.bg_state, res->lay.bg_pitch, res->sizes.num_bgcells, host_out);
+}
+
+int gecut_subcell_to_inout(const gecut_result* res, const int32_t* program, int len, int8_t* host_out) {
+  if (!res) return GECUT_ERR_INVALID;
+  return eval_rows_to_host(res, program, len, res->lay.sc_state, res->lay.sc_pitch, res->sizes.num_subcells, host_out);
+}
+
+int gecut_select_cells(const gecut_result* res, int kind, const int32_t* program, int len, int side,
+                       gecut_selection** out) {
+  if (!res || !out) return GECUT_ERR_INVALID;
+  gecut_ctx* ctx = res->ctx;
+  *out = nullptr;
+  if (kind == GECUT_SEL_BOUNDARY || kind < 0 || kind > GECUT_SEL_BGONLY) {
+    ctx->err = "invalid selection kind";
+    return GECUT_ERR_INVALID;
+  }
+  if (side != GECUT_IN && side != GECUT_OUT) {
+    ctx->err = "side must be GECUT_IN or GECUT_OUT";
+    return GECUT_ERR_INVALID;
+  }
+  DeviceGuard guard(ctx->device);
+  gecut_selection* sel = new (std::nothrow) gecut_selection();
+  if (!sel) return GECUT_ERR_OOM;
+  sel->res = res;
+  sel->kind = kind;
+  sel->side = side;
+  int st = make_program(ctx, program, len, res->L, &sel->prog);
+  if (st == GECUT_OK) st = gc_select_cells(ctx, sel);
+  if (st == GECUT_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = GECUT_ERR_CUDA;
+  if (st != GECUT_OK) {
+    gecut_selection_free(sel);
+    return st;
+  }
+  *out = sel;
+  return GECUT_OK;
+}
+
+int gecut_select_boundary(const gecut_result* res, const int32_t* program1, int len1, const int32_t* program2, int len2,
+                          gecut_selection** out) {
+  if (!res || !out) return GECUT_ERR_INVALID;
+  gecut_ctx* ctx = res->ctx;
+  *out = nullptr;
+  DeviceGuard guard(ctx->device);
+  gecut_selection* sel = new (std::nothrow) gecut_selection();
+  if (!sel) return GECUT_ERR_OOM;
+  sel->res = res;
+  sel->kind = GECUT_SEL_BOUNDARY;
+  int st = make_program(ctx, program1, len1, res->L, &sel->prog);
+  if (st == GECUT_OK && program2) {
+    st = make_program(ctx, program2, len2, res->L, &sel->prog2);
+    sel->has_prog2 = true;
+  }
+  if (st == GECUT_OK) st = gc_select_boundary(ctx, sel);
+  if (st == GECUT_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = GECUT_ERR_CUDA;
+  if (st != GECUT_OK) {
+    gecut_selection_free(sel);
+    return st;
+  }
+  *out = sel;
+  return GECUT_OK;
+}
+
+int gecut_selection_free(gecut_selection* sel) {
+  if (!sel) return GECUT_OK;
+  gecut_ctx* ctx = sel->res->ctx;
+  DeviceGuard guard(ctx->device);
+  gc_free(ctx, sel->sub_ids);
+  gc_free(ctx, sel->orientation);
+  gc_free(ctx, sel->bg_ids);
+  gc_free(ctx, sel->K_cut);
+  delete sel;
+  return GECUT_OK;
+}
+
+int gecut_selection_sizes(const gecut_selection* sel, int64_t* n_sub, int64_t* n_bg) {
+  if (!sel) return GECUT_ERR_INVALID;
+  if (n_sub) *n_sub = sel->n_sub;
+  if (n_bg) *n_bg = sel->n_bg;
+  return GECUT_OK;
+}
+
+int gecut_selection_copy(const gecut_selection* sel_c, int32_t* sub_ids, int8_t* orientation, int32_t* bg_ids) {
+  if (!sel_c) return GECUT_ERR_INVALID;
+  gecut_selection* sel = const_cast<gecut_selection*>(sel_c);
+  gecut_ctx* ctx = sel->res->ctx;
+  DeviceGuard guard(ctx->device);
+  GC_CHECK(copy_to_host(ctx, sub_ids, sel->sub_ids, sel->n_sub));
+  if (orientation && sel->kind != GECUT_SEL_BOUNDARY) {
+    ctx->err = "orientation is only defined for boundary selections";
+    return GECUT_ERR_INVALID;
+  }
+  GC_CHECK(copy_to_host(ctx, orientation, sel->orientation, sel->n_sub));
+  if (bg_ids && sel->n_bg > 0) {
+    GC_CHECK(gc_materialize_bg_ids(ctx, sel));
+    GC_CHECK(copy_to_host(ctx, bg_ids, sel->bg_ids, sel->n_bg));
+  }
+  GC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GECUT_OK;
+}
+
+int gecut_selection_gather(const gecut_selection* sel, int32_t* to_points, int32_t* to_bgcell, double* normals) {
+  if (!sel) return GECUT_ERR_INVALID;
+  gecut_ctx* ctx = sel->res->ctx;
+  DeviceGuard guard(ctx->device);
+  const int64_t n = sel->n_sub;
+  if (n == 0) return GECUT_OK;
+  const int D = sel->res->grid.D;
+  const bool boundary = sel->kind == GECUT_SEL_BOUNDARY;
+  const int stride = boundary ? D : D + 1;
+  if (normals && !boundary) {
+    ctx->err = "normals are only defined for boundary selections";
+    return GECUT_ERR_INVALID;
+  }
+  int32_t *d_tp = nullptr, *d_tb = nullptr;
+  double* d_n = nullptr;
+  int st = GECUT_OK;
+  if (to_points) st = gc_malloc(ctx, (void**)&d_tp, sizeof(int32_t) * n * stride);
+  if (st == GECUT_OK && to_bgcell) st = gc_malloc(ctx, (void**)&d_tb, sizeof(int32_t) * n);
+  if (st == GECUT_OK && normals) st = gc_malloc(ctx, (void**)&d_n, sizeof(double) * n * D);
+  if (st == GECUT_OK) st = gc_selection_gather(ctx, sel, d_tp, d_tb, d_n);
+  if (st == GECUT_OK) st = copy_to_host(ctx, to_points, d_tp, n * stride);
+  if (st == GECUT_OK) st = copy_to_host(ctx, to_bgcell, d_tb, n);
+  if (st == GECUT_OK) st = copy_to_host(ctx, normals, d_n, n * D);
+  if (st == GECUT_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = GECUT_ERR_CUDA;
+  gc_free(ctx, d_tp);
+  gc_free(ctx, d_tb);
+  gc_free(ctx, d_n);
+  return st;
+}
+
+int gecut_integrate_measure(const gecut_selection* sel, double* values, double* total) {
+  if (!sel || !total) return GECUT_ERR_INVALID;
+  gecut_ctx* ctx = sel->res->ctx;
+  DeviceGuard guard(ctx->device);
+  double* d_vals = nullptr;
+  const int64_t n = sel->n_sub;
+  if (values && n > 0) GC_CHECK(gc_malloc(ctx, (void**)&d_vals, sizeof(double) * n));
+  int st = gc_integrate_measure(ctx, sel, d_vals, total);
+  if (st == GECUT_OK && values && n > 0) {
+    st = copy_to_host(ctx, values, d_vals, n);
+    if (st == GECUT_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = GECUT_ERR_CUDA;
+  }
+  gc_free(ctx, d_vals);
+  return st;
+}
+
+int gecut_integrate_laplacian(const gecut_selection* sel_c, double* K_cut, double* K_bg) {
+  if (!sel_c) return GECUT_ERR_INVALID;
+  gecut_selection* sel = const_cast<gecut_selection*>(sel_c);
+  gecut_ctx* ctx = sel->res->ctx;
+  if (sel->kind != GECUT_SEL_PHYSICAL && sel->kind != GECUT_SEL_CUTONLY) {
+    ctx->err = "laplacian integration needs a PHYSICAL or CUT selection";
+    return GECUT_ERR_INVALID;
+  }
+  DeviceGuard guard(ctx->device);
+  GC_CHECK(gc_integrate_laplacian(ctx, sel, K_bg));
+  const int nn = sel->res->grid.nv * sel->res->grid.nv;
+  GC_CHECK(copy_to_host(ctx, K_cut, sel->K_cut, sel->res->sizes.num_cutcells * nn));
+  GC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GECUT_OK;
+}
+
+int gecut_selection_device_laplacian(const gecut_selection* sel, double** K_cut_dev) {
+  if (!sel || !K_cut_dev) return GECUT_ERR_INVALID;
+  *K_cut_dev = sel->K_cut;
+  return GECUT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,441 @@
+// gecut_classify.cu -- K1+K2 fused: level-set evaluation at the background nodes and IN/OUT/CUT classification
+// of every background cell, plus the stable compaction of the cut-cell list.
+//
+// Reference path replaced:
+//   discretize(geo, grid)                 src/LevelSetCutters/DiscreteGeometries.jl:48-63   (L x Nn FP64 evaluations)
+//   _compute_in_out_or_cut per level set  src/LevelSetCutters/CutTriangulations.jl:619-640  (compute_case, LookupTables.jl:19-33)
+//   _find_cut_cells                       src/LevelSetCutters/CutTriangulations.jl:481-493  (ascending ids)
+//
+// B200 design: only the SIGN of a node value decides the classification (`isout(v) = v > 0`, LookupTables.jl:40-42),
+// so node values never go to HBM.  A warp evaluates 32 consecutive nodes of an x-row and `__ballot_sync` packs their
+// signs into one 32-bit word kept in shared memory; a block marches through the layers of the last direction keeping
+// two node planes of sign words, and one thread then classifies 32 cells at once with bit-parallel AND/OR over the
+// vertex words.  HBM traffic: L bytes per cell written (+ 8 L bytes per node read for NODAL leaves) + 1 bit per cell.
+#include "gecut_internal.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan of uint32 (3 phases, 2048 items per block)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// exclusive scan across the block of one value per thread; returns the exclusive prefix, *total = block sum
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t wsum[33];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nw = blockDim.x >> 5;
+  uint32_t inc = warp_incl_scan(v);
+  if (lane == 31) wsum[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t s = lane < nw ? wsum[lane] : 0;
+    uint32_t si = warp_incl_scan(s);
+    wsum[lane] = si - s;
+    if (lane == 31) wsum[32] = si;
+  }
+  __syncthreads();
+  uint32_t excl = wsum[wid] + inc - v;
+  *total = wsum[32];
+  __syncthreads();
+  return excl;
+}
+
+__global__ void k_scan_reduce(const uint32_t* __restrict__ in, int64_t n, uint64_t* __restrict__ blocksums) {
+  int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    int64_t idx = base + (int64_t)i * SCAN_THREADS + threadIdx.x;
+    if (idx < n) s += in[idx];
+  }
+  uint32_t tot;
+  block_excl_scan(s, &tot);
+  if (threadIdx.x == 0) blocksums[blockIdx.x] = tot;
+}
+
+// single block: exclusive scan of the block sums (uint64), grand total out
+__global__ void k_scan_blocksums(uint64_t* __restrict__ blocksums, int64_t nb, uint64_t* __restrict__ total) {
+  __shared__ uint64_t carry_s;
+  __shared__ uint64_t wsum[32];
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int64_t start = 0; start < nb; start += blockDim.x) {
+    int64_t idx = start + threadIdx.x;
+    uint64_t v = idx < nb ? blocksums[idx] : 0;
+    uint64_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      uint64_t s = lane < (blockDim.x >> 5) ? wsum[lane] : 0;
+      uint64_t si = s;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint64_t t = __shfl_up_sync(0xffffffffu, si, o);
+        if (lane >= o) si += t;
+      }
+      wsum[lane] = si - s;
+    }
+    __syncthreads();
+    uint64_t excl = carry_s + wsum[wid] + inc - v;
+    if (idx < nb) blocksums[idx] = excl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry_s;
+}
+
+__global__ void k_scan_apply(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t n,
+                             const uint64_t* __restrict__ blocksums) {
+  // blocked arrangement: thread t owns items [t*ITEMS, (t+1)*ITEMS) of the tile so that the order is preserved
+  int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS];
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    int64_t idx = base + i;
+    v[i] = idx < n ? in[idx] : 0;
+    s += v[i];
+  }
+  uint32_t tot;
+  uint32_t excl = block_excl_scan(s, &tot);
+  uint32_t run = (uint32_t)blocksums[blockIdx.x] + excl;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    int64_t idx = base + i;
+    if (idx < n) out[idx] = run;
+    run += v[i];
+  }
+}
+
+}  // namespace
+
+int gc_exclusive_scan_u32(gecut_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n, uint64_t* total_dev) {
+  if (n <= 0) {
+    GC_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(uint64_t), ctx->stream));
+    return GECUT_OK;
+  }
+  int64_t nb = gc_div_up(n, SCAN_TILE);
+  uint64_t* blocksums = nullptr;
+  GC_CHECK(gc_malloc(ctx, (void**)&blocksums, sizeof(uint64_t) * nb));
+  k_scan_reduce<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(in, n, blocksums);
+  k_scan_blocksums<<<1, 1024, 0, ctx->stream>>>(blocksums, nb, total_dev);
+  k_scan_apply<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, blocksums);
+  ctx->launches += 3;
+  int st = gc_launch_check(ctx, "scan");
+  gc_free(ctx, blocksums);
+  return st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused node evaluation + classification
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+template <int D>
+struct ClsCfg {
+  static constexpr int WX = (D == 3) ? 4 : 16;  // x words (32 cells each) per block tile
+  static constexpr int TY = (D == 3) ? 8 : 1;   // cell rows per tile (3-D only)
+  static constexpr int RY = (D == 3) ? TY + 1 : 1;  // node rows per plane
+  static constexpr int ZS = 32;                 // layers of the last direction marched by one block
+  static constexpr int THREADS = (D == 3) ? 256 : 128;
+};
+
+// words per x-row of the cut mask
+__host__ __device__ inline int gc_words_per_row(int nx) { return (nx + 31) / 32; }
+
+template <int D, bool SIMPLEX>
+__global__ void __launch_bounds__(ClsCfg<D>::THREADS)
+k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64_t pitch,
+           uint32_t* __restrict__ cutmask, const uint8_t* __restrict__ simplexify_raw) {
+  using C = ClsCfg<D>;
+  constexpr int WX = C::WX, TY = C::TY, RY = C::RY, ZS = C::ZS;
+  constexpr int NVC = 1 << D;                         // vertices of the n-cube
+  constexpr int CPC = SIMPLEX ? (D == 3 ? 6 : 2) : 1;  // bg cells per n-cube
+  constexpr int NW = C::THREADS / 32;
+  extern __shared__ uint32_t planes[];  // [2][L][RY][WX+1] sign words
+  __shared__ uint8_t s_tets[6][4];
+  const int L = lv.L;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nx = g.n[0];
+  const int ny = (D == 3) ? g.n[1] : 1;
+  const int wxtot = gc_words_per_row(nx);
+  const int w0 = blockIdx.x * WX;   // first x word of the tile
+  const int j0 = (D == 3) ? blockIdx.y * TY : 0;
+  const int kz0 = g.k0 + ((D == 3) ? blockIdx.z : blockIdx.y) * ZS;  // first layer (global index)
+  const int kz1 = min(kz0 + ZS, g.k1);
+  if (SIMPLEX && threadIdx.x < 24) s_tets[threadIdx.x / 4][threadIdx.x % 4] = simplexify_raw[(D - 2) * 24 + threadIdx.x];
+  const int plane_words = L * RY * (WX + 1);
+
+  for (int kp = kz0; kp <= kz1; ++kp) {  // node planes kz0..kz1
+    uint32_t* P = planes + ((kp - kz0) & 1) * plane_words;
+    // ---- evaluate the signs of node plane kp: one ballot per (row, word) task and level set
+    for (int task = wid; task < RY * (WX + 1); task += NW) {
+      const int r = task / (WX + 1), ww = task % (WX + 1);
+      const int i = 32 * (w0 + ww) + lane;
+      const int j = j0 + r;
+      const bool valid = (i < g.nn[0]) && (D == 2 || j < g.nn[1]);
+      double x[3];
+      x[0] = gc_coord(g, 0, i);
+      if (D == 3) {
+        x[1] = gc_coord(g, 1, j);
+        x[2] = gc_coord(g, 2, kp);
+      } else {
+        x[1] = gc_coord(g, 1, kp);
+        x[2] = 0.0;
+      }
+      const int64_t node = (D == 3) ? ((int64_t)i + (int64_t)g.nn[0] * ((int64_t)j + (int64_t)g.nn[1] * kp))
+                                    : ((int64_t)i + (int64_t)g.nn[0] * kp);
+      for (int ls = 0; ls < L; ++ls) {
+        double v = -1.0;
+        if (valid) {
+          if (lv.leaf[ls].kind == GECUT_LEAF_NODAL)
+            v = __ldg(lv.nodal[ls] + node);
+          else
+            v = gc_eval_leaf(lv.leaf[ls], x, D);
+        }
+        uint32_t word = __ballot_sync(0xffffffffu, valid && (v > 0.0));
+        if (lane == 0) P[(ls * RY + r) * (WX + 1) + ww] = word;
+      }
+    }
+    __syncthreads();
+    if (kp > kz0) {
+      // ---- classify layer kp-1 from planes (kp-1) [lo] and kp [hi]
+      const uint32_t* P0 = planes + ((kp - 1 - kz0) & 1) * plane_words;
+      const uint32_t* P1 = P;
+      const int kc = kp - 1;  // global layer index
+      for (int task = threadIdx.x; task < TY * WX * L; task += C::THREADS) {
+        const int ls = task / (TY * WX);
+        const int rem = task % (TY * WX);
+        const int r = rem / WX, ww = rem % WX;
+        const int jc = j0 + r;
+        const int i0 = 32 * (w0 + ww);
+        if (i0 >= nx || jc >= ny) continue;
+        // vertex words: V[lv] bit c = sign of local vertex lv of cell i0+c
+        uint32_t V[NVC];
+#pragma unroll
+        for (int v = 0; v < NVC; ++v) {
+          const int xo = v & 1;
+          const int ro = (D == 3) ? ((v >> 1) & 1) : 0;
+          const int po = (D == 3) ? ((v >> 2) & 1) : ((v >> 1) & 1);
+          const uint32_t* Pp = po ? P1 : P0;
+          const uint32_t* row = Pp + (ls * RY + r + ro) * (WX + 1);
+          uint32_t a = row[ww];
+          if (xo) a = (a >> 1) | (row[ww + 1] << 31);
+          V[v] = a;
+        }
+        const int ncell = min(32, nx - i0);
+        const uint32_t live = ncell == 32 ? 0xffffffffu : ((1u << ncell) - 1u);
+        const int64_t rowid = (D == 3) ? ((int64_t)(kc - g.k0) * ny + jc) : (int64_t)(kc - g.k0);
+        const int64_t cube0 = rowid * nx + i0;
+        int8_t* out = states + (int64_t)ls * pitch + cube0 * CPC;
+        uint32_t* cm = cutmask + (rowid * wxtot + (w0 + ww)) * CPC;
+#pragma unroll
+        for (int t = 0; t < CPC; ++t) {
+          uint32_t any, all;
+          if (SIMPLEX) {
+            any = 0u;
+            all = 0xffffffffu;
+#pragma unroll
+            for (int m = 0; m <= D; ++m) {
+              uint32_t a = V[s_tets[t][m]];
+              any |= a;
+              all &= a;
+            }
+          } else {
+            any = 0u;
+            all = 0xffffffffu;
+#pragma unroll
+            for (int v = 0; v < NVC; ++v) {
+              any |= V[v];
+              all &= V[v];
+            }
+          }
+          const uint32_t cutw = any & ~all & live;
+          // accumulate "cut by any level set"; tasks of different ls of the same word are different threads
+          if (L == 1)
+            cm[t] = cutw;
+          else if (cutw)
+            atomicOr(cm + t, cutw);
+          if (CPC == 1 && (nx & 3) == 0) {
+            // 4 states per 32-bit store: OUT(1) where all, IN(-1 = 0xFF) where !any, CUT(0) otherwise
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (4 * q < ncell) {
+                uint32_t o4 = (all >> (4 * q)) & 0xFu, n4 = (~any >> (4 * q)) & 0xFu;
+                uint32_t so = (o4 * 0x00204081u) & 0x01010101u;
+                uint32_t si = ((n4 * 0x00204081u) & 0x01010101u) * 0xFFu;
+                reinterpret_cast<uint32_t*>(out)[q] = so | si;
+              }
+            }
+          } else {
+            for (int c = 0; c < ncell; ++c) {
+              int8_t s = ((all >> c) & 1u) ? (int8_t)GC_OUT : (((any >> c) & 1u) ? (int8_t)GC_CUT : (int8_t)GC_IN);
+              out[(int64_t)c * CPC + t] = s;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- compaction of the cut mask -------------------------------------------------------------------
+template <int CPC>
+__global__ void k_cutmask_count(const uint32_t* __restrict__ cutmask, int64_t ngroups, uint32_t* __restrict__ counts) {
+  int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gidx >= ngroups) return;
+  uint32_t c = 0;
+#pragma unroll
+  for (int t = 0; t < CPC; ++t) c += __popc(cutmask[gidx * CPC + t]);
+  counts[gidx] = c;
+}
+
+template <int CPC>
+__global__ void k_cutmask_emit(const uint32_t* __restrict__ cutmask, int64_t ngroups, const uint32_t* __restrict__ offs,
+                               int nx, int wxtot, int32_t* __restrict__ cutcells) {
+  int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gidx >= ngroups) return;
+  uint32_t m[CPC];
+  uint32_t any = 0;
+#pragma unroll
+  for (int t = 0; t < CPC; ++t) {
+    m[t] = cutmask[gidx * CPC + t];
+    any |= m[t];
+  }
+  if (!any) return;
+  int64_t rowid = gidx / wxtot;
+  int w = (int)(gidx % wxtot);
+  int64_t cube0 = rowid * nx + 32 * (int64_t)w;
+  uint32_t o = offs[gidx];
+  while (any) {
+    int c = __ffs(any) - 1;
+    any &= any - 1;
+#pragma unroll
+    for (int t = 0; t < CPC; ++t)
+      if ((m[t] >> c) & 1u) cutcells[o++] = (int32_t)((cube0 + c) * CPC + t + 1);
+  }
+}
+
+template <int D>
+__global__ void k_eval_leaf_nodes(const GcGrid g, const gecut_leaf leaf, double* __restrict__ out) {
+  int64_t node = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)g.nn[0] * g.nn[1] * (D == 3 ? g.nn[2] : 1);
+  if (node >= total) return;
+  int i = (int)(node % g.nn[0]);
+  int j = (int)((node / g.nn[0]) % g.nn[1]);
+  int k = (D == 3) ? (int)(node / ((int64_t)g.nn[0] * g.nn[1])) : 0;
+  double x[3] = {gc_coord(g, 0, i), gc_coord(g, 1, j), D == 3 ? gc_coord(g, 2, k) : 0.0};
+  out[node] = gc_eval_leaf(leaf, x, D);
+}
+
+}  // namespace
+
+int gc_classify(gecut_ctx* ctx, gecut_result* res) {
+  const GcGrid& g = res->grid;
+  const int L = res->L;
+  const int nx = g.n[0];
+  const int wxtot = gc_words_per_row(nx);
+  const int nlayers = g.k1 - g.k0;
+  auto launch = [&](auto Dtag, auto Stag) {
+    constexpr int D = decltype(Dtag)::value;
+    constexpr bool S = decltype(Stag)::value;
+    using C = ClsCfg<D>;
+    dim3 grid;
+    grid.x = (unsigned)gc_div_up(wxtot, C::WX);
+    if (D == 3) {
+      grid.y = (unsigned)gc_div_up(g.n[1], C::TY);
+      grid.z = (unsigned)gc_div_up(nlayers, C::ZS);
+    } else {
+      grid.y = (unsigned)gc_div_up(nlayers, C::ZS);
+      grid.z = 1;
+    }
+    size_t smem = sizeof(uint32_t) * 2 * L * C::RY * (C::WX + 1);
+    k_classify<D, S><<<grid, C::THREADS, smem, ctx->stream>>>(g, res->leaves, res->lay.bg_state, res->lay.bg_pitch,
+                                                              res->cutmask, ctx->d_simplexify_raw);
+  };
+  if (g.D == 3) {
+    if (g.simplexified)
+      launch(std::integral_constant<int, 3>{}, std::true_type{});
+    else
+      launch(std::integral_constant<int, 3>{}, std::false_type{});
+  } else {
+    if (g.simplexified)
+      launch(std::integral_constant<int, 2>{}, std::true_type{});
+    else
+      launch(std::integral_constant<int, 2>{}, std::false_type{});
+  }
+  ctx->launches += 1;
+  return gc_launch_check(ctx, "k_classify");
+}
+
+int gc_compact_cutcells(gecut_ctx* ctx, gecut_result* res) {
+  const GcGrid& g = res->grid;
+  const int nx = g.n[0];
+  const int wxtot = gc_words_per_row(nx);
+  const int64_t rows = (g.D == 3) ? (int64_t)(g.k1 - g.k0) * g.n[1] : (int64_t)(g.k1 - g.k0);
+  const int64_t ngroups = rows * wxtot;
+  uint32_t* counts = nullptr;
+  uint64_t* total_dev = nullptr;
+  GC_CHECK(gc_malloc(ctx, (void**)&counts, sizeof(uint32_t) * ngroups));
+  GC_CHECK(gc_malloc(ctx, (void**)&total_dev, sizeof(uint64_t)));
+  const int T = 256;
+  const unsigned nb = (unsigned)gc_div_up(ngroups, T);
+  switch (g.cpc) {
+    case 1: k_cutmask_count<1><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts); break;
+    case 2: k_cutmask_count<2><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts); break;
+    default: k_cutmask_count<6><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts); break;
+  }
+  ctx->launches += 1;
+  GC_CHECK(gc_exclusive_scan_u32(ctx, counts, counts, ngroups, total_dev));
+  uint64_t* h = (uint64_t*)ctx->h_pinned;
+  GC_CUDA(cudaMemcpyAsync(h, total_dev, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  GC_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int64_t ncut = (int64_t)h[0];
+  res->sizes.num_cutcells = ncut;
+  if (ncut > 0) {
+    GC_CHECK(gc_malloc(ctx, (void**)&res->lay.cutcells, sizeof(int32_t) * ncut));
+    switch (g.cpc) {
+      case 1: k_cutmask_emit<1><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts, nx, wxtot, res->lay.cutcells); break;
+      case 2: k_cutmask_emit<2><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts, nx, wxtot, res->lay.cutcells); break;
+      default: k_cutmask_emit<6><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts, nx, wxtot, res->lay.cutcells); break;
+    }
+    ctx->launches += 1;
+  }
+  int st = gc_launch_check(ctx, "cutmask compaction");
+  gc_free(ctx, counts);
+  gc_free(ctx, total_dev);
+  return st;
+}
+
+int gc_eval_leaf_nodes(gecut_ctx* ctx, const GcGrid& g, const gecut_leaf& leaf, double* out_dev) {
+  int64_t total = (int64_t)g.nn[0] * g.nn[1] * (g.D == 3 ? g.nn[2] : 1);
+  const int T = 256;
+  unsigned nb = (unsigned)gc_div_up(total, T);
+  if (g.D == 3)
+    k_eval_leaf_nodes<3><<<nb, T, 0, ctx->stream>>>(g, leaf, out_dev);
+  else
+    k_eval_leaf_nodes<2><<<nb, T, 0, ctx->stream>>>(g, leaf, out_dev);
+  ctx->launches += 1;
+  return gc_launch_check(ctx, "k_eval_leaf_nodes");
+}

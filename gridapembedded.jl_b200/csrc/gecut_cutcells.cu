@@ -1,0 +1,479 @@
+// gecut_cutcells.cu -- K3: marching-simplex subtriangulation of the cut background cells.
+//
+// Reference path replaced (src/LevelSetCutters/CutTriangulations.jl):
+//   _simplexify_and_isolate_cells_in_cutgrid / _simplexify   :505-617   stage-0 mesh of the cut cells
+//   cut_sub_triangulation_with_boundary_several_levelsets    :309-343   for ls = L..1: count -> allocate -> fill
+//   _cut_cell! / set_point_data!                             :179-222, 123-135  connectivity, vertex copies, edge lerps
+//   _cut_cell_boundary! / _setup_normal                      :268-292, LookupTables.jl:304-347  facets + normals
+//   cut_sub_triangulation_several_levelsets (facet re-cuts)  :294-307, 405-441
+//   merge_sub_face_data                                      src/Interfaces/SubFacetTriangulations.jl:161-208
+//
+// B200 design: the reference re-emits the WHOLE sub-mesh once per level set (O(L * Nsub) traffic and 2L passes).
+// Every stage keeps the children of a cell contiguous and in order, so the final arrays are exactly the depth-first
+// traversal of each stage-0 simplex' refinement tree; the facets of level set ls are the depth-first traversal of the
+// facet re-cut trees hanging off depth L-ls.  One thread walks the tree of one stage-0 simplex twice: a counting walk
+// (reference: count_sub_triangulation_with_boundary :238-251), an exclusive scan of the counters over the simplices
+// (stable: preserves the reference ordering), and a filling walk that writes the final layout only.  Node values are
+// recomputed from the leaf records (bit-identical to the classification pass) or gathered from the NODAL vectors.
+#include "gecut_internal.cuh"
+
+namespace {
+
+template <int D, int LM>
+struct Pt {
+  double x[D];
+  double r[D];
+  double w[LM];
+};
+
+template <int D>
+struct WalkCfg {
+  static constexpr int NPC = (D == 3) ? 8 : 5;  // max points of a cut D-simplex (vertices + cut edges)
+  static constexpr int NPF = (D == 3) ? 5 : 3;  // max points of a cut (D-1)-simplex
+};
+
+template <int D>
+__device__ __forceinline__ void unit_normal(const double* p1, const double* p2, const double* p3, double orient, double* n) {
+  // _setup_normal / _normal_vector / _orthogonal_vector (LookupTables.jl:309-360), then orientation*normal (:287-288)
+  if (D == 2) {
+    double v1 = __dsub_rn(p2[0], p1[0]), v2 = __dsub_rn(p2[1], p1[1]);
+    double w1 = v2, w2 = -v1;
+    double m = __dsqrt_rn(__dadd_rn(__dmul_rn(w1, w1), __dmul_rn(w2, w2)));
+    if (m < 2.220446049250313e-16) {
+      n[0] = __dmul_rn(orient, 0.0);
+      n[1] = __dmul_rn(orient, 0.0);
+    } else {
+      n[0] = __dmul_rn(orient, __ddiv_rn(w1, m));
+      n[1] = __dmul_rn(orient, __ddiv_rn(w2, m));
+    }
+  } else {
+    double a0 = __dsub_rn(p2[0], p1[0]), a1 = __dsub_rn(p2[1], p1[1]), a2 = __dsub_rn(p2[2], p1[2]);
+    double b0 = __dsub_rn(p3[0], p1[0]), b1 = __dsub_rn(p3[1], p1[1]), b2 = __dsub_rn(p3[2], p1[2]);
+    double w1 = __dsub_rn(__dmul_rn(a1, b2), __dmul_rn(a2, b1));
+    double w2 = __dsub_rn(__dmul_rn(a2, b0), __dmul_rn(a0, b2));
+    double w3 = __dsub_rn(__dmul_rn(a0, b1), __dmul_rn(a1, b0));
+    double m = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(w1, w1), __dmul_rn(w2, w2)), __dmul_rn(w3, w3)));
+    if (m < 2.220446049250313e-16) {
+      n[0] = __dmul_rn(orient, 0.0);
+      n[1] = __dmul_rn(orient, 0.0);
+      n[2] = __dmul_rn(orient, 0.0);
+    } else {
+      n[0] = __dmul_rn(orient, __ddiv_rn(w1, m));
+      n[1] = __dmul_rn(orient, __ddiv_rn(w2, m));
+      n[2] = __dmul_rn(orient, __ddiv_rn(w3, m));
+    }
+  }
+}
+
+// new point on the edge (a,b) cut by level set `ls` (_cut_cell!, CutTriangulations.jl:206-218)
+template <int D, int LM>
+__device__ __forceinline__ void cut_point(const Pt<D, LM>& a, const Pt<D, LM>& b, int ls, int L, Pt<D, LM>& o) {
+  double w1 = fabs(a.w[ls]), w2 = fabs(b.w[ls]);
+  double coeff = __ddiv_rn(w1, __dadd_rn(w1, w2));
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    o.x[d] = gc_lerp(a.x[d], b.x[d], coeff);
+    o.r[d] = gc_lerp(a.r[d], b.r[d], coeff);
+  }
+  for (int k = 0; k < L; ++k) o.w[k] = gc_lerp(a.w[k], b.w[k], coeff);
+}
+
+// Stage-0 simplex `t` of the cut bg cell `cell0` (0-based, slab-local): points with coordinates, reference coordinates of
+// the bg polytope and all L level-set values; first two vertices swapped when det J < 0 in physical space
+// (_simplexify :562-617, _ensure_positive_jacobians! :532-533 -> LookupTables.jl:199-216).
+template <int D, int LM>
+__device__ __forceinline__ void setup_stage0(const GcGrid& g, const GcLeaves& lv, int64_t cell0, int t,
+                                             const uint8_t* simp_raw, const uint8_t* simp_pos, Pt<D, LM>* S) {
+  const int L = lv.L;
+  const int64_t cube = cell0 / g.cpc;
+  const int typ = (int)(cell0 % g.cpc);
+  int ijk[3];
+  ijk[0] = (int)(cube % g.n[0]);
+  if (D == 3) {
+    ijk[1] = (int)((cube / g.n[0]) % g.n[1]);
+    ijk[2] = (int)(cube / ((int64_t)g.n[0] * g.n[1])) + g.k0;
+  } else {
+    ijk[1] = (int)(cube / g.n[0]) + g.k0;
+    ijk[2] = 0;
+  }
+#pragma unroll
+  for (int m = 0; m <= D; ++m) {
+    int lvid;
+    if (g.simplexified) {
+      lvid = simp_raw[(D - 2) * 24 + typ * 4 + m];
+    } else {
+      lvid = simp_pos[(D - 2) * 24 + t * 4 + m];
+    }
+    int nijk[3] = {ijk[0] + (lvid & 1), ijk[1] + ((lvid >> 1) & 1), ijk[2] + ((lvid >> 2) & 1)};
+    double x[3] = {gc_coord(g, 0, nijk[0]), gc_coord(g, 1, nijk[1]), D == 3 ? gc_coord(g, 2, nijk[2]) : 0.0};
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      S[m].x[d] = x[d];
+      if (g.simplexified)
+        S[m].r[d] = (m == d + 1) ? 1.0 : 0.0;  // simplex vertices: origin then unit axes
+      else
+        S[m].r[d] = (double)((lvid >> d) & 1);  // n-cube vertices, x fastest
+    }
+    const int64_t node = (D == 3) ? ((int64_t)nijk[0] + (int64_t)g.nn[0] * ((int64_t)nijk[1] + (int64_t)g.nn[1] * nijk[2]))
+                                  : ((int64_t)nijk[0] + (int64_t)g.nn[0] * nijk[1]);
+    for (int ls = 0; ls < L; ++ls) {
+      if (lv.leaf[ls].kind == GECUT_LEAF_NODAL)
+        S[m].w[ls] = __ldg(lv.nodal[ls] + node);
+      else
+        S[m].w[ls] = gc_eval_leaf(lv.leaf[ls], x, D);
+    }
+  }
+  // J[a][b] = x_{a+1}[b] - x_0[b]; flip iff det(J) < 0
+  double J[3][3];
+#pragma unroll
+  for (int a = 0; a < D; ++a)
+#pragma unroll
+    for (int b = 0; b < D; ++b) J[a][b] = __dsub_rn(S[a + 1].x[b], S[0].x[b]);
+  double dV;
+  if (D == 2) {
+    dV = __dsub_rn(__dmul_rn(J[0][0], J[1][1]), __dmul_rn(J[0][1], J[1][0]));
+  } else {
+    double p1 = __dmul_rn(__dmul_rn(J[0][0], J[1][1]), J[2][2]);
+    double p2 = __dmul_rn(__dmul_rn(J[0][1], J[1][2]), J[2][0]);
+    double p3 = __dmul_rn(__dmul_rn(J[0][2], J[1][0]), J[2][1]);
+    double q1 = __dmul_rn(__dmul_rn(J[0][0], J[1][2]), J[2][1]);
+    double q2 = __dmul_rn(__dmul_rn(J[0][1], J[1][0]), J[2][2]);
+    double q3 = __dmul_rn(__dmul_rn(J[0][2], J[1][1]), J[2][0]);
+    dV = __dsub_rn(__dadd_rn(__dadd_rn(p1, p2), p3), __dadd_rn(__dadd_rn(q1, q2), q3));
+  }
+  if (dV < 0.0) {
+    Pt<D, LM> tmp = S[0];
+    S[0] = S[1];
+    S[1] = tmp;
+  }
+}
+
+template <int D, int LM, bool FILL>
+__global__ void __launch_bounds__(64)
+k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
+           const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
+           const int32_t* __restrict__ cutcells, int64_t nsimp, GcCounters cn, GcLayout lay) {
+  constexpr int NPC = WalkCfg<D>::NPC, NPF = WalkCfg<D>::NPF;
+  __shared__ GcSimplexTable s_tab[2];  // [0]: D-simplex (cells), [1]: (D-1)-simplex (facet re-cuts)
+  {
+    const uint32_t* src0 = reinterpret_cast<const uint32_t*>(tables + (D - 1));
+    const uint32_t* src1 = reinterpret_cast<const uint32_t*>(tables + (D - 2));
+    uint32_t* dst0 = reinterpret_cast<uint32_t*>(&s_tab[0]);
+    uint32_t* dst1 = reinterpret_cast<uint32_t*>(&s_tab[1]);
+    for (int i = threadIdx.x; i < (int)(sizeof(GcSimplexTable) / 4); i += blockDim.x) {
+      dst0[i] = src0[i];
+      dst1[i] = src1[i];
+    }
+  }
+  __syncthreads();
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nsimp) return;
+  const GcSimplexTable& TC = s_tab[0];
+  const GcSimplexTable& TF = s_tab[1];
+  const int L = lv.L;
+  const int64_t kcut = s / g.nt0;
+  const int t = (int)(s % g.nt0);
+  const int32_t bgcell1 = cutcells[kcut];
+
+  // running output positions (FILL) / counters (!FILL)
+  uint32_t cell_off = 0, pt_off = 0;
+  uint32_t fac_off[LM], fpt_off[LM];
+#pragma unroll
+  for (int k = 0; k < LM; ++k) {
+    fac_off[k] = 0;
+    fpt_off[k] = 0;
+  }
+  if (FILL) {
+    cell_off = cn.cells[s];
+    pt_off = cn.points[s];
+    for (int k = 0; k < L; ++k) {
+      fac_off[k] = cn.fac_base[k] + cn.fac[k][s];
+      if (L > 1) fpt_off[k] = cn.fpt_base[k] + cn.fpt[k][s];
+    }
+  }
+
+  Pt<D, LM> E[LM][NPC];
+  Pt<D, LM> FE[(LM > 1) ? LM - 1 : 1][NPF];
+  int8_t child[LM], cs[LM], npE[LM], st[LM];
+  int8_t fchild[LM], fcs[LM], fnp[LM], fst[LM];
+
+  setup_stage0<D, LM>(g, lv, bgcell1 - 1, t, simp_raw, simp_pos, E[0]);
+
+  int depth = 0;
+  child[0] = -1;
+  while (depth >= 0) {
+    const int ls = L - 1 - depth;
+    if (child[depth] < 0) {
+      // ---- enter: case, cut points (CutTriangulations.jl:179-222)
+      int c = 0;
+#pragma unroll
+      for (int i = 0; i <= D; ++i)
+        if (E[depth][i].w[ls] > 0.0) c |= 1 << i;
+      cs[depth] = (int8_t)c;
+      int np = D + 1;
+      if (TC.inoutcut[c] == GC_CUT) {
+        for (int e = 0; e < TC.nedges; ++e) {
+          const int a = TC.edges[e][0], b = TC.edges[e][1];
+          if ((E[depth][a].w[ls] > 0.0) != (E[depth][b].w[ls] > 0.0)) {
+            cut_point<D, LM>(E[depth][a], E[depth][b], ls, L, E[depth][np]);
+            np++;
+          }
+        }
+      }
+      npE[depth] = (int8_t)np;
+      const int nfac = TC.nfac[c];
+      // ---- boundary facets of this stage (CutTriangulations.jl:268-292)
+      if (L == 1) {
+        if (FILL) {
+          for (int f = 0; f < nfac; ++f) {
+            const uint32_t fid = fac_off[0] + f;
+            const uint8_t* fp = TC.fac_pts[c][f];
+            double nrm[3];
+            unit_normal<D>(E[depth][fp[0]].x, E[depth][fp[1]].x, E[depth][fp[D - 1]].x, (double)TC.fac_orient[c][f], nrm);
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+              lay.sf_c2p[(int64_t)fid * D + i] = (int32_t)(pt_off + fp[i] + 1);
+              lay.sf_N[(int64_t)fid * D + i] = nrm[i];
+            }
+            lay.sf_c2bg[fid] = bgcell1;
+            lay.sf_state[fid] = (int8_t)GECUT_INTERFACE;
+          }
+        }
+        fac_off[0] += nfac;
+      } else {
+        for (int f = 0; f < nfac; ++f) {
+          const uint8_t* fp = TC.fac_pts[c][f];
+          double nrm[3];
+          unit_normal<D>(E[depth][fp[0]].x, E[depth][fp[1]].x, E[depth][fp[D - 1]].x, (double)TC.fac_orient[c][f], nrm);
+#pragma unroll
+          for (int i = 0; i < D; ++i) FE[0][i] = E[depth][fp[i]];
+          // ---- re-cut the facet by every other level set, last to first (CutTriangulations.jl:294-307,324-327)
+          int fdepth = 0;
+          fchild[0] = -1;
+          while (fdepth >= 0) {
+            // k-th other level set, taken from the last: indices L-1, L-2, ... skipping ls
+            int k = L - 1 - fdepth;
+            if (k <= ls) k -= 1;
+            if (fchild[fdepth] < 0) {
+              int fc = 0;
+#pragma unroll
+              for (int i = 0; i < D; ++i)
+                if (FE[fdepth][i].w[k] > 0.0) fc |= 1 << i;
+              fcs[fdepth] = (int8_t)fc;
+              int fn = D;
+              if (TF.inoutcut[fc] == GC_CUT) {
+                for (int e = 0; e < TF.nedges; ++e) {
+                  const int a = TF.edges[e][0], b = TF.edges[e][1];
+                  if ((FE[fdepth][a].w[k] > 0.0) != (FE[fdepth][b].w[k] > 0.0)) {
+                    cut_point<D, LM>(FE[fdepth][a], FE[fdepth][b], k, L, FE[fdepth][fn]);
+                    fn++;
+                  }
+                }
+              }
+              fnp[fdepth] = (int8_t)fn;
+              if (fdepth == L - 2) {
+                // final facets of level set ls: point block + children
+                const int nsf = TF.nsub[fc];
+                if (FILL) {
+                  const uint32_t pb = fpt_off[ls];
+                  for (int p = 0; p < fn; ++p)
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                      lay.sf_X[(int64_t)(pb + p) * D + d] = FE[fdepth][p].x[d];
+                      lay.sf_R[(int64_t)(pb + p) * D + d] = FE[fdepth][p].r[d];
+                    }
+                  for (int j = 0; j < nsf; ++j) {
+                    const uint32_t fid = fac_off[ls] + j;
+#pragma unroll
+                    for (int i = 0; i < D; ++i) {
+                      lay.sf_c2p[(int64_t)fid * D + i] = (int32_t)(pb + TF.sub_pts[fc][j][i] + 1);
+                      lay.sf_N[(int64_t)fid * D + i] = nrm[i];
+                    }
+                    lay.sf_c2bg[fid] = bgcell1;
+                    for (int kk = 0; kk < L; ++kk) {
+                      int8_t v = (kk == ls) ? (int8_t)GECUT_INTERFACE : ((kk == k) ? TF.sub_inout[fc][j] : fst[kk]);
+                      lay.sf_state[(int64_t)kk * lay.sf_pitch + fid] = v;
+                    }
+                  }
+                }
+                fac_off[ls] += nsf;
+                fpt_off[ls] += fn;
+                fdepth--;
+                continue;
+              }
+              fchild[fdepth] = 0;
+            }
+            const int fc = fcs[fdepth];
+            if (fchild[fdepth] < TF.nsub[fc]) {
+              const int j = fchild[fdepth]++;
+              fst[k] = TF.sub_inout[fc][j];
+#pragma unroll
+              for (int i = 0; i < D; ++i) FE[fdepth + 1][i] = FE[fdepth][TF.sub_pts[fc][j][i]];
+              fchild[fdepth + 1] = -1;
+              fdepth++;
+            } else {
+              fdepth--;
+            }
+          }
+        }
+      }
+      if (ls == 0) {
+        // ---- final subcells of this branch: point block + children (CutTriangulations.jl:186-203)
+        const int nsub = TC.nsub[c];
+        if (FILL) {
+          for (int p = 0; p < np; ++p)
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+              lay.sc_X[(int64_t)(pt_off + p) * D + d] = E[depth][p].x[d];
+              lay.sc_R[(int64_t)(pt_off + p) * D + d] = E[depth][p].r[d];
+              if (L == 1) {  // the facets of a single level set share the subcell points (CutTriangulations.jl:365-378)
+                lay.sf_X[(int64_t)(pt_off + p) * D + d] = E[depth][p].x[d];
+                lay.sf_R[(int64_t)(pt_off + p) * D + d] = E[depth][p].r[d];
+              }
+            }
+          for (int j = 0; j < nsub; ++j) {
+            const uint32_t cid = cell_off + j;
+#pragma unroll
+            for (int i = 0; i <= D; ++i) lay.sc_c2p[(int64_t)cid * (D + 1) + i] = (int32_t)(pt_off + TC.sub_pts[c][j][i] + 1);
+            lay.sc_c2bg[cid] = bgcell1;
+            lay.sc_state[cid] = TC.sub_inout[c][j];
+            for (int kk = 1; kk < L; ++kk) lay.sc_state[(int64_t)kk * lay.sc_pitch + cid] = st[kk];
+          }
+        }
+        cell_off += nsub;
+        pt_off += np;
+        depth--;
+        continue;
+      }
+      child[depth] = 0;
+    }
+    const int c = cs[depth];
+    if (child[depth] < TC.nsub[c]) {
+      const int j = child[depth]++;
+      st[ls] = TC.sub_inout[c][j];
+#pragma unroll
+      for (int i = 0; i <= D; ++i) E[depth + 1][i] = E[depth][TC.sub_pts[c][j][i]];
+      child[depth + 1] = -1;
+      depth++;
+    } else {
+      depth--;
+    }
+  }
+
+  if (!FILL) {
+    cn.cells[s] = cell_off;
+    cn.points[s] = pt_off;
+    for (int k = 0; k < L; ++k) {
+      cn.fac[k][s] = fac_off[k];
+      if (L > 1) cn.fpt[k][s] = fpt_off[k];
+    }
+  }
+}
+
+template <int D, int LM>
+void launch_walk(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcCounters& cn, bool fill) {
+  const int T = 64;
+  const unsigned nb = (unsigned)gc_div_up(nsimp, T);
+  if (fill)
+    k_cut_walk<D, LM, true><<<nb, T, 0, ctx->stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
+                                                       ctx->d_simplexify_pos, res->lay.cutcells, nsimp, cn, res->lay);
+  else
+    k_cut_walk<D, LM, false><<<nb, T, 0, ctx->stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
+                                                        ctx->d_simplexify_pos, res->lay.cutcells, nsimp, cn, res->lay);
+  ctx->launches += 1;
+}
+
+void dispatch_walk(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcCounters& cn, bool fill) {
+  const int L = res->L;
+  const int D = res->grid.D;
+#define GC_WALK(DD, LL) launch_walk<DD, LL>(ctx, res, nsimp, cn, fill)
+  if (D == 2) {
+    if (L <= 1) GC_WALK(2, 1);
+    else if (L <= 2) GC_WALK(2, 2);
+    else if (L <= 4) GC_WALK(2, 4);
+    else if (L <= 8) GC_WALK(2, 8);
+    else GC_WALK(2, 16);
+  } else {
+    if (L <= 1) GC_WALK(3, 1);
+    else if (L <= 2) GC_WALK(3, 2);
+    else if (L <= 4) GC_WALK(3, 4);
+    else if (L <= 8) GC_WALK(3, 8);
+    else GC_WALK(3, 16);
+  }
+#undef GC_WALK
+}
+
+}  // namespace
+
+static inline int64_t pad_pitch(int64_t n) { return ((n + 255) / 256) * 256; }
+
+int gc_cut_cells(gecut_ctx* ctx, gecut_result* res) {
+  const GcGrid& g = res->grid;
+  const int L = res->L, D = g.D;
+  const int64_t ncut = res->sizes.num_cutcells;
+  const int64_t nsimp = ncut * g.nt0;
+  gecut_sizes& sz = res->sizes;
+  sz.num_subcells = sz.num_subcell_points = sz.num_subfacets = sz.num_subfacet_points = 0;
+  if (nsimp == 0) return GECUT_OK;
+  // counters: cells, points, fac[L], fpt[L] (fpt unused for L == 1)
+  const int narr = 2 + L + (L > 1 ? L : 0);
+  uint32_t* pool = nullptr;
+  uint64_t* totals_dev = nullptr;
+  GC_CHECK(gc_malloc(ctx, (void**)&pool, sizeof(uint32_t) * nsimp * narr));
+  GC_CHECK(gc_malloc(ctx, (void**)&totals_dev, sizeof(uint64_t) * narr));
+  GcCounters cn{};
+  cn.cells = pool;
+  cn.points = pool + nsimp;
+  for (int k = 0; k < L; ++k) {
+    cn.fac[k] = pool + (2 + k) * nsimp;
+    cn.fpt[k] = (L > 1) ? pool + (2 + L + k) * nsimp : nullptr;
+  }
+  dispatch_walk(ctx, res, nsimp, cn, false);
+  GC_CHECK(gc_launch_check(ctx, "k_cut_walk(count)"));
+  for (int a = 0; a < narr; ++a) GC_CHECK(gc_exclusive_scan_u32(ctx, pool + a * nsimp, pool + a * nsimp, nsimp, totals_dev + a));
+  uint64_t* h = (uint64_t*)ctx->h_pinned;
+  GC_CUDA(cudaMemcpyAsync(h, totals_dev, sizeof(uint64_t) * narr, cudaMemcpyDeviceToHost, ctx->stream));
+  GC_CUDA(cudaStreamSynchronize(ctx->stream));
+  uint64_t nsc = h[0], nscp = h[1], nsf = 0, nsfp = 0;
+  for (int k = 0; k < L; ++k) {
+    cn.fac_base[k] = (uint32_t)nsf;
+    cn.fpt_base[k] = (uint32_t)nsfp;
+    nsf += h[2 + k];
+    if (L > 1) nsfp += h[2 + L + k];
+  }
+  if (L == 1) nsfp = nscp;
+  const uint64_t lim = 2147483647ull;
+  if (nsc * (uint64_t)(D + 1) >= lim || nscp > lim || nsf > lim || nsfp > lim || nsc > lim) {
+    ctx->err = "Int32 ids of the SubCellData/SubFacetData layout would overflow";
+    gc_free(ctx, pool);
+    gc_free(ctx, totals_dev);
+    return GECUT_ERR_OVERFLOW;
+  }
+  sz.num_subcells = (int64_t)nsc;
+  sz.num_subcell_points = (int64_t)nscp;
+  sz.num_subfacets = (int64_t)nsf;
+  sz.num_subfacet_points = (int64_t)nsfp;
+  GcLayout& lay = res->lay;
+  lay.sc_pitch = pad_pitch((int64_t)nsc);
+  lay.sf_pitch = pad_pitch((int64_t)nsf);
+  GC_CHECK(gc_malloc(ctx, (void**)&lay.sc_c2p, sizeof(int32_t) * nsc * (D + 1)));
+  GC_CHECK(gc_malloc(ctx, (void**)&lay.sc_c2bg, sizeof(int32_t) * nsc));
+  GC_CHECK(gc_malloc(ctx, (void**)&lay.sc_X, sizeof(double) * nscp * D));
+  GC_CHECK(gc_malloc(ctx, (void**)&lay.sc_R, sizeof(double) * nscp * D));
+  GC_CHECK(gc_malloc(ctx, (void**)&lay.sc_state, (size_t)lay.sc_pitch * L));
+  if (nsf > 0) {
+    GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_c2p, sizeof(int32_t) * nsf * D));
+    GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_c2bg, sizeof(int32_t) * nsf));
+    GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_N, sizeof(double) * nsf * D));
+    GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_state, (size_t)lay.sf_pitch * L));
+  }
+  if (nsfp > 0) {
+    GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_X, sizeof(double) * nsfp * D));
+    GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_R, sizeof(double) * nsfp * D));
+  }
+  dispatch_walk(ctx, res, nsimp, cn, true);
+  int st = gc_launch_check(ctx, "k_cut_walk(fill)");
+  gc_free(ctx, pool);
+  gc_free(ctx, totals_dev);
+  return st;
+}

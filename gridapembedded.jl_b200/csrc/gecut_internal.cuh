@@ -1,0 +1,298 @@
+// gecut_internal.cuh -- shared declarations of the B200 cutting library (not part of the ABI).
+//
+// Data layout in HBM (all arrays device resident):
+//   ls_to_bgcell_to_inoutcut  L rows of Nc Int8, row pitch padded to 256 B
+//   cutmask                   1 bit per bg cell ("CUT by any level set"), grouped as [row][x-word][cell type]
+//   cutcell_to_cell           Ncut Int32 (1-based, ascending)
+//   SubCellData / SubFacetData arrays exactly as the reference structs (Int32 1-based ids, Float64 AoS points)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "gecut.h"
+#include "gecut_tables.h"
+
+#define GC_LMAX GECUT_MAX_LEVELSETS
+#define GC_IN (-1)
+#define GC_OUT 1
+#define GC_CUT 0
+
+// ------------------------------------------------------------------------------------------------
+// Grid descriptor handed to kernels (by value).
+// ------------------------------------------------------------------------------------------------
+struct GcGrid {
+  int D;
+  int simplexified;
+  double pmin[3], dx[3];
+  int n[3];    // n-cubes per direction (whole model)
+  int nn[3];   // nodes per direction (whole model)
+  int k0, k1;  // slab: n-cube layers [k0,k1) of the last direction
+  int nv;      // vertices per bg cell
+  int nt;      // simplices per n-cube (2 / 6)
+  int cpc;     // bg cells per n-cube (1, or nt when simplexified)
+  int nt0;     // stage-0 simplices per bg cell (nt for n-cubes, 1 for simplices)
+  int64_t layer_cubes;  // n-cubes per layer of the last direction
+  int64_t layer_nodes;  // nodes per plane of the last direction
+  int64_t num_cubes, num_cells, num_nodes;  // of the slab
+};
+
+struct GcLeaves {
+  int L;
+  gecut_leaf leaf[GC_LMAX];
+  const double* nodal[GC_LMAX];  // device pointers (whole-model node numbering) for NODAL leaves
+};
+
+struct GcProgram {
+  int len;
+  int8_t tok[GECUT_MAX_PROGRAM];
+};
+
+// Device pointers of the result layout.
+struct GcLayout {
+  int8_t* bg_state;
+  int64_t bg_pitch;
+  int32_t* cutcells;
+  int32_t* sc_c2p;
+  int32_t* sc_c2bg;
+  double* sc_X;
+  double* sc_R;
+  int8_t* sc_state;
+  int64_t sc_pitch;
+  int32_t* sf_c2p;
+  int32_t* sf_c2bg;
+  double* sf_N;
+  double* sf_X;
+  double* sf_R;
+  int8_t* sf_state;
+  int64_t sf_pitch;
+};
+
+// Per stage-0-simplex counters (pass 1) / exclusive offsets (pass 2).
+struct GcCounters {
+  uint32_t* cells;
+  uint32_t* points;
+  uint32_t* fac[GC_LMAX];
+  uint32_t* fpt[GC_LMAX];
+  uint32_t fac_base[GC_LMAX];  // global offset of the facets of level set ls (merge_sub_face_data order)
+  uint32_t fpt_base[GC_LMAX];
+};
+
+// ------------------------------------------------------------------------------------------------
+// Context / result / selection objects behind the opaque ABI handles.
+// ------------------------------------------------------------------------------------------------
+struct gecut_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  GcSimplexTable* d_tables = nullptr;  // [3] on the device
+  uint8_t* d_simplexify_raw = nullptr;  // [2][6][4]
+  uint8_t* d_simplexify_pos = nullptr;  // [2][6][4]
+  void* h_pinned = nullptr;             // small pinned staging buffer for scalar read-backs
+  size_t h_pinned_bytes = 0;
+};
+
+struct gecut_result {
+  gecut_ctx* ctx = nullptr;
+  GcGrid grid{};
+  int L = 0;
+  GcLeaves leaves{};
+  gecut_sizes sizes{};
+  GcLayout lay{};
+  uint32_t* cutmask = nullptr;
+  bool owns_nodal[GC_LMAX] = {false};
+  double* nodal_dev[GC_LMAX] = {nullptr};
+};
+
+struct gecut_selection {
+  const gecut_result* res = nullptr;
+  int kind = 0;
+  int side = 0;
+  GcProgram prog{};
+  GcProgram prog2{};
+  bool has_prog2 = false;
+  int64_t n_sub = 0;  // selected subcells / subfacets
+  int64_t n_bg = 0;   // selected bg cells
+  int32_t* sub_ids = nullptr;
+  int8_t* orientation = nullptr;
+  int32_t* bg_ids = nullptr;  // materialised lazily
+  int64_t bg_type_count[8] = {0};
+  double* K_cut = nullptr;  // Ncut x nv x nv of the last laplacian integration
+};
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+#define GC_CUDA(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t _e = (call);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e);                           \
+      return (_e == cudaErrorMemoryAllocation) ? GECUT_ERR_OOM : GECUT_ERR_CUDA;               \
+    }                                                                                          \
+  } while (0)
+
+#define GC_CHECK(st)          \
+  do {                        \
+    int _s = (st);            \
+    if (_s != GECUT_OK) return _s; \
+  } while (0)
+
+static inline int64_t gc_div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+int gc_malloc(gecut_ctx* ctx, void** p, size_t bytes);
+void gc_free(gecut_ctx* ctx, void* p);
+int gc_launch_check(gecut_ctx* ctx, const char* what);
+
+// ---- scan (gecut_classify.cu) ----
+// exclusive prefix sum of n uint32 (in place allowed); *total_dev (uint64, device) receives the grand total
+int gc_exclusive_scan_u32(gecut_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n, uint64_t* total_dev);
+
+// ---- classification (gecut_classify.cu) ----
+int gc_classify(gecut_ctx* ctx, gecut_result* res);        // states + cutmask
+int gc_compact_cutcells(gecut_ctx* ctx, gecut_result* res);  // cutmask -> cutcell_to_cell, sizes.num_cutcells
+int gc_eval_leaf_nodes(gecut_ctx* ctx, const GcGrid& g, const gecut_leaf& leaf, double* out_dev);
+
+// ---- subtriangulation (gecut_cutcells.cu) ----
+int gc_cut_cells(gecut_ctx* ctx, gecut_result* res);
+
+// ---- selectors (gecut_select.cu) ----
+int gc_eval_rows(gecut_ctx* ctx, const int8_t* rows, int64_t pitch, int64_t n, const GcProgram& prog, int8_t* out_dev);
+int gc_select_cells(gecut_ctx* ctx, gecut_selection* sel);
+int gc_select_boundary(gecut_ctx* ctx, gecut_selection* sel);
+int gc_materialize_bg_ids(gecut_ctx* ctx, gecut_selection* sel);
+int gc_selection_gather(gecut_ctx* ctx, const gecut_selection* sel, int32_t* to_points_dev, int32_t* to_bgcell_dev,
+                        double* normals_dev);
+
+// ---- integration (gecut_integrate.cu) ----
+int gc_integrate_measure(gecut_ctx* ctx, const gecut_selection* sel, double* values_dev, double* total_host);
+int gc_integrate_laplacian(gecut_ctx* ctx, gecut_selection* sel, double* K_bg_host);
+
+// ------------------------------------------------------------------------------------------------
+// device helpers shared by the kernels
+// ------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// Leaf formulas (AnalyticalGeometries.jl:75-78,146-198) with explicit round-to-nearest intrinsics: Julia never
+// contracts a*b+c into an FMA, so neither may we (IN/OUT of nodes lying on a surface flips on one ulp).
+__device__ __forceinline__ double gc_dot3(const double* a, const double* b, int D) {
+  double s = __dmul_rn(a[0], b[0]);
+  s = __dadd_rn(s, __dmul_rn(a[1], b[1]));
+  if (D == 3) s = __dadd_rn(s, __dmul_rn(a[2], b[2]));
+  return s;
+}
+
+__device__ __forceinline__ double gc_eval_leaf(const gecut_leaf& lf, const double* x, int D) {
+  double w[3];
+  w[0] = __dsub_rn(x[0], lf.x0[0]);
+  w[1] = __dsub_rn(x[1], lf.x0[1]);
+  w[2] = (D == 3) ? __dsub_rn(x[2], lf.x0[2]) : 0.0;
+  switch (lf.kind) {
+    case GECUT_LEAF_SPHERE:
+      return __dsub_rn(gc_dot3(w, w, D), __dmul_rn(lf.R, lf.R));
+    case GECUT_LEAF_CYLINDER: {
+      double A = gc_dot3(w, lf.v, D);
+      double H2 = gc_dot3(w, w, D);
+      double B = __dsub_rn(H2, __dmul_rn(A, A));
+      return __dsub_rn(B, __dmul_rn(lf.R, lf.R));
+    }
+    case GECUT_LEAF_PLANE:
+      return gc_dot3(w, lf.v, D);
+    case GECUT_LEAF_DOUGHNUT: {
+      double t = __dsub_rn(lf.R, __dsqrt_rn(__dadd_rn(__dmul_rn(w[0], w[0]), __dmul_rn(w[1], w[1]))));
+      return __dsub_rn(__dadd_rn(__dmul_rn(t, t), __dmul_rn(w[2], w[2])), __dmul_rn(lf.r, lf.r));
+    }
+    default:
+      return 0.0;
+  }
+}
+
+// CartesianCoordinates getindex: x0[d] + (I[d]-1)*dx[d] (Gridap, assumption A4)
+__device__ __forceinline__ double gc_coord(const GcGrid& g, int d, int i) {
+  return __dadd_rn(g.pmin[d], __dmul_rn((double)i, g.dx[d]));
+}
+
+// a + c*(b-a)  (set_point_data!, CutTriangulations.jl:123-135)
+__device__ __forceinline__ double gc_lerp(double a, double b, double c) {
+  return __dadd_rn(a, __dmul_rn(c, __dsub_rn(b, a)));
+}
+
+// 3-valued boolean tables (EmbeddedDiscretizations.jl:136-177)
+__device__ __forceinline__ int gc_io_union(int a, int b) {
+  if (a == GC_OUT && b == GC_OUT) return GC_OUT;
+  if ((a == GC_CUT && b == GC_CUT) || (a == GC_CUT && b == GC_OUT) || (a == GC_OUT && b == GC_CUT)) return GC_CUT;
+  return GC_IN;
+}
+__device__ __forceinline__ int gc_io_intersection(int a, int b) {
+  if (a == GC_IN && b == GC_IN) return GC_IN;
+  if ((a == GC_CUT && b == GC_CUT) || (a == GC_CUT && b == GC_IN) || (a == GC_IN && b == GC_CUT)) return GC_CUT;
+  return GC_OUT;
+}
+__device__ __forceinline__ int gc_io_setdiff(int a, int b) {
+  if (a == GC_IN && b == GC_OUT) return GC_IN;
+  if ((a == GC_CUT && b == GC_CUT) || (a == GC_CUT && b == GC_OUT) || (a == GC_IN && b == GC_CUT)) return GC_CUT;
+  return GC_OUT;
+}
+__device__ __forceinline__ int gc_io_complementary(int a) {
+  if (a == GC_OUT) return GC_IN;
+  if (a == GC_IN) return GC_OUT;
+  return GC_CUT;
+}
+
+// compute_inoutcut(tree) (EmbeddedDiscretizations.jl:107-134) on element e of `rows`
+__device__ __forceinline__ int gc_eval_inoutcut(const GcProgram& p, const int8_t* rows, int64_t pitch, int64_t e) {
+  int8_t st[GECUT_MAX_PROGRAM / 2 + 2];
+  int sp = 0;
+  for (int t = 0; t < p.len; ++t) {
+    int tok = p.tok[t];
+    if (tok >= 0) {
+      st[sp++] = rows[(int64_t)tok * pitch + e];
+    } else if (tok == GECUT_OP_COMPLEMENT) {
+      st[sp - 1] = (int8_t)gc_io_complementary(st[sp - 1]);
+    } else {
+      int b = st[--sp], a = st[--sp];
+      st[sp++] = (int8_t)(tok == GECUT_OP_UNION ? gc_io_union(a, b)
+                                                : (tok == GECUT_OP_INTERSECT ? gc_io_intersection(a, b) : gc_io_setdiff(a, b)));
+    }
+  }
+  return st[0];
+}
+
+// compute_inoutboundary(tree) (EmbeddedDiscretizations.jl:179-245): state and orientation
+__device__ __forceinline__ void gc_eval_inoutboundary(const GcProgram& p, const int8_t* rows, int64_t pitch, int64_t e,
+                                                      int* state, int* orientation) {
+  int8_t st[GECUT_MAX_PROGRAM / 2 + 2], orr[GECUT_MAX_PROGRAM / 2 + 2];
+  int sp = 0;
+  for (int t = 0; t < p.len; ++t) {
+    int tok = p.tok[t];
+    if (tok >= 0) {
+      st[sp] = rows[(int64_t)tok * pitch + e];
+      orr[sp] = 1;
+      sp++;
+    } else if (tok == GECUT_OP_COMPLEMENT) {
+      if (st[sp - 1] == GECUT_INTERFACE) orr[sp - 1] = (int8_t)-orr[sp - 1];
+      st[sp - 1] = (int8_t)gc_io_complementary(st[sp - 1]);
+    } else {
+      int b = st[sp - 1], a = st[sp - 2];
+      int d2 = orr[sp - 1], d1 = orr[sp - 2];
+      sp -= 2;
+      int rs, ro;
+      if (tok == GECUT_OP_SETDIFF) {
+        rs = gc_io_setdiff(a, b);
+        ro = (a == GECUT_INTERFACE) ? d1 : ((b == GECUT_INTERFACE) ? -d2 : d1);
+      } else {
+        rs = tok == GECUT_OP_UNION ? gc_io_union(a, b) : gc_io_intersection(a, b);
+        ro = (a == GECUT_INTERFACE) ? d1 : ((b == GECUT_INTERFACE) ? d2 : d1);
+      }
+      st[sp] = (int8_t)rs;
+      orr[sp] = (int8_t)ro;
+      sp++;
+    }
+  }
+  *state = st[0];
+  *orientation = orr[0];
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,235 @@
+// gecut_select.cu -- selectors: boolean programs over the IN/OUT/CUT rows, masks and stable compaction.
+//
+// Reference path replaced (src/Interfaces/EmbeddedDiscretizations.jl):
+//   compute_bgcell_to_inoutcut / compute_inoutcut + truth tables   :91-177
+//   compute_subcell_to_inout                                       :325-339
+//   Triangulation(cut, CutInOrOut / Integer / ActiveInOrOut, geo)  :297-323   (mask + findall)
+//   compute_inoutboundary + orientation rules, EmbeddedBoundary    :179-245, 408-463
+//   SubCellData(st,ids) / SubFacetData(st,ids,orientation)         SubCellTriangulations.jl:9-17, SubFacetTriangulations.jl:10-21
+//
+// The reference evaluates the CSG tree by broadcasting over whole state vectors (one temporary vector per tree node);
+// here the tree is a postfix program evaluated per element in registers, fused with the mask, and `findall` is a
+// flag -> exclusive scan -> scatter (stable, so ids come out ascending like the reference).
+#include <algorithm>
+
+#include "gecut_internal.cuh"
+
+namespace {
+
+__global__ void k_eval_rows(const int8_t* __restrict__ rows, int64_t pitch, int64_t n, const GcProgram prog,
+                            int8_t* __restrict__ out) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  out[e] = (int8_t)gc_eval_inoutcut(prog, rows, pitch, e);
+}
+
+// flags for Triangulation(cut,CutInOrOut(side),geo): bg state == CUT && subcell state == side
+__global__ void k_flag_subcells(const GcLayout lay, int64_t nsc, const GcProgram prog, int side,
+                                uint32_t* __restrict__ flags) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nsc) return;
+  int bg = gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, (int64_t)lay.sc_c2bg[e] - 1);
+  int sc = gc_eval_inoutcut(prog, lay.sc_state, lay.sc_pitch, e);
+  flags[e] = (bg == GC_CUT && sc == side) ? 1u : 0u;
+}
+
+// bg cells: count per cell type of the cells with state == side (mode 0) or CUT||side (mode 1); optionally flags
+__global__ void k_count_bgcells(const GcLayout lay, int64_t nc, const GcProgram prog, int side, int mode, int cpc,
+                                unsigned long long* __restrict__ counts, uint32_t* __restrict__ flags) {
+  __shared__ unsigned int s_cnt[8];
+  if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nc; e += (int64_t)gridDim.x * blockDim.x) {
+    int bg = gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, e);
+    bool keep = mode == 0 ? (bg == side) : (bg == GC_CUT || bg == side);
+    if (flags) flags[e] = keep ? 1u : 0u;
+    if (keep) atomicAdd(&s_cnt[(int)(e % cpc)], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < 8 && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+}
+
+__global__ void k_flag_boundary(const GcLayout lay, int64_t nsf, const GcProgram prog1, const GcProgram prog2,
+                                int has2, uint32_t* __restrict__ flags, int8_t* __restrict__ orient_all) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nsf) return;
+  int s1, o1;
+  gc_eval_inoutboundary(prog1, lay.sf_state, lay.sf_pitch, e, &s1, &o1);
+  bool keep = s1 == GECUT_INTERFACE;
+  if (keep && has2) keep = gc_eval_inoutcut(prog2, lay.sf_state, lay.sf_pitch, e) == GECUT_INTERFACE;
+  flags[e] = keep ? 1u : 0u;
+  orient_all[e] = (int8_t)o1;
+}
+
+// scatter of the flagged elements: ids[offs[e]] = e+1 (1-based), optional orientation
+__global__ void k_scatter_ids(const uint32_t* __restrict__ flags_scanned, const uint32_t* __restrict__ flags_raw_next,
+                              int64_t n, uint64_t total, int32_t* __restrict__ ids, const int8_t* __restrict__ orient_all,
+                              int8_t* __restrict__ orient) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  uint32_t o = flags_scanned[e];
+  uint32_t nxt = (e + 1 < n) ? flags_scanned[e + 1] : (uint32_t)total;
+  if (nxt != o) {
+    ids[o] = (int32_t)(e + 1);
+    if (orient) orient[o] = orient_all[e];
+  }
+  (void)flags_raw_next;
+}
+
+template <int STRIDE>
+__global__ void k_gather_rows(const int32_t* __restrict__ ids, int64_t n, const int32_t* __restrict__ c2p,
+                              const int32_t* __restrict__ c2bg, const double* __restrict__ normals,
+                              const int8_t* __restrict__ orient, int D, int32_t* __restrict__ out_c2p,
+                              int32_t* __restrict__ out_c2bg, double* __restrict__ out_normals) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t e = (int64_t)ids[i] - 1;
+  if (out_c2p)
+#pragma unroll
+    for (int k = 0; k < STRIDE; ++k) out_c2p[i * STRIDE + k] = c2p[e * STRIDE + k];
+  if (out_c2bg) out_c2bg[i] = c2bg[e];
+  if (out_normals) {
+    double o = (double)orient[i];
+    for (int d = 0; d < D; ++d) out_normals[i * D + d] = __dmul_rn(normals[e * D + d], o);
+  }
+}
+
+}  // namespace
+
+int gc_eval_rows(gecut_ctx* ctx, const int8_t* rows, int64_t pitch, int64_t n, const GcProgram& prog, int8_t* out_dev) {
+  if (n <= 0) return GECUT_OK;
+  const int T = 256;
+  k_eval_rows<<<(unsigned)gc_div_up(n, T), T, 0, ctx->stream>>>(rows, pitch, n, prog, out_dev);
+  ctx->launches += 1;
+  return gc_launch_check(ctx, "k_eval_rows");
+}
+
+// flags (uint32, n) -> ids (1-based, ascending); *count out.  flags buffer is consumed (scanned in place).
+static int compact_flags(gecut_ctx* ctx, uint32_t* flags, int64_t n, int32_t** ids_out, int64_t* count,
+                         const int8_t* orient_all, int8_t** orient_out) {
+  *ids_out = nullptr;
+  if (orient_out) *orient_out = nullptr;
+  *count = 0;
+  if (n <= 0) return GECUT_OK;
+  uint64_t* total_dev = nullptr;
+  GC_CHECK(gc_malloc(ctx, (void**)&total_dev, sizeof(uint64_t)));
+  GC_CHECK(gc_exclusive_scan_u32(ctx, flags, flags, n, total_dev));
+  uint64_t* h = (uint64_t*)ctx->h_pinned;
+  GC_CUDA(cudaMemcpyAsync(h, total_dev, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  GC_CUDA(cudaStreamSynchronize(ctx->stream));
+  uint64_t total = h[0];
+  gc_free(ctx, total_dev);
+  *count = (int64_t)total;
+  if (total == 0) return GECUT_OK;
+  GC_CHECK(gc_malloc(ctx, (void**)ids_out, sizeof(int32_t) * total));
+  if (orient_out) GC_CHECK(gc_malloc(ctx, (void**)orient_out, sizeof(int8_t) * total));
+  const int T = 256;
+  k_scatter_ids<<<(unsigned)gc_div_up(n, T), T, 0, ctx->stream>>>(flags, nullptr, n, total, *ids_out, orient_all,
+                                                                  orient_out ? *orient_out : nullptr);
+  ctx->launches += 1;
+  return gc_launch_check(ctx, "k_scatter_ids");
+}
+
+int gc_select_cells(gecut_ctx* ctx, gecut_selection* sel) {
+  const gecut_result* res = sel->res;
+  const GcLayout& lay = res->lay;
+  const int64_t nsc = res->sizes.num_subcells, nc = res->sizes.num_bgcells;
+  const int T = 256;
+  const bool want_sub = sel->kind == GECUT_SEL_PHYSICAL || sel->kind == GECUT_SEL_CUTONLY;
+  const bool want_bg = sel->kind == GECUT_SEL_PHYSICAL || sel->kind == GECUT_SEL_ACTIVE || sel->kind == GECUT_SEL_BGONLY;
+  if (want_sub && nsc > 0) {
+    uint32_t* flags = nullptr;
+    GC_CHECK(gc_malloc(ctx, (void**)&flags, sizeof(uint32_t) * nsc));
+    k_flag_subcells<<<(unsigned)gc_div_up(nsc, T), T, 0, ctx->stream>>>(lay, nsc, sel->prog, sel->side, flags);
+    ctx->launches += 1;
+    int st = compact_flags(ctx, flags, nsc, &sel->sub_ids, &sel->n_sub, nullptr, nullptr);
+    gc_free(ctx, flags);
+    GC_CHECK(st);
+  }
+  if (want_bg && nc > 0) {
+    unsigned long long* counts = nullptr;
+    GC_CHECK(gc_malloc(ctx, (void**)&counts, sizeof(unsigned long long) * 8));
+    GC_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * 8, ctx->stream));
+    const int mode = sel->kind == GECUT_SEL_ACTIVE ? 1 : 0;
+    unsigned nb = (unsigned)std::min<int64_t>(gc_div_up(nc, T), 148 * 16);
+    k_count_bgcells<<<nb, T, 0, ctx->stream>>>(lay, nc, sel->prog, sel->side, mode, res->grid.cpc, counts, nullptr);
+    ctx->launches += 1;
+    uint64_t* h = (uint64_t*)ctx->h_pinned;
+    GC_CUDA(cudaMemcpyAsync(h, counts, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    GC_CUDA(cudaStreamSynchronize(ctx->stream));
+    sel->n_bg = 0;
+    for (int t = 0; t < 8; ++t) {
+      sel->bg_type_count[t] = (int64_t)h[t];
+      sel->n_bg += (int64_t)h[t];
+    }
+    gc_free(ctx, counts);
+  }
+  return gc_launch_check(ctx, "select_cells");
+}
+
+int gc_materialize_bg_ids(gecut_ctx* ctx, gecut_selection* sel) {
+  if (sel->bg_ids || sel->n_bg == 0) return GECUT_OK;
+  const gecut_result* res = sel->res;
+  const int64_t nc = res->sizes.num_bgcells;
+  const int T = 256;
+  uint32_t* flags = nullptr;
+  unsigned long long* counts = nullptr;
+  GC_CHECK(gc_malloc(ctx, (void**)&flags, sizeof(uint32_t) * nc));
+  GC_CHECK(gc_malloc(ctx, (void**)&counts, sizeof(unsigned long long) * 8));
+  GC_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * 8, ctx->stream));
+  const int mode = sel->kind == GECUT_SEL_ACTIVE ? 1 : 0;
+  unsigned nb = (unsigned)std::min<int64_t>(gc_div_up(nc, T), 148 * 16);
+  k_count_bgcells<<<nb, T, 0, ctx->stream>>>(res->lay, nc, sel->prog, sel->side, mode, res->grid.cpc, counts, flags);
+  ctx->launches += 1;
+  int64_t n = 0;
+  int st = compact_flags(ctx, flags, nc, &sel->bg_ids, &n, nullptr, nullptr);
+  gc_free(ctx, flags);
+  gc_free(ctx, counts);
+  return st;
+}
+
+int gc_select_boundary(gecut_ctx* ctx, gecut_selection* sel) {
+  const gecut_result* res = sel->res;
+  const int64_t nsf = res->sizes.num_subfacets;
+  if (nsf <= 0) return GECUT_OK;
+  const int T = 256;
+  uint32_t* flags = nullptr;
+  int8_t* orient_all = nullptr;
+  GC_CHECK(gc_malloc(ctx, (void**)&flags, sizeof(uint32_t) * nsf));
+  GC_CHECK(gc_malloc(ctx, (void**)&orient_all, sizeof(int8_t) * nsf));
+  k_flag_boundary<<<(unsigned)gc_div_up(nsf, T), T, 0, ctx->stream>>>(res->lay, nsf, sel->prog, sel->prog2,
+                                                                      sel->has_prog2 ? 1 : 0, flags, orient_all);
+  ctx->launches += 1;
+  int st = compact_flags(ctx, flags, nsf, &sel->sub_ids, &sel->n_sub, orient_all, &sel->orientation);
+  gc_free(ctx, flags);
+  gc_free(ctx, orient_all);
+  return st;
+}
+
+int gc_selection_gather(gecut_ctx* ctx, const gecut_selection* sel, int32_t* to_points_dev, int32_t* to_bgcell_dev,
+                        double* normals_dev) {
+  const gecut_result* res = sel->res;
+  const int64_t n = sel->n_sub;
+  if (n <= 0) return GECUT_OK;
+  const int D = res->grid.D;
+  const int T = 256;
+  const unsigned nb = (unsigned)gc_div_up(n, T);
+  const GcLayout& lay = res->lay;
+  if (sel->kind == GECUT_SEL_BOUNDARY) {
+    if (D == 2)
+      k_gather_rows<2><<<nb, T, 0, ctx->stream>>>(sel->sub_ids, n, lay.sf_c2p, lay.sf_c2bg, lay.sf_N, sel->orientation, D,
+                                                  to_points_dev, to_bgcell_dev, normals_dev);
+    else
+      k_gather_rows<3><<<nb, T, 0, ctx->stream>>>(sel->sub_ids, n, lay.sf_c2p, lay.sf_c2bg, lay.sf_N, sel->orientation, D,
+                                                  to_points_dev, to_bgcell_dev, normals_dev);
+  } else {
+    if (D == 2)
+      k_gather_rows<3><<<nb, T, 0, ctx->stream>>>(sel->sub_ids, n, lay.sc_c2p, lay.sc_c2bg, nullptr, nullptr, D,
+                                                  to_points_dev, to_bgcell_dev, nullptr);
+    else
+      k_gather_rows<4><<<nb, T, 0, ctx->stream>>>(sel->sub_ids, n, lay.sc_c2p, lay.sc_c2bg, nullptr, nullptr, D,
+                                                  to_points_dev, to_bgcell_dev, nullptr);
+  }
+  ctx->launches += 1;
+  return gc_launch_check(ctx, "k_gather_rows");
+}

@@ -1,0 +1,305 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bar (BASELINE.json north_star): bit-exact IN/OUT/CUT classification, subcell/subfacet counts, connectivity and ordering;
+<= 1e-12 relative on coordinates, normals, measures and element matrices.  Coordinates/normals are in fact compared for
+exact equality first (both sides use the same IEEE operations without FMA contraction) and only then with the tolerance.
+"""
+import numpy as np
+import pytest
+
+import gecut
+from gecut import (CartesianDiscreteModel, simplexify, disk, sphere, cube, cylinder, plane, doughnut, olympic_rings,
+                   quadrilateral, square, tube, popcorn, union, intersect, setdiff, complement, get_geometry,
+                   DiscreteGeometry, AnalyticalGeometry, LevelSetCutter, cut, Triangulation, EmbeddedBoundary, Measure,
+                   PHYSICAL, PHYSICAL_IN, PHYSICAL_OUT, ACTIVE, ACTIVE_OUT, CUT_IN, IN, OUT)
+from gecut.csg import compile_postfix
+from gecut.measures import integrate_measure, integrate_laplacian
+from gecut.discretizations import compute_bgcell_to_inoutcut, compute_subcell_to_inout
+import oracle_binding as ob
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def csg_geometry():
+    R = 0.5
+    geo1 = cylinder(R, v=(1, 0, 0))
+    geo2 = cylinder(R, v=(0, 1, 0))
+    geo3 = cylinder(R, v=(0, 0, 1))
+    geo4 = union(union(geo1, geo2), geo3, name="source")
+    geo5 = sphere(1)
+    geo6 = cube(L=1.5)
+    geo7 = intersect(geo6, geo5)
+    return setdiff(geo7, geo4, name="csg")
+
+
+def stokes_geometry():
+    # examples/StokesTubeWithObstacleCutFEM/StokesTubeWithObstacleCutFEM.jl:17-28,51
+    R, L = 0.3, 2.0
+    x0 = (0.0, 0.0, 0.0)
+    geo2 = tube(R, L, x0=x0)
+    geo3 = sphere(0.3 * R, x0=(L / 3, 0.0, 0.0))
+    geo4 = complement(get_geometry(geo2, "walls"))
+    geo5 = union(geo3, geo4, name="solid")
+    geo1 = setdiff(geo2, geo3, name="fluid")
+    m = 0.05
+    pmin = (x0[0] - m, x0[1] - R, x0[2] - R)
+    pmax = (x0[0] + m + L, x0[1] + R, x0[2] + R)
+    return union(geo1, geo5), pmin, pmax
+
+
+def three_disks():
+    # test/LevelSetCuttersTests/CutTriangulationsTests.jl:15-30
+    R = 0.85
+    geo1 = disk(R, name="disk1")
+    geo2 = disk(R, x0=(1, 1), name="disk2")
+    geo3 = disk(R, x0=(1, 0), name="disk3")
+    geo5 = union(geo1, geo2)
+    return union(geo5, geo3)
+
+
+def bimaterial():
+    R = 0.4
+    geo1 = cylinder(R, x0=(0.0, 1.0, 0.7))
+    geo2 = cylinder(R, x0=(0.0, 1.0, 2.3))
+    geo3 = union(geo1, geo2, name="steel")
+    geo4 = complement(geo3, name="concrete")
+    return union(geo3, geo4)
+
+
+def box_model(geo, part, simplex=False):
+    box = gecut.get_metadata(geo)
+    m = CartesianDiscreteModel(box.pmin, box.pmax, part)
+    return simplexify(m) if simplex else m
+
+
+CASES = {
+    "disk_quad_50": lambda: (box_model(disk(0.7), (50, 50)), disk(0.7)),
+    "disk_tri_50": lambda: (box_model(disk(0.7), (50, 50), True), disk(0.7)),
+    "disk_quad_odd": lambda: (box_model(disk(0.7), (37, 45)), disk(0.7)),
+    "sphere_hex_12": lambda: (box_model(sphere(0.7), (12, 12, 12)), sphere(0.7)),
+    "sphere_tet_12": lambda: (box_model(sphere(0.7), (12, 12, 12), True), sphere(0.7)),
+    "sphere_hex_odd": lambda: (box_model(sphere(0.7), (37, 21, 13)), sphere(0.7)),
+    "sphere_tet_odd": lambda: (box_model(sphere(0.7), (35, 9, 17), True), sphere(0.7)),
+    "csg_hex_10": lambda: (CartesianDiscreteModel((-0.8,) * 3, (0.8,) * 3, (10, 10, 10)), csg_geometry()),
+    "csg_hex_20": lambda: (CartesianDiscreteModel((-0.8,) * 3, (0.8,) * 3, (20, 20, 20)), csg_geometry()),
+    "csg_tet_8": lambda: (simplexify(CartesianDiscreteModel((-0.8,) * 3, (0.8,) * 3, (8, 8, 8))), csg_geometry()),
+    "three_disks_40": lambda: (CartesianDiscreteModel((-1, -1), (2, 2), (40, 40)), three_disks()),
+    "three_disks_tri": lambda: (simplexify(CartesianDiscreteModel((-1, -1), (2, 2), (33, 20))), three_disks()),
+    "square_2d": lambda: (CartesianDiscreteModel((-1, -1), (1, 1), (24, 24)), square(L=1.1)),
+    "quadrilateral": lambda: (CartesianDiscreteModel((-0.01, 2.01, -0.01, 3.01), (5, 5)),
+                              quadrilateral(x0=(0, 0), d1=(1, 1), d2=(1, 2))),
+    "bimaterial": lambda: (CartesianDiscreteModel((0., 0., 0.), (3., 2., 3.), (9, 12, 18)), bimaterial()),
+    "doughnut": lambda: (box_model(doughnut(0.6, 0.25), (20, 20, 8)), doughnut(0.6, 0.25)),
+    "olympic": lambda: (box_model(olympic_rings(0.6, 0.1), (40, 20, 4)), olympic_rings(0.6, 0.1)),
+    "stokes_tet": lambda: (lambda g: (simplexify(CartesianDiscreteModel(g[1], g[2], (16, 4, 4))), g[0]))(stokes_geometry()),
+    "stokes_hex": lambda: (lambda g: (CartesianDiscreteModel(g[1], g[2], (24, 6, 6)), g[0]))(stokes_geometry()),
+    "no_cut": lambda: (CartesianDiscreteModel((2, 2, 2), (3, 3, 3), (6, 5, 4)), sphere(0.7)),
+    "all_in": lambda: (CartesianDiscreteModel((-.1, -.1), (.1, .1), (7, 3)), disk(0.7)),
+}
+
+
+def assert_float_equal(a, b, what):
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    if np.array_equal(a, b):
+        return
+    scale = max(np.abs(b).max(), 1e-300) if b.size else 1.0
+    err = np.abs(a - b).max() / scale
+    assert err <= RTOL, f"{what}: max relative error {err:.3e} > {RTOL}"
+
+
+def compare_layout(gd, oc):
+    s = gd.sizes
+    D, L = oc.D, oc.L
+    assert (s.num_bgcells, s.num_cutcells, s.num_subcells, s.num_subcell_points, s.num_subfacets,
+            s.num_subfacet_points, s.num_levelsets) == (oc.Nc, oc.Ncut, oc.Nsc, oc.Nscp, oc.Nsf, oc.Nsfp, oc.L)
+    h = gd.to_host()
+    assert np.array_equal(h["ls_to_bgcell_to_inoutcut"], oc.rows("ls_to_bgcell_to_inoutcut"))
+    assert np.array_equal(h["cutcell_to_cell"], oc.array("cutcell_to_cell"))
+    assert np.array_equal(h["sc_cell_to_points"].ravel(), oc.array("subcells.cell_to_points"))
+    assert np.array_equal(h["sc_cell_to_bgcell"], oc.array("subcells.cell_to_bgcell"))
+    assert np.array_equal(h["ls_to_subcell_to_inout"], oc.rows("ls_to_subcell_to_inout").reshape(L, -1))
+    assert np.array_equal(h["sf_facet_to_points"].ravel(), oc.array("subfacets.facet_to_points"))
+    assert np.array_equal(h["sf_facet_to_bgcell"], oc.array("subfacets.facet_to_bgcell"))
+    assert np.array_equal(h["ls_to_subfacet_to_inout"], oc.rows("ls_to_subfacet_to_inout").reshape(L, -1))
+    assert_float_equal(h["sc_point_to_coords"].ravel(), oc.array("subcells.point_to_coords"), "subcell coords")
+    assert_float_equal(h["sc_point_to_rcoords"].ravel(), oc.array("subcells.point_to_rcoords"), "subcell rcoords")
+    assert_float_equal(h["sf_point_to_coords"].ravel(), oc.array("subfacets.point_to_coords"), "subfacet coords")
+    assert_float_equal(h["sf_point_to_rcoords"].ravel(), oc.array("subfacets.point_to_rcoords"), "subfacet rcoords")
+    assert_float_equal(h["sf_facet_to_normal"].ravel(), oc.array("subfacets.facet_to_normal"), "normals")
+
+
+def named_programs(gd):
+    names = [None] + [n for n in gecut.get_geometry_names(gd.geo)]
+    return names
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_cut_layout_matches_oracle(case):
+    model, geo = CASES[case]()
+    oc = ob.oracle_cut(model, geo)
+    gd = cut(model, geo)
+    compare_layout(gd, oc)
+
+
+@pytest.mark.parametrize("case", ["disk_quad_50", "disk_tri_50", "sphere_hex_12", "sphere_tet_12", "csg_hex_10",
+                                  "three_disks_40", "bimaterial", "stokes_tet", "no_cut", "all_in"])
+def test_selectors_and_integrals_match_oracle(case):
+    model, geo = CASES[case]()
+    oc = ob.oracle_cut(model, geo)
+    gd = cut(model, geo)
+    oid = {k: v for k, v in gd.oid_to_ls.items()}
+    names = named_programs(gd)
+    for name in names:
+        prog = gd.program(name)
+        assert np.array_equal(compute_bgcell_to_inoutcut(gd, name), oc.bgcell_to_inoutcut(prog))
+        if oc.Nsc:
+            assert np.array_equal(compute_subcell_to_inout(gd, name), oc.subcell_to_inout(prog))
+        for side, sel in ((IN, PHYSICAL_IN), (OUT, PHYSICAL_OUT)):
+            t = Triangulation(gd, sel, name)
+            ids = oc.select_subcells(prog, side)
+            bg = oc.select_bgcells(prog, side)
+            assert np.array_equal(t.sub_ids, ids)
+            assert np.array_equal(t.bg_ids, bg)
+            if len(ids):
+                g = t.gather()
+                c2p = oc.array("subcells.cell_to_points").reshape(-1, oc.D + 1)
+                assert np.array_equal(g.cell_to_points, c2p[ids - 1])
+                assert np.array_equal(g.cell_to_bgcell, oc.array("subcells.cell_to_bgcell")[ids - 1])
+            total, vals = integrate_measure(Measure(t, 2), return_values=True)
+            ovals = oc.subcell_measures(ids)
+            assert_float_equal(vals, ovals, "subcell measures")
+            ototal = ovals.sum() + sum(oc.bgcell_measure(int(c)) for c in bg)
+            assert abs(total - ototal) <= RTOL * max(abs(ototal), 1e-300)
+            K_cut, K_bg = integrate_laplacian(Measure(t, 2))
+            oK = oc.cutcell_laplacian(ids)
+            assert_float_equal(K_cut, oK, "cut-cell laplacian")
+            ntypes = K_bg.shape[0]
+            for ty in range(ntypes):
+                assert_float_equal(K_bg[ty], oc.bgcell_laplacian(ty + 1), "bg laplacian")
+        ta = Triangulation(gd, ACTIVE, name)
+        assert np.array_equal(ta.bg_ids, oc.select_bgcells(prog, IN, active=True))
+        tb = EmbeddedBoundary(gd, name)
+        fids, ori = oc.select_boundary(prog)
+        assert np.array_equal(tb.sub_ids, fids)
+        assert np.array_equal(tb.orientation, ori)
+        surf, fvals = integrate_measure(Measure(tb, 2), return_values=True)
+        assert_float_equal(fvals, oc.subfacet_measures(fids), "subfacet measures")
+        if len(fids):
+            g = tb.gather()
+            f2n = oc.array("subfacets.facet_to_normal").reshape(-1, oc.D)
+            assert_float_equal(g.facet_to_normal, f2n[fids - 1] * ori[:, None], "oriented normals")
+    # two-geometry boundaries
+    if len(names) > 2:
+        a, b = names[1], names[2]
+        tb = EmbeddedBoundary(gd, a, b)
+        fids, ori = oc.select_boundary(gd.program(a), gd.program(b))
+        assert np.array_equal(tb.sub_ids, fids)
+        assert np.array_equal(tb.orientation, ori)
+
+
+def test_known_answers_on_gpu():
+    # test/InterfacesTests/EmbeddedDiscretizationsTests.jl:48-56 through the public API
+    R = 0.7
+    for simplex in (False, True):
+        geo = disk(R)
+        model = box_model(geo, (50, 50), simplex)
+        cutgeo = cut(model, geo)
+        vol = integrate_measure(Measure(Triangulation(cutgeo, PHYSICAL), 2))
+        surf = integrate_measure(Measure(EmbeddedBoundary(cutgeo), 2))
+        assert abs(np.pi * R ** 2 - vol) < 1.0e-3
+        assert abs(surf - 2 * np.pi * R) < 1.0e-3
+
+
+def test_discrete_geometry_matches_analytical():
+    """DiscreteGeometry (NODAL values) of discretize(geo) gives the same cut as the analytical tree
+    (src/LevelSetCutters/DiscreteGeometries.jl:36-63; CutTriangulations.jl:443-454)."""
+    import torch
+    g, pmin, pmax = stokes_geometry()
+    model = CartesianDiscreteModel(pmin, pmax, (16, 5, 4))
+    dgeo = gecut.discretize(g, model)
+    a = cut(model, g)
+    b = cut(model, dgeo)
+    ha, hb = a.to_host(), b.to_host()
+    for k in ha:
+        assert np.array_equal(ha[k], hb[k]), k
+    # host numpy nodal values too
+    vals = ob.node_values(model, ob.make_leaf(0, R=0.7))
+    dg = DiscreteGeometry(vals, CartesianDiscreteModel((-1, -1, -1), (1, 1, 1), (9, 8, 7)), name="ball") \
+        if False else None
+    model2 = CartesianDiscreteModel((-1, -1, -1), (1, 1, 1), (9, 8, 7))
+    vals = ob.node_values(model2, ob.make_leaf(0, R=0.7))
+    c1 = cut(model2, DiscreteGeometry(vals, model2, name="ball"))
+    c2 = cut(model2, sphere(0.7))
+    h1, h2 = c1.to_host(), c2.to_host()
+    for k in h1:
+        assert np.array_equal(h1[k], h2[k]), k
+    c3 = cut(model2, DiscreteGeometry(torch.from_numpy(vals).cuda(), model2, name="ball"))
+    h3 = c3.to_host()
+    for k in h1:
+        assert np.array_equal(h1[k], h3[k]), k
+
+
+def test_host_function_geometry_popcorn():
+    geo = popcorn()
+    model = box_model(geo, (14, 14, 14))
+    oc = ob.oracle_cut(model, geo)
+    gd = cut(model, geo)
+    compare_layout(gd, oc)
+
+
+def test_node_evaluation_kernel_bit_exact():
+    """K1 alone: discretize(geo,model) on the device equals the oracle's leaf formulas bit for bit."""
+    model = CartesianDiscreteModel((-0.8,) * 3, (0.8,) * 3, (13, 11, 7))
+    geo = csg_geometry()
+    leaves, _, _ = gecut.cutters.flatten_geometry(model, geo)
+    vals = gecut.cutters.evaluate_leaves_at_nodes(model, leaves, device_output=False)
+    for lf, v in zip(leaves, vals):
+        ref = ob.node_values(model, ob.make_leaf(lf.kind, lf.x0, lf.v, lf.R, lf.r))
+        assert np.array_equal(v, ref)
+    lf = gecut.doughnut(0.6, 0.25).get_tree().data[0]
+    v = gecut.cutters.evaluate_leaves_at_nodes(model, [lf], device_output=False)[0]
+    assert np.array_equal(v, ob.node_values(model, ob.make_leaf(lf.kind, lf.x0, lf.v, lf.R, lf.r)))
+
+
+@pytest.mark.parametrize("case", ["sphere_hex_12", "sphere_tet_12", "csg_hex_10", "disk_quad_50"])
+def test_slab_cut_is_a_slice_of_the_whole_cut(case):
+    """z-slab partition (src/Distributed/DistributedDiscretizations.jl:29-40): cutting layers [k0,k1) gives exactly the
+    part of the whole cut that lives in those layers (ids shifted by the slab offsets)."""
+    model, geo = CASES[case]()
+    whole = cut(model, geo)
+    hw = whole.to_host()
+    nlast = model.partition[-1]
+    k0, k1 = nlast // 3, nlast - nlast // 4
+    part = LevelSetCutter(slab=(k0, k1)).cut(model, geo)
+    hp = part.to_host()
+    off = int(part.sizes.cell_offset)
+    nc = int(part.sizes.num_bgcells)
+    assert np.array_equal(hp["ls_to_bgcell_to_inoutcut"], hw["ls_to_bgcell_to_inoutcut"][:, off:off + nc])
+    cw = hw["cutcell_to_cell"]
+    mask = (cw > off) & (cw <= off + nc)
+    assert np.array_equal(hp["cutcell_to_cell"] + off, cw[mask])
+    scm = (hw["sc_cell_to_bgcell"] > off) & (hw["sc_cell_to_bgcell"] <= off + nc)
+    assert np.array_equal(hp["sc_cell_to_bgcell"] + off, hw["sc_cell_to_bgcell"][scm])
+    first = np.flatnonzero(scm)[0] if scm.any() else 0
+    p0 = hw["sc_cell_to_points"][first].min() - hp["sc_cell_to_points"][0].min() if scm.any() else 0
+    assert np.array_equal(hp["sc_cell_to_points"] + p0, hw["sc_cell_to_points"][scm])
+    npts = hp["sc_point_to_coords"].shape[0]
+    pstart = hw["sc_cell_to_points"][scm].min() - 1 if scm.any() else 0
+    assert np.array_equal(hp["sc_point_to_coords"], hw["sc_point_to_coords"][pstart:pstart + npts])
+    assert np.array_equal(hp["ls_to_subcell_to_inout"], hw["ls_to_subcell_to_inout"][:, scm])
+
+
+def test_error_paths():
+    model = CartesianDiscreteModel((0, 0), (1, 1), (4, 4))
+    with pytest.raises(ValueError):
+        cut(model, sphere(0.5))  # 3-D leaf on a 2-D model
+    with pytest.raises(Exception):
+        CartesianDiscreteModel((0, 0), (1, 1), (4, 0))
+    with pytest.raises(NotImplementedError):
+        Measure(Triangulation(cut(model, disk(0.3, x0=(0.5, 0.5))), PHYSICAL), 4)
+    geo = disk(0.3, x0=(0.5, 0.5))
+    cg = cut(model, geo)
+    with pytest.raises(KeyError):
+        Triangulation(cg, PHYSICAL, "nope")
