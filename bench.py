@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""bench.py -- background cells/s through cut() + ∫dΩ on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one synthetic background model:
+    cutgeo = cut(LevelSetCutter(), bgmodel, geo)             (classification + subtriangulation, all outputs in HBM)
+    Ω = Triangulation(cutgeo, PHYSICAL); Γ = EmbeddedBoundary(cutgeo)
+    sum(∫1 dΩ), sum(∫1 dΓ), cut-cell Laplacian element matrices of ∫∇v·∇u dΩ
+Workload (config.workload): BASELINE.json configs[2] -- sphere R=0.7 on the n^3 Cartesian box ±0.707 (n=512 per GPU),
+simplexified (6 TET per HEX) by default, z-slab sharded over the ranks with the global model growing with N (weak
+scaling: N=8 -> 1024^3).  `value` counts n^3 n-cube cells per second (NOT the 6x larger number of simplices).
+
+Lines printed: rank 0 prints ONE JSON line (see the keys required by the driver contract in the task statement).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "bg cells/s through cut()+∫dΩ at n³"
+UNIT = "cells/s"
+
+
+# --------------------------------------------------------------------------------------------------------------------
+def make_workload(name, n, world):
+    import gecut
+    from gecut import CartesianDiscreteModel, simplexify, sphere, disk
+    if name in ("c3_tet", "c3_hex"):
+        geo = sphere(0.7)
+        box = gecut.get_metadata(geo)
+        mult = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}.get(world)
+        if mult is None:
+            raise SystemExit("--gpus must be 1, 2, 4 or 8")
+        part = tuple(n * m for m in mult)
+        model = CartesianDiscreteModel(box.pmin, box.pmax, part)
+        if name == "c3_tet":
+            model = simplexify(model)
+        desc = (f"BASELINE configs[2]: sphere(R=0.7) on {part[0]}x{part[1]}x{part[2]} Cartesian box ±0.707"
+                f"{', simplexified (6 TET/HEX)' if name == 'c3_tet' else ' (HEX, Q1)'}; cut + PHYSICAL volume + "
+                f"EmbeddedBoundary area + cut-cell {'P1 4x4' if name == 'c3_tet' else 'Q1 8x8'} Laplacian matrices")
+        return model, geo, desc
+    if name == "c2_disk":
+        geo = disk(0.7)
+        box = gecut.get_metadata(geo)
+        mult = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}[world]
+        part = tuple(n * m for m in mult)
+        model = CartesianDiscreteModel(box.pmin, box.pmax, part)
+        return model, geo, f"BASELINE configs[1]: disk(R=0.7) on {part[0]}x{part[1]} quads: cut + area + perimeter + Q1 4x4 matrices"
+    raise SystemExit(f"unknown workload {name}")
+
+
+def slab_of(model, rank, world):
+    nl = model.partition[-1]
+    assert nl % world == 0
+    per = nl // world
+    return (rank * per, (rank + 1) * per)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------------------------
+def layout_bytes(s):
+    """bytes of every output array of the layout (B_cut + states)"""
+    D, L = int(s.D), int(s.num_levelsets)
+    b = {}
+    b["bg_state"] = L * s.num_bgcells
+    b["cutcells"] = 4 * s.num_cutcells
+    b["subcells"] = s.num_subcells * (4 * (D + 1) + 4 + L) + s.num_subcell_points * 16 * D
+    b["subfacets"] = s.num_subfacets * (4 * D + 4 + 8 * D + L) + s.num_subfacet_points * 16 * D
+    return {k: int(v) for k, v in b.items()}
+
+
+def algorithmic_bytes(s, model, nsel, nfsel, nodal=False):
+    """ALGORITHMIC bytes per kernel and per step (DESIGN.md section 'Roofline accounting')."""
+    D, L = int(s.D), int(s.num_levelsets)
+    nv = int(s.num_vertices_per_bgcell)
+    Nc, Nn, Ncut = int(s.num_bgcells), int(s.num_bgnodes), int(s.num_cutcells)
+    lb = layout_bytes(s)
+    nt0 = 1 if model.simplexified else (2 if D == 2 else 6)
+    nsimp = Ncut * nt0
+    narr = 2 + L + (L if L > 1 else 0)
+    k = {}
+    k["k_classify"] = L * Nc + Nc // 8 + (8 * L * Nn if nodal else 0)
+    k["k_cut_walk_count"] = 4 * Ncut + 4 * narr * nsimp
+    k["k_cut_walk_fill"] = 4 * Ncut + 4 * narr * nsimp + lb["subcells"] + lb["subfacets"]
+    k["k_count_bgcells"] = L * Nc
+    k["k_flag_subcells"] = int(s.num_subcells) * (4 + 2 * L + 4)
+    k["k_flag_boundary"] = int(s.num_subfacets) * (L + 4 + 1)
+    k["k_measures"] = nsel * (4 + 4 * (D + 1) + 8 * D * (D + 1) + 8) + nfsel * (4 + 4 * D + 8 * D * D + 8)
+    k["k_cutcell_laplacian"] = nsel * (4 + 4 + 4 * (D + 1) + 16 * D * (D + 1)) + 8 * nv * nv * Ncut + 4 * Ncut
+    # whole step, SURVEY.md section 8(d): B_sweep + B_cut + B_int (node values are never materialised: 16*L*Nn of the
+    # survey's B_sweep is not moved at all, so it is NOT counted here)
+    step = (L * Nc + Nc // 8) + lb["cutcells"] + lb["subcells"] + lb["subfacets"] + 8 * (nsel + nfsel) + 8 * nv * nv * Ncut
+    return k, int(step)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3_tet", choices=["c3_tet", "c3_hex", "c2_disk"])
+    ap.add_argument("--n", type=int, default=None, help="cells per direction per GPU (default 512; 4096 for c2_disk)")
+    ap.add_argument("--cpu-n", type=int, default=None, help="size of the bounded CPU sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"WORLD_SIZE={world} does not match --gpus {args.gpus}")
+    n = args.n or (4096 if args.workload == "c2_disk" else 512)
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference(args, n)
+        return
+    run_b200(args, n, rank, world, local_rank)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+def cpu_sample(workload, n_cpu, steps=1):
+    """The CPU restatement of the reference (oracle/, 1 thread = the reference's execution model) on a bounded sample of
+    the same workload.  Returns (cells/s, description)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_binding as ob
+    model, geo, _ = make_workload(workload, n_cpu, 1)
+    best = None
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        oc = ob.oracle_cut(model, geo)
+        prog = [0]
+        ids = oc.select_subcells(prog, -1)
+        nbg = len(oc.select_bgcells(prog, -1))
+        vol = oc.subcell_measures(ids).sum() + nbg * oc.bgcell_measure(1)
+        fids, _ = oc.select_boundary(prog)
+        surf = oc.subfacet_measures(fids).sum()
+        K = oc.cutcell_laplacian(ids)
+        dt = time.perf_counter() - t0
+        del oc, K
+        best = dt if best is None else min(best, dt)
+    cubes = model.num_cubes
+    return cubes / best, best, (f"same geometry at {'x'.join(str(p) for p in model.partition)} "
+                                f"({'simplexified' if model.simplexified else 'n-cubes'}), full cut + selectors + integrals, "
+                                f"oracle/gecut_oracle.cpp -O2 single thread (the reference is serial Julia; it cannot run here)")
+
+
+def run_reference(args, n):
+    n_cpu = args.cpu_n or (1024 if args.workload == "c2_disk" else 128)
+    model, geo, desc = make_workload(args.workload, n_cpu, 1)
+    for _ in range(args.warmup):
+        cpu_sample(args.workload, n_cpu)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        val, dt, sample = cpu_sample(args.workload, n_cpu)
+    elapsed = time.perf_counter() - t0
+    cubes = model.num_cubes
+    value = cubes * args.steps / elapsed
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "note": "bounded CPU sample of the same workload; rank 0 only"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+def run_b200(args, n, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    import gecut
+    from gecut import LevelSetCutter, Triangulation, EmbeddedBoundary, Measure, PHYSICAL
+    from gecut import _lib
+    from gecut.measures import integrate_measure
+    import ctypes as C
+
+    model, geo, desc = make_workload(args.workload, n, world)
+    slab = slab_of(model, rank, world) if world > 1 else None
+    stream = torch.cuda.current_stream()
+    ctx = _lib.Context(local_rank, stream.cuda_stream)
+    cutter = LevelSetCutter(ctx, slab=slab)
+    red = torch.zeros(4, dtype=torch.float64, device=f"cuda:{local_rank}")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    state = {}
+
+    def step(e2e=False, host=None):
+        cg = cutter.cut(model, geo)
+        om = Triangulation(cg, PHYSICAL)
+        ga = EmbeddedBoundary(cg)
+        vol = integrate_measure(Measure(om, 2))
+        surf = integrate_measure(Measure(ga, 2))
+        ctx.check(ctx._lib.gecut_integrate_laplacian(om.handle, host["K_cut"].ctypes.data if e2e else None, None),
+                  "gecut_integrate_laplacian")
+        if e2e:
+            cg.to_host(buffers=host["layout"])
+        if world > 1:  # global integrals + counts: the only data-path collective
+            red[0], red[1], red[2], red[3] = vol, surf, float(cg.num_cutcells), float(cg.sizes.num_subcells)
+            dist.all_reduce(red)
+            if e2e:
+                _ = red.cpu()
+            vol, surf = float(red[0]), float(red[1])
+        state.update(sizes=cg.sizes, nsel=om.num_sub, nfsel=ga.num_sub, vol=vol, surf=surf)
+        om.close()
+        ga.close()
+        cg.close()
+        return vol, surf
+
+    # ---- device-resident throughput ----------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 1)):
+        step()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    l0 = ctx.launch_count
+    if sampler:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = ctx.launch_count - l0
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms[0])
+    cubes_total = model.num_cubes  # all ranks together
+    value = cubes_total * args.steps / (ms_total * 1e-3)
+    s = state["sizes"]
+
+    # ---- per-kernel timing for the roofline (CUDA events around every launch, same stream) -------------------------
+    PROF_STEPS = 3
+    ctx.profile(True)
+    for _ in range(PROF_STEPS):
+        step()
+    rep = ctx.profile_report()
+    ctx.profile(False)
+    kbytes, step_bytes = algorithmic_bytes(s, model, state["nsel"], state["nfsel"])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    kernels = []
+    for name, (cnt, tot) in rep.items():
+        per_step_ms = tot / PROF_STEPS
+        kb = kbytes.get(name)
+        kernels.append({"name": name, "launches_per_step": cnt / PROF_STEPS, "ms_per_step": round(per_step_ms, 4),
+                        "alg_bytes_per_step": kb,
+                        "gbs": round(kb / (per_step_ms * 1e-3) / 1e9, 1) if kb and per_step_ms > 0 else None})
+    kernels.sort(key=lambda k: -k["ms_per_step"])
+    top = kernels[0]
+    top_launches = max(1.0, top["launches_per_step"])
+    achieved = (top["alg_bytes_per_step"] or 0) / (top["ms_per_step"] * 1e-3) / 1e9 if top["ms_per_step"] > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": top["name"], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_kind,
+                "alg_bytes_per_launch": int((top["alg_bytes_per_step"] or 0) / top_launches),
+                "ms_per_launch": round(top["ms_per_step"] / top_launches, 4),
+                "kernel_share_of_step": round(top["ms_per_step"] / sum(k["ms_per_step"] for k in kernels), 3)}
+    ms_step = ms_total / args.steps
+    step_roofline = {"alg_bytes_per_step": step_bytes, "achieved": round(step_bytes / (ms_step * 1e-3) / 1e9, 1),
+                     "peak": peak, "unit": "GB/s", "frac": round(step_bytes / (ms_step * 1e-3) / 1e9 / peak, 4)}
+
+    # ---- end to end through the C ABI with HOST buffers ------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        D, L = int(s.D), int(s.num_levelsets)
+        nv = int(s.num_vertices_per_bgcell)
+        host = {"layout": {}, "K_cut": None}
+        shapes = {
+            "ls_to_bgcell_to_inoutcut": ((L, s.num_bgcells), np.int8), "cutcell_to_cell": ((s.num_cutcells,), np.int32),
+            "sc_cell_to_points": ((s.num_subcells, D + 1), np.int32), "sc_cell_to_bgcell": ((s.num_subcells,), np.int32),
+            "sc_point_to_coords": ((s.num_subcell_points, D), np.float64),
+            "sc_point_to_rcoords": ((s.num_subcell_points, D), np.float64),
+            "ls_to_subcell_to_inout": ((L, s.num_subcells), np.int8),
+            "sf_facet_to_points": ((s.num_subfacets, D), np.int32), "sf_facet_to_bgcell": ((s.num_subfacets,), np.int32),
+            "sf_facet_to_normal": ((s.num_subfacets, D), np.float64),
+            "sf_point_to_coords": ((s.num_subfacet_points, D), np.float64),
+            "sf_point_to_rcoords": ((s.num_subfacet_points, D), np.float64),
+            "ls_to_subfacet_to_inout": ((L, s.num_subfacets), np.int8)}
+        tdt = {np.int8: torch.int8, np.int32: torch.int32, np.float64: torch.float64}
+        d2h = 0
+        for k, (shape, dt) in shapes.items():
+            t = torch.empty(tuple(int(x) for x in shape), dtype=tdt[dt], pin_memory=True)
+            host["layout"][k] = t.numpy()
+            d2h += t.numel() * t.element_size()
+        kt = torch.empty((int(s.num_cutcells), nv, nv), dtype=torch.float64, pin_memory=True)
+        host["K_cut"] = kt.numpy()
+        d2h += kt.numel() * 8 + 16
+        h2d = C.sizeof(_lib.Grid) + L * C.sizeof(_lib.LeafRec) + 3 * 4 * 8  # grid + leaf records + 3 boolean programs
+        e2e_steps = max(1, min(args.steps, 3))
+        step(True, host)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(e2e_steps):
+            step(True, host)
+        e1.record(stream)
+        barrier()
+        ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e = {"value": cubes_total * e2e_steps / (float(ems[0]) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": float(ems[0]) / e2e_steps,
+               "what": "gecut_cut + selectors + integrals through the C ABI, whole EmbeddedDiscretization layout and the "
+                       "element matrices copied into pinned HOST buffers every step; the input is an AnalyticalGeometry "
+                       "(a few hundred bytes of leaf records), exactly what the reference API receives"}
+
+    # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        n_cpu = args.cpu_n or (2048 if args.workload == "c2_disk" else 224)
+        v, dt, sample = cpu_sample(args.workload, n_cpu)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample, "seconds": round(dt, 2)}
+
+    if rank == 0:
+        lb = layout_bytes(s)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": desc, "cells_per_gpu": int(model.num_cubes // world),
+                       "bg_simplices_per_gpu": int(s.num_bgcells), "partition": list(model.partition),
+                       "parallelism": f"z-slab x{world}" if world > 1 else "single GPU",
+                       "l2": "no L2 flush needed: every step rewrites its whole working set "
+                             f"({(sum(lb.values())) / 1e9:.2f} GB of outputs per GPU >> 126 MB L2), nothing is reused across steps",
+                       "per_gpu_counts": {"cut_cells": int(s.num_cutcells), "subcells": int(s.num_subcells),
+                                          "subcell_points": int(s.num_subcell_points), "subfacets": int(s.num_subfacets)},
+                       "integrals": {"volume": state["vol"], "surface": state["surf"]}},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "step_roofline": step_roofline, "kernels": kernels[:12], "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -130,6 +130,10 @@ def lib():
     L.gecut_last_error.restype = C.c_char_p
     L.gecut_launch_count.argtypes = [vp]
     L.gecut_launch_count.restype = i64
+    L.gecut_profile.argtypes = [vp, cint]
+    L.gecut_profile.restype = cint
+    L.gecut_profile_report.argtypes = [vp]
+    L.gecut_profile_report.restype = C.c_char_p
     L.gecut_cut.argtypes = [vp, P(Grid), P(LeafRec), cint, P(vp), cint, P(vp)]
     L.gecut_classify.argtypes = [vp, P(Grid), P(LeafRec), cint, P(vp), cint, P(vp)]
     L.gecut_eval_leaf_at_nodes.argtypes = [vp, P(Grid), P(LeafRec), vp, cint]
@@ -160,6 +164,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = ["gecut_create", "gecut_destroy", "gecut_set_stream", "gecut_last_error", "gecut_launch_count",
+                    "gecut_profile", "gecut_profile_report",
                     "gecut_cut", "gecut_classify", "gecut_eval_leaf_at_nodes", "gecut_result_free",
                     "gecut_result_sizes", "gecut_result_device_ptrs", "gecut_result_copy", "gecut_bgcell_to_inoutcut",
                     "gecut_subcell_to_inout", "gecut_select_cells", "gecut_select_boundary", "gecut_selection_free",
@@ -193,6 +198,18 @@ class Context:
     @property
     def handle(self):
         return self._h
+
+    def profile(self, enable: bool):
+        self.check(self._lib.gecut_profile(self._h, 1 if enable else 0), "gecut_profile")
+
+    def profile_report(self) -> dict:
+        """{kernel name: (launches, total ms)} since profile(True)."""
+        txt = self._lib.gecut_profile_report(self._h).decode()
+        out = {}
+        for line in txt.splitlines():
+            name, cnt, ms = line.split()
+            out[name] = (int(cnt), float(ms))
+        return out
 
     def close(self):
         if self._h:

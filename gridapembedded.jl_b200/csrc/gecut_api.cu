@@ -3,6 +3,8 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <utility>
+#include <vector>
 
 #include "gecut_internal.cuh"
 
@@ -37,6 +39,17 @@ int gc_launch_check(gecut_ctx* ctx, const char* what) {
 }
 
 static inline int64_t pad_pitch(int64_t n) { return ((n + 255) / 256) * 256; }
+
+void gc_prof_before(gecut_ctx* ctx, const char* name) {
+  GcProfRec r;
+  r.name = name;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, ctx->stream);
+  ctx->prof.push_back(r);
+}
+
+void gc_prof_after(gecut_ctx* ctx) { cudaEventRecord(ctx->prof.back().b, ctx->stream); }
 
 namespace {
 
@@ -352,6 +365,47 @@ int gecut_set_stream(gecut_ctx* ctx, void* cuda_stream) {
 const char* gecut_last_error(const gecut_ctx* ctx) { return ctx ? ctx->err.c_str() : "NULL context"; }
 
 int64_t gecut_launch_count(const gecut_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int gecut_profile(gecut_ctx* ctx, int enable) {
+  if (!ctx) return GECUT_ERR_INVALID;
+  DeviceGuard guard(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& r : ctx->prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  ctx->prof.clear();
+  ctx->prof_on = enable != 0;
+  return GECUT_OK;
+}
+
+const char* gecut_profile_report(gecut_ctx* ctx) {
+  if (!ctx) return "";
+  DeviceGuard guard(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  // aggregate by kernel name, in order of first launch: "name count total_ms\n"
+  std::vector<std::pair<std::string, std::pair<int, double>>> agg;
+  for (auto& r : ctx->prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    bool found = false;
+    for (auto& a : agg)
+      if (a.first == r.name) {
+        a.second.first++;
+        a.second.second += ms;
+        found = true;
+        break;
+      }
+    if (!found) agg.push_back({r.name, {1, (double)ms}});
+  }
+  ctx->prof_report.clear();
+  char buf[256];
+  for (auto& a : agg) {
+    snprintf(buf, sizeof(buf), "%s %d %.6f\n", a.first.c_str(), a.second.first, a.second.second);
+    ctx->prof_report += buf;
+  }
+  return ctx->prof_report.c_str();
+}
 
 int gecut_cut(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* leaves, int num_leaves,
               const double* const* nodal_values, int nodal_on_device, gecut_result** out) {

@@ -137,10 +137,9 @@ int gc_exclusive_scan_u32(gecut_ctx* ctx, const uint32_t* in, uint32_t* out, int
   int64_t nb = gc_div_up(n, SCAN_TILE);
   uint64_t* blocksums = nullptr;
   GC_CHECK(gc_malloc(ctx, (void**)&blocksums, sizeof(uint64_t) * nb));
-  k_scan_reduce<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(in, n, blocksums);
-  k_scan_blocksums<<<1, 1024, 0, ctx->stream>>>(blocksums, nb, total_dev);
-  k_scan_apply<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, blocksums);
-  ctx->launches += 3;
+  GC_LAUNCH(ctx, "k_scan_reduce", k_scan_reduce<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(in, n, blocksums));
+  GC_LAUNCH(ctx, "k_scan_blocksums", k_scan_blocksums<<<1, 1024, 0, ctx->stream>>>(blocksums, nb, total_dev));
+  GC_LAUNCH(ctx, "k_scan_apply", k_scan_apply<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, blocksums));
   int st = gc_launch_check(ctx, "scan");
   gc_free(ctx, blocksums);
   return st;
@@ -371,8 +370,8 @@ int gc_classify(gecut_ctx* ctx, gecut_result* res) {
       grid.z = 1;
     }
     size_t smem = sizeof(uint32_t) * 2 * L * C::RY * (C::WX + 1);
-    k_classify<D, S><<<grid, C::THREADS, smem, ctx->stream>>>(g, res->leaves, res->lay.bg_state, res->lay.bg_pitch,
-                                                              res->cutmask, ctx->d_simplexify_raw);
+    GC_LAUNCH(ctx, "k_classify", k_classify<D, S><<<grid, C::THREADS, smem, ctx->stream>>>(g, res->leaves, res->lay.bg_state, res->lay.bg_pitch,
+                                                              res->cutmask, ctx->d_simplexify_raw));
   };
   if (g.D == 3) {
     if (g.simplexified)
@@ -385,7 +384,6 @@ int gc_classify(gecut_ctx* ctx, gecut_result* res) {
     else
       launch(std::integral_constant<int, 2>{}, std::false_type{});
   }
-  ctx->launches += 1;
   return gc_launch_check(ctx, "k_classify");
 }
 
@@ -402,11 +400,10 @@ int gc_compact_cutcells(gecut_ctx* ctx, gecut_result* res) {
   const int T = 256;
   const unsigned nb = (unsigned)gc_div_up(ngroups, T);
   switch (g.cpc) {
-    case 1: k_cutmask_count<1><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts); break;
-    case 2: k_cutmask_count<2><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts); break;
-    default: k_cutmask_count<6><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts); break;
+    case 1: GC_LAUNCH(ctx, "k_cutmask_count", k_cutmask_count<1><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts)); break;
+    case 2: GC_LAUNCH(ctx, "k_cutmask_count", k_cutmask_count<2><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts)); break;
+    default: GC_LAUNCH(ctx, "k_cutmask_count", k_cutmask_count<6><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts)); break;
   }
-  ctx->launches += 1;
   GC_CHECK(gc_exclusive_scan_u32(ctx, counts, counts, ngroups, total_dev));
   uint64_t* h = (uint64_t*)ctx->h_pinned;
   GC_CUDA(cudaMemcpyAsync(h, total_dev, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -416,11 +413,10 @@ int gc_compact_cutcells(gecut_ctx* ctx, gecut_result* res) {
   if (ncut > 0) {
     GC_CHECK(gc_malloc(ctx, (void**)&res->lay.cutcells, sizeof(int32_t) * ncut));
     switch (g.cpc) {
-      case 1: k_cutmask_emit<1><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts, nx, wxtot, res->lay.cutcells); break;
-      case 2: k_cutmask_emit<2><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts, nx, wxtot, res->lay.cutcells); break;
-      default: k_cutmask_emit<6><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts, nx, wxtot, res->lay.cutcells); break;
+      case 1: GC_LAUNCH(ctx, "k_cutmask_emit", k_cutmask_emit<1><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts, nx, wxtot, res->lay.cutcells)); break;
+      case 2: GC_LAUNCH(ctx, "k_cutmask_emit", k_cutmask_emit<2><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts, nx, wxtot, res->lay.cutcells)); break;
+      default: GC_LAUNCH(ctx, "k_cutmask_emit", k_cutmask_emit<6><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts, nx, wxtot, res->lay.cutcells)); break;
     }
-    ctx->launches += 1;
   }
   int st = gc_launch_check(ctx, "cutmask compaction");
   gc_free(ctx, counts);
@@ -433,9 +429,8 @@ int gc_eval_leaf_nodes(gecut_ctx* ctx, const GcGrid& g, const gecut_leaf& leaf, 
   const int T = 256;
   unsigned nb = (unsigned)gc_div_up(total, T);
   if (g.D == 3)
-    k_eval_leaf_nodes<3><<<nb, T, 0, ctx->stream>>>(g, leaf, out_dev);
+    GC_LAUNCH(ctx, "k_eval_leaf_nodes", k_eval_leaf_nodes<3><<<nb, T, 0, ctx->stream>>>(g, leaf, out_dev));
   else
-    k_eval_leaf_nodes<2><<<nb, T, 0, ctx->stream>>>(g, leaf, out_dev);
-  ctx->launches += 1;
+    GC_LAUNCH(ctx, "k_eval_leaf_nodes", k_eval_leaf_nodes<2><<<nb, T, 0, ctx->stream>>>(g, leaf, out_dev));
   return gc_launch_check(ctx, "k_eval_leaf_nodes");
 }

@@ -375,12 +375,11 @@ void launch_walk(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const G
   const int T = 64;
   const unsigned nb = (unsigned)gc_div_up(nsimp, T);
   if (fill)
-    k_cut_walk<D, LM, true><<<nb, T, 0, ctx->stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
-                                                       ctx->d_simplexify_pos, res->lay.cutcells, nsimp, cn, res->lay);
+    GC_LAUNCH(ctx, "k_cut_walk_fill", k_cut_walk<D, LM, true><<<nb, T, 0, ctx->stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
+                                                       ctx->d_simplexify_pos, res->lay.cutcells, nsimp, cn, res->lay));
   else
-    k_cut_walk<D, LM, false><<<nb, T, 0, ctx->stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
-                                                        ctx->d_simplexify_pos, res->lay.cutcells, nsimp, cn, res->lay);
-  ctx->launches += 1;
+    GC_LAUNCH(ctx, "k_cut_walk_count", k_cut_walk<D, LM, false><<<nb, T, 0, ctx->stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
+                                                        ctx->d_simplexify_pos, res->lay.cutcells, nsimp, cn, res->lay));
 }
 
 void dispatch_walk(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcCounters& cn, bool fill) {

@@ -389,21 +389,20 @@ int gc_integrate_measure(gecut_ctx* ctx, const gecut_selection* sel, double* val
     const unsigned nb = (unsigned)gc_div_up(n, T);
     if (sel->kind == GECUT_SEL_BOUNDARY) {
       if (g.D == 2)
-        k_measures<2, 1><<<nb, T, 0, ctx->stream>>>(sel->sub_ids, n, lay.sf_c2p, lay.sf_X, vals);
+        GC_LAUNCH(ctx, "k_measures", k_measures<2, 1><<<nb, T, 0, ctx->stream>>>(sel->sub_ids, n, lay.sf_c2p, lay.sf_X, vals));
       else
-        k_measures<3, 2><<<nb, T, 0, ctx->stream>>>(sel->sub_ids, n, lay.sf_c2p, lay.sf_X, vals);
+        GC_LAUNCH(ctx, "k_measures", k_measures<3, 2><<<nb, T, 0, ctx->stream>>>(sel->sub_ids, n, lay.sf_c2p, lay.sf_X, vals));
     } else {
       if (g.D == 2)
-        k_measures<2, 2><<<nb, T, 0, ctx->stream>>>(sel->sub_ids, n, lay.sc_c2p, lay.sc_X, vals);
+        GC_LAUNCH(ctx, "k_measures", k_measures<2, 2><<<nb, T, 0, ctx->stream>>>(sel->sub_ids, n, lay.sc_c2p, lay.sc_X, vals));
       else
-        k_measures<3, 3><<<nb, T, 0, ctx->stream>>>(sel->sub_ids, n, lay.sc_c2p, lay.sc_X, vals);
+        GC_LAUNCH(ctx, "k_measures", k_measures<3, 3><<<nb, T, 0, ctx->stream>>>(sel->sub_ids, n, lay.sc_c2p, lay.sc_X, vals));
     }
     const int NB = (int)std::min<int64_t>(1024, gc_div_up(n, 1024));
     double* partial = nullptr;
     GC_CHECK(gc_malloc(ctx, (void**)&partial, sizeof(double) * (NB + 1)));
-    k_block_sums<<<NB, 256, 0, ctx->stream>>>(vals, n, partial);
-    k_final_sum<<<1, 256, 0, ctx->stream>>>(partial, NB, partial + NB);
-    ctx->launches += 3;
+    GC_LAUNCH(ctx, "k_block_sums", k_block_sums<<<NB, 256, 0, ctx->stream>>>(vals, n, partial));
+    GC_LAUNCH(ctx, "k_final_sum", k_final_sum<<<1, 256, 0, ctx->stream>>>(partial, NB, partial + NB));
     double* h = (double*)ctx->h_pinned;
     GC_CUDA(cudaMemcpyAsync(h, partial + NB, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     GC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -433,11 +432,10 @@ int gc_integrate_laplacian(gecut_ctx* ctx, gecut_selection* sel, double* K_bg_ho
   const int T = 128;
   const unsigned nb = (unsigned)gc_div_up(ncut * 32, T);
   if (g.D == 2)
-    k_cutcell_laplacian<2><<<nb, T, 0, ctx->stream>>>(g, res->lay, sel->sub_ids, sel->n_sub, ncut, ctx->d_simplexify_raw,
-                                                      sel->K_cut);
+    GC_LAUNCH(ctx, "k_cutcell_laplacian", k_cutcell_laplacian<2><<<nb, T, 0, ctx->stream>>>(g, res->lay, sel->sub_ids, sel->n_sub, ncut, ctx->d_simplexify_raw,
+                                                      sel->K_cut));
   else
-    k_cutcell_laplacian<3><<<nb, T, 0, ctx->stream>>>(g, res->lay, sel->sub_ids, sel->n_sub, ncut, ctx->d_simplexify_raw,
-                                                      sel->K_cut);
-  ctx->launches += 1;
+    GC_LAUNCH(ctx, "k_cutcell_laplacian", k_cutcell_laplacian<3><<<nb, T, 0, ctx->stream>>>(g, res->lay, sel->sub_ids, sel->n_sub, ncut, ctx->d_simplexify_raw,
+                                                      sel->K_cut));
   return gc_launch_check(ctx, "k_cutcell_laplacian");
 }

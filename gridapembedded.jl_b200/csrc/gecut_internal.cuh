@@ -10,6 +10,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "gecut.h"
 #include "gecut_tables.h"
@@ -82,11 +83,20 @@ struct GcCounters {
 // ------------------------------------------------------------------------------------------------
 // Context / result / selection objects behind the opaque ABI handles.
 // ------------------------------------------------------------------------------------------------
+// per-kernel CUDA-event timing (bench.py roofline leg): off by default, zero cost when off
+struct GcProfRec {
+  const char* name;
+  cudaEvent_t a, b;
+};
+
 struct gecut_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   std::string err;
   int64_t launches = 0;
+  bool prof_on = false;
+  std::vector<GcProfRec> prof;
+  std::string prof_report;
   GcSimplexTable* d_tables = nullptr;  // [3] on the device
   uint8_t* d_simplexify_raw = nullptr;  // [2][6][4]
   uint8_t* d_simplexify_pos = nullptr;  // [2][6][4]
@@ -141,6 +151,17 @@ struct gecut_selection {
   } while (0)
 
 static inline int64_t gc_div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+void gc_prof_before(gecut_ctx* ctx, const char* name);
+void gc_prof_after(gecut_ctx* ctx);
+// every kernel launch of the library goes through this macro (launch counter + optional event timing)
+#define GC_LAUNCH(ctx, name, ...)            \
+  do {                                       \
+    if ((ctx)->prof_on) gc_prof_before(ctx, name); \
+    __VA_ARGS__;                             \
+    if ((ctx)->prof_on) gc_prof_after(ctx);  \
+    (ctx)->launches++;                       \
+  } while (0)
 
 int gc_malloc(gecut_ctx* ctx, void** p, size_t bytes);
 void gc_free(gecut_ctx* ctx, void* p);

@@ -99,8 +99,7 @@ __global__ void k_gather_rows(const int32_t* __restrict__ ids, int64_t n, const 
 int gc_eval_rows(gecut_ctx* ctx, const int8_t* rows, int64_t pitch, int64_t n, const GcProgram& prog, int8_t* out_dev) {
   if (n <= 0) return GECUT_OK;
   const int T = 256;
-  k_eval_rows<<<(unsigned)gc_div_up(n, T), T, 0, ctx->stream>>>(rows, pitch, n, prog, out_dev);
-  ctx->launches += 1;
+  GC_LAUNCH(ctx, "k_eval_rows", k_eval_rows<<<(unsigned)gc_div_up(n, T), T, 0, ctx->stream>>>(rows, pitch, n, prog, out_dev));
   return gc_launch_check(ctx, "k_eval_rows");
 }
 
@@ -124,9 +123,8 @@ static int compact_flags(gecut_ctx* ctx, uint32_t* flags, int64_t n, int32_t** i
   GC_CHECK(gc_malloc(ctx, (void**)ids_out, sizeof(int32_t) * total));
   if (orient_out) GC_CHECK(gc_malloc(ctx, (void**)orient_out, sizeof(int8_t) * total));
   const int T = 256;
-  k_scatter_ids<<<(unsigned)gc_div_up(n, T), T, 0, ctx->stream>>>(flags, nullptr, n, total, *ids_out, orient_all,
-                                                                  orient_out ? *orient_out : nullptr);
-  ctx->launches += 1;
+  GC_LAUNCH(ctx, "k_scatter_ids", k_scatter_ids<<<(unsigned)gc_div_up(n, T), T, 0, ctx->stream>>>(flags, nullptr, n, total, *ids_out, orient_all,
+                                                                  orient_out ? *orient_out : nullptr));
   return gc_launch_check(ctx, "k_scatter_ids");
 }
 
@@ -140,8 +138,7 @@ int gc_select_cells(gecut_ctx* ctx, gecut_selection* sel) {
   if (want_sub && nsc > 0) {
     uint32_t* flags = nullptr;
     GC_CHECK(gc_malloc(ctx, (void**)&flags, sizeof(uint32_t) * nsc));
-    k_flag_subcells<<<(unsigned)gc_div_up(nsc, T), T, 0, ctx->stream>>>(lay, nsc, sel->prog, sel->side, flags);
-    ctx->launches += 1;
+    GC_LAUNCH(ctx, "k_flag_subcells", k_flag_subcells<<<(unsigned)gc_div_up(nsc, T), T, 0, ctx->stream>>>(lay, nsc, sel->prog, sel->side, flags));
     int st = compact_flags(ctx, flags, nsc, &sel->sub_ids, &sel->n_sub, nullptr, nullptr);
     gc_free(ctx, flags);
     GC_CHECK(st);
@@ -152,8 +149,7 @@ int gc_select_cells(gecut_ctx* ctx, gecut_selection* sel) {
     GC_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * 8, ctx->stream));
     const int mode = sel->kind == GECUT_SEL_ACTIVE ? 1 : 0;
     unsigned nb = (unsigned)std::min<int64_t>(gc_div_up(nc, T), 148 * 16);
-    k_count_bgcells<<<nb, T, 0, ctx->stream>>>(lay, nc, sel->prog, sel->side, mode, res->grid.cpc, counts, nullptr);
-    ctx->launches += 1;
+    GC_LAUNCH(ctx, "k_count_bgcells", k_count_bgcells<<<nb, T, 0, ctx->stream>>>(lay, nc, sel->prog, sel->side, mode, res->grid.cpc, counts, nullptr));
     uint64_t* h = (uint64_t*)ctx->h_pinned;
     GC_CUDA(cudaMemcpyAsync(h, counts, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     GC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -179,8 +175,7 @@ int gc_materialize_bg_ids(gecut_ctx* ctx, gecut_selection* sel) {
   GC_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * 8, ctx->stream));
   const int mode = sel->kind == GECUT_SEL_ACTIVE ? 1 : 0;
   unsigned nb = (unsigned)std::min<int64_t>(gc_div_up(nc, T), 148 * 16);
-  k_count_bgcells<<<nb, T, 0, ctx->stream>>>(res->lay, nc, sel->prog, sel->side, mode, res->grid.cpc, counts, flags);
-  ctx->launches += 1;
+  GC_LAUNCH(ctx, "k_count_bgcells", k_count_bgcells<<<nb, T, 0, ctx->stream>>>(res->lay, nc, sel->prog, sel->side, mode, res->grid.cpc, counts, flags));
   int64_t n = 0;
   int st = compact_flags(ctx, flags, nc, &sel->bg_ids, &n, nullptr, nullptr);
   gc_free(ctx, flags);
@@ -197,9 +192,8 @@ int gc_select_boundary(gecut_ctx* ctx, gecut_selection* sel) {
   int8_t* orient_all = nullptr;
   GC_CHECK(gc_malloc(ctx, (void**)&flags, sizeof(uint32_t) * nsf));
   GC_CHECK(gc_malloc(ctx, (void**)&orient_all, sizeof(int8_t) * nsf));
-  k_flag_boundary<<<(unsigned)gc_div_up(nsf, T), T, 0, ctx->stream>>>(res->lay, nsf, sel->prog, sel->prog2,
-                                                                      sel->has_prog2 ? 1 : 0, flags, orient_all);
-  ctx->launches += 1;
+  GC_LAUNCH(ctx, "k_flag_boundary", k_flag_boundary<<<(unsigned)gc_div_up(nsf, T), T, 0, ctx->stream>>>(res->lay, nsf, sel->prog, sel->prog2,
+                                                                      sel->has_prog2 ? 1 : 0, flags, orient_all));
   int st = compact_flags(ctx, flags, nsf, &sel->sub_ids, &sel->n_sub, orient_all, &sel->orientation);
   gc_free(ctx, flags);
   gc_free(ctx, orient_all);
@@ -217,19 +211,18 @@ int gc_selection_gather(gecut_ctx* ctx, const gecut_selection* sel, int32_t* to_
   const GcLayout& lay = res->lay;
   if (sel->kind == GECUT_SEL_BOUNDARY) {
     if (D == 2)
-      k_gather_rows<2><<<nb, T, 0, ctx->stream>>>(sel->sub_ids, n, lay.sf_c2p, lay.sf_c2bg, lay.sf_N, sel->orientation, D,
-                                                  to_points_dev, to_bgcell_dev, normals_dev);
+      GC_LAUNCH(ctx, "k_gather_rows", k_gather_rows<2><<<nb, T, 0, ctx->stream>>>(sel->sub_ids, n, lay.sf_c2p, lay.sf_c2bg, lay.sf_N, sel->orientation, D,
+                                                  to_points_dev, to_bgcell_dev, normals_dev));
     else
-      k_gather_rows<3><<<nb, T, 0, ctx->stream>>>(sel->sub_ids, n, lay.sf_c2p, lay.sf_c2bg, lay.sf_N, sel->orientation, D,
-                                                  to_points_dev, to_bgcell_dev, normals_dev);
+      GC_LAUNCH(ctx, "k_gather_rows", k_gather_rows<3><<<nb, T, 0, ctx->stream>>>(sel->sub_ids, n, lay.sf_c2p, lay.sf_c2bg, lay.sf_N, sel->orientation, D,
+                                                  to_points_dev, to_bgcell_dev, normals_dev));
   } else {
     if (D == 2)
-      k_gather_rows<3><<<nb, T, 0, ctx->stream>>>(sel->sub_ids, n, lay.sc_c2p, lay.sc_c2bg, nullptr, nullptr, D,
-                                                  to_points_dev, to_bgcell_dev, nullptr);
+      GC_LAUNCH(ctx, "k_gather_rows", k_gather_rows<3><<<nb, T, 0, ctx->stream>>>(sel->sub_ids, n, lay.sc_c2p, lay.sc_c2bg, nullptr, nullptr, D,
+                                                  to_points_dev, to_bgcell_dev, nullptr));
     else
-      k_gather_rows<4><<<nb, T, 0, ctx->stream>>>(sel->sub_ids, n, lay.sc_c2p, lay.sc_c2bg, nullptr, nullptr, D,
-                                                  to_points_dev, to_bgcell_dev, nullptr);
+      GC_LAUNCH(ctx, "k_gather_rows", k_gather_rows<4><<<nb, T, 0, ctx->stream>>>(sel->sub_ids, n, lay.sc_c2p, lay.sc_c2bg, nullptr, nullptr, D,
+                                                  to_points_dev, to_bgcell_dev, nullptr));
   }
-  ctx->launches += 1;
   return gc_launch_check(ctx, "k_gather_rows");
 }

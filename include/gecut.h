@@ -134,6 +134,12 @@ const char* gecut_last_error(const gecut_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's `gpu_launches`). */
 int64_t gecut_launch_count(const gecut_ctx* ctx);
 
+/* Per-kernel CUDA-event timing for the benchmark's roofline leg: gecut_profile(ctx,1) starts recording every kernel
+ * launch of this context, gecut_profile_report returns "kernel_name launches total_ms\n" lines (valid until the next
+ * call), gecut_profile(ctx,0) stops and clears. */
+int gecut_profile(gecut_ctx* ctx, int enable);
+const char* gecut_profile_report(gecut_ctx* ctx);
+
 /* ---- cut ------------------------------------------------------------------------------------------------------ */
 /* cut(::LevelSetCutter, bgmodel, geo)  (src/LevelSetCutters/LevelSetCutters.jl:79-105 -> CutTriangulations.jl:443-460,
  * 309-343): evaluates the L unique leaves at the nodes, classifies every bg cell per level set, extracts + simplexifies
