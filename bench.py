@@ -65,55 +65,65 @@ def slab_of(model, rank, world):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe), read through NVML in-process
+    (pynvml / nvidia-ml-py) every 50 ms: the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*`
+    prints, without the heavy per-sample cost of the nvidia-smi loop (which was measured to stretch 5.5 ms steps to
+    10-16 ms).  Falls back to one `nvidia-smi` query after the timed region if NVML is unavailable."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.reasons = set()
+        self.smax = None
+        self.stop_flag = False
+        self.thread = None
+        self.nvml = None
 
     def start(self):
-        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.nvml = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _loop(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def clear(self):
+        self.samples.clear()
+        self.reasons.clear()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
+        if self.nvml is None:
             try:
-                sm.append(float(f[1]))
-                smax = float(f[2])
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=10).stdout
+                a, b = [float(x) for x in out.strip().split(",")]
+                return {"sm_mhz": a, "sm_max_mhz": b, "reasons": [], "samples": 1, "source": "nvidia-smi after the run"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
+        self.stop_flag = True
+        self.thread.join(timeout=1)
+        sm = sorted(self.samples)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.smax, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": "NVML in-process, 50 ms period"}
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -124,7 +134,10 @@ def layout_bytes(s):
     b["bg_state"] = L * s.num_bgcells
     b["cutcells"] = 4 * s.num_cutcells
     b["subcells"] = s.num_subcells * (4 * (D + 1) + 4 + L) + s.num_subcell_points * 16 * D
-    b["subfacets"] = s.num_subfacets * (4 * D + 4 + 8 * D + L) + s.num_subfacet_points * 16 * D
+    # one level set: the subfacet point arrays alias the subcell point arrays on the device (the reference aliases them
+    # too until merge_sub_face_data copies them), so they are not moved a second time
+    sfp = 0 if L == 1 else s.num_subfacet_points
+    b["subfacets"] = s.num_subfacets * (4 * D + 4 + 8 * D + L) + sfp * 16 * D
     return {k: int(v) for k, v in b.items()}
 
 
@@ -141,21 +154,30 @@ def algorithmic_bytes(s, model, nsel, nfsel, nodal=False):
     k["k_classify"] = L * Nc + Nc // 8 + (8 * L * Nn if nodal else 0)
     k["k_cut_walk_count"] = 4 * Ncut + 4 * narr * nsimp
     k["k_cut_walk_fill"] = 4 * Ncut + 4 * narr * nsimp + lb["subcells"] + lb["subfacets"]
+    ntiles = (nsimp + 127) // 128
+    k["k_cut1_count"] = 4 * Ncut + 12 * ntiles
+    meas = 8 * (int(s.num_subcells) + int(s.num_subfacets))  # per-entity measures written next to the layout
+    k["k_cut1_fill"] = 4 * Ncut + 12 * ntiles + lb["subcells"] + lb["subfacets"] + 4 * Ncut + meas
+    k["k_cut_walk_fill"] += meas
     k["k_count_bgcells"] = L * Nc
     k["k_flag_subcells"] = int(s.num_subcells) * (4 + 2 * L + 4)
     k["k_flag_boundary"] = int(s.num_subfacets) * (L + 4 + 1)
-    k["k_measures"] = nsel * (4 + 4 * (D + 1) + 8 * D * (D + 1) + 8) + nfsel * (4 + 4 * D + 8 * D * D + 8)
-    k["k_cutcell_laplacian"] = nsel * (4 + 4 + 4 * (D + 1) + 16 * D * (D + 1)) + 8 * nv * nv * Ncut + 4 * Ncut
+    k["k_measures"] = (nsel + nfsel) * (4 + 8 + 8)  # id + gathered measure + value
+    nsc = int(s.num_subcells)
+    if model.simplexified:  # P1: states + measures of the cut cells' subcells, matrices out
+        k["k_cutcell_laplacian"] = nsc * L + nsel * 8 + 8 * nv * nv * Ncut + 8 * Ncut
+    else:  # Q1: + connectivity and reference coordinates of the selected subcells
+        k["k_cutcell_laplacian"] = nsc * L + nsel * (8 + 4 * (D + 1) + 8 * D * (D + 1)) + 8 * nv * nv * Ncut + 8 * Ncut
     # whole step, SURVEY.md section 8(d): B_sweep + B_cut + B_int (node values are never materialised: 16*L*Nn of the
     # survey's B_sweep is not moved at all, so it is NOT counted here)
-    step = (L * Nc + Nc // 8) + lb["cutcells"] + lb["subcells"] + lb["subfacets"] + 8 * (nsel + nfsel) + 8 * nv * nv * Ncut
+    step = (L * Nc + Nc // 8) + lb["cutcells"] + lb["subcells"] + lb["subfacets"] + meas + 8 * (nsel + nfsel) + 8 * nv * nv * Ncut
     return k, int(step)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3_tet", choices=["c3_tet", "c3_hex", "c2_disk"])
@@ -257,14 +279,23 @@ def run_b200(args, n, rank, world, local_rank):
 
     state = {}
 
+    dbg = []
+
     def step(e2e=False, host=None):
+        t = [time.perf_counter()]
         cg = cutter.cut(model, geo)
+        t.append(time.perf_counter())
         om = Triangulation(cg, PHYSICAL)
+        t.append(time.perf_counter())
         ga = EmbeddedBoundary(cg)
+        t.append(time.perf_counter())
         vol = integrate_measure(Measure(om, 2))
         surf = integrate_measure(Measure(ga, 2))
+        t.append(time.perf_counter())
         ctx.check(ctx._lib.gecut_integrate_laplacian(om.handle, host["K_cut"].ctypes.data if e2e else None, None),
                   "gecut_integrate_laplacian")
+        t.append(time.perf_counter())
+        dbg.append([round((b - a) * 1e3, 2) for a, b in zip(t[:-1], t[1:])])
         if e2e:
             cg.to_host(buffers=host["layout"])
         if world > 1:  # global integrals + counts: the only data-path collective
@@ -280,18 +311,30 @@ def run_b200(args, n, rank, world, local_rank):
         return vol, surf
 
     # ---- device-resident throughput ----------------------------------------------------------------------------
-    for _ in range(max(args.warmup, 1)):
-        step()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    barrier()
-    l0 = ctx.launch_count
+    # the clock sampler is started BEFORE the warm-up: nvidia-smi's start-up (NVML init) stalls the driver for ~100 ms,
+    # which must not land inside the (few ms per step) timed region; it keeps sampling during the timed steps
+    sampler = ClockSampler(local_rank) if (rank == 0 and not os.environ.get("GECUT_NO_SAMPLER")) else None
     if sampler:
         sampler.start()
+    for _ in range(max(args.warmup, 1)):
+        step()
+    barrier()
+    if sampler:
+        sampler.clear()
+    l0 = ctx.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
+    wall = []
     for _ in range(args.steps):
+        t0 = time.perf_counter()
         step()
+        wall.append((time.perf_counter() - t0) * 1e3)
     ev1.record(stream)
+    if os.environ.get("GECUT_BENCH_DEBUG"):
+        sys.stderr.write("per-step wall ms: " + " ".join(f"{w:.1f}" for w in wall) + "\n")
+        sys.stderr.write("per-call [cut, physical, boundary, measures, laplacian] ms of the timed steps:\n")
+        for row in dbg[-args.steps:]:
+            sys.stderr.write("   " + str(row) + "\n")
     barrier()
     clocks = sampler.stop() if sampler else None
     launches = ctx.launch_count - l0

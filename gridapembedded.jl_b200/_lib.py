@@ -62,12 +62,26 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xcompiler", "-ffp-contract=off"]
 
 
+def _source_hash() -> str:
+    """Content hash of everything the library is built from (mtimes do not survive the copy to the GPU box)."""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(INCLUDE, "gecut.h")]
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+HASH_PATH = os.path.join(LIB_DIR, "BUILD_HASH")
+
+
 def _needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, "gecut.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return open(HASH_PATH).read().strip() != _source_hash()
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
@@ -100,6 +114,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         raise GecutError(f"nvcc failed for {failed}")
     cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
+    with open(HASH_PATH, "w") as fh:
+        fh.write(_source_hash())
     return LIB_PATH
 
 
@@ -130,6 +146,8 @@ def lib():
     L.gecut_last_error.restype = C.c_char_p
     L.gecut_launch_count.argtypes = [vp]
     L.gecut_launch_count.restype = i64
+    L.gecut_trim.argtypes = [vp]
+    L.gecut_trim.restype = cint
     L.gecut_profile.argtypes = [vp, cint]
     L.gecut_profile.restype = cint
     L.gecut_profile_report.argtypes = [vp]
@@ -164,7 +182,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = ["gecut_create", "gecut_destroy", "gecut_set_stream", "gecut_last_error", "gecut_launch_count",
-                    "gecut_profile", "gecut_profile_report",
+                    "gecut_profile", "gecut_profile_report", "gecut_trim",
                     "gecut_cut", "gecut_classify", "gecut_eval_leaf_at_nodes", "gecut_result_free",
                     "gecut_result_sizes", "gecut_result_device_ptrs", "gecut_result_copy", "gecut_bgcell_to_inoutcut",
                     "gecut_subcell_to_inout", "gecut_select_cells", "gecut_select_boundary", "gecut_selection_free",
@@ -198,6 +216,10 @@ class Context:
     @property
     def handle(self):
         return self._h
+
+    def trim(self):
+        """Return the context's cached device blocks to the driver."""
+        self.check(self._lib.gecut_trim(self._h), "gecut_trim")
 
     def profile(self, enable: bool):
         self.check(self._lib.gecut_profile(self._h, 1 if enable else 0), "gecut_profile")

@@ -11,22 +11,52 @@
 // ------------------------------------------------------------------------------------------------
 // memory: stream-ordered pool allocations so that repeated cuts reuse memory without cudaMalloc round trips
 // ------------------------------------------------------------------------------------------------
+void gc_trim(gecut_ctx* ctx) {
+  if (ctx->cache.empty()) return;
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->cache) cudaFree(kv.second);
+  ctx->cache.clear();
+  ctx->cached_bytes = 0;
+}
+
 int gc_malloc(gecut_ctx* ctx, void** p, size_t bytes) {
   *p = nullptr;
   if (bytes == 0) bytes = 16;
-  cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+  bytes = (bytes + 255) & ~(size_t)255;
+  // smallest cached block that fits without wasting more than 1/8 of it
+  auto it = ctx->cache.lower_bound(bytes);
+  if (it != ctx->cache.end() && it->first <= bytes + bytes / 8 + 4096) {
+    *p = it->second;
+    ctx->cached_bytes -= it->first;
+    ctx->live[*p] = it->first;
+    ctx->cache.erase(it);
+    return GECUT_OK;
+  }
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) {  // give the cached blocks back and retry once
+    (void)cudaGetLastError();
+    gc_trim(ctx);
+    e = cudaMalloc(p, bytes);
+  }
   if (e != cudaSuccess) {
     (void)cudaGetLastError();
     char buf[128];
     snprintf(buf, sizeof(buf), "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
     ctx->err = buf;
+    *p = nullptr;
     return e == cudaErrorMemoryAllocation ? GECUT_ERR_OOM : GECUT_ERR_CUDA;
   }
+  ctx->live[*p] = bytes;
   return GECUT_OK;
 }
 
 void gc_free(gecut_ctx* ctx, void* p) {
-  if (p) cudaFreeAsync(p, ctx->stream);
+  if (!p) return;
+  auto it = ctx->live.find(p);
+  if (it == ctx->live.end()) return;  // not ours (or already freed)
+  ctx->cache.insert({it->second, p});
+  ctx->cached_bytes += it->second;
+  ctx->live.erase(it);
 }
 
 int gc_launch_check(gecut_ctx* ctx, const char* what) {
@@ -135,10 +165,16 @@ void free_result_arrays(gecut_result* r) {
   gc_free(ctx, l.sf_c2p);
   gc_free(ctx, l.sf_c2bg);
   gc_free(ctx, l.sf_N);
-  gc_free(ctx, l.sf_X);
-  gc_free(ctx, l.sf_R);
+  if (!r->sf_points_alias) {
+    gc_free(ctx, l.sf_X);
+    gc_free(ctx, l.sf_R);
+  }
   gc_free(ctx, l.sf_state);
+  gc_free(ctx, l.sc_meas);
+  gc_free(ctx, l.sf_meas);
   gc_free(ctx, r->cutmask);
+  gc_free(ctx, r->cut_sc_ptr);
+  r->cut_sc_ptr = nullptr;
   for (int i = 0; i < GC_LMAX; ++i)
     if (r->owns_nodal[i]) gc_free(ctx, r->nodal_dev[i]);
   l = GcLayout{};
@@ -346,6 +382,9 @@ int gecut_destroy(gecut_ctx* ctx) {
   if (!ctx) return GECUT_OK;
   DeviceGuard guard(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  gc_trim(ctx);
+  for (auto& kv : ctx->live) cudaFree(kv.first);
+  ctx->live.clear();
   cudaFree(ctx->d_tables);
   cudaFree(ctx->d_simplexify_raw);
   cudaFree(ctx->d_simplexify_pos);
@@ -365,6 +404,13 @@ int gecut_set_stream(gecut_ctx* ctx, void* cuda_stream) {
 const char* gecut_last_error(const gecut_ctx* ctx) { return ctx ? ctx->err.c_str() : "NULL context"; }
 
 int64_t gecut_launch_count(const gecut_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int gecut_trim(gecut_ctx* ctx) {
+  if (!ctx) return GECUT_ERR_INVALID;
+  DeviceGuard guard(ctx->device);
+  gc_trim(ctx);
+  return GECUT_OK;
+}
 
 int gecut_profile(gecut_ctx* ctx, int enable) {
   if (!ctx) return GECUT_ERR_INVALID;

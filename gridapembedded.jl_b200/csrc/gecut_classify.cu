@@ -171,7 +171,12 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
   constexpr int NVC = 1 << D;                         // vertices of the n-cube
   constexpr int CPC = SIMPLEX ? (D == 3 ? 6 : 2) : 1;  // bg cells per n-cube
   constexpr int NW = C::THREADS / 32;
+  constexpr int NTASK = TY * WX;                      // (row, x-word) tasks of one layer: 32 cells each
+  static_assert(NTASK * 8 == C::THREADS, "phase B maps one thread to 4 cells");
   extern __shared__ uint32_t planes[];  // [2][L][RY][WX+1] sign words
+  // phase A -> phase B hand-over, double buffered by level-set parity
+  __shared__ uint32_t s_words[2][NTASK][SIMPLEX ? NVC : 2];  // simplex: vertex sign words; n-cube: (any, all)
+  __shared__ unsigned long long s_lut[SIMPLEX ? (1 << NVC) : 1];  // sign byte of an n-cube -> states of its CPC simplices
   __shared__ uint8_t s_tets[6][4];
   const int L = lv.L;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -182,7 +187,25 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
   const int j0 = (D == 3) ? blockIdx.y * TY : 0;
   const int kz0 = g.k0 + ((D == 3) ? blockIdx.z : blockIdx.y) * ZS;  // first layer (global index)
   const int kz1 = min(kz0 + ZS, g.k1);
-  if (SIMPLEX && threadIdx.x < 24) s_tets[threadIdx.x / 4][threadIdx.x % 4] = simplexify_raw[(D - 2) * 24 + threadIdx.x];
+  const bool vec_ok = (nx & 3) == 0;
+  if (SIMPLEX) {
+    if (threadIdx.x < 24) s_tets[threadIdx.x / 4][threadIdx.x % 4] = simplexify_raw[(D - 2) * 24 + threadIdx.x];
+    __syncthreads();
+    for (int sb = threadIdx.x; sb < (1 << NVC); sb += C::THREADS) {
+      unsigned long long e = 0ull;
+      for (int t = 0; t < CPC; ++t) {
+        bool any = false, all = true;
+        for (int m = 0; m <= D; ++m) {
+          const bool o = (sb >> s_tets[t][m]) & 1;
+          any |= o;
+          all &= o;
+        }
+        const unsigned long long st = all ? 0x01ull : (any ? 0x00ull : 0xFFull);  // OUT / CUT / IN
+        e |= st << (8 * t);
+      }
+      s_lut[sb] = e;
+    }
+  }
   const int plane_words = L * RY * (WX + 1);
 
   for (int kp = kz0; kp <= kz1; ++kp) {  // node planes kz0..kz1
@@ -222,80 +245,117 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
       const uint32_t* P0 = planes + ((kp - 1 - kz0) & 1) * plane_words;
       const uint32_t* P1 = P;
       const int kc = kp - 1;  // global layer index
-      for (int task = threadIdx.x; task < TY * WX * L; task += C::THREADS) {
-        const int ls = task / (TY * WX);
-        const int rem = task % (TY * WX);
-        const int r = rem / WX, ww = rem % WX;
-        const int jc = j0 + r;
-        const int i0 = 32 * (w0 + ww);
-        if (i0 >= nx || jc >= ny) continue;
-        // vertex words: V[lv] bit c = sign of local vertex lv of cell i0+c
-        uint32_t V[NVC];
-#pragma unroll
-        for (int v = 0; v < NVC; ++v) {
-          const int xo = v & 1;
-          const int ro = (D == 3) ? ((v >> 1) & 1) : 0;
-          const int po = (D == 3) ? ((v >> 2) & 1) : ((v >> 1) & 1);
-          const uint32_t* Pp = po ? P1 : P0;
-          const uint32_t* row = Pp + (ls * RY + r + ro) * (WX + 1);
-          uint32_t a = row[ww];
-          if (xo) a = (a >> 1) | (row[ww + 1] << 31);
-          V[v] = a;
-        }
-        const int ncell = min(32, nx - i0);
-        const uint32_t live = ncell == 32 ? 0xffffffffu : ((1u << ncell) - 1u);
-        const int64_t rowid = (D == 3) ? ((int64_t)(kc - g.k0) * ny + jc) : (int64_t)(kc - g.k0);
-        const int64_t cube0 = rowid * nx + i0;
-        int8_t* out = states + (int64_t)ls * pitch + cube0 * CPC;
-        uint32_t* cm = cutmask + (rowid * wxtot + (w0 + ww)) * CPC;
-#pragma unroll
-        for (int t = 0; t < CPC; ++t) {
-          uint32_t any, all;
-          if (SIMPLEX) {
-            any = 0u;
-            all = 0xffffffffu;
-#pragma unroll
-            for (int m = 0; m <= D; ++m) {
-              uint32_t a = V[s_tets[t][m]];
-              any |= a;
-              all &= a;
-            }
-          } else {
-            any = 0u;
-            all = 0xffffffffu;
+      for (int ls = 0; ls < L; ++ls) {
+        // phase A: one thread per (row, word): vertex sign words, cut mask, hand-over to phase B
+        if (threadIdx.x < NTASK) {
+          const int r = threadIdx.x / WX, ww = threadIdx.x % WX;
+          const int jc = j0 + r;
+          const int i0 = 32 * (w0 + ww);
+          if (i0 < nx && jc < ny) {
+            uint32_t V[NVC];
 #pragma unroll
             for (int v = 0; v < NVC; ++v) {
-              any |= V[v];
-              all &= V[v];
+              const int xo = v & 1;
+              const int ro = (D == 3) ? ((v >> 1) & 1) : 0;
+              const int po = (D == 3) ? ((v >> 2) & 1) : ((v >> 1) & 1);
+              const uint32_t* row = (po ? P1 : P0) + (ls * RY + r + ro) * (WX + 1);
+              uint32_t a = row[ww];
+              if (xo) a = (a >> 1) | (row[ww + 1] << 31);
+              V[v] = a;
+            }
+            const int ncell = min(32, nx - i0);
+            const uint32_t live = ncell == 32 ? 0xffffffffu : ((1u << ncell) - 1u);
+            const int64_t rowid = (D == 3) ? ((int64_t)(kc - g.k0) * ny + jc) : (int64_t)(kc - g.k0);
+            uint32_t* cm = cutmask + (rowid * wxtot + (w0 + ww)) * CPC;
+            if (SIMPLEX) {
+#pragma unroll
+              for (int v = 0; v < NVC; ++v) s_words[ls & 1][threadIdx.x][v] = V[v];
+#pragma unroll
+              for (int t = 0; t < CPC; ++t) {
+                uint32_t any = 0u, all = 0xffffffffu;
+#pragma unroll
+                for (int m = 0; m <= D; ++m) {
+                  const uint32_t a = V[s_tets[t][m]];
+                  any |= a;
+                  all &= a;
+                }
+                const uint32_t cutw = any & ~all & live;
+                if (L == 1 || ls == 0)
+                  cm[t] = cutw;
+                else if (cutw)
+                  cm[t] |= cutw;  // same thread owns this word for every ls of the layer
+              }
+            } else {
+              uint32_t any = 0u, all = 0xffffffffu;
+#pragma unroll
+              for (int v = 0; v < NVC; ++v) {
+                any |= V[v];
+                all &= V[v];
+              }
+              s_words[ls & 1][threadIdx.x][0] = any;
+              s_words[ls & 1][threadIdx.x][1] = all;
+              const uint32_t cutw = any & ~all & live;
+              if (L == 1 || ls == 0)
+                cm[0] = cutw;
+              else if (cutw)
+                cm[0] |= cutw;
             }
           }
-          const uint32_t cutw = any & ~all & live;
-          // accumulate "cut by any level set"; tasks of different ls of the same word are different threads
-          if (L == 1)
-            cm[t] = cutw;
-          else if (cutw)
-            atomicOr(cm + t, cutw);
-          if (CPC == 1 && (nx & 3) == 0) {
-            // 4 states per 32-bit store: OUT(1) where all, IN(-1 = 0xFF) where !any, CUT(0) otherwise
+        }
+        __syncthreads();
+        // phase B: one thread per 4 consecutive cells: state bytes (coalesced 4/8-byte stores)
+        {
+          const int task = threadIdx.x >> 3, quad = threadIdx.x & 7;
+          const int r = task / WX, ww = task % WX;
+          const int jc = j0 + r;
+          const int i0 = 32 * (w0 + ww);
+          const int c0 = 4 * quad;
+          if (i0 + c0 < nx && jc < ny) {
+            const int ncq = min(4, nx - (i0 + c0));
+            const int64_t rowid = (D == 3) ? ((int64_t)(kc - g.k0) * ny + jc) : (int64_t)(kc - g.k0);
+            const int64_t cube0 = rowid * nx + i0 + c0;
+            int8_t* out = states + (int64_t)ls * pitch + cube0 * CPC;
+            if (SIMPLEX) {
+              unsigned long long e[4];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              if (4 * q < ncell) {
-                uint32_t o4 = (all >> (4 * q)) & 0xFu, n4 = (~any >> (4 * q)) & 0xFu;
-                uint32_t so = (o4 * 0x00204081u) & 0x01010101u;
-                uint32_t si = ((n4 * 0x00204081u) & 0x01010101u) * 0xFFu;
-                reinterpret_cast<uint32_t*>(out)[q] = so | si;
+              for (int c = 0; c < 4; ++c) {
+                uint32_t sb = 0;
+#pragma unroll
+                for (int v = 0; v < NVC; ++v) sb |= ((s_words[ls & 1][task][v] >> (c0 + c)) & 1u) << v;
+                e[c] = s_lut[sb];
               }
-            }
-          } else {
-            for (int c = 0; c < ncell; ++c) {
-              int8_t s = ((all >> c) & 1u) ? (int8_t)GC_OUT : (((any >> c) & 1u) ? (int8_t)GC_CUT : (int8_t)GC_IN);
-              out[(int64_t)c * CPC + t] = s;
+              if (vec_ok) {
+                if (CPC == 6) {  // 4 cells x 6 bytes = 24 bytes = three 8-byte stores
+                  unsigned long long* o8 = reinterpret_cast<unsigned long long*>(out);
+                  o8[0] = (e[0] & 0xFFFFFFFFFFFFull) | (e[1] << 48);
+                  o8[1] = ((e[1] >> 16) & 0xFFFFFFFFull) | (e[2] << 32);
+                  o8[2] = ((e[2] >> 32) & 0xFFFFull) | (e[3] << 16);
+                } else {  // 4 cells x 2 bytes
+                  *reinterpret_cast<unsigned long long*>(out) =
+                      (e[0] & 0xFFFFull) | ((e[1] & 0xFFFFull) << 16) | ((e[2] & 0xFFFFull) << 32) | ((e[3] & 0xFFFFull) << 48);
+                }
+              } else {
+                for (int c = 0; c < ncq; ++c)
+                  for (int t = 0; t < CPC; ++t) out[c * CPC + t] = (int8_t)((e[c] >> (8 * t)) & 0xFFull);
+              }
+            } else {
+              const uint32_t any = s_words[ls & 1][task][0], all = s_words[ls & 1][task][1];
+              const uint32_t o4 = (all >> c0) & 0xFu, n4 = (~any >> c0) & 0xFu;
+              const uint32_t so = (o4 * 0x00204081u) & 0x01010101u;
+              const uint32_t si = ((n4 * 0x00204081u) & 0x01010101u) * 0xFFu;
+              const uint32_t w = so | si;  // OUT(1) where all, IN(0xFF) where !any, CUT(0) otherwise
+              if (vec_ok) {
+                *reinterpret_cast<uint32_t*>(out) = w;
+              } else {
+                for (int c = 0; c < ncq; ++c) out[c] = (int8_t)((w >> (8 * c)) & 0xFFu);
+              }
             }
           }
         }
       }
     }
-    __syncthreads();
+    // no barrier needed here: the next plane goes to the buffer last read by phase A (which is followed by a barrier),
+    // and s_words is only rewritten after the barrier that follows the next evaluation
   }
 }
 

@@ -236,6 +236,14 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
               lay.sf_N[(int64_t)fid * D + i] = nrm[i];
             }
             lay.sf_c2bg[fid] = bgcell1;
+            {
+              double pf[D][3];
+#pragma unroll
+              for (int v = 0; v < D; ++v)
+#pragma unroll
+                for (int d = 0; d < D; ++d) pf[v][d] = E[depth][fp[v]].x[d];
+              lay.sf_meas[fid] = integrate_one<D - 1>(simplex_meas<D, D - 1>(pf));
+            }
             lay.sf_state[fid] = (int8_t)GECUT_INTERFACE;
           }
         }
@@ -290,6 +298,14 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
                       lay.sf_N[(int64_t)fid * D + i] = nrm[i];
                     }
                     lay.sf_c2bg[fid] = bgcell1;
+                    {
+                      double pf[D][3];
+#pragma unroll
+                      for (int v = 0; v < D; ++v)
+#pragma unroll
+                        for (int d = 0; d < D; ++d) pf[v][d] = FE[fdepth][TF.sub_pts[fc][j][v]].x[d];
+                      lay.sf_meas[fid] = integrate_one<D - 1>(simplex_meas<D, D - 1>(pf));
+                    }
                     for (int kk = 0; kk < L; ++kk) {
                       int8_t v = (kk == ls) ? (int8_t)GECUT_INTERFACE : ((kk == k) ? TF.sub_inout[fc][j] : fst[kk]);
                       lay.sf_state[(int64_t)kk * lay.sf_pitch + fid] = v;
@@ -336,6 +352,14 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
 #pragma unroll
             for (int i = 0; i <= D; ++i) lay.sc_c2p[(int64_t)cid * (D + 1) + i] = (int32_t)(pt_off + TC.sub_pts[c][j][i] + 1);
             lay.sc_c2bg[cid] = bgcell1;
+            {
+              double pc[D + 1][3];
+#pragma unroll
+              for (int v = 0; v <= D; ++v)
+#pragma unroll
+                for (int d = 0; d < D; ++d) pc[v][d] = E[depth][TC.sub_pts[c][j][v]].x[d];
+              lay.sc_meas[cid] = integrate_one<D>(simplex_meas<D, D>(pc));
+            }
             lay.sc_state[cid] = TC.sub_inout[c][j];
             for (int kk = 1; kk < L; ++kk) lay.sc_state[(int64_t)kk * lay.sc_pitch + cid] = st[kk];
           }
@@ -368,6 +392,258 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
       if (L > 1) cn.fpt[k][s] = fpt_off[k];
     }
   }
+}
+
+// ================================================================================================
+// L == 1 fast path (one level set: BASELINE configs 2 and 3).  The refinement tree has depth one, so a stage-0 simplex
+// needs no stack: case -> table row.  Blocks own tiles of CUT1_TILE consecutive stage-0 simplices:
+//   k_cut1_count : per-tile totals (subcells, points, facets)                      -> exclusive scan over the tiles
+//   k_cut1_fill  : recomputes the case, block-scans the three counters (packed in one word), stages the tile's output
+//                  in shared memory and writes every array of the layout with fully coalesced stores.
+// No per-simplex offset ever goes to HBM.  The facet point arrays of a single level set are the subcell point arrays
+// (CutTriangulations.jl:365-378 aliases them; merge_sub_face_data copies them): on the device they stay aliased.
+// ================================================================================================
+constexpr int CUT1_TILE = 128;
+
+__device__ __forceinline__ uint32_t cut1_pack(int ncell, int npt, int nfac) {
+  return (uint32_t)nfac | ((uint32_t)npt << 10) | ((uint32_t)ncell << 21);
+}
+
+// exclusive scan of one packed word per thread across a block of CUT1_TILE threads
+__device__ __forceinline__ uint32_t cut1_block_scan(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t wsum[CUT1_TILE / 32 + 1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) wsum[wid] = inc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int w = 0; w < CUT1_TILE / 32; ++w) {
+      uint32_t t = wsum[w];
+      wsum[w] = run;
+      run += t;
+    }
+    wsum[CUT1_TILE / 32] = run;
+  }
+  __syncthreads();
+  *total = wsum[CUT1_TILE / 32];
+  return wsum[wid] + inc - v;
+}
+
+template <int D>
+__device__ __forceinline__ int cut1_case(const Pt<D, 1>* S) {
+  int c = 0;
+#pragma unroll
+  for (int i = 0; i <= D; ++i)
+    if (S[i].w[0] > 0.0) c |= 1 << i;
+  return c;
+}
+
+template <int D>
+__global__ void __launch_bounds__(CUT1_TILE)
+k_cut1_count(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
+             const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
+             const int32_t* __restrict__ cutcells, int64_t nsimp, uint32_t* __restrict__ tile_cells,
+             uint32_t* __restrict__ tile_points, uint32_t* __restrict__ tile_facets) {
+  const GcSimplexTable* T = tables + (D - 1);
+  const int64_t s = (int64_t)blockIdx.x * CUT1_TILE + threadIdx.x;
+  uint32_t packed = 0;
+  if (s < nsimp) {
+    Pt<D, 1> S[D + 1];
+    setup_stage0<D, 1>(g, lv, (int64_t)cutcells[s / g.nt0] - 1, (int)(s % g.nt0), simp_raw, simp_pos, S);
+    const int c = cut1_case<D>(S);
+    packed = cut1_pack(T->nsub[c], T->npts[c], T->nfac[c]);
+  }
+  uint32_t total;
+  cut1_block_scan(packed, &total);
+  if (threadIdx.x == 0) {
+    tile_cells[blockIdx.x] = total >> 21;
+    tile_points[blockIdx.x] = (total >> 10) & 0x7FFu;
+    tile_facets[blockIdx.x] = total & 0x3FFu;
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(CUT1_TILE, 6)
+k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
+            const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
+            const int32_t* __restrict__ cutcells, int64_t nsimp, const uint32_t* __restrict__ tile_cells,
+            const uint32_t* __restrict__ tile_points, const uint32_t* __restrict__ tile_facets, GcLayout lay,
+            uint32_t* __restrict__ sc_ptr) {
+  constexpr int NPC = WalkCfg<D>::NPC;
+  constexpr int NSUB = (D == 3) ? 6 : 3, NFAC = (D == 3) ? 2 : 1, NE = (D == 3) ? 6 : 3;
+  // one staging buffer, used in turn for point_to_coords, point_to_rcoords and the integer arrays
+  extern __shared__ double stage[];  // [CUT1_TILE*NPC][D] doubles
+  __shared__ GcSimplexTable s_tab;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(tables + (D - 1));
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
+    for (int i = threadIdx.x; i < (int)(sizeof(GcSimplexTable) / 4); i += CUT1_TILE) dst[i] = src[i];
+  }
+  __syncthreads();
+  const GcSimplexTable& TC = s_tab;
+  const int64_t s = (int64_t)blockIdx.x * CUT1_TILE + threadIdx.x;
+  const bool valid = s < nsimp;
+  Pt<D, 1> S[D + 1];
+  int c = 0, nsub = 0, np = 0, nfac = 0;
+  int32_t bgcell1 = 0;
+  if (valid) {
+    bgcell1 = cutcells[s / g.nt0];
+    setup_stage0<D, 1>(g, lv, (int64_t)bgcell1 - 1, (int)(s % g.nt0), simp_raw, simp_pos, S);
+    c = cut1_case<D>(S);
+    nsub = TC.nsub[c];
+    np = TC.npts[c];
+    nfac = TC.nfac[c];
+  }
+  uint32_t total;
+  const uint32_t excl = cut1_block_scan(valid ? cut1_pack(nsub, np, nfac) : 0u, &total);
+  const uint32_t lc = excl >> 21, lp = (excl >> 10) & 0x7FFu, lf = excl & 0x3FFu;    // tile-local offsets
+  const uint32_t tc = total >> 21, tp = (total >> 10) & 0x7FFu, tf = total & 0x3FFu;  // tile totals
+  const uint32_t gc = tile_cells[blockIdx.x], gp = tile_points[blockIdx.x], gf = tile_facets[blockIdx.x];  // tile bases
+  // Gridap edge order of the simplex: TRI [1,2],[1,3],[2,3]; TET [1,2],[1,3],[2,3],[1,4],[2,4],[3,4]
+  double coeff[NE];
+  const bool iscut = valid && TC.inoutcut[c] == GC_CUT;
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    const int a = (D == 3) ? (e == 0 ? 0 : e == 1 ? 0 : e == 2 ? 1 : e == 3 ? 0 : e == 4 ? 1 : 2) : (e == 0 ? 0 : e == 1 ? 0 : 1);
+    const int b = (D == 3) ? (e == 0 ? 1 : e == 1 ? 2 : e == 2 ? 2 : 3) : (e == 0 ? 1 : 2);
+    const double v1 = S[a].w[0], v2 = S[b].w[0];
+    coeff[e] = -1.0;  // edge not cut
+    if (iscut && ((v1 > 0.0) != (v2 > 0.0))) {
+      const double w1 = fabs(v1), w2 = fabs(v2);
+      coeff[e] = __ddiv_rn(w1, __dadd_rn(w1, w2));  // (CutTriangulations.jl:213-215)
+    }
+  }
+  // ---- phase 1: physical coordinates: vertex copies, then one point per cut edge in edge order (:199-219)
+  if (valid) {
+    if (s % g.nt0 == 0) sc_ptr[s / g.nt0] = gc + lc;
+    if (s == nsimp - 1) sc_ptr[s / g.nt0 + 1] = gc + lc + nsub;
+#pragma unroll
+    for (int i = 0; i <= D; ++i)
+#pragma unroll
+      for (int d = 0; d < D; ++d) stage[(lp + i) * D + d] = S[i].x[d];
+    int q = D + 1;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const int a = (D == 3) ? (e == 0 ? 0 : e == 1 ? 0 : e == 2 ? 1 : e == 3 ? 0 : e == 4 ? 1 : 2) : (e == 0 ? 0 : e == 1 ? 0 : 1);
+      const int b = (D == 3) ? (e == 0 ? 1 : e == 1 ? 2 : e == 2 ? 2 : 3) : (e == 0 ? 1 : 2);
+      if (coeff[e] >= 0.0) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) stage[(lp + q) * D + d] = gc_lerp(S[a].x[d], S[b].x[d], coeff[e]);
+        q++;
+      }
+    }
+    // facet normals and measures, subcell measures: from this thread's own staged points, written directly
+    for (int f = 0; f < nfac; ++f) {
+      const uint8_t* fp = TC.fac_pts[c][f];
+      double nrm[3];
+      unit_normal<D>(&stage[(lp + fp[0]) * D], &stage[(lp + fp[1]) * D], &stage[(lp + fp[D - 1]) * D],
+                     (double)TC.fac_orient[c][f], nrm);
+      double pf[D][3];
+#pragma unroll
+      for (int v = 0; v < D; ++v)
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          pf[v][d] = stage[(lp + fp[v]) * D + d];
+          if (v == 0) lay.sf_N[(int64_t)(gf + lf + f) * D + d] = nrm[d];
+        }
+      lay.sf_meas[gf + lf + f] = integrate_one<D - 1>(simplex_meas<D, D - 1>(pf));
+    }
+    for (int j = 0; j < nsub; ++j) {
+      double pc[D + 1][3];
+#pragma unroll
+      for (int v = 0; v <= D; ++v)
+#pragma unroll
+        for (int d = 0; d < D; ++d) pc[v][d] = stage[(lp + TC.sub_pts[c][j][v]) * D + d];
+      lay.sc_meas[gc + lc + j] = integrate_one<D>(simplex_meas<D, D>(pc));
+    }
+  }
+  __syncthreads();
+  {
+    double* gX = lay.sc_X + (int64_t)gp * D;
+    for (uint32_t i = threadIdx.x; i < tp * D; i += CUT1_TILE) gX[i] = stage[i];
+  }
+  __syncthreads();
+  // ---- phase 2: reference coordinates
+  if (valid) {
+#pragma unroll
+    for (int i = 0; i <= D; ++i)
+#pragma unroll
+      for (int d = 0; d < D; ++d) stage[(lp + i) * D + d] = S[i].r[d];
+    int q = D + 1;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const int a = (D == 3) ? (e == 0 ? 0 : e == 1 ? 0 : e == 2 ? 1 : e == 3 ? 0 : e == 4 ? 1 : 2) : (e == 0 ? 0 : e == 1 ? 0 : 1);
+      const int b = (D == 3) ? (e == 0 ? 1 : e == 1 ? 2 : e == 2 ? 2 : 3) : (e == 0 ? 1 : 2);
+      if (coeff[e] >= 0.0) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) stage[(lp + q) * D + d] = gc_lerp(S[a].r[d], S[b].r[d], coeff[e]);
+        q++;
+      }
+    }
+  }
+  __syncthreads();
+  {
+    double* gR = lay.sc_R + (int64_t)gp * D;
+    for (uint32_t i = threadIdx.x; i < tp * D; i += CUT1_TILE) gR[i] = stage[i];
+  }
+  __syncthreads();
+  // ---- phase 3: integer arrays, staged in the same shared memory
+  int32_t* st_c2p = reinterpret_cast<int32_t*>(stage);           // [CUT1_TILE*NSUB][D+1]
+  int32_t* st_c2bg = st_c2p + CUT1_TILE * NSUB * (D + 1);        // [CUT1_TILE*NSUB]
+  int32_t* st_f2p = st_c2bg + CUT1_TILE * NSUB;                  // [CUT1_TILE*NFAC][D]
+  int32_t* st_f2bg = st_f2p + CUT1_TILE * NFAC * D;              // [CUT1_TILE*NFAC]
+  int8_t* st_state = reinterpret_cast<int8_t*>(st_f2bg + CUT1_TILE * NFAC);  // [CUT1_TILE*NSUB]
+  if (valid) {
+    const int32_t pbase = (int32_t)(gp + lp) + 1;  // 1-based id of the first point of this simplex' block
+    for (int j = 0; j < nsub; ++j) {
+#pragma unroll
+      for (int i = 0; i <= D; ++i) st_c2p[(lc + j) * (D + 1) + i] = pbase + TC.sub_pts[c][j][i];
+      st_c2bg[lc + j] = bgcell1;
+      st_state[lc + j] = TC.sub_inout[c][j];
+    }
+    for (int f = 0; f < nfac; ++f) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) st_f2p[(lf + f) * D + i] = pbase + TC.fac_pts[c][f][i];
+      st_f2bg[lf + f] = bgcell1;
+    }
+  }
+  __syncthreads();
+  {
+    int32_t* g_c2p = lay.sc_c2p + (int64_t)gc * (D + 1);
+    for (uint32_t i = threadIdx.x; i < tc * (D + 1); i += CUT1_TILE) g_c2p[i] = st_c2p[i];
+    int32_t* g_c2bg = lay.sc_c2bg + gc;
+    int8_t* g_state = lay.sc_state + gc;
+    for (uint32_t i = threadIdx.x; i < tc; i += CUT1_TILE) {
+      g_c2bg[i] = st_c2bg[i];
+      g_state[i] = st_state[i];
+    }
+    int32_t* g_f2p = lay.sf_c2p + (int64_t)gf * D;
+    for (uint32_t i = threadIdx.x; i < tf * D; i += CUT1_TILE) g_f2p[i] = st_f2p[i];
+    int32_t* g_f2bg = lay.sf_c2bg + gf;
+    int8_t* g_fstate = lay.sf_state + gf;
+    for (uint32_t i = threadIdx.x; i < tf; i += CUT1_TILE) {
+      g_f2bg[i] = st_f2bg[i];
+      g_fstate[i] = (int8_t)GECUT_INTERFACE;
+    }
+  }
+}
+
+template <int D>
+size_t cut1_fill_smem() {
+  return sizeof(double) * (CUT1_TILE * WalkCfg<D>::NPC * D);
+}
+
+__global__ void k_extract_sc_ptr(const uint32_t* __restrict__ cell_offs, int nt0, int64_t ncut, uint32_t total,
+                                 uint32_t* __restrict__ ptr) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < ncut) ptr[k] = cell_offs[k * nt0];
+  if (k == ncut) ptr[k] = total;
 }
 
 template <int D, int LM>
@@ -406,6 +682,75 @@ void dispatch_walk(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const
 
 static inline int64_t pad_pitch(int64_t n) { return ((n + 255) / 256) * 256; }
 
+// L == 1: tile totals -> scan over tiles -> allocate -> fill (see the fast-path kernels above)
+static int gc_cut_cells_l1(gecut_ctx* ctx, gecut_result* res) {
+  const GcGrid& g = res->grid;
+  const int D = g.D;
+  const int64_t ncut = res->sizes.num_cutcells;
+  const int64_t nsimp = ncut * g.nt0;
+  const int64_t ntiles = gc_div_up(nsimp, CUT1_TILE);
+  gecut_sizes& sz = res->sizes;
+  uint32_t* tiles = nullptr;
+  uint64_t* totals_dev = nullptr;
+  GC_CHECK(gc_malloc(ctx, (void**)&tiles, sizeof(uint32_t) * ntiles * 3));
+  GC_CHECK(gc_malloc(ctx, (void**)&totals_dev, sizeof(uint64_t) * 3));
+  uint32_t *t_cells = tiles, *t_points = tiles + ntiles, *t_facets = tiles + 2 * ntiles;
+  if (D == 2)
+    GC_LAUNCH(ctx, "k_cut1_count", k_cut1_count<2><<<(unsigned)ntiles, CUT1_TILE, 0, ctx->stream>>>(
+        g, res->leaves, ctx->d_tables, ctx->d_simplexify_raw, ctx->d_simplexify_pos, res->lay.cutcells, nsimp, t_cells, t_points, t_facets));
+  else
+    GC_LAUNCH(ctx, "k_cut1_count", k_cut1_count<3><<<(unsigned)ntiles, CUT1_TILE, 0, ctx->stream>>>(
+        g, res->leaves, ctx->d_tables, ctx->d_simplexify_raw, ctx->d_simplexify_pos, res->lay.cutcells, nsimp, t_cells, t_points, t_facets));
+  GC_CHECK(gc_launch_check(ctx, "k_cut1_count"));
+  for (int a = 0; a < 3; ++a) GC_CHECK(gc_exclusive_scan_u32(ctx, tiles + a * ntiles, tiles + a * ntiles, ntiles, totals_dev + a));
+  uint64_t* h = (uint64_t*)ctx->h_pinned;
+  GC_CUDA(cudaMemcpyAsync(h, totals_dev, sizeof(uint64_t) * 3, cudaMemcpyDeviceToHost, ctx->stream));
+  GC_CUDA(cudaStreamSynchronize(ctx->stream));
+  const uint64_t nsc = h[0], nscp = h[1], nsf = h[2];
+  const uint64_t lim = 2147483647ull;
+  if (nsc * (uint64_t)(D + 1) >= lim || nscp > lim || nsf > lim) {
+    ctx->err = "Int32 ids of the SubCellData/SubFacetData layout would overflow";
+    gc_free(ctx, tiles);
+    gc_free(ctx, totals_dev);
+    return GECUT_ERR_OVERFLOW;
+  }
+  sz.num_subcells = (int64_t)nsc;
+  sz.num_subcell_points = (int64_t)nscp;
+  sz.num_subfacets = (int64_t)nsf;
+  sz.num_subfacet_points = (int64_t)nscp;  // the facets of a single level set share the subcell points
+  GcLayout& lay = res->lay;
+  lay.sc_pitch = pad_pitch((int64_t)nsc);
+  lay.sf_pitch = pad_pitch((int64_t)nsf);
+  GC_CHECK(gc_malloc(ctx, (void**)&lay.sc_c2p, sizeof(int32_t) * nsc * (D + 1)));
+  GC_CHECK(gc_malloc(ctx, (void**)&lay.sc_c2bg, sizeof(int32_t) * nsc));
+  GC_CHECK(gc_malloc(ctx, (void**)&lay.sc_X, sizeof(double) * nscp * D));
+  GC_CHECK(gc_malloc(ctx, (void**)&lay.sc_R, sizeof(double) * nscp * D));
+  GC_CHECK(gc_malloc(ctx, (void**)&lay.sc_state, (size_t)lay.sc_pitch));
+  GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_c2p, sizeof(int32_t) * nsf * D));
+  GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_c2bg, sizeof(int32_t) * nsf));
+  GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_N, sizeof(double) * nsf * D));
+  GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_state, (size_t)lay.sf_pitch));
+  GC_CHECK(gc_malloc(ctx, (void**)&lay.sc_meas, sizeof(double) * nsc));
+  GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_meas, sizeof(double) * nsf));
+  lay.sf_X = lay.sc_X;  // device-side alias (read-only results); the host copy-out writes both destinations
+  lay.sf_R = lay.sc_R;
+  res->sf_points_alias = true;
+  GC_CHECK(gc_malloc(ctx, (void**)&res->cut_sc_ptr, sizeof(uint32_t) * (ncut + 1)));
+  if (D == 2) {
+    const size_t smem = cut1_fill_smem<2>();
+    GC_LAUNCH(ctx, "k_cut1_fill", k_cut1_fill<2><<<(unsigned)ntiles, CUT1_TILE, smem, ctx->stream>>>(
+        g, res->leaves, ctx->d_tables, ctx->d_simplexify_raw, ctx->d_simplexify_pos, lay.cutcells, nsimp, t_cells, t_points, t_facets, lay, res->cut_sc_ptr));
+  } else {
+    const size_t smem = cut1_fill_smem<3>();
+    GC_LAUNCH(ctx, "k_cut1_fill", k_cut1_fill<3><<<(unsigned)ntiles, CUT1_TILE, smem, ctx->stream>>>(
+        g, res->leaves, ctx->d_tables, ctx->d_simplexify_raw, ctx->d_simplexify_pos, lay.cutcells, nsimp, t_cells, t_points, t_facets, lay, res->cut_sc_ptr));
+  }
+  int st = gc_launch_check(ctx, "k_cut1_fill");
+  gc_free(ctx, tiles);
+  gc_free(ctx, totals_dev);
+  return st;
+}
+
 int gc_cut_cells(gecut_ctx* ctx, gecut_result* res) {
   const GcGrid& g = res->grid;
   const int L = res->L, D = g.D;
@@ -414,6 +759,7 @@ int gc_cut_cells(gecut_ctx* ctx, gecut_result* res) {
   gecut_sizes& sz = res->sizes;
   sz.num_subcells = sz.num_subcell_points = sz.num_subfacets = sz.num_subfacet_points = 0;
   if (nsimp == 0) return GECUT_OK;
+  if (L == 1) return gc_cut_cells_l1(ctx, res);
   // counters: cells, points, fac[L], fpt[L] (fpt unused for L == 1)
   const int narr = 2 + L + (L > 1 ? L : 0);
   uint32_t* pool = nullptr;
@@ -460,6 +806,8 @@ int gc_cut_cells(gecut_ctx* ctx, gecut_result* res) {
   GC_CHECK(gc_malloc(ctx, (void**)&lay.sc_X, sizeof(double) * nscp * D));
   GC_CHECK(gc_malloc(ctx, (void**)&lay.sc_R, sizeof(double) * nscp * D));
   GC_CHECK(gc_malloc(ctx, (void**)&lay.sc_state, (size_t)lay.sc_pitch * L));
+  GC_CHECK(gc_malloc(ctx, (void**)&lay.sc_meas, sizeof(double) * nsc));
+  GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_meas, sizeof(double) * nsf));
   if (nsf > 0) {
     GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_c2p, sizeof(int32_t) * nsf * D));
     GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_c2bg, sizeof(int32_t) * nsf));
@@ -470,6 +818,9 @@ int gc_cut_cells(gecut_ctx* ctx, gecut_result* res) {
     GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_X, sizeof(double) * nsfp * D));
     GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_R, sizeof(double) * nsfp * D));
   }
+  GC_CHECK(gc_malloc(ctx, (void**)&res->cut_sc_ptr, sizeof(uint32_t) * (ncut + 1)));
+  GC_LAUNCH(ctx, "k_extract_sc_ptr", k_extract_sc_ptr<<<(unsigned)gc_div_up(ncut + 1, 256), 256, 0, ctx->stream>>>(
+      cn.cells, g.nt0, ncut, (uint32_t)nsc, res->cut_sc_ptr));
   dispatch_walk(ctx, res, nsimp, cn, true);
   int st = gc_launch_check(ctx, "k_cut_walk(fill)");
   gc_free(ctx, pool);

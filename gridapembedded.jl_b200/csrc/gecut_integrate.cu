@@ -9,63 +9,19 @@
 // SubCellTriangulations.jl:63-72).  No step is a dense contraction, so tensor cores are deliberately unused.
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 #include "gecut_internal.cuh"
 
 namespace {
 
-__host__ __device__ inline double det2x2(const double J[3][3]) { return J[0][0] * J[1][1] - J[0][1] * J[1][0]; }
-__host__ __device__ inline double det3x3(const double J[3][3]) {
-  return J[0][0] * J[1][1] * J[2][2] + J[0][1] * J[1][2] * J[2][0] + J[0][2] * J[1][0] * J[2][1] -
-         (J[0][0] * J[1][2] * J[2][1] + J[0][1] * J[1][0] * J[2][2] + J[0][2] * J[1][1] * J[2][0]);
-}
-
-// |det J| of a D-simplex / sqrt(det JtJ) of a (D-1)-simplex whose vertices are p[0..ds] (D doubles each)
-template <int D, int DS>
-__device__ __forceinline__ double simplex_meas(const double (*p)[3]) {
-  if (DS == D) {
-    double J[3][3];
-#pragma unroll
-    for (int i = 0; i < D; ++i)
-#pragma unroll
-      for (int d = 0; d < D; ++d) J[i][d] = p[i + 1][d] - p[0][d];
-    return fabs(D == 2 ? det2x2(J) : det3x3(J));
-  }
-  if (D == 2) {
-    double a = p[1][0] - p[0][0], b = p[1][1] - p[0][1];
-    return sqrt(a * a + b * b);
-  }
-  double a[3] = {p[1][0] - p[0][0], p[1][1] - p[0][1], p[1][2] - p[0][2]};
-  double b[3] = {p[2][0] - p[0][0], p[2][1] - p[0][1], p[2][2] - p[0][2]};
-  double n1 = a[1] * b[2] - a[2] * b[1], n2 = a[2] * b[0] - a[0] * b[2], n3 = a[0] * b[1] - a[1] * b[0];
-  return sqrt(n1 * n1 + n2 * n2 + n3 * n3);
-}
-
-// sum_q w_q * meas with the degree-2 rule of the DS-simplex (weights 1/2 x2, 1/6 x3, 1/24 x4)
-template <int DS>
-__device__ __forceinline__ double integrate_one(double meas) {
-  const double w = DS == 1 ? 0.5 : (DS == 2 ? 1.0 / 6 : 1.0 / 24);
-  const int nq = DS + 1;
-  double s = 0.0;
-#pragma unroll
-  for (int q = 0; q < nq; ++q) s += w * meas;
-  return s;
-}
-
-template <int D, int DS>
-__global__ void k_measures(const int32_t* __restrict__ ids, int64_t n, const int32_t* __restrict__ c2p,
-                           const double* __restrict__ X, double* __restrict__ values) {
+// per-entity measures (integral of 1 with the degree-2 rule) are produced by the subtriangulation kernels while the
+// vertices are on chip; a Measure over a selection only gathers them
+__global__ void k_measures(const int32_t* __restrict__ ids, int64_t n, const double* __restrict__ meas,
+                           double* __restrict__ values) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  int64_t e = (int64_t)ids[i] - 1;
-  double p[DS + 1][3];
-#pragma unroll
-  for (int v = 0; v <= DS; ++v) {
-    int64_t pid = (int64_t)c2p[e * (DS + 1) + v] - 1;
-#pragma unroll
-    for (int d = 0; d < D; ++d) p[v][d] = X[pid * D + d];
-  }
-  values[i] = integrate_one<DS>(simplex_meas<D, DS>(p));
+  values[i] = meas[(int64_t)ids[i] - 1];
 }
 
 // deterministic two-level sum
@@ -216,99 +172,163 @@ inline QuadRule ncube_rule_deg2(int D) {
   return q;
 }
 
-// One warp per cut bg cell: lanes own entries (a,b) of the nv x nv matrix and loop over the selected subcells of the
-// cell (a contiguous run of the selection, found by binary search on the bg cell id) and the quadrature points.
+// One warp per cut bg cell.  The selection (bg state CUT && subcell state == side, EmbeddedDiscretizations.jl:303-311) is
+// evaluated on the fly from the state rows, so the kernel reads each subcell of the cell exactly once.
+//   * n-cube cells (Q1): the integrand grad(phi_a).grad(phi_b) is a tensor-product polynomial; with
+//     P_0(t)=(1-t)^2, P_1(t)=t(1-t), P_2(t)=t^2 it only needs the moments
+//       M_d[i][j] = sum_{s,q} w_q |J_s| P_i(eta_e) P_j(eta_f)   ((e,f) = the directions other than d)
+//     (27 numbers in 3-D, 6 in 2-D), accumulated per lane over (subcell, quadrature point) items, reduced across the warp
+//     through shared memory, and K_ab = sum_d sgn_a sgn_b / h_d^2 * M_d[a_e+b_e][a_f+b_f].
+//   * simplex cells (P1): gradients are constant, K_ab = (g_a.g_b) * sum_s sum_q w_q |J_s|.
+constexpr int LAP_WARPS = 4;
+
 template <int D>
-__global__ void __launch_bounds__(128)
-k_cutcell_laplacian(const GcGrid g, const GcLayout lay, const int32_t* __restrict__ sel_ids, int64_t nsel,
-                    int64_t ncut, const uint8_t* __restrict__ simp_raw, double* __restrict__ K) {
-  const int lane = threadIdx.x & 31;
-  const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (k >= ncut) return;
-  const int nv = g.nv, nn = nv * nv;
-  const int32_t bg = lay.cutcells[k];
-  // run [lo,hi) of the selection with cell_to_bgcell == bg
-  int64_t lo, hi;
-  {
-    int64_t a = 0, b = nsel;
-    while (a < b) {
-      int64_t m = (a + b) >> 1;
-      if (lay.sc_c2bg[(int64_t)sel_ids[m] - 1] < bg) a = m + 1; else b = m;
-    }
-    lo = a;
-    b = nsel;
-    while (a < b) {
-      int64_t m = (a + b) >> 1;
-      if (lay.sc_c2bg[(int64_t)sel_ids[m] - 1] <= bg) a = m + 1; else b = m;
-    }
-    hi = a;
-  }
-  double acc[2] = {0.0, 0.0};
-  if (hi > lo) {
+__global__ void __launch_bounds__(LAP_WARPS * 32)
+k_cutcell_laplacian_q1(const GcGrid g, const GcLayout lay, const uint32_t* __restrict__ sc_ptr, int64_t ncut,
+                    const GcProgram prog, int side, const uint8_t* __restrict__ simp_raw, double* __restrict__ K) {
+  constexpr int NV = 1 << D;
+  constexpr int NQ = D + 1;
+  constexpr int NM = D == 3 ? 27 : 6;
+  constexpr int NN = NV * NV;
+  __shared__ double red[LAP_WARPS][NM][33];
+  __shared__ double tot[LAP_WARPS][NM];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t nwarps = (int64_t)gridDim.x * LAP_WARPS;
+  const double qa = D == 3 ? (5.0 - sqrt(5.0)) / 20.0 : 1.0 / 6;
+  const double qb = D == 3 ? (5.0 + 3.0 * sqrt(5.0)) / 20.0 : 2.0 / 3;
+  const double qw = D == 3 ? 1.0 / 24 : 1.0 / 6;
+  for (int64_t k = (int64_t)blockIdx.x * LAP_WARPS + wid; k < ncut; k += nwarps) {
+    const int32_t bg = lay.cutcells[k];
     const int64_t cell0 = (int64_t)bg - 1;
-    const int64_t cube = cell0 / g.cpc;
-    const int typ = (int)(cell0 % g.cpc);
-    int ijk[3];
-    ijk[0] = (int)(cube % g.n[0]);
-    if (D == 3) {
-      ijk[1] = (int)((cube / g.n[0]) % g.n[1]);
-      ijk[2] = (int)(cube / ((int64_t)g.n[0] * g.n[1])) + g.k0;
-    } else {
-      ijk[1] = (int)(cube / g.n[0]) + g.k0;
-      ijk[2] = 0;
-    }
-    double xv[8][3], invJt[3][3];
-    bgcell_vertices(g, ijk, typ, simp_raw, xv);
-    bgcell_inv_jt(g, xv, invJt);
-    const QuadRule q = simplex_rule_deg2(D);
-    for (int64_t s = lo; s < hi; ++s) {
-      const int64_t e = (int64_t)sel_ids[s] - 1;
-      double p[D + 1][3], r[D + 1][3];
+    const int bgstate = gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, cell0);
+    double M[NM];
 #pragma unroll
-      for (int v = 0; v <= D; ++v) {
-        int64_t pid = (int64_t)lay.sc_c2p[e * (D + 1) + v] - 1;
+    for (int m = 0; m < NM; ++m) M[m] = 0.0;
+    if (bgstate == GC_CUT) {
+      const uint32_t s0 = sc_ptr[k], s1 = sc_ptr[k + 1];
+      for (uint32_t it = s0 + lane; it < s1; it += 32) {
+        const int64_t e = (int64_t)it;
+        if (gc_eval_inoutcut(prog, lay.sc_state, lay.sc_pitch, e) != side) continue;
+        double r[D + 1][3];
+#pragma unroll
+        for (int v = 0; v <= D; ++v) {
+          const int64_t pid = (int64_t)lay.sc_c2p[e * (D + 1) + v] - 1;
+#pragma unroll
+          for (int d = 0; d < D; ++d) r[v][d] = lay.sc_R[pid * D + d];
+        }
+        const double wdV = lay.sc_meas[e] * (1.0 / NQ);  // sc_meas = sum_q w_q |J_s| (all weights equal)
+        double rs[3];
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-          p[v][d] = lay.sc_X[pid * D + d];
-          r[v][d] = lay.sc_R[pid * D + d];
-        }
-      }
-      const double dV = simplex_meas<D, D>(p);
-      for (int iq = 0; iq < q.n; ++iq) {
-        double N[4];
-        double sm = 0;
-        for (int d = 0; d < D; ++d) sm += q.xi[iq][d];
-        N[0] = 1.0 - sm;
-        for (int d = 0; d < D; ++d) N[d + 1] = q.xi[iq][d];
-        double eta[3] = {0, 0, 0};
-        for (int i = 0; i <= D; ++i)
-          for (int d = 0; d < D; ++d) eta[d] += N[i] * r[i][d];
-        double gr[8][3], gx[8][3];
-        bg_ref_grads(D, g.simplexified != 0, eta, gr);
-        for (int a = 0; a < nv; ++a)
-          for (int d = 0; d < D; ++d) {
-            double v = 0;
-            for (int e2 = 0; e2 < D; ++e2) v += invJt[d][e2] * gr[a][e2];
-            gx[a][d] = v;
-          }
-        const double wdV = q.w[iq] * dV;
+          double t = r[0][d];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          int idx = lane + 32 * u;
-          if (idx < nn) {
-            int a = idx / nv, b = idx % nv;
-            double dd = 0;
-            for (int d = 0; d < D; ++d) dd += gx[a][d] * gx[b][d];
-            acc[u] += wdV * dd;
+          for (int i = 1; i <= D; ++i) t += r[i][d];
+          rs[d] = qa * t;
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          double P[3][3];
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            // eta_q = sum_i N_i(xi_q) R_i with N_i = qb for i == q and qa otherwise
+            const double t = rs[d] + (qb - qa) * r[q][d], u = 1.0 - t;
+            P[d][0] = u * u;
+            P[d][1] = t * u;
+            P[d][2] = t * t;
+          }
+          if (D == 3) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              const int e1 = d == 0 ? 1 : 0, f1 = d == 2 ? 1 : 2;
+#pragma unroll
+              for (int i = 0; i < 3; ++i) {
+                const double wp = wdV * P[e1][i];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) M[d * 9 + i * 3 + j] = fma(wp, P[f1][j], M[d * 9 + i * 3 + j]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+              const int e1 = 1 - d;
+#pragma unroll
+              for (int i = 0; i < 3; ++i) M[d * 3 + i] = fma(wdV, P[e1][i], M[d * 3 + i]);
+            }
           }
         }
       }
     }
-  }
+    // ---- reduce the moments across the warp
 #pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    int idx = lane + 32 * u;
-    if (idx < nn) K[k * nn + idx] = acc[u];
+    for (int m = 0; m < NM; ++m) red[wid][m][lane] = M[m];
+    __syncwarp();
+    if (lane < NM) {
+      double sacc = 0.0;
+      for (int j = 0; j < 32; ++j) sacc += red[wid][lane][j];
+      tot[wid][lane] = sacc;
+    }
+    __syncwarp();
+    // ---- element matrix
+    {
+#pragma unroll
+      for (int u = 0; u < (NN + 31) / 32; ++u) {
+        const int idx = lane + 32 * u;
+        if (idx < NN) {
+          const int a = idx / NV, b = idx % NV;
+          double val = 0.0;
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            const double sg = (((a >> d) & 1) == ((b >> d) & 1)) ? 1.0 : -1.0;
+            const double ih2 = 1.0 / (g.dx[d] * g.dx[d]);
+            int mi;
+            if (D == 3) {
+              const int e1 = d == 0 ? 1 : 0, f1 = d == 2 ? 1 : 2;
+              mi = d * 9 + (((a >> e1) & 1) + ((b >> e1) & 1)) * 3 + (((a >> f1) & 1) + ((b >> f1) & 1));
+            } else {
+              const int e1 = 1 - d;
+              mi = d * 3 + (((a >> e1) & 1) + ((b >> e1) & 1));
+            }
+            val += sg * ih2 * tot[wid][mi];
+          }
+          K[k * NN + idx] = val;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Simplex bg cells (P1): one thread per cut cell accumulates V = sum over its selected subcells of sum_q w_q |J_s|; the
+// matrix is V * (g_a.g_b) with the constant gradient products of the cell type (6 TET / 2 TRI types of a Cartesian
+// n-cube), written warp-cooperatively so that the 32 matrices of a warp go out as contiguous 256-byte stores.
+template <int D>
+__global__ void __launch_bounds__(128)
+k_cutcell_laplacian_p1(const GcGrid g, const GcLayout lay, const uint32_t* __restrict__ sc_ptr, int64_t ncut,
+                       const GcProgram prog, int side, const double* __restrict__ graddots, double* __restrict__ K) {
+  constexpr int NV = D + 1, NN = NV * NV;
+  const int lane = threadIdx.x & 31;
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double V = 0.0;
+  int ty = 0;
+  if (k < ncut) {
+    const int64_t cell0 = (int64_t)lay.cutcells[k] - 1;
+    ty = (int)(cell0 % g.cpc);
+    if (gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, cell0) == GC_CUT) {
+      const uint32_t s0 = sc_ptr[k], s1 = sc_ptr[k + 1];
+      for (uint32_t e = s0; e < s1; ++e) {
+        if (gc_eval_inoutcut(prog, lay.sc_state, lay.sc_pitch, (int64_t)e) != side) continue;
+        V += lay.sc_meas[e];
+      }
+    }
+  }
+  const int64_t wbase = k - lane;
+#pragma unroll
+  for (int j = 0; j < NN; ++j) {
+    const int idx = lane + 32 * j;
+    const int cl = idx / NN, en = idx % NN;
+    const double v = __shfl_sync(0xffffffffu, V, cl);
+    const int t = __shfl_sync(0xffffffffu, ty, cl);
+    if (wbase + cl < ncut) K[wbase * NN + idx] = v * graddots[t * NN + en];
   }
 }
 
@@ -375,6 +395,29 @@ static void host_bgcell_laplacian(const GcGrid& g, int typ, double* K) {
   }
 }
 
+// g_a.g_b of the P1 shape functions of an uncut simplex cell of type `typ` (host)
+static void host_bgcell_graddots(const GcGrid& g, int typ, double* G) {
+  const int D = g.D, nv = g.nv;
+  int ijk[3] = {0, 0, 0};
+  ijk[D - 1] = g.k0;
+  double x[8][3], invJt[3][3], gr[8][3], gx[8][3];
+  bgcell_vertices(g, ijk, typ, &GC_SIMPLEXIFY_RAW[0][0][0], x);
+  bgcell_inv_jt(g, x, invJt);
+  bg_ref_grads(D, true, nullptr, gr);
+  for (int a = 0; a < nv; ++a)
+    for (int d = 0; d < D; ++d) {
+      double v = 0;
+      for (int e = 0; e < D; ++e) v += invJt[d][e] * gr[a][e];
+      gx[a][d] = v;
+    }
+  for (int a = 0; a < nv; ++a)
+    for (int b = 0; b < nv; ++b) {
+      double dd = 0;
+      for (int d = 0; d < D; ++d) dd += gx[a][d] * gx[b][d];
+      G[a * nv + b] = dd;
+    }
+}
+
 int gc_integrate_measure(gecut_ctx* ctx, const gecut_selection* sel, double* values_dev, double* total_host) {
   const gecut_result* res = sel->res;
   const GcGrid& g = res->grid;
@@ -387,17 +430,8 @@ int gc_integrate_measure(gecut_ctx* ctx, const gecut_selection* sel, double* val
     if (!vals) GC_CHECK(gc_malloc(ctx, (void**)&vals, sizeof(double) * n));
     const int T = 256;
     const unsigned nb = (unsigned)gc_div_up(n, T);
-    if (sel->kind == GECUT_SEL_BOUNDARY) {
-      if (g.D == 2)
-        GC_LAUNCH(ctx, "k_measures", k_measures<2, 1><<<nb, T, 0, ctx->stream>>>(sel->sub_ids, n, lay.sf_c2p, lay.sf_X, vals));
-      else
-        GC_LAUNCH(ctx, "k_measures", k_measures<3, 2><<<nb, T, 0, ctx->stream>>>(sel->sub_ids, n, lay.sf_c2p, lay.sf_X, vals));
-    } else {
-      if (g.D == 2)
-        GC_LAUNCH(ctx, "k_measures", k_measures<2, 2><<<nb, T, 0, ctx->stream>>>(sel->sub_ids, n, lay.sc_c2p, lay.sc_X, vals));
-      else
-        GC_LAUNCH(ctx, "k_measures", k_measures<3, 3><<<nb, T, 0, ctx->stream>>>(sel->sub_ids, n, lay.sc_c2p, lay.sc_X, vals));
-    }
+    GC_LAUNCH(ctx, "k_measures", k_measures<<<nb, T, 0, ctx->stream>>>(
+        sel->sub_ids, n, sel->kind == GECUT_SEL_BOUNDARY ? lay.sf_meas : lay.sc_meas, vals));
     const int NB = (int)std::min<int64_t>(1024, gc_div_up(n, 1024));
     double* partial = nullptr;
     GC_CHECK(gc_malloc(ctx, (void**)&partial, sizeof(double) * (NB + 1)));
@@ -429,13 +463,31 @@ int gc_integrate_laplacian(gecut_ctx* ctx, gecut_selection* sel, double* K_bg_ho
     for (int t = 0; t < g.cpc; ++t) host_bgcell_laplacian(g, t, K_bg_host + (size_t)t * nn);
   if (ncut == 0) return GECUT_OK;
   if (!sel->K_cut) GC_CHECK(gc_malloc(ctx, (void**)&sel->K_cut, sizeof(double) * ncut * nn));
-  const int T = 128;
-  const unsigned nb = (unsigned)gc_div_up(ncut * 32, T);
+  if (g.simplexified) {
+    double Gh[6 * 16];
+    for (int t = 0; t < g.cpc; ++t) host_bgcell_graddots(g, t, Gh + (size_t)t * nn);
+    double* Gd = nullptr;
+    GC_CHECK(gc_malloc(ctx, (void**)&Gd, sizeof(Gh)));
+    // pinned staging so that the async copy does not read a dead stack frame
+    memcpy((char*)ctx->h_pinned + 1024, Gh, sizeof(double) * g.cpc * nn);
+    GC_CUDA(cudaMemcpyAsync(Gd, (char*)ctx->h_pinned + 1024, sizeof(double) * g.cpc * nn, cudaMemcpyHostToDevice, ctx->stream));
+    const unsigned nb1 = (unsigned)gc_div_up(ncut, 128);
+    if (g.D == 2)
+      GC_LAUNCH(ctx, "k_cutcell_laplacian", k_cutcell_laplacian_p1<2><<<nb1, 128, 0, ctx->stream>>>(
+          g, res->lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, Gd, sel->K_cut));
+    else
+      GC_LAUNCH(ctx, "k_cutcell_laplacian", k_cutcell_laplacian_p1<3><<<nb1, 128, 0, ctx->stream>>>(
+          g, res->lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, Gd, sel->K_cut));
+    gc_free(ctx, Gd);
+    return gc_launch_check(ctx, "k_cutcell_laplacian_p1");
+  }
+  const int T = LAP_WARPS * 32;
+  const unsigned nb = (unsigned)std::min<int64_t>(gc_div_up(ncut, LAP_WARPS), 148 * 64);
   if (g.D == 2)
-    GC_LAUNCH(ctx, "k_cutcell_laplacian", k_cutcell_laplacian<2><<<nb, T, 0, ctx->stream>>>(g, res->lay, sel->sub_ids, sel->n_sub, ncut, ctx->d_simplexify_raw,
-                                                      sel->K_cut));
+    GC_LAUNCH(ctx, "k_cutcell_laplacian", k_cutcell_laplacian_q1<2><<<nb, T, 0, ctx->stream>>>(
+        g, res->lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, ctx->d_simplexify_raw, sel->K_cut));
   else
-    GC_LAUNCH(ctx, "k_cutcell_laplacian", k_cutcell_laplacian<3><<<nb, T, 0, ctx->stream>>>(g, res->lay, sel->sub_ids, sel->n_sub, ncut, ctx->d_simplexify_raw,
-                                                      sel->K_cut));
+    GC_LAUNCH(ctx, "k_cutcell_laplacian", k_cutcell_laplacian_q1<3><<<nb, T, 0, ctx->stream>>>(
+        g, res->lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, ctx->d_simplexify_raw, sel->K_cut));
   return gc_launch_check(ctx, "k_cutcell_laplacian");
 }

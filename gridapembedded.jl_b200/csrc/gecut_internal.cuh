@@ -9,7 +9,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "gecut.h"
@@ -68,6 +70,10 @@ struct GcLayout {
   double* sf_R;
   int8_t* sf_state;
   int64_t sf_pitch;
+  // not part of the reference layout: integral of 1 over every subcell / subfacet with the degree-2 rule
+  // (sum_q w_q*meas(J)), written by the subtriangulation kernels while the vertices are on chip
+  double* sc_meas;
+  double* sf_meas;
 };
 
 // Per stage-0-simplex counters (pass 1) / exclusive offsets (pass 2).
@@ -94,6 +100,13 @@ struct gecut_ctx {
   cudaStream_t stream = nullptr;
   std::string err;
   int64_t launches = 0;
+  // caching device allocator: blocks freed by results / selections are kept and handed out again to requests of the
+  // same size.  A cut step asks for the same sizes every time, so after the first step no driver allocation (and none
+  // of its multi-millisecond stalls) happens inside the hot path.  All work of a context is ordered on one stream,
+  // which makes immediate reuse safe.
+  std::unordered_map<void*, size_t> live;
+  std::multimap<size_t, void*> cache;
+  size_t cached_bytes = 0;
   bool prof_on = false;
   std::vector<GcProfRec> prof;
   std::string prof_report;
@@ -112,6 +125,8 @@ struct gecut_result {
   gecut_sizes sizes{};
   GcLayout lay{};
   uint32_t* cutmask = nullptr;
+  uint32_t* cut_sc_ptr = nullptr;  // Ncut+1: first subcell (0-based) of every cut bg cell
+  bool sf_points_alias = false;    // L == 1: the subfacet point arrays ARE the subcell point arrays on the device
   bool owns_nodal[GC_LMAX] = {false};
   double* nodal_dev[GC_LMAX] = {nullptr};
 };
@@ -165,6 +180,7 @@ void gc_prof_after(gecut_ctx* ctx);
 
 int gc_malloc(gecut_ctx* ctx, void** p, size_t bytes);
 void gc_free(gecut_ctx* ctx, void* p);
+void gc_trim(gecut_ctx* ctx);  // give every cached block back to the driver
 int gc_launch_check(gecut_ctx* ctx, const char* what);
 
 // ---- scan (gecut_classify.cu) ----
@@ -195,6 +211,47 @@ int gc_integrate_laplacian(gecut_ctx* ctx, gecut_selection* sel, double* K_bg_ho
 // device helpers shared by the kernels
 // ------------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// ---- measures of simplices (Gridap `meas`: |det J| resp. sqrt(det JtJ)); plain operators, the library is compiled
+//      with --fmad=false so that host (oracle-like) and device evaluation orders coincide
+__host__ __device__ inline double det2x2(const double J[3][3]) { return J[0][0] * J[1][1] - J[0][1] * J[1][0]; }
+__host__ __device__ inline double det3x3(const double J[3][3]) {
+  return J[0][0] * J[1][1] * J[2][2] + J[0][1] * J[1][2] * J[2][0] + J[0][2] * J[1][0] * J[2][1] -
+         (J[0][0] * J[1][2] * J[2][1] + J[0][1] * J[1][0] * J[2][2] + J[0][2] * J[1][1] * J[2][0]);
+}
+
+// |det J| of a D-simplex / sqrt(det JtJ) of a (D-1)-simplex whose vertices are p[0..ds] (D doubles each)
+template <int D, int DS>
+__device__ __forceinline__ double simplex_meas(const double (*p)[3]) {
+  if (DS == D) {
+    double J[3][3];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int d = 0; d < D; ++d) J[i][d] = p[i + 1][d] - p[0][d];
+    return fabs(D == 2 ? det2x2(J) : det3x3(J));
+  }
+  if (D == 2) {
+    double a = p[1][0] - p[0][0], b = p[1][1] - p[0][1];
+    return sqrt(a * a + b * b);
+  }
+  double a[3] = {p[1][0] - p[0][0], p[1][1] - p[0][1], p[1][2] - p[0][2]};
+  double b[3] = {p[2][0] - p[0][0], p[2][1] - p[0][1], p[2][2] - p[0][2]};
+  double n1 = a[1] * b[2] - a[2] * b[1], n2 = a[2] * b[0] - a[0] * b[2], n3 = a[0] * b[1] - a[1] * b[0];
+  return sqrt(n1 * n1 + n2 * n2 + n3 * n3);
+}
+
+// sum_q w_q * meas with the degree-2 rule of the DS-simplex (weights 1/2 x2, 1/6 x3, 1/24 x4)
+template <int DS>
+__device__ __forceinline__ double integrate_one(double meas) {
+  const double w = DS == 1 ? 0.5 : (DS == 2 ? 1.0 / 6 : 1.0 / 24);
+  const int nq = DS + 1;
+  double s = 0.0;
+#pragma unroll
+  for (int q = 0; q < nq; ++q) s += w * meas;
+  return s;
+}
+
 
 // Leaf formulas (AnalyticalGeometries.jl:75-78,146-198) with explicit round-to-nearest intrinsics: Julia never
 // contracts a*b+c into an FMA, so neither may we (IN/OUT of nodes lying on a surface flips on one ulp).
@@ -270,6 +327,25 @@ __device__ __forceinline__ int gc_eval_inoutcut(const GcProgram& p, const int8_t
     int tok = p.tok[t];
     if (tok >= 0) {
       st[sp++] = rows[(int64_t)tok * pitch + e];
+    } else if (tok == GECUT_OP_COMPLEMENT) {
+      st[sp - 1] = (int8_t)gc_io_complementary(st[sp - 1]);
+    } else {
+      int b = st[--sp], a = st[--sp];
+      st[sp++] = (int8_t)(tok == GECUT_OP_UNION ? gc_io_union(a, b)
+                                                : (tok == GECUT_OP_INTERSECT ? gc_io_intersection(a, b) : gc_io_setdiff(a, b)));
+    }
+  }
+  return st[0];
+}
+
+// same program on explicit per-level-set values
+__device__ __forceinline__ int gc_eval_inoutcut_vals(const GcProgram& p, const int8_t* vals) {
+  int8_t st[GECUT_MAX_PROGRAM / 2 + 2];
+  int sp = 0;
+  for (int t = 0; t < p.len; ++t) {
+    int tok = p.tok[t];
+    if (tok >= 0) {
+      st[sp++] = vals[tok];
     } else if (tok == GECUT_OP_COMPLEMENT) {
       st[sp - 1] = (int8_t)gc_io_complementary(st[sp - 1]);
     } else {

@@ -131,6 +131,10 @@ int gecut_create(int device, void* cuda_stream, gecut_ctx** ctx);
 int gecut_destroy(gecut_ctx* ctx);
 int gecut_set_stream(gecut_ctx* ctx, void* cuda_stream);
 const char* gecut_last_error(const gecut_ctx* ctx);
+/* Device memory freed by gecut_result_free / gecut_selection_free is cached by the context and reused by later calls
+ * (a cut step asks for the same sizes every time); gecut_trim returns the cached blocks to the driver.  Results and
+ * selections must be freed before their context is destroyed. */
+int gecut_trim(gecut_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's `gpu_launches`). */
 int64_t gecut_launch_count(const gecut_ctx* ctx);
 
