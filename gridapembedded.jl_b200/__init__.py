@@ -5,7 +5,7 @@ booleans, `cut`, `LevelSetCutter`, `Triangulation(cutgeo, PHYSICAL, name)`, `Emb
 `Measure`.  All compute goes through the C ABI of `libgecut.so` (include/gecut.h); there is no CPU
 fallback -- importing this package works without a GPU, calling `cut` does not.
 """
-from . import csg, geometries, cartesian, cutters, discretizations, measures  # noqa: F401
+from . import csg, geometries, cartesian, cutters, discretizations, measures, distributed  # noqa: F401
 from .csg import (Node, Leaf, Geometry, union, intersect, intersection, setdiff, complement, get_geometry,
                   get_geometry_names, get_tree, get_name, get_metadata, replace_metadata, replace_data)
 from .geometries import (AnalyticalGeometry, DiscreteGeometry, BoundingBox, discretize, doughnut, popcorn, sphere,
@@ -16,3 +16,4 @@ from .discretizations import (IN, OUT, CUT, INTERFACE, CUT_IN, CUT_OUT, PHYSICAL
                               ACTIVE_IN, ACTIVE_OUT, EmbeddedDiscretization, SubCellData, SubFacetData,
                               Triangulation, EmbeddedBoundary)
 from .measures import Measure, integrate_measure, integrate_laplacian
+from .distributed import DistributedLevelSetCutter, slab_range

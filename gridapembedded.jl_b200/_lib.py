@@ -29,7 +29,8 @@ class GecutError(RuntimeError):
 
 class Grid(C.Structure):
     _fields_ = [("D", C.c_int32), ("simplexified", C.c_int32), ("pmin", C.c_double * 3), ("pmax", C.c_double * 3),
-                ("partition", C.c_int32 * 3), ("slab_begin", C.c_int32), ("slab_end", C.c_int32), ("pad", C.c_int32)]
+                ("partition", C.c_int32 * 3), ("slab_begin", C.c_int32), ("slab_end", C.c_int32),
+                ("nodal_slab_local", C.c_int32)]
 
 
 class LeafRec(C.Structure):

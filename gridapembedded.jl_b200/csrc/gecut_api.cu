@@ -212,7 +212,9 @@ int do_cut(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* leaves, int
   };
   // leaves
   r->leaves.L = L;
-  const int64_t nn_total = g.layer_nodes * g.nn[g.D - 1];
+  const bool nodal_local = grid->nodal_slab_local != 0;
+  r->leaves.nodal_base = nodal_local ? (int64_t)g.k0 * g.layer_nodes : 0;
+  const int64_t nn_total = nodal_local ? g.num_nodes : g.layer_nodes * g.nn[g.D - 1];
   for (int i = 0; i < L; ++i) {
     r->leaves.leaf[i] = leaves[i];
     r->leaves.nodal[i] = nullptr;

@@ -231,7 +231,7 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
         double v = -1.0;
         if (valid) {
           if (lv.leaf[ls].kind == GECUT_LEAF_NODAL)
-            v = __ldg(lv.nodal[ls] + node);
+            v = __ldg(lv.nodal[ls] + (node - lv.nodal_base));
           else
             v = gc_eval_leaf(lv.leaf[ls], x, D);
         }

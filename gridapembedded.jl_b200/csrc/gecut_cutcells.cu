@@ -118,7 +118,7 @@ __device__ __forceinline__ void setup_stage0(const GcGrid& g, const GcLeaves& lv
                                   : ((int64_t)nijk[0] + (int64_t)g.nn[0] * nijk[1]);
     for (int ls = 0; ls < L; ++ls) {
       if (lv.leaf[ls].kind == GECUT_LEAF_NODAL)
-        S[m].w[ls] = __ldg(lv.nodal[ls] + node);
+        S[m].w[ls] = __ldg(lv.nodal[ls] + (node - lv.nodal_base));
       else
         S[m].w[ls] = gc_eval_leaf(lv.leaf[ls], x, D);
     }

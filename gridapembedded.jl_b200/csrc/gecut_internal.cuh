@@ -44,7 +44,8 @@ struct GcGrid {
 struct GcLeaves {
   int L;
   gecut_leaf leaf[GC_LMAX];
-  const double* nodal[GC_LMAX];  // device pointers (whole-model node numbering) for NODAL leaves
+  const double* nodal[GC_LMAX];  // device pointers for NODAL leaves
+  int64_t nodal_base;            // global id of the first node the NODAL vectors hold (0: whole model; slab node offset)
 };
 
 struct GcProgram {

@@ -37,7 +37,7 @@ def _is_torch_tensor(x) -> bool:
     return type(x).__module__.startswith("torch")
 
 
-def flatten_geometry(model, geo: Geometry, host_only: bool = False):
+def flatten_geometry(model, geo: Geometry, host_only: bool = False, num_nodal: Optional[int] = None):
     """Host half of `initial_sub_triangulation` (`CutTriangulations.jl:443-454`): the unique leaves of the tree in
     `_find_unique_leaves` order as leaf records, plus per-leaf nodal values for NODAL leaves.
 
@@ -62,8 +62,9 @@ def flatten_geometry(model, geo: Geometry, host_only: bool = False):
                 nodal.append(None)
         else:  # vector of nodal values (DiscreteGeometry leaf)
             n = p.shape[0]
-            if n != model.num_nodes:
-                raise ValueError(f"expected {model.num_nodes} nodal values, got {n}")
+            expected = model.num_nodes if num_nodal is None else num_nodal
+            if n != expected:
+                raise ValueError(f"expected {expected} nodal values, got {n}")
             if host_only and _is_torch_tensor(p):
                 p = p.detach().cpu().numpy()
             leaves.append(LeafFunction(LEAF_NODAL, model.D))
@@ -128,9 +129,11 @@ class LevelSetCutter(Cutter):
     `ctx`: a `_lib.Context` (default: one per LOCAL_RANK device).  `slab=(k0,k1)`: cut only the n-cubes whose last
     index lies in [k0,k1) (multi-GPU z-slab partition)."""
 
-    def __init__(self, ctx: Optional[_lib.Context] = None, slab: Optional[Tuple[int, int]] = None):
+    def __init__(self, ctx: Optional[_lib.Context] = None, slab: Optional[Tuple[int, int]] = None,
+                 nodal_slab_local: bool = False):
         self._ctx = ctx
         self.slab = slab
+        self.nodal_slab_local = bool(nodal_slab_local)  # NODAL vectors hold only the node planes slab[0]..slab[1]
 
     @property
     def ctx(self) -> _lib.Context:
@@ -141,8 +144,13 @@ class LevelSetCutter(Cutter):
     def _call(self, fn_name: str, background, geom):
         from .discretizations import EmbeddedDiscretization
         model = background
-        leaves, nodal, oid_to_ls = flatten_geometry(model, geom)
+        num_nodal = None
+        if self.nodal_slab_local and self.slab is not None:
+            layer_nodes = model.num_nodes // (model.partition[-1] + 1)
+            num_nodal = layer_nodes * (self.slab[1] - self.slab[0] + 1)
+        leaves, nodal, oid_to_ls = flatten_geometry(model, geom, num_nodal=num_nodal)
         grid = make_grid(model, self.slab)
+        grid.nodal_slab_local = 1 if num_nodal is not None else 0
         recs = make_leaf_records(leaves)
         ptrs, on_device, keep = _nodal_pointers(self.ctx, model, nodal)
         out = C.c_void_p()

@@ -325,9 +325,9 @@ class DiscreteGeometry(Geometry):
             self.tree = geo.tree
         else:
             vals = values_or_tree
-            n = vals.shape[0] if hasattr(vals, "shape") else len(vals)
-            if n != model.num_nodes:
-                raise ValueError(f"expected {model.num_nodes} nodal values, got {n}")
+            if not hasattr(vals, "shape"):
+                vals = np.asarray(vals, dtype=np.float64)
+            # the length is checked at cut time (whole model, or one z-slab of it for a distributed cut)
             self.tree = Leaf((vals, name, None))
 
     def get_tree(self):

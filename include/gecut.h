@@ -73,7 +73,8 @@ typedef struct {
   int32_t partition[3];
   int32_t slab_begin;
   int32_t slab_end;
-  int32_t pad;
+  int32_t nodal_slab_local; /* 0: NODAL vectors hold every node of the model; 1: only the nodes of the slab
+                               (planes slab_begin..slab_end of the last direction, num_bgnodes values)            */
 } gecut_grid;
 
 /* One unique leaf of the CSG tree, in `_find_unique_leaves` order (DiscreteGeometries.jl:65-74). */
@@ -148,8 +149,9 @@ const char* gecut_profile_report(gecut_ctx* ctx);
 /* cut(::LevelSetCutter, bgmodel, geo)  (src/LevelSetCutters/LevelSetCutters.jl:79-105 -> CutTriangulations.jl:443-460,
  * 309-343): evaluates the L unique leaves at the nodes, classifies every bg cell per level set, extracts + simplexifies
  * the cut cells and cuts them sequentially by every level set (ls = L..1), producing subcells, boundary subfacets with
- * normals, and the IN/OUT rows.  `nodal_values[ls]` is read only for NODAL leaves: Nn doubles (whole model, node ids
- * lexicographic x fastest), resident on the device if `nodal_on_device` else on the host. */
+ * normals, and the IN/OUT rows.  `nodal_values[ls]` is read only for NODAL leaves: one double per node (node ids
+ * lexicographic x fastest) of the whole model, or of the slab when grid->nodal_slab_local is set; resident on the device
+ * if `nodal_on_device` else on the host. */
 int gecut_cut(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* leaves, int num_leaves,
               const double* const* nodal_values, int nodal_on_device, gecut_result** out);
 /* compute_bgcell_to_inoutcut(::LevelSetCutter, bgmodel, geo) (LevelSetCutters.jl:154-157,175-205): classification only
