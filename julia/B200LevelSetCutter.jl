@@ -1,0 +1,188 @@
+# B200LevelSetCutter.jl -- reference-side binding of libgecut.so (SOURCE ONLY: Julia is not available in the build
+# image, so this file has never been executed; it documents the drop-in a GridapEmbedded maintainer would add).
+#
+# It implements the `Cutter` plugin API of the reference (src/Interfaces/Cutters.jl:22-60) for Cartesian background
+# models: `cut(cutter, bgmodel, geo)` and `compute_bgcell_to_inoutcut(cutter, bgmodel, geo)`, returning the unchanged
+# `EmbeddedDiscretization` layout (src/Interfaces/EmbeddedDiscretizations.jl:36-45) so that Triangulation(cutgeo,...),
+# EmbeddedBoundary, AgFEM etc. run on it as they do on the result of the in-tree LevelSetCutter.
+module B200LevelSetCutters
+
+using Gridap, Gridap.Geometry, Gridap.Arrays, Gridap.ReferenceFEs
+using GridapEmbedded.Interfaces, GridapEmbedded.CSG, GridapEmbedded.LevelSetCutters
+using GridapEmbedded.Interfaces: SubCellData, SubFacetData, EmbeddedDiscretization
+using GridapEmbedded.LevelSetCutters: _find_unique_leaves, discretize
+import GridapEmbedded.Interfaces: cut, compute_bgcell_to_inoutcut
+
+const libgecut = get(ENV, "GECUT_LIB", "libgecut.so")
+
+# ---- mirrors of the C structs of include/gecut.h -----------------------------------------------------------------
+struct GecutGrid
+  D::Int32; simplexified::Int32
+  pmin::NTuple{3,Float64}; pmax::NTuple{3,Float64}
+  partition::NTuple{3,Int32}; slab_begin::Int32; slab_end::Int32; nodal_slab_local::Int32
+end
+struct GecutLeaf
+  kind::Int32; pad::Int32
+  x0::NTuple{3,Float64}; v::NTuple{3,Float64}; R::Float64; r::Float64
+end
+struct GecutSizes
+  num_bgcells::Int64; num_bgnodes::Int64; num_cutcells::Int64; num_subcells::Int64; num_subcell_points::Int64
+  num_subfacets::Int64; num_subfacet_points::Int64; cell_offset::Int64; node_offset::Int64
+  num_levelsets::Int32; D::Int32; num_vertices_per_bgcell::Int32; pad::Int32
+end
+mutable struct GecutBuffers
+  ls_to_bgcell_to_inoutcut::Ptr{Int8}; cutcell_to_cell::Ptr{Int32}
+  sc_cell_to_points::Ptr{Int32}; sc_cell_to_bgcell::Ptr{Int32}; sc_point_to_coords::Ptr{Float64}; sc_point_to_rcoords::Ptr{Float64}
+  ls_to_subcell_to_inout::Ptr{Int8}
+  sf_facet_to_points::Ptr{Int32}; sf_facet_to_bgcell::Ptr{Int32}; sf_facet_to_normal::Ptr{Float64}
+  sf_point_to_coords::Ptr{Float64}; sf_point_to_rcoords::Ptr{Float64}; ls_to_subfacet_to_inout::Ptr{Int8}
+  state_pitch_bgcell::Int64; state_pitch_subcell::Int64; state_pitch_subfacet::Int64
+end
+
+const LEAF_NODAL = Int32(4)
+
+"""
+    struct B200LevelSetCutter <: Cutter
+
+`device`: CUDA device ordinal.  The context is created lazily and kept for the lifetime of the cutter.
+"""
+mutable struct B200LevelSetCutter <: Cutter
+  device::Int
+  ctx::Ptr{Cvoid}
+  B200LevelSetCutter(device::Integer=0) = new(device, C_NULL)
+end
+
+function _ctx(c::B200LevelSetCutter)
+  if c.ctx == C_NULL
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    st = ccall((:gecut_create, libgecut), Cint, (Cint, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), c.device, C_NULL, r)
+    st == 0 || error("gecut_create failed with status $st (no CUDA device: there is no CPU fallback)")
+    c.ctx = r[]
+    finalizer(x -> ccall((:gecut_destroy, libgecut), Cint, (Ptr{Cvoid},), x.ctx), c)
+  end
+  c.ctx
+end
+
+_check(c, st, what) = st == 0 || error("$what failed ($st): " *
+  unsafe_string(ccall((:gecut_last_error, libgecut), Cstring, (Ptr{Cvoid},), c.ctx)))
+
+_pad3(x, z) = ntuple(i -> i <= length(x) ? x[i] : z, 3)
+
+# Cartesian descriptor of the background model (only CartesianDiscreteModel and simplexify(CartesianDiscreteModel)
+# are accelerated; everything else mirrors @notimplementedif of CutTriangulations.jl:495-503)
+function _grid(model::CartesianDiscreteModel)
+  desc = get_cartesian_descriptor(model)
+  D = length(desc.partition)
+  pmin = Tuple(desc.origin); pmax = Tuple(desc.origin .+ desc.sizes .* desc.partition)
+  GecutGrid(D, 0, _pad3(Float64.(pmin), 0.0), _pad3(Float64.(pmax), 0.0), _pad3(Int32.(desc.partition), Int32(1)), 0, 0, 0)
+end
+
+# Leaf records: closed-form leaves are recognised by the closure's captured fields (spherefun, cylinderfun, planefun,
+# doughnutfun of src/LevelSetCutters/AnalyticalGeometries.jl:57-59,130-132,167-169,186-188); anything else -- arbitrary
+# closures, popcorn, DiscreteGeometry payloads -- is passed as NODAL values evaluated on the host
+# (j_to_ls = fun.(point_to_coords), DiscreteGeometries.jl:51).
+function _leaf_record(f, point_to_coords)
+  n = nameof(typeof(f))
+  s = string(n)
+  if occursin("spherefun", s) || occursin("diskfun", s)
+    return GecutLeaf(0, 0, _pad3(Float64.(Tuple(f.x0)), 0.0), (0.0, 0.0, 0.0), Float64(f.R), 0.0), nothing
+  elseif occursin("cylinderfun", s)
+    return GecutLeaf(1, 0, _pad3(Float64.(Tuple(f.x0)), 0.0), _pad3(Float64.(Tuple(f.d)), 0.0), Float64(f.R), 0.0), nothing
+  elseif occursin("planefun", s)
+    return GecutLeaf(2, 0, _pad3(Float64.(Tuple(f.x0)), 0.0), _pad3(Float64.(Tuple(f.v)), 0.0), 0.0, 0.0), nothing
+  elseif occursin("doughnutfun", s)
+    return GecutLeaf(3, 0, _pad3(Float64.(Tuple(f.x0)), 0.0), (0.0, 0.0, 0.0), Float64(f.R), Float64(f.r)), nothing
+  elseif f isa AbstractVector
+    return GecutLeaf(LEAF_NODAL, 0, (0.0, 0.0, 0.0), (0.0, 0.0, 0.0), 0.0, 0.0), collect(Float64, f)
+  else
+    return GecutLeaf(LEAF_NODAL, 0, (0.0, 0.0, 0.0), (0.0, 0.0, 0.0), 0.0, 0.0), Float64[f(x) for x in point_to_coords]
+  end
+end
+
+function _run(cutter::B200LevelSetCutter, fname::Symbol, bgmodel, geom, simplexified::Bool, cartesian)
+  ctx = _ctx(cutter)
+  j_to_fun, oid_to_ls = _find_unique_leaves(get_tree(geom))
+  coords = collect1d(get_node_coordinates(get_grid(bgmodel)))
+  recs = GecutLeaf[]; nodal = Vector{Union{Nothing,Vector{Float64}}}()
+  for f in j_to_fun
+    r, v = _leaf_record(f, coords); push!(recs, r); push!(nodal, v)
+  end
+  g = _grid(cartesian)
+  g = GecutGrid(g.D, simplexified ? 1 : 0, g.pmin, g.pmax, g.partition, 0, 0, 0)
+  ptrs = Ptr{Float64}[v === nothing ? C_NULL : pointer(v) for v in nodal]
+  res = Ref{Ptr{Cvoid}}(C_NULL)
+  GC.@preserve nodal begin
+    st = ccall((fname, libgecut), Cint,
+               (Ptr{Cvoid}, Ref{GecutGrid}, Ptr{GecutLeaf}, Cint, Ptr{Ptr{Float64}}, Cint, Ptr{Ptr{Cvoid}}),
+               ctx, g, recs, length(recs), ptrs, 0, res)
+  end
+  _check(cutter, st, string(fname))
+  res[], oid_to_ls
+end
+
+function _copy_out(cutter, res)
+  sz = Ref{GecutSizes}()
+  _check(cutter, ccall((:gecut_result_sizes, libgecut), Cint, (Ptr{Cvoid}, Ref{GecutSizes}), res, sz), "gecut_result_sizes")
+  s = sz[]; D = Int(s.D); L = Int(s.num_levelsets)
+  bg  = Matrix{Int8}(undef, s.num_bgcells, L)
+  c2p = Vector{Int32}(undef, s.num_subcells*(D+1)); c2b = Vector{Int32}(undef, s.num_subcells)
+  X = Vector{Float64}(undef, s.num_subcell_points*D); R = similar(X)
+  sci = Matrix{Int8}(undef, s.num_subcells, L)
+  f2p = Vector{Int32}(undef, s.num_subfacets*D); f2b = Vector{Int32}(undef, s.num_subfacets)
+  N = Vector{Float64}(undef, s.num_subfacets*D)
+  fX = Vector{Float64}(undef, s.num_subfacet_points*D); fR = similar(fX)
+  sfi = Matrix{Int8}(undef, s.num_subfacets, L)
+  b = GecutBuffers(pointer(bg), C_NULL, pointer(c2p), pointer(c2b), pointer(X), pointer(R), pointer(sci),
+                   pointer(f2p), pointer(f2b), pointer(N), pointer(fX), pointer(fR), pointer(sfi), 0, 0, 0)
+  GC.@preserve bg c2p c2b X R sci f2p f2b N fX fR sfi begin
+    _check(cutter, ccall((:gecut_result_copy, libgecut), Cint, (Ptr{Cvoid}, Ref{GecutBuffers}), res, b), "gecut_result_copy")
+  end
+  pts(v) = collect(reinterpret(Point{D,Float64}, v))
+  table(data, n, stride) = Table(data, collect(Int32, 1:stride:(n*stride+1)))
+  subcells  = SubCellData(table(c2p, s.num_subcells, D+1), c2b, pts(X), pts(R))
+  subfacets = SubFacetData(table(f2p, s.num_subfacets, D), pts(N), f2b, pts(fX), pts(fR))
+  rows(m) = [m[:, ls] for ls in 1:L]
+  rows(bg), subcells, rows(sci), subfacets, rows(sfi)
+end
+
+_cartesian(m::CartesianDiscreteModel) = (m, false)
+# simplexify(CartesianDiscreteModel) keeps no descriptor: the caller passes it, see INTEGRATION.md
+struct SimplexifiedCartesian{M}; model::M; cartesian::CartesianDiscreteModel; end
+
+function cut(cutter::B200LevelSetCutter, bgmodel::CartesianDiscreteModel, geom)
+  res, oid_to_ls = _run(cutter, :gecut_cut, bgmodel, geom, false, bgmodel)
+  data = _copy_out(cutter, res)
+  ccall((:gecut_result_free, libgecut), Cint, (Ptr{Cvoid},), res)
+  EmbeddedDiscretization(bgmodel, data..., oid_to_ls, geom)
+end
+
+function cut(cutter::B200LevelSetCutter, bg::SimplexifiedCartesian, geom)
+  res, oid_to_ls = _run(cutter, :gecut_cut, bg.model, geom, true, bg.cartesian)
+  data = _copy_out(cutter, res)
+  ccall((:gecut_result_free, libgecut), Cint, (Ptr{Cvoid},), res)
+  EmbeddedDiscretization(bg.model, data..., oid_to_ls, geom)
+end
+
+function compute_bgcell_to_inoutcut(cutter::B200LevelSetCutter, bgmodel::CartesianDiscreteModel, geom)
+  res, oid_to_ls = _run(cutter, :gecut_classify, bgmodel, geom, false, bgmodel)
+  # boolean tree on the device: postfix program over the level-set rows (compute_inoutcut, EmbeddedDiscretizations.jl:107-177)
+  prog = Int32[]
+  function rec(n)
+    if n.leftchild === nothing
+      push!(prog, Int32(oid_to_ls[objectid(first(n.data))] - 1))
+    else
+      rec(n.leftchild); n.rightchild === nothing || rec(n.rightchild)
+      push!(prog, Dict(:∪ => Int32(-1), :∩ => Int32(-2), :- => Int32(-3), :! => Int32(-4))[first(n.data)])
+    end
+  end
+  rec(get_tree(geom))
+  out = Vector{Int8}(undef, num_cells(bgmodel))
+  _check(cutter, ccall((:gecut_bgcell_to_inoutcut, libgecut), Cint, (Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Int8}),
+                       res, prog, length(prog), out), "gecut_bgcell_to_inoutcut")
+  ccall((:gecut_result_free, libgecut), Cint, (Ptr{Cvoid},), res)
+  out
+end
+
+export B200LevelSetCutter, SimplexifiedCartesian
+
+end # module
