@@ -175,6 +175,8 @@ void free_result_arrays(gecut_result* r) {
   gc_free(ctx, r->cutmask);
   gc_free(ctx, r->cut_sc_ptr);
   r->cut_sc_ptr = nullptr;
+  gc_free(ctx, r->bg_counts_dev);
+  r->bg_counts_dev = nullptr;
   for (int i = 0; i < GC_LMAX; ++i)
     if (r->owns_nodal[i]) gc_free(ctx, r->nodal_dev[i]);
   l = GcLayout{};
@@ -274,6 +276,12 @@ int do_cut(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* leaves, int
       ctx->err = std::string("memset: ") + cudaGetErrorString(e);
       return fail(GECUT_ERR_CUDA);
     }
+  }
+  st = gc_malloc(ctx, (void**)&r->bg_counts_dev, sizeof(unsigned long long) * GC_LMAX * 12);
+  if (st != GECUT_OK) return fail(st);
+  if (cudaMemsetAsync(r->bg_counts_dev, 0, sizeof(unsigned long long) * GC_LMAX * 12, ctx->stream) != cudaSuccess) {
+    ctx->err = "memset of the bg counters failed";
+    return fail(GECUT_ERR_CUDA);
   }
   st = gc_classify(ctx, r);
   if (st != GECUT_OK) return fail(st);

@@ -165,7 +165,8 @@ __host__ __device__ inline int gc_words_per_row(int nx) { return (nx + 31) / 32;
 template <int D, bool SIMPLEX>
 __global__ void __launch_bounds__(ClsCfg<D>::THREADS)
 k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64_t pitch,
-           uint32_t* __restrict__ cutmask, const uint8_t* __restrict__ simplexify_raw) {
+           uint32_t* __restrict__ cutmask, const uint8_t* __restrict__ simplexify_raw,
+           unsigned long long* __restrict__ bg_counts /* [L][2][6]: IN / OUT cells per level set and cell type */) {
   using C = ClsCfg<D>;
   constexpr int WX = C::WX, TY = C::TY, RY = C::RY, ZS = C::ZS;
   constexpr int NVC = 1 << D;                         // vertices of the n-cube
@@ -178,8 +179,10 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
   __shared__ uint32_t s_words[2][NTASK][SIMPLEX ? NVC : 2];  // simplex: vertex sign words; n-cube: (any, all)
   __shared__ unsigned long long s_lut[SIMPLEX ? (1 << NVC) : 1];  // sign byte of an n-cube -> states of its CPC simplices
   __shared__ uint8_t s_tets[6][4];
+  __shared__ unsigned int s_cnt[GC_LMAX * 12];
   const int L = lv.L;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < L * 12; i += C::THREADS) s_cnt[i] = 0u;
   const int nx = g.n[0];
   const int ny = (D == 3) ? g.n[1] : 1;
   const int wxtot = gc_words_per_row(nx);
@@ -207,15 +210,21 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
     }
   }
   const int plane_words = L * RY * (WX + 1);
+  // packed per-type tallies (one byte per cell type; <= 4 cells x 32 layers = 128 per byte, n-cubes: plain counters)
+  unsigned long long acc_in = 0ull, acc_out = 0ull;
 
   for (int kp = kz0; kp <= kz1; ++kp) {  // node planes kz0..kz1
     uint32_t* P = planes + ((kp - kz0) & 1) * plane_words;
-    // ---- evaluate the signs of node plane kp: one ballot per (row, word) task and level set
-    for (int task = wid; task < RY * (WX + 1); task += NW) {
-      const int r = task / (WX + 1), ww = task % (WX + 1);
-      const int i = 32 * (w0 + ww) + lane;
+    // ---- evaluate the signs of node plane kp: one ballot per (row, word) task and level set.  Of the word right of the
+    //      tile only bit 0 is needed (x+1 vertices of the last cell column): one transposed task evaluates that node
+    //      column for all RY rows at once instead of RY mostly wasted row tasks.
+    for (int task = wid; task < RY * WX + 1; task += NW) {
+      const bool halo = task == RY * WX;
+      const int r = halo ? lane : task / WX;
+      const int ww = halo ? WX : task % WX;
+      const int i = halo ? 32 * (w0 + WX) : 32 * (w0 + ww) + lane;
       const int j = j0 + r;
-      const bool valid = (i < g.nn[0]) && (D == 2 || j < g.nn[1]);
+      const bool valid = (i < g.nn[0]) && (D == 2 || j < g.nn[1]) && (!halo || lane < RY);
       double x[3];
       x[0] = gc_coord(g, 0, i);
       if (D == 3) {
@@ -235,8 +244,12 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
           else
             v = gc_eval_leaf(lv.leaf[ls], x, D);
         }
-        uint32_t word = __ballot_sync(0xffffffffu, valid && (v > 0.0));
-        if (lane == 0) P[(ls * RY + r) * (WX + 1) + ww] = word;
+        const uint32_t word = __ballot_sync(0xffffffffu, valid && (v > 0.0));
+        if (!halo) {
+          if (lane == 0) P[(ls * RY + r) * (WX + 1) + ww] = word;
+        } else if (lane < RY) {
+          P[(ls * RY + lane) * (WX + 1) + WX] = (word >> lane) & 1u;
+        }
       }
     }
     __syncthreads();
@@ -303,13 +316,15 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
           }
         }
         __syncthreads();
-        // phase B: one thread per 4 consecutive cells: state bytes (coalesced 4/8-byte stores)
+        // phase B: one thread per 4 consecutive cells: state bytes (coalesced 4/8-byte stores) and IN/OUT tallies
         {
           const int task = threadIdx.x >> 3, quad = threadIdx.x & 7;
           const int r = task / WX, ww = task % WX;
           const int jc = j0 + r;
           const int i0 = 32 * (w0 + ww);
           const int c0 = 4 * quad;
+          // IN / OUT tallies of this thread's 4 cells, one byte per cell type (IN = 0xFF, OUT = 0x01, CUT = 0x00)
+          unsigned long long pin = 0ull, pout = 0ull;
           if (i0 + c0 < nx && jc < ny) {
             const int ncq = min(4, nx - (i0 + c0));
             const int64_t rowid = (D == 3) ? ((int64_t)(kc - g.k0) * ny + jc) : (int64_t)(kc - g.k0);
@@ -323,6 +338,11 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
 #pragma unroll
                 for (int v = 0; v < NVC; ++v) sb |= ((s_words[ls & 1][task][v] >> (c0 + c)) & 1u) << v;
                 e[c] = s_lut[sb];
+                if (c < ncq) {
+                  const unsigned long long hi = (e[c] >> 7) & 0x010101010101ull;  // bit 7 set: IN
+                  pin += hi;
+                  pout += (e[c] & 0x010101010101ull) & ~hi;                       // bit 0 set, bit 7 clear: OUT
+                }
               }
               if (vec_ok) {
                 if (CPC == 6) {  // 4 cells x 6 bytes = 24 bytes = three 8-byte stores
@@ -340,7 +360,10 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
               }
             } else {
               const uint32_t any = s_words[ls & 1][task][0], all = s_words[ls & 1][task][1];
+              const uint32_t vm = (1u << ncq) - 1u;
               const uint32_t o4 = (all >> c0) & 0xFu, n4 = (~any >> c0) & 0xFu;
+              pin = __popc(n4 & vm);
+              pout = __popc(o4 & vm);
               const uint32_t so = (o4 * 0x00204081u) & 0x01010101u;
               const uint32_t si = ((n4 * 0x00204081u) & 0x01010101u) * 0xFFu;
               const uint32_t w = so | si;  // OUT(1) where all, IN(0xFF) where !any, CUT(0) otherwise
@@ -351,12 +374,42 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
               }
             }
           }
+          if (L == 1) {  // one level set: keep the packed tallies in registers until the end of the block
+            acc_in += pin;
+            acc_out += pout;
+          } else {
+#pragma unroll
+            for (int t = 0; t < CPC; ++t) {
+              const unsigned int a = __reduce_add_sync(0xffffffffu, (unsigned int)(pin >> (8 * t)) & 0xFFu);
+              const unsigned int b = __reduce_add_sync(0xffffffffu, (unsigned int)(pout >> (8 * t)) & 0xFFu);
+              if (lane == 0) {
+                if (a) atomicAdd(&s_cnt[ls * 12 + t], a);
+                if (b) atomicAdd(&s_cnt[ls * 12 + 6 + t], b);
+              }
+            }
+          }
         }
       }
     }
     // no barrier needed here: the next plane goes to the buffer last read by phase A (which is followed by a barrier),
     // and s_words is only rewritten after the barrier that follows the next evaluation
   }
+  if (L == 1) {
+#pragma unroll
+    for (int t = 0; t < CPC; ++t) {
+      const unsigned int vi = SIMPLEX ? (unsigned int)(acc_in >> (8 * t)) & 0xFFu : (unsigned int)acc_in;
+      const unsigned int vo = SIMPLEX ? (unsigned int)(acc_out >> (8 * t)) & 0xFFu : (unsigned int)acc_out;
+      const unsigned int a = __reduce_add_sync(0xffffffffu, vi);
+      const unsigned int b = __reduce_add_sync(0xffffffffu, vo);
+      if (lane == 0) {
+        if (a) atomicAdd(&s_cnt[t], a);
+        if (b) atomicAdd(&s_cnt[6 + t], b);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < L * 12; i += C::THREADS)
+    if (s_cnt[i]) atomicAdd(&bg_counts[i], (unsigned long long)s_cnt[i]);
 }
 
 // ---- compaction of the cut mask -------------------------------------------------------------------
@@ -431,7 +484,7 @@ int gc_classify(gecut_ctx* ctx, gecut_result* res) {
     }
     size_t smem = sizeof(uint32_t) * 2 * L * C::RY * (C::WX + 1);
     GC_LAUNCH(ctx, "k_classify", k_classify<D, S><<<grid, C::THREADS, smem, ctx->stream>>>(g, res->leaves, res->lay.bg_state, res->lay.bg_pitch,
-                                                              res->cutmask, ctx->d_simplexify_raw));
+                                                              res->cutmask, ctx->d_simplexify_raw, res->bg_counts_dev));
   };
   if (g.D == 3) {
     if (g.simplexified)
@@ -467,8 +520,10 @@ int gc_compact_cutcells(gecut_ctx* ctx, gecut_result* res) {
   GC_CHECK(gc_exclusive_scan_u32(ctx, counts, counts, ngroups, total_dev));
   uint64_t* h = (uint64_t*)ctx->h_pinned;
   GC_CUDA(cudaMemcpyAsync(h, total_dev, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  GC_CUDA(cudaMemcpyAsync(h + 1, res->bg_counts_dev, sizeof(uint64_t) * res->L * 12, cudaMemcpyDeviceToHost, ctx->stream));
   GC_CUDA(cudaStreamSynchronize(ctx->stream));
   const int64_t ncut = (int64_t)h[0];
+  for (int i = 0; i < res->L * 12; ++i) res->bg_counts[i] = (int64_t)h[1 + i];
   res->sizes.num_cutcells = ncut;
   if (ncut > 0) {
     GC_CHECK(gc_malloc(ctx, (void**)&res->lay.cutcells, sizeof(int32_t) * ncut));

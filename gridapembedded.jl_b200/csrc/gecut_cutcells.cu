@@ -521,8 +521,14 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
   }
   // ---- phase 1: physical coordinates: vertex copies, then one point per cut edge in edge order (:199-219)
   if (valid) {
-    if (s % g.nt0 == 0) sc_ptr[s / g.nt0] = gc + lc;
-    if (s == nsimp - 1) sc_ptr[s / g.nt0 + 1] = gc + lc + nsub;
+    if (s % g.nt0 == 0) {  // first subcell / first point of this cut cell
+      sc_ptr[2 * (s / g.nt0)] = gc + lc;
+      sc_ptr[2 * (s / g.nt0) + 1] = gp + lp;
+    }
+    if (s == nsimp - 1) {
+      sc_ptr[2 * (s / g.nt0) + 2] = gc + lc + nsub;
+      sc_ptr[2 * (s / g.nt0) + 3] = gp + lp + np;
+    }
 #pragma unroll
     for (int i = 0; i <= D; ++i)
 #pragma unroll
@@ -639,11 +645,17 @@ size_t cut1_fill_smem() {
   return sizeof(double) * (CUT1_TILE * WalkCfg<D>::NPC * D);
 }
 
-__global__ void k_extract_sc_ptr(const uint32_t* __restrict__ cell_offs, int nt0, int64_t ncut, uint32_t total,
-                                 uint32_t* __restrict__ ptr) {
+__global__ void k_extract_sc_ptr(const uint32_t* __restrict__ cell_offs, const uint32_t* __restrict__ point_offs, int nt0,
+                                 int64_t ncut, uint32_t total_cells, uint32_t total_points, uint32_t* __restrict__ ptr) {
   int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < ncut) ptr[k] = cell_offs[k * nt0];
-  if (k == ncut) ptr[k] = total;
+  if (k < ncut) {
+    ptr[2 * k] = cell_offs[k * nt0];
+    ptr[2 * k + 1] = point_offs[k * nt0];
+  }
+  if (k == ncut) {
+    ptr[2 * k] = total_cells;
+    ptr[2 * k + 1] = total_points;
+  }
 }
 
 template <int D, int LM>
@@ -735,7 +747,7 @@ static int gc_cut_cells_l1(gecut_ctx* ctx, gecut_result* res) {
   lay.sf_X = lay.sc_X;  // device-side alias (read-only results); the host copy-out writes both destinations
   lay.sf_R = lay.sc_R;
   res->sf_points_alias = true;
-  GC_CHECK(gc_malloc(ctx, (void**)&res->cut_sc_ptr, sizeof(uint32_t) * (ncut + 1)));
+  GC_CHECK(gc_malloc(ctx, (void**)&res->cut_sc_ptr, sizeof(uint32_t) * 2 * (ncut + 1)));
   if (D == 2) {
     const size_t smem = cut1_fill_smem<2>();
     GC_LAUNCH(ctx, "k_cut1_fill", k_cut1_fill<2><<<(unsigned)ntiles, CUT1_TILE, smem, ctx->stream>>>(
@@ -818,9 +830,9 @@ int gc_cut_cells(gecut_ctx* ctx, gecut_result* res) {
     GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_X, sizeof(double) * nsfp * D));
     GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_R, sizeof(double) * nsfp * D));
   }
-  GC_CHECK(gc_malloc(ctx, (void**)&res->cut_sc_ptr, sizeof(uint32_t) * (ncut + 1)));
+  GC_CHECK(gc_malloc(ctx, (void**)&res->cut_sc_ptr, sizeof(uint32_t) * 2 * (ncut + 1)));
   GC_LAUNCH(ctx, "k_extract_sc_ptr", k_extract_sc_ptr<<<(unsigned)gc_div_up(ncut + 1, 256), 256, 0, ctx->stream>>>(
-      cn.cells, g.nt0, ncut, (uint32_t)nsc, res->cut_sc_ptr));
+      cn.cells, cn.points, g.nt0, ncut, (uint32_t)nsc, (uint32_t)nscp, res->cut_sc_ptr));
   dispatch_walk(ctx, res, nsimp, cn, true);
   int st = gc_launch_check(ctx, "k_cut_walk(fill)");
   gc_free(ctx, pool);

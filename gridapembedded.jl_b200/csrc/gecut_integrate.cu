@@ -180,121 +180,120 @@ inline QuadRule ncube_rule_deg2(int D) {
 //     (27 numbers in 3-D, 6 in 2-D), accumulated per lane over (subcell, quadrature point) items, reduced across the warp
 //     through shared memory, and K_ab = sum_d sgn_a sgn_b / h_d^2 * M_d[a_e+b_e][a_f+b_f].
 //   * simplex cells (P1): gradients are constant, K_ab = (g_a.g_b) * sum_s sum_q w_q |J_s|.
-constexpr int LAP_WARPS = 4;
-
+// One THREAD per cut cell: it walks the cell's subcells (a contiguous run) and keeps the 27 (6) moments in registers, so
+// there is no cross-lane reduction at all and a warp has 32 cells' worth of independent loads in flight.
 template <int D>
-__global__ void __launch_bounds__(LAP_WARPS * 32)
+__global__ void __launch_bounds__(128)
 k_cutcell_laplacian_q1(const GcGrid g, const GcLayout lay, const uint32_t* __restrict__ sc_ptr, int64_t ncut,
-                    const GcProgram prog, int side, const uint8_t* __restrict__ simp_raw, double* __restrict__ K) {
+                       const GcProgram prog, int side, double* __restrict__ K) {
   constexpr int NV = 1 << D;
   constexpr int NQ = D + 1;
   constexpr int NM = D == 3 ? 27 : 6;
   constexpr int NN = NV * NV;
-  __shared__ double red[LAP_WARPS][NM][33];
-  __shared__ double tot[LAP_WARPS][NM];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int64_t nwarps = (int64_t)gridDim.x * LAP_WARPS;
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= ncut) return;
   const double qa = D == 3 ? (5.0 - sqrt(5.0)) / 20.0 : 1.0 / 6;
   const double qb = D == 3 ? (5.0 + 3.0 * sqrt(5.0)) / 20.0 : 2.0 / 3;
-  const double qw = D == 3 ? 1.0 / 24 : 1.0 / 6;
-  for (int64_t k = (int64_t)blockIdx.x * LAP_WARPS + wid; k < ncut; k += nwarps) {
-    const int32_t bg = lay.cutcells[k];
-    const int64_t cell0 = (int64_t)bg - 1;
-    const int bgstate = gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, cell0);
-    double M[NM];
+  const int64_t cell0 = (int64_t)lay.cutcells[k] - 1;
+  double M[NM];
 #pragma unroll
-    for (int m = 0; m < NM; ++m) M[m] = 0.0;
-    if (bgstate == GC_CUT) {
-      const uint32_t s0 = sc_ptr[k], s1 = sc_ptr[k + 1];
-      for (uint32_t it = s0 + lane; it < s1; it += 32) {
-        const int64_t e = (int64_t)it;
-        if (gc_eval_inoutcut(prog, lay.sc_state, lay.sc_pitch, e) != side) continue;
-        double r[D + 1][3];
+  for (int m = 0; m < NM; ++m) M[m] = 0.0;
+  if (gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, cell0) == GC_CUT) {
+    const uint32_t s0 = sc_ptr[2 * k], s1 = sc_ptr[2 * k + 2];
+    for (uint32_t it = s0; it < s1; ++it) {
+      const int64_t e = (int64_t)it;
+      if (gc_eval_inoutcut(prog, lay.sc_state, lay.sc_pitch, e) != side) continue;
+      int32_t ids[D + 1];
+      if (D == 3) {
+        const int4 q4 = *reinterpret_cast<const int4*>(lay.sc_c2p + e * 4);
+        ids[0] = q4.x;
+        ids[1] = q4.y;
+        ids[2] = q4.z;
+        ids[D] = q4.w;
+      } else {
 #pragma unroll
-        for (int v = 0; v <= D; ++v) {
-          const int64_t pid = (int64_t)lay.sc_c2p[e * (D + 1) + v] - 1;
+        for (int v = 0; v <= D; ++v) ids[v] = lay.sc_c2p[e * (D + 1) + v];
+      }
+      double r[D + 1][3];
 #pragma unroll
-          for (int d = 0; d < D; ++d) r[v][d] = lay.sc_R[pid * D + d];
-        }
-        const double wdV = lay.sc_meas[e] * (1.0 / NQ);  // sc_meas = sum_q w_q |J_s| (all weights equal)
-        double rs[3];
+      for (int v = 0; v <= D; ++v) {
+        const int64_t pid = (int64_t)ids[v] - 1;
+#pragma unroll
+        for (int d = 0; d < D; ++d) r[v][d] = lay.sc_R[pid * D + d];
+      }
+      const double wdV = lay.sc_meas[e] * (1.0 / NQ);  // sc_meas = sum_q w_q |J_s| (all weights equal)
+      double rs[3];
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        double t = r[0][d];
+#pragma unroll
+        for (int i = 1; i <= D; ++i) t += r[i][d];
+        rs[d] = qa * t;
+      }
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        double P[3][3];
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-          double t = r[0][d];
-#pragma unroll
-          for (int i = 1; i <= D; ++i) t += r[i][d];
-          rs[d] = qa * t;
+          // eta_q = sum_i N_i(xi_q) R_i with N_i = qb for i == q and qa otherwise
+          const double t = rs[d] + (qb - qa) * r[q][d], u = 1.0 - t;
+          P[d][0] = u * u;
+          P[d][1] = t * u;
+          P[d][2] = t * t;
         }
+        if (D == 3) {
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-          double P[3][3];
+          for (int d = 0; d < 3; ++d) {
+            const int e1 = d == 0 ? 1 : 0, f1 = d == 2 ? 1 : 2;
 #pragma unroll
-          for (int d = 0; d < D; ++d) {
-            // eta_q = sum_i N_i(xi_q) R_i with N_i = qb for i == q and qa otherwise
-            const double t = rs[d] + (qb - qa) * r[q][d], u = 1.0 - t;
-            P[d][0] = u * u;
-            P[d][1] = t * u;
-            P[d][2] = t * t;
+            for (int i = 0; i < 3; ++i) {
+              const double wp = wdV * P[e1][i];
+#pragma unroll
+              for (int j = 0; j < 3; ++j) M[d * 9 + i * 3 + j] = fma(wp, P[f1][j], M[d * 9 + i * 3 + j]);
+            }
           }
+        } else {
+#pragma unroll
+          for (int d = 0; d < 2; ++d) {
+            const int e1 = 1 - d;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) M[d * 3 + i] = fma(wdV, P[e1][i], M[d * 3 + i]);
+          }
+        }
+      }
+    }
+  }
+  // ---- element matrix from the moments (static indices: everything stays in registers)
+  double ih2[3];
+#pragma unroll
+  for (int d = 0; d < D; ++d) ih2[d] = 1.0 / (g.dx[d] * g.dx[d]);
+  double* out = K + k * NN;
+#pragma unroll
+  for (int a = 0; a < NV; ++a) {
+#pragma unroll
+    for (int b = 0; b < NV; b += 2) {
+      double v2[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int bb = b + u;
+        double val = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const double sg = (((a >> d) & 1) == ((bb >> d) & 1)) ? 1.0 : -1.0;
+          int mi;
           if (D == 3) {
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-              const int e1 = d == 0 ? 1 : 0, f1 = d == 2 ? 1 : 2;
-#pragma unroll
-              for (int i = 0; i < 3; ++i) {
-                const double wp = wdV * P[e1][i];
-#pragma unroll
-                for (int j = 0; j < 3; ++j) M[d * 9 + i * 3 + j] = fma(wp, P[f1][j], M[d * 9 + i * 3 + j]);
-              }
-            }
+            const int e1 = d == 0 ? 1 : 0, f1 = d == 2 ? 1 : 2;
+            mi = d * 9 + (((a >> e1) & 1) + ((bb >> e1) & 1)) * 3 + (((a >> f1) & 1) + ((bb >> f1) & 1));
           } else {
-#pragma unroll
-            for (int d = 0; d < 2; ++d) {
-              const int e1 = 1 - d;
-#pragma unroll
-              for (int i = 0; i < 3; ++i) M[d * 3 + i] = fma(wdV, P[e1][i], M[d * 3 + i]);
-            }
+            const int e1 = 1 - d;
+            mi = d * 3 + (((a >> e1) & 1) + ((bb >> e1) & 1));
           }
+          val += sg * ih2[d] * M[mi];
         }
+        v2[u] = val;
       }
+      *reinterpret_cast<double2*>(out + a * NV + b) = make_double2(v2[0], v2[1]);
     }
-    // ---- reduce the moments across the warp
-#pragma unroll
-    for (int m = 0; m < NM; ++m) red[wid][m][lane] = M[m];
-    __syncwarp();
-    if (lane < NM) {
-      double sacc = 0.0;
-      for (int j = 0; j < 32; ++j) sacc += red[wid][lane][j];
-      tot[wid][lane] = sacc;
-    }
-    __syncwarp();
-    // ---- element matrix
-    {
-#pragma unroll
-      for (int u = 0; u < (NN + 31) / 32; ++u) {
-        const int idx = lane + 32 * u;
-        if (idx < NN) {
-          const int a = idx / NV, b = idx % NV;
-          double val = 0.0;
-#pragma unroll
-          for (int d = 0; d < D; ++d) {
-            const double sg = (((a >> d) & 1) == ((b >> d) & 1)) ? 1.0 : -1.0;
-            const double ih2 = 1.0 / (g.dx[d] * g.dx[d]);
-            int mi;
-            if (D == 3) {
-              const int e1 = d == 0 ? 1 : 0, f1 = d == 2 ? 1 : 2;
-              mi = d * 9 + (((a >> e1) & 1) + ((b >> e1) & 1)) * 3 + (((a >> f1) & 1) + ((b >> f1) & 1));
-            } else {
-              const int e1 = 1 - d;
-              mi = d * 3 + (((a >> e1) & 1) + ((b >> e1) & 1));
-            }
-            val += sg * ih2 * tot[wid][mi];
-          }
-          K[k * NN + idx] = val;
-        }
-      }
-    }
-    __syncwarp();
   }
 }
 
@@ -314,7 +313,7 @@ k_cutcell_laplacian_p1(const GcGrid g, const GcLayout lay, const uint32_t* __res
     const int64_t cell0 = (int64_t)lay.cutcells[k] - 1;
     ty = (int)(cell0 % g.cpc);
     if (gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, cell0) == GC_CUT) {
-      const uint32_t s0 = sc_ptr[k], s1 = sc_ptr[k + 1];
+      const uint32_t s0 = sc_ptr[2 * k], s1 = sc_ptr[2 * k + 2];
       for (uint32_t e = s0; e < s1; ++e) {
         if (gc_eval_inoutcut(prog, lay.sc_state, lay.sc_pitch, (int64_t)e) != side) continue;
         V += lay.sc_meas[e];
@@ -481,13 +480,13 @@ int gc_integrate_laplacian(gecut_ctx* ctx, gecut_selection* sel, double* K_bg_ho
     gc_free(ctx, Gd);
     return gc_launch_check(ctx, "k_cutcell_laplacian_p1");
   }
-  const int T = LAP_WARPS * 32;
-  const unsigned nb = (unsigned)std::min<int64_t>(gc_div_up(ncut, LAP_WARPS), 148 * 64);
+  const int T = 128;
+  const unsigned nb = (unsigned)gc_div_up(ncut, T);
   if (g.D == 2)
     GC_LAUNCH(ctx, "k_cutcell_laplacian", k_cutcell_laplacian_q1<2><<<nb, T, 0, ctx->stream>>>(
-        g, res->lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, ctx->d_simplexify_raw, sel->K_cut));
+        g, res->lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, sel->K_cut));
   else
     GC_LAUNCH(ctx, "k_cutcell_laplacian", k_cutcell_laplacian_q1<3><<<nb, T, 0, ctx->stream>>>(
-        g, res->lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, ctx->d_simplexify_raw, sel->K_cut));
+        g, res->lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, sel->K_cut));
   return gc_launch_check(ctx, "k_cutcell_laplacian");
 }

@@ -126,7 +126,9 @@ struct gecut_result {
   gecut_sizes sizes{};
   GcLayout lay{};
   uint32_t* cutmask = nullptr;
-  uint32_t* cut_sc_ptr = nullptr;  // Ncut+1: first subcell (0-based) of every cut bg cell
+  uint32_t* cut_sc_ptr = nullptr;  // 2*(Ncut+1): (first subcell, first subcell point) (0-based) of every cut bg cell
+  unsigned long long* bg_counts_dev = nullptr;  // [L][2][6] IN / OUT bg cells per level set and cell type
+  int64_t bg_counts[GC_LMAX * 12] = {0};        // host copy (filled with the cut-cell count read-back)
   bool sf_points_alias = false;    // L == 1: the subfacet point arrays ARE the subcell point arrays on the device
   bool owns_nodal[GC_LMAX] = {false};
   double* nodal_dev[GC_LMAX] = {nullptr};

@@ -189,7 +189,32 @@ int gc_select_cells(gecut_ctx* ctx, gecut_selection* sel) {
     gc_free(ctx, flags);
     GC_CHECK(st);
   }
+  // single-leaf programs ([ls] or [ls, !]): the classification kernel already tallied IN / OUT cells per level set and
+  // cell type, no pass over the Nc state bytes is needed
+  bool from_tally = false;
   if (want_bg && nc > 0) {
+    const GcProgram& p = sel->prog;
+    const bool leaf = p.len == 1 && p.tok[0] >= 0;
+    const bool notleaf = p.len == 2 && p.tok[0] >= 0 && p.tok[1] == GECUT_OP_COMPLEMENT;
+    if (leaf || notleaf) {
+      const int ls = p.tok[0];
+      const int side_eff = notleaf ? -sel->side : sel->side;
+      const int64_t* cin = res->bg_counts + ls * 12;
+      const int64_t* cout = cin + 6;
+      sel->n_bg = 0;
+      for (int t = 0; t < res->grid.cpc; ++t) {
+        int64_t c;
+        if (sel->kind == GECUT_SEL_ACTIVE)  // CUT or side  =  all cells of the type minus the other side
+          c = res->grid.num_cubes - (side_eff == GECUT_IN ? cout[t] : cin[t]);
+        else
+          c = side_eff == GECUT_IN ? cin[t] : cout[t];
+        sel->bg_type_count[t] = c;
+        sel->n_bg += c;
+      }
+      from_tally = true;
+    }
+  }
+  if (want_bg && nc > 0 && !from_tally) {
     unsigned long long* counts = nullptr;
     GC_CHECK(gc_malloc(ctx, (void**)&counts, sizeof(unsigned long long) * 8));
     GC_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * 8, ctx->stream));
