@@ -53,7 +53,10 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total)
   return excl;
 }
 
+// all three kernels take `nch` arrays of n elements stored back to back (blockIdx.y = channel)
 __global__ void k_scan_reduce(const uint32_t* __restrict__ in, int64_t n, uint64_t* __restrict__ blocksums) {
+  in += (int64_t)blockIdx.y * n;
+  blocksums += (int64_t)blockIdx.y * gridDim.x;
   int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
   uint32_t s = 0;
 #pragma unroll
@@ -68,6 +71,8 @@ __global__ void k_scan_reduce(const uint32_t* __restrict__ in, int64_t n, uint64
 
 // single block: exclusive scan of the block sums (uint64), grand total out
 __global__ void k_scan_blocksums(uint64_t* __restrict__ blocksums, int64_t nb, uint64_t* __restrict__ total) {
+  blocksums += (int64_t)blockIdx.x * nb;
+  total += blockIdx.x;
   __shared__ uint64_t carry_s;
   __shared__ uint64_t wsum[32];
   if (threadIdx.x == 0) carry_s = 0;
@@ -106,6 +111,9 @@ __global__ void k_scan_blocksums(uint64_t* __restrict__ blocksums, int64_t nb, u
 
 __global__ void k_scan_apply(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t n,
                              const uint64_t* __restrict__ blocksums) {
+  in += (int64_t)blockIdx.y * n;
+  out += (int64_t)blockIdx.y * n;
+  blocksums += (int64_t)blockIdx.y * gridDim.x;
   // blocked arrangement: thread t owns items [t*ITEMS, (t+1)*ITEMS) of the tile so that the order is preserved
   int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
   uint32_t v[SCAN_ITEMS];
@@ -129,20 +137,25 @@ __global__ void k_scan_apply(const uint32_t* __restrict__ in, uint32_t* __restri
 
 }  // namespace
 
-int gc_exclusive_scan_u32(gecut_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n, uint64_t* total_dev) {
+int gc_exclusive_scan_u32_multi(gecut_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n, int nch, uint64_t* totals_dev) {
   if (n <= 0) {
-    GC_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(uint64_t), ctx->stream));
+    GC_CUDA(cudaMemsetAsync(totals_dev, 0, sizeof(uint64_t) * nch, ctx->stream));
     return GECUT_OK;
   }
   int64_t nb = gc_div_up(n, SCAN_TILE);
   uint64_t* blocksums = nullptr;
-  GC_CHECK(gc_malloc(ctx, (void**)&blocksums, sizeof(uint64_t) * nb));
-  GC_LAUNCH(ctx, "k_scan_reduce", k_scan_reduce<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(in, n, blocksums));
-  GC_LAUNCH(ctx, "k_scan_blocksums", k_scan_blocksums<<<1, 1024, 0, ctx->stream>>>(blocksums, nb, total_dev));
-  GC_LAUNCH(ctx, "k_scan_apply", k_scan_apply<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, blocksums));
+  GC_CHECK(gc_malloc(ctx, (void**)&blocksums, sizeof(uint64_t) * nb * nch));
+  dim3 grid((unsigned)nb, (unsigned)nch);
+  GC_LAUNCH(ctx, "k_scan_reduce", k_scan_reduce<<<grid, SCAN_THREADS, 0, ctx->stream>>>(in, n, blocksums));
+  GC_LAUNCH(ctx, "k_scan_blocksums", k_scan_blocksums<<<nch, 1024, 0, ctx->stream>>>(blocksums, nb, totals_dev));
+  GC_LAUNCH(ctx, "k_scan_apply", k_scan_apply<<<grid, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, blocksums));
   int st = gc_launch_check(ctx, "scan");
   gc_free(ctx, blocksums);
   return st;
+}
+
+int gc_exclusive_scan_u32(gecut_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n, uint64_t* total_dev) {
+  return gc_exclusive_scan_u32_multi(ctx, in, out, n, 1, total_dev);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -162,7 +175,11 @@ struct ClsCfg {
 // words per x-row of the cut mask
 __host__ __device__ inline int gc_words_per_row(int nx) { return (nx + 31) / 32; }
 
-template <int D, bool SIMPLEX>
+// LH > 0: "hoisted" evaluation for models with at most LH level sets.  Every closed-form leaf splits into a part that
+// depends on the in-plane coordinates only (constant while the block marches through the layers) and the marching
+// coordinate: e.g. sphere ((wx*wx + wy*wy) + wz*wz) - R*R  =  (pa + wz*wz) - RR with pa kept in a register per task.
+// The association of the reference formulas is preserved exactly (same rounding), only loop-invariant operations move.
+template <int D, bool SIMPLEX, int LH>
 __global__ void __launch_bounds__(ClsCfg<D>::THREADS)
 k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64_t pitch,
            uint32_t* __restrict__ cutmask, const uint8_t* __restrict__ simplexify_raw,
@@ -212,43 +229,146 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
   const int plane_words = L * RY * (WX + 1);
   // packed per-type tallies (one byte per cell type; <= 4 cells x 32 layers = 128 per byte, n-cubes: plain counters)
   unsigned long long acc_in = 0ull, acc_out = 0ull;
-
-  for (int kp = kz0; kp <= kz1; ++kp) {  // node planes kz0..kz1
-    uint32_t* P = planes + ((kp - kz0) & 1) * plane_words;
-    // ---- evaluate the signs of node plane kp: one ballot per (row, word) task and level set.  Of the word right of the
-    //      tile only bit 0 is needed (x+1 vertices of the last cell column): one transposed task evaluates that node
-    //      column for all RY rows at once instead of RY mostly wasted row tasks.
-    for (int task = wid; task < RY * WX + 1; task += NW) {
+  // hoisted (plane-invariant) parts of the leaf formulas per evaluation task of this warp
+  constexpr int NSLOT = (RY * WX + 1 + NW - 1) / NW;
+  constexpr int LHS = LH > 0 ? LH : 1;
+  double h_pa[NSLOT][LHS], h_pb[NSLOT][LHS], h_c[LHS];
+  uint32_t h_valid = 0u;  // bit k: this lane evaluates a real node in task slot k
+  if (LH > 0) {
+#pragma unroll
+    for (int ls = 0; ls < LH; ++ls) {
+      h_c[ls] = 0.0;
+      if (ls < L) {
+        const int kind = lv.leaf[ls].kind;
+        h_c[ls] = kind == GECUT_LEAF_DOUGHNUT ? __dmul_rn(lv.leaf[ls].r, lv.leaf[ls].r) : __dmul_rn(lv.leaf[ls].R, lv.leaf[ls].R);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NSLOT; ++k) {
+      const int task = wid + k * NW;
       const bool halo = task == RY * WX;
       const int r = halo ? lane : task / WX;
       const int ww = halo ? WX : task % WX;
       const int i = halo ? 32 * (w0 + WX) : 32 * (w0 + ww) + lane;
       const int j = j0 + r;
-      const bool valid = (i < g.nn[0]) && (D == 2 || j < g.nn[1]) && (!halo || lane < RY);
-      double x[3];
-      x[0] = gc_coord(g, 0, i);
-      if (D == 3) {
-        x[1] = gc_coord(g, 1, j);
-        x[2] = gc_coord(g, 2, kp);
-      } else {
-        x[1] = gc_coord(g, 1, kp);
-        x[2] = 0.0;
-      }
-      const int64_t node = (D == 3) ? ((int64_t)i + (int64_t)g.nn[0] * ((int64_t)j + (int64_t)g.nn[1] * kp))
-                                    : ((int64_t)i + (int64_t)g.nn[0] * kp);
-      for (int ls = 0; ls < L; ++ls) {
-        double v = -1.0;
-        if (valid) {
-          if (lv.leaf[ls].kind == GECUT_LEAF_NODAL)
-            v = __ldg(lv.nodal[ls] + (node - lv.nodal_base));
-          else
-            v = gc_eval_leaf(lv.leaf[ls], x, D);
+      if ((task < RY * WX + 1) && (i < g.nn[0]) && (D == 2 || j < g.nn[1]) && (!halo || lane < RY)) h_valid |= 1u << k;
+      const double xc = gc_coord(g, 0, i);
+      const double yc = (D == 3) ? gc_coord(g, 1, j) : 0.0;
+#pragma unroll
+      for (int ls = 0; ls < LH; ++ls) {
+        h_pa[k][ls] = 0.0;
+        h_pb[k][ls] = 0.0;
+        if (ls < L) {
+          const gecut_leaf& lf = lv.leaf[ls];
+          const double wx = __dsub_rn(xc, lf.x0[0]);
+          const double wy = (D == 3) ? __dsub_rn(yc, lf.x0[1]) : 0.0;
+          // in-plane partial sums, associated exactly like gc_dot3: (a0*b0 + a1*b1) [+ a2*b2 added per plane]
+          const double ww2 = (D == 3) ? __dadd_rn(__dmul_rn(wx, wx), __dmul_rn(wy, wy)) : __dmul_rn(wx, wx);
+          const double wv = (D == 3) ? __dadd_rn(__dmul_rn(wx, lf.v[0]), __dmul_rn(wy, lf.v[1])) : __dmul_rn(wx, lf.v[0]);
+          if (lf.kind == GECUT_LEAF_SPHERE) {
+            h_pa[k][ls] = ww2;
+          } else if (lf.kind == GECUT_LEAF_PLANE) {
+            h_pa[k][ls] = wv;
+          } else if (lf.kind == GECUT_LEAF_CYLINDER) {
+            h_pa[k][ls] = wv;
+            h_pb[k][ls] = ww2;
+          } else if (lf.kind == GECUT_LEAF_DOUGHNUT) {
+            const double t = __dsub_rn(lf.R, __dsqrt_rn(ww2));
+            h_pa[k][ls] = __dmul_rn(t, t);
+          }
         }
-        const uint32_t word = __ballot_sync(0xffffffffu, valid && (v > 0.0));
-        if (!halo) {
-          if (lane == 0) P[(ls * RY + r) * (WX + 1) + ww] = word;
-        } else if (lane < RY) {
-          P[(ls * RY + lane) * (WX + 1) + WX] = (word >> lane) & 1u;
+      }
+    }
+  }
+
+  for (int kp = kz0; kp <= kz1; ++kp) {  // node planes kz0..kz1
+    uint32_t* P = planes + ((kp - kz0) & 1) * plane_words;
+    if (LH > 0) {
+      // ---- hoisted evaluation: per plane only the marching coordinate enters
+      const double zc = gc_coord(g, D - 1, kp);
+      double wz[LH > 0 ? LH : 1], wz2[LH > 0 ? LH : 1], wzv[LH > 0 ? LH : 1];
+#pragma unroll
+      for (int ls = 0; ls < LH; ++ls) {
+        if (ls < L) {
+          wz[ls] = __dsub_rn(zc, lv.leaf[ls].x0[D - 1]);
+          wz2[ls] = __dmul_rn(wz[ls], wz[ls]);
+          wzv[ls] = __dmul_rn(wz[ls], lv.leaf[ls].v[D - 1]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NSLOT; ++k) {
+        const int task = wid + k * NW;
+        if (task < RY * WX + 1) {
+          const bool halo = task == RY * WX;
+          const int r = halo ? lane : task / WX;
+          const int ww = halo ? WX : task % WX;
+#pragma unroll
+          for (int ls = 0; ls < LH; ++ls) {
+            if (ls < L) {
+              const int kind = lv.leaf[ls].kind;
+              double v;
+              if (kind == GECUT_LEAF_SPHERE) {
+                v = __dsub_rn(__dadd_rn(h_pa[k][ls], wz2[ls]), h_c[ls]);
+              } else if (kind == GECUT_LEAF_PLANE) {
+                v = __dadd_rn(h_pa[k][ls], wzv[ls]);
+              } else if (kind == GECUT_LEAF_CYLINDER) {
+                const double A = __dadd_rn(h_pa[k][ls], wzv[ls]);
+                const double H2 = __dadd_rn(h_pb[k][ls], wz2[ls]);
+                v = __dsub_rn(__dsub_rn(H2, __dmul_rn(A, A)), h_c[ls]);
+              } else if (kind == GECUT_LEAF_DOUGHNUT) {
+                v = __dsub_rn(__dadd_rn(h_pa[k][ls], wz2[ls]), h_c[ls]);
+              } else {
+                const int i = halo ? 32 * (w0 + WX) : 32 * (w0 + ww) + lane;
+                const int64_t node = (D == 3) ? ((int64_t)i + (int64_t)g.nn[0] * ((int64_t)(j0 + r) + (int64_t)g.nn[1] * kp))
+                                              : ((int64_t)i + (int64_t)g.nn[0] * kp);
+                v = ((h_valid >> k) & 1u) ? __ldg(lv.nodal[ls] + (node - lv.nodal_base)) : -1.0;
+              }
+              const uint32_t word = __ballot_sync(0xffffffffu, ((h_valid >> k) & 1u) && (v > 0.0));
+              if (!halo) {
+                if (lane == 0) P[(ls * RY + r) * (WX + 1) + ww] = word;
+              } else if (lane < RY) {
+                P[(ls * RY + lane) * (WX + 1) + WX] = (word >> lane) & 1u;
+              }
+            }
+          }
+        }
+      }
+    } else {
+    // ---- evaluate the signs of node plane kp: one ballot per (row, word) task and level set.  Of the word right of the
+      //      tile only bit 0 is needed (x+1 vertices of the last cell column): one transposed task evaluates that node
+      //      column for all RY rows at once instead of RY mostly wasted row tasks.
+      for (int task = wid; task < RY * WX + 1; task += NW) {
+        const bool halo = task == RY * WX;
+        const int r = halo ? lane : task / WX;
+        const int ww = halo ? WX : task % WX;
+        const int i = halo ? 32 * (w0 + WX) : 32 * (w0 + ww) + lane;
+        const int j = j0 + r;
+        const bool valid = (i < g.nn[0]) && (D == 2 || j < g.nn[1]) && (!halo || lane < RY);
+        double x[3];
+        x[0] = gc_coord(g, 0, i);
+        if (D == 3) {
+          x[1] = gc_coord(g, 1, j);
+          x[2] = gc_coord(g, 2, kp);
+        } else {
+          x[1] = gc_coord(g, 1, kp);
+          x[2] = 0.0;
+        }
+        const int64_t node = (D == 3) ? ((int64_t)i + (int64_t)g.nn[0] * ((int64_t)j + (int64_t)g.nn[1] * kp))
+                                      : ((int64_t)i + (int64_t)g.nn[0] * kp);
+        for (int ls = 0; ls < L; ++ls) {
+          double v = -1.0;
+          if (valid) {
+            if (lv.leaf[ls].kind == GECUT_LEAF_NODAL)
+              v = __ldg(lv.nodal[ls] + (node - lv.nodal_base));
+            else
+              v = gc_eval_leaf(lv.leaf[ls], x, D);
+          }
+          const uint32_t word = __ballot_sync(0xffffffffu, valid && (v > 0.0));
+          if (!halo) {
+            if (lane == 0) P[(ls * RY + r) * (WX + 1) + ww] = word;
+          } else if (lane < RY) {
+            P[(ls * RY + lane) * (WX + 1) + WX] = (word >> lane) & 1u;
+          }
         }
       }
     }
@@ -483,8 +603,15 @@ int gc_classify(gecut_ctx* ctx, gecut_result* res) {
       grid.z = 1;
     }
     size_t smem = sizeof(uint32_t) * 2 * L * C::RY * (C::WX + 1);
-    GC_LAUNCH(ctx, "k_classify", k_classify<D, S><<<grid, C::THREADS, smem, ctx->stream>>>(g, res->leaves, res->lay.bg_state, res->lay.bg_pitch,
-                                                              res->cutmask, ctx->d_simplexify_raw, res->bg_counts_dev));
+    if (L == 1)
+      GC_LAUNCH(ctx, "k_classify", k_classify<D, S, 1><<<grid, C::THREADS, smem, ctx->stream>>>(
+          g, res->leaves, res->lay.bg_state, res->lay.bg_pitch, res->cutmask, ctx->d_simplexify_raw, res->bg_counts_dev));
+    else if (L == 2)
+      GC_LAUNCH(ctx, "k_classify", k_classify<D, S, 2><<<grid, C::THREADS, smem, ctx->stream>>>(
+          g, res->leaves, res->lay.bg_state, res->lay.bg_pitch, res->cutmask, ctx->d_simplexify_raw, res->bg_counts_dev));
+    else
+      GC_LAUNCH(ctx, "k_classify", k_classify<D, S, 0><<<grid, C::THREADS, smem, ctx->stream>>>(
+          g, res->leaves, res->lay.bg_state, res->lay.bg_pitch, res->cutmask, ctx->d_simplexify_raw, res->bg_counts_dev));
   };
   if (g.D == 3) {
     if (g.simplexified)

@@ -435,6 +435,73 @@ __device__ __forceinline__ uint32_t cut1_block_scan(uint32_t v, uint32_t* total)
   return wsum[wid] + inc - v;
 }
 
+// Lean stage-0 set-up of the fast path: physical coordinates, the single level-set value and, instead of the reference
+// coordinates, one small integer per vertex whose bit d IS the d-th reference coordinate (n-cube vertices are {0,1}^D,
+// simplex vertices are the origin and the unit axes) -- 24 fewer live registers than carrying the doubles around.
+template <int D>
+__device__ __forceinline__ void setup_stage0_l1(const GcGrid& g, const GcLeaves& lv, int64_t cell0, int t,
+                                                const uint8_t* simp_raw, const uint8_t* simp_pos, double (*x)[D],
+                                                double* w, int* rv) {
+  const int64_t cube = cell0 / g.cpc;
+  const int typ = (int)(cell0 % g.cpc);
+  int ijk[3];
+  ijk[0] = (int)(cube % g.n[0]);
+  if (D == 3) {
+    ijk[1] = (int)((cube / g.n[0]) % g.n[1]);
+    ijk[2] = (int)(cube / ((int64_t)g.n[0] * g.n[1])) + g.k0;
+  } else {
+    ijk[1] = (int)(cube / g.n[0]) + g.k0;
+    ijk[2] = 0;
+  }
+#pragma unroll
+  for (int m = 0; m <= D; ++m) {
+    const int lvid = g.simplexified ? simp_raw[(D - 2) * 24 + typ * 4 + m] : simp_pos[(D - 2) * 24 + t * 4 + m];
+    const int nijk[3] = {ijk[0] + (lvid & 1), ijk[1] + ((lvid >> 1) & 1), ijk[2] + ((lvid >> 2) & 1)};
+    double xx[3] = {gc_coord(g, 0, nijk[0]), gc_coord(g, 1, nijk[1]), D == 3 ? gc_coord(g, 2, nijk[2]) : 0.0};
+#pragma unroll
+    for (int d = 0; d < D; ++d) x[m][d] = xx[d];
+    rv[m] = g.simplexified ? (m == 0 ? 0 : (1 << (m - 1))) : lvid;
+    if (lv.leaf[0].kind == GECUT_LEAF_NODAL) {
+      const int64_t node = (D == 3) ? ((int64_t)nijk[0] + (int64_t)g.nn[0] * ((int64_t)nijk[1] + (int64_t)g.nn[1] * nijk[2]))
+                                    : ((int64_t)nijk[0] + (int64_t)g.nn[0] * nijk[1]);
+      w[m] = __ldg(lv.nodal[0] + (node - lv.nodal_base));
+    } else {
+      w[m] = gc_eval_leaf(lv.leaf[0], xx, D);
+    }
+  }
+  double J[3][3];
+#pragma unroll
+  for (int a = 0; a < D; ++a)
+#pragma unroll
+    for (int b = 0; b < D; ++b) J[a][b] = __dsub_rn(x[a + 1][b], x[0][b]);
+  double dV;
+  if (D == 2) {
+    dV = __dsub_rn(__dmul_rn(J[0][0], J[1][1]), __dmul_rn(J[0][1], J[1][0]));
+  } else {
+    const double p1 = __dmul_rn(__dmul_rn(J[0][0], J[1][1]), J[2][2]);
+    const double p2 = __dmul_rn(__dmul_rn(J[0][1], J[1][2]), J[2][0]);
+    const double p3 = __dmul_rn(__dmul_rn(J[0][2], J[1][0]), J[2][1]);
+    const double q1 = __dmul_rn(__dmul_rn(J[0][0], J[1][2]), J[2][1]);
+    const double q2 = __dmul_rn(__dmul_rn(J[0][1], J[1][0]), J[2][2]);
+    const double q3 = __dmul_rn(__dmul_rn(J[0][2], J[1][1]), J[2][0]);
+    dV = __dsub_rn(__dadd_rn(__dadd_rn(p1, p2), p3), __dadd_rn(__dadd_rn(q1, q2), q3));
+  }
+  if (dV < 0.0) {  // _ensure_positive_jacobians!: swap the first two vertices
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const double tx = x[0][d];
+      x[0][d] = x[1][d];
+      x[1][d] = tx;
+    }
+    const double tw = w[0];
+    w[0] = w[1];
+    w[1] = tw;
+    const int tr = rv[0];
+    rv[0] = rv[1];
+    rv[1] = tr;
+  }
+}
+
 template <int D>
 __device__ __forceinline__ int cut1_case(const Pt<D, 1>* S) {
   int c = 0;
@@ -469,7 +536,7 @@ k_cut1_count(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict
 }
 
 template <int D>
-__global__ void __launch_bounds__(CUT1_TILE, 6)
+__global__ void __launch_bounds__(CUT1_TILE, 5)
 k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
             const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
             const int32_t* __restrict__ cutcells, int64_t nsimp, const uint32_t* __restrict__ tile_cells,
@@ -489,13 +556,23 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
   const GcSimplexTable& TC = s_tab;
   const int64_t s = (int64_t)blockIdx.x * CUT1_TILE + threadIdx.x;
   const bool valid = s < nsimp;
-  Pt<D, 1> S[D + 1];
+  double X[D + 1][D], W[D + 1];
+  int rv[D + 1];
   int c = 0, nsub = 0, np = 0, nfac = 0;
   int32_t bgcell1 = 0;
+#pragma unroll
+  for (int i = 0; i <= D; ++i) {
+    W[i] = 0.0;
+    rv[i] = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) X[i][d] = 0.0;
+  }
   if (valid) {
     bgcell1 = cutcells[s / g.nt0];
-    setup_stage0<D, 1>(g, lv, (int64_t)bgcell1 - 1, (int)(s % g.nt0), simp_raw, simp_pos, S);
-    c = cut1_case<D>(S);
+    setup_stage0_l1<D>(g, lv, (int64_t)bgcell1 - 1, (int)(s % g.nt0), simp_raw, simp_pos, X, W, rv);
+#pragma unroll
+    for (int i = 0; i <= D; ++i)
+      if (W[i] > 0.0) c |= 1 << i;
     nsub = TC.nsub[c];
     np = TC.npts[c];
     nfac = TC.nfac[c];
@@ -512,7 +589,7 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
   for (int e = 0; e < NE; ++e) {
     const int a = (D == 3) ? (e == 0 ? 0 : e == 1 ? 0 : e == 2 ? 1 : e == 3 ? 0 : e == 4 ? 1 : 2) : (e == 0 ? 0 : e == 1 ? 0 : 1);
     const int b = (D == 3) ? (e == 0 ? 1 : e == 1 ? 2 : e == 2 ? 2 : 3) : (e == 0 ? 1 : 2);
-    const double v1 = S[a].w[0], v2 = S[b].w[0];
+    const double v1 = W[a], v2 = W[b];
     coeff[e] = -1.0;  // edge not cut
     if (iscut && ((v1 > 0.0) != (v2 > 0.0))) {
       const double w1 = fabs(v1), w2 = fabs(v2);
@@ -532,7 +609,7 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
 #pragma unroll
     for (int i = 0; i <= D; ++i)
 #pragma unroll
-      for (int d = 0; d < D; ++d) stage[(lp + i) * D + d] = S[i].x[d];
+      for (int d = 0; d < D; ++d) stage[(lp + i) * D + d] = X[i][d];
     int q = D + 1;
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
@@ -540,7 +617,7 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
       const int b = (D == 3) ? (e == 0 ? 1 : e == 1 ? 2 : e == 2 ? 2 : 3) : (e == 0 ? 1 : 2);
       if (coeff[e] >= 0.0) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) stage[(lp + q) * D + d] = gc_lerp(S[a].x[d], S[b].x[d], coeff[e]);
+        for (int d = 0; d < D; ++d) stage[(lp + q) * D + d] = gc_lerp(X[a][d], X[b][d], coeff[e]);
         q++;
       }
     }
@@ -580,7 +657,7 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
 #pragma unroll
     for (int i = 0; i <= D; ++i)
 #pragma unroll
-      for (int d = 0; d < D; ++d) stage[(lp + i) * D + d] = S[i].r[d];
+      for (int d = 0; d < D; ++d) stage[(lp + i) * D + d] = (double)((rv[i] >> d) & 1);
     int q = D + 1;
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
@@ -588,7 +665,8 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
       const int b = (D == 3) ? (e == 0 ? 1 : e == 1 ? 2 : e == 2 ? 2 : 3) : (e == 0 ? 1 : 2);
       if (coeff[e] >= 0.0) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) stage[(lp + q) * D + d] = gc_lerp(S[a].r[d], S[b].r[d], coeff[e]);
+        for (int d = 0; d < D; ++d)
+          stage[(lp + q) * D + d] = gc_lerp((double)((rv[a] >> d) & 1), (double)((rv[b] >> d) & 1), coeff[e]);
         q++;
       }
     }
@@ -714,7 +792,7 @@ static int gc_cut_cells_l1(gecut_ctx* ctx, gecut_result* res) {
     GC_LAUNCH(ctx, "k_cut1_count", k_cut1_count<3><<<(unsigned)ntiles, CUT1_TILE, 0, ctx->stream>>>(
         g, res->leaves, ctx->d_tables, ctx->d_simplexify_raw, ctx->d_simplexify_pos, res->lay.cutcells, nsimp, t_cells, t_points, t_facets));
   GC_CHECK(gc_launch_check(ctx, "k_cut1_count"));
-  for (int a = 0; a < 3; ++a) GC_CHECK(gc_exclusive_scan_u32(ctx, tiles + a * ntiles, tiles + a * ntiles, ntiles, totals_dev + a));
+  GC_CHECK(gc_exclusive_scan_u32_multi(ctx, tiles, tiles, ntiles, 3, totals_dev));
   uint64_t* h = (uint64_t*)ctx->h_pinned;
   GC_CUDA(cudaMemcpyAsync(h, totals_dev, sizeof(uint64_t) * 3, cudaMemcpyDeviceToHost, ctx->stream));
   GC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -787,7 +865,7 @@ int gc_cut_cells(gecut_ctx* ctx, gecut_result* res) {
   }
   dispatch_walk(ctx, res, nsimp, cn, false);
   GC_CHECK(gc_launch_check(ctx, "k_cut_walk(count)"));
-  for (int a = 0; a < narr; ++a) GC_CHECK(gc_exclusive_scan_u32(ctx, pool + a * nsimp, pool + a * nsimp, nsimp, totals_dev + a));
+  GC_CHECK(gc_exclusive_scan_u32_multi(ctx, pool, pool, nsimp, narr, totals_dev));
   uint64_t* h = (uint64_t*)ctx->h_pinned;
   GC_CUDA(cudaMemcpyAsync(h, totals_dev, sizeof(uint64_t) * narr, cudaMemcpyDeviceToHost, ctx->stream));
   GC_CUDA(cudaStreamSynchronize(ctx->stream));

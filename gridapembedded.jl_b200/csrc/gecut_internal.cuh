@@ -189,6 +189,8 @@ int gc_launch_check(gecut_ctx* ctx, const char* what);
 // ---- scan (gecut_classify.cu) ----
 // exclusive prefix sum of n uint32 (in place allowed); *total_dev (uint64, device) receives the grand total
 int gc_exclusive_scan_u32(gecut_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n, uint64_t* total_dev);
+// the same for `nch` arrays of n elements stored back to back (one launch set for all channels)
+int gc_exclusive_scan_u32_multi(gecut_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n, int nch, uint64_t* totals_dev);
 
 // ---- classification (gecut_classify.cu) ----
 int gc_classify(gecut_ctx* ctx, gecut_result* res);        // states + cutmask
@@ -324,6 +326,8 @@ __device__ __forceinline__ int gc_io_complementary(int a) {
 
 // compute_inoutcut(tree) (EmbeddedDiscretizations.jl:107-134) on element e of `rows`
 __device__ __forceinline__ int gc_eval_inoutcut(const GcProgram& p, const int8_t* rows, int64_t pitch, int64_t e) {
+  if (p.len == 1) return rows[(int64_t)p.tok[0] * pitch + e];  // single leaf: no stack machine
+  if (p.len == 2 && p.tok[1] == GECUT_OP_COMPLEMENT) return gc_io_complementary(rows[(int64_t)p.tok[0] * pitch + e]);
   int8_t st[GECUT_MAX_PROGRAM / 2 + 2];
   int sp = 0;
   for (int t = 0; t < p.len; ++t) {
@@ -363,6 +367,11 @@ __device__ __forceinline__ int gc_eval_inoutcut_vals(const GcProgram& p, const i
 // compute_inoutboundary(tree) (EmbeddedDiscretizations.jl:179-245): state and orientation
 __device__ __forceinline__ void gc_eval_inoutboundary(const GcProgram& p, const int8_t* rows, int64_t pitch, int64_t e,
                                                       int* state, int* orientation) {
+  if (p.len == 1) {  // single leaf: orientation +1
+    *state = rows[(int64_t)p.tok[0] * pitch + e];
+    *orientation = 1;
+    return;
+  }
   int8_t st[GECUT_MAX_PROGRAM / 2 + 2], orr[GECUT_MAX_PROGRAM / 2 + 2];
   int sp = 0;
   for (int t = 0; t < p.len; ++t) {

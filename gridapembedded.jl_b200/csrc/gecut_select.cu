@@ -33,6 +33,29 @@ __global__ void k_flag_subcells(const GcLayout lay, int64_t nsc, const GcProgram
   flags[e] = (bg == GC_CUT && sc == side) ? 1u : 0u;
 }
 
+// Triangulation(cut,CutInOrOut(side),geo) by cut cell: the subcells of a cut cell are a contiguous run (cut_sc_ptr), so
+// the bg state is evaluated once per cut cell and no per-subcell flag array / bgcell gather is needed.
+// EMIT == false: number of selected subcells per cut cell; EMIT == true: their 1-based ids at the scanned offsets.
+template <bool EMIT>
+__global__ void k_select_subcells(const GcLayout lay, const uint32_t* __restrict__ sc_ptr, int64_t ncut,
+                                  const GcProgram prog, int side, uint32_t* __restrict__ counts_or_offs,
+                                  int32_t* __restrict__ ids) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= ncut) return;
+  uint32_t c = 0;
+  uint32_t o = EMIT ? counts_or_offs[k] : 0u;
+  if (gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, (int64_t)lay.cutcells[k] - 1) == GC_CUT) {
+    const uint32_t s0 = sc_ptr[2 * k], s1 = sc_ptr[2 * k + 2];
+    for (uint32_t e = s0; e < s1; ++e) {
+      if (gc_eval_inoutcut(prog, lay.sc_state, lay.sc_pitch, (int64_t)e) == side) {
+        if (EMIT) ids[o++] = (int32_t)(e + 1);
+        c++;
+      }
+    }
+  }
+  if (!EMIT) counts_or_offs[k] = c;
+}
+
 // bg cells: count per cell type of the cells with state == side (mode 0) or CUT||side (mode 1); optionally flags
 __global__ void k_count_bgcells(const GcLayout lay, int64_t nc, const GcProgram prog, int side, int mode, int cpc,
                                 unsigned long long* __restrict__ counts, uint32_t* __restrict__ flags) {
@@ -181,13 +204,27 @@ int gc_select_cells(gecut_ctx* ctx, gecut_selection* sel) {
   const int T = 256;
   const bool want_sub = sel->kind == GECUT_SEL_PHYSICAL || sel->kind == GECUT_SEL_CUTONLY;
   const bool want_bg = sel->kind == GECUT_SEL_PHYSICAL || sel->kind == GECUT_SEL_ACTIVE || sel->kind == GECUT_SEL_BGONLY;
-  if (want_sub && nsc > 0) {
-    uint32_t* flags = nullptr;
-    GC_CHECK(gc_malloc(ctx, (void**)&flags, sizeof(uint32_t) * nsc));
-    GC_LAUNCH(ctx, "k_flag_subcells", k_flag_subcells<<<(unsigned)gc_div_up(nsc, T), T, 0, ctx->stream>>>(lay, nsc, sel->prog, sel->side, flags));
-    int st = compact_flags(ctx, flags, nsc, &sel->sub_ids, &sel->n_sub, nullptr, nullptr);
-    gc_free(ctx, flags);
-    GC_CHECK(st);
+  if (want_sub && nsc > 0 && res->cut_sc_ptr) {
+    const int64_t ncut = res->sizes.num_cutcells;
+    uint32_t* counts = nullptr;
+    uint64_t* total_dev = nullptr;
+    GC_CHECK(gc_malloc(ctx, (void**)&counts, sizeof(uint32_t) * ncut));
+    GC_CHECK(gc_malloc(ctx, (void**)&total_dev, sizeof(uint64_t)));
+    const unsigned nbk = (unsigned)gc_div_up(ncut, T);
+    GC_LAUNCH(ctx, "k_select_subcells", k_select_subcells<false><<<nbk, T, 0, ctx->stream>>>(
+        lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, counts, nullptr));
+    GC_CHECK(gc_exclusive_scan_u32(ctx, counts, counts, ncut, total_dev));
+    uint64_t* h = (uint64_t*)ctx->h_pinned;
+    GC_CUDA(cudaMemcpyAsync(h, total_dev, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GC_CUDA(cudaStreamSynchronize(ctx->stream));
+    sel->n_sub = (int64_t)h[0];
+    if (sel->n_sub > 0) {
+      GC_CHECK(gc_malloc(ctx, (void**)&sel->sub_ids, sizeof(int32_t) * sel->n_sub));
+      GC_LAUNCH(ctx, "k_select_subcells", k_select_subcells<true><<<nbk, T, 0, ctx->stream>>>(
+          lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, counts, sel->sub_ids));
+    }
+    gc_free(ctx, counts);
+    gc_free(ctx, total_dev);
   }
   // single-leaf programs ([ls] or [ls, !]): the classification kernel already tallied IN / OUT cells per level set and
   // cell type, no pass over the Nc state bytes is needed
