@@ -511,27 +511,74 @@ __device__ __forceinline__ int cut1_case(const Pt<D, 1>* S) {
   return c;
 }
 
+// Tile totals.  The three counters of a stage-0 simplex depend only on HOW MANY of its vertices are OUT (the table
+// rows of a k-vs-(D+1-k) split all have the same sizes), so one thread per cut bg cell evaluates the cell's nodes once,
+// takes the popcount of each of its stage-0 simplices and adds the packed counters to the tile the simplex falls in.
+// A block owns BC cells with BC*nt0 a multiple of CUT1_TILE, i.e. a whole number of tiles.
 template <int D>
-__global__ void __launch_bounds__(CUT1_TILE)
-k_cut1_count(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
-             const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
-             const int32_t* __restrict__ cutcells, int64_t nsimp, uint32_t* __restrict__ tile_cells,
-             uint32_t* __restrict__ tile_points, uint32_t* __restrict__ tile_facets) {
-  const GcSimplexTable* T = tables + (D - 1);
-  const int64_t s = (int64_t)blockIdx.x * CUT1_TILE + threadIdx.x;
-  uint32_t packed = 0;
-  if (s < nsimp) {
-    Pt<D, 1> S[D + 1];
-    setup_stage0<D, 1>(g, lv, (int64_t)cutcells[s / g.nt0] - 1, (int)(s % g.nt0), simp_raw, simp_pos, S);
-    const int c = cut1_case<D>(S);
-    packed = cut1_pack(T->nsub[c], T->npts[c], T->nfac[c]);
+__global__ void __launch_bounds__(128)
+k_cut1_count(const GcGrid g, const GcLeaves lv, const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
+             const int32_t* __restrict__ cutcells, int64_t ncut, int cells_per_block, uint32_t* __restrict__ tile_cells,
+             uint32_t* __restrict__ tile_points, uint32_t* __restrict__ tile_facets, int64_t ntiles) {
+  __shared__ uint32_t s_tile[8];
+  if (threadIdx.x < 8) s_tile[threadIdx.x] = 0u;
+  __syncthreads();
+  const int64_t k = (int64_t)blockIdx.x * cells_per_block + threadIdx.x;
+  const int tiles_per_block = cells_per_block * g.nt0 / CUT1_TILE;
+  if ((int)threadIdx.x < cells_per_block && k < ncut) {
+    const int64_t cell0 = (int64_t)cutcells[k] - 1;
+    const int64_t cube = cell0 / g.cpc;
+    const int typ = (int)(cell0 % g.cpc);
+    int ijk[3];
+    ijk[0] = (int)(cube % g.n[0]);
+    if (D == 3) {
+      ijk[1] = (int)((cube / g.n[0]) % g.n[1]);
+      ijk[2] = (int)(cube / ((int64_t)g.n[0] * g.n[1])) + g.k0;
+    } else {
+      ijk[1] = (int)(cube / g.n[0]) + g.k0;
+      ijk[2] = 0;
+    }
+    // sign bits of the bg cell's vertices (local vertex ids of the n-cube)
+    uint32_t bits = 0;
+    const int nvb = g.simplexified ? D + 1 : (1 << D);
+    for (int m = 0; m < nvb; ++m) {
+      const int lvid = g.simplexified ? simp_raw[(D - 2) * 24 + typ * 4 + m] : m;
+      const int nijk[3] = {ijk[0] + (lvid & 1), ijk[1] + ((lvid >> 1) & 1), ijk[2] + ((lvid >> 2) & 1)};
+      double v;
+      if (lv.leaf[0].kind == GECUT_LEAF_NODAL) {
+        const int64_t node = (D == 3) ? ((int64_t)nijk[0] + (int64_t)g.nn[0] * ((int64_t)nijk[1] + (int64_t)g.nn[1] * nijk[2]))
+                                      : ((int64_t)nijk[0] + (int64_t)g.nn[0] * nijk[1]);
+        v = __ldg(lv.nodal[0] + (node - lv.nodal_base));
+      } else {
+        const double xx[3] = {gc_coord(g, 0, nijk[0]), gc_coord(g, 1, nijk[1]), D == 3 ? gc_coord(g, 2, nijk[2]) : 0.0};
+        v = gc_eval_leaf(lv.leaf[0], xx, D);
+      }
+      if (v > 0.0) bits |= 1u << m;
+    }
+    for (int t = 0; t < g.nt0; ++t) {
+      int nout;
+      if (g.simplexified) {
+        nout = __popc(bits);
+      } else {
+        nout = 0;
+        for (int m = 0; m <= D; ++m) nout += (bits >> simp_pos[(D - 2) * 24 + t * 4 + m]) & 1u;
+      }
+      const int kk = min(nout, D + 1 - nout);  // 0: uncut, 1: one vertex split off, 2: two-two split (TET only)
+      const uint32_t pk = (D == 3) ? (kk == 0 ? cut1_pack(1, 4, 0) : kk == 1 ? cut1_pack(4, 7, 1) : cut1_pack(6, 8, 2))
+                                   : (kk == 0 ? cut1_pack(1, 3, 0) : cut1_pack(3, 5, 1));
+      const int64_t sidx = k * g.nt0 + t;
+      atomicAdd(&s_tile[(int)(sidx / CUT1_TILE - (int64_t)blockIdx.x * tiles_per_block)], pk);
+    }
   }
-  uint32_t total;
-  cut1_block_scan(packed, &total);
-  if (threadIdx.x == 0) {
-    tile_cells[blockIdx.x] = total >> 21;
-    tile_points[blockIdx.x] = (total >> 10) & 0x7FFu;
-    tile_facets[blockIdx.x] = total & 0x3FFu;
+  __syncthreads();
+  if ((int)threadIdx.x < tiles_per_block) {
+    const int64_t tile = (int64_t)blockIdx.x * tiles_per_block + threadIdx.x;
+    if (tile < ntiles) {
+      const uint32_t total = s_tile[threadIdx.x];
+      tile_cells[tile] = total >> 21;
+      tile_points[tile] = (total >> 10) & 0x7FFu;
+      tile_facets[tile] = total & 0x3FFu;
+    }
   }
 }
 
@@ -785,12 +832,17 @@ static int gc_cut_cells_l1(gecut_ctx* ctx, gecut_result* res) {
   GC_CHECK(gc_malloc(ctx, (void**)&tiles, sizeof(uint32_t) * ntiles * 3));
   GC_CHECK(gc_malloc(ctx, (void**)&totals_dev, sizeof(uint64_t) * 3));
   uint32_t *t_cells = tiles, *t_points = tiles + ntiles, *t_facets = tiles + 2 * ntiles;
-  if (D == 2)
-    GC_LAUNCH(ctx, "k_cut1_count", k_cut1_count<2><<<(unsigned)ntiles, CUT1_TILE, 0, ctx->stream>>>(
-        g, res->leaves, ctx->d_tables, ctx->d_simplexify_raw, ctx->d_simplexify_pos, res->lay.cutcells, nsimp, t_cells, t_points, t_facets));
-  else
-    GC_LAUNCH(ctx, "k_cut1_count", k_cut1_count<3><<<(unsigned)ntiles, CUT1_TILE, 0, ctx->stream>>>(
-        g, res->leaves, ctx->d_tables, ctx->d_simplexify_raw, ctx->d_simplexify_pos, res->lay.cutcells, nsimp, t_cells, t_points, t_facets));
+  {
+    // cells per block so that a block covers whole tiles: CUT1_TILE / gcd(CUT1_TILE, nt0)
+    const int cpb = g.nt0 == 1 ? 128 : 64;  // nt0 in {1, 2, 6}: 128*1, 64*2, 64*6 are multiples of 128
+    const unsigned nbc = (unsigned)gc_div_up(ncut, cpb);
+    if (D == 2)
+      GC_LAUNCH(ctx, "k_cut1_count", k_cut1_count<2><<<nbc, 128, 0, ctx->stream>>>(
+          g, res->leaves, ctx->d_simplexify_raw, ctx->d_simplexify_pos, res->lay.cutcells, ncut, cpb, t_cells, t_points, t_facets, ntiles));
+    else
+      GC_LAUNCH(ctx, "k_cut1_count", k_cut1_count<3><<<nbc, 128, 0, ctx->stream>>>(
+          g, res->leaves, ctx->d_simplexify_raw, ctx->d_simplexify_pos, res->lay.cutcells, ncut, cpb, t_cells, t_points, t_facets, ntiles));
+  }
   GC_CHECK(gc_launch_check(ctx, "k_cut1_count"));
   GC_CHECK(gc_exclusive_scan_u32_multi(ctx, tiles, tiles, ntiles, 3, totals_dev));
   uint64_t* h = (uint64_t*)ctx->h_pinned;
