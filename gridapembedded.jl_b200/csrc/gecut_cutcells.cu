@@ -148,12 +148,20 @@ __device__ __forceinline__ void setup_stage0(const GcGrid& g, const GcLeaves& lv
   }
 }
 
+// Generic walk (any L): index-based depth-first traversal.  All points a thread ever needs live in one per-thread pool
+// (stage-0 vertices, then the cut points of the levels on the current path, then the cut points of the facet being
+// re-cut); frames only hold small indices into the pool, so descending a level copies D+1 bytes, not D+1 points, and a
+// level that does not cut the simplex costs one case evaluation and an index permutation.  The pool shrinks back when
+// the walk returns from a level.
 template <int D, int LM, bool FILL>
 __global__ void __launch_bounds__(64)
 k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
            const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
            const int32_t* __restrict__ cutcells, int64_t nsimp, GcCounters cn, GcLayout lay) {
   constexpr int NPC = WalkCfg<D>::NPC, NPF = WalkCfg<D>::NPF;
+  constexpr int CE = NPC - (D + 1), FE = NPF - D;  // max new points per cell / facet cut
+  constexpr int NPOOL = (D + 1) + CE * LM + FE * (LM > 1 ? LM - 1 : 1);
+  constexpr int LF = (LM > 1) ? LM - 1 : 1;
   __shared__ GcSimplexTable s_tab[2];  // [0]: D-simplex (cells), [1]: (D-1)-simplex (facet re-cuts)
   {
     const uint32_t* src0 = reinterpret_cast<const uint32_t*>(tables + (D - 1));
@@ -192,12 +200,16 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
     }
   }
 
-  Pt<D, LM> E[LM][NPC];
-  Pt<D, LM> FE[(LM > 1) ? LM - 1 : 1][NPF];
-  int8_t child[LM], cs[LM], npE[LM], st[LM];
-  int8_t fchild[LM], fcs[LM], fnp[LM], fst[LM];
+  Pt<D, LM> pool[NPOOL];
+  uint8_t v[LM][D + 1], e[LM][NPC];      // simplex vertices / expanded point set of every level on the path
+  uint8_t fv[LF][D], fe[LF][NPF];         // the same for the facet being re-cut
+  int8_t child[LM], cs[LM], npE[LM], st[LM], ptop_at[LM];
+  int8_t fchild[LF], fcs[LF], fptop_at[LF], fst[LM];
 
-  setup_stage0<D, LM>(g, lv, bgcell1 - 1, t, simp_raw, simp_pos, E[0]);
+  setup_stage0<D, LM>(g, lv, bgcell1 - 1, t, simp_raw, simp_pos, pool);
+  int ptop = D + 1;
+#pragma unroll
+  for (int i = 0; i <= D; ++i) v[0][i] = (uint8_t)i;
 
   int depth = 0;
   child[0] = -1;
@@ -207,16 +219,19 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
       // ---- enter: case, cut points (CutTriangulations.jl:179-222)
       int c = 0;
 #pragma unroll
-      for (int i = 0; i <= D; ++i)
-        if (E[depth][i].w[ls] > 0.0) c |= 1 << i;
+      for (int i = 0; i <= D; ++i) {
+        e[depth][i] = v[depth][i];
+        if (pool[v[depth][i]].w[ls] > 0.0) c |= 1 << i;
+      }
       cs[depth] = (int8_t)c;
+      ptop_at[depth] = (int8_t)ptop;
       int np = D + 1;
       if (TC.inoutcut[c] == GC_CUT) {
-        for (int e = 0; e < TC.nedges; ++e) {
-          const int a = TC.edges[e][0], b = TC.edges[e][1];
-          if ((E[depth][a].w[ls] > 0.0) != (E[depth][b].w[ls] > 0.0)) {
-            cut_point<D, LM>(E[depth][a], E[depth][b], ls, L, E[depth][np]);
-            np++;
+        for (int ed = 0; ed < TC.nedges; ++ed) {
+          const int a = e[depth][TC.edges[ed][0]], b = e[depth][TC.edges[ed][1]];
+          if ((pool[a].w[ls] > 0.0) != (pool[b].w[ls] > 0.0)) {
+            cut_point<D, LM>(pool[a], pool[b], ls, L, pool[ptop]);
+            e[depth][np++] = (uint8_t)ptop++;
           }
         }
       }
@@ -229,21 +244,18 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
             const uint32_t fid = fac_off[0] + f;
             const uint8_t* fp = TC.fac_pts[c][f];
             double nrm[3];
-            unit_normal<D>(E[depth][fp[0]].x, E[depth][fp[1]].x, E[depth][fp[D - 1]].x, (double)TC.fac_orient[c][f], nrm);
+            unit_normal<D>(pool[e[depth][fp[0]]].x, pool[e[depth][fp[1]]].x, pool[e[depth][fp[D - 1]]].x,
+                           (double)TC.fac_orient[c][f], nrm);
+            double pf[D][3];
 #pragma unroll
             for (int i = 0; i < D; ++i) {
               lay.sf_c2p[(int64_t)fid * D + i] = (int32_t)(pt_off + fp[i] + 1);
               lay.sf_N[(int64_t)fid * D + i] = nrm[i];
+#pragma unroll
+              for (int d = 0; d < D; ++d) pf[i][d] = pool[e[depth][fp[i]]].x[d];
             }
             lay.sf_c2bg[fid] = bgcell1;
-            {
-              double pf[D][3];
-#pragma unroll
-              for (int v = 0; v < D; ++v)
-#pragma unroll
-                for (int d = 0; d < D; ++d) pf[v][d] = E[depth][fp[v]].x[d];
-              lay.sf_meas[fid] = integrate_one<D - 1>(simplex_meas<D, D - 1>(pf));
-            }
+            lay.sf_meas[fid] = integrate_one<D - 1>(simplex_meas<D, D - 1>(pf));
             lay.sf_state[fid] = (int8_t)GECUT_INTERFACE;
           }
         }
@@ -252,33 +264,36 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
         for (int f = 0; f < nfac; ++f) {
           const uint8_t* fp = TC.fac_pts[c][f];
           double nrm[3];
-          unit_normal<D>(E[depth][fp[0]].x, E[depth][fp[1]].x, E[depth][fp[D - 1]].x, (double)TC.fac_orient[c][f], nrm);
+          unit_normal<D>(pool[e[depth][fp[0]]].x, pool[e[depth][fp[1]]].x, pool[e[depth][fp[D - 1]]].x,
+                         (double)TC.fac_orient[c][f], nrm);
 #pragma unroll
-          for (int i = 0; i < D; ++i) FE[0][i] = E[depth][fp[i]];
+          for (int i = 0; i < D; ++i) fv[0][i] = e[depth][fp[i]];
           // ---- re-cut the facet by every other level set, last to first (CutTriangulations.jl:294-307,324-327)
+          const int ptop_cell = ptop;
           int fdepth = 0;
           fchild[0] = -1;
           while (fdepth >= 0) {
-            // k-th other level set, taken from the last: indices L-1, L-2, ... skipping ls
-            int k = L - 1 - fdepth;
+            int k = L - 1 - fdepth;  // fdepth-th other level set, taken from the last, skipping ls
             if (k <= ls) k -= 1;
             if (fchild[fdepth] < 0) {
               int fc = 0;
 #pragma unroll
-              for (int i = 0; i < D; ++i)
-                if (FE[fdepth][i].w[k] > 0.0) fc |= 1 << i;
+              for (int i = 0; i < D; ++i) {
+                fe[fdepth][i] = fv[fdepth][i];
+                if (pool[fv[fdepth][i]].w[k] > 0.0) fc |= 1 << i;
+              }
               fcs[fdepth] = (int8_t)fc;
+              fptop_at[fdepth] = (int8_t)ptop;
               int fn = D;
               if (TF.inoutcut[fc] == GC_CUT) {
-                for (int e = 0; e < TF.nedges; ++e) {
-                  const int a = TF.edges[e][0], b = TF.edges[e][1];
-                  if ((FE[fdepth][a].w[k] > 0.0) != (FE[fdepth][b].w[k] > 0.0)) {
-                    cut_point<D, LM>(FE[fdepth][a], FE[fdepth][b], k, L, FE[fdepth][fn]);
-                    fn++;
+                for (int ed = 0; ed < TF.nedges; ++ed) {
+                  const int a = fe[fdepth][TF.edges[ed][0]], b = fe[fdepth][TF.edges[ed][1]];
+                  if ((pool[a].w[k] > 0.0) != (pool[b].w[k] > 0.0)) {
+                    cut_point<D, LM>(pool[a], pool[b], k, L, pool[ptop]);
+                    fe[fdepth][fn++] = (uint8_t)ptop++;
                   }
                 }
               }
-              fnp[fdepth] = (int8_t)fn;
               if (fdepth == L - 2) {
                 // final facets of level set ls: point block + children
                 const int nsf = TF.nsub[fc];
@@ -287,33 +302,30 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
                   for (int p = 0; p < fn; ++p)
 #pragma unroll
                     for (int d = 0; d < D; ++d) {
-                      lay.sf_X[(int64_t)(pb + p) * D + d] = FE[fdepth][p].x[d];
-                      lay.sf_R[(int64_t)(pb + p) * D + d] = FE[fdepth][p].r[d];
+                      lay.sf_X[(int64_t)(pb + p) * D + d] = pool[fe[fdepth][p]].x[d];
+                      lay.sf_R[(int64_t)(pb + p) * D + d] = pool[fe[fdepth][p]].r[d];
                     }
                   for (int j = 0; j < nsf; ++j) {
                     const uint32_t fid = fac_off[ls] + j;
+                    double pf[D][3];
 #pragma unroll
                     for (int i = 0; i < D; ++i) {
                       lay.sf_c2p[(int64_t)fid * D + i] = (int32_t)(pb + TF.sub_pts[fc][j][i] + 1);
                       lay.sf_N[(int64_t)fid * D + i] = nrm[i];
+#pragma unroll
+                      for (int d = 0; d < D; ++d) pf[i][d] = pool[fe[fdepth][TF.sub_pts[fc][j][i]]].x[d];
                     }
                     lay.sf_c2bg[fid] = bgcell1;
-                    {
-                      double pf[D][3];
-#pragma unroll
-                      for (int v = 0; v < D; ++v)
-#pragma unroll
-                        for (int d = 0; d < D; ++d) pf[v][d] = FE[fdepth][TF.sub_pts[fc][j][v]].x[d];
-                      lay.sf_meas[fid] = integrate_one<D - 1>(simplex_meas<D, D - 1>(pf));
-                    }
+                    lay.sf_meas[fid] = integrate_one<D - 1>(simplex_meas<D, D - 1>(pf));
                     for (int kk = 0; kk < L; ++kk) {
-                      int8_t v = (kk == ls) ? (int8_t)GECUT_INTERFACE : ((kk == k) ? TF.sub_inout[fc][j] : fst[kk]);
-                      lay.sf_state[(int64_t)kk * lay.sf_pitch + fid] = v;
+                      int8_t val = (kk == ls) ? (int8_t)GECUT_INTERFACE : ((kk == k) ? TF.sub_inout[fc][j] : fst[kk]);
+                      lay.sf_state[(int64_t)kk * lay.sf_pitch + fid] = val;
                     }
                   }
                 }
                 fac_off[ls] += nsf;
                 fpt_off[ls] += fn;
+                ptop = fptop_at[fdepth];
                 fdepth--;
                 continue;
               }
@@ -324,13 +336,15 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
               const int j = fchild[fdepth]++;
               fst[k] = TF.sub_inout[fc][j];
 #pragma unroll
-              for (int i = 0; i < D; ++i) FE[fdepth + 1][i] = FE[fdepth][TF.sub_pts[fc][j][i]];
+              for (int i = 0; i < D; ++i) fv[fdepth + 1][i] = fe[fdepth][TF.sub_pts[fc][j][i]];
               fchild[fdepth + 1] = -1;
               fdepth++;
             } else {
+              ptop = fptop_at[fdepth];
               fdepth--;
             }
           }
+          ptop = ptop_cell;
         }
       }
       if (ls == 0) {
@@ -340,32 +354,27 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
           for (int p = 0; p < np; ++p)
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-              lay.sc_X[(int64_t)(pt_off + p) * D + d] = E[depth][p].x[d];
-              lay.sc_R[(int64_t)(pt_off + p) * D + d] = E[depth][p].r[d];
-              if (L == 1) {  // the facets of a single level set share the subcell points (CutTriangulations.jl:365-378)
-                lay.sf_X[(int64_t)(pt_off + p) * D + d] = E[depth][p].x[d];
-                lay.sf_R[(int64_t)(pt_off + p) * D + d] = E[depth][p].r[d];
-              }
+              lay.sc_X[(int64_t)(pt_off + p) * D + d] = pool[e[depth][p]].x[d];
+              lay.sc_R[(int64_t)(pt_off + p) * D + d] = pool[e[depth][p]].r[d];
             }
           for (int j = 0; j < nsub; ++j) {
             const uint32_t cid = cell_off + j;
+            double pc[D + 1][3];
 #pragma unroll
-            for (int i = 0; i <= D; ++i) lay.sc_c2p[(int64_t)cid * (D + 1) + i] = (int32_t)(pt_off + TC.sub_pts[c][j][i] + 1);
-            lay.sc_c2bg[cid] = bgcell1;
-            {
-              double pc[D + 1][3];
+            for (int i = 0; i <= D; ++i) {
+              lay.sc_c2p[(int64_t)cid * (D + 1) + i] = (int32_t)(pt_off + TC.sub_pts[c][j][i] + 1);
 #pragma unroll
-              for (int v = 0; v <= D; ++v)
-#pragma unroll
-                for (int d = 0; d < D; ++d) pc[v][d] = E[depth][TC.sub_pts[c][j][v]].x[d];
-              lay.sc_meas[cid] = integrate_one<D>(simplex_meas<D, D>(pc));
+              for (int d = 0; d < D; ++d) pc[i][d] = pool[e[depth][TC.sub_pts[c][j][i]]].x[d];
             }
+            lay.sc_c2bg[cid] = bgcell1;
+            lay.sc_meas[cid] = integrate_one<D>(simplex_meas<D, D>(pc));
             lay.sc_state[cid] = TC.sub_inout[c][j];
             for (int kk = 1; kk < L; ++kk) lay.sc_state[(int64_t)kk * lay.sc_pitch + cid] = st[kk];
           }
         }
         cell_off += nsub;
         pt_off += np;
+        ptop = ptop_at[depth];
         depth--;
         continue;
       }
@@ -376,10 +385,11 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
       const int j = child[depth]++;
       st[ls] = TC.sub_inout[c][j];
 #pragma unroll
-      for (int i = 0; i <= D; ++i) E[depth + 1][i] = E[depth][TC.sub_pts[c][j][i]];
+      for (int i = 0; i <= D; ++i) v[depth + 1][i] = e[depth][TC.sub_pts[c][j][i]];
       child[depth + 1] = -1;
       depth++;
     } else {
+      ptop = ptop_at[depth];
       depth--;
     }
   }
@@ -804,12 +814,14 @@ void dispatch_walk(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const
     else if (L <= 2) GC_WALK(2, 2);
     else if (L <= 4) GC_WALK(2, 4);
     else if (L <= 8) GC_WALK(2, 8);
+    else if (L <= 12) GC_WALK(2, 12);
     else GC_WALK(2, 16);
   } else {
     if (L <= 1) GC_WALK(3, 1);
     else if (L <= 2) GC_WALK(3, 2);
     else if (L <= 4) GC_WALK(3, 4);
     else if (L <= 8) GC_WALK(3, 8);
+    else if (L <= 12) GC_WALK(3, 12);
     else GC_WALK(3, 16);
   }
 #undef GC_WALK
