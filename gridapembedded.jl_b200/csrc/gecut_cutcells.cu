@@ -413,36 +413,24 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
 // No per-simplex offset ever goes to HBM.  The facet point arrays of a single level set are the subcell point arrays
 // (CutTriangulations.jl:365-378 aliases them; merge_sub_face_data copies them): on the device they stay aliased.
 // ================================================================================================
-constexpr int CUT1_TILE = 128;
+constexpr int CUT1_TILE = 32;    // one warp = one tile: warps run their phases independently (no block barriers)
+constexpr int CUT1_BLOCK = 128;  // threads per block of the fill kernel (4 independent tiles)
 
 __device__ __forceinline__ uint32_t cut1_pack(int ncell, int npt, int nfac) {
   return (uint32_t)nfac | ((uint32_t)npt << 10) | ((uint32_t)ncell << 21);
 }
 
-// exclusive scan of one packed word per thread across a block of CUT1_TILE threads
-__device__ __forceinline__ uint32_t cut1_block_scan(uint32_t v, uint32_t* total) {
-  __shared__ uint32_t wsum[CUT1_TILE / 32 + 1];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+// exclusive scan of one packed word per lane across the warp (= the tile); *total = tile sum
+__device__ __forceinline__ uint32_t cut1_warp_scan(uint32_t v, uint32_t* total) {
+  const int lane = threadIdx.x & 31;
   uint32_t inc = v;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
     if (lane >= o) inc += t;
   }
-  if (lane == 31) wsum[wid] = inc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t run = 0;
-    for (int w = 0; w < CUT1_TILE / 32; ++w) {
-      uint32_t t = wsum[w];
-      wsum[w] = run;
-      run += t;
-    }
-    wsum[CUT1_TILE / 32] = run;
-  }
-  __syncthreads();
-  *total = wsum[CUT1_TILE / 32];
-  return wsum[wid] + inc - v;
+  *total = __shfl_sync(0xffffffffu, inc, 31);
+  return inc - v;
 }
 
 // Lean stage-0 set-up of the fast path: physical coordinates, the single level-set value and, instead of the reference
@@ -452,15 +440,19 @@ template <int D>
 __device__ __forceinline__ void setup_stage0_l1(const GcGrid& g, const GcLeaves& lv, int64_t cell0, int t,
                                                 const uint8_t* simp_raw, const uint8_t* simp_pos, double (*x)[D],
                                                 double* w, int* rv) {
-  const int64_t cube = cell0 / g.cpc;
-  const int typ = (int)(cell0 % g.cpc);
+  // slab-local cell ids fit in 32 bits (checked at cut time): 32-bit divisions are ~4x cheaper than 64-bit ones
+  const uint32_t cell = (uint32_t)cell0;
+  const uint32_t cube = cell / (uint32_t)g.cpc;
+  const int typ = (int)(cell - cube * (uint32_t)g.cpc);
   int ijk[3];
-  ijk[0] = (int)(cube % g.n[0]);
+  const uint32_t row = cube / (uint32_t)g.n[0];
+  ijk[0] = (int)(cube - row * (uint32_t)g.n[0]);
   if (D == 3) {
-    ijk[1] = (int)((cube / g.n[0]) % g.n[1]);
-    ijk[2] = (int)(cube / ((int64_t)g.n[0] * g.n[1])) + g.k0;
+    const uint32_t lay3 = row / (uint32_t)g.n[1];
+    ijk[1] = (int)(row - lay3 * (uint32_t)g.n[1]);
+    ijk[2] = (int)lay3 + g.k0;
   } else {
-    ijk[1] = (int)(cube / g.n[0]) + g.k0;
+    ijk[1] = (int)row + g.k0;
     ijk[2] = 0;
   }
 #pragma unroll
@@ -530,8 +522,8 @@ __global__ void __launch_bounds__(128)
 k_cut1_count(const GcGrid g, const GcLeaves lv, const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
              const int32_t* __restrict__ cutcells, int64_t ncut, int cells_per_block, uint32_t* __restrict__ tile_cells,
              uint32_t* __restrict__ tile_points, uint32_t* __restrict__ tile_facets, int64_t ntiles) {
-  __shared__ uint32_t s_tile[8];
-  if (threadIdx.x < 8) s_tile[threadIdx.x] = 0u;
+  __shared__ uint32_t s_tile[32];
+  if (threadIdx.x < 32) s_tile[threadIdx.x] = 0u;
   __syncthreads();
   const int64_t k = (int64_t)blockIdx.x * cells_per_block + threadIdx.x;
   const int tiles_per_block = cells_per_block * g.nt0 / CUT1_TILE;
@@ -592,8 +584,21 @@ k_cut1_count(const GcGrid g, const GcLeaves lv, const uint8_t* __restrict__ simp
   }
 }
 
+// warp copy of n doubles from shared to global memory with 16-byte accesses; src/dst have the same 16-byte phase
+// (`odd` = the first element sits on an odd 8-byte slot)
+__device__ __forceinline__ void cut1_copy_doubles(double* __restrict__ dst, const double* __restrict__ src, uint32_t n,
+                                                  uint32_t odd, int lane) {
+  const uint32_t start = (odd && n > 0) ? 1u : 0u;
+  if (start && lane == 0) dst[0] = src[0];
+  const uint32_t nvec = (n - start) >> 1;
+  double2* d2 = reinterpret_cast<double2*>(dst + start);
+  const double2* s2 = reinterpret_cast<const double2*>(src + start);
+  for (uint32_t i = lane; i < nvec; i += 32) d2[i] = s2[i];
+  if (((n - start) & 1u) && lane == 0) dst[n - 1] = src[n - 1];
+}
+
 template <int D>
-__global__ void __launch_bounds__(CUT1_TILE, 5)
+__global__ void __launch_bounds__(CUT1_BLOCK, 5)
 k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
             const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
             const int32_t* __restrict__ cutcells, int64_t nsimp, const uint32_t* __restrict__ tile_cells,
@@ -602,16 +607,19 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
   constexpr int NPC = WalkCfg<D>::NPC;
   constexpr int NSUB = (D == 3) ? 6 : 3, NFAC = (D == 3) ? 2 : 1, NE = (D == 3) ? 6 : 3;
   // one staging buffer, used in turn for point_to_coords, point_to_rcoords and the integer arrays
-  extern __shared__ double stage[];  // [CUT1_TILE*NPC][D] doubles
+  extern __shared__ double stage_all[];  // per warp: [CUT1_TILE*NPC][D] doubles
   __shared__ GcSimplexTable s_tab;
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(tables + (D - 1));
     uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
-    for (int i = threadIdx.x; i < (int)(sizeof(GcSimplexTable) / 4); i += CUT1_TILE) dst[i] = src[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(GcSimplexTable) / 4); i += CUT1_BLOCK) dst[i] = src[i];
   }
   __syncthreads();
   const GcSimplexTable& TC = s_tab;
-  const int64_t s = (int64_t)blockIdx.x * CUT1_TILE + threadIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double* stage = stage_all + (size_t)wid * (CUT1_TILE * NPC * D + 2);
+  const int64_t tile = (int64_t)blockIdx.x * (CUT1_BLOCK / CUT1_TILE) + wid;
+  const int64_t s = tile * CUT1_TILE + lane;
   const bool valid = s < nsimp;
   double X[D + 1][D], W[D + 1];
   int rv[D + 1];
@@ -635,10 +643,14 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
     nfac = TC.nfac[c];
   }
   uint32_t total;
-  const uint32_t excl = cut1_block_scan(valid ? cut1_pack(nsub, np, nfac) : 0u, &total);
+  const uint32_t excl = cut1_warp_scan(valid ? cut1_pack(nsub, np, nfac) : 0u, &total);
   const uint32_t lc = excl >> 21, lp = (excl >> 10) & 0x7FFu, lf = excl & 0x3FFu;    // tile-local offsets
   const uint32_t tc = total >> 21, tp = (total >> 10) & 0x7FFu, tf = total & 0x3FFu;  // tile totals
-  const uint32_t gc = tile_cells[blockIdx.x], gp = tile_points[blockIdx.x], gf = tile_facets[blockIdx.x];  // tile bases
+  if (tile * CUT1_TILE >= nsimp) return;  // whole warp beyond the end
+  const uint32_t gc = tile_cells[tile], gp = tile_points[tile], gf = tile_facets[tile];  // tile bases
+  // staged doubles start at `pad` so that shared and global memory have the same 16-byte phase (vector copy-out)
+  const uint32_t pad = (uint32_t)(((uint64_t)gp * D) & 1u);
+  double* stage_p = stage + pad;
   // Gridap edge order of the simplex: TRI [1,2],[1,3],[2,3]; TET [1,2],[1,3],[2,3],[1,4],[2,4],[3,4]
   double coeff[NE];
   const bool iscut = valid && TC.inoutcut[c] == GC_CUT;
@@ -666,7 +678,7 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
 #pragma unroll
     for (int i = 0; i <= D; ++i)
 #pragma unroll
-      for (int d = 0; d < D; ++d) stage[(lp + i) * D + d] = X[i][d];
+      for (int d = 0; d < D; ++d) stage_p[(lp + i) * D + d] = X[i][d];
     int q = D + 1;
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
@@ -674,7 +686,7 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
       const int b = (D == 3) ? (e == 0 ? 1 : e == 1 ? 2 : e == 2 ? 2 : 3) : (e == 0 ? 1 : 2);
       if (coeff[e] >= 0.0) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) stage[(lp + q) * D + d] = gc_lerp(X[a][d], X[b][d], coeff[e]);
+        for (int d = 0; d < D; ++d) stage_p[(lp + q) * D + d] = gc_lerp(X[a][d], X[b][d], coeff[e]);
         q++;
       }
     }
@@ -682,14 +694,14 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
     for (int f = 0; f < nfac; ++f) {
       const uint8_t* fp = TC.fac_pts[c][f];
       double nrm[3];
-      unit_normal<D>(&stage[(lp + fp[0]) * D], &stage[(lp + fp[1]) * D], &stage[(lp + fp[D - 1]) * D],
+      unit_normal<D>(&stage_p[(lp + fp[0]) * D], &stage_p[(lp + fp[1]) * D], &stage_p[(lp + fp[D - 1]) * D],
                      (double)TC.fac_orient[c][f], nrm);
       double pf[D][3];
 #pragma unroll
       for (int v = 0; v < D; ++v)
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-          pf[v][d] = stage[(lp + fp[v]) * D + d];
+          pf[v][d] = stage_p[(lp + fp[v]) * D + d];
           if (v == 0) lay.sf_N[(int64_t)(gf + lf + f) * D + d] = nrm[d];
         }
       lay.sf_meas[gf + lf + f] = integrate_one<D - 1>(simplex_meas<D, D - 1>(pf));
@@ -699,22 +711,19 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
 #pragma unroll
       for (int v = 0; v <= D; ++v)
 #pragma unroll
-        for (int d = 0; d < D; ++d) pc[v][d] = stage[(lp + TC.sub_pts[c][j][v]) * D + d];
+        for (int d = 0; d < D; ++d) pc[v][d] = stage_p[(lp + TC.sub_pts[c][j][v]) * D + d];
       lay.sc_meas[gc + lc + j] = integrate_one<D>(simplex_meas<D, D>(pc));
     }
   }
-  __syncthreads();
-  {
-    double* gX = lay.sc_X + (int64_t)gp * D;
-    for (uint32_t i = threadIdx.x; i < tp * D; i += CUT1_TILE) gX[i] = stage[i];
-  }
-  __syncthreads();
+  __syncwarp();
+  cut1_copy_doubles(lay.sc_X + (int64_t)gp * D, stage_p, tp * D, pad, lane);
+  __syncwarp();
   // ---- phase 2: reference coordinates
   if (valid) {
 #pragma unroll
     for (int i = 0; i <= D; ++i)
 #pragma unroll
-      for (int d = 0; d < D; ++d) stage[(lp + i) * D + d] = (double)((rv[i] >> d) & 1);
+      for (int d = 0; d < D; ++d) stage_p[(lp + i) * D + d] = (double)((rv[i] >> d) & 1);
     int q = D + 1;
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
@@ -723,17 +732,14 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
       if (coeff[e] >= 0.0) {
 #pragma unroll
         for (int d = 0; d < D; ++d)
-          stage[(lp + q) * D + d] = gc_lerp((double)((rv[a] >> d) & 1), (double)((rv[b] >> d) & 1), coeff[e]);
+          stage_p[(lp + q) * D + d] = gc_lerp((double)((rv[a] >> d) & 1), (double)((rv[b] >> d) & 1), coeff[e]);
         q++;
       }
     }
   }
-  __syncthreads();
-  {
-    double* gR = lay.sc_R + (int64_t)gp * D;
-    for (uint32_t i = threadIdx.x; i < tp * D; i += CUT1_TILE) gR[i] = stage[i];
-  }
-  __syncthreads();
+  __syncwarp();
+  cut1_copy_doubles(lay.sc_R + (int64_t)gp * D, stage_p, tp * D, pad, lane);
+  __syncwarp();
   // ---- phase 3: integer arrays, staged in the same shared memory
   int32_t* st_c2p = reinterpret_cast<int32_t*>(stage);           // [CUT1_TILE*NSUB][D+1]
   int32_t* st_c2bg = st_c2p + CUT1_TILE * NSUB * (D + 1);        // [CUT1_TILE*NSUB]
@@ -754,21 +760,26 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
       st_f2bg[lf + f] = bgcell1;
     }
   }
-  __syncthreads();
+  __syncwarp();
   {
     int32_t* g_c2p = lay.sc_c2p + (int64_t)gc * (D + 1);
-    for (uint32_t i = threadIdx.x; i < tc * (D + 1); i += CUT1_TILE) g_c2p[i] = st_c2p[i];
+    if (D == 3) {  // rows of 4 ids: 16-byte aligned on both sides
+      for (uint32_t i = lane; i < tc; i += CUT1_TILE)
+        reinterpret_cast<int4*>(g_c2p)[i] = reinterpret_cast<const int4*>(st_c2p)[i];
+    } else {
+      for (uint32_t i = lane; i < tc * (D + 1); i += CUT1_TILE) g_c2p[i] = st_c2p[i];
+    }
     int32_t* g_c2bg = lay.sc_c2bg + gc;
     int8_t* g_state = lay.sc_state + gc;
-    for (uint32_t i = threadIdx.x; i < tc; i += CUT1_TILE) {
+    for (uint32_t i = lane; i < tc; i += CUT1_TILE) {
       g_c2bg[i] = st_c2bg[i];
       g_state[i] = st_state[i];
     }
     int32_t* g_f2p = lay.sf_c2p + (int64_t)gf * D;
-    for (uint32_t i = threadIdx.x; i < tf * D; i += CUT1_TILE) g_f2p[i] = st_f2p[i];
+    for (uint32_t i = lane; i < tf * D; i += CUT1_TILE) g_f2p[i] = st_f2p[i];
     int32_t* g_f2bg = lay.sf_c2bg + gf;
     int8_t* g_fstate = lay.sf_state + gf;
-    for (uint32_t i = threadIdx.x; i < tf; i += CUT1_TILE) {
+    for (uint32_t i = lane; i < tf; i += CUT1_TILE) {
       g_f2bg[i] = st_f2bg[i];
       g_fstate[i] = (int8_t)GECUT_INTERFACE;
     }
@@ -777,7 +788,7 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
 
 template <int D>
 size_t cut1_fill_smem() {
-  return sizeof(double) * (CUT1_TILE * WalkCfg<D>::NPC * D);
+  return sizeof(double) * (CUT1_BLOCK / CUT1_TILE) * (CUT1_TILE * WalkCfg<D>::NPC * D + 2);  // per warp, + phase pad
 }
 
 __global__ void k_extract_sc_ptr(const uint32_t* __restrict__ cell_offs, const uint32_t* __restrict__ point_offs, int nt0,
@@ -845,8 +856,8 @@ static int gc_cut_cells_l1(gecut_ctx* ctx, gecut_result* res) {
   GC_CHECK(gc_malloc(ctx, (void**)&totals_dev, sizeof(uint64_t) * 3));
   uint32_t *t_cells = tiles, *t_points = tiles + ntiles, *t_facets = tiles + 2 * ntiles;
   {
-    // cells per block so that a block covers whole tiles: CUT1_TILE / gcd(CUT1_TILE, nt0)
-    const int cpb = g.nt0 == 1 ? 128 : 64;  // nt0 in {1, 2, 6}: 128*1, 64*2, 64*6 are multiples of 128
+    // 128 cells per block = 128*nt0/32 whole tiles (nt0 in {1, 2, 6})
+    const int cpb = 128;
     const unsigned nbc = (unsigned)gc_div_up(ncut, cpb);
     if (D == 2)
       GC_LAUNCH(ctx, "k_cut1_count", k_cut1_count<2><<<nbc, 128, 0, ctx->stream>>>(
@@ -892,11 +903,11 @@ static int gc_cut_cells_l1(gecut_ctx* ctx, gecut_result* res) {
   GC_CHECK(gc_malloc(ctx, (void**)&res->cut_sc_ptr, sizeof(uint32_t) * 2 * (ncut + 1)));
   if (D == 2) {
     const size_t smem = cut1_fill_smem<2>();
-    GC_LAUNCH(ctx, "k_cut1_fill", k_cut1_fill<2><<<(unsigned)ntiles, CUT1_TILE, smem, ctx->stream>>>(
+    GC_LAUNCH(ctx, "k_cut1_fill", k_cut1_fill<2><<<(unsigned)gc_div_up(ntiles, CUT1_BLOCK / CUT1_TILE), CUT1_BLOCK, smem, ctx->stream>>>(
         g, res->leaves, ctx->d_tables, ctx->d_simplexify_raw, ctx->d_simplexify_pos, lay.cutcells, nsimp, t_cells, t_points, t_facets, lay, res->cut_sc_ptr));
   } else {
     const size_t smem = cut1_fill_smem<3>();
-    GC_LAUNCH(ctx, "k_cut1_fill", k_cut1_fill<3><<<(unsigned)ntiles, CUT1_TILE, smem, ctx->stream>>>(
+    GC_LAUNCH(ctx, "k_cut1_fill", k_cut1_fill<3><<<(unsigned)gc_div_up(ntiles, CUT1_BLOCK / CUT1_TILE), CUT1_BLOCK, smem, ctx->stream>>>(
         g, res->leaves, ctx->d_tables, ctx->d_simplexify_raw, ctx->d_simplexify_pos, lay.cutcells, nsimp, t_cells, t_points, t_facets, lay, res->cut_sc_ptr));
   }
   int st = gc_launch_check(ctx, "k_cut1_fill");
