@@ -303,3 +303,82 @@ def test_error_paths():
     cg = cut(model, geo)
     with pytest.raises(KeyError):
         Triangulation(cg, PHYSICAL, "nope")
+
+
+# ---- BASELINE.json full sizes: size-independent properties (the oracle would take minutes to hours there) -----------
+
+def _measures(cg, name=None):
+    om, oo, ga = Triangulation(cg, PHYSICAL_IN, name), Triangulation(cg, PHYSICAL_OUT, name), EmbeddedBoundary(cg, name)
+    out = (integrate_measure(Measure(om, 2)), integrate_measure(Measure(oo, 2)), integrate_measure(Measure(ga, 2)))
+    for t in (om, oo, ga):
+        t.close()
+    return out
+
+
+def test_full_size_disk_4096():
+    """BASELINE configs[1]: disk on 4096^2.  Area and perimeter converge at O(h^2) (the reference asserts 1e-3 at 50^2,
+    test/InterfacesTests/EmbeddedDiscretizationsTests.jl:55-56); IN + OUT partition the box to round-off."""
+    R = 0.7
+    geo = disk(R)
+    model = box_model(geo, (4096, 4096))
+    cg = cut(model, geo)
+    vin, vout, surf = _measures(cg)
+    box = (2 * 1.01 * R) ** 2
+    assert abs(vin + vout - box) <= 1e-12 * box
+    assert abs(vin - np.pi * R ** 2) < 2e-7 and abs(surf - 2 * np.pi * R) < 2e-7
+    s = cg.sizes
+    assert s.num_subcells == 3 * (2 * s.num_cutcells) - 2 * (2 * s.num_cutcells - s.num_subfacets)  # 1 or 3 per triangle
+    # sortedness / idempotence of the layout
+    h = cg.to_host()
+    assert np.all(np.diff(h["cutcell_to_cell"]) > 0) and np.all(np.diff(h["sc_cell_to_bgcell"]) >= 0)
+    cg2 = cut(model, geo)
+    h2 = cg2.to_host()
+    assert all(np.array_equal(h[k], h2[k]) for k in h)
+    cg.close(); cg2.close()
+
+
+@pytest.mark.parametrize("simplex", [False, True])
+def test_full_size_sphere_256(simplex):
+    """BASELINE configs[2] at 256^3 (the bench runs 512^3): volume/surface convergence, partition of the box, every
+    cut cell's subcells tile the cell exactly, checksums of the connectivity."""
+    R = 0.7
+    geo = sphere(R)
+    model = box_model(geo, (256, 256, 256), simplex)
+    cg = cut(model, geo)
+    vin, vout, surf = _measures(cg)
+    box = (2 * 1.01 * R) ** 3
+    assert abs(vin + vout - box) <= 1e-12 * box
+    assert abs(vin - 4 / 3 * np.pi * R ** 3) < 2e-4 and abs(surf - 4 * np.pi * R ** 2) < 1e-3  # O(h^2), h = 5.5e-3
+    h = cg.to_host()
+    c2p, c2bg = h["sc_cell_to_points"], h["sc_cell_to_bgcell"]
+    assert c2p.min() == 1 and c2p.max() == h["sc_point_to_coords"].shape[0]
+    assert np.all(np.diff(c2bg) >= 0) and np.array_equal(np.unique(c2bg), h["cutcell_to_cell"])
+    # per cut cell: sum of |subcell volumes| == bg cell volume (subcells tile the cut cell)
+    X = h["sc_point_to_coords"][c2p - 1]
+    vol = np.abs(np.linalg.det(X[:, 1:, :] - X[:, :1, :])) / 6.0
+    idx = np.searchsorted(h["cutcell_to_cell"], c2bg)
+    per_cell = np.bincount(idx, weights=vol, minlength=len(h["cutcell_to_cell"]))
+    cellvol = np.prod(model.sizes) / (6.0 if simplex else 1.0)
+    assert np.abs(per_cell - cellvol).max() <= 1e-12 * cellvol * 8
+    # unit normals point from IN to OUT: away from the sphere centre
+    f2p = h["sf_facet_to_points"]
+    cen = h["sf_point_to_coords"][f2p - 1].mean(1)
+    nrm = h["sf_facet_to_normal"]
+    assert np.abs(np.linalg.norm(nrm, axis=1) - 1).max() < 1e-12
+    assert np.all((nrm * cen).sum(1) > 0)
+    cg.close()
+
+
+def test_max_levelsets_and_limits():
+    """GECUT_MAX_LEVELSETS = 16 unique leaves work (generic walk, LM = 16); 17 are rejected like @notimplementedif."""
+    model = CartesianDiscreteModel((-1, -1), (1, 1), (24, 24))
+    geos = [disk(0.25 + 0.03 * i, x0=(-0.5 + 0.06 * i, 0.1 * np.sin(i)), name=f"d{i}") for i in range(17)]
+    g16 = geos[0]
+    for g in geos[1:16]:
+        g16 = union(g16, g)
+    oc = ob.oracle_cut(model, g16)
+    gd = cut(model, g16)
+    assert gd.L == 16
+    compare_layout(gd, oc)
+    with pytest.raises(NotImplementedError):
+        cut(model, union(g16, geos[16]))
