@@ -196,6 +196,7 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
   __shared__ uint32_t s_words[2][NTASK][SIMPLEX ? NVC : 2];  // simplex: vertex sign words; n-cube: (any, all)
   __shared__ unsigned long long s_lut[SIMPLEX ? (1 << NVC) : 1];  // sign byte of an n-cube -> states of its CPC simplices
   __shared__ uint8_t s_tets[6][4];
+  __shared__ uint8_t s_uni[2][NTASK];  // per 32-cell group: 0 mixed, 1 every vertex IN, 2 every vertex OUT
   __shared__ unsigned int s_cnt[GC_LMAX * 12];
   const int L = lv.L;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -401,8 +402,14 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
             const int64_t rowid = (D == 3) ? ((int64_t)(kc - g.k0) * ny + jc) : (int64_t)(kc - g.k0);
             uint32_t* cm = cutmask + (rowid * wxtot + (w0 + ww)) * CPC;
             if (SIMPLEX) {
+              uint32_t vor = 0u, vand = 0xffffffffu;
 #pragma unroll
-              for (int v = 0; v < NVC; ++v) s_words[ls & 1][threadIdx.x][v] = V[v];
+              for (int v = 0; v < NVC; ++v) {
+                s_words[ls & 1][threadIdx.x][v] = V[v];
+                vor |= V[v];
+                vand &= V[v];
+              }
+              s_uni[ls & 1][threadIdx.x] = ((vor & live) == 0u) ? 1 : (((vand & live) == live) ? 2 : 0);
 #pragma unroll
               for (int t = 0; t < CPC; ++t) {
                 uint32_t any = 0u, all = 0xffffffffu;
@@ -452,16 +459,25 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
             int8_t* out = states + (int64_t)ls * pitch + cube0 * CPC;
             if (SIMPLEX) {
               unsigned long long e[4];
+              const int uni = s_uni[ls & 1][task];
+              if (uni) {  // uniform group (the common case away from the surfaces): constant states, no gather
+                constexpr unsigned long long ONES = CPC == 6 ? 0x010101010101ull : 0x0101ull;
+                const unsigned long long pat = uni == 1 ? ONES * 0xFFull : ONES;
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                uint32_t sb = 0;
+                for (int c = 0; c < 4; ++c) e[c] = pat;
+                if (uni == 1) pin = ONES * (unsigned long long)ncq; else pout = ONES * (unsigned long long)ncq;
+              } else {
 #pragma unroll
-                for (int v = 0; v < NVC; ++v) sb |= ((s_words[ls & 1][task][v] >> (c0 + c)) & 1u) << v;
-                e[c] = s_lut[sb];
-                if (c < ncq) {
-                  const unsigned long long hi = (e[c] >> 7) & 0x010101010101ull;  // bit 7 set: IN
-                  pin += hi;
-                  pout += (e[c] & 0x010101010101ull) & ~hi;                       // bit 0 set, bit 7 clear: OUT
+                for (int c = 0; c < 4; ++c) {
+                  uint32_t sb = 0;
+#pragma unroll
+                  for (int v = 0; v < NVC; ++v) sb |= ((s_words[ls & 1][task][v] >> (c0 + c)) & 1u) << v;
+                  e[c] = s_lut[sb];
+                  if (c < ncq) {
+                    const unsigned long long hi = (e[c] >> 7) & 0x010101010101ull;  // bit 7 set: IN
+                    pin += hi;
+                    pout += (e[c] & 0x010101010101ull) & ~hi;                       // bit 0 set, bit 7 clear: OUT
+                  }
                 }
               }
               if (vec_ok) {

@@ -17,11 +17,26 @@ namespace {
 
 // per-entity measures (integral of 1 with the degree-2 rule) are produced by the subtriangulation kernels while the
 // vertices are on chip; a Measure over a selection only gathers them
-__global__ void k_measures(const int32_t* __restrict__ ids, int64_t n, const double* __restrict__ meas,
-                           double* __restrict__ values) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  values[i] = meas[(int64_t)ids[i] - 1];
+__global__ void __launch_bounds__(256)
+k_measures(const int32_t* __restrict__ ids, int64_t n, const double* __restrict__ meas, double* __restrict__ values,
+           double* __restrict__ partial) {
+  // gather + deterministic block partial sums (fixed element -> thread -> tree order); values may be NULL
+  __shared__ double sh[256];
+  double s = 0.0;
+  const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = per * blockIdx.x, hi = lo + per < n ? lo + per : n;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const double v = meas[(int64_t)ids[i] - 1];
+    if (values) values[i] = v;
+    s += v;
+  }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
 
 // deterministic two-level sum
@@ -425,23 +440,17 @@ int gc_integrate_measure(gecut_ctx* ctx, const gecut_selection* sel, double* val
   double total = 0.0;
   const bool use_sub = sel->kind == GECUT_SEL_PHYSICAL || sel->kind == GECUT_SEL_CUTONLY || sel->kind == GECUT_SEL_BOUNDARY;
   if (use_sub && n > 0) {
-    double* vals = values_dev;
-    if (!vals) GC_CHECK(gc_malloc(ctx, (void**)&vals, sizeof(double) * n));
-    const int T = 256;
-    const unsigned nb = (unsigned)gc_div_up(n, T);
-    GC_LAUNCH(ctx, "k_measures", k_measures<<<nb, T, 0, ctx->stream>>>(
-        sel->sub_ids, n, sel->kind == GECUT_SEL_BOUNDARY ? lay.sf_meas : lay.sc_meas, vals));
-    const int NB = (int)std::min<int64_t>(1024, gc_div_up(n, 1024));
+    const int NB = (int)std::min<int64_t>(1184, gc_div_up(n, 1024));
     double* partial = nullptr;
     GC_CHECK(gc_malloc(ctx, (void**)&partial, sizeof(double) * (NB + 1)));
-    GC_LAUNCH(ctx, "k_block_sums", k_block_sums<<<NB, 256, 0, ctx->stream>>>(vals, n, partial));
+    GC_LAUNCH(ctx, "k_measures", k_measures<<<NB, 256, 0, ctx->stream>>>(
+        sel->sub_ids, n, sel->kind == GECUT_SEL_BOUNDARY ? lay.sf_meas : lay.sc_meas, values_dev, partial));
     GC_LAUNCH(ctx, "k_final_sum", k_final_sum<<<1, 256, 0, ctx->stream>>>(partial, NB, partial + NB));
     double* h = (double*)ctx->h_pinned;
     GC_CUDA(cudaMemcpyAsync(h, partial + NB, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     GC_CUDA(cudaStreamSynchronize(ctx->stream));
     total += h[0];
     gc_free(ctx, partial);
-    if (!values_dev) gc_free(ctx, vals);
     GC_CHECK(gc_launch_check(ctx, "k_measures"));
   }
   const bool use_bg = sel->kind == GECUT_SEL_PHYSICAL || sel->kind == GECUT_SEL_ACTIVE || sel->kind == GECUT_SEL_BGONLY;

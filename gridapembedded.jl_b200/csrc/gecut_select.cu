@@ -292,11 +292,27 @@ int gc_materialize_bg_ids(gecut_ctx* ctx, gecut_selection* sel) {
   return st;
 }
 
+__global__ void k_iota_boundary(int64_t n, int32_t* __restrict__ ids, int8_t* __restrict__ orient) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  ids[e] = (int32_t)(e + 1);
+  orient[e] = 1;
+}
+
 int gc_select_boundary(gecut_ctx* ctx, gecut_selection* sel) {
   const gecut_result* res = sel->res;
   const int64_t nsf = res->sizes.num_subfacets;
   if (nsf <= 0) return GECUT_OK;
   const int T = 256;
+  // one level set, program = that leaf (and no second geometry, or the same leaf): every subfacet is INTERFACE with
+  // orientation +1 (compute_inoutboundary of a Leaf, EmbeddedDiscretizations.jl:179-182) -> the selection is 1..Nsf
+  if (res->L == 1 && sel->prog.len == 1 && (!sel->has_prog2 || sel->prog2.len == 1)) {
+    GC_CHECK(gc_malloc(ctx, (void**)&sel->sub_ids, sizeof(int32_t) * nsf));
+    GC_CHECK(gc_malloc(ctx, (void**)&sel->orientation, sizeof(int8_t) * nsf));
+    GC_LAUNCH(ctx, "k_iota_boundary", k_iota_boundary<<<(unsigned)gc_div_up(nsf, T), T, 0, ctx->stream>>>(nsf, sel->sub_ids, sel->orientation));
+    sel->n_sub = nsf;
+    return gc_launch_check(ctx, "k_iota_boundary");
+  }
   uint32_t* flags = nullptr;
   int8_t* orient_all = nullptr;
   GC_CHECK(gc_malloc(ctx, (void**)&flags, sizeof(uint32_t) * nsf));
