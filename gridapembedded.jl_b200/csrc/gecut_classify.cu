@@ -192,11 +192,8 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
   constexpr int NTASK = TY * WX;                      // (row, x-word) tasks of one layer: 32 cells each
   static_assert(NTASK * 8 == C::THREADS, "phase B maps one thread to 4 cells");
   extern __shared__ uint32_t planes[];  // [2][L][RY][WX+1] sign words
-  // phase A -> phase B hand-over, double buffered by level-set parity
-  __shared__ uint32_t s_words[2][NTASK][SIMPLEX ? NVC : 2];  // simplex: vertex sign words; n-cube: (any, all)
   __shared__ unsigned long long s_lut[SIMPLEX ? (1 << NVC) : 1];  // sign byte of an n-cube -> states of its CPC simplices
   __shared__ uint8_t s_tets[6][4];
-  __shared__ uint8_t s_uni[2][NTASK];  // per 32-cell group: 0 mixed, 1 every vertex IN, 2 every vertex OUT
   __shared__ unsigned int s_cnt[GC_LMAX * 12];
   const int L = lv.L;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -380,98 +377,81 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
       const uint32_t* P1 = P;
       const int kc = kp - 1;  // global layer index
       for (int ls = 0; ls < L; ++ls) {
-        // phase A: one thread per (row, word): vertex sign words, cut mask, hand-over to phase B
-        if (threadIdx.x < NTASK) {
-          const int r = threadIdx.x / WX, ww = threadIdx.x % WX;
-          const int jc = j0 + r;
-          const int i0 = 32 * (w0 + ww);
-          if (i0 < nx && jc < ny) {
-            uint32_t V[NVC];
+        // One thread per 4 consecutive cells (8 threads share a 32-cell group).  Every thread rebuilds the vertex sign
+        // words of its group from the two planes (16 mostly broadcast shared loads) -- redundant across the 8 threads
+        // but parallel, which removes the former single-warp "phase A" and one block barrier per layer and level set.
+        const int task = threadIdx.x >> 3, quad = threadIdx.x & 7;
+        const int r = task / WX, ww = task % WX;
+        const int jc = j0 + r;
+        const int i0 = 32 * (w0 + ww);
+        const int c0 = 4 * quad;
+        unsigned long long pin = 0ull, pout = 0ull;  // IN / OUT tallies, one byte per cell type
+        if (i0 < nx && jc < ny) {
+          uint32_t V[NVC];
 #pragma unroll
-            for (int v = 0; v < NVC; ++v) {
-              const int xo = v & 1;
-              const int ro = (D == 3) ? ((v >> 1) & 1) : 0;
-              const int po = (D == 3) ? ((v >> 2) & 1) : ((v >> 1) & 1);
-              const uint32_t* row = (po ? P1 : P0) + (ls * RY + r + ro) * (WX + 1);
-              uint32_t a = row[ww];
-              if (xo) a = (a >> 1) | (row[ww + 1] << 31);
-              V[v] = a;
-            }
-            const int ncell = min(32, nx - i0);
-            const uint32_t live = ncell == 32 ? 0xffffffffu : ((1u << ncell) - 1u);
-            const int64_t rowid = (D == 3) ? ((int64_t)(kc - g.k0) * ny + jc) : (int64_t)(kc - g.k0);
-            uint32_t* cm = cutmask + (rowid * wxtot + (w0 + ww)) * CPC;
+          for (int v = 0; v < NVC; ++v) {
+            const int xo = v & 1;
+            const int ro = (D == 3) ? ((v >> 1) & 1) : 0;
+            const int po = (D == 3) ? ((v >> 2) & 1) : ((v >> 1) & 1);
+            const uint32_t* row = (po ? P1 : P0) + (ls * RY + r + ro) * (WX + 1);
+            uint32_t a = row[ww];
+            if (xo) a = (a >> 1) | (row[ww + 1] << 31);
+            V[v] = a;
+          }
+          const int ncell = min(32, nx - i0);
+          const uint32_t live = ncell == 32 ? 0xffffffffu : ((1u << ncell) - 1u);
+          const int64_t rowid = (D == 3) ? ((int64_t)(kc - g.k0) * ny + jc) : (int64_t)(kc - g.k0);
+          uint32_t* cm = cutmask + (rowid * wxtot + (w0 + ww)) * CPC;
+          // ---- "cut by any level set" mask of the group: thread `quad` owns cell type t = quad
+          if (quad < CPC) {
+            uint32_t any = 0u, all = 0xffffffffu;
             if (SIMPLEX) {
-              uint32_t vor = 0u, vand = 0xffffffffu;
 #pragma unroll
-              for (int v = 0; v < NVC; ++v) {
-                s_words[ls & 1][threadIdx.x][v] = V[v];
-                vor |= V[v];
-                vand &= V[v];
-              }
-              s_uni[ls & 1][threadIdx.x] = ((vor & live) == 0u) ? 1 : (((vand & live) == live) ? 2 : 0);
-#pragma unroll
-              for (int t = 0; t < CPC; ++t) {
-                uint32_t any = 0u, all = 0xffffffffu;
-#pragma unroll
-                for (int m = 0; m <= D; ++m) {
-                  const uint32_t a = V[s_tets[t][m]];
-                  any |= a;
-                  all &= a;
-                }
-                const uint32_t cutw = any & ~all & live;
-                if (L == 1 || ls == 0)
-                  cm[t] = cutw;
-                else if (cutw)
-                  cm[t] |= cutw;  // same thread owns this word for every ls of the layer
+              for (int m = 0; m <= D; ++m) {
+                const uint32_t a = V[s_tets[quad][m]];
+                any |= a;
+                all &= a;
               }
             } else {
-              uint32_t any = 0u, all = 0xffffffffu;
 #pragma unroll
               for (int v = 0; v < NVC; ++v) {
                 any |= V[v];
                 all &= V[v];
               }
-              s_words[ls & 1][threadIdx.x][0] = any;
-              s_words[ls & 1][threadIdx.x][1] = all;
-              const uint32_t cutw = any & ~all & live;
-              if (L == 1 || ls == 0)
-                cm[0] = cutw;
-              else if (cutw)
-                cm[0] |= cutw;
             }
+            const uint32_t cutw = any & ~all & live;
+            if (L == 1 || ls == 0)
+              cm[quad] = cutw;
+            else if (cutw)
+              cm[quad] |= cutw;  // the same thread owns this word for every ls of the layer
           }
-        }
-        __syncthreads();
-        // phase B: one thread per 4 consecutive cells: state bytes (coalesced 4/8-byte stores) and IN/OUT tallies
-        {
-          const int task = threadIdx.x >> 3, quad = threadIdx.x & 7;
-          const int r = task / WX, ww = task % WX;
-          const int jc = j0 + r;
-          const int i0 = 32 * (w0 + ww);
-          const int c0 = 4 * quad;
-          // IN / OUT tallies of this thread's 4 cells, one byte per cell type (IN = 0xFF, OUT = 0x01, CUT = 0x00)
-          unsigned long long pin = 0ull, pout = 0ull;
-          if (i0 + c0 < nx && jc < ny) {
-            const int ncq = min(4, nx - (i0 + c0));
-            const int64_t rowid = (D == 3) ? ((int64_t)(kc - g.k0) * ny + jc) : (int64_t)(kc - g.k0);
+          // ---- state bytes of this thread's 4 cells
+          if (c0 < ncell) {
+            const int ncq = min(4, ncell - c0);
             const int64_t cube0 = rowid * nx + i0 + c0;
             int8_t* out = states + (int64_t)ls * pitch + cube0 * CPC;
             if (SIMPLEX) {
+              uint32_t vor = 0u, vand = 0xffffffffu;
+#pragma unroll
+              for (int v = 0; v < NVC; ++v) {
+                vor |= V[v];
+                vand &= V[v];
+              }
               unsigned long long e[4];
-              const int uni = s_uni[ls & 1][task];
-              if (uni) {  // uniform group (the common case away from the surfaces): constant states, no gather
+              if ((vor & live) == 0u || (vand & live) == live) {
+                // uniform group (the common case away from the surfaces): constant states, no gather
                 constexpr unsigned long long ONES = CPC == 6 ? 0x010101010101ull : 0x0101ull;
-                const unsigned long long pat = uni == 1 ? ONES * 0xFFull : ONES;
+                const bool in = (vor & live) == 0u;
+                const unsigned long long pat = in ? ONES * 0xFFull : ONES;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) e[c] = pat;
-                if (uni == 1) pin = ONES * (unsigned long long)ncq; else pout = ONES * (unsigned long long)ncq;
+                if (in) pin = ONES * (unsigned long long)ncq; else pout = ONES * (unsigned long long)ncq;
               } else {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                   uint32_t sb = 0;
 #pragma unroll
-                  for (int v = 0; v < NVC; ++v) sb |= ((s_words[ls & 1][task][v] >> (c0 + c)) & 1u) << v;
+                  for (int v = 0; v < NVC; ++v) sb |= ((V[v] >> (c0 + c)) & 1u) << v;
                   e[c] = s_lut[sb];
                   if (c < ncq) {
                     const unsigned long long hi = (e[c] >> 7) & 0x010101010101ull;  // bit 7 set: IN
@@ -495,7 +475,12 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
                   for (int t = 0; t < CPC; ++t) out[c * CPC + t] = (int8_t)((e[c] >> (8 * t)) & 0xFFull);
               }
             } else {
-              const uint32_t any = s_words[ls & 1][task][0], all = s_words[ls & 1][task][1];
+              uint32_t any = 0u, all = 0xffffffffu;
+#pragma unroll
+              for (int v = 0; v < NVC; ++v) {
+                any |= V[v];
+                all &= V[v];
+              }
               const uint32_t vm = (1u << ncq) - 1u;
               const uint32_t o4 = (all >> c0) & 0xFu, n4 = (~any >> c0) & 0xFu;
               pin = __popc(n4 & vm);
@@ -510,25 +495,25 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
               }
             }
           }
-          if (L == 1) {  // one level set: keep the packed tallies in registers until the end of the block
-            acc_in += pin;
-            acc_out += pout;
-          } else {
+        }
+        if (L == 1) {  // one level set: keep the packed tallies in registers until the end of the block
+          acc_in += pin;
+          acc_out += pout;
+        } else {
 #pragma unroll
-            for (int t = 0; t < CPC; ++t) {
-              const unsigned int a = __reduce_add_sync(0xffffffffu, (unsigned int)(pin >> (8 * t)) & 0xFFu);
-              const unsigned int b = __reduce_add_sync(0xffffffffu, (unsigned int)(pout >> (8 * t)) & 0xFFu);
-              if (lane == 0) {
-                if (a) atomicAdd(&s_cnt[ls * 12 + t], a);
-                if (b) atomicAdd(&s_cnt[ls * 12 + 6 + t], b);
-              }
+          for (int t = 0; t < CPC; ++t) {
+            const unsigned int a = __reduce_add_sync(0xffffffffu, (unsigned int)(pin >> (8 * t)) & 0xFFu);
+            const unsigned int b = __reduce_add_sync(0xffffffffu, (unsigned int)(pout >> (8 * t)) & 0xFFu);
+            if (lane == 0) {
+              if (a) atomicAdd(&s_cnt[ls * 12 + t], a);
+              if (b) atomicAdd(&s_cnt[ls * 12 + 6 + t], b);
             }
           }
         }
       }
     }
-    // no barrier needed here: the next plane goes to the buffer last read by phase A (which is followed by a barrier),
-    // and s_words is only rewritten after the barrier that follows the next evaluation
+    // one barrier per layer: the next plane goes to the buffer this classification step has just read
+    __syncthreads();
   }
   if (L == 1) {
 #pragma unroll
