@@ -372,8 +372,15 @@ def run_b200(args, n, rank, world, local_rank):
     top = kernels[0]
     top_launches = max(1.0, top["launches_per_step"])
     achieved = (top["alg_bytes_per_step"] or 0) / (top["ms_per_step"] * 1e-3) / 1e9 if top["ms_per_step"] > 0 else 0.0
+    traffic = None
+    try:  # DRAM bytes per launch of this kernel from the committed ncu --set full capture (not measured live)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"{args.workload}:{top['name']}")
+        if world > 1 or n != 512:
+            traffic = None  # the capture was taken on the single-GPU 512^3 workload
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": top["name"], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_kind,
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_kind,
                 "alg_bytes_per_launch": int((top["alg_bytes_per_step"] or 0) / top_launches),
                 "ms_per_launch": round(top["ms_per_step"] / top_launches, 4),
                 "kernel_share_of_step": round(top["ms_per_step"] / sum(k["ms_per_step"] for k in kernels), 3)}
@@ -401,6 +408,8 @@ def run_b200(args, n, rank, world, local_rank):
         tdt = {np.int8: torch.int8, np.int32: torch.int32, np.float64: torch.float64}
         d2h = 0
         for k, (shape, dt) in shapes.items():
+            if int(s.subfacet_points_alias) and k in ("sf_point_to_coords", "sf_point_to_rcoords"):
+                continue  # one level set: these ARE the subcell point arrays; the binding shares one host array
             t = torch.empty(tuple(int(x) for x in shape), dtype=tdt[dt], pin_memory=True)
             host["layout"][k] = t.numpy()
             d2h += t.numel() * t.element_size()
@@ -429,7 +438,7 @@ def run_b200(args, n, rank, world, local_rank):
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        n_cpu = args.cpu_n or (2048 if args.workload == "c2_disk" else 224)
+        n_cpu = args.cpu_n or (4096 if args.workload == "c2_disk" else 320)
         v, dt, sample = cpu_sample(args.workload, n_cpu)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample, "seconds": round(dt, 2)}
 

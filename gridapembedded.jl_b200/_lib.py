@@ -43,7 +43,7 @@ class Sizes(C.Structure):
                 ("num_subcells", C.c_int64), ("num_subcell_points", C.c_int64), ("num_subfacets", C.c_int64),
                 ("num_subfacet_points", C.c_int64), ("cell_offset", C.c_int64), ("node_offset", C.c_int64),
                 ("num_levelsets", C.c_int32), ("D", C.c_int32), ("num_vertices_per_bgcell", C.c_int32),
-                ("pad", C.c_int32)]
+                ("subfacet_points_alias", C.c_int32)]
 
 
 BUFFER_FIELDS = ["ls_to_bgcell_to_inoutcut", "cutcell_to_cell", "sc_cell_to_points", "sc_cell_to_bgcell",

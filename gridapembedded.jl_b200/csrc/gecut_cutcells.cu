@@ -900,6 +900,7 @@ static int gc_cut_cells_l1(gecut_ctx* ctx, gecut_result* res) {
   lay.sf_X = lay.sc_X;  // device-side alias (read-only results); the host copy-out writes both destinations
   lay.sf_R = lay.sc_R;
   res->sf_points_alias = true;
+  sz.subfacet_points_alias = 1;
   GC_CHECK(gc_malloc(ctx, (void**)&res->cut_sc_ptr, sizeof(uint32_t) * 2 * (ncut + 1)));
   if (D == 2) {
     const size_t smem = cut1_fill_smem<2>();

@@ -138,7 +138,7 @@ class EmbeddedDiscretization:
         return b
 
     # ---- host copy ------------------------------------------------------------------------------
-    def to_host(self, pinned: bool = False, buffers: Optional[dict] = None) -> dict:
+    def to_host(self, pinned: bool = False, buffers: Optional[dict] = None, share_aliased_points: bool = True) -> dict:
         """Copy the whole layout to the host (the arrays a Julia `EmbeddedDiscretization` owns)."""
         if self._host is not None and buffers is None:
             return self._host
@@ -161,12 +161,20 @@ class EmbeddedDiscretization:
         }
         host = buffers if buffers is not None else {}
         b = _lib.Buffers()
+        # one level set: the subfacet point arrays are the subcell point arrays (the reference aliases them until
+        # merge_sub_face_data copies them); share ONE host array for both instead of copying 2 x Nscp x D doubles twice
+        alias = bool(s.subfacet_points_alias) and share_aliased_points
+        skip = {"sf_point_to_coords": "sc_point_to_coords", "sf_point_to_rcoords": "sc_point_to_rcoords"} if alias else {}
         for name, (shape, dt) in shapes.items():
+            if name in skip:
+                continue
             if name not in host:
                 host[name] = _alloc(tuple(int(x) for x in shape), dt, pinned)
             a = host[name]
             setattr(b, name, a.ctypes.data if a.size else None)
         self.ctx.check(self.ctx._lib.gecut_result_copy(self._h, C.byref(b)), "gecut_result_copy")
+        for name, src in skip.items():
+            host[name] = host[src]
         if buffers is None:
             self._host = host
         return host

@@ -100,7 +100,9 @@ typedef struct {
   int32_t num_levelsets;        /* L                                                                               */
   int32_t D;
   int32_t num_vertices_per_bgcell; /* nv                                                                           */
-  int32_t pad;
+  int32_t subfacet_points_alias;   /* 1: one level set -- the subfacet point arrays ARE the subcell point arrays    */
+                                   /* (CutTriangulations.jl:365-378); a binding may share one host array for both   */
+                                   /* and pass NULL for sf_point_to_coords / sf_point_to_rcoords to gecut_result_copy */
 } gecut_sizes;
 
 /* Pointers to the arrays of the layout.  Used both to hand out device pointers (gecut_result_device_ptrs) and to name

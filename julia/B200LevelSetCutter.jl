@@ -28,7 +28,7 @@ end
 struct GecutSizes
   num_bgcells::Int64; num_bgnodes::Int64; num_cutcells::Int64; num_subcells::Int64; num_subcell_points::Int64
   num_subfacets::Int64; num_subfacet_points::Int64; cell_offset::Int64; node_offset::Int64
-  num_levelsets::Int32; D::Int32; num_vertices_per_bgcell::Int32; pad::Int32
+  num_levelsets::Int32; D::Int32; num_vertices_per_bgcell::Int32; subfacet_points_alias::Int32
 end
 mutable struct GecutBuffers
   ls_to_bgcell_to_inoutcut::Ptr{Int8}; cutcell_to_cell::Ptr{Int32}
@@ -130,10 +130,13 @@ function _copy_out(cutter, res)
   sci = Matrix{Int8}(undef, s.num_subcells, L)
   f2p = Vector{Int32}(undef, s.num_subfacets*D); f2b = Vector{Int32}(undef, s.num_subfacets)
   N = Vector{Float64}(undef, s.num_subfacets*D)
-  fX = Vector{Float64}(undef, s.num_subfacet_points*D); fR = similar(fX)
+  # one level set: the subfacet points ARE the subcell points (CutTriangulations.jl:365-378): share the host arrays
+  alias = s.subfacet_points_alias != 0
+  fX = alias ? X : Vector{Float64}(undef, s.num_subfacet_points*D); fR = alias ? R : similar(fX)
   sfi = Matrix{Int8}(undef, s.num_subfacets, L)
   b = GecutBuffers(pointer(bg), C_NULL, pointer(c2p), pointer(c2b), pointer(X), pointer(R), pointer(sci),
-                   pointer(f2p), pointer(f2b), pointer(N), pointer(fX), pointer(fR), pointer(sfi), 0, 0, 0)
+                   pointer(f2p), pointer(f2b), pointer(N), alias ? Ptr{Float64}(C_NULL) : pointer(fX),
+                   alias ? Ptr{Float64}(C_NULL) : pointer(fR), pointer(sfi), 0, 0, 0)
   GC.@preserve bg c2p c2b X R sci f2p f2b N fX fR sfi begin
     _check(cutter, ccall((:gecut_result_copy, libgecut), Cint, (Ptr{Cvoid}, Ref{GecutBuffers}), res, b), "gecut_result_copy")
   end
