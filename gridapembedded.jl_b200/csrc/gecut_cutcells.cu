@@ -66,14 +66,17 @@ __device__ __forceinline__ void unit_normal(const double* p1, const double* p2, 
 }
 
 // new point on the edge (a,b) cut by level set `ls` (_cut_cell!, CutTriangulations.jl:206-218)
-template <int D, int LM>
+// WITH_XR = false (counting walk): only the level-set values are interpolated -- the tree shape depends on nothing else
+template <int D, int LM, bool WITH_XR = true>
 __device__ __forceinline__ void cut_point(const Pt<D, LM>& a, const Pt<D, LM>& b, int ls, int L, Pt<D, LM>& o) {
   double w1 = fabs(a.w[ls]), w2 = fabs(b.w[ls]);
   double coeff = __ddiv_rn(w1, __dadd_rn(w1, w2));
+  if (WITH_XR) {
 #pragma unroll
-  for (int d = 0; d < D; ++d) {
-    o.x[d] = gc_lerp(a.x[d], b.x[d], coeff);
-    o.r[d] = gc_lerp(a.r[d], b.r[d], coeff);
+    for (int d = 0; d < D; ++d) {
+      o.x[d] = gc_lerp(a.x[d], b.x[d], coeff);
+      o.r[d] = gc_lerp(a.r[d], b.r[d], coeff);
+    }
   }
   for (int k = 0; k < L; ++k) o.w[k] = gc_lerp(a.w[k], b.w[k], coeff);
 }
@@ -230,7 +233,7 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
         for (int ed = 0; ed < TC.nedges; ++ed) {
           const int a = e[depth][TC.edges[ed][0]], b = e[depth][TC.edges[ed][1]];
           if ((pool[a].w[ls] > 0.0) != (pool[b].w[ls] > 0.0)) {
-            cut_point<D, LM>(pool[a], pool[b], ls, L, pool[ptop]);
+            cut_point<D, LM, FILL>(pool[a], pool[b], ls, L, pool[ptop]);
             e[depth][np++] = (uint8_t)ptop++;
           }
         }
@@ -263,9 +266,10 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
       } else {
         for (int f = 0; f < nfac; ++f) {
           const uint8_t* fp = TC.fac_pts[c][f];
-          double nrm[3];
-          unit_normal<D>(pool[e[depth][fp[0]]].x, pool[e[depth][fp[1]]].x, pool[e[depth][fp[D - 1]]].x,
-                         (double)TC.fac_orient[c][f], nrm);
+          double nrm[3] = {0.0, 0.0, 0.0};
+          if (FILL)
+            unit_normal<D>(pool[e[depth][fp[0]]].x, pool[e[depth][fp[1]]].x, pool[e[depth][fp[D - 1]]].x,
+                           (double)TC.fac_orient[c][f], nrm);
 #pragma unroll
           for (int i = 0; i < D; ++i) fv[0][i] = e[depth][fp[i]];
           // ---- re-cut the facet by every other level set, last to first (CutTriangulations.jl:294-307,324-327)
@@ -289,7 +293,7 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
                 for (int ed = 0; ed < TF.nedges; ++ed) {
                   const int a = fe[fdepth][TF.edges[ed][0]], b = fe[fdepth][TF.edges[ed][1]];
                   if ((pool[a].w[k] > 0.0) != (pool[b].w[k] > 0.0)) {
-                    cut_point<D, LM>(pool[a], pool[b], k, L, pool[ptop]);
+                    cut_point<D, LM, FILL>(pool[a], pool[b], k, L, pool[ptop]);
                     fe[fdepth][fn++] = (uint8_t)ptop++;
                   }
                 }

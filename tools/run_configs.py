@@ -58,7 +58,8 @@ def report(name, model, geo, omega_names, check_oracle=False):
 
 which = sys.argv[1:] or ["c1", "c2", "c4", "c5"]
 if "c1" in which:
-    report("C1 PoissonCSGCutFEM 40^3 L=10", CartesianDiscreteModel((-0.8,) * 3, (0.8,) * 3, (40, 40, 40)), csg_geometry(), ["csg"], check_oracle=True)
+    n1 = int(os.environ.get("C1_N", "40"))
+    report(f"C1 PoissonCSGCutFEM {n1}^3 L=10", CartesianDiscreteModel((-0.8,) * 3, (0.8,) * 3, (n1, n1, n1)), csg_geometry(), ["csg"], check_oracle=(n1 <= 48))
 if "c2" in which:
     g = disk(0.7); b = get_metadata(g)
     l = report("C2 disk 4096^2", CartesianDiscreteModel(b.pmin, b.pmax, (4096, 4096)), g, [None])
