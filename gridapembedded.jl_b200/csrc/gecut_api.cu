@@ -173,6 +173,7 @@ void free_result_arrays(gecut_result* r) {
   gc_free(ctx, l.sc_meas);
   gc_free(ctx, l.sf_meas);
   gc_free(ctx, r->cutmask);
+  gc_free(ctx, r->cutcount);
   gc_free(ctx, r->cut_sc_ptr);
   r->cut_sc_ptr = nullptr;
   gc_free(ctx, r->bg_counts_dev);
@@ -181,6 +182,7 @@ void free_result_arrays(gecut_result* r) {
     if (r->owns_nodal[i]) gc_free(ctx, r->nodal_dev[i]);
   l = GcLayout{};
   r->cutmask = nullptr;
+  r->cutcount = nullptr;
 }
 
 int do_cut(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* leaves, int L, const double* const* nodal_values,
@@ -270,13 +272,6 @@ int do_cut(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* leaves, int
   const size_t mask_bytes = sizeof(uint32_t) * rows * wxtot * g.cpc;
   st = gc_malloc(ctx, (void**)&r->cutmask, mask_bytes);
   if (st != GECUT_OK) return fail(st);
-  if (L > 1) {
-    cudaError_t e = cudaMemsetAsync(r->cutmask, 0, mask_bytes, ctx->stream);
-    if (e != cudaSuccess) {
-      ctx->err = std::string("memset: ") + cudaGetErrorString(e);
-      return fail(GECUT_ERR_CUDA);
-    }
-  }
   st = gc_malloc(ctx, (void**)&r->bg_counts_dev, sizeof(unsigned long long) * GC_LMAX * 12);
   if (st != GECUT_OK) return fail(st);
   if (cudaMemsetAsync(r->bg_counts_dev, 0, sizeof(unsigned long long) * GC_LMAX * 12, ctx->stream) != cudaSuccess) {

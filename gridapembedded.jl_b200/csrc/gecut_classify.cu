@@ -163,53 +163,85 @@ int gc_exclusive_scan_u32(gecut_ctx* ctx, const uint32_t* in, uint32_t* out, int
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-template <int D>
+// Warp-autonomous marching: every warp owns a tile of WXT x-words (32 cubes each) x TY cell rows and marches through
+// ZS layers of the last direction.  No block barrier in the loop (only __syncwarp); two node planes of sign words per
+// level set live in a warp-private slice of shared memory.
+template <int D, bool SIMPLEX>
 struct ClsCfg {
-  static constexpr int WX = (D == 3) ? 4 : 16;  // x words (32 cells each) per block tile
-  static constexpr int TY = (D == 3) ? 8 : 1;   // cell rows per tile (3-D only)
-  static constexpr int RY = (D == 3) ? TY + 1 : 1;  // node rows per plane
-  static constexpr int ZS = 32;                 // layers of the last direction marched by one block
-  static constexpr int THREADS = (D == 3) ? 256 : 128;
+  static constexpr int NVC = 1 << D;                             // vertices of the n-cube
+  static constexpr int CPC = SIMPLEX ? (D == 3 ? 6 : 2) : 1;     // bg cells per n-cube
+  static constexpr int LPW = (D == 3) ? (SIMPLEX ? 2 : 1) : 4;   // lanes sharing one 32-cube word
+  static constexpr int CPL = 32 / LPW;                           // cubes per lane and layer
+  static constexpr int NTASK = 32 / LPW;                         // words per warp and layer
+  static constexpr int WXT = (D == 3) ? (SIMPLEX ? 2 : 4) : 8;   // x words of the warp tile
+  static constexpr int TY = NTASK / WXT;                         // cell rows of the warp tile
+  static constexpr int RY = (D == 3) ? TY + 1 : 1;               // node rows per plane
+  static constexpr int PW = RY * (WXT + 1);                      // sign words per plane and level set (+ x halo bit)
+  static constexpr int OUTB = CPL * CPC;                         // state bytes per lane and layer: 32 / 96 / 8 / 16
+  static constexpr int NQ = OUTB / 8;                            // ... in 64-bit words
+  static constexpr int WARPS = 4;
 };
 
+#ifndef CLS_MIN_BLOCKS
+#define CLS_MIN_BLOCKS 4
+#endif
 // words per x-row of the cut mask
 __host__ __device__ inline int gc_words_per_row(int nx) { return (nx + 31) / 32; }
 
-// LH > 0: "hoisted" evaluation for models with at most LH level sets.  Every closed-form leaf splits into a part that
-// depends on the in-plane coordinates only (constant while the block marches through the layers) and the marching
-// coordinate: e.g. sphere ((wx*wx + wy*wy) + wz*wz) - R*R  =  (pa + wz*wz) - RR with pa kept in a register per task.
-// The association of the reference formulas is preserved exactly (same rounding), only loop-invariant operations move.
+// NQ 64-bit words to 8*NQ contiguous bytes with the widest store the size allows (32-byte stores: whole sectors)
+template <int NQ>
+__device__ __forceinline__ void cls_store(int8_t* out, const unsigned long long* e) {
+  if constexpr (NQ % 4 == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; q += 4)
+      asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(out + 8 * q), "l"(e[q]), "l"(e[q + 1]), "l"(e[q + 2]),
+                   "l"(e[q + 3])
+                   : "memory");
+  } else if constexpr (NQ == 2) {
+    *reinterpret_cast<ulonglong2*>(out) = make_ulonglong2(e[0], e[1]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) reinterpret_cast<unsigned long long*>(out)[q] = e[q];
+  }
+}
+
+// scalar fall-back when rows are not 32-byte aligned (nx not a multiple of 32): the first nbytes bytes of e[]
+template <int NQ>
+__device__ __forceinline__ void cls_store_bytes(int8_t* out, const unsigned long long* e, int nbytes) {
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (q * 8 + k < nbytes) out[q * 8 + k] = (int8_t)((e[q] >> (8 * k)) & 0xFFull);
+}
+
+// LH > 0: "hoisted" evaluation for models with at most LH level sets.  SPHERE / PLANE / CYLINDER split into parts that
+// depend on one coordinate only: the x parts live in registers (per x word of the tile), the y parts in shared memory
+// (per node row), the marching coordinate enters once per plane.  The association of the reference formulas
+// (gc_eval_leaf) is preserved exactly -- same operations, same rounding -- only loop-invariant ones move.
 template <int D, bool SIMPLEX, int LH>
-__global__ void __launch_bounds__(ClsCfg<D>::THREADS)
+__global__ void __launch_bounds__(ClsCfg<D, SIMPLEX>::WARPS * 32, CLS_MIN_BLOCKS)
 k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64_t pitch,
-           uint32_t* __restrict__ cutmask, const uint8_t* __restrict__ simplexify_raw,
-           unsigned long long* __restrict__ bg_counts /* [L][2][6]: IN / OUT cells per level set and cell type */) {
-  using C = ClsCfg<D>;
-  constexpr int WX = C::WX, TY = C::TY, RY = C::RY, ZS = C::ZS;
-  constexpr int NVC = 1 << D;                         // vertices of the n-cube
-  constexpr int CPC = SIMPLEX ? (D == 3 ? 6 : 2) : 1;  // bg cells per n-cube
-  constexpr int NW = C::THREADS / 32;
-  constexpr int NTASK = TY * WX;                      // (row, x-word) tasks of one layer: 32 cells each
-  static_assert(NTASK * 8 == C::THREADS, "phase B maps one thread to 4 cells");
-  extern __shared__ uint32_t planes[];  // [2][L][RY][WX+1] sign words
+           uint32_t* __restrict__ cutmask, uint32_t* __restrict__ cutcount, const uint8_t* __restrict__ simplexify_raw,
+           unsigned long long* __restrict__ bg_counts /* [L][2][6]: IN / OUT cells per level set and cell type */,
+           int ZS, int ntx, int nty, int64_t ntiles) {
+  using C = ClsCfg<D, SIMPLEX>;
+  constexpr int NVC = C::NVC, CPC = C::CPC, LPW = C::LPW, CPL = C::CPL, WXT = C::WXT, TY = C::TY, RY = C::RY;
+  constexpr int PW = C::PW, NQ = C::NQ, WARPS = C::WARPS;
+  constexpr int LHS = LH > 0 ? LH : 1;
+  constexpr int ROWD = 1 + 2 * (LH > 0 ? LH : 0);  // doubles per node row: y, then (wy^2, wy*vy) per hoisted level set
+  constexpr uint32_t FULL = 0xffffffffu;
+  extern __shared__ __align__(16) unsigned char cls_smem[];
   __shared__ unsigned long long s_lut[SIMPLEX ? (1 << NVC) : 1];  // sign byte of an n-cube -> states of its CPC simplices
   __shared__ uint8_t s_tets[6][4];
-  __shared__ unsigned int s_cnt[GC_LMAX * 12];
+  __shared__ unsigned int s_cnt[GC_LMAX * 14];  // per level set: IN[6], OUT[6] per cell type, + IN/OUT of uniform groups
   const int L = lv.L;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < L * 12; i += C::THREADS) s_cnt[i] = 0u;
-  const int nx = g.n[0];
-  const int ny = (D == 3) ? g.n[1] : 1;
-  const int wxtot = gc_words_per_row(nx);
-  const int w0 = blockIdx.x * WX;   // first x word of the tile
-  const int j0 = (D == 3) ? blockIdx.y * TY : 0;
-  const int kz0 = g.k0 + ((D == 3) ? blockIdx.z : blockIdx.y) * ZS;  // first layer (global index)
-  const int kz1 = min(kz0 + ZS, g.k1);
-  const bool vec_ok = (nx & 3) == 0;
+  for (int i = threadIdx.x; i < L * 14; i += WARPS * 32) s_cnt[i] = 0u;
   if (SIMPLEX) {
     if (threadIdx.x < 24) s_tets[threadIdx.x / 4][threadIdx.x % 4] = simplexify_raw[(D - 2) * 24 + threadIdx.x];
     __syncthreads();
-    for (int sb = threadIdx.x; sb < (1 << NVC); sb += C::THREADS) {
+    for (int sb = threadIdx.x; sb < (1 << NVC); sb += WARPS * 32) {
       unsigned long long e = 0ull;
       for (int t = 0; t < CPC; ++t) {
         bool any = false, all = true;
@@ -224,326 +256,357 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
       s_lut[sb] = e;
     }
   }
-  const int plane_words = L * RY * (WX + 1);
-  // packed per-type tallies (one byte per cell type; <= 4 cells x 32 layers = 128 per byte, n-cubes: plain counters)
-  unsigned long long acc_in = 0ull, acc_out = 0ull;
-  // hoisted (plane-invariant) parts of the leaf formulas per evaluation task of this warp
-  constexpr int NSLOT = (RY * WX + 1 + NW - 1) / NW;
-  constexpr int LHS = LH > 0 ? LH : 1;
-  double h_pa[NSLOT][LHS], h_pb[NSLOT][LHS], h_c[LHS];
-  uint32_t h_valid = 0u;  // bit k: this lane evaluates a real node in task slot k
-  if (LH > 0) {
-#pragma unroll
-    for (int ls = 0; ls < LH; ++ls) {
-      h_c[ls] = 0.0;
-      if (ls < L) {
-        const int kind = lv.leaf[ls].kind;
-        h_c[ls] = kind == GECUT_LEAF_DOUGHNUT ? __dmul_rn(lv.leaf[ls].r, lv.leaf[ls].r) : __dmul_rn(lv.leaf[ls].R, lv.leaf[ls].R);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < NSLOT; ++k) {
-      const int task = wid + k * NW;
-      const bool halo = task == RY * WX;
-      const int r = halo ? lane : task / WX;
-      const int ww = halo ? WX : task % WX;
-      const int i = halo ? 32 * (w0 + WX) : 32 * (w0 + ww) + lane;
-      const int j = j0 + r;
-      if ((task < RY * WX + 1) && (i < g.nn[0]) && (D == 2 || j < g.nn[1]) && (!halo || lane < RY)) h_valid |= 1u << k;
-      const double xc = gc_coord(g, 0, i);
-      const double yc = (D == 3) ? gc_coord(g, 1, j) : 0.0;
-#pragma unroll
-      for (int ls = 0; ls < LH; ++ls) {
-        h_pa[k][ls] = 0.0;
-        h_pb[k][ls] = 0.0;
-        if (ls < L) {
-          const gecut_leaf& lf = lv.leaf[ls];
-          const double wx = __dsub_rn(xc, lf.x0[0]);
-          const double wy = (D == 3) ? __dsub_rn(yc, lf.x0[1]) : 0.0;
-          // in-plane partial sums, associated exactly like gc_dot3: (a0*b0 + a1*b1) [+ a2*b2 added per plane]
-          const double ww2 = (D == 3) ? __dadd_rn(__dmul_rn(wx, wx), __dmul_rn(wy, wy)) : __dmul_rn(wx, wx);
-          const double wv = (D == 3) ? __dadd_rn(__dmul_rn(wx, lf.v[0]), __dmul_rn(wy, lf.v[1])) : __dmul_rn(wx, lf.v[0]);
-          if (lf.kind == GECUT_LEAF_SPHERE) {
-            h_pa[k][ls] = ww2;
-          } else if (lf.kind == GECUT_LEAF_PLANE) {
-            h_pa[k][ls] = wv;
-          } else if (lf.kind == GECUT_LEAF_CYLINDER) {
-            h_pa[k][ls] = wv;
-            h_pb[k][ls] = ww2;
-          } else if (lf.kind == GECUT_LEAF_DOUGHNUT) {
-            const double t = __dsub_rn(lf.R, __dsqrt_rn(ww2));
-            h_pa[k][ls] = __dmul_rn(t, t);
-          }
-        }
-      }
-    }
-  }
+  __syncthreads();
 
-  for (int kp = kz0; kp <= kz1; ++kp) {  // node planes kz0..kz1
-    uint32_t* P = planes + ((kp - kz0) & 1) * plane_words;
-    if (LH > 0) {
-      // ---- hoisted evaluation: per plane only the marching coordinate enters
-      const double zc = gc_coord(g, D - 1, kp);
-      double wz[LH > 0 ? LH : 1], wz2[LH > 0 ? LH : 1], wzv[LH > 0 ? LH : 1];
+  const int64_t tile = (int64_t)blockIdx.x * WARPS + wid;
+  if (tile < ntiles) {
+    const int nx = g.n[0];
+    const int ny = (D == 3) ? g.n[1] : 1;
+    const int wxtot = gc_words_per_row(nx);
+    const int tx = (int)(tile % ntx);
+    const int ty = (int)((tile / ntx) % nty);
+    const int tz = (int)(tile / ((int64_t)ntx * nty));
+    const int w0 = tx * WXT;
+    const int j0 = ty * TY;
+    const int kz0 = g.k0 + tz * ZS;
+    const int kz1 = min(kz0 + ZS, g.k1);
+    const bool vec_ok = (nx & 31) == 0;
+    // warp-private shared memory: row doubles, then the sign planes [2][L][PW]
+    const size_t per_warp = sizeof(double) * RY * ROWD + sizeof(uint32_t) * 2 * L * PW;
+    double* rowd = reinterpret_cast<double*>(cls_smem + (size_t)wid * ((per_warp + 15) & ~(size_t)15));
+    uint32_t* planes = reinterpret_cast<uint32_t*>(rowd + RY * ROWD);
+
+    // ---- evaluation set-up: this lane's node column of every x word, the halo node column (lane = node row)
+    double xw[WXT];
+    uint32_t xmask = 0u;  // bit ww: this lane's node of word ww exists
 #pragma unroll
-      for (int ls = 0; ls < LH; ++ls) {
-        if (ls < L) {
-          wz[ls] = __dsub_rn(zc, lv.leaf[ls].x0[D - 1]);
-          wz2[ls] = __dmul_rn(wz[ls], wz[ls]);
-          wzv[ls] = __dmul_rn(wz[ls], lv.leaf[ls].v[D - 1]);
+    for (int ww = 0; ww < WXT; ++ww) {
+      const int i = 32 * (w0 + ww) + lane;
+      xw[ww] = gc_coord(g, 0, i);
+      if (i < g.nn[0]) xmask |= 1u << ww;
+    }
+    const int ih = 32 * (w0 + WXT);
+    const bool hvalid = (ih < g.nn[0]) && (lane < RY) && (D == 2 || j0 + lane < g.nn[1]);
+    const double xh = gc_coord(g, 0, ih);
+    const double yh = (D == 3) ? gc_coord(g, 1, j0 + lane) : 0.0;
+    uint32_t rowmask = 0u;  // bit r: node row r exists
+#pragma unroll
+    for (int r = 0; r < RY; ++r)
+      if (D == 2 || j0 + r < g.nn[1]) rowmask |= 1u << r;
+    if (D == 3 && lane < RY) {
+      rowd[lane * ROWD] = yh;
+      if (LH > 0) {
+#pragma unroll
+        for (int ls = 0; ls < LH; ++ls) {
+          const double wy = ls < L ? __dsub_rn(yh, lv.leaf[ls].x0[1]) : 0.0;
+          rowd[lane * ROWD + 1 + 2 * ls] = __dmul_rn(wy, wy);
+          rowd[lane * ROWD + 2 + 2 * ls] = ls < L ? __dmul_rn(wy, lv.leaf[ls].v[1]) : 0.0;
         }
       }
+    }
+    double hxa[LHS][WXT], hxb[LHS][WXT], ha[LHS], hb[LHS], hc[LHS];
+    if (LH > 0) {
 #pragma unroll
-      for (int k = 0; k < NSLOT; ++k) {
-        const int task = wid + k * NW;
-        if (task < RY * WX + 1) {
-          const bool halo = task == RY * WX;
-          const int r = halo ? lane : task / WX;
-          const int ww = halo ? WX : task % WX;
+      for (int ls = 0; ls < LH; ++ls) {
+        const bool on = ls < L;
+        const double x00 = on ? lv.leaf[ls].x0[0] : 0.0, x01 = on ? lv.leaf[ls].x0[1] : 0.0;
+        const double v0 = on ? lv.leaf[ls].v[0] : 0.0, v1 = on ? lv.leaf[ls].v[1] : 0.0;
+        hc[ls] = on ? __dmul_rn(lv.leaf[ls].R, lv.leaf[ls].R) : 0.0;
 #pragma unroll
-          for (int ls = 0; ls < LH; ++ls) {
-            if (ls < L) {
-              const int kind = lv.leaf[ls].kind;
-              double v;
-              if (kind == GECUT_LEAF_SPHERE) {
-                v = __dsub_rn(__dadd_rn(h_pa[k][ls], wz2[ls]), h_c[ls]);
-              } else if (kind == GECUT_LEAF_PLANE) {
-                v = __dadd_rn(h_pa[k][ls], wzv[ls]);
-              } else if (kind == GECUT_LEAF_CYLINDER) {
-                const double A = __dadd_rn(h_pa[k][ls], wzv[ls]);
-                const double H2 = __dadd_rn(h_pb[k][ls], wz2[ls]);
-                v = __dsub_rn(__dsub_rn(H2, __dmul_rn(A, A)), h_c[ls]);
-              } else if (kind == GECUT_LEAF_DOUGHNUT) {
-                v = __dsub_rn(__dadd_rn(h_pa[k][ls], wz2[ls]), h_c[ls]);
-              } else {
-                const int i = halo ? 32 * (w0 + WX) : 32 * (w0 + ww) + lane;
-                const int64_t node = (D == 3) ? ((int64_t)i + (int64_t)g.nn[0] * ((int64_t)(j0 + r) + (int64_t)g.nn[1] * kp))
-                                              : ((int64_t)i + (int64_t)g.nn[0] * kp);
-                v = ((h_valid >> k) & 1u) ? __ldg(lv.nodal[ls] + (node - lv.nodal_base)) : -1.0;
+        for (int ww = 0; ww < WXT; ++ww) {
+          const double wx = __dsub_rn(xw[ww], x00);
+          hxa[ls][ww] = __dmul_rn(wx, wx);
+          hxb[ls][ww] = __dmul_rn(wx, v0);
+        }
+        const double wx = __dsub_rn(xh, x00);
+        const double wy = __dsub_rn(yh, x01);
+        // in-plane partial sums of the halo column, associated like gc_dot3: (a0*b0 + a1*b1) [+ a2*b2 per plane]
+        ha[ls] = (D == 3) ? __dadd_rn(__dmul_rn(wx, wx), __dmul_rn(wy, wy)) : __dmul_rn(wx, wx);
+        hb[ls] = (D == 3) ? __dadd_rn(__dmul_rn(wx, v0), __dmul_rn(wy, v1)) : __dmul_rn(wx, v0);
+      }
+    }
+    __syncwarp();
+
+    // ---- classification set-up: lane -> (word task, part of the word)
+    const int task = lane / LPW, sub = lane % LPW;
+    const int ww_c = task % WXT, r_c = task / WXT;
+    const int c0 = sub * CPL;
+    const int i0 = 32 * (w0 + ww_c);
+    const int jc = j0 + r_c;
+    const int ncw = max(0, min(32, nx - i0));                              // live cubes of the word
+    const uint32_t livew = ncw == 32 ? FULL : ((1u << ncw) - 1u);
+    const int nl = max(0, min(CPL, ncw - c0));                             // live cubes of this lane
+    const uint32_t livel = nl == 32 ? FULL : ((1u << nl) - 1u);
+    const bool lane_on = nl > 0 && jc < ny;
+    const bool word_on = sub == 0 && ncw > 0 && jc < ny;
+    const int pofs = r_c * (WXT + 1) + ww_c;
+    const int64_t layer_rows = (D == 3) ? ny : 1;
+    unsigned int cnt_in[CPC], cnt_out[CPC], uni_in = 0u, uni_out = 0u;
+#pragma unroll
+    for (int t = 0; t < CPC; ++t) cnt_in[t] = cnt_out[t] = 0u;
+    bool slow_seen = false;
+
+    auto flush_counts = [&](int ls) {
+      const unsigned int a = __reduce_add_sync(FULL, uni_in), b = __reduce_add_sync(FULL, uni_out);
+      if (lane == 0) {
+        if (a) atomicAdd(&s_cnt[ls * 14 + 12], a);
+        if (b) atomicAdd(&s_cnt[ls * 14 + 13], b);
+      }
+      uni_in = uni_out = 0u;
+      if (slow_seen) {
+#pragma unroll
+        for (int t = 0; t < CPC; ++t) {
+          const unsigned int ai = __reduce_add_sync(FULL, cnt_in[t]), ao = __reduce_add_sync(FULL, cnt_out[t]);
+          if (lane == 0) {
+            if (ai) atomicAdd(&s_cnt[ls * 14 + t], ai);
+            if (ao) atomicAdd(&s_cnt[ls * 14 + 6 + t], ao);
+          }
+          cnt_in[t] = cnt_out[t] = 0u;
+        }
+        slow_seen = false;
+      }
+    };
+
+    for (int kp = kz0; kp <= kz1; ++kp) {  // node planes kz0..kz1
+      uint32_t* Pk = planes + ((kp - kz0) & 1) * L * PW;
+      const double zc = gc_coord(g, D - 1, kp);
+      // ================= signs of node plane kp: one ballot per (node row, x word) and level set
+      for (int ls = 0; ls < L; ++ls) {
+        uint32_t* P = Pk + ls * PW;
+        const int kind = lv.leaf[ls].kind;
+        // rows x words with a value functor f(ww2, wv, r, ww) (in-plane partial sums) -- fully unrolled
+        auto sweep = [&](auto f) {
+#pragma unroll
+          for (int r = 0; r < RY; ++r) {
+            double wy2 = 0.0, wyv = 0.0;
+            if (D == 3 && LH > 0) {
+              const int lsh = ls < LHS ? ls : 0;
+              wy2 = rowd[r * ROWD + 1 + 2 * lsh];
+              wyv = rowd[r * ROWD + 2 + 2 * lsh];
+            }
+#pragma unroll
+            for (int ww = 0; ww < WXT; ++ww) {
+              const int lsh = (LH > 0 && ls < LHS) ? ls : 0;
+              double a = 0.0, b = 0.0;
+              if (LH > 0) {
+                // select the registers of level set ls without dynamic indexing
+                a = hxa[0][ww];
+                b = hxb[0][ww];
+#pragma unroll
+                for (int q = 1; q < LHS; ++q)
+                  if (lsh == q) {
+                    a = hxa[q][ww];
+                    b = hxb[q][ww];
+                  }
               }
-              const uint32_t word = __ballot_sync(0xffffffffu, ((h_valid >> k) & 1u) && (v > 0.0));
-              if (!halo) {
-                if (lane == 0) P[(ls * RY + r) * (WX + 1) + ww] = word;
-              } else if (lane < RY) {
-                P[(ls * RY + lane) * (WX + 1) + WX] = (word >> lane) & 1u;
-              }
+              const double ww2 = (D == 3) ? __dadd_rn(a, wy2) : a;
+              const double wv = (D == 3) ? __dadd_rn(b, wyv) : b;
+              const double v = f(ww2, wv, r, ww, false);
+              const bool ok = ((rowmask >> r) & 1u) && ((xmask >> ww) & 1u);
+              const uint32_t word = __ballot_sync(FULL, ok && (v > 0.0));
+              if (lane == 0) P[r * (WXT + 1) + ww] = word;
             }
           }
-        }
-      }
-    } else {
-    // ---- evaluate the signs of node plane kp: one ballot per (row, word) task and level set.  Of the word right of the
-      //      tile only bit 0 is needed (x+1 vertices of the last cell column): one transposed task evaluates that node
-      //      column for all RY rows at once instead of RY mostly wasted row tasks.
-      for (int task = wid; task < RY * WX + 1; task += NW) {
-        const bool halo = task == RY * WX;
-        const int r = halo ? lane : task / WX;
-        const int ww = halo ? WX : task % WX;
-        const int i = halo ? 32 * (w0 + WX) : 32 * (w0 + ww) + lane;
-        const int j = j0 + r;
-        const bool valid = (i < g.nn[0]) && (D == 2 || j < g.nn[1]) && (!halo || lane < RY);
-        double x[3];
-        x[0] = gc_coord(g, 0, i);
-        if (D == 3) {
-          x[1] = gc_coord(g, 1, j);
-          x[2] = gc_coord(g, 2, kp);
+          {  // x halo: the node column right of the tile, lane = node row
+            double a = 0.0, b = 0.0;
+            if (LH > 0) {
+              const int lsh = ls < LHS ? ls : 0;
+              a = ha[0];
+              b = hb[0];
+#pragma unroll
+              for (int q = 1; q < LHS; ++q)
+                if (lsh == q) {
+                  a = ha[q];
+                  b = hb[q];
+                }
+            }
+            const double v = f(a, b, lane, WXT, true);
+            const uint32_t word = __ballot_sync(FULL, hvalid && (v > 0.0));
+            if (lane < RY) P[lane * (WXT + 1) + WXT] = (word >> lane) & 1u;
+          }
+        };
+        // generic value of one node: closed-form leaf or NODAL vector
+        auto node_value = [&](int r, int ww, bool halo) -> double {
+          const int i = halo ? ih : 32 * (w0 + ww) + lane;
+          const int j = (D == 3) ? j0 + r : 0;
+          if (kind == GECUT_LEAF_NODAL) {
+            const bool ok = halo ? hvalid : (((rowmask >> (r & 31)) & 1u) && (i < g.nn[0]));
+            const int64_t node = (D == 3) ? ((int64_t)i + (int64_t)g.nn[0] * ((int64_t)j + (int64_t)g.nn[1] * kp))
+                                          : ((int64_t)i + (int64_t)g.nn[0] * kp);
+            return ok ? __ldg(lv.nodal[ls] + (node - lv.nodal_base)) : -1.0;
+          }
+          double x[3];
+          x[0] = halo ? xh : gc_coord(g, 0, i);
+          if (D == 3) {
+            x[1] = halo ? yh : rowd[(r < RY ? r : 0) * ROWD];
+            x[2] = zc;
+          } else {
+            x[1] = zc;
+            x[2] = 0.0;
+          }
+          return gc_eval_leaf(lv.leaf[ls], x, D);
+        };
+        if (LH > 0 && ls < LHS && (kind == GECUT_LEAF_SPHERE || kind == GECUT_LEAF_PLANE || kind == GECUT_LEAF_CYLINDER)) {
+          const double wz = __dsub_rn(zc, lv.leaf[ls].x0[D - 1]);
+          const double wz2 = __dmul_rn(wz, wz);
+          const double wzv = __dmul_rn(wz, lv.leaf[ls].v[D - 1]);
+          double c = hc[0];
+#pragma unroll
+          for (int q = 1; q < LHS; ++q)
+            if (ls == q) c = hc[q];
+          if (kind == GECUT_LEAF_SPHERE) {
+            sweep([&](double ww2, double, int, int, bool) { return __dsub_rn(__dadd_rn(ww2, wz2), c); });
+          } else if (kind == GECUT_LEAF_PLANE) {
+            sweep([&](double, double wv, int, int, bool) { return __dadd_rn(wv, wzv); });
+          } else {
+            sweep([&](double ww2, double wv, int, int, bool) {
+              const double A = __dadd_rn(wv, wzv);
+              const double H2 = __dadd_rn(ww2, wz2);
+              return __dsub_rn(__dsub_rn(H2, __dmul_rn(A, A)), c);
+            });
+          }
         } else {
-          x[1] = gc_coord(g, 1, kp);
-          x[2] = 0.0;
-        }
-        const int64_t node = (D == 3) ? ((int64_t)i + (int64_t)g.nn[0] * ((int64_t)j + (int64_t)g.nn[1] * kp))
-                                      : ((int64_t)i + (int64_t)g.nn[0] * kp);
-        for (int ls = 0; ls < L; ++ls) {
-          double v = -1.0;
-          if (valid) {
-            if (lv.leaf[ls].kind == GECUT_LEAF_NODAL)
-              v = __ldg(lv.nodal[ls] + (node - lv.nodal_base));
-            else
-              v = gc_eval_leaf(lv.leaf[ls], x, D);
-          }
-          const uint32_t word = __ballot_sync(0xffffffffu, valid && (v > 0.0));
-          if (!halo) {
-            if (lane == 0) P[(ls * RY + r) * (WX + 1) + ww] = word;
-          } else if (lane < RY) {
-            P[(ls * RY + lane) * (WX + 1) + WX] = (word >> lane) & 1u;
-          }
+          sweep([&](double, double, int r, int ww, bool halo) { return node_value(r, ww, halo); });
         }
       }
-    }
-    __syncthreads();
-    if (kp > kz0) {
-      // ---- classify layer kp-1 from planes (kp-1) [lo] and kp [hi]
-      const uint32_t* P0 = planes + ((kp - 1 - kz0) & 1) * plane_words;
-      const uint32_t* P1 = P;
-      const int kc = kp - 1;  // global layer index
-      for (int ls = 0; ls < L; ++ls) {
-        // One thread per 4 consecutive cells (8 threads share a 32-cell group).  Every thread rebuilds the vertex sign
-        // words of its group from the two planes (16 mostly broadcast shared loads) -- redundant across the 8 threads
-        // but parallel, which removes the former single-warp "phase A" and one block barrier per layer and level set.
-        const int task = threadIdx.x >> 3, quad = threadIdx.x & 7;
-        const int r = task / WX, ww = task % WX;
-        const int jc = j0 + r;
-        const int i0 = 32 * (w0 + ww);
-        const int c0 = 4 * quad;
-        unsigned long long pin = 0ull, pout = 0ull;  // IN / OUT tallies, one byte per cell type
-        if (i0 < nx && jc < ny) {
+      __syncwarp();
+      if (kp > kz0) {
+        // ================= classify layer kp-1 from planes kp-1 [lo] and kp [hi]
+        const int kc = kp - 1;  // global layer index
+        const uint32_t* Q0 = planes + ((kp - 1 - kz0) & 1) * L * PW;
+        const uint32_t* Q1 = Pk;
+        const int64_t rowid = (int64_t)(kc - g.k0) * layer_rows + jc;
+        const int64_t cube0 = rowid * nx + i0 + c0;
+        const int64_t gidx = rowid * wxtot + (w0 + ww_c);
+        uint32_t cutacc[CPC];
+#pragma unroll
+        for (int t = 0; t < CPC; ++t) cutacc[t] = 0u;
+        for (int ls = 0; ls < L; ++ls) {
           uint32_t V[NVC];
 #pragma unroll
           for (int v = 0; v < NVC; ++v) {
             const int xo = v & 1;
             const int ro = (D == 3) ? ((v >> 1) & 1) : 0;
             const int po = (D == 3) ? ((v >> 2) & 1) : ((v >> 1) & 1);
-            const uint32_t* row = (po ? P1 : P0) + (ls * RY + r + ro) * (WX + 1);
-            uint32_t a = row[ww];
-            if (xo) a = (a >> 1) | (row[ww + 1] << 31);
-            V[v] = a;
+            const uint32_t* row = (po ? Q1 : Q0) + ls * PW + pofs + ro * (WXT + 1);
+            V[v] = xo ? __funnelshift_r(row[0], row[1], 1) : row[0];
           }
-          const int ncell = min(32, nx - i0);
-          const uint32_t live = ncell == 32 ? 0xffffffffu : ((1u << ncell) - 1u);
-          const int64_t rowid = (D == 3) ? ((int64_t)(kc - g.k0) * ny + jc) : (int64_t)(kc - g.k0);
-          uint32_t* cm = cutmask + (rowid * wxtot + (w0 + ww)) * CPC;
-          // ---- "cut by any level set" mask of the group: thread `quad` owns cell type t = quad
-          if (quad < CPC) {
-            uint32_t any = 0u, all = 0xffffffffu;
-            if (SIMPLEX) {
+          uint32_t vor = 0u, vand = FULL;
 #pragma unroll
-              for (int m = 0; m <= D; ++m) {
-                const uint32_t a = V[s_tets[quad][m]];
-                any |= a;
-                all &= a;
-              }
-            } else {
+          for (int v = 0; v < NVC; ++v) {
+            vor |= V[v];
+            vand &= V[v];
+          }
+          const uint32_t lor = (vor >> c0) & livel, land = (vand >> c0) & livel;
+          const bool u_in = lor == 0u, u_out = land == livel;
+          const bool w_uni = ((vor & livew) == 0u) || ((vand & livew) == livew);
+          const bool fast = (!lane_on || u_in || u_out) && (!word_on || w_uni);
+          int8_t* out = states + (int64_t)ls * pitch + cube0 * CPC;
+          unsigned long long e[NQ];
+          if (vec_ok && __all_sync(FULL, fast)) {
+            // uniform everywhere in the warp tile (the common case away from the surfaces): constant states
+            if (lane_on) {
+              const unsigned long long pat = u_in ? 0xFFFFFFFFFFFFFFFFull : 0x0101010101010101ull;
 #pragma unroll
-              for (int v = 0; v < NVC; ++v) {
-                any |= V[v];
-                all &= V[v];
-              }
+              for (int q = 0; q < NQ; ++q) e[q] = pat;
+              cls_store<NQ>(out, e);
+              if (u_in) uni_in += (unsigned int)nl; else uni_out += (unsigned int)nl;
             }
-            const uint32_t cutw = any & ~all & live;
-            if (L == 1 || ls == 0)
-              cm[quad] = cutw;
-            else if (cutw)
-              cm[quad] |= cutw;  // the same thread owns this word for every ls of the layer
-          }
-          // ---- state bytes of this thread's 4 cells
-          if (c0 < ncell) {
-            const int ncq = min(4, ncell - c0);
-            const int64_t cube0 = rowid * nx + i0 + c0;
-            int8_t* out = states + (int64_t)ls * pitch + cube0 * CPC;
+          } else {
+            slow_seen = true;
             if (SIMPLEX) {
-              uint32_t vor = 0u, vand = 0xffffffffu;
+              // per cell type: any / all over the simplex' vertices -> cut mask word and tallies
 #pragma unroll
-              for (int v = 0; v < NVC; ++v) {
-                vor |= V[v];
-                vand &= V[v];
-              }
-              unsigned long long e[4];
-              if ((vor & live) == 0u || (vand & live) == live) {
-                // uniform group (the common case away from the surfaces): constant states, no gather
-                constexpr unsigned long long ONES = CPC == 6 ? 0x010101010101ull : 0x0101ull;
-                const bool in = (vor & live) == 0u;
-                const unsigned long long pat = in ? ONES * 0xFFull : ONES;
+              for (int t = 0; t < CPC; ++t) {
+                uint32_t any = 0u, all = FULL;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) e[c] = pat;
-                if (in) pin = ONES * (unsigned long long)ncq; else pout = ONES * (unsigned long long)ncq;
-              } else {
+                for (int m = 0; m <= D; ++m) {
+                  const int lv_id = s_tets[t][m];
+                  uint32_t a = V[0];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  uint32_t sb = 0;
-#pragma unroll
-                  for (int v = 0; v < NVC; ++v) sb |= ((V[v] >> (c0 + c)) & 1u) << v;
-                  e[c] = s_lut[sb];
-                  if (c < ncq) {
-                    const unsigned long long hi = (e[c] >> 7) & 0x010101010101ull;  // bit 7 set: IN
-                    pin += hi;
-                    pout += (e[c] & 0x010101010101ull) & ~hi;                       // bit 0 set, bit 7 clear: OUT
-                  }
+                  for (int v = 1; v < NVC; ++v)
+                    if (lv_id == v) a = V[v];
+                  any |= a;
+                  all &= a;
+                }
+                cutacc[t] |= any & ~all & livew;
+                if (lane_on) {
+                  cnt_in[t] += __popc((~any >> c0) & livel);
+                  cnt_out[t] += __popc((all >> c0) & livel);
                 }
               }
-              if (vec_ok) {
-                if (CPC == 6) {  // 4 cells x 6 bytes = 24 bytes = three 8-byte stores
-                  unsigned long long* o8 = reinterpret_cast<unsigned long long*>(out);
-                  o8[0] = (e[0] & 0xFFFFFFFFFFFFull) | (e[1] << 48);
-                  o8[1] = ((e[1] >> 16) & 0xFFFFFFFFull) | (e[2] << 32);
-                  o8[2] = ((e[2] >> 32) & 0xFFFFull) | (e[3] << 16);
-                } else {  // 4 cells x 2 bytes
-                  *reinterpret_cast<unsigned long long*>(out) =
-                      (e[0] & 0xFFFFull) | ((e[1] & 0xFFFFull) << 16) | ((e[2] & 0xFFFFull) << 32) | ((e[3] & 0xFFFFull) << 48);
+              // state bytes: sign byte of every cube (bit v = vertex v OUT) -> LUT row
+#pragma unroll
+              for (int q4 = 0; q4 < CPL / 4; ++q4) {
+                uint32_t acc = 0u;
+#pragma unroll
+                for (int v = 0; v < NVC; ++v) {
+                  const uint32_t nib = (V[v] >> (c0 + 4 * q4)) & 0xFu;
+                  acc += ((nib * 0x00204081u) & 0x01010101u) << v;
                 }
-              } else {
-                for (int c = 0; c < ncq; ++c)
-                  for (int t = 0; t < CPC; ++t) out[c * CPC + t] = (int8_t)((e[c] >> (8 * t)) & 0xFFull);
+                const unsigned long long e0 = s_lut[acc & 0xFFu], e1 = s_lut[(acc >> 8) & 0xFFu];
+                const unsigned long long e2 = s_lut[(acc >> 16) & 0xFFu], e3 = s_lut[acc >> 24];
+                if (CPC == 6) {
+                  e[3 * q4 + 0] = e0 | (e1 << 48);
+                  e[3 * q4 + 1] = (e1 >> 16) | (e2 << 32);
+                  e[3 * q4 + 2] = (e2 >> 32) | (e3 << 16);
+                } else {
+                  e[q4] = e0 | (e1 << 16) | (e2 << 32) | (e3 << 48);
+                }
               }
             } else {
-              uint32_t any = 0u, all = 0xffffffffu;
-#pragma unroll
-              for (int v = 0; v < NVC; ++v) {
-                any |= V[v];
-                all &= V[v];
+              cutacc[0] |= vor & ~vand & livew;
+              if (lane_on) {
+                cnt_in[0] += __popc(~lor & livel);
+                cnt_out[0] += __popc(land);
               }
-              const uint32_t vm = (1u << ncq) - 1u;
-              const uint32_t o4 = (all >> c0) & 0xFu, n4 = (~any >> c0) & 0xFu;
-              pin = __popc(n4 & vm);
-              pout = __popc(o4 & vm);
-              const uint32_t so = (o4 * 0x00204081u) & 0x01010101u;
-              const uint32_t si = ((n4 * 0x00204081u) & 0x01010101u) * 0xFFu;
-              const uint32_t w = so | si;  // OUT(1) where all, IN(0xFF) where !any, CUT(0) otherwise
-              if (vec_ok) {
-                *reinterpret_cast<uint32_t*>(out) = w;
-              } else {
-                for (int c = 0; c < ncq; ++c) out[c] = (int8_t)((w >> (8 * c)) & 0xFFu);
+              const uint32_t o = vand >> c0, n = ~vor >> c0;
+#pragma unroll
+              for (int q = 0; q < NQ; ++q) {
+                unsigned long long w8 = 0ull;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const uint32_t o4 = (o >> (8 * q + 4 * h)) & 0xFu, n4 = (n >> (8 * q + 4 * h)) & 0xFu;
+                  const uint32_t so = (o4 * 0x00204081u) & 0x01010101u;
+                  const uint32_t si = ((n4 * 0x00204081u) & 0x01010101u) * 0xFFu;
+                  w8 |= (unsigned long long)(so | si) << (32 * h);  // OUT(1) where all, IN(0xFF) where !any, CUT(0) otherwise
+                }
+                e[q] = w8;
               }
             }
+            if (lane_on) {
+              if (vec_ok) cls_store<NQ>(out, e);
+              else cls_store_bytes<NQ>(out, e, nl * CPC);
+            }
           }
+          if (L > 1) flush_counts(ls);
         }
-        if (L == 1) {  // one level set: keep the packed tallies in registers until the end of the block
-          acc_in += pin;
-          acc_out += pout;
-        } else {
+        if (word_on) {
+          uint32_t* cm = cutmask + gidx * CPC;
+          uint32_t n = 0u;
 #pragma unroll
           for (int t = 0; t < CPC; ++t) {
-            const unsigned int a = __reduce_add_sync(0xffffffffu, (unsigned int)(pin >> (8 * t)) & 0xFFu);
-            const unsigned int b = __reduce_add_sync(0xffffffffu, (unsigned int)(pout >> (8 * t)) & 0xFFu);
-            if (lane == 0) {
-              if (a) atomicAdd(&s_cnt[ls * 12 + t], a);
-              if (b) atomicAdd(&s_cnt[ls * 12 + 6 + t], b);
-            }
+            cm[t] = cutacc[t];
+            n += __popc(cutacc[t]);
           }
+          cutcount[gidx] = n;
         }
       }
+      __syncwarp();  // the next plane overwrites the buffer this step has just read
     }
-    // one barrier per layer: the next plane goes to the buffer this classification step has just read
-    __syncthreads();
-  }
-  if (L == 1) {
-#pragma unroll
-    for (int t = 0; t < CPC; ++t) {
-      const unsigned int vi = SIMPLEX ? (unsigned int)(acc_in >> (8 * t)) & 0xFFu : (unsigned int)acc_in;
-      const unsigned int vo = SIMPLEX ? (unsigned int)(acc_out >> (8 * t)) & 0xFFu : (unsigned int)acc_out;
-      const unsigned int a = __reduce_add_sync(0xffffffffu, vi);
-      const unsigned int b = __reduce_add_sync(0xffffffffu, vo);
-      if (lane == 0) {
-        if (a) atomicAdd(&s_cnt[t], a);
-        if (b) atomicAdd(&s_cnt[6 + t], b);
-      }
-    }
+    if (L == 1) flush_counts(0);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < L * 12; i += C::THREADS)
-    if (s_cnt[i]) atomicAdd(&bg_counts[i], (unsigned long long)s_cnt[i]);
+  for (int i = threadIdx.x; i < L * 12; i += WARPS * 32) {
+    const unsigned int v = s_cnt[(i / 12) * 14 + (i % 12)] + s_cnt[(i / 12) * 14 + 12 + (i % 12) / 6];
+    // uniform groups count for every cell type of the n-cube
+    const bool type_exists = (i % 6) < CPC;
+    if (type_exists && v) atomicAdd(&bg_counts[i], (unsigned long long)v);
+  }
 }
+
 
 // ---- compaction of the cut mask -------------------------------------------------------------------
-template <int CPC>
-__global__ void k_cutmask_count(const uint32_t* __restrict__ cutmask, int64_t ngroups, uint32_t* __restrict__ counts) {
-  int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gidx >= ngroups) return;
-  uint32_t c = 0;
-#pragma unroll
-  for (int t = 0; t < CPC; ++t) c += __popc(cutmask[gidx * CPC + t]);
-  counts[gidx] = c;
-}
-
 template <int CPC>
 __global__ void k_cutmask_emit(const uint32_t* __restrict__ cutmask, int64_t ngroups, const uint32_t* __restrict__ offs,
                                int nx, int wxtot, int32_t* __restrict__ cutcells) {
@@ -584,35 +647,55 @@ __global__ void k_eval_leaf_nodes(const GcGrid g, const gecut_leaf leaf, double*
 
 }  // namespace
 
+// number of layers one warp tile marches: few enough tiles per resident warp leave SMs idle at the end (tail), short
+// marches re-evaluate the shared node plane more often ((ZS+1)/ZS); pick the best product of the two efficiencies
+static int cls_pick_zs(int64_t tiles_per_slab, int nlayers, int64_t resident_warps) {
+  int best = 8;
+  double best_score = -1.0;
+  for (int zs = 4; zs <= 32; ++zs) {
+    const int64_t n = tiles_per_slab * gc_div_up(nlayers, zs);
+    const double waves = (double)n / (double)resident_warps;
+    const double tail = waves / ceil(waves);
+    const double score = tail * (double)zs / (double)(zs + 1);
+    if (score > best_score + 1e-9) {
+      best_score = score;
+      best = zs;
+    }
+  }
+  return best;
+}
+
 int gc_classify(gecut_ctx* ctx, gecut_result* res) {
   const GcGrid& g = res->grid;
   const int L = res->L;
   const int nx = g.n[0];
   const int wxtot = gc_words_per_row(nx);
   const int nlayers = g.k1 - g.k0;
+  const int64_t rows = (g.D == 3) ? (int64_t)nlayers * g.n[1] : (int64_t)nlayers;
+  GC_CHECK(gc_malloc(ctx, (void**)&res->cutcount, sizeof(uint32_t) * rows * wxtot));
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
   auto launch = [&](auto Dtag, auto Stag) {
     constexpr int D = decltype(Dtag)::value;
     constexpr bool S = decltype(Stag)::value;
-    using C = ClsCfg<D>;
-    dim3 grid;
-    grid.x = (unsigned)gc_div_up(wxtot, C::WX);
-    if (D == 3) {
-      grid.y = (unsigned)gc_div_up(g.n[1], C::TY);
-      grid.z = (unsigned)gc_div_up(nlayers, C::ZS);
-    } else {
-      grid.y = (unsigned)gc_div_up(nlayers, C::ZS);
-      grid.z = 1;
-    }
-    size_t smem = sizeof(uint32_t) * 2 * L * C::RY * (C::WX + 1);
-    if (L == 1)
-      GC_LAUNCH(ctx, "k_classify", k_classify<D, S, 1><<<grid, C::THREADS, smem, ctx->stream>>>(
-          g, res->leaves, res->lay.bg_state, res->lay.bg_pitch, res->cutmask, ctx->d_simplexify_raw, res->bg_counts_dev));
-    else if (L == 2)
-      GC_LAUNCH(ctx, "k_classify", k_classify<D, S, 2><<<grid, C::THREADS, smem, ctx->stream>>>(
-          g, res->leaves, res->lay.bg_state, res->lay.bg_pitch, res->cutmask, ctx->d_simplexify_raw, res->bg_counts_dev));
-    else
-      GC_LAUNCH(ctx, "k_classify", k_classify<D, S, 0><<<grid, C::THREADS, smem, ctx->stream>>>(
-          g, res->leaves, res->lay.bg_state, res->lay.bg_pitch, res->cutmask, ctx->d_simplexify_raw, res->bg_counts_dev));
+    using C = ClsCfg<D, S>;
+    const int ntx = (int)gc_div_up(wxtot, C::WXT);
+    const int nty = (D == 3) ? (int)gc_div_up(g.n[1], C::TY) : 1;
+    const int LH = L <= 2 ? L : 0;
+    const int rowd = 1 + 2 * LH;
+    const size_t per_warp = (sizeof(double) * C::RY * rowd + sizeof(uint32_t) * 2 * L * C::PW + 15) & ~(size_t)15;
+    const size_t smem = per_warp * C::WARPS;
+    const int zs = cls_pick_zs((int64_t)ntx * nty, nlayers, (int64_t)nsm * CLS_MIN_BLOCKS * C::WARPS);
+    const int64_t ntiles = (int64_t)ntx * nty * gc_div_up(nlayers, zs);
+    const unsigned nb = (unsigned)gc_div_up(ntiles, C::WARPS);
+#define GC_CLS(LHV)                                                                                                   \
+  GC_LAUNCH(ctx, "k_classify", k_classify<D, S, LHV><<<nb, C::WARPS * 32, smem, ctx->stream>>>(                        \
+      g, res->leaves, res->lay.bg_state, res->lay.bg_pitch, res->cutmask, res->cutcount, ctx->d_simplexify_raw,       \
+      res->bg_counts_dev, zs, ntx, nty, ntiles))
+    if (L == 1) GC_CLS(1);
+    else if (L == 2) GC_CLS(2);
+    else GC_CLS(0);
+#undef GC_CLS
   };
   if (g.D == 3) {
     if (g.simplexified)
@@ -634,17 +717,11 @@ int gc_compact_cutcells(gecut_ctx* ctx, gecut_result* res) {
   const int wxtot = gc_words_per_row(nx);
   const int64_t rows = (g.D == 3) ? (int64_t)(g.k1 - g.k0) * g.n[1] : (int64_t)(g.k1 - g.k0);
   const int64_t ngroups = rows * wxtot;
-  uint32_t* counts = nullptr;
+  uint32_t* counts = res->cutcount;  // cut cells per 32-cube group, written by k_classify
   uint64_t* total_dev = nullptr;
-  GC_CHECK(gc_malloc(ctx, (void**)&counts, sizeof(uint32_t) * ngroups));
   GC_CHECK(gc_malloc(ctx, (void**)&total_dev, sizeof(uint64_t)));
   const int T = 256;
   const unsigned nb = (unsigned)gc_div_up(ngroups, T);
-  switch (g.cpc) {
-    case 1: GC_LAUNCH(ctx, "k_cutmask_count", k_cutmask_count<1><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts)); break;
-    case 2: GC_LAUNCH(ctx, "k_cutmask_count", k_cutmask_count<2><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts)); break;
-    default: GC_LAUNCH(ctx, "k_cutmask_count", k_cutmask_count<6><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts)); break;
-  }
   GC_CHECK(gc_exclusive_scan_u32(ctx, counts, counts, ngroups, total_dev));
   uint64_t* h = (uint64_t*)ctx->h_pinned;
   GC_CUDA(cudaMemcpyAsync(h, total_dev, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -662,7 +739,8 @@ int gc_compact_cutcells(gecut_ctx* ctx, gecut_result* res) {
     }
   }
   int st = gc_launch_check(ctx, "cutmask compaction");
-  gc_free(ctx, counts);
+  gc_free(ctx, res->cutcount);
+  res->cutcount = nullptr;
   gc_free(ctx, total_dev);
   return st;
 }

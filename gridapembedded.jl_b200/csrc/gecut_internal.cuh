@@ -126,6 +126,7 @@ struct gecut_result {
   gecut_sizes sizes{};
   GcLayout lay{};
   uint32_t* cutmask = nullptr;
+  uint32_t* cutcount = nullptr;   // cut cells per 32-cube group (k_classify -> compaction, then freed)
   uint32_t* cut_sc_ptr = nullptr;  // 2*(Ncut+1): (first subcell, first subcell point) (0-based) of every cut bg cell
   unsigned long long* bg_counts_dev = nullptr;  // [L][2][6] IN / OUT bg cells per level set and cell type
   int64_t bg_counts[GC_LMAX * 12] = {0};        // host copy (filled with the cut-cell count read-back)
