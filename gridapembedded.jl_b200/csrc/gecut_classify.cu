@@ -53,85 +53,94 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total)
   return excl;
 }
 
-// all three kernels take `nch` arrays of n elements stored back to back (blockIdx.y = channel)
-__global__ void k_scan_reduce(const uint32_t* __restrict__ in, int64_t n, uint64_t* __restrict__ blocksums) {
-  in += (int64_t)blockIdx.y * n;
-  blocksums += (int64_t)blockIdx.y * gridDim.x;
-  int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
-  uint32_t s = 0;
-#pragma unroll
-  for (int i = 0; i < SCAN_ITEMS; ++i) {
-    int64_t idx = base + (int64_t)i * SCAN_THREADS + threadIdx.x;
-    if (idx < n) s += in[idx];
-  }
-  uint32_t tot;
-  block_excl_scan(s, &tot);
-  if (threadIdx.x == 0) blocksums[blockIdx.x] = tot;
-}
+// Single-pass exclusive scan (decoupled look-back): one launch, every element read once and written once.  Tiles are
+// handed out in launch order by a ticket counter, so a tile only ever waits on tiles that are already running; tile t
+// publishes its aggregate, warp 0 walks back over the 32 closest predecessors at a time until it meets an inclusive
+// prefix, then publishes its own.  state word = value (62 bits) | flag (0: not ready, 1: aggregate, 2: inclusive prefix);
+// value and flag travel in one 64-bit store, so no fence is needed.  `nch` arrays of n elements stored back to back
+// (blockIdx.y = channel).  in == out is allowed.
+#define SCAN_AGG (1ull << 62)
+#define SCAN_PRE (2ull << 62)
+#define SCAN_VAL ((1ull << 62) - 1ull)
 
-// single block: exclusive scan of the block sums (uint64), grand total out
-__global__ void k_scan_blocksums(uint64_t* __restrict__ blocksums, int64_t nb, uint64_t* __restrict__ total) {
-  blocksums += (int64_t)blockIdx.x * nb;
-  total += blockIdx.x;
-  __shared__ uint64_t carry_s;
-  __shared__ uint64_t wsum[32];
-  if (threadIdx.x == 0) carry_s = 0;
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_lookback(const uint32_t* in, uint32_t* out, int64_t n, int64_t nb, unsigned long long* state, uint32_t* ticket,
+                uint64_t* __restrict__ totals) {
+  const int ch = blockIdx.y;
+  in += (int64_t)ch * n;
+  out += (int64_t)ch * n;
+  volatile unsigned long long* st = state + (int64_t)ch * nb;
+  __shared__ uint32_t s_tile;
+  __shared__ unsigned long long s_excl;
+  if (threadIdx.x == 0) s_tile = atomicAdd(&ticket[ch], 1u);
   __syncthreads();
+  const int64_t tile = s_tile;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int64_t start = 0; start < nb; start += blockDim.x) {
-    int64_t idx = start + threadIdx.x;
-    uint64_t v = idx < nb ? blocksums[idx] : 0;
-    uint64_t inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (lane == 31) wsum[wid] = inc;
-    __syncthreads();
-    if (wid == 0) {
-      uint64_t s = lane < (blockDim.x >> 5) ? wsum[lane] : 0;
-      uint64_t si = s;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint64_t t = __shfl_up_sync(0xffffffffu, si, o);
-        if (lane >= o) si += t;
-      }
-      wsum[lane] = si - s;
-    }
-    __syncthreads();
-    uint64_t excl = carry_s + wsum[wid] + inc - v;
-    if (idx < nb) blocksums[idx] = excl;
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) carry_s = excl + v;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *total = carry_s;
-}
-
-__global__ void k_scan_apply(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t n,
-                             const uint64_t* __restrict__ blocksums) {
-  in += (int64_t)blockIdx.y * n;
-  out += (int64_t)blockIdx.y * n;
-  blocksums += (int64_t)blockIdx.y * gridDim.x;
   // blocked arrangement: thread t owns items [t*ITEMS, (t+1)*ITEMS) of the tile so that the order is preserved
-  int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  const int64_t base = tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
   uint32_t v[SCAN_ITEMS];
   uint32_t s = 0;
+  if (base + SCAN_ITEMS <= n && ((reinterpret_cast<uintptr_t>(in + base) & 15) == 0)) {
 #pragma unroll
-  for (int i = 0; i < SCAN_ITEMS; ++i) {
-    int64_t idx = base + i;
-    v[i] = idx < n ? in[idx] : 0;
-    s += v[i];
+    for (int i = 0; i < SCAN_ITEMS; i += 4) {
+      const uint4 q = *reinterpret_cast<const uint4*>(in + base + i);
+      v[i] = q.x;
+      v[i + 1] = q.y;
+      v[i + 2] = q.z;
+      v[i + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) v[i] = (base + i < n) ? in[base + i] : 0u;
   }
-  uint32_t tot;
-  uint32_t excl = block_excl_scan(s, &tot);
-  uint32_t run = (uint32_t)blocksums[blockIdx.x] + excl;
 #pragma unroll
-  for (int i = 0; i < SCAN_ITEMS; ++i) {
-    int64_t idx = base + i;
-    if (idx < n) out[idx] = run;
-    run += v[i];
+  for (int i = 0; i < SCAN_ITEMS; ++i) s += v[i];
+  uint32_t tot;
+  const uint32_t excl_in_tile = block_excl_scan(s, &tot);
+  if (wid == 0) {
+    if (lane == 0) st[tile] = (tile == 0 ? SCAN_PRE : SCAN_AGG) | (unsigned long long)tot;
+    unsigned long long excl = 0ull;
+    if (tile > 0) {
+      int64_t j = tile - 1 - lane;
+      while (true) {
+        unsigned long long sv = j >= 0 ? st[j] : SCAN_PRE;  // before the first tile: inclusive prefix 0
+        while (__any_sync(0xffffffffu, (sv >> 62) == 0ull))
+          if ((sv >> 62) == 0ull) sv = st[j];
+        const uint32_t pre = __ballot_sync(0xffffffffu, (sv >> 62) == 2ull);
+        const int first = pre ? __ffs(pre) - 1 : 31;  // the closest predecessor that already knows its prefix
+        unsigned long long val = lane <= first ? (sv & SCAN_VAL) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        excl += val;
+        if (pre) break;
+        j -= 32;
+      }
+      if (lane == 0) st[tile] = SCAN_PRE | (excl + (unsigned long long)tot);
+    }
+    if (lane == 0) {
+      s_excl = excl;
+      if (tile == nb - 1) totals[ch] = excl + (unsigned long long)tot;
+    }
+  }
+  __syncthreads();
+  uint32_t run = (uint32_t)s_excl + excl_in_tile;
+  if (base + SCAN_ITEMS <= n && ((reinterpret_cast<uintptr_t>(out + base) & 15) == 0)) {
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i += 4) {
+      uint4 q;
+      q.x = run;
+      q.y = q.x + v[i];
+      q.z = q.y + v[i + 1];
+      q.w = q.z + v[i + 2];
+      run = q.w + v[i + 3];
+      *reinterpret_cast<uint4*>(out + base + i) = q;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+      if (base + i < n) out[base + i] = run;
+      run += v[i];
+    }
   }
 }
 
@@ -142,15 +151,16 @@ int gc_exclusive_scan_u32_multi(gecut_ctx* ctx, const uint32_t* in, uint32_t* ou
     GC_CUDA(cudaMemsetAsync(totals_dev, 0, sizeof(uint64_t) * nch, ctx->stream));
     return GECUT_OK;
   }
-  int64_t nb = gc_div_up(n, SCAN_TILE);
-  uint64_t* blocksums = nullptr;
-  GC_CHECK(gc_malloc(ctx, (void**)&blocksums, sizeof(uint64_t) * nb * nch));
+  const int64_t nb = gc_div_up(n, SCAN_TILE);
+  unsigned long long* state = nullptr;  // [nch][nb] tile states, then nch tickets
+  const size_t bytes = sizeof(unsigned long long) * (nb * nch + nch);
+  GC_CHECK(gc_malloc(ctx, (void**)&state, bytes));
+  GC_CUDA(cudaMemsetAsync(state, 0, bytes, ctx->stream));
+  uint32_t* ticket = reinterpret_cast<uint32_t*>(state + nb * nch);
   dim3 grid((unsigned)nb, (unsigned)nch);
-  GC_LAUNCH(ctx, "k_scan_reduce", k_scan_reduce<<<grid, SCAN_THREADS, 0, ctx->stream>>>(in, n, blocksums));
-  GC_LAUNCH(ctx, "k_scan_blocksums", k_scan_blocksums<<<nch, 1024, 0, ctx->stream>>>(blocksums, nb, totals_dev));
-  GC_LAUNCH(ctx, "k_scan_apply", k_scan_apply<<<grid, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, blocksums));
+  GC_LAUNCH(ctx, "k_scan_lookback", k_scan_lookback<<<grid, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, nb, state, ticket, totals_dev));
   int st = gc_launch_check(ctx, "scan");
-  gc_free(ctx, blocksums);
+  gc_free(ctx, state);
   return st;
 }
 
@@ -233,20 +243,21 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
   constexpr uint32_t FULL = 0xffffffffu;
   extern __shared__ __align__(16) unsigned char cls_smem[];
   __shared__ unsigned long long s_lut[SIMPLEX ? (1 << NVC) : 1];  // sign byte of an n-cube -> states of its CPC simplices
-  __shared__ uint8_t s_tets[6][4];
-  __shared__ unsigned int s_cnt[GC_LMAX * 14];  // per level set: IN[6], OUT[6] per cell type, + IN/OUT of uniform groups
+  // per warp and level set: IN[6], OUT[6] per cell type, + IN/OUT of uniform groups (warp-private: no block barrier)
+  __shared__ unsigned int s_cnt_all[WARPS][GC_LMAX * 14];
   const int L = lv.L;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < L * 14; i += WARPS * 32) s_cnt[i] = 0u;
+  unsigned int* s_cnt = s_cnt_all[wid];
+  for (int i = lane; i < L * 14; i += 32) s_cnt[i] = 0u;
   if (SIMPLEX) {
-    if (threadIdx.x < 24) s_tets[threadIdx.x / 4][threadIdx.x % 4] = simplexify_raw[(D - 2) * 24 + threadIdx.x];
-    __syncthreads();
     for (int sb = threadIdx.x; sb < (1 << NVC); sb += WARPS * 32) {
       unsigned long long e = 0ull;
+#pragma unroll
       for (int t = 0; t < CPC; ++t) {
         bool any = false, all = true;
+#pragma unroll
         for (int m = 0; m <= D; ++m) {
-          const bool o = (sb >> s_tets[t][m]) & 1;
+          const bool o = (sb >> gc_simplexify_raw(D - 2, t, m)) & 1;
           any |= o;
           all &= o;
         }
@@ -521,11 +532,7 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
                 uint32_t any = 0u, all = FULL;
 #pragma unroll
                 for (int m = 0; m <= D; ++m) {
-                  const int lv_id = s_tets[t][m];
-                  uint32_t a = V[0];
-#pragma unroll
-                  for (int v = 1; v < NVC; ++v)
-                    if (lv_id == v) a = V[v];
+                  const uint32_t a = V[gc_simplexify_raw(D - 2, t, m)];  // compile-time index
                   any |= a;
                   all &= a;
                 }
@@ -596,8 +603,8 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
     }
     if (L == 1) flush_counts(0);
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < L * 12; i += WARPS * 32) {
+  __syncwarp();
+  for (int i = lane; i < L * 12; i += 32) {
     const unsigned int v = s_cnt[(i / 12) * 14 + (i % 12)] + s_cnt[(i / 12) * 14 + 12 + (i % 12) / 6];
     // uniform groups count for every cell type of the n-cube
     const bool type_exists = (i % 6) < CPC;

@@ -532,16 +532,19 @@ k_cut1_count(const GcGrid g, const GcLeaves lv, const uint8_t* __restrict__ simp
   const int64_t k = (int64_t)blockIdx.x * cells_per_block + threadIdx.x;
   const int tiles_per_block = cells_per_block * g.nt0 / CUT1_TILE;
   if ((int)threadIdx.x < cells_per_block && k < ncut) {
-    const int64_t cell0 = (int64_t)cutcells[k] - 1;
-    const int64_t cube = cell0 / g.cpc;
-    const int typ = (int)(cell0 % g.cpc);
+    // slab-local cell ids fit in 32 bits (checked at cut time)
+    const uint32_t cell = (uint32_t)(cutcells[k] - 1);
+    const uint32_t cube = cell / (uint32_t)g.cpc;
+    const int typ = (int)(cell - cube * (uint32_t)g.cpc);
     int ijk[3];
-    ijk[0] = (int)(cube % g.n[0]);
+    const uint32_t row = cube / (uint32_t)g.n[0];
+    ijk[0] = (int)(cube - row * (uint32_t)g.n[0]);
     if (D == 3) {
-      ijk[1] = (int)((cube / g.n[0]) % g.n[1]);
-      ijk[2] = (int)(cube / ((int64_t)g.n[0] * g.n[1])) + g.k0;
+      const uint32_t lay3 = row / (uint32_t)g.n[1];
+      ijk[1] = (int)(row - lay3 * (uint32_t)g.n[1]);
+      ijk[2] = (int)lay3 + g.k0;
     } else {
-      ijk[1] = (int)(cube / g.n[0]) + g.k0;
+      ijk[1] = (int)row + g.k0;
       ijk[2] = 0;
     }
     // sign bits of the bg cell's vertices (local vertex ids of the n-cube)

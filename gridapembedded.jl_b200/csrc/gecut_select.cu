@@ -33,27 +33,72 @@ __global__ void k_flag_subcells(const GcLayout lay, int64_t nsc, const GcProgram
   flags[e] = (bg == GC_CUT && sc == side) ? 1u : 0u;
 }
 
-// Triangulation(cut,CutInOrOut(side),geo) by cut cell: the subcells of a cut cell are a contiguous run (cut_sc_ptr), so
-// the bg state is evaluated once per cut cell and no per-subcell flag array / bgcell gather is needed.
-// EMIT == false: number of selected subcells per cut cell; EMIT == true: their 1-based ids at the scanned offsets.
+// Triangulation(cut,CutInOrOut(side),geo): bg state == CUT && subcell state == side, as a stream compaction over the
+// subcells: 16 consecutive subcells per thread (one 128-bit load of the state row for single-leaf programs), 4096 per
+// block.  check_bg == 0 (one level set: every cut cell is CUT for every program over it) skips the bg-cell gather.
+// EMIT == false: number of selected subcells per block; EMIT == true: their 1-based ids at the scanned block offsets.
+constexpr int SELSC_T = 256, SELSC_PER = 16;
+
 template <bool EMIT>
-__global__ void k_select_subcells(const GcLayout lay, const uint32_t* __restrict__ sc_ptr, int64_t ncut,
-                                  const GcProgram prog, int side, uint32_t* __restrict__ counts_or_offs,
-                                  int32_t* __restrict__ ids) {
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= ncut) return;
-  uint32_t c = 0;
-  uint32_t o = EMIT ? counts_or_offs[k] : 0u;
-  if (gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, (int64_t)lay.cutcells[k] - 1) == GC_CUT) {
-    const uint32_t s0 = sc_ptr[2 * k], s1 = sc_ptr[2 * k + 2];
-    for (uint32_t e = s0; e < s1; ++e) {
-      if (gc_eval_inoutcut(prog, lay.sc_state, lay.sc_pitch, (int64_t)e) == side) {
-        if (EMIT) ids[o++] = (int32_t)(e + 1);
-        c++;
+__global__ void __launch_bounds__(SELSC_T)
+k_select_subcells(const GcLayout lay, int64_t nsc, const GcProgram prog, int side, int check_bg,
+                  uint32_t* __restrict__ counts_or_offs, int32_t* __restrict__ ids) {
+  __shared__ uint32_t s_w[SELSC_T / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t e0 = ((int64_t)blockIdx.x * SELSC_T + threadIdx.x) * SELSC_PER;
+  uint32_t bits = 0u;  // bit i: subcell e0+i is selected
+  if (e0 < nsc) {
+    const bool leaf1 = prog.len == 1 || (prog.len == 2 && prog.tok[1] == GECUT_OP_COMPLEMENT);
+    if (leaf1) {
+      const int want = prog.len == 2 ? -side : side;  // complement swaps IN and OUT
+      // rows are padded to a multiple of 256 bytes: the vector load may run past nsc
+      const uint4 q = *reinterpret_cast<const uint4*>(lay.sc_state + (int64_t)prog.tok[0] * lay.sc_pitch + e0);
+      const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+      const uint32_t pat = (uint32_t)(uint8_t)(int8_t)want * 0x01010101u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t x = w4[j] ^ pat;  // zero byte <=> state == want
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (((x >> (8 * i)) & 0xFFu) == 0u) bits |= 1u << (4 * j + i);
+      }
+    } else {
+#pragma unroll 4
+      for (int i = 0; i < SELSC_PER; ++i)
+        if (e0 + i < nsc && gc_eval_inoutcut(prog, lay.sc_state, lay.sc_pitch, e0 + i) == side) bits |= 1u << i;
+    }
+    const int64_t left = nsc - e0;
+    if (left < SELSC_PER) bits &= (1u << (int)left) - 1u;
+    if (check_bg) {
+      for (uint32_t m = bits; m; m &= m - 1) {
+        const int i = __ffs(m) - 1;
+        if (gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, (int64_t)lay.sc_c2bg[e0 + i] - 1) != GC_CUT) bits &= ~(1u << i);
       }
     }
   }
-  if (!EMIT) counts_or_offs[k] = c;
+  const uint32_t cnt = __popc(bits);
+  // block-level exclusive prefix of the per-thread counts (thread order = ascending subcell ids)
+  uint32_t inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_w[wid] = inc;
+  __syncthreads();
+  uint32_t wbase = 0u, total = 0u;
+#pragma unroll
+  for (int k = 0; k < SELSC_T / 32; ++k) {
+    const uint32_t v = s_w[k];
+    if (k < wid) wbase += v;
+    total += v;
+  }
+  if (!EMIT) {
+    if (threadIdx.x == 0) counts_or_offs[blockIdx.x] = total;
+  } else {
+    uint32_t o = counts_or_offs[blockIdx.x] + wbase + inc - cnt;
+    for (uint32_t m = bits; m; m &= m - 1) ids[o++] = (int32_t)(e0 + (__ffs(m) - 1) + 1);
+  }
 }
 
 // bg cells: count per cell type of the cells with state == side (mode 0) or CUT||side (mode 1); optionally flags
@@ -228,24 +273,25 @@ int gc_select_cells(gecut_ctx* ctx, gecut_selection* sel) {
   const int T = 256;
   const bool want_sub = sel->kind == GECUT_SEL_PHYSICAL || sel->kind == GECUT_SEL_CUTONLY;
   const bool want_bg = sel->kind == GECUT_SEL_PHYSICAL || sel->kind == GECUT_SEL_ACTIVE || sel->kind == GECUT_SEL_BGONLY;
-  if (want_sub && nsc > 0 && res->cut_sc_ptr) {
-    const int64_t ncut = res->sizes.num_cutcells;
+  if (want_sub && nsc > 0) {
+    const int64_t nblk = gc_div_up(nsc, (int64_t)SELSC_T * SELSC_PER);
+    const int check_bg = res->L > 1 ? 1 : 0;  // one level set: every cut cell is CUT for every program over it
     uint32_t* counts = nullptr;
     uint64_t* total_dev = nullptr;
-    GC_CHECK(gc_malloc(ctx, (void**)&counts, sizeof(uint32_t) * ncut));
+    GC_CHECK(gc_malloc(ctx, (void**)&counts, sizeof(uint32_t) * nblk));
     GC_CHECK(gc_malloc(ctx, (void**)&total_dev, sizeof(uint64_t)));
-    const unsigned nbk = (unsigned)gc_div_up(ncut, T);
-    GC_LAUNCH(ctx, "k_select_subcells", k_select_subcells<false><<<nbk, T, 0, ctx->stream>>>(
-        lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, counts, nullptr));
-    GC_CHECK(gc_exclusive_scan_u32(ctx, counts, counts, ncut, total_dev));
+    const unsigned nbk = (unsigned)nblk;
+    GC_LAUNCH(ctx, "k_select_subcells", k_select_subcells<false><<<nbk, SELSC_T, 0, ctx->stream>>>(
+        lay, nsc, sel->prog, sel->side, check_bg, counts, nullptr));
+    GC_CHECK(gc_exclusive_scan_u32(ctx, counts, counts, nblk, total_dev));
     uint64_t* h = (uint64_t*)ctx->h_pinned;
     GC_CUDA(cudaMemcpyAsync(h, total_dev, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     GC_CUDA(cudaStreamSynchronize(ctx->stream));
     sel->n_sub = (int64_t)h[0];
     if (sel->n_sub > 0) {
       GC_CHECK(gc_malloc(ctx, (void**)&sel->sub_ids, sizeof(int32_t) * sel->n_sub));
-      GC_LAUNCH(ctx, "k_select_subcells", k_select_subcells<true><<<nbk, T, 0, ctx->stream>>>(
-          lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, counts, sel->sub_ids));
+      GC_LAUNCH(ctx, "k_select_subcells", k_select_subcells<true><<<nbk, SELSC_T, 0, ctx->stream>>>(
+          lay, nsc, sel->prog, sel->side, check_bg, counts, sel->sub_ids));
     }
     gc_free(ctx, counts);
     gc_free(ctx, total_dev);
