@@ -419,6 +419,16 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
 // ================================================================================================
 constexpr int CUT1_TILE = 32;    // one warp = one tile: warps run their phases independently (no block barriers)
 constexpr int CUT1_BLOCK = 128;  // threads per block of the fill kernel (4 independent tiles)
+#ifndef CUT1_MINB
+#define CUT1_MINB 5
+#endif
+
+// shared memory of one warp of the fill kernel: staged points (+ phase pad), 16-byte records, owner maps; 32-byte multiple
+template <int D>
+__host__ __device__ constexpr int cut1_warp_bytes() {
+  return (((CUT1_TILE * ((D == 3) ? 8 : 5) * D + 4) * 8 + CUT1_TILE * 16 + CUT1_TILE * ((D == 3) ? 6 : 3) +
+           CUT1_TILE * ((D == 3) ? 2 : 1)) + 31) / 32 * 32;
+}
 
 __device__ __forceinline__ uint32_t cut1_pack(int ncell, int npt, int nfac) {
   return (uint32_t)nfac | ((uint32_t)npt << 10) | ((uint32_t)ncell << 21);
@@ -435,77 +445,6 @@ __device__ __forceinline__ uint32_t cut1_warp_scan(uint32_t v, uint32_t* total) 
   }
   *total = __shfl_sync(0xffffffffu, inc, 31);
   return inc - v;
-}
-
-// Lean stage-0 set-up of the fast path: physical coordinates, the single level-set value and, instead of the reference
-// coordinates, one small integer per vertex whose bit d IS the d-th reference coordinate (n-cube vertices are {0,1}^D,
-// simplex vertices are the origin and the unit axes) -- 24 fewer live registers than carrying the doubles around.
-template <int D>
-__device__ __forceinline__ void setup_stage0_l1(const GcGrid& g, const GcLeaves& lv, int64_t cell0, int t,
-                                                const uint8_t* simp_raw, const uint8_t* simp_pos, double (*x)[D],
-                                                double* w, int* rv) {
-  // slab-local cell ids fit in 32 bits (checked at cut time): 32-bit divisions are ~4x cheaper than 64-bit ones
-  const uint32_t cell = (uint32_t)cell0;
-  const uint32_t cube = cell / (uint32_t)g.cpc;
-  const int typ = (int)(cell - cube * (uint32_t)g.cpc);
-  int ijk[3];
-  const uint32_t row = cube / (uint32_t)g.n[0];
-  ijk[0] = (int)(cube - row * (uint32_t)g.n[0]);
-  if (D == 3) {
-    const uint32_t lay3 = row / (uint32_t)g.n[1];
-    ijk[1] = (int)(row - lay3 * (uint32_t)g.n[1]);
-    ijk[2] = (int)lay3 + g.k0;
-  } else {
-    ijk[1] = (int)row + g.k0;
-    ijk[2] = 0;
-  }
-#pragma unroll
-  for (int m = 0; m <= D; ++m) {
-    const int lvid = g.simplexified ? simp_raw[(D - 2) * 24 + typ * 4 + m] : simp_pos[(D - 2) * 24 + t * 4 + m];
-    const int nijk[3] = {ijk[0] + (lvid & 1), ijk[1] + ((lvid >> 1) & 1), ijk[2] + ((lvid >> 2) & 1)};
-    double xx[3] = {gc_coord(g, 0, nijk[0]), gc_coord(g, 1, nijk[1]), D == 3 ? gc_coord(g, 2, nijk[2]) : 0.0};
-#pragma unroll
-    for (int d = 0; d < D; ++d) x[m][d] = xx[d];
-    rv[m] = g.simplexified ? (m == 0 ? 0 : (1 << (m - 1))) : lvid;
-    if (lv.leaf[0].kind == GECUT_LEAF_NODAL) {
-      const int64_t node = (D == 3) ? ((int64_t)nijk[0] + (int64_t)g.nn[0] * ((int64_t)nijk[1] + (int64_t)g.nn[1] * nijk[2]))
-                                    : ((int64_t)nijk[0] + (int64_t)g.nn[0] * nijk[1]);
-      w[m] = __ldg(lv.nodal[0] + (node - lv.nodal_base));
-    } else {
-      w[m] = gc_eval_leaf(lv.leaf[0], xx, D);
-    }
-  }
-  double J[3][3];
-#pragma unroll
-  for (int a = 0; a < D; ++a)
-#pragma unroll
-    for (int b = 0; b < D; ++b) J[a][b] = __dsub_rn(x[a + 1][b], x[0][b]);
-  double dV;
-  if (D == 2) {
-    dV = __dsub_rn(__dmul_rn(J[0][0], J[1][1]), __dmul_rn(J[0][1], J[1][0]));
-  } else {
-    const double p1 = __dmul_rn(__dmul_rn(J[0][0], J[1][1]), J[2][2]);
-    const double p2 = __dmul_rn(__dmul_rn(J[0][1], J[1][2]), J[2][0]);
-    const double p3 = __dmul_rn(__dmul_rn(J[0][2], J[1][0]), J[2][1]);
-    const double q1 = __dmul_rn(__dmul_rn(J[0][0], J[1][2]), J[2][1]);
-    const double q2 = __dmul_rn(__dmul_rn(J[0][1], J[1][0]), J[2][2]);
-    const double q3 = __dmul_rn(__dmul_rn(J[0][2], J[1][1]), J[2][0]);
-    dV = __dsub_rn(__dadd_rn(__dadd_rn(p1, p2), p3), __dadd_rn(__dadd_rn(q1, q2), q3));
-  }
-  if (dV < 0.0) {  // _ensure_positive_jacobians!: swap the first two vertices
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      const double tx = x[0][d];
-      x[0][d] = x[1][d];
-      x[1][d] = tx;
-    }
-    const double tw = w[0];
-    w[0] = w[1];
-    w[1] = tw;
-    const int tr = rv[0];
-    rv[0] = rv[1];
-    rv[1] = tr;
-  }
 }
 
 template <int D>
@@ -591,57 +530,167 @@ k_cut1_count(const GcGrid g, const GcLeaves lv, const uint8_t* __restrict__ simp
   }
 }
 
-// warp copy of n doubles from shared to global memory with 16-byte accesses; src/dst have the same 16-byte phase
-// (`odd` = the first element sits on an odd 8-byte slot)
+// warp copy of n doubles from the staging buffer to global memory with 32-byte stores (whole sectors).  The caller
+// staged element k at src[k] with src = stage + (global index of element 0 mod 4), so both sides share the 32-byte phase.
 __device__ __forceinline__ void cut1_copy_doubles(double* __restrict__ dst, const double* __restrict__ src, uint32_t n,
-                                                  uint32_t odd, int lane) {
-  const uint32_t start = (odd && n > 0) ? 1u : 0u;
-  if (start && lane == 0) dst[0] = src[0];
-  const uint32_t nvec = (n - start) >> 1;
-  double2* d2 = reinterpret_cast<double2*>(dst + start);
-  const double2* s2 = reinterpret_cast<const double2*>(src + start);
-  for (uint32_t i = lane; i < nvec; i += 32) d2[i] = s2[i];
-  if (((n - start) & 1u) && lane == 0) dst[n - 1] = src[n - 1];
+                                                  uint32_t phase, int lane) {
+  const uint32_t head = min(n, (4u - phase) & 3u);  // elements before the first 32-byte boundary
+  if ((uint32_t)lane < head) dst[lane] = src[lane];
+  const uint32_t nvec = (n - head) >> 2;
+  const double* s4 = src + head;
+  double* d4 = dst + head;
+  for (uint32_t i = lane; i < nvec; i += 32) {
+    const double2 a = *reinterpret_cast<const double2*>(s4 + 4 * i);
+    const double2 b = *reinterpret_cast<const double2*>(s4 + 4 * i + 2);
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(d4 + 4 * i), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+  }
+  const uint32_t tail = (n - head) & 3u;
+  if ((uint32_t)lane < tail) dst[head + 4 * nvec + lane] = src[head + 4 * nvec + lane];
 }
 
+// edge e of the simplex in Gridap order: TRI [1,2],[1,3],[2,3]; TET [1,2],[1,3],[2,3],[1,4],[2,4],[3,4] (0-based ends)
 template <int D>
-__global__ void __launch_bounds__(CUT1_BLOCK, 5)
+__device__ __forceinline__ constexpr int cut1_edge_a(int e) {
+  return (D == 3) ? (e == 0 ? 0 : e == 1 ? 0 : e == 2 ? 1 : e == 3 ? 0 : e == 4 ? 1 : 2) : (e == 0 ? 0 : e == 1 ? 0 : 1);
+}
+template <int D>
+__device__ __forceinline__ constexpr int cut1_edge_b(int e) {
+  return (D == 3) ? (e == 0 ? 1 : e == 1 ? 2 : e == 2 ? 2 : 3) : (e == 0 ? 1 : 2);
+}
+
+// Fill of the single-level-set layout.  One warp = one tile of 32 consecutive stage-0 simplices, four phases:
+//   A  lane = simplex : stage-0 set-up (vertices, level-set values), case, warp scan of the three counters, edge
+//                       coefficients, physical points into the staging buffer, one 16-byte record per simplex
+//   X  warp           : point_to_coords of the tile leaves the staging buffer with 32-byte stores
+//   C  lane = subcell : connectivity row, bg cell, IN/OUT state and measure, written directly (lane-contiguous)
+//   D  lane = subfacet: connectivity row, unit normal, bg cell, measure
+//   R  lane = simplex : reference points into the staging buffer (an edge point is 0, 1, c or 1-c per direction),
+//                       then the same warp copy
+// Phases C and D have no divergent trip counts: every lane owns one output entity and finds its simplex through a
+// byte map written in phase A.
+template <int D, bool SX>
+__global__ void __launch_bounds__(CUT1_BLOCK, CUT1_MINB)
 k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
             const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
             const int32_t* __restrict__ cutcells, int64_t nsimp, const uint32_t* __restrict__ tile_cells,
             const uint32_t* __restrict__ tile_points, const uint32_t* __restrict__ tile_facets, GcLayout lay,
             uint32_t* __restrict__ sc_ptr) {
+  constexpr int NT0 = SX ? 1 : (D == 3 ? 6 : 2);   // stage-0 simplices per bg cell
+  constexpr int CPC = SX ? (D == 3 ? 6 : 2) : 1;   // bg cells per n-cube
   constexpr int NPC = WalkCfg<D>::NPC;
   constexpr int NSUB = (D == 3) ? 6 : 3, NFAC = (D == 3) ? 2 : 1, NE = (D == 3) ? 6 : 3;
-  // one staging buffer, used in turn for point_to_coords, point_to_rcoords and the integer arrays
-  extern __shared__ double stage_all[];  // per warp: [CUT1_TILE*NPC][D] doubles
+  constexpr int STG = CUT1_TILE * NPC * D + 4;     // staged doubles per warp (+ phase pad)
+  constexpr int WBYTES = cut1_warp_bytes<D>();
+  extern __shared__ __align__(32) unsigned char fill_smem[];
   __shared__ GcSimplexTable s_tab;
+  __shared__ uint8_t s_swap[8];
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(tables + (D - 1));
     uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
     for (int i = threadIdx.x; i < (int)(sizeof(GcSimplexTable) / 4); i += CUT1_BLOCK) dst[i] = src[i];
   }
+  const uint8_t* vtab = (SX ? simp_raw : simp_pos) + (D - 2) * 24;  // rows of 4 local vertex ids of the n-cube
+  if (threadIdx.x < (SX ? CPC : NT0)) {
+    // _ensure_positive_jacobians! (CutTriangulations.jl:512-514): on a Cartesian grid the sign of the stage-0 Jacobian
+    // depends on the simplex type only (every entry of J is 0 or +-(one grid step)), so it is decided once per block
+    double x[D + 1][D];
+#pragma unroll
+    for (int m = 0; m <= D; ++m) {
+      const int lvid = vtab[threadIdx.x * 4 + m];
+#pragma unroll
+      for (int d = 0; d < D; ++d) x[m][d] = gc_coord(g, d, (d == D - 1 ? g.k0 : 0) + ((lvid >> d) & 1));
+    }
+    double J[3][3];
+#pragma unroll
+    for (int a = 0; a < D; ++a)
+#pragma unroll
+      for (int b = 0; b < D; ++b) J[a][b] = __dsub_rn(x[a + 1][b], x[0][b]);
+    double dV;
+    if (D == 2) {
+      dV = __dsub_rn(__dmul_rn(J[0][0], J[1][1]), __dmul_rn(J[0][1], J[1][0]));
+    } else {
+      const double p1 = __dmul_rn(__dmul_rn(J[0][0], J[1][1]), J[2][2]);
+      const double p2 = __dmul_rn(__dmul_rn(J[0][1], J[1][2]), J[2][0]);
+      const double p3 = __dmul_rn(__dmul_rn(J[0][2], J[1][0]), J[2][1]);
+      const double q1 = __dmul_rn(__dmul_rn(J[0][0], J[1][2]), J[2][1]);
+      const double q2 = __dmul_rn(__dmul_rn(J[0][1], J[1][0]), J[2][2]);
+      const double q3 = __dmul_rn(__dmul_rn(J[0][2], J[1][1]), J[2][0]);
+      dV = __dsub_rn(__dadd_rn(__dadd_rn(p1, p2), p3), __dadd_rn(__dadd_rn(q1, q2), q3));
+    }
+    s_swap[threadIdx.x] = dV < 0.0 ? 1 : 0;
+  }
   __syncthreads();
   const GcSimplexTable& TC = s_tab;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double* stage = stage_all + (size_t)wid * (CUT1_TILE * NPC * D + 2);
+  unsigned char* wbase = fill_smem + (size_t)wid * WBYTES;
+  double* stage = reinterpret_cast<double*>(wbase);
+  uint4* rec = reinterpret_cast<uint4*>(wbase + sizeof(double) * STG);
+  uint8_t* own_c = reinterpret_cast<uint8_t*>(rec + CUT1_TILE);
+  uint8_t* own_f = own_c + CUT1_TILE * NSUB;
   const int64_t tile = (int64_t)blockIdx.x * (CUT1_BLOCK / CUT1_TILE) + wid;
+  if (tile * CUT1_TILE >= nsimp) return;  // whole warp beyond the end (no block barrier below)
   const int64_t s = tile * CUT1_TILE + lane;
   const bool valid = s < nsimp;
+
+  // ======================================== phase A: lane = stage-0 simplex
   double X[D + 1][D], W[D + 1];
-  int rv[D + 1];
+  uint32_t rv4 = 0u;  // byte m: reference coordinates of vertex m, one bit per direction
   int c = 0, nsub = 0, np = 0, nfac = 0;
   int32_t bgcell1 = 0;
+  int64_t kcut = 0;
+  int t0 = 0;
 #pragma unroll
   for (int i = 0; i <= D; ++i) {
     W[i] = 0.0;
-    rv[i] = 0;
 #pragma unroll
     for (int d = 0; d < D; ++d) X[i][d] = 0.0;
   }
   if (valid) {
-    bgcell1 = cutcells[s / g.nt0];
-    setup_stage0_l1<D>(g, lv, (int64_t)bgcell1 - 1, (int)(s % g.nt0), simp_raw, simp_pos, X, W, rv);
+    kcut = s / NT0;
+    t0 = (int)(s - kcut * NT0);
+    bgcell1 = cutcells[kcut];
+    // slab-local cell ids fit in 32 bits (checked at cut time)
+    const uint32_t cell = (uint32_t)(bgcell1 - 1);
+    const uint32_t cube = cell / (uint32_t)CPC;
+    const int row_id = SX ? (int)(cell - cube * (uint32_t)CPC) : t0;  // row of the vertex table
+    int ijk[3];
+    const uint32_t row = cube / (uint32_t)g.n[0];
+    ijk[0] = (int)(cube - row * (uint32_t)g.n[0]);
+    if (D == 3) {
+      const uint32_t lay3 = row / (uint32_t)g.n[1];
+      ijk[1] = (int)(row - lay3 * (uint32_t)g.n[1]);
+      ijk[2] = (int)lay3 + g.k0;
+    } else {
+      ijk[1] = (int)row + g.k0;
+      ijk[2] = 0;
+    }
+    uint32_t lv4 = *reinterpret_cast<const uint32_t*>(vtab + row_id * 4);
+    rv4 = SX ? 0x04020100u : lv4;  // simplex cells: origin + unit axes; n-cube cells: the cube vertex itself
+    if (s_swap[row_id]) {          // swap the first two vertices
+      lv4 = __byte_perm(lv4, 0u, 0x3201);
+      rv4 = __byte_perm(rv4, 0u, 0x3201);
+    }
+    const double RR = __dmul_rn(lv.leaf[0].R, lv.leaf[0].R);
+#pragma unroll
+    for (int m = 0; m <= D; ++m) {
+      const int lvid = (lv4 >> (8 * m)) & 0xFFu;
+      const int nijk[3] = {ijk[0] + (lvid & 1), ijk[1] + ((lvid >> 1) & 1), ijk[2] + ((lvid >> 2) & 1)};
+      double xx[3] = {gc_coord(g, 0, nijk[0]), gc_coord(g, 1, nijk[1]), D == 3 ? gc_coord(g, 2, nijk[2]) : 0.0};
+#pragma unroll
+      for (int d = 0; d < D; ++d) X[m][d] = xx[d];
+      const int kind = lv.leaf[0].kind;
+      if (kind == GECUT_LEAF_NODAL) {
+        const int64_t node = (D == 3) ? ((int64_t)nijk[0] + (int64_t)g.nn[0] * ((int64_t)nijk[1] + (int64_t)g.nn[1] * nijk[2]))
+                                      : ((int64_t)nijk[0] + (int64_t)g.nn[0] * nijk[1]);
+        W[m] = __ldg(lv.nodal[0] + (node - lv.nodal_base));
+      } else if (kind == GECUT_LEAF_SPHERE) {  // gc_eval_leaf with R*R hoisted
+        double w[3] = {__dsub_rn(xx[0], lv.leaf[0].x0[0]), __dsub_rn(xx[1], lv.leaf[0].x0[1]),
+                       D == 3 ? __dsub_rn(xx[2], lv.leaf[0].x0[2]) : 0.0};
+        W[m] = __dsub_rn(gc_dot3(w, w, D), RR);
+      } else {
+        W[m] = gc_eval_leaf(lv.leaf[0], xx, D);
+      }
+    }
 #pragma unroll
     for (int i = 0; i <= D; ++i)
       if (W[i] > 0.0) c |= 1 << i;
@@ -653,35 +702,31 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
   const uint32_t excl = cut1_warp_scan(valid ? cut1_pack(nsub, np, nfac) : 0u, &total);
   const uint32_t lc = excl >> 21, lp = (excl >> 10) & 0x7FFu, lf = excl & 0x3FFu;    // tile-local offsets
   const uint32_t tc = total >> 21, tp = (total >> 10) & 0x7FFu, tf = total & 0x3FFu;  // tile totals
-  if (tile * CUT1_TILE >= nsimp) return;  // whole warp beyond the end
   const uint32_t gc = tile_cells[tile], gp = tile_points[tile], gf = tile_facets[tile];  // tile bases
-  // staged doubles start at `pad` so that shared and global memory have the same 16-byte phase (vector copy-out)
-  const uint32_t pad = (uint32_t)(((uint64_t)gp * D) & 1u);
-  double* stage_p = stage + pad;
-  // Gridap edge order of the simplex: TRI [1,2],[1,3],[2,3]; TET [1,2],[1,3],[2,3],[1,4],[2,4],[3,4]
+  // staged doubles start at `phase` so that shared and global memory have the same 32-byte phase (vector copy-out)
+  const uint32_t phase = (uint32_t)(((uint64_t)gp * D) & 3u);
+  double* stage_p = stage + phase;
   double coeff[NE];
   const bool iscut = valid && TC.inoutcut[c] == GC_CUT;
 #pragma unroll
   for (int e = 0; e < NE; ++e) {
-    const int a = (D == 3) ? (e == 0 ? 0 : e == 1 ? 0 : e == 2 ? 1 : e == 3 ? 0 : e == 4 ? 1 : 2) : (e == 0 ? 0 : e == 1 ? 0 : 1);
-    const int b = (D == 3) ? (e == 0 ? 1 : e == 1 ? 2 : e == 2 ? 2 : 3) : (e == 0 ? 1 : 2);
-    const double v1 = W[a], v2 = W[b];
+    const double v1 = W[cut1_edge_a<D>(e)], v2 = W[cut1_edge_b<D>(e)];
     coeff[e] = -1.0;  // edge not cut
     if (iscut && ((v1 > 0.0) != (v2 > 0.0))) {
       const double w1 = fabs(v1), w2 = fabs(v2);
       coeff[e] = __ddiv_rn(w1, __dadd_rn(w1, w2));  // (CutTriangulations.jl:213-215)
     }
   }
-  // ---- phase 1: physical coordinates: vertex copies, then one point per cut edge in edge order (:199-219)
   if (valid) {
-    if (s % g.nt0 == 0) {  // first subcell / first point of this cut cell
-      sc_ptr[2 * (s / g.nt0)] = gc + lc;
-      sc_ptr[2 * (s / g.nt0) + 1] = gp + lp;
+    if (t0 == 0) {  // first subcell / first point of this cut cell
+      sc_ptr[2 * kcut] = gc + lc;
+      sc_ptr[2 * kcut + 1] = gp + lp;
     }
     if (s == nsimp - 1) {
-      sc_ptr[2 * (s / g.nt0) + 2] = gc + lc + nsub;
-      sc_ptr[2 * (s / g.nt0) + 3] = gp + lp + np;
+      sc_ptr[2 * kcut + 2] = gc + lc + nsub;
+      sc_ptr[2 * kcut + 3] = gp + lp + np;
     }
+    // physical coordinates: vertex copies, then one point per cut edge in edge order (:199-219)
 #pragma unroll
     for (int i = 0; i <= D; ++i)
 #pragma unroll
@@ -689,113 +734,100 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
     int q = D + 1;
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
-      const int a = (D == 3) ? (e == 0 ? 0 : e == 1 ? 0 : e == 2 ? 1 : e == 3 ? 0 : e == 4 ? 1 : 2) : (e == 0 ? 0 : e == 1 ? 0 : 1);
-      const int b = (D == 3) ? (e == 0 ? 1 : e == 1 ? 2 : e == 2 ? 2 : 3) : (e == 0 ? 1 : 2);
       if (coeff[e] >= 0.0) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) stage_p[(lp + q) * D + d] = gc_lerp(X[a][d], X[b][d], coeff[e]);
+        for (int d = 0; d < D; ++d)
+          stage_p[(lp + q) * D + d] = gc_lerp(X[cut1_edge_a<D>(e)][d], X[cut1_edge_b<D>(e)][d], coeff[e]);
         q++;
       }
     }
-    // facet normals and measures, subcell measures: from this thread's own staged points, written directly
-    for (int f = 0; f < nfac; ++f) {
-      const uint8_t* fp = TC.fac_pts[c][f];
-      double nrm[3];
-      unit_normal<D>(&stage_p[(lp + fp[0]) * D], &stage_p[(lp + fp[1]) * D], &stage_p[(lp + fp[D - 1]) * D],
-                     (double)TC.fac_orient[c][f], nrm);
-      double pf[D][3];
+    rec[lane] = make_uint4((uint32_t)c | (lp << 4) | (lf << 16), lc, gp + lp + 1u, (uint32_t)bgcell1);
 #pragma unroll
-      for (int v = 0; v < D; ++v)
+    for (int j = 0; j < NSUB; ++j)
+      if (j < nsub) own_c[lc + j] = (uint8_t)lane;
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-          pf[v][d] = stage_p[(lp + fp[v]) * D + d];
-          if (v == 0) lay.sf_N[(int64_t)(gf + lf + f) * D + d] = nrm[d];
-        }
-      lay.sf_meas[gf + lf + f] = integrate_one<D - 1>(simplex_meas<D, D - 1>(pf));
-    }
-    for (int j = 0; j < nsub; ++j) {
-      double pc[D + 1][3];
-#pragma unroll
-      for (int v = 0; v <= D; ++v)
-#pragma unroll
-        for (int d = 0; d < D; ++d) pc[v][d] = stage_p[(lp + TC.sub_pts[c][j][v]) * D + d];
-      lay.sc_meas[gc + lc + j] = integrate_one<D>(simplex_meas<D, D>(pc));
-    }
+    for (int f = 0; f < NFAC; ++f)
+      if (f < nfac) own_f[lf + f] = (uint8_t)lane;
   }
   __syncwarp();
-  cut1_copy_doubles(lay.sc_X + (int64_t)gp * D, stage_p, tp * D, pad, lane);
+  // ======================================== phase X: point_to_coords of the tile
+  cut1_copy_doubles(lay.sc_X + (int64_t)gp * D, stage_p, tp * D, phase, lane);
+  // ======================================== phase C: lane = subcell
+  for (uint32_t idx = lane; idx < tc; idx += CUT1_TILE) {
+    const uint4 r = rec[own_c[idx]];
+    const int cc = r.x & 15u;
+    const uint32_t plo = (r.x >> 4) & 0xFFFu;
+    const int j = (int)(idx - r.y);
+    const uint32_t pts = *reinterpret_cast<const uint32_t*>(TC.sub_pts[cc][j]);  // D+1 local point ids
+    double pc[D + 1][3];
+#pragma unroll
+    for (int v = 0; v <= D; ++v) {
+      const double* pv = stage_p + (plo + ((pts >> (8 * v)) & 0xFFu)) * D;
+#pragma unroll
+      for (int d = 0; d < D; ++d) pc[v][d] = pv[d];
+    }
+    const int64_t o = (int64_t)gc + idx;
+    if (D == 3) {
+      reinterpret_cast<int4*>(lay.sc_c2p)[o] =
+          make_int4((int)(r.z + (pts & 0xFFu)), (int)(r.z + ((pts >> 8) & 0xFFu)), (int)(r.z + ((pts >> 16) & 0xFFu)),
+                    (int)(r.z + (pts >> 24)));
+    } else {
+#pragma unroll
+      for (int v = 0; v <= D; ++v) lay.sc_c2p[o * (D + 1) + v] = (int)(r.z + ((pts >> (8 * v)) & 0xFFu));
+    }
+    lay.sc_c2bg[o] = (int32_t)r.w;
+    lay.sc_state[o] = TC.sub_inout[cc][j];
+    lay.sc_meas[o] = integrate_one<D>(simplex_meas<D, D>(pc));
+  }
+  // ======================================== phase D: lane = subfacet
+  for (uint32_t idx = lane; idx < tf; idx += CUT1_TILE) {
+    const uint4 r = rec[own_f[idx]];
+    const int cc = r.x & 15u;
+    const uint32_t plo = (r.x >> 4) & 0xFFFu;
+    const int f = (int)(idx - (r.x >> 16));
+    const uint8_t* fp = TC.fac_pts[cc][f];
+    double pf[D][3];
+#pragma unroll
+    for (int v = 0; v < D; ++v)
+#pragma unroll
+      for (int d = 0; d < D; ++d) pf[v][d] = stage_p[(plo + fp[v]) * D + d];
+    double nrm[3];
+    unit_normal<D>(pf[0], pf[1], pf[D - 1], (double)TC.fac_orient[cc][f], nrm);
+    const int64_t o = (int64_t)gf + idx;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      lay.sf_c2p[o * D + d] = (int)(r.z + fp[d]);
+      lay.sf_N[o * D + d] = nrm[d];
+    }
+    lay.sf_c2bg[o] = (int32_t)r.w;
+    lay.sf_state[o] = (int8_t)GECUT_INTERFACE;
+    lay.sf_meas[o] = integrate_one<D - 1>(simplex_meas<D, D - 1>(pf));
+  }
   __syncwarp();
-  // ---- phase 2: reference coordinates
+  // ======================================== phase R: reference coordinates (lane = simplex), same staging buffer
   if (valid) {
 #pragma unroll
     for (int i = 0; i <= D; ++i)
 #pragma unroll
-      for (int d = 0; d < D; ++d) stage_p[(lp + i) * D + d] = (double)((rv[i] >> d) & 1);
+      for (int d = 0; d < D; ++d) stage_p[(lp + i) * D + d] = (double)((rv4 >> (8 * i + d)) & 1u);
     int q = D + 1;
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
-      const int a = (D == 3) ? (e == 0 ? 0 : e == 1 ? 0 : e == 2 ? 1 : e == 3 ? 0 : e == 4 ? 1 : 2) : (e == 0 ? 0 : e == 1 ? 0 : 1);
-      const int b = (D == 3) ? (e == 0 ? 1 : e == 1 ? 2 : e == 2 ? 2 : 3) : (e == 0 ? 1 : 2);
       if (coeff[e] >= 0.0) {
+        // gc_lerp(ra, rb, c) with ra, rb in {0, 1}: ra (equal ends), c (0 -> 1) or 1 - c (1 -> 0), bit for bit
+        const double cf = coeff[e], omc = __dsub_rn(1.0, cf);
+        const uint32_t ra = (rv4 >> (8 * cut1_edge_a<D>(e))) & 0xFFu, rb = (rv4 >> (8 * cut1_edge_b<D>(e))) & 0xFFu;
 #pragma unroll
-        for (int d = 0; d < D; ++d)
-          stage_p[(lp + q) * D + d] = gc_lerp((double)((rv[a] >> d) & 1), (double)((rv[b] >> d) & 1), coeff[e]);
+        for (int d = 0; d < D; ++d) {
+          const uint32_t a = (ra >> d) & 1u, b = (rb >> d) & 1u;
+          stage_p[(lp + q) * D + d] = a == b ? (double)a : (a ? omc : cf);
+        }
         q++;
       }
     }
   }
   __syncwarp();
-  cut1_copy_doubles(lay.sc_R + (int64_t)gp * D, stage_p, tp * D, pad, lane);
-  __syncwarp();
-  // ---- phase 3: integer arrays, staged in the same shared memory
-  int32_t* st_c2p = reinterpret_cast<int32_t*>(stage);           // [CUT1_TILE*NSUB][D+1]
-  int32_t* st_c2bg = st_c2p + CUT1_TILE * NSUB * (D + 1);        // [CUT1_TILE*NSUB]
-  int32_t* st_f2p = st_c2bg + CUT1_TILE * NSUB;                  // [CUT1_TILE*NFAC][D]
-  int32_t* st_f2bg = st_f2p + CUT1_TILE * NFAC * D;              // [CUT1_TILE*NFAC]
-  int8_t* st_state = reinterpret_cast<int8_t*>(st_f2bg + CUT1_TILE * NFAC);  // [CUT1_TILE*NSUB]
-  if (valid) {
-    const int32_t pbase = (int32_t)(gp + lp) + 1;  // 1-based id of the first point of this simplex' block
-    for (int j = 0; j < nsub; ++j) {
-#pragma unroll
-      for (int i = 0; i <= D; ++i) st_c2p[(lc + j) * (D + 1) + i] = pbase + TC.sub_pts[c][j][i];
-      st_c2bg[lc + j] = bgcell1;
-      st_state[lc + j] = TC.sub_inout[c][j];
-    }
-    for (int f = 0; f < nfac; ++f) {
-#pragma unroll
-      for (int i = 0; i < D; ++i) st_f2p[(lf + f) * D + i] = pbase + TC.fac_pts[c][f][i];
-      st_f2bg[lf + f] = bgcell1;
-    }
-  }
-  __syncwarp();
-  {
-    int32_t* g_c2p = lay.sc_c2p + (int64_t)gc * (D + 1);
-    if (D == 3) {  // rows of 4 ids: 16-byte aligned on both sides
-      for (uint32_t i = lane; i < tc; i += CUT1_TILE)
-        reinterpret_cast<int4*>(g_c2p)[i] = reinterpret_cast<const int4*>(st_c2p)[i];
-    } else {
-      for (uint32_t i = lane; i < tc * (D + 1); i += CUT1_TILE) g_c2p[i] = st_c2p[i];
-    }
-    int32_t* g_c2bg = lay.sc_c2bg + gc;
-    int8_t* g_state = lay.sc_state + gc;
-    for (uint32_t i = lane; i < tc; i += CUT1_TILE) {
-      g_c2bg[i] = st_c2bg[i];
-      g_state[i] = st_state[i];
-    }
-    int32_t* g_f2p = lay.sf_c2p + (int64_t)gf * D;
-    for (uint32_t i = lane; i < tf * D; i += CUT1_TILE) g_f2p[i] = st_f2p[i];
-    int32_t* g_f2bg = lay.sf_c2bg + gf;
-    int8_t* g_fstate = lay.sf_state + gf;
-    for (uint32_t i = lane; i < tf; i += CUT1_TILE) {
-      g_f2bg[i] = st_f2bg[i];
-      g_fstate[i] = (int8_t)GECUT_INTERFACE;
-    }
-  }
-}
-
-template <int D>
-size_t cut1_fill_smem() {
-  return sizeof(double) * (CUT1_BLOCK / CUT1_TILE) * (CUT1_TILE * WalkCfg<D>::NPC * D + 2);  // per warp, + phase pad
+  cut1_copy_doubles(lay.sc_R + (int64_t)gp * D, stage_p, tp * D, phase, lane);
 }
 
 __global__ void k_extract_sc_ptr(const uint32_t* __restrict__ cell_offs, const uint32_t* __restrict__ point_offs, int nt0,
@@ -909,14 +941,19 @@ static int gc_cut_cells_l1(gecut_ctx* ctx, gecut_result* res) {
   res->sf_points_alias = true;
   sz.subfacet_points_alias = 1;
   GC_CHECK(gc_malloc(ctx, (void**)&res->cut_sc_ptr, sizeof(uint32_t) * 2 * (ncut + 1)));
-  if (D == 2) {
-    const size_t smem = cut1_fill_smem<2>();
-    GC_LAUNCH(ctx, "k_cut1_fill", k_cut1_fill<2><<<(unsigned)gc_div_up(ntiles, CUT1_BLOCK / CUT1_TILE), CUT1_BLOCK, smem, ctx->stream>>>(
-        g, res->leaves, ctx->d_tables, ctx->d_simplexify_raw, ctx->d_simplexify_pos, lay.cutcells, nsimp, t_cells, t_points, t_facets, lay, res->cut_sc_ptr));
-  } else {
-    const size_t smem = cut1_fill_smem<3>();
-    GC_LAUNCH(ctx, "k_cut1_fill", k_cut1_fill<3><<<(unsigned)gc_div_up(ntiles, CUT1_BLOCK / CUT1_TILE), CUT1_BLOCK, smem, ctx->stream>>>(
-        g, res->leaves, ctx->d_tables, ctx->d_simplexify_raw, ctx->d_simplexify_pos, lay.cutcells, nsimp, t_cells, t_points, t_facets, lay, res->cut_sc_ptr));
+  {
+    const unsigned nbf = (unsigned)gc_div_up(ntiles, CUT1_BLOCK / CUT1_TILE);
+#define GC_FILL1(DD, SXV)                                                                                              \
+  GC_LAUNCH(ctx, "k_cut1_fill",                                                                                        \
+            k_cut1_fill<DD, SXV><<<nbf, CUT1_BLOCK, (size_t)cut1_warp_bytes<DD>() * (CUT1_BLOCK / CUT1_TILE), ctx->stream>>>( \
+                g, res->leaves, ctx->d_tables, ctx->d_simplexify_raw, ctx->d_simplexify_pos, lay.cutcells, nsimp, t_cells,   \
+                t_points, t_facets, lay, res->cut_sc_ptr))
+    if (D == 2) {
+      if (g.simplexified) GC_FILL1(2, true); else GC_FILL1(2, false);
+    } else {
+      if (g.simplexified) GC_FILL1(3, true); else GC_FILL1(3, false);
+    }
+#undef GC_FILL1
   }
   int st = gc_launch_check(ctx, "k_cut1_fill");
   gc_free(ctx, tiles);
