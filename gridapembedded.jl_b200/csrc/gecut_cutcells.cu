@@ -15,6 +15,8 @@
 // (reference: count_sub_triangulation_with_boundary :238-251), an exclusive scan of the counters over the simplices
 // (stable: preserves the reference ordering), and a filling walk that writes the final layout only.  Node values are
 // recomputed from the leaf records (bit-identical to the classification pass) or gathered from the NODAL vectors.
+#include <cstdlib>
+
 #include "gecut_internal.cuh"
 
 namespace {
@@ -423,11 +425,12 @@ constexpr int CUT1_BLOCK = 128;  // threads per block of the fill kernel (4 inde
 #define CUT1_MINB 5
 #endif
 
-// shared memory of one warp of the fill kernel: staged points (+ phase pad), 16-byte records, owner maps; 32-byte multiple
+// shared memory of one warp of the fill kernel: staged points (+ phase pad), cut-edge coefficients, 16-byte records,
+// owner maps; 32-byte multiple
 template <int D>
 __host__ __device__ constexpr int cut1_warp_bytes() {
-  return (((CUT1_TILE * ((D == 3) ? 8 : 5) * D + 4) * 8 + CUT1_TILE * 16 + CUT1_TILE * ((D == 3) ? 6 : 3) +
-           CUT1_TILE * ((D == 3) ? 2 : 1)) + 31) / 32 * 32;
+  return (((CUT1_TILE * ((D == 3) ? 8 : 5) * D + 4) * 8 + CUT1_TILE * ((D == 3) ? 4 : 2) * 8 + CUT1_TILE * 16 +
+           CUT1_TILE * ((D == 3) ? 6 : 3) + CUT1_TILE * ((D == 3) ? 2 : 1)) + 31) / 32 * 32;
 }
 
 __device__ __forceinline__ uint32_t cut1_pack(int ncell, int npt, int nfac) {
@@ -530,22 +533,19 @@ k_cut1_count(const GcGrid g, const GcLeaves lv, const uint8_t* __restrict__ simp
   }
 }
 
-// warp copy of n doubles from the staging buffer to global memory with 32-byte stores (whole sectors).  The caller
-// staged element k at src[k] with src = stage + (global index of element 0 mod 4), so both sides share the 32-byte phase.
+// warp copy of n doubles from the staging buffer to global memory: every instruction moves 512 contiguous bytes
+// (16 per lane), which is conflict-free on the shared-memory side and whole sectors on the global side.  The caller
+// staged element k at src[k] with src = stage + (global index of element 0 mod 4), so both sides share the 16-byte phase.
 __device__ __forceinline__ void cut1_copy_doubles(double* __restrict__ dst, const double* __restrict__ src, uint32_t n,
                                                   uint32_t phase, int lane) {
-  const uint32_t head = min(n, (4u - phase) & 3u);  // elements before the first 32-byte boundary
-  if ((uint32_t)lane < head) dst[lane] = src[lane];
-  const uint32_t nvec = (n - head) >> 2;
-  const double* s4 = src + head;
-  double* d4 = dst + head;
-  for (uint32_t i = lane; i < nvec; i += 32) {
-    const double2 a = *reinterpret_cast<const double2*>(s4 + 4 * i);
-    const double2 b = *reinterpret_cast<const double2*>(s4 + 4 * i + 2);
-    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(d4 + 4 * i), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
-  }
-  const uint32_t tail = (n - head) & 3u;
-  if ((uint32_t)lane < tail) dst[head + 4 * nvec + lane] = src[head + 4 * nvec + lane];
+  const uint32_t head = min(n, phase & 1u);  // element before the first 16-byte boundary
+  if (head && lane == 0) dst[0] = src[0];
+  const uint32_t nvec = (n - head) >> 1;
+  const double2* s2 = reinterpret_cast<const double2*>(src + head);
+  double2* d2 = reinterpret_cast<double2*>(dst + head);
+#pragma unroll 2
+  for (uint32_t i = lane; i < nvec; i += 32) d2[i] = s2[i];
+  if (((n - head) & 1u) && lane == 0) dst[n - 1] = src[n - 1];
 }
 
 // edge e of the simplex in Gridap order: TRI [1,2],[1,3],[2,3]; TET [1,2],[1,3],[2,3],[1,4],[2,4],[3,4] (0-based ends)
@@ -568,8 +568,8 @@ __device__ __forceinline__ constexpr int cut1_edge_b(int e) {
 //                       then the same warp copy
 // Phases C and D have no divergent trip counts: every lane owns one output entity and finds its simplex through a
 // byte map written in phase A.
-template <int D, bool SX>
-__global__ void __launch_bounds__(CUT1_BLOCK, CUT1_MINB)
+template <int D, bool SX, int MB>
+__global__ void __launch_bounds__(CUT1_BLOCK, MB)
 k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
             const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
             const int32_t* __restrict__ cutcells, int64_t nsimp, const uint32_t* __restrict__ tile_cells,
@@ -624,7 +624,9 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   unsigned char* wbase = fill_smem + (size_t)wid * WBYTES;
   double* stage = reinterpret_cast<double*>(wbase);
-  uint4* rec = reinterpret_cast<uint4*>(wbase + sizeof(double) * STG);
+  constexpr int NCE = (D == 3) ? 4 : 2;  // a cut simplex has at most NCE cut edges
+  double* cstash = stage + STG;          // [NCE][32] coefficients of the cut edges, parked here between phases A and R
+  uint4* rec = reinterpret_cast<uint4*>(wbase + sizeof(double) * (STG + NCE * CUT1_TILE));
   uint8_t* own_c = reinterpret_cast<uint8_t*>(rec + CUT1_TILE);
   uint8_t* own_f = own_c + CUT1_TILE * NSUB;
   const int64_t tile = (int64_t)blockIdx.x * (CUT1_BLOCK / CUT1_TILE) + wid;
@@ -738,6 +740,7 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
 #pragma unroll
         for (int d = 0; d < D; ++d)
           stage_p[(lp + q) * D + d] = gc_lerp(X[cut1_edge_a<D>(e)][d], X[cut1_edge_b<D>(e)][d], coeff[e]);
+        cstash[(q - (D + 1)) * CUT1_TILE + lane] = coeff[e];
         q++;
       }
     }
@@ -811,11 +814,12 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
 #pragma unroll
       for (int d = 0; d < D; ++d) stage_p[(lp + i) * D + d] = (double)((rv4 >> (8 * i + d)) & 1u);
     int q = D + 1;
+    const bool iscut_r = TC.inoutcut[c] == GC_CUT;
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
-      if (coeff[e] >= 0.0) {
+      if (iscut_r && (((c >> cut1_edge_a<D>(e)) ^ (c >> cut1_edge_b<D>(e))) & 1)) {  // edge e is cut
         // gc_lerp(ra, rb, c) with ra, rb in {0, 1}: ra (equal ends), c (0 -> 1) or 1 - c (1 -> 0), bit for bit
-        const double cf = coeff[e], omc = __dsub_rn(1.0, cf);
+        const double cf = cstash[(q - (D + 1)) * CUT1_TILE + lane], omc = __dsub_rn(1.0, cf);
         const uint32_t ra = (rv4 >> (8 * cut1_edge_a<D>(e))) & 0xFFu, rb = (rv4 >> (8 * cut1_edge_b<D>(e))) & 0xFFu;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
@@ -943,16 +947,18 @@ static int gc_cut_cells_l1(gecut_ctx* ctx, gecut_result* res) {
   GC_CHECK(gc_malloc(ctx, (void**)&res->cut_sc_ptr, sizeof(uint32_t) * 2 * (ncut + 1)));
   {
     const unsigned nbf = (unsigned)gc_div_up(ntiles, CUT1_BLOCK / CUT1_TILE);
-#define GC_FILL1(DD, SXV)                                                                                              \
+#define GC_FILL1(DD, SXV, MB)                                                                                          \
   GC_LAUNCH(ctx, "k_cut1_fill",                                                                                        \
-            k_cut1_fill<DD, SXV><<<nbf, CUT1_BLOCK, (size_t)cut1_warp_bytes<DD>() * (CUT1_BLOCK / CUT1_TILE), ctx->stream>>>( \
+            k_cut1_fill<DD, SXV, MB><<<nbf, CUT1_BLOCK, (size_t)cut1_warp_bytes<DD>() * (CUT1_BLOCK / CUT1_TILE), ctx->stream>>>( \
                 g, res->leaves, ctx->d_tables, ctx->d_simplexify_raw, ctx->d_simplexify_pos, lay.cutcells, nsimp, t_cells,   \
                 t_points, t_facets, lay, res->cut_sc_ptr))
+#define GC_FILL2(DD, SXV) GC_FILL1(DD, SXV, CUT1_MINB)
     if (D == 2) {
-      if (g.simplexified) GC_FILL1(2, true); else GC_FILL1(2, false);
+      if (g.simplexified) GC_FILL2(2, true); else GC_FILL2(2, false);
     } else {
-      if (g.simplexified) GC_FILL1(3, true); else GC_FILL1(3, false);
+      if (g.simplexified) GC_FILL2(3, true); else GC_FILL2(3, false);
     }
+#undef GC_FILL2
 #undef GC_FILL1
   }
   int st = gc_launch_check(ctx, "k_cut1_fill");
