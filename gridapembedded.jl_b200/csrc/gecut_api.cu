@@ -321,6 +321,50 @@ int make_program(gecut_ctx* ctx, const int32_t* program, int len, int L, GcProgr
   }
   if (depth != 1) goto bad;
   p->len = len;
+  p->lut = nullptr;
+  p->nused = 0;
+  if (len >= 3) {
+    // truth table over the level sets the program uses (EmbeddedDiscretizations.jl:136-177 evaluated 3^nused times, once)
+    bool seen[GC_LMAX] = {false};
+    for (int i = 0; i < len; ++i)
+      if (program[i] >= 0) seen[program[i]] = true;
+    int nused = 0;
+    for (int ls = 0; ls < L; ++ls)
+      if (seen[ls]) {
+        if (nused < GC_LUT_MAXUSED) p->used[nused] = (int8_t)ls;
+        nused++;
+      }
+    if (nused <= GC_LUT_MAXUSED) {
+      p->nused = nused;
+      const std::string key(reinterpret_cast<const char*>(p->tok), (size_t)len);
+      auto it = ctx->lut_cache.find(key);
+      if (it == ctx->lut_cache.end()) {
+        size_t n = 1;
+        for (int k = 0; k < nused; ++k) n *= 3;
+        std::vector<int8_t> tab(n);
+        int8_t vals[GC_LMAX] = {0};
+        for (size_t idx = 0; idx < n; ++idx) {
+          size_t r = idx;
+          for (int k = 0; k < nused; ++k) {
+            vals[p->used[k]] = (int8_t)((int)(r % 3) - 1);
+            r /= 3;
+          }
+          tab[idx] = (int8_t)gc_eval_inoutcut_vals(*p, vals);
+        }
+        int8_t* d = nullptr;
+        if (cudaMalloc((void**)&d, n) != cudaSuccess) {
+          ctx->err = "out of device memory (truth table)";
+          return GECUT_ERR_OOM;
+        }
+        it = ctx->lut_cache.emplace(key, std::make_pair(d, std::move(tab))).first;
+        if (cudaMemcpyAsync(d, it->second.second.data(), n, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+          ctx->err = "upload of the truth table failed";
+          return GECUT_ERR_CUDA;
+        }
+      }
+      p->lut = it->second.first;
+    }
+  }
   return GECUT_OK;
 bad:
   ctx->err = "malformed boolean program";
@@ -393,6 +437,7 @@ int gecut_destroy(gecut_ctx* ctx) {
   cudaFree(ctx->d_tables);
   cudaFree(ctx->d_simplexify_raw);
   cudaFree(ctx->d_simplexify_pos);
+  for (auto& kv : ctx->lut_cache) cudaFree(kv.second.first);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   delete ctx;
   return GECUT_OK;

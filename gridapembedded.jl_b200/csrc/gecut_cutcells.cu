@@ -70,7 +70,7 @@ __device__ __forceinline__ void unit_normal(const double* p1, const double* p2, 
 // new point on the edge (a,b) cut by level set `ls` (_cut_cell!, CutTriangulations.jl:206-218)
 // WITH_XR = false (counting walk): only the level-set values are interpolated -- the tree shape depends on nothing else
 template <int D, int LM, bool WITH_XR = true>
-__device__ __forceinline__ void cut_point(const Pt<D, LM>& a, const Pt<D, LM>& b, int ls, int L, Pt<D, LM>& o) {
+__device__ __forceinline__ void cut_point(const Pt<D, LM>& a, const Pt<D, LM>& b, int ls, uint32_t wmask, Pt<D, LM>& o) {
   double w1 = fabs(a.w[ls]), w2 = fabs(b.w[ls]);
   double coeff = __ddiv_rn(w1, __dadd_rn(w1, w2));
   if (WITH_XR) {
@@ -80,7 +80,11 @@ __device__ __forceinline__ void cut_point(const Pt<D, LM>& a, const Pt<D, LM>& b
       o.r[d] = gc_lerp(a.r[d], b.r[d], coeff);
     }
   }
-  for (int k = 0; k < L; ++k) o.w[k] = gc_lerp(a.w[k], b.w[k], coeff);
+  // only the level sets that can still be looked at further down the tree (wmask) need their values carried along
+  for (uint32_t m = wmask; m; m &= m - 1) {
+    const int k = __ffs(m) - 1;
+    o.w[k] = gc_lerp(a.w[k], b.w[k], coeff);
+  }
 }
 
 // Stage-0 simplex `t` of the cut bg cell `cell0` (0-based, slab-local): points with coordinates, reference coordinates of
@@ -216,10 +220,59 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
 #pragma unroll
   for (int i = 0; i <= D; ++i) v[0][i] = (uint8_t)i;
 
+  // Level compression.  A level set whose values have one sign on the D+1 vertices of the stage-0 simplex has that sign
+  // on every point of the refinement tree (cut points are convex combinations), so its stage never cuts anything: every
+  // simplex goes through it as the single child of the all-IN / all-OUT table row, i.e. with its vertices permuted by
+  // that row and a constant state.  The walk therefore visits only the level sets with mixed signs (plus the last one
+  // of each sequence, where the output is emitted) and applies the permutations of the skipped stages in between.
+  int8_t lsd[LM], fk[LF];
+  uint32_t mixed = 0u, outm = 0u;
+  for (int k = 0; k < L; ++k) {
+    bool any = false, all = true;
+#pragma unroll
+    for (int i = 0; i <= D; ++i) {
+      const bool o = pool[i].w[k] > 0.0;
+      any |= o;
+      all &= o;
+    }
+    if (any && !all) mixed |= 1u << k;
+    if (all) outm |= 1u << k;
+    st[k] = all ? (int8_t)GC_OUT : (int8_t)GC_IN;   // overwritten on the way down for the visited level sets
+    fst[k] = st[k];
+  }
+  const uint32_t wmask = (mixed | 3u) & ((1u << L) - 1u);  // values needed: visited level sets (0 and 1 are emission stages)
+  const int c_allout = (1 << (D + 1)) - 1, fc_allout = (1 << D) - 1;
+  // skipped cell stages hi-1 ... lo+1 applied to a vertex list
+  auto skip_cell_stages = [&](uint8_t* vl, int hi, int lo) {
+    for (int k = hi - 1; k > lo; --k) {
+      const uint8_t* pm = TC.sub_pts[((outm >> k) & 1u) ? c_allout : 0][0];
+      uint8_t tmp[D + 1];
+#pragma unroll
+      for (int i = 0; i <= D; ++i) tmp[i] = vl[pm[i]];
+#pragma unroll
+      for (int i = 0; i <= D; ++i) vl[i] = tmp[i];
+    }
+  };
+  // the same for the facet re-cut stages (level set `skip` is not part of that sequence)
+  auto skip_facet_stages = [&](uint8_t* vl, int hi, int lo, int skip) {
+    for (int k = hi - 1; k > lo; --k) {
+      if (k == skip) continue;
+      const uint8_t* pm = TF.sub_pts[((outm >> k) & 1u) ? fc_allout : 0][0];
+      uint8_t tmp[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) tmp[i] = vl[pm[i]];
+#pragma unroll
+      for (int i = 0; i < D; ++i) vl[i] = tmp[i];
+    }
+  };
+  const uint32_t cmask = (mixed | 1u) & ((1u << L) - 1u);  // visited cell stages
+  lsd[0] = (int8_t)(31 - __clz(cmask));
+  skip_cell_stages(v[0], L, lsd[0]);
+
   int depth = 0;
   child[0] = -1;
   while (depth >= 0) {
-    const int ls = L - 1 - depth;
+    const int ls = lsd[depth];
     if (child[depth] < 0) {
       // ---- enter: case, cut points (CutTriangulations.jl:179-222)
       int c = 0;
@@ -235,7 +288,7 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
         for (int ed = 0; ed < TC.nedges; ++ed) {
           const int a = e[depth][TC.edges[ed][0]], b = e[depth][TC.edges[ed][1]];
           if ((pool[a].w[ls] > 0.0) != (pool[b].w[ls] > 0.0)) {
-            cut_point<D, LM, FILL>(pool[a], pool[b], ls, L, pool[ptop]);
+            cut_point<D, LM, FILL>(pool[a], pool[b], ls, wmask, pool[ptop]);
             e[depth][np++] = (uint8_t)ptop++;
           }
         }
@@ -274,13 +327,17 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
                            (double)TC.fac_orient[c][f], nrm);
 #pragma unroll
           for (int i = 0; i < D; ++i) fv[0][i] = e[depth][fp[i]];
-          // ---- re-cut the facet by every other level set, last to first (CutTriangulations.jl:294-307,324-327)
+          // ---- re-cut the facet by every other level set, last to first (CutTriangulations.jl:294-307,324-327);
+          //      visited: the other level sets with mixed signs + the last one of the sequence (emission)
           const int ptop_cell = ptop;
+          const int klast = ls == 0 ? 1 : 0;
+          const uint32_t fmask = ((mixed & ~(1u << ls)) | (1u << klast)) & ((1u << L) - 1u);
+          fk[0] = (int8_t)(31 - __clz(fmask));
+          skip_facet_stages(fv[0], L, fk[0], ls);
           int fdepth = 0;
           fchild[0] = -1;
           while (fdepth >= 0) {
-            int k = L - 1 - fdepth;  // fdepth-th other level set, taken from the last, skipping ls
-            if (k <= ls) k -= 1;
+            const int k = fk[fdepth];
             if (fchild[fdepth] < 0) {
               int fc = 0;
 #pragma unroll
@@ -295,12 +352,12 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
                 for (int ed = 0; ed < TF.nedges; ++ed) {
                   const int a = fe[fdepth][TF.edges[ed][0]], b = fe[fdepth][TF.edges[ed][1]];
                   if ((pool[a].w[k] > 0.0) != (pool[b].w[k] > 0.0)) {
-                    cut_point<D, LM, FILL>(pool[a], pool[b], k, L, pool[ptop]);
+                    cut_point<D, LM, FILL>(pool[a], pool[b], k, wmask, pool[ptop]);
                     fe[fdepth][fn++] = (uint8_t)ptop++;
                   }
                 }
               }
-              if (fdepth == L - 2) {
+              if (k == klast) {
                 // final facets of level set ls: point block + children
                 const int nsf = TF.nsub[fc];
                 if (FILL) {
@@ -343,6 +400,8 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
               fst[k] = TF.sub_inout[fc][j];
 #pragma unroll
               for (int i = 0; i < D; ++i) fv[fdepth + 1][i] = fe[fdepth][TF.sub_pts[fc][j][i]];
+              fk[fdepth + 1] = (int8_t)(31 - __clz(fmask & ((1u << k) - 1u)));
+              skip_facet_stages(fv[fdepth + 1], k, fk[fdepth + 1], ls);
               fchild[fdepth + 1] = -1;
               fdepth++;
             } else {
@@ -392,6 +451,8 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
       st[ls] = TC.sub_inout[c][j];
 #pragma unroll
       for (int i = 0; i <= D; ++i) v[depth + 1][i] = e[depth][TC.sub_pts[c][j][i]];
+      lsd[depth + 1] = (int8_t)(31 - __clz(cmask & ((1u << ls) - 1u)));
+      skip_cell_stages(v[depth + 1], ls, lsd[depth + 1]);
       child[depth + 1] = -1;
       depth++;
     } else {

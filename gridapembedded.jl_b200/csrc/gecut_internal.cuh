@@ -12,6 +12,7 @@
 #include <map>
 #include <string>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "gecut.h"
@@ -48,9 +49,16 @@ struct GcLeaves {
   int64_t nodal_base;            // global id of the first node the NODAL vectors hold (0: whole model; slab node offset)
 };
 
+// Postfix boolean program over the level-set rows.  Programs with more than one operator also carry a truth table:
+// `lut` (device memory, owned by the context cache) has 3^nused entries indexed by the base-3 digits state+1 of the
+// level sets the program uses (used[0] = least significant), so that evaluating the CSG tree is one gather.
+constexpr int GC_LUT_MAXUSED = 10;  // 3^10 = 59049 bytes
 struct GcProgram {
   int len;
   int8_t tok[GECUT_MAX_PROGRAM];
+  const int8_t* lut;
+  int nused;
+  int8_t used[GC_LUT_MAXUSED];
 };
 
 // Device pointers of the result layout.
@@ -114,6 +122,8 @@ struct gecut_ctx {
   GcSimplexTable* d_tables = nullptr;  // [3] on the device
   uint8_t* d_simplexify_raw = nullptr;  // [2][6][4]
   uint8_t* d_simplexify_pos = nullptr;  // [2][6][4]
+  // truth tables of boolean programs, keyed by the token string (device copy + the host copy the upload reads from)
+  std::map<std::string, std::pair<int8_t*, std::vector<int8_t>>> lut_cache;
   void* h_pinned = nullptr;             // small pinned staging buffer for scalar read-backs
   size_t h_pinned_bytes = 0;
 };
@@ -304,22 +314,22 @@ __device__ __forceinline__ double gc_lerp(double a, double b, double c) {
 }
 
 // 3-valued boolean tables (EmbeddedDiscretizations.jl:136-177)
-__device__ __forceinline__ int gc_io_union(int a, int b) {
+__host__ __device__ __forceinline__ int gc_io_union(int a, int b) {
   if (a == GC_OUT && b == GC_OUT) return GC_OUT;
   if ((a == GC_CUT && b == GC_CUT) || (a == GC_CUT && b == GC_OUT) || (a == GC_OUT && b == GC_CUT)) return GC_CUT;
   return GC_IN;
 }
-__device__ __forceinline__ int gc_io_intersection(int a, int b) {
+__host__ __device__ __forceinline__ int gc_io_intersection(int a, int b) {
   if (a == GC_IN && b == GC_IN) return GC_IN;
   if ((a == GC_CUT && b == GC_CUT) || (a == GC_CUT && b == GC_IN) || (a == GC_IN && b == GC_CUT)) return GC_CUT;
   return GC_OUT;
 }
-__device__ __forceinline__ int gc_io_setdiff(int a, int b) {
+__host__ __device__ __forceinline__ int gc_io_setdiff(int a, int b) {
   if (a == GC_IN && b == GC_OUT) return GC_IN;
   if ((a == GC_CUT && b == GC_CUT) || (a == GC_CUT && b == GC_OUT) || (a == GC_IN && b == GC_CUT)) return GC_CUT;
   return GC_OUT;
 }
-__device__ __forceinline__ int gc_io_complementary(int a) {
+__host__ __device__ __forceinline__ int gc_io_complementary(int a) {
   if (a == GC_OUT) return GC_IN;
   if (a == GC_IN) return GC_OUT;
   return GC_CUT;
@@ -329,6 +339,11 @@ __device__ __forceinline__ int gc_io_complementary(int a) {
 __device__ __forceinline__ int gc_eval_inoutcut(const GcProgram& p, const int8_t* rows, int64_t pitch, int64_t e) {
   if (p.len == 1) return rows[(int64_t)p.tok[0] * pitch + e];  // single leaf: no stack machine
   if (p.len == 2 && p.tok[1] == GECUT_OP_COMPLEMENT) return gc_io_complementary(rows[(int64_t)p.tok[0] * pitch + e]);
+  if (p.lut) {  // truth table: base-3 index from the states of the used level sets
+    int idx = 0;
+    for (int k = p.nused - 1; k >= 0; --k) idx = idx * 3 + (rows[(int64_t)p.used[k] * pitch + e] + 1);
+    return __ldg(p.lut + idx);
+  }
   int8_t st[GECUT_MAX_PROGRAM / 2 + 2];
   int sp = 0;
   for (int t = 0; t < p.len; ++t) {
@@ -347,7 +362,14 @@ __device__ __forceinline__ int gc_eval_inoutcut(const GcProgram& p, const int8_t
 }
 
 // same program on explicit per-level-set values
-__device__ __forceinline__ int gc_eval_inoutcut_vals(const GcProgram& p, const int8_t* vals) {
+__host__ __device__ __forceinline__ int gc_eval_inoutcut_vals(const GcProgram& p, const int8_t* vals) {
+#ifdef __CUDA_ARCH__
+  if (p.lut) {
+    int idx = 0;
+    for (int k = p.nused - 1; k >= 0; --k) idx = idx * 3 + (vals[p.used[k]] + 1);
+    return __ldg(p.lut + idx);
+  }
+#endif
   int8_t st[GECUT_MAX_PROGRAM / 2 + 2];
   int sp = 0;
   for (int t = 0; t < p.len; ++t) {

@@ -141,25 +141,21 @@ k_count_bgcells_vec(const GcLayout lay, int64_t nc, int L, const GcProgram prog,
         for (int t = 0; t < 6; ++t) loc[t] += (keep && t == ty) ? 1u : 0u;
         ty = (ty + 1 == cpc) ? 0 : ty + 1;
       }
-    } else if (L <= 4) {
-      // few level sets: 128-bit loads of every row, then the program per byte
-      uint32_t w4[4][4];
+    } else if (prog.lut) {
+      // truth table: one 128-bit load per used level-set row, base-3 index per cell, one gather
+      uint32_t idx[16];
 #pragma unroll
-      for (int ls = 0; ls < 4; ++ls) {
-        if (ls < L) {
-          const uint4 r4 = *reinterpret_cast<const uint4*>(lay.bg_state + (int64_t)ls * lay.bg_pitch + e0);
-          w4[ls][0] = r4.x;
-          w4[ls][1] = r4.y;
-          w4[ls][2] = r4.z;
-          w4[ls][3] = r4.w;
-        }
+      for (int c = 0; c < 16; ++c) idx[c] = 0u;
+      for (int k = prog.nused - 1; k >= 0; --k) {
+        const uint4 r4 = *reinterpret_cast<const uint4*>(lay.bg_state + (int64_t)prog.used[k] * lay.bg_pitch + e0);
+        const uint32_t w4[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          idx[c] = idx[c] * 3u + (uint32_t)((int)(int8_t)((w4[c >> 2] >> (8 * (c & 3))) & 0xFFu) + 1);
       }
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
-        int8_t vals[4];
-#pragma unroll
-        for (int ls = 0; ls < 4; ++ls) vals[ls] = ls < L ? (int8_t)((w4[ls][c >> 2] >> (8 * (c & 3))) & 0xFFu) : (int8_t)0;
-        const int bg = gc_eval_inoutcut_vals(prog, vals);
+        const int bg = c < nvalid ? (int)__ldg(prog.lut + idx[c]) : GC_OUT;
         const bool keep = (c < nvalid) && (mode == 0 ? (bg == side) : (bg == GC_CUT || bg == side));
 #pragma unroll
         for (int t = 0; t < 6; ++t) loc[t] += (keep && t == ty) ? 1u : 0u;
