@@ -93,6 +93,7 @@ struct GcCounters {
   uint32_t* fpt[GC_LMAX];
   uint32_t fac_base[GC_LMAX];  // global offset of the facets of level set ls (merge_sub_face_data order)
   uint32_t fpt_base[GC_LMAX];
+  uint32_t total_points;  // subcell points of the whole result (end of the last warp's range in the fill walk)
 };
 
 // ------------------------------------------------------------------------------------------------
