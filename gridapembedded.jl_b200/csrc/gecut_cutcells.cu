@@ -92,7 +92,8 @@ __device__ __forceinline__ void cut_point(const Pt<D, LM>& a, const Pt<D, LM>& b
 // (_simplexify :562-617, _ensure_positive_jacobians! :532-533 -> LookupTables.jl:199-216).
 template <int D, int LM>
 __device__ __forceinline__ void setup_stage0(const GcGrid& g, const GcLeaves& lv, int64_t cell0, int t,
-                                             const uint8_t* simp_raw, const uint8_t* simp_pos, Pt<D, LM>* S) {
+                                             const uint8_t* simp_raw, const uint8_t* simp_pos,
+                                             const int8_t* __restrict__ bg_state, int64_t bg_pitch, Pt<D, LM>* S) {
   const int L = lv.L;
   const int64_t cube = cell0 / g.cpc;
   const int typ = (int)(cell0 % g.cpc);
@@ -126,7 +127,12 @@ __device__ __forceinline__ void setup_stage0(const GcGrid& g, const GcLeaves& lv
     const int64_t node = (D == 3) ? ((int64_t)nijk[0] + (int64_t)g.nn[0] * ((int64_t)nijk[1] + (int64_t)g.nn[1] * nijk[2]))
                                   : ((int64_t)nijk[0] + (int64_t)g.nn[0] * nijk[1]);
     for (int ls = 0; ls < L; ++ls) {
-      if (lv.leaf[ls].kind == GECUT_LEAF_NODAL)
+      // a level set that does not cut the bg cell has one sign on all its vertices: only that sign is ever looked at
+      // (such a stage never produces a cut point), so the evaluation is skipped
+      const int bgst = bg_state[(int64_t)ls * bg_pitch + cell0];
+      if (bgst != GC_CUT)
+        S[m].w[ls] = bgst == GC_OUT ? 1.0 : -1.0;
+      else if (lv.leaf[ls].kind == GECUT_LEAF_NODAL)
         S[m].w[ls] = __ldg(lv.nodal[ls] + (node - lv.nodal_base));
       else
         S[m].w[ls] = gc_eval_leaf(lv.leaf[ls], x, D);
@@ -154,6 +160,17 @@ __device__ __forceinline__ void setup_stage0(const GcGrid& g, const GcLeaves& lv
     Pt<D, LM> tmp = S[0];
     S[0] = S[1];
     S[1] = tmp;
+  }
+}
+
+// one row of cell_to_points: a single 16-byte store for tetrahedra
+template <int D>
+__device__ __forceinline__ void store_c2p_row(int32_t* __restrict__ c2p, uint32_t cid, const int32_t* row) {
+  if (D == 3) {
+    reinterpret_cast<int4*>(c2p)[cid] = make_int4(row[0], row[1], row[2], row[3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i <= D; ++i) c2p[(int64_t)cid * (D + 1) + i] = row[i];
   }
 }
 
@@ -248,7 +265,7 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
   int8_t fchild[LF], fcs[LF], fptop_at[LF], fst[LM];
 
   if (valid) {
-  setup_stage0<D, LM>(g, lv, bgcell1 - 1, t, simp_raw, simp_pos, pool);
+  setup_stage0<D, LM>(g, lv, bgcell1 - 1, t, simp_raw, simp_pos, lay.bg_state, lay.bg_pitch, pool);
   int ptop = D + 1;
 #pragma unroll
   for (int i = 0; i <= D; ++i) v[0][i] = (uint8_t)i;
@@ -408,13 +425,15 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
         for (int j = 0; j < nsub; ++j) {
           const uint32_t cid = cell_off + j;
           double pc[D + 1][3];
+          int32_t row[D + 1];
 #pragma unroll
           for (int i = 0; i <= D; ++i) {
             const int li = TC.sub_pts[c][j][i];
-            lay.sc_c2p[(int64_t)cid * (D + 1) + i] = (int32_t)(pt_off + li + 1);
+            row[i] = (int32_t)(pt_off + li + 1);
 #pragma unroll
             for (int d = 0; d < D; ++d) pc[i][d] = sget(li, d);
           }
+          store_c2p_row<D>(lay.sc_c2p, cid, row);
           lay.sc_c2bg[cid] = bgcell1;
           lay.sc_meas[cid] = integrate_one<D>(simplex_meas<D, D>(pc));
           lay.sc_state[cid] = TC.sub_inout[c][j];
@@ -446,13 +465,15 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
             }
           }
           double pc[D + 1][3];
+          int32_t row[D + 1];
 #pragma unroll
           for (int i = 0; i <= D; ++i) {
             const int li = TC.sub_pts[c0][0][i];
-            lay.sc_c2p[(int64_t)cid * (D + 1) + i] = (int32_t)(pb + li + 1);
+            row[i] = (int32_t)(pb + li + 1);
 #pragma unroll
             for (int d = 0; d < D; ++d) pc[i][d] = sget(cv[li], d);
           }
+          store_c2p_row<D>(lay.sc_c2p, cid, row);
           lay.sc_c2bg[cid] = bgcell1;
           lay.sc_meas[cid] = integrate_one<D>(simplex_meas<D, D>(pc));
           lay.sc_state[cid] = TC.sub_inout[c0][0];
