@@ -15,5 +15,5 @@ from .cutters import Cutter, LevelSetCutter, cut, compute_bgcell_to_inoutcut
 from .discretizations import (IN, OUT, CUT, INTERFACE, CUT_IN, CUT_OUT, PHYSICAL, PHYSICAL_IN, PHYSICAL_OUT, ACTIVE,
                               ACTIVE_IN, ACTIVE_OUT, EmbeddedDiscretization, SubCellData, SubFacetData,
                               Triangulation, EmbeddedBoundary)
-from .measures import Measure, integrate_measure, integrate_laplacian
+from .measures import Measure, integrate_measure, integrate_laplacian, get_cell_measure
 from .distributed import DistributedLevelSetCutter, slab_range

@@ -18,6 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(HERE, "..", "include")
 
 GECUT_OK = 0
+GECUT_ERR_INVALID, GECUT_ERR_NOTIMPLEMENTED, GECUT_ERR_CUDA, GECUT_ERR_OOM, GECUT_ERR_OVERFLOW = 1, 2, 3, 4, 5
 SEL_PHYSICAL, SEL_ACTIVE, SEL_BOUNDARY, SEL_CUTONLY, SEL_BGONLY = 0, 1, 2, 3, 4
 MAX_LEVELSETS = 16
 MAX_PROGRAM = 64
@@ -171,12 +172,13 @@ def lib():
     L.gecut_integrate_measure.argtypes = [vp, vp, P(C.c_double)]
     L.gecut_integrate_laplacian.argtypes = [vp, vp, vp]
     L.gecut_selection_device_laplacian.argtypes = [vp, P(vp)]
+    L.gecut_cell_measure.argtypes = [vp, vp, C.c_int]
     for name in ("gecut_create", "gecut_destroy", "gecut_set_stream", "gecut_cut", "gecut_classify",
                  "gecut_eval_leaf_at_nodes", "gecut_result_free", "gecut_result_sizes", "gecut_result_device_ptrs",
                  "gecut_result_copy", "gecut_bgcell_to_inoutcut", "gecut_subcell_to_inout", "gecut_select_cells",
                  "gecut_select_boundary", "gecut_selection_free", "gecut_selection_sizes", "gecut_selection_copy",
                  "gecut_selection_gather", "gecut_integrate_measure", "gecut_integrate_laplacian",
-                 "gecut_selection_device_laplacian"):
+                 "gecut_selection_device_laplacian", "gecut_cell_measure"):
         getattr(L, name).restype = cint
     _lib = L
     return L
@@ -188,7 +190,8 @@ EXPORTED_SYMBOLS = ["gecut_create", "gecut_destroy", "gecut_set_stream", "gecut_
                     "gecut_result_sizes", "gecut_result_device_ptrs", "gecut_result_copy", "gecut_bgcell_to_inoutcut",
                     "gecut_subcell_to_inout", "gecut_select_cells", "gecut_select_boundary", "gecut_selection_free",
                     "gecut_selection_sizes", "gecut_selection_copy", "gecut_selection_gather",
-                    "gecut_integrate_measure", "gecut_integrate_laplacian", "gecut_selection_device_laplacian"]
+                    "gecut_integrate_measure", "gecut_integrate_laplacian", "gecut_selection_device_laplacian",
+                    "gecut_cell_measure"]
 
 
 class Context:
@@ -206,6 +209,10 @@ class Context:
         if rc != GECUT_OK:
             msg = self._lib.gecut_last_error(self._h)
             raise GecutError(f"{what} failed with status {rc}: {msg.decode() if msg else ''}")
+
+    def last_error(self) -> str:
+        msg = self._lib.gecut_last_error(self._h)
+        return msg.decode() if msg else ""
 
     def set_stream(self, stream: int):
         self.check(self._lib.gecut_set_stream(self._h, C.c_void_p(stream or 0)), "gecut_set_stream")

@@ -801,6 +801,29 @@ int gecut_integrate_laplacian(const gecut_selection* sel_c, double* K_cut, doubl
   return GECUT_OK;
 }
 
+int gecut_cell_measure(const gecut_selection* sel, double* values, int values_on_device) {
+  if (!sel || !values) return GECUT_ERR_INVALID;
+  gecut_ctx* ctx = sel->res->ctx;
+  if (sel->kind != GECUT_SEL_PHYSICAL && sel->kind != GECUT_SEL_CUTONLY && sel->kind != GECUT_SEL_BGONLY) {
+    ctx->err = "cell measures need a PHYSICAL, CUT or bg-cell selection";
+    return GECUT_ERR_INVALID;
+  }
+  DeviceGuard guard(ctx->device);
+  const int64_t nc = sel->res->sizes.num_bgcells;
+  if (values_on_device) {
+    GC_CHECK(gc_cell_measure(ctx, sel, values));
+    GC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GECUT_OK;
+  }
+  double* d = nullptr;
+  GC_CHECK(gc_malloc(ctx, (void**)&d, sizeof(double) * std::max<int64_t>(nc, 1)));
+  int st = gc_cell_measure(ctx, sel, d);
+  if (st == GECUT_OK) st = copy_to_host(ctx, values, d, nc);
+  if (st == GECUT_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = GECUT_ERR_CUDA;
+  gc_free(ctx, d);
+  return st;
+}
+
 int gecut_selection_device_laplacian(const gecut_selection* sel, double** K_cut_dev) {
   if (!sel || !K_cut_dev) return GECUT_ERR_INVALID;
   *K_cut_dev = sel->K_cut;

@@ -346,6 +346,30 @@ k_cutcell_laplacian_p1(const GcGrid g, const GcLayout lay, const uint32_t* __res
   }
 }
 
+// get_cell_measure: uncut cells (whole-cell measure per cell type when the state is `side`, else 0) ...
+__global__ void k_bgcell_measure(const GcLayout lay, int64_t nc, const GcProgram prog, int side, int cpc, int use_bg,
+                                 const double* __restrict__ type_meas, double* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nc) return;
+  double v = 0.0;
+  if (use_bg && gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, e) == side) v = type_meas[e % cpc];
+  out[e] = v;
+}
+
+// ... then the cut cells: sum of the selected subcells in subcell order (move_contributions)
+__global__ void k_cutcell_measure(const GcLayout lay, const uint32_t* __restrict__ sc_ptr, int64_t ncut, const GcProgram prog,
+                                  int side, double* __restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= ncut) return;
+  const int64_t cell0 = (int64_t)lay.cutcells[k] - 1;
+  if (gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, cell0) != GC_CUT) return;
+  double V = 0.0;
+  const uint32_t s0 = sc_ptr[2 * k], s1 = sc_ptr[2 * k + 2];
+  for (uint32_t e = s0; e < s1; ++e)
+    if (gc_eval_inoutcut(prog, lay.sc_state, lay.sc_pitch, (int64_t)e) == side) V += lay.sc_meas[e];
+  out[cell0] = V;
+}
+
 }  // namespace
 
 // measure of an uncut bg cell of type `typ` (host; tensor Gauss for n-cubes, degree-2 simplex rule otherwise)
@@ -498,4 +522,27 @@ int gc_integrate_laplacian(gecut_ctx* ctx, gecut_selection* sel, double* K_bg_ho
     GC_LAUNCH(ctx, "k_cutcell_laplacian", k_cutcell_laplacian_q1<3><<<nb, T, 0, ctx->stream>>>(
         g, res->lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, sel->K_cut));
   return gc_launch_check(ctx, "k_cutcell_laplacian");
+}
+
+int gc_cell_measure(gecut_ctx* ctx, const gecut_selection* sel, double* values_dev) {
+  const gecut_result* res = sel->res;
+  const GcGrid& g = res->grid;
+  const int64_t nc = res->sizes.num_bgcells, ncut = res->sizes.num_cutcells;
+  if (nc == 0) return GECUT_OK;
+  const bool use_bg = sel->kind == GECUT_SEL_PHYSICAL || sel->kind == GECUT_SEL_BGONLY;
+  const bool use_sub = sel->kind == GECUT_SEL_PHYSICAL || sel->kind == GECUT_SEL_CUTONLY;
+  double* tm = nullptr;
+  GC_CHECK(gc_malloc(ctx, (void**)&tm, sizeof(double) * 8));
+  double* hm = reinterpret_cast<double*>((char*)ctx->h_pinned + 2048);
+  for (int t = 0; t < 8; ++t) hm[t] = t < g.cpc ? host_bgcell_measure(g, t) : 0.0;
+  GC_CUDA(cudaMemcpyAsync(tm, hm, sizeof(double) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  const int T = 256;
+  GC_LAUNCH(ctx, "k_bgcell_measure", k_bgcell_measure<<<(unsigned)gc_div_up(nc, T), T, 0, ctx->stream>>>(
+      res->lay, nc, sel->prog, sel->side, g.cpc, use_bg ? 1 : 0, tm, values_dev));
+  if (use_sub && ncut > 0 && res->cut_sc_ptr)
+    GC_LAUNCH(ctx, "k_cutcell_measure", k_cutcell_measure<<<(unsigned)gc_div_up(ncut, T), T, 0, ctx->stream>>>(
+        res->lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, values_dev));
+  int st = gc_launch_check(ctx, "cell_measure");
+  gc_free(ctx, tm);
+  return st;
 }

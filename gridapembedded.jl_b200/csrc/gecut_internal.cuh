@@ -223,6 +223,7 @@ int gc_selection_gather(gecut_ctx* ctx, const gecut_selection* sel, int32_t* to_
 // ---- integration (gecut_integrate.cu) ----
 int gc_integrate_measure(gecut_ctx* ctx, const gecut_selection* sel, double* values_dev, double* total_host);
 int gc_integrate_laplacian(gecut_ctx* ctx, gecut_selection* sel, double* K_bg_host);
+int gc_cell_measure(gecut_ctx* ctx, const gecut_selection* sel, double* values_dev);
 
 // ------------------------------------------------------------------------------------------------
 // device helpers shared by the kernels

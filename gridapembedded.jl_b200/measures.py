@@ -55,3 +55,17 @@ def integrate_laplacian(dΩ: Measure) -> Tuple[np.ndarray, np.ndarray]:
     t.ctx.check(t.ctx._lib.gecut_integrate_laplacian(
         t.handle, K_cut.ctypes.data if K_cut.size else None, K_bg.ctypes.data), "gecut_integrate_laplacian")
     return K_cut, K_bg
+
+
+def get_cell_measure(trian: CutTriangulation, device_output: bool = False):
+    """`get_cell_measure(trian, bgtrian)` (`src/AgFEM/CellAggregation.jl:111-113`): measure of `trian` per background
+    cell (slab-local numbering) -- the input of the AgFEM aggregation.  numpy array, or a CUDA torch tensor."""
+    nc = int(trian.cut.sizes.num_bgcells)
+    if device_output:
+        import torch
+        out = torch.empty(nc, dtype=torch.float64, device=f"cuda:{trian.ctx.device}")
+        trian.ctx.check(trian.ctx._lib.gecut_cell_measure(trian.handle, C.c_void_p(out.data_ptr()), 1), "gecut_cell_measure")
+        return out
+    out = np.empty(nc, np.float64)
+    trian.ctx.check(trian.ctx._lib.gecut_cell_measure(trian.handle, C.c_void_p(out.ctypes.data), 0), "gecut_cell_measure")
+    return out

@@ -206,6 +206,11 @@ int gecut_integrate_measure(const gecut_selection* sel, double* values, double* 
  * subcell); `K_bg` (host, NULL skipped) is ntypes x nv x nv for the uncut cells (ntypes = 1 for n-cubes, 2/6 for
  * simplexified models, type = (cell-1) mod ntypes). */
 int gecut_integrate_laplacian(const gecut_selection* sel, double* K_cut, double* K_bg);
+/* get_cell_measure(trian, bgtrian) (the aggregation input of AgFEM, src/AgFEM/CellAggregation.jl:111-113): measure of the
+ * selected triangulation per bg cell -- the whole cell for selected uncut cells, the sum over the selected subcells (in
+ * subcell order) for cut cells, 0 elsewhere.  `values` has num_bgcells entries; host memory, or device memory when
+ * values_on_device != 0.  PHYSICAL, CUT-only and bg-only selections. */
+int gecut_cell_measure(const gecut_selection* sel, double* values, int values_on_device);
 /* device pointer to the Ncut x nv x nv matrices of the last gecut_integrate_laplacian on this selection */
 int gecut_selection_device_laplacian(const gecut_selection* sel, double** K_cut_dev);
 

@@ -382,3 +382,125 @@ def test_max_levelsets_and_limits():
     compare_layout(gd, oc)
     with pytest.raises(NotImplementedError):
         cut(model, union(g16, geos[16]))
+
+
+# ---- widening: aggregation input, re-cut loop, slab-local nodal values, classification-only verb, raw ABI ----
+
+@pytest.mark.parametrize("case", ["sphere_hex_12", "sphere_tet_12", "csg_hex_10", "disk_quad_50", "bimaterial"])
+def test_cell_measure_matches_oracle(case):
+    """get_cell_measure(trian, bgtrian) (src/AgFEM/CellAggregation.jl:111-113): per-bg-cell measure of the physical
+    triangulation = whole cell for IN cells, sum of the selected subcells (subcell order) for cut cells."""
+    from gecut.measures import get_cell_measure
+    model, geo = CASES[case]()
+    oc = ob.oracle_cut(model, geo)
+    gd = cut(model, geo)
+    name = named_programs(gd)[0]
+    prog = gd.program(name)
+    for side, sel in ((IN, PHYSICAL_IN), (OUT, PHYSICAL_OUT)):
+        t = Triangulation(gd, sel, name)
+        got = get_cell_measure(t)
+        want = np.zeros(model.num_cells)
+        for c in oc.select_bgcells(prog, side):
+            want[c - 1] = oc.bgcell_measure(int(c))
+        ids = oc.select_subcells(prog, side)
+        if len(ids):
+            bg = oc.array("subcells.cell_to_bgcell")[ids - 1]
+            np.add.at(want, bg - 1, oc.subcell_measures(ids))  # unbuffered, in subcell order
+        assert_float_equal(got, want, "cell measures")
+        dev = get_cell_measure(t, device_output=True)
+        assert np.array_equal(dev.cpu().numpy(), got)
+    # the unit cut measures of IN + OUT partition every cell
+    tin, tout = Triangulation(gd, PHYSICAL_IN, name), Triangulation(gd, PHYSICAL_OUT, name)
+    both = get_cell_measure(tin) + get_cell_measure(tout)
+    cellvol = np.array([oc.bgcell_measure(c + 1) for c in range(min(model.num_cells, 12))])
+    assert np.allclose(both[:len(cellvol)], cellvol, rtol=1e-10, atol=0)
+
+
+def test_recut_loop_with_device_resident_levelset():
+    """Re-cut on an updated level set (src/LevelSetCutters/DifferentiableTriangulations.jl:55-59): the nodal
+    values live on the device, every iteration cuts again in the same context; each result equals the oracle's and the
+    context stops asking the driver for memory after the first iteration."""
+    import torch
+    model = CartesianDiscreteModel((-1, -1, -1), (1, 1, 1), (14, 12, 10))
+    X = ob.node_coords(model)
+    ctx = gecut._lib.default_context()
+    launches = []
+    for it, R in enumerate((0.55, 0.6, 0.65, 0.7)):
+        vals = (X ** 2).sum(1) - R * R
+        dgeo = DiscreteGeometry(torch.from_numpy(vals).cuda(), model, name="ball")
+        cg = cut(model, dgeo)
+        oc = ob.OracleCut(model, [ob.make_leaf(4)], [vals])
+        compare_layout(cg, oc)
+        vol = integrate_measure(Measure(Triangulation(cg, PHYSICAL, "ball"), 2))
+        assert abs(vol - 4 / 3 * np.pi * R ** 3) < 0.1 * (4 / 3 * np.pi * R ** 3)  # coarse grid, quadratic level set
+        launches.append(ctx.launch_count)
+        cg.close()
+    assert launches[-1] > launches[0]  # the native kernels ran every iteration
+
+
+def test_slab_local_nodal_values():
+    """A rank that owns only the node planes of its slab (+ the ghost plane) cuts the same as a rank holding the whole
+    vector (src/Distributed/DistributedDiscretizations.jl:164-170: ghost values come from the neighbour)."""
+    model = CartesianDiscreteModel((-1, -1, -1), (1, 1, 1), (10, 9, 12))
+    vals = ob.node_values(model, ob.make_leaf(0, R=0.7))
+    k0, k1 = 3, 9
+    layer_nodes = model.num_nodes // (model.partition[-1] + 1)
+    whole = LevelSetCutter(slab=(k0, k1)).cut(model, DiscreteGeometry(vals, model, name="ball"))
+    local_vals = np.ascontiguousarray(vals[k0 * layer_nodes:(k1 + 1) * layer_nodes])
+    part = LevelSetCutter(slab=(k0, k1), nodal_slab_local=True).cut(model, DiscreteGeometry(local_vals, model, name="ball"))
+    hw, hp = whole.to_host(), part.to_host()
+    for k in hw:
+        assert np.array_equal(hw[k], hp[k]), k
+
+
+@pytest.mark.parametrize("case", ["sphere_hex_12", "csg_hex_10", "stokes_tet", "disk_tri_50"])
+def test_classification_only_verb(case):
+    """compute_bgcell_to_inoutcut(cutter, model, geo) (LevelSetCutters.jl:154-188) without building the sub-triangulation."""
+    model, geo = CASES[case]()
+    oc = ob.oracle_cut(model, geo)
+    got = LevelSetCutter().compute_bgcell_to_inoutcut(model, geo)
+    tree = geo.get_tree()
+    from gecut.csg import find_unique_leaves
+    _, oid_to_ls = find_unique_leaves(tree)
+    prog = compile_postfix(tree, oid_to_ls)
+    assert np.array_equal(got, oc.bgcell_to_inoutcut(prog))
+
+
+def test_raw_abi_error_codes():
+    """Status codes and gecut_last_error through ctypes, the way a foreign binding sees them."""
+    import ctypes as C
+    from gecut import _lib
+    L = _lib.lib()
+    ctx = _lib.default_context()
+    out = C.c_void_p()
+    assert L.gecut_cut(None, None, None, 0, None, 0, C.byref(out)) == _lib.GECUT_ERR_INVALID
+    g = _lib.Grid()
+    g.D = 4
+    rec = (_lib.LeafRec * 1)()
+    assert L.gecut_cut(ctx.handle, C.byref(g), rec, 1, None, 0, C.byref(out)) != 0
+    assert len(ctx.last_error()) > 0
+    g.D = 2
+    g.partition[0], g.partition[1] = 4, 4
+    g.pmax[0] = g.pmax[1] = 1.0
+    assert L.gecut_cut(ctx.handle, C.byref(g), rec, 17, None, 0, C.byref(out)) != 0  # more level sets than GC_LMAX
+    rec[0].kind = 4  # NODAL without values
+    ptrs = (C.c_void_p * 1)()
+    assert L.gecut_cut(ctx.handle, C.byref(g), rec, 1, ptrs, 0, C.byref(out)) == _lib.GECUT_ERR_INVALID
+    # a valid cut, then malformed selector programs
+    rec[0].kind = 0
+    rec[0].x0[0] = rec[0].x0[1] = 0.5
+    rec[0].R = 0.3
+    assert L.gecut_cut(ctx.handle, C.byref(g), rec, 1, None, 0, C.byref(out)) == 0
+    sel = C.c_void_p()
+    bad = (C.c_int32 * 2)(0, -2)  # binary operator with one operand
+    assert L.gecut_select_cells(out, 0, bad, 2, -1, C.byref(sel)) == _lib.GECUT_ERR_INVALID
+    bad2 = (C.c_int32 * 1)(3)    # level set that does not exist
+    assert L.gecut_select_cells(out, 0, bad2, 1, -1, C.byref(sel)) == _lib.GECUT_ERR_INVALID
+    ok = (C.c_int32 * 1)(0)
+    assert L.gecut_select_cells(out, 0, ok, 1, -1, C.byref(sel)) == 0
+    tot = C.c_double()
+    assert L.gecut_integrate_measure(sel, None, C.byref(tot)) == 0
+    assert 0.15 < tot.value < 0.35  # disk of radius 0.3 on a 4 x 4 grid: pi*0.09 = 0.283 up to the coarse polygon
+    assert L.gecut_cell_measure(sel, None, 0) == _lib.GECUT_ERR_INVALID
+    L.gecut_selection_free(sel)
+    L.gecut_result_free(out)
