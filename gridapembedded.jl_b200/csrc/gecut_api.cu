@@ -725,6 +725,7 @@ int gecut_selection_copy(const gecut_selection* sel_c, int32_t* sub_ids, int8_t*
   gecut_selection* sel = const_cast<gecut_selection*>(sel_c);
   gecut_ctx* ctx = sel->res->ctx;
   DeviceGuard guard(ctx->device);
+  if (sub_ids || orientation) GC_CHECK(gc_materialize_sub_ids(ctx, sel));
   GC_CHECK(copy_to_host(ctx, sub_ids, sel->sub_ids, sel->n_sub));
   if (orientation && sel->kind != GECUT_SEL_BOUNDARY) {
     ctx->err = "orientation is only defined for boundary selections";

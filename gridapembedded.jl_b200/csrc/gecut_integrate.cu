@@ -26,7 +26,7 @@ k_measures(const int32_t* __restrict__ ids, int64_t n, const double* __restrict_
   const int64_t per = (n + gridDim.x - 1) / gridDim.x;
   const int64_t lo = per * blockIdx.x, hi = lo + per < n ? lo + per : n;
   for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const double v = meas[(int64_t)ids[i] - 1];
+    const double v = meas[ids ? (int64_t)ids[i] - 1 : i];  // ids == NULL: the selection is 1..n
     if (values) values[i] = v;
     s += v;
   }
@@ -200,7 +200,7 @@ inline QuadRule ncube_rule_deg2(int D) {
 template <int D>
 __global__ void __launch_bounds__(128)
 k_cutcell_laplacian_q1(const GcGrid g, const GcLayout lay, const uint32_t* __restrict__ sc_ptr, int64_t ncut,
-                       const GcProgram prog, int side, double* __restrict__ K) {
+                       const GcProgram prog, int side, int check_bg, double* __restrict__ K) {
   constexpr int NV = 1 << D;
   constexpr int NQ = D + 1;
   constexpr int NM = D == 3 ? 27 : 6;
@@ -213,7 +213,7 @@ k_cutcell_laplacian_q1(const GcGrid g, const GcLayout lay, const uint32_t* __res
   double M[NM];
 #pragma unroll
   for (int m = 0; m < NM; ++m) M[m] = 0.0;
-  if (gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, cell0) == GC_CUT) {
+  if (!check_bg || gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, cell0) == GC_CUT) {
     const uint32_t s0 = sc_ptr[2 * k], s1 = sc_ptr[2 * k + 2];
     for (uint32_t it = s0; it < s1; ++it) {
       const int64_t e = (int64_t)it;
@@ -318,7 +318,8 @@ k_cutcell_laplacian_q1(const GcGrid g, const GcLayout lay, const uint32_t* __res
 template <int D>
 __global__ void __launch_bounds__(128)
 k_cutcell_laplacian_p1(const GcGrid g, const GcLayout lay, const uint32_t* __restrict__ sc_ptr, int64_t ncut,
-                       const GcProgram prog, int side, const double* __restrict__ graddots, double* __restrict__ K) {
+                       const GcProgram prog, int side, int check_bg, const double* __restrict__ graddots,
+                       double* __restrict__ K) {
   constexpr int NV = D + 1, NN = NV * NV;
   const int lane = threadIdx.x & 31;
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -327,7 +328,8 @@ k_cutcell_laplacian_p1(const GcGrid g, const GcLayout lay, const uint32_t* __res
   if (k < ncut) {
     const int64_t cell0 = (int64_t)lay.cutcells[k] - 1;
     ty = (int)(cell0 % g.cpc);
-    if (gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, cell0) == GC_CUT) {
+    // one level set: every cut cell is CUT for every program over it, no need to look at the bg state row
+    if (!check_bg || gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, cell0) == GC_CUT) {
       const uint32_t s0 = sc_ptr[2 * k], s1 = sc_ptr[2 * k + 2];
       for (uint32_t e = s0; e < s1; ++e) {
         if (gc_eval_inoutcut(prog, lay.sc_state, lay.sc_pitch, (int64_t)e) != side) continue;
@@ -495,6 +497,7 @@ int gc_integrate_laplacian(gecut_ctx* ctx, gecut_selection* sel, double* K_bg_ho
     for (int t = 0; t < g.cpc; ++t) host_bgcell_laplacian(g, t, K_bg_host + (size_t)t * nn);
   if (ncut == 0) return GECUT_OK;
   if (!sel->K_cut) GC_CHECK(gc_malloc(ctx, (void**)&sel->K_cut, sizeof(double) * ncut * nn));
+  const int check_bg = res->L > 1 ? 1 : 0;
   if (g.simplexified) {
     double Gh[6 * 16];
     for (int t = 0; t < g.cpc; ++t) host_bgcell_graddots(g, t, Gh + (size_t)t * nn);
@@ -506,10 +509,10 @@ int gc_integrate_laplacian(gecut_ctx* ctx, gecut_selection* sel, double* K_bg_ho
     const unsigned nb1 = (unsigned)gc_div_up(ncut, 128);
     if (g.D == 2)
       GC_LAUNCH(ctx, "k_cutcell_laplacian", k_cutcell_laplacian_p1<2><<<nb1, 128, 0, ctx->stream>>>(
-          g, res->lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, Gd, sel->K_cut));
+          g, res->lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, check_bg, Gd, sel->K_cut));
     else
       GC_LAUNCH(ctx, "k_cutcell_laplacian", k_cutcell_laplacian_p1<3><<<nb1, 128, 0, ctx->stream>>>(
-          g, res->lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, Gd, sel->K_cut));
+          g, res->lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, check_bg, Gd, sel->K_cut));
     gc_free(ctx, Gd);
     return gc_launch_check(ctx, "k_cutcell_laplacian_p1");
   }
@@ -517,10 +520,10 @@ int gc_integrate_laplacian(gecut_ctx* ctx, gecut_selection* sel, double* K_bg_ho
   const unsigned nb = (unsigned)gc_div_up(ncut, T);
   if (g.D == 2)
     GC_LAUNCH(ctx, "k_cutcell_laplacian", k_cutcell_laplacian_q1<2><<<nb, T, 0, ctx->stream>>>(
-        g, res->lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, sel->K_cut));
+        g, res->lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, check_bg, sel->K_cut));
   else
     GC_LAUNCH(ctx, "k_cutcell_laplacian", k_cutcell_laplacian_q1<3><<<nb, T, 0, ctx->stream>>>(
-        g, res->lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, sel->K_cut));
+        g, res->lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, check_bg, sel->K_cut));
   return gc_launch_check(ctx, "k_cutcell_laplacian");
 }
 

@@ -157,6 +157,7 @@ struct gecut_selection {
   int64_t n_bg = 0;   // selected bg cells
   int32_t* sub_ids = nullptr;
   int8_t* orientation = nullptr;
+  bool sub_identity = false;  // the selection is 1..n_sub with orientation +1; ids are materialised only on demand
   int32_t* bg_ids = nullptr;  // materialised lazily
   int64_t bg_type_count[8] = {0};
   double* K_cut = nullptr;  // Ncut x nv x nv of the last laplacian integration
@@ -217,6 +218,7 @@ int gc_eval_rows(gecut_ctx* ctx, const int8_t* rows, int64_t pitch, int64_t n, c
 int gc_select_cells(gecut_ctx* ctx, gecut_selection* sel);
 int gc_select_boundary(gecut_ctx* ctx, gecut_selection* sel);
 int gc_materialize_bg_ids(gecut_ctx* ctx, gecut_selection* sel);
+int gc_materialize_sub_ids(gecut_ctx* ctx, gecut_selection* sel);
 int gc_selection_gather(gecut_ctx* ctx, const gecut_selection* sel, int32_t* to_points_dev, int32_t* to_bgcell_dev,
                         double* normals_dev);
 

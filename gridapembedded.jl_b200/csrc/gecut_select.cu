@@ -373,11 +373,9 @@ int gc_select_boundary(gecut_ctx* ctx, gecut_selection* sel) {
   // one level set, program = that leaf (and no second geometry, or the same leaf): every subfacet is INTERFACE with
   // orientation +1 (compute_inoutboundary of a Leaf, EmbeddedDiscretizations.jl:179-182) -> the selection is 1..Nsf
   if (res->L == 1 && sel->prog.len == 1 && (!sel->has_prog2 || sel->prog2.len == 1)) {
-    GC_CHECK(gc_malloc(ctx, (void**)&sel->sub_ids, sizeof(int32_t) * nsf));
-    GC_CHECK(gc_malloc(ctx, (void**)&sel->orientation, sizeof(int8_t) * nsf));
-    GC_LAUNCH(ctx, "k_iota_boundary", k_iota_boundary<<<(unsigned)gc_div_up(nsf, T), T, 0, ctx->stream>>>(nsf, sel->sub_ids, sel->orientation));
     sel->n_sub = nsf;
-    return gc_launch_check(ctx, "k_iota_boundary");
+    sel->sub_identity = true;  // ids / orientation are written when somebody asks for them (gc_materialize_sub_ids)
+    return GECUT_OK;
   }
   uint32_t* flags = nullptr;
   int8_t* orient_all = nullptr;
@@ -391,11 +389,22 @@ int gc_select_boundary(gecut_ctx* ctx, gecut_selection* sel) {
   return st;
 }
 
+int gc_materialize_sub_ids(gecut_ctx* ctx, gecut_selection* sel) {
+  if (!sel->sub_identity || sel->sub_ids || sel->n_sub <= 0) return GECUT_OK;
+  const int64_t n = sel->n_sub;
+  const int T = 256;
+  GC_CHECK(gc_malloc(ctx, (void**)&sel->sub_ids, sizeof(int32_t) * n));
+  GC_CHECK(gc_malloc(ctx, (void**)&sel->orientation, sizeof(int8_t) * n));
+  GC_LAUNCH(ctx, "k_iota_boundary", k_iota_boundary<<<(unsigned)gc_div_up(n, T), T, 0, ctx->stream>>>(n, sel->sub_ids, sel->orientation));
+  return gc_launch_check(ctx, "k_iota_boundary");
+}
+
 int gc_selection_gather(gecut_ctx* ctx, const gecut_selection* sel, int32_t* to_points_dev, int32_t* to_bgcell_dev,
                         double* normals_dev) {
   const gecut_result* res = sel->res;
   const int64_t n = sel->n_sub;
   if (n <= 0) return GECUT_OK;
+  GC_CHECK(gc_materialize_sub_ids(ctx, const_cast<gecut_selection*>(sel)));
   const int D = res->grid.D;
   const int T = 256;
   const unsigned nb = (unsigned)gc_div_up(n, T);
