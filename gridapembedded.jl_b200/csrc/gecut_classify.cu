@@ -225,6 +225,42 @@ __device__ __forceinline__ void cls_store_bytes(int8_t* out, const unsigned long
       if (q * 8 + k < nbytes) out[q * 8 + k] = (int8_t)((e[q] >> (8 * k)) & 0xFFull);
 }
 
+// the first nbytes bytes of e[] to `out` with the widest stores the address allows: whole 32-byte sectors when the row
+// segment is aligned (grids whose x size is a multiple of 32 always are), else 8- or 4-byte words and a byte tail
+template <int NQ>
+__device__ __forceinline__ void cls_store_any(int8_t* out, const unsigned long long* e, int nbytes) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(out);
+  constexpr uintptr_t VMASK = (NQ % 4 == 0) ? 31 : (NQ == 2 ? 15 : 7);
+  if (nbytes == 8 * NQ && (a & VMASK) == 0) {
+    cls_store<NQ>(out, e);
+  } else if ((a & 7) == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      if (8 * (q + 1) <= nbytes) {
+        reinterpret_cast<unsigned long long*>(out)[q] = e[q];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (q * 8 + k < nbytes) out[q * 8 + k] = (int8_t)((e[q] >> (8 * k)) & 0xFFull);
+      }
+    }
+  } else if ((a & 3) == 0) {
+#pragma unroll
+    for (int w = 0; w < 2 * NQ; ++w) {
+      const uint32_t v = (uint32_t)(e[w >> 1] >> (32 * (w & 1)));
+      if (4 * (w + 1) <= nbytes) {
+        reinterpret_cast<uint32_t*>(out)[w] = v;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (w * 4 + k < nbytes) out[w * 4 + k] = (int8_t)((v >> (8 * k)) & 0xFFu);
+      }
+    }
+  } else {
+    cls_store_bytes<NQ>(out, e, nbytes);
+  }
+}
+
 // LH > 0: "hoisted" evaluation for models with at most LH level sets.  SPHERE / PLANE / CYLINDER split into parts that
 // depend on one coordinate only: the x parts live in registers (per x word of the tile), the y parts in shared memory
 // (per node row), the marching coordinate enters once per plane.  The association of the reference formulas
@@ -514,13 +550,14 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
           const bool fast = (!lane_on || u_in || u_out) && (!word_on || w_uni);
           int8_t* out = states + (int64_t)ls * pitch + cube0 * CPC;
           unsigned long long e[NQ];
-          if (vec_ok && __all_sync(FULL, fast)) {
+          if (__all_sync(FULL, fast)) {
             // uniform everywhere in the warp tile (the common case away from the surfaces): constant states
             if (lane_on) {
               const unsigned long long pat = u_in ? 0xFFFFFFFFFFFFFFFFull : 0x0101010101010101ull;
 #pragma unroll
               for (int q = 0; q < NQ; ++q) e[q] = pat;
-              cls_store<NQ>(out, e);
+              if (vec_ok) cls_store<NQ>(out, e);
+              else cls_store_any<NQ>(out, e, nl * CPC);
               if (u_in) uni_in += (unsigned int)nl; else uni_out += (unsigned int)nl;
             }
           } else {
@@ -583,7 +620,7 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
             }
             if (lane_on) {
               if (vec_ok) cls_store<NQ>(out, e);
-              else cls_store_bytes<NQ>(out, e, nl * CPC);
+              else cls_store_any<NQ>(out, e, nl * CPC);
             }
           }
           if (L > 1) flush_counts(ls);
