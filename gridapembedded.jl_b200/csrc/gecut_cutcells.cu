@@ -185,7 +185,11 @@ template <int D, int LM, bool FILL>
 __global__ void __launch_bounds__(WALK_T)
 k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
            const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
-           const int32_t* __restrict__ cutcells, int64_t nsimp, GcCounters cn, GcLayout lay) {
+           const int32_t* __restrict__ cutcells, int64_t nsimp, GcCounters cn, GcLayout lay, int mode,
+           uint32_t* __restrict__ slow_list, uint32_t* __restrict__ slow_count) {
+  // mode 1: all simplices, but those cut by two or more level sets are only recorded in slow_list (count walk) / skipped
+  //         (fill walk); mode 2: the recorded simplices, one per thread -- so that the tree walk, which is an order of
+  //         magnitude longer than the no-tree path, runs in full warps instead of stalling 31 finished lanes each time
   constexpr int NPC = WalkCfg<D>::NPC, NPF = WalkCfg<D>::NPF;
   constexpr int CE = NPC - (D + 1), FE = NPF - D;  // max new points per cell / facet cut
   constexpr int NPOOL = (D + 1) + CE * LM + FE * (LM > 1 ? LM - 1 : 1);
@@ -205,9 +209,11 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
   }
   __syncthreads();
   const int64_t s_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = s_raw < nsimp;
+  const int64_t nwork = mode == 2 ? (int64_t)*slow_count : nsimp;
+  const bool valid = s_raw < nwork;
   if (!FILL && !valid) return;
-  const int64_t s = valid ? s_raw : nsimp - 1;  // lanes past the end idle but take part in the warp-level copy-out
+  // lanes past the end idle but take part in the warp-level copy-out
+  const int64_t s = mode == 2 ? (int64_t)slow_list[valid ? s_raw : 0] : (valid ? s_raw : nsimp - 1);
   const GcSimplexTable& TC = s_tab[0];
   const GcSimplexTable& TF = s_tab[1];
   const int L = lv.L;
@@ -244,7 +250,7 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
   uint16_t* pmap = walk_pmap + (FILL && LM > 1 ? (threadIdx.x >> 5) * PCAP : 0);
   uint32_t wbase = 0, wcount = 0;
   bool staged = false;
-  if (FILL && LM > 1) {
+  if (FILL && LM > 1 && mode != 2) {
     const int64_t s0 = s_raw - lane;
     wbase = cn.points[s0 < nsimp ? s0 : nsimp - 1];
     const uint32_t wend = (s0 + 32 < nsimp) ? cn.points[s0 + 32] : cn.total_points;
@@ -321,6 +327,12 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
 
   int depth = 0;
   child[0] = -1;
+  bool deferred = false;
+  if (mode == 1 && __popc(mixed) > 1) {
+    if (!FILL) slow_list[atomicAdd(slow_count, 1u)] = (uint32_t)s;
+    deferred = true;
+    depth = -1;
+  }
   if (L > 1 && __popc(mixed) <= 1) {
     // ---- at most one level set cuts this stage-0 simplex (the bulk of every multi-level-set model): no tree, no stack.
     // The simplex reaches the cutting stage `a` with permuted vertices, is cut there exactly like in the single-level-set
@@ -676,6 +688,14 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
     }
   }
 
+  if (!FILL && !deferred) {
+    cn.cells[s] = cell_off;
+    cn.points[s] = pt_off;
+    for (int k = 0; k < L; ++k) {
+      cn.fac[k][s] = fac_off[k];
+      if (L > 1) cn.fpt[k][s] = fpt_off[k];
+    }
+  }
   }  // valid
   if (FILL && LM > 1) {
     __syncwarp();
@@ -694,12 +714,398 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
       }
     }
   }
-  if (!FILL) {
-    cn.cells[s] = cell_off;
-    cn.points[s] = pt_off;
+}
+
+// ================================================================================================
+// L > 1, simplices cut by AT MOST ONE level set (the bulk of every multi-level-set model): no tree, no stack, no local
+// memory.  Pass 1 evaluates every level set at the D+1 vertices and keeps only the sign bits; a simplex with two or
+// more mixed-sign level sets is recorded for the tree walk (k_cut_walk, mode 2).  Otherwise the simplex reaches the
+// cutting stage `a` with its vertices permuted by the skipped stages, is cut there exactly like in the single-level-set
+// path, and its children (a > 0) or itself (a == 0, or nothing cuts it) are emitted at stage 0; the facets of `a` pass
+// through the other stages unchanged but for the permutations.  The <= 8 points (x and r) live in a per-thread slice of
+// shared memory with an odd stride (conflict-free); subcell points leave through the warp-level copy-out.
+// ================================================================================================
+template <int D, bool FILL>
+__global__ void __launch_bounds__(WALK_T)
+k_cut_fast(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
+           const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
+           const int32_t* __restrict__ cutcells, int64_t nsimp, GcCounters cn, GcLayout lay,
+           uint32_t* __restrict__ slow_list, uint32_t* __restrict__ slow_count) {
+  constexpr int NPC = WalkCfg<D>::NPC;
+  constexpr int PCAP = 1024;
+  constexpr int SSTR = NPC * 2 * D + 1;
+  __shared__ GcSimplexTable s_tab[2];  // [0]: D-simplex (cells), [1]: (D-1)-simplex (facet pass-through rows)
+  __shared__ double scratch[FILL ? SSTR * WALK_T : 1];
+  __shared__ __align__(16) uint16_t pmap_all[FILL ? (WALK_T / 32) * PCAP : 8];
+  __shared__ uint8_t s_swap[8];
+  {
+    const uint32_t* src0 = reinterpret_cast<const uint32_t*>(tables + (D - 1));
+    const uint32_t* src1 = reinterpret_cast<const uint32_t*>(tables + (D - 2));
+    uint32_t* dst0 = reinterpret_cast<uint32_t*>(&s_tab[0]);
+    uint32_t* dst1 = reinterpret_cast<uint32_t*>(&s_tab[1]);
+    for (int i = threadIdx.x; i < (int)(sizeof(GcSimplexTable) / 4); i += blockDim.x) {
+      dst0[i] = src0[i];
+      dst1[i] = src1[i];
+    }
+  }
+  const uint8_t* vtab = (g.simplexified ? simp_raw : simp_pos) + (D - 2) * 24;  // rows of local vertex ids of the n-cube
+  if ((int)threadIdx.x < (g.simplexified ? g.cpc : g.nt0)) {
+    // _ensure_positive_jacobians! in physical space: decided once per simplex type (see k_cut1_fill)
+    double x[D + 1][D];
+#pragma unroll
+    for (int m = 0; m <= D; ++m) {
+      const int lvid = vtab[threadIdx.x * 4 + m];
+#pragma unroll
+      for (int d = 0; d < D; ++d) x[m][d] = gc_coord(g, d, (d == D - 1 ? g.k0 : 0) + ((lvid >> d) & 1));
+    }
+    double J[3][3];
+#pragma unroll
+    for (int a = 0; a < D; ++a)
+#pragma unroll
+      for (int b = 0; b < D; ++b) J[a][b] = __dsub_rn(x[a + 1][b], x[0][b]);
+    double dV;
+    if (D == 2) {
+      dV = __dsub_rn(__dmul_rn(J[0][0], J[1][1]), __dmul_rn(J[0][1], J[1][0]));
+    } else {
+      const double p1 = __dmul_rn(__dmul_rn(J[0][0], J[1][1]), J[2][2]);
+      const double p2 = __dmul_rn(__dmul_rn(J[0][1], J[1][2]), J[2][0]);
+      const double p3 = __dmul_rn(__dmul_rn(J[0][2], J[1][0]), J[2][1]);
+      const double q1 = __dmul_rn(__dmul_rn(J[0][0], J[1][2]), J[2][1]);
+      const double q2 = __dmul_rn(__dmul_rn(J[0][1], J[1][0]), J[2][2]);
+      const double q3 = __dmul_rn(__dmul_rn(J[0][2], J[1][1]), J[2][0]);
+      dV = __dsub_rn(__dadd_rn(__dadd_rn(p1, p2), p3), __dadd_rn(__dadd_rn(q1, q2), q3));
+    }
+    s_swap[threadIdx.x] = dV < 0.0 ? 1 : 0;
+  }
+  __syncthreads();
+  const GcSimplexTable& TC = s_tab[0];
+  const GcSimplexTable& TF = s_tab[1];
+  const int L = lv.L;
+  const int lane = threadIdx.x & 31;
+  const int64_t s_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = s_raw < nsimp;
+  if (!FILL && !valid) return;
+  const int64_t s = valid ? s_raw : nsimp - 1;  // lanes past the end idle but take part in the warp-level copy-out
+
+  // ---- warp-level copy-out state (see k_cut_walk)
+  uint16_t* pmap = pmap_all + (FILL ? (threadIdx.x >> 5) * PCAP : 0);
+  uint32_t wbase = 0, wcount = 0;
+  bool staged = false;
+  if (FILL) {
+    const int64_t s0 = s_raw - lane;
+    wbase = cn.points[s0 < nsimp ? s0 : nsimp - 1];
+    const uint32_t wend = (s0 + 32 < nsimp) ? cn.points[s0 + 32] : cn.total_points;
+    wcount = wend - wbase;
+    staged = wcount <= (uint32_t)PCAP;
+    if (staged) {
+      uint4* pm4 = reinterpret_cast<uint4*>(pmap) + lane * (PCAP / 256);
+#pragma unroll
+      for (int i = 0; i < PCAP / 256; ++i) pm4[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    }
+    __syncwarp();
+  }
+
+  if (valid) {
+    const int64_t kcut = s / g.nt0;
+    const int t0 = (int)(s - kcut * g.nt0);
+    const int32_t bgcell1 = cutcells[kcut];
+    const uint32_t cell = (uint32_t)(bgcell1 - 1);  // slab-local cell ids fit in 32 bits (checked at cut time)
+    const uint32_t cube = cell / (uint32_t)g.cpc;
+    const int row_id = g.simplexified ? (int)(cell - cube * (uint32_t)g.cpc) : t0;
+    int ijk[3];
+    {
+      const uint32_t row = cube / (uint32_t)g.n[0];
+      ijk[0] = (int)(cube - row * (uint32_t)g.n[0]);
+      if (D == 3) {
+        const uint32_t lay3 = row / (uint32_t)g.n[1];
+        ijk[1] = (int)(row - lay3 * (uint32_t)g.n[1]);
+        ijk[2] = (int)lay3 + g.k0;
+      } else {
+        ijk[1] = (int)row + g.k0;
+        ijk[2] = 0;
+      }
+    }
+    uint32_t lv4 = *reinterpret_cast<const uint32_t*>(vtab + row_id * 4);
+    uint32_t rv4 = g.simplexified ? 0x04020100u : lv4;  // reference coordinates, one bit per direction
+    if (s_swap[row_id]) {                               // swap the first two vertices
+      lv4 = __byte_perm(lv4, 0u, 0x3201);
+      rv4 = __byte_perm(rv4, 0u, 0x3201);
+    }
+    double X[D + 1][3];
+    int64_t node[D + 1];
+#pragma unroll
+    for (int m = 0; m <= D; ++m) {
+      const int lvid = (lv4 >> (8 * m)) & 0xFFu;
+      const int nijk[3] = {ijk[0] + (lvid & 1), ijk[1] + ((lvid >> 1) & 1), ijk[2] + ((lvid >> 2) & 1)};
+      X[m][0] = gc_coord(g, 0, nijk[0]);
+      X[m][1] = gc_coord(g, 1, nijk[1]);
+      X[m][2] = D == 3 ? gc_coord(g, 2, nijk[2]) : 0.0;
+      node[m] = (D == 3) ? ((int64_t)nijk[0] + (int64_t)g.nn[0] * ((int64_t)nijk[1] + (int64_t)g.nn[1] * nijk[2]))
+                         : ((int64_t)nijk[0] + (int64_t)g.nn[0] * nijk[1]);
+    }
+    auto value = [&](int ls, int m) -> double {
+      if (lv.leaf[ls].kind == GECUT_LEAF_NODAL) return __ldg(lv.nodal[ls] + (node[m] - lv.nodal_base));
+      return gc_eval_leaf(lv.leaf[ls], X[m], D);
+    };
+    // ---- pass 1: sign bits of every level set
+    uint32_t mixed = 0u, outm = 0u;
     for (int k = 0; k < L; ++k) {
-      cn.fac[k][s] = fac_off[k];
-      if (L > 1) cn.fpt[k][s] = fpt_off[k];
+      bool any = false, all = true;
+#pragma unroll
+      for (int m = 0; m <= D; ++m) {
+        const bool o = value(k, m) > 0.0;
+        any |= o;
+        all &= o;
+      }
+      if (any && !all) mixed |= 1u << k;
+      if (all) outm |= 1u << k;
+    }
+    uint32_t cell_off = 0, pt_off = 0;
+    if (__popc(mixed) > 1) {
+      if (!FILL) slow_list[atomicAdd(slow_count, 1u)] = (uint32_t)s;
+    } else {
+      const int a = mixed ? (31 - __clz(mixed)) : 0;  // the only stage that can cut (stage 0 is visited in any case)
+      auto cstate = [&](int k) -> int8_t { return ((outm >> k) & 1u) ? (int8_t)GC_OUT : (int8_t)GC_IN; };
+      const int c_allout = (1 << (D + 1)) - 1, fc_allout = (1 << D) - 1;
+      auto skip_cell_stages = [&](uint8_t* vl, int hi, int lo) {
+        for (int k = hi - 1; k > lo; --k) {
+          const uint8_t* pm = TC.sub_pts[((outm >> k) & 1u) ? c_allout : 0][0];
+          uint8_t tmp[D + 1];
+#pragma unroll
+          for (int i = 0; i <= D; ++i) tmp[i] = vl[pm[i]];
+#pragma unroll
+          for (int i = 0; i <= D; ++i) vl[i] = tmp[i];
+        }
+      };
+      auto skip_facet_stages = [&](uint8_t* vl, int hi, int lo, int skip) {
+        for (int k = hi - 1; k > lo; --k) {
+          if (k == skip) continue;
+          const uint8_t* pm = TF.sub_pts[((outm >> k) & 1u) ? fc_allout : 0][0];
+          uint8_t tmp[D];
+#pragma unroll
+          for (int i = 0; i < D; ++i) tmp[i] = vl[pm[i]];
+#pragma unroll
+          for (int i = 0; i < D; ++i) vl[i] = tmp[i];
+        }
+      };
+      uint8_t vl[D + 1];  // vertex order when the simplex arrives at stage a
+#pragma unroll
+      for (int i = 0; i <= D; ++i) vl[i] = (uint8_t)i;
+      skip_cell_stages(vl, L, a);
+      // ---- pass 2: values of level set a (signs are enough when nothing cuts), in arrival order
+      double W[D + 1];
+      {
+        double W0[D + 1];
+#pragma unroll
+        for (int m = 0; m <= D; ++m) W0[m] = mixed ? value(a, m) : (((outm >> a) & 1u) ? 1.0 : -1.0);
+#pragma unroll
+        for (int i = 0; i <= D; ++i) {
+          double w = W0[0];
+#pragma unroll
+          for (int m = 1; m <= D; ++m)
+            if (vl[i] == m) w = W0[m];
+          W[i] = w;
+        }
+      }
+      int c = 0;
+#pragma unroll
+      for (int i = 0; i <= D; ++i)
+        if (W[i] > 0.0) c |= 1 << i;
+      const int nsub = TC.nsub[c], nfac = TC.nfac[c];
+      int np = D + 1;
+      double* SX = scratch + (FILL ? threadIdx.x * SSTR : 0);  // component q (x then r) of slot p at SX[p * 2 * D + q]
+      auto sget = [&](int slot, int q) -> double { return SX[slot * 2 * D + q]; };
+      if (FILL) {
+        // vertices in original order to the upper slots, then permuted into slots 0..D (no dynamic register indexing)
+#pragma unroll
+        for (int m = 0; m <= D; ++m)
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            SX[(NPC - 1 - D + m) * 2 * D + d] = X[m][d];
+            SX[(NPC - 1 - D + m) * 2 * D + D + d] = (double)((rv4 >> (8 * m + d)) & 1u);
+          }
+        double tmp[D + 1][2 * D];
+#pragma unroll
+        for (int i = 0; i <= D; ++i)
+#pragma unroll
+          for (int q = 0; q < 2 * D; ++q) tmp[i][q] = SX[(NPC - 1 - D + vl[i]) * 2 * D + q];
+#pragma unroll
+        for (int i = 0; i <= D; ++i)
+#pragma unroll
+          for (int q = 0; q < 2 * D; ++q) SX[i * 2 * D + q] = tmp[i][q];
+      }
+      if (TC.inoutcut[c] == GC_CUT) {
+        for (int ed = 0; ed < TC.nedges; ++ed) {
+          const int ia = TC.edges[ed][0], ib = TC.edges[ed][1];
+          double wa = W[0], wb = W[0];
+#pragma unroll
+          for (int m = 1; m <= D; ++m) {
+            if (ia == m) wa = W[m];
+            if (ib == m) wb = W[m];
+          }
+          if ((wa > 0.0) != (wb > 0.0)) {
+            if (FILL) {
+              const double w1 = fabs(wa), w2 = fabs(wb);
+              const double coeff = __ddiv_rn(w1, __dadd_rn(w1, w2));
+#pragma unroll
+              for (int q = 0; q < 2 * D; ++q) SX[np * 2 * D + q] = gc_lerp(sget(ia, q), sget(ib, q), coeff);
+            }
+            np++;
+          }
+        }
+      }
+      uint32_t fac_off = 0, fpt_off = 0;
+      if (FILL) {
+        cell_off = cn.cells[s];
+        pt_off = cn.points[s];
+        fac_off = cn.fac_base[a] + cn.fac[a][s];
+        fpt_off = cn.fpt_base[a] + cn.fpt[a][s];
+      }
+      // ---- facets of level set a: one final facet each, emitted at the last other stage
+      if (FILL) {
+        const int klast = a == 0 ? 1 : 0;
+        const int fc = ((outm >> klast) & 1u) ? fc_allout : 0;
+        for (int f = 0; f < nfac; ++f) {
+          const uint8_t* fp = TC.fac_pts[c][f];
+          double q1[3], q2[3], q3[3], nrm[3];
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            q1[d] = sget(fp[0], d);
+            q2[d] = sget(fp[1], d);
+            q3[d] = sget(fp[D - 1], d);
+          }
+          unit_normal<D>(q1, q2, q3, (double)TC.fac_orient[c][f], nrm);
+          uint8_t fvl[D];
+#pragma unroll
+          for (int i = 0; i < D; ++i) fvl[i] = fp[i];
+          skip_facet_stages(fvl, L, klast, a);
+          const uint32_t pb = fpt_off + (uint32_t)f * D, fid = fac_off + (uint32_t)f;
+#pragma unroll
+          for (int pnt = 0; pnt < D; ++pnt)
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+              lay.sf_X[(int64_t)(pb + pnt) * D + d] = sget(fvl[pnt], d);
+              lay.sf_R[(int64_t)(pb + pnt) * D + d] = sget(fvl[pnt], D + d);
+            }
+          double pf[D][3];
+#pragma unroll
+          for (int i = 0; i < D; ++i) {
+            const int li = TF.sub_pts[fc][0][i];
+            lay.sf_c2p[(int64_t)fid * D + i] = (int32_t)(pb + li + 1);
+            lay.sf_N[(int64_t)fid * D + i] = nrm[i];
+#pragma unroll
+            for (int d = 0; d < D; ++d) pf[i][d] = sget(fvl[li], d);
+          }
+          lay.sf_c2bg[fid] = bgcell1;
+          lay.sf_meas[fid] = integrate_one<D - 1>(simplex_meas<D, D - 1>(pf));
+          for (int kk = 0; kk < L; ++kk)
+            lay.sf_state[(int64_t)kk * lay.sf_pitch + fid] =
+                (kk == a) ? (int8_t)GECUT_INTERFACE : ((kk == klast) ? TF.sub_inout[fc][0] : cstate(kk));
+        }
+      }
+      // ---- cells
+      uint32_t ncell_out, npt_out;
+      if (a == 0) {
+        // cut (or not) at the emission stage itself: one point block, nsub children (CutTriangulations.jl:186-203)
+        if (FILL) {
+          for (int pnt = 0; pnt < np; ++pnt) {
+            if (staged) {
+              pmap[pt_off + pnt - wbase] = (uint16_t)((lane << 3) | pnt);
+            } else {
+#pragma unroll
+              for (int d = 0; d < D; ++d) {
+                lay.sc_X[(int64_t)(pt_off + pnt) * D + d] = sget(pnt, d);
+                lay.sc_R[(int64_t)(pt_off + pnt) * D + d] = sget(pnt, D + d);
+              }
+            }
+          }
+          for (int j = 0; j < nsub; ++j) {
+            const uint32_t cid = cell_off + j;
+            double pc[D + 1][3];
+            int32_t row[D + 1];
+#pragma unroll
+            for (int i = 0; i <= D; ++i) {
+              const int li = TC.sub_pts[c][j][i];
+              row[i] = (int32_t)(pt_off + li + 1);
+#pragma unroll
+              for (int d = 0; d < D; ++d) pc[i][d] = sget(li, d);
+            }
+            store_c2p_row<D>(lay.sc_c2p, cid, row);
+            lay.sc_c2bg[cid] = bgcell1;
+            lay.sc_meas[cid] = integrate_one<D>(simplex_meas<D, D>(pc));
+            lay.sc_state[cid] = TC.sub_inout[c][j];
+            for (int kk = 1; kk < L; ++kk) lay.sc_state[(int64_t)kk * lay.sc_pitch + cid] = cstate(kk);
+          }
+        }
+        ncell_out = nsub;
+        npt_out = np;
+      } else {
+        // cut at stage a > 0: every child goes down to stage 0 alone and is emitted there as an uncut simplex
+        const int c0 = (outm & 1u) ? c_allout : 0;
+        if (FILL) {
+          for (int j = 0; j < nsub; ++j) {
+            uint8_t cv[D + 1];
+#pragma unroll
+            for (int i = 0; i <= D; ++i) cv[i] = TC.sub_pts[c][j][i];
+            skip_cell_stages(cv, a, 0);
+            const uint32_t pb = pt_off + (uint32_t)j * (D + 1), cid = cell_off + j;
+#pragma unroll
+            for (int pnt = 0; pnt <= D; ++pnt) {
+              if (staged) {
+                pmap[pb + pnt - wbase] = (uint16_t)((lane << 3) | cv[pnt]);
+              } else {
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                  lay.sc_X[(int64_t)(pb + pnt) * D + d] = sget(cv[pnt], d);
+                  lay.sc_R[(int64_t)(pb + pnt) * D + d] = sget(cv[pnt], D + d);
+                }
+              }
+            }
+            double pc[D + 1][3];
+            int32_t row[D + 1];
+#pragma unroll
+            for (int i = 0; i <= D; ++i) {
+              const int li = TC.sub_pts[c0][0][i];
+              row[i] = (int32_t)(pb + li + 1);
+#pragma unroll
+              for (int d = 0; d < D; ++d) pc[i][d] = sget(cv[li], d);
+            }
+            store_c2p_row<D>(lay.sc_c2p, cid, row);
+            lay.sc_c2bg[cid] = bgcell1;
+            lay.sc_meas[cid] = integrate_one<D>(simplex_meas<D, D>(pc));
+            lay.sc_state[cid] = TC.sub_inout[c0][0];
+            for (int kk = 1; kk < L; ++kk)
+              lay.sc_state[(int64_t)kk * lay.sc_pitch + cid] = (kk == a) ? TC.sub_inout[c][j] : cstate(kk);
+          }
+        }
+        ncell_out = nsub;
+        npt_out = nsub * (D + 1);
+      }
+      if (!FILL) {
+        cn.cells[s] = ncell_out;
+        cn.points[s] = npt_out;
+        for (int k = 0; k < L; ++k) {
+          cn.fac[k][s] = (k == a) ? (uint32_t)nfac : 0u;
+          cn.fpt[k][s] = (k == a) ? (uint32_t)(nfac * D) : 0u;
+        }
+      }
+    }
+  }  // valid
+  if (FILL) {
+    __syncwarp();
+    if (staged) {
+      const double* SW = scratch + (threadIdx.x & ~31) * SSTR;  // scratch of lane 0 of this warp
+      double* gX = lay.sc_X + (int64_t)wbase * D;
+      double* gR = lay.sc_R + (int64_t)wbase * D;
+      for (uint32_t q = lane; q < wcount * D; q += 32) {
+        const uint32_t pnt = q / D, d = q - pnt * D;
+        const uint32_t m = pmap[pnt];
+        if (m != 0xFFFFu) {
+          const double* src = SW + (m >> 3) * SSTR + (m & 7u) * 2 * D;
+          gX[q] = src[d];
+          gR[q] = src[D + d];
+        }
+      }
     }
   }
 }
@@ -1218,21 +1624,40 @@ __global__ void k_extract_sc_ptr(const uint32_t* __restrict__ cell_offs, const u
 }
 
 template <int D, int LM>
-void launch_walk(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcCounters& cn, bool fill) {
+void launch_walk(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcCounters& cn, bool fill, int mode,
+                 int64_t nwork, uint32_t* slow_list, uint32_t* slow_count) {
   const int T = WALK_T;
-  const unsigned nb = (unsigned)gc_div_up(nsimp, T);
+  const unsigned nb = (unsigned)gc_div_up(nwork, T);
+  if (nb == 0) return;
   if (fill)
-    GC_LAUNCH(ctx, "k_cut_walk_fill", k_cut_walk<D, LM, true><<<nb, T, 0, ctx->stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
-                                                       ctx->d_simplexify_pos, res->lay.cutcells, nsimp, cn, res->lay));
+    GC_LAUNCH(ctx, mode == 2 ? "k_cut_walk_fill_tree" : "k_cut_walk_fill", k_cut_walk<D, LM, true><<<nb, T, 0, ctx->stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
+                                                       ctx->d_simplexify_pos, res->lay.cutcells, nsimp, cn, res->lay, mode, slow_list, slow_count));
   else
-    GC_LAUNCH(ctx, "k_cut_walk_count", k_cut_walk<D, LM, false><<<nb, T, 0, ctx->stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
-                                                        ctx->d_simplexify_pos, res->lay.cutcells, nsimp, cn, res->lay));
+    GC_LAUNCH(ctx, mode == 2 ? "k_cut_walk_count_tree" : "k_cut_walk_count", k_cut_walk<D, LM, false><<<nb, T, 0, ctx->stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
+                                                        ctx->d_simplexify_pos, res->lay.cutcells, nsimp, cn, res->lay, mode, slow_list, slow_count));
 }
 
-void dispatch_walk(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcCounters& cn, bool fill) {
+void launch_fast(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcCounters& cn, bool fill,
+                 uint32_t* slow_list, uint32_t* slow_count) {
+  const unsigned nb = (unsigned)gc_div_up(nsimp, WALK_T);
+#define GC_FAST(DD, FF, NAME)                                                                                      \
+  GC_LAUNCH(ctx, NAME, k_cut_fast<DD, FF><<<nb, WALK_T, 0, ctx->stream>>>(res->grid, res->leaves, ctx->d_tables,      \
+                                                                        ctx->d_simplexify_raw, ctx->d_simplexify_pos, \
+                                                                        res->lay.cutcells, nsimp, cn, res->lay,     \
+                                                                        slow_list, slow_count))
+  if (res->grid.D == 2) {
+    if (fill) GC_FAST(2, true, "k_cut_fast_fill"); else GC_FAST(2, false, "k_cut_fast_count");
+  } else {
+    if (fill) GC_FAST(3, true, "k_cut_fast_fill"); else GC_FAST(3, false, "k_cut_fast_count");
+  }
+#undef GC_FAST
+}
+
+void dispatch_walk(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcCounters& cn, bool fill, int mode,
+                   int64_t nwork, uint32_t* slow_list, uint32_t* slow_count) {
   const int L = res->L;
   const int D = res->grid.D;
-#define GC_WALK(DD, LL) launch_walk<DD, LL>(ctx, res, nsimp, cn, fill)
+#define GC_WALK(DD, LL) launch_walk<DD, LL>(ctx, res, nsimp, cn, fill, mode, nwork, slow_list, slow_count)
   if (D == 2) {
     if (L <= 1) GC_WALK(2, 1);
     else if (L <= 2) GC_WALK(2, 2);
@@ -1368,7 +1793,21 @@ int gc_cut_cells(gecut_ctx* ctx, gecut_result* res) {
     cn.fac[k] = pool + (2 + k) * nsimp;
     cn.fpt[k] = (L > 1) ? pool + (2 + L + k) * nsimp : nullptr;
   }
-  dispatch_walk(ctx, res, nsimp, cn, false);
+  // simplices cut by two or more level sets are collected and walked by a second, dense launch
+  uint32_t* slow_list = nullptr;
+  uint32_t* slow_count = nullptr;
+  GC_CHECK(gc_malloc(ctx, (void**)&slow_list, sizeof(uint32_t) * nsimp));
+  GC_CHECK(gc_malloc(ctx, (void**)&slow_count, sizeof(uint32_t) * 2));
+  GC_CUDA(cudaMemsetAsync(slow_count, 0, sizeof(uint32_t) * 2, ctx->stream));
+  launch_fast(ctx, res, nsimp, cn, false, slow_list, slow_count);
+  int64_t nslow = 0;
+  {
+    uint32_t* hs = (uint32_t*)ctx->h_pinned;
+    GC_CUDA(cudaMemcpyAsync(hs, slow_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GC_CUDA(cudaStreamSynchronize(ctx->stream));
+    nslow = (int64_t)hs[0];
+  }
+  dispatch_walk(ctx, res, nsimp, cn, false, 2, nslow, slow_list, slow_count);
   GC_CHECK(gc_launch_check(ctx, "k_cut_walk(count)"));
   GC_CHECK(gc_exclusive_scan_u32_multi(ctx, pool, pool, nsimp, narr, totals_dev));
   uint64_t* h = (uint64_t*)ctx->h_pinned;
@@ -1388,6 +1827,8 @@ int gc_cut_cells(gecut_ctx* ctx, gecut_result* res) {
     ctx->err = "Int32 ids of the SubCellData/SubFacetData layout would overflow";
     gc_free(ctx, pool);
     gc_free(ctx, totals_dev);
+    gc_free(ctx, slow_list);
+    gc_free(ctx, slow_count);
     return GECUT_ERR_OVERFLOW;
   }
   sz.num_subcells = (int64_t)nsc;
@@ -1417,9 +1858,12 @@ int gc_cut_cells(gecut_ctx* ctx, gecut_result* res) {
   GC_CHECK(gc_malloc(ctx, (void**)&res->cut_sc_ptr, sizeof(uint32_t) * 2 * (ncut + 1)));
   GC_LAUNCH(ctx, "k_extract_sc_ptr", k_extract_sc_ptr<<<(unsigned)gc_div_up(ncut + 1, 256), 256, 0, ctx->stream>>>(
       cn.cells, cn.points, g.nt0, ncut, (uint32_t)nsc, (uint32_t)nscp, res->cut_sc_ptr));
-  dispatch_walk(ctx, res, nsimp, cn, true);
+  launch_fast(ctx, res, nsimp, cn, true, slow_list, slow_count);
+  dispatch_walk(ctx, res, nsimp, cn, true, 2, nslow, slow_list, slow_count);
   int st = gc_launch_check(ctx, "k_cut_walk(fill)");
   gc_free(ctx, pool);
   gc_free(ctx, totals_dev);
+  gc_free(ctx, slow_list);
+  gc_free(ctx, slow_count);
   return st;
 }

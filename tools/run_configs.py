@@ -36,7 +36,7 @@ def report(name, model, geo, omega_names, check_oracle=False):
     ms, _ = timed(step)
     ctx = gecut._lib.default_context()
     ctx.profile(True); step(); rep = ctx.profile_report(); ctx.profile(False)
-    top = sorted(rep.items(), key=lambda kv: -kv[1][1])[:4]
+    top = sorted(rep.items(), key=lambda kv: -kv[1][1])[:int(os.environ.get("TOPK", "4"))]
     out, cg = step(keep=True)
     s = out["sizes"]
     box = float(np.prod(np.asarray(model.pmax) - np.asarray(model.pmin)))
