@@ -215,28 +215,52 @@ k_cutcell_laplacian_q1(const GcGrid g, const GcLayout lay, const uint32_t* __res
   for (int m = 0; m < NM; ++m) M[m] = 0.0;
   if (!check_bg || gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, cell0) == GC_CUT) {
     const uint32_t s0 = sc_ptr[2 * k], s1 = sc_ptr[2 * k + 2];
-    for (uint32_t it = s0; it < s1; ++it) {
-      const int64_t e = (int64_t)it;
-      if (gc_eval_inoutcut(prog, lay.sc_state, lay.sc_pitch, e) != side) continue;
-      int32_t ids[D + 1];
+    // software pipeline: connectivity row, state and measure of the NEXT subcell are requested while the current one
+    // is processed, so an iteration waits for one memory round trip (the reference points), not two
+    struct Ids {
+      int32_t v[4];
+    };
+    auto load_ids = [&](int64_t e) -> Ids {
+      Ids o;
       if (D == 3) {
         const int4 q4 = *reinterpret_cast<const int4*>(lay.sc_c2p + e * 4);
-        ids[0] = q4.x;
-        ids[1] = q4.y;
-        ids[2] = q4.z;
-        ids[D] = q4.w;
+        o.v[0] = q4.x;
+        o.v[1] = q4.y;
+        o.v[2] = q4.z;
+        o.v[3] = q4.w;
       } else {
 #pragma unroll
-        for (int v = 0; v <= D; ++v) ids[v] = lay.sc_c2p[e * (D + 1) + v];
+        for (int v = 0; v <= D; ++v) o.v[v] = lay.sc_c2p[e * (D + 1) + v];
+        o.v[3] = 0;
       }
+      return o;
+    };
+    Ids nids{};
+    int nstate = 0;
+    double nmeas = 0.0;
+    if (s0 < s1) {
+      nids = load_ids((int64_t)s0);
+      nstate = gc_eval_inoutcut(prog, lay.sc_state, lay.sc_pitch, (int64_t)s0);
+      nmeas = lay.sc_meas[s0];
+    }
+    for (uint32_t it = s0; it < s1; ++it) {
+      const Ids ids_s = nids;
+      const int state = nstate;
+      const double meas = nmeas;
+      if (it + 1 < s1) {
+        nids = load_ids((int64_t)it + 1);
+        nstate = gc_eval_inoutcut(prog, lay.sc_state, lay.sc_pitch, (int64_t)it + 1);
+        nmeas = lay.sc_meas[it + 1];
+      }
+      if (state != side) continue;
       double r[D + 1][3];
 #pragma unroll
       for (int v = 0; v <= D; ++v) {
-        const int64_t pid = (int64_t)ids[v] - 1;
+        const int64_t pid = (int64_t)ids_s.v[v] - 1;
 #pragma unroll
         for (int d = 0; d < D; ++d) r[v][d] = lay.sc_R[pid * D + d];
       }
-      const double wdV = lay.sc_meas[e] * (1.0 / NQ);  // sc_meas = sum_q w_q |J_s| (all weights equal)
+      const double wdV = meas * (1.0 / NQ);  // sc_meas = sum_q w_q |J_s| (all weights equal)
       double rs[3];
 #pragma unroll
       for (int d = 0; d < D; ++d) {
