@@ -185,18 +185,17 @@ template <int D, int LM, bool FILL>
 __global__ void __launch_bounds__(WALK_T)
 k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
            const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
-           const int32_t* __restrict__ cutcells, int64_t nsimp, GcCounters cn, GcLayout lay, int mode,
-           uint32_t* __restrict__ slow_list, uint32_t* __restrict__ slow_count) {
-  // mode 1: all simplices, but those cut by two or more level sets are only recorded in slow_list (count walk) / skipped
-  //         (fill walk); mode 2: the recorded simplices, one per thread -- so that the tree walk, which is an order of
-  //         magnitude longer than the no-tree path, runs in full warps instead of stalling 31 finished lanes each time
+           const int32_t* __restrict__ cutcells, int64_t nsimp, GcCounters cn, GcLayout lay,
+           const uint32_t* __restrict__ slow_list, const uint32_t* __restrict__ slow_count) {
+  // One thread per RECORDED simplex (those cut by two or more level sets, listed by k_cut_fast): the tree walk is an
+  // order of magnitude longer than the no-tree path, so it runs in its own dense launch instead of stalling the 31
+  // finished lanes of a mixed warp.
   constexpr int NPC = WalkCfg<D>::NPC, NPF = WalkCfg<D>::NPF;
   constexpr int CE = NPC - (D + 1), FE = NPF - D;  // max new points per cell / facet cut
-  constexpr int NPOOL = (D + 1) + CE * LM + FE * (LM > 1 ? LM - 1 : 1);
-  constexpr int LF = (LM > 1) ? LM - 1 : 1;
+  constexpr int NPOOL = (D + 1) + CE * LM + FE * (LM - 1);
+  constexpr int LF = LM - 1;
+  static_assert(LM >= 2, "one level set takes the k_cut1_* path");
   __shared__ GcSimplexTable s_tab[2];  // [0]: D-simplex (cells), [1]: (D-1)-simplex (facet re-cuts)
-  // fast path scratch: the <= NPC points (x and r) of one cut simplex per thread, transposed (conflict-free)
-  __shared__ double walk_scratch[(FILL && LM > 1) ? (NPC * 2 * D + 1) * WALK_T : 1];
   {
     const uint32_t* src0 = reinterpret_cast<const uint32_t*>(tables + (D - 1));
     const uint32_t* src1 = reinterpret_cast<const uint32_t*>(tables + (D - 2));
@@ -208,12 +207,9 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
     }
   }
   __syncthreads();
-  const int64_t s_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t nwork = mode == 2 ? (int64_t)*slow_count : nsimp;
-  const bool valid = s_raw < nwork;
-  if (!FILL && !valid) return;
-  // lanes past the end idle but take part in the warp-level copy-out
-  const int64_t s = mode == 2 ? (int64_t)slow_list[valid ? s_raw : 0] : (valid ? s_raw : nsimp - 1);
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)*slow_count) return;
+  const int64_t s = (int64_t)slow_list[idx];
   const GcSimplexTable& TC = s_tab[0];
   const GcSimplexTable& TF = s_tab[1];
   const int L = lv.L;
@@ -234,34 +230,8 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
     pt_off = cn.points[s];
     for (int k = 0; k < L; ++k) {
       fac_off[k] = cn.fac_base[k] + cn.fac[k][s];
-      if (L > 1) fpt_off[k] = cn.fpt_base[k] + cn.fpt[k][s];
+      fpt_off[k] = cn.fpt_base[k] + cn.fpt[k][s];
     }
-  }
-
-  // Warp-level copy-out of the subcell points (fill walk, L > 1): the point range of the warp's 32 simplices is
-  // contiguous; lanes on the no-tree path leave their points in the shared scratch and only record (lane, slot) per
-  // output point in a 16-bit map, then the whole warp writes point_to_coords / point_to_rcoords one double per lane, fully
-  // coalesced.  Lanes on the tree walk write their points directly (map entries stay 0xFFFF).  Ranges longer than the map
-  // fall back to direct stores for the whole warp.
-  constexpr int PCAP = 1024;
-  constexpr int SSTR = NPC * 2 * D + 1;  // odd stride: conflict-free per-slot writes and per-point reads
-  __shared__ __align__(16) uint16_t walk_pmap[(FILL && LM > 1) ? (WALK_T / 32) * PCAP : 8];
-  const int lane = threadIdx.x & 31;
-  uint16_t* pmap = walk_pmap + (FILL && LM > 1 ? (threadIdx.x >> 5) * PCAP : 0);
-  uint32_t wbase = 0, wcount = 0;
-  bool staged = false;
-  if (FILL && LM > 1 && mode != 2) {
-    const int64_t s0 = s_raw - lane;
-    wbase = cn.points[s0 < nsimp ? s0 : nsimp - 1];
-    const uint32_t wend = (s0 + 32 < nsimp) ? cn.points[s0 + 32] : cn.total_points;
-    wcount = wend - wbase;
-    staged = wcount <= (uint32_t)PCAP;
-    if (staged) {
-      uint4* pm4 = reinterpret_cast<uint4*>(pmap) + lane * (PCAP / 256);
-#pragma unroll
-      for (int i = 0; i < PCAP / 256; ++i) pm4[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-    }
-    __syncwarp();
   }
 
   Pt<D, LM> pool[NPOOL];
@@ -270,7 +240,6 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
   int8_t child[LM], cs[LM], npE[LM], st[LM], ptop_at[LM];
   int8_t fchild[LF], fcs[LF], fptop_at[LF], fst[LM];
 
-  if (valid) {
   setup_stage0<D, LM>(g, lv, bgcell1 - 1, t, simp_raw, simp_pos, lay.bg_state, lay.bg_pitch, pool);
   int ptop = D + 1;
 #pragma unroll
@@ -327,177 +296,6 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
 
   int depth = 0;
   child[0] = -1;
-  bool deferred = false;
-  if (mode == 1 && __popc(mixed) > 1) {
-    if (!FILL) slow_list[atomicAdd(slow_count, 1u)] = (uint32_t)s;
-    deferred = true;
-    depth = -1;
-  }
-  if (L > 1 && __popc(mixed) <= 1) {
-    // ---- at most one level set cuts this stage-0 simplex (the bulk of every multi-level-set model): no tree, no stack.
-    // The simplex reaches the cutting stage `a` with permuted vertices, is cut there exactly like in the single-level-set
-    // path, and its children (a > 0) or itself (a == 0, or nothing cuts it) are emitted at stage 0; the facets of `a` pass
-    // through the other stages unchanged but for the permutations.  The <= 8 points live in a transposed shared-memory
-    // scratch (no local memory), no level-set value is ever interpolated.
-    const int a = mixed ? (31 - __clz(mixed)) : 0;  // the only stage that can cut (stage 0 is visited in any case)
-    double* SX = walk_scratch + threadIdx.x * SSTR;  // component q (x then r) of slot p at SX[p * 2 * D + q]
-    auto sget = [&](int slot, int q) -> double { return SX[slot * 2 * D + q]; };
-    const uint8_t* vl = v[0];                      // vertex order when the simplex arrives at stage a
-    int c = 0;
-#pragma unroll
-    for (int i = 0; i <= D; ++i)
-      if (pool[vl[i]].w[a] > 0.0) c |= 1 << i;
-    const int nsub = TC.nsub[c], nfac = TC.nfac[c];
-    int np = D + 1;
-    if (FILL) {
-#pragma unroll
-      for (int i = 0; i <= D; ++i)
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-          SX[i * 2 * D + d] = pool[vl[i]].x[d];
-          SX[i * 2 * D + D + d] = pool[vl[i]].r[d];
-        }
-    }
-    if (TC.inoutcut[c] == GC_CUT) {
-      for (int ed = 0; ed < TC.nedges; ++ed) {
-        const int ia = TC.edges[ed][0], ib = TC.edges[ed][1];
-        const double wa = pool[vl[ia]].w[a], wb = pool[vl[ib]].w[a];
-        if ((wa > 0.0) != (wb > 0.0)) {
-          if (FILL) {
-            const double w1 = fabs(wa), w2 = fabs(wb);
-            const double coeff = __ddiv_rn(w1, __dadd_rn(w1, w2));
-#pragma unroll
-            for (int q = 0; q < 2 * D; ++q) SX[np * 2 * D + q] = gc_lerp(sget(ia, q), sget(ib, q), coeff);
-          }
-          np++;
-        }
-      }
-    }
-    // ---- facets of level set a: one final facet each (no other stage cuts it), emitted at the last other stage
-    {
-      const int klast = a == 0 ? 1 : 0;
-      const int fc = ((outm >> klast) & 1u) ? fc_allout : 0;
-      if (FILL) {
-        for (int f = 0; f < nfac; ++f) {
-          const uint8_t* fp = TC.fac_pts[c][f];
-          double q1[3], q2[3], q3[3], nrm[3];
-#pragma unroll
-          for (int d = 0; d < D; ++d) {
-            q1[d] = sget(fp[0], d);
-            q2[d] = sget(fp[1], d);
-            q3[d] = sget(fp[D - 1], d);
-          }
-          unit_normal<D>(q1, q2, q3, (double)TC.fac_orient[c][f], nrm);
-          uint8_t fvl[D];
-#pragma unroll
-          for (int i = 0; i < D; ++i) fvl[i] = fp[i];
-          skip_facet_stages(fvl, L, klast, a);
-          const uint32_t pb = fpt_off[a] + (uint32_t)f * D, fid = fac_off[a] + (uint32_t)f;
-#pragma unroll
-          for (int pnt = 0; pnt < D; ++pnt)
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-              lay.sf_X[(int64_t)(pb + pnt) * D + d] = sget(fvl[pnt], d);
-              lay.sf_R[(int64_t)(pb + pnt) * D + d] = sget(fvl[pnt], D + d);
-            }
-          double pf[D][3];
-#pragma unroll
-          for (int i = 0; i < D; ++i) {
-            const int li = TF.sub_pts[fc][0][i];
-            lay.sf_c2p[(int64_t)fid * D + i] = (int32_t)(pb + li + 1);
-            lay.sf_N[(int64_t)fid * D + i] = nrm[i];
-#pragma unroll
-            for (int d = 0; d < D; ++d) pf[i][d] = sget(fvl[li], d);
-          }
-          lay.sf_c2bg[fid] = bgcell1;
-          lay.sf_meas[fid] = integrate_one<D - 1>(simplex_meas<D, D - 1>(pf));
-          for (int kk = 0; kk < L; ++kk)
-            lay.sf_state[(int64_t)kk * lay.sf_pitch + fid] =
-                (kk == a) ? (int8_t)GECUT_INTERFACE : ((kk == klast) ? TF.sub_inout[fc][0] : fst[kk]);
-        }
-      }
-      fac_off[a] += nfac;
-      fpt_off[a] += nfac * D;
-    }
-    // ---- cells
-    if (a == 0) {
-      // cut (or not) at the emission stage itself: one point block, nsub children (CutTriangulations.jl:186-203)
-      if (FILL) {
-        for (int pnt = 0; pnt < np; ++pnt) {
-          if (staged) {
-            pmap[pt_off + pnt - wbase] = (uint16_t)((lane << 3) | pnt);
-          } else {
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-              lay.sc_X[(int64_t)(pt_off + pnt) * D + d] = sget(pnt, d);
-              lay.sc_R[(int64_t)(pt_off + pnt) * D + d] = sget(pnt, D + d);
-            }
-          }
-        }
-        for (int j = 0; j < nsub; ++j) {
-          const uint32_t cid = cell_off + j;
-          double pc[D + 1][3];
-          int32_t row[D + 1];
-#pragma unroll
-          for (int i = 0; i <= D; ++i) {
-            const int li = TC.sub_pts[c][j][i];
-            row[i] = (int32_t)(pt_off + li + 1);
-#pragma unroll
-            for (int d = 0; d < D; ++d) pc[i][d] = sget(li, d);
-          }
-          store_c2p_row<D>(lay.sc_c2p, cid, row);
-          lay.sc_c2bg[cid] = bgcell1;
-          lay.sc_meas[cid] = integrate_one<D>(simplex_meas<D, D>(pc));
-          lay.sc_state[cid] = TC.sub_inout[c][j];
-          for (int kk = 1; kk < L; ++kk) lay.sc_state[(int64_t)kk * lay.sc_pitch + cid] = st[kk];
-        }
-      }
-      cell_off += nsub;
-      pt_off += np;
-    } else {
-      // cut at stage a > 0: every child goes down to stage 0 alone and is emitted there as an uncut simplex
-      const int c0 = (outm & 1u) ? c_allout : 0;
-      if (FILL) {
-        for (int j = 0; j < nsub; ++j) {
-          uint8_t cv[D + 1];
-#pragma unroll
-          for (int i = 0; i <= D; ++i) cv[i] = TC.sub_pts[c][j][i];
-          skip_cell_stages(cv, a, 0);
-          const uint32_t pb = pt_off + (uint32_t)j * (D + 1), cid = cell_off + j;
-#pragma unroll
-          for (int pnt = 0; pnt <= D; ++pnt) {
-            if (staged) {
-              pmap[pb + pnt - wbase] = (uint16_t)((lane << 3) | cv[pnt]);
-            } else {
-#pragma unroll
-              for (int d = 0; d < D; ++d) {
-                lay.sc_X[(int64_t)(pb + pnt) * D + d] = sget(cv[pnt], d);
-                lay.sc_R[(int64_t)(pb + pnt) * D + d] = sget(cv[pnt], D + d);
-              }
-            }
-          }
-          double pc[D + 1][3];
-          int32_t row[D + 1];
-#pragma unroll
-          for (int i = 0; i <= D; ++i) {
-            const int li = TC.sub_pts[c0][0][i];
-            row[i] = (int32_t)(pb + li + 1);
-#pragma unroll
-            for (int d = 0; d < D; ++d) pc[i][d] = sget(cv[li], d);
-          }
-          store_c2p_row<D>(lay.sc_c2p, cid, row);
-          lay.sc_c2bg[cid] = bgcell1;
-          lay.sc_meas[cid] = integrate_one<D>(simplex_meas<D, D>(pc));
-          lay.sc_state[cid] = TC.sub_inout[c0][0];
-          for (int kk = 1; kk < L; ++kk)
-            lay.sc_state[(int64_t)kk * lay.sc_pitch + cid] = (kk == a) ? TC.sub_inout[c][j] : st[kk];
-        }
-      }
-      cell_off += nsub;
-      pt_off += nsub * (D + 1);
-    }
-    depth = -1;  // skip the tree walk
-  }
   while (depth >= 0) {
     const int ls = lsd[depth];
     if (child[depth] < 0) {
@@ -523,29 +321,7 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
       npE[depth] = (int8_t)np;
       const int nfac = TC.nfac[c];
       // ---- boundary facets of this stage (CutTriangulations.jl:268-292)
-      if (L == 1) {
-        if (FILL) {
-          for (int f = 0; f < nfac; ++f) {
-            const uint32_t fid = fac_off[0] + f;
-            const uint8_t* fp = TC.fac_pts[c][f];
-            double nrm[3];
-            unit_normal<D>(pool[e[depth][fp[0]]].x, pool[e[depth][fp[1]]].x, pool[e[depth][fp[D - 1]]].x,
-                           (double)TC.fac_orient[c][f], nrm);
-            double pf[D][3];
-#pragma unroll
-            for (int i = 0; i < D; ++i) {
-              lay.sf_c2p[(int64_t)fid * D + i] = (int32_t)(pt_off + fp[i] + 1);
-              lay.sf_N[(int64_t)fid * D + i] = nrm[i];
-#pragma unroll
-              for (int d = 0; d < D; ++d) pf[i][d] = pool[e[depth][fp[i]]].x[d];
-            }
-            lay.sf_c2bg[fid] = bgcell1;
-            lay.sf_meas[fid] = integrate_one<D - 1>(simplex_meas<D, D - 1>(pf));
-            lay.sf_state[fid] = (int8_t)GECUT_INTERFACE;
-          }
-        }
-        fac_off[0] += nfac;
-      } else {
+      {
         for (int f = 0; f < nfac; ++f) {
           const uint8_t* fp = TC.fac_pts[c][f];
           double nrm[3] = {0.0, 0.0, 0.0};
@@ -688,30 +464,12 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
     }
   }
 
-  if (!FILL && !deferred) {
+  if (!FILL) {
     cn.cells[s] = cell_off;
     cn.points[s] = pt_off;
     for (int k = 0; k < L; ++k) {
       cn.fac[k][s] = fac_off[k];
-      if (L > 1) cn.fpt[k][s] = fpt_off[k];
-    }
-  }
-  }  // valid
-  if (FILL && LM > 1) {
-    __syncwarp();
-    if (staged) {
-      const double* SW = walk_scratch + (threadIdx.x & ~31) * SSTR;  // scratch of lane 0 of this warp
-      double* gX = lay.sc_X + (int64_t)wbase * D;
-      double* gR = lay.sc_R + (int64_t)wbase * D;
-      for (uint32_t q = lane; q < wcount * D; q += 32) {
-        const uint32_t pnt = q / D, d = q - pnt * D;
-        const uint32_t m = pmap[pnt];
-        if (m != 0xFFFFu) {
-          const double* src = SW + (m >> 3) * SSTR + (m & 7u) * 2 * D;
-          gX[q] = src[d];
-          gR[q] = src[D + d];
-        }
-      }
+      cn.fpt[k][s] = fpt_off[k];
     }
   }
 }
@@ -1148,15 +906,6 @@ __device__ __forceinline__ uint32_t cut1_warp_scan(uint32_t v, uint32_t* total) 
   }
   *total = __shfl_sync(0xffffffffu, inc, 31);
   return inc - v;
-}
-
-template <int D>
-__device__ __forceinline__ int cut1_case(const Pt<D, 1>* S) {
-  int c = 0;
-#pragma unroll
-  for (int i = 0; i <= D; ++i)
-    if (S[i].w[0] > 0.0) c |= 1 << i;
-  return c;
 }
 
 // Tile totals.  The three counters of a stage-0 simplex depend only on HOW MANY of its vertices are OUT (the table
@@ -1624,17 +1373,17 @@ __global__ void k_extract_sc_ptr(const uint32_t* __restrict__ cell_offs, const u
 }
 
 template <int D, int LM>
-void launch_walk(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcCounters& cn, bool fill, int mode,
-                 int64_t nwork, uint32_t* slow_list, uint32_t* slow_count) {
+void launch_walk(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcCounters& cn, bool fill, int64_t nslow,
+                 const uint32_t* slow_list, const uint32_t* slow_count) {
   const int T = WALK_T;
-  const unsigned nb = (unsigned)gc_div_up(nwork, T);
+  const unsigned nb = (unsigned)gc_div_up(nslow, T);
   if (nb == 0) return;
   if (fill)
-    GC_LAUNCH(ctx, mode == 2 ? "k_cut_walk_fill_tree" : "k_cut_walk_fill", k_cut_walk<D, LM, true><<<nb, T, 0, ctx->stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
-                                                       ctx->d_simplexify_pos, res->lay.cutcells, nsimp, cn, res->lay, mode, slow_list, slow_count));
+    GC_LAUNCH(ctx, "k_cut_walk_fill", k_cut_walk<D, LM, true><<<nb, T, 0, ctx->stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
+                                                       ctx->d_simplexify_pos, res->lay.cutcells, nsimp, cn, res->lay, slow_list, slow_count));
   else
-    GC_LAUNCH(ctx, mode == 2 ? "k_cut_walk_count_tree" : "k_cut_walk_count", k_cut_walk<D, LM, false><<<nb, T, 0, ctx->stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
-                                                        ctx->d_simplexify_pos, res->lay.cutcells, nsimp, cn, res->lay, mode, slow_list, slow_count));
+    GC_LAUNCH(ctx, "k_cut_walk_count", k_cut_walk<D, LM, false><<<nb, T, 0, ctx->stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
+                                                        ctx->d_simplexify_pos, res->lay.cutcells, nsimp, cn, res->lay, slow_list, slow_count));
 }
 
 void launch_fast(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcCounters& cn, bool fill,
@@ -1653,21 +1402,19 @@ void launch_fast(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const G
 #undef GC_FAST
 }
 
-void dispatch_walk(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcCounters& cn, bool fill, int mode,
-                   int64_t nwork, uint32_t* slow_list, uint32_t* slow_count) {
+void dispatch_walk(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcCounters& cn, bool fill, int64_t nslow,
+                   const uint32_t* slow_list, const uint32_t* slow_count) {
   const int L = res->L;
   const int D = res->grid.D;
-#define GC_WALK(DD, LL) launch_walk<DD, LL>(ctx, res, nsimp, cn, fill, mode, nwork, slow_list, slow_count)
+#define GC_WALK(DD, LL) launch_walk<DD, LL>(ctx, res, nsimp, cn, fill, nslow, slow_list, slow_count)
   if (D == 2) {
-    if (L <= 1) GC_WALK(2, 1);
-    else if (L <= 2) GC_WALK(2, 2);
+    if (L <= 2) GC_WALK(2, 2);
     else if (L <= 4) GC_WALK(2, 4);
     else if (L <= 8) GC_WALK(2, 8);
     else if (L <= 12) GC_WALK(2, 12);
     else GC_WALK(2, 16);
   } else {
-    if (L <= 1) GC_WALK(3, 1);
-    else if (L <= 2) GC_WALK(3, 2);
+    if (L <= 2) GC_WALK(3, 2);
     else if (L <= 4) GC_WALK(3, 4);
     else if (L <= 8) GC_WALK(3, 8);
     else if (L <= 12) GC_WALK(3, 12);
@@ -1807,7 +1554,7 @@ int gc_cut_cells(gecut_ctx* ctx, gecut_result* res) {
     GC_CUDA(cudaStreamSynchronize(ctx->stream));
     nslow = (int64_t)hs[0];
   }
-  dispatch_walk(ctx, res, nsimp, cn, false, 2, nslow, slow_list, slow_count);
+  dispatch_walk(ctx, res, nsimp, cn, false, nslow, slow_list, slow_count);
   GC_CHECK(gc_launch_check(ctx, "k_cut_walk(count)"));
   GC_CHECK(gc_exclusive_scan_u32_multi(ctx, pool, pool, nsimp, narr, totals_dev));
   uint64_t* h = (uint64_t*)ctx->h_pinned;
@@ -1859,7 +1606,7 @@ int gc_cut_cells(gecut_ctx* ctx, gecut_result* res) {
   GC_LAUNCH(ctx, "k_extract_sc_ptr", k_extract_sc_ptr<<<(unsigned)gc_div_up(ncut + 1, 256), 256, 0, ctx->stream>>>(
       cn.cells, cn.points, g.nt0, ncut, (uint32_t)nsc, (uint32_t)nscp, res->cut_sc_ptr));
   launch_fast(ctx, res, nsimp, cn, true, slow_list, slow_count);
-  dispatch_walk(ctx, res, nsimp, cn, true, 2, nslow, slow_list, slow_count);
+  dispatch_walk(ctx, res, nsimp, cn, true, nslow, slow_list, slow_count);
   int st = gc_launch_check(ctx, "k_cut_walk(fill)");
   gc_free(ctx, pool);
   gc_free(ctx, totals_dev);

@@ -40,20 +40,6 @@ k_measures(const int32_t* __restrict__ ids, int64_t n, const double* __restrict_
 }
 
 // deterministic two-level sum
-__global__ void k_block_sums(const double* __restrict__ v, int64_t n, double* __restrict__ partial) {
-  __shared__ double sh[256];
-  double s = 0.0;
-  int64_t per = (n + gridDim.x - 1) / gridDim.x;
-  int64_t lo = per * blockIdx.x, hi = lo + per < n ? lo + per : n;
-  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) s += v[i];
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
-}
 __global__ void k_final_sum(const double* __restrict__ partial, int nb, double* __restrict__ out) {
   __shared__ double sh[256];
   double s = 0.0;

@@ -23,16 +23,6 @@ __global__ void k_eval_rows(const int8_t* __restrict__ rows, int64_t pitch, int6
   out[e] = (int8_t)gc_eval_inoutcut(prog, rows, pitch, e);
 }
 
-// flags for Triangulation(cut,CutInOrOut(side),geo): bg state == CUT && subcell state == side
-__global__ void k_flag_subcells(const GcLayout lay, int64_t nsc, const GcProgram prog, int side,
-                                uint32_t* __restrict__ flags) {
-  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= nsc) return;
-  int bg = gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, (int64_t)lay.sc_c2bg[e] - 1);
-  int sc = gc_eval_inoutcut(prog, lay.sc_state, lay.sc_pitch, e);
-  flags[e] = (bg == GC_CUT && sc == side) ? 1u : 0u;
-}
-
 // Triangulation(cut,CutInOrOut(side),geo): bg state == CUT && subcell state == side, as a stream compaction over the
 // subcells: 16 consecutive subcells per thread (one 128-bit load of the state row for single-leaf programs), 4096 per
 // block.  check_bg == 0 (one level set: every cut cell is CUT for every program over it) skips the bg-cell gather.
