@@ -11,12 +11,14 @@
 // B200 design: the reference re-emits the WHOLE sub-mesh once per level set (O(L * Nsub) traffic and 2L passes).
 // Every stage keeps the children of a cell contiguous and in order, so the final arrays are exactly the depth-first
 // traversal of each stage-0 simplex' refinement tree; the facets of level set ls are the depth-first traversal of the
-// facet re-cut trees hanging off depth L-ls.  One thread walks the tree of one stage-0 simplex twice: a counting walk
-// (reference: count_sub_triangulation_with_boundary :238-251), an exclusive scan of the counters over the simplices
-// (stable: preserves the reference ordering), and a filling walk that writes the final layout only.  Node values are
-// recomputed from the leaf records (bit-identical to the classification pass) or gathered from the NODAL vectors.
-#include <cstdlib>
-
+// facet re-cut trees hanging off depth L-ls.  Counting pass (reference: count_sub_triangulation_with_boundary :238-251),
+// exclusive scan (stable: preserves the reference ordering), filling pass that writes the final layout only.  Node
+// values are recomputed from the leaf records (bit-identical to the classification pass) or gathered from NODAL vectors.
+//
+//   L == 1 : k_cut1_count(_sx) -> scan over tiles of 32 simplices -> k_cut1_fill   (no tree: case -> table row)
+//   L  > 1 : k_cut_fast<count> (+ k_cut_walk<count> for the recorded simplices) -> scan over simplices ->
+//            k_cut_fast<fill> (+ k_cut_walk<fill>).  k_cut_fast handles the simplices cut by at most one level set
+//            without a tree; k_cut_walk is the generic depth-first walk, restricted to the level sets with mixed signs.
 #include "gecut_internal.cuh"
 
 namespace {
