@@ -438,6 +438,11 @@ int gecut_destroy(gecut_ctx* ctx) {
   cudaFree(ctx->d_simplexify_raw);
   cudaFree(ctx->d_simplexify_pos);
   for (auto& kv : ctx->lut_cache) cudaFree(kv.second.first);
+  for (int i = 0; i < 8; ++i) {
+    if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
+    if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   delete ctx;
   return GECUT_OK;

@@ -19,6 +19,9 @@
 //   L  > 1 : k_cut_fast<count> (+ k_cut_walk<count> for the recorded simplices) -> scan over simplices ->
 //            k_cut_fast<fill> (+ k_cut_walk<fill>).  k_cut_fast handles the simplices cut by at most one level set
 //            without a tree; k_cut_walk is the generic depth-first walk, restricted to the level sets with mixed signs.
+#include <cstdio>
+#include <cstdlib>
+
 #include "gecut_internal.cuh"
 
 namespace {
@@ -69,11 +72,12 @@ __device__ __forceinline__ void unit_normal(const double* p1, const double* p2, 
   }
 }
 
-// new point on the edge (a,b) cut by level set `ls` (_cut_cell!, CutTriangulations.jl:206-218)
+// new point on the edge (a,b) cut by the level set in value slot `sl` (_cut_cell!, CutTriangulations.jl:206-218).
+// Points carry the values of the nw level sets that can still be looked at further down the tree, in compact slots.
 // WITH_XR = false (counting walk): only the level-set values are interpolated -- the tree shape depends on nothing else
-template <int D, int LM, bool WITH_XR = true>
-__device__ __forceinline__ void cut_point(const Pt<D, LM>& a, const Pt<D, LM>& b, int ls, uint32_t wmask, Pt<D, LM>& o) {
-  double w1 = fabs(a.w[ls]), w2 = fabs(b.w[ls]);
+template <int D, int NW, bool WITH_XR = true>
+__device__ __forceinline__ void cut_point(const Pt<D, NW>& a, const Pt<D, NW>& b, int sl, int nw, Pt<D, NW>& o) {
+  double w1 = fabs(a.w[sl]), w2 = fabs(b.w[sl]);
   double coeff = __ddiv_rn(w1, __dadd_rn(w1, w2));
   if (WITH_XR) {
 #pragma unroll
@@ -82,20 +86,19 @@ __device__ __forceinline__ void cut_point(const Pt<D, LM>& a, const Pt<D, LM>& b
       o.r[d] = gc_lerp(a.r[d], b.r[d], coeff);
     }
   }
-  // only the level sets that can still be looked at further down the tree (wmask) need their values carried along
-  for (uint32_t m = wmask; m; m &= m - 1) {
-    const int k = __ffs(m) - 1;
-    o.w[k] = gc_lerp(a.w[k], b.w[k], coeff);
-  }
+  for (int j = 0; j < nw; ++j) o.w[j] = gc_lerp(a.w[j], b.w[j], coeff);
 }
 
-// Stage-0 simplex `t` of the cut bg cell `cell0` (0-based, slab-local): points with coordinates, reference coordinates of
-// the bg polytope and all L level-set values; first two vertices swapped when det J < 0 in physical space
-// (_simplexify :562-617, _ensure_positive_jacobians! :532-533 -> LookupTables.jl:199-216).
-template <int D, int LM>
+// Stage-0 simplex `t` of the cut bg cell `cell0` (0-based, slab-local): points with coordinates and reference coordinates
+// of the bg polytope; first two vertices swapped when det J < 0 in physical space (_simplexify :562-617,
+// _ensure_positive_jacobians! :532-533 -> LookupTables.jl:199-216).  Every level set is evaluated at the D+1 vertices:
+// *mixed / *outm get one bit per level set (mixed signs / all OUT); the values of the level sets in
+// wmask = mixed | {0, 1} are kept, in ascending level order, in the compact slots w[0..nw).
+template <int D, int NW>
 __device__ __forceinline__ void setup_stage0(const GcGrid& g, const GcLeaves& lv, int64_t cell0, int t,
                                              const uint8_t* simp_raw, const uint8_t* simp_pos,
-                                             const int8_t* __restrict__ bg_state, int64_t bg_pitch, Pt<D, LM>* S) {
+                                             const int8_t* __restrict__ bg_state, int64_t bg_pitch, Pt<D, NW>* S,
+                                             uint32_t* mixed_out, uint32_t* outm_out) {
   const int L = lv.L;
   const int64_t cube = cell0 / g.cpc;
   const int typ = (int)(cell0 % g.cpc);
@@ -108,6 +111,7 @@ __device__ __forceinline__ void setup_stage0(const GcGrid& g, const GcLeaves& lv
     ijk[1] = (int)(cube / g.n[0]) + g.k0;
     ijk[2] = 0;
   }
+  int64_t node[D + 1];
 #pragma unroll
   for (int m = 0; m <= D; ++m) {
     int lvid;
@@ -126,20 +130,43 @@ __device__ __forceinline__ void setup_stage0(const GcGrid& g, const GcLeaves& lv
       else
         S[m].r[d] = (double)((lvid >> d) & 1);  // n-cube vertices, x fastest
     }
-    const int64_t node = (D == 3) ? ((int64_t)nijk[0] + (int64_t)g.nn[0] * ((int64_t)nijk[1] + (int64_t)g.nn[1] * nijk[2]))
-                                  : ((int64_t)nijk[0] + (int64_t)g.nn[0] * nijk[1]);
-    for (int ls = 0; ls < L; ++ls) {
-      // a level set that does not cut the bg cell has one sign on all its vertices: only that sign is ever looked at
-      // (such a stage never produces a cut point), so the evaluation is skipped
-      const int bgst = bg_state[(int64_t)ls * bg_pitch + cell0];
-      if (bgst != GC_CUT)
-        S[m].w[ls] = bgst == GC_OUT ? 1.0 : -1.0;
-      else if (lv.leaf[ls].kind == GECUT_LEAF_NODAL)
-        S[m].w[ls] = __ldg(lv.nodal[ls] + (node - lv.nodal_base));
-      else
-        S[m].w[ls] = gc_eval_leaf(lv.leaf[ls], x, D);
+    node[m] = (D == 3) ? ((int64_t)nijk[0] + (int64_t)g.nn[0] * ((int64_t)nijk[1] + (int64_t)g.nn[1] * nijk[2]))
+                       : ((int64_t)nijk[0] + (int64_t)g.nn[0] * nijk[1]);
+  }
+  uint32_t mixed = 0u, outm = 0u;
+  int slot = 0;
+  for (int ls = 0; ls < L; ++ls) {
+    double val[D + 1];
+    bool any = false, all = true;
+    // a level set that does not cut the bg cell has one sign on all its vertices and only that sign is ever looked at
+    // (its stage never produces a cut point): no evaluation
+    const int bgst = bg_state[(int64_t)ls * bg_pitch + cell0];
+#pragma unroll
+    for (int m = 0; m <= D; ++m) {
+      if (bgst != GC_CUT) {
+        val[m] = bgst == GC_OUT ? 1.0 : -1.0;
+      } else if (lv.leaf[ls].kind == GECUT_LEAF_NODAL) {
+        val[m] = __ldg(lv.nodal[ls] + (node[m] - lv.nodal_base));
+      } else {
+        const double x[3] = {S[m].x[0], S[m].x[1], D == 3 ? S[m].x[2] : 0.0};
+        val[m] = gc_eval_leaf(lv.leaf[ls], x, D);
+      }
+      const bool o = val[m] > 0.0;
+      any |= o;
+      all &= o;
+    }
+    if (any && !all) mixed |= 1u << ls;
+    if (all) outm |= 1u << ls;
+    if (ls < 2 || (any && !all)) {
+      if (slot < NW) {
+#pragma unroll
+        for (int m = 0; m <= D; ++m) S[m].w[slot] = val[m];
+      }
+      slot++;
     }
   }
+  *mixed_out = mixed;
+  *outm_out = outm;
   // J[a][b] = x_{a+1}[b] - x_0[b]; flip iff det(J) < 0
   double J[3][3];
 #pragma unroll
@@ -159,7 +186,7 @@ __device__ __forceinline__ void setup_stage0(const GcGrid& g, const GcLeaves& lv
     dV = __dsub_rn(__dadd_rn(__dadd_rn(p1, p2), p3), __dadd_rn(__dadd_rn(q1, q2), q3));
   }
   if (dV < 0.0) {
-    Pt<D, LM> tmp = S[0];
+    Pt<D, NW> tmp = S[0];
     S[0] = S[1];
     S[1] = tmp;
   }
@@ -182,8 +209,11 @@ __device__ __forceinline__ void store_c2p_row(int32_t* __restrict__ c2p, uint32_
 // level that does not cut the simplex costs one case evaluation and an index permutation.  The pool shrinks back when
 // the walk returns from a level.
 constexpr int WALK_T = 64;  // threads per block of the generic walk
+// tree-walk launch buckets: level sets tracked per recorded simplex (mixed signs + the emission stages 0 and 1)
+constexpr int WALK_NB = 5;
+__host__ __device__ constexpr int walk_nw(int b) { return b == 0 ? 4 : b == 1 ? 6 : b == 2 ? 8 : b == 3 ? 12 : GC_LMAX; }
 
-template <int D, int LM, bool FILL>
+template <int D, int NW, bool FILL>
 __global__ void __launch_bounds__(WALK_T)
 k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
            const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
@@ -194,9 +224,11 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
   // finished lanes of a mixed warp.
   constexpr int NPC = WalkCfg<D>::NPC, NPF = WalkCfg<D>::NPF;
   constexpr int CE = NPC - (D + 1), FE = NPF - D;  // max new points per cell / facet cut
-  constexpr int NPOOL = (D + 1) + CE * LM + FE * (LM - 1);
-  constexpr int LF = LM - 1;
-  static_assert(LM >= 2, "one level set takes the k_cut1_* path");
+  // NW bounds the level sets a recorded simplex tracks (mixed signs + the two emission stages 0 and 1), hence the depth
+  // of both walks and the size of the per-thread point pool; level-set IDS still run up to GC_LMAX.
+  constexpr int LM = GC_LMAX;
+  constexpr int NPOOL = (D + 1) + CE * NW + FE * NW;
+  constexpr int LF = NW;
   __shared__ GcSimplexTable s_tab[2];  // [0]: D-simplex (cells), [1]: (D-1)-simplex (facet re-cuts)
   {
     const uint32_t* src0 = reinterpret_cast<const uint32_t*>(tables + (D - 1));
@@ -236,13 +268,14 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
     }
   }
 
-  Pt<D, LM> pool[NPOOL];
-  uint8_t v[LM][D + 1], e[LM][NPC];      // simplex vertices / expanded point set of every level on the path
+  Pt<D, NW> pool[NPOOL];
+  uint8_t v[NW][D + 1], e[NW][NPC];      // simplex vertices / expanded point set of every visited stage on the path
   uint8_t fv[LF][D], fe[LF][NPF];         // the same for the facet being re-cut
-  int8_t child[LM], cs[LM], npE[LM], st[LM], ptop_at[LM];
+  int8_t child[NW], cs[NW], npE[NW], st[LM], ptop_at[NW];
   int8_t fchild[LF], fcs[LF], fptop_at[LF], fst[LM];
 
-  setup_stage0<D, LM>(g, lv, bgcell1 - 1, t, simp_raw, simp_pos, lay.bg_state, lay.bg_pitch, pool);
+  uint32_t mixed = 0u, outm = 0u;
+  setup_stage0<D, NW>(g, lv, bgcell1 - 1, t, simp_raw, simp_pos, lay.bg_state, lay.bg_pitch, pool, &mixed, &outm);
   int ptop = D + 1;
 #pragma unroll
   for (int i = 0; i <= D; ++i) v[0][i] = (uint8_t)i;
@@ -252,22 +285,15 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
   // simplex goes through it as the single child of the all-IN / all-OUT table row, i.e. with its vertices permuted by
   // that row and a constant state.  The walk therefore visits only the level sets with mixed signs (plus the last one
   // of each sequence, where the output is emitted) and applies the permutations of the skipped stages in between.
-  int8_t lsd[LM], fk[LF];
-  uint32_t mixed = 0u, outm = 0u;
+  int8_t lsd[NW], fk[LF];
   for (int k = 0; k < L; ++k) {
-    bool any = false, all = true;
-#pragma unroll
-    for (int i = 0; i <= D; ++i) {
-      const bool o = pool[i].w[k] > 0.0;
-      any |= o;
-      all &= o;
-    }
-    if (any && !all) mixed |= 1u << k;
-    if (all) outm |= 1u << k;
-    st[k] = all ? (int8_t)GC_OUT : (int8_t)GC_IN;   // overwritten on the way down for the visited level sets
+    st[k] = ((outm >> k) & 1u) ? (int8_t)GC_OUT : (int8_t)GC_IN;  // overwritten on the way down for the visited level sets
     fst[k] = st[k];
   }
-  const uint32_t wmask = (mixed | 3u) & ((1u << L) - 1u);  // values needed: visited level sets (0 and 1 are emission stages)
+  const uint32_t wmask = (mixed | 3u) & ((1u << L) - 1u);  // tracked level sets: mixed signs + the emission stages 0 and 1
+  const int nw = __popc(wmask);
+  if (nw > NW) return;  // cannot happen: the launch bucket is chosen from the same count (k_cut_fast)
+  auto ws = [&](int k) -> int { return __popc(wmask & ((1u << k) - 1u)); };  // value slot of level set k
   const int c_allout = (1 << (D + 1)) - 1, fc_allout = (1 << D) - 1;
   // skipped cell stages hi-1 ... lo+1 applied to a vertex list
   auto skip_cell_stages = [&](uint8_t* vl, int hi, int lo) {
@@ -300,13 +326,14 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
   child[0] = -1;
   while (depth >= 0) {
     const int ls = lsd[depth];
+    const int wls = ws(ls);
     if (child[depth] < 0) {
       // ---- enter: case, cut points (CutTriangulations.jl:179-222)
       int c = 0;
 #pragma unroll
       for (int i = 0; i <= D; ++i) {
         e[depth][i] = v[depth][i];
-        if (pool[v[depth][i]].w[ls] > 0.0) c |= 1 << i;
+        if (pool[v[depth][i]].w[wls] > 0.0) c |= 1 << i;
       }
       cs[depth] = (int8_t)c;
       ptop_at[depth] = (int8_t)ptop;
@@ -314,8 +341,8 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
       if (TC.inoutcut[c] == GC_CUT) {
         for (int ed = 0; ed < TC.nedges; ++ed) {
           const int a = e[depth][TC.edges[ed][0]], b = e[depth][TC.edges[ed][1]];
-          if ((pool[a].w[ls] > 0.0) != (pool[b].w[ls] > 0.0)) {
-            cut_point<D, LM, FILL>(pool[a], pool[b], ls, wmask, pool[ptop]);
+          if ((pool[a].w[wls] > 0.0) != (pool[b].w[wls] > 0.0)) {
+            cut_point<D, NW, FILL>(pool[a], pool[b], wls, nw, pool[ptop]);
             e[depth][np++] = (uint8_t)ptop++;
           }
         }
@@ -343,12 +370,13 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
           fchild[0] = -1;
           while (fdepth >= 0) {
             const int k = fk[fdepth];
+            const int wk = ws(k);
             if (fchild[fdepth] < 0) {
               int fc = 0;
 #pragma unroll
               for (int i = 0; i < D; ++i) {
                 fe[fdepth][i] = fv[fdepth][i];
-                if (pool[fv[fdepth][i]].w[k] > 0.0) fc |= 1 << i;
+                if (pool[fv[fdepth][i]].w[wk] > 0.0) fc |= 1 << i;
               }
               fcs[fdepth] = (int8_t)fc;
               fptop_at[fdepth] = (int8_t)ptop;
@@ -356,8 +384,8 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
               if (TF.inoutcut[fc] == GC_CUT) {
                 for (int ed = 0; ed < TF.nedges; ++ed) {
                   const int a = fe[fdepth][TF.edges[ed][0]], b = fe[fdepth][TF.edges[ed][1]];
-                  if ((pool[a].w[k] > 0.0) != (pool[b].w[k] > 0.0)) {
-                    cut_point<D, LM, FILL>(pool[a], pool[b], k, wmask, pool[ptop]);
+                  if ((pool[a].w[wk] > 0.0) != (pool[b].w[wk] > 0.0)) {
+                    cut_point<D, NW, FILL>(pool[a], pool[b], wk, nw, pool[ptop]);
                     fe[fdepth][fn++] = (uint8_t)ptop++;
                   }
                 }
@@ -622,7 +650,13 @@ k_cut_fast(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
     }
     uint32_t cell_off = 0, pt_off = 0;
     if (__popc(mixed) > 1) {
-      if (!FILL) slow_list[atomicAdd(slow_count, 1u)] = (uint32_t)s;
+      if (!FILL) {
+        // recorded for the tree walk, bucketed by the number of level sets the walk has to track
+        const int nw = __popc((mixed | 3u) & ((1u << L) - 1u));
+        int bucket = 0;
+        while (nw > walk_nw(bucket)) bucket++;
+        slow_list[(int64_t)bucket * nsimp + atomicAdd(&slow_count[bucket], 1u)] = (uint32_t)s;
+      }
     } else {
       const int a = mixed ? (31 - __clz(mixed)) : 0;  // the only stage that can cut (stage 0 is visited in any case)
       auto cstate = [&](int k) -> int8_t { return ((outm >> k) & 1u) ? (int8_t)GC_OUT : (int8_t)GC_IN; };
@@ -1374,17 +1408,17 @@ __global__ void k_extract_sc_ptr(const uint32_t* __restrict__ cell_offs, const u
   }
 }
 
-template <int D, int LM>
+template <int D, int NW>
 void launch_walk(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcCounters& cn, bool fill, int64_t nslow,
-                 const uint32_t* slow_list, const uint32_t* slow_count) {
+                 const uint32_t* slow_list, const uint32_t* slow_count, cudaStream_t stream) {
   const int T = WALK_T;
   const unsigned nb = (unsigned)gc_div_up(nslow, T);
   if (nb == 0) return;
   if (fill)
-    GC_LAUNCH(ctx, "k_cut_walk_fill", k_cut_walk<D, LM, true><<<nb, T, 0, ctx->stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
+    GC_LAUNCH(ctx, "k_cut_walk_fill", k_cut_walk<D, NW, true><<<nb, T, 0, stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
                                                        ctx->d_simplexify_pos, res->lay.cutcells, nsimp, cn, res->lay, slow_list, slow_count));
   else
-    GC_LAUNCH(ctx, "k_cut_walk_count", k_cut_walk<D, LM, false><<<nb, T, 0, ctx->stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
+    GC_LAUNCH(ctx, "k_cut_walk_count", k_cut_walk<D, NW, false><<<nb, T, 0, stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
                                                         ctx->d_simplexify_pos, res->lay.cutcells, nsimp, cn, res->lay, slow_list, slow_count));
 }
 
@@ -1404,25 +1438,50 @@ void launch_fast(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const G
 #undef GC_FAST
 }
 
-void dispatch_walk(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcCounters& cn, bool fill, int64_t nslow,
-                   const uint32_t* slow_list, const uint32_t* slow_count) {
-  const int L = res->L;
+// one dense launch per bucket of recorded simplices (nslow[b] of them in slow_list + b*nsimp).  The buckets are
+// independent and each launch lasts as long as its slowest thread, so they run concurrently on side streams.
+int dispatch_walk(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcCounters& cn, bool fill,
+                  const int64_t* nslow, const uint32_t* slow_list, const uint32_t* slow_count) {
   const int D = res->grid.D;
-#define GC_WALK(DD, LL) launch_walk<DD, LL>(ctx, res, nsimp, cn, fill, nslow, slow_list, slow_count)
+  int nonempty = 0;
+  for (int b = 0; b < WALK_NB; ++b) nonempty += nslow[b] > 0 ? 1 : 0;
+  const bool fork = nonempty > 1 && !ctx->prof_on;  // per-kernel profiling times launches on the main stream
+  if (fork) {
+    if (!ctx->ev_fork) GC_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    for (int b = 0; b < WALK_NB; ++b) {
+      if (!ctx->side[b]) GC_CUDA(cudaStreamCreateWithFlags(&ctx->side[b], cudaStreamNonBlocking));
+      if (!ctx->ev_join[b]) GC_CUDA(cudaEventCreateWithFlags(&ctx->ev_join[b], cudaEventDisableTiming));
+    }
+    GC_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  }
+  auto stream_of = [&](int b) -> cudaStream_t {
+    if (!fork || nslow[b] == 0) return ctx->stream;
+    cudaStreamWaitEvent(ctx->side[b], ctx->ev_fork, 0);
+    return ctx->side[b];
+  };
+#define GC_WALK(DD, B) launch_walk<DD, walk_nw(B)>(ctx, res, nsimp, cn, fill, nslow[B], slow_list + (int64_t)(B) * nsimp, slow_count + (B), stream_of(B))
   if (D == 2) {
-    if (L <= 2) GC_WALK(2, 2);
-    else if (L <= 4) GC_WALK(2, 4);
-    else if (L <= 8) GC_WALK(2, 8);
-    else if (L <= 12) GC_WALK(2, 12);
-    else GC_WALK(2, 16);
+    GC_WALK(2, 0);
+    GC_WALK(2, 1);
+    GC_WALK(2, 2);
+    GC_WALK(2, 3);
+    GC_WALK(2, 4);
   } else {
-    if (L <= 2) GC_WALK(3, 2);
-    else if (L <= 4) GC_WALK(3, 4);
-    else if (L <= 8) GC_WALK(3, 8);
-    else if (L <= 12) GC_WALK(3, 12);
-    else GC_WALK(3, 16);
+    GC_WALK(3, 0);
+    GC_WALK(3, 1);
+    GC_WALK(3, 2);
+    GC_WALK(3, 3);
+    GC_WALK(3, 4);
   }
 #undef GC_WALK
+  if (fork) {
+    for (int b = 0; b < WALK_NB; ++b) {
+      if (nslow[b] == 0) continue;
+      GC_CUDA(cudaEventRecord(ctx->ev_join[b], ctx->side[b]));
+      GC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[b], 0));
+    }
+  }
+  return GECUT_OK;
 }
 
 }  // namespace
@@ -1545,18 +1604,19 @@ int gc_cut_cells(gecut_ctx* ctx, gecut_result* res) {
   // simplices cut by two or more level sets are collected and walked by a second, dense launch
   uint32_t* slow_list = nullptr;
   uint32_t* slow_count = nullptr;
-  GC_CHECK(gc_malloc(ctx, (void**)&slow_list, sizeof(uint32_t) * nsimp));
-  GC_CHECK(gc_malloc(ctx, (void**)&slow_count, sizeof(uint32_t) * 2));
-  GC_CUDA(cudaMemsetAsync(slow_count, 0, sizeof(uint32_t) * 2, ctx->stream));
+  GC_CHECK(gc_malloc(ctx, (void**)&slow_list, sizeof(uint32_t) * nsimp * WALK_NB));
+  GC_CHECK(gc_malloc(ctx, (void**)&slow_count, sizeof(uint32_t) * 8));
+  GC_CUDA(cudaMemsetAsync(slow_count, 0, sizeof(uint32_t) * 8, ctx->stream));
   launch_fast(ctx, res, nsimp, cn, false, slow_list, slow_count);
-  int64_t nslow = 0;
+  int64_t nslow[WALK_NB];
   {
     uint32_t* hs = (uint32_t*)ctx->h_pinned;
-    GC_CUDA(cudaMemcpyAsync(hs, slow_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GC_CUDA(cudaMemcpyAsync(hs, slow_count, sizeof(uint32_t) * WALK_NB, cudaMemcpyDeviceToHost, ctx->stream));
     GC_CUDA(cudaStreamSynchronize(ctx->stream));
-    nslow = (int64_t)hs[0];
+    for (int b = 0; b < WALK_NB; ++b) nslow[b] = (int64_t)hs[b];
   }
-  dispatch_walk(ctx, res, nsimp, cn, false, nslow, slow_list, slow_count);
+  if (getenv("GECUT_WALK_DEBUG")) fprintf(stderr, "[gecut] tree-walk buckets: %lld %lld %lld %lld %lld of %lld simplices\n", (long long)nslow[0], (long long)nslow[1], (long long)nslow[2], (long long)nslow[3], (long long)nslow[4], (long long)nsimp);
+  GC_CHECK(dispatch_walk(ctx, res, nsimp, cn, false, nslow, slow_list, slow_count));
   GC_CHECK(gc_launch_check(ctx, "k_cut_walk(count)"));
   GC_CHECK(gc_exclusive_scan_u32_multi(ctx, pool, pool, nsimp, narr, totals_dev));
   uint64_t* h = (uint64_t*)ctx->h_pinned;
@@ -1608,7 +1668,7 @@ int gc_cut_cells(gecut_ctx* ctx, gecut_result* res) {
   GC_LAUNCH(ctx, "k_extract_sc_ptr", k_extract_sc_ptr<<<(unsigned)gc_div_up(ncut + 1, 256), 256, 0, ctx->stream>>>(
       cn.cells, cn.points, g.nt0, ncut, (uint32_t)nsc, (uint32_t)nscp, res->cut_sc_ptr));
   launch_fast(ctx, res, nsimp, cn, true, slow_list, slow_count);
-  dispatch_walk(ctx, res, nsimp, cn, true, nslow, slow_list, slow_count);
+  GC_CHECK(dispatch_walk(ctx, res, nsimp, cn, true, nslow, slow_list, slow_count));
   int st = gc_launch_check(ctx, "k_cut_walk(fill)");
   gc_free(ctx, pool);
   gc_free(ctx, totals_dev);

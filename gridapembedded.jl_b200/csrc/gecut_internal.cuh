@@ -108,6 +108,10 @@ struct GcProfRec {
 struct gecut_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // side streams + events: the tree-walk buckets of a multi-level-set cut are independent launches whose run time is set by
+  // their slowest thread, so they run concurrently (fork from / join into `stream`)
+  cudaStream_t side[8] = {nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[8] = {nullptr};
   std::string err;
   int64_t launches = 0;
   // caching device allocator: blocks freed by results / selections are kept and handed out again to requests of the
