@@ -213,15 +213,20 @@ constexpr int WALK_T = 64;  // threads per block of the generic walk
 constexpr int WALK_NB = 5;
 __host__ __device__ constexpr int walk_nw(int b) { return b == 0 ? 4 : b == 1 ? 6 : b == 2 ? 8 : b == 3 ? 12 : GC_LMAX; }
 
+// Work split: a recorded simplex is walked by WALK_ITEMS = 8 lanes.  Every lane enters the top visited stage (case, cut
+// points: cheap and redundant), then lane j < 6 walks only the subtree of top-stage child j and lanes 6, 7 only the
+// re-cut trees of the top stage's facets 0, 1.  The subtrees write disjoint, consecutive ranges: children in order for
+// the cell / point arrays and the facet arrays of the lower level sets, the top-stage facets alone own the facet arrays
+// of the top level set.  walk_item<FILL=false> returns the item's counters; the count kernel adds them up per simplex,
+// the fill kernel turns them into the item's start offsets with an 8-lane exclusive scan and walks again, writing.
+constexpr int WALK_ITEMS = 8;
+
 template <int D, int NW, bool FILL>
-__global__ void __launch_bounds__(WALK_T)
-k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
-           const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
-           const int32_t* __restrict__ cutcells, int64_t nsimp, GcCounters cn, GcLayout lay,
-           const uint32_t* __restrict__ slow_list, const uint32_t* __restrict__ slow_count) {
-  // One thread per RECORDED simplex (those cut by two or more level sets, listed by k_cut_fast): the tree walk is an
-  // order of magnitude longer than the no-tree path, so it runs in its own dense launch instead of stalling the 31
-  // finished lanes of a mixed warp.
+__device__ __forceinline__ void walk_item(const GcGrid& g, const GcLeaves& lv, const GcSimplexTable& TC,
+                                          const GcSimplexTable& TF, const uint8_t* __restrict__ simp_raw,
+                                          const uint8_t* __restrict__ simp_pos, const GcLayout& lay, int64_t s,
+                                          int32_t bgcell1, int item, uint32_t& cell_off, uint32_t& pt_off,
+                                          uint32_t* fac_off, uint32_t* fpt_off) {
   constexpr int NPC = WalkCfg<D>::NPC, NPF = WalkCfg<D>::NPF;
   constexpr int CE = NPC - (D + 1), FE = NPF - D;  // max new points per cell / facet cut
   // NW bounds the level sets a recorded simplex tracks (mixed signs + the two emission stages 0 and 1), hence the depth
@@ -229,44 +234,8 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
   constexpr int LM = GC_LMAX;
   constexpr int NPOOL = (D + 1) + CE * NW + FE * NW;
   constexpr int LF = NW;
-  __shared__ GcSimplexTable s_tab[2];  // [0]: D-simplex (cells), [1]: (D-1)-simplex (facet re-cuts)
-  {
-    const uint32_t* src0 = reinterpret_cast<const uint32_t*>(tables + (D - 1));
-    const uint32_t* src1 = reinterpret_cast<const uint32_t*>(tables + (D - 2));
-    uint32_t* dst0 = reinterpret_cast<uint32_t*>(&s_tab[0]);
-    uint32_t* dst1 = reinterpret_cast<uint32_t*>(&s_tab[1]);
-    for (int i = threadIdx.x; i < (int)(sizeof(GcSimplexTable) / 4); i += blockDim.x) {
-      dst0[i] = src0[i];
-      dst1[i] = src1[i];
-    }
-  }
-  __syncthreads();
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)*slow_count) return;
-  const int64_t s = (int64_t)slow_list[idx];
-  const GcSimplexTable& TC = s_tab[0];
-  const GcSimplexTable& TF = s_tab[1];
   const int L = lv.L;
-  const int64_t kcut = s / g.nt0;
   const int t = (int)(s % g.nt0);
-  const int32_t bgcell1 = cutcells[kcut];
-
-  // running output positions (FILL) / counters (!FILL)
-  uint32_t cell_off = 0, pt_off = 0;
-  uint32_t fac_off[LM], fpt_off[LM];
-#pragma unroll
-  for (int k = 0; k < LM; ++k) {
-    fac_off[k] = 0;
-    fpt_off[k] = 0;
-  }
-  if (FILL) {
-    cell_off = cn.cells[s];
-    pt_off = cn.points[s];
-    for (int k = 0; k < L; ++k) {
-      fac_off[k] = cn.fac_base[k] + cn.fac[k][s];
-      fpt_off[k] = cn.fpt_base[k] + cn.fpt[k][s];
-    }
-  }
 
   Pt<D, NW> pool[NPOOL];
   uint8_t v[NW][D + 1], e[NW][NPC];      // simplex vertices / expanded point set of every visited stage on the path
@@ -349,9 +318,10 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
       }
       npE[depth] = (int8_t)np;
       const int nfac = TC.nfac[c];
-      // ---- boundary facets of this stage (CutTriangulations.jl:268-292)
+      // ---- boundary facets of this stage (CutTriangulations.jl:268-292); at the top stage only by their own lanes
       {
         for (int f = 0; f < nfac; ++f) {
+          if (depth == 0 && item != 6 + f) continue;
           const uint8_t* fp = TC.fac_pts[c][f];
           double nrm[3] = {0.0, 0.0, 0.0};
           if (FILL)
@@ -479,6 +449,11 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
       child[depth] = 0;
     }
     const int c = cs[depth];
+    if (depth == 0) {
+      // top stage: this lane owns child `item` only
+      if (child[0] != 0 || item >= TC.nsub[c]) break;
+      child[0] = (int8_t)item;
+    }
     if (child[depth] < TC.nsub[c]) {
       const int j = child[depth]++;
       st[ls] = TC.sub_inout[c][j];
@@ -494,12 +469,81 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
     }
   }
 
+}
+
+template <int D, int NW, bool FILL>
+__global__ void __launch_bounds__(WALK_T)
+k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
+           const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
+           const int32_t* __restrict__ cutcells, int64_t nsimp, GcCounters cn, GcLayout lay,
+           const uint32_t* __restrict__ slow_list, const uint32_t* __restrict__ slow_count) {
+  // WALK_ITEMS lanes per RECORDED simplex (those cut by two or more level sets, listed by k_cut_fast): the tree walk is
+  // an order of magnitude longer than the no-tree path, so it runs in its own dense launches.
+  constexpr int LM = GC_LMAX;
+  __shared__ GcSimplexTable s_tab[2];  // [0]: D-simplex (cells), [1]: (D-1)-simplex (facet re-cuts)
+  {
+    const uint32_t* src0 = reinterpret_cast<const uint32_t*>(tables + (D - 1));
+    const uint32_t* src1 = reinterpret_cast<const uint32_t*>(tables + (D - 2));
+    uint32_t* dst0 = reinterpret_cast<uint32_t*>(&s_tab[0]);
+    uint32_t* dst1 = reinterpret_cast<uint32_t*>(&s_tab[1]);
+    for (int i = threadIdx.x; i < (int)(sizeof(GcSimplexTable) / 4); i += blockDim.x) {
+      dst0[i] = src0[i];
+      dst1[i] = src1[i];
+    }
+  }
+  __syncthreads();
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t idx = gtid / WALK_ITEMS;
+  const int item = (int)(gtid % WALK_ITEMS);
+  const bool valid = idx < (int64_t)*slow_count;  // idle lanes still take part in the shuffles
+  const int64_t s = valid ? (int64_t)slow_list[idx] : 0;
+  const int L = lv.L;
+  const int32_t bgcell1 = cutcells[s / g.nt0];
+  // counting walk of this item
+  uint32_t n_cells = 0, n_pts = 0, n_fac[LM], n_fpt[LM];
+#pragma unroll
+  for (int k = 0; k < LM; ++k) n_fac[k] = n_fpt[k] = 0;
+  if (valid) walk_item<D, NW, false>(g, lv, s_tab[0], s_tab[1], simp_raw, simp_pos, lay, s, bgcell1, item, n_cells, n_pts, n_fac, n_fpt);
+  // inclusive scan over the WALK_ITEMS lanes of the simplex
+  const int lane = threadIdx.x & 31;
+  auto seg_scan = [&](uint32_t v) -> uint32_t {
+#pragma unroll
+    for (int o = 1; o < WALK_ITEMS; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, v, o);
+      if ((lane & (WALK_ITEMS - 1)) >= o) v += up;
+    }
+    return v;
+  };
   if (!FILL) {
-    cn.cells[s] = cell_off;
-    cn.points[s] = pt_off;
+    const uint32_t tc = seg_scan(n_cells), tp = seg_scan(n_pts);
+    if (valid && item == WALK_ITEMS - 1) {
+      cn.cells[s] = tc;
+      cn.points[s] = tp;
+    }
     for (int k = 0; k < L; ++k) {
-      cn.fac[k][s] = fac_off[k];
-      cn.fpt[k][s] = fpt_off[k];
+      const uint32_t tf = seg_scan(n_fac[k]), tq = seg_scan(n_fpt[k]);
+      if (valid && item == WALK_ITEMS - 1) {
+        cn.fac[k][s] = tf;
+        cn.fpt[k][s] = tq;
+      }
+    }
+  } else {
+    uint32_t cell_off = seg_scan(n_cells) - n_cells, pt_off = seg_scan(n_pts) - n_pts;
+    uint32_t fac_off[LM], fpt_off[LM];
+#pragma unroll
+    for (int k = 0; k < LM; ++k) fac_off[k] = fpt_off[k] = 0;
+    for (int k = 0; k < L; ++k) {
+      fac_off[k] = seg_scan(n_fac[k]) - n_fac[k];
+      fpt_off[k] = seg_scan(n_fpt[k]) - n_fpt[k];
+    }
+    if (valid) {
+      cell_off += cn.cells[s];
+      pt_off += cn.points[s];
+      for (int k = 0; k < L; ++k) {
+        fac_off[k] += cn.fac_base[k] + cn.fac[k][s];
+        fpt_off[k] += cn.fpt_base[k] + cn.fpt[k][s];
+      }
+      walk_item<D, NW, true>(g, lv, s_tab[0], s_tab[1], simp_raw, simp_pos, lay, s, bgcell1, item, cell_off, pt_off, fac_off, fpt_off);
     }
   }
 }
@@ -1412,7 +1456,7 @@ template <int D, int NW>
 void launch_walk(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcCounters& cn, bool fill, int64_t nslow,
                  const uint32_t* slow_list, const uint32_t* slow_count, cudaStream_t stream) {
   const int T = WALK_T;
-  const unsigned nb = (unsigned)gc_div_up(nslow, T);
+  const unsigned nb = (unsigned)gc_div_up(nslow * WALK_ITEMS, T);
   if (nb == 0) return;
   if (fill)
     GC_LAUNCH(ctx, "k_cut_walk_fill", k_cut_walk<D, NW, true><<<nb, T, 0, stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
