@@ -60,9 +60,17 @@ k_select_subcells(const GcLayout lay, int64_t nsc, const GcProgram prog, int sid
     const int64_t left = nsc - e0;
     if (left < SELSC_PER) bits &= (1u << (int)left) - 1u;
     if (check_bg) {
+      // consecutive subcells mostly share their bg cell: the state of the last one looked up is kept
+      int32_t last_bg = 0;
+      bool last_ok = false;
       for (uint32_t m = bits; m; m &= m - 1) {
         const int i = __ffs(m) - 1;
-        if (gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, (int64_t)lay.sc_c2bg[e0 + i] - 1) != GC_CUT) bits &= ~(1u << i);
+        const int32_t bgc = lay.sc_c2bg[e0 + i];
+        if (bgc != last_bg) {
+          last_bg = bgc;
+          last_ok = gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, (int64_t)bgc - 1) == GC_CUT;
+        }
+        if (!last_ok) bits &= ~(1u << i);
       }
     }
   }
@@ -115,6 +123,11 @@ k_count_bgcells_vec(const GcLayout lay, int64_t nc, int L, const GcProgram prog,
   if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   unsigned int loc[6] = {0, 0, 0, 0, 0, 0};
+  // per group of 16 cells the per-type tallies are packed one byte per cell type (<= 16 each) and unpacked once
+  auto unpack = [&](unsigned long long pk) {
+#pragma unroll
+    for (int t = 0; t < 6; ++t) loc[t] += (unsigned int)(pk >> (8 * t)) & 0xFFu;
+  };
   const int64_t ngroups = (nc + 15) / 16;
   for (int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups; gi += (int64_t)gridDim.x * blockDim.x) {
     const int64_t e0 = gi * 16;
@@ -123,14 +136,15 @@ k_count_bgcells_vec(const GcLayout lay, int64_t nc, int L, const GcProgram prog,
     if (prog.len == 1) {
       const uint4 r4 = *reinterpret_cast<const uint4*>(lay.bg_state + (int64_t)prog.tok[0] * lay.bg_pitch + e0);
       const uint32_t w4[4] = {r4.x, r4.y, r4.z, r4.w};
+      unsigned long long pk = 0ull;
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         const int bg = (int)(int8_t)((w4[c >> 2] >> (8 * (c & 3))) & 0xFFu);
         const bool keep = (c < nvalid) && (mode == 0 ? (bg == side) : (bg == GC_CUT || bg == side));
-#pragma unroll
-        for (int t = 0; t < 6; ++t) loc[t] += (keep && t == ty) ? 1u : 0u;
+        pk += (unsigned long long)(keep ? 1u : 0u) << (8 * ty);
         ty = (ty + 1 == cpc) ? 0 : ty + 1;
       }
+      unpack(pk);
     } else if (prog.lut) {
       // truth table: one 128-bit load per used level-set row, base-3 index per cell, one gather
       uint32_t idx[16];
@@ -143,14 +157,15 @@ k_count_bgcells_vec(const GcLayout lay, int64_t nc, int L, const GcProgram prog,
         for (int c = 0; c < 16; ++c)
           idx[c] = idx[c] * 3u + (uint32_t)((int)(int8_t)((w4[c >> 2] >> (8 * (c & 3))) & 0xFFu) + 1);
       }
+      unsigned long long pk = 0ull;
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         const int bg = c < nvalid ? (int)__ldg(prog.lut + idx[c]) : GC_OUT;
         const bool keep = (c < nvalid) && (mode == 0 ? (bg == side) : (bg == GC_CUT || bg == side));
-#pragma unroll
-        for (int t = 0; t < 6; ++t) loc[t] += (keep && t == ty) ? 1u : 0u;
+        pk += (unsigned long long)(keep ? 1u : 0u) << (8 * ty);
         ty = (ty + 1 == cpc) ? 0 : ty + 1;
       }
+      unpack(pk);
     } else {
       for (int c = 0; c < nvalid; ++c) {
         int8_t vals[GC_LMAX];
@@ -312,7 +327,7 @@ int gc_select_cells(gecut_ctx* ctx, gecut_selection* sel) {
     GC_CHECK(gc_malloc(ctx, (void**)&counts, sizeof(unsigned long long) * 8));
     GC_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * 8, ctx->stream));
     const int mode = sel->kind == GECUT_SEL_ACTIVE ? 1 : 0;
-    unsigned nb = (unsigned)std::min<int64_t>(gc_div_up(gc_div_up(nc, 16), T), 148 * 8);
+    unsigned nb = (unsigned)std::min<int64_t>(gc_div_up(gc_div_up(nc, 16), T), 148 * 64);
     GC_LAUNCH(ctx, "k_count_bgcells", k_count_bgcells_vec<<<nb, T, 0, ctx->stream>>>(lay, nc, res->L, sel->prog, sel->side, mode,
                                                                                    res->grid.cpc, counts));
     uint64_t* h = (uint64_t*)ctx->h_pinned;

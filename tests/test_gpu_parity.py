@@ -504,3 +504,58 @@ def test_raw_abi_error_codes():
     assert L.gecut_cell_measure(sel, None, 0) == _lib.GECUT_ERR_INVALID
     L.gecut_selection_free(sel)
     L.gecut_result_free(out)
+
+
+@pytest.mark.parametrize("case", ["bimaterial_160", "csg_96", "stokes_tet_64"])
+def test_multi_levelset_properties_at_scale(case):
+    """BASELINE configs 1, 4, 5 at sizes the oracle would need minutes for: IN + OUT partition the box for every named
+    geometry, the subcells of every cut cell tile it, the facets of a level set are INTERFACE for it, and the
+    two-launch cut (no-tree kernel + 8-lane tree walk) agrees with the slab-by-slab cut."""
+    if case == "bimaterial_160":
+        geo = bimaterial()
+        model = CartesianDiscreteModel((0, 0, 0), (3, 2, 3), (160, 96, 160))
+        names = ["steel", "concrete"]
+    elif case == "csg_96":
+        geo = csg_geometry()
+        model = CartesianDiscreteModel((-0.8, -0.8, -0.8), (0.8, 0.8, 0.8), (96, 96, 96))
+        names = ["csg"]
+    else:
+        geo, pmin, pmax = stokes_geometry()
+        model = simplexify(CartesianDiscreteModel(pmin, pmax, (128, 40, 40)))
+        names = ["fluid"]
+    cg = cut(model, geo)
+    box = float(np.prod(np.asarray(model.pmax) - np.asarray(model.pmin)))
+    for nm in names:
+        vin, vout, surf = _measures(cg, nm)
+        assert abs(vin + vout - box) <= 1e-11 * box, (nm, vin, vout)
+        assert surf > 0
+    h = cg.to_host()
+    c2p, c2bg = h["sc_cell_to_points"], h["sc_cell_to_bgcell"]
+    assert c2p.min() == 1 and c2p.max() == h["sc_point_to_coords"].shape[0]
+    assert np.all(np.diff(c2bg) >= 0) and np.array_equal(np.unique(c2bg), h["cutcell_to_cell"])
+    X = h["sc_point_to_coords"][c2p - 1]
+    vol = np.abs(np.linalg.det(X[:, 1:, :] - X[:, :1, :])) / 6.0
+    idx = np.searchsorted(h["cutcell_to_cell"], c2bg)
+    per_cell = np.bincount(idx, weights=vol, minlength=len(h["cutcell_to_cell"]))
+    cellvol = np.prod(model.sizes) / (6.0 if model.simplexified else 1.0)
+    assert np.abs(per_cell - cellvol).max() <= 1e-11 * cellvol * 8
+    # ls-major facet order, INTERFACE row
+    fst = h["ls_to_subfacet_to_inout"]
+    own = np.argmax(fst == 0, axis=0)
+    assert np.all(fst[own, np.arange(fst.shape[1])] == 0) and np.all(np.diff(own) >= 0)
+    assert np.abs(np.linalg.norm(h["sf_facet_to_normal"], axis=1) - 1).max() < 1e-12
+    # slab by slab == whole (the recorded-simplex lists differ per slab, the layout must not)
+    nlast = model.partition[-1]
+    k0 = nlast // 2
+    parts = [LevelSetCutter(slab=(0, k0)).cut(model, geo), LevelSetCutter(slab=(k0, nlast)).cut(model, geo)]
+    hp = [p.to_host() for p in parts]
+    assert hp[0]["sc_cell_to_points"].shape[0] + hp[1]["sc_cell_to_points"].shape[0] == c2p.shape[0]
+    assert np.array_equal(np.concatenate([hp[0]["sc_point_to_coords"], hp[1]["sc_point_to_coords"]]), h["sc_point_to_coords"])
+    assert np.array_equal(np.concatenate([hp[0]["ls_to_subcell_to_inout"], hp[1]["ls_to_subcell_to_inout"]], axis=1),
+                          h["ls_to_subcell_to_inout"])
+    assert np.array_equal(np.concatenate([hp[0]["sf_facet_to_normal"][hp[0]["ls_to_subfacet_to_inout"][0] == 0],
+                                          hp[1]["sf_facet_to_normal"][hp[1]["ls_to_subfacet_to_inout"][0] == 0]]),
+                          h["sf_facet_to_normal"][fst[0] == 0])
+    for p in parts:
+        p.close()
+    cg.close()
