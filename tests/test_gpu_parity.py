@@ -543,7 +543,12 @@ def test_multi_levelset_properties_at_scale(case):
     fst = h["ls_to_subfacet_to_inout"]
     own = np.argmax(fst == 0, axis=0)
     assert np.all(fst[own, np.arange(fst.shape[1])] == 0) and np.all(np.diff(own) >= 0)
-    assert np.abs(np.linalg.norm(h["sf_facet_to_normal"], axis=1) - 1).max() < 1e-12
+    # unit normals, except on degenerate facets (a grid node exactly on a surface gives a cut point at coefficient 0): the
+    # reference returns the zero vector when the cross product is shorter than eps (LookupTables.jl:309-360)
+    nn = np.linalg.norm(h["sf_facet_to_normal"], axis=1)
+    P = h["sf_point_to_coords"][h["sf_facet_to_points"] - 1]
+    area = 0.5 * np.linalg.norm(np.cross(P[:, 1] - P[:, 0], P[:, 2] - P[:, 0]), axis=1)
+    assert np.all((np.abs(nn - 1) < 1e-12) | ((nn == 0) & (area < 1e-15)))
     # slab by slab == whole (the recorded-simplex lists differ per slab, the layout must not)
     nlast = model.partition[-1]
     k0 = nlast // 2
