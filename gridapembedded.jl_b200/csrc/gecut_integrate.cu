@@ -19,9 +19,11 @@ namespace {
 // vertices are on chip; a Measure over a selection only gathers them
 __global__ void __launch_bounds__(256)
 k_measures(const int32_t* __restrict__ ids, int64_t n, const double* __restrict__ meas, double* __restrict__ values,
-           double* __restrict__ partial) {
-  // gather + deterministic block partial sums (fixed element -> thread -> tree order); values may be NULL
+           double* __restrict__ partial, unsigned int* __restrict__ ticket, double* __restrict__ out) {
+  // gather + deterministic two-level sum: fixed element -> thread -> tree order inside a block, and the block that
+  // finishes last adds the block partials in index order (no second launch); values may be NULL
   __shared__ double sh[256];
+  __shared__ bool s_last;
   double s = 0.0;
   const int64_t per = (n + gridDim.x - 1) / gridDim.x;
   const int64_t lo = per * blockIdx.x, hi = lo + per < n ? lo + per : n;
@@ -36,15 +38,17 @@ k_measures(const int32_t* __restrict__ ids, int64_t n, const double* __restrict_
     if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
-}
-
-// deterministic two-level sum
-__global__ void k_final_sum(const double* __restrict__ partial, int nb, double* __restrict__ out) {
-  __shared__ double sh[256];
-  double s = 0.0;
-  for (int i = threadIdx.x; i < nb; i += blockDim.x) s += partial[i];
-  sh[threadIdx.x] = s;
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = sh[0];
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double t = 0.0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += reinterpret_cast<volatile double*>(partial)[i];
+  sh[threadIdx.x] = t;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
     if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
@@ -477,11 +481,13 @@ int gc_integrate_measure(gecut_ctx* ctx, const gecut_selection* sel, double* val
   const bool use_sub = sel->kind == GECUT_SEL_PHYSICAL || sel->kind == GECUT_SEL_CUTONLY || sel->kind == GECUT_SEL_BOUNDARY;
   if (use_sub && n > 0) {
     const int NB = (int)std::min<int64_t>(1184, gc_div_up(n, 1024));
-    double* partial = nullptr;
-    GC_CHECK(gc_malloc(ctx, (void**)&partial, sizeof(double) * (NB + 1)));
+    double* partial = nullptr;  // NB block partials, the total, the completion ticket
+    GC_CHECK(gc_malloc(ctx, (void**)&partial, sizeof(double) * (NB + 2)));
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(partial + NB + 1);
+    GC_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), ctx->stream));
     GC_LAUNCH(ctx, "k_measures", k_measures<<<NB, 256, 0, ctx->stream>>>(
-        sel->sub_ids, n, sel->kind == GECUT_SEL_BOUNDARY ? lay.sf_meas : lay.sc_meas, values_dev, partial));
-    GC_LAUNCH(ctx, "k_final_sum", k_final_sum<<<1, 256, 0, ctx->stream>>>(partial, NB, partial + NB));
+        sel->sub_ids, n, sel->kind == GECUT_SEL_BOUNDARY ? lay.sf_meas : lay.sc_meas, values_dev, partial, ticket,
+        partial + NB));
     double* h = (double*)ctx->h_pinned;
     GC_CUDA(cudaMemcpyAsync(h, partial + NB, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     GC_CUDA(cudaStreamSynchronize(ctx->stream));
