@@ -803,6 +803,11 @@ k_cut_fast(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
       if (FILL) {
         const int klast = a == 0 ? 1 : 0;
         const int fc = ((outm >> klast) & 1u) ? fc_allout : 0;
+        // the skipped stages are the same for every facet: their permutations are composed once
+        uint8_t qf[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) qf[i] = (uint8_t)i;
+        skip_facet_stages(qf, L, klast, a);
         for (int f = 0; f < nfac; ++f) {
           const uint8_t* fp = TC.fac_pts[c][f];
           double q1[3], q2[3], q3[3], nrm[3];
@@ -815,8 +820,7 @@ k_cut_fast(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
           unit_normal<D>(q1, q2, q3, (double)TC.fac_orient[c][f], nrm);
           uint8_t fvl[D];
 #pragma unroll
-          for (int i = 0; i < D; ++i) fvl[i] = fp[i];
-          skip_facet_stages(fvl, L, klast, a);
+          for (int i = 0; i < D; ++i) fvl[i] = fp[qf[i]];
           const uint32_t pb = fpt_off + (uint32_t)f * D, fid = fac_off + (uint32_t)f;
 #pragma unroll
           for (int pnt = 0; pnt < D; ++pnt)
@@ -881,11 +885,14 @@ k_cut_fast(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
         // cut at stage a > 0: every child goes down to stage 0 alone and is emitted there as an uncut simplex
         const int c0 = (outm & 1u) ? c_allout : 0;
         if (FILL) {
+          uint8_t qc[D + 1];  // composed permutations of the stages a-1 ... 1 (the same for every child)
+#pragma unroll
+          for (int i = 0; i <= D; ++i) qc[i] = (uint8_t)i;
+          skip_cell_stages(qc, a, 0);
           for (int j = 0; j < nsub; ++j) {
             uint8_t cv[D + 1];
 #pragma unroll
-            for (int i = 0; i <= D; ++i) cv[i] = TC.sub_pts[c][j][i];
-            skip_cell_stages(cv, a, 0);
+            for (int i = 0; i <= D; ++i) cv[i] = TC.sub_pts[c][j][qc[i]];
             const uint32_t pb = pt_off + (uint32_t)j * (D + 1), cid = cell_off + j;
 #pragma unroll
             for (int pnt = 0; pnt <= D; ++pnt) {
