@@ -174,6 +174,11 @@ void free_result_arrays(gecut_result* r) {
   gc_free(ctx, l.sf_meas);
   gc_free(ctx, r->cutmask);
   gc_free(ctx, r->cutcount);
+  for (auto& kv : r->prog_rows) {
+    gc_free(ctx, kv.second.first);
+    gc_free(ctx, kv.second.second);
+  }
+  r->prog_rows.clear();
   gc_free(ctx, r->cut_sc_ptr);
   r->cut_sc_ptr = nullptr;
   gc_free(ctx, r->bg_counts_dev);
@@ -323,6 +328,7 @@ int make_program(gecut_ctx* ctx, const int32_t* program, int len, int L, GcProgr
   p->len = len;
   p->lut = nullptr;
   p->nused = 0;
+  p->sc_base = p->sc_row = p->bg_base = p->bg_row = nullptr;
   if (len >= 3) {
     // truth table over the level sets the program uses (EmbeddedDiscretizations.jl:136-177 evaluated 3^nused times, once)
     bool seen[GC_LMAX] = {false};
@@ -369,6 +375,35 @@ int make_program(gecut_ctx* ctx, const int32_t* program, int len, int L, GcProgr
 bad:
   ctx->err = "malformed boolean program";
   return GECUT_ERR_INVALID;
+}
+
+// Multi-operator programs: evaluate once over the subcell and bg-cell rows of `res`, keep the two Int8 rows with the
+// result and let every later evaluation of the same program read them (selections of both sides, measures, Laplacian).
+int attach_program_rows(gecut_ctx* ctx, const gecut_result* res_c, GcProgram* p) {
+  // single-leaf programs read one state row anyway, and with few level sets the truth-table gather over the rows is
+  // cheaper than a pass that writes a new row
+  if (!p->lut || p->nused <= 4) return GECUT_OK;
+  gecut_result* res = const_cast<gecut_result*>(res_c);
+  const std::string key(reinterpret_cast<const char*>(p->tok), (size_t)p->len);
+  auto it = res->prog_rows.find(key);
+  if (it == res->prog_rows.end()) {
+    const int64_t nsc = res->sizes.num_subcells, nc = res->sizes.num_bgcells;
+    int8_t *sc = nullptr, *bg = nullptr;
+    if (nsc > 0) {
+      GC_CHECK(gc_malloc(ctx, (void**)&sc, (size_t)pad_pitch(nsc)));  // padded: consumers read 16-byte vectors
+      GC_CHECK(gc_eval_rows(ctx, res->lay.sc_state, res->lay.sc_pitch, nsc, *p, sc, true));
+    }
+    if (nc > 0) {
+      GC_CHECK(gc_malloc(ctx, (void**)&bg, (size_t)pad_pitch(nc)));
+      GC_CHECK(gc_eval_rows(ctx, res->lay.bg_state, res->lay.bg_pitch, nc, *p, bg, true));
+    }
+    it = res->prog_rows.emplace(key, std::make_pair(sc, bg)).first;
+  }
+  p->sc_base = res->lay.sc_state;
+  p->sc_row = it->second.first;
+  p->bg_base = res->lay.bg_state;
+  p->bg_row = it->second.second;
+  return GECUT_OK;
 }
 
 int copy_rows_to_host(gecut_ctx* ctx, int8_t* host, const int8_t* dev, int64_t pitch, int64_t n, int L) {
@@ -671,6 +706,7 @@ int gecut_select_cells(const gecut_result* res, int kind, const int32_t* program
   sel->kind = kind;
   sel->side = side;
   int st = make_program(ctx, program, len, res->L, &sel->prog);
+  if (st == GECUT_OK) st = attach_program_rows(ctx, res, &sel->prog);
   if (st == GECUT_OK) st = gc_select_cells(ctx, sel);
   if (st == GECUT_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = GECUT_ERR_CUDA;
   if (st != GECUT_OK) {

@@ -59,6 +59,9 @@ struct GcProgram {
   const int8_t* lut;
   int nused;
   int8_t used[GC_LUT_MAXUSED];
+  // memoised results of this program over the subcell / bg-cell state rows of one result (device, owned by the result):
+  // when `rows` of an evaluation is sc_base (bg_base) the answer is sc_row[e] (bg_row[e])
+  const int8_t *sc_base, *sc_row, *bg_base, *bg_row;
 };
 
 // Device pointers of the result layout.
@@ -142,6 +145,9 @@ struct gecut_result {
   GcLayout lay{};
   uint32_t* cutmask = nullptr;
   uint32_t* cutcount = nullptr;   // cut cells per 32-cube group (k_classify -> compaction, then freed)
+  // memoised program rows (key = program tokens): results of multi-operator boolean programs over the subcell and the
+  // bg-cell state rows, evaluated once and shared by every selection / integration that uses the same geometry
+  std::map<std::string, std::pair<int8_t*, int8_t*>> prog_rows;
   uint32_t* cut_sc_ptr = nullptr;  // 2*(Ncut+1): (first subcell, first subcell point) (0-based) of every cut bg cell
   unsigned long long* bg_counts_dev = nullptr;  // [L][2][6] IN / OUT bg cells per level set and cell type
   int64_t bg_counts[GC_LMAX * 12] = {0};        // host copy (filled with the cut-cell count read-back)
@@ -218,7 +224,8 @@ int gc_eval_leaf_nodes(gecut_ctx* ctx, const GcGrid& g, const gecut_leaf& leaf, 
 int gc_cut_cells(gecut_ctx* ctx, gecut_result* res);
 
 // ---- selectors (gecut_select.cu) ----
-int gc_eval_rows(gecut_ctx* ctx, const int8_t* rows, int64_t pitch, int64_t n, const GcProgram& prog, int8_t* out_dev);
+int gc_eval_rows(gecut_ctx* ctx, const int8_t* rows, int64_t pitch, int64_t n, const GcProgram& prog, int8_t* out_dev,
+                 bool out_padded = false);  // out_padded: out_dev holds a multiple of 16 bytes
 int gc_select_cells(gecut_ctx* ctx, gecut_selection* sel);
 int gc_select_boundary(gecut_ctx* ctx, gecut_selection* sel);
 int gc_materialize_bg_ids(gecut_ctx* ctx, gecut_selection* sel);
@@ -347,6 +354,8 @@ __host__ __device__ __forceinline__ int gc_io_complementary(int a) {
 __device__ __forceinline__ int gc_eval_inoutcut(const GcProgram& p, const int8_t* rows, int64_t pitch, int64_t e) {
   if (p.len == 1) return rows[(int64_t)p.tok[0] * pitch + e];  // single leaf: no stack machine
   if (p.len == 2 && p.tok[1] == GECUT_OP_COMPLEMENT) return gc_io_complementary(rows[(int64_t)p.tok[0] * pitch + e]);
+  if (p.sc_row && rows == p.sc_base) return p.sc_row[e];  // memoised program row
+  if (p.bg_row && rows == p.bg_base) return p.bg_row[e];
   if (p.lut) {  // truth table: base-3 index from the states of the used level sets
     int idx = 0;
     for (int k = p.nused - 1; k >= 0; --k) idx = idx * 3 + (rows[(int64_t)p.used[k] * pitch + e] + 1);

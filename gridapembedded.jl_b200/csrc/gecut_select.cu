@@ -23,6 +23,30 @@ __global__ void k_eval_rows(const int8_t* __restrict__ rows, int64_t pitch, int6
   out[e] = (int8_t)gc_eval_inoutcut(prog, rows, pitch, e);
 }
 
+// truth-table programs, 16 elements per thread: one 128-bit load per used state row, one 128-bit store (rows and `out`
+// are padded to 16 bytes)
+__global__ void __launch_bounds__(256)
+k_eval_rows_lut16(const int8_t* __restrict__ rows, int64_t pitch, int64_t n, const GcProgram prog, int8_t* __restrict__ out) {
+  const int64_t e0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (e0 >= n) return;
+  uint32_t idx[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) idx[c] = 0u;
+  for (int k = prog.nused - 1; k >= 0; --k) {
+    const uint4 r4 = *reinterpret_cast<const uint4*>(rows + (int64_t)prog.used[k] * pitch + e0);
+    const uint32_t w4[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+    for (int c = 0; c < 16; ++c) idx[c] = idx[c] * 3u + (uint32_t)((int)(int8_t)((w4[c >> 2] >> (8 * (c & 3))) & 0xFFu) + 1);
+  }
+  uint32_t o4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const uint32_t v = e0 + c < n ? (uint32_t)(uint8_t)__ldg(prog.lut + idx[c]) : 0u;
+    o4[c >> 2] |= v << (8 * (c & 3));
+  }
+  *reinterpret_cast<uint4*>(out + e0) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+}
+
 // Triangulation(cut,CutInOrOut(side),geo): bg state == CUT && subcell state == side, as a stream compaction over the
 // subcells: 16 consecutive subcells per thread (one 128-bit load of the state row for single-leaf programs), 4096 per
 // block.  check_bg == 0 (one level set: every cut cell is CUT for every program over it) skips the bg-cell gather.
@@ -39,10 +63,11 @@ k_select_subcells(const GcLayout lay, int64_t nsc, const GcProgram prog, int sid
   uint32_t bits = 0u;  // bit i: subcell e0+i is selected
   if (e0 < nsc) {
     const bool leaf1 = prog.len == 1 || (prog.len == 2 && prog.tok[1] == GECUT_OP_COMPLEMENT);
-    if (leaf1) {
-      const int want = prog.len == 2 ? -side : side;  // complement swaps IN and OUT
-      // rows are padded to a multiple of 256 bytes: the vector load may run past nsc
-      const uint4 q = *reinterpret_cast<const uint4*>(lay.sc_state + (int64_t)prog.tok[0] * lay.sc_pitch + e0);
+    if (leaf1 || prog.sc_row) {
+      const int want = (!prog.sc_row && prog.len == 2) ? -side : side;  // complement swaps IN and OUT
+      // rows are padded to a multiple of 256 bytes: the vector load may run past nsc (memoised rows: allocation granularity)
+      const int8_t* row = prog.sc_row ? prog.sc_row : lay.sc_state + (int64_t)prog.tok[0] * lay.sc_pitch;
+      const uint4 q = *reinterpret_cast<const uint4*>(row + e0);
       const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
       const uint32_t pat = (uint32_t)(uint8_t)(int8_t)want * 0x01010101u;
 #pragma unroll
@@ -133,8 +158,9 @@ k_count_bgcells_vec(const GcLayout lay, int64_t nc, int L, const GcProgram prog,
     const int64_t e0 = gi * 16;
     const int nvalid = (int)(nc - e0 < 16 ? nc - e0 : 16);
     int ty = (int)(e0 % cpc);
-    if (prog.len == 1) {
-      const uint4 r4 = *reinterpret_cast<const uint4*>(lay.bg_state + (int64_t)prog.tok[0] * lay.bg_pitch + e0);
+    if (prog.len == 1 || prog.bg_row) {
+      const int8_t* row = prog.bg_row ? prog.bg_row : lay.bg_state + (int64_t)prog.tok[0] * lay.bg_pitch;
+      const uint4 r4 = *reinterpret_cast<const uint4*>(row + e0);
       const uint32_t w4[4] = {r4.x, r4.y, r4.z, r4.w};
       unsigned long long pk = 0ull;
 #pragma unroll
@@ -235,10 +261,14 @@ __global__ void k_gather_rows(const int32_t* __restrict__ ids, int64_t n, const 
 
 }  // namespace
 
-int gc_eval_rows(gecut_ctx* ctx, const int8_t* rows, int64_t pitch, int64_t n, const GcProgram& prog, int8_t* out_dev) {
+int gc_eval_rows(gecut_ctx* ctx, const int8_t* rows, int64_t pitch, int64_t n, const GcProgram& prog, int8_t* out_dev,
+                 bool out_padded) {
   if (n <= 0) return GECUT_OK;
   const int T = 256;
-  GC_LAUNCH(ctx, "k_eval_rows", k_eval_rows<<<(unsigned)gc_div_up(n, T), T, 0, ctx->stream>>>(rows, pitch, n, prog, out_dev));
+  if (prog.lut && out_padded && (reinterpret_cast<uintptr_t>(out_dev) & 15) == 0)
+    GC_LAUNCH(ctx, "k_eval_rows", k_eval_rows_lut16<<<(unsigned)gc_div_up(gc_div_up(n, 16), T), T, 0, ctx->stream>>>(rows, pitch, n, prog, out_dev));
+  else
+    GC_LAUNCH(ctx, "k_eval_rows", k_eval_rows<<<(unsigned)gc_div_up(n, T), T, 0, ctx->stream>>>(rows, pitch, n, prog, out_dev));
   return gc_launch_check(ctx, "k_eval_rows");
 }
 
