@@ -569,6 +569,10 @@ k_cut_fast(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
   __shared__ GcSimplexTable s_tab[2];  // [0]: D-simplex (cells), [1]: (D-1)-simplex (facet pass-through rows)
   __shared__ double scratch[FILL ? SSTR * WALK_T : 1];
   __shared__ __align__(16) uint16_t pmap_all[FILL ? (WALK_T / 32) * PCAP : 8];
+  // per-lane stash of the <= 2 facets of a simplex (unit normal, measure, point slots) for the warp-level facet emission
+  __shared__ double fstash[FILL ? WALK_T : 1][8];
+  __shared__ uint8_t fslots[FILL ? WALK_T : 1][8];
+  __shared__ uint8_t fitem_all[FILL ? WALK_T * 2 : 8];
   __shared__ uint8_t s_swap[8];
   {
     const uint32_t* src0 = reinterpret_cast<const uint32_t*>(tables + (D - 1));
@@ -637,6 +641,10 @@ k_cut_fast(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
     __syncwarp();
   }
 
+  // what the warp-level facet emission needs from every lane (0 facets for idle lanes and recorded simplices)
+  int w_a = 0, w_nfac = 0, w_fc = 0;
+  uint32_t w_outm = 0u, w_fac_off = 0u, w_fpt_off = 0u;
+  int32_t w_bg = 0;
   if (valid) {
     const int64_t kcut = s / g.nt0;
     const int t0 = (int)(s - kcut * g.nt0);
@@ -821,29 +829,27 @@ k_cut_fast(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
           uint8_t fvl[D];
 #pragma unroll
           for (int i = 0; i < D; ++i) fvl[i] = fp[qf[i]];
-          const uint32_t pb = fpt_off + (uint32_t)f * D, fid = fac_off + (uint32_t)f;
-#pragma unroll
-          for (int pnt = 0; pnt < D; ++pnt)
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-              lay.sf_X[(int64_t)(pb + pnt) * D + d] = sget(fvl[pnt], d);
-              lay.sf_R[(int64_t)(pb + pnt) * D + d] = sget(fvl[pnt], D + d);
-            }
           double pf[D][3];
 #pragma unroll
           for (int i = 0; i < D; ++i) {
             const int li = TF.sub_pts[fc][0][i];
-            lay.sf_c2p[(int64_t)fid * D + i] = (int32_t)(pb + li + 1);
-            lay.sf_N[(int64_t)fid * D + i] = nrm[i];
 #pragma unroll
             for (int d = 0; d < D; ++d) pf[i][d] = sget(fvl[li], d);
           }
-          lay.sf_c2bg[fid] = bgcell1;
-          lay.sf_meas[fid] = integrate_one<D - 1>(simplex_meas<D, D - 1>(pf));
-          for (int kk = 0; kk < L; ++kk)
-            lay.sf_state[(int64_t)kk * lay.sf_pitch + fid] =
-                (kk == a) ? (int8_t)GECUT_INTERFACE : ((kk == klast) ? TF.sub_inout[fc][0] : cstate(kk));
+          // parked for the warp-level emission below
+#pragma unroll
+          for (int d = 0; d < D; ++d) fstash[threadIdx.x][f * 4 + d] = nrm[d];
+          fstash[threadIdx.x][f * 4 + 3] = integrate_one<D - 1>(simplex_meas<D, D - 1>(pf));
+#pragma unroll
+          for (int i = 0; i < D; ++i) fslots[threadIdx.x][f * 4 + i] = fvl[i];
         }
+        w_a = a;
+        w_nfac = nfac;
+        w_fc = fc;
+        w_outm = outm;
+        w_fac_off = fac_off;
+        w_fpt_off = fpt_off;
+        w_bg = bgcell1;
       }
       // ---- cells
       uint32_t ncell_out, npt_out;
@@ -938,6 +944,70 @@ k_cut_fast(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
   }  // valid
   if (FILL) {
     __syncwarp();
+    // ---- warp-level facet emission: the facets of the warp's simplices form (per level set) runs of consecutive ids,
+    // so one facet entity per lane writes point blocks, normals, connectivity, bg cells, measures and state rows with
+    // neighbouring lanes on neighbouring addresses (the per-lane loops above scattered 8-byte stores over 32 sectors)
+    {
+      constexpr uint32_t FULLM = 0xffffffffu;
+      const uint32_t lt = (1u << lane) - 1u;
+      const uint32_t b1 = __ballot_sync(FULLM, w_nfac >= 1), b2 = __ballot_sync(FULLM, w_nfac >= 2);
+      const int T = __popc(b1) + __popc(b2);
+      uint8_t* fitem = fitem_all + (threadIdx.x & ~31) * 2;
+      const int first = __popc(b1 & lt) + __popc(b2 & lt);
+      for (int f = 0; f < w_nfac; ++f) fitem[first + f] = (uint8_t)(lane * 2 + f);
+      __syncwarp();
+      const int wt0 = threadIdx.x & ~31;                   // thread index of lane 0 of this warp
+      const double* SW = scratch + wt0 * SSTR;
+      // point blocks: D points x D coordinates per facet
+      for (int q0 = 0; q0 < T * D * D; q0 += 32) {
+        const int q = q0 + lane;
+        const bool on = q < T * D * D;
+        const int item = on ? q / (D * D) : 0;
+        const int r = q - item * (D * D), pnt = r / D, d = r - pnt * D;
+        const int it = fitem[item], o = it >> 1, f = it & 1;
+        const uint32_t fpo = __shfl_sync(FULLM, w_fpt_off, o);
+        if (on) {
+          const double* src = SW + o * SSTR + fslots[wt0 + o][f * 4 + pnt] * 2 * D;
+          const int64_t dst = (int64_t)(fpo + (uint32_t)(f * D + pnt)) * D + d;
+          lay.sf_X[dst] = src[d];
+          lay.sf_R[dst] = src[D + d];
+        }
+      }
+      // normals and connectivity: D entries per facet
+      for (int q0 = 0; q0 < T * D; q0 += 32) {
+        const int q = q0 + lane;
+        const bool on = q < T * D;
+        const int item = on ? q / D : 0;
+        const int d = q - item * D;
+        const int it = fitem[item], o = it >> 1, f = it & 1;
+        const uint32_t fpo = __shfl_sync(FULLM, w_fpt_off, o), fao = __shfl_sync(FULLM, w_fac_off, o);
+        const int fco = __shfl_sync(FULLM, w_fc, o);
+        if (on) {
+          const int64_t dst = (int64_t)(fao + (uint32_t)f) * D + d;
+          lay.sf_N[dst] = fstash[wt0 + o][f * 4 + d];
+          lay.sf_c2p[dst] = (int32_t)(fpo + (uint32_t)(f * D) + TF.sub_pts[fco][0][d] + 1);
+        }
+      }
+      // per facet: bg cell, measure, state rows
+      for (int q0 = 0; q0 < T; q0 += 32) {
+        const int q = q0 + lane;
+        const bool on = q < T;
+        const int it = fitem[on ? q : 0], o = it >> 1, f = it & 1;
+        const uint32_t fao = __shfl_sync(FULLM, w_fac_off, o), om = __shfl_sync(FULLM, w_outm, o);
+        const int fco = __shfl_sync(FULLM, w_fc, o), ao = __shfl_sync(FULLM, w_a, o);
+        const int32_t bgo = __shfl_sync(FULLM, w_bg, o);
+        if (on) {
+          const int64_t fid = (int64_t)fao + f;
+          lay.sf_c2bg[fid] = bgo;
+          lay.sf_meas[fid] = fstash[wt0 + o][f * 4 + 3];
+          const int klast = ao == 0 ? 1 : 0;
+          for (int kk = 0; kk < L; ++kk)
+            lay.sf_state[(int64_t)kk * lay.sf_pitch + fid] =
+                (kk == ao) ? (int8_t)GECUT_INTERFACE
+                           : ((kk == klast) ? TF.sub_inout[fco][0] : (((om >> kk) & 1u) ? (int8_t)GC_OUT : (int8_t)GC_IN));
+        }
+      }
+    }
     if (staged) {
       const double* SW = scratch + (threadIdx.x & ~31) * SSTR;  // scratch of lane 0 of this warp
       double* gX = lay.sc_X + (int64_t)wbase * D;
