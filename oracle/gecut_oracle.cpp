@@ -188,6 +188,8 @@ struct BgGrid {
 struct Mesh {
   int ds = 0;  // dimension of the simplices (Dc for subcells, Dp-1 for subfacets)
   int dp = 0;  // dimension of the points
+  int dr = -1; // dimension of the reference coordinates (-1: dp; ds for the sub-mesh of a bg FACET grid)
+  int rdim() const { return dr < 0 ? dp : dr; }
   bool is_facets = false;
   std::vector<int32_t> c2p;   // Table data, (ds+1) ids per cell, 1-based
   std::vector<int32_t> c2bg;  // cell_to_bgcell / facet_to_bgcell, 1-based
@@ -265,12 +267,13 @@ void cut_stage(const Mesh& m, const std::vector<double>& val, bool with_boundary
   s = Mesh();
   s.ds = m.ds;
   s.dp = m.dp;
+  s.dr = m.dr;
   s.is_facets = m.is_facets;
   s.c2p.assign(n_scells * nlp, 0);
   s.c2bg.assign(n_scells, 0);
   if (m.is_facets) s.c2n.assign(n_scells * m.dp, 0.0);
   s.X.assign(n_spoints * m.dp, 0.0);
-  s.R.assign(n_spoints * m.dp, 0.0);
+  s.R.assign(n_spoints * m.rdim(), 0.0);
   s.done.assign(m.done.size(), std::vector<int8_t>(n_scells, 0));
   s.pending.assign(m.pending.size(), std::vector<double>(n_spoints, 0.0));
   scell_to_inoutcut.assign(n_scells, 0);
@@ -287,13 +290,11 @@ void cut_stage(const Mesh& m, const std::vector<double>& val, bool with_boundary
   }
   // cut_sub_triangulation(_with_boundary)! (CutTriangulations.jl:168-177,253-266)
   int64_t scell = 0, spoint = 0, q = 0, sfacet = 0, z = 0;
-  const int dp = m.dp;
+  const int dp = m.dp, dr = m.rdim();
   auto copy_point = [&](int64_t sp1, int64_t mp1) {  // set_point_data! (CutTriangulations.jl:93-101,113-121)
     for (size_t l = 0; l < s.pending.size(); ++l) s.pending[l][sp1 - 1] = m.pending[l][mp1 - 1];
-    for (int d = 0; d < dp; ++d) {
-      s.X[(sp1 - 1) * dp + d] = m.X[(mp1 - 1) * dp + d];
-      s.R[(sp1 - 1) * dp + d] = m.R[(mp1 - 1) * dp + d];
-    }
+    for (int d = 0; d < dp; ++d) s.X[(sp1 - 1) * dp + d] = m.X[(mp1 - 1) * dp + d];
+    for (int d = 0; d < dr; ++d) s.R[(sp1 - 1) * dr + d] = m.R[(mp1 - 1) * dr + d];
   };
   auto lerp_point = [&](int64_t sp1, int64_t mp1, int64_t mp2, double coeff) {  // CutTriangulations.jl:123-135
     for (size_t l = 0; l < s.pending.size(); ++l) {
@@ -303,8 +304,10 @@ void cut_stage(const Mesh& m, const std::vector<double>& val, bool with_boundary
     for (int d = 0; d < dp; ++d) {
       double a = m.X[(mp1 - 1) * dp + d], b = m.X[(mp2 - 1) * dp + d];
       s.X[(sp1 - 1) * dp + d] = a + coeff * (b - a);
-      double ra = m.R[(mp1 - 1) * dp + d], rb = m.R[(mp2 - 1) * dp + d];
-      s.R[(sp1 - 1) * dp + d] = ra + coeff * (rb - ra);
+    }
+    for (int d = 0; d < dr; ++d) {
+      double ra = m.R[(mp1 - 1) * dr + d], rb = m.R[(mp2 - 1) * dr + d];
+      s.R[(sp1 - 1) * dr + d] = ra + coeff * (rb - ra);
     }
   };
   for (int64_t mcell = 0; mcell < m.ncells(); ++mcell) {
@@ -554,6 +557,155 @@ Result* do_cut(const OGrid& og, const OLeaf* leaves, int L, const double* const*
   m.pending.clear();
   r->subcells = std::move(m);
   r->subfacets = std::move(fst);
+  return r;
+}
+
+// ----------------------------------------------------------------------------
+// cut_facets(LevelSetCutter(), bgmodel, geo) (LevelSetCutters.jl:107-142):
+// the same machinery on `Grid(ReferenceFE{D-1}, model)`, without boundary.
+// Result = EmbeddedFacetDiscretization (EmbeddedFacetDiscretizations.jl:28-35).
+//
+// Assumption A8 (Gridap 0.20.x, not vendored, unpinned by the reference tests):
+//  * facets of the model are numbered by first encounter over (cell ascending,
+//    local facet ascending) (`generate_cell_to_faces`), and a facet takes the
+//    node order of the local facet of the cell that meets it first;
+//  * local facets of the n-cubes: QUAD [[1,2],[3,4],[1,3],[2,4]],
+//    HEX [[1,2,3,4],[5,6,7,8],[1,2,5,6],[3,4,7,8],[1,3,5,7],[2,4,6,8]].
+// Only n-cube (not simplexified) Cartesian models.
+// ----------------------------------------------------------------------------
+static const std::vector<std::vector<int>> LFACETS_QUAD = {{1, 2}, {3, 4}, {1, 3}, {2, 4}};
+static const std::vector<std::vector<int>> LFACETS_HEX = {{1, 2, 3, 4}, {5, 6, 7, 8}, {1, 2, 5, 6},
+                                                          {3, 4, 7, 8}, {1, 3, 5, 7}, {2, 4, 6, 8}};
+static const std::vector<std::vector<int>> SIMPLEXIFY_POS_SEGMENT = {{1, 2}};
+static const std::vector<std::vector<double>> VERTICES_SEGMENT = {{0.0}, {1.0}};
+
+struct FacetResult {
+  BgGrid grid;
+  int L;
+  int nvf;                                    // nodes per bg facet
+  std::vector<int64_t> facet_nodes;           // nvf 0-based node ids per bg facet
+  std::vector<int8_t> facet_is_boundary;      // 1: the facet belongs to one cell only
+  std::vector<std::vector<int8_t>> ls_to_facet_to_inoutcut;
+  std::vector<int32_t> cutfacet_to_facet;     // 1-based, ascending
+  Mesh subfacets;                             // SubCellData{D-1,D}
+  std::vector<std::vector<int8_t>> ls_to_subfacet_to_inout;
+  explicit FacetResult(const OGrid& g) : grid(g), L(0), nvf(0) {}
+};
+
+FacetResult* do_cut_facets(const OGrid& og, const OLeaf* leaves, int L, const double* const* nodal_values) {
+  FacetResult* r = new FacetResult(og);
+  const BgGrid& g = r->grid;
+  if (g.simplexified) return r;  // not covered (nvf == 0 marks it)
+  r->L = L;
+  const int D = g.D, nvf = 1 << (D - 1);
+  r->nvf = nvf;
+  // ---- Grid(ReferenceFE{D-1}, model): first-encounter numbering (A8)
+  const std::vector<std::vector<int>>& lfacets = D == 2 ? LFACETS_QUAD : LFACETS_HEX;
+  {
+    std::map<std::array<int64_t, 4>, int32_t> seen;
+    for (int64_t cell = 0; cell < g.num_cells; ++cell) {
+      int64_t nodes[8];
+      g.cell_nodes(cell, nodes);
+      for (const std::vector<int>& lf : lfacets) {
+        std::array<int64_t, 4> key = {-1, -1, -1, -1};
+        for (int i = 0; i < nvf; ++i) key[i] = nodes[lf[i] - 1];
+        std::array<int64_t, 4> sorted = key;
+        std::sort(sorted.begin(), sorted.end());
+        auto it = seen.find(sorted);
+        if (it == seen.end()) {
+          seen.emplace(sorted, (int32_t)r->facet_is_boundary.size());
+          for (int i = 0; i < nvf; ++i) r->facet_nodes.push_back(key[i]);
+          r->facet_is_boundary.push_back(1);
+        } else {
+          r->facet_is_boundary[it->second] = 0;
+        }
+      }
+    }
+  }
+  const int64_t nfacets = (int64_t)r->facet_is_boundary.size();
+  // ---- discretize (DiscreteGeometries.jl:48-63)
+  std::vector<std::vector<double>> ls_to_point_to_value(L);
+  for (int ls = 0; ls < L; ++ls) {
+    std::vector<double>& v = ls_to_point_to_value[ls];
+    v.resize(g.num_nodes);
+    if (leaves[ls].kind == NODAL) {
+      std::memcpy(v.data(), nodal_values[ls], sizeof(double) * g.num_nodes);
+    } else {
+      for (int64_t node = 0; node < g.num_nodes; ++node) {
+        double x[3];
+        g.node_coords(node, x);
+        v[node] = eval_leaf(leaves[ls], x, D);
+      }
+    }
+  }
+  // ---- _extract_grid_of_cut_cells on the facet grid (CutTriangulations.jl:462-493)
+  r->ls_to_facet_to_inoutcut.assign(L, std::vector<int8_t>(nfacets, 0));
+  for (int ls = 0; ls < L; ++ls)
+    for (int64_t f = 0; f < nfacets; ++f) {
+      int c = 1;
+      for (int i = 0; i < nvf; ++i)
+        if (isout(ls_to_point_to_value[ls][r->facet_nodes[f * nvf + i]])) c += 1 << i;
+      r->ls_to_facet_to_inoutcut[ls][f] = (int8_t)case_to_inoutcut_ncube(c, nvf);
+    }
+  for (int64_t f = 0; f < nfacets; ++f) {
+    bool iscut = false;
+    for (int ls = 0; ls < L; ++ls)
+      if (r->ls_to_facet_to_inoutcut[ls][f] == CUT) iscut = true;
+    if (iscut) r->cutfacet_to_facet.push_back((int32_t)(f + 1));
+  }
+  // ---- _simplexify_and_isolate_cells_in_cutgrid (CutTriangulations.jl:505-548), Dc = D-1, Dp = D
+  const std::vector<std::vector<int>>& lt = D == 2 ? SIMPLEXIFY_POS_SEGMENT : SIMPLEXIFY_POS_QUAD;
+  const std::vector<std::vector<double>>& verts = D == 2 ? VERTICES_SEGMENT : VERTICES_QUAD;
+  const int nlt = (int)lt.size(), nsp = D, ds = D - 1;
+  const int64_t ncut = (int64_t)r->cutfacet_to_facet.size();
+  Mesh m0;
+  m0.ds = ds;
+  m0.dp = D;
+  m0.dr = ds;
+  m0.c2p.assign(ncut * nlt * nsp, 0);
+  m0.c2bg.assign(ncut * nlt, 0);
+  m0.X.assign(ncut * nvf * D, 0.0);
+  m0.R.assign(ncut * nvf * ds, 0.0);
+  m0.pending.assign(L, std::vector<double>(ncut * nvf, 0.0));
+  int64_t tpoint = 0, tcell = 0;
+  for (int64_t k = 0; k < ncut; ++k) {
+    const int64_t f = r->cutfacet_to_facet[k] - 1;
+    for (int ltc = 0; ltc < nlt; ++ltc) {
+      tcell += 1;
+      for (int j = 0; j < nsp; ++j) m0.c2p[(tcell - 1) * nsp + j] = (int32_t)(tpoint + lt[ltc][j]);
+      m0.c2bg[tcell - 1] = (int32_t)(f + 1);
+    }
+    for (int lpoint = 0; lpoint < nvf; ++lpoint) {
+      tpoint += 1;
+      const int64_t node = r->facet_nodes[f * nvf + lpoint];
+      double x[3];
+      g.node_coords(node, x);
+      for (int d = 0; d < D; ++d) m0.X[(tpoint - 1) * D + d] = x[d];
+      for (int d = 0; d < ds; ++d) m0.R[(tpoint - 1) * ds + d] = verts[lpoint][d];
+      for (int ls = 0; ls < L; ++ls) m0.pending[ls][tpoint - 1] = ls_to_point_to_value[ls][node];
+    }
+  }
+  // _ensure_positive_jacobians_facets! (CutTriangulations.jl:642-683): swap the first two ids when the Jacobian of the
+  // sub-simplex and the Jacobian of the bg facet map (both at the first reference node) have a negative inner product
+  for (int64_t t = 0; t < m0.ncells(); ++t) {
+    int32_t* p = &m0.c2p[t * nsp];
+    const int64_t k = t / nlt;  // tcell_to_cutcell
+    const double* q0 = &m0.X[(k * nvf + 0) * D];
+    double dot = 0.0;
+    for (int a = 0; a < ds; ++a) {
+      const double* xa = &m0.X[(int64_t)(p[a + 1] - 1) * D];
+      const double* x0 = &m0.X[(int64_t)(p[0] - 1) * D];
+      const double* qa = &m0.X[(k * nvf + (1 << a)) * D];  // d x / d xi_a of the n-cube map at the origin
+      for (int d = 0; d < D; ++d) dot += (xa[d] - x0[d]) * (qa[d] - q0[d]);
+    }
+    if (dot < 0) std::swap(p[0], p[1]);
+  }
+  // ---- cut_sub_triangulation_several_levelsets (CutTriangulations.jl:294-307)
+  std::vector<std::vector<double>> pending = std::move(m0.pending);
+  m0.pending.clear();
+  Mesh out;
+  cut_several_levelsets(std::move(m0), std::move(pending), out, r->ls_to_subfacet_to_inout);
+  r->subfacets = std::move(out);
   return r;
 }
 
@@ -1035,6 +1187,112 @@ void gecut_oracle_cutcell_laplacian(void* h, const int32_t* ids, int64_t n, doub
 void gecut_oracle_bgcell_laplacian(void* h, int32_t cell1, double* K) { bgcell_laplacian(((Result*)h)->grid, cell1 - 1, K); }
 
 // leaf evaluation at arbitrary points (for the K1 parity test)
+// ---- cut_facets ---------------------------------------------------------------------------------------------
+void* gecut_oracle_cut_facets(const OGrid* grid, const OLeaf* leaves, int L, const double* const* nodal_values) {
+  return do_cut_facets(*grid, leaves, L, nodal_values);
+}
+void gecut_oracle_facets_free(void* h) { delete (FacetResult*)h; }
+// sizes: [Nf, Ncutf, Nsf, Nsfp, L, D, nvf, Nboundary]
+void gecut_oracle_facets_sizes(void* h, int64_t* out) {
+  FacetResult* r = (FacetResult*)h;
+  out[0] = (int64_t)r->facet_is_boundary.size();
+  out[1] = (int64_t)r->cutfacet_to_facet.size();
+  out[2] = r->subfacets.ncells();
+  out[3] = r->subfacets.c2p.empty() ? 0 : r->subfacets.npoints();
+  out[4] = r->L;
+  out[5] = r->grid.D;
+  out[6] = r->nvf;
+  int64_t nb = 0;
+  for (int8_t b : r->facet_is_boundary) nb += b;
+  out[7] = nb;
+}
+const void* gecut_oracle_facets_array(void* h, const char* name, int ls, int64_t* n) {
+  FacetResult* r = (FacetResult*)h;
+  std::string s(name);
+#define RET(vec)                 \
+  {                              \
+    *n = (int64_t)(vec).size();  \
+    return (const void*)(vec).data(); \
+  }
+  if (s == "ls_to_facet_to_inoutcut") RET(r->ls_to_facet_to_inoutcut[ls]);
+  if (s == "cutfacet_to_facet") RET(r->cutfacet_to_facet);
+  if (s == "facet_is_boundary") RET(r->facet_is_boundary);
+  if (s == "facet_nodes") RET(r->facet_nodes);
+  if (s == "subfacets.cell_to_points") RET(r->subfacets.c2p);
+  if (s == "subfacets.cell_to_bgcell") RET(r->subfacets.c2bg);
+  if (s == "subfacets.point_to_coords") RET(r->subfacets.X);
+  if (s == "subfacets.point_to_rcoords") RET(r->subfacets.R);
+  if (s == "ls_to_subfacet_to_inout") RET(r->ls_to_subfacet_to_inout[ls]);
+#undef RET
+  *n = -1;
+  return nullptr;
+}
+// compute_bgfacet_to_inoutcut(cut,geo) / compute_subfacet_to_inout(cut,geo) (EmbeddedFacetDiscretizations.jl:216-248)
+void gecut_oracle_bgfacet_to_inoutcut(void* h, const int32_t* prog, int len, int8_t* out) {
+  FacetResult* r = (FacetResult*)h;
+  for (int64_t f = 0; f < (int64_t)r->facet_is_boundary.size(); ++f)
+    out[f] = eval_inoutcut(prog, len, r->ls_to_facet_to_inoutcut, f);
+}
+void gecut_oracle_facets_subfacet_to_inout(void* h, const int32_t* prog, int len, int8_t* out) {
+  FacetResult* r = (FacetResult*)h;
+  for (int64_t f = 0; f < r->subfacets.ncells(); ++f) out[f] = eval_inoutcut(prog, len, r->ls_to_subfacet_to_inout, f);
+}
+// BoundaryTriangulation(facets,cut,in_or_out,geo) (EmbeddedFacetDiscretizations.jl:147-201) on the boundary facets
+// (which = 0) or on one side of SkeletonTriangulation (which = 1: interior facets).  mode 0: CutInOrOut(side) ->
+// subfacets; mode 1: Integer side -> bg facets with state == side; mode 2: ActiveInOrOut(side) -> bg facets CUT or side.
+int64_t gecut_oracle_select_facets(void* h, const int32_t* prog, int len, int which, int mode, int side, int32_t* ids) {
+  FacetResult* r = (FacetResult*)h;
+  int64_t n = 0;
+  auto in_trian = [&](int64_t f0) { return which == 0 ? r->facet_is_boundary[f0] == 1 : r->facet_is_boundary[f0] == 0; };
+  if (mode == 0) {
+    for (int64_t sf = 0; sf < r->subfacets.ncells(); ++sf) {
+      const int64_t f0 = r->subfacets.c2bg[sf] - 1;
+      const int a = eval_inoutcut(prog, len, r->ls_to_facet_to_inoutcut, f0);
+      const int b = eval_inoutcut(prog, len, r->ls_to_subfacet_to_inout, sf);
+      if (in_trian(f0) && a == CUT && b == side) {
+        if (ids) ids[n] = (int32_t)(sf + 1);
+        n++;
+      }
+    }
+  } else {
+    for (int64_t f0 = 0; f0 < (int64_t)r->facet_is_boundary.size(); ++f0) {
+      const int a = eval_inoutcut(prog, len, r->ls_to_facet_to_inoutcut, f0);
+      const bool ok = mode == 1 ? a == side : (a == CUT || a == side);
+      if (in_trian(f0) && ok) {
+        if (ids) ids[n] = (int32_t)(f0 + 1);
+        n++;
+      }
+    }
+  }
+  return n;
+}
+void gecut_oracle_facets_subfacet_measures(void* h, const int32_t* ids, int64_t n, double* out) {
+  FacetResult* r = (FacetResult*)h;
+  for (int64_t i = 0; i < n; ++i) out[i] = integrate_one(r->subfacets, ids[i] - 1);
+}
+// integral of 1 over a whole bg facet (tensor Gauss rule of degree 2 on the (D-1)-cube; the map is affine)
+double gecut_oracle_bgfacet_measure(void* h, int32_t facet1) {
+  FacetResult* r = (FacetResult*)h;
+  const BgGrid& g = r->grid;
+  const int nvf = r->nvf, D = g.D;
+  double x[4][3];
+  for (int i = 0; i < nvf; ++i) g.node_coords(r->facet_nodes[(int64_t)(facet1 - 1) * nvf + i], x[i]);
+  double meas;
+  if (D == 2) {
+    double a = x[1][0] - x[0][0], b = x[1][1] - x[0][1];
+    meas = std::sqrt(a * a + b * b);
+  } else {
+    double a[3] = {x[1][0] - x[0][0], x[1][1] - x[0][1], x[1][2] - x[0][2]};
+    double b[3] = {x[2][0] - x[0][0], x[2][1] - x[0][1], x[2][2] - x[0][2]};
+    double n1 = a[1] * b[2] - a[2] * b[1], n2 = a[2] * b[0] - a[0] * b[2], n3 = a[0] * b[1] - a[1] * b[0];
+    meas = std::sqrt(n1 * n1 + n2 * n2 + n3 * n3);
+  }
+  Rule q = ncube_rule_deg2(D - 1);
+  double s = 0;
+  for (int i = 0; i < q.n; ++i) s += q.w[i] * meas;
+  return s;
+}
+
 void gecut_oracle_eval_leaf(const OLeaf* leaf, int D, const double* x, int64_t n, double* out) {
   for (int64_t i = 0; i < n; ++i) out[i] = eval_leaf(*leaf, x + i * D, D);
 }

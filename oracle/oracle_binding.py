@@ -68,6 +68,19 @@ def lib():
         L.gecut_oracle_eval_leaf.argtypes = [C.POINTER(OLeaf), C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
         L.gecut_oracle_node_values.argtypes = [C.POINTER(OGrid), C.POINTER(OLeaf), C.c_void_p]
         L.gecut_oracle_node_coords.argtypes = [C.POINTER(OGrid), C.c_void_p]
+        L.gecut_oracle_cut_facets.restype = C.c_void_p
+        L.gecut_oracle_cut_facets.argtypes = [C.POINTER(OGrid), C.POINTER(OLeaf), C.c_int, C.POINTER(C.c_void_p)]
+        L.gecut_oracle_facets_free.argtypes = [C.c_void_p]
+        L.gecut_oracle_facets_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.gecut_oracle_facets_array.restype = C.c_void_p
+        L.gecut_oracle_facets_array.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int64)]
+        L.gecut_oracle_bgfacet_to_inoutcut.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.gecut_oracle_facets_subfacet_to_inout.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.gecut_oracle_select_facets.restype = C.c_int64
+        L.gecut_oracle_select_facets.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.gecut_oracle_facets_subfacet_measures.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.gecut_oracle_bgfacet_measure.restype = C.c_double
+        L.gecut_oracle_bgfacet_measure.argtypes = [C.c_void_p, C.c_int32]
         _lib = L
     return _lib
 
@@ -219,6 +232,103 @@ class OracleCut:
         K = np.zeros((self.nv, self.nv), np.float64)
         lib().gecut_oracle_bgcell_laplacian(self.h, int(cell1), K.ctypes.data)
         return K
+
+
+_FACET_DTYPES = {
+    "ls_to_facet_to_inoutcut": np.int8, "cutfacet_to_facet": np.int32, "facet_is_boundary": np.int8,
+    "facet_nodes": np.int64,
+    "subfacets.cell_to_points": np.int32, "subfacets.cell_to_bgcell": np.int32,
+    "subfacets.point_to_coords": np.float64, "subfacets.point_to_rcoords": np.float64,
+    "ls_to_subfacet_to_inout": np.int8,
+}
+
+BOUNDARY_FACETS, SKELETON_FACETS = 0, 1
+SEL_CUT, SEL_BG, SEL_ACTIVE = 0, 1, 2
+
+
+class OracleFacetCut:
+    """Result of the oracle's `cut_facets(LevelSetCutter(), model, geo)`: the arrays of the
+    `EmbeddedFacetDiscretization` (EmbeddedFacetDiscretizations.jl:28-35) as numpy copies."""
+
+    def __init__(self, model, leaves: Sequence[OLeaf], nodal_values: Optional[List[Optional[np.ndarray]]] = None):
+        L = len(leaves)
+        arr = (OLeaf * L)(*leaves)
+        ptrs = (C.c_void_p * L)()
+        self._keep = []
+        for i in range(L):
+            if nodal_values is not None and nodal_values[i] is not None:
+                a = np.ascontiguousarray(nodal_values[i], dtype=np.float64)
+                assert a.shape[0] == model.num_nodes
+                self._keep.append(a)
+                ptrs[i] = a.ctypes.data
+            else:
+                ptrs[i] = None
+        self.model = model
+        self.grid = make_grid(model)
+        self.h = lib().gecut_oracle_cut_facets(C.byref(self.grid), arr, L, ptrs)
+        s = (C.c_int64 * 8)()
+        lib().gecut_oracle_facets_sizes(self.h, s)
+        (self.Nf, self.Ncutf, self.Nsf, self.Nsfp, self.L, self.D, self.nvf, self.Nboundary) = [int(x) for x in s]
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().gecut_oracle_facets_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def array(self, name: str, ls: int = 0) -> np.ndarray:
+        n = C.c_int64()
+        p = lib().gecut_oracle_facets_array(self.h, name.encode(), ls, C.byref(n))
+        if n.value < 0:
+            raise KeyError(name)
+        dt = np.dtype(_FACET_DTYPES[name])
+        if n.value == 0:
+            return np.zeros(0, dtype=dt)
+        buf = (C.c_char * (n.value * dt.itemsize)).from_address(p)
+        return np.frombuffer(buf, dtype=dt).copy()
+
+    def rows(self, name: str) -> np.ndarray:
+        return np.stack([self.array(name, ls) for ls in range(self.L)])
+
+    def bgfacet_to_inoutcut(self, prog) -> np.ndarray:
+        a, p, n = OracleCut._prog(prog)
+        out = np.zeros(self.Nf, np.int8)
+        lib().gecut_oracle_bgfacet_to_inoutcut(self.h, p, n, out.ctypes.data)
+        return out
+
+    def subfacet_to_inout(self, prog) -> np.ndarray:
+        a, p, n = OracleCut._prog(prog)
+        out = np.zeros(self.Nsf, np.int8)
+        lib().gecut_oracle_facets_subfacet_to_inout(self.h, p, n, out.ctypes.data)
+        return out
+
+    def select(self, prog, which: int, mode: int, side: int) -> np.ndarray:
+        a, p, n = OracleCut._prog(prog)
+        ids = np.zeros(max(self.Nsf, self.Nf, 1), np.int32)
+        k = lib().gecut_oracle_select_facets(self.h, p, n, which, mode, side, ids.ctypes.data)
+        return ids[:k].copy()
+
+    def subfacet_measures(self, ids) -> np.ndarray:
+        ids = np.ascontiguousarray(ids, np.int32)
+        out = np.zeros(ids.size, np.float64)
+        lib().gecut_oracle_facets_subfacet_measures(self.h, ids.ctypes.data, ids.size, out.ctypes.data)
+        return out
+
+    def bgfacet_measure(self, facet1: int) -> float:
+        return float(lib().gecut_oracle_bgfacet_measure(self.h, int(facet1)))
+
+
+def oracle_cut_facets(model, geo) -> "OracleFacetCut":
+    import importlib
+    gecut = importlib.import_module("gecut")
+    leaves, nodal, oid_to_ls = gecut.cutters.flatten_geometry(model, geo, host_only=True)
+    oleaves = [make_leaf(l.kind, l.x0, l.v, l.R, l.r) for l in leaves]
+    oc = OracleFacetCut(model, oleaves, nodal)
+    oc.oid_to_ls = oid_to_ls
+    oc.geo = geo
+    return oc
 
 
 def node_values(model, leaf: OLeaf) -> np.ndarray:
