@@ -59,7 +59,25 @@ class Buffers(C.Structure):
                                                            ("state_pitch_subfacet", C.c_int64)]
 
 
-SOURCES = ["gecut_api.cu", "gecut_classify.cu", "gecut_cutcells.cu", "gecut_select.cu", "gecut_integrate.cu"]
+class FacetSizes(C.Structure):
+    _fields_ = [("num_bgfacets", C.c_int64), ("num_boundary_facets", C.c_int64), ("num_cutfacets", C.c_int64),
+                ("num_subfacets", C.c_int64), ("num_subfacet_points", C.c_int64), ("num_levelsets", C.c_int32),
+                ("D", C.c_int32), ("num_vertices_per_bgfacet", C.c_int32), ("pad", C.c_int32)]
+
+
+FACET_BUFFER_FIELDS = ["ls_to_facet_to_inoutcut", "cutfacet_to_facet", "facet_to_nodes", "facet_is_boundary",
+                       "sf_cell_to_points", "sf_cell_to_bgcell", "sf_point_to_coords", "sf_point_to_rcoords",
+                       "ls_to_subfacet_to_inout"]
+
+
+class FacetBuffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in FACET_BUFFER_FIELDS]
+
+
+FACETS_BOUNDARY, FACETS_SKELETON = 0, 1
+
+SOURCES = ["gecut_api.cu", "gecut_classify.cu", "gecut_cutcells.cu", "gecut_select.cu", "gecut_integrate.cu",
+           "gecut_facets.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xcompiler", "-ffp-contract=off"]
 
@@ -173,6 +191,19 @@ def lib():
     L.gecut_integrate_laplacian.argtypes = [vp, vp, vp]
     L.gecut_selection_device_laplacian.argtypes = [vp, P(vp)]
     L.gecut_cell_measure.argtypes = [vp, vp, C.c_int]
+    L.gecut_cut_facets.argtypes = [vp, P(Grid), P(LeafRec), cint, P(vp), cint, cint, P(vp)]
+    L.gecut_facet_result_free.argtypes = [vp]
+    L.gecut_facet_result_sizes.argtypes = [vp, P(FacetSizes)]
+    L.gecut_facet_result_copy.argtypes = [vp, P(FacetBuffers)]
+    L.gecut_bgfacet_to_inoutcut.argtypes = [vp, vp, cint, vp]
+    L.gecut_subfacet_to_inout.argtypes = [vp, vp, cint, vp]
+    L.gecut_select_facets.argtypes = [vp, cint, cint, vp, cint, cint, P(vp)]
+    L.gecut_facet_selection_free.argtypes = [vp]
+    L.gecut_facet_selection_sizes.argtypes = [vp, P(i64), P(i64)]
+    L.gecut_facet_selection_copy.argtypes = [vp, vp, vp]
+    L.gecut_facet_selection_measure.argtypes = [vp, vp, P(C.c_double)]
+    for name in FACET_SYMBOLS:
+        getattr(L, name).restype = cint
     for name in ("gecut_create", "gecut_destroy", "gecut_set_stream", "gecut_cut", "gecut_classify",
                  "gecut_eval_leaf_at_nodes", "gecut_result_free", "gecut_result_sizes", "gecut_result_device_ptrs",
                  "gecut_result_copy", "gecut_bgcell_to_inoutcut", "gecut_subcell_to_inout", "gecut_select_cells",
@@ -184,7 +215,12 @@ def lib():
     return L
 
 
-EXPORTED_SYMBOLS = ["gecut_create", "gecut_destroy", "gecut_set_stream", "gecut_last_error", "gecut_launch_count",
+FACET_SYMBOLS = ["gecut_cut_facets", "gecut_facet_result_free", "gecut_facet_result_sizes", "gecut_facet_result_copy",
+                 "gecut_bgfacet_to_inoutcut", "gecut_subfacet_to_inout", "gecut_select_facets",
+                 "gecut_facet_selection_free", "gecut_facet_selection_sizes", "gecut_facet_selection_copy",
+                 "gecut_facet_selection_measure"]
+
+EXPORTED_SYMBOLS = FACET_SYMBOLS + ["gecut_create", "gecut_destroy", "gecut_set_stream", "gecut_last_error", "gecut_launch_count",
                     "gecut_profile", "gecut_profile_report", "gecut_trim",
                     "gecut_cut", "gecut_classify", "gecut_eval_leaf_at_nodes", "gecut_result_free",
                     "gecut_result_sizes", "gecut_result_device_ptrs", "gecut_result_copy", "gecut_bgcell_to_inoutcut",

@@ -83,19 +83,6 @@ void gc_prof_after(gecut_ctx* ctx) { cudaEventRecord(ctx->prof.back().b, ctx->st
 
 namespace {
 
-struct DeviceGuard {
-  int prev = -1;
-  explicit DeviceGuard(int dev) {
-    cudaGetDevice(&prev);
-    if (prev != dev) cudaSetDevice(dev);
-  }
-  ~DeviceGuard() {
-    int cur = -1;
-    cudaGetDevice(&cur);
-    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
-  }
-};
-
 int make_grid(gecut_ctx* ctx, const gecut_grid* in, GcGrid* g) {
   if (!in) {
     ctx->err = "grid is NULL";
@@ -420,6 +407,12 @@ int copy_to_host(gecut_ctx* ctx, T* host, const T* dev, int64_t count) {
 }
 
 }  // namespace
+
+// shared with gecut_facets.cu
+int gc_make_grid(gecut_ctx* ctx, const gecut_grid* in, GcGrid* g) { return make_grid(ctx, in, g); }
+int gc_make_program(gecut_ctx* ctx, const int32_t* program, int len, int L, GcProgram* p) {
+  return make_program(ctx, program, len, L, p);
+}
 
 // ------------------------------------------------------------------------------------------------
 // ABI

@@ -209,6 +209,22 @@ void gc_free(gecut_ctx* ctx, void* p);
 void gc_trim(gecut_ctx* ctx);  // give every cached block back to the driver
 int gc_launch_check(gecut_ctx* ctx, const char* what);
 
+// ---- host helpers of gecut_api.cu shared with gecut_facets.cu ----
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+int gc_make_grid(gecut_ctx* ctx, const gecut_grid* in, GcGrid* g);
+int gc_make_program(gecut_ctx* ctx, const int32_t* program, int len, int L, GcProgram* p);
+
 // ---- scan (gecut_classify.cu) ----
 // exclusive prefix sum of n uint32 (in place allowed); *total_dev (uint64, device) receives the grand total
 int gc_exclusive_scan_u32(gecut_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n, uint64_t* total_dev);
@@ -226,6 +242,9 @@ int gc_cut_cells(gecut_ctx* ctx, gecut_result* res);
 // ---- selectors (gecut_select.cu) ----
 int gc_eval_rows(gecut_ctx* ctx, const int8_t* rows, int64_t pitch, int64_t n, const GcProgram& prog, int8_t* out_dev,
                  bool out_padded = false);  // out_padded: out_dev holds a multiple of 16 bytes
+// flags (uint32, n) -> ids (1-based, ascending); the flags buffer is consumed (scanned in place)
+int gc_compact_flags(gecut_ctx* ctx, uint32_t* flags, int64_t n, int32_t** ids_out, int64_t* count,
+                     const int8_t* orient_all, int8_t** orient_out);
 int gc_select_cells(gecut_ctx* ctx, gecut_selection* sel);
 int gc_select_boundary(gecut_ctx* ctx, gecut_selection* sel);
 int gc_materialize_bg_ids(gecut_ctx* ctx, gecut_selection* sel);

@@ -273,8 +273,8 @@ int gc_eval_rows(gecut_ctx* ctx, const int8_t* rows, int64_t pitch, int64_t n, c
 }
 
 // flags (uint32, n) -> ids (1-based, ascending); *count out.  flags buffer is consumed (scanned in place).
-static int compact_flags(gecut_ctx* ctx, uint32_t* flags, int64_t n, int32_t** ids_out, int64_t* count,
-                         const int8_t* orient_all, int8_t** orient_out) {
+int gc_compact_flags(gecut_ctx* ctx, uint32_t* flags, int64_t n, int32_t** ids_out, int64_t* count,
+                     const int8_t* orient_all, int8_t** orient_out) {
   *ids_out = nullptr;
   if (orient_out) *orient_out = nullptr;
   *count = 0;
@@ -387,7 +387,7 @@ int gc_materialize_bg_ids(gecut_ctx* ctx, gecut_selection* sel) {
   unsigned nb = (unsigned)std::min<int64_t>(gc_div_up(nc, T), 148 * 16);
   GC_LAUNCH(ctx, "k_count_bgcells", k_count_bgcells<<<nb, T, 0, ctx->stream>>>(res->lay, nc, sel->prog, sel->side, mode, res->grid.cpc, counts, flags));
   int64_t n = 0;
-  int st = compact_flags(ctx, flags, nc, &sel->bg_ids, &n, nullptr, nullptr);
+  int st = gc_compact_flags(ctx, flags, nc, &sel->bg_ids, &n, nullptr, nullptr);
   gc_free(ctx, flags);
   gc_free(ctx, counts);
   return st;
@@ -418,7 +418,7 @@ int gc_select_boundary(gecut_ctx* ctx, gecut_selection* sel) {
   GC_CHECK(gc_malloc(ctx, (void**)&orient_all, sizeof(int8_t) * nsf));
   GC_LAUNCH(ctx, "k_flag_boundary", k_flag_boundary<<<(unsigned)gc_div_up(nsf, T), T, 0, ctx->stream>>>(res->lay, nsf, sel->prog, sel->prog2,
                                                                       sel->has_prog2 ? 1 : 0, flags, orient_all));
-  int st = compact_flags(ctx, flags, nsf, &sel->sub_ids, &sel->n_sub, orient_all, &sel->orientation);
+  int st = gc_compact_flags(ctx, flags, nsf, &sel->sub_ids, &sel->n_sub, orient_all, &sel->orientation);
   gc_free(ctx, flags);
   gc_free(ctx, orient_all);
   return st;

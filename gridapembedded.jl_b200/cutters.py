@@ -27,10 +27,10 @@ class Cutter:
         raise NotImplementedError("abstract method")
 
     def cut_facets(self, background, geom):
-        raise NotImplementedError("cut_facets is outside the accelerated path (SURVEY.md section 8f)")
+        raise NotImplementedError("abstract method")
 
     def compute_bgfacet_to_inoutcut(self, background, geom):
-        raise NotImplementedError("compute_bgfacet_to_inoutcut is outside the accelerated path (SURVEY.md section 8f)")
+        raise NotImplementedError("abstract method")
 
 
 def _is_torch_tensor(x) -> bool:

@@ -214,6 +214,67 @@ int gecut_cell_measure(const gecut_selection* sel, double* values, int values_on
 /* device pointer to the Ncut x nv x nv matrices of the last gecut_integrate_laplacian on this selection */
 int gecut_selection_device_laplacian(const gecut_selection* sel, double** K_cut_dev);
 
+/* ---- cut_facets ----------------------------------------------------------------------------- */
+/* cut_facets(::LevelSetCutter, bgmodel, geo) (src/LevelSetCutters/LevelSetCutters.jl:107-142): the marching-simplex
+ * machinery on Grid(ReferenceFE{D-1}, bgmodel) without boundary -> EmbeddedFacetDiscretization
+ * (src/Interfaces/EmbeddedFacetDiscretizations.jl:28-35).  n-cube Cartesian models, whole model (no slab) only.
+ * Facet numbering (Gridap `generate_cell_to_faces`, assumption A8 in DESIGN.md): first encounter over (cell ascending,
+ * local facet ascending), local facets QUAD [1,2],[3,4],[1,3],[2,4] / HEX [1,2,3,4],[5,6,7,8],[1,2,5,6],[3,4,7,8],
+ * [1,3,5,7],[2,4,6,8]; a facet keeps the node order of the local facet of the cell that meets it first. */
+typedef struct gecut_facet_result gecut_facet_result;       /* device-resident EmbeddedFacetDiscretization          */
+typedef struct gecut_facet_selection gecut_facet_selection; /* BoundaryTriangulation / SkeletonTriangulation(cut_facets,...) */
+
+typedef struct {
+  int64_t num_bgfacets;         /* Nf                                                                              */
+  int64_t num_boundary_facets;  /* facets with one cell around                                                     */
+  int64_t num_cutfacets;        /* facets CUT by at least one level set                                            */
+  int64_t num_subfacets;        /* Nsf: (D-1)-simplices of the cut facets                                          */
+  int64_t num_subfacet_points;  /* Nsfp                                                                            */
+  int32_t num_levelsets;
+  int32_t D;
+  int32_t num_vertices_per_bgfacet; /* 2 (SEGMENT) or 4 (QUAD)                                                     */
+  int32_t pad;
+} gecut_facet_sizes;
+
+/* host destinations (NULL entries skipped) of gecut_facet_result_copy */
+typedef struct {
+  int8_t* ls_to_facet_to_inoutcut;  /* L x Nf                                                                      */
+  int32_t* cutfacet_to_facet;       /* Ncutf, ascending, 1-based                                                    */
+  int32_t* facet_to_nodes;          /* Nf x nvf, 1-based node ids (Grid(ReferenceFE{D-1},model) connectivity)       */
+  int8_t* facet_is_boundary;        /* Nf                                                                          */
+  int32_t* sf_cell_to_points;       /* Nsf*D   SubCellData{D-1,D}.cell_to_points data                              */
+  int32_t* sf_cell_to_bgcell;       /* Nsf     bg FACET ids                                                        */
+  double* sf_point_to_coords;       /* Nsfp*D                                                                      */
+  double* sf_point_to_rcoords;      /* Nsfp*(D-1)  reference coordinates in the bg facet                           */
+  int8_t* ls_to_subfacet_to_inout;  /* L x Nsf                                                                     */
+} gecut_facet_buffers;
+
+/* classify_only != 0: compute_bgfacet_to_inoutcut(::LevelSetCutter, bgmodel, geo) (LevelSetCutters.jl:169-173) -- states
+ * and the cut facet list, no sub-facets. */
+int gecut_cut_facets(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* leaves, int num_leaves,
+                     const double* const* nodal_values, int nodal_on_device, int classify_only,
+                     gecut_facet_result** out);
+int gecut_facet_result_free(gecut_facet_result* res);
+int gecut_facet_result_sizes(const gecut_facet_result* res, gecut_facet_sizes* sizes);
+int gecut_facet_result_copy(const gecut_facet_result* res, const gecut_facet_buffers* host);
+/* compute_bgfacet_to_inoutcut(cut, geo) / compute_subfacet_to_inout(cut, geo) (EmbeddedFacetDiscretizations.jl:216-248) */
+int gecut_bgfacet_to_inoutcut(const gecut_facet_result* res, const int32_t* program, int len, int8_t* host_out);
+int gecut_subfacet_to_inout(const gecut_facet_result* res, const int32_t* program, int len, int8_t* host_out);
+
+#define GECUT_FACETS_BOUNDARY 0 /* BoundaryTriangulation(cut_facets, in_or_out, geo)   (:112-201)                      */
+#define GECUT_FACETS_SKELETON 1 /* one side of SkeletonTriangulation(cut_facets, in_or_out, geo) (:54-103)             */
+/* kind = GECUT_SEL_PHYSICAL (sub-facets of CUT facets with state == side + facets with state == side), GECUT_SEL_CUTONLY,
+ * GECUT_SEL_BGONLY or GECUT_SEL_ACTIVE (facets CUT or side), restricted to the boundary / interior facets. */
+int gecut_select_facets(const gecut_facet_result* res, int which, int kind, const int32_t* program, int len, int side,
+                        gecut_facet_selection** out);
+int gecut_facet_selection_free(gecut_facet_selection* sel);
+int gecut_facet_selection_sizes(const gecut_facet_selection* sel, int64_t* n_sub, int64_t* n_bg);
+/* host copies (NULL skipped): 1-based ids of the selected sub-facets / bg facets, ascending */
+int gecut_facet_selection_copy(const gecut_facet_selection* sel, int32_t* sub_ids, int32_t* bg_ids);
+/* sum(∫(1)dΓ) over the selection with Measure(trian,2): `sub_values` (host, NULL skipped) one value per selected
+ * sub-facet; *total also includes the selected whole facets */
+int gecut_facet_selection_measure(const gecut_facet_selection* sel, double* sub_values, double* total);
+
 #ifdef __cplusplus
 }
 #endif

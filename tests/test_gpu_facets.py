@@ -1,0 +1,204 @@
+"""GPU parity of `cut_facets` (EmbeddedFacetDiscretization): the CUDA path through the C ABI
+against the CPU oracle on the same inputs -- bit-exact states, facet numbering, connectivity and ordering; coordinates
+compared for equality first and within 1e-12 relative otherwise -- plus size-independent properties at scale."""
+import numpy as np
+import pytest
+
+import gecut
+from gecut import (CartesianDiscreteModel, disk, sphere, cube, cylinder, plane, union, intersect, setdiff, complement,
+                   get_geometry, DiscreteGeometry, cut, cut_facets, compute_bgfacet_to_inoutcut,
+                   compute_subfacet_to_inout, BoundaryTriangulation, SkeletonTriangulation, Triangulation,
+                   EmbeddedBoundary, Measure, LevelSetCutter, PHYSICAL, PHYSICAL_IN, PHYSICAL_OUT, ACTIVE, ACTIVE_OUT,
+                   CUT_IN, CUT_OUT, IN, OUT)
+from gecut import _lib
+from gecut.measures import integrate_measure
+import oracle_binding as ob
+from test_gpu_parity import csg_geometry, stokes_geometry, three_disks, bimaterial
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+def two_disks_plane():
+    return setdiff(intersect(disk(0.45, x0=(0.5, 0.5)), plane(x0=(0.5, 0.7), v=(0.2, 1.0))), disk(0.2, x0=(0.4, 0.4)))
+
+
+def stokes_model(n):
+    geo, pmin, pmax = stokes_geometry()
+    return CartesianDiscreteModel(pmin, pmax, n), geo
+
+
+CASES = {
+    "disk_corner_10": lambda: (CartesianDiscreteModel((0, 1, 0, 1), (10, 10)), disk(0.72, x0=(1, 1))),
+    "disk_odd": lambda: (CartesianDiscreteModel((-0.8, 0.9, -0.7, 0.75), (37, 45)), disk(0.7)),
+    "disk_1xN": lambda: (CartesianDiscreteModel((-1, 1, -1, 1), (1, 7)), disk(0.7)),
+    "three_disks": lambda: (CartesianDiscreteModel((-1, 2, -1, 2), (23, 19)), three_disks()),
+    "csg2d": lambda: (CartesianDiscreteModel((0, 1, 0, 1), (33, 31)), two_disks_plane()),
+    "sphere_face": lambda: (CartesianDiscreteModel((0, 1, 0, 1, 0, 1), (8, 8, 8)), sphere(0.37, x0=(0.5, 0.5, 1.0))),
+    "sphere_odd": lambda: (CartesianDiscreteModel((-0.8, 0.9, -0.7, 0.75, -0.9, 0.8), (13, 9, 11)), sphere(0.7)),
+    "sphere_1x1xN": lambda: (CartesianDiscreteModel((-0.2, 0.3, -0.2, 0.3, -1, 1), (1, 1, 9)), sphere(0.7)),
+    "csg_10": lambda: (CartesianDiscreteModel((-0.8,) * 3, (0.8,) * 3, (10, 10, 10)), csg_geometry()),
+    "stokes": lambda: stokes_model((20, 8, 8)),
+    "bimaterial": lambda: (CartesianDiscreteModel((0., 0., 0.), (3., 2., 3.), (9, 6, 9)), bimaterial()),
+    "empty_cut": lambda: (CartesianDiscreteModel((2, 3, 2, 3), (5, 5)), disk(0.7)),
+    "all_in": lambda: (CartesianDiscreteModel((-0.1, 0.1, -0.1, 0.1, -0.1, 0.1), (3, 3, 3)), sphere(0.7)),
+}
+
+
+def assert_close(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape
+    if not np.array_equal(a, b):
+        assert np.allclose(a, b, rtol=RTOL, atol=1e-300)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_facet_layout_parity(name):
+    model, geo = CASES[name]()
+    fc = cut_facets(model, geo)
+    oc = ob.oracle_cut_facets(model, geo)
+    h = fc.to_host(topology=True)
+    s = fc.sizes
+    assert (s.num_bgfacets, s.num_cutfacets, s.num_subfacets, s.num_subfacet_points, s.num_boundary_facets) == \
+        (oc.Nf, oc.Ncutf, oc.Nsf, oc.Nsfp, oc.Nboundary)
+    D = model.D
+    assert np.array_equal(h["facet_to_nodes"], oc.array("facet_nodes").reshape(-1, oc.nvf) + 1)
+    assert np.array_equal(h["facet_is_boundary"], oc.array("facet_is_boundary"))
+    assert np.array_equal(h["ls_to_facet_to_inoutcut"], oc.rows("ls_to_facet_to_inoutcut"))
+    assert np.array_equal(h["cutfacet_to_facet"], oc.array("cutfacet_to_facet"))
+    assert np.array_equal(h["sf_cell_to_points"].ravel(), oc.array("subfacets.cell_to_points"))
+    assert np.array_equal(h["sf_cell_to_bgcell"], oc.array("subfacets.cell_to_bgcell"))
+    assert np.array_equal(h["ls_to_subfacet_to_inout"], oc.rows("ls_to_subfacet_to_inout").reshape(oc.L, -1))
+    assert_close(h["sf_point_to_coords"].ravel(), oc.array("subfacets.point_to_coords"))
+    assert_close(h["sf_point_to_rcoords"].ravel(), oc.array("subfacets.point_to_rcoords"))
+    fc.close()
+
+
+@pytest.mark.parametrize("name", ["disk_corner_10", "three_disks", "csg2d", "sphere_face", "csg_10", "stokes", "bimaterial"])
+def test_facet_selectors_and_measures(name):
+    model, geo = CASES[name]()
+    fc = cut_facets(model, geo)
+    oc = ob.oracle_cut_facets(model, geo)
+    names = [None]
+    if name == "csg_10":
+        names += ["csg", "source"]
+    if name == "stokes":
+        names += ["fluid", "solid"]
+    if name == "bimaterial":
+        names += ["steel", "concrete"]
+    if name == "three_disks":
+        names += ["disk1", "disk3"]
+    for nm in names:
+        prog = fc.program(nm)
+        assert np.array_equal(compute_bgfacet_to_inoutcut(fc, nm), oc.bgfacet_to_inoutcut(prog))
+        assert np.array_equal(compute_subfacet_to_inout(fc, nm), oc.subfacet_to_inout(prog))
+        for ctor, which in ((BoundaryTriangulation, ob.BOUNDARY_FACETS), (SkeletonTriangulation, ob.SKELETON_FACETS)):
+            for sel, side in ((PHYSICAL_IN, IN), (PHYSICAL_OUT, OUT)):
+                t = ctor(fc, sel, nm)
+                sub = oc.select(prog, which, ob.SEL_CUT, side)
+                bg = oc.select(prog, which, ob.SEL_BG, side)
+                assert np.array_equal(t.sub_ids, sub)
+                assert np.array_equal(t.bg_ids, bg)
+                tot, vals = t.measure(return_values=True)
+                ovals = oc.subfacet_measures(sub)
+                assert_close(vals, ovals)
+                ref = ovals.sum() + sum(oc.bgfacet_measure(int(f)) for f in bg)
+                assert abs(tot - ref) <= 1e-12 * max(abs(ref), 1e-300)
+                t.close()
+            t = ctor(fc, ACTIVE, nm)
+            assert t.num_sub == 0 and np.array_equal(t.bg_ids, oc.select(prog, which, ob.SEL_ACTIVE, IN))
+            t.close()
+            t = ctor(fc, CUT_OUT, nm)
+            assert t.num_bg == 0 and np.array_equal(t.sub_ids, oc.select(prog, which, ob.SEL_CUT, OUT))
+            t.close()
+            t = ctor(fc, OUT, nm)
+            assert t.num_sub == 0 and np.array_equal(t.bg_ids, oc.select(prog, which, ob.SEL_BG, OUT))
+            t.close()
+    fc.close()
+
+
+def test_facets_discrete_geometry_and_classify_only():
+    model, geo = stokes_model((12, 6, 6))
+    dgeo = gecut.discretize(geo, model)
+    fc = cut_facets(model, dgeo)
+    fa = cut_facets(model, geo)
+    ha, hd = fa.to_host(), fc.to_host()
+    for k in ha:
+        assert np.array_equal(ha[k], hd[k]), k
+    st = compute_bgfacet_to_inoutcut(model, geo)  # classification-only entry point
+    assert np.array_equal(st, compute_bgfacet_to_inoutcut(fa, geo))
+    # cut_facets(cut::EmbeddedDiscretization, geo) and cut_facets(cut_facets) forwards (LevelSetCutters.jl:122-128)
+    cg = cut(model, geo)
+    f2 = cut_facets(cg, geo)
+    assert np.array_equal(f2.to_host()["sf_cell_to_points"], ha["sf_cell_to_points"])
+    assert cut_facets(f2) is f2
+    for x in (fc, fa, f2, cg):
+        x.close()
+
+
+def test_facets_unsupported_inputs():
+    from gecut import simplexify
+    model = simplexify(CartesianDiscreteModel((0, 1, 0, 1), (4, 4)))
+    with pytest.raises(NotImplementedError):
+        cut_facets(model, disk(0.3, x0=(0.5, 0.5)))
+    m = CartesianDiscreteModel((0, 1, 0, 1), (4, 4))
+    with pytest.raises(NotImplementedError):
+        LevelSetCutter(slab=(0, 2)).cut_facets(m, disk(0.3, x0=(0.5, 0.5)))
+    # raw ABI: simplexified grids are refused with NOTIMPLEMENTED, not silently mis-numbered
+    ctx = _lib.default_context()
+    import ctypes as C
+    from gecut.cutters import make_grid, make_leaf_records, flatten_geometry
+    leaves, nodal, _ = flatten_geometry(model, disk(0.3, x0=(0.5, 0.5)))
+    out = C.c_void_p()
+    g = make_grid(model)
+    rc = ctx._lib.gecut_cut_facets(ctx.handle, C.byref(g), make_leaf_records(leaves), 1, None, 0, 0, C.byref(out))
+    assert rc == _lib.GECUT_ERR_NOTIMPLEMENTED and "n-cube" in ctx.last_error()
+
+
+@pytest.mark.parametrize("case", ["disk_2048", "sphere_160", "csg_64"])
+def test_facets_properties_at_scale(case):
+    """Size-independent properties where the oracle is too slow: IN + OUT parts of every cut facet add up to the facet,
+    boundary/skeleton split, agreement of the facet states with the cell states of cut(), boundary IN measure against
+    the analytic value."""
+    if case == "disk_2048":
+        model, geo = CartesianDiscreteModel((0, 1, 0, 1), (2048, 2048)), disk(0.72, x0=(1, 1))
+    elif case == "sphere_160":
+        model, geo = CartesianDiscreteModel((0, 1, 0, 1, 0, 1), (160, 160, 160)), sphere(0.37, x0=(0.5, 0.5, 1.0))
+    else:
+        model, geo = CartesianDiscreteModel((-0.8,) * 3, (0.8,) * 3, (64, 64, 64)), csg_geometry()
+    D = model.D
+    fc = cut_facets(model, geo)
+    nm = "csg" if case == "csg_64" else None
+    h = np.asarray(model.sizes)
+    n = np.asarray(model.partition)
+    tot_b = {}
+    for ctor, key in ((BoundaryTriangulation, "b"), (SkeletonTriangulation, "s")):
+        tin = ctor(fc, PHYSICAL_IN, nm)
+        tout = ctor(fc, PHYSICAL_OUT, nm)
+        m_in, m_out = tin.measure(), tout.measure()
+        # total measure of the boundary / interior facets of the box
+        if key == "b":
+            whole = 2 * sum(np.prod(np.delete(h * n, d)) for d in range(D))
+        else:
+            whole = sum((n[d] - 1) * np.prod(np.delete(h * n, d)) for d in range(D))
+        assert abs(m_in + m_out - whole) <= 1e-11 * whole
+        assert tin.num_sub + tout.num_sub > 0 or (key == "b" and case == "csg_64")  # the CSG body stays inside the box
+        tot_b[key] = m_in
+        tin.close()
+        tout.close()
+    if case == "disk_2048":  # quarter disk of radius 0.72 centred on the corner: two boundary segments of length R
+        assert abs(tot_b["b"] - 2 * 0.72) < 1e-6
+    if case == "sphere_160":  # disk of radius R on the z-max face
+        assert abs(tot_b["b"] - np.pi * 0.37 ** 2) / (np.pi * 0.37 ** 2) < 2e-3
+    # sub-facets are grouped by ascending cut facet; ids within range; states +-1
+    hh = fc.to_host()
+    c2bg = hh["sf_cell_to_bgcell"]
+    assert np.all(np.diff(c2bg) >= 0)
+    assert np.array_equal(np.unique(c2bg), hh["cutfacet_to_facet"])
+    assert np.all(np.diff(hh["cutfacet_to_facet"]) > 0)
+    assert hh["sf_cell_to_points"].min() == 1 and hh["sf_cell_to_points"].max() == fc.sizes.num_subfacet_points
+    assert set(np.unique(hh["ls_to_subfacet_to_inout"]).tolist()) <= {-1, 1}
+    # every cut facet belongs to a facet the classification calls CUT for some level set
+    anycut = (hh["ls_to_facet_to_inoutcut"] == 0).any(0)
+    assert np.array_equal(np.nonzero(anycut)[0] + 1, hh["cutfacet_to_facet"])
+    fc.close()
