@@ -16,6 +16,7 @@
 // facets are then walked depth-first, one thread per stage-0 simplex (2 per QUAD facet, 1 per SEGMENT): the final arrays
 // of the reference's stage-major loop are exactly the depth-first order of each simplex' refinement tree, so only the
 // final layout is written (count walk -> exclusive scan -> fill walk).
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -46,7 +47,6 @@ struct gecut_facet_result {
   GcLeaves leaves{};
   gecut_facet_sizes sizes{};
   GcFacetLayout lay{};
-  uint32_t* cutmask = nullptr;
   bool owns_nodal[GC_LMAX] = {false};
   double* nodal_dev[GC_LMAX] = {nullptr};
 };
@@ -58,6 +58,7 @@ struct gecut_facet_selection {
   int32_t* sub_ids = nullptr;
   int32_t* bg_ids = nullptr;
   int64_t bg_dir_count[3] = {0, 0, 0};  // selected whole facets per normal direction
+  GcProgram prog{};                     // for the lazy materialisation of bg_ids
 };
 
 namespace {
@@ -177,62 +178,215 @@ __device__ __forceinline__ double leaf_at_node(const GcGrid& g, const GcLeaves& 
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1: states of every facet per level set (_compute_in_out_or_cut on the facet grid, CutTriangulations.jl:619-640),
-//     cut mask + cut facets per block
+// K1: sign bit of every level set at every node (discretize + isout, DiscreteGeometries.jl:48-63, LookupTables.jl:40-42):
+//     one evaluation per node, 32 x-consecutive nodes -> one ballot word.  A warp owns a word column and marches through
+//     NS_KCH planes of the last direction; the in-plane partial sums of the closed-form leaves are hoisted out of the
+//     march with the association of the reference ((w1*w1 + w2*w2) + w3*w3, gc_dot3), so a node costs 3-6 FP64
+//     operations.  The bit planes (Nn/8 bytes per level set, 17 MB at 513^3) stay in L2 for the next pass; node VALUES
+//     never touch HBM.
 // ------------------------------------------------------------------------------------------------
-constexpr int FC_T = 256;
+constexpr int NS_KCH = 32;
 
 template <int D>
-__global__ void __launch_bounds__(FC_T)
-k_facet_classify(const GcGrid g, const GcLeaves lv, int64_t nf, int8_t* __restrict__ state, int64_t pitch,
-                 uint32_t* __restrict__ cutmask, uint32_t* __restrict__ block_counts) {
-  constexpr int NVF = 1 << (D - 1);
-  __shared__ uint32_t s_cnt;
-  if (threadIdx.x == 0) s_cnt = 0;
-  __syncthreads();
-  const int64_t f = (int64_t)blockIdx.x * FC_T + threadIdx.x;
-  bool anycut = false;
-  if (f < nf) {
-    const FacetIdx fi = facet_decode<D>(g, (uint32_t)f);
-    int nijk[NVF][3];
-#pragma unroll
-    for (int m = 0; m < NVF; ++m) facet_node<D>(fi, m, nijk[m]);
-    for (int ls = 0; ls < lv.L; ++ls) {
-      bool any = false, all = true;
-#pragma unroll
-      for (int m = 0; m < NVF; ++m) {
-        const bool o = leaf_at_node<D>(g, lv, ls, nijk[m]) > 0.0;  // isout (LookupTables.jl:40-42)
-        any |= o;
-        all &= o;
+__global__ void __launch_bounds__(256)
+k_node_signs(const GcGrid g, const GcLeaves lv, int wxt, uint32_t* __restrict__ signs, int64_t ls_stride) {
+  constexpr int M = D - 1;  // marching direction
+  const int wx = blockIdx.x;
+  int j = 0, kbeg;
+  if (D == 3) {
+    j = blockIdx.y * 8 + threadIdx.y;
+    if (j >= g.nn[1]) return;  // a warp is one threadIdx.y: it leaves as a whole
+    kbeg = blockIdx.z * NS_KCH;
+  } else {
+    kbeg = (blockIdx.y * 8 + threadIdx.y) * NS_KCH;
+    if (kbeg >= g.nn[1]) return;
+  }
+  const int kend = min(kbeg + NS_KCH, g.nn[M]);
+  const int i = wx * 32 + threadIdx.x;
+  const bool valid = i < g.nn[0];
+  const int ic = valid ? i : g.nn[0] - 1;
+  const double x = gc_coord(g, 0, ic);
+  const double y = D == 3 ? gc_coord(g, 1, j) : 0.0;
+  for (int ls = 0; ls < lv.L; ++ls) {
+    const gecut_leaf& lf = lv.leaf[ls];
+    const int kind = lf.kind;
+    uint32_t* out = signs + (int64_t)ls * ls_stride + wx;
+    if (kind == GECUT_LEAF_NODAL) {
+      for (int k = kbeg; k < kend; ++k) {
+        const int64_t nrow = D == 3 ? (int64_t)k * g.nn[1] + j : (int64_t)k;
+        const double val = __ldg(lv.nodal[ls] + nrow * g.nn[0] + ic);
+        const uint32_t word = __ballot_sync(0xffffffffu, valid && val > 0.0);
+        if (threadIdx.x == 0) out[nrow * wxt] = word;
       }
-      const int8_t st = all ? (int8_t)GC_OUT : (any ? (int8_t)GC_CUT : (int8_t)GC_IN);
-      state[(int64_t)ls * pitch + f] = st;
-      anycut |= (st == GC_CUT);
+      continue;
+    }
+    const double w0 = __dsub_rn(x, lf.x0[0]);
+    const double w1 = D == 3 ? __dsub_rn(y, lf.x0[1]) : 0.0;
+    double ww = __dmul_rn(w0, w0), wv = __dmul_rn(w0, lf.v[0]);
+    if (D == 3) {
+      ww = __dadd_rn(ww, __dmul_rn(w1, w1));
+      wv = __dadd_rn(wv, __dmul_rn(w1, lf.v[1]));
+    }
+    const double R2 = __dmul_rn(lf.R, lf.R), r2 = __dmul_rn(lf.r, lf.r);
+    const double tt = kind == GECUT_LEAF_DOUGHNUT ? __dsub_rn(lf.R, __dsqrt_rn(ww)) : 0.0;
+    const double t2 = __dmul_rn(tt, tt);
+    for (int k = kbeg; k < kend; ++k) {
+      const double wl = __dsub_rn(gc_coord(g, M, k), lf.x0[M]);
+      double val;
+      if (kind == GECUT_LEAF_SPHERE) {
+        val = __dsub_rn(__dadd_rn(ww, __dmul_rn(wl, wl)), R2);
+      } else if (kind == GECUT_LEAF_PLANE) {
+        val = __dadd_rn(wv, __dmul_rn(wl, lf.v[M]));
+      } else if (kind == GECUT_LEAF_CYLINDER) {
+        const double A = __dadd_rn(wv, __dmul_rn(wl, lf.v[M]));
+        const double H2 = __dadd_rn(ww, __dmul_rn(wl, wl));
+        val = __dsub_rn(__dsub_rn(H2, __dmul_rn(A, A)), R2);
+      } else {  // DOUGHNUT (3-D only)
+        val = __dsub_rn(__dadd_rn(t2, __dmul_rn(wl, wl)), r2);
+      }
+      const uint32_t word = __ballot_sync(0xffffffffu, valid && val > 0.0);
+      const int64_t nrow = D == 3 ? (int64_t)k * g.nn[1] + j : (int64_t)k;
+      if (threadIdx.x == 0) out[nrow * wxt] = word;
     }
   }
-  const uint32_t word = __ballot_sync(0xffffffffu, anycut);
-  if ((threadIdx.x & 31) == 0) {
-    if (f < nf) cutmask[f >> 5] = word;
-    if (word) atomicAdd(&s_cnt, (uint32_t)__popc(word));
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) block_counts[blockIdx.x] = s_cnt;
 }
 
-// K2: ascending list of the cut facets (_find_cut_cells, CutTriangulations.jl:481-493)
-__global__ void __launch_bounds__(FC_T)
-k_facet_emit(int64_t nf, const uint32_t* __restrict__ cutmask, const uint32_t* __restrict__ block_offs,
-             int32_t* __restrict__ cutfacets) {
-  const int64_t f = (int64_t)blockIdx.x * FC_T + threadIdx.x;
-  if (f >= nf) return;
-  const int64_t w0 = ((int64_t)blockIdx.x * FC_T) >> 5;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t word = cutmask[w0 + warp];
-  if (!((word >> lane) & 1u)) return;
-  uint32_t pos = block_offs[blockIdx.x];
-  for (int w = 0; w < warp; ++w) pos += (uint32_t)__popc(cutmask[w0 + w]);
-  pos += (uint32_t)__popc(word & ((1u << lane) - 1u));
-  cutfacets[pos] = (int32_t)(f + 1);
+// first facet id (0-based) of the row of cells (j,k)
+template <int D>
+__host__ __device__ inline int64_t facet_row_base(const GcGrid& g, int j, int k) {
+  int64_t b = 0;
+  if (D == 3 && k > 0) b += facets_per_layer(g, 0) + (int64_t)(k - 1) * facets_per_layer(g, 1);
+  if (j > 0) b += facets_per_row<D>(g, 0, k) + (int64_t)(j - 1) * facets_per_row<D>(g, 1, k);
+  return b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: states of every facet per level set (_compute_in_out_or_cut on the facet grid, CutTriangulations.jl:619-640) and
+//     the ascending list of the cut facets (_find_cut_cells :481-493).  The facets a row of cells meets first are a
+//     contiguous id range (closed form, no division).  A warp owns a segment of FR_SEG cells of one row and walks it in
+//     chunks of 128 cells: a lane derives the states of the D..D+3 new facets of a cell from the 2^D corner sign bits
+//     (warp-uniform, L2-resident sign words).  EMIT = false: the states are staged in the warp's slice of shared memory
+//     with the 16-byte alignment of their global destination and leave as 16-byte stores (no block barrier); the
+//     segment's number of cut facets is recorded.  EMIT = true (after the scan over segments): the cut facets of the
+//     segment are written in id order.
+// ------------------------------------------------------------------------------------------------
+constexpr int FR_SEG = 1024;  // cells per warp segment
+constexpr int FR_WCH = 128;   // cells per warp iteration
+constexpr int FR_STAGE = FR_WCH * 5 + 1 + 16 + 15;
+
+template <int D, bool EMIT>
+__global__ void __launch_bounds__(256)
+k_facet_rows(const GcGrid g, int L, int wxt, const uint32_t* __restrict__ signs, int64_t ls_stride,
+             int8_t* __restrict__ state, int64_t pitch, uint32_t* __restrict__ seg_counts,
+             int32_t* __restrict__ cutfacets, int nseg_per_row, int64_t nsegs) {
+  constexpr int NR = 1 << (D - 1);
+  __shared__ __align__(16) uint8_t s_stage[EMIT ? 1 : 8][EMIT ? 16 : ((FR_STAGE + 15) & ~15)];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t gw = (int64_t)blockIdx.x * 8 + warp;
+  if (gw >= nsegs) return;
+  const int row = (int)(gw / nseg_per_row), seg = (int)(gw % nseg_per_row);
+  const int j = D == 3 ? row % g.n[1] : row;
+  const int k = D == 3 ? row / g.n[1] : 0;
+  const int per = D + (j == 0 ? 1 : 0) + ((D == 3 && k == 0) ? 1 : 0);
+  const int64_t rowbase = facet_row_base<D>(g, j, k);
+  const int nx = g.n[0];
+  const int i_beg = seg * FR_SEG, i_end = min(nx, i_beg + FR_SEG);
+  uint8_t* stage = s_stage[EMIT ? 0 : warp];
+  int64_t nrow[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) nrow[r] = ((int64_t)(k + (r >> 1)) * g.nn[1] + (j + (r & 1))) * wxt;
+  uint32_t running = EMIT ? seg_counts[gw] : 0u, total = 0u;
+  for (int i0 = i_beg; i0 < i_end; i0 += FR_WCH) {
+    const int chunk_off = i0 * per + (i0 > 0 ? 1 : 0);
+    const int chunk_len = min(FR_WCH, i_end - i0) * per + (i0 == 0 ? 1 : 0);
+    const int align = (int)((rowbase + chunk_off) & 15);
+    uint32_t anybits[4] = {0u, 0u, 0u, 0u};
+    const int w0 = i0 >> 5;
+    for (int ls = 0; ls < L; ++ls) {
+      const uint32_t* sg = signs + (int64_t)ls * ls_stride;
+      uint32_t lo[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) lo[r] = __ldg(sg + nrow[r] + w0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = i0 + q * 32 + lane;
+        uint32_t sm = 0u;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const uint32_t hi = (w0 + q + 1 < wxt) ? __ldg(sg + nrow[r] + w0 + q + 1) : 0u;
+          sm |= (__funnelshift_r(lo[r], hi, lane) & 3u) << (2 * r);
+          lo[r] = hi;
+        }
+        if (i < i_end) {
+          const int loc = i * per + (i > 0 ? 1 : 0) - chunk_off + align;
+          int t = 0;
+#pragma unroll
+          for (int d = D - 1; d >= 0; --d) {
+            const int idx = d == 0 ? i : (d == 1 ? j : k);
+            const uint32_t mlow = D == 3 ? (d == 0 ? 0x55u : (d == 1 ? 0x33u : 0x0Fu)) : (d == 0 ? 0x5u : 0x3u);
+            const uint32_t mhigh = D == 3 ? (d == 0 ? 0xAAu : (d == 1 ? 0xCCu : 0xF0u)) : (d == 0 ? 0xAu : 0xCu);
+            if (idx == 0) {
+              const uint32_t v = sm & mlow;
+              const int8_t st = v == 0u ? (int8_t)GC_IN : (v == mlow ? (int8_t)GC_OUT : (int8_t)GC_CUT);
+              if (st == GC_CUT) anybits[q] |= 1u << t;
+              if (!EMIT) stage[loc + t] = (uint8_t)st;
+              t++;
+            }
+            const uint32_t v = sm & mhigh;
+            const int8_t st = v == 0u ? (int8_t)GC_IN : (v == mhigh ? (int8_t)GC_OUT : (int8_t)GC_CUT);
+            if (st == GC_CUT) anybits[q] |= 1u << t;
+            if (!EMIT) stage[loc + t] = (uint8_t)st;
+            t++;
+          }
+        }
+      }
+      if (!EMIT) {
+        __syncwarp();
+        // stage[align + q] <-> global g0 + q; 16-byte blocks that lie inside the chunk leave as one store
+        int8_t* g0 = state + (int64_t)ls * pitch + rowbase + chunk_off - align;
+        const int end = align + chunk_len;
+        for (int p0 = lane * 16; p0 < end; p0 += 512) {
+          if (p0 >= align && p0 + 16 <= end) {
+            *reinterpret_cast<uint4*>(g0 + p0) = *reinterpret_cast<const uint4*>(stage + p0);
+          } else {
+            for (int p = max(p0, align); p < min(p0 + 16, end); ++p) g0[p] = (int8_t)stage[p];
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (!EMIT) {
+      total += (uint32_t)(__popc(anybits[0]) + __popc(anybits[1]) + __popc(anybits[2]) + __popc(anybits[3]));
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t cnt = (uint32_t)__popc(anybits[q]);
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += up;
+        }
+        const uint32_t qtot = __shfl_sync(0xffffffffu, inc, 31);
+        if (qtot) {
+          const int i = i0 + q * 32 + lane;
+          uint32_t pos = running + inc - cnt;
+          uint32_t bits = anybits[q];
+          while (bits) {
+            const int t = __ffs(bits) - 1;
+            bits &= bits - 1u;
+            cutfacets[pos++] = (int32_t)(rowbase + (int64_t)i * per + (i > 0 ? 1 : 0) + t + 1);
+          }
+          running += qtot;
+        }
+      }
+    }
+  }
+  if (!EMIT) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (lane == 0) seg_counts[gw] = total;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -412,26 +566,97 @@ k_facet_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict
 // ------------------------------------------------------------------------------------------------
 // selectors (EmbeddedFacetDiscretizations.jl:147-201) and measures
 // ------------------------------------------------------------------------------------------------
+// whole facets of a selection, counted per normal direction (the measure needs nothing else).  `row` is ONE Int8 state
+// row (a level set's row, or the memoised row of a multi-operator program); a warp owns a segment of a row of cells and
+// reads its facets' states as aligned 16-byte vectors, the direction and boundary flag of a byte follow from its offset
+// in the row (division by the warp-uniform facets-per-cell through constant divisors)
+template <int PER>
+__device__ __forceinline__ void divmod_per(uint32_t u, uint32_t& q, uint32_t& r) {
+  q = u / (uint32_t)PER;
+  r = u - q * (uint32_t)PER;
+}
+
 template <int D>
-__global__ void k_facet_flag_bg(const GcGrid g, const int8_t* __restrict__ rows, int64_t pitch, int64_t nf,
-                                const GcProgram prog, int which, int mode, int side, uint32_t* __restrict__ flags,
-                                unsigned long long* __restrict__ dir_counts) {
-  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool ok = false;
-  int dir = 0;
-  if (f < nf) {
-    const FacetIdx fi = facet_decode<D>(g, (uint32_t)f);
-    const bool in_trian = facet_is_boundary<D>(g, fi) == (which == GECUT_FACETS_BOUNDARY);
-    const int a = gc_eval_inoutcut(prog, rows, pitch, f);
-    ok = in_trian && (mode == 1 ? a == side : (a == GC_CUT || a == side));
-    flags[f] = ok ? 1u : 0u;
-    dir = fi.d;
+__global__ void __launch_bounds__(256)
+k_facet_rows_count(const GcGrid g, const int8_t* __restrict__ row_state, int which, int mode, int side,
+                   unsigned long long* __restrict__ dir_counts, int nseg_per_row, int64_t nsegs) {
+  __shared__ uint32_t s_cnt[3];
+  if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0u;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t gw = (int64_t)blockIdx.x * 8 + warp;
+  uint32_t cnt[3] = {0u, 0u, 0u};
+  if (gw < nsegs) {
+    const int row = (int)(gw / nseg_per_row), seg = (int)(gw % nseg_per_row);
+    const int j = D == 3 ? row % g.n[1] : row;
+    const int k = D == 3 ? row / g.n[1] : 0;
+    const int per = D + (j == 0 ? 1 : 0) + ((D == 3 && k == 0) ? 1 : 0);
+    const int64_t rowbase = facet_row_base<D>(g, j, k);
+    const int nx = g.n[0];
+    const int i_beg = seg * FR_SEG, i_end = min(nx, i_beg + FR_SEG);
+    // full local sequence of a cell: [z-low], z-high, [y-low], y-high, x-low, x-high (per + 1 entries); 3 bits each:
+    // direction (2) | side (1)
+    uint32_t code = 0u;
+    {
+      int t = 0;
+      for (int d = D - 1; d >= 0; --d) {
+        const int idx = d == 0 ? 0 : (d == 1 ? j : k);
+        if (idx == 0) code |= (uint32_t)(d << 1) << (3 * t++);
+        code |= (uint32_t)((d << 1) | 1) << (3 * t++);
+      }
+    }
+    const bool row_b1 = j == g.n[1] - 1, row_b2 = D == 3 && k == g.n[2] - 1;
+    const int64_t t_beg = (int64_t)i_beg * per + (i_beg > 0 ? 1 : 0), t_end = (int64_t)i_end * per + 1;
+    const int64_t p_beg = rowbase + t_beg, p_end = rowbase + t_end;
+    for (int64_t blk = (p_beg & ~(int64_t)15) + lane * 16; blk < p_end; blk += 512) {
+      const uint4 v = *reinterpret_cast<const uint4*>(row_state + blk);
+      const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int b = 0; b < 16; ++b) {
+        const int64_t p = blk + b;
+        if (p < p_beg || p >= p_end) continue;
+        const int a = (int)(int8_t)((wv[b >> 2] >> (8 * (b & 3))) & 0xffu);
+        if (!(mode == 1 ? a == side : (a == GC_CUT || a == side))) continue;
+        const uint32_t t = (uint32_t)(p - rowbase);
+        uint32_t i = 0u, sq = t;  // cell, index in the full sequence
+        if (t > (uint32_t)per) {
+          uint32_t loc;
+          switch (per) {
+            case 2: divmod_per<2>(t - 1u, i, loc); break;
+            case 3: divmod_per<3>(t - 1u, i, loc); break;
+            case 4: divmod_per<4>(t - 1u, i, loc); break;
+            default: divmod_per<5>(t - 1u, i, loc); break;
+          }
+          sq = loc < (uint32_t)per - 1u ? loc : (uint32_t)per;  // cells i > 0 have no x-low facet
+        }
+        const uint32_t c = (code >> (3u * sq)) & 7u;
+        const int d = (int)(c >> 1);
+        const bool isb = (c & 1u) == 0u || (d == 0 ? (int)i == nx - 1 : (d == 1 ? row_b1 : row_b2));
+        if (isb == (which == GECUT_FACETS_BOUNDARY)) cnt[d]++;
+      }
+    }
   }
 #pragma unroll
   for (int d = 0; d < D; ++d) {
-    const uint32_t m = __ballot_sync(0xffffffffu, ok && dir == d);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&dir_counts[d], (unsigned long long)__popc(m));
+    uint32_t v = cnt[d];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && v) atomicAdd(&s_cnt[d], v);
   }
+  __syncthreads();
+  if (threadIdx.x < D && s_cnt[threadIdx.x]) atomicAdd(&dir_counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+}
+
+// ids of the selected whole facets, materialised only when a caller asks for them
+template <int D>
+__global__ void k_facet_flag_bg(const GcGrid g, const int8_t* __restrict__ rows, int64_t pitch, int64_t nf,
+                                const GcProgram prog, int which, int mode, int side, uint32_t* __restrict__ flags) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nf) return;
+  const FacetIdx fi = facet_decode<D>(g, (uint32_t)f);
+  const bool in_trian = facet_is_boundary<D>(g, fi) == (which == GECUT_FACETS_BOUNDARY);
+  const int a = gc_eval_inoutcut(prog, rows, pitch, f);
+  flags[f] = (in_trian && (mode == 1 ? a == side : (a == GC_CUT || a == side))) ? 1u : 0u;
 }
 
 template <int D>
@@ -516,11 +741,9 @@ void free_facet_arrays(gecut_facet_result* r) {
   gc_free(ctx, l.R);
   gc_free(ctx, l.state);
   gc_free(ctx, l.meas);
-  gc_free(ctx, r->cutmask);
   for (int i = 0; i < GC_LMAX; ++i)
     if (r->owns_nodal[i]) gc_free(ctx, r->nodal_dev[i]);
   l = GcFacetLayout{};
-  r->cutmask = nullptr;
 }
 
 int read_u64(gecut_ctx* ctx, const uint64_t* dev, int n, uint64_t* out) {
@@ -534,28 +757,50 @@ int read_u64(gecut_ctx* ctx, const uint64_t* dev, int n, uint64_t* out) {
 template <int D>
 int classify_facets(gecut_ctx* ctx, gecut_facet_result* r) {
   const GcGrid& g = r->grid;
-  const int64_t nf = r->sizes.num_bgfacets;
-  const int64_t nblocks = gc_div_up(nf, FC_T);
-  uint32_t* block_counts = nullptr;
+  const int L = r->L;
+  const int wxt = (g.nn[0] + 31) / 32;
+  const int64_t node_rows = D == 3 ? (int64_t)g.nn[1] * g.nn[2] : (int64_t)g.nn[1];
+  const int64_t ls_stride = node_rows * wxt;
+  const int64_t nrows = D == 3 ? (int64_t)g.n[1] * g.n[2] : (int64_t)g.n[1];
+  const int nseg_per_row = (int)gc_div_up(g.n[0], FR_SEG);
+  const int64_t nsegs = nrows * nseg_per_row;
+  dim3 sgrid((unsigned)wxt, 1u, 1u), sblock(32, 8);
+  if (D == 3) {
+    sgrid.y = (unsigned)gc_div_up(g.nn[1], 8);
+    sgrid.z = (unsigned)gc_div_up(g.nn[2], NS_KCH);
+  } else {
+    sgrid.y = (unsigned)gc_div_up(gc_div_up(g.nn[1], NS_KCH), 8);
+  }
+  if (sgrid.y > 65535u || sgrid.z > 65535u) {
+    ctx->err = "cut_facets: model too large for the node-sign grid";
+    return GECUT_ERR_NOTIMPLEMENTED;
+  }
+  uint32_t* signs = nullptr;
+  uint32_t* seg_counts = nullptr;
   uint64_t* total_dev = nullptr;
-  GC_CHECK(gc_malloc(ctx, (void**)&block_counts, sizeof(uint32_t) * nblocks));
+  GC_CHECK(gc_malloc(ctx, (void**)&signs, sizeof(uint32_t) * ls_stride * L));
+  GC_CHECK(gc_malloc(ctx, (void**)&seg_counts, sizeof(uint32_t) * nsegs));
   GC_CHECK(gc_malloc(ctx, (void**)&total_dev, sizeof(uint64_t)));
-  GC_CHECK(gc_malloc(ctx, (void**)&r->cutmask, sizeof(uint32_t) * gc_div_up(nf, 32)));
-  GC_LAUNCH(ctx, "k_facet_classify",
-            k_facet_classify<D><<<(unsigned)nblocks, FC_T, 0, ctx->stream>>>(g, r->leaves, nf, r->lay.bg_state, r->lay.bg_pitch,
-                                                                            r->cutmask, block_counts));
-  GC_CHECK(gc_launch_check(ctx, "k_facet_classify"));
-  GC_CHECK(gc_exclusive_scan_u32(ctx, block_counts, block_counts, nblocks, total_dev));
+  GC_LAUNCH(ctx, "k_node_signs", k_node_signs<D><<<sgrid, sblock, 0, ctx->stream>>>(g, r->leaves, wxt, signs, ls_stride));
+  GC_CHECK(gc_launch_check(ctx, "k_node_signs"));
+  const unsigned nb = (unsigned)gc_div_up(nsegs, 8);
+  GC_LAUNCH(ctx, "k_facet_rows",
+            (k_facet_rows<D, false><<<nb, 256, 0, ctx->stream>>>(g, L, wxt, signs, ls_stride, r->lay.bg_state, r->lay.bg_pitch,
+                                                               seg_counts, nullptr, nseg_per_row, nsegs)));
+  GC_CHECK(gc_launch_check(ctx, "k_facet_rows"));
+  GC_CHECK(gc_exclusive_scan_u32(ctx, seg_counts, seg_counts, nsegs, total_dev));
   uint64_t total = 0;
   GC_CHECK(read_u64(ctx, total_dev, 1, &total));
   r->sizes.num_cutfacets = (int64_t)total;
   if (total > 0) {
     GC_CHECK(gc_malloc(ctx, (void**)&r->lay.cutfacets, sizeof(int32_t) * total));
-    GC_LAUNCH(ctx, "k_facet_emit",
-              k_facet_emit<<<(unsigned)nblocks, FC_T, 0, ctx->stream>>>(nf, r->cutmask, block_counts, r->lay.cutfacets));
-    GC_CHECK(gc_launch_check(ctx, "k_facet_emit"));
+    GC_LAUNCH(ctx, "k_facet_rows_emit",
+              (k_facet_rows<D, true><<<nb, 256, 0, ctx->stream>>>(g, L, wxt, signs, ls_stride, nullptr, 0, seg_counts,
+                                                                r->lay.cutfacets, nseg_per_row, nsegs)));
+    GC_CHECK(gc_launch_check(ctx, "k_facet_rows_emit"));
   }
-  gc_free(ctx, block_counts);
+  gc_free(ctx, signs);
+  gc_free(ctx, seg_counts);
   gc_free(ctx, total_dev);
   return GECUT_OK;
 }
@@ -841,6 +1086,7 @@ int gecut_select_facets(const gecut_facet_result* res, int which, int kind, cons
   sel->which = which;
   sel->kind = kind;
   sel->side = side;
+  sel->prog = p;
   auto fail = [&](int code) {
     gc_free(ctx, sel->sub_ids);
     gc_free(ctx, sel->bg_ids);
@@ -865,29 +1111,49 @@ int gecut_select_facets(const gecut_facet_result* res, int which, int kind, cons
     if (st != GECUT_OK) return fail(st);
   }
   if (kind != GECUT_SEL_CUTONLY && nf > 0) {
-    uint32_t* flags = nullptr;
     unsigned long long* dirc = nullptr;
-    st = gc_malloc(ctx, (void**)&flags, sizeof(uint32_t) * nf);
-    if (st != GECUT_OK) return fail(st);
     st = gc_malloc(ctx, (void**)&dirc, sizeof(unsigned long long) * 3);
-    if (st != GECUT_OK) {
-      gc_free(ctx, flags);
-      return fail(st);
-    }
+    if (st != GECUT_OK) return fail(st);
     cudaMemsetAsync(dirc, 0, sizeof(unsigned long long) * 3, ctx->stream);
     const int mode = kind == GECUT_SEL_ACTIVE ? 2 : 1;
+    const GcGrid& g = res->grid;
+    const int64_t nrows = D == 3 ? (int64_t)g.n[1] * g.n[2] : (int64_t)g.n[1];
+    const int nseg_per_row = (int)gc_div_up(g.n[0], FR_SEG);
+    const int64_t nsegs = nrows * nseg_per_row;
+    // one state row: the level set's own row (single leaf, complement = the other side), else the program's row
+    const int8_t* row = nullptr;
+    int8_t* tmp = nullptr;
+    int eff_side = side;
+    if (p.len == 1) {
+      row = res->lay.bg_state + (int64_t)p.tok[0] * res->lay.bg_pitch;
+    } else if (p.len == 2 && p.tok[1] == GECUT_OP_COMPLEMENT) {
+      row = res->lay.bg_state + (int64_t)p.tok[0] * res->lay.bg_pitch;
+      eff_side = -side;
+    } else {
+      st = gc_malloc(ctx, (void**)&tmp, (size_t)pad_pitch(nf));
+      if (st == GECUT_OK) st = gc_eval_rows(ctx, res->lay.bg_state, res->lay.bg_pitch, nf, p, tmp, true);
+      if (st != GECUT_OK) {
+        gc_free(ctx, tmp);
+        gc_free(ctx, dirc);
+        return fail(st);
+      }
+      row = tmp;
+    }
+    const unsigned nb = (unsigned)gc_div_up(nsegs, 8);
     if (D == 2)
-      GC_LAUNCH(ctx, "k_facet_flag_bg", k_facet_flag_bg<2><<<(unsigned)gc_div_up(nf, T), T, 0, ctx->stream>>>(res->grid, res->lay.bg_state, res->lay.bg_pitch, nf, p, which, mode, side, flags, dirc));
+      GC_LAUNCH(ctx, "k_facet_rows_count", k_facet_rows_count<2><<<nb, 256, 0, ctx->stream>>>(g, row, which, mode, eff_side, dirc, nseg_per_row, nsegs));
     else
-      GC_LAUNCH(ctx, "k_facet_flag_bg", k_facet_flag_bg<3><<<(unsigned)gc_div_up(nf, T), T, 0, ctx->stream>>>(res->grid, res->lay.bg_state, res->lay.bg_pitch, nf, p, which, mode, side, flags, dirc));
-    st = gc_launch_check(ctx, "k_facet_flag_bg");
-    if (st == GECUT_OK) st = gc_compact_flags(ctx, flags, nf, &sel->bg_ids, &sel->n_bg, nullptr, nullptr);
+      GC_LAUNCH(ctx, "k_facet_rows_count", k_facet_rows_count<3><<<nb, 256, 0, ctx->stream>>>(g, row, which, mode, eff_side, dirc, nseg_per_row, nsegs));
+    gc_free(ctx, tmp);
+    st = gc_launch_check(ctx, "k_facet_rows_count");
     if (st == GECUT_OK) {
       uint64_t h[3];
       st = read_u64(ctx, (const uint64_t*)dirc, 3, h);
-      for (int d = 0; d < 3; ++d) sel->bg_dir_count[d] = (int64_t)h[d];
+      for (int d = 0; d < 3; ++d) {
+        sel->bg_dir_count[d] = (int64_t)h[d];
+        sel->n_bg += (int64_t)h[d];
+      }
     }
-    gc_free(ctx, flags);
     gc_free(ctx, dirc);
     if (st != GECUT_OK) return fail(st);
   }
@@ -916,10 +1182,33 @@ int gecut_facet_selection_sizes(const gecut_facet_selection* sel, int64_t* n_sub
   return GECUT_OK;
 }
 
-int gecut_facet_selection_copy(const gecut_facet_selection* sel, int32_t* sub_ids, int32_t* bg_ids) {
-  if (!sel) return GECUT_ERR_INVALID;
-  gecut_ctx* ctx = sel->res->ctx;
+int gecut_facet_selection_copy(const gecut_facet_selection* sel_c, int32_t* sub_ids, int32_t* bg_ids) {
+  if (!sel_c) return GECUT_ERR_INVALID;
+  gecut_facet_selection* sel = const_cast<gecut_facet_selection*>(sel_c);
+  const gecut_facet_result* res = sel->res;
+  gecut_ctx* ctx = res->ctx;
   DeviceGuard guard(ctx->device);
+  if (bg_ids && sel->n_bg > 0 && !sel->bg_ids) {
+    // ids of the whole facets: flags over all facets -> scan -> scatter (only when somebody wants the list)
+    const int64_t nf = res->sizes.num_bgfacets;
+    const int mode = sel->kind == GECUT_SEL_ACTIVE ? 2 : 1;
+    const int T = 256;
+    uint32_t* flags = nullptr;
+    GC_CHECK(gc_malloc(ctx, (void**)&flags, sizeof(uint32_t) * nf));
+    if (res->sizes.D == 2)
+      GC_LAUNCH(ctx, "k_facet_flag_bg", k_facet_flag_bg<2><<<(unsigned)gc_div_up(nf, T), T, 0, ctx->stream>>>(res->grid, res->lay.bg_state, res->lay.bg_pitch, nf, sel->prog, sel->which, mode, sel->side, flags));
+    else
+      GC_LAUNCH(ctx, "k_facet_flag_bg", k_facet_flag_bg<3><<<(unsigned)gc_div_up(nf, T), T, 0, ctx->stream>>>(res->grid, res->lay.bg_state, res->lay.bg_pitch, nf, sel->prog, sel->which, mode, sel->side, flags));
+    int st = gc_launch_check(ctx, "k_facet_flag_bg");
+    int64_t n = 0;
+    if (st == GECUT_OK) st = gc_compact_flags(ctx, flags, nf, &sel->bg_ids, &n, nullptr, nullptr);
+    gc_free(ctx, flags);
+    GC_CHECK(st);
+    if (n != sel->n_bg) {
+      ctx->err = "facet selection: id list and count disagree";
+      return GECUT_ERR_CUDA;
+    }
+  }
   GC_CHECK(to_host(ctx, sub_ids, sel->sub_ids, sel->n_sub));
   GC_CHECK(to_host(ctx, bg_ids, sel->bg_ids, sel->n_bg));
   GC_CUDA(cudaStreamSynchronize(ctx->stream));
