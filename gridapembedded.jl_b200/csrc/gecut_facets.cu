@@ -47,6 +47,7 @@ struct gecut_facet_result {
   GcLeaves leaves{};
   gecut_facet_sizes sizes{};
   GcFacetLayout lay{};
+  int64_t tallies[GC_LMAX * 12] = {0};  // whole facets per level set: ((s*3 + d)*2 + isb), s = 0 IN / 1 OUT (k_facet_rows)
   bool owns_nodal[GC_LMAX] = {false};
   double* nodal_dev[GC_LMAX] = {nullptr};
 };
@@ -274,118 +275,247 @@ constexpr int FR_SEG = 1024;  // cells per warp segment
 constexpr int FR_WCH = 128;   // cells per warp iteration
 constexpr int FR_STAGE = FR_WCH * 5 + 1 + 16 + 15;
 
+// tallies of the whole facets per level set, fused into K2: index ((s*3 + d)*2 + isb), s = 0 IN / 1 OUT, d = normal
+// direction, isb = facet on the boundary of the model.  A selection over a single-leaf geometry reads its whole-facet
+// counts from here (no pass over the facets at all).
+constexpr int FT_N = 12;
+
+// 12 tallies packed in 16-bit fields of three 64-bit words (a warp segment has at most 2 * FR_SEG facets per field)
+struct Tally3 {
+  unsigned long long w0, w1, w2;
+  __device__ __forceinline__ void add(int c, uint32_t n) {
+    const unsigned long long inc = (unsigned long long)n << (16 * (c & 3));
+    const int wi = c >> 2;
+    w0 += wi == 0 ? inc : 0ull;
+    w1 += wi == 1 ? inc : 0ull;
+    w2 += wi == 2 ? inc : 0ull;
+  }
+  __device__ __forceinline__ uint32_t get(int c) const {
+    const unsigned long long w = (c >> 2) == 0 ? w0 : ((c >> 2) == 1 ? w1 : w2);
+    return (uint32_t)((w >> (16 * (c & 3))) & 0xffffull);
+  }
+};
+
 template <int D, bool EMIT>
 __global__ void __launch_bounds__(256)
 k_facet_rows(const GcGrid g, int L, int wxt, const uint32_t* __restrict__ signs, int64_t ls_stride,
              int8_t* __restrict__ state, int64_t pitch, uint32_t* __restrict__ seg_counts,
-             int32_t* __restrict__ cutfacets, int nseg_per_row, int64_t nsegs) {
+             int32_t* __restrict__ cutfacets, int nseg_per_row, int64_t nsegs,
+             unsigned long long* __restrict__ tallies) {
   constexpr int NR = 1 << (D - 1);
   __shared__ __align__(16) uint8_t s_stage[EMIT ? 1 : 8][EMIT ? 16 : ((FR_STAGE + 15) & ~15)];
+  __shared__ uint32_t s_tally[EMIT ? 1 : GC_LMAX * FT_N];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (!EMIT) {
+    for (int c = threadIdx.x; c < GC_LMAX * FT_N; c += blockDim.x) s_tally[c] = 0u;
+    __syncthreads();
+  }
   const int64_t gw = (int64_t)blockIdx.x * 8 + warp;
-  if (gw >= nsegs) return;
-  const int row = (int)(gw / nseg_per_row), seg = (int)(gw % nseg_per_row);
-  const int j = D == 3 ? row % g.n[1] : row;
-  const int k = D == 3 ? row / g.n[1] : 0;
-  const int per = D + (j == 0 ? 1 : 0) + ((D == 3 && k == 0) ? 1 : 0);
-  const int64_t rowbase = facet_row_base<D>(g, j, k);
-  const int nx = g.n[0];
-  const int i_beg = seg * FR_SEG, i_end = min(nx, i_beg + FR_SEG);
-  uint8_t* stage = s_stage[EMIT ? 0 : warp];
-  int64_t nrow[NR];
+  if (gw < nsegs) {
+    const int row = (int)(gw / nseg_per_row), seg = (int)(gw % nseg_per_row);
+    const int j = D == 3 ? row % g.n[1] : row;
+    const int k = D == 3 ? row / g.n[1] : 0;
+    const int per = D + (j == 0 ? 1 : 0) + ((D == 3 && k == 0) ? 1 : 0);
+    const int64_t rowbase = facet_row_base<D>(g, j, k);
+    const int nx = g.n[0];
+    const int i_beg = seg * FR_SEG, i_end = min(nx, i_beg + FR_SEG);
+    uint8_t* stage = s_stage[EMIT ? 0 : warp];
+    int64_t nrow[NR];
 #pragma unroll
-  for (int r = 0; r < NR; ++r) nrow[r] = ((int64_t)(k + (r >> 1)) * g.nn[1] + (j + (r & 1))) * wxt;
-  uint32_t running = EMIT ? seg_counts[gw] : 0u, total = 0u;
-  for (int i0 = i_beg; i0 < i_end; i0 += FR_WCH) {
-    const int chunk_off = i0 * per + (i0 > 0 ? 1 : 0);
-    const int chunk_len = min(FR_WCH, i_end - i0) * per + (i0 == 0 ? 1 : 0);
-    const int align = (int)((rowbase + chunk_off) & 15);
-    uint32_t anybits[4] = {0u, 0u, 0u, 0u};
-    const int w0 = i0 >> 5;
-    for (int ls = 0; ls < L; ++ls) {
-      const uint32_t* sg = signs + (int64_t)ls * ls_stride;
-      uint32_t lo[NR];
-#pragma unroll
-      for (int r = 0; r < NR; ++r) lo[r] = __ldg(sg + nrow[r] + w0);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int i = i0 + q * 32 + lane;
-        uint32_t sm = 0u;
+    for (int r = 0; r < NR; ++r) nrow[r] = ((int64_t)(k + (r >> 1)) * g.nn[1] + (j + (r & 1))) * wxt;
+    const bool hi1 = j == g.n[1] - 1, hi2 = D == 3 && k == g.n[2] - 1;  // the row's y-high / z-high facets are boundary
+    uint32_t running = EMIT ? seg_counts[gw] : 0u, total = 0u;
+    Tally3 acc = {0ull, 0ull, 0ull};  // lane ls holds the tallies of level set ls
+    // tallies of `nc` consecutive cells from `first`, all of whose facets have state index sidx (warp-uniform)
+    auto tally_uniform = [&](Tally3& t, int sidx, int first, int nc) {
+      if (D == 3) {
+        if (k == 0) t.add((sidx * 3 + 2) * 2 + 1, nc);
+        t.add((sidx * 3 + 2) * 2 + (hi2 ? 1 : 0), nc);
+      }
+      if (j == 0) t.add((sidx * 3 + 1) * 2 + 1, nc);
+      t.add((sidx * 3 + 1) * 2 + (hi1 ? 1 : 0), nc);
+      const uint32_t last = first + nc == nx ? 1u : 0u;  // x-high of the last cell of the row is a boundary facet
+      t.add((sidx * 3 + 0) * 2 + 1, (first == 0 ? 1u : 0u) + last);
+      t.add((sidx * 3 + 0) * 2 + 0, (uint32_t)nc - last);
+    };
+    for (int i0 = i_beg; i0 < i_end; i0 += FR_WCH) {
+      const int chunk_cells = min(FR_WCH, i_end - i0);
+      const int chunk_off = i0 * per + (i0 > 0 ? 1 : 0);
+      const int chunk_len = chunk_cells * per + (i0 == 0 ? 1 : 0);
+      const int align = (int)((rowbase + chunk_off) & 15);
+      uint32_t anybits[4] = {0u, 0u, 0u, 0u};
+      const int w0 = i0 >> 5;
+      for (int ls = 0; ls < L; ++ls) {
+        const uint32_t* sg = signs + (int64_t)ls * ls_stride;
+        uint32_t W[NR][5];
+        // sign of the 33 nodes of every 32-cell group: 0 mixed, 1 all IN, 2 all OUT (warp-uniform)
+        uint32_t g_or[4] = {0u, 0u, 0u, 0u}, g_and[4] = {~0u, ~0u, ~0u, ~0u};
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-          const uint32_t hi = (w0 + q + 1 < wxt) ? __ldg(sg + nrow[r] + w0 + q + 1) : 0u;
-          sm |= (__funnelshift_r(lo[r], hi, lane) & 3u) << (2 * r);
-          lo[r] = hi;
+#pragma unroll
+          for (int q = 0; q < 5; ++q) W[r][q] = (w0 + q < wxt) ? __ldg(sg + nrow[r] + w0 + q) : 0u;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            g_or[q] |= W[r][q] | (W[r][q + 1] & 1u);
+            g_and[q] &= W[r][q] & (W[r][q + 1] | ~1u);
+          }
         }
-        if (i < i_end) {
+        int gu[4];
+        bool all_in = chunk_cells == FR_WCH, all_out = chunk_cells == FR_WCH;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bool full = i0 + q * 32 + 32 <= i_end;
+          gu[q] = !full ? 0 : (g_or[q] == 0u ? 1 : (g_and[q] == 0xffffffffu ? 2 : 0));
+          all_in &= gu[q] == 1;
+          all_out &= gu[q] == 2;
+        }
+        // ---- whole chunk on one side (the bulk of the model): constant 16-byte stores, closed-form tallies
+        if (all_in || all_out) {
+          if (!EMIT) {
+            const uint32_t b4 = all_in ? 0xffffffffu : 0x01010101u;
+            const uint4 cv = make_uint4(b4, b4, b4, b4);
+            int8_t* g0 = state + (int64_t)ls * pitch + rowbase + chunk_off - align;
+            const int end = align + chunk_len;
+            for (int p0 = lane * 16; p0 + 16 <= end; p0 += 512)
+              if (p0 >= align) *reinterpret_cast<uint4*>(g0 + p0) = cv;
+            if (align != 0 && lane >= align && lane < 16 && lane < end) g0[lane] = (int8_t)(b4 & 0xffu);
+            {
+              const int tail0 = end & ~15;
+              const int p = tail0 + (lane & 15);
+              if (lane >= 16 && p < end && p >= align && (tail0 > 0 || align == 0)) g0[p] = (int8_t)(b4 & 0xffu);
+            }
+            if (lane == ls) tally_uniform(acc, all_in ? 0 : 1, i0, FR_WCH);
+          }
+          continue;
+        }
+        // ---- general path: a lane per cell, 4 cells per lane; 32-cell groups on one side skip the corner logic.
+        //      Tallies come from warp ballots (warp-uniform adds, no reduction)
+        Tally3 tu = {0ull, 0ull, 0ull};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = i0 + q * 32 + lane;
           const int loc = i * per + (i > 0 ? 1 : 0) - chunk_off + align;
+          if (gu[q] != 0) {
+            if (!EMIT) {
+              const uint8_t b = gu[q] == 1 ? (uint8_t)0xff : (uint8_t)0x01;
+              const int nfac = per + (i == 0 ? 1 : 0);
+#pragma unroll
+              for (int t = 0; t < D + 3; ++t)
+                if (t < nfac) stage[loc + t] = b;
+              tally_uniform(tu, gu[q] - 1, i0 + q * 32, 32);
+            }
+            continue;
+          }
+          uint32_t sm = 0u;
+#pragma unroll
+          for (int r = 0; r < NR; ++r) sm |= (__funnelshift_r(W[r][q], W[r][q + 1], lane) & 3u) << (2 * r);
+          const bool valid = i < i_end;
+          const uint32_t lastm = __ballot_sync(0xffffffffu, valid && i == nx - 1);
           int t = 0;
 #pragma unroll
           for (int d = D - 1; d >= 0; --d) {
-            const int idx = d == 0 ? i : (d == 1 ? j : k);
+            const bool hib = d == 1 ? hi1 : hi2;  // d >= 1 only
             const uint32_t mlow = D == 3 ? (d == 0 ? 0x55u : (d == 1 ? 0x33u : 0x0Fu)) : (d == 0 ? 0x5u : 0x3u);
             const uint32_t mhigh = D == 3 ? (d == 0 ? 0xAAu : (d == 1 ? 0xCCu : 0xF0u)) : (d == 0 ? 0xAu : 0xCu);
-            if (idx == 0) {
-              const uint32_t v = sm & mlow;
-              const int8_t st = v == 0u ? (int8_t)GC_IN : (v == mlow ? (int8_t)GC_OUT : (int8_t)GC_CUT);
-              if (st == GC_CUT) anybits[q] |= 1u << t;
-              if (!EMIT) stage[loc + t] = (uint8_t)st;
-              t++;
+#pragma unroll
+            for (int sd = 0; sd < 2; ++sd) {
+              // low facets: rows with index 0 along d (warp-uniform for d >= 1; the cell i == 0 alone for d == 0)
+              if (sd == 0 && d >= 1 && (d == 1 ? j : k) != 0) continue;
+              const uint32_t m = sd == 0 ? mlow : mhigh;
+              const uint32_t v = sm & m;
+              const int8_t st = v == 0u ? (int8_t)GC_IN : (v == m ? (int8_t)GC_OUT : (int8_t)GC_CUT);
+              const bool mine = valid && !(sd == 0 && d == 0 && i != 0);
+              if (mine) {
+                if (st == GC_CUT) anybits[q] |= 1u << t;
+                if (!EMIT) stage[loc + t] = (uint8_t)st;
+                t++;
+              }
+              if (!EMIT) {
+                const uint32_t m_in = __ballot_sync(0xffffffffu, mine && st == GC_IN);
+                const uint32_t m_out = __ballot_sync(0xffffffffu, mine && st == GC_OUT);
+                if (d >= 1) {
+                  const int isb = (sd == 0 || hib) ? 1 : 0;
+                  tu.add((0 * 3 + d) * 2 + isb, (uint32_t)__popc(m_in));
+                  tu.add((1 * 3 + d) * 2 + isb, (uint32_t)__popc(m_out));
+                } else if (sd == 0) {
+                  tu.add((0 * 3 + 0) * 2 + 1, (uint32_t)__popc(m_in));
+                  tu.add((1 * 3 + 0) * 2 + 1, (uint32_t)__popc(m_out));
+                } else {
+                  tu.add((0 * 3 + 0) * 2 + 1, (uint32_t)__popc(m_in & lastm));
+                  tu.add((0 * 3 + 0) * 2 + 0, (uint32_t)__popc(m_in & ~lastm));
+                  tu.add((1 * 3 + 0) * 2 + 1, (uint32_t)__popc(m_out & lastm));
+                  tu.add((1 * 3 + 0) * 2 + 0, (uint32_t)__popc(m_out & ~lastm));
+                }
+              }
             }
-            const uint32_t v = sm & mhigh;
-            const int8_t st = v == 0u ? (int8_t)GC_IN : (v == mhigh ? (int8_t)GC_OUT : (int8_t)GC_CUT);
-            if (st == GC_CUT) anybits[q] |= 1u << t;
-            if (!EMIT) stage[loc + t] = (uint8_t)st;
-            t++;
           }
+        }
+        if (!EMIT) {
+          __syncwarp();
+          // stage[align + q] <-> global g0 + q: aligned 16-byte blocks inside the chunk leave as one store, the bytes
+          // of the head and tail blocks one per lane
+          int8_t* g0 = state + (int64_t)ls * pitch + rowbase + chunk_off - align;
+          const int end = align + chunk_len;
+          for (int p0 = lane * 16; p0 + 16 <= end; p0 += 512)
+            if (p0 >= align) *reinterpret_cast<uint4*>(g0 + p0) = *reinterpret_cast<const uint4*>(stage + p0);
+          if (align != 0 && lane >= align && lane < 16 && lane < end) g0[lane] = (int8_t)stage[lane];
+          {
+            const int tail0 = end & ~15;
+            const int p = tail0 + (lane & 15);
+            if (lane >= 16 && p < end && p >= align && (tail0 > 0 || align == 0)) g0[p] = (int8_t)stage[p];
+          }
+          if (lane == ls) {
+            acc.w0 += tu.w0;
+            acc.w1 += tu.w1;
+            acc.w2 += tu.w2;
+          }
+          __syncwarp();
         }
       }
       if (!EMIT) {
-        __syncwarp();
-        // stage[align + q] <-> global g0 + q; 16-byte blocks that lie inside the chunk leave as one store
-        int8_t* g0 = state + (int64_t)ls * pitch + rowbase + chunk_off - align;
-        const int end = align + chunk_len;
-        for (int p0 = lane * 16; p0 < end; p0 += 512) {
-          if (p0 >= align && p0 + 16 <= end) {
-            *reinterpret_cast<uint4*>(g0 + p0) = *reinterpret_cast<const uint4*>(stage + p0);
-          } else {
-            for (int p = max(p0, align); p < min(p0 + 16, end); ++p) g0[p] = (int8_t)stage[p];
+        total += (uint32_t)(__popc(anybits[0]) + __popc(anybits[1]) + __popc(anybits[2]) + __popc(anybits[3]));
+      } else if (__any_sync(0xffffffffu, (anybits[0] | anybits[1] | anybits[2] | anybits[3]) != 0u)) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t cnt = (uint32_t)__popc(anybits[q]);
+          uint32_t inc = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += up;
+          }
+          const uint32_t qtot = __shfl_sync(0xffffffffu, inc, 31);
+          if (qtot) {
+            const int i = i0 + q * 32 + lane;
+            uint32_t pos = running + inc - cnt;
+            uint32_t bits = anybits[q];
+            while (bits) {
+              const int t = __ffs(bits) - 1;
+              bits &= bits - 1u;
+              cutfacets[pos++] = (int32_t)(rowbase + (int64_t)i * per + (i > 0 ? 1 : 0) + t + 1);
+            }
+            running += qtot;
           }
         }
-        __syncwarp();
       }
     }
     if (!EMIT) {
-      total += (uint32_t)(__popc(anybits[0]) + __popc(anybits[1]) + __popc(anybits[2]) + __popc(anybits[3]));
-    } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t cnt = (uint32_t)__popc(anybits[q]);
-        uint32_t inc = cnt;
+      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+      if (lane == 0) seg_counts[gw] = total;
+      if (lane < L) {
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
-          if (lane >= o) inc += up;
-        }
-        const uint32_t qtot = __shfl_sync(0xffffffffu, inc, 31);
-        if (qtot) {
-          const int i = i0 + q * 32 + lane;
-          uint32_t pos = running + inc - cnt;
-          uint32_t bits = anybits[q];
-          while (bits) {
-            const int t = __ffs(bits) - 1;
-            bits &= bits - 1u;
-            cutfacets[pos++] = (int32_t)(rowbase + (int64_t)i * per + (i > 0 ? 1 : 0) + t + 1);
-          }
-          running += qtot;
+        for (int c = 0; c < FT_N; ++c) {
+          const uint32_t v = acc.get(c);
+          if (v) atomicAdd(&s_tally[lane * FT_N + c], v);
         }
       }
     }
   }
   if (!EMIT) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-    if (lane == 0) seg_counts[gw] = total;
+    __syncthreads();
+    for (int c = threadIdx.x; c < L * FT_N; c += blockDim.x)
+      if (s_tally[c]) atomicAdd(&tallies[c], (unsigned long long)s_tally[c]);
   }
 }
 
@@ -780,23 +910,27 @@ int classify_facets(gecut_ctx* ctx, gecut_facet_result* r) {
   uint64_t* total_dev = nullptr;
   GC_CHECK(gc_malloc(ctx, (void**)&signs, sizeof(uint32_t) * ls_stride * L));
   GC_CHECK(gc_malloc(ctx, (void**)&seg_counts, sizeof(uint32_t) * nsegs));
-  GC_CHECK(gc_malloc(ctx, (void**)&total_dev, sizeof(uint64_t)));
+  GC_CHECK(gc_malloc(ctx, (void**)&total_dev, sizeof(uint64_t) * (1 + GC_LMAX * FT_N)));
+  GC_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(uint64_t) * (1 + GC_LMAX * FT_N), ctx->stream));
   GC_LAUNCH(ctx, "k_node_signs", k_node_signs<D><<<sgrid, sblock, 0, ctx->stream>>>(g, r->leaves, wxt, signs, ls_stride));
   GC_CHECK(gc_launch_check(ctx, "k_node_signs"));
   const unsigned nb = (unsigned)gc_div_up(nsegs, 8);
   GC_LAUNCH(ctx, "k_facet_rows",
             (k_facet_rows<D, false><<<nb, 256, 0, ctx->stream>>>(g, L, wxt, signs, ls_stride, r->lay.bg_state, r->lay.bg_pitch,
-                                                               seg_counts, nullptr, nseg_per_row, nsegs)));
+                                                               seg_counts, nullptr, nseg_per_row, nsegs,
+                                                               (unsigned long long*)(total_dev + 1))));
   GC_CHECK(gc_launch_check(ctx, "k_facet_rows"));
   GC_CHECK(gc_exclusive_scan_u32(ctx, seg_counts, seg_counts, nsegs, total_dev));
-  uint64_t total = 0;
-  GC_CHECK(read_u64(ctx, total_dev, 1, &total));
+  uint64_t hbuf[1 + GC_LMAX * FT_N];
+  GC_CHECK(read_u64(ctx, total_dev, 1 + L * FT_N, hbuf));
+  const uint64_t total = hbuf[0];
+  for (int c = 0; c < L * FT_N; ++c) r->tallies[c] = (int64_t)hbuf[1 + c];
   r->sizes.num_cutfacets = (int64_t)total;
   if (total > 0) {
     GC_CHECK(gc_malloc(ctx, (void**)&r->lay.cutfacets, sizeof(int32_t) * total));
     GC_LAUNCH(ctx, "k_facet_rows_emit",
               (k_facet_rows<D, true><<<nb, 256, 0, ctx->stream>>>(g, L, wxt, signs, ls_stride, nullptr, 0, seg_counts,
-                                                                r->lay.cutfacets, nseg_per_row, nsegs)));
+                                                                r->lay.cutfacets, nseg_per_row, nsegs, nullptr)));
     GC_CHECK(gc_launch_check(ctx, "k_facet_rows_emit"));
   }
   gc_free(ctx, signs);
@@ -1111,25 +1245,35 @@ int gecut_select_facets(const gecut_facet_result* res, int which, int kind, cons
     if (st != GECUT_OK) return fail(st);
   }
   if (kind != GECUT_SEL_CUTONLY && nf > 0) {
-    unsigned long long* dirc = nullptr;
-    st = gc_malloc(ctx, (void**)&dirc, sizeof(unsigned long long) * 3);
-    if (st != GECUT_OK) return fail(st);
-    cudaMemsetAsync(dirc, 0, sizeof(unsigned long long) * 3, ctx->stream);
     const int mode = kind == GECUT_SEL_ACTIVE ? 2 : 1;
     const GcGrid& g = res->grid;
-    const int64_t nrows = D == 3 ? (int64_t)g.n[1] * g.n[2] : (int64_t)g.n[1];
-    const int nseg_per_row = (int)gc_div_up(g.n[0], FR_SEG);
-    const int64_t nsegs = nrows * nseg_per_row;
-    // one state row: the level set's own row (single leaf, complement = the other side), else the program's row
-    const int8_t* row = nullptr;
-    int8_t* tmp = nullptr;
-    int eff_side = side;
-    if (p.len == 1) {
-      row = res->lay.bg_state + (int64_t)p.tok[0] * res->lay.bg_pitch;
-    } else if (p.len == 2 && p.tok[1] == GECUT_OP_COMPLEMENT) {
-      row = res->lay.bg_state + (int64_t)p.tok[0] * res->lay.bg_pitch;
-      eff_side = -side;
+    const bool single = p.len == 1 || (p.len == 2 && p.tok[1] == GECUT_OP_COMPLEMENT);
+    if (single) {
+      // single leaf (or its complement = the other side): the tallies of the classification pass answer directly
+      const int ls = p.tok[0];
+      const int eff_side = p.len == 1 ? side : -side;
+      const int isb = which == GECUT_FACETS_BOUNDARY ? 1 : 0;
+      const int64_t* tl = res->tallies + (size_t)ls * 12;
+      for (int d = 0; d < D; ++d) {
+        int64_t others = 1;
+        for (int e = 0; e < D; ++e)
+          if (e != d) others *= g.n[e];
+        const int64_t all = isb ? 2 * others : (int64_t)(g.n[d] - 1) * others;
+        const int s_same = eff_side == GECUT_IN ? 0 : 1;
+        const int64_t c = mode == 1 ? tl[(s_same * 3 + d) * 2 + isb] : all - tl[((1 - s_same) * 3 + d) * 2 + isb];
+        sel->bg_dir_count[d] = c;
+        sel->n_bg += c;
+      }
     } else {
+      unsigned long long* dirc = nullptr;
+      st = gc_malloc(ctx, (void**)&dirc, sizeof(unsigned long long) * 3);
+      if (st != GECUT_OK) return fail(st);
+      cudaMemsetAsync(dirc, 0, sizeof(unsigned long long) * 3, ctx->stream);
+      const int64_t nrows = D == 3 ? (int64_t)g.n[1] * g.n[2] : (int64_t)g.n[1];
+      const int nseg_per_row = (int)gc_div_up(g.n[0], FR_SEG);
+      const int64_t nsegs = nrows * nseg_per_row;
+      // the program's own Int8 row first (truth-table gather over the level-set rows), then one pass over that row
+      int8_t* tmp = nullptr;
       st = gc_malloc(ctx, (void**)&tmp, (size_t)pad_pitch(nf));
       if (st == GECUT_OK) st = gc_eval_rows(ctx, res->lay.bg_state, res->lay.bg_pitch, nf, p, tmp, true);
       if (st != GECUT_OK) {
@@ -1137,25 +1281,24 @@ int gecut_select_facets(const gecut_facet_result* res, int which, int kind, cons
         gc_free(ctx, dirc);
         return fail(st);
       }
-      row = tmp;
-    }
-    const unsigned nb = (unsigned)gc_div_up(nsegs, 8);
-    if (D == 2)
-      GC_LAUNCH(ctx, "k_facet_rows_count", k_facet_rows_count<2><<<nb, 256, 0, ctx->stream>>>(g, row, which, mode, eff_side, dirc, nseg_per_row, nsegs));
-    else
-      GC_LAUNCH(ctx, "k_facet_rows_count", k_facet_rows_count<3><<<nb, 256, 0, ctx->stream>>>(g, row, which, mode, eff_side, dirc, nseg_per_row, nsegs));
-    gc_free(ctx, tmp);
-    st = gc_launch_check(ctx, "k_facet_rows_count");
-    if (st == GECUT_OK) {
-      uint64_t h[3];
-      st = read_u64(ctx, (const uint64_t*)dirc, 3, h);
-      for (int d = 0; d < 3; ++d) {
-        sel->bg_dir_count[d] = (int64_t)h[d];
-        sel->n_bg += (int64_t)h[d];
+      const unsigned nb = (unsigned)gc_div_up(nsegs, 8);
+      if (D == 2)
+        GC_LAUNCH(ctx, "k_facet_rows_count", k_facet_rows_count<2><<<nb, 256, 0, ctx->stream>>>(g, tmp, which, mode, side, dirc, nseg_per_row, nsegs));
+      else
+        GC_LAUNCH(ctx, "k_facet_rows_count", k_facet_rows_count<3><<<nb, 256, 0, ctx->stream>>>(g, tmp, which, mode, side, dirc, nseg_per_row, nsegs));
+      gc_free(ctx, tmp);
+      st = gc_launch_check(ctx, "k_facet_rows_count");
+      if (st == GECUT_OK) {
+        uint64_t h[3];
+        st = read_u64(ctx, (const uint64_t*)dirc, 3, h);
+        for (int d = 0; d < 3; ++d) {
+          sel->bg_dir_count[d] = (int64_t)h[d];
+          sel->n_bg += (int64_t)h[d];
+        }
       }
+      gc_free(ctx, dirc);
+      if (st != GECUT_OK) return fail(st);
     }
-    gc_free(ctx, dirc);
-    if (st != GECUT_OK) return fail(st);
   }
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
     ctx->err = "facet selection failed";
