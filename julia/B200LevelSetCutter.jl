@@ -2,16 +2,17 @@
 # image, so this file has never been executed; it documents the drop-in a GridapEmbedded maintainer would add).
 #
 # It implements the `Cutter` plugin API of the reference (src/Interfaces/Cutters.jl:22-60) for Cartesian background
-# models: `cut(cutter, bgmodel, geo)` and `compute_bgcell_to_inoutcut(cutter, bgmodel, geo)`, returning the unchanged
+# models: `cut(cutter, bgmodel, geo)`, `compute_bgcell_to_inoutcut(cutter, bgmodel, geo)`, `cut_facets(cutter, bgmodel, geo)`
+# and `compute_bgfacet_to_inoutcut(cutter, bgmodel, geo)`, returning the unchanged
 # `EmbeddedDiscretization` layout (src/Interfaces/EmbeddedDiscretizations.jl:36-45) so that Triangulation(cutgeo,...),
 # EmbeddedBoundary, AgFEM etc. run on it as they do on the result of the in-tree LevelSetCutter.
 module B200LevelSetCutters
 
 using Gridap, Gridap.Geometry, Gridap.Arrays, Gridap.ReferenceFEs
 using GridapEmbedded.Interfaces, GridapEmbedded.CSG, GridapEmbedded.LevelSetCutters
-using GridapEmbedded.Interfaces: SubCellData, SubFacetData, EmbeddedDiscretization
+using GridapEmbedded.Interfaces: SubCellData, SubFacetData, EmbeddedDiscretization, EmbeddedFacetDiscretization
 using GridapEmbedded.LevelSetCutters: _find_unique_leaves, discretize
-import GridapEmbedded.Interfaces: cut, compute_bgcell_to_inoutcut
+import GridapEmbedded.Interfaces: cut, compute_bgcell_to_inoutcut, cut_facets, compute_bgfacet_to_inoutcut
 
 const libgecut = get(ENV, "GECUT_LIB", "libgecut.so")
 
@@ -184,6 +185,85 @@ function compute_bgcell_to_inoutcut(cutter::B200LevelSetCutter, bgmodel::Cartesi
                        res, prog, length(prog), out), "gecut_bgcell_to_inoutcut")
   ccall((:gecut_result_free, libgecut), Cint, (Ptr{Cvoid},), res)
   out
+end
+
+# ---- cut_facets (LevelSetCutters.jl:107-110 -> EmbeddedFacetDiscretization, EmbeddedFacetDiscretizations.jl:28-35) -------
+struct GecutFacetSizes
+  num_bgfacets::Int64; num_boundary_facets::Int64; num_cutfacets::Int64; num_subfacets::Int64
+  num_subfacet_points::Int64; num_levelsets::Int32; D::Int32; num_vertices_per_bgfacet::Int32; pad::Int32
+end
+struct GecutFacetBuffers
+  ls_to_facet_to_inoutcut::Ptr{Int8}; cutfacet_to_facet::Ptr{Int32}; facet_to_nodes::Ptr{Int32}
+  facet_is_boundary::Ptr{Int8}; sf_cell_to_points::Ptr{Int32}; sf_cell_to_bgcell::Ptr{Int32}
+  sf_point_to_coords::Ptr{Float64}; sf_point_to_rcoords::Ptr{Float64}; ls_to_subfacet_to_inout::Ptr{Int8}
+end
+
+function _run_facets(cutter::B200LevelSetCutter, bgmodel::CartesianDiscreteModel, geom, classify_only::Bool)
+  ctx = _ctx(cutter)
+  j_to_fun, oid_to_ls = _find_unique_leaves(get_tree(geom))
+  coords = collect1d(get_node_coordinates(get_grid(bgmodel)))
+  recs = GecutLeaf[]; nodal = Vector{Union{Nothing,Vector{Float64}}}()
+  for f in j_to_fun
+    r, v = _leaf_record(f, coords); push!(recs, r); push!(nodal, v)
+  end
+  g = _grid(bgmodel)
+  ptrs = Ptr{Float64}[v === nothing ? C_NULL : pointer(v) for v in nodal]
+  res = Ref{Ptr{Cvoid}}(C_NULL)
+  GC.@preserve nodal begin
+    st = ccall((:gecut_cut_facets, libgecut), Cint,
+               (Ptr{Cvoid}, Ref{GecutGrid}, Ptr{GecutLeaf}, Cint, Ptr{Ptr{Float64}}, Cint, Cint, Ptr{Ptr{Cvoid}}),
+               ctx, g, recs, length(recs), ptrs, 0, classify_only ? 1 : 0, res)
+  end
+  _check(cutter, st, "gecut_cut_facets")
+  res[], oid_to_ls
+end
+
+# The facet ids of the library follow Gridap's own numbering of Grid(ReferenceFE{D-1}, model) (first encounter over
+# (cell, local facet), DESIGN.md assumption A8), so `cell_to_bgcell` indexes get_face_nodes(model, D-1) directly.
+function cut_facets(cutter::B200LevelSetCutter, bgmodel::CartesianDiscreteModel, geom)
+  res, oid_to_ls = _run_facets(cutter, bgmodel, geom, false)
+  sz = Ref{GecutFacetSizes}()
+  _check(cutter, ccall((:gecut_facet_result_sizes, libgecut), Cint, (Ptr{Cvoid}, Ref{GecutFacetSizes}), res, sz),
+         "gecut_facet_result_sizes")
+  s = sz[]; D = Int(s.D); L = Int(s.num_levelsets)
+  bg  = Matrix{Int8}(undef, s.num_bgfacets, L)
+  c2p = Vector{Int32}(undef, s.num_subfacets*D); c2b = Vector{Int32}(undef, s.num_subfacets)
+  X = Vector{Float64}(undef, s.num_subfacet_points*D); R = Vector{Float64}(undef, s.num_subfacet_points*(D-1))
+  sfi = Matrix{Int8}(undef, s.num_subfacets, L)
+  b = GecutFacetBuffers(pointer(bg), C_NULL, C_NULL, C_NULL, pointer(c2p), pointer(c2b), pointer(X), pointer(R), pointer(sfi))
+  GC.@preserve bg c2p c2b X R sfi begin
+    _check(cutter, ccall((:gecut_facet_result_copy, libgecut), Cint, (Ptr{Cvoid}, Ref{GecutFacetBuffers}), res, b),
+           "gecut_facet_result_copy")
+  end
+  ccall((:gecut_facet_result_free, libgecut), Cint, (Ptr{Cvoid},), res)
+  subfacets = SubCellData(Table(c2p, collect(Int32, 1:D:(s.num_subfacets*D+1))), c2b,
+                          collect(reinterpret(Point{D,Float64}, X)), collect(reinterpret(Point{D-1,Float64}, R)))
+  EmbeddedFacetDiscretization(bgmodel, [bg[:, ls] for ls in 1:L], subfacets, [sfi[:, ls] for ls in 1:L], oid_to_ls, geom)
+end
+
+function compute_bgfacet_to_inoutcut(cutter::B200LevelSetCutter, bgmodel::CartesianDiscreteModel, geom)
+  res, oid_to_ls = _run_facets(cutter, bgmodel, geom, true)
+  prog = _postfix(get_tree(geom), oid_to_ls)
+  out = Vector{Int8}(undef, num_facets(bgmodel))
+  _check(cutter, ccall((:gecut_bgfacet_to_inoutcut, libgecut), Cint, (Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Int8}),
+                       res, prog, length(prog), out), "gecut_bgfacet_to_inoutcut")
+  ccall((:gecut_facet_result_free, libgecut), Cint, (Ptr{Cvoid},), res)
+  out
+end
+
+# postfix program of a CSG tree over the 0-based level-set rows (compute_inoutcut, EmbeddedDiscretizations.jl:107-177)
+function _postfix(tree, oid_to_ls)
+  prog = Int32[]
+  function rec(n)
+    if n.leftchild === nothing
+      push!(prog, Int32(oid_to_ls[objectid(first(n.data))] - 1))
+    else
+      rec(n.leftchild); n.rightchild === nothing || rec(n.rightchild)
+      push!(prog, Dict(:∪ => Int32(-1), :∩ => Int32(-2), :- => Int32(-3), :! => Int32(-4))[first(n.data)])
+    end
+  end
+  rec(tree)
+  prog
 end
 
 export B200LevelSetCutter, SimplexifiedCartesian
