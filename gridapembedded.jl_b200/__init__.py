@@ -5,7 +5,7 @@ booleans, `cut`, `LevelSetCutter`, `Triangulation(cutgeo, PHYSICAL, name)`, `Emb
 `Measure`.  All compute goes through the C ABI of `libgecut.so` (include/gecut.h); there is no CPU
 fallback -- importing this package works without a GPU, calling `cut` does not.
 """
-from . import csg, geometries, cartesian, cutters, discretizations, measures, distributed, facets  # noqa: F401
+from . import csg, geometries, cartesian, cutters, discretizations, measures, distributed, facets, agfem  # noqa: F401
 from .csg import (Node, Leaf, Geometry, union, intersect, intersection, setdiff, complement, get_geometry,
                   get_geometry_names, get_tree, get_name, get_metadata, replace_metadata, replace_data)
 from .geometries import (AnalyticalGeometry, DiscreteGeometry, BoundingBox, discretize, doughnut, popcorn, sphere,
@@ -19,3 +19,4 @@ from .measures import Measure, integrate_measure, integrate_laplacian, get_cell_
 from .distributed import DistributedLevelSetCutter, slab_range
 from .facets import (EmbeddedFacetDiscretization, cut_facets, compute_bgfacet_to_inoutcut, compute_subfacet_to_inout,
                      BoundaryTriangulation, SkeletonTriangulation)
+from .agfem import AggregateCutCellsByThreshold, AggregateAllCutCells, aggregate

@@ -77,7 +77,7 @@ class FacetBuffers(C.Structure):
 FACETS_BOUNDARY, FACETS_SKELETON = 0, 1
 
 SOURCES = ["gecut_api.cu", "gecut_classify.cu", "gecut_cutcells.cu", "gecut_select.cu", "gecut_integrate.cu",
-           "gecut_facets.cu"]
+           "gecut_facets.cu", "gecut_aggregate.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xcompiler", "-ffp-contract=off"]
 
@@ -202,6 +202,7 @@ def lib():
     L.gecut_facet_selection_sizes.argtypes = [vp, P(i64), P(i64)]
     L.gecut_facet_selection_copy.argtypes = [vp, vp, vp]
     L.gecut_facet_selection_measure.argtypes = [vp, vp, P(C.c_double)]
+    L.gecut_aggregate.argtypes = [vp, vp, vp, cint, cint, C.c_double, vp, cint]
     for name in FACET_SYMBOLS:
         getattr(L, name).restype = cint
     for name in ("gecut_create", "gecut_destroy", "gecut_set_stream", "gecut_cut", "gecut_classify",
@@ -218,7 +219,7 @@ def lib():
 FACET_SYMBOLS = ["gecut_cut_facets", "gecut_facet_result_free", "gecut_facet_result_sizes", "gecut_facet_result_copy",
                  "gecut_bgfacet_to_inoutcut", "gecut_subfacet_to_inout", "gecut_select_facets",
                  "gecut_facet_selection_free", "gecut_facet_selection_sizes", "gecut_facet_selection_copy",
-                 "gecut_facet_selection_measure"]
+                 "gecut_facet_selection_measure", "gecut_aggregate"]
 
 EXPORTED_SYMBOLS = FACET_SYMBOLS + ["gecut_create", "gecut_destroy", "gecut_set_stream", "gecut_last_error", "gecut_launch_count",
                     "gecut_profile", "gecut_profile_report", "gecut_trim",

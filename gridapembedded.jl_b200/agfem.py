@@ -1,0 +1,74 @@
+"""AgFEM cell aggregation (host mirror of `src/AgFEM/CellAggregation.jl:1-102`).
+
+`aggregate(strategy, cut[, cut_facets][, geo or name][, in_or_out])` returns `cell_to_cellin` (Int32, 1-based root cell of
+every active cell, 0 for the others), computed on the device by `gecut_aggregate`; the neighbour search uses the closed
+form topology of the Cartesian model, the facet states come from `cut_facets` / `compute_bgfacet_to_inoutcut`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from .csg import Geometry
+from .cutters import LevelSetCutter
+from .discretizations import IN, OUT, EmbeddedDiscretization
+from .facets import EmbeddedFacetDiscretization, _call_cut_facets
+
+
+class AggregateCutCellsByThreshold:
+    """`AggregateCutCellsByThreshold(threshold)` (`CellAggregation.jl:64-68`)."""
+
+    def __init__(self, threshold: float):
+        if threshold < 0.0 or threshold > 1.0:
+            raise ValueError("Agg. threshold must be in [0,1]")
+        self.threshold = float(threshold)
+
+
+def AggregateAllCutCells() -> AggregateCutCellsByThreshold:
+    """`AggregateAllCutCells() = AggregateCutCellsByThreshold(1.0)` (`CellAggregation.jl:70`)."""
+    return AggregateCutCellsByThreshold(1.0)
+
+
+def aggregate(strategy: AggregateCutCellsByThreshold, cut: EmbeddedDiscretization, *args, device_output: bool = False):
+    """`aggregate(strategy, cut)`, `(strategy, cut, geo)`, `(strategy, cut, name, in_or_out)`,
+    `(strategy, cut, geo, in_or_out)`, `(strategy, cut, cut_facets[, geo or name[, in_or_out]])`
+    (`CellAggregation.jl:1-102`)."""
+    args = list(args)
+    facets: Optional[EmbeddedFacetDiscretization] = None
+    if args and isinstance(args[0], EmbeddedFacetDiscretization):
+        facets = args.pop(0)
+    geo = args.pop(0) if args else None
+    in_or_out = args.pop(0) if args else IN
+    if args:
+        raise TypeError("too many arguments")
+    if in_or_out not in (IN, OUT):
+        raise ValueError("in_or_out must be IN or OUT")
+    if not isinstance(strategy, AggregateCutCellsByThreshold):
+        raise NotImplementedError("abstract method")  # CellAggregation.jl:14-16
+    own = None
+    if facets is None:
+        # compute_bgfacet_to_inoutcut(cut.bgmodel, geo) (`CellAggregation.jl:79`): classification of the facet grid only
+        # (of the WHOLE geometry, so that the level-set rows line up with cut.program(geo))
+        own = facets = _call_cut_facets(LevelSetCutter(cut.ctx), cut.bgmodel, cut.geo, True)
+    prog = cut.program(geo)
+    ctx = cut.ctx
+    nc = cut.num_bgcells
+    try:
+        if device_output:
+            import torch
+            out = torch.empty(nc, dtype=torch.int32, device=f"cuda:{ctx.device}")
+            ctx.check(ctx._lib.gecut_aggregate(cut.handle, facets.handle, prog.ctypes.data, prog.size, int(in_or_out),
+                                               C.c_double(strategy.threshold), C.c_void_p(out.data_ptr()), 1),
+                      "gecut_aggregate")
+        else:
+            out = np.empty(nc, np.int32)
+            ctx.check(ctx._lib.gecut_aggregate(cut.handle, facets.handle, prog.ctypes.data, prog.size, int(in_or_out),
+                                               C.c_double(strategy.threshold), C.c_void_p(out.ctypes.data), 0),
+                      "gecut_aggregate")
+    finally:
+        if own is not None:
+            own.close()
+    return out

@@ -23,149 +23,9 @@
 #include <string>
 
 #include "gecut_internal.cuh"
-
-// ------------------------------------------------------------------------------------------------
-// objects behind the opaque handles
-// ------------------------------------------------------------------------------------------------
-struct GcFacetLayout {
-  int8_t* bg_state;   // L x Nf (pitched)
-  int64_t bg_pitch;
-  int32_t* cutfacets; // Ncutf, 1-based ascending
-  int32_t* c2p;       // Nsf * D
-  int32_t* c2bg;      // Nsf (bg facet ids, 1-based)
-  double* X;          // Nsfp * D
-  double* R;          // Nsfp * (D-1)
-  int8_t* state;      // L x Nsf (pitched)
-  int64_t pitch;
-  double* meas;       // Nsf: integral of 1 with the degree-2 rule
-};
-
-struct gecut_facet_result {
-  gecut_ctx* ctx = nullptr;
-  GcGrid grid{};
-  int L = 0;
-  GcLeaves leaves{};
-  gecut_facet_sizes sizes{};
-  GcFacetLayout lay{};
-  int64_t tallies[GC_LMAX * 12] = {0};  // whole facets per level set: ((s*3 + d)*2 + isb), s = 0 IN / 1 OUT (k_facet_rows)
-  bool owns_nodal[GC_LMAX] = {false};
-  double* nodal_dev[GC_LMAX] = {nullptr};
-};
-
-struct gecut_facet_selection {
-  const gecut_facet_result* res = nullptr;
-  int which = 0, kind = 0, side = 0;
-  int64_t n_sub = 0, n_bg = 0;
-  int32_t* sub_ids = nullptr;
-  int32_t* bg_ids = nullptr;
-  int64_t bg_dir_count[3] = {0, 0, 0};  // selected whole facets per normal direction
-  GcProgram prog{};                     // for the lazy materialisation of bg_ids
-};
+#include "gecut_facets.cuh"
 
 namespace {
-
-// ------------------------------------------------------------------------------------------------
-// Facet numbering of a Cartesian model (Gridap generate_cell_to_faces: first encounter over (cell, local facet)).
-// Local facets, highest direction first: lf = 2*(D-1-d) + side (side 0: low face, 1: high face); the low face of
-// direction d is new only for cells with index 0 along d.
-// ------------------------------------------------------------------------------------------------
-struct FacetIdx {
-  int ijk[3];  // cell
-  int d;       // direction the facet is normal to
-  int side;    // 0 low, 1 high
-};
-
-template <int D>
-__host__ __device__ inline int64_t facets_per_row(const GcGrid& g, int j, int k) {
-  // cells of a row: D new facets each (high faces) + low faces of the higher directions; +1 for the x-low face of cell 0
-  return (int64_t)g.n[0] * (D + (j == 0 ? 1 : 0) + ((D == 3 && k == 0) ? 1 : 0)) + 1;
-}
-__host__ __device__ inline int64_t facets_per_layer(const GcGrid& g, int k) {
-  return facets_per_row<3>(g, 0, k) + (int64_t)(g.n[1] - 1) * facets_per_row<3>(g, 1, k);
-}
-template <int D>
-__host__ __device__ inline int64_t num_facets(const GcGrid& g) {
-  if (D == 2) return facets_per_row<2>(g, 0, 0) + (int64_t)(g.n[1] - 1) * facets_per_row<2>(g, 1, 0);
-  return facets_per_layer(g, 0) + (int64_t)(g.n[2] - 1) * facets_per_layer(g, 1);
-}
-
-template <int D>
-__device__ __forceinline__ FacetIdx facet_decode(const GcGrid& g, uint32_t f) {
-  FacetIdx r;
-  uint32_t rem = f;
-  int k = 0;
-  if (D == 3) {
-    const uint32_t L0 = (uint32_t)facets_per_layer(g, 0);
-    if (rem >= L0) {
-      const uint32_t L1 = (uint32_t)facets_per_layer(g, 1);
-      rem -= L0;
-      k = 1 + (int)(rem / L1);
-      rem = rem % L1;
-    }
-  }
-  int j = 0;
-  const uint32_t R0 = (uint32_t)facets_per_row<D>(g, 0, k);
-  if (rem >= R0) {
-    const uint32_t R1 = (uint32_t)facets_per_row<D>(g, 1, k);
-    rem -= R0;
-    j = 1 + (int)(rem / R1);
-    rem = rem % R1;
-  }
-  const uint32_t per = (uint32_t)(D + (j == 0 ? 1 : 0) + ((D == 3 && k == 0) ? 1 : 0));
-  int i = 0;
-  if (rem >= per + 1) {
-    rem -= per + 1;
-    i = 1 + (int)(rem / per);
-    rem = rem % per;
-  }
-  r.ijk[0] = i;
-  r.ijk[1] = j;
-  r.ijk[2] = k;
-  // rem-th NEW facet of the cell, local order: [z-low], z-high, [y-low], y-high, [x-low], x-high
-  int t = (int)rem;
-  r.d = 0;
-  r.side = 1;
-#pragma unroll
-  for (int d = D - 1; d >= 0; --d) {
-    const int idx = d == 0 ? i : (d == 1 ? j : k);
-    if (idx == 0) {
-      if (t == 0) {
-        r.d = d;
-        r.side = 0;
-        return r;
-      }
-      t--;
-    }
-    if (t == 0) {
-      r.d = d;
-      r.side = 1;
-      return r;
-    }
-    t--;
-  }
-  return r;
-}
-
-// multi-index of local node m (0 .. 2^(D-1)-1) of the facet: the free directions ascending, lower one fastest
-template <int D>
-__device__ __forceinline__ void facet_node(const FacetIdx& fi, int m, int* nijk) {
-  nijk[0] = fi.ijk[0];
-  nijk[1] = fi.ijk[1];
-  nijk[2] = D == 3 ? fi.ijk[2] : 0;
-  nijk[fi.d] += fi.side;
-  int bit = 0;
-#pragma unroll
-  for (int d = 0; d < D; ++d) {
-    if (d == fi.d) continue;
-    nijk[d] += (m >> bit) & 1;
-    bit++;
-  }
-}
-
-template <int D>
-__device__ __forceinline__ bool facet_is_boundary(const GcGrid& g, const FacetIdx& fi) {
-  return fi.side == 0 || fi.ijk[fi.d] == g.n[fi.d] - 1;
-}
 
 template <int D>
 __device__ __forceinline__ double leaf_at_node(const GcGrid& g, const GcLeaves& lv, int ls, const int* nijk) {
@@ -250,15 +110,6 @@ k_node_signs(const GcGrid g, const GcLeaves lv, int wxt, uint32_t* __restrict__ 
       if (threadIdx.x == 0) out[nrow * wxt] = word;
     }
   }
-}
-
-// first facet id (0-based) of the row of cells (j,k)
-template <int D>
-__host__ __device__ inline int64_t facet_row_base(const GcGrid& g, int j, int k) {
-  int64_t b = 0;
-  if (D == 3 && k > 0) b += facets_per_layer(g, 0) + (int64_t)(k - 1) * facets_per_layer(g, 1);
-  if (j > 0) b += facets_per_row<D>(g, 0, k) + (int64_t)(j - 1) * facets_per_row<D>(g, 1, k);
-  return b;
 }
 
 // ------------------------------------------------------------------------------------------------

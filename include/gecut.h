@@ -275,6 +275,17 @@ int gecut_facet_selection_copy(const gecut_facet_selection* sel, int32_t* sub_id
  * sub-facet; *total also includes the selected whole facets */
 int gecut_facet_selection_measure(const gecut_facet_selection* sel, double* sub_values, double* total);
 
+/* ---- AgFEM aggregation ------------------------------------------------------------------------ */
+/* aggregate(AggregateCutCellsByThreshold(threshold), cut, cut_facets, geo, in_or_out) (src/AgFEM/CellAggregation.jl:72-189):
+ * `cell_to_cellin` (num_bgcells Int32; host memory, or device memory when on_device != 0) receives for every cell the
+ * 1-based root cell it is aggregated to -- itself for cells whose unit cut measure is >= threshold, the root of the best
+ * touched face neighbour (closest root, ties by Gridap's local facet order) for the other CUT cells, 0 elsewhere.
+ * `facets` may be a classification-only facet result (compute_bgfacet_to_inoutcut).  threshold = 1 is
+ * AggregateAllCutCells().  Fails with GECUT_ERR_INVALID when 20 sweeps do not aggregate every cut cell (the reference's
+ * @assert all_aggregated).  Whole n-cube Cartesian models. */
+int gecut_aggregate(const gecut_result* cut, const gecut_facet_result* facets, const int32_t* program, int len, int side,
+                    double threshold, int32_t* cell_to_cellin, int on_device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1293,6 +1293,118 @@ double gecut_oracle_bgfacet_measure(void* h, int32_t facet1) {
   return s;
 }
 
+// ---- AgFEM aggregation (src/AgFEM/CellAggregation.jl:104-242) --------------------------------------------------
+// aggregate(AggregateCutCellsByThreshold(threshold), cut, cut_facets, geo, loc): `cell_to_cellin` (Int32, 1-based root
+// cell of every active cell, 0 elsewhere).  Topology from the facet grid of the FacetResult (Gridap: cell_to_faces in
+// local facet order, face_to_cells ascending).  Returns 0, or 1 when the 20 iterations did not aggregate every cut cell
+// (the reference's @assert all_aggregated).
+int gecut_oracle_aggregate(void* hc, void* hf, const int32_t* prog, int len, int loc, double threshold, int32_t* out) {
+  Result* r = (Result*)hc;
+  FacetResult* fr = (FacetResult*)hf;
+  const BgGrid& g = r->grid;
+  const int D = g.D, nvf = fr->nvf, nv = g.nv;
+  const int64_t n_cells = g.num_cells, n_facets = (int64_t)fr->facet_is_boundary.size();
+  // get_faces(topo,D,D-1) / get_faces(topo,D-1,D)
+  const std::vector<std::vector<int>>& lfacets = D == 2 ? LFACETS_QUAD : LFACETS_HEX;
+  const int nlf = (int)lfacets.size();
+  std::map<std::array<int64_t, 4>, int32_t> facet_of;
+  for (int64_t f = 0; f < n_facets; ++f) {
+    std::array<int64_t, 4> key = {-1, -1, -1, -1};
+    for (int i = 0; i < nvf; ++i) key[i] = fr->facet_nodes[f * nvf + i];
+    std::sort(key.begin(), key.end());
+    facet_of[key] = (int32_t)f;
+  }
+  std::vector<int32_t> cell_to_faces(n_cells * nlf);
+  std::vector<std::vector<int32_t>> face_to_cells(n_facets);
+  for (int64_t cell = 0; cell < n_cells; ++cell) {
+    int64_t nodes[8];
+    g.cell_nodes(cell, nodes);
+    for (int lf = 0; lf < nlf; ++lf) {
+      std::array<int64_t, 4> key = {-1, -1, -1, -1};
+      for (int i = 0; i < nvf; ++i) key[i] = nodes[lfacets[lf][i] - 1];
+      std::sort(key.begin(), key.end());
+      const int32_t f = facet_of.at(key);
+      cell_to_faces[cell * nlf + lf] = f;
+      face_to_cells[f].push_back((int32_t)cell);
+    }
+  }
+  // _aggregate_by_threshold (:104-131): unit cut measures, states
+  std::vector<double> unit(n_cells, 0.0);
+  std::vector<int8_t> cell_to_inoutcut(n_cells), facet_to_inoutcut(n_facets);
+  for (int64_t c = 0; c < n_cells; ++c) {
+    cell_to_inoutcut[c] = eval_inoutcut(prog, len, r->ls_to_bgcell_to_inoutcut, c);
+    if (cell_to_inoutcut[c] == loc) unit[c] = bgcell_volume(g, c);
+  }
+  for (int64_t sc = 0; sc < r->subcells.ncells(); ++sc) {
+    const int64_t c = r->subcells.c2bg[sc] - 1;
+    if (cell_to_inoutcut[c] == CUT && eval_inoutcut(prog, len, r->ls_to_subcell_to_inout, sc) == loc)
+      unit[c] += integrate_one(r->subcells, sc);
+  }
+  for (int64_t c = 0; c < n_cells; ++c) unit[c] = unit[c] / bgcell_volume(g, c);
+  for (int64_t f = 0; f < n_facets; ++f) facet_to_inoutcut[f] = eval_inoutcut(prog, len, fr->ls_to_facet_to_inoutcut, f);
+  // _aggregate_by_threshold_barrier (:133-189)
+  std::vector<int32_t> cell_to_cellin(n_cells, 0);
+  std::vector<char> touched(n_cells, 0);
+  for (int64_t c = 0; c < n_cells; ++c)
+    if (unit[c] >= threshold) {
+      cell_to_cellin[c] = (int32_t)(c + 1);
+      touched[c] = 1;
+    }
+  auto coords = [&](int64_t cell, double x[8][3]) {
+    int64_t nodes[8];
+    g.cell_nodes(cell, nodes);
+    for (int i = 0; i < nv; ++i) {
+      x[i][0] = x[i][1] = x[i][2] = 0.0;
+      g.node_coords(nodes[i], x[i]);
+    }
+  };
+  bool all_aggregated = false;
+  for (int iter = 0; iter < 20; ++iter) {
+    all_aggregated = true;
+    for (int64_t cell = 0; cell < n_cells; ++cell) {
+      if (touched[cell] || cell_to_inoutcut[cell] != CUT) continue;
+      // _find_best_neighbor (:191-233)
+      double dmin = std::numeric_limits<double>::infinity();
+      int64_t best = -1;
+      double xi[8][3], xj[8][3];
+      coords(cell, xi);
+      for (int lf = 0; lf < nlf; ++lf) {
+        const int32_t face = cell_to_faces[cell * nlf + lf];
+        const int io = facet_to_inoutcut[face];
+        if (io != CUT && io != loc) continue;
+        for (int32_t neigh : face_to_cells[face]) {
+          if (neigh == cell || !touched[neigh]) continue;
+          const int64_t cellin = cell_to_cellin[neigh] - 1;
+          coords(cellin, xj);
+          double d = 0.0;
+          for (int p = 0; p < nv; ++p)
+            for (int q = 0; q < nv; ++q) {
+              double s2 = 0.0;
+              for (int c = 0; c < D; ++c) {
+                const double w = xi[p][c] - xj[q][c];
+                s2 += w * w;
+              }
+              d = std::max(d, std::sqrt(s2));
+            }
+          if ((1.0 + 1.0e-9) * d < dmin) {
+            dmin = d;
+            best = neigh;
+          }
+        }
+      }
+      if (best >= 0)
+        cell_to_cellin[cell] = cell_to_cellin[best];
+      else
+        all_aggregated = false;
+    }
+    if (all_aggregated) break;
+    for (int64_t c = 0; c < n_cells; ++c)  // _touch_aggregated_cells! (:235-241)
+      if (cell_to_cellin[c] > 0) touched[c] = 1;
+  }
+  std::memcpy(out, cell_to_cellin.data(), sizeof(int32_t) * n_cells);
+  return all_aggregated ? 0 : 1;
+}
+
 void gecut_oracle_eval_leaf(const OLeaf* leaf, int D, const double* x, int64_t n, double* out) {
   for (int64_t i = 0; i < n; ++i) out[i] = eval_leaf(*leaf, x + i * D, D);
 }

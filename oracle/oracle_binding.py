@@ -79,6 +79,8 @@ def lib():
         L.gecut_oracle_select_facets.restype = C.c_int64
         L.gecut_oracle_select_facets.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.gecut_oracle_facets_subfacet_measures.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.gecut_oracle_aggregate.restype = C.c_int
+        L.gecut_oracle_aggregate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]
         L.gecut_oracle_bgfacet_measure.restype = C.c_double
         L.gecut_oracle_bgfacet_measure.argtypes = [C.c_void_p, C.c_int32]
         _lib = L
@@ -318,6 +320,15 @@ class OracleFacetCut:
 
     def bgfacet_measure(self, facet1: int) -> float:
         return float(lib().gecut_oracle_bgfacet_measure(self.h, int(facet1)))
+
+
+def oracle_aggregate(oc: "OracleCut", fc: "OracleFacetCut", prog, loc: int = IN, threshold: float = 1.0):
+    """`aggregate(AggregateCutCellsByThreshold(threshold), cut, cut_facets, geo, loc)` (CellAggregation.jl:83-189):
+    returns (cell_to_cellin Int32 1-based, all_aggregated)."""
+    a, p, n = OracleCut._prog(prog)
+    out = np.zeros(oc.Nc, np.int32)
+    rc = lib().gecut_oracle_aggregate(oc.h, fc.h, p, n, int(loc), float(threshold), out.ctypes.data)
+    return out, rc == 0
 
 
 def oracle_cut_facets(model, geo) -> "OracleFacetCut":

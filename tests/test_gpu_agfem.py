@@ -1,0 +1,95 @@
+"""GPU parity of the AgFEM aggregation (`gecut_aggregate`) against the CPU oracle: `cell_to_cellin` must be identical
+(Int32, bit-exact), through every call path of the reference's own test (`test/AgFEMTests/CellAggregationTests.jl`)."""
+import numpy as np
+import pytest
+
+import gecut
+from gecut import (CartesianDiscreteModel, disk, sphere, cut, cut_facets, aggregate, AggregateAllCutCells,
+                   AggregateCutCellsByThreshold, get_geometry, simplexify, IN, OUT)
+import oracle_binding as ob
+from test_gpu_parity import csg_geometry, stokes_geometry, bimaterial, three_disks
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "disk_30": lambda: (CartesianDiscreteModel((0, 1, 0, 1), (30, 30)), disk(0.4, x0=(0.5, 0.5)), None),
+    "disk_corner": lambda: (CartesianDiscreteModel((0, 1, 0, 1), (17, 23)), disk(0.72, x0=(1, 1)), None),
+    "three_disks": lambda: (CartesianDiscreteModel((-1, 2, -1, 2), (23, 19)), three_disks(), None),
+    "sphere": lambda: (CartesianDiscreteModel((-1, 1, -1, 1, -1, 1), (9, 8, 7)), sphere(0.7), None),
+    "csg": lambda: (CartesianDiscreteModel((-0.8,) * 3, (0.8,) * 3, (12, 12, 12)), csg_geometry(), "csg"),
+    "bimaterial": lambda: (CartesianDiscreteModel((0., 0., 0.), (3., 2., 3.), (18, 12, 18)), bimaterial(), "steel"),
+    # too coarse for an IN root inside the cylinders: the reference's @assert all_aggregated fires
+    "bimaterial_coarse": lambda: (CartesianDiscreteModel((0., 0., 0.), (3., 2., 3.), (9, 6, 9)), bimaterial(), "steel"),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("thr", [1.0, 0.4])
+def test_aggregate_parity(name, thr):
+    model, geo, nm = CASES[name]()
+    cg = cut(model, geo)
+    fc = cut_facets(model, geo)
+    oc = ob.oracle_cut(model, geo)
+    ofc = ob.oracle_cut_facets(model, geo)
+    prog = cg.program(nm)
+    strategy = AggregateCutCellsByThreshold(thr)
+    for loc in (IN, OUT):
+        ref, ok = ob.oracle_aggregate(oc, ofc, prog, loc, thr)
+        if not ok:  # the reference asserts; the library reports the same condition as an error
+            with pytest.raises(gecut._lib.GecutError, match="not all cut cells"):
+                aggregate(strategy, cg, fc, nm, loc)
+            continue
+        a1 = aggregate(strategy, cg, fc, nm, loc)          # with an EmbeddedFacetDiscretization
+        a2 = aggregate(strategy, cg, nm, loc)               # compute_bgfacet_to_inoutcut(cut.bgmodel, geo) inside
+        assert a1.dtype == np.int32 and np.array_equal(a1, ref)
+        assert np.array_equal(a2, ref)
+    if ob.oracle_aggregate(oc, ofc, prog, IN, thr)[1]:
+        a3 = aggregate(strategy, cg, fc, nm, IN, device_output=True)
+        assert np.array_equal(a3.cpu().numpy(), aggregate(strategy, cg, fc, nm, IN))
+    cg.close()
+    fc.close()
+
+
+def test_aggregate_defaults_and_errors():
+    model = CartesianDiscreteModel((0, 1, 0, 1), (30, 30))
+    geo = disk(0.4, x0=(0.5, 0.5))
+    cg = cut(model, geo)
+    fc = cut_facets(model, geo)
+    a = aggregate(AggregateAllCutCells(), cg)               # aggregate(strategy, cut) (CellAggregation.jl:1-3)
+    assert np.array_equal(a, aggregate(AggregateAllCutCells(), cg, fc))
+    assert np.array_equal(a, aggregate(AggregateAllCutCells(), cg, geo, IN))
+    with pytest.raises(ValueError):
+        AggregateCutCellsByThreshold(1.5)
+    # simplexified models: not implemented (needs the facet grid of the simplexified model)
+    ms = simplexify(model)
+    cs = cut(ms, geo)
+    with pytest.raises((NotImplementedError, gecut._lib.GecutError)):
+        aggregate(AggregateAllCutCells(), cs)
+    for x in (cg, fc, cs):
+        x.close()
+
+
+def test_aggregate_at_scale():
+    """256^3 sphere: invariants without the oracle (roots are fixed points, every CUT cell has an IN root at most a few
+    cells away, OUT cells are 0) and the time of the whole aggregation."""
+    n = 256
+    g = sphere(0.7)
+    b = gecut.get_metadata(g)
+    model = CartesianDiscreteModel(b.pmin, b.pmax, (n, n, n))
+    cg = cut(model, g)
+    fc = cut_facets(model, g)
+    agg = aggregate(AggregateAllCutCells(), cg, fc)
+    st = gecut.compute_bgcell_to_inoutcut(cg, g)
+    cells = np.arange(1, model.num_cells + 1, dtype=np.int64)
+    assert np.all(agg[st == OUT] == 0)
+    assert np.all(agg[st == IN] == cells[st == IN])
+    cutm = st == 0
+    assert np.all(agg[cutm] > 0) and np.all(st[agg[cutm] - 1] == IN)
+    # distance (in cells) between a cut cell and its root
+    def ijk(c):
+        c = c - 1
+        return np.stack([c % n, (c // n) % n, c // (n * n)], 1)
+    dist = np.abs(ijk(cells[cutm]) - ijk(agg[cutm].astype(np.int64))).max(1)
+    assert dist.max() <= 3
+    cg.close()
+    fc.close()

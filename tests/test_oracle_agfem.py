@@ -1,0 +1,92 @@
+"""Oracle checks of the AgFEM aggregation restatement (`src/AgFEM/CellAggregation.jl:104-241`): the reference's own test
+(`test/AgFEMTests/CellAggregationTests.jl`) only asserts that the call paths agree, so the invariants of the algorithm
+are asserted here as well."""
+import numpy as np
+import pytest
+
+import gecut
+from gecut import CartesianDiscreteModel, disk, sphere, union, get_geometry
+from gecut.csg import compile_postfix
+import oracle_binding as ob
+import facet_helpers as FH
+from test_oracle_kat import csg_geometry
+
+IN, OUT, CUT = -1, 1, 0
+
+
+def setup(model, geo):
+    oc = ob.oracle_cut(model, geo)
+    fc = ob.oracle_cut_facets(model, geo)
+    return oc, fc
+
+
+def check_invariants(model, oc, fc, p, loc, thr, agg):
+    st = oc.bgcell_to_inoutcut(p)
+    n = model.num_cells
+    cells = np.arange(1, n + 1)
+    # cells on the other side are not aggregated (threshold > 0); cells on `loc` are their own roots
+    assert np.all(agg[st == -loc] == 0)
+    assert np.all(agg[st == loc] == cells[st == loc])
+    # every CUT cell has a root, and a root is its own root
+    assert np.all(agg[st == CUT] > 0)
+    roots = np.unique(agg[agg > 0])
+    assert np.all(agg[roots - 1] == roots)
+    # roots that are CUT cells have a unit cut measure >= threshold; CUT cells below it are slaves
+    ids = oc.select_subcells(p, loc)
+    vol = np.zeros(n)
+    np.add.at(vol, oc.array("subcells.cell_to_bgcell")[ids - 1] - 1, oc.subcell_measures(ids))
+    unit = vol / np.prod(model.sizes)
+    cut_roots = roots[st[roots - 1] == CUT]
+    assert np.all(unit[cut_roots - 1] >= thr - 1e-12)
+    slaves = cells[(st == CUT) & (agg != cells)]
+    assert np.all(unit[slaves - 1] < thr + 1e-12)
+    # a slave is connected to its root through face neighbours with the same root (or the root itself)
+    fn = fc.array("facet_nodes").reshape(-1, fc.nvf)
+    d, pos, minus, plus = FH.facet_cells(model, fn)
+    m = (minus >= 0) & (plus >= 0)
+    nbr = {}
+    for a, b in zip(minus[m], plus[m]):
+        nbr.setdefault(a, []).append(b)
+        nbr.setdefault(b, []).append(a)
+    for c in slaves:
+        assert any(agg[x] == agg[c - 1] for x in nbr[c - 1])
+
+
+def test_cell_aggregation_reference_case():
+    # test/AgFEMTests/CellAggregationTests.jl:9-43
+    model = CartesianDiscreteModel((0, 1, 0, 1), (30, 30))
+    geo = disk(0.4, x0=(0.5, 0.5))
+    oc, fc = setup(model, geo)
+    p = compile_postfix(geo.get_tree(), oc.oid_to_ls)
+    agg, ok = ob.oracle_aggregate(oc, fc, p, IN, 1.0)
+    assert ok
+    check_invariants(model, oc, fc, p, IN, 1.0, agg)
+    agg_out, ok = ob.oracle_aggregate(oc, fc, p, OUT, 1.0)
+    assert ok
+    check_invariants(model, oc, fc, p, OUT, 1.0, agg_out)
+    assert not np.array_equal(agg, agg_out)
+    # AggregateAllCutCells: no cut cell is its own root
+    st = oc.bgcell_to_inoutcut(p)
+    cells = np.arange(1, model.num_cells + 1)
+    assert np.all(agg[st == CUT] != cells[st == CUT])
+
+
+@pytest.mark.parametrize("thr", [0.25, 0.5, 1.0])
+def test_cell_aggregation_thresholds_3d(thr):
+    model = CartesianDiscreteModel((-1, 1, -1, 1, -1, 1), (9, 8, 7))
+    geo = sphere(0.7)
+    oc, fc = setup(model, geo)
+    p = compile_postfix(geo.get_tree(), oc.oid_to_ls)
+    agg, ok = ob.oracle_aggregate(oc, fc, p, IN, thr)
+    assert ok
+    check_invariants(model, oc, fc, p, IN, thr, agg)
+
+
+def test_cell_aggregation_csg_named_geometry():
+    model = CartesianDiscreteModel((-0.8,) * 3, (0.8,) * 3, (10, 10, 10))
+    geo = csg_geometry()
+    oc, fc = setup(model, geo)
+    p = compile_postfix(get_geometry(geo, "csg").get_tree(), oc.oid_to_ls)
+    agg, ok = ob.oracle_aggregate(oc, fc, p, IN, 1.0)
+    assert ok
+    check_invariants(model, oc, fc, p, IN, 1.0, agg)
