@@ -203,6 +203,7 @@ def lib():
     L.gecut_facet_selection_copy.argtypes = [vp, vp, vp]
     L.gecut_facet_selection_measure.argtypes = [vp, vp, P(C.c_double)]
     L.gecut_aggregate.argtypes = [vp, vp, vp, cint, cint, C.c_double, vp, cint]
+    L.gecut_ghost_skeleton.argtypes = [vp, vp, cint, cint, P(i64), vp, vp]
     for name in FACET_SYMBOLS:
         getattr(L, name).restype = cint
     for name in ("gecut_create", "gecut_destroy", "gecut_set_stream", "gecut_cut", "gecut_classify",
@@ -219,7 +220,7 @@ def lib():
 FACET_SYMBOLS = ["gecut_cut_facets", "gecut_facet_result_free", "gecut_facet_result_sizes", "gecut_facet_result_copy",
                  "gecut_bgfacet_to_inoutcut", "gecut_subfacet_to_inout", "gecut_select_facets",
                  "gecut_facet_selection_free", "gecut_facet_selection_sizes", "gecut_facet_selection_copy",
-                 "gecut_facet_selection_measure", "gecut_aggregate"]
+                 "gecut_facet_selection_measure", "gecut_aggregate", "gecut_ghost_skeleton"]
 
 EXPORTED_SYMBOLS = FACET_SYMBOLS + ["gecut_create", "gecut_destroy", "gecut_set_stream", "gecut_last_error", "gecut_launch_count",
                     "gecut_profile", "gecut_profile_report", "gecut_trim",

@@ -72,3 +72,37 @@ def aggregate(strategy: AggregateCutCellsByThreshold, cut: EmbeddedDiscretizatio
         if own is not None:
             own.close()
     return out
+
+
+def GhostSkeleton(cut: EmbeddedDiscretization, in_or_out=None, geo=None, ids: bool = False):
+    """`GhostSkeleton(cut[, in_or_out=ACTIVE_IN][, geo or name])` (`EmbeddedDiscretizations.jl:465-543`): the
+    `facet_to_mask` (bool per bg facet, Gridap facet numbering) the reference hands to `SkeletonTriangulation(model, mask)`;
+    with `ids=True` the ascending 1-based facet ids instead."""
+    from .discretizations import ACTIVE_IN, ActiveInOrOut, CutInOrOut
+    if isinstance(in_or_out, (str, Geometry)) and geo is None:
+        in_or_out, geo = None, in_or_out
+    if in_or_out is None:
+        in_or_out = ACTIVE_IN
+    if isinstance(in_or_out, tuple):  # PHYSICAL_IN / PHYSICAL_OUT (`:508`)
+        raise NotImplementedError("Not implemented but not needed in practice. Ghost stabilization can be integrated in "
+                                  "full facets.")
+    side = in_or_out if isinstance(in_or_out, int) else in_or_out.in_or_out
+    if side not in (IN, OUT, 0):
+        raise ValueError("in_or_out must be ACTIVE_IN, ACTIVE_OUT or IN / OUT / CUT")
+    prog = cut.program(geo)
+    ctx = cut.ctx
+    n = C.c_int64()
+    if ids:
+        ctx.check(ctx._lib.gecut_ghost_skeleton(cut.handle, prog.ctypes.data, prog.size, int(side), C.byref(n), None, None),
+                  "gecut_ghost_skeleton")
+        out = np.empty(int(n.value), np.int32)
+        if out.size:
+            ctx.check(ctx._lib.gecut_ghost_skeleton(cut.handle, prog.ctypes.data, prog.size, int(side), C.byref(n), None,
+                                                    C.c_void_p(out.ctypes.data)), "gecut_ghost_skeleton")
+        return out
+    m = cut.bgmodel
+    nf = sum(int(np.prod([m.partition[e] + (1 if e == d else 0) for e in range(m.D)])) for d in range(m.D))
+    mask = np.empty(nf, np.int8)
+    ctx.check(ctx._lib.gecut_ghost_skeleton(cut.handle, prog.ctypes.data, prog.size, int(side), C.byref(n),
+                                            C.c_void_p(mask.ctypes.data), None), "gecut_ghost_skeleton")
+    return mask.astype(bool)

@@ -1,4 +1,4 @@
-// gecut_aggregate.cu -- AgFEM cell aggregation on the device.
+// gecut_aggregate.cu -- AgFEM cell aggregation and the GhostSkeleton facet mask on the device.
 //
 // Reference path replaced (src/AgFEM/CellAggregation.jl):
 //   aggregate(::AggregateCutCellsByThreshold, cut, [cut_facets,] geo, in_or_out)   :72-102
@@ -120,9 +120,127 @@ __global__ void k_agg_touch(const GcLayout lay, int64_t ncut, const int32_t* __r
   if (cellin[cell] > 0) touched[cell] = 1;
 }
 
+// GhostSkeleton mask (_fill_ghost_skeleton_mask!, src/Interfaces/EmbeddedDiscretizations.jl:520-543): interior facets
+// with at least one CUT cell around and both cells active (CUT or `side`).  Every such facet touches a CUT cell, so
+// the O(n^2) cut cells drive the pass; a facet between two CUT cells is written by both with the same value.
+template <int D>
+__global__ void k_ghost_mask(const GcGrid g, const GcLayout lay, int64_t ncut, const GcProgram prog, int side,
+                             int8_t* __restrict__ mask, unsigned long long* __restrict__ count) {
+  const int64_t kk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (kk >= ncut) return;
+  const int64_t cell = (int64_t)lay.cutcells[kk] - 1;
+  if (gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, cell) != GC_CUT) return;
+  int c[3];
+  c[0] = (int)(cell % g.n[0]);
+  c[1] = D == 3 ? (int)((cell / g.n[0]) % g.n[1]) : (int)(cell / g.n[0]);
+  c[2] = D == 3 ? (int)(cell / ((int64_t)g.n[0] * g.n[1])) : 0;
+#pragma unroll
+  for (int d = D - 1; d >= 0; --d) {
+#pragma unroll
+    for (int sd = 0; sd < 2; ++sd) {
+      int nb[3] = {c[0], c[1], c[2]};
+      nb[d] += sd == 0 ? -1 : 1;
+      if (nb[d] < 0 || nb[d] >= g.n[d]) continue;
+      const int64_t neigh = (int64_t)nb[0] + (int64_t)g.n[0] * ((int64_t)nb[1] + (int64_t)g.n[1] * nb[2]);
+      const int st = gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, neigh);
+      if (st != GC_CUT && st != side) continue;
+      mask[facet_id_of<D>(g, c[0], c[1], c[2], d, sd)] = 1;
+      // counted once: by the CUT cell on the low side, or by this cell when the neighbour is not CUT
+      if (st != GC_CUT || sd == 1) atomicAdd(count, 1ull);
+    }
+  }
+}
+
+__global__ void k_mask_to_flags(const int8_t* __restrict__ mask, int64_t n, uint32_t* __restrict__ flags) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = mask[i] ? 1u : 0u;
+}
+
 inline int64_t pad_pitch(int64_t n) { return ((n + 255) / 256) * 256; }
 
 }  // namespace
+
+extern "C" int gecut_ghost_skeleton(const gecut_result* cut, const int32_t* program, int len, int side, int64_t* n_ghost,
+                                    int8_t* facet_to_mask, int32_t* facet_ids) {
+  if (!cut) return GECUT_ERR_INVALID;
+  gecut_ctx* ctx = cut->ctx;
+  const GcGrid& g = cut->grid;
+  if (side != GECUT_IN && side != GECUT_OUT && side != GECUT_CUT) {
+    ctx->err = "ghost skeleton: in_or_out must be IN, OUT or CUT";
+    return GECUT_ERR_INVALID;
+  }
+  if (g.simplexified || g.k0 != 0 || g.k1 != g.n[g.D - 1]) {
+    ctx->err = "GhostSkeleton is implemented for whole n-cube Cartesian models";
+    return GECUT_ERR_NOTIMPLEMENTED;
+  }
+  DeviceGuard guard(ctx->device);
+  GcProgram p;
+  GC_CHECK(gc_make_program(ctx, program, len, cut->L, &p));
+  const int D = g.D;
+  const int64_t nf = D == 2 ? num_facets<2>(g) : num_facets<3>(g);
+  const int64_t ncut = cut->sizes.num_cutcells;
+  int8_t* mask = nullptr;
+  unsigned long long* cnt = nullptr;
+  GC_CHECK(gc_malloc(ctx, (void**)&mask, (size_t)pad_pitch(nf)));
+  int st = gc_malloc(ctx, (void**)&cnt, sizeof(unsigned long long));
+  auto done = [&](int code) {
+    gc_free(ctx, mask);
+    gc_free(ctx, cnt);
+    return code;
+  };
+  if (st != GECUT_OK) return done(st);
+  if (cudaMemsetAsync(mask, 0, (size_t)nf, ctx->stream) != cudaSuccess ||
+      cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), ctx->stream) != cudaSuccess) {
+    ctx->err = "ghost skeleton: memset failed";
+    return done(GECUT_ERR_CUDA);
+  }
+  const int T = 256;
+  if (ncut > 0) {
+    if (D == 2)
+      GC_LAUNCH(ctx, "k_ghost_mask", k_ghost_mask<2><<<(unsigned)gc_div_up(ncut, T), T, 0, ctx->stream>>>(g, cut->lay, ncut, p, side, mask, cnt));
+    else
+      GC_LAUNCH(ctx, "k_ghost_mask", k_ghost_mask<3><<<(unsigned)gc_div_up(ncut, T), T, 0, ctx->stream>>>(g, cut->lay, ncut, p, side, mask, cnt));
+    st = gc_launch_check(ctx, "k_ghost_mask");
+    if (st != GECUT_OK) return done(st);
+  }
+  uint64_t* h = (uint64_t*)ctx->h_pinned;
+  if (cudaMemcpyAsync(h, cnt, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+      cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    ctx->err = "ghost skeleton failed";
+    return done(GECUT_ERR_CUDA);
+  }
+  const int64_t total = (int64_t)h[0];
+  if (n_ghost) *n_ghost = total;
+  if (facet_to_mask && cudaMemcpyAsync(facet_to_mask, mask, (size_t)nf, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) {
+    ctx->err = "ghost skeleton: D2H copy failed";
+    return done(GECUT_ERR_CUDA);
+  }
+  if (facet_ids && total > 0) {
+    uint32_t* flags = nullptr;
+    int32_t* ids = nullptr;
+    int64_t n = 0;
+    st = gc_malloc(ctx, (void**)&flags, sizeof(uint32_t) * nf);
+    if (st != GECUT_OK) return done(st);
+    GC_LAUNCH(ctx, "k_mask_to_flags", k_mask_to_flags<<<(unsigned)gc_div_up(nf, T), T, 0, ctx->stream>>>(mask, nf, flags));
+    st = gc_launch_check(ctx, "k_mask_to_flags");
+    if (st == GECUT_OK) st = gc_compact_flags(ctx, flags, nf, &ids, &n, nullptr, nullptr);
+    gc_free(ctx, flags);
+    if (st == GECUT_OK && n != total) {
+      ctx->err = "ghost skeleton: id list and count disagree";
+      st = GECUT_ERR_CUDA;
+    }
+    if (st == GECUT_OK && cudaMemcpyAsync(facet_ids, ids, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+      st = GECUT_ERR_CUDA;
+    cudaStreamSynchronize(ctx->stream);
+    gc_free(ctx, ids);
+    if (st != GECUT_OK) return done(st);
+  }
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    ctx->err = "ghost skeleton failed";
+    return done(GECUT_ERR_CUDA);
+  }
+  return done(GECUT_OK);
+}
 
 extern "C" int gecut_aggregate(const gecut_result* cut, const gecut_facet_result* facets, const int32_t* program,
                                int len, int side, double threshold, int32_t* cell_to_cellin, int on_device) {

@@ -286,6 +286,15 @@ int gecut_facet_selection_measure(const gecut_facet_selection* sel, double* sub_
 int gecut_aggregate(const gecut_result* cut, const gecut_facet_result* facets, const int32_t* program, int len, int side,
                     double threshold, int32_t* cell_to_cellin, int on_device);
 
+/* GhostSkeleton(cut, in_or_out, geo) (src/Interfaces/EmbeddedDiscretizations.jl:504-543): the interior facets with at
+ * least one CUT cell around and both cells active (CUT or `side`; side = GECUT_IN / GECUT_OUT for ACTIVE_IN / ACTIVE_OUT,
+ * GECUT_CUT for the cut cells alone).  *n_ghost = number of such facets; `facet_to_mask` (host, num_bgfacets Int8, NULL
+ * skipped) is the mask handed to SkeletonTriangulation(model, facet_to_mask); `facet_ids` (host, *n_ghost Int32 from a
+ * previous call, NULL skipped) the same facets as an ascending 1-based list.  Facet numbering as in gecut_cut_facets.
+ * Whole n-cube Cartesian models. */
+int gecut_ghost_skeleton(const gecut_result* cut, const int32_t* program, int len, int side, int64_t* n_ghost,
+                         int8_t* facet_to_mask, int32_t* facet_ids);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1405,6 +1405,44 @@ int gecut_oracle_aggregate(void* hc, void* hf, const int32_t* prog, int len, int
   return all_aggregated ? 0 : 1;
 }
 
+// GhostSkeleton(cut,in_or_out,geo) (EmbeddedDiscretizations.jl:504-543): facet_to_mask via _fill_ghost_skeleton_mask!
+// with face_to_cells of the facet grid of `hf`
+void gecut_oracle_ghost_skeleton(void* hc, void* hf, const int32_t* prog, int len, int in_or_out, int8_t* mask) {
+  Result* r = (Result*)hc;
+  FacetResult* fr = (FacetResult*)hf;
+  const BgGrid& g = r->grid;
+  const int D = g.D, nvf = fr->nvf;
+  const int64_t n_cells = g.num_cells, n_facets = (int64_t)fr->facet_is_boundary.size();
+  const std::vector<std::vector<int>>& lfacets = D == 2 ? LFACETS_QUAD : LFACETS_HEX;
+  std::map<std::array<int64_t, 4>, int32_t> facet_of;
+  for (int64_t f = 0; f < n_facets; ++f) {
+    std::array<int64_t, 4> key = {-1, -1, -1, -1};
+    for (int i = 0; i < nvf; ++i) key[i] = fr->facet_nodes[f * nvf + i];
+    std::sort(key.begin(), key.end());
+    facet_of[key] = (int32_t)f;
+  }
+  std::vector<std::vector<int32_t>> facet_to_cells(n_facets);
+  for (int64_t cell = 0; cell < n_cells; ++cell) {
+    int64_t nodes[8];
+    g.cell_nodes(cell, nodes);
+    for (const std::vector<int>& lf : lfacets) {
+      std::array<int64_t, 4> key = {-1, -1, -1, -1};
+      for (int i = 0; i < nvf; ++i) key[i] = nodes[lf[i] - 1];
+      std::sort(key.begin(), key.end());
+      facet_to_cells[facet_of.at(key)].push_back((int32_t)cell);
+    }
+  }
+  for (int64_t facet = 0; facet < n_facets; ++facet) {
+    int ncells_around_cut = 0, ncells_around_active = 0;
+    for (int32_t cell : facet_to_cells[facet]) {
+      const int inoutcut = eval_inoutcut(prog, len, r->ls_to_bgcell_to_inoutcut, cell);
+      if (inoutcut == CUT) ncells_around_cut += 1;
+      if (inoutcut == CUT || inoutcut == in_or_out) ncells_around_active += 1;
+    }
+    mask[facet] = (ncells_around_cut > 0 && ncells_around_active == 2) ? 1 : 0;
+  }
+}
+
 void gecut_oracle_eval_leaf(const OLeaf* leaf, int D, const double* x, int64_t n, double* out) {
   for (int64_t i = 0; i < n; ++i) out[i] = eval_leaf(*leaf, x + i * D, D);
 }

@@ -79,6 +79,7 @@ def lib():
         L.gecut_oracle_select_facets.restype = C.c_int64
         L.gecut_oracle_select_facets.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.gecut_oracle_facets_subfacet_measures.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.gecut_oracle_ghost_skeleton.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.gecut_oracle_aggregate.restype = C.c_int
         L.gecut_oracle_aggregate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]
         L.gecut_oracle_bgfacet_measure.restype = C.c_double
@@ -329,6 +330,14 @@ def oracle_aggregate(oc: "OracleCut", fc: "OracleFacetCut", prog, loc: int = IN,
     out = np.zeros(oc.Nc, np.int32)
     rc = lib().gecut_oracle_aggregate(oc.h, fc.h, p, n, int(loc), float(threshold), out.ctypes.data)
     return out, rc == 0
+
+
+def oracle_ghost_skeleton(oc: "OracleCut", fc: "OracleFacetCut", prog, in_or_out: int = IN) -> np.ndarray:
+    """`facet_to_mask` of `GhostSkeleton(cut, ActiveInOrOut(in_or_out), geo)` (EmbeddedDiscretizations.jl:504-543)."""
+    a, p, n = OracleCut._prog(prog)
+    out = np.zeros(fc.Nf, np.int8)
+    lib().gecut_oracle_ghost_skeleton(oc.h, fc.h, p, n, int(in_or_out), out.ctypes.data)
+    return out.astype(bool)
 
 
 def oracle_cut_facets(model, geo) -> "OracleFacetCut":

@@ -93,3 +93,23 @@ def test_aggregate_at_scale():
     assert dist.max() <= 3
     cg.close()
     fc.close()
+
+
+@pytest.mark.parametrize("name", ["disk_30", "disk_corner", "three_disks", "sphere", "csg", "bimaterial"])
+def test_ghost_skeleton_parity(name):
+    from gecut import GhostSkeleton, ACTIVE_IN, ACTIVE_OUT, PHYSICAL_IN
+    model, geo, nm = CASES[name]()
+    cg = cut(model, geo)
+    oc = ob.oracle_cut(model, geo)
+    ofc = ob.oracle_cut_facets(model, geo)
+    prog = cg.program(nm)
+    for sel, side in ((ACTIVE_IN, IN), (ACTIVE_OUT, OUT), (0, 0)):
+        ref = ob.oracle_ghost_skeleton(oc, ofc, prog, side)
+        mask = GhostSkeleton(cg, sel, nm)
+        assert mask.dtype == bool and np.array_equal(mask, ref)
+        ids = GhostSkeleton(cg, sel, nm, ids=True)
+        assert np.array_equal(ids, np.nonzero(ref)[0] + 1)
+    assert np.array_equal(GhostSkeleton(cg) if nm is None else GhostSkeleton(cg, nm), ob.oracle_ghost_skeleton(oc, ofc, prog, IN))
+    with pytest.raises(NotImplementedError):
+        GhostSkeleton(cg, PHYSICAL_IN, nm)
+    cg.close()

@@ -90,3 +90,25 @@ def test_cell_aggregation_csg_named_geometry():
     agg, ok = ob.oracle_aggregate(oc, fc, p, IN, 1.0)
     assert ok
     check_invariants(model, oc, fc, p, IN, 1.0, agg)
+
+
+def test_ghost_skeleton_mask():
+    # EmbeddedDiscretizations.jl:504-543: interior facets next to a CUT cell whose two cells are active
+    model = CartesianDiscreteModel((0, 1, 0, 1), (30, 30))
+    geo = disk(0.4, x0=(0.5, 0.5))
+    oc, fc = setup(model, geo)
+    p = compile_postfix(geo.get_tree(), oc.oid_to_ls)
+    st = oc.bgcell_to_inoutcut(p)
+    fn = fc.array("facet_nodes").reshape(-1, fc.nvf)
+    d, pos, minus, plus = FH.facet_cells(model, fn)
+    for side in (IN, OUT, CUT):
+        mask = ob.oracle_ghost_skeleton(oc, fc, p, side)
+        interior = (minus >= 0) & (plus >= 0)
+        assert not mask[~interior].any()
+        a, b = st[minus[interior]], st[plus[interior]]
+        act = lambda s: (s == CUT) | (s == side)
+        expect = ((a == CUT) | (b == CUT)) & act(a) & act(b)
+        assert np.array_equal(mask[interior], expect)
+        assert mask.sum() > 0
+    # ACTIVE_IN ghosts contain the CUT-only ghosts
+    assert np.all(ob.oracle_ghost_skeleton(oc, fc, p, IN)[ob.oracle_ghost_skeleton(oc, fc, p, CUT)])
