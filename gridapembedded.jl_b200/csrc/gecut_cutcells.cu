@@ -19,6 +19,7 @@
 //   L  > 1 : k_cut_fast<count> (+ k_cut_walk<count> for the recorded simplices) -> scan over simplices ->
 //            k_cut_fast<fill> (+ k_cut_walk<fill>).  k_cut_fast handles the simplices cut by at most one level set
 //            without a tree; k_cut_walk is the generic depth-first walk, restricted to the level sets with mixed signs.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -1256,7 +1257,7 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
             const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
             const int32_t* __restrict__ cutcells, int64_t nsimp, const uint32_t* __restrict__ tile_cells,
             const uint32_t* __restrict__ tile_points, const uint32_t* __restrict__ tile_facets, GcLayout lay,
-            uint32_t* __restrict__ sc_ptr) {
+            uint32_t* __restrict__ sc_ptr, double4* __restrict__ tile_stats) {
   constexpr int NT0 = SX ? 1 : (D == 3 ? 6 : 2);   // stage-0 simplices per bg cell
   constexpr int CPC = SX ? (D == 3 ? 6 : 2) : 1;   // bg cells per n-cube
   constexpr int NPC = WalkCfg<D>::NPC;
@@ -1438,6 +1439,10 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
   // ======================================== phase X: point_to_coords of the tile
   cut1_copy_doubles(lay.sc_X + (int64_t)gp * D, stage_p, tp * D, phase, lane);
   // ======================================== phase C: lane = subcell
+  // tile statistics for the selections of a single-leaf geometry (no pass over the subcells later): measure of the IN and
+  // of the OUT subcells, measure of the subfacets, number of IN subcells
+  double st_in = 0.0, st_out = 0.0, st_surf = 0.0;
+  uint32_t st_nin = 0u;
   for (uint32_t idx = lane; idx < tc; idx += CUT1_TILE) {
     const uint4 r = rec[own_c[idx]];
     const int cc = r.x & 15u;
@@ -1461,8 +1466,16 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
       for (int v = 0; v <= D; ++v) lay.sc_c2p[o * (D + 1) + v] = (int)(r.z + ((pts >> (8 * v)) & 0xFFu));
     }
     lay.sc_c2bg[o] = (int32_t)r.w;
-    lay.sc_state[o] = TC.sub_inout[cc][j];
-    lay.sc_meas[o] = integrate_one<D>(simplex_meas<D, D>(pc));
+    const int8_t io = TC.sub_inout[cc][j];
+    const double ms = integrate_one<D>(simplex_meas<D, D>(pc));
+    lay.sc_state[o] = io;
+    lay.sc_meas[o] = ms;
+    if (io == GC_IN) {
+      st_in += ms;
+      st_nin++;
+    } else {
+      st_out += ms;
+    }
   }
   // ======================================== phase D: lane = subfacet
   for (uint32_t idx = lane; idx < tf; idx += CUT1_TILE) {
@@ -1486,8 +1499,19 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
     }
     lay.sf_c2bg[o] = (int32_t)r.w;
     lay.sf_state[o] = (int8_t)GECUT_INTERFACE;
-    lay.sf_meas[o] = integrate_one<D - 1>(simplex_meas<D, D - 1>(pf));
+    const double mf = integrate_one<D - 1>(simplex_meas<D, D - 1>(pf));
+    lay.sf_meas[o] = mf;
+    st_surf += mf;
   }
+  // fixed lane assignment + fixed shuffle tree: the tile sums are reproducible
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    st_in += __shfl_xor_sync(0xffffffffu, st_in, o);
+    st_out += __shfl_xor_sync(0xffffffffu, st_out, o);
+    st_surf += __shfl_xor_sync(0xffffffffu, st_surf, o);
+    st_nin += __shfl_xor_sync(0xffffffffu, st_nin, o);
+  }
+  if (lane == 0) tile_stats[tile] = make_double4(st_in, st_out, st_surf, (double)st_nin);
   __syncwarp();
   // ======================================== phase R: reference coordinates (lane = simplex), same staging buffer
   if (valid) {
@@ -1607,6 +1631,56 @@ int dispatch_walk(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const 
 
 }  // namespace
 
+// deterministic sum of the tile statistics: fixed element -> thread -> tree order inside a block, the block that finishes
+// last adds the block partials in index order
+__global__ void __launch_bounds__(256)
+k_tile_stats_reduce(const double4* __restrict__ tile_stats, int64_t ntiles, double4* __restrict__ partial,
+                    unsigned int* __restrict__ ticket, double4* __restrict__ out) {
+  __shared__ double4 sh[256];
+  __shared__ bool s_last;
+  double4 a = make_double4(0.0, 0.0, 0.0, 0.0);
+  const int64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = per * blockIdx.x, hi = lo + per < ntiles ? lo + per : ntiles;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const double4 v = tile_stats[i];
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      double4 u = sh[threadIdx.x], v = sh[threadIdx.x + o];
+      u.x += v.x; u.y += v.y; u.z += v.z; u.w += v.w;
+      sh[threadIdx.x] = u;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = sh[0];
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double4 t = make_double4(0.0, 0.0, 0.0, 0.0);
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+    const volatile double* pv = reinterpret_cast<const volatile double*>(partial + i);
+    t.x += pv[0]; t.y += pv[1]; t.z += pv[2]; t.w += pv[3];
+  }
+  sh[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      double4 u = sh[threadIdx.x], v = sh[threadIdx.x + o];
+      u.x += v.x; u.y += v.y; u.z += v.z; u.w += v.w;
+      sh[threadIdx.x] = u;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
+}
+
 static inline int64_t pad_pitch(int64_t n) { return ((n + 255) / 256) * 256; }
 
 // L == 1: tile totals -> scan over tiles -> allocate -> fill (see the fast-path kernels above)
@@ -1678,13 +1752,21 @@ static int gc_cut_cells_l1(gecut_ctx* ctx, gecut_result* res) {
   res->sf_points_alias = true;
   sz.subfacet_points_alias = 1;
   GC_CHECK(gc_malloc(ctx, (void**)&res->cut_sc_ptr, sizeof(uint32_t) * 2 * (ncut + 1)));
+  // tile statistics -> four sums (IN / OUT subcell measure, subfacet measure, IN subcells), read back with the result
+  const int NBR = (int)std::min<int64_t>(592, gc_div_up(ntiles, 256));
+  double4* tile_stats = nullptr;
+  GC_CHECK(gc_malloc(ctx, (void**)&tile_stats, sizeof(double4) * (ntiles + NBR + 2)));
+  double4* st_partial = tile_stats + ntiles;
+  double4* st_out = st_partial + NBR;
+  unsigned int* st_ticket = reinterpret_cast<unsigned int*>(st_out + 1);
+  GC_CUDA(cudaMemsetAsync(st_ticket, 0, sizeof(unsigned int), ctx->stream));
   {
     const unsigned nbf = (unsigned)gc_div_up(ntiles, CUT1_BLOCK / CUT1_TILE);
 #define GC_FILL1(DD, SXV, MB)                                                                                          \
   GC_LAUNCH(ctx, "k_cut1_fill",                                                                                        \
             k_cut1_fill<DD, SXV, MB><<<nbf, CUT1_BLOCK, (size_t)cut1_warp_bytes<DD>() * (CUT1_BLOCK / CUT1_TILE), ctx->stream>>>( \
                 g, res->leaves, ctx->d_tables, ctx->d_simplexify_raw, ctx->d_simplexify_pos, lay.cutcells, nsimp, t_cells,   \
-                t_points, t_facets, lay, res->cut_sc_ptr))
+                t_points, t_facets, lay, res->cut_sc_ptr, tile_stats))
 #define GC_FILL2(DD, SXV) GC_FILL1(DD, SXV, CUT1_MINB)
     if (D == 2) {
       if (g.simplexified) GC_FILL2(2, true); else GC_FILL2(2, false);
@@ -1695,6 +1777,17 @@ static int gc_cut_cells_l1(gecut_ctx* ctx, gecut_result* res) {
 #undef GC_FILL1
   }
   int st = gc_launch_check(ctx, "k_cut1_fill");
+  if (st == GECUT_OK) {
+    GC_LAUNCH(ctx, "k_tile_stats_reduce", k_tile_stats_reduce<<<NBR, 256, 0, ctx->stream>>>(tile_stats, ntiles, st_partial, st_ticket, st_out));
+    st = gc_launch_check(ctx, "k_tile_stats_reduce");
+    // the copy completes before gecut_cut returns (stream synchronisation at the end of the cut)
+    if (st == GECUT_OK && cudaMemcpyAsync(res->l1_stats_pinned(), st_out, sizeof(double4), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) {
+      ctx->err = "read-back of the tile statistics failed";
+      st = GECUT_ERR_CUDA;
+    }
+    res->has_l1_stats = st == GECUT_OK;
+  }
+  gc_free(ctx, tile_stats);
   gc_free(ctx, tiles);
   gc_free(ctx, totals_dev);
   return st;

@@ -479,7 +479,13 @@ int gc_integrate_measure(gecut_ctx* ctx, const gecut_selection* sel, double* val
   const int64_t n = sel->n_sub;
   double total = 0.0;
   const bool use_sub = sel->kind == GECUT_SEL_PHYSICAL || sel->kind == GECUT_SEL_CUTONLY || sel->kind == GECUT_SEL_BOUNDARY;
-  if (use_sub && n > 0) {
+  // one level set: the sums of the fill kernel answer without a pass (per-entity values still need the gather)
+  const bool from_stats = res->has_l1_stats && !values_dev &&
+                          ((sel->sub_lazy && sel->kind != GECUT_SEL_BOUNDARY) || (sel->sub_identity && sel->kind == GECUT_SEL_BOUNDARY));
+  if (use_sub && n > 0 && from_stats) {
+    total += sel->kind == GECUT_SEL_BOUNDARY ? res->l1_stats[2] : res->l1_stats[sel->lazy_side == GECUT_IN ? 0 : 1];
+  } else if (use_sub && n > 0) {
+    GC_CHECK(gc_materialize_sub_ids(ctx, const_cast<gecut_selection*>(sel)));
     const int NB = (int)std::min<int64_t>(1184, gc_div_up(n, 1024));
     double* partial = nullptr;  // NB block partials, the total, the completion ticket
     GC_CHECK(gc_malloc(ctx, (void**)&partial, sizeof(double) * (NB + 2)));

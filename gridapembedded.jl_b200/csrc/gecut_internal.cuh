@@ -151,6 +151,11 @@ struct gecut_result {
   uint32_t* cut_sc_ptr = nullptr;  // 2*(Ncut+1): (first subcell, first subcell point) (0-based) of every cut bg cell
   unsigned long long* bg_counts_dev = nullptr;  // [L][2][6] IN / OUT bg cells per level set and cell type
   int64_t bg_counts[GC_LMAX * 12] = {0};        // host copy (filled with the cut-cell count read-back)
+  // one level set: sums written by the fill kernel ([0] measure of the IN subcells, [1] of the OUT subcells, [2] of the
+  // subfacets, [3] number of IN subcells); selections over the single leaf need no pass over the subcells
+  bool has_l1_stats = false;
+  double l1_stats[4] = {0, 0, 0, 0};
+  double* l1_stats_pinned() { return l1_stats; }
   bool sf_points_alias = false;    // L == 1: the subfacet point arrays ARE the subcell point arrays on the device
   bool owns_nodal[GC_LMAX] = {false};
   double* nodal_dev[GC_LMAX] = {nullptr};
@@ -167,6 +172,10 @@ struct gecut_selection {
   int64_t n_bg = 0;   // selected bg cells
   int32_t* sub_ids = nullptr;
   int8_t* orientation = nullptr;
+  // one level set, single-leaf program: the selected subcells are those with state == lazy_side; count and measure come
+  // from the result's tile statistics, the id list is written only when somebody asks for it
+  bool sub_lazy = false;
+  int lazy_side = 0;
   bool sub_identity = false;  // the selection is 1..n_sub with orientation +1; ids are materialised only on demand
   int32_t* bg_ids = nullptr;  // materialised lazily
   int64_t bg_type_count[8] = {0};

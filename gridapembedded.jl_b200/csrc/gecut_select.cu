@@ -297,14 +297,12 @@ int gc_compact_flags(gecut_ctx* ctx, uint32_t* flags, int64_t n, int32_t** ids_o
   return gc_launch_check(ctx, "k_scatter_ids");
 }
 
-int gc_select_cells(gecut_ctx* ctx, gecut_selection* sel) {
+// count -> scan -> emit of the selected subcells (ascending ids = findall)
+static int select_subcells_now(gecut_ctx* ctx, gecut_selection* sel) {
   const gecut_result* res = sel->res;
   const GcLayout& lay = res->lay;
-  const int64_t nsc = res->sizes.num_subcells, nc = res->sizes.num_bgcells;
-  const int T = 256;
-  const bool want_sub = sel->kind == GECUT_SEL_PHYSICAL || sel->kind == GECUT_SEL_CUTONLY;
-  const bool want_bg = sel->kind == GECUT_SEL_PHYSICAL || sel->kind == GECUT_SEL_ACTIVE || sel->kind == GECUT_SEL_BGONLY;
-  if (want_sub && nsc > 0) {
+  const int64_t nsc = res->sizes.num_subcells;
+  {
     const int64_t nblk = gc_div_up(nsc, (int64_t)SELSC_T * SELSC_PER);
     const int check_bg = res->L > 1 ? 1 : 0;  // one level set: every cut cell is CUT for every program over it
     uint32_t* counts = nullptr;
@@ -326,6 +324,29 @@ int gc_select_cells(gecut_ctx* ctx, gecut_selection* sel) {
     }
     gc_free(ctx, counts);
     gc_free(ctx, total_dev);
+  }
+  return gc_launch_check(ctx, "select_subcells");
+}
+
+int gc_select_cells(gecut_ctx* ctx, gecut_selection* sel) {
+  const gecut_result* res = sel->res;
+  const GcLayout& lay = res->lay;
+  const int64_t nsc = res->sizes.num_subcells, nc = res->sizes.num_bgcells;
+  const int T = 256;
+  const bool want_sub = sel->kind == GECUT_SEL_PHYSICAL || sel->kind == GECUT_SEL_CUTONLY;
+  const bool want_bg = sel->kind == GECUT_SEL_PHYSICAL || sel->kind == GECUT_SEL_ACTIVE || sel->kind == GECUT_SEL_BGONLY;
+  if (want_sub && nsc > 0) {
+    const GcProgram& p = sel->prog;
+    const bool leaf1 = (p.len == 1 && p.tok[0] >= 0) || (p.len == 2 && p.tok[0] >= 0 && p.tok[1] == GECUT_OP_COMPLEMENT);
+    if (res->has_l1_stats && leaf1) {
+      // one level set: count (and measure) were summed by the fill kernel; ids on demand (gc_materialize_sub_ids)
+      sel->sub_lazy = true;
+      sel->lazy_side = p.len == 1 ? sel->side : -sel->side;
+      const int64_t n_in = (int64_t)res->l1_stats[3];
+      sel->n_sub = sel->lazy_side == GECUT_IN ? n_in : nsc - n_in;
+    } else {
+      GC_CHECK(select_subcells_now(ctx, sel));
+    }
   }
   // single-leaf programs ([ls] or [ls, !]): the classification kernel already tallied IN / OUT cells per level set and
   // cell type, no pass over the Nc state bytes is needed
@@ -425,6 +446,15 @@ int gc_select_boundary(gecut_ctx* ctx, gecut_selection* sel) {
 }
 
 int gc_materialize_sub_ids(gecut_ctx* ctx, gecut_selection* sel) {
+  if (sel->sub_lazy && !sel->sub_ids && sel->n_sub > 0) {
+    const int64_t expect = sel->n_sub;
+    GC_CHECK(select_subcells_now(ctx, sel));
+    if (sel->n_sub != expect) {
+      ctx->err = "selection: id list and tile statistics disagree";
+      return GECUT_ERR_CUDA;
+    }
+    return GECUT_OK;
+  }
   if (!sel->sub_identity || sel->sub_ids || sel->n_sub <= 0) return GECUT_OK;
   const int64_t n = sel->n_sub;
   const int T = 256;
