@@ -158,13 +158,17 @@ def algorithmic_bytes(s, model, nsel, nfsel, nodal=False):
     k["k_cut1_count"] = 4 * Ncut + 12 * ntiles
     meas = 8 * (int(s.num_subcells) + int(s.num_subfacets))  # per-entity measures written next to the layout
     k["k_cut1_fill"] = 4 * Ncut + 12 * ntiles + lb["subcells"] + lb["subfacets"] + 4 * Ncut + meas
+    if L == 1:  # tile statistics (4 doubles per 32-simplex tile) and, for simplex bg cells, (IN, OUT) measure per cut cell
+        k["k_cut1_fill"] += 32 * ((nsimp + 31) // 32) + (16 * Ncut if model.simplexified else 0)
     k["k_cut_walk_fill"] += meas
     k["k_count_bgcells"] = L * Nc
     k["k_flag_subcells"] = int(s.num_subcells) * (4 + 2 * L + 4)
     k["k_flag_boundary"] = int(s.num_subfacets) * (L + 4 + 1)
     k["k_measures"] = (nsel + nfsel) * (4 + 8 + 8)  # id + gathered measure + value
     nsc = int(s.num_subcells)
-    if model.simplexified:  # P1: states + measures of the cut cells' subcells, matrices out
+    if model.simplexified and L == 1:  # P1, one level set: (IN, OUT) measure + id of every cut cell in, matrices out
+        k["k_cutcell_laplacian"] = (16 + 4) * Ncut + 8 * nv * nv * Ncut
+    elif model.simplexified:  # P1: states + measures of the cut cells' subcells, matrices out
         k["k_cutcell_laplacian"] = nsc * L + nsel * 8 + 8 * nv * nv * Ncut + 8 * Ncut
     else:  # Q1: + connectivity and reference coordinates of the selected subcells
         k["k_cutcell_laplacian"] = nsc * L + nsel * (8 + 4 * (D + 1) + 8 * D * (D + 1)) + 8 * nv * nv * Ncut + 8 * Ncut

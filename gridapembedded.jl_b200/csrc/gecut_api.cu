@@ -168,6 +168,8 @@ void free_result_arrays(gecut_result* r) {
   r->prog_rows.clear();
   gc_free(ctx, r->cut_sc_ptr);
   r->cut_sc_ptr = nullptr;
+  gc_free(ctx, r->cell_vio);
+  r->cell_vio = nullptr;
   gc_free(ctx, r->bg_counts_dev);
   r->bg_counts_dev = nullptr;
   for (int i = 0; i < GC_LMAX; ++i)

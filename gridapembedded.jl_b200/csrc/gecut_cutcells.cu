@@ -1042,10 +1042,11 @@ constexpr int CUT1_BLOCK = 128;  // threads per block of the fill kernel (4 inde
 #endif
 
 // shared memory of one warp of the fill kernel: staged points (+ phase pad), cut-edge coefficients, 16-byte records,
-// owner maps; 32-byte multiple
+// subcell measures, owner maps; 32-byte multiple
 template <int D>
 __host__ __device__ constexpr int cut1_warp_bytes() {
   return (((CUT1_TILE * ((D == 3) ? 8 : 5) * D + 4) * 8 + CUT1_TILE * ((D == 3) ? 4 : 2) * 8 + CUT1_TILE * 16 +
+           CUT1_TILE * ((D == 3) ? 6 : 3) * 8 +  // signed subcell measures of the tile (per-cell IN / OUT sums)
            CUT1_TILE * ((D == 3) ? 6 : 3) + CUT1_TILE * ((D == 3) ? 2 : 1)) + 31) / 32 * 32;
 }
 
@@ -1257,7 +1258,7 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
             const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
             const int32_t* __restrict__ cutcells, int64_t nsimp, const uint32_t* __restrict__ tile_cells,
             const uint32_t* __restrict__ tile_points, const uint32_t* __restrict__ tile_facets, GcLayout lay,
-            uint32_t* __restrict__ sc_ptr, double4* __restrict__ tile_stats) {
+            uint32_t* __restrict__ sc_ptr, double4* __restrict__ tile_stats, double2* __restrict__ cell_vio) {
   constexpr int NT0 = SX ? 1 : (D == 3 ? 6 : 2);   // stage-0 simplices per bg cell
   constexpr int CPC = SX ? (D == 3 ? 6 : 2) : 1;   // bg cells per n-cube
   constexpr int NPC = WalkCfg<D>::NPC;
@@ -1310,7 +1311,8 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
   constexpr int NCE = (D == 3) ? 4 : 2;  // a cut simplex has at most NCE cut edges
   double* cstash = stage + STG;          // [NCE][32] coefficients of the cut edges, parked here between phases A and R
   uint4* rec = reinterpret_cast<uint4*>(wbase + sizeof(double) * (STG + NCE * CUT1_TILE));
-  uint8_t* own_c = reinterpret_cast<uint8_t*>(rec + CUT1_TILE);
+  double* vstage = reinterpret_cast<double*>(rec + CUT1_TILE);  // [NSUB*32] measure of every subcell, sign bit = OUT
+  uint8_t* own_c = reinterpret_cast<uint8_t*>(vstage + CUT1_TILE * NSUB);
   uint8_t* own_f = own_c + CUT1_TILE * NSUB;
   const int64_t tile = (int64_t)blockIdx.x * (CUT1_BLOCK / CUT1_TILE) + wid;
   if (tile * CUT1_TILE >= nsimp) return;  // whole warp beyond the end (no block barrier below)
@@ -1476,6 +1478,7 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
     } else {
       st_out += ms;
     }
+    if (SX) vstage[idx] = io == GC_IN ? ms : -ms;
   }
   // ======================================== phase D: lane = subfacet
   for (uint32_t idx = lane; idx < tf; idx += CUT1_TILE) {
@@ -1513,6 +1516,18 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
   }
   if (lane == 0) tile_stats[tile] = make_double4(st_in, st_out, st_surf, (double)st_nin);
   __syncwarp();
+  if (SX && valid) {
+    // simplex bg cells: a lane is a cut cell; IN / OUT measure of the cell in subcell order (the input of the P1
+    // Laplacian and of get_cell_measure, no pass over the subcells later)
+    const uint4 rr = rec[lane];  // case and first subcell of this lane's simplex (phase A)
+    const int ns = TC.nsub[rr.x & 15u];
+    double vi = 0.0, vo = 0.0;
+    for (int j = 0; j < ns; ++j) {
+      const double v = vstage[rr.y + j];
+      if (signbit(v)) vo += -v; else vi += v;
+    }
+    cell_vio[s] = make_double2(vi, vo);  // SX: one stage-0 simplex per cut cell
+  }
   // ======================================== phase R: reference coordinates (lane = simplex), same staging buffer
   if (valid) {
 #pragma unroll
@@ -1752,6 +1767,7 @@ static int gc_cut_cells_l1(gecut_ctx* ctx, gecut_result* res) {
   res->sf_points_alias = true;
   sz.subfacet_points_alias = 1;
   GC_CHECK(gc_malloc(ctx, (void**)&res->cut_sc_ptr, sizeof(uint32_t) * 2 * (ncut + 1)));
+  if (g.simplexified) GC_CHECK(gc_malloc(ctx, (void**)&res->cell_vio, sizeof(double2) * ncut));
   // tile statistics -> four sums (IN / OUT subcell measure, subfacet measure, IN subcells), read back with the result
   const int NBR = (int)std::min<int64_t>(592, gc_div_up(ntiles, 256));
   double4* tile_stats = nullptr;
@@ -1766,7 +1782,7 @@ static int gc_cut_cells_l1(gecut_ctx* ctx, gecut_result* res) {
   GC_LAUNCH(ctx, "k_cut1_fill",                                                                                        \
             k_cut1_fill<DD, SXV, MB><<<nbf, CUT1_BLOCK, (size_t)cut1_warp_bytes<DD>() * (CUT1_BLOCK / CUT1_TILE), ctx->stream>>>( \
                 g, res->leaves, ctx->d_tables, ctx->d_simplexify_raw, ctx->d_simplexify_pos, lay.cutcells, nsimp, t_cells,   \
-                t_points, t_facets, lay, res->cut_sc_ptr, tile_stats))
+                t_points, t_facets, lay, res->cut_sc_ptr, tile_stats, res->cell_vio))
 #define GC_FILL2(DD, SXV) GC_FILL1(DD, SXV, CUT1_MINB)
     if (D == 2) {
       if (g.simplexified) GC_FILL2(2, true); else GC_FILL2(2, false);

@@ -362,6 +362,33 @@ k_cutcell_laplacian_p1(const GcGrid g, const GcLayout lay, const uint32_t* __res
   }
 }
 
+// the same with the per-cell (IN, OUT) measures the fill kernel left behind (one level set, single-leaf geometry):
+// 16 bytes read per cut cell instead of its subcell range
+template <int D>
+__global__ void __launch_bounds__(128)
+k_cutcell_laplacian_p1_vio(const GcLayout lay, int cpc, const double2* __restrict__ cell_vio, int64_t ncut, int side,
+                           const double* __restrict__ graddots, double* __restrict__ K) {
+  constexpr int NV = D + 1, NN = NV * NV;
+  const int lane = threadIdx.x & 31;
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double V = 0.0;
+  int ty = 0;
+  if (k < ncut) {
+    ty = (int)(((int64_t)lay.cutcells[k] - 1) % cpc);
+    const double2 v = cell_vio[k];
+    V = side == GC_IN ? v.x : v.y;
+  }
+  const int64_t wbase = k - lane;
+#pragma unroll
+  for (int j = 0; j < NN; ++j) {
+    const int idx = lane + 32 * j;
+    const int cl = idx / NN, en = idx % NN;
+    const double v = __shfl_sync(0xffffffffu, V, cl);
+    const int t = __shfl_sync(0xffffffffu, ty, cl);
+    if (wbase + cl < ncut) K[wbase * NN + idx] = v * graddots[t * NN + en];
+  }
+}
+
 // get_cell_measure: uncut cells (whole-cell measure per cell type when the state is `side`, else 0) ...
 __global__ void k_bgcell_measure(const GcLayout lay, int64_t nc, const GcProgram prog, int side, int cpc, int use_bg,
                                  const double* __restrict__ type_meas, double* __restrict__ out) {
@@ -529,6 +556,19 @@ int gc_integrate_laplacian(gecut_ctx* ctx, gecut_selection* sel, double* K_bg_ho
     memcpy((char*)ctx->h_pinned + 1024, Gh, sizeof(double) * g.cpc * nn);
     GC_CUDA(cudaMemcpyAsync(Gd, (char*)ctx->h_pinned + 1024, sizeof(double) * g.cpc * nn, cudaMemcpyHostToDevice, ctx->stream));
     const unsigned nb1 = (unsigned)gc_div_up(ncut, 128);
+    const GcProgram& pp = sel->prog;
+    const bool leaf1 = (pp.len == 1 && pp.tok[0] >= 0) || (pp.len == 2 && pp.tok[0] >= 0 && pp.tok[1] == GECUT_OP_COMPLEMENT);
+    if (res->cell_vio && res->L == 1 && leaf1) {
+      const int eff = pp.len == 1 ? sel->side : -sel->side;
+      if (g.D == 2)
+        GC_LAUNCH(ctx, "k_cutcell_laplacian", k_cutcell_laplacian_p1_vio<2><<<nb1, 128, 0, ctx->stream>>>(
+            res->lay, g.cpc, res->cell_vio, ncut, eff, Gd, sel->K_cut));
+      else
+        GC_LAUNCH(ctx, "k_cutcell_laplacian", k_cutcell_laplacian_p1_vio<3><<<nb1, 128, 0, ctx->stream>>>(
+            res->lay, g.cpc, res->cell_vio, ncut, eff, Gd, sel->K_cut));
+      gc_free(ctx, Gd);
+      return gc_launch_check(ctx, "k_cutcell_laplacian_p1_vio");
+    }
     if (g.D == 2)
       GC_LAUNCH(ctx, "k_cutcell_laplacian", k_cutcell_laplacian_p1<2><<<nb1, 128, 0, ctx->stream>>>(
           g, res->lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, check_bg, Gd, sel->K_cut));

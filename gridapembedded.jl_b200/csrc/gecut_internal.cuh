@@ -153,6 +153,7 @@ struct gecut_result {
   int64_t bg_counts[GC_LMAX * 12] = {0};        // host copy (filled with the cut-cell count read-back)
   // one level set: sums written by the fill kernel ([0] measure of the IN subcells, [1] of the OUT subcells, [2] of the
   // subfacets, [3] number of IN subcells); selections over the single leaf need no pass over the subcells
+  double2* cell_vio = nullptr;  // one level set, simplex bg cells: (IN, OUT) subcell measure of every cut cell (fill kernel)
   bool has_l1_stats = false;
   double l1_stats[4] = {0, 0, 0, 0};
   double* l1_stats_pinned() { return l1_stats; }
