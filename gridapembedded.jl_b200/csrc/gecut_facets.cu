@@ -115,46 +115,46 @@ k_node_signs(const GcGrid g, const GcLeaves lv, int wxt, uint32_t* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 // K2: states of every facet per level set (_compute_in_out_or_cut on the facet grid, CutTriangulations.jl:619-640) and
 //     the ascending list of the cut facets (_find_cut_cells :481-493).  The facets a row of cells meets first are a
-//     contiguous id range (closed form, no division).  A warp owns a segment of FR_SEG cells of one row and walks it in
-//     chunks of 128 cells: a lane derives the states of the D..D+3 new facets of a cell from the 2^D corner sign bits
-//     (warp-uniform, L2-resident sign words).  EMIT = false: the states are staged in the warp's slice of shared memory
-//     with the 16-byte alignment of their global destination and leave as 16-byte stores (no block barrier); the
-//     segment's number of cut facets is recorded.  EMIT = true (after the scan over segments): the cut facets of the
-//     segment are written in id order.
+//     contiguous id range (closed form), and consecutive rows are consecutive ranges, so the model's facets are ONE byte
+//     stream ordered by (row, x word).  A lane owns a word = 32 cells of a row and works bit-parallel: the "all OUT" /
+//     "any OUT" masks of a facet kind are AND / OR of the node sign words of the rows it touches (x+1 by funnel shift),
+//     3-5 kinds per word.  A warp owns 32 consecutive words = one contiguous piece of the stream.
+//       EMIT = false: pieces with one sign on all nodes (all but the O(n^2) pieces a surface crosses) are written as
+//       constant 16-byte stores; otherwise lanes expand their masks into the warp's shared-memory slice (constant fill for
+//       lanes with one sign) and the piece leaves as aligned 16-byte stores.  Tallies (IN/OUT x direction x boundary) are
+//       popcounts; the number of cut facets of every piece is recorded.
+//       EMIT = true (after the scan over pieces): the cut facets of the piece are written in id order.
 // ------------------------------------------------------------------------------------------------
-constexpr int FR_SEG = 1024;  // cells per warp segment
-constexpr int FR_WCH = 128;   // cells per warp iteration
-constexpr int FR_STAGE = FR_WCH * 5 + 1 + 16 + 15;
+constexpr int FR_SEG = 1024;  // cells per warp segment (k_facet_rows_count)
+constexpr int FW_ITER = 4;    // pieces per warp
 
 // tallies of the whole facets per level set, fused into K2: index ((s*3 + d)*2 + isb), s = 0 IN / 1 OUT, d = normal
 // direction, isb = facet on the boundary of the model.  A selection over a single-leaf geometry reads its whole-facet
 // counts from here (no pass over the facets at all).
 constexpr int FT_N = 12;
 
-// 12 tallies packed in 16-bit fields of three 64-bit words (a warp segment has at most 2 * FR_SEG facets per field)
-struct Tally3 {
-  unsigned long long w0, w1, w2;
-  __device__ __forceinline__ void add(int c, uint32_t n) {
-    const unsigned long long inc = (unsigned long long)n << (16 * (c & 3));
-    const int wi = c >> 2;
-    w0 += wi == 0 ? inc : 0ull;
-    w1 += wi == 1 ? inc : 0ull;
-    w2 += wi == 2 ? inc : 0ull;
-  }
-  __device__ __forceinline__ uint32_t get(int c) const {
-    const unsigned long long w = (c >> 2) == 0 ? w0 : ((c >> 2) == 1 ? w1 : w2);
-    return (uint32_t)((w >> (16 * (c & 3))) & 0xffffull);
-  }
-};
+template <int D>
+__host__ __device__ constexpr int fw_stage_bytes() { return 32 * (32 * (D + 2) + 1) + 32; }
+
+// `len` copies of byte b at dst (shared memory, any alignment): bytes up to the first 4-byte boundary, then words
+__device__ __forceinline__ void fw_fill(uint8_t* dst, int len, uint8_t b) {
+  int p = 0;
+  while (p < len && ((reinterpret_cast<uintptr_t>(dst + p)) & 3u)) dst[p++] = b;
+  const uint32_t b4 = (uint32_t)b * 0x01010101u;
+  for (; p + 4 <= len; p += 4) *reinterpret_cast<uint32_t*>(dst + p) = b4;
+  for (; p < len; ++p) dst[p] = b;
+}
 
 template <int D, bool EMIT>
 __global__ void __launch_bounds__(256)
-k_facet_rows(const GcGrid g, int L, int wxt, const uint32_t* __restrict__ signs, int64_t ls_stride,
-             int8_t* __restrict__ state, int64_t pitch, uint32_t* __restrict__ seg_counts,
-             int32_t* __restrict__ cutfacets, int nseg_per_row, int64_t nsegs,
-             unsigned long long* __restrict__ tallies) {
+k_facet_words(const GcGrid g, int L, int wxt, int wpr, const uint32_t* __restrict__ signs, int64_t ls_stride,
+              int8_t* __restrict__ state, int64_t pitch, uint32_t* __restrict__ piece_counts,
+              int32_t* __restrict__ cutfacets, int64_t nitems, int64_t npieces, unsigned long long* __restrict__ tallies) {
   constexpr int NR = 1 << (D - 1);
-  __shared__ __align__(16) uint8_t s_stage[EMIT ? 1 : 8][EMIT ? 16 : ((FR_STAGE + 15) & ~15)];
+  // fixed slots of the facet kinds in local order: (low, high) of the directions D-1 .. 1, then x-high; the low slots
+  // exist only in rows with index 0 along that direction, the x-low facet only for cell 0 of a row (handled apart)
+  constexpr int NKS = 2 * (D - 1) + 1;
+  __shared__ __align__(16) uint8_t s_stage[EMIT ? 1 : 8][EMIT ? 16 : ((fw_stage_bytes<D>() + 15) & ~15)];
   __shared__ uint32_t s_tally[EMIT ? 1 : GC_LMAX * FT_N];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (!EMIT) {
@@ -162,203 +162,201 @@ k_facet_rows(const GcGrid g, int L, int wxt, const uint32_t* __restrict__ signs,
     __syncthreads();
   }
   const int64_t gw = (int64_t)blockIdx.x * 8 + warp;
-  if (gw < nsegs) {
-    const int row = (int)(gw / nseg_per_row), seg = (int)(gw % nseg_per_row);
-    const int j = D == 3 ? row % g.n[1] : row;
-    const int k = D == 3 ? row / g.n[1] : 0;
-    const int per = D + (j == 0 ? 1 : 0) + ((D == 3 && k == 0) ? 1 : 0);
-    const int64_t rowbase = facet_row_base<D>(g, j, k);
-    const int nx = g.n[0];
-    const int i_beg = seg * FR_SEG, i_end = min(nx, i_beg + FR_SEG);
-    uint8_t* stage = s_stage[EMIT ? 0 : warp];
+  uint8_t* stage = s_stage[EMIT ? 0 : warp];
+  const int nx = g.n[0];
+  for (int it = 0; it < FW_ITER; ++it) {
+    const int64_t piece = gw * FW_ITER + it;
+    if (piece >= npieces) break;  // warp-uniform
+    const int64_t t = piece * 32 + lane;
+    const bool valid = t < nitems;
+    // ---- this lane's word: row (j,k), word w, cells, position in the facet stream
+    const uint32_t tt = valid ? (uint32_t)t : (uint32_t)(nitems - 1);
+    const uint32_t row = tt / (uint32_t)wpr;
+    const int w = (int)(tt - row * (uint32_t)wpr);
+    const int j = D == 3 ? (int)(row % (uint32_t)g.n[1]) : (int)row;
+    const int k = D == 3 ? (int)(row / (uint32_t)g.n[1]) : 0;
+    const bool lowp[3] = {false, j == 0, D == 3 && k == 0};  // low facets present, by direction
+    const bool hib[3] = {false, j == g.n[1] - 1, D == 3 && k == g.n[2] - 1};  // high facets of the row on the boundary
+    const int per = D + (lowp[1] ? 1 : 0) + (lowp[2] ? 1 : 0);
+    const int ncell = valid ? min(32, nx - 32 * w) : 0;
+    const uint32_t cmask = ncell == 32 ? 0xffffffffu : ((1u << ncell) - 1u);
+    const int64_t start = facet_row_base<D>(g, j, k) + (int64_t)32 * w * per + (w > 0 ? 1 : 0);
+    const int len = valid ? ncell * per + (w == 0 ? 1 : 0) : 0;
+    const int64_t start0 = __shfl_sync(0xffffffffu, start, 0);
+    // lanes are consecutive words of the stream: the piece is [start0, start of the last valid lane + its length)
+    const int last = (int)min((int64_t)31, nitems - 1 - piece * 32);
+    const int total_len = (int)(__shfl_sync(0xffffffffu, start, last) - start0) + __shfl_sync(0xffffffffu, len, last);
+    const int align = (int)(start0 & 15);
+    const int off = (int)(start - start0) + align;  // of this lane's first byte in the staging slice
+    const bool has_xl = valid && w == 0;
+    const bool lastword = valid && 32 * w + ncell == nx;  // the x-high facet of its last cell is a boundary facet
     int64_t nrow[NR];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) nrow[r] = ((int64_t)(k + (r >> 1)) * g.nn[1] + (j + (r & 1))) * wxt;
-    const bool hi1 = j == g.n[1] - 1, hi2 = D == 3 && k == g.n[2] - 1;  // the row's y-high / z-high facets are boundary
-    uint32_t running = EMIT ? seg_counts[gw] : 0u, total = 0u;
-    Tally3 acc = {0ull, 0ull, 0ull};  // lane ls holds the tallies of level set ls
-    // tallies of `nc` consecutive cells from `first`, all of whose facets have state index sidx (warp-uniform)
-    auto tally_uniform = [&](Tally3& t, int sidx, int first, int nc) {
-      if (D == 3) {
-        if (k == 0) t.add((sidx * 3 + 2) * 2 + 1, nc);
-        t.add((sidx * 3 + 2) * 2 + (hi2 ? 1 : 0), nc);
+    for (int r = 0; r < NR; ++r) nrow[r] = ((int64_t)(k + (r >> 1)) * g.nn[1] + (j + (r & 1))) * wxt + w;
+    uint32_t cut[NKS];  // cut facets of this word per slot, over all level sets
+#pragma unroll
+    for (int q = 0; q < NKS; ++q) cut[q] = 0u;
+    bool xl_cut = false;
+    for (int ls = 0; ls < L; ++ls) {
+      const uint32_t* sg = signs + (int64_t)ls * ls_stride;
+      uint32_t S[NR], X[NR];
+      uint32_t n_or = 0u, n_and = 0xffffffffu;  // over the (ncell + 1) x NR nodes of the word
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        S[r] = valid ? __ldg(sg + nrow[r]) : 0u;
+        const uint32_t nxt = (valid && w + 1 < wxt) ? __ldg(sg + nrow[r] + 1) : 0u;
+        X[r] = __funnelshift_r(S[r], nxt, 1);  // bit c = sign of node 32w + c + 1
+        n_or |= (S[r] | X[r]) & cmask;
+        n_and &= (S[r] & X[r]) | ~cmask;
       }
-      if (j == 0) t.add((sidx * 3 + 1) * 2 + 1, nc);
-      t.add((sidx * 3 + 1) * 2 + (hi1 ? 1 : 0), nc);
-      const uint32_t last = first + nc == nx ? 1u : 0u;  // x-high of the last cell of the row is a boundary facet
-      t.add((sidx * 3 + 0) * 2 + 1, (first == 0 ? 1u : 0u) + last);
-      t.add((sidx * 3 + 0) * 2 + 0, (uint32_t)nc - last);
-    };
-    for (int i0 = i_beg; i0 < i_end; i0 += FR_WCH) {
-      const int chunk_cells = min(FR_WCH, i_end - i0);
-      const int chunk_off = i0 * per + (i0 > 0 ? 1 : 0);
-      const int chunk_len = chunk_cells * per + (i0 == 0 ? 1 : 0);
-      const int align = (int)((rowbase + chunk_off) & 15);
-      uint32_t anybits[4] = {0u, 0u, 0u, 0u};
-      const int w0 = i0 >> 5;
-      for (int ls = 0; ls < L; ++ls) {
-        const uint32_t* sg = signs + (int64_t)ls * ls_stride;
-        uint32_t W[NR][5];
-        // sign of the 33 nodes of every 32-cell group: 0 mixed, 1 all IN, 2 all OUT (warp-uniform)
-        uint32_t g_or[4] = {0u, 0u, 0u, 0u}, g_and[4] = {~0u, ~0u, ~0u, ~0u};
+      const bool u_in = n_or == 0u, u_out = n_and == 0xffffffffu;
+      const bool w_in = __all_sync(0xffffffffu, u_in || !valid), w_out = __all_sync(0xffffffffu, u_out || !valid);
+      uint32_t all[NKS], any[NKS];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
+      for (int q = 0; q < NKS; ++q) {
+        uint32_t a = 0xffffffffu, o = 0u;
+        if (q < 2 * (D - 1)) {
+          const int d = D - 1 - q / 2, sd = q & 1;  // node rows on side sd of direction d: bit (d-1) of r
 #pragma unroll
-          for (int q = 0; q < 5; ++q) W[r][q] = (w0 + q < wxt) ? __ldg(sg + nrow[r] + w0 + q) : 0u;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            g_or[q] |= W[r][q] | (W[r][q + 1] & 1u);
-            g_and[q] &= W[r][q] & (W[r][q + 1] | ~1u);
-          }
-        }
-        int gu[4];
-        bool all_in = chunk_cells == FR_WCH, all_out = chunk_cells == FR_WCH;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const bool full = i0 + q * 32 + 32 <= i_end;
-          gu[q] = !full ? 0 : (g_or[q] == 0u ? 1 : (g_and[q] == 0xffffffffu ? 2 : 0));
-          all_in &= gu[q] == 1;
-          all_out &= gu[q] == 2;
-        }
-        // ---- whole chunk on one side (the bulk of the model): constant 16-byte stores, closed-form tallies
-        if (all_in || all_out) {
-          if (!EMIT) {
-            const uint32_t b4 = all_in ? 0xffffffffu : 0x01010101u;
-            const uint4 cv = make_uint4(b4, b4, b4, b4);
-            int8_t* g0 = state + (int64_t)ls * pitch + rowbase + chunk_off - align;
-            const int end = align + chunk_len;
-            for (int p0 = lane * 16; p0 + 16 <= end; p0 += 512)
-              if (p0 >= align) *reinterpret_cast<uint4*>(g0 + p0) = cv;
-            if (align != 0 && lane >= align && lane < 16 && lane < end) g0[lane] = (int8_t)(b4 & 0xffu);
-            {
-              const int tail0 = end & ~15;
-              const int p = tail0 + (lane & 15);
-              if (lane >= 16 && p < end && p >= align && (tail0 > 0 || align == 0)) g0[p] = (int8_t)(b4 & 0xffu);
+          for (int r = 0; r < NR; ++r)
+            if (((r >> (d - 1)) & 1) == sd) {
+              a &= S[r] & X[r];
+              o |= S[r] | X[r];
             }
-            if (lane == ls) tally_uniform(acc, all_in ? 0 : 1, i0, FR_WCH);
+        } else {
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            a &= X[r];
+            o |= X[r];
           }
-          continue;
         }
-        // ---- general path: a lane per cell, 4 cells per lane; 32-cell groups on one side skip the corner logic.
-        //      Tallies come from warp ballots (warp-uniform adds, no reduction)
-        Tally3 tu = {0ull, 0ull, 0ull};
+        all[q] = a & cmask;
+        any[q] = o & cmask;
+      }
+      uint32_t xl_all = 1u, xl_any = 0u;  // x-low facet of cell 0 (word 0 only): nodes i = 0 of all rows
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int i = i0 + q * 32 + lane;
-          const int loc = i * per + (i > 0 ? 1 : 0) - chunk_off + align;
-          if (gu[q] != 0) {
-            if (!EMIT) {
-              const uint8_t b = gu[q] == 1 ? (uint8_t)0xff : (uint8_t)0x01;
-              const int nfac = per + (i == 0 ? 1 : 0);
+      for (int r = 0; r < NR; ++r) {
+        xl_all &= S[r] & 1u;
+        xl_any |= S[r] & 1u;
+      }
 #pragma unroll
-              for (int t = 0; t < D + 3; ++t)
-                if (t < nfac) stage[loc + t] = b;
-              tally_uniform(tu, gu[q] - 1, i0 + q * 32, 32);
-            }
-            continue;
+      for (int q = 0; q < NKS; ++q) {
+        const bool present = q >= 2 * (D - 1) || (q & 1) || lowp[D - 1 - q / 2];
+        if (present) cut[q] |= any[q] & ~all[q];
+      }
+      if (has_xl && xl_any && !xl_all) xl_cut = true;
+      if (!EMIT) {
+        // ---- tallies of this level set: popcounts, summed over the warp
+        uint32_t tl[FT_N];
+#pragma unroll
+        for (int c = 0; c < FT_N; ++c) tl[c] = 0u;
+#pragma unroll
+        for (int q = 0; q < NKS; ++q) {
+          const uint32_t nin = (uint32_t)__popc(~any[q] & cmask), nout = (uint32_t)__popc(all[q]);
+          if (q < 2 * (D - 1)) {
+            const int d = D - 1 - q / 2;
+            const bool low = (q & 1) == 0;
+            if (low && !lowp[d]) continue;
+            const bool isb = low || hib[d];
+            tl[(0 * 3 + d) * 2 + 0] += isb ? 0u : nin;
+            tl[(0 * 3 + d) * 2 + 1] += isb ? nin : 0u;
+            tl[(1 * 3 + d) * 2 + 0] += isb ? 0u : nout;
+            tl[(1 * 3 + d) * 2 + 1] += isb ? nout : 0u;
+          } else {
+            const uint32_t lb = lastword ? (1u << (ncell - 1)) : 0u;  // the boundary x-high facet
+            const uint32_t bin = (~any[q] & lb) ? 1u : 0u, bout = (all[q] & lb) ? 1u : 0u;
+            tl[(0 * 3 + 0) * 2 + 0] += nin - bin;
+            tl[(0 * 3 + 0) * 2 + 1] += bin;
+            tl[(1 * 3 + 0) * 2 + 0] += nout - bout;
+            tl[(1 * 3 + 0) * 2 + 1] += bout;
           }
-          uint32_t sm = 0u;
+        }
+        if (has_xl) {
+          if (!xl_any) tl[(0 * 3 + 0) * 2 + 1] += 1u;
+          if (xl_all) tl[(1 * 3 + 0) * 2 + 1] += 1u;
+        }
 #pragma unroll
-          for (int r = 0; r < NR; ++r) sm |= (__funnelshift_r(W[r][q], W[r][q + 1], lane) & 3u) << (2 * r);
-          const bool valid = i < i_end;
-          const uint32_t lastm = __ballot_sync(0xffffffffu, valid && i == nx - 1);
-          int t = 0;
+        for (int c = 0; c < FT_N; ++c) {
+          if (D == 2 && ((c >> 1) % 3) == 2) continue;  // no z direction
+          const uint32_t v = __reduce_add_sync(0xffffffffu, tl[c]);
+          if (lane == 0 && v) atomicAdd(&s_tally[ls * FT_N + c], v);
+        }
+        // ---- states
+        int8_t* g0 = state + (int64_t)ls * pitch + start0 - align;
+        const int end = align + total_len;
+        if (w_in || w_out) {
+          const uint32_t b4 = w_in ? 0xffffffffu : 0x01010101u;
+          const uint4 cv = make_uint4(b4, b4, b4, b4);
+          for (int p0 = lane * 16; p0 + 16 <= end; p0 += 512)
+            if (p0 >= align) *reinterpret_cast<uint4*>(g0 + p0) = cv;
+          if (align != 0 && lane >= align && lane < 16 && lane < end) g0[lane] = (int8_t)(b4 & 0xffu);
+          const int tail0 = end & ~15;
+          const int p = tail0 + (lane & 15);
+          if (lane >= 16 && p < end && p >= align && (tail0 > 0 || align == 0)) g0[p] = (int8_t)(b4 & 0xffu);
+        } else {
+          if (valid) {
+            if (u_in || u_out) {
+              fw_fill(stage + off, len, u_in ? (uint8_t)0xff : (uint8_t)0x01);
+            } else {
+              int p = off;
+              for (int c = 0; c < ncell; ++c) {
 #pragma unroll
-          for (int d = D - 1; d >= 0; --d) {
-            const bool hib = d == 1 ? hi1 : hi2;  // d >= 1 only
-            const uint32_t mlow = D == 3 ? (d == 0 ? 0x55u : (d == 1 ? 0x33u : 0x0Fu)) : (d == 0 ? 0x5u : 0x3u);
-            const uint32_t mhigh = D == 3 ? (d == 0 ? 0xAAu : (d == 1 ? 0xCCu : 0xF0u)) : (d == 0 ? 0xAu : 0xCu);
-#pragma unroll
-            for (int sd = 0; sd < 2; ++sd) {
-              // low facets: rows with index 0 along d (warp-uniform for d >= 1; the cell i == 0 alone for d == 0)
-              if (sd == 0 && d >= 1 && (d == 1 ? j : k) != 0) continue;
-              const uint32_t m = sd == 0 ? mlow : mhigh;
-              const uint32_t v = sm & m;
-              const int8_t st = v == 0u ? (int8_t)GC_IN : (v == m ? (int8_t)GC_OUT : (int8_t)GC_CUT);
-              const bool mine = valid && !(sd == 0 && d == 0 && i != 0);
-              if (mine) {
-                if (st == GC_CUT) anybits[q] |= 1u << t;
-                if (!EMIT) stage[loc + t] = (uint8_t)st;
-                t++;
-              }
-              if (!EMIT) {
-                const uint32_t m_in = __ballot_sync(0xffffffffu, mine && st == GC_IN);
-                const uint32_t m_out = __ballot_sync(0xffffffffu, mine && st == GC_OUT);
-                if (d >= 1) {
-                  const int isb = (sd == 0 || hib) ? 1 : 0;
-                  tu.add((0 * 3 + d) * 2 + isb, (uint32_t)__popc(m_in));
-                  tu.add((1 * 3 + d) * 2 + isb, (uint32_t)__popc(m_out));
-                } else if (sd == 0) {
-                  tu.add((0 * 3 + 0) * 2 + 1, (uint32_t)__popc(m_in));
-                  tu.add((1 * 3 + 0) * 2 + 1, (uint32_t)__popc(m_out));
-                } else {
-                  tu.add((0 * 3 + 0) * 2 + 1, (uint32_t)__popc(m_in & lastm));
-                  tu.add((0 * 3 + 0) * 2 + 0, (uint32_t)__popc(m_in & ~lastm));
-                  tu.add((1 * 3 + 0) * 2 + 1, (uint32_t)__popc(m_out & lastm));
-                  tu.add((1 * 3 + 0) * 2 + 0, (uint32_t)__popc(m_out & ~lastm));
+                for (int q = 0; q < NKS; ++q) {
+                  const bool present = q >= 2 * (D - 1) || (q & 1) || lowp[D - 1 - q / 2];
+                  if (!present) continue;
+                  if (q == NKS - 1 && c == 0 && has_xl)  // x-low of cell 0 sits before its x-high
+                    stage[p++] = xl_all ? (uint8_t)0x01 : (xl_any ? (uint8_t)0x00 : (uint8_t)0xff);
+                  const uint32_t ab = (all[q] >> c) & 1u, ob = (any[q] >> c) & 1u;
+                  stage[p++] = ab ? (uint8_t)0x01 : (ob ? (uint8_t)0x00 : (uint8_t)0xff);
                 }
               }
             }
           }
-        }
-        if (!EMIT) {
           __syncwarp();
-          // stage[align + q] <-> global g0 + q: aligned 16-byte blocks inside the chunk leave as one store, the bytes
-          // of the head and tail blocks one per lane
-          int8_t* g0 = state + (int64_t)ls * pitch + rowbase + chunk_off - align;
-          const int end = align + chunk_len;
           for (int p0 = lane * 16; p0 + 16 <= end; p0 += 512)
             if (p0 >= align) *reinterpret_cast<uint4*>(g0 + p0) = *reinterpret_cast<const uint4*>(stage + p0);
           if (align != 0 && lane >= align && lane < 16 && lane < end) g0[lane] = (int8_t)stage[lane];
-          {
-            const int tail0 = end & ~15;
-            const int p = tail0 + (lane & 15);
-            if (lane >= 16 && p < end && p >= align && (tail0 > 0 || align == 0)) g0[p] = (int8_t)stage[p];
-          }
-          if (lane == ls) {
-            acc.w0 += tu.w0;
-            acc.w1 += tu.w1;
-            acc.w2 += tu.w2;
-          }
+          const int tail0 = end & ~15;
+          const int p = tail0 + (lane & 15);
+          if (lane >= 16 && p < end && p >= align && (tail0 > 0 || align == 0)) g0[p] = (int8_t)stage[p];
           __syncwarp();
         }
       }
-      if (!EMIT) {
-        total += (uint32_t)(__popc(anybits[0]) + __popc(anybits[1]) + __popc(anybits[2]) + __popc(anybits[3]));
-      } else if (__any_sync(0xffffffffu, (anybits[0] | anybits[1] | anybits[2] | anybits[3]) != 0u)) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t cnt = (uint32_t)__popc(anybits[q]);
-          uint32_t inc = cnt;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += up;
-          }
-          const uint32_t qtot = __shfl_sync(0xffffffffu, inc, 31);
-          if (qtot) {
-            const int i = i0 + q * 32 + lane;
-            uint32_t pos = running + inc - cnt;
-            uint32_t bits = anybits[q];
-            while (bits) {
-              const int t = __ffs(bits) - 1;
-              bits &= bits - 1u;
-              cutfacets[pos++] = (int32_t)(rowbase + (int64_t)i * per + (i > 0 ? 1 : 0) + t + 1);
-            }
-            running += qtot;
-          }
-        }
-      }
     }
+    // ---- cut facets of the piece
+    uint32_t cnt = xl_cut ? 1u : 0u;
+#pragma unroll
+    for (int q = 0; q < NKS; ++q) cnt += (uint32_t)__popc(cut[q]);
     if (!EMIT) {
+      const uint32_t tot = __reduce_add_sync(0xffffffffu, cnt);
+      if (lane == 0) piece_counts[piece] = tot;
+    } else {
+      uint32_t inc = cnt;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-      if (lane == 0) seg_counts[gw] = total;
-      if (lane < L) {
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += up;
+      }
+      if (cnt) {
+        uint32_t pos = piece_counts[piece] + inc - cnt;
+        uint32_t m = xl_cut ? 1u : 0u;
 #pragma unroll
-        for (int c = 0; c < FT_N; ++c) {
-          const uint32_t v = acc.get(c);
-          if (v) atomicAdd(&s_tally[lane * FT_N + c], v);
+        for (int q = 0; q < NKS; ++q) m |= cut[q];
+        while (m) {
+          const int c = __ffs(m) - 1;
+          m &= m - 1u;
+          int64_t f = start + (int64_t)c * per + ((w == 0 && c > 0) ? 1 : 0);
+#pragma unroll
+          for (int q = 0; q < NKS; ++q) {
+            const bool present = q >= 2 * (D - 1) || (q & 1) || lowp[D - 1 - q / 2];
+            if (!present) continue;
+            if (q == NKS - 1 && c == 0 && w == 0) {  // x-low of cell 0
+              if (xl_cut) cutfacets[pos++] = (int32_t)(f + 1);
+              f++;
+            }
+            if ((cut[q] >> c) & 1u) cutfacets[pos++] = (int32_t)(f + 1);
+            f++;
+          }
         }
       }
     }
@@ -743,8 +741,13 @@ int classify_facets(gecut_ctx* ctx, gecut_facet_result* r) {
   const int64_t node_rows = D == 3 ? (int64_t)g.nn[1] * g.nn[2] : (int64_t)g.nn[1];
   const int64_t ls_stride = node_rows * wxt;
   const int64_t nrows = D == 3 ? (int64_t)g.n[1] * g.n[2] : (int64_t)g.n[1];
-  const int nseg_per_row = (int)gc_div_up(g.n[0], FR_SEG);
-  const int64_t nsegs = nrows * nseg_per_row;
+  const int wpr = (int)gc_div_up(g.n[0], 32);  // cell words per row
+  const int64_t nitems = nrows * wpr;
+  const int64_t npieces = gc_div_up(nitems, 32);
+  if (nitems >= 4294967295ll) {
+    ctx->err = "cut_facets: model too large";
+    return GECUT_ERR_OVERFLOW;
+  }
   dim3 sgrid((unsigned)wxt, 1u, 1u), sblock(32, 8);
   if (D == 3) {
     sgrid.y = (unsigned)gc_div_up(g.nn[1], 8);
@@ -760,18 +763,18 @@ int classify_facets(gecut_ctx* ctx, gecut_facet_result* r) {
   uint32_t* seg_counts = nullptr;
   uint64_t* total_dev = nullptr;
   GC_CHECK(gc_malloc(ctx, (void**)&signs, sizeof(uint32_t) * ls_stride * L));
-  GC_CHECK(gc_malloc(ctx, (void**)&seg_counts, sizeof(uint32_t) * nsegs));
+  GC_CHECK(gc_malloc(ctx, (void**)&seg_counts, sizeof(uint32_t) * npieces));
   GC_CHECK(gc_malloc(ctx, (void**)&total_dev, sizeof(uint64_t) * (1 + GC_LMAX * FT_N)));
   GC_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(uint64_t) * (1 + GC_LMAX * FT_N), ctx->stream));
   GC_LAUNCH(ctx, "k_node_signs", k_node_signs<D><<<sgrid, sblock, 0, ctx->stream>>>(g, r->leaves, wxt, signs, ls_stride));
   GC_CHECK(gc_launch_check(ctx, "k_node_signs"));
-  const unsigned nb = (unsigned)gc_div_up(nsegs, 8);
-  GC_LAUNCH(ctx, "k_facet_rows",
-            (k_facet_rows<D, false><<<nb, 256, 0, ctx->stream>>>(g, L, wxt, signs, ls_stride, r->lay.bg_state, r->lay.bg_pitch,
-                                                               seg_counts, nullptr, nseg_per_row, nsegs,
-                                                               (unsigned long long*)(total_dev + 1))));
-  GC_CHECK(gc_launch_check(ctx, "k_facet_rows"));
-  GC_CHECK(gc_exclusive_scan_u32(ctx, seg_counts, seg_counts, nsegs, total_dev));
+  const unsigned nb = (unsigned)gc_div_up(gc_div_up(npieces, FW_ITER), 8);
+  GC_LAUNCH(ctx, "k_facet_words",
+            (k_facet_words<D, false><<<nb, 256, 0, ctx->stream>>>(g, L, wxt, wpr, signs, ls_stride, r->lay.bg_state,
+                                                                r->lay.bg_pitch, seg_counts, nullptr, nitems, npieces,
+                                                                (unsigned long long*)(total_dev + 1))));
+  GC_CHECK(gc_launch_check(ctx, "k_facet_words"));
+  GC_CHECK(gc_exclusive_scan_u32(ctx, seg_counts, seg_counts, npieces, total_dev));
   uint64_t hbuf[1 + GC_LMAX * FT_N];
   GC_CHECK(read_u64(ctx, total_dev, 1 + L * FT_N, hbuf));
   const uint64_t total = hbuf[0];
@@ -779,10 +782,10 @@ int classify_facets(gecut_ctx* ctx, gecut_facet_result* r) {
   r->sizes.num_cutfacets = (int64_t)total;
   if (total > 0) {
     GC_CHECK(gc_malloc(ctx, (void**)&r->lay.cutfacets, sizeof(int32_t) * total));
-    GC_LAUNCH(ctx, "k_facet_rows_emit",
-              (k_facet_rows<D, true><<<nb, 256, 0, ctx->stream>>>(g, L, wxt, signs, ls_stride, nullptr, 0, seg_counts,
-                                                                r->lay.cutfacets, nseg_per_row, nsegs, nullptr)));
-    GC_CHECK(gc_launch_check(ctx, "k_facet_rows_emit"));
+    GC_LAUNCH(ctx, "k_facet_words_emit",
+              (k_facet_words<D, true><<<nb, 256, 0, ctx->stream>>>(g, L, wxt, wpr, signs, ls_stride, nullptr, 0, seg_counts,
+                                                                 r->lay.cutfacets, nitems, npieces, nullptr)));
+    GC_CHECK(gc_launch_check(ctx, "k_facet_words_emit"));
   }
   gc_free(ctx, signs);
   gc_free(ctx, seg_counts);
