@@ -511,6 +511,7 @@ k_facet_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict
             }
             lay.c2bg[cid] = facet1;
             lay.meas[cid] = integrate_one<DS>(simplex_meas<D, DS>(pc));
+            lay.isb[cid] = facet_is_boundary<D>(g, fi) ? 1 : 0;
             lay.state[cid] = T.sub_inout[c][j];
             for (int kk = 1; kk < L; ++kk) lay.state[(int64_t)kk * lay.pitch + cid] = st[kk];
           }
@@ -638,17 +639,80 @@ __global__ void k_facet_flag_bg(const GcGrid g, const int8_t* __restrict__ rows,
   flags[f] = (in_trian && (mode == 1 ? a == side : (a == GC_CUT || a == side))) ? 1u : 0u;
 }
 
-template <int D>
-__global__ void k_facet_flag_sub(const GcGrid g, const GcFacetLayout lay, int64_t nsf, const GcProgram prog, int which,
-                                 int side, uint32_t* __restrict__ flags) {
+// sub-facet e belongs to BoundaryTriangulation / SkeletonTriangulation(cut_facets, CutInOrOut(side), geo)
+// (EmbeddedFacetDiscretizations.jl:167-190): bg facet CUT, sub-facet on `side`, bg facet in the triangulation
+__device__ __forceinline__ bool facet_sub_selected(const GcFacetLayout& lay, int L, const GcProgram& prog, int which, int side,
+                                                   int64_t e) {
+  if ((lay.isb[e] != 0) != (which == GECUT_FACETS_BOUNDARY)) return false;
+  if (gc_eval_inoutcut(prog, lay.state, lay.pitch, e) != side) return false;
+  // one level set: a sub-facet only exists in a facet that level set cuts
+  return L == 1 || gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, (int64_t)lay.c2bg[e] - 1) == GC_CUT;
+}
+
+__global__ void k_facet_flag_sub(const GcFacetLayout lay, int L, int64_t nsf, const GcProgram prog, int which, int side,
+                                 uint32_t* __restrict__ flags) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nsf) return;
-  const int64_t f = (int64_t)lay.c2bg[e] - 1;
-  const FacetIdx fi = facet_decode<D>(g, (uint32_t)f);
-  const bool in_trian = facet_is_boundary<D>(g, fi) == (which == GECUT_FACETS_BOUNDARY);
-  const int a = gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, f);
-  const int b = gc_eval_inoutcut(prog, lay.state, lay.pitch, e);
-  flags[e] = (in_trian && a == GC_CUT && b == side) ? 1u : 0u;
+  flags[e] = facet_sub_selected(lay, L, prog, which, side, e) ? 1u : 0u;
+}
+
+// number and measure of the selected sub-facets in one pass (the id list is not needed for either): fixed element ->
+// thread -> tree order inside a block, the block that finishes last adds the block partials in index order
+__global__ void __launch_bounds__(256)
+k_facet_sub_count_sum(const GcFacetLayout lay, int L, int64_t nsf, const GcProgram prog, int which, int side,
+                      double* __restrict__ partial, unsigned long long* __restrict__ pcount, unsigned int* __restrict__ ticket,
+                      double* __restrict__ out_sum, unsigned long long* __restrict__ out_count) {
+  __shared__ double sh[256];
+  __shared__ unsigned long long shc[256];
+  __shared__ bool s_last;
+  double a = 0.0;
+  unsigned long long c = 0ull;
+  const int64_t per = (nsf + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = per * blockIdx.x, hi = lo + per < nsf ? lo + per : nsf;
+  for (int64_t e = lo + threadIdx.x; e < hi; e += blockDim.x)
+    if (facet_sub_selected(lay, L, prog, which, side, e)) {
+      a += lay.meas[e];
+      c++;
+    }
+  sh[threadIdx.x] = a;
+  shc[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      sh[threadIdx.x] += sh[threadIdx.x + o];
+      shc[threadIdx.x] += shc[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = sh[0];
+    pcount[blockIdx.x] = shc[0];
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  a = 0.0;
+  c = 0ull;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+    a += reinterpret_cast<volatile double*>(partial)[i];
+    c += reinterpret_cast<volatile unsigned long long*>(pcount)[i];
+  }
+  sh[threadIdx.x] = a;
+  shc[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      sh[threadIdx.x] += sh[threadIdx.x + o];
+      shc[threadIdx.x] += shc[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *out_sum = sh[0];
+    *out_count = shc[0];
+  }
 }
 
 // deterministic sum of meas[ids[i]-1]: block partials in a fixed order, the last block adds them up
@@ -720,6 +784,7 @@ void free_facet_arrays(gecut_facet_result* r) {
   gc_free(ctx, l.R);
   gc_free(ctx, l.state);
   gc_free(ctx, l.meas);
+  gc_free(ctx, l.isb);
   for (int i = 0; i < GC_LMAX; ++i)
     if (r->owns_nodal[i]) gc_free(ctx, r->nodal_dev[i]);
   l = GcFacetLayout{};
@@ -823,6 +888,7 @@ int walk_facets_nw(gecut_ctx* ctx, gecut_facet_result* r) {
   GC_CHECK(gc_malloc(ctx, (void**)&l.c2p, sizeof(int32_t) * tot[0] * D));
   GC_CHECK(gc_malloc(ctx, (void**)&l.c2bg, sizeof(int32_t) * tot[0]));
   GC_CHECK(gc_malloc(ctx, (void**)&l.meas, sizeof(double) * tot[0]));
+  GC_CHECK(gc_malloc(ctx, (void**)&l.isb, (size_t)tot[0]));
   GC_CHECK(gc_malloc(ctx, (void**)&l.state, (size_t)l.pitch * L));
   GC_CHECK(gc_malloc(ctx, (void**)&l.X, sizeof(double) * tot[1] * D));
   GC_CHECK(gc_malloc(ctx, (void**)&l.R, sizeof(double) * tot[1] * (D - 1)));
@@ -1086,16 +1152,26 @@ int gecut_select_facets(const gecut_facet_result* res, int which, int kind, cons
   int st = GECUT_OK;
   const int64_t nsf = res->sizes.num_subfacets, nf = res->sizes.num_bgfacets;
   if ((kind == GECUT_SEL_PHYSICAL || kind == GECUT_SEL_CUTONLY) && nsf > 0) {
-    uint32_t* flags = nullptr;
-    st = gc_malloc(ctx, (void**)&flags, sizeof(uint32_t) * nsf);
+    // count and measure in one pass; the id list is materialised by gecut_facet_selection_copy / per-entity values
+    const int NB = (int)std::min<int64_t>(1184, gc_div_up(nsf, 1024));
+    double* partial = nullptr;
+    st = gc_malloc(ctx, (void**)&partial, sizeof(double) * (2 * NB + 3));
     if (st != GECUT_OK) return fail(st);
-    if (D == 2)
-      GC_LAUNCH(ctx, "k_facet_flag_sub", k_facet_flag_sub<2><<<(unsigned)gc_div_up(nsf, T), T, 0, ctx->stream>>>(res->grid, res->lay, nsf, p, which, side, flags));
-    else
-      GC_LAUNCH(ctx, "k_facet_flag_sub", k_facet_flag_sub<3><<<(unsigned)gc_div_up(nsf, T), T, 0, ctx->stream>>>(res->grid, res->lay, nsf, p, which, side, flags));
-    st = gc_launch_check(ctx, "k_facet_flag_sub");
-    if (st == GECUT_OK) st = gc_compact_flags(ctx, flags, nsf, &sel->sub_ids, &sel->n_sub, nullptr, nullptr);
-    gc_free(ctx, flags);
+    unsigned long long* pcount = reinterpret_cast<unsigned long long*>(partial + NB);
+    double* out_sum = partial + 2 * NB;
+    unsigned long long* out_count = reinterpret_cast<unsigned long long*>(partial + 2 * NB + 1);
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(partial + 2 * NB + 2);
+    cudaMemsetAsync(ticket, 0, sizeof(unsigned int), ctx->stream);
+    GC_LAUNCH(ctx, "k_facet_sub_count_sum", k_facet_sub_count_sum<<<NB, 256, 0, ctx->stream>>>(res->lay, res->L, nsf, p, which, side, partial, pcount, ticket, out_sum, out_count));
+    st = gc_launch_check(ctx, "k_facet_sub_count_sum");
+    if (st == GECUT_OK) {
+      uint64_t h[2];
+      st = read_u64(ctx, (const uint64_t*)out_sum, 2, h);
+      memcpy(&sel->sub_measure, &h[0], sizeof(double));
+      sel->n_sub = (int64_t)h[1];
+      sel->sub_lazy = true;
+    }
+    gc_free(ctx, partial);
     if (st != GECUT_OK) return fail(st);
   }
   if (kind != GECUT_SEL_CUTONLY && nf > 0) {
@@ -1179,6 +1255,26 @@ int gecut_facet_selection_sizes(const gecut_facet_selection* sel, int64_t* n_sub
   return GECUT_OK;
 }
 
+static int facet_materialize_sub_ids(gecut_ctx* ctx, gecut_facet_selection* sel) {
+  if (!sel->sub_lazy || sel->sub_ids || sel->n_sub <= 0) return GECUT_OK;
+  const gecut_facet_result* res = sel->res;
+  const int64_t nsf = res->sizes.num_subfacets;
+  const int T = 256;
+  uint32_t* flags = nullptr;
+  GC_CHECK(gc_malloc(ctx, (void**)&flags, sizeof(uint32_t) * nsf));
+  GC_LAUNCH(ctx, "k_facet_flag_sub", k_facet_flag_sub<<<(unsigned)gc_div_up(nsf, T), T, 0, ctx->stream>>>(res->lay, res->L, nsf, sel->prog, sel->which, sel->side, flags));
+  int st = gc_launch_check(ctx, "k_facet_flag_sub");
+  int64_t n = 0;
+  if (st == GECUT_OK) st = gc_compact_flags(ctx, flags, nsf, &sel->sub_ids, &n, nullptr, nullptr);
+  gc_free(ctx, flags);
+  GC_CHECK(st);
+  if (n != sel->n_sub) {
+    ctx->err = "facet selection: sub-facet id list and count disagree";
+    return GECUT_ERR_CUDA;
+  }
+  return GECUT_OK;
+}
+
 int gecut_facet_selection_copy(const gecut_facet_selection* sel_c, int32_t* sub_ids, int32_t* bg_ids) {
   if (!sel_c) return GECUT_ERR_INVALID;
   gecut_facet_selection* sel = const_cast<gecut_facet_selection*>(sel_c);
@@ -1206,6 +1302,7 @@ int gecut_facet_selection_copy(const gecut_facet_selection* sel_c, int32_t* sub_
       return GECUT_ERR_CUDA;
     }
   }
+  if (sub_ids) GC_CHECK(facet_materialize_sub_ids(ctx, sel));
   GC_CHECK(to_host(ctx, sub_ids, sel->sub_ids, sel->n_sub));
   GC_CHECK(to_host(ctx, bg_ids, sel->bg_ids, sel->n_bg));
   GC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1218,7 +1315,10 @@ int gecut_facet_selection_measure(const gecut_facet_selection* sel, double* sub_
   gecut_ctx* ctx = res->ctx;
   DeviceGuard guard(ctx->device);
   double sum = 0.0;
-  if (sel->n_sub > 0) {
+  if (sel->n_sub > 0 && sel->sub_lazy && !sub_values) {
+    sum = sel->sub_measure;  // summed by the selection pass
+  } else if (sel->n_sub > 0) {
+    GC_CHECK(facet_materialize_sub_ids(ctx, const_cast<gecut_facet_selection*>(sel)));
     const int64_t n = sel->n_sub;
     const int64_t nb = gc_div_up(n, (int64_t)SUM_T * SUM_PER);
     double *partial = nullptr, *vals = nullptr;

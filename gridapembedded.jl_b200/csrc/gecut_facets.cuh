@@ -17,6 +17,7 @@ struct GcFacetLayout {
   int8_t* state;      // L x Nsf (pitched)
   int64_t pitch;
   double* meas;       // Nsf: integral of 1 with the degree-2 rule
+  uint8_t* isb;       // Nsf: 1 when the bg facet of the sub-facet lies on the boundary of the model
 };
 
 struct gecut_facet_result {
@@ -38,6 +39,8 @@ struct gecut_facet_selection {
   int32_t* sub_ids = nullptr;
   int32_t* bg_ids = nullptr;
   int64_t bg_dir_count[3] = {0, 0, 0};  // selected whole facets per normal direction
+  bool sub_lazy = false;                // n_sub / sub_measure known, the id list is written only on demand
+  double sub_measure = 0.0;             // sum of the measures of the selected sub-facets
   GcProgram prog{};                     // for the lazy materialisation of bg_ids
 };
 
