@@ -318,6 +318,7 @@ def run_b200(args, n, rank, world, local_rank):
     ctx = _lib.Context(local_rank, stream.cuda_stream)
     cutter = LevelSetCutter(ctx, slab=slab)
     red = torch.zeros(4, dtype=torch.float64, device=f"cuda:{local_rank}")
+    red_host = torch.zeros(4, dtype=torch.float64, pin_memory=True)
 
     def barrier():
         if world > 1:
@@ -346,11 +347,13 @@ def run_b200(args, n, rank, world, local_rank):
         if e2e:
             cg.to_host(buffers=host["layout"])
         if world > 1:  # global integrals + counts: the only data-path collective
-            red[0], red[1], red[2], red[3] = vol, surf, float(cg.num_cutcells), float(cg.sizes.num_subcells)
+            # one H2D copy of the four local numbers, the all-reduce, one read-back of the global ones
+            red_host[0], red_host[1] = vol, surf
+            red_host[2], red_host[3] = float(cg.num_cutcells), float(cg.sizes.num_subcells)
+            red.copy_(red_host, non_blocking=True)
             dist.all_reduce(red)
-            if e2e:
-                _ = red.cpu()
-            vol, surf = float(red[0]), float(red[1])
+            glob = red.cpu()
+            vol, surf = float(glob[0]), float(glob[1])
         state.update(sizes=cg.sizes, nsel=om.num_sub, nfsel=ga.num_sub, vol=vol, surf=surf)
         om.close()
         ga.close()
