@@ -54,7 +54,55 @@ def make_workload(name, n, world):
         part = tuple(n * m for m in mult)
         model = CartesianDiscreteModel(box.pmin, box.pmax, part)
         return model, geo, f"BASELINE configs[1]: disk(R=0.7) on {part[0]}x{part[1]} quads: cut + area + perimeter + Q1 4x4 matrices"
+    if name == "c5_bimaterial":
+        # BimaterialLinElastCutFEM.jl:16-37,56: two steel cylinders (axis x) in a concrete block, tree union(steel, !steel)
+        from gecut import cylinder, union, complement
+        geo1 = cylinder(0.4, x0=(0.0, 1.0, 0.7))
+        geo2 = cylinder(0.4, x0=(0.0, 1.0, 2.3))
+        steel = union(geo1, geo2, name="steel")
+        geo = union(steel, complement(steel, name="concrete"))
+        mult = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}.get(world)
+        if mult is None:
+            raise SystemExit("--gpus must be 1, 2, 4 or 8")
+        part = tuple(n * m for m in mult)
+        model = CartesianDiscreteModel((0.0, 0.0, 0.0), (3.0, 2.0, 3.0), part)
+        desc = (f"BASELINE configs[4]: BimaterialLinElastCutFEM two-phase interface (2 cylinders, L=2) on "
+                f"{part[0]}x{part[1]}x{part[2]} HEX box [0,3]x[0,2]x[0,3]; cut + steel (IN) and concrete (OUT) PHYSICAL "
+                f"volumes + interface area + cut-cell Q1 8x8 Laplacian matrices of both phases")
+        return model, geo, desc
     raise SystemExit(f"unknown workload {name}")
+
+
+def workload_plan(name):
+    """(cell selections [(sub-geometry name, side)], boundary names) integrated by one step; side -1 = IN, +1 = OUT."""
+    if name == "c5_bimaterial":
+        return [("steel", -1), ("steel", 1)], ["steel"]
+    return [(None, -1)], [None]
+
+
+def host_program(model, geo, name):
+    """postfix program of the (named sub-)geometry over the unique leaves, compiled on the host (CPU arms)"""
+    import gecut
+    from gecut.csg import compile_postfix, get_geometry
+    _, _, oid_to_ls = gecut.cutters.flatten_geometry(model, geo, host_only=True)
+    g = geo if name is None else get_geometry(geo, name)
+    return [int(x) for x in compile_postfix(g.get_tree(), oid_to_ls)]
+
+
+def oracle_step(oc, model, geo, workload):
+    """one step of the workload on an oracle cut: (volumes per cell selection, areas per boundary, matrices)"""
+    cells, bnds = workload_plan(workload)
+    vols, surfs, nK = [], [], 0
+    for name, side in cells:
+        prog = host_program(model, geo, name)
+        ids = oc.select_subcells(prog, side)
+        bg = oc.select_bgcells(prog, side)
+        vols.append(float(oc.subcell_measures(ids).sum() + len(bg) * oc.bgcell_measure(1)))
+        nK += int(oc.cutcell_laplacian(ids).shape[0])
+    for name in bnds:
+        fids, _ = oc.select_boundary(host_program(model, geo, name))
+        surfs.append(float(oc.subfacet_measures(fids).sum()))
+    return vols, surfs, nK
 
 
 def slab_of(model, rank, world):
@@ -141,7 +189,7 @@ def layout_bytes(s):
     return {k: int(v) for k, v in b.items()}
 
 
-def algorithmic_bytes(s, model, nsel, nfsel, nodal=False):
+def algorithmic_bytes(s, model, nsel, nfsel, nodal=False, ncellsel=1):
     """ALGORITHMIC bytes per kernel and per step (DESIGN.md section 'Roofline accounting')."""
     D, L = int(s.D), int(s.num_levelsets)
     nv = int(s.num_vertices_per_bgcell)
@@ -161,7 +209,12 @@ def algorithmic_bytes(s, model, nsel, nfsel, nodal=False):
     if L == 1:  # tile statistics (4 doubles per 32-simplex tile) and, for simplex bg cells, (IN, OUT) measure per cut cell
         k["k_cut1_fill"] += 32 * ((nsimp + 31) // 32) + (16 * Ncut if model.simplexified else 0)
     k["k_cut_walk_fill"] += meas
-    k["k_count_bgcells"] = L * Nc
+    # L > 1: k_cut_fast writes the layout of the simplices cut by at most one level set (the bulk), k_cut_walk the rest;
+    # the whole layout is attributed to the fast kernel (the walk's share is not subtracted: an upper bound of its GB/s)
+    k["k_cut_fast_count"] = k["k_cut_walk_count"]
+    k["k_cut_fast_fill"] = k["k_cut_walk_fill"]
+    k["k_count_bgcells"] = L * Nc * ncellsel
+    k["k_select_subcells"] = int(s.num_subcells) * L * 2 * ncellsel + 4 * nsel
     k["k_flag_subcells"] = int(s.num_subcells) * (4 + 2 * L + 4)
     k["k_flag_boundary"] = int(s.num_subfacets) * (L + 4 + 1)
     k["k_measures"] = (nsel + nfsel) * (4 + 8 + 8)  # id + gathered measure + value
@@ -169,12 +222,13 @@ def algorithmic_bytes(s, model, nsel, nfsel, nodal=False):
     if model.simplexified and L == 1:  # P1, one level set: (IN, OUT) measure + id of every cut cell in, matrices out
         k["k_cutcell_laplacian"] = (16 + 4) * Ncut + 8 * nv * nv * Ncut
     elif model.simplexified:  # P1: states + measures of the cut cells' subcells, matrices out
-        k["k_cutcell_laplacian"] = nsc * L + nsel * 8 + 8 * nv * nv * Ncut + 8 * Ncut
+        k["k_cutcell_laplacian"] = ncellsel * (nsc * L + 8 * nv * nv * Ncut + 8 * Ncut) + nsel * 8
     else:  # Q1: + connectivity and reference coordinates of the selected subcells
-        k["k_cutcell_laplacian"] = nsc * L + nsel * (8 + 4 * (D + 1) + 8 * D * (D + 1)) + 8 * nv * nv * Ncut + 8 * Ncut
+        k["k_cutcell_laplacian"] = (ncellsel * (nsc * L + 8 * nv * nv * Ncut + 8 * Ncut) +
+                                    nsel * (8 + 4 * (D + 1) + 8 * D * (D + 1)))
     # whole step, SURVEY.md section 8(d): B_sweep + B_cut + B_int (node values are never materialised: 16*L*Nn of the
     # survey's B_sweep is not moved at all, so it is NOT counted here)
-    step = (L * Nc + Nc // 8) + lb["cutcells"] + lb["subcells"] + lb["subfacets"] + meas + 8 * (nsel + nfsel) + 8 * nv * nv * Ncut
+    step = (L * Nc + Nc // 8) + lb["cutcells"] + lb["subcells"] + lb["subfacets"] + meas + 8 * (nsel + nfsel) + 8 * nv * nv * Ncut * ncellsel
     return k, int(step)
 
 
@@ -184,7 +238,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3_tet", choices=["c3_tet", "c3_hex", "c2_disk"])
+    ap.add_argument("--workload", default="c3_tet", choices=["c3_tet", "c3_hex", "c2_disk", "c5_bimaterial"])
     ap.add_argument("--n", type=int, default=None, help="cells per direction per GPU (default 512; 4096 for c2_disk)")
     ap.add_argument("--cpu-n", type=int, default=None, help="size of the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
@@ -214,15 +268,9 @@ def cpu_sample(workload, n_cpu, steps=1):
     for _ in range(steps):
         t0 = time.perf_counter()
         oc = ob.oracle_cut(model, geo)
-        prog = [0]
-        ids = oc.select_subcells(prog, -1)
-        nbg = len(oc.select_bgcells(prog, -1))
-        vol = oc.subcell_measures(ids).sum() + nbg * oc.bgcell_measure(1)
-        fids, _ = oc.select_boundary(prog)
-        surf = oc.subfacet_measures(fids).sum()
-        K = oc.cutcell_laplacian(ids)
+        oracle_step(oc, model, geo, workload)
         dt = time.perf_counter() - t0
-        del oc, K
+        del oc
         best = dt if best is None else min(best, dt)
     cubes = model.num_cubes
     return cubes / best, best, (f"same geometry at {'x'.join(str(p) for p in model.partition)} "
@@ -247,14 +295,8 @@ def _cpu_slab_job(job):
     part[D - 1] = k1 - k0
     sub = gecut.CartesianDiscreteModel(tuple(pmin), tuple(pmax), tuple(part), simplexified=model.simplexified)
     oc = ob.oracle_cut(sub, geo)
-    prog = [0]
-    ids = oc.select_subcells(prog, -1)
-    nbg = len(oc.select_bgcells(prog, -1))
-    vol = oc.subcell_measures(ids).sum() + nbg * oc.bgcell_measure(1)
-    fids, _ = oc.select_boundary(prog)
-    surf = oc.subfacet_measures(fids).sum()
-    K = oc.cutcell_laplacian(ids)
-    return float(vol), float(surf), int(K.shape[0])
+    vols, surfs, nK = oracle_step(oc, sub, geo, workload)
+    return float(vols[0]), float(surfs[0]), nK
 
 
 def run_reference(args, n):
@@ -262,7 +304,7 @@ def run_reference(args, n):
     reference itself uses many cores (one rank per slab; the library has no threading)."""
     import concurrent.futures as cf
     cores = max(1, min(os.cpu_count() or 1, 64))
-    n_cpu = args.cpu_n or (2048 if args.workload == "c2_disk" else (256 if cores >= 32 else 192))
+    n_cpu = args.cpu_n or {"c2_disk": 2048, "c5_bimaterial": 128}.get(args.workload, 256 if cores >= 32 else 192)
     model, geo, desc = make_workload(args.workload, n_cpu, 1)
     nz = model.partition[model.D - 1]
     cores = min(cores, nz)
@@ -317,8 +359,8 @@ def run_b200(args, n, rank, world, local_rank):
     stream = torch.cuda.current_stream()
     ctx = _lib.Context(local_rank, stream.cuda_stream)
     cutter = LevelSetCutter(ctx, slab=slab)
-    red = torch.zeros(4, dtype=torch.float64, device=f"cuda:{local_rank}")
-    red_host = torch.zeros(4, dtype=torch.float64, pin_memory=True)
+    red = torch.zeros(5, dtype=torch.float64, device=f"cuda:{local_rank}")
+    red_host = torch.zeros(5, dtype=torch.float64, pin_memory=True)
 
     def barrier():
         if world > 1:
@@ -329,34 +371,42 @@ def run_b200(args, n, rank, world, local_rank):
 
     dbg = []
 
+    cells_plan, bnd_plan = workload_plan(args.workload)
+    SIDE = {-1: gecut.PHYSICAL_IN, 1: gecut.PHYSICAL_OUT}
+
     def step(e2e=False, host=None):
         t = [time.perf_counter()]
         cg = cutter.cut(model, geo)
         t.append(time.perf_counter())
-        om = Triangulation(cg, PHYSICAL)
+        oms = [Triangulation(cg, SIDE[side], name) for name, side in cells_plan]
         t.append(time.perf_counter())
-        ga = EmbeddedBoundary(cg)
+        gas = [EmbeddedBoundary(cg, name) for name in bnd_plan]
         t.append(time.perf_counter())
-        vol = integrate_measure(Measure(om, 2))
-        surf = integrate_measure(Measure(ga, 2))
+        vols = [integrate_measure(Measure(om, 2)) for om in oms]
+        surfs = [integrate_measure(Measure(ga, 2)) for ga in gas]
         t.append(time.perf_counter())
-        ctx.check(ctx._lib.gecut_integrate_laplacian(om.handle, host["K_cut"].ctypes.data if e2e else None, None),
-                  "gecut_integrate_laplacian")
+        for i, om in enumerate(oms):
+            ctx.check(ctx._lib.gecut_integrate_laplacian(om.handle, host["K_cut"][i].ctypes.data if e2e else None, None),
+                      "gecut_integrate_laplacian")
         t.append(time.perf_counter())
         dbg.append([round((b - a) * 1e3, 2) for a, b in zip(t[:-1], t[1:])])
         if e2e:
             cg.to_host(buffers=host["layout"])
+        vol, surf = vols[0], surfs[0]
         if world > 1:  # global integrals + counts: the only data-path collective
-            # one H2D copy of the four local numbers, the all-reduce, one read-back of the global ones
+            # one H2D copy of the local numbers, the all-reduce, one read-back of the global ones
             red_host[0], red_host[1] = vol, surf
             red_host[2], red_host[3] = float(cg.num_cutcells), float(cg.sizes.num_subcells)
+            red_host[4] = vols[-1]
             red.copy_(red_host, non_blocking=True)
             dist.all_reduce(red)
             glob = red.cpu()
             vol, surf = float(glob[0]), float(glob[1])
-        state.update(sizes=cg.sizes, nsel=om.num_sub, nfsel=ga.num_sub, vol=vol, surf=surf)
-        om.close()
-        ga.close()
+            vols = [vol] + ([float(glob[4])] if len(vols) > 1 else [])
+        state.update(sizes=cg.sizes, nsel=sum(om.num_sub for om in oms), nfsel=sum(ga.num_sub for ga in gas), vol=vol,
+                     surf=surf, vols=[float(v) for v in vols])
+        for o in oms + gas:
+            o.close()
         cg.close()
         return vol, surf
 
@@ -403,7 +453,7 @@ def run_b200(args, n, rank, world, local_rank):
         step()
     rep = ctx.profile_report()
     ctx.profile(False)
-    kbytes, step_bytes = algorithmic_bytes(s, model, state["nsel"], state["nfsel"])
+    kbytes, step_bytes = algorithmic_bytes(s, model, state["nsel"], state["nfsel"], ncellsel=len(cells_plan))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -463,9 +513,11 @@ def run_b200(args, n, rank, world, local_rank):
             t = torch.empty(tuple(int(x) for x in shape), dtype=tdt[dt], pin_memory=True)
             host["layout"][k] = t.numpy()
             d2h += t.numel() * t.element_size()
-        kt = torch.empty((int(s.num_cutcells), nv, nv), dtype=torch.float64, pin_memory=True)
-        host["K_cut"] = kt.numpy()
-        d2h += kt.numel() * 8 + 16
+        host["K_cut"] = []
+        for _ in cells_plan:
+            kt = torch.empty((int(s.num_cutcells), nv, nv), dtype=torch.float64, pin_memory=True)
+            host["K_cut"].append(kt.numpy())
+            d2h += kt.numel() * 8 + 16
         h2d = C.sizeof(_lib.Grid) + L * C.sizeof(_lib.LeafRec) + 3 * 4 * 8  # grid + leaf records + 3 boolean programs
         e2e_steps = max(1, min(args.steps, 3))
         step(True, host)
@@ -488,7 +540,7 @@ def run_b200(args, n, rank, world, local_rank):
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        n_cpu = args.cpu_n or (4096 if args.workload == "c2_disk" else 320)
+        n_cpu = args.cpu_n or {"c2_disk": 4096, "c5_bimaterial": 128}.get(args.workload, 320)
         v, dt, sample = cpu_sample(args.workload, n_cpu)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample, "seconds": round(dt, 2)}
 
@@ -505,7 +557,7 @@ def run_b200(args, n, rank, world, local_rank):
                              f"({(sum(lb.values())) / 1e9:.2f} GB of outputs per GPU >> 126 MB L2), nothing is reused across steps",
                        "per_gpu_counts": {"cut_cells": int(s.num_cutcells), "subcells": int(s.num_subcells),
                                           "subcell_points": int(s.num_subcell_points), "subfacets": int(s.num_subfacets)},
-                       "integrals": {"volume": state["vol"], "surface": state["surf"]}},
+                       "integrals": {"volume": state["vol"], "surface": state["surf"], "volumes": state["vols"]}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "step_roofline": step_roofline, "kernels": kernels[:12], "cpu_baseline": cpu,
         }
