@@ -185,28 +185,39 @@ inline QuadRule ncube_rule_deg2(int D) {
 //     (27 numbers in 3-D, 6 in 2-D), accumulated per lane over (subcell, quadrature point) items, reduced across the warp
 //     through shared memory, and K_ab = sum_d sgn_a sgn_b / h_d^2 * M_d[a_e+b_e][a_f+b_f].
 //   * simplex cells (P1): gradients are constant, K_ab = (g_a.g_b) * sum_s sum_q w_q |J_s|.
-// One THREAD per cut cell: it walks the cell's subcells (a contiguous run) and keeps the 27 (6) moments in registers, so
-// there is no cross-lane reduction at all and a warp has 32 cells' worth of independent loads in flight.
+// G LANES per cut cell (G = 4): lane g of the group walks the subcells s0+g, s0+g+G, ... of the cell's contiguous run with
+// the 27 (6) moments in registers, the G partial sums are added with a fixed butterfly (reproducible), the moments of the
+// warp's 32/G cells are parked in shared memory and the warp writes their matrices as contiguous 256-byte stores (lane =
+// matrix entry).  Compared with one thread per cell: G times more warps and G times shorter dependent gather chains
+// (ids -> reference points), and the trip counts inside a warp differ by the subcell count / G instead of the subcell
+// count itself (cut hexes carry 6 .. 36 subcells).
+constexpr int LAPQ_G = 4;
+constexpr int LAPQ_T = 128;
+
 template <int D>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(LAPQ_T)
 k_cutcell_laplacian_q1(const GcGrid g, const GcLayout lay, const uint32_t* __restrict__ sc_ptr, int64_t ncut,
                        const GcProgram prog, int side, int check_bg, double* __restrict__ K) {
+  constexpr int G = LAPQ_G;
+  constexpr int CW = 32 / G;  // cells per warp
   constexpr int NV = 1 << D;
   constexpr int NQ = D + 1;
   constexpr int NM = D == 3 ? 27 : 6;
   constexpr int NN = NV * NV;
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= ncut) return;
+  __shared__ double s_M[LAPQ_T / 32][CW][NM + 1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int gl = lane % G, cw = lane / G;
+  const int64_t kw0 = ((int64_t)blockIdx.x * (LAPQ_T / 32) + wid) * CW;  // first cell of this warp
+  const int64_t k = kw0 + cw;
   const double qa = D == 3 ? (5.0 - sqrt(5.0)) / 20.0 : 1.0 / 6;
   const double qb = D == 3 ? (5.0 + 3.0 * sqrt(5.0)) / 20.0 : 2.0 / 3;
-  const int64_t cell0 = (int64_t)lay.cutcells[k] - 1;
   double M[NM];
 #pragma unroll
   for (int m = 0; m < NM; ++m) M[m] = 0.0;
-  if (!check_bg || gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, cell0) == GC_CUT) {
-    const uint32_t s0 = sc_ptr[2 * k], s1 = sc_ptr[2 * k + 2];
-    // software pipeline: connectivity row, state and measure of the NEXT subcell are requested while the current one
-    // is processed, so an iteration waits for one memory round trip (the reference points), not two
+  if (k < ncut && (!check_bg || gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, (int64_t)lay.cutcells[k] - 1) == GC_CUT)) {
+    const uint32_t s0 = sc_ptr[2 * k] + (uint32_t)gl, s1 = sc_ptr[2 * k + 2];
+    // software pipeline: connectivity row, state and measure of this lane's NEXT subcell are requested while the current
+    // one is processed, so an iteration waits for one memory round trip (the reference points), not two
     struct Ids {
       int32_t v[4];
     };
@@ -233,14 +244,14 @@ k_cutcell_laplacian_q1(const GcGrid g, const GcLayout lay, const uint32_t* __res
       nstate = gc_eval_inoutcut(prog, lay.sc_state, lay.sc_pitch, (int64_t)s0);
       nmeas = lay.sc_meas[s0];
     }
-    for (uint32_t it = s0; it < s1; ++it) {
+    for (uint32_t it = s0; it < s1; it += G) {
       const Ids ids_s = nids;
       const int state = nstate;
       const double meas = nmeas;
-      if (it + 1 < s1) {
-        nids = load_ids((int64_t)it + 1);
-        nstate = gc_eval_inoutcut(prog, lay.sc_state, lay.sc_pitch, (int64_t)it + 1);
-        nmeas = lay.sc_meas[it + 1];
+      if (it + G < s1) {
+        nids = load_ids((int64_t)it + G);
+        nstate = gc_eval_inoutcut(prog, lay.sc_state, lay.sc_pitch, (int64_t)it + G);
+        nmeas = lay.sc_meas[it + G];
       }
       if (state != side) continue;
       double r[D + 1][3];
@@ -292,37 +303,43 @@ k_cutcell_laplacian_q1(const GcGrid g, const GcLayout lay, const uint32_t* __res
       }
     }
   }
-  // ---- element matrix from the moments (static indices: everything stays in registers)
-  double ih2[3];
+  // ---- the G partial sums of a cell: fixed butterfly, then lane 0 of the group parks the moments
 #pragma unroll
-  for (int d = 0; d < D; ++d) ih2[d] = 1.0 / (g.dx[d] * g.dx[d]);
-  double* out = K + k * NN;
+  for (int o = 1; o < G; o <<= 1)
 #pragma unroll
-  for (int a = 0; a < NV; ++a) {
+    for (int m = 0; m < NM; ++m) M[m] += __shfl_xor_sync(0xffffffffu, M[m], o);
+  if (gl == 0) {
 #pragma unroll
-    for (int b = 0; b < NV; b += 2) {
-      double v2[2];
+    for (int m = 0; m < NM; ++m) s_M[wid][cw][m] = M[m];
+  }
+  __syncwarp();
+  // ---- element matrices of the warp's cells from the moments: lane = entry of the contiguous output
+  double sih2[3];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int bb = b + u;
-        double val = 0.0;
+  for (int d = 0; d < D; ++d) sih2[d] = 1.0 / (g.dx[d] * g.dx[d]);
+  double* out = K + kw0 * NN;
+  const int64_t nvalid = (ncut - kw0) * NN;  // entries of existing cells
+#pragma unroll 4
+  for (int j = 0; j < CW * NN / 32; ++j) {
+    const int e = lane + 32 * j;
+    const int cl = e / NN, idx = e % NN;
+    const int a = idx / NV, bb = idx % NV;
+    const double* Mc = s_M[wid][cl];
+    double val = 0.0;
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-          const double sg = (((a >> d) & 1) == ((bb >> d) & 1)) ? 1.0 : -1.0;
-          int mi;
-          if (D == 3) {
-            const int e1 = d == 0 ? 1 : 0, f1 = d == 2 ? 1 : 2;
-            mi = d * 9 + (((a >> e1) & 1) + ((bb >> e1) & 1)) * 3 + (((a >> f1) & 1) + ((bb >> f1) & 1));
-          } else {
-            const int e1 = 1 - d;
-            mi = d * 3 + (((a >> e1) & 1) + ((bb >> e1) & 1));
-          }
-          val += sg * ih2[d] * M[mi];
-        }
-        v2[u] = val;
+    for (int d = 0; d < D; ++d) {
+      const double sg = (((a >> d) & 1) == ((bb >> d) & 1)) ? sih2[d] : -sih2[d];
+      int mi;
+      if (D == 3) {
+        const int e1 = d == 0 ? 1 : 0, f1 = d == 2 ? 1 : 2;
+        mi = d * 9 + (((a >> e1) & 1) + ((bb >> e1) & 1)) * 3 + (((a >> f1) & 1) + ((bb >> f1) & 1));
+      } else {
+        const int e1 = 1 - d;
+        mi = d * 3 + (((a >> e1) & 1) + ((bb >> e1) & 1));
       }
-      *reinterpret_cast<double2*>(out + a * NV + b) = make_double2(v2[0], v2[1]);
+      val += sg * Mc[mi];
     }
+    if (e < nvalid) out[e] = val;
   }
 }
 
@@ -578,8 +595,8 @@ int gc_integrate_laplacian(gecut_ctx* ctx, gecut_selection* sel, double* K_bg_ho
     gc_free(ctx, Gd);
     return gc_launch_check(ctx, "k_cutcell_laplacian_p1");
   }
-  const int T = 128;
-  const unsigned nb = (unsigned)gc_div_up(ncut, T);
+  const int T = LAPQ_T;
+  const unsigned nb = (unsigned)gc_div_up(ncut, T / LAPQ_G);
   if (g.D == 2)
     GC_LAUNCH(ctx, "k_cutcell_laplacian", k_cutcell_laplacian_q1<2><<<nb, T, 0, ctx->stream>>>(
         g, res->lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, check_bg, sel->K_cut));

@@ -77,6 +77,34 @@ k_select_subcells(const GcLayout lay, int64_t nsc, const GcProgram prog, int sid
         for (int i = 0; i < 4; ++i)
           if (((x >> (8 * i)) & 0xFFu) == 0u) bits |= 1u << (4 * j + i);
       }
+    } else if (prog.lut) {
+      // truth table: one 128-bit load per used state row (rows are padded), base-3 index per subcell, one gather; runs of
+      // 16 subcells with one state per row need a single gather
+      bool uni = true;
+      uint32_t idx0 = 0u;
+      for (int k = prog.nused - 1; k >= 0; --k) {
+        const uint4 q = *reinterpret_cast<const uint4*>(lay.sc_state + (int64_t)prog.used[k] * lay.sc_pitch + e0);
+        uni = uni && q.x == q.y && q.y == q.z && q.z == q.w && q.x == (q.x & 0xFFu) * 0x01010101u;
+        idx0 = idx0 * 3u + (uint32_t)((int)(int8_t)(q.x & 0xFFu) + 1);
+      }
+      if (uni) {
+        bits = ((int)__ldg(prog.lut + idx0) == side) ? 0xFFFFu : 0u;
+      } else {
+        uint32_t idx[SELSC_PER];
+#pragma unroll
+        for (int c = 0; c < SELSC_PER; ++c) idx[c] = 0u;
+        for (int k = prog.nused - 1; k >= 0; --k) {
+          const uint4 q = *reinterpret_cast<const uint4*>(lay.sc_state + (int64_t)prog.used[k] * lay.sc_pitch + e0);
+          const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int c = 0; c < SELSC_PER; ++c)
+            idx[c] = idx[c] * 3u + (uint32_t)((int)(int8_t)((w4[c >> 2] >> (8 * (c & 3))) & 0xFFu) + 1);
+        }
+        const int nval = (int)(nsc - e0 < SELSC_PER ? nsc - e0 : SELSC_PER);  // bytes past nsc are padding: no gather
+#pragma unroll
+        for (int c = 0; c < SELSC_PER; ++c)
+          if (c < nval && (int)__ldg(prog.lut + idx[c]) == side) bits |= 1u << c;
+      }
     } else {
 #pragma unroll 4
       for (int i = 0; i < SELSC_PER; ++i)
@@ -172,6 +200,33 @@ k_count_bgcells_vec(const GcLayout lay, int64_t nc, int L, const GcProgram prog,
       }
       unpack(pk);
     } else if (prog.lut) {
+      // groups whose 16 cells have the same state in every used row (all but the ones a surface crosses): one gather
+      {
+        bool uni = nvalid == 16;
+        uint32_t idx0 = 0u;
+        for (int k = prog.nused - 1; k >= 0; --k) {
+          const uint4 r4 = *reinterpret_cast<const uint4*>(lay.bg_state + (int64_t)prog.used[k] * lay.bg_pitch + e0);
+          uni = uni && r4.x == r4.y && r4.y == r4.z && r4.z == r4.w && r4.x == (r4.x & 0xFFu) * 0x01010101u;
+          idx0 = idx0 * 3u + (uint32_t)((int)(int8_t)(r4.x & 0xFFu) + 1);
+        }
+        if (uni) {
+          const int bg = (int)__ldg(prog.lut + idx0);
+          if (mode == 0 ? (bg == side) : (bg == GC_CUT || bg == side)) {
+            if (cpc == 1) {
+              loc[0] += 16u;
+            } else {
+              const int base = 16 / cpc, rem = 16 % cpc;
+#pragma unroll
+              for (int t = 0; t < 6; ++t) {
+                int dlt = t - ty;
+                if (dlt < 0) dlt += cpc;
+                if (t < cpc) loc[t] += (unsigned int)(base + (dlt < rem ? 1 : 0));
+              }
+            }
+          }
+          continue;
+        }
+      }
       // truth table: one 128-bit load per used level-set row, base-3 index per cell, one gather
       uint32_t idx[16];
 #pragma unroll
