@@ -700,10 +700,13 @@ int gecut_select_cells(const gecut_result* res, int kind, const int32_t* program
   sel->res = res;
   sel->kind = kind;
   sel->side = side;
+  const int64_t launches0 = ctx->launches;
   int st = make_program(ctx, program, len, res->L, &sel->prog);
   if (st == GECUT_OK) st = attach_program_rows(ctx, res, &sel->prog);
   if (st == GECUT_OK) st = gc_select_cells(ctx, sel);
-  if (st == GECUT_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = GECUT_ERR_CUDA;
+  // selections answered from the tallies of the cut (no kernel queued by this call) do not wait for earlier
+  // stream-ordered work of the context (the device-resident Laplacian)
+  if (st == GECUT_OK && ctx->launches != launches0 && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = GECUT_ERR_CUDA;
   if (st != GECUT_OK) {
     gecut_selection_free(sel);
     return st;
@@ -722,13 +725,14 @@ int gecut_select_boundary(const gecut_result* res, const int32_t* program1, int 
   if (!sel) return GECUT_ERR_OOM;
   sel->res = res;
   sel->kind = GECUT_SEL_BOUNDARY;
+  const int64_t launches0 = ctx->launches;
   int st = make_program(ctx, program1, len1, res->L, &sel->prog);
   if (st == GECUT_OK && program2) {
     st = make_program(ctx, program2, len2, res->L, &sel->prog2);
     sel->has_prog2 = true;
   }
   if (st == GECUT_OK) st = gc_select_boundary(ctx, sel);
-  if (st == GECUT_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = GECUT_ERR_CUDA;
+  if (st == GECUT_OK && ctx->launches != launches0 && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = GECUT_ERR_CUDA;
   if (st != GECUT_OK) {
     gecut_selection_free(sel);
     return st;
@@ -833,6 +837,10 @@ int gecut_integrate_laplacian(const gecut_selection* sel_c, double* K_cut, doubl
   DeviceGuard guard(ctx->device);
   GC_CHECK(gc_integrate_laplacian(ctx, sel, K_bg));
   const int nn = sel->res->grid.nv * sel->res->grid.nv;
+  // K_cut == NULL: the matrices stay on the device (gecut_selection_device_laplacian) and the call is stream-ordered --
+  // it returns once the kernel is queued, so host work of the caller overlaps it; every later call on this context (and
+  // anything the caller queues on the context's stream) sees the finished matrices
+  if (!K_cut) return GECUT_OK;
   GC_CHECK(copy_to_host(ctx, K_cut, sel->K_cut, sel->res->sizes.num_cutcells * nn));
   GC_CUDA(cudaStreamSynchronize(ctx->stream));
   return GECUT_OK;

@@ -343,15 +343,24 @@ k_cutcell_laplacian_q1(const GcGrid g, const GcLayout lay, const uint32_t* __res
   }
 }
 
+// constant gradient products g_a.g_b of the 6 (2) simplex types of a Cartesian n-cube: a kernel parameter (no H2D copy, so
+// the device-resident Laplacian can return without synchronising), staged into shared memory by the kernels
+struct GcGradDots {
+  double v[6 * 16];
+};
+
 // Simplex bg cells (P1): one thread per cut cell accumulates V = sum over its selected subcells of sum_q w_q |J_s|; the
 // matrix is V * (g_a.g_b) with the constant gradient products of the cell type (6 TET / 2 TRI types of a Cartesian
 // n-cube), written warp-cooperatively so that the 32 matrices of a warp go out as contiguous 256-byte stores.
 template <int D>
 __global__ void __launch_bounds__(128)
 k_cutcell_laplacian_p1(const GcGrid g, const GcLayout lay, const uint32_t* __restrict__ sc_ptr, int64_t ncut,
-                       const GcProgram prog, int side, int check_bg, const double* __restrict__ graddots,
+                       const GcProgram prog, int side, int check_bg, const GcGradDots gd,
                        double* __restrict__ K) {
   constexpr int NV = D + 1, NN = NV * NV;
+  __shared__ double graddots[6 * 16];
+  if (threadIdx.x < 6 * 16) graddots[threadIdx.x] = gd.v[threadIdx.x];
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double V = 0.0;
@@ -384,8 +393,11 @@ k_cutcell_laplacian_p1(const GcGrid g, const GcLayout lay, const uint32_t* __res
 template <int D>
 __global__ void __launch_bounds__(128)
 k_cutcell_laplacian_p1_vio(const GcLayout lay, int cpc, const double2* __restrict__ cell_vio, int64_t ncut, int side,
-                           const double* __restrict__ graddots, double* __restrict__ K) {
+                           const GcGradDots gd, double* __restrict__ K) {
   constexpr int NV = D + 1, NN = NV * NV;
+  __shared__ double graddots[6 * 16];
+  if (threadIdx.x < 6 * 16) graddots[threadIdx.x] = gd.v[threadIdx.x];
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double V = 0.0;
@@ -565,13 +577,8 @@ int gc_integrate_laplacian(gecut_ctx* ctx, gecut_selection* sel, double* K_bg_ho
   if (!sel->K_cut) GC_CHECK(gc_malloc(ctx, (void**)&sel->K_cut, sizeof(double) * ncut * nn));
   const int check_bg = res->L > 1 ? 1 : 0;
   if (g.simplexified) {
-    double Gh[6 * 16];
-    for (int t = 0; t < g.cpc; ++t) host_bgcell_graddots(g, t, Gh + (size_t)t * nn);
-    double* Gd = nullptr;
-    GC_CHECK(gc_malloc(ctx, (void**)&Gd, sizeof(Gh)));
-    // pinned staging so that the async copy does not read a dead stack frame
-    memcpy((char*)ctx->h_pinned + 1024, Gh, sizeof(double) * g.cpc * nn);
-    GC_CUDA(cudaMemcpyAsync(Gd, (char*)ctx->h_pinned + 1024, sizeof(double) * g.cpc * nn, cudaMemcpyHostToDevice, ctx->stream));
+    GcGradDots Gd{};
+    for (int t = 0; t < g.cpc; ++t) host_bgcell_graddots(g, t, Gd.v + (size_t)t * nn);
     const unsigned nb1 = (unsigned)gc_div_up(ncut, 128);
     const GcProgram& pp = sel->prog;
     const bool leaf1 = (pp.len == 1 && pp.tok[0] >= 0) || (pp.len == 2 && pp.tok[0] >= 0 && pp.tok[1] == GECUT_OP_COMPLEMENT);
@@ -583,7 +590,6 @@ int gc_integrate_laplacian(gecut_ctx* ctx, gecut_selection* sel, double* K_bg_ho
       else
         GC_LAUNCH(ctx, "k_cutcell_laplacian", k_cutcell_laplacian_p1_vio<3><<<nb1, 128, 0, ctx->stream>>>(
             res->lay, g.cpc, res->cell_vio, ncut, eff, Gd, sel->K_cut));
-      gc_free(ctx, Gd);
       return gc_launch_check(ctx, "k_cutcell_laplacian_p1_vio");
     }
     if (g.D == 2)
@@ -592,7 +598,6 @@ int gc_integrate_laplacian(gecut_ctx* ctx, gecut_selection* sel, double* K_bg_ho
     else
       GC_LAUNCH(ctx, "k_cutcell_laplacian", k_cutcell_laplacian_p1<3><<<nb1, 128, 0, ctx->stream>>>(
           g, res->lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, check_bg, Gd, sel->K_cut));
-    gc_free(ctx, Gd);
     return gc_launch_check(ctx, "k_cutcell_laplacian_p1");
   }
   const int T = LAPQ_T;

@@ -204,7 +204,9 @@ int gecut_integrate_measure(const gecut_selection* sel, double* values, double* 
  * subcells accumulated per cut bg cell in subcell order (move_contributions, SubCellTriangulations.jl:63-72):
  * `K_cut` (host, NULL skipped) is Ncut x nv x nv, row k belongs to cutcell_to_cell[k] (zero if the cell has no selected
  * subcell); `K_bg` (host, NULL skipped) is ntypes x nv x nv for the uncut cells (ntypes = 1 for n-cubes, 2/6 for
- * simplexified models, type = (cell-1) mod ntypes). */
+ * simplexified models, type = (cell-1) mod ntypes).  With K_cut == NULL the matrices stay on the device
+ * (gecut_selection_device_laplacian) and the call is STREAM-ORDERED: it returns once the kernel is queued on the
+ * context's stream; later calls on the context and work queued on that stream see the finished matrices. */
 int gecut_integrate_laplacian(const gecut_selection* sel, double* K_cut, double* K_bg);
 /* get_cell_measure(trian, bgtrian) (the aggregation input of AgFEM, src/AgFEM/CellAggregation.jl:111-113): measure of the
  * selected triangulation per bg cell -- the whole cell for selected uncut cells, the sum over the selected subcells (in
