@@ -199,7 +199,10 @@ def algorithmic_bytes(s, model, nsel, nfsel, nodal=False, ncellsel=1):
     nsimp = Ncut * nt0
     narr = 2 + L + (L if L > 1 else 0)
     k = {}
-    k["k_classify"] = L * Nc + Nc // 8 + (8 * L * Nn if nodal else 0)
+    # NODAL leaves (DiscreteGeometry): k_nodal_signs streams the values once (8 B per node in, 1 bit out), the marching
+    # kernel then reads the bits
+    k["k_classify"] = L * Nc + Nc // 8 + (L * Nn // 8 if nodal else 0)
+    k["k_nodal_signs"] = (8 * L * Nn + L * Nn // 8) if nodal else 0
     k["k_cut_walk_count"] = 4 * Ncut + 4 * narr * nsimp
     k["k_cut_walk_fill"] = 4 * Ncut + 4 * narr * nsimp + lb["subcells"] + lb["subfacets"]
     ntiles = (nsimp + 127) // 128
@@ -228,7 +231,7 @@ def algorithmic_bytes(s, model, nsel, nfsel, nodal=False, ncellsel=1):
                                     nsel * (8 + 4 * (D + 1) + 8 * D * (D + 1)))
     # whole step, SURVEY.md section 8(d): B_sweep + B_cut + B_int (node values are never materialised: 16*L*Nn of the
     # survey's B_sweep is not moved at all, so it is NOT counted here)
-    step = (L * Nc + Nc // 8) + lb["cutcells"] + lb["subcells"] + lb["subfacets"] + meas + 8 * (nsel + nfsel) + 8 * nv * nv * Ncut * ncellsel
+    step = (L * Nc + Nc // 8) + (8 * L * Nn if nodal else 0) + lb["cutcells"] + lb["subcells"] + lb["subfacets"] + meas + 8 * (nsel + nfsel) + 8 * nv * nv * Ncut * ncellsel
     return k, int(step)
 
 
@@ -241,6 +244,9 @@ def main():
     ap.add_argument("--workload", default="c3_tet", choices=["c3_tet", "c3_hex", "c2_disk", "c5_bimaterial"])
     ap.add_argument("--n", type=int, default=None, help="cells per direction per GPU (default 512; 4096 for c2_disk)")
     ap.add_argument("--cpu-n", type=int, default=None, help="size of the bounded CPU sample")
+    ap.add_argument("--nodal", action="store_true",
+                    help="feed the level sets as a DiscreteGeometry: slab-local nodal vectors resident on each GPU, ghost "
+                         "node plane from the next rank by NCCL send/recv every step (SURVEY 8e)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -371,11 +377,38 @@ def run_b200(args, n, rank, world, local_rank):
 
     dbg = []
 
+    # ---- DiscreteGeometry input: every rank holds the nodal values of its own node planes; the ghost plane (first plane of
+    # the next rank) arrives by NCCL send/recv inside every step, as in a re-cut loop on an evolving level set
+    nodal_bufs, layer_nodes = [], 0
+    if args.nodal:
+        from gecut import DiscreteGeometry
+        from gecut.cutters import evaluate_leaves_at_nodes
+        from gecut.csg import find_unique_leaves, replace_data
+        from gecut.distributed import exchange_ghost_plane_
+        tree = geo.get_tree()
+        payloads, oid_to_j = find_unique_leaves(tree)
+        layer_nodes = model.num_nodes // (model.partition[-1] + 1)
+        k0, k1 = slab if slab is not None else (0, model.partition[-1])
+        for pl in payloads:
+            (full,) = evaluate_leaves_at_nodes(model, [pl], ctx=ctx, device_output=True)
+            buf = full[k0 * layer_nodes:(k1 + 1) * layer_nodes].clone()
+            if world > 1 and rank < world - 1:
+                buf[-layer_nodes:] = float("nan")  # the ghost plane is NOT known locally: it must come from the neighbour
+            nodal_bufs.append(buf)
+            del full
+        torch.cuda.empty_cache()
+        geo = DiscreteGeometry(replace_data(lambda d: d, lambda d: (nodal_bufs[oid_to_j[id(d[0])]], d[1], d[2]), tree), model)
+        cutter = LevelSetCutter(ctx, slab=slab, nodal_slab_local=slab is not None)
+        desc += "; level sets given as a DiscreteGeometry (device-resident slab-local nodal values, NCCL ghost-plane exchange per step)"
+
     cells_plan, bnd_plan = workload_plan(args.workload)
     SIDE = {-1: gecut.PHYSICAL_IN, 1: gecut.PHYSICAL_OUT}
 
     def step(e2e=False, host=None):
         t = [time.perf_counter()]
+        if nodal_bufs and world > 1:
+            for buf in nodal_bufs:
+                exchange_ghost_plane_(buf, layer_nodes)
         cg = cutter.cut(model, geo)
         t.append(time.perf_counter())
         oms = [Triangulation(cg, SIDE[side], name) for name, side in cells_plan]
@@ -455,7 +488,7 @@ def run_b200(args, n, rank, world, local_rank):
         step()
     rep = ctx.profile_report()
     ctx.profile(False)
-    kbytes, step_bytes = algorithmic_bytes(s, model, state["nsel"], state["nfsel"], ncellsel=len(cells_plan))
+    kbytes, step_bytes = algorithmic_bytes(s, model, state["nsel"], state["nfsel"], ncellsel=len(cells_plan), nodal=bool(nodal_bufs))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

@@ -423,6 +423,20 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
       for (int ls = 0; ls < L; ++ls) {
         uint32_t* P = Pk + ls * PW;
         const int kind = lv.leaf[ls].kind;
+        if (lv.signs[ls]) {
+          // NODAL leaf: the sign words were written by k_nodal_signs at full streaming bandwidth; a lane fetches one
+          // word of the plane (node row r, x word ww; the halo column only needs bit 0 of the next word)
+          const int wpr = lv.signs_wpr;
+          const uint32_t* S = lv.signs[ls] + (int64_t)(kp - g.k0) * ((D == 3) ? g.nn[1] : 1) * wpr;
+          for (int idx = lane; idx < PW; idx += 32) {
+            const int r = idx / (WXT + 1), ww = idx - r * (WXT + 1);
+            const int j = (D == 3) ? j0 + r : 0, wx = w0 + ww;
+            uint32_t word = 0u;
+            if ((D == 2 || j < g.nn[1]) && wx < wpr) word = __ldg(S + (int64_t)j * wpr + wx);
+            P[idx] = (ww == WXT) ? (word & 1u) : word;
+          }
+          continue;
+        }
         // rows x words with a value functor f(ww2, wv, r, ww) (in-plane partial sums) -- fully unrolled
         auto sweep = [&](auto f) {
 #pragma unroll
@@ -679,6 +693,44 @@ __global__ void k_cutmask_emit(const uint32_t* __restrict__ cutmask, int64_t ngr
   }
 }
 
+// Sign words of a NODAL level set (DiscreteGeometry): 8 bytes per node are read exactly once with eight independent
+// 256-byte warp loads in flight per warp, one bit per node is written.  word (row, wx) covers the nodes 32*wx .. 32*wx+31
+// of node row `row` (rows = the slab's node planes k0..k1 x the node rows of a plane); bits of nodes past the row end are 0.
+constexpr int NSG_WPI = 8;    // words per warp iteration
+constexpr int NSG_ITERS = 2;  // iterations per warp
+
+__global__ void __launch_bounds__(256)
+k_nodal_signs(const double* __restrict__ vals /* first node of the slab's first plane */, int nn0, int wpr, int64_t nwords,
+              uint32_t* __restrict__ signs) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t W0 = warp * (NSG_WPI * NSG_ITERS);
+#pragma unroll 1
+  for (int it = 0; it < NSG_ITERS; ++it, W0 += NSG_WPI) {
+    if (W0 >= nwords) return;
+    double v[NSG_WPI];
+    int64_t row = W0 / wpr;  // one division per iteration, then incremental (row, wx)
+    int wx = (int)(W0 - row * wpr);
+    const double* rp = vals + row * nn0;
+#pragma unroll
+    for (int q = 0; q < NSG_WPI; ++q) {
+      const int i = wx * 32 + lane;
+      v[q] = (W0 + q < nwords && i < nn0) ? __ldg(rp + i) : -1.0;
+      if (++wx == wpr) {
+        wx = 0;
+        rp += nn0;
+      }
+    }
+    uint32_t mine = 0u;
+#pragma unroll
+    for (int q = 0; q < NSG_WPI; ++q) {
+      const uint32_t word = __ballot_sync(0xffffffffu, v[q] > 0.0);
+      if (lane == q) mine = word;
+    }
+    if (lane < NSG_WPI && W0 + lane < nwords) signs[W0 + lane] = mine;
+  }
+}
+
 template <int D>
 __global__ void k_eval_leaf_nodes(const GcGrid g, const gecut_leaf leaf, double* __restrict__ out) {
   int64_t node = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -730,6 +782,30 @@ int gc_classify(gecut_ctx* ctx, gecut_result* res) {
     closed_form = closed_form && (k == GECUT_LEAF_SPHERE || k == GECUT_LEAF_PLANE || k == GECUT_LEAF_CYLINDER);
   }
   const int chunk = (L > 2 && closed_form) ? 2 : L;
+  // NODAL leaves: sign words first (streaming pass), the marching kernel then reads 1 bit per node instead of 8 bytes
+  const int swpr = (g.nn[0] + 31) / 32;
+  const int64_t srows = (int64_t)(nlayers + 1) * ((g.D == 3) ? g.nn[1] : 1);
+  const int64_t swords = srows * swpr;
+  uint32_t* sign_pool = nullptr;
+  const uint32_t* sign_of[GC_LMAX] = {};
+  {
+    int nnod = 0;
+    for (int i = 0; i < L; ++i) nnod += res->leaves.leaf[i].kind == GECUT_LEAF_NODAL ? 1 : 0;
+    if (nnod > 0) {
+      GC_CHECK(gc_malloc(ctx, (void**)&sign_pool, sizeof(uint32_t) * swords * nnod));
+      const int64_t layer_nodes = (int64_t)g.nn[0] * ((g.D == 3) ? g.nn[1] : 1);
+      const unsigned nbs = (unsigned)gc_div_up(swords, (int64_t)(256 / 32) * NSG_WPI * NSG_ITERS);
+      int q = 0;
+      for (int i = 0; i < L; ++i) {
+        if (res->leaves.leaf[i].kind != GECUT_LEAF_NODAL) continue;
+        uint32_t* dst = sign_pool + (int64_t)q++ * swords;
+        const double* first = res->leaves.nodal[i] + ((int64_t)g.k0 * layer_nodes - res->leaves.nodal_base);
+        GC_LAUNCH(ctx, "k_nodal_signs", k_nodal_signs<<<nbs, 256, 0, ctx->stream>>>(first, g.nn[0], swpr, swords, dst));
+        sign_of[i] = dst;
+      }
+      GC_CHECK(gc_launch_check(ctx, "k_nodal_signs"));
+    }
+  }
   auto launch = [&](auto Dtag, auto Stag) {
     constexpr int D = decltype(Dtag)::value;
     constexpr bool S = decltype(Stag)::value;
@@ -747,7 +823,9 @@ int gc_classify(gecut_ctx* ctx, gecut_result* res) {
       for (int i = 0; i < nl; ++i) {
         lv.leaf[i] = res->leaves.leaf[ls0 + i];
         lv.nodal[i] = res->leaves.nodal[ls0 + i];
+        lv.signs[i] = sign_of[ls0 + i];
       }
+      lv.signs_wpr = swpr;
       const int LH = nl <= 2 ? nl : 0;
       const int rowd = 1 + 2 * LH;
       const size_t per_warp = (sizeof(double) * C::RY * rowd + sizeof(uint32_t) * 2 * nl * C::PW + 15) & ~(size_t)15;
@@ -776,6 +854,7 @@ int gc_classify(gecut_ctx* ctx, gecut_result* res) {
     else
       launch(std::integral_constant<int, 2>{}, std::false_type{});
   }
+  gc_free(ctx, sign_pool);  // stream-ordered cache: the block is not handed out before the launches above have run
   return gc_launch_check(ctx, "k_classify");
 }
 

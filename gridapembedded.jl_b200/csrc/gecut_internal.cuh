@@ -47,6 +47,10 @@ struct GcLeaves {
   gecut_leaf leaf[GC_LMAX];
   const double* nodal[GC_LMAX];  // device pointers for NODAL leaves
   int64_t nodal_base;            // global id of the first node the NODAL vectors hold (0: whole model; slab node offset)
+  // classification only: sign words of NODAL leaves written by k_nodal_signs (bit b of word (row, wx) = value of node
+  // 32*wx+b of node row `row` is > 0; rows = node planes k0..k1 of the slab x node rows of a plane), else nullptr
+  const uint32_t* signs[GC_LMAX];
+  int signs_wpr;                 // words per node row
 };
 
 // Postfix boolean program over the level-set rows.  Programs with more than one operator also carry a truth table:

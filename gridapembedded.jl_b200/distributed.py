@@ -109,6 +109,29 @@ def exchange_ghost_plane(owned_values, layer_nodes: int, group=None):
     return owned_values if ghost is None else torch.cat([owned_values, ghost])
 
 
+def exchange_ghost_plane_(slab_values, layer_nodes: int, group=None):
+    """In-place form of `exchange_ghost_plane` for a re-cut loop: `slab_values` is the persistent (k1-k0+1)-plane buffer of
+    this rank (torch tensor); its first plane is sent to the previous rank and its last plane is overwritten with the
+    first plane of the next rank (the last rank owns its top plane).  No allocation, one send + one recv of layer_nodes
+    doubles per rank boundary."""
+    if not _active(group):
+        return slab_values
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+
+    def grank(r):
+        return dist.get_global_rank(group, r) if group is not None else r
+
+    reqs = []
+    if rank > 0:
+        reqs.append(dist.isend(slab_values[:layer_nodes], dst=grank(rank - 1), group=group))
+    if rank < world - 1:
+        reqs.append(dist.irecv(slab_values[slab_values.numel() - layer_nodes:], src=grank(rank + 1), group=group))
+    for r in reqs:
+        r.wait()
+    return slab_values
+
+
 class DistributedLevelSetCutter:
     """`cut(::DistributedDiscreteModel, geo)` analogue: each rank cuts its z-slab on its own GPU."""
 

@@ -86,6 +86,13 @@ def _worker(rank, world, port, q):
         owned = torch.from_numpy(vals[k0 * layer_nodes: top * layer_nodes].copy())
         full = exchange_ghost_plane(owned, layer_nodes)
         assert np.array_equal(full.numpy(), vals[k0 * layer_nodes: (k1 + 1) * layer_nodes])
+        # in-place form (persistent slab buffer of a re-cut loop): the ghost plane is unknown (NaN) before the exchange
+        from gecut.distributed import exchange_ghost_plane_
+        buf = torch.from_numpy(vals[k0 * layer_nodes: (k1 + 1) * layer_nodes].copy())
+        if rank < world - 1:
+            buf[-layer_nodes:] = float("nan")
+        exchange_ghost_plane_(buf, layer_nodes)
+        assert np.array_equal(buf.numpy(), vals[k0 * layer_nodes: (k1 + 1) * layer_nodes])
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
