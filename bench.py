@@ -247,6 +247,7 @@ def main():
     ap.add_argument("--nodal", action="store_true",
                     help="feed the level sets as a DiscreteGeometry: slab-local nodal vectors resident on each GPU, ghost "
                          "node plane from the next rank by NCCL send/recv every step (SURVEY 8e)")
+    ap.add_argument("--uniform-slabs", action="store_true", help="even z-slabs instead of the work-balanced partition")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -361,7 +362,19 @@ def run_b200(args, n, rank, world, local_rank):
     import ctypes as C
 
     model, geo, desc = make_workload(args.workload, n, world)
-    slab = slab_of(model, rank, world) if world > 1 else None
+    # z-slabs: work-balanced by default (even layers of classification + cut cells weighted by their measured cost; every
+    # rank derives the same partition from the geometry, no communication), --uniform-slabs for the even split
+    slab, slab_kind = None, "single GPU"
+    if world > 1:
+        if args.uniform_slabs:
+            slab, slab_kind = slab_of(model, rank, world), f"z-slab x{world} (even layers)"
+        else:
+            from gecut.distributed import balanced_slab_ranges
+            cw = {"c3_tet": 300.0, "c3_hex": 760.0, "c5_bimaterial": 1400.0}.get(args.workload, 600.0)
+            ranges = balanced_slab_ranges(model, geo, world, cut_weight=cw)
+            slab = ranges[rank]
+            slab_kind = (f"z-slab x{world}, work-balanced (layers per rank {[b - a for a, b in ranges]}; cut cell = "
+                         f"{cw:g} cells of classification)")
     stream = torch.cuda.current_stream()
     ctx = _lib.Context(local_rank, stream.cuda_stream)
     cutter = LevelSetCutter(ctx, slab=slab)
@@ -585,9 +598,9 @@ def run_b200(args, n, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": desc, "cells_per_gpu": int(model.num_cubes // world),
+            "config": {"workload": desc, "cells_per_gpu": int(model.num_cubes // world), "cells_rank0": int(model.num_cubes // model.partition[-1] * ((slab[1] - slab[0]) if slab else model.partition[-1])),
                        "bg_simplices_per_gpu": int(s.num_bgcells), "partition": list(model.partition),
-                       "parallelism": f"z-slab x{world}" if world > 1 else "single GPU",
+                       "parallelism": slab_kind,
                        "l2": "no L2 flush needed: every step rewrites its whole working set "
                              f"({(sum(lb.values())) / 1e9:.2f} GB of outputs per GPU >> 126 MB L2), nothing is reused across steps",
                        "per_gpu_counts": {"cut_cells": int(s.num_cutcells), "subcells": int(s.num_subcells),

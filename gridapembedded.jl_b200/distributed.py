@@ -32,6 +32,70 @@ def slab_range(nlast: int, rank: int, world: int) -> Tuple[int, int]:
     return k0, k0 + base + (1 if rank < rem else 0)
 
 
+def estimate_cut_cells_per_layer(model, geo, coarse: int = 128):
+    """Host estimate of the number of cut n-cubes in every layer of the last direction, from the signs of the level sets
+    on a coarse node grid: blocks of f x f (x f) fine cells with the SAME f in every direction (f = ceil(max partition /
+    coarse); anisotropic blocks would weight the surface orientations differently from the fine cells).  A block with
+    mixed signs for some level set stands for about f^(D-1) fine cut cells (cut cells scale like area / h^2) spread over
+    its f fine layers.  Needs closed-form or host-callable leaves; returns None for value-vector (DiscreteGeometry) leaves."""
+    import numpy as np
+    from .csg import find_unique_leaves
+    from .geometries import LeafFunction
+    payloads, _ = find_unique_leaves(geo.get_tree())
+    if not all(isinstance(p, LeafFunction) for p in payloads):
+        return None
+    D = model.D
+    part = list(model.partition)
+    f = max(1, -(-max(part) // max(1, coarse)))
+    cpart = [-(-n // f) for n in part]
+    h = [(model.pmax[d] - model.pmin[d]) / part[d] for d in range(D)]
+    axes = [model.pmin[d] + f * h[d] * np.arange(cpart[d] + 1) for d in range(D)]
+    grids = np.meshgrid(*axes, indexing="ij")
+    x = np.stack([g.ravel() for g in grids], axis=1)
+    shape = tuple(c + 1 for c in cpart)
+    cut = np.zeros(tuple(cpart), dtype=bool)
+    for p in payloads:
+        out = (p(x) > 0.0).reshape(shape)
+        any_ = np.zeros(tuple(cpart), dtype=bool)
+        all_ = np.ones(tuple(cpart), dtype=bool)
+        for corner in range(1 << D):
+            sl = tuple(slice((corner >> d) & 1, ((corner >> d) & 1) + cpart[d]) for d in range(D))
+            any_ |= out[sl]
+            all_ &= out[sl]
+        cut |= any_ & ~all_
+    per_block_layer = cut.reshape(-1, cpart[-1]).sum(axis=0).astype(np.float64)
+    per_fine_layer = per_block_layer * float(f) ** (D - 1) / f  # f^(D-1) fine cut cells per block over f layers
+    return np.repeat(per_fine_layer, f)[:part[-1]]
+
+
+def balanced_slab_ranges(model, geo, world: int, cut_weight: float = 600.0, coarse: int = 128) -> List[Tuple[int, int]]:
+    """Work-balanced z-slabs: contiguous layer ranges [k0,k1) per rank such that the estimated work
+    `layers * cubes_per_layer + cut_weight * cut cubes` is as even as possible (the classification sweep costs the same
+    for every cube, the subtriangulation and the integrals are proportional to the cut cells -- SURVEY.md section 8e:
+    "load is unbalanced in the cut work").  Deterministic and communication-free: every rank computes the same
+    partition from the geometry.  Falls back to the even split when the level sets cannot be evaluated on the host."""
+    import numpy as np
+    nz = model.partition[-1]
+    if world > nz:
+        raise ValueError("more ranks than layers")
+    est = estimate_cut_cells_per_layer(model, geo, coarse) if world > 1 else None
+    if est is None:
+        return [slab_range(nz, r, world) for r in range(world)]
+    cubes_per_layer = model.num_cubes // nz
+    w = cubes_per_layer + float(cut_weight) * est
+    pre = np.concatenate([[0.0], np.cumsum(w)])
+    bounds = [0]
+    for r in range(1, world):
+        target = pre[-1] * r / world
+        k = int(np.searchsorted(pre, target, side="left"))
+        if k > 0 and abs(pre[k - 1] - target) < abs(pre[min(k, nz)] - target):
+            k -= 1
+        k = max(bounds[-1] + 1, min(k, nz - (world - r)))  # every rank keeps at least one layer
+        bounds.append(k)
+    bounds.append(nz)
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
 def slab_cell_offset(model, k0: int) -> int:
     """Global id offset of the first cell of the slab starting at layer k0."""
     layer_cubes = model.num_cubes // model.partition[-1]

@@ -114,3 +114,34 @@ def test_two_ranks_gloo():
         p.join(timeout=60)
     for rank, msg in res:
         assert msg == "ok", f"rank {rank}: {msg}"
+
+
+def test_balanced_slabs_cover_the_layers_and_even_out_the_estimated_work():
+    """Work-balanced z-slabs (the cut work is surface-proportional): contiguous, non-empty, covering; the
+    estimated work of the most loaded rank drops for the two-cylinder model whose cylinders cross only some slabs."""
+    import gecut as G
+    from gecut.distributed import balanced_slab_ranges, estimate_cut_cells_per_layer, slab_range
+    steel = G.union(G.cylinder(0.4, x0=(0.0, 1.0, 0.7)), G.cylinder(0.4, x0=(0.0, 1.0, 2.3)), name="steel")
+    geo = G.union(steel, G.complement(steel, name="concrete"))
+    model = G.CartesianDiscreteModel((0.0, 0.0, 0.0), (3.0, 2.0, 3.0), (96, 96, 96))
+    est = estimate_cut_cells_per_layer(model, geo, coarse=32)
+    assert est.shape == (96,) and est.min() == 0.0 and est.max() > 0.0
+    cpl = model.num_cubes // 96
+
+    def worst(ranges, cw):
+        return max((b - a) * cpl + cw * est[a:b].sum() for a, b in ranges)
+
+    for world in (2, 3, 8):
+        rs = balanced_slab_ranges(model, geo, world, cut_weight=1400.0, coarse=32)
+        assert rs[0][0] == 0 and rs[-1][1] == 96 and all(a < b for a, b in rs)
+        assert all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
+        even = [slab_range(96, r, world) for r in range(world)]
+        assert worst(rs, 1400.0) <= worst(even, 1400.0) + 1e-9
+    assert worst(balanced_slab_ranges(model, geo, 8, 1400.0, coarse=32), 1400.0) < 0.8 * worst([slab_range(96, r, 8) for r in range(8)], 1400.0)
+    # value-vector leaves cannot be evaluated on the host: even split
+    dg = G.DiscreteGeometry(np.zeros(model.num_nodes), model, name="d")
+    assert balanced_slab_ranges(model, dg, 4) == [slab_range(96, r, 4) for r in range(4)]
+    # more ranks than layers is an error, one rank owns everything
+    assert balanced_slab_ranges(model, geo, 1) == [(0, 96)]
+    with pytest.raises(ValueError):
+        balanced_slab_ranges(model, geo, 97)
