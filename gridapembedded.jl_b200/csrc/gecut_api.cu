@@ -316,6 +316,7 @@ int make_program(gecut_ctx* ctx, const int32_t* program, int len, int L, GcProgr
   if (depth != 1) goto bad;
   p->len = len;
   p->lut = nullptr;
+  p->blut = nullptr;
   p->nused = 0;
   p->sc_base = p->sc_row = p->bg_base = p->bg_row = nullptr;
   if (len >= 3) {
@@ -364,6 +365,42 @@ int make_program(gecut_ctx* ctx, const int32_t* program, int len, int L, GcProgr
 bad:
   ctx->err = "malformed boolean program";
   return GECUT_ERR_INVALID;
+}
+
+// compute_inoutboundary (EmbeddedDiscretizations.jl:179-245) as a truth table over the level sets the program uses: entry =
+// (state + 1) | (orientation + 1) << 2, same base-3 index as `lut` (subfacet states are IN / OUT / INTERFACE = -1 / 1 / 0)
+static int attach_boundary_lut(gecut_ctx* ctx, GcProgram* p) {
+  if (p->len < 3 || p->nused <= 0 || p->nused > GC_LUT_MAXUSED) return GECUT_OK;  // single leaf: no table needed
+  const std::string key = "B" + std::string(reinterpret_cast<const char*>(p->tok), (size_t)p->len);
+  auto it = ctx->lut_cache.find(key);
+  if (it == ctx->lut_cache.end()) {
+    size_t n = 1;
+    for (int k = 0; k < p->nused; ++k) n *= 3;
+    std::vector<int8_t> tab(n);
+    int8_t vals[GC_LMAX] = {0};
+    for (size_t idx = 0; idx < n; ++idx) {
+      size_t r = idx;
+      for (int k = 0; k < p->nused; ++k) {
+        vals[p->used[k]] = (int8_t)((int)(r % 3) - 1);
+        r /= 3;
+      }
+      int st = 0, orient = 1;
+      gc_eval_inoutboundary_vals(*p, vals, &st, &orient);
+      tab[idx] = (int8_t)((st + 1) | ((orient + 1) << 2));
+    }
+    int8_t* d = nullptr;
+    if (cudaMalloc((void**)&d, n) != cudaSuccess) {
+      ctx->err = "out of device memory (boundary truth table)";
+      return GECUT_ERR_OOM;
+    }
+    it = ctx->lut_cache.emplace(key, std::make_pair(d, std::move(tab))).first;
+    if (cudaMemcpyAsync(d, it->second.second.data(), n, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+      ctx->err = "upload of the boundary truth table failed";
+      return GECUT_ERR_CUDA;
+    }
+  }
+  p->blut = it->second.first;
+  return GECUT_OK;
 }
 
 // Multi-operator programs: evaluate once over the subcell and bg-cell rows of `res`, keep the two Int8 rows with the
@@ -727,6 +764,7 @@ int gecut_select_boundary(const gecut_result* res, const int32_t* program1, int 
   sel->kind = GECUT_SEL_BOUNDARY;
   const int64_t launches0 = ctx->launches;
   int st = make_program(ctx, program1, len1, res->L, &sel->prog);
+  if (st == GECUT_OK) st = attach_boundary_lut(ctx, &sel->prog);
   if (st == GECUT_OK && program2) {
     st = make_program(ctx, program2, len2, res->L, &sel->prog2);
     sel->has_prog2 = true;

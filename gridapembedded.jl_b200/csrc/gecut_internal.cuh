@@ -61,6 +61,7 @@ struct GcProgram {
   int len;
   int8_t tok[GECUT_MAX_PROGRAM];
   const int8_t* lut;
+  const int8_t* blut;  // boundary programs: (state + 1) | (orientation + 1) << 2 of compute_inoutboundary, same index
   int nused;
   int8_t used[GC_LUT_MAXUSED];
   // memoised results of this program over the subcell / bg-cell state rows of one result (device, owned by the result):
@@ -451,6 +452,41 @@ __device__ __forceinline__ void gc_eval_inoutboundary(const GcProgram& p, const 
     int tok = p.tok[t];
     if (tok >= 0) {
       st[sp] = rows[(int64_t)tok * pitch + e];
+      orr[sp] = 1;
+      sp++;
+    } else if (tok == GECUT_OP_COMPLEMENT) {
+      if (st[sp - 1] == GECUT_INTERFACE) orr[sp - 1] = (int8_t)-orr[sp - 1];
+      st[sp - 1] = (int8_t)gc_io_complementary(st[sp - 1]);
+    } else {
+      int b = st[sp - 1], a = st[sp - 2];
+      int d2 = orr[sp - 1], d1 = orr[sp - 2];
+      sp -= 2;
+      int rs, ro;
+      if (tok == GECUT_OP_SETDIFF) {
+        rs = gc_io_setdiff(a, b);
+        ro = (a == GECUT_INTERFACE) ? d1 : ((b == GECUT_INTERFACE) ? -d2 : d1);
+      } else {
+        rs = tok == GECUT_OP_UNION ? gc_io_union(a, b) : gc_io_intersection(a, b);
+        ro = (a == GECUT_INTERFACE) ? d1 : ((b == GECUT_INTERFACE) ? d2 : d1);
+      }
+      st[sp] = (int8_t)rs;
+      orr[sp] = (int8_t)ro;
+      sp++;
+    }
+  }
+  *state = st[0];
+  *orientation = orr[0];
+}
+
+// the same on explicit per-level-set values (host: builds the boundary truth table)
+__host__ __device__ __forceinline__ void gc_eval_inoutboundary_vals(const GcProgram& p, const int8_t* vals, int* state,
+                                                                    int* orientation) {
+  int8_t st[GECUT_MAX_PROGRAM / 2 + 2], orr[GECUT_MAX_PROGRAM / 2 + 2];
+  int sp = 0;
+  for (int t = 0; t < p.len; ++t) {
+    int tok = p.tok[t];
+    if (tok >= 0) {
+      st[sp] = vals[tok];
       orr[sp] = 1;
       sp++;
     } else if (tok == GECUT_OP_COMPLEMENT) {

@@ -274,7 +274,15 @@ __global__ void k_flag_boundary(const GcLayout lay, int64_t nsf, const GcProgram
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nsf) return;
   int s1, o1;
-  gc_eval_inoutboundary(prog1, lay.sf_state, lay.sf_pitch, e, &s1, &o1);
+  if (prog1.blut) {  // truth table: one gather instead of the stack machine (whose stacks live in local memory)
+    int idx = 0;
+    for (int k = prog1.nused - 1; k >= 0; --k) idx = idx * 3 + (lay.sf_state[(int64_t)prog1.used[k] * lay.sf_pitch + e] + 1);
+    const int v = __ldg(prog1.blut + idx);
+    s1 = (v & 3) - 1;
+    o1 = (v >> 2) - 1;
+  } else {
+    gc_eval_inoutboundary(prog1, lay.sf_state, lay.sf_pitch, e, &s1, &o1);
+  }
   bool keep = s1 == GECUT_INTERFACE;
   if (keep && has2) keep = gc_eval_inoutcut(prog2, lay.sf_state, lay.sf_pitch, e) == GECUT_INTERFACE;
   flags[e] = keep ? 1u : 0u;

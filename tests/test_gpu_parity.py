@@ -241,6 +241,40 @@ def test_discrete_geometry_matches_analytical():
         assert np.array_equal(h1[k], h3[k]), k
 
 
+@pytest.mark.parametrize("part,simplex,slab", [((70, 45), False, None), ((33, 64), True, (5, 40)), ((65, 31, 9), False, None),
+                                               ((31, 33, 12), True, (2, 11)), ((96, 8, 8), False, (0, 3)),
+                                               ((5, 4, 3), True, None)])
+def test_nodal_sign_words_classify_like_the_closed_form(part, simplex, slab):
+    """NODAL level sets go through k_nodal_signs (one streaming pass: value vector -> sign words) and the marching kernel
+    reads bits; the whole result must equal the cut of the same level sets in closed form, bit for bit -- row lengths that
+    are not multiples of 32 nodes, 2-D and 3-D, n-cube and simplex cells, whole model and z-slabs (device and host
+    vectors, two level sets so that chunked and NODAL rows mix with an analytical one)."""
+    import torch
+    D = len(part)
+    if D == 2:
+        g1, g2 = disk(0.62, x0=(0.05, -0.1)), disk(0.3, x0=(-0.4, 0.35))
+        model = CartesianDiscreteModel((-1.0, -0.9), (1.0, 0.9), part)
+    else:
+        g1, g2 = sphere(0.62, x0=(0.05, -0.1, 0.02)), cylinder(0.3, x0=(-0.4, 0.35, 0.0), v=(0.0, 0.0, 1.0))
+        model = CartesianDiscreteModel((-1.0, -0.9, -0.8), (1.0, 0.9, 0.8), part)
+    if simplex:
+        model = simplexify(model)
+    geo = union(g1, g2, name="both")
+    leaves, _, _ = gecut.cutters.flatten_geometry(model, geo)
+    v1, v2 = gecut.cutters.evaluate_leaves_at_nodes(model, leaves, device_output=False)
+    cutter = LevelSetCutter(slab=slab)
+    ref = cutter.cut(model, geo).to_host()
+    # both NODAL (host vectors), NODAL + closed form (device vector)
+    d_both = union(DiscreteGeometry(v1, model, name="a"), DiscreteGeometry(v2, model, name="b"), name="both")
+    d_mix = union(DiscreteGeometry(torch.from_numpy(v1).cuda(), model, name="a"), g2, name="both")
+    for dg in (d_both, d_mix):
+        got = cutter.cut(model, dg).to_host()
+        for k in ref:
+            assert np.array_equal(ref[k], got[k]), k
+    # classification-only verb on the NODAL geometry
+    assert np.array_equal(cutter.compute_bgcell_to_inoutcut(model, d_both), cutter.compute_bgcell_to_inoutcut(model, geo))
+
+
 def test_host_function_geometry_popcorn():
     geo = popcorn()
     model = box_model(geo, (14, 14, 14))
