@@ -406,9 +406,12 @@ static int attach_boundary_lut(gecut_ctx* ctx, GcProgram* p) {
 // Multi-operator programs: evaluate once over the subcell and bg-cell rows of `res`, keep the two Int8 rows with the
 // result and let every later evaluation of the same program read them (selections of both sides, measures, Laplacian).
 int attach_program_rows(gecut_ctx* ctx, const gecut_result* res_c, GcProgram* p) {
-  // single-leaf programs read one state row anyway, and with few level sets the truth-table gather over the rows is
-  // cheaper than a pass that writes a new row
-  if (!p->lut || p->nused <= 4) return GECUT_OK;
+  // single-leaf programs read one state row anyway.  Multi-operator programs: the SUBCELL row is always memoised (O(Nsc)
+  // bytes, one short pass; every later consumer -- both sides' selections, the Laplacian's per-subcell test -- reads one byte
+  // instead of the dependent chain state rows -> truth-table gather); the BG-CELL row (a pass over all Nc cells) only when
+  // the program uses more than four level sets, else the truth-table gather over the rows is cheaper than writing a new row
+  if (!p->lut) return GECUT_OK;
+  const bool want_bg = p->nused > 4;
   gecut_result* res = const_cast<gecut_result*>(res_c);
   const std::string key(reinterpret_cast<const char*>(p->tok), (size_t)p->len);
   auto it = res->prog_rows.find(key);
@@ -419,7 +422,7 @@ int attach_program_rows(gecut_ctx* ctx, const gecut_result* res_c, GcProgram* p)
       GC_CHECK(gc_malloc(ctx, (void**)&sc, (size_t)pad_pitch(nsc)));  // padded: consumers read 16-byte vectors
       GC_CHECK(gc_eval_rows(ctx, res->lay.sc_state, res->lay.sc_pitch, nsc, *p, sc, true));
     }
-    if (nc > 0) {
+    if (nc > 0 && want_bg) {
       GC_CHECK(gc_malloc(ctx, (void**)&bg, (size_t)pad_pitch(nc)));
       GC_CHECK(gc_eval_rows(ctx, res->lay.bg_state, res->lay.bg_pitch, nc, *p, bg, true));
     }
