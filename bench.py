@@ -208,6 +208,8 @@ def algorithmic_bytes(s, model, nsel, nfsel, nodal=False, ncellsel=1):
     ntiles = (nsimp + 127) // 128
     k["k_cut1_count"] = 4 * Ncut + 12 * ntiles
     meas = 8 * (int(s.num_subcells) + int(s.num_subfacets))  # per-entity measures written next to the layout
+    if model.simplexified and L == 1:
+        meas = 0  # simplex cells, one level set: summed on chip (tile statistics, per-cell IN / OUT), per entity on demand
     k["k_cut1_fill"] = 4 * Ncut + 12 * ntiles + lb["subcells"] + lb["subfacets"] + 4 * Ncut + meas
     if L == 1:  # tile statistics (4 doubles per 32-simplex tile) and, for simplex bg cells, (IN, OUT) measure per cut cell
         k["k_cut1_fill"] += 32 * ((nsimp + 31) // 32) + (16 * Ncut if model.simplexified else 0)

@@ -319,6 +319,8 @@ extern "C" int gecut_aggregate(const gecut_result* cut, const gecut_facet_result
     const double w = D == 2 ? 0.25 : 0.125;
     double cell_meas = 0.0;
     for (int q = 0; q < nq; ++q) cell_meas += w * fabs(detJ);
+    st = gc_ensure_measures(ctx, cut);
+    if (st != GECUT_OK) return done(st);
     GC_LAUNCH(ctx, "k_agg_init_cut", k_agg_init_cut<<<(unsigned)gc_div_up(ncut, T), T, 0, ctx->stream>>>(
         cut->lay, cut->cut_sc_ptr, ncut, p, side, threshold, cell_meas, cellin, touched));
     st = gc_launch_check(ctx, "k_agg_init_cut");

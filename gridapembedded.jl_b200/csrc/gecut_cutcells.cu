@@ -1252,7 +1252,7 @@ __device__ __forceinline__ constexpr int cut1_edge_b(int e) {
 //                       then the same warp copy
 // Phases C and D have no divergent trip counts: every lane owns one output entity and finds its simplex through a
 // byte map written in phase A.
-template <int D, bool SX, int MB>
+template <int D, bool SX, int MB, bool WM = true>
 __global__ void __launch_bounds__(CUT1_BLOCK, MB)
 k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
             const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
@@ -1471,7 +1471,7 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
     const int8_t io = TC.sub_inout[cc][j];
     const double ms = integrate_one<D>(simplex_meas<D, D>(pc));
     lay.sc_state[o] = io;
-    lay.sc_meas[o] = ms;
+    if (WM) lay.sc_meas[o] = ms;
     if (io == GC_IN) {
       st_in += ms;
       st_nin++;
@@ -1503,7 +1503,7 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
     lay.sf_c2bg[o] = (int32_t)r.w;
     lay.sf_state[o] = (int8_t)GECUT_INTERFACE;
     const double mf = integrate_one<D - 1>(simplex_meas<D, D - 1>(pf));
-    lay.sf_meas[o] = mf;
+    if (WM) lay.sf_meas[o] = mf;
     st_surf += mf;
   }
   // fixed lane assignment + fixed shuffle tree: the tile sums are reproducible
@@ -1698,6 +1698,51 @@ k_tile_stats_reduce(const double4* __restrict__ tile_stats, int64_t ntiles, doub
 
 static inline int64_t pad_pitch(int64_t n) { return ((n + 255) / 256) * 256; }
 
+// Per-entity measures on demand.  Simplex bg cells with one level set: everything the default consumers need (the three
+// global sums, the (IN, OUT) measure of every cut cell) is summed by the fill kernel while the vertices are on chip, so the
+// 8 bytes per subcell / subfacet are not written at cut time; whoever asks for per-entity values (gecut_integrate_measure
+// with `values`, non-leaf selections, get_cell_measure) gets them from this pass -- the same simplex_meas / integrate_one
+// on the same stored coordinates, hence the same bits as the fill kernel would have written.
+template <int D, int DS>
+__global__ void __launch_bounds__(256)
+k_entity_measures(const int32_t* __restrict__ c2p, const double* __restrict__ X, int64_t n, double* __restrict__ meas) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  double pc[DS + 1][3];
+#pragma unroll
+  for (int v = 0; v <= DS; ++v) {
+    const int64_t pid = (int64_t)c2p[e * (DS + 1) + v] - 1;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) pc[v][d] = d < D ? X[pid * D + d] : 0.0;
+  }
+  meas[e] = integrate_one<DS>(simplex_meas<D, DS>(pc));
+}
+
+int gc_ensure_measures(gecut_ctx* ctx, const gecut_result* res_c) {
+  gecut_result* res = const_cast<gecut_result*>(res_c);
+  GcLayout& lay = res->lay;
+  const int D = res->grid.D;
+  const int64_t nsc = res->sizes.num_subcells, nsf = res->sizes.num_subfacets;
+  const int T = 256;
+  if (!lay.sc_meas && nsc > 0) {
+    GC_CHECK(gc_malloc(ctx, (void**)&lay.sc_meas, sizeof(double) * nsc));
+    const unsigned nb = (unsigned)gc_div_up(nsc, T);
+    if (D == 2)
+      GC_LAUNCH(ctx, "k_entity_measures", k_entity_measures<2, 2><<<nb, T, 0, ctx->stream>>>(lay.sc_c2p, lay.sc_X, nsc, lay.sc_meas));
+    else
+      GC_LAUNCH(ctx, "k_entity_measures", k_entity_measures<3, 3><<<nb, T, 0, ctx->stream>>>(lay.sc_c2p, lay.sc_X, nsc, lay.sc_meas));
+  }
+  if (!lay.sf_meas && nsf > 0) {
+    GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_meas, sizeof(double) * nsf));
+    const unsigned nb = (unsigned)gc_div_up(nsf, T);
+    if (D == 2)
+      GC_LAUNCH(ctx, "k_entity_measures", k_entity_measures<2, 1><<<nb, T, 0, ctx->stream>>>(lay.sf_c2p, lay.sf_X, nsf, lay.sf_meas));
+    else
+      GC_LAUNCH(ctx, "k_entity_measures", k_entity_measures<3, 2><<<nb, T, 0, ctx->stream>>>(lay.sf_c2p, lay.sf_X, nsf, lay.sf_meas));
+  }
+  return gc_launch_check(ctx, "k_entity_measures");
+}
+
 // L == 1: tile totals -> scan over tiles -> allocate -> fill (see the fast-path kernels above)
 static int gc_cut_cells_l1(gecut_ctx* ctx, gecut_result* res) {
   const GcGrid& g = res->grid;
@@ -1760,8 +1805,12 @@ static int gc_cut_cells_l1(gecut_ctx* ctx, gecut_result* res) {
   GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_c2bg, sizeof(int32_t) * nsf));
   GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_N, sizeof(double) * nsf * D));
   GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_state, (size_t)lay.sf_pitch));
-  GC_CHECK(gc_malloc(ctx, (void**)&lay.sc_meas, sizeof(double) * nsc));
-  GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_meas, sizeof(double) * nsf));
+  // simplex bg cells: per-entity measures are not written at cut time (gc_ensure_measures computes them on demand)
+  const bool lazy_meas = g.simplexified != 0;
+  if (!lazy_meas) {
+    GC_CHECK(gc_malloc(ctx, (void**)&lay.sc_meas, sizeof(double) * nsc));
+    GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_meas, sizeof(double) * nsf));
+  }
   lay.sf_X = lay.sc_X;  // device-side alias (read-only results); the host copy-out writes both destinations
   lay.sf_R = lay.sc_R;
   res->sf_points_alias = true;
@@ -1780,7 +1829,7 @@ static int gc_cut_cells_l1(gecut_ctx* ctx, gecut_result* res) {
     const unsigned nbf = (unsigned)gc_div_up(ntiles, CUT1_BLOCK / CUT1_TILE);
 #define GC_FILL1(DD, SXV, MB)                                                                                          \
   GC_LAUNCH(ctx, "k_cut1_fill",                                                                                        \
-            k_cut1_fill<DD, SXV, MB><<<nbf, CUT1_BLOCK, (size_t)cut1_warp_bytes<DD>() * (CUT1_BLOCK / CUT1_TILE), ctx->stream>>>( \
+            k_cut1_fill<DD, SXV, MB, !SXV><<<nbf, CUT1_BLOCK, (size_t)cut1_warp_bytes<DD>() * (CUT1_BLOCK / CUT1_TILE), ctx->stream>>>( \
                 g, res->leaves, ctx->d_tables, ctx->d_simplexify_raw, ctx->d_simplexify_pos, lay.cutcells, nsimp, t_cells,   \
                 t_points, t_facets, lay, res->cut_sc_ptr, tile_stats, res->cell_vio))
 #define GC_FILL2(DD, SXV) GC_FILL1(DD, SXV, CUT1_MINB)

@@ -542,6 +542,7 @@ int gc_integrate_measure(gecut_ctx* ctx, const gecut_selection* sel, double* val
     total += sel->kind == GECUT_SEL_BOUNDARY ? res->l1_stats[2] : res->l1_stats[sel->lazy_side == GECUT_IN ? 0 : 1];
   } else if (use_sub && n > 0) {
     GC_CHECK(gc_materialize_sub_ids(ctx, const_cast<gecut_selection*>(sel)));
+    GC_CHECK(gc_ensure_measures(ctx, res));  // simplex cells, one level set: not written at cut time
     const int NB = (int)std::min<int64_t>(1184, gc_div_up(n, 1024));
     double* partial = nullptr;  // NB block partials, the total, the completion ticket
     GC_CHECK(gc_malloc(ctx, (void**)&partial, sizeof(double) * (NB + 2)));
@@ -592,6 +593,7 @@ int gc_integrate_laplacian(gecut_ctx* ctx, gecut_selection* sel, double* K_bg_ho
             res->lay, g.cpc, res->cell_vio, ncut, eff, Gd, sel->K_cut));
       return gc_launch_check(ctx, "k_cutcell_laplacian_p1_vio");
     }
+    GC_CHECK(gc_ensure_measures(ctx, res));
     if (g.D == 2)
       GC_LAUNCH(ctx, "k_cutcell_laplacian", k_cutcell_laplacian_p1<2><<<nb1, 128, 0, ctx->stream>>>(
           g, res->lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, check_bg, Gd, sel->K_cut));
@@ -600,6 +602,7 @@ int gc_integrate_laplacian(gecut_ctx* ctx, gecut_selection* sel, double* K_bg_ho
           g, res->lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, check_bg, Gd, sel->K_cut));
     return gc_launch_check(ctx, "k_cutcell_laplacian_p1");
   }
+  GC_CHECK(gc_ensure_measures(ctx, res));
   const int T = LAPQ_T;
   const unsigned nb = (unsigned)gc_div_up(ncut, T / LAPQ_G);
   if (g.D == 2)
@@ -626,6 +629,7 @@ int gc_cell_measure(gecut_ctx* ctx, const gecut_selection* sel, double* values_d
   const int T = 256;
   GC_LAUNCH(ctx, "k_bgcell_measure", k_bgcell_measure<<<(unsigned)gc_div_up(nc, T), T, 0, ctx->stream>>>(
       res->lay, nc, sel->prog, sel->side, g.cpc, use_bg ? 1 : 0, tm, values_dev));
+  if (use_sub && ncut > 0 && res->cut_sc_ptr) GC_CHECK(gc_ensure_measures(ctx, res));
   if (use_sub && ncut > 0 && res->cut_sc_ptr)
     GC_LAUNCH(ctx, "k_cutcell_measure", k_cutcell_measure<<<(unsigned)gc_div_up(ncut, T), T, 0, ctx->stream>>>(
         res->lay, res->cut_sc_ptr, ncut, sel->prog, sel->side, values_dev));

@@ -223,6 +223,8 @@ int gc_malloc(gecut_ctx* ctx, void** p, size_t bytes);
 void gc_free(gecut_ctx* ctx, void* p);
 void gc_trim(gecut_ctx* ctx);  // give every cached block back to the driver
 int gc_launch_check(gecut_ctx* ctx, const char* what);
+// per-entity measures of results that did not write them at cut time (simplex bg cells, one level set)
+int gc_ensure_measures(gecut_ctx* ctx, const struct gecut_result* res);
 
 // ---- host helpers of gecut_api.cu shared with gecut_facets.cu ----
 struct DeviceGuard {

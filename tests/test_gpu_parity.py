@@ -275,6 +275,34 @@ def test_nodal_sign_words_classify_like_the_closed_form(part, simplex, slab):
     assert np.array_equal(cutter.compute_bgcell_to_inoutcut(model, d_both), cutter.compute_bgcell_to_inoutcut(model, geo))
 
 
+@pytest.mark.parametrize("case", ["disk_tri_50", "sphere_tet_12", "sphere_tet_odd", "sphere_hex_12"])
+def test_per_entity_measures_on_demand(case):
+    """Simplex bg cells with one level set do not write the per-entity measures at cut time (the sums come from the fill
+    kernel's tile statistics); per-entity values, cell measures and the matrices of a complemented selection are computed
+    on demand and must be the bits the oracle integrates (n-cube cells, which do write them, run the same assertions)."""
+    model, geo = CASES[case]()
+    oc = ob.oracle_cut(model, geo)
+    gd = cut(model, geo)
+    prog = gd.program(None)
+    for side, sel in ((IN, PHYSICAL_IN), (OUT, PHYSICAL_OUT)):
+        t = Triangulation(gd, sel)
+        ids = oc.select_subcells(prog, side)
+        total_fast = integrate_measure(Measure(t, 2))                     # tile statistics, no per-entity array
+        total, vals = integrate_measure(Measure(t, 2), return_values=True)  # per-entity values on demand
+        ref = oc.subcell_measures(ids)
+        assert np.array_equal(vals, ref)
+        bg = oc.select_bgcells(prog, side)
+        expect = ref.sum() + sum(oc.bgcell_measure(int(c)) for c in bg)
+        assert abs(total - expect) <= 1e-12 * abs(expect) and abs(total_fast - expect) <= 1e-12 * abs(expect)
+        K_cut, _ = integrate_laplacian(Measure(t, 2))
+        assert np.allclose(K_cut, oc.cutcell_laplacian(ids), rtol=1e-12, atol=1e-14)
+    ga = EmbeddedBoundary(gd)
+    fids, _ = oc.select_boundary(prog)
+    tot, fvals = integrate_measure(Measure(ga, 2), return_values=True)
+    assert np.array_equal(fvals, oc.subfacet_measures(fids))
+    assert abs(tot - integrate_measure(Measure(ga, 2))) <= 1e-12 * abs(tot)
+
+
 def test_host_function_geometry_popcorn():
     geo = popcorn()
     model = box_model(geo, (14, 14, 14))
