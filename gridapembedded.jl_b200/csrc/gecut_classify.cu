@@ -267,7 +267,7 @@ __device__ __forceinline__ void cls_store_any(int8_t* out, const unsigned long l
 // depend on one coordinate only: the x parts live in registers (per x word of the tile), the y parts in shared memory
 // (per node row), the marching coordinate enters once per plane.  The association of the reference formulas
 // (gc_eval_leaf) is preserved exactly -- same operations, same rounding -- only loop-invariant ones move.
-template <int D, bool SIMPLEX, int LH>
+template <int D, bool SIMPLEX, int LH, bool SG /* some level set of the launch comes as precomputed sign words */>
 __global__ void __launch_bounds__(ClsCfg<D, SIMPLEX>::WARPS * 32, CLS_MIN_BLOCKS)
 k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64_t pitch,
            uint32_t* __restrict__ cutmask, uint32_t* __restrict__ cutcount, const uint8_t* __restrict__ simplexify_raw,
@@ -423,7 +423,7 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
       for (int ls = 0; ls < L; ++ls) {
         uint32_t* P = Pk + ls * PW;
         const int kind = lv.leaf[ls].kind;
-        if (lv.signs[ls]) {
+        if (SG && lv.signs[ls]) {
           // NODAL leaf: the sign words were written by k_nodal_signs at full streaming bandwidth; a lane fetches one
           // word of the plane (node row r, x word ww; the halo column only needs bit 0 of the next word)
           const int wpr = lv.signs_wpr;
@@ -833,13 +833,22 @@ int gc_classify(gecut_ctx* ctx, gecut_result* res) {
       int8_t* states = res->lay.bg_state + (int64_t)ls0 * res->lay.bg_pitch;
       unsigned long long* counts = res->bg_counts_dev + (int64_t)ls0 * 12;
       const int acc = ls0 > 0 ? 1 : 0;
-#define GC_CLS(LHV)                                                                                                   \
-  GC_LAUNCH(ctx, "k_classify", k_classify<D, S, LHV><<<nb, C::WARPS * 32, smem, ctx->stream>>>(                        \
+      bool any_signs = false;
+      for (int i = 0; i < nl; ++i) any_signs = any_signs || lv.signs[i] != nullptr;
+#define GC_CLS(LHV, SGV)                                                                                              \
+  GC_LAUNCH(ctx, "k_classify", k_classify<D, S, LHV, SGV><<<nb, C::WARPS * 32, smem, ctx->stream>>>(                   \
       g, lv, states, res->lay.bg_pitch, res->cutmask, res->cutcount, ctx->d_simplexify_raw, counts, zs, ntx, nty,     \
       ntiles, acc))
-      if (nl == 1) GC_CLS(1);
-      else if (nl == 2) GC_CLS(2);
-      else GC_CLS(0);
+      // the sign-word branch is compiled out of the closed-form instances (it cost the tet kernel 24 bytes of spills)
+      if (any_signs) {
+        if (nl == 1) GC_CLS(1, true);
+        else if (nl == 2) GC_CLS(2, true);
+        else GC_CLS(0, true);
+      } else {
+        if (nl == 1) GC_CLS(1, false);
+        else if (nl == 2) GC_CLS(2, false);
+        else GC_CLS(0, false);
+      }
 #undef GC_CLS
     }
   };
