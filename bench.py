@@ -114,7 +114,7 @@ def slab_of(model, rank, world):
 
 class ClockSampler:
     """SM clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe), read through NVML in-process
-    (pynvml / nvidia-ml-py) every 50 ms: the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*`
+    (pynvml / nvidia-ml-py) every 20 ms: the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*`
     prints, without the heavy per-sample cost of the nvidia-smi loop (which was measured to stretch 5.5 ms steps to
     10-16 ms).  Falls back to one `nvidia-smi` query after the timed region if NVML is unavailable."""
 
@@ -152,7 +152,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.02)
 
     def clear(self):
         self.samples.clear()
@@ -171,7 +171,7 @@ class ClockSampler:
         self.thread.join(timeout=1)
         sm = sorted(self.samples)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.smax, "reasons": sorted(self.reasons),
-                "samples": len(sm), "source": "NVML in-process, 50 ms period"}
+                "samples": len(sm), "source": "NVML in-process, 20 ms period"}
 
 
 # --------------------------------------------------------------------------------------------------------------------
