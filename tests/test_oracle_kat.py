@@ -168,6 +168,9 @@ def test_csg_multi_levelset_divergence_theorem():
     p = prog(oc, "csg")
     a, b = divergence_theorem(oc, model, p, p, gradu=[1, 1, -1], facet_degree=4)
     assert abs(a - b) < 1.0e-9
+    # ... and through the Q1 element matrices of the ten-level-set cut (AffineFEOperator's input in the example)
+    a_mat = matrix_form(oc, model, p, [1, 1, -1])
+    assert abs(a_mat - a) < 1e-12 * max(1.0, abs(a)) and abs(a_mat - b) < 1.0e-9
     # the Dirichlet boundary of the example: EmbeddedBoundary(cutgeo,"csg","source") is part of the whole boundary
     f_all, _ = oc.select_boundary(p)
     f_src, _ = oc.select_boundary(p, prog(oc, "source"))
@@ -205,3 +208,45 @@ def test_two_phase_union_with_complement():
     f1, o1 = oc.select_boundary(ps, pc)
     f2, o2 = oc.select_boundary(pc, ps)
     assert len(f1) > 0 and np.array_equal(f1, f2) and np.array_equal(o1, -o2)
+
+
+def matrix_form(oc, model, p, gradu, seed=1234):
+    """sum over the active cells of v_c^T K_c u_c with the element matrices of the path (cut cells: contributions of the
+    selected subcells moved to their bg cell; uncut IN cells: the bg-cell matrix), u = gradu·x, v as in divergence_theorem()."""
+    rng = np.random.default_rng(seed)
+    vn = rng.random(model.num_nodes)
+    un = model.node_coordinates() @ np.asarray(gradu, float)
+    cn = model.cell_node_ids()
+    K_cut = oc.cutcell_laplacian(oc.select_subcells(p, IN))
+    nodes = cn[oc.array("cutcell_to_cell") - 1] - 1
+    a_mat = np.einsum("ka,kab,kb->", vn[nodes], K_cut, un[nodes])
+    for c in oc.select_bgcells(p, IN):
+        nd = cn[int(c) - 1] - 1
+        a_mat += vn[nd] @ oc.bgcell_laplacian(int(c)) @ un[nd]
+    return float(a_mat)
+
+
+@pytest.mark.parametrize("dim,simplex", [(2, False), (2, True), (3, False), (3, True)])
+def test_element_matrices_reproduce_the_divergence_theorem(dim, simplex):
+    """The reference checks the divergence theorem once more AFTER `move_contributions` has gathered the sub-cell integrals
+    of ∫∇v·∇u per background cell (test/InterfacesTests/EmbeddedDiscretizationsTests.jl:96-110).  The per-cut-cell element
+    matrices of this path ARE those moved contributions (in matrix form), so with u linear (exactly representable in the
+    Q1 / P1 background space) and v a random background FE function
+        sum_cells v_c^T K_c u_c  ==  ∫_Ω ∇v·∇u  ==  ∫_Γ v n·∇u          (1e-9, the reference's tolerance)
+    which pins the matrices -- shape-function gradients at the glued reference points, quadrature, subcell -> bg cell
+    accumulation -- to the reference's own known answer, not only to the oracle."""
+    if dim == 2:
+        geom, part, gradu, fdeg = disk(0.7), (50, 50), [1.0, 1.0], 2
+    else:
+        geom, part, gradu, fdeg = sphere(0.7), (12, 12, 12), [1.0, 1.0, -1.0], 4
+    box = gecut.get_metadata(geom)
+    model = CartesianDiscreteModel(box.pmin, box.pmax, part)
+    if simplex:
+        model = simplexify(model)
+    oc = ocut(model, geom)
+    p = prog(oc)
+    a, b = divergence_theorem(oc, model, p, p, gradu=gradu, facet_degree=fdeg)
+    a_mat = matrix_form(oc, model, p, gradu)
+    assert abs(a_mat - a) < 1e-12 * max(1.0, abs(a))
+    assert abs(a_mat - b) < 1.0e-9
+    assert abs(a_mat) > 1e-3
