@@ -1,0 +1,124 @@
+"""A downstream consumer of the cut in numpy: the Nitsche + ghost-penalty CutFEM Poisson problem of the reference's
+test/GridapEmbeddedTests/PoissonCutFEMTests.jl (manufactured solution u = x + y - z on the sphere R = 0.7, Q1 background
+space on the ACTIVE cells), assembled from exactly what this path hands to Gridap:
+
+  * ∫ ∇v·∇u dΩ            -- the element matrices of the path (cut cells: K_cut, uncut IN cells: K_bg),
+  * the Nitsche terms on Γ -- from the SubFacetData layout (points, reference points through the glue, normals, bg cell),
+  * the ghost penalty      -- on the interior facets between two active cells one of which is cut (GhostSkeleton).
+
+The reference asserts el2/ul2 < 1e-8 and eh1/uh1 < 1e-7 (PoissonCutFEMTests.jl:116-117); u lies in the discrete space, so
+the discrete solution reproduces it as long as the layout, the glue, the normals and the matrices are mutually consistent.
+The same function serves the CPU oracle (tests without a GPU) and the device results (gpu tests)."""
+import numpy as np
+
+import helpers as H
+
+IN, OUT, CUT = -1, 1, 0
+
+
+def u_exact(x):
+    return x[:, 0] + x[:, 1] - x[:, 2]
+
+
+GRAD_U = np.array([1.0, 1.0, -1.0])
+
+
+def solve_poisson_cutfem(model, bg_state, cutcells, K_cut, K_bg, sub, fac, gamma_d=10.0, gamma_g=0.1):
+    """bg_state: Int8 per bg cell (state of the geometry); cutcells: 1-based ids (rows of K_cut); K_bg: nv x nv matrix of an
+    uncut cell; sub = dict(c2p, c2bg, X, R) of the PHYSICAL subcells; fac = dict(c2p, c2bg, X, R, N) of the embedded boundary
+    (normals already oriented).  Returns (el2/ul2, eh1/uh1, number of ghost facets)."""
+    D = model.D
+    assert D == 3 and not model.simplexified
+    nv = 1 << D
+    cn = model.cell_node_ids() - 1
+    xn = model.node_coordinates()
+    hvec = np.asarray(model.sizes, float)
+    h = hvec[0]
+    nn = model.num_nodes
+    A = np.zeros((nn, nn))
+    rhs = np.zeros(nn)
+
+    def add(cells0, Ke):
+        for c, K in zip(cells0, Ke):
+            A[np.ix_(cn[c], cn[c])] += K
+
+    # ---- ∫ ∇v·∇u dΩ from the element matrices of the path
+    add(cutcells - 1, K_cut)
+    in_cells = np.flatnonzero(bg_state == IN)
+    add(in_cells, np.broadcast_to(K_bg, (len(in_cells), nv, nv)))
+    # ---- Nitsche terms on the embedded boundary (degree-4 rule: v restricted to a plane is cubic)
+    xi, w = H.simplex_rule(D - 1, 4)
+    Nq = H.p1_shape(xi)  # (nq, D)
+    P = fac["X"][fac["c2p"] - 1]   # (nf, D, D)
+    Rr = fac["R"][fac["c2p"] - 1]
+    meas = H.simplex_meas(P)
+    nrm = fac["N"]
+    fc = fac["c2bg"] - 1
+    for q in range(len(w)):
+        eta = np.einsum("i,nid->nd", Nq[q], Rr)
+        x = np.einsum("i,nid->nd", Nq[q], P)
+        phi, dphi = H.q1_shape_and_grad(eta)
+        dn = np.einsum("nad,nd->na", dphi / hvec[None, None, :], nrm)  # n·∇φ_a
+        wq = w[q] * meas
+        Ke = wq[:, None, None] * ((gamma_d / h) * phi[:, :, None] * phi[:, None, :] - phi[:, :, None] * dn[:, None, :]
+                                  - dn[:, :, None] * phi[:, None, :])
+        ud = u_exact(x)
+        re = wq[:, None] * ((gamma_d / h) * phi * ud[:, None] - dn * ud[:, None])
+        for f in range(len(fc)):
+            nd = cn[fc[f]]
+            A[np.ix_(nd, nd)] += Ke[f]
+            rhs[nd] += re[f]
+    # ---- ghost penalty on the interior facets between two active cells, at least one of them cut
+    n = model.partition
+    active = (bg_state != OUT).reshape(n[2], n[1], n[0])
+    iscut = (bg_state == CUT).reshape(n[2], n[1], n[0])
+    cid = np.arange(model.num_cells).reshape(n[2], n[1], n[0])
+    g2 = H.GAUSS2
+    nghost = 0
+    for d in range(3):
+        ax = 2 - d  # array axis of direction d
+        lo = [slice(None)] * 3
+        hi = [slice(None)] * 3
+        lo[ax] = slice(0, -1)
+        hi[ax] = slice(1, None)
+        lo, hi = tuple(lo), tuple(hi)
+        sel = active[lo] & active[hi] & (iscut[lo] | iscut[hi])
+        c1 = cid[lo][sel]
+        c2 = cid[hi][sel]
+        nghost += len(c1)
+        others = [e for e in range(3) if e != d]
+        area = hvec[others[0]] * hvec[others[1]]
+        G = np.zeros((2 * nv, 2 * nv))
+        for qa in range(2):
+            for qb in range(2):
+                eta1 = np.zeros((1, 3))
+                eta2 = np.zeros((1, 3))
+                eta1[0, d], eta2[0, d] = 1.0, 0.0
+                eta1[0, others[0]] = eta2[0, others[0]] = g2[qa]
+                eta1[0, others[1]] = eta2[0, others[1]] = g2[qb]
+                _, d1 = H.q1_shape_and_grad(eta1)
+                _, d2 = H.q1_shape_and_grad(eta2)
+                g = np.concatenate([d1[0, :, d], -d2[0, :, d]]) / hvec[d]  # jump of n·∇φ over the two cells
+                G += 0.25 * area * np.outer(g, g)
+        G *= gamma_g * h
+        for a, b in zip(c1, c2):
+            nd = np.concatenate([cn[a], cn[b]])  # the two cells share the nodes of the facet: accumulate duplicates
+            np.add.at(A, np.ix_(nd, nd), G)
+    # ---- solve on the nodes of the active cells
+    act_nodes = np.unique(cn[np.flatnonzero(bg_state != OUT)])
+    uh = np.zeros(nn)
+    uh[act_nodes] = np.linalg.solve(A[np.ix_(act_nodes, act_nodes)], rhs[act_nodes])
+    # ---- errors over Ω (PHYSICAL subcells + IN cells), degree-2 rules as in the reference
+    en = u_exact(xn) - uh
+    cn1 = model.cell_node_ids()
+
+    def sq(vn, with_grad):
+        def f(bgcell, eta, x):
+            v, g = H.bg_field_at(model, cn1, bgcell, eta, vn)
+            return v * v + ((g * g).sum(1) if with_grad else 0.0)
+        return (H.integrate_on_simplices(model, cn1, sub["c2p"], sub["c2bg"], sub["X"], sub["R"], f)
+                + H.integrate_on_bgcells(model, cn1, in_cells + 1, f))
+
+    el2, ul2 = np.sqrt(sq(en, False)), np.sqrt(sq(uh, False))
+    eh1, uh1 = np.sqrt(sq(en, True)), np.sqrt(sq(uh, True))
+    return el2 / ul2, eh1 / uh1, nghost

@@ -1,0 +1,68 @@
+"""The reference's PDE known answer for this path (test/GridapEmbeddedTests/PoissonCutFEMTests.jl:116-117): Nitsche +
+ghost-penalty CutFEM Poisson on the sphere with a manufactured linear solution, el2/ul2 < 1e-8 and eh1/uh1 < 1e-7,
+assembled in numpy (tests/poisson_helpers.py) from what the path hands downstream -- the element matrices, the
+SubFacetData layout with its glue and normals, the ghost skeleton.  CPU: the oracle.  GPU: the device results."""
+import numpy as np
+import pytest
+
+import gecut
+from gecut import CartesianDiscreteModel, sphere
+from gecut.csg import compile_postfix
+import oracle_binding as ob
+import poisson_helpers as PH
+
+IN, OUT, CUT = -1, 1, 0
+
+
+def _model(n=10):
+    geom = sphere(0.7)
+    box = gecut.get_metadata(geom)
+    return CartesianDiscreteModel(box.pmin, box.pmax, (n, n, n)), geom
+
+
+def test_poisson_cutfem_manufactured_solution_oracle():
+    model, geom = _model()
+    oc = ob.oracle_cut(model, geom)
+    p = compile_postfix(geom.get_tree(), oc.oid_to_ls)
+    D = 3
+    ids = oc.select_subcells(p, IN)
+    fids, ori = oc.select_boundary(p)
+    sub = {"c2p": oc.array("subcells.cell_to_points").reshape(-1, D + 1)[ids - 1],
+           "c2bg": oc.array("subcells.cell_to_bgcell")[ids - 1],
+           "X": oc.array("subcells.point_to_coords").reshape(-1, D),
+           "R": oc.array("subcells.point_to_rcoords").reshape(-1, D)}
+    fac = {"c2p": oc.array("subfacets.facet_to_points").reshape(-1, D)[fids - 1],
+           "c2bg": oc.array("subfacets.facet_to_bgcell")[fids - 1],
+           "X": oc.array("subfacets.point_to_coords").reshape(-1, D),
+           "R": oc.array("subfacets.point_to_rcoords").reshape(-1, D),
+           "N": oc.array("subfacets.facet_to_normal").reshape(-1, D)[fids - 1] * ori[:, None]}
+    bg_state = oc.bgcell_to_inoutcut(p)
+    el2, eh1, nghost = PH.solve_poisson_cutfem(model, bg_state, oc.array("cutcell_to_cell"), oc.cutcell_laplacian(ids),
+                                               oc.bgcell_laplacian(1), sub, fac)
+    assert el2 < 1.0e-8 and eh1 < 1.0e-7, (el2, eh1)
+    # the ghost facets of the assembly are the ones GhostSkeleton(cutgeo) marks
+    ofc = ob.oracle_cut_facets(model, geom)
+    assert nghost == int(np.count_nonzero(ob.oracle_ghost_skeleton(oc, ofc, p, IN)))
+
+
+@pytest.mark.gpu
+def test_poisson_cutfem_manufactured_solution_gpu():
+    from gecut import cut, Triangulation, EmbeddedBoundary, Measure, PHYSICAL, GhostSkeleton
+    from gecut.measures import integrate_laplacian
+    from gecut.discretizations import compute_bgcell_to_inoutcut
+    model, geom = _model()
+    cg = cut(model, geom)
+    h = cg.to_host()
+    om = Triangulation(cg, PHYSICAL)
+    ga = EmbeddedBoundary(cg)
+    K_cut, K_bg = integrate_laplacian(Measure(om, 2))
+    ids, fids, ori = om.sub_ids, ga.sub_ids, ga.orientation
+    sub = {"c2p": h["sc_cell_to_points"][ids - 1], "c2bg": h["sc_cell_to_bgcell"][ids - 1],
+           "X": h["sc_point_to_coords"], "R": h["sc_point_to_rcoords"]}
+    fac = {"c2p": h["sf_facet_to_points"][fids - 1], "c2bg": h["sf_facet_to_bgcell"][fids - 1],
+           "X": h["sf_point_to_coords"], "R": h["sf_point_to_rcoords"],
+           "N": h["sf_facet_to_normal"][fids - 1] * ori[:, None].astype(np.float64)}
+    el2, eh1, nghost = PH.solve_poisson_cutfem(model, compute_bgcell_to_inoutcut(cg), h["cutcell_to_cell"], K_cut, K_bg[0],
+                                               sub, fac)
+    assert el2 < 1.0e-8 and eh1 < 1.0e-7, (el2, eh1)
+    assert nghost == int(np.count_nonzero(GhostSkeleton(cg)))
