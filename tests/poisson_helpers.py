@@ -122,3 +122,97 @@ def solve_poisson_cutfem(model, bg_state, cutcells, K_cut, K_bg, sub, fac, gamma
     el2, ul2 = np.sqrt(sq(en, False)), np.sqrt(sq(uh, False))
     eh1, uh1 = np.sqrt(sq(en, True)), np.sqrt(sq(uh, True))
     return el2 / ul2, eh1 / uh1, nghost
+
+
+# --------------------------------------------------------------------------------------------------------------------
+def solve_bimaterial_poisson(model, state1, cutcells, K1_cut, K2_cut, K_bg, meas_K1, meas_K2, sub1, sub2, fac,
+                             alpha1=4.0, alpha2=3.0, gamma_hat=2.0):
+    """test/GridapEmbeddedTests/BimaterialPoissonCutFEMTests.jl: two unfitted P1 fields u1 (disk, ACTIVE geo1 cells) and u2
+    (the rest, ACTIVE !geo1 cells, Dirichlet on the box boundary) coupled by the Nitsche interface terms of the CutFEM
+    paper, manufactured solution u = x - y/2 in both materials (fluxes jump by (alpha1 - alpha2)∇u).
+
+    state1: Int8 per bg simplex (state of geo1); K1_cut / K2_cut: P1 matrices of the PHYSICAL IN / OUT subcells per cut
+    cell (rows = cutcells, 1-based ids); K_bg[type]: matrix of an uncut simplex of that type; meas_K1 / meas_K2:
+    get_cell_measure(Ω1 / Ω2, Ω_bg) per bg cell; sub1 / sub2: dict(c2p, c2bg, X, R) of the PHYSICAL subcells of each side;
+    fac: dict(c2p, c2bg, X, R, N) of EmbeddedBoundary(cutgeo, geo1, geo2).  Returns (el2/ul2, eh1/uh1)."""
+    D = model.D
+    assert D == 2 and model.simplexified
+    cn1 = model.cell_node_ids()
+    cn = cn1 - 1
+    xn = model.node_coordinates()
+    nn = model.num_nodes
+    ntypes = model.simplices_per_cube
+
+    def u_ex(x):
+        return x[:, 0] - 0.5 * x[:, 1]
+
+    gradu = np.array([1.0, -0.5])
+    A = np.zeros((2 * nn, 2 * nn))
+    rhs = np.zeros(2 * nn)
+    # ---- bulk terms from the element matrices of the path
+    for side, (alpha, Kc, off, st) in enumerate(((alpha1, K1_cut, 0, IN), (alpha2, K2_cut, nn, OUT))):
+        for k, c in enumerate(cutcells - 1):
+            nd = cn[c] + off
+            A[np.ix_(nd, nd)] += alpha * Kc[k]
+        for c in np.flatnonzero(state1 == st):
+            nd = cn[c] + off
+            A[np.ix_(nd, nd)] += alpha * K_bg[c % ntypes]
+    # ---- interface terms (degree-2 rule on the segments: products of two linear functions)
+    fc = fac["c2bg"] - 1
+    meas_KG = np.bincount(fc, weights=0.5 * H.simplex_meas(fac["X"][fac["c2p"] - 1]) * 2.0, minlength=len(state1))
+    k1 = (alpha2 * meas_K1) / np.where(state1 == CUT, alpha2 * meas_K1 + alpha1 * meas_K2, 1.0)
+    k2 = (alpha1 * meas_K2) / np.where(state1 == CUT, alpha2 * meas_K1 + alpha1 * meas_K2, 1.0)
+    beta = (gamma_hat * meas_KG) / np.where(state1 == CUT, meas_K1 / alpha1 + meas_K2 / alpha2, 1.0)
+    # constant physical gradients of the P1 shape functions of every bg cell
+    Xc = xn[cn]                                   # (nc, 3, 2)
+    Jt = Xc[:, 1:, :] - Xc[:, :1, :]              # rows: x_i - x_0
+    gref = np.array([[-1.0, -1.0], [1.0, 0.0], [0.0, 1.0]])
+    gphys = np.einsum("nij,aj->nai", np.linalg.inv(Jt), gref)   # (nc, 3, 2): ∇φ_a
+    xi, w = H.simplex_rule(1, 2)
+    Nq = H.p1_shape(xi)
+    P = fac["X"][fac["c2p"] - 1]
+    Rr = fac["R"][fac["c2p"] - 1]
+    meas = H.simplex_meas(P)
+    nrm = fac["N"]
+    for f in range(len(fc)):
+        c = fc[f]
+        dn = gphys[c] @ nrm[f]                    # n·∇φ_a (3,)
+        nd1, nd2 = cn[c], cn[c] + nn
+        nd = np.concatenate([nd1, nd2])
+        for q in range(len(w)):
+            eta = Nq[q] @ Rr[f]
+            phi = np.array([1.0 - eta[0] - eta[1], eta[0], eta[1]])
+            wq = w[q] * meas[f]
+            jump = np.concatenate([phi, -phi])                                  # [v] = v1 - v2
+            meanq = np.concatenate([k1[c] * alpha1 * dn, k2[c] * alpha2 * dn])  # n·mean_q
+            meanu = np.concatenate([k2[c] * phi, k1[c] * phi])                  # mean_u
+            A[np.ix_(nd, nd)] += wq * (beta[c] * np.outer(jump, jump) - np.outer(jump, meanq) - np.outer(meanq, jump))
+            rhs[nd] += wq * meanu * ((alpha1 - alpha2) * (nrm[f] @ gradu))
+    # ---- spaces: u1 on the nodes of the cells active for geo1, u2 on those active for !geo1, Dirichlet on the box boundary
+    act1 = np.unique(cn[np.flatnonzero(state1 != OUT)])
+    act2 = np.unique(cn[np.flatnonzero(state1 != IN)])
+    lo, hi = np.asarray(model.pmin), np.asarray(model.pmax)
+    on_bnd = np.any((np.abs(xn - lo) < 1e-12) | (np.abs(xn - hi) < 1e-12), axis=1)
+    free2 = act2[~on_bnd[act2]]
+    fixed2 = act2[on_bnd[act2]]
+    U = np.zeros(2 * nn)
+    U[fixed2 + nn] = u_ex(xn[fixed2])
+    free = np.concatenate([act1, free2 + nn])
+    b = rhs[free] - A[np.ix_(free, fixed2 + nn)] @ U[fixed2 + nn]
+    U[free] = np.linalg.solve(A[np.ix_(free, free)], b)
+    # ---- errors
+    ue = u_ex(xn)
+
+    def sq(vn, sub, st, with_grad):
+        def fun(bgcell, eta, x):
+            v, g = H.bg_field_at(model, cn1, bgcell, eta, vn)
+            return v * v + ((g * g).sum(1) if with_grad else 0.0)
+        return (H.integrate_on_simplices(model, cn1, sub["c2p"], sub["c2bg"], sub["X"], sub["R"], fun)
+                + H.integrate_on_bgcells(model, cn1, np.flatnonzero(state1 == st) + 1, fun))
+
+    u1, u2 = U[:nn], U[nn:]
+    el2 = np.sqrt(sq(ue - u1, sub1, IN, False) + sq(ue - u2, sub2, OUT, False))
+    ul2 = np.sqrt(sq(u1, sub1, IN, False) + sq(u2, sub2, OUT, False))
+    eh1 = np.sqrt(sq(ue - u1, sub1, IN, True) + sq(ue - u2, sub2, OUT, True))
+    uh1 = np.sqrt(sq(u1, sub1, IN, True) + sq(u2, sub2, OUT, True))
+    return el2 / ul2, eh1 / uh1

@@ -66,3 +66,77 @@ def test_poisson_cutfem_manufactured_solution_gpu():
                                                sub, fac)
     assert el2 < 1.0e-8 and eh1 < 1.0e-7, (el2, eh1)
     assert nghost == int(np.count_nonzero(GhostSkeleton(cg)))
+
+
+def _bimaterial_model(n=30):
+    from gecut import disk, complement, union, simplexify
+    geo1 = disk(0.7, name="geo1")
+    geo2 = complement(geo1, name="geo2")
+    model = simplexify(CartesianDiscreteModel((-1.0, 1.0, -1.0, 1.0), (n, n)))
+    return model, union(geo1, geo2), geo1, geo2
+
+
+def test_bimaterial_poisson_manufactured_solution_oracle():
+    """BimaterialPoissonCutFEMTests.jl:137-138 on the oracle: P1 matrices of both sides, get_cell_measure of both sides and
+    of the interface (the stabilisation weights), EmbeddedBoundary(cutgeo, geo1, geo2) with its normals."""
+    model, geo, geo1, geo2 = _bimaterial_model()
+    oc = ob.oracle_cut(model, geo)
+    assert oc.L == 1
+    p1 = compile_postfix(geo1.get_tree(), oc.oid_to_ls)
+    p2 = compile_postfix(geo2.get_tree(), oc.oid_to_ls)
+    D = 2
+    c2p = oc.array("subcells.cell_to_points").reshape(-1, D + 1)
+    c2bg = oc.array("subcells.cell_to_bgcell")
+    X, R = oc.array("subcells.point_to_coords").reshape(-1, D), oc.array("subcells.point_to_rcoords").reshape(-1, D)
+    ids1, ids2 = oc.select_subcells(p1, IN), oc.select_subcells(p2, IN)
+    assert np.array_equal(ids2, oc.select_subcells(p1, OUT))
+    sub1 = {"c2p": c2p[ids1 - 1], "c2bg": c2bg[ids1 - 1], "X": X, "R": R}
+    sub2 = {"c2p": c2p[ids2 - 1], "c2bg": c2bg[ids2 - 1], "X": X, "R": R}
+    fids, ori = oc.select_boundary(p1, p2)
+    fac = {"c2p": oc.array("subfacets.facet_to_points").reshape(-1, D)[fids - 1],
+           "c2bg": oc.array("subfacets.facet_to_bgcell")[fids - 1],
+           "X": oc.array("subfacets.point_to_coords").reshape(-1, D),
+           "R": oc.array("subfacets.point_to_rcoords").reshape(-1, D),
+           "N": oc.array("subfacets.facet_to_normal").reshape(-1, D)[fids - 1] * ori[:, None]}
+    state1 = oc.bgcell_to_inoutcut(p1)
+    nc = len(state1)
+
+    def cell_measure(ids, st):
+        m = np.bincount(c2bg[ids - 1] - 1, weights=oc.subcell_measures(ids), minlength=nc)
+        for c in np.flatnonzero(state1 == st):
+            m[c] = oc.bgcell_measure(int(c) + 1)
+        return m
+
+    K_bg = np.stack([oc.bgcell_laplacian(t + 1) for t in range(model.simplices_per_cube)])
+    el2, eh1 = PH.solve_bimaterial_poisson(model, state1, oc.array("cutcell_to_cell"), oc.cutcell_laplacian(ids1),
+                                           oc.cutcell_laplacian(ids2), K_bg, cell_measure(ids1, IN), cell_measure(ids2, OUT),
+                                           sub1, sub2, fac)
+    assert el2 < 1.0e-8 and eh1 < 1.0e-7, (el2, eh1)
+
+
+@pytest.mark.gpu
+def test_bimaterial_poisson_manufactured_solution_gpu():
+    """The same known answer from the device results: Triangulation(cutgeo, PHYSICAL, geo1 / geo2), the two-geometry
+    EmbeddedBoundary, get_cell_measure of both sides and the P1 element matrices of both sides."""
+    from gecut import cut, Triangulation, EmbeddedBoundary, Measure, PHYSICAL_IN
+    from gecut.measures import integrate_laplacian, get_cell_measure
+    from gecut.discretizations import compute_bgcell_to_inoutcut
+    model, geo, geo1, geo2 = _bimaterial_model()
+    cg = cut(model, geo)
+    h = cg.to_host()
+    t1 = Triangulation(cg, PHYSICAL_IN, "geo1")
+    t2 = Triangulation(cg, PHYSICAL_IN, "geo2")
+    ga = EmbeddedBoundary(cg, "geo1", "geo2")
+    K1_cut, K_bg = integrate_laplacian(Measure(t1, 2))
+    K2_cut, _ = integrate_laplacian(Measure(t2, 2))
+    ids1, ids2, fids, ori = t1.sub_ids, t2.sub_ids, ga.sub_ids, ga.orientation
+    sub1 = {"c2p": h["sc_cell_to_points"][ids1 - 1], "c2bg": h["sc_cell_to_bgcell"][ids1 - 1],
+            "X": h["sc_point_to_coords"], "R": h["sc_point_to_rcoords"]}
+    sub2 = {"c2p": h["sc_cell_to_points"][ids2 - 1], "c2bg": h["sc_cell_to_bgcell"][ids2 - 1],
+            "X": h["sc_point_to_coords"], "R": h["sc_point_to_rcoords"]}
+    fac = {"c2p": h["sf_facet_to_points"][fids - 1], "c2bg": h["sf_facet_to_bgcell"][fids - 1],
+           "X": h["sf_point_to_coords"], "R": h["sf_point_to_rcoords"],
+           "N": h["sf_facet_to_normal"][fids - 1] * ori[:, None].astype(np.float64)}
+    el2, eh1 = PH.solve_bimaterial_poisson(model, compute_bgcell_to_inoutcut(cg, "geo1"), h["cutcell_to_cell"], K1_cut, K2_cut,
+                                           K_bg, get_cell_measure(t1), get_cell_measure(t2), sub1, sub2, fac)
+    assert el2 < 1.0e-8 and eh1 < 1.0e-7, (el2, eh1)
