@@ -216,3 +216,91 @@ def solve_bimaterial_poisson(model, state1, cutcells, K1_cut, K2_cut, K_bg, meas
     eh1 = np.sqrt(sq(ue - u1, sub1, IN, True) + sq(ue - u2, sub2, OUT, True))
     uh1 = np.sqrt(sq(u1, sub1, IN, True) + sq(u2, sub2, OUT, True))
     return el2 / ul2, eh1 / uh1
+
+
+# --------------------------------------------------------------------------------------------------------------------
+def solve_poisson_agfem_2d(model, bg_state, cutcells, K_cut, K_bg, cell_to_cellin, sub, fac, gamma_d=10.0):
+    """test/GridapEmbeddedTests/PoissonAgFEMTests.jl: Nitsche Poisson WITHOUT ghost penalty on the aggregated Q1 space
+    (AgFEMSpace, src/AgFEM/AgFEMSpaces.jl:57-150): a node all of whose active cells are cut (aggregated) cells is
+    constrained to the extension of the shape functions of the root cell of its owner (the touching active cell with the
+    largest id); u = x - y.  Returns (el2/ul2, eh1/uh1, number of constrained nodes)."""
+    D = model.D
+    assert D == 2 and not model.simplexified
+    nv = 4
+    cn1 = model.cell_node_ids()
+    cn = cn1 - 1
+    xn = model.node_coordinates()
+    hvec = np.asarray(model.sizes, float)
+    h = hvec[0]
+    nn = model.num_nodes
+
+    def u_ex(x):
+        return x[:, 0] - x[:, 1]
+
+    A = np.zeros((nn, nn))
+    rhs = np.zeros(nn)
+    for k, c in enumerate(cutcells - 1):
+        A[np.ix_(cn[c], cn[c])] += K_cut[k]
+    in_cells = np.flatnonzero(bg_state == IN)
+    for c in in_cells:
+        A[np.ix_(cn[c], cn[c])] += K_bg
+    xi, w = H.simplex_rule(1, 2)
+    Nq = H.p1_shape(xi)
+    P = fac["X"][fac["c2p"] - 1]
+    Rr = fac["R"][fac["c2p"] - 1]
+    meas = H.simplex_meas(P)
+    nrm = fac["N"]
+    fc = fac["c2bg"] - 1
+    for q in range(len(w)):
+        eta = np.einsum("i,nid->nd", Nq[q], Rr)
+        x = np.einsum("i,nid->nd", Nq[q], P)
+        phi, dphi = H.q1_shape_and_grad(eta)
+        dn = np.einsum("nad,nd->na", dphi / hvec[None, None, :], nrm)
+        wq = w[q] * meas
+        Ke = wq[:, None, None] * ((gamma_d / h) * phi[:, :, None] * phi[:, None, :] - phi[:, :, None] * dn[:, None, :]
+                                  - dn[:, :, None] * phi[:, None, :])
+        ud = u_ex(x)
+        re = wq[:, None] * ((gamma_d / h) * phi * ud[:, None] - dn * ud[:, None])
+        for f in range(len(fc)):
+            nd = cn[fc[f]]
+            A[np.ix_(nd, nd)] += Ke[f]
+            rhs[nd] += re[f]
+    # ---- AgFEM constraints
+    active = np.flatnonzero(bg_state != OUT)
+    node_isagg = np.ones(nn, bool)
+    node_owner = np.full(nn, -1)
+    touched = np.zeros(nn, bool)
+    for c in active:  # ascending ids: the last writer is the touching active cell with the largest id
+        aggregated = cell_to_cellin[c] != c + 1
+        for nd in cn[c]:
+            touched[nd] = True
+            node_isagg[nd] &= aggregated
+            node_owner[nd] = c
+    act_nodes = np.flatnonzero(touched)
+    masters = act_nodes[~node_isagg[act_nodes]]
+    col = -np.ones(nn, int)
+    col[masters] = np.arange(len(masters))
+    T = np.zeros((nn, len(masters)))
+    T[masters, col[masters]] = 1.0
+    slaves = act_nodes[node_isagg[act_nodes]]
+    for nd in slaves:
+        root = cell_to_cellin[node_owner[nd]] - 1
+        rn = cn[root]
+        assert np.all(col[rn] >= 0)  # the nodes of a root cell are never constrained
+        eta = ((xn[nd] - xn[rn[0]]) / hvec)[None, :]  # reference point of the node in the ROOT cell (outside [0,1]^2)
+        phi, _ = H.q1_shape_and_grad(eta)
+        T[nd, col[rn]] = phi[0]
+    Ar = T.T @ A @ T
+    br = T.T @ rhs
+    uh = T @ np.linalg.solve(Ar, br)
+    # ---- errors over Ω
+    en = u_ex(xn) - uh
+
+    def sq(vn, with_grad):
+        def fun(bgcell, eta, x):
+            v, g = H.bg_field_at(model, cn1, bgcell, eta, vn)
+            return v * v + ((g * g).sum(1) if with_grad else 0.0)
+        return (H.integrate_on_simplices(model, cn1, sub["c2p"], sub["c2bg"], sub["X"], sub["R"], fun)
+                + H.integrate_on_bgcells(model, cn1, in_cells + 1, fun))
+
+    return (np.sqrt(sq(en, False)) / np.sqrt(sq(uh, False)), np.sqrt(sq(en, True)) / np.sqrt(sq(uh, True)), len(slaves))

@@ -140,3 +140,35 @@ def test_bimaterial_poisson_manufactured_solution_gpu():
     el2, eh1 = PH.solve_bimaterial_poisson(model, compute_bgcell_to_inoutcut(cg, "geo1"), h["cutcell_to_cell"], K1_cut, K2_cut,
                                            K_bg, get_cell_measure(t1), get_cell_measure(t2), sub1, sub2, fac)
     assert el2 < 1.0e-8 and eh1 < 1.0e-7, (el2, eh1)
+
+
+def test_poisson_agfem_manufactured_solution_oracle():
+    """PoissonAgFEMTests.jl:80-81 on the oracle: setdiff of two disks (two level sets), AggregateAllCutCells, Nitsche
+    Poisson on the aggregated Q1 space without ghost penalty -- the consumer of `aggregate`."""
+    from gecut import disk, setdiff
+    R = 0.5
+    geo3 = setdiff(disk(R, x0=(0.0, 0.0)), disk(R, x0=(0.8 * 2 * R, 0.0)))
+    t = 1.01
+    model = CartesianDiscreteModel((-t * R, -t * R), (t * R, t * R), (30, 30))
+    oc = ob.oracle_cut(model, geo3)
+    assert oc.L == 2
+    fcut = ob.oracle_cut_facets(model, geo3)
+    p = compile_postfix(geo3.get_tree(), oc.oid_to_ls)
+    D = 2
+    ids = oc.select_subcells(p, IN)
+    fids, ori = oc.select_boundary(p)
+    sub = {"c2p": oc.array("subcells.cell_to_points").reshape(-1, D + 1)[ids - 1],
+           "c2bg": oc.array("subcells.cell_to_bgcell")[ids - 1],
+           "X": oc.array("subcells.point_to_coords").reshape(-1, D),
+           "R": oc.array("subcells.point_to_rcoords").reshape(-1, D)}
+    fac = {"c2p": oc.array("subfacets.facet_to_points").reshape(-1, D)[fids - 1],
+           "c2bg": oc.array("subfacets.facet_to_bgcell")[fids - 1],
+           "X": oc.array("subfacets.point_to_coords").reshape(-1, D),
+           "R": oc.array("subfacets.point_to_rcoords").reshape(-1, D),
+           "N": oc.array("subfacets.facet_to_normal").reshape(-1, D)[fids - 1] * ori[:, None]}
+    agg, ok = ob.oracle_aggregate(oc, fcut, p, IN, 1.0)
+    assert ok
+    el2, eh1, nslaves = PH.solve_poisson_agfem_2d(model, oc.bgcell_to_inoutcut(p), oc.array("cutcell_to_cell"),
+                                                  oc.cutcell_laplacian(ids), oc.bgcell_laplacian(1), agg, sub, fac)
+    assert nslaves > 0
+    assert el2 < 1.0e-8 and eh1 < 1.0e-7, (el2, eh1)
