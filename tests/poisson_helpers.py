@@ -304,3 +304,71 @@ def solve_poisson_agfem_2d(model, bg_state, cutcells, K_cut, K_bg, cell_to_celli
                 + H.integrate_on_bgcells(model, cn1, in_cells + 1, fun))
 
     return (np.sqrt(sq(en, False)) / np.sqrt(sq(uh, False)), np.sqrt(sq(en, True)) / np.sqrt(sq(uh, True)), len(slaves))
+
+
+# --------------------------------------------------------------------------------------------------------------------
+def solve_tracefem_projection_2d(model, bg_state, fac, gamma_d=10.0, gamma_g=0.1):
+    """test/GridapEmbeddedTests/TraceFEMTests.jl: L2 projection of ud = x - y onto the P1 space of the CUT cells, posed on
+    the embedded boundary Γ and stabilised by the gradient jumps over the interior edges between two CUT cells
+    (GhostSkeleton(cutgeom, CUT, geom)).  Returns (l2 error on Γ, number of ghost edges)."""
+    assert model.D == 2 and model.simplexified
+    cn1 = model.cell_node_ids()
+    cn = cn1 - 1
+    xn = model.node_coordinates()
+    nn = model.num_nodes
+    h = float(model.sizes[0])
+
+    def ud(x):
+        return x[:, 0] - x[:, 1]
+
+    A = np.zeros((nn, nn))
+    rhs = np.zeros(nn)
+    xi, w = H.simplex_rule(1, 2)
+    Nq = H.p1_shape(xi)
+    P = fac["X"][fac["c2p"] - 1]
+    Rr = fac["R"][fac["c2p"] - 1]
+    meas = H.simplex_meas(P)
+    fc = fac["c2bg"] - 1
+    for f in range(len(fc)):
+        nd = cn[fc[f]]
+        for q in range(len(w)):
+            eta = Nq[q] @ Rr[f]
+            x = (Nq[q] @ P[f])[None, :]
+            phi = np.array([1.0 - eta[0] - eta[1], eta[0], eta[1]])
+            A[np.ix_(nd, nd)] += w[q] * meas[f] * (gamma_d / h) * np.outer(phi, phi)
+            rhs[nd] += w[q] * meas[f] * (gamma_d / h) * phi * ud(x)[0]
+    # ---- ghost penalty over the interior edges shared by two CUT cells
+    cut_cells = np.flatnonzero(bg_state == CUT)
+    Xc = xn[cn]
+    Jt = Xc[:, 1:, :] - Xc[:, :1, :]
+    gref = np.array([[-1.0, -1.0], [1.0, 0.0], [0.0, 1.0]])
+    gphys = np.einsum("nij,aj->nai", np.linalg.inv(Jt), gref)
+    edge_to_cells = {}
+    for c in cut_cells:
+        for a, b in ((0, 1), (0, 2), (1, 2)):
+            key = tuple(sorted((cn[c][a], cn[c][b])))
+            edge_to_cells.setdefault(key, []).append(c)
+    nghost = 0
+    for (na, nb), cells in edge_to_cells.items():
+        if len(cells) != 2:
+            continue
+        nghost += 1
+        c1, c2 = cells
+        t = xn[nb] - xn[na]
+        length = np.linalg.norm(t)
+        nrm = np.array([t[1], -t[0]]) / length
+        g = np.concatenate([gphys[c1] @ nrm, -(gphys[c2] @ nrm)])  # jump of n·∇φ (constant along the edge)
+        nd = np.concatenate([cn[c1], cn[c2]])
+        np.add.at(A, np.ix_(nd, nd), gamma_g * h * length * np.outer(g, g))
+    act = np.unique(cn[cut_cells])
+    uh = np.zeros(nn)
+    uh[act] = np.linalg.solve(A[np.ix_(act, act)], rhs[act])
+    en = uh - ud(xn)
+    err2 = 0.0
+    for f in range(len(fc)):
+        nd = cn[fc[f]]
+        for q in range(len(w)):
+            eta = Nq[q] @ Rr[f]
+            phi = np.array([1.0 - eta[0] - eta[1], eta[0], eta[1]])
+            err2 += w[q] * meas[f] * float(phi @ en[nd]) ** 2
+    return np.sqrt(err2), nghost

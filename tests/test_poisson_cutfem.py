@@ -172,3 +172,26 @@ def test_poisson_agfem_manufactured_solution_oracle():
                                                   oc.cutcell_laplacian(ids), oc.bgcell_laplacian(1), agg, sub, fac)
     assert nslaves > 0
     assert el2 < 1.0e-8 and eh1 < 1.0e-7, (el2, eh1)
+
+
+def test_tracefem_projection_oracle():
+    """TraceFEMTests.jl:53-54 on the oracle: a problem posed on the embedded boundary alone (P1 background functions of the
+    CUT cells traced on Γ through the glue of the SubFacetData) with the CUT-cell ghost skeleton; l2 error on Γ < 1e-10."""
+    from gecut import disk, simplexify
+    geom = disk(0.7)
+    box = gecut.get_metadata(geom)
+    model = simplexify(CartesianDiscreteModel(box.pmin, box.pmax, (10, 10)))
+    oc = ob.oracle_cut(model, geom)
+    p = compile_postfix(geom.get_tree(), oc.oid_to_ls)
+    D = 2
+    fids, ori = oc.select_boundary(p)
+    fac = {"c2p": oc.array("subfacets.facet_to_points").reshape(-1, D)[fids - 1],
+           "c2bg": oc.array("subfacets.facet_to_bgcell")[fids - 1],
+           "X": oc.array("subfacets.point_to_coords").reshape(-1, D),
+           "R": oc.array("subfacets.point_to_rcoords").reshape(-1, D)}
+    state = oc.bgcell_to_inoutcut(p)
+    # every bg cell that carries a piece of Γ is a CUT cell (Triangulation(cutgeom, CUT, geom) is the support of the space)
+    assert np.all(state[fac["c2bg"] - 1] == CUT)
+    err, nghost = PH.solve_tracefem_projection_2d(model, state, fac)
+    assert nghost > 0
+    assert err < 1.0e-10, err
