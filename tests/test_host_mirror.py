@@ -156,6 +156,19 @@ def test_c_abi_library_exports_every_declared_symbol():
     assert ctypes.sizeof(_lib.Sizes) == 9 * 8 + 4 * 4  # incl. subfacet_points_alias and ctypes.sizeof(_lib.Buffers) == 13 * 8 + 3 * 8
 
 
+def test_julia_shim_binds_only_exported_symbols():
+    """The reference-side binding (julia/B200LevelSetCutter.jl, delivered as source: there is no Julia here) `ccall`s only
+    entry points the library really exports, and the statuses / leaf kinds it hard-codes are the header's."""
+    src = open(os.path.join(ROOT, "julia", "B200LevelSetCutter.jl")).read()
+    used = set(re.findall(r":(gecut_[a-z0-9_]+)", src))
+    assert len(used) >= 10 and used <= set(_lib.EXPORTED_SYMBOLS), used - set(_lib.EXPORTED_SYMBOLS)
+    assert {"gecut_create", "gecut_cut", "gecut_classify", "gecut_result_sizes", "gecut_result_copy",
+            "gecut_cut_facets"} <= used
+    header = open(os.path.join(ROOT, "include", "gecut.h")).read()
+    for name in re.findall(r"\b(GECUT_LEAF_[A-Z]+)\b", src):
+        assert re.search(r"#define\s+%s\b" % name, header) or re.search(r"\b%s\b" % name, header), name
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
     if torch.cuda.is_available():
