@@ -266,6 +266,120 @@ function _postfix(tree, oid_to_ls)
   prog
 end
 
+# ---- device-resident quadrature path ---------------------------------------------------------------------------------
+# For consumers that do not need the EmbeddedDiscretization on the host at all (volume / surface functionals, cut-cell
+# element matrices, aggregation): the result stays on the GPU, selections are boolean programs, only the integrals and
+# the matrices come back.  Replaces, for this path, Triangulation(cutgeo,PHYSICAL,geo) + Measure + ∫ / get_cell_measure
+# (EmbeddedDiscretizations.jl:297-323, CellAggregation.jl:111-113) and aggregate (CellAggregation.jl:72-189).
+mutable struct B200DeviceCut
+  cutter::B200LevelSetCutter
+  res::Ptr{Cvoid}
+  oid_to_ls::Dict{UInt,Int}
+  geom
+  bgmodel
+end
+
+function device_cut(cutter::B200LevelSetCutter, bgmodel::CartesianDiscreteModel, geom)
+  res, oid_to_ls = _run(cutter, :gecut_cut, bgmodel, geom, false, bgmodel)
+  d = B200DeviceCut(cutter, res, oid_to_ls, geom, bgmodel)
+  finalizer(x -> ccall((:gecut_result_free, libgecut), Cint, (Ptr{Cvoid},), x.res), d)
+  d
+end
+
+_program(d::B200DeviceCut, geo) = _postfix(get_tree(geo), d.oid_to_ls)
+_program(d::B200DeviceCut, name::String) = _program(d, get_geometry(d.geom, name))
+
+const SEL_PHYSICAL = Cint(0)
+
+function _select_cells(d::B200DeviceCut, geo, side::Integer)
+  prog = _program(d, geo)
+  sel = Ref{Ptr{Cvoid}}(C_NULL)
+  _check(d.cutter, ccall((:gecut_select_cells, libgecut), Cint, (Ptr{Cvoid}, Cint, Ptr{Int32}, Cint, Cint, Ptr{Ptr{Cvoid}}),
+                         d.res, SEL_PHYSICAL, prog, length(prog), side, sel), "gecut_select_cells")
+  sel[]
+end
+
+_free_selection(sel) = ccall((:gecut_selection_free, libgecut), Cint, (Ptr{Cvoid},), sel)
+
+"sum(∫(1)dΩ) over Triangulation(cutgeo,PHYSICAL_IN/OUT,geo), Measure(Ω,2)"
+function physical_measure(d::B200DeviceCut, geo=d.geom; side::Integer=IN)
+  sel = _select_cells(d, geo, side)
+  total = Ref{Float64}(0.0)
+  _check(d.cutter, ccall((:gecut_integrate_measure, libgecut), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
+                         sel, C_NULL, total), "gecut_integrate_measure")
+  _free_selection(sel)
+  total[]
+end
+
+"sum(∫(1)dΓ) over EmbeddedBoundary(cutgeo,geo1[,geo2]), Measure(Γ,2)"
+function boundary_measure(d::B200DeviceCut, geo1=d.geom, geo2=nothing)
+  p1 = _program(d, geo1)
+  p2 = geo2 === nothing ? Int32[] : _program(d, geo2)
+  sel = Ref{Ptr{Cvoid}}(C_NULL)
+  _check(d.cutter, ccall((:gecut_select_boundary, libgecut), Cint,
+                         (Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Int32}, Cint, Ptr{Ptr{Cvoid}}),
+                         d.res, p1, length(p1), geo2 === nothing ? C_NULL : pointer(p2), length(p2), sel),
+         "gecut_select_boundary")
+  total = Ref{Float64}(0.0)
+  _check(d.cutter, ccall((:gecut_integrate_measure, libgecut), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
+                         sel[], C_NULL, total), "gecut_integrate_measure")
+  _free_selection(sel[])
+  total[]
+end
+
+"get_cell_measure(Triangulation(cutgeo,PHYSICAL,geo), Ω_bg): one value per background cell"
+function cell_measure(d::B200DeviceCut, geo=d.geom; side::Integer=IN)
+  sel = _select_cells(d, geo, side)
+  out = Vector{Float64}(undef, num_cells(d.bgmodel))
+  _check(d.cutter, ccall((:gecut_cell_measure, libgecut), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint), sel, out, 0),
+         "gecut_cell_measure")
+  _free_selection(sel)
+  out
+end
+
+"""
+Element matrices of ∫(∇(v)⋅∇(u))dΩ for the background shape functions: `K_cut[:,:,k]` is the contribution of the selected
+subcells of cut cell `cutcell_to_cell[k]` (move_contributions), `K_bg` the matrix of an uncut cell.
+"""
+function cutcell_laplacian(d::B200DeviceCut, geo=d.geom; side::Integer=IN)
+  sz = Ref(GecutSizes(ntuple(_ -> 0, fieldcount(GecutSizes))...))
+  ccall((:gecut_result_sizes, libgecut), Cint, (Ptr{Cvoid}, Ptr{GecutSizes}), d.res, sz)
+  nv = 2^num_cell_dims(d.bgmodel)
+  ncut = Int(sz[].num_cutcells)
+  K_cut = Array{Float64}(undef, nv, nv, ncut)   # column-major: K_cut[b,a,k] = row-major (k,a,b) of the library; symmetric
+  K_bg = Array{Float64}(undef, nv, nv)
+  sel = _select_cells(d, geo, side)
+  _check(d.cutter, ccall((:gecut_integrate_laplacian, libgecut), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
+                         sel, K_cut, K_bg), "gecut_integrate_laplacian")
+  _free_selection(sel)
+  K_cut, K_bg
+end
+
+"aggregate(AggregateCutCellsByThreshold(threshold), cutgeo, cutgeo_facets, geo, in_or_out) on the device"
+function device_aggregate(d::B200DeviceCut, geo=d.geom; side::Integer=IN, threshold::Real=1.0)
+  fres, _ = _run_facets(d.cutter, d.bgmodel, d.geom, true)   # classification of the facets is all the aggregation needs
+  prog = _program(d, geo)
+  out = Vector{Int32}(undef, num_cells(d.bgmodel))
+  st = ccall((:gecut_aggregate, libgecut), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Cint, Cint, Cdouble, Ptr{Int32}, Cint),
+             d.res, fres, prog, length(prog), side, threshold, out, 0)
+  ccall((:gecut_facet_result_free, libgecut), Cint, (Ptr{Cvoid},), fres)
+  _check(d.cutter, st, "gecut_aggregate")
+  out
+end
+
+"facet_to_mask of GhostSkeleton(cutgeo, in_or_out, geo)"
+function ghost_skeleton_mask(d::B200DeviceCut, geo=d.geom; side::Integer=IN)
+  prog = _program(d, geo)
+  n = Ref{Int64}(0)
+  mask = Vector{Int8}(undef, num_faces(d.bgmodel, num_cell_dims(d.bgmodel) - 1))
+  _check(d.cutter, ccall((:gecut_ghost_skeleton, libgecut), Cint,
+                         (Ptr{Cvoid}, Ptr{Int32}, Cint, Cint, Ptr{Int64}, Ptr{Int8}, Ptr{Int32}),
+                         d.res, prog, length(prog), side, n, mask, C_NULL), "gecut_ghost_skeleton")
+  Vector{Bool}(mask .!= 0)
+end
+
 export B200LevelSetCutter, SimplexifiedCartesian
+export B200DeviceCut, device_cut, physical_measure, boundary_measure, cell_measure, cutcell_laplacian
+export device_aggregate, ghost_skeleton_mask
 
 end # module
