@@ -245,7 +245,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3_tet", choices=["c3_tet", "c3_hex", "c2_disk", "c5_bimaterial"])
     ap.add_argument("--n", type=int, default=None, help="cells per direction per GPU (default 512; 4096 for c2_disk)")
-    ap.add_argument("--cpu-n", type=int, default=None, help="size of the bounded CPU sample")
+    ap.add_argument("--cpu-n", type=int, default=None, help="size of the bounded CPU sample (default: the GPU arm's n)")
+    ap.add_argument("--cpu-stride", type=int, default=None,
+                    help="reference arm: a step covers every m-th thin z-slab of the model (default: chosen so that a step "
+                         "takes a few seconds; 1 = the whole model)")
     ap.add_argument("--nodal", action="store_true",
                     help="feed the level sets as a DiscreteGeometry: slab-local nodal vectors resident on each GPU, ghost "
                          "node plane from the next rank by NCCL send/recv every step (SURVEY 8e)")
@@ -288,14 +291,14 @@ def cpu_sample(workload, n_cpu, steps=1):
 
 
 def _cpu_slab_job(job):
-    """One z-slab of the model through the oracle (a worker process = one rank of the reference's distributed mode,
+    """One thin z-slab of the model through the oracle (a worker process = one rank of the reference's distributed mode,
     src/Distributed/DistributedDiscretizations.jl:29-40: every rank cuts its own part of the Cartesian model)."""
-    workload, n_cpu, k0, k1 = job
+    workload, n, world, k0, k1 = job
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     sys.path.insert(0, ROOT)
     import oracle_binding as ob
     import gecut
-    model, geo, _ = make_workload(workload, n_cpu, 1)
+    model, geo, _ = make_workload(workload, n, world)
     D = model.D
     dz = model.sizes[D - 1]
     pmin, pmax, part = list(model.pmin), list(model.pmax), list(model.partition)
@@ -309,18 +312,29 @@ def _cpu_slab_job(job):
 
 
 def run_reference(args, n):
-    """Reference arm: the CPU restatement on ALL host cores -- z-slabs of the model in worker processes, the way the
-    reference itself uses many cores (one rank per slab; the library has no threading)."""
+    """Reference arm: the CPU restatement on ALL host cores, on the SAME model as the GPU arm (same n, same geometry, same
+    --gpus multiplier): thin z-slabs of the model are dealt to one worker process per core, the way the reference itself
+    uses many cores (one rank per part, src/Distributed; the library has no threading).  When a whole pass would take more
+    than a few seconds (N > 1: up to 1024^3 cells) a step covers every m-th thin slab -- a bounded sample of the same
+    model at the same resolution, spread evenly over the slab direction -- and the value is sample cells / time."""
     import concurrent.futures as cf
     cores = max(1, min(os.cpu_count() or 1, 64))
-    n_cpu = args.cpu_n or {"c2_disk": 2048, "c5_bimaterial": 128}.get(args.workload, 256 if cores >= 32 else 192)
-    model, geo, desc = make_workload(args.workload, n_cpu, 1)
+    n_cpu = args.cpu_n or n
+    model, geo, desc = make_workload(args.workload, n_cpu, args.gpus)
     nz = model.partition[model.D - 1]
-    cores = min(cores, nz)
-    cuts = [(args.workload, n_cpu, (nz * r) // cores, (nz * (r + 1)) // cores) for r in range(cores)]
+    layer_cubes = model.num_cubes // nz
+    chunk = max(1, nz // (cores * 4))
+    chunks = [(k, min(k + chunk, nz)) for k in range(0, nz, chunk)]
+    # predicted seconds of a whole pass at ~6e7 cells/s per 16 cores (measured round 1: 4.1e7 at 192^3, growing with n)
+    pred = model.num_cubes / (6.0e7 * cores / 16.0)
+    m = args.cpu_stride or max(1, int(-(-pred // 4.0)))
+    picked = chunks[::m]
+    cores = min(cores, len(picked))
+    jobs = [(args.workload, n_cpu, args.gpus, a, b) for a, b in picked]
+    sample_cubes = sum(b - a for a, b in picked) * layer_cubes
     with cf.ProcessPoolExecutor(max_workers=cores) as pool:
         def one_step():
-            res = list(pool.map(_cpu_slab_job, cuts))
+            res = list(pool.map(_cpu_slab_job, jobs))
             return sum(r[0] for r in res), sum(r[1] for r in res)
         for _ in range(max(args.warmup, 1)):
             one_step()
@@ -328,23 +342,167 @@ def run_reference(args, n):
         for _ in range(args.steps):
             vol, surf = one_step()
         elapsed = time.perf_counter() - t0
-    cubes = model.num_cubes
-    value = cubes * args.steps / elapsed
-    sample = (f"same geometry at {'x'.join(str(p) for p in model.partition)} "
-              f"({'simplexified' if model.simplexified else 'n-cubes'}), full cut + selectors + integrals per step, "
-              f"oracle/gecut_oracle.cpp -O2 on {cores} worker processes (one z-slab each, as the reference's distributed mode "
-              f"would use the cores; the reference is Julia and cannot run here)")
+    value = sample_cubes * args.steps / elapsed
+    whole = m == 1
+    sample = (("the whole model" if whole else f"every {m}-th thin z-slab ({len(picked)} of {len(chunks)} slabs of {chunk} "
+               f"layers = {sample_cubes / model.num_cubes:.3f} of the cells)") +
+              f" of the same model as the GPU arm ({'x'.join(str(p) for p in model.partition)}, "
+              f"{'simplexified' if model.simplexified else 'n-cubes'}), full cut + selectors + integrals per step, "
+              f"oracle/gecut_oracle.cpp -O2 on {cores} worker processes (one thin z-slab at a time each, as the reference's "
+              f"distributed mode would use the cores; the reference is Julia and cannot run here)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "note": "bounded CPU sample of the same workload; rank 0 only",
+        "config": {"workload": desc, "same_size_as_gpu_arm": True, "partition": list(model.partition),
+                   "sample_fraction": sample_cubes / model.num_cubes,
+                   "note": "same size as the GPU arm; rank 0 only, host cores",
                    "integrals": {"volume": vol, "surface": surf}},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+def multi_gpu_legs(args, n, rank, world, local_rank, ctx, model, geo, slab, state, step_bytes, ms_step, peak, barrier, stream):
+    """N > 1 only.  (1) Every number the ranks all-reduced through the library's NCCL communicator is recomputed by rank 0
+    alone, slab by slab on its own GPU, and must agree (counts exactly, integrals to 1e-12).  (2) iso-work efficiency: the
+    mean per-GPU fraction of the HBM roofline at N ranks over the fraction one GPU reaches on the N = 1 model, measured in
+    this same process (per-GPU algorithmic bytes shrink with N because the surface work is proportional to n^2 / N, so the
+    driver's cells/s ratio overstates the scaling).  (3) DiscreteGeometry leg: the same model with the level sets given as
+    slab-local nodal vectors -- ghost node planes by ncclSend/ncclRecv and the consistency guard inside every step."""
+    import torch
+    import torch.distributed as dist
+    import gecut
+    from gecut import LevelSetCutter, Triangulation, EmbeddedBoundary, Measure
+    from gecut.measures import integrate_measure
+    SIDE = {-1: gecut.PHYSICAL_IN, 1: gecut.PHYSICAL_OUT}
+    cells_plan, bnd_plan = workload_plan(args.workload)
+    dev = f"cuda:{local_rank}"
+
+    def one(cutter, mdl, g, lap=True):
+        cg = cutter.cut(mdl, g)
+        oms = [Triangulation(cg, SIDE[side], name) for name, side in cells_plan]
+        if lap:
+            for om in oms:
+                ctx.check(ctx._lib.gecut_integrate_laplacian(om.handle, None, None), "gecut_integrate_laplacian")
+        gas = [EmbeddedBoundary(cg, name) for name in bnd_plan]
+        vols = [integrate_measure(Measure(om, 2)) for om in oms]
+        surfs = [integrate_measure(Measure(ga, 2)) for ga in gas]
+        out = [vols[0], surfs[0], float(cg.num_cutcells), float(cg.sizes.num_subcells), vols[-1]]
+        for o in oms + gas:
+            o.close()
+        cg.close()
+        return out
+
+    # ---- (1) slab-by-slab on one GPU
+    slabs = [None] * world
+    dist.all_gather_object(slabs, tuple(slab))
+    check = None
+    if rank == 0:
+        tot = [0.0] * 5
+        for sl in slabs:
+            part = one(LevelSetCutter(ctx, slab=tuple(sl)), model, geo, lap=False)
+            tot = [a + b for a, b in zip(tot, part)]
+        glob = [state["vol"], state["surf"], float(state["global_counts"]["cut_cells"]),
+                float(state["global_counts"]["subcells"]), state["vols"][-1]]
+        ok = (tot[2] == glob[2] and tot[3] == glob[3] and
+              all(abs(a - b) <= 1e-12 * abs(a) for a, b in ((tot[0], glob[0]), (tot[1], glob[1]), (tot[4], glob[4]))))
+        check = {"ok": bool(ok), "nccl": glob, "single_gpu_slab_by_slab": tot}
+        if not ok:
+            raise SystemExit(f"the {world}-rank NCCL result differs from the single-GPU slab-by-slab result: {check}")
+    barrier()
+
+    # ---- (2) iso-work efficiency
+    bytes_t = torch.tensor([float(step_bytes)], dtype=torch.float64, device=dev)
+    dist.all_reduce(bytes_t)
+    frac_n = float(bytes_t[0]) / world / (ms_step * 1e-3) / 1e9 / peak
+    iso = None
+    model1, geo1, _ = make_workload(args.workload, n, 1)
+    if rank == 0:
+        c1 = LevelSetCutter(ctx)
+        for _ in range(3):
+            one(c1, model1, geo1)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        K = max(5, min(args.steps, 20))
+        a.record(stream)
+        for _ in range(K):
+            one(c1, model1, geo1)
+        b.record(stream)
+        torch.cuda.synchronize()
+        ms1 = a.elapsed_time(b) / K
+        # algorithmic bytes of the N = 1 model from its own counts
+        cg = c1.cut(model1, geo1)
+        oms = [Triangulation(cg, SIDE[side], name) for name, side in cells_plan]
+        gas = [EmbeddedBoundary(cg, name) for name in bnd_plan]
+        _, b1 = algorithmic_bytes(cg.sizes, model1, sum(o.num_sub for o in oms), sum(g_.num_sub for g_ in gas),
+                                  ncellsel=len(cells_plan))
+        for o in oms + gas:
+            o.close()
+        cg.close()
+        frac_1 = b1 / (ms1 * 1e-3) / 1e9 / peak
+        iso = {"frac_per_gpu_at_n": round(frac_n, 4), "frac_single_gpu_model": round(frac_1, 4),
+               "iso_work_efficiency": round(frac_n / frac_1, 4), "single_gpu_ms_per_step": round(ms1, 4),
+               "note": "mean per-GPU step_roofline.frac at N ranks / the same fraction of the N = 1 model timed on rank 0 in "
+                       "this run (device-resident laplacian, same kernels)"}
+    barrier()
+
+    # ---- (3) DiscreteGeometry leg (skipped when the main leg already ran --nodal)
+    nodal = None
+    if not args.nodal:
+        from gecut import DiscreteGeometry
+        from gecut.cutters import evaluate_leaves_at_nodes
+        from gecut.csg import find_unique_leaves, replace_data
+        tree = geo.get_tree()
+        payloads, oid_to_j = find_unique_leaves(tree)
+        layer_nodes = model.num_nodes // (model.partition[-1] + 1)
+        # DiscreteGeometry data cannot be re-balanced from the geometry: even slabs (DESIGN section 6)
+        k0, k1 = slab_of(model, rank, world)
+        bufs = []
+        for pl in payloads:
+            (buf,) = evaluate_leaves_at_nodes(model, [pl], ctx=ctx, device_output=True, slab=(k0, k1))
+            if rank < world - 1:
+                buf[-layer_nodes:] = float("nan")  # the ghost plane must come from the neighbour
+            bufs.append(buf)
+        dgeo = DiscreteGeometry(replace_data(lambda d: d, lambda d: (bufs[oid_to_j[id(d[0])]], d[1], d[2]), tree), model)
+        ncut = LevelSetCutter(ctx, slab=(k0, k1), nodal_slab_local=True)
+        red2 = torch.zeros(16, dtype=torch.float64, device=dev)
+
+        def nstep():
+            ctx.comm_exchange_ghost_planes(bufs, layer_nodes)
+            if not ctx.comm_check_consistency(bufs, layer_nodes):
+                raise SystemExit("inconsistent ghost planes")
+            loc = one(ncut, model, dgeo)
+            ctx.comm_allreduce_sum(loc, red2.data_ptr())
+        for _ in range(3):
+            nstep()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(args.steps):
+            nstep()
+        b.record(stream)
+        barrier()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        g2 = ctx.comm_fetch(red2.data_ptr(), 5)
+        same = (g2[2] == float(state["global_counts"]["cut_cells"]) and g2[3] == float(state["global_counts"]["subcells"]) and
+                abs(g2[0] - state["vol"]) <= 1e-12 * abs(state["vol"]) and abs(g2[1] - state["surf"]) <= 1e-12 * abs(state["surf"]))
+        if not same:
+            raise SystemExit(f"DiscreteGeometry leg: global numbers {g2} differ from the closed-form leg")
+        msn = float(t[0]) / args.steps
+        nodal = {"ms_per_step": msn, "value": model.num_cubes / (msn * 1e-3), "unit": UNIT, "slabs": "even layers",
+                 "ghost_plane_bytes_per_step_per_boundary": int(8 * layer_nodes * len(bufs)),
+                 "what": "same model, level sets as a DiscreteGeometry: slab-local device-resident nodal vectors (ghost plane "
+                         "poisoned with NaN at start), per step: grouped ncclSend/ncclRecv of the ghost node planes + the "
+                         "consistency guard (sign compare + ncclAllReduce(min)) + cut + integrals + ncclAllReduce(sum); "
+                         "global integrals and counts equal the closed-form leg's"}
+        del bufs
+    return {"check_vs_single_gpu": check, "iso_work": iso, "discrete_geometry_leg": nodal,
+            "collectives": "inside libgecut.so (gecut_comm_*): NCCL on the context's stream, no host round trip per step"}
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -380,8 +538,12 @@ def run_b200(args, n, rank, world, local_rank):
     stream = torch.cuda.current_stream()
     ctx = _lib.Context(local_rank, stream.cuda_stream)
     cutter = LevelSetCutter(ctx, slab=slab)
-    red = torch.zeros(5, dtype=torch.float64, device=f"cuda:{local_rank}")
-    red_host = torch.zeros(5, dtype=torch.float64, pin_memory=True)
+    # global integrals + counts: all-reduced INSIDE the library (gecut_comm_allreduce_sum: the local numbers travel as kernel
+    # arguments, ncclAllReduce on the context's stream, nothing waits on the host); read back once after the loop
+    red = torch.zeros(16, dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        from gecut.distributed import init_library_communicator
+        init_library_communicator(ctx)
 
     def barrier():
         if world > 1:
@@ -399,19 +561,15 @@ def run_b200(args, n, rank, world, local_rank):
         from gecut import DiscreteGeometry
         from gecut.cutters import evaluate_leaves_at_nodes
         from gecut.csg import find_unique_leaves, replace_data
-        from gecut.distributed import exchange_ghost_plane_
         tree = geo.get_tree()
         payloads, oid_to_j = find_unique_leaves(tree)
         layer_nodes = model.num_nodes // (model.partition[-1] + 1)
         k0, k1 = slab if slab is not None else (0, model.partition[-1])
         for pl in payloads:
-            (full,) = evaluate_leaves_at_nodes(model, [pl], ctx=ctx, device_output=True)
-            buf = full[k0 * layer_nodes:(k1 + 1) * layer_nodes].clone()
+            (buf,) = evaluate_leaves_at_nodes(model, [pl], ctx=ctx, device_output=True, slab=(k0, k1))
             if world > 1 and rank < world - 1:
                 buf[-layer_nodes:] = float("nan")  # the ghost plane is NOT known locally: it must come from the neighbour
             nodal_bufs.append(buf)
-            del full
-        torch.cuda.empty_cache()
         geo = DiscreteGeometry(replace_data(lambda d: d, lambda d: (nodal_bufs[oid_to_j[id(d[0])]], d[1], d[2]), tree), model)
         cutter = LevelSetCutter(ctx, slab=slab, nodal_slab_local=slab is not None)
         desc += "; level sets given as a DiscreteGeometry (device-resident slab-local nodal values, NCCL ghost-plane exchange per step)"
@@ -422,8 +580,11 @@ def run_b200(args, n, rank, world, local_rank):
     def step(e2e=False, host=None):
         t = [time.perf_counter()]
         if nodal_bufs and world > 1:
-            for buf in nodal_bufs:
-                exchange_ghost_plane_(buf, layer_nodes)
+            # ghost node planes of the slab-local level sets: grouped ncclSend/ncclRecv inside the library, stream-ordered
+            # before the cut; then the reference's guard (isconsistent_bgcell_to_inoutcut) on the shared planes
+            ctx.comm_exchange_ghost_planes(nodal_bufs, layer_nodes)
+            if not ctx.comm_check_consistency(nodal_bufs, layer_nodes):
+                raise SystemExit("inconsistent ghost planes")
         cg = cutter.cut(model, geo)
         t.append(time.perf_counter())
         oms = [Triangulation(cg, SIDE[side], name) for name, side in cells_plan]
@@ -443,18 +604,11 @@ def run_b200(args, n, rank, world, local_rank):
         if e2e:
             cg.to_host(buffers=host["layout"])
         vol, surf = vols[0], surfs[0]
-        if world > 1:  # global integrals + counts: the only data-path collective
-            # one H2D copy of the local numbers, the all-reduce, one read-back of the global ones
-            red_host[0], red_host[1] = vol, surf
-            red_host[2], red_host[3] = float(cg.num_cutcells), float(cg.sizes.num_subcells)
-            red_host[4] = vols[-1]
-            red.copy_(red_host, non_blocking=True)
-            dist.all_reduce(red)
-            glob = red.cpu()
-            vol, surf = float(glob[0]), float(glob[1])
-            vols = [vol] + ([float(glob[4])] if len(vols) > 1 else [])
+        local = [vol, surf, float(cg.num_cutcells), float(cg.sizes.num_subcells), vols[-1]]
+        if world > 1:  # global integrals + counts: the only data-path collective, device resident
+            ctx.comm_allreduce_sum(local, red.data_ptr())
         state.update(sizes=cg.sizes, nsel=sum(om.num_sub for om in oms), nfsel=sum(ga.num_sub for ga in gas), vol=vol,
-                     surf=surf, vols=[float(v) for v in vols])
+                     surf=surf, vols=[float(v) for v in vols], local=local)
         for o in oms + gas:
             o.close()
         cg.close()
@@ -486,8 +640,12 @@ def run_b200(args, n, rank, world, local_rank):
         for row in dbg[-args.steps:]:
             sys.stderr.write("   " + str(row) + "\n")
     barrier()
-    clocks = sampler.stop() if sampler else None
+    timed_clock_samples = len(sampler.samples) if sampler else 0
     launches = ctx.launch_count - l0
+    glob = ctx.comm_fetch(red.data_ptr(), 5) if world > 1 else list(state["local"])
+    state["vol"], state["surf"] = glob[0], glob[1]
+    state["vols"] = [glob[0]] + ([glob[4]] if len(state["vols"]) > 1 else [])
+    state["global_counts"] = {"cut_cells": int(glob[2]), "subcells": int(glob[3])}
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -537,6 +695,12 @@ def run_b200(args, n, rank, world, local_rank):
     ms_step = ms_total / args.steps
     step_roofline = {"alg_bytes_per_step": step_bytes, "achieved": round(step_bytes / (ms_step * 1e-3) / 1e9, 1),
                      "peak": peak, "unit": "GB/s", "frac": round(step_bytes / (ms_step * 1e-3) / 1e9 / peak, 4)}
+
+    # ---- multi-GPU: the N-rank result against a single-GPU slab-by-slab run, iso-work efficiency, DiscreteGeometry leg ----
+    multi = None
+    if world > 1:
+        multi = multi_gpu_legs(args, n, rank, world, local_rank, ctx, model, geo, slab, state, step_bytes, ms_step, peak,
+                               barrier, stream)
 
     # ---- end to end through the C ABI with HOST buffers ------------------------------------------------------------
     e2e = None
@@ -594,6 +758,12 @@ def run_b200(args, n, rank, world, local_rank):
         v, dt, sample = cpu_sample(args.workload, n_cpu)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample, "seconds": round(dt, 2)}
 
+    clocks = None
+    if sampler:
+        clocks = sampler.stop()
+        clocks["samples_timed_region"] = timed_clock_samples
+        clocks["note"] = ("sampled from the first timed step to the end of the end-to-end leg (the device-resident timed "
+                          "region alone lasts tens of ms = 1-2 samples at the 20 ms period)")
     if rank == 0:
         lb = layout_bytes(s)
         line = {
@@ -607,8 +777,9 @@ def run_b200(args, n, rank, world, local_rank):
                              f"({(sum(lb.values())) / 1e9:.2f} GB of outputs per GPU >> 126 MB L2), nothing is reused across steps",
                        "per_gpu_counts": {"cut_cells": int(s.num_cutcells), "subcells": int(s.num_subcells),
                                           "subcell_points": int(s.num_subcell_points), "subfacets": int(s.num_subfacets)},
+                       "global_counts": state["global_counts"],
                        "integrals": {"volume": state["vol"], "surface": state["surf"], "volumes": state["vols"]}},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "multi_gpu": multi,
             "roofline": roofline, "step_roofline": step_roofline, "kernels": kernels[:12], "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

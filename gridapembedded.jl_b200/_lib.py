@@ -18,7 +18,8 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(HERE, "..", "include")
 
 GECUT_OK = 0
-GECUT_ERR_INVALID, GECUT_ERR_NOTIMPLEMENTED, GECUT_ERR_CUDA, GECUT_ERR_OOM, GECUT_ERR_OVERFLOW = 1, 2, 3, 4, 5
+GECUT_ERR_INVALID, GECUT_ERR_NOTIMPLEMENTED, GECUT_ERR_CUDA, GECUT_ERR_OOM, GECUT_ERR_OVERFLOW, GECUT_ERR_COMM = 1, 2, 3, 4, 5, 6
+COMM_ID_BYTES, COMM_MAX_VALUES = 128, 16
 SEL_PHYSICAL, SEL_ACTIVE, SEL_BOUNDARY, SEL_CUTONLY, SEL_BGONLY = 0, 1, 2, 3, 4
 MAX_LEVELSETS = 16
 MAX_PROGRAM = 64
@@ -77,12 +78,30 @@ class FacetBuffers(C.Structure):
 FACETS_BOUNDARY, FACETS_SKELETON = 0, 1
 
 SOURCES = ["gecut_api.cu", "gecut_classify.cu", "gecut_cutcells.cu", "gecut_select.cu", "gecut_integrate.cu",
-           "gecut_facets.cu", "gecut_aggregate.cu"]
+           "gecut_facets.cu", "gecut_aggregate.cu", "gecut_comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xcompiler", "-ffp-contract=off"]
 
 
-def _source_hash() -> str:
+def _nvcc() -> str:
+    return os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+
+_nvcc_version_cache = None
+
+
+def _nvcc_version() -> str:
+    global _nvcc_version_cache
+    if _nvcc_version_cache is None:
+        try:
+            out = subprocess.run([_nvcc(), "--version"], capture_output=True, text=True, timeout=30).stdout
+            _nvcc_version_cache = out.strip().splitlines()[-1] if out.strip() else "unknown"
+        except Exception:
+            _nvcc_version_cache = "absent"
+    return _nvcc_version_cache
+
+
+def _source_hash(with_compiler: bool = True) -> str:
     """Content hash of everything the library is built from (mtimes do not survive the copy to the GPU box)."""
     import hashlib
     h = hashlib.sha256()
@@ -92,6 +111,8 @@ def _source_hash() -> str:
         with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
+    if with_compiler:
+        h.update(_nvcc_version().encode())
     return h.hexdigest()
 
 
@@ -106,36 +127,53 @@ def _needs_build() -> bool:
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a (`--fmad=false`: the reference's Julia arithmetic never fuses
-    a*b+c and IN/OUT decisions of nodes lying on a surface depend on it) and link libgecut.so in-tree."""
+    a*b+c and IN/OUT decisions of nodes lying on a surface depend on it) and link libgecut.so in-tree.
+
+    Safe under torchrun: the ranks serialise on a file lock, the first one builds into a private directory and moves the
+    finished library into place atomically, the others find an up-to-date library when they get the lock."""
     if not force and not _needs_build():
         return LIB_PATH
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    import fcntl
+    import shutil
+    import tempfile
     os.makedirs(LIB_DIR, exist_ok=True)
-    objdir = os.path.join(LIB_DIR, "obj")
-    os.makedirs(objdir, exist_ok=True)
-    procs = []
-    objs = []
-    for src in SOURCES:
-        obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
-        if verbose:
-            cmd.insert(1, "-Xptxas")
-            cmd.insert(2, "-v")
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
-    failed = []
-    for src, p in procs:
-        out, _ = p.communicate()
-        if verbose or p.returncode != 0:
-            sys.stderr.write(out.decode(errors="replace"))
-        if p.returncode != 0:
-            failed.append(src)
-    if failed:
-        raise GecutError(f"nvcc failed for {failed}")
-    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-lcudart"]
-    subprocess.check_call(cmd)
-    with open(HASH_PATH, "w") as fh:
-        fh.write(_source_hash())
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _needs_build():  # another rank built it while this one waited
+                return LIB_PATH
+            nvcc = _nvcc()
+            tmp = tempfile.mkdtemp(prefix=".build-", dir=LIB_DIR)
+            try:
+                procs = []
+                objs = []
+                for src in SOURCES:
+                    obj = os.path.join(tmp, src.replace(".cu", ".o"))
+                    objs.append(obj)
+                    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
+                    if verbose:
+                        cmd.insert(1, "-Xptxas")
+                        cmd.insert(2, "-v")
+                    procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+                failed = []
+                for src, p in procs:
+                    out, _ = p.communicate()
+                    if verbose or p.returncode != 0:
+                        sys.stderr.write(out.decode(errors="replace"))
+                    if p.returncode != 0:
+                        failed.append(src)
+                if failed:
+                    raise GecutError(f"nvcc failed for {failed}")
+                so = os.path.join(tmp, "libgecut.so")
+                subprocess.check_call([nvcc, "-shared", "-o", so] + objs + ["-lcudart", "-lnccl"])
+                os.replace(so, LIB_PATH)
+                with open(os.path.join(tmp, "BUILD_HASH"), "w") as fh:
+                    fh.write(_source_hash())
+                os.replace(os.path.join(tmp, "BUILD_HASH"), HASH_PATH)
+            finally:
+                shutil.rmtree(tmp, ignore_errors=True)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
@@ -153,6 +191,12 @@ def lib():
     except FileNotFoundError as e:  # no nvcc on this machine: use the prebuilt library if there is one
         if not os.path.exists(LIB_PATH):
             raise GecutError(f"libgecut.so is missing and nvcc is unavailable: {e}")
+    # libgecut.so needs libnccl.so.2.  PyTorch ships its own copy under the same SONAME: load torch first so that one
+    # process never maps two NCCL versions (whichever is mapped first serves both).
+    try:
+        import torch  # noqa: F401
+    except Exception:
+        pass
     try:
         L = C.CDLL(LIB_PATH)
     except OSError as e:
@@ -202,9 +246,18 @@ def lib():
     L.gecut_facet_selection_sizes.argtypes = [vp, P(i64), P(i64)]
     L.gecut_facet_selection_copy.argtypes = [vp, vp, vp]
     L.gecut_facet_selection_measure.argtypes = [vp, vp, P(C.c_double)]
-    L.gecut_aggregate.argtypes = [vp, vp, vp, cint, cint, C.c_double, vp, cint]
+    L.gecut_aggregate.argtypes = [vp, vp, vp, cint, vp, cint, cint, C.c_double, vp, cint]
     L.gecut_ghost_skeleton.argtypes = [vp, vp, cint, cint, P(i64), vp, vp]
-    for name in FACET_SYMBOLS:
+    L.gecut_comm_unique_id.argtypes = [vp]
+    L.gecut_comm_init.argtypes = [vp, vp, cint, cint]
+    L.gecut_comm_free.argtypes = [vp]
+    L.gecut_comm_rank.argtypes = [vp, P(cint), P(cint)]
+    L.gecut_comm_exchange_ghost_planes.argtypes = [vp, P(vp), cint, i64, i64]
+    L.gecut_comm_check_consistency.argtypes = [vp, P(vp), cint, i64, i64, P(cint)]
+    L.gecut_comm_allreduce_sum.argtypes = [vp, P(C.c_double), cint, vp]
+    L.gecut_comm_fetch.argtypes = [vp, vp, cint, P(C.c_double)]
+    L.gecut_comm_allgather_sizes.argtypes = [vp, vp, P(Sizes)]
+    for name in FACET_SYMBOLS + COMM_SYMBOLS:
         getattr(L, name).restype = cint
     for name in ("gecut_create", "gecut_destroy", "gecut_set_stream", "gecut_cut", "gecut_classify",
                  "gecut_eval_leaf_at_nodes", "gecut_result_free", "gecut_result_sizes", "gecut_result_device_ptrs",
@@ -222,7 +275,11 @@ FACET_SYMBOLS = ["gecut_cut_facets", "gecut_facet_result_free", "gecut_facet_res
                  "gecut_facet_selection_free", "gecut_facet_selection_sizes", "gecut_facet_selection_copy",
                  "gecut_facet_selection_measure", "gecut_aggregate", "gecut_ghost_skeleton"]
 
-EXPORTED_SYMBOLS = FACET_SYMBOLS + ["gecut_create", "gecut_destroy", "gecut_set_stream", "gecut_last_error", "gecut_launch_count",
+COMM_SYMBOLS = ["gecut_comm_unique_id", "gecut_comm_init", "gecut_comm_free", "gecut_comm_rank",
+                "gecut_comm_exchange_ghost_planes", "gecut_comm_check_consistency", "gecut_comm_allreduce_sum",
+                "gecut_comm_fetch", "gecut_comm_allgather_sizes"]
+
+EXPORTED_SYMBOLS = FACET_SYMBOLS + COMM_SYMBOLS + ["gecut_create", "gecut_destroy", "gecut_set_stream", "gecut_last_error", "gecut_launch_count",
                     "gecut_profile", "gecut_profile_report", "gecut_trim",
                     "gecut_cut", "gecut_classify", "gecut_eval_leaf_at_nodes", "gecut_result_free",
                     "gecut_result_sizes", "gecut_result_device_ptrs", "gecut_result_copy", "gecut_bgcell_to_inoutcut",
@@ -278,6 +335,74 @@ class Context:
             name, cnt, ms = line.split()
             out[name] = (int(cnt), float(ms))
         return out
+
+    # ---- multi-GPU (include/gecut.h "multi-GPU"): NCCL collectives enqueued on this context's stream -------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128 bytes to hand to every rank's `comm_init` (rank 0 creates them; the host program distributes them)."""
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        rc = lib().gecut_comm_unique_id(buf)
+        if rc != GECUT_OK:
+            raise GecutError(f"gecut_comm_unique_id failed with status {rc}")
+        return buf.raw
+
+    def comm_init(self, uid: bytes, rank: int, world: int):
+        if len(uid) != COMM_ID_BYTES:
+            raise ValueError("the communicator id has GECUT_COMM_ID_BYTES bytes")
+        self.check(self._lib.gecut_comm_init(self._h, C.c_char_p(uid), int(rank), int(world)), "gecut_comm_init")
+
+    def comm_free(self):
+        self.check(self._lib.gecut_comm_free(self._h), "gecut_comm_free")
+
+    @property
+    def comm_rank_world(self):
+        r, w = C.c_int(), C.c_int()
+        self.check(self._lib.gecut_comm_rank(self._h, C.byref(r), C.byref(w)), "gecut_comm_rank")
+        return int(r.value), int(w.value)
+
+    def comm_exchange_ghost_planes(self, slab_values, layer_nodes: int):
+        """In-place ghost update of slab-local nodal vectors (CUDA float64 torch tensors of num_planes * layer_nodes values)."""
+        vecs = [v for v in slab_values]
+        if not vecs:
+            return
+        n = int(vecs[0].numel())
+        if any(int(v.numel()) != n or n % layer_nodes for v in vecs):
+            raise ValueError("every vector holds the same whole number of node planes")
+        ptrs = (C.c_void_p * len(vecs))(*[v.data_ptr() for v in vecs])
+        self.check(self._lib.gecut_comm_exchange_ghost_planes(self._h, ptrs, len(vecs), int(layer_nodes), n // layer_nodes),
+                   "gecut_comm_exchange_ghost_planes")
+
+    def comm_check_consistency(self, slab_values=(), layer_nodes: int = 0) -> bool:
+        """`isconsistent_bgcell_to_inoutcut` (DistributedDiscretizations.jl:136-174) for the slab partition."""
+        vecs = [v for v in slab_values]
+        ok = C.c_int(0)
+        if vecs:
+            n = int(vecs[0].numel())
+            ptrs = (C.c_void_p * len(vecs))(*[v.data_ptr() for v in vecs])
+            rc = self._lib.gecut_comm_check_consistency(self._h, ptrs, len(vecs), int(layer_nodes), n // layer_nodes,
+                                                        C.byref(ok))
+        else:
+            rc = self._lib.gecut_comm_check_consistency(self._h, None, 0, 0, 0, C.byref(ok))
+        self.check(rc, "gecut_comm_check_consistency")
+        return bool(ok.value)
+
+    def comm_allreduce_sum(self, values, result_dev_ptr: int):
+        """Global sums of a few doubles into device memory at `result_dev_ptr`, stream-ordered (no host wait)."""
+        n = len(values)
+        arr = (C.c_double * n)(*[float(v) for v in values])
+        self.check(self._lib.gecut_comm_allreduce_sum(self._h, arr, n, C.c_void_p(result_dev_ptr)),
+                   "gecut_comm_allreduce_sum")
+
+    def comm_fetch(self, dev_ptr: int, n: int):
+        out = (C.c_double * n)()
+        self.check(self._lib.gecut_comm_fetch(self._h, C.c_void_p(dev_ptr), n, out), "gecut_comm_fetch")
+        return [float(x) for x in out]
+
+    def comm_allgather_sizes(self, result_handle):
+        _, w = self.comm_rank_world
+        arr = (Sizes * w)()
+        self.check(self._lib.gecut_comm_allgather_sizes(self._h, result_handle, arr), "gecut_comm_allgather_sizes")
+        return list(arr)
 
     def close(self):
         if self._h:

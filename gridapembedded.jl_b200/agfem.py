@@ -54,19 +54,24 @@ def aggregate(strategy: AggregateCutCellsByThreshold, cut: EmbeddedDiscretizatio
         # (of the WHOLE geometry, so that the level-set rows line up with cut.program(geo))
         own = facets = _call_cut_facets(LevelSetCutter(cut.ctx), cut.bgmodel, cut.geo, True)
     prog = cut.program(geo)
+    # compute_bgfacet_to_inoutcut(cut_facets, geo) uses cut_facets' OWN oid_to_ls (`CellAggregation.jl:90`): the facet
+    # discretization may come from another Geometry object or leaf order, so the geometry is compiled a second time over it
+    fprog = facets.program(geo)
     ctx = cut.ctx
     nc = cut.num_bgcells
     try:
         if device_output:
             import torch
             out = torch.empty(nc, dtype=torch.int32, device=f"cuda:{ctx.device}")
-            ctx.check(ctx._lib.gecut_aggregate(cut.handle, facets.handle, prog.ctypes.data, prog.size, int(in_or_out),
-                                               C.c_double(strategy.threshold), C.c_void_p(out.data_ptr()), 1),
+            ctx.check(ctx._lib.gecut_aggregate(cut.handle, facets.handle, prog.ctypes.data, prog.size, fprog.ctypes.data,
+                                               fprog.size, int(in_or_out), C.c_double(strategy.threshold),
+                                               C.c_void_p(out.data_ptr()), 1),
                       "gecut_aggregate")
         else:
             out = np.empty(nc, np.int32)
-            ctx.check(ctx._lib.gecut_aggregate(cut.handle, facets.handle, prog.ctypes.data, prog.size, int(in_or_out),
-                                               C.c_double(strategy.threshold), C.c_void_p(out.ctypes.data), 0),
+            ctx.check(ctx._lib.gecut_aggregate(cut.handle, facets.handle, prog.ctypes.data, prog.size, fprog.ctypes.data,
+                                               fprog.size, int(in_or_out), C.c_double(strategy.threshold),
+                                               C.c_void_p(out.ctypes.data), 0),
                       "gecut_aggregate")
     finally:
         if own is not None:

@@ -75,10 +75,16 @@ class CartesianDiscreteModel:
         return (self.pmin, self.pmax, self.partition) == (other.pmin, other.pmax, other.partition)
 
     # ---- small-model helpers (host, tests and host-evaluated leaves) ----------------------
-    def node_coordinates(self) -> np.ndarray:
-        """(num_nodes, D) float64, `x0[d] + (I[d]-1)*dx[d]`."""
+    def node_coordinates(self, planes=None) -> np.ndarray:
+        """(num_nodes, D) float64, `x0[d] + (I[d]-1)*dx[d]`.  `planes=(k0,k1)`: only the node planes k0..k1 (inclusive) of
+        the last direction -- the nodes a z-slab [k0,k1) of cells touches, in the same (global) order."""
         axes = [self.pmin[d] + np.arange(self.partition[d] + 1, dtype=np.float64) * self.sizes[d]
                 for d in range(self.D)]
+        if planes is not None:
+            k0, k1 = int(planes[0]), int(planes[1])
+            if not (0 <= k0 <= k1 <= self.partition[-1]):
+                raise ValueError("node plane range out of bounds")
+            axes[-1] = axes[-1][k0:k1 + 1]
         grids = np.meshgrid(*axes, indexing="ij")
         # x fastest -> Fortran order of the (i,j,k) index space
         return np.stack([g.reshape(-1, order="F") for g in grids], axis=1)

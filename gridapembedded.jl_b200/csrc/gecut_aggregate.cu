@@ -243,7 +243,8 @@ extern "C" int gecut_ghost_skeleton(const gecut_result* cut, const int32_t* prog
 }
 
 extern "C" int gecut_aggregate(const gecut_result* cut, const gecut_facet_result* facets, const int32_t* program,
-                               int len, int side, double threshold, int32_t* cell_to_cellin, int on_device) {
+                               int len, const int32_t* facet_program, int facet_len, int side, double threshold,
+                               int32_t* cell_to_cellin, int on_device) {
   if (!cut || !facets || !cell_to_cellin) return GECUT_ERR_INVALID;
   gecut_ctx* ctx = cut->ctx;
   if (facets->ctx != ctx) {
@@ -271,6 +272,10 @@ extern "C" int gecut_aggregate(const gecut_result* cut, const gecut_facet_result
   DeviceGuard guard(ctx->device);
   GcProgram p;
   GC_CHECK(gc_make_program(ctx, program, len, cut->L, &p));
+  // compute_bgfacet_to_inoutcut(cut_facets, geo) evaluates the geometry over cut_facets' OWN oid_to_ls (CellAggregation.jl:90):
+  // its level-set rows may be numbered differently from the cell discretization's
+  GcProgram pf = p;
+  if (facet_program) GC_CHECK(gc_make_program(ctx, facet_program, facet_len, facets->L, &pf));
   const int64_t nc = cut->sizes.num_bgcells, ncut = cut->sizes.num_cutcells, nf = facets->sizes.num_bgfacets;
   const int D = g.D;
   int32_t* cellin = nullptr;
@@ -296,11 +301,11 @@ extern "C" int gecut_aggregate(const gecut_result* cut, const gecut_facet_result
   if (st != GECUT_OK) return done(st);
   // compute_bgfacet_to_inoutcut(cut_facets, geo): the level set's own row for a single leaf, else the program's row
   const int8_t* facet_state = nullptr;
-  if (p.len == 1) {
-    facet_state = facets->lay.bg_state + (int64_t)p.tok[0] * facets->lay.bg_pitch;
+  if (pf.len == 1) {
+    facet_state = facets->lay.bg_state + (int64_t)pf.tok[0] * facets->lay.bg_pitch;
   } else {
     st = gc_malloc(ctx, (void**)&frow, (size_t)pad_pitch(nf));
-    if (st == GECUT_OK) st = gc_eval_rows(ctx, facets->lay.bg_state, facets->lay.bg_pitch, nf, p, frow, true);
+    if (st == GECUT_OK) st = gc_eval_rows(ctx, facets->lay.bg_state, facets->lay.bg_pitch, nf, pf, frow, true);
     if (st != GECUT_OK) return done(st);
     facet_state = frow;
   }

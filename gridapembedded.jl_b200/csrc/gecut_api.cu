@@ -501,6 +501,7 @@ int gecut_destroy(gecut_ctx* ctx) {
   if (!ctx) return GECUT_OK;
   DeviceGuard guard(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  gecut_comm_free(ctx);
   gc_trim(ctx);
   for (auto& kv : ctx->live) cudaFree(kv.first);
   ctx->live.clear();
@@ -591,7 +592,7 @@ int gecut_classify(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* lea
 int gecut_eval_leaf_at_nodes(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* leaf, double* values,
                              int on_device) {
   if (!ctx) return GECUT_ERR_INVALID;
-  if (!leaf || !values) {
+  if (!grid || !leaf || !values) {
     ctx->err = "NULL argument";
     return GECUT_ERR_INVALID;
   }
@@ -602,12 +603,14 @@ int gecut_eval_leaf_at_nodes(gecut_ctx* ctx, const gecut_grid* grid, const gecut
   DeviceGuard guard(ctx->device);
   GcGrid g;
   gecut_grid gg = *grid;
-  gg.slab_begin = gg.slab_end = 0;
+  // nodal_slab_local: only the node planes slab_begin..slab_end (what a rank of the z-slab partition owns + its ghost plane)
+  const bool slab_only = gg.nodal_slab_local != 0 && !(gg.slab_begin == 0 && gg.slab_end == 0);
+  if (!slab_only) gg.slab_begin = gg.slab_end = 0;
   GC_CHECK(make_grid(ctx, &gg, &g));
-  const int64_t nn = g.layer_nodes * g.nn[g.D - 1];
+  const int64_t nn = slab_only ? g.num_nodes : g.layer_nodes * g.nn[g.D - 1];
   double* d = values;
   if (!on_device) GC_CHECK(gc_malloc(ctx, (void**)&d, sizeof(double) * nn));
-  int st = gc_eval_leaf_nodes(ctx, g, *leaf, d);
+  int st = gc_eval_leaf_nodes(ctx, g, *leaf, d, slab_only);
   if (st == GECUT_OK && !on_device) {
     cudaError_t e = cudaMemcpyAsync(values, d, sizeof(double) * nn, cudaMemcpyDeviceToHost, ctx->stream);
     if (e != cudaSuccess) {
@@ -626,6 +629,10 @@ int gecut_eval_leaf_at_nodes(gecut_ctx* ctx, const gecut_grid* grid, const gecut
 
 int gecut_result_free(gecut_result* res) {
   if (!res) return GECUT_OK;
+  if (res->live_selections > 0) {  // deferred: the last selection of this result releases it
+    res->free_requested = true;
+    return GECUT_OK;
+  }
   DeviceGuard guard(res->ctx->device);
   free_result_arrays(res);
   delete res;
@@ -735,9 +742,14 @@ int gecut_select_cells(const gecut_result* res, int kind, const int32_t* program
     return GECUT_ERR_INVALID;
   }
   DeviceGuard guard(ctx->device);
+  if (res->free_requested) {
+    ctx->err = "the result has been freed";
+    return GECUT_ERR_INVALID;
+  }
   gecut_selection* sel = new (std::nothrow) gecut_selection();
   if (!sel) return GECUT_ERR_OOM;
   sel->res = res;
+  res->live_selections++;
   sel->kind = kind;
   sel->side = side;
   const int64_t launches0 = ctx->launches;
@@ -761,9 +773,14 @@ int gecut_select_boundary(const gecut_result* res, const int32_t* program1, int 
   gecut_ctx* ctx = res->ctx;
   *out = nullptr;
   DeviceGuard guard(ctx->device);
+  if (res->free_requested) {
+    ctx->err = "the result has been freed";
+    return GECUT_ERR_INVALID;
+  }
   gecut_selection* sel = new (std::nothrow) gecut_selection();
   if (!sel) return GECUT_ERR_OOM;
   sel->res = res;
+  res->live_selections++;
   sel->kind = GECUT_SEL_BOUNDARY;
   const int64_t launches0 = ctx->launches;
   int st = make_program(ctx, program1, len1, res->L, &sel->prog);
@@ -790,7 +807,9 @@ int gecut_selection_free(gecut_selection* sel) {
   gc_free(ctx, sel->orientation);
   gc_free(ctx, sel->bg_ids);
   gc_free(ctx, sel->K_cut);
+  gecut_result* res = const_cast<gecut_result*>(sel->res);
   delete sel;
+  if (--res->live_selections == 0 && res->free_requested) return gecut_result_free(res);
   return GECUT_OK;
 }
 

@@ -731,14 +731,14 @@ k_nodal_signs(const double* __restrict__ vals /* first node of the slab's first 
   }
 }
 
+// `plane0`: index (last direction) of the first node plane written, `total` nodes from there on (whole model: 0 / all)
 template <int D>
-__global__ void k_eval_leaf_nodes(const GcGrid g, const gecut_leaf leaf, double* __restrict__ out) {
+__global__ void k_eval_leaf_nodes(const GcGrid g, const gecut_leaf leaf, int plane0, int64_t total, double* __restrict__ out) {
   int64_t node = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t total = (int64_t)g.nn[0] * g.nn[1] * (D == 3 ? g.nn[2] : 1);
   if (node >= total) return;
   int i = (int)(node % g.nn[0]);
-  int j = (int)((node / g.nn[0]) % g.nn[1]);
-  int k = (D == 3) ? (int)(node / ((int64_t)g.nn[0] * g.nn[1])) : 0;
+  int j = (D == 3) ? (int)((node / g.nn[0]) % g.nn[1]) : (int)(node / g.nn[0]) + plane0;
+  int k = (D == 3) ? (int)(node / ((int64_t)g.nn[0] * g.nn[1])) + plane0 : 0;
   double x[3] = {gc_coord(g, 0, i), gc_coord(g, 1, j), D == 3 ? gc_coord(g, 2, k) : 0.0};
   out[node] = gc_eval_leaf(leaf, x, D);
 }
@@ -901,13 +901,15 @@ int gc_compact_cutcells(gecut_ctx* ctx, gecut_result* res) {
   return st;
 }
 
-int gc_eval_leaf_nodes(gecut_ctx* ctx, const GcGrid& g, const gecut_leaf& leaf, double* out_dev) {
-  int64_t total = (int64_t)g.nn[0] * g.nn[1] * (g.D == 3 ? g.nn[2] : 1);
+int gc_eval_leaf_nodes(gecut_ctx* ctx, const GcGrid& g, const gecut_leaf& leaf, double* out_dev, bool slab_only) {
+  // whole model, or only the node planes k0..k1 of the slab (slab-local DiscreteGeometry vectors)
+  const int plane0 = slab_only ? g.k0 : 0;
+  const int64_t total = slab_only ? g.num_nodes : g.layer_nodes * (int64_t)g.nn[g.D - 1];
   const int T = 256;
   unsigned nb = (unsigned)gc_div_up(total, T);
   if (g.D == 3)
-    GC_LAUNCH(ctx, "k_eval_leaf_nodes", k_eval_leaf_nodes<3><<<nb, T, 0, ctx->stream>>>(g, leaf, out_dev));
+    GC_LAUNCH(ctx, "k_eval_leaf_nodes", k_eval_leaf_nodes<3><<<nb, T, 0, ctx->stream>>>(g, leaf, plane0, total, out_dev));
   else
-    GC_LAUNCH(ctx, "k_eval_leaf_nodes", k_eval_leaf_nodes<2><<<nb, T, 0, ctx->stream>>>(g, leaf, out_dev));
+    GC_LAUNCH(ctx, "k_eval_leaf_nodes", k_eval_leaf_nodes<2><<<nb, T, 0, ctx->stream>>>(g, leaf, plane0, total, out_dev));
   return gc_launch_check(ctx, "k_eval_leaf_nodes");
 }

@@ -1751,10 +1751,11 @@ static int gc_cut_cells_l1(gecut_ctx* ctx, gecut_result* res) {
   const int64_t nsimp = ncut * g.nt0;
   const int64_t ntiles = gc_div_up(nsimp, CUT1_TILE);
   gecut_sizes& sz = res->sizes;
+  GcScratch scratch(ctx);  // tiles, totals, tile statistics: released on every exit path
   uint32_t* tiles = nullptr;
   uint64_t* totals_dev = nullptr;
-  GC_CHECK(gc_malloc(ctx, (void**)&tiles, sizeof(uint32_t) * ntiles * 3));
-  GC_CHECK(gc_malloc(ctx, (void**)&totals_dev, sizeof(uint64_t) * 3));
+  GC_CHECK(scratch.alloc(&tiles, sizeof(uint32_t) * ntiles * 3));
+  GC_CHECK(scratch.alloc(&totals_dev, sizeof(uint64_t) * 3));
   uint32_t *t_cells = tiles, *t_points = tiles + ntiles, *t_facets = tiles + 2 * ntiles;
   {
     // 128 cells per block = 128*nt0/32 whole tiles (nt0 in {1, 2, 6})
@@ -1785,8 +1786,6 @@ static int gc_cut_cells_l1(gecut_ctx* ctx, gecut_result* res) {
   const uint64_t lim = 2147483647ull;
   if (nsc * (uint64_t)(D + 1) >= lim || nscp > lim || nsf > lim) {
     ctx->err = "Int32 ids of the SubCellData/SubFacetData layout would overflow";
-    gc_free(ctx, tiles);
-    gc_free(ctx, totals_dev);
     return GECUT_ERR_OVERFLOW;
   }
   sz.num_subcells = (int64_t)nsc;
@@ -1820,7 +1819,7 @@ static int gc_cut_cells_l1(gecut_ctx* ctx, gecut_result* res) {
   // tile statistics -> four sums (IN / OUT subcell measure, subfacet measure, IN subcells), read back with the result
   const int NBR = (int)std::min<int64_t>(592, gc_div_up(ntiles, 256));
   double4* tile_stats = nullptr;
-  GC_CHECK(gc_malloc(ctx, (void**)&tile_stats, sizeof(double4) * (ntiles + NBR + 2)));
+  GC_CHECK(scratch.alloc(&tile_stats, sizeof(double4) * (ntiles + NBR + 2)));
   double4* st_partial = tile_stats + ntiles;
   double4* st_out = st_partial + NBR;
   unsigned int* st_ticket = reinterpret_cast<unsigned int*>(st_out + 1);
@@ -1852,9 +1851,6 @@ static int gc_cut_cells_l1(gecut_ctx* ctx, gecut_result* res) {
     }
     res->has_l1_stats = st == GECUT_OK;
   }
-  gc_free(ctx, tile_stats);
-  gc_free(ctx, tiles);
-  gc_free(ctx, totals_dev);
   return st;
 }
 

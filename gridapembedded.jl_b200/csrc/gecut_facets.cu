@@ -824,12 +824,13 @@ int classify_facets(gecut_ctx* ctx, gecut_facet_result* r) {
     ctx->err = "cut_facets: model too large for the node-sign grid";
     return GECUT_ERR_NOTIMPLEMENTED;
   }
+  GcScratch scratch(ctx);  // released on every exit path
   uint32_t* signs = nullptr;
   uint32_t* seg_counts = nullptr;
   uint64_t* total_dev = nullptr;
-  GC_CHECK(gc_malloc(ctx, (void**)&signs, sizeof(uint32_t) * ls_stride * L));
-  GC_CHECK(gc_malloc(ctx, (void**)&seg_counts, sizeof(uint32_t) * npieces));
-  GC_CHECK(gc_malloc(ctx, (void**)&total_dev, sizeof(uint64_t) * (1 + GC_LMAX * FT_N)));
+  GC_CHECK(scratch.alloc(&signs, sizeof(uint32_t) * ls_stride * L));
+  GC_CHECK(scratch.alloc(&seg_counts, sizeof(uint32_t) * npieces));
+  GC_CHECK(scratch.alloc(&total_dev, sizeof(uint64_t) * (1 + GC_LMAX * FT_N)));
   GC_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(uint64_t) * (1 + GC_LMAX * FT_N), ctx->stream));
   GC_LAUNCH(ctx, "k_node_signs", k_node_signs<D><<<sgrid, sblock, 0, ctx->stream>>>(g, r->leaves, wxt, signs, ls_stride));
   GC_CHECK(gc_launch_check(ctx, "k_node_signs"));
@@ -852,9 +853,6 @@ int classify_facets(gecut_ctx* ctx, gecut_facet_result* r) {
                                                                  r->lay.cutfacets, nitems, npieces, nullptr)));
     GC_CHECK(gc_launch_check(ctx, "k_facet_words_emit"));
   }
-  gc_free(ctx, signs);
-  gc_free(ctx, seg_counts);
-  gc_free(ctx, total_dev);
   return GECUT_OK;
 }
 
@@ -863,10 +861,11 @@ int walk_facets_nw(gecut_ctx* ctx, gecut_facet_result* r) {
   constexpr int NT0 = D == 3 ? 2 : 1;
   const int64_t nsimp = r->sizes.num_cutfacets * NT0;
   const int L = r->L;
+  GcScratch scratch(ctx);
   uint32_t* cnt = nullptr;
   uint64_t* totals_dev = nullptr;
-  GC_CHECK(gc_malloc(ctx, (void**)&cnt, sizeof(uint32_t) * 2 * nsimp));
-  GC_CHECK(gc_malloc(ctx, (void**)&totals_dev, sizeof(uint64_t) * 2));
+  GC_CHECK(scratch.alloc(&cnt, sizeof(uint32_t) * 2 * nsimp));
+  GC_CHECK(scratch.alloc(&totals_dev, sizeof(uint64_t) * 2));
   const unsigned nb = (unsigned)gc_div_up(nsimp, FW_T);
   GC_LAUNCH(ctx, "k_facet_walk_count",
             (k_facet_walk<D, NW, false><<<nb, FW_T, 0, ctx->stream>>>(r->grid, r->leaves, ctx->d_tables, r->lay.cutfacets, nsimp,
@@ -877,8 +876,6 @@ int walk_facets_nw(gecut_ctx* ctx, gecut_facet_result* r) {
   GC_CHECK(read_u64(ctx, totals_dev, 2, tot));
   if (tot[0] >= 2147483647ull || tot[1] >= 2147483647ull) {
     ctx->err = "sub-facet ids overflow Int32";
-    gc_free(ctx, cnt);
-    gc_free(ctx, totals_dev);
     return GECUT_ERR_OVERFLOW;
   }
   r->sizes.num_subfacets = (int64_t)tot[0];
@@ -896,8 +893,6 @@ int walk_facets_nw(gecut_ctx* ctx, gecut_facet_result* r) {
             (k_facet_walk<D, NW, true><<<nb, FW_T, 0, ctx->stream>>>(r->grid, r->leaves, ctx->d_tables, r->lay.cutfacets, nsimp,
                                                                     cnt, r->lay)));
   GC_CHECK(gc_launch_check(ctx, "k_facet_walk_fill"));
-  gc_free(ctx, cnt);
-  gc_free(ctx, totals_dev);
   return GECUT_OK;
 }
 
@@ -1059,6 +1054,10 @@ int gecut_cut_facets(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* l
 
 int gecut_facet_result_free(gecut_facet_result* res) {
   if (!res) return GECUT_OK;
+  if (res->live_selections > 0) {  // deferred: the last selection of this result releases it
+    res->free_requested = true;
+    return GECUT_OK;
+  }
   DeviceGuard guard(res->ctx->device);
   free_facet_arrays(res);
   delete res;
@@ -1085,13 +1084,14 @@ int gecut_facet_result_copy(const gecut_facet_result* res, const gecut_facet_buf
   GC_CHECK(to_host(ctx, host->sf_point_to_coords, l.X, s.num_subfacet_points * D));
   GC_CHECK(to_host(ctx, host->sf_point_to_rcoords, l.R, s.num_subfacet_points * (D - 1)));
   GC_CHECK(rows_to_host(ctx, host->ls_to_subfacet_to_inout, l.state, l.pitch, s.num_subfacets, L));
+  GcScratch scratch(ctx);  // released on every exit path
   int32_t* nodes = nullptr;
   int8_t* isb = nullptr;
   if (host->facet_to_nodes || host->facet_is_boundary) {
     const int64_t nf = s.num_bgfacets;
     const int nvf = s.num_vertices_per_bgfacet;
-    if (host->facet_to_nodes) GC_CHECK(gc_malloc(ctx, (void**)&nodes, sizeof(int32_t) * nf * nvf));
-    if (host->facet_is_boundary) GC_CHECK(gc_malloc(ctx, (void**)&isb, (size_t)nf));
+    if (host->facet_to_nodes) GC_CHECK(scratch.alloc(&nodes, sizeof(int32_t) * nf * nvf));
+    if (host->facet_is_boundary) GC_CHECK(scratch.alloc(&isb, (size_t)nf));
     const int T = 256;
     if (D == 2)
       GC_LAUNCH(ctx, "k_facet_topology", k_facet_topology<2><<<(unsigned)gc_div_up(nf, T), T, 0, ctx->stream>>>(res->grid, nf, nodes, isb));
@@ -1102,8 +1102,6 @@ int gecut_facet_result_copy(const gecut_facet_result* res, const gecut_facet_buf
     GC_CHECK(to_host(ctx, host->facet_is_boundary, isb, nf));
   }
   GC_CUDA(cudaStreamSynchronize(ctx->stream));
-  gc_free(ctx, nodes);
-  gc_free(ctx, isb);
   return GECUT_OK;
 }
 
@@ -1134,9 +1132,14 @@ int gecut_select_facets(const gecut_facet_result* res, int which, int kind, cons
   DeviceGuard guard(ctx->device);
   GcProgram p;
   GC_CHECK(gc_make_program(ctx, program, len, res->L, &p));
+  if (res->free_requested) {
+    ctx->err = "the facet result has been freed";
+    return GECUT_ERR_INVALID;
+  }
   gecut_facet_selection* sel = new (std::nothrow) gecut_facet_selection();
   if (!sel) return GECUT_ERR_OOM;
   sel->res = res;
+  res->live_selections++;
   sel->which = which;
   sel->kind = kind;
   sel->side = side;
@@ -1145,6 +1148,7 @@ int gecut_select_facets(const gecut_facet_result* res, int which, int kind, cons
     gc_free(ctx, sel->sub_ids);
     gc_free(ctx, sel->bg_ids);
     delete sel;
+    res->live_selections--;
     return code;
   };
   const int D = res->sizes.D;
@@ -1244,7 +1248,9 @@ int gecut_facet_selection_free(gecut_facet_selection* sel) {
   DeviceGuard guard(ctx->device);
   gc_free(ctx, sel->sub_ids);
   gc_free(ctx, sel->bg_ids);
+  gecut_facet_result* res = const_cast<gecut_facet_result*>(sel->res);
   delete sel;
+  if (--res->live_selections == 0 && res->free_requested) return gecut_facet_result_free(res);
   return GECUT_OK;
 }
 
@@ -1321,9 +1327,10 @@ int gecut_facet_selection_measure(const gecut_facet_selection* sel, double* sub_
     GC_CHECK(facet_materialize_sub_ids(ctx, const_cast<gecut_facet_selection*>(sel)));
     const int64_t n = sel->n_sub;
     const int64_t nb = gc_div_up(n, (int64_t)SUM_T * SUM_PER);
+    GcScratch scratch(ctx);
     double *partial = nullptr, *vals = nullptr;
-    GC_CHECK(gc_malloc(ctx, (void**)&partial, sizeof(double) * (nb + 1)));
-    if (sub_values) GC_CHECK(gc_malloc(ctx, (void**)&vals, sizeof(double) * n));
+    GC_CHECK(scratch.alloc(&partial, sizeof(double) * (nb + 1)));
+    if (sub_values) GC_CHECK(scratch.alloc(&vals, sizeof(double) * n));
     GC_LAUNCH(ctx, "k_facet_gather_sum",
               k_facet_gather_sum<<<(unsigned)nb, SUM_T, 0, ctx->stream>>>(sel->sub_ids, n, res->lay.meas, vals, partial));
     GC_CHECK(gc_launch_check(ctx, "k_facet_gather_sum"));
@@ -1334,8 +1341,6 @@ int gecut_facet_selection_measure(const gecut_facet_selection* sel, double* sub_
     GC_CHECK(to_host(ctx, sub_values, vals, n));
     GC_CUDA(cudaStreamSynchronize(ctx->stream));
     sum = h[0];
-    gc_free(ctx, partial);
-    gc_free(ctx, vals);
   }
   // whole facets: tensor Gauss rule of degree 2 on the (D-1)-cube, sum_q w_q * meas (the facet map is affine)
   const GcGrid& g = res->grid;

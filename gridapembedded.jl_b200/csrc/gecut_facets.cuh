@@ -22,6 +22,8 @@ struct GcFacetLayout {
 
 struct gecut_facet_result {
   gecut_ctx* ctx = nullptr;
+  mutable int live_selections = 0;  // see gecut_result: a result outlives its selections
+  bool free_requested = false;
   GcGrid grid{};
   int L = 0;
   GcLeaves leaves{};

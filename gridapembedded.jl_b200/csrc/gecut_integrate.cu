@@ -582,8 +582,9 @@ int gc_integrate_measure(gecut_ctx* ctx, const gecut_selection* sel, double* val
     GC_CHECK(gc_materialize_sub_ids(ctx, const_cast<gecut_selection*>(sel)));
     GC_CHECK(gc_ensure_measures(ctx, res));  // simplex cells, one level set: not written at cut time
     const int NB = (int)std::min<int64_t>(1184, gc_div_up(n, 1024));
+    GcScratch scratch(ctx);
     double* partial = nullptr;  // NB block partials, the total, the completion ticket
-    GC_CHECK(gc_malloc(ctx, (void**)&partial, sizeof(double) * (NB + 2)));
+    GC_CHECK(scratch.alloc(&partial, sizeof(double) * (NB + 2)));
     unsigned int* ticket = reinterpret_cast<unsigned int*>(partial + NB + 1);
     GC_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), ctx->stream));
     GC_LAUNCH(ctx, "k_measures", k_measures<<<NB, 256, 0, ctx->stream>>>(
@@ -593,7 +594,6 @@ int gc_integrate_measure(gecut_ctx* ctx, const gecut_selection* sel, double* val
     GC_CUDA(cudaMemcpyAsync(h, partial + NB, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     GC_CUDA(cudaStreamSynchronize(ctx->stream));
     total += h[0];
-    gc_free(ctx, partial);
     GC_CHECK(gc_launch_check(ctx, "k_measures"));
   }
   const bool use_bg = sel->kind == GECUT_SEL_PHYSICAL || sel->kind == GECUT_SEL_ACTIVE || sel->kind == GECUT_SEL_BGONLY;

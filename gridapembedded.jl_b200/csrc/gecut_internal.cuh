@@ -139,10 +139,20 @@ struct gecut_ctx {
   std::map<std::string, std::pair<int8_t*, std::vector<int8_t>>> lut_cache;
   void* h_pinned = nullptr;             // small pinned staging buffer for scalar read-backs
   size_t h_pinned_bytes = 0;
+  // multi-GPU (gecut_comm.cu): ncclComm_t of this rank, flag + scratch plane of the consistency guard
+  void* comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
+  int* comm_flag = nullptr;
+  double* comm_plane = nullptr;
+  size_t comm_plane_bytes = 0;
 };
 
 struct gecut_result {
   gecut_ctx* ctx = nullptr;
+  // selections made from this result keep it alive: gecut_result_free with live selections only marks the result, the
+  // last gecut_selection_free releases it (host finalizers -- Julia's GC, Python's __del__ -- run in no particular order)
+  mutable int live_selections = 0;
+  bool free_requested = false;
   GcGrid grid{};
   int L = 0;
   GcLeaves leaves{};
@@ -223,6 +233,31 @@ int gc_malloc(gecut_ctx* ctx, void** p, size_t bytes);
 void gc_free(gecut_ctx* ctx, void* p);
 void gc_trim(gecut_ctx* ctx);  // give every cached block back to the driver
 int gc_launch_check(gecut_ctx* ctx, const char* what);
+
+// Scratch blocks of one call: handed back to the context's cache on EVERY exit path (GC_CHECK / GC_CUDA return early), so a
+// failed call -- typically an allocation failure of the layout at large sizes -- pins nothing and the documented recovery
+// (gecut_trim, then a smaller slab) has the memory to work with.  `keep` releases a block from the guard (it became part
+// of a result).
+struct GcScratch {
+  gecut_ctx* ctx;
+  std::vector<void*> blocks;
+  explicit GcScratch(gecut_ctx* c) : ctx(c) {}
+  GcScratch(const GcScratch&) = delete;
+  GcScratch& operator=(const GcScratch&) = delete;
+  ~GcScratch() {
+    for (void* p : blocks) gc_free(ctx, p);
+  }
+  template <class T>
+  int alloc(T** p, size_t bytes) {
+    const int st = gc_malloc(ctx, reinterpret_cast<void**>(p), bytes);
+    if (st == GECUT_OK) blocks.push_back(*p);
+    return st;
+  }
+  void keep(void* p) {
+    for (auto& b : blocks)
+      if (b == p) b = nullptr;
+  }
+};
 // per-entity measures of results that did not write them at cut time (simplex bg cells, one level set)
 int gc_ensure_measures(gecut_ctx* ctx, const struct gecut_result* res);
 
@@ -251,7 +286,7 @@ int gc_exclusive_scan_u32_multi(gecut_ctx* ctx, const uint32_t* in, uint32_t* ou
 // ---- classification (gecut_classify.cu) ----
 int gc_classify(gecut_ctx* ctx, gecut_result* res);        // states + cutmask
 int gc_compact_cutcells(gecut_ctx* ctx, gecut_result* res);  // cutmask -> cutcell_to_cell, sizes.num_cutcells
-int gc_eval_leaf_nodes(gecut_ctx* ctx, const GcGrid& g, const gecut_leaf& leaf, double* out_dev);
+int gc_eval_leaf_nodes(gecut_ctx* ctx, const GcGrid& g, const gecut_leaf& leaf, double* out_dev, bool slab_only = false);
 
 // ---- subtriangulation (gecut_cutcells.cu) ----
 int gc_cut_cells(gecut_ctx* ctx, gecut_result* res);

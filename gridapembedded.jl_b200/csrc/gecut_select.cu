@@ -342,14 +342,14 @@ int gc_compact_flags(gecut_ctx* ctx, uint32_t* flags, int64_t n, int32_t** ids_o
   if (orient_out) *orient_out = nullptr;
   *count = 0;
   if (n <= 0) return GECUT_OK;
+  GcScratch scratch(ctx);  // released on every exit path
   uint64_t* total_dev = nullptr;
-  GC_CHECK(gc_malloc(ctx, (void**)&total_dev, sizeof(uint64_t)));
+  GC_CHECK(scratch.alloc(&total_dev, sizeof(uint64_t)));
   GC_CHECK(gc_exclusive_scan_u32(ctx, flags, flags, n, total_dev));
   uint64_t* h = (uint64_t*)ctx->h_pinned;
   GC_CUDA(cudaMemcpyAsync(h, total_dev, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   GC_CUDA(cudaStreamSynchronize(ctx->stream));
   uint64_t total = h[0];
-  gc_free(ctx, total_dev);
   *count = (int64_t)total;
   if (total == 0) return GECUT_OK;
   GC_CHECK(gc_malloc(ctx, (void**)ids_out, sizeof(int32_t) * total));
@@ -368,10 +368,11 @@ static int select_subcells_now(gecut_ctx* ctx, gecut_selection* sel) {
   {
     const int64_t nblk = gc_div_up(nsc, (int64_t)SELSC_T * SELSC_PER);
     const int check_bg = res->L > 1 ? 1 : 0;  // one level set: every cut cell is CUT for every program over it
+    GcScratch scratch(ctx);
     uint32_t* counts = nullptr;
     uint64_t* total_dev = nullptr;
-    GC_CHECK(gc_malloc(ctx, (void**)&counts, sizeof(uint32_t) * nblk));
-    GC_CHECK(gc_malloc(ctx, (void**)&total_dev, sizeof(uint64_t)));
+    GC_CHECK(scratch.alloc(&counts, sizeof(uint32_t) * nblk));
+    GC_CHECK(scratch.alloc(&total_dev, sizeof(uint64_t)));
     const unsigned nbk = (unsigned)nblk;
     GC_LAUNCH(ctx, "k_select_subcells", k_select_subcells<false><<<nbk, SELSC_T, 0, ctx->stream>>>(
         lay, nsc, sel->prog, sel->side, check_bg, counts, nullptr));
@@ -385,8 +386,6 @@ static int select_subcells_now(gecut_ctx* ctx, gecut_selection* sel) {
       GC_LAUNCH(ctx, "k_select_subcells", k_select_subcells<true><<<nbk, SELSC_T, 0, ctx->stream>>>(
           lay, nsc, sel->prog, sel->side, check_bg, counts, sel->sub_ids));
     }
-    gc_free(ctx, counts);
-    gc_free(ctx, total_dev);
   }
   return gc_launch_check(ctx, "select_subcells");
 }
@@ -437,8 +436,9 @@ int gc_select_cells(gecut_ctx* ctx, gecut_selection* sel) {
     }
   }
   if (want_bg && nc > 0 && !from_tally) {
+    GcScratch scratch(ctx);
     unsigned long long* counts = nullptr;
-    GC_CHECK(gc_malloc(ctx, (void**)&counts, sizeof(unsigned long long) * 8));
+    GC_CHECK(scratch.alloc(&counts, sizeof(unsigned long long) * 8));
     GC_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * 8, ctx->stream));
     const int mode = sel->kind == GECUT_SEL_ACTIVE ? 1 : 0;
     unsigned nb = (unsigned)std::min<int64_t>(gc_div_up(gc_div_up(nc, 16), T), 148 * 64);
@@ -452,7 +452,6 @@ int gc_select_cells(gecut_ctx* ctx, gecut_selection* sel) {
       sel->bg_type_count[t] = (int64_t)h[t];
       sel->n_bg += (int64_t)h[t];
     }
-    gc_free(ctx, counts);
   }
   return gc_launch_check(ctx, "select_cells");
 }
@@ -462,19 +461,17 @@ int gc_materialize_bg_ids(gecut_ctx* ctx, gecut_selection* sel) {
   const gecut_result* res = sel->res;
   const int64_t nc = res->sizes.num_bgcells;
   const int T = 256;
+  GcScratch scratch(ctx);
   uint32_t* flags = nullptr;
   unsigned long long* counts = nullptr;
-  GC_CHECK(gc_malloc(ctx, (void**)&flags, sizeof(uint32_t) * nc));
-  GC_CHECK(gc_malloc(ctx, (void**)&counts, sizeof(unsigned long long) * 8));
+  GC_CHECK(scratch.alloc(&flags, sizeof(uint32_t) * nc));
+  GC_CHECK(scratch.alloc(&counts, sizeof(unsigned long long) * 8));
   GC_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * 8, ctx->stream));
   const int mode = sel->kind == GECUT_SEL_ACTIVE ? 1 : 0;
   unsigned nb = (unsigned)std::min<int64_t>(gc_div_up(nc, T), 148 * 16);
   GC_LAUNCH(ctx, "k_count_bgcells", k_count_bgcells<<<nb, T, 0, ctx->stream>>>(res->lay, nc, sel->prog, sel->side, mode, res->grid.cpc, counts, flags));
   int64_t n = 0;
-  int st = gc_compact_flags(ctx, flags, nc, &sel->bg_ids, &n, nullptr, nullptr);
-  gc_free(ctx, flags);
-  gc_free(ctx, counts);
-  return st;
+  return gc_compact_flags(ctx, flags, nc, &sel->bg_ids, &n, nullptr, nullptr);
 }
 
 __global__ void k_iota_boundary(int64_t n, int32_t* __restrict__ ids, int8_t* __restrict__ orient) {
@@ -496,16 +493,14 @@ int gc_select_boundary(gecut_ctx* ctx, gecut_selection* sel) {
     sel->sub_identity = true;  // ids / orientation are written when somebody asks for them (gc_materialize_sub_ids)
     return GECUT_OK;
   }
+  GcScratch scratch(ctx);
   uint32_t* flags = nullptr;
   int8_t* orient_all = nullptr;
-  GC_CHECK(gc_malloc(ctx, (void**)&flags, sizeof(uint32_t) * nsf));
-  GC_CHECK(gc_malloc(ctx, (void**)&orient_all, sizeof(int8_t) * nsf));
+  GC_CHECK(scratch.alloc(&flags, sizeof(uint32_t) * nsf));
+  GC_CHECK(scratch.alloc(&orient_all, sizeof(int8_t) * nsf));
   GC_LAUNCH(ctx, "k_flag_boundary", k_flag_boundary<<<(unsigned)gc_div_up(nsf, T), T, 0, ctx->stream>>>(res->lay, nsf, sel->prog, sel->prog2,
                                                                       sel->has_prog2 ? 1 : 0, flags, orient_all));
-  int st = gc_compact_flags(ctx, flags, nsf, &sel->sub_ids, &sel->n_sub, orient_all, &sel->orientation);
-  gc_free(ctx, flags);
-  gc_free(ctx, orient_all);
-  return st;
+  return gc_compact_flags(ctx, flags, nsf, &sel->sub_ids, &sel->n_sub, orient_all, &sel->orientation);
 }
 
 int gc_materialize_sub_ids(gecut_ctx* ctx, gecut_selection* sel) {

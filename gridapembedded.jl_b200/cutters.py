@@ -37,9 +37,14 @@ def _is_torch_tensor(x) -> bool:
     return type(x).__module__.startswith("torch")
 
 
-def flatten_geometry(model, geo: Geometry, host_only: bool = False, num_nodal: Optional[int] = None):
+def flatten_geometry(model, geo: Geometry, host_only: bool = False, num_nodal: Optional[int] = None,
+                     nodal_planes: Optional[Tuple[int, int]] = None):
     """Host half of `initial_sub_triangulation` (`CutTriangulations.jl:443-454`): the unique leaves of the tree in
     `_find_unique_leaves` order as leaf records, plus per-leaf nodal values for NODAL leaves.
+
+    `nodal_planes=(k0,k1)` (slab-local NODAL mode): value vectors hold, and host-callable leaves (popcorn, arbitrary
+    closures) are evaluated on, only the node planes k0..k1 of the last direction -- every NODAL vector handed to the
+    library then has the same slab-local extent `num_nodal`.
 
     Returns (leaves: List[LeafFunction-like], nodal: List[array|None], oid_to_ls: dict id(payload)->ls (0-based))."""
     tree = geo.get_tree()
@@ -50,8 +55,8 @@ def flatten_geometry(model, geo: Geometry, host_only: bool = False, num_nodal: O
     for p in payloads:
         if isinstance(p, LeafFunction):
             if p.kind == LEAF_NODAL:
-                vals = np.ascontiguousarray(p(model.node_coordinates()), dtype=np.float64)
-                if vals.shape != (model.num_nodes,):
+                vals = np.ascontiguousarray(p(model.node_coordinates(nodal_planes)), dtype=np.float64)
+                if vals.shape != (model.num_nodes if num_nodal is None else num_nodal,):
                     raise ValueError("a host level-set function must return one value per node")
                 leaves.append(p)
                 nodal.append(vals)
@@ -144,11 +149,12 @@ class LevelSetCutter(Cutter):
     def _call(self, fn_name: str, background, geom):
         from .discretizations import EmbeddedDiscretization
         model = background
-        num_nodal = None
+        num_nodal, planes = None, None
         if self.nodal_slab_local and self.slab is not None:
             layer_nodes = model.num_nodes // (model.partition[-1] + 1)
             num_nodal = layer_nodes * (self.slab[1] - self.slab[0] + 1)
-        leaves, nodal, oid_to_ls = flatten_geometry(model, geom, num_nodal=num_nodal)
+            planes = (self.slab[0], self.slab[1])
+        leaves, nodal, oid_to_ls = flatten_geometry(model, geom, num_nodal=num_nodal, nodal_planes=planes)
         grid = make_grid(model, self.slab)
         grid.nodal_slab_local = 1 if num_nodal is not None else 0
         recs = make_leaf_records(leaves)
@@ -190,28 +196,36 @@ def compute_bgcell_to_inoutcut(*args):
     return cutter.compute_bgcell_to_inoutcut(background, geom)
 
 
-def evaluate_leaves_at_nodes(model, payloads, ctx: Optional[_lib.Context] = None, device_output: bool = True):
+def evaluate_leaves_at_nodes(model, payloads, ctx: Optional[_lib.Context] = None, device_output: bool = True,
+                             slab: Optional[Tuple[int, int]] = None):
     """`j_to_ls = [fun.(point_to_coords) for fun in j_to_fun]` (`DiscreteGeometries.jl:51`) on the device.
-    Returns one vector per payload: CUDA torch tensors (device_output) or numpy arrays."""
+    Returns one vector per payload: CUDA torch tensors (device_output) or numpy arrays.  `slab=(k0,k1)`: only the node
+    planes k0..k1 of the last direction (the slab-local vectors of a rank of the z-slab partition)."""
     ctx = ctx or _lib.default_context()
-    grid = make_grid(model)
+    grid = make_grid(model, slab)
+    num = model.num_nodes
+    planes = None
+    if slab is not None:
+        grid.nodal_slab_local = 1
+        planes = (int(slab[0]), int(slab[1]))
+        num = (model.num_nodes // (model.partition[-1] + 1)) * (planes[1] - planes[0] + 1)
     out = []
     for p in payloads:
         if not isinstance(p, LeafFunction):
             out.append(p)
             continue
         if p.kind == LEAF_NODAL:
-            out.append(np.ascontiguousarray(p(model.node_coordinates()), dtype=np.float64))
+            out.append(np.ascontiguousarray(p(model.node_coordinates(planes)), dtype=np.float64))
             continue
         rec = make_leaf_records([p])
         if device_output:
             import torch
-            t = torch.empty(model.num_nodes, dtype=torch.float64, device=f"cuda:{ctx.device}")
+            t = torch.empty(num, dtype=torch.float64, device=f"cuda:{ctx.device}")
             rc = ctx._lib.gecut_eval_leaf_at_nodes(ctx.handle, C.byref(grid), rec, C.c_void_p(t.data_ptr()), 1)
             ctx.check(rc, "gecut_eval_leaf_at_nodes")
             out.append(t)
         else:
-            a = np.empty(model.num_nodes, dtype=np.float64)
+            a = np.empty(num, dtype=np.float64)
             rc = ctx._lib.gecut_eval_leaf_at_nodes(ctx.handle, C.byref(grid), rec, C.c_void_p(a.ctypes.data), 0)
             ctx.check(rc, "gecut_eval_leaf_at_nodes")
             out.append(a)

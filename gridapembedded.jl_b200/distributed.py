@@ -196,6 +196,22 @@ def exchange_ghost_plane_(slab_values, layer_nodes: int, group=None):
     return slab_values
 
 
+def init_library_communicator(ctx, group=None):
+    """Give `ctx` its own NCCL communicator (the library's, `gecut_comm_init`) over the ranks of a torch.distributed group:
+    rank 0 creates the unique id, the 128 bytes travel by one `broadcast_object_list` (gloo or nccl -- the host program's
+    existing channel, MPI.Bcast in the Julia host), every rank joins.  After this the data path of a multi-GPU step
+    (ghost planes, global sums, consistency flag, sizes) runs inside libgecut.so on the context's stream."""
+    dist = _dist()
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("torch.distributed is not initialised")
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [ctx.comm_unique_id() if rank == 0 else None]
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    dist.broadcast_object_list(box, src=src, group=group)
+    ctx.comm_init(box[0], rank, world)
+    return rank, world
+
+
 class DistributedLevelSetCutter:
     """`cut(::DistributedDiscreteModel, geo)` analogue: each rank cuts its z-slab on its own GPU."""
 

@@ -32,6 +32,7 @@ extern "C" {
 #define GECUT_ERR_CUDA 3           /* CUDA runtime failure (message in gecut_last_error)                             */
 #define GECUT_ERR_OOM 4            /* device allocation failed                                                        */
 #define GECUT_ERR_OVERFLOW 5       /* an Int32 id of the reference layout would overflow                             */
+#define GECUT_ERR_COMM 6           /* NCCL failure (message in gecut_last_error)                                     */
 
 /* ---- states (src/Interfaces/Interfaces.jl:70-73) ----------------------------------------------------------------- */
 #define GECUT_IN (-1)
@@ -161,9 +162,13 @@ int gecut_cut(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* leaves, 
 int gecut_classify(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* leaves, int num_leaves,
                    const double* const* nodal_values, int nodal_on_device, gecut_result** out);
 /* discretize(geo, model) (src/LevelSetCutters/DiscreteGeometries.jl:48-63): leaf `leaf` at every node of the model into
- * `values` (Nn doubles, device pointer if on_device else host). */
+ * `values` (Nn doubles, device pointer if on_device else host).  With a slab and grid->nodal_slab_local set: only the node
+ * planes slab_begin..slab_end (the slab-local vector gecut_cut accepts, (slab_end-slab_begin+1) planes). */
 int gecut_eval_leaf_at_nodes(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* leaf, double* values,
                              int on_device);
+/* Selections made from a result keep it alive: freeing a result that still has selections only marks it, the last
+ * gecut_selection_free releases it (finalizers of a garbage-collected host run in no particular order); no new selection
+ * can be made from a result after gecut_result_free.  The same holds for facet results and facet selections. */
 int gecut_result_free(gecut_result* res);
 int gecut_result_sizes(const gecut_result* res, gecut_sizes* sizes);
 int gecut_result_device_ptrs(const gecut_result* res, gecut_buffers* dev);
@@ -282,11 +287,14 @@ int gecut_facet_selection_measure(const gecut_facet_selection* sel, double* sub_
  * `cell_to_cellin` (num_bgcells Int32; host memory, or device memory when on_device != 0) receives for every cell the
  * 1-based root cell it is aggregated to -- itself for cells whose unit cut measure is >= threshold, the root of the best
  * touched face neighbour (closest root, ties by Gridap's local facet order) for the other CUT cells, 0 elsewhere.
- * `facets` may be a classification-only facet result (compute_bgfacet_to_inoutcut).  threshold = 1 is
+ * `facets` may be a classification-only facet result (compute_bgfacet_to_inoutcut).  `facet_program` is the same geometry
+ * compiled over the FACET discretization's own level-set numbering (its oid_to_ls, CellAggregation.jl:90); NULL = the
+ * two discretizations number their level sets alike and `program` serves both.  threshold = 1 is
  * AggregateAllCutCells().  Fails with GECUT_ERR_INVALID when 20 sweeps do not aggregate every cut cell (the reference's
  * @assert all_aggregated).  Whole n-cube Cartesian models. */
-int gecut_aggregate(const gecut_result* cut, const gecut_facet_result* facets, const int32_t* program, int len, int side,
-                    double threshold, int32_t* cell_to_cellin, int on_device);
+int gecut_aggregate(const gecut_result* cut, const gecut_facet_result* facets, const int32_t* program, int len,
+                    const int32_t* facet_program, int facet_len, int side, double threshold, int32_t* cell_to_cellin,
+                    int on_device);
 
 /* GhostSkeleton(cut, in_or_out, geo) (src/Interfaces/EmbeddedDiscretizations.jl:504-543): the interior facets with at
  * least one CUT cell around and both cells active (CUT or `side`; side = GECUT_IN / GECUT_OUT for ACTIVE_IN / ACTIVE_OUT,
@@ -296,6 +304,40 @@ int gecut_aggregate(const gecut_result* cut, const gecut_facet_result* facets, c
  * Whole n-cube Cartesian models. */
 int gecut_ghost_skeleton(const gecut_result* cut, const int32_t* program, int len, int side, int64_t* n_ghost,
                          int8_t* facet_to_mask, int32_t* facet_ids);
+
+/* ---- multi-GPU: z-slab partition, one context per GPU / process ------------------------------ */
+/* cut(cutter, bgmodel::DistributedDiscreteModel, geo) (src/Distributed/DistributedDiscretizations.jl:33-40): every rank
+ * cuts its own slab (gecut_grid.slab_begin/end) -- no data-path collective.  What does cross ranks is enqueued on the
+ * context's stream by the calls below (NCCL over NVLink); a host language needs nothing but these entry points:
+ *   rank 0: gecut_comm_unique_id(id); the host program distributes the GECUT_COMM_ID_BYTES bytes with what it already has
+ *   (MPI.Bcast in GridapDistributed, a file, torch.distributed ...); every rank: gecut_comm_init(ctx, id, rank, world). */
+#define GECUT_COMM_ID_BYTES 128
+#define GECUT_COMM_MAX_VALUES 16
+int gecut_comm_unique_id(void* id);
+int gecut_comm_init(gecut_ctx* ctx, const void* id, int rank, int world);
+int gecut_comm_free(gecut_ctx* ctx);
+int gecut_comm_rank(const gecut_ctx* ctx, int* rank, int* world);
+/* Ghost update of level sets that exist only as slab-local nodal vectors (`consistent!`, :164-170): `slab_values[i]`
+ * (device) holds num_planes = slab_end - slab_begin + 1 node planes of layer_nodes doubles; the first plane goes to rank-1,
+ * the last plane is overwritten with the first plane of rank+1 (the last rank owns its top plane).  NULL entries are
+ * skipped.  Stream-ordered: returns once the grouped send/recv is queued; a following gecut_cut on this context sees it. */
+int gecut_comm_exchange_ghost_planes(gecut_ctx* ctx, double* const* slab_values, int num_vectors, int64_t layer_nodes,
+                                     int64_t num_planes);
+/* isconsistent_bgcell_to_inoutcut (:136-174): the reference compares every rank's ghost-cell states with the owner's and
+ * reduces with &.  In the slab partition the only data two ranks both classify with is their shared node plane, so the
+ * guard compares the SIGNS (what compute_case reads) of this rank's copy (last plane) with the owner's (first plane of
+ * rank+1) for every vector, then all-reduces the flag with min.  Closed-form leaves are recomputed from global indices
+ * and cannot disagree: pass num_vectors = 0 (the flag is still reduced, so a rank that failed elsewhere may lower it).
+ * Blocking; *consistent = 1 or 0 on every rank. */
+int gecut_comm_check_consistency(gecut_ctx* ctx, const double* const* slab_values, int num_vectors, int64_t layer_nodes,
+                                 int64_t num_planes, int* consistent);
+/* sum over the ranks of n <= GECUT_COMM_MAX_VALUES doubles (global integrals and counts, the `sum(∫...)` of a distributed
+ * triangulation): `host_values` (NULL: result_dev already holds the local numbers) are placed in `result_dev` (device) as
+ * kernel arguments and all-reduced in place.  Stream-ordered, no host synchronisation; read with gecut_comm_fetch. */
+int gecut_comm_allreduce_sum(gecut_ctx* ctx, const double* host_values, int n, double* result_dev);
+int gecut_comm_fetch(gecut_ctx* ctx, const double* values_dev, int n, double* host_out);
+/* sizes of every rank's result (all_sizes[world]): offsets of the rank-major global layout = exclusive sums.  Blocking. */
+int gecut_comm_allgather_sizes(gecut_ctx* ctx, const gecut_result* res, gecut_sizes* all_sizes);
 
 #ifdef __cplusplus
 }

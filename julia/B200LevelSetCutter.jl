@@ -360,8 +360,10 @@ function device_aggregate(d::B200DeviceCut, geo=d.geom; side::Integer=IN, thresh
   fres, _ = _run_facets(d.cutter, d.bgmodel, d.geom, true)   # classification of the facets is all the aggregation needs
   prog = _program(d, geo)
   out = Vector{Int32}(undef, num_cells(d.bgmodel))
-  st = ccall((:gecut_aggregate, libgecut), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Cint, Cint, Cdouble, Ptr{Int32}, Cint),
-             d.res, fres, prog, length(prog), side, threshold, out, 0)
+  # the facet result was cut from the same geometry object, so both discretizations share oid_to_ls: no second program
+  st = ccall((:gecut_aggregate, libgecut), Cint,
+             (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Int32}, Cint, Cint, Cdouble, Ptr{Int32}, Cint),
+             d.res, fres, prog, length(prog), C_NULL, 0, side, threshold, out, 0)
   ccall((:gecut_facet_result_free, libgecut), Cint, (Ptr{Cvoid},), fres)
   _check(d.cutter, st, "gecut_aggregate")
   out

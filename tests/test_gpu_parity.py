@@ -626,3 +626,78 @@ def test_multi_levelset_properties_at_scale(case):
     for p in parts:
         p.close()
     cg.close()
+
+
+# ---- BASELINE.json configurations at their own sizes: the whole layout against the oracle ------------------------------
+# (one-ulp sign flips of nodes lying on a surface are what grows with n, so the sizes matter)
+
+BASELINE_CASES = {
+    # configs[0]: PoissonCSGCutFEM.jl:9-23, test/LevelSetCuttersTests/AnalyticalGeometriesTests.jl:147-166 (40^3, L = 10)
+    "c1_csg_40": lambda: (CartesianDiscreteModel((-0.8,) * 3, (0.8,) * 3, (40, 40, 40)), csg_geometry()),
+    # configs[1]: disk on 4096^2 quads
+    "c2_disk_4096": lambda: (box_model(disk(0.7), (4096, 4096)), disk(0.7)),
+    # configs[2] at 256^3 (the oracle needs ~6 s and 2.3 GB there; 512^3 = the bench size would need 20 GB of host memory)
+    "c3_sphere_hex_256": lambda: (box_model(sphere(0.7), (256, 256, 256)), sphere(0.7)),
+    "c3_sphere_tet_256": lambda: (box_model(sphere(0.7), (256, 256, 256), True), sphere(0.7)),
+    # configs[4] geometry (two cylinders, union(steel, !steel)) at 256^3 per GPU
+    "c5_bimaterial_256": lambda: (CartesianDiscreteModel((0., 0., 0.), (3., 2., 3.), (256, 256, 256)), bimaterial()),
+}
+
+
+@pytest.mark.parametrize("case", sorted(BASELINE_CASES))
+def test_baseline_size_layout_matches_oracle(case):
+    model, geo = BASELINE_CASES[case]()
+    oc = ob.oracle_cut(model, geo)
+    gd = cut(model, geo)
+    compare_layout(gd, oc)
+    # the integrals of the step the benchmark times, on the same result
+    for name in named_programs(gd)[:2]:
+        prog = gd.program(name)
+        for side, sel in ((IN, PHYSICAL_IN), (OUT, PHYSICAL_OUT)):
+            t = Triangulation(gd, sel, name)
+            ids = oc.select_subcells(prog, side)
+            assert np.array_equal(t.sub_ids, ids)
+            bg = oc.select_bgcells(prog, side)
+            assert t.num_bg == len(bg)
+            total = integrate_measure(Measure(t, 2))
+            ntypes = 1 if not model.simplexified else (2 if model.D == 2 else 6)  # cell type = (cell - 1) mod ntypes
+            ototal = oc.subcell_measures(ids).sum() + sum(
+                np.count_nonzero((bg - 1) % ntypes == ty) * oc.bgcell_measure(ty + 1) for ty in range(ntypes))
+            assert abs(total - ototal) <= 1e-12 * abs(ototal)
+            K_cut, _ = integrate_laplacian(Measure(t, 2))
+            assert_float_equal(K_cut, oc.cutcell_laplacian(ids), "cut-cell laplacian")
+            t.close()
+        tb = EmbeddedBoundary(gd, name)
+        fids, ori = oc.select_boundary(prog)
+        assert np.array_equal(tb.sub_ids, fids) and np.array_equal(tb.orientation, ori)
+        surf = integrate_measure(Measure(tb, 2))
+        osurf = oc.subfacet_measures(fids).sum()
+        assert abs(surf - osurf) <= 1e-12 * abs(osurf)
+        tb.close()
+    gd.close()
+
+
+def test_baseline_c4_stokes_discrete_geometry_256():
+    """configs[3]: StokesTubeWithObstacleCutFEM tube + obstacle as a DiscreteGeometry (Q1 nodal values, L = 4) on the
+    simplexified 256^3 model: PHYSICAL "fluid" subcells, EmbeddedBoundary("fluid","inlet") / ("fluid","solid") with
+    normals -- the whole layout and the selections against the oracle (StokesTubeWithObstacleCutFEM.jl:17-28,48-60)."""
+    g, pmin, pmax = stokes_geometry()
+    model = simplexify(CartesianDiscreteModel(pmin, pmax, (256, 256, 256)))
+    dgeo = gecut.discretize(g, model)  # nodal values evaluated on the device (bit-exact, test_node_evaluation_kernel_bit_exact)
+    gd = cut(model, dgeo)
+    oc = ob.oracle_cut(model, g)
+    compare_layout(gd, oc)
+    prog = gd.program("fluid")
+    t = Triangulation(gd, PHYSICAL, "fluid")
+    assert np.array_equal(t.sub_ids, oc.select_subcells(prog, IN))
+    assert np.array_equal(t.bg_ids, oc.select_bgcells(prog, IN))
+    for other in ("inlet", "solid"):
+        tb = EmbeddedBoundary(gd, "fluid", other)
+        fids, ori = oc.select_boundary(prog, gd.program(other))
+        assert np.array_equal(tb.sub_ids, fids) and np.array_equal(tb.orientation, ori)
+        if len(fids):
+            f2n = oc.array("subfacets.facet_to_normal").reshape(-1, 3)
+            assert_float_equal(tb.gather().facet_to_normal, f2n[fids - 1] * ori[:, None], "oriented normals")
+        tb.close()
+    t.close()
+    gd.close()
