@@ -54,6 +54,22 @@ def make_workload(name, n, world):
         part = tuple(n * m for m in mult)
         model = CartesianDiscreteModel(box.pmin, box.pmax, part)
         return model, geo, f"BASELINE configs[1]: disk(R=0.7) on {part[0]}x{part[1]} quads: cut + area + perimeter + Q1 4x4 matrices"
+    if name == "c1_csg":
+        # PoissonCSGCutFEM.jl:9-23 (BASELINE configs[0], the north-star "512^3 3-D CSG cut"): box ∩ sphere − 3 cylinders,
+        # ten unique level sets (6 planes of the cube, the sphere, 3 cylinders) on [-0.8, 0.8]^3
+        from gecut import cylinder, cube, union, intersect, setdiff
+        R = 0.5
+        src = union(union(cylinder(R, v=(1, 0, 0)), cylinder(R, v=(0, 1, 0))), cylinder(R, v=(0, 0, 1)), name="source")
+        geo = setdiff(intersect(cube(L=1.5), sphere(1)), src, name="csg")
+        mult = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}.get(world)
+        if mult is None:
+            raise SystemExit("--gpus must be 1, 2, 4 or 8")
+        part = tuple(n * m for m in mult)
+        model = CartesianDiscreteModel((-0.8,) * 3, (0.8,) * 3, part)
+        desc = (f"BASELINE configs[0] at the north-star size: PoissonCSGCutFEM geometry (box ∩ sphere − 3 cylinders, L=10) on "
+                f"{part[0]}x{part[1]}x{part[2]} HEX box [-0.8,0.8]^3; cut + PHYSICAL \"csg\" volume + EmbeddedBoundary(\"csg\") "
+                f"area + cut-cell Q1 8x8 Laplacian matrices")
+        return model, geo, desc
     if name == "c5_bimaterial":
         # BimaterialLinElastCutFEM.jl:16-37,56: two steel cylinders (axis x) in a concrete block, tree union(steel, !steel)
         from gecut import cylinder, union, complement
@@ -77,6 +93,8 @@ def workload_plan(name):
     """(cell selections [(sub-geometry name, side)], boundary names) integrated by one step; side -1 = IN, +1 = OUT."""
     if name == "c5_bimaterial":
         return [("steel", -1), ("steel", 1)], ["steel"]
+    if name == "c1_csg":
+        return [("csg", -1)], ["csg"]
     return [(None, -1)], [None]
 
 
@@ -203,8 +221,10 @@ def algorithmic_bytes(s, model, nsel, nfsel, nodal=False, ncellsel=1):
     # kernel then reads the bits
     k["k_classify"] = L * Nc + Nc // 8 + (L * Nn // 8 if nodal else 0)
     k["k_nodal_signs"] = (8 * L * Nn + L * Nn // 8) if nodal else 0
-    k["k_cut_walk_count"] = 4 * Ncut + 4 * narr * nsimp
-    k["k_cut_walk_fill"] = 4 * Ncut + 4 * narr * nsimp + lb["subcells"] + lb["subfacets"]
+    ntile32 = (nsimp + 31) // 32
+    # L > 1: one info word per stage-0 simplex and narr totals per 32-simplex tile (no per-simplex counters)
+    k["k_cutm_count"] = 4 * Ncut + 4 * nsimp + 4 * narr * ntile32
+    k["k_cutm_fill"] = 4 * Ncut + 4 * nsimp + 4 * narr * ntile32 + lb["subcells"] + lb["subfacets"] + 8 * Ncut
     ntiles = (nsimp + 127) // 128
     k["k_cut1_count"] = 4 * Ncut + 12 * ntiles
     meas = 8 * (int(s.num_subcells) + int(s.num_subfacets))  # per-entity measures written next to the layout
@@ -213,11 +233,9 @@ def algorithmic_bytes(s, model, nsel, nfsel, nodal=False, ncellsel=1):
     k["k_cut1_fill"] = 4 * Ncut + 12 * ntiles + lb["subcells"] + lb["subfacets"] + 4 * Ncut + meas
     if L == 1:  # tile statistics (4 doubles per 32-simplex tile) and, for simplex bg cells, (IN, OUT) measure per cut cell
         k["k_cut1_fill"] += 32 * ((nsimp + 31) // 32) + (16 * Ncut if model.simplexified else 0)
-    k["k_cut_walk_fill"] += meas
-    # L > 1: k_cut_fast writes the layout of the simplices cut by at most one level set (the bulk), k_cut_walk the rest;
-    # the whole layout is attributed to the fast kernel (the walk's share is not subtracted: an upper bound of its GB/s)
-    k["k_cut_fast_count"] = k["k_cut_walk_count"]
-    k["k_cut_fast_fill"] = k["k_cut_walk_fill"]
+    # L > 1: k_cutm_fill writes the layout of the simplices cut by at most one level set (the bulk), k_cut_walk the rest;
+    # the whole layout is attributed to the tile kernel (the walk's share is not subtracted: an upper bound of its GB/s)
+    k["k_cutm_fill"] += meas
     k["k_count_bgcells"] = L * Nc * ncellsel
     k["k_select_subcells"] = int(s.num_subcells) * L * 2 * ncellsel + 4 * nsel
     k["k_flag_subcells"] = int(s.num_subcells) * (4 + 2 * L + 4)
@@ -243,7 +261,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3_tet", choices=["c3_tet", "c3_hex", "c2_disk", "c5_bimaterial"])
+    ap.add_argument("--workload", default="c3_tet", choices=["c3_tet", "c3_hex", "c2_disk", "c5_bimaterial", "c1_csg"])
     ap.add_argument("--n", type=int, default=None, help="cells per direction per GPU (default 512; 4096 for c2_disk)")
     ap.add_argument("--cpu-n", type=int, default=None, help="size of the bounded CPU sample (default: the GPU arm's n)")
     ap.add_argument("--cpu-stride", type=int, default=None,
@@ -530,7 +548,7 @@ def run_b200(args, n, rank, world, local_rank):
             slab, slab_kind = slab_of(model, rank, world), f"z-slab x{world} (even layers)"
         else:
             from gecut.distributed import balanced_slab_ranges
-            cw = {"c3_tet": 300.0, "c3_hex": 760.0, "c5_bimaterial": 1400.0}.get(args.workload, 600.0)
+            cw = {"c3_tet": 300.0, "c3_hex": 760.0, "c5_bimaterial": 1400.0, "c1_csg": 1400.0}.get(args.workload, 600.0)
             ranges = balanced_slab_ranges(model, geo, world, cut_weight=cw)
             slab = ranges[rank]
             slab_kind = (f"z-slab x{world}, work-balanced (layers per rank {[b - a for a, b in ranges]}; cut cell = "
@@ -754,7 +772,7 @@ def run_b200(args, n, rank, world, local_rank):
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        n_cpu = args.cpu_n or {"c2_disk": 4096, "c5_bimaterial": 128}.get(args.workload, 320)
+        n_cpu = args.cpu_n or {"c2_disk": 4096, "c5_bimaterial": 128, "c1_csg": 64}.get(args.workload, 320)
         v, dt, sample = cpu_sample(args.workload, n_cpu)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample, "seconds": round(dt, 2)}
 

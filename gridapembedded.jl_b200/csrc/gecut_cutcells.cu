@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "gecut_internal.cuh"
 
@@ -472,13 +473,35 @@ __device__ __forceinline__ void walk_item(const GcGrid& g, const GcLeaves& lv, c
 
 }
 
+// ---- bookkeeping of the multi-level-set cut (L > 1), tile design of the single-level-set path -------------------------
+// A warp owns a TILE of 32 consecutive stage-0 simplices.  Channels: 0 subcells, 1 subcell points, 2+k subfacets of level
+// set k, 2+L+k subfacet points of level set k.  The count pass leaves one TOTAL per tile and channel (not per simplex),
+// an exclusive scan over the tiles turns them into tile bases, and the fill pass rebuilds the offsets of the 32 simplices
+// of a tile with warp scans.  Simplices cut by two or more level sets ("recorded", walked by k_cut_walk) get a slot:
+// their counters live in slot-indexed arrays, are added to the tile totals with atomics (integer sums: order-free) and are
+// replaced by their start offsets by the fill kernel of the tile before the walk writes.
+constexpr uint32_t CM_SLOW = 0x80000000u;  // sinfo: recorded simplex, low bits = slot
+struct GcMulti {
+  int nch;                // 2 + 2L
+  int64_t ntiles;
+  uint32_t* tile;         // [nch][ntiles] totals (count pass) -> exclusive bases (scan)
+  uint32_t* sinfo;        // [nsimp] fast: outm | a << 16 | case << 20 | mixed << 24; recorded: CM_SLOW | slot
+  uint32_t* slow_simp;    // [slot] -> stage-0 simplex
+  uint8_t* slow_bucket;   // [slot] -> launch bucket of the walk
+  uint32_t* slow_val;     // [nch][slow_n] counters (walk count) -> start offsets (fill of the tile)
+  int64_t slow_n;
+  uint32_t* slow_count;   // [WALK_NB] recorded simplices per bucket, [WALK_NB] their total (slot allocator)
+  uint32_t fac_base[GC_LMAX];  // global offset of the facets of level set ls (merge_sub_face_data order)
+  uint32_t fpt_base[GC_LMAX];
+};
+
 template <int D, int NW, bool FILL>
 __global__ void __launch_bounds__(WALK_T)
 k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
            const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
-           const int32_t* __restrict__ cutcells, int64_t nsimp, GcCounters cn, GcLayout lay,
-           const uint32_t* __restrict__ slow_list, const uint32_t* __restrict__ slow_count) {
-  // WALK_ITEMS lanes per RECORDED simplex (those cut by two or more level sets, listed by k_cut_fast): the tree walk is
+           const int32_t* __restrict__ cutcells, GcMulti mu, GcLayout lay,
+           const uint32_t* __restrict__ slots, int64_t nslots) {
+  // WALK_ITEMS lanes per RECORDED simplex (those cut by two or more level sets, listed by k_cutm_count): the tree walk is
   // an order of magnitude longer than the no-tree path, so it runs in its own dense launches.
   constexpr int LM = GC_LMAX;
   __shared__ GcSimplexTable s_tab[2];  // [0]: D-simplex (cells), [1]: (D-1)-simplex (facet re-cuts)
@@ -496,10 +519,12 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t idx = gtid / WALK_ITEMS;
   const int item = (int)(gtid % WALK_ITEMS);
-  const bool valid = idx < (int64_t)*slow_count;  // idle lanes still take part in the shuffles
-  const int64_t s = valid ? (int64_t)slow_list[idx] : 0;
+  const bool valid = idx < nslots;  // idle lanes still take part in the shuffles
+  const uint32_t slot = valid ? slots[idx] : 0u;
+  const int64_t s = valid ? (int64_t)mu.slow_simp[slot] : 0;
   const int L = lv.L;
   const int32_t bgcell1 = cutcells[s / g.nt0];
+  uint32_t* val = mu.slow_val + slot;  // channel ch at val[ch * slow_n]
   // counting walk of this item
   uint32_t n_cells = 0, n_pts = 0, n_fac[LM], n_fpt[LM];
 #pragma unroll
@@ -516,16 +541,23 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
     return v;
   };
   if (!FILL) {
+    // per-slot counters + the simplex' share of its tile's totals
+    const int64_t tile = s / 32;
+    const bool last = valid && item == WALK_ITEMS - 1;
     const uint32_t tc = seg_scan(n_cells), tp = seg_scan(n_pts);
-    if (valid && item == WALK_ITEMS - 1) {
-      cn.cells[s] = tc;
-      cn.points[s] = tp;
+    if (last) {
+      val[0] = tc;
+      val[mu.slow_n] = tp;
+      atomicAdd(mu.tile + tile, tc);
+      atomicAdd(mu.tile + mu.ntiles + tile, tp);
     }
     for (int k = 0; k < L; ++k) {
       const uint32_t tf = seg_scan(n_fac[k]), tq = seg_scan(n_fpt[k]);
-      if (valid && item == WALK_ITEMS - 1) {
-        cn.fac[k][s] = tf;
-        cn.fpt[k][s] = tq;
+      if (last) {
+        val[(int64_t)(2 + k) * mu.slow_n] = tf;
+        val[(int64_t)(2 + L + k) * mu.slow_n] = tq;
+        if (tf) atomicAdd(mu.tile + (int64_t)(2 + k) * mu.ntiles + tile, tf);
+        if (tq) atomicAdd(mu.tile + (int64_t)(2 + L + k) * mu.ntiles + tile, tq);
       }
     }
   } else {
@@ -538,56 +570,55 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
       fpt_off[k] = seg_scan(n_fpt[k]) - n_fpt[k];
     }
     if (valid) {
-      cell_off += cn.cells[s];
-      pt_off += cn.points[s];
+      // start offsets of the simplex, left by the fill kernel of its tile (k_cutm_fill)
+      cell_off += val[0];
+      pt_off += val[mu.slow_n];
       for (int k = 0; k < L; ++k) {
-        fac_off[k] += cn.fac_base[k] + cn.fac[k][s];
-        fpt_off[k] += cn.fpt_base[k] + cn.fpt[k][s];
+        fac_off[k] += mu.fac_base[k] + val[(int64_t)(2 + k) * mu.slow_n];
+        fpt_off[k] += mu.fpt_base[k] + val[(int64_t)(2 + L + k) * mu.slow_n];
       }
       walk_item<D, NW, true>(g, lv, s_tab[0], s_tab[1], simp_raw, simp_pos, lay, s, bgcell1, item, cell_off, pt_off, fac_off, fpt_off);
     }
   }
 }
 
+// recorded simplices -> one dense slot list per launch bucket (any order inside a bucket)
+__global__ void k_cutm_bucketize(const uint8_t* __restrict__ slow_bucket, int64_t n, const uint32_t* __restrict__ base,
+                                 uint32_t* __restrict__ cursor, uint32_t* __restrict__ lists) {
+  const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n) return;
+  const int b = slow_bucket[slot];
+  lists[base[b] + atomicAdd(cursor + b, 1u)] = (uint32_t)slot;
+}
+
 // ================================================================================================
 // L > 1, simplices cut by AT MOST ONE level set (the bulk of every multi-level-set model): no tree, no stack, no local
-// memory.  Pass 1 evaluates every level set at the D+1 vertices and keeps only the sign bits; a simplex with two or
-// more mixed-sign level sets is recorded for the tree walk (k_cut_walk, mode 2).  Otherwise the simplex reaches the
-// cutting stage `a` with its vertices permuted by the skipped stages, is cut there exactly like in the single-level-set
-// path, and its children (a > 0) or itself (a == 0, or nothing cuts it) are emitted at stage 0; the facets of `a` pass
-// through the other stages unchanged but for the permutations.  The <= 8 points (x and r) live in a per-thread slice of
-// shared memory with an odd stride (conflict-free); subcell points leave through the warp-level copy-out.
+// memory.  Such a simplex reaches the cutting stage `a` with its vertices permuted by the skipped stages, is cut there
+// exactly like in the single-level-set path, and its children (a > 0) or itself (a == 0, or nothing cuts it) are emitted
+// at stage 0; the facets of `a` pass through the other stages unchanged but for the permutations.
+//   k_cutm_count : lane = simplex.  Sign bits of every level set at the D+1 vertices -> the cutting stage, the case and
+//                  the all-OUT mask in ONE word per simplex (sinfo: the fill kernel does not evaluate L level sets again),
+//                  tile totals per channel with warp reductions; simplices with two or more mixed-sign level sets are
+//                  recorded for the tree walk.
+//   k_cutm_fill  : the single-level-set phases: A lane = simplex (points into a per-lane slice of shared memory, facet
+//                  normals, warp scans of the counters -> offsets), F lane = subfacet element, P warp copy-out of the
+//                  subcell points through a point map, C lane = subcell (connectivity row, bg cell, measure, L state
+//                  bytes: neighbouring lanes write neighbouring addresses).
 // ================================================================================================
-template <int D, bool FILL>
-__global__ void __launch_bounds__(WALK_T)
-k_cut_fast(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
-           const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
-           const int32_t* __restrict__ cutcells, int64_t nsimp, GcCounters cn, GcLayout lay,
-           uint32_t* __restrict__ slow_list, uint32_t* __restrict__ slow_count) {
-  constexpr int NPC = WalkCfg<D>::NPC;
-  constexpr int PCAP = 1024;
-  constexpr int SSTR = NPC * 2 * D + 1;
-  __shared__ GcSimplexTable s_tab[2];  // [0]: D-simplex (cells), [1]: (D-1)-simplex (facet pass-through rows)
-  __shared__ double scratch[FILL ? SSTR * WALK_T : 1];
-  __shared__ __align__(16) uint16_t pmap_all[FILL ? (WALK_T / 32) * PCAP : 8];
-  // per-lane stash of the <= 2 facets of a simplex (unit normal, measure, point slots) for the warp-level facet emission
-  __shared__ double fstash[FILL ? WALK_T : 1][8];
-  __shared__ uint8_t fslots[FILL ? WALK_T : 1][8];
-  __shared__ uint8_t fitem_all[FILL ? WALK_T * 2 : 8];
-  __shared__ uint8_t s_swap[8];
-  {
-    const uint32_t* src0 = reinterpret_cast<const uint32_t*>(tables + (D - 1));
-    const uint32_t* src1 = reinterpret_cast<const uint32_t*>(tables + (D - 2));
-    uint32_t* dst0 = reinterpret_cast<uint32_t*>(&s_tab[0]);
-    uint32_t* dst1 = reinterpret_cast<uint32_t*>(&s_tab[1]);
-    for (int i = threadIdx.x; i < (int)(sizeof(GcSimplexTable) / 4); i += blockDim.x) {
-      dst0[i] = src0[i];
-      dst1[i] = src1[i];
-    }
-  }
-  const uint8_t* vtab = (g.simplexified ? simp_raw : simp_pos) + (D - 2) * 24;  // rows of local vertex ids of the n-cube
+constexpr int CM_T = 64;  // threads per block: 2 independent warp tiles
+
+template <int D>
+struct CmLane {
+  int ijk[3];
+  uint32_t lv4;  // local vertex ids of the n-cube, one byte per simplex vertex (first two swapped when det J < 0)
+  uint32_t rv4;  // reference coordinates of the vertices in the bg cell, one bit per direction
+  int32_t bgcell1;
+};
+
+// Jacobian sign of every stage-0 simplex type (_ensure_positive_jacobians! in physical space, see k_cut1_fill)
+template <int D>
+__device__ __forceinline__ void cm_swap_flags(const GcGrid& g, const uint8_t* vtab, uint8_t* s_swap) {
   if ((int)threadIdx.x < (g.simplexified ? g.cpc : g.nt0)) {
-    // _ensure_positive_jacobians! in physical space: decided once per simplex type (see k_cut1_fill)
     double x[D + 1][D];
 #pragma unroll
     for (int m = 0; m <= D; ++m) {
@@ -614,361 +645,460 @@ k_cut_fast(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
     }
     s_swap[threadIdx.x] = dV < 0.0 ? 1 : 0;
   }
+}
+
+template <int D>
+__device__ __forceinline__ void cm_lane_setup(const GcGrid& g, const uint8_t* vtab, const uint8_t* s_swap,
+                                              const int32_t* __restrict__ cutcells, int64_t s, CmLane<D>& o) {
+  const int64_t kcut = s / g.nt0;
+  const int t0 = (int)(s - kcut * g.nt0);
+  o.bgcell1 = cutcells[kcut];
+  const uint32_t cell = (uint32_t)(o.bgcell1 - 1);  // slab-local cell ids fit in 32 bits (checked at cut time)
+  const uint32_t cube = cell / (uint32_t)g.cpc;
+  const int row_id = g.simplexified ? (int)(cell - cube * (uint32_t)g.cpc) : t0;
+  const uint32_t row = cube / (uint32_t)g.n[0];
+  o.ijk[0] = (int)(cube - row * (uint32_t)g.n[0]);
+  if (D == 3) {
+    const uint32_t lay3 = row / (uint32_t)g.n[1];
+    o.ijk[1] = (int)(row - lay3 * (uint32_t)g.n[1]);
+    o.ijk[2] = (int)lay3 + g.k0;
+  } else {
+    o.ijk[1] = (int)row + g.k0;
+    o.ijk[2] = 0;
+  }
+  o.lv4 = *reinterpret_cast<const uint32_t*>(vtab + row_id * 4);
+  o.rv4 = g.simplexified ? 0x04020100u : o.lv4;  // simplex cells: origin + unit axes; n-cube cells: the cube vertex
+  if (s_swap[row_id]) {                          // swap the first two vertices
+    o.lv4 = __byte_perm(o.lv4, 0u, 0x3201);
+    o.rv4 = __byte_perm(o.rv4, 0u, 0x3201);
+  }
+}
+
+// vertex order in which a simplex arrives at stage `lo` after the all-IN / all-OUT stages hi-1 ... lo+1 (each a vertex
+// permutation = the single child of that table row), as 2-bit entries
+template <int D>
+__device__ __forceinline__ uint32_t cm_skip_cell_stages(const GcSimplexTable& TC, uint32_t outm, int hi, int lo) {
+  const int c_allout = (1 << (D + 1)) - 1;
+  uint8_t vl[D + 1];
+#pragma unroll
+  for (int i = 0; i <= D; ++i) vl[i] = (uint8_t)i;
+  for (int k = hi - 1; k > lo; --k) {
+    const uint8_t* pm = TC.sub_pts[((outm >> k) & 1u) ? c_allout : 0][0];
+    uint8_t tmp[D + 1];
+#pragma unroll
+    for (int i = 0; i <= D; ++i) tmp[i] = vl[pm[i]];
+#pragma unroll
+    for (int i = 0; i <= D; ++i) vl[i] = tmp[i];
+  }
+  uint32_t q = 0;
+#pragma unroll
+  for (int i = 0; i <= D; ++i) q |= (uint32_t)vl[i] << (2 * i);
+  return q;
+}
+
+template <int D>
+__device__ __forceinline__ uint32_t cm_skip_facet_stages(const GcSimplexTable& TF, uint32_t outm, int hi, int lo, int skip) {
+  const int fc_allout = (1 << D) - 1;
+  uint8_t vl[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) vl[i] = (uint8_t)i;
+  for (int k = hi - 1; k > lo; --k) {
+    if (k == skip) continue;
+    const uint8_t* pm = TF.sub_pts[((outm >> k) & 1u) ? fc_allout : 0][0];
+    uint8_t tmp[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) tmp[i] = vl[pm[i]];
+#pragma unroll
+    for (int i = 0; i < D; ++i) vl[i] = tmp[i];
+  }
+  uint32_t q = 0;
+#pragma unroll
+  for (int i = 0; i < D; ++i) q |= (uint32_t)vl[i] << (2 * i);
+  return q;
+}
+
+template <int D>
+__global__ void __launch_bounds__(CM_T)
+k_cutm_count(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
+             const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
+             const int32_t* __restrict__ cutcells, int64_t nsimp, GcMulti mu) {
+  __shared__ GcSimplexTable s_tab;
+  __shared__ uint8_t s_swap[8];
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(tables + (D - 1));
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
+    for (int i = threadIdx.x; i < (int)(sizeof(GcSimplexTable) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  const uint8_t* vtab = (g.simplexified ? simp_raw : simp_pos) + (D - 2) * 24;
+  cm_swap_flags<D>(g, vtab, s_swap);
   __syncthreads();
-  const GcSimplexTable& TC = s_tab[0];
-  const GcSimplexTable& TF = s_tab[1];
+  const GcSimplexTable& TC = s_tab;
   const int L = lv.L;
   const int lane = threadIdx.x & 31;
-  const int64_t s_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = s_raw < nsimp;
-  if (!FILL && !valid) return;
-  const int64_t s = valid ? s_raw : nsimp - 1;  // lanes past the end idle but take part in the warp-level copy-out
-
-  // ---- warp-level copy-out state (see k_cut_walk)
-  uint16_t* pmap = pmap_all + (FILL ? (threadIdx.x >> 5) * PCAP : 0);
-  uint32_t wbase = 0, wcount = 0;
-  bool staged = false;
-  if (FILL) {
-    const int64_t s0 = s_raw - lane;
-    wbase = cn.points[s0 < nsimp ? s0 : nsimp - 1];
-    const uint32_t wend = (s0 + 32 < nsimp) ? cn.points[s0 + 32] : cn.total_points;
-    wcount = wend - wbase;
-    staged = wcount <= (uint32_t)PCAP;
-    if (staged) {
-      uint4* pm4 = reinterpret_cast<uint4*>(pmap) + lane * (PCAP / 256);
-#pragma unroll
-      for (int i = 0; i < PCAP / 256; ++i) pm4[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-    }
-    __syncwarp();
-  }
-
-  // what the warp-level facet emission needs from every lane (0 facets for idle lanes and recorded simplices)
-  int w_a = 0, w_nfac = 0, w_fc = 0;
-  uint32_t w_outm = 0u, w_fac_off = 0u, w_fpt_off = 0u;
-  int32_t w_bg = 0;
-  if (valid) {
-    const int64_t kcut = s / g.nt0;
-    const int t0 = (int)(s - kcut * g.nt0);
-    const int32_t bgcell1 = cutcells[kcut];
-    const uint32_t cell = (uint32_t)(bgcell1 - 1);  // slab-local cell ids fit in 32 bits (checked at cut time)
-    const uint32_t cube = cell / (uint32_t)g.cpc;
-    const int row_id = g.simplexified ? (int)(cell - cube * (uint32_t)g.cpc) : t0;
-    int ijk[3];
-    {
-      const uint32_t row = cube / (uint32_t)g.n[0];
-      ijk[0] = (int)(cube - row * (uint32_t)g.n[0]);
-      if (D == 3) {
-        const uint32_t lay3 = row / (uint32_t)g.n[1];
-        ijk[1] = (int)(row - lay3 * (uint32_t)g.n[1]);
-        ijk[2] = (int)lay3 + g.k0;
-      } else {
-        ijk[1] = (int)row + g.k0;
-        ijk[2] = 0;
-      }
-    }
-    uint32_t lv4 = *reinterpret_cast<const uint32_t*>(vtab + row_id * 4);
-    uint32_t rv4 = g.simplexified ? 0x04020100u : lv4;  // reference coordinates, one bit per direction
-    if (s_swap[row_id]) {                               // swap the first two vertices
-      lv4 = __byte_perm(lv4, 0u, 0x3201);
-      rv4 = __byte_perm(rv4, 0u, 0x3201);
-    }
+  const int64_t tile = (int64_t)blockIdx.x * (CM_T / 32) + (threadIdx.x >> 5);
+  if (tile * 32 >= nsimp) return;  // whole warp beyond the end (no block barrier below)
+  const int64_t s = tile * 32 + lane;
+  uint32_t ncell = 0, npt = 0, nfac = 0;
+  int a = -1;  // cutting stage of a fast simplex with facets
+  if (s < nsimp) {
+    CmLane<D> ln;
+    cm_lane_setup<D>(g, vtab, s_swap, cutcells, s, ln);
     double X[D + 1][3];
     int64_t node[D + 1];
 #pragma unroll
     for (int m = 0; m <= D; ++m) {
-      const int lvid = (lv4 >> (8 * m)) & 0xFFu;
-      const int nijk[3] = {ijk[0] + (lvid & 1), ijk[1] + ((lvid >> 1) & 1), ijk[2] + ((lvid >> 2) & 1)};
+      const int lvid = (ln.lv4 >> (8 * m)) & 0xFFu;
+      const int nijk[3] = {ln.ijk[0] + (lvid & 1), ln.ijk[1] + ((lvid >> 1) & 1), ln.ijk[2] + ((lvid >> 2) & 1)};
       X[m][0] = gc_coord(g, 0, nijk[0]);
       X[m][1] = gc_coord(g, 1, nijk[1]);
       X[m][2] = D == 3 ? gc_coord(g, 2, nijk[2]) : 0.0;
       node[m] = (D == 3) ? ((int64_t)nijk[0] + (int64_t)g.nn[0] * ((int64_t)nijk[1] + (int64_t)g.nn[1] * nijk[2]))
                          : ((int64_t)nijk[0] + (int64_t)g.nn[0] * nijk[1]);
     }
-    auto value = [&](int ls, int m) -> double {
-      if (lv.leaf[ls].kind == GECUT_LEAF_NODAL) return __ldg(lv.nodal[ls] + (node[m] - lv.nodal_base));
-      return gc_eval_leaf(lv.leaf[ls], X[m], D);
-    };
-    // ---- pass 1: sign bits of every level set
-    uint32_t mixed = 0u, outm = 0u;
+    // sign bits of every level set at the vertices (in stage-0 order): one nibble per level set is enough for the case
+    uint32_t mixed = 0u, outm = 0u, sa = 0u;
     for (int k = 0; k < L; ++k) {
-      bool any = false, all = true;
+      uint32_t sb = 0u;
 #pragma unroll
       for (int m = 0; m <= D; ++m) {
-        const bool o = value(k, m) > 0.0;
-        any |= o;
-        all &= o;
+        const double v = lv.leaf[k].kind == GECUT_LEAF_NODAL ? __ldg(lv.nodal[k] + (node[m] - lv.nodal_base))
+                                                              : gc_eval_leaf(lv.leaf[k], X[m], D);
+        sb |= (v > 0.0 ? 1u : 0u) << m;
       }
-      if (any && !all) mixed |= 1u << k;
-      if (all) outm |= 1u << k;
+      const uint32_t full = (1u << (D + 1)) - 1u;
+      if (sb == full) outm |= 1u << k;
+      else if (sb != 0u) {
+        mixed |= 1u << k;
+        sa = sb;  // the highest mixed level set stays
+      }
     }
-    uint32_t cell_off = 0, pt_off = 0;
     if (__popc(mixed) > 1) {
-      if (!FILL) {
-        // recorded for the tree walk, bucketed by the number of level sets the walk has to track
-        const int nw = __popc((mixed | 3u) & ((1u << L) - 1u));
-        int bucket = 0;
-        while (nw > walk_nw(bucket)) bucket++;
-        slow_list[(int64_t)bucket * nsimp + atomicAdd(&slow_count[bucket], 1u)] = (uint32_t)s;
-      }
+      // recorded for the tree walk, bucketed by the number of level sets the walk has to track
+      const int nw = __popc((mixed | 3u) & ((1u << L) - 1u));
+      int bucket = 0;
+      while (nw > walk_nw(bucket)) bucket++;
+      atomicAdd(&mu.slow_count[bucket], 1u);
+      const uint32_t slot = atomicAdd(&mu.slow_count[WALK_NB], 1u);
+      mu.slow_simp[slot] = (uint32_t)s;
+      mu.slow_bucket[slot] = (uint8_t)bucket;
+      mu.sinfo[s] = CM_SLOW | slot;
     } else {
-      const int a = mixed ? (31 - __clz(mixed)) : 0;  // the only stage that can cut (stage 0 is visited in any case)
-      auto cstate = [&](int k) -> int8_t { return ((outm >> k) & 1u) ? (int8_t)GC_OUT : (int8_t)GC_IN; };
-      const int c_allout = (1 << (D + 1)) - 1, fc_allout = (1 << D) - 1;
-      auto skip_cell_stages = [&](uint8_t* vl, int hi, int lo) {
-        for (int k = hi - 1; k > lo; --k) {
-          const uint8_t* pm = TC.sub_pts[((outm >> k) & 1u) ? c_allout : 0][0];
-          uint8_t tmp[D + 1];
+      const int aa = mixed ? (31 - __clz(mixed)) : 0;  // the only stage that can cut (stage 0 is visited in any case)
+      const uint32_t vl = cm_skip_cell_stages<D>(TC, outm, L, aa);
+      if (!mixed) sa = ((outm >> aa) & 1u) ? (1u << (D + 1)) - 1u : 0u;
+      int c = 0;  // case in arrival order
 #pragma unroll
-          for (int i = 0; i <= D; ++i) tmp[i] = vl[pm[i]];
+      for (int i = 0; i <= D; ++i) c |= (int)((sa >> ((vl >> (2 * i)) & 3u)) & 1u) << i;
+      ncell = TC.nsub[c];
+      nfac = TC.nfac[c];
+      npt = aa == 0 ? TC.npts[c] : ncell * (D + 1);
+      if (nfac) a = aa;
+      mu.sinfo[s] = outm | ((uint32_t)aa << 16) | ((uint32_t)c << 20) | (mixed ? 1u << 24 : 0u);
+    }
+  }
+  // tile totals of the fast simplices (the walk adds the recorded ones)
+  const uint32_t tc = __reduce_add_sync(0xffffffffu, ncell), tp = __reduce_add_sync(0xffffffffu, npt);
+  const uint32_t present = __reduce_or_sync(0xffffffffu, a >= 0 ? 1u << a : 0u);
+  if (lane == 0) {
+    mu.tile[tile] = tc;
+    mu.tile[mu.ntiles + tile] = tp;
+  }
+  for (int k = 0; k < L; ++k) {
+    uint32_t tf = 0u;
+    if ((present >> k) & 1u) tf = __reduce_add_sync(0xffffffffu, a == k ? nfac : 0u);
+    if (lane == 0) {
+      mu.tile[(int64_t)(2 + k) * mu.ntiles + tile] = tf;
+      mu.tile[(int64_t)(2 + L + k) * mu.ntiles + tile] = tf * D;  // a passed-through facet keeps its D points
+    }
+  }
+}
+
+// shared memory of one warp of k_cutm_fill
+template <int D>
+struct CmSmem {
+  static constexpr int NPC = WalkCfg<D>::NPC;
+  static constexpr int SSTR = NPC * 2 * D + 1;  // doubles per lane: x then r of <= NPC points, odd stride
+  static constexpr int PCAP = 1024;             // points of a tile that go through the staged copy-out
+  static constexpr int NSUBMAX = (D == 3) ? 6 : 3;
+  double sx[32 * SSTR];
+  double fstash[32][8];   // <= 2 facets per lane: unit normal (D) + measure
+  uint4 rec[32];          // per lane: case | a << 4 | qc << 8 | first fast subcell << 16, outm, first subcell, first point
+  int32_t bg[32];
+  uint16_t pmap[PCAP];    // tile point -> (lane << 3 | slot) of the staged copy
+  uint8_t fslots[32][8];  // point slots of the <= 2 facets of a lane
+  uint8_t own_c[32 * NSUBMAX];  // fast subcell of the tile -> lane
+  uint8_t fitem[64];
+};
+
+template <int D>
+__global__ void __launch_bounds__(CM_T)
+k_cutm_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
+            const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
+            const int32_t* __restrict__ cutcells, int64_t nsimp, GcMulti mu, GcLayout lay,
+            uint32_t* __restrict__ sc_ptr) {
+  using SM = CmSmem<D>;
+  constexpr int SSTR = SM::SSTR, PCAP = SM::PCAP;
+  constexpr uint32_t FULLM = 0xffffffffu;
+  extern __shared__ __align__(16) unsigned char cm_smem[];
+  __shared__ GcSimplexTable s_tab[2];  // [0]: D-simplex (cells), [1]: (D-1)-simplex (facet pass-through rows)
+  __shared__ uint8_t s_swap[8];
+  {
+    const uint32_t* src0 = reinterpret_cast<const uint32_t*>(tables + (D - 1));
+    const uint32_t* src1 = reinterpret_cast<const uint32_t*>(tables + (D - 2));
+    uint32_t* dst0 = reinterpret_cast<uint32_t*>(&s_tab[0]);
+    uint32_t* dst1 = reinterpret_cast<uint32_t*>(&s_tab[1]);
+    for (int i = threadIdx.x; i < (int)(sizeof(GcSimplexTable) / 4); i += blockDim.x) {
+      dst0[i] = src0[i];
+      dst1[i] = src1[i];
+    }
+  }
+  const uint8_t* vtab = (g.simplexified ? simp_raw : simp_pos) + (D - 2) * 24;
+  cm_swap_flags<D>(g, vtab, s_swap);
+  __syncthreads();
+  const GcSimplexTable& TC = s_tab[0];
+  const GcSimplexTable& TF = s_tab[1];
+  const int L = lv.L;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  SM& sm = *reinterpret_cast<SM*>(cm_smem + (size_t)wid * sizeof(SM));
+  const int64_t tile = (int64_t)blockIdx.x * (CM_T / 32) + wid;
+  if (tile * 32 >= nsimp) return;  // whole warp beyond the end (no block barrier below)
+  const int64_t s = tile * 32 + lane;
+  const bool valid = s < nsimp;
+  const uint32_t lt = (1u << lane) - 1u;
+  const int c_allout = (1 << (D + 1)) - 1, fc_allout = (1 << D) - 1;
+
+  // ======================================== phase A: lane = stage-0 simplex
+  const uint32_t info = valid ? mu.sinfo[s] : 0u;
+  const bool slow = valid && (info & CM_SLOW);
+  const bool fast = valid && !slow;
+  const uint32_t slot = info & ~CM_SLOW;
+  const uint32_t outm = info & 0xFFFFu;
+  const int a = fast ? (int)((info >> 16) & 15u) : 0;
+  const int c = fast ? (int)((info >> 20) & 15u) : 0;
+  uint32_t ncell = 0, npt = 0, nfac = 0;
+  if (fast) {
+    ncell = TC.nsub[c];
+    nfac = TC.nfac[c];
+    npt = a == 0 ? TC.npts[c] : ncell * (D + 1);
+  } else if (slow) {
+    ncell = mu.slow_val[slot];
+    npt = mu.slow_val[mu.slow_n + slot];
+  }
+  // warp scans: all subcells / all points (recorded simplices included: they own ranges of the same arrays), and the
+  // fast-only subcell index of the lane-per-subcell phase
+  auto excl_scan = [&](uint32_t v, uint32_t* total) -> uint32_t {
+    uint32_t inc = v;
 #pragma unroll
-          for (int i = 0; i <= D; ++i) vl[i] = tmp[i];
-        }
-      };
-      auto skip_facet_stages = [&](uint8_t* vl, int hi, int lo, int skip) {
-        for (int k = hi - 1; k > lo; --k) {
-          if (k == skip) continue;
-          const uint8_t* pm = TF.sub_pts[((outm >> k) & 1u) ? fc_allout : 0][0];
-          uint8_t tmp[D];
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(FULLM, inc, o);
+      if (lane >= o) inc += t;
+    }
+    *total = __shfl_sync(FULLM, inc, 31);
+    return inc - v;
+  };
+  uint32_t tcells, tpts, tcf;
+  const uint32_t lc = excl_scan(ncell, &tcells), lp = excl_scan(npt, &tpts);
+  const uint32_t lcf = excl_scan(fast ? ncell : 0u, &tcf);
+  const uint32_t cell_off = mu.tile[tile] + lc, pt_off = mu.tile[mu.ntiles + tile] + lp;
+  const uint32_t wbase = pt_off - lp, wcount = tpts;  // point range of the tile
+  const bool staged = wcount <= (uint32_t)PCAP;
+  // facets: offsets inside the arrays of level set a
+  uint32_t fac_off = 0, fpt_off = 0;
+  const uint32_t any_slow = __ballot_sync(FULLM, slow);
+  if (!any_slow) {
+    const uint32_t peers = __match_any_sync(FULLM, nfac ? a : 31);
+    const uint32_t b1 = __ballot_sync(FULLM, nfac >= 1), b2 = __ballot_sync(FULLM, nfac >= 2);
+    const uint32_t before = (uint32_t)(__popc(peers & b1 & lt) + __popc(peers & b2 & lt));
+    if (nfac) {
+      fac_off = mu.fac_base[a] + mu.tile[(int64_t)(2 + a) * mu.ntiles + tile] + before;
+      fpt_off = mu.fpt_base[a] + mu.tile[(int64_t)(2 + L + a) * mu.ntiles + tile] + before * D;
+    }
+  } else {
+    // a tile with recorded simplices: they own facet ranges of several level sets -> one scan per level set and array
+    for (int k = 0; k < L; ++k) {
+      uint32_t tot;
+      const uint32_t vf = fast ? (a == k ? nfac : 0u) : (slow ? mu.slow_val[(int64_t)(2 + k) * mu.slow_n + slot] : 0u);
+      const uint32_t ef = excl_scan(vf, &tot);
+      const uint32_t vq = fast ? (a == k ? nfac * D : 0u) : (slow ? mu.slow_val[(int64_t)(2 + L + k) * mu.slow_n + slot] : 0u);
+      const uint32_t eq = excl_scan(vq, &tot);
+      const uint32_t bf = mu.tile[(int64_t)(2 + k) * mu.ntiles + tile] + ef;
+      const uint32_t bq = mu.tile[(int64_t)(2 + L + k) * mu.ntiles + tile] + eq;
+      if (fast && a == k && nfac) {
+        fac_off = mu.fac_base[k] + bf;
+        fpt_off = mu.fpt_base[k] + bq;
+      }
+      if (slow) {  // counters -> start offsets (without the level-set base: the walk adds it)
+        mu.slow_val[(int64_t)(2 + k) * mu.slow_n + slot] = bf;
+        mu.slow_val[(int64_t)(2 + L + k) * mu.slow_n + slot] = bq;
+      }
+    }
+  }
+  if (slow) {
+    mu.slow_val[slot] = cell_off;
+    mu.slow_val[mu.slow_n + slot] = pt_off;
+  }
+  if (valid) {  // first subcell / first point of every cut cell (consumers: Laplacian, cell measures)
+    const int64_t kcut = s / g.nt0;
+    if (s - kcut * g.nt0 == 0) {
+      sc_ptr[2 * kcut] = cell_off;
+      sc_ptr[2 * kcut + 1] = pt_off;
+    }
+    if (s == nsimp - 1) {
+      sc_ptr[2 * kcut + 2] = cell_off + ncell;
+      sc_ptr[2 * kcut + 3] = pt_off + npt;
+    }
+  }
+  if (staged) {
+    uint4* pm4 = reinterpret_cast<uint4*>(sm.pmap) + lane * (PCAP / 256);
 #pragma unroll
-          for (int i = 0; i < D; ++i) tmp[i] = vl[pm[i]];
+    for (int i = 0; i < PCAP / 256; ++i) pm4[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+  }
+  __syncwarp();
+  double* SX = sm.sx + lane * SSTR;  // component q (x then r) of slot p at SX[p * 2 * D + q]
+  int w_fc = 0;
+  if (fast) {
+    CmLane<D> ln;
+    cm_lane_setup<D>(g, vtab, s_swap, cutcells, s, ln);
+    const bool mixed = (info >> 24) & 1u;
+    const uint32_t vl = cm_skip_cell_stages<D>(TC, outm, L, a);
+    // vertices in arrival order into slots 0..D; values of level set a (the only one whose values matter) alongside
+    double W[D + 1];
 #pragma unroll
-          for (int i = 0; i < D; ++i) vl[i] = tmp[i];
-        }
-      };
-      uint8_t vl[D + 1];  // vertex order when the simplex arrives at stage a
+    for (int i = 0; i <= D; ++i) {
+      const int m = (vl >> (2 * i)) & 3u;
+      const int lvid = (ln.lv4 >> (8 * m)) & 0xFFu;
+      const int nijk[3] = {ln.ijk[0] + (lvid & 1), ln.ijk[1] + ((lvid >> 1) & 1), ln.ijk[2] + ((lvid >> 2) & 1)};
+      const double x[3] = {gc_coord(g, 0, nijk[0]), gc_coord(g, 1, nijk[1]), D == 3 ? gc_coord(g, 2, nijk[2]) : 0.0};
 #pragma unroll
-      for (int i = 0; i <= D; ++i) vl[i] = (uint8_t)i;
-      skip_cell_stages(vl, L, a);
-      // ---- pass 2: values of level set a (signs are enough when nothing cuts), in arrival order
-      double W[D + 1];
-      {
-        double W0[D + 1];
-#pragma unroll
-        for (int m = 0; m <= D; ++m) W0[m] = mixed ? value(a, m) : (((outm >> a) & 1u) ? 1.0 : -1.0);
-#pragma unroll
-        for (int i = 0; i <= D; ++i) {
-          double w = W0[0];
-#pragma unroll
-          for (int m = 1; m <= D; ++m)
-            if (vl[i] == m) w = W0[m];
-          W[i] = w;
+      for (int d = 0; d < D; ++d) {
+        SX[i * 2 * D + d] = x[d];
+        SX[i * 2 * D + D + d] = (double)((ln.rv4 >> (8 * m + d)) & 1u);
+      }
+      W[i] = 0.0;
+      if (mixed) {
+        if (lv.leaf[a].kind == GECUT_LEAF_NODAL) {
+          const int64_t node = (D == 3) ? ((int64_t)nijk[0] + (int64_t)g.nn[0] * ((int64_t)nijk[1] + (int64_t)g.nn[1] * nijk[2]))
+                                        : ((int64_t)nijk[0] + (int64_t)g.nn[0] * nijk[1]);
+          W[i] = __ldg(lv.nodal[a] + (node - lv.nodal_base));
+        } else {
+          W[i] = gc_eval_leaf(lv.leaf[a], x, D);
         }
       }
-      int c = 0;
-#pragma unroll
-      for (int i = 0; i <= D; ++i)
-        if (W[i] > 0.0) c |= 1 << i;
-      const int nsub = TC.nsub[c], nfac = TC.nfac[c];
-      int np = D + 1;
-      double* SX = scratch + (FILL ? threadIdx.x * SSTR : 0);  // component q (x then r) of slot p at SX[p * 2 * D + q]
-      auto sget = [&](int slot, int q) -> double { return SX[slot * 2 * D + q]; };
-      if (FILL) {
-        // vertices in original order to the upper slots, then permuted into slots 0..D (no dynamic register indexing)
-#pragma unroll
-        for (int m = 0; m <= D; ++m)
-#pragma unroll
-          for (int d = 0; d < D; ++d) {
-            SX[(NPC - 1 - D + m) * 2 * D + d] = X[m][d];
-            SX[(NPC - 1 - D + m) * 2 * D + D + d] = (double)((rv4 >> (8 * m + d)) & 1u);
-          }
-        double tmp[D + 1][2 * D];
-#pragma unroll
-        for (int i = 0; i <= D; ++i)
-#pragma unroll
-          for (int q = 0; q < 2 * D; ++q) tmp[i][q] = SX[(NPC - 1 - D + vl[i]) * 2 * D + q];
-#pragma unroll
-        for (int i = 0; i <= D; ++i)
-#pragma unroll
-          for (int q = 0; q < 2 * D; ++q) SX[i * 2 * D + q] = tmp[i][q];
-      }
-      if (TC.inoutcut[c] == GC_CUT) {
-        for (int ed = 0; ed < TC.nedges; ++ed) {
-          const int ia = TC.edges[ed][0], ib = TC.edges[ed][1];
+    }
+    int np = D + 1;
+    if (TC.inoutcut[c] == GC_CUT) {
+      for (int ed = 0; ed < TC.nedges; ++ed) {
+        const int ia = TC.edges[ed][0], ib = TC.edges[ed][1];
+        if (((c >> ia) ^ (c >> ib)) & 1) {
           double wa = W[0], wb = W[0];
 #pragma unroll
           for (int m = 1; m <= D; ++m) {
             if (ia == m) wa = W[m];
             if (ib == m) wb = W[m];
           }
-          if ((wa > 0.0) != (wb > 0.0)) {
-            if (FILL) {
-              const double w1 = fabs(wa), w2 = fabs(wb);
-              const double coeff = __ddiv_rn(w1, __dadd_rn(w1, w2));
+          const double w1 = fabs(wa), w2 = fabs(wb);
+          const double coeff = __ddiv_rn(w1, __dadd_rn(w1, w2));
 #pragma unroll
-              for (int q = 0; q < 2 * D; ++q) SX[np * 2 * D + q] = gc_lerp(sget(ia, q), sget(ib, q), coeff);
-            }
-            np++;
-          }
-        }
-      }
-      uint32_t fac_off = 0, fpt_off = 0;
-      if (FILL) {
-        cell_off = cn.cells[s];
-        pt_off = cn.points[s];
-        fac_off = cn.fac_base[a] + cn.fac[a][s];
-        fpt_off = cn.fpt_base[a] + cn.fpt[a][s];
-      }
-      // ---- facets of level set a: one final facet each, emitted at the last other stage
-      if (FILL) {
-        const int klast = a == 0 ? 1 : 0;
-        const int fc = ((outm >> klast) & 1u) ? fc_allout : 0;
-        // the skipped stages are the same for every facet: their permutations are composed once
-        uint8_t qf[D];
-#pragma unroll
-        for (int i = 0; i < D; ++i) qf[i] = (uint8_t)i;
-        skip_facet_stages(qf, L, klast, a);
-        for (int f = 0; f < nfac; ++f) {
-          const uint8_t* fp = TC.fac_pts[c][f];
-          double q1[3], q2[3], q3[3], nrm[3];
-#pragma unroll
-          for (int d = 0; d < D; ++d) {
-            q1[d] = sget(fp[0], d);
-            q2[d] = sget(fp[1], d);
-            q3[d] = sget(fp[D - 1], d);
-          }
-          unit_normal<D>(q1, q2, q3, (double)TC.fac_orient[c][f], nrm);
-          uint8_t fvl[D];
-#pragma unroll
-          for (int i = 0; i < D; ++i) fvl[i] = fp[qf[i]];
-          double pf[D][3];
-#pragma unroll
-          for (int i = 0; i < D; ++i) {
-            const int li = TF.sub_pts[fc][0][i];
-#pragma unroll
-            for (int d = 0; d < D; ++d) pf[i][d] = sget(fvl[li], d);
-          }
-          // parked for the warp-level emission below
-#pragma unroll
-          for (int d = 0; d < D; ++d) fstash[threadIdx.x][f * 4 + d] = nrm[d];
-          fstash[threadIdx.x][f * 4 + 3] = integrate_one<D - 1>(simplex_meas<D, D - 1>(pf));
-#pragma unroll
-          for (int i = 0; i < D; ++i) fslots[threadIdx.x][f * 4 + i] = fvl[i];
-        }
-        w_a = a;
-        w_nfac = nfac;
-        w_fc = fc;
-        w_outm = outm;
-        w_fac_off = fac_off;
-        w_fpt_off = fpt_off;
-        w_bg = bgcell1;
-      }
-      // ---- cells
-      uint32_t ncell_out, npt_out;
-      if (a == 0) {
-        // cut (or not) at the emission stage itself: one point block, nsub children (CutTriangulations.jl:186-203)
-        if (FILL) {
-          for (int pnt = 0; pnt < np; ++pnt) {
-            if (staged) {
-              pmap[pt_off + pnt - wbase] = (uint16_t)((lane << 3) | pnt);
-            } else {
-#pragma unroll
-              for (int d = 0; d < D; ++d) {
-                lay.sc_X[(int64_t)(pt_off + pnt) * D + d] = sget(pnt, d);
-                lay.sc_R[(int64_t)(pt_off + pnt) * D + d] = sget(pnt, D + d);
-              }
-            }
-          }
-          for (int j = 0; j < nsub; ++j) {
-            const uint32_t cid = cell_off + j;
-            double pc[D + 1][3];
-            int32_t row[D + 1];
-#pragma unroll
-            for (int i = 0; i <= D; ++i) {
-              const int li = TC.sub_pts[c][j][i];
-              row[i] = (int32_t)(pt_off + li + 1);
-#pragma unroll
-              for (int d = 0; d < D; ++d) pc[i][d] = sget(li, d);
-            }
-            store_c2p_row<D>(lay.sc_c2p, cid, row);
-            lay.sc_c2bg[cid] = bgcell1;
-            lay.sc_meas[cid] = integrate_one<D>(simplex_meas<D, D>(pc));
-            lay.sc_state[cid] = TC.sub_inout[c][j];
-            for (int kk = 1; kk < L; ++kk) lay.sc_state[(int64_t)kk * lay.sc_pitch + cid] = cstate(kk);
-          }
-        }
-        ncell_out = nsub;
-        npt_out = np;
-      } else {
-        // cut at stage a > 0: every child goes down to stage 0 alone and is emitted there as an uncut simplex
-        const int c0 = (outm & 1u) ? c_allout : 0;
-        if (FILL) {
-          uint8_t qc[D + 1];  // composed permutations of the stages a-1 ... 1 (the same for every child)
-#pragma unroll
-          for (int i = 0; i <= D; ++i) qc[i] = (uint8_t)i;
-          skip_cell_stages(qc, a, 0);
-          for (int j = 0; j < nsub; ++j) {
-            uint8_t cv[D + 1];
-#pragma unroll
-            for (int i = 0; i <= D; ++i) cv[i] = TC.sub_pts[c][j][qc[i]];
-            const uint32_t pb = pt_off + (uint32_t)j * (D + 1), cid = cell_off + j;
-#pragma unroll
-            for (int pnt = 0; pnt <= D; ++pnt) {
-              if (staged) {
-                pmap[pb + pnt - wbase] = (uint16_t)((lane << 3) | cv[pnt]);
-              } else {
-#pragma unroll
-                for (int d = 0; d < D; ++d) {
-                  lay.sc_X[(int64_t)(pb + pnt) * D + d] = sget(cv[pnt], d);
-                  lay.sc_R[(int64_t)(pb + pnt) * D + d] = sget(cv[pnt], D + d);
-                }
-              }
-            }
-            double pc[D + 1][3];
-            int32_t row[D + 1];
-#pragma unroll
-            for (int i = 0; i <= D; ++i) {
-              const int li = TC.sub_pts[c0][0][i];
-              row[i] = (int32_t)(pb + li + 1);
-#pragma unroll
-              for (int d = 0; d < D; ++d) pc[i][d] = sget(cv[li], d);
-            }
-            store_c2p_row<D>(lay.sc_c2p, cid, row);
-            lay.sc_c2bg[cid] = bgcell1;
-            lay.sc_meas[cid] = integrate_one<D>(simplex_meas<D, D>(pc));
-            lay.sc_state[cid] = TC.sub_inout[c0][0];
-            for (int kk = 1; kk < L; ++kk)
-              lay.sc_state[(int64_t)kk * lay.sc_pitch + cid] = (kk == a) ? TC.sub_inout[c][j] : cstate(kk);
-          }
-        }
-        ncell_out = nsub;
-        npt_out = nsub * (D + 1);
-      }
-      if (!FILL) {
-        cn.cells[s] = ncell_out;
-        cn.points[s] = npt_out;
-        for (int k = 0; k < L; ++k) {
-          cn.fac[k][s] = (k == a) ? (uint32_t)nfac : 0u;
-          cn.fpt[k][s] = (k == a) ? (uint32_t)(nfac * D) : 0u;
+          for (int q = 0; q < 2 * D; ++q) SX[np * 2 * D + q] = gc_lerp(SX[ia * 2 * D + q], SX[ib * 2 * D + q], coeff);
+          np++;
         }
       }
     }
-  }  // valid
-  if (FILL) {
-    __syncwarp();
-    // ---- warp-level facet emission: the facets of the warp's simplices form (per level set) runs of consecutive ids,
-    // so one facet entity per lane writes point blocks, normals, connectivity, bg cells, measures and state rows with
-    // neighbouring lanes on neighbouring addresses (the per-lane loops above scattered 8-byte stores over 32 sectors)
-    {
-      constexpr uint32_t FULLM = 0xffffffffu;
-      const uint32_t lt = (1u << lane) - 1u;
-      const uint32_t b1 = __ballot_sync(FULLM, w_nfac >= 1), b2 = __ballot_sync(FULLM, w_nfac >= 2);
-      const int T = __popc(b1) + __popc(b2);
-      uint8_t* fitem = fitem_all + (threadIdx.x & ~31) * 2;
+    // ---- facets of level set a: one final facet each, emitted at the last other stage
+    if (nfac) {
+      const int klast = a == 0 ? 1 : 0;
+      const int fc = ((outm >> klast) & 1u) ? fc_allout : 0;
+      w_fc = fc;
+      const uint32_t qf = cm_skip_facet_stages<D>(TF, outm, L, klast, a);  // the same for every facet of the simplex
+      for (int f = 0; f < (int)nfac; ++f) {
+        const uint8_t* fp = TC.fac_pts[c][f];
+        double q1[3], q2[3], q3[3], nrm[3];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          q1[d] = SX[fp[0] * 2 * D + d];
+          q2[d] = SX[fp[1] * 2 * D + d];
+          q3[d] = SX[fp[D - 1] * 2 * D + d];
+        }
+        unit_normal<D>(q1, q2, q3, (double)TC.fac_orient[c][f], nrm);
+        uint8_t fvl[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) fvl[i] = fp[(qf >> (2 * i)) & 3u];
+        double pf[D][3];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          const int li = TF.sub_pts[fc][0][i];
+#pragma unroll
+          for (int d = 0; d < D; ++d) pf[i][d] = SX[fvl[li] * 2 * D + d];
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) sm.fstash[lane][f * 4 + d] = nrm[d];
+        sm.fstash[lane][f * 4 + 3] = integrate_one<D - 1>(simplex_meas<D, D - 1>(pf));
+#pragma unroll
+        for (int i = 0; i < D; ++i) sm.fslots[lane][f * 4 + i] = fvl[i];
+      }
+    }
+    // ---- subcell points: where every point of the final layout comes from (slot of this lane's slice)
+    uint32_t qc = 0;
+    if (a == 0) {
+      for (int pnt = 0; pnt < np; ++pnt) {
+        if (staged) {
+          sm.pmap[pt_off + pnt - wbase] = (uint16_t)((lane << 3) | pnt);
+        } else {
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            lay.sc_X[(int64_t)(pt_off + pnt) * D + d] = SX[pnt * 2 * D + d];
+            lay.sc_R[(int64_t)(pt_off + pnt) * D + d] = SX[pnt * 2 * D + D + d];
+          }
+        }
+      }
+    } else {
+      // cut at stage a > 0: every child goes down to stage 0 alone (composed permutations of the stages a-1 ... 1, the
+      // same for every child) and is emitted there as an uncut simplex with its own copy of its D+1 points
+      qc = cm_skip_cell_stages<D>(TC, outm, a, 0);
+      for (int j = 0; j < (int)ncell; ++j) {
+        const uint32_t pb = pt_off + (uint32_t)j * (D + 1);
+#pragma unroll
+        for (int pnt = 0; pnt <= D; ++pnt) {
+          const int sl = TC.sub_pts[c][j][(qc >> (2 * pnt)) & 3u];
+          if (staged) {
+            sm.pmap[pb + pnt - wbase] = (uint16_t)((lane << 3) | sl);
+          } else {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+              lay.sc_X[(int64_t)(pb + pnt) * D + d] = SX[sl * 2 * D + d];
+              lay.sc_R[(int64_t)(pb + pnt) * D + d] = SX[sl * 2 * D + D + d];
+            }
+          }
+        }
+      }
+    }
+    sm.rec[lane] = make_uint4((uint32_t)c | ((uint32_t)a << 4) | (qc << 8) | (lcf << 16), outm, cell_off, pt_off);
+    sm.bg[lane] = ln.bgcell1;
+    for (int j = 0; j < (int)ncell; ++j) sm.own_c[lcf + j] = (uint8_t)lane;
+  }
+  __syncwarp();
+  const double* SW = sm.sx;
+  // ======================================== phase F: lane = element of the tile's subfacets
+  // the facets of the warp's simplices form (per level set) runs of consecutive ids, so one facet entity per lane writes
+  // point blocks, normals, connectivity, bg cells, measures and state rows with neighbouring lanes on neighbouring addresses
+  {
+    const uint32_t b1 = __ballot_sync(FULLM, fast && nfac >= 1), b2 = __ballot_sync(FULLM, fast && nfac >= 2);
+    const int T = __popc(b1) + __popc(b2);
+    if (T) {
       const int first = __popc(b1 & lt) + __popc(b2 & lt);
-      for (int f = 0; f < w_nfac; ++f) fitem[first + f] = (uint8_t)(lane * 2 + f);
+      if (fast)
+        for (int f = 0; f < (int)nfac; ++f) sm.fitem[first + f] = (uint8_t)(lane * 2 + f);
       __syncwarp();
-      const int wt0 = threadIdx.x & ~31;                   // thread index of lane 0 of this warp
-      const double* SW = scratch + wt0 * SSTR;
       // point blocks: D points x D coordinates per facet
       for (int q0 = 0; q0 < T * D * D; q0 += 32) {
         const int q = q0 + lane;
         const bool on = q < T * D * D;
         const int item = on ? q / (D * D) : 0;
         const int r = q - item * (D * D), pnt = r / D, d = r - pnt * D;
-        const int it = fitem[item], o = it >> 1, f = it & 1;
-        const uint32_t fpo = __shfl_sync(FULLM, w_fpt_off, o);
+        const int it = sm.fitem[item], o = it >> 1, f = it & 1;
+        const uint32_t fpo = __shfl_sync(FULLM, fpt_off, o);
         if (on) {
-          const double* src = SW + o * SSTR + fslots[wt0 + o][f * 4 + pnt] * 2 * D;
+          const double* src = SW + o * SSTR + sm.fslots[o][f * 4 + pnt] * 2 * D;
           const int64_t dst = (int64_t)(fpo + (uint32_t)(f * D + pnt)) * D + d;
           lay.sf_X[dst] = src[d];
           lay.sf_R[dst] = src[D + d];
@@ -980,12 +1110,12 @@ k_cut_fast(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
         const bool on = q < T * D;
         const int item = on ? q / D : 0;
         const int d = q - item * D;
-        const int it = fitem[item], o = it >> 1, f = it & 1;
-        const uint32_t fpo = __shfl_sync(FULLM, w_fpt_off, o), fao = __shfl_sync(FULLM, w_fac_off, o);
+        const int it = sm.fitem[item], o = it >> 1, f = it & 1;
+        const uint32_t fpo = __shfl_sync(FULLM, fpt_off, o), fao = __shfl_sync(FULLM, fac_off, o);
         const int fco = __shfl_sync(FULLM, w_fc, o);
         if (on) {
           const int64_t dst = (int64_t)(fao + (uint32_t)f) * D + d;
-          lay.sf_N[dst] = fstash[wt0 + o][f * 4 + d];
+          lay.sf_N[dst] = sm.fstash[o][f * 4 + d];
           lay.sf_c2p[dst] = (int32_t)(fpo + (uint32_t)(f * D) + TF.sub_pts[fco][0][d] + 1);
         }
       }
@@ -993,14 +1123,13 @@ k_cut_fast(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
       for (int q0 = 0; q0 < T; q0 += 32) {
         const int q = q0 + lane;
         const bool on = q < T;
-        const int it = fitem[on ? q : 0], o = it >> 1, f = it & 1;
-        const uint32_t fao = __shfl_sync(FULLM, w_fac_off, o), om = __shfl_sync(FULLM, w_outm, o);
-        const int fco = __shfl_sync(FULLM, w_fc, o), ao = __shfl_sync(FULLM, w_a, o);
-        const int32_t bgo = __shfl_sync(FULLM, w_bg, o);
+        const int it = sm.fitem[on ? q : 0], o = it >> 1, f = it & 1;
+        const uint32_t fao = __shfl_sync(FULLM, fac_off, o), om = __shfl_sync(FULLM, outm, o);
+        const int fco = __shfl_sync(FULLM, w_fc, o), ao = __shfl_sync(FULLM, a, o);
         if (on) {
           const int64_t fid = (int64_t)fao + f;
-          lay.sf_c2bg[fid] = bgo;
-          lay.sf_meas[fid] = fstash[wt0 + o][f * 4 + 3];
+          lay.sf_c2bg[fid] = sm.bg[o];
+          lay.sf_meas[fid] = sm.fstash[o][f * 4 + 3];
           const int klast = ao == 0 ? 1 : 0;
           for (int kk = 0; kk < L; ++kk)
             lay.sf_state[(int64_t)kk * lay.sf_pitch + fid] =
@@ -1009,20 +1138,65 @@ k_cut_fast(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
         }
       }
     }
-    if (staged) {
-      const double* SW = scratch + (threadIdx.x & ~31) * SSTR;  // scratch of lane 0 of this warp
-      double* gX = lay.sc_X + (int64_t)wbase * D;
-      double* gR = lay.sc_R + (int64_t)wbase * D;
-      for (uint32_t q = lane; q < wcount * D; q += 32) {
-        const uint32_t pnt = q / D, d = q - pnt * D;
-        const uint32_t m = pmap[pnt];
-        if (m != 0xFFFFu) {
-          const double* src = SW + (m >> 3) * SSTR + (m & 7u) * 2 * D;
-          gX[q] = src[d];
-          gR[q] = src[D + d];
-        }
+  }
+  // ======================================== phase P: subcell points of the tile leave through the point map
+  if (staged) {
+    double* gX = lay.sc_X + (int64_t)wbase * D;
+    double* gR = lay.sc_R + (int64_t)wbase * D;
+    for (uint32_t q = lane; q < wcount * D; q += 32) {
+      const uint32_t pnt = q / D, d = q - pnt * D;
+      const uint32_t m = sm.pmap[pnt];
+      if (m != 0xFFFFu) {  // points of recorded simplices are written by the walk
+        const double* src = SW + (m >> 3) * SSTR + (m & 7u) * 2 * D;
+        gX[q] = src[d];
+        gR[q] = src[D + d];
       }
     }
+  }
+  // ======================================== phase C: lane = subcell of a fast simplex
+  for (uint32_t idx = lane; idx < tcf; idx += 32) {
+    const int o = sm.own_c[idx];
+    const uint4 r = sm.rec[o];
+    const int cc = r.x & 15u, aa = (r.x >> 4) & 15u;
+    const uint32_t qc = (r.x >> 8) & 0xFFu;
+    const int j = (int)(idx - ((r.x >> 16) & 0xFFu));
+    const uint32_t om = r.y;
+    const int64_t cid = (int64_t)r.z + j;
+    const double* SXo = SW + o * SSTR;
+    const uint32_t ptsj = *reinterpret_cast<const uint32_t*>(TC.sub_pts[cc][j]);
+    int32_t row[D + 1];
+    double pc[D + 1][3];
+    int8_t s0;
+    if (aa == 0) {
+#pragma unroll
+      for (int i = 0; i <= D; ++i) {
+        const uint32_t li = (ptsj >> (8 * i)) & 0xFFu;
+        row[i] = (int32_t)(r.w + li + 1u);
+#pragma unroll
+        for (int d = 0; d < D; ++d) pc[i][d] = SXo[li * 2 * D + d];
+      }
+      s0 = TC.sub_inout[cc][j];
+    } else {
+      const int c0 = (om & 1u) ? c_allout : 0;
+      const uint32_t pts0 = *reinterpret_cast<const uint32_t*>(TC.sub_pts[c0][0]);
+      const uint32_t pb = r.w + (uint32_t)j * (D + 1);
+#pragma unroll
+      for (int i = 0; i <= D; ++i) {
+        const uint32_t li = (pts0 >> (8 * i)) & 0xFFu;
+        row[i] = (int32_t)(pb + li + 1u);
+        const uint32_t sl = (ptsj >> (8 * ((qc >> (2 * li)) & 3u))) & 0xFFu;
+#pragma unroll
+        for (int d = 0; d < D; ++d) pc[i][d] = SXo[sl * 2 * D + d];
+      }
+      s0 = TC.sub_inout[c0][0];
+    }
+    store_c2p_row<D>(lay.sc_c2p, (uint32_t)cid, row);
+    lay.sc_c2bg[cid] = sm.bg[o];
+    lay.sc_meas[cid] = integrate_one<D>(simplex_meas<D, D>(pc));
+    lay.sc_state[cid] = s0;
+    for (int kk = 1; kk < L; ++kk)
+      lay.sc_state[(int64_t)kk * lay.sc_pitch + cid] =
+          (kk == aa) ? TC.sub_inout[cc][j] : (((om >> kk) & 1u) ? (int8_t)GC_OUT : (int8_t)GC_IN);
   }
 }
 
@@ -1555,56 +1729,50 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
   cut1_copy_doubles(lay.sc_R + (int64_t)gp * D, stage_p, tp * D, phase, lane);
 }
 
-__global__ void k_extract_sc_ptr(const uint32_t* __restrict__ cell_offs, const uint32_t* __restrict__ point_offs, int nt0,
-                                 int64_t ncut, uint32_t total_cells, uint32_t total_points, uint32_t* __restrict__ ptr) {
-  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < ncut) {
-    ptr[2 * k] = cell_offs[k * nt0];
-    ptr[2 * k + 1] = point_offs[k * nt0];
-  }
-  if (k == ncut) {
-    ptr[2 * k] = total_cells;
-    ptr[2 * k + 1] = total_points;
-  }
-}
-
 template <int D, int NW>
-void launch_walk(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcCounters& cn, bool fill, int64_t nslow,
-                 const uint32_t* slow_list, const uint32_t* slow_count, cudaStream_t stream) {
+void launch_walk(gecut_ctx* ctx, const gecut_result* res, const GcMulti& mu, bool fill, int64_t nslots,
+                 const uint32_t* slots, cudaStream_t stream) {
   const int T = WALK_T;
-  const unsigned nb = (unsigned)gc_div_up(nslow * WALK_ITEMS, T);
+  const unsigned nb = (unsigned)gc_div_up(nslots * WALK_ITEMS, T);
   if (nb == 0) return;
   if (fill)
     GC_LAUNCH(ctx, "k_cut_walk_fill", k_cut_walk<D, NW, true><<<nb, T, 0, stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
-                                                       ctx->d_simplexify_pos, res->lay.cutcells, nsimp, cn, res->lay, slow_list, slow_count));
+                                                       ctx->d_simplexify_pos, res->lay.cutcells, mu, res->lay, slots, nslots));
   else
     GC_LAUNCH(ctx, "k_cut_walk_count", k_cut_walk<D, NW, false><<<nb, T, 0, stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
-                                                        ctx->d_simplexify_pos, res->lay.cutcells, nsimp, cn, res->lay, slow_list, slow_count));
+                                                        ctx->d_simplexify_pos, res->lay.cutcells, mu, res->lay, slots, nslots));
 }
 
-void launch_fast(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcCounters& cn, bool fill,
-                 uint32_t* slow_list, uint32_t* slow_count) {
-  const unsigned nb = (unsigned)gc_div_up(nsimp, WALK_T);
-#define GC_FAST(DD, FF, NAME)                                                                                      \
-  GC_LAUNCH(ctx, NAME, k_cut_fast<DD, FF><<<nb, WALK_T, 0, ctx->stream>>>(res->grid, res->leaves, ctx->d_tables,      \
-                                                                        ctx->d_simplexify_raw, ctx->d_simplexify_pos, \
-                                                                        res->lay.cutcells, nsimp, cn, res->lay,     \
-                                                                        slow_list, slow_count))
-  if (res->grid.D == 2) {
-    if (fill) GC_FAST(2, true, "k_cut_fast_fill"); else GC_FAST(2, false, "k_cut_fast_count");
-  } else {
-    if (fill) GC_FAST(3, true, "k_cut_fast_fill"); else GC_FAST(3, false, "k_cut_fast_count");
-  }
-#undef GC_FAST
+void launch_fast_count(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcMulti& mu) {
+  const unsigned nb = (unsigned)gc_div_up(mu.ntiles, CM_T / 32);
+  if (res->grid.D == 2)
+    GC_LAUNCH(ctx, "k_cutm_count", k_cutm_count<2><<<nb, CM_T, 0, ctx->stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
+                                                                               ctx->d_simplexify_pos, res->lay.cutcells, nsimp, mu));
+  else
+    GC_LAUNCH(ctx, "k_cutm_count", k_cutm_count<3><<<nb, CM_T, 0, ctx->stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
+                                                                               ctx->d_simplexify_pos, res->lay.cutcells, nsimp, mu));
 }
 
-// one dense launch per bucket of recorded simplices (nslow[b] of them in slow_list + b*nsimp).  The buckets are
+void launch_fast_fill(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcMulti& mu) {
+  const unsigned nb = (unsigned)gc_div_up(mu.ntiles, CM_T / 32);
+  if (res->grid.D == 2)
+    GC_LAUNCH(ctx, "k_cutm_fill", k_cutm_fill<2><<<nb, CM_T, sizeof(CmSmem<2>) * (CM_T / 32), ctx->stream>>>(
+        res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw, ctx->d_simplexify_pos, res->lay.cutcells, nsimp, mu, res->lay,
+        res->cut_sc_ptr));
+  else
+    GC_LAUNCH(ctx, "k_cutm_fill", k_cutm_fill<3><<<nb, CM_T, sizeof(CmSmem<3>) * (CM_T / 32), ctx->stream>>>(
+        res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw, ctx->d_simplexify_pos, res->lay.cutcells, nsimp, mu, res->lay,
+        res->cut_sc_ptr));
+}
+
+// one dense launch per bucket of recorded simplices (nslow[b] slots starting at lists + base[b]).  The buckets are
 // independent and each launch lasts as long as its slowest thread, so they run concurrently on side streams.
-int dispatch_walk(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcCounters& cn, bool fill,
-                  const int64_t* nslow, const uint32_t* slow_list, const uint32_t* slow_count) {
+int dispatch_walk(gecut_ctx* ctx, const gecut_result* res, const GcMulti& mu, bool fill, const int64_t* nslow,
+                  const uint32_t* lists) {
   const int D = res->grid.D;
   int nonempty = 0;
   for (int b = 0; b < WALK_NB; ++b) nonempty += nslow[b] > 0 ? 1 : 0;
+  if (nonempty == 0) return GECUT_OK;
   const bool fork = nonempty > 1 && !ctx->prof_on;  // per-kernel profiling times launches on the main stream
   if (fork) {
     if (!ctx->ev_fork) GC_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
@@ -1619,7 +1787,10 @@ int dispatch_walk(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const 
     cudaStreamWaitEvent(ctx->side[b], ctx->ev_fork, 0);
     return ctx->side[b];
   };
-#define GC_WALK(DD, B) launch_walk<DD, walk_nw(B)>(ctx, res, nsimp, cn, fill, nslow[B], slow_list + (int64_t)(B) * nsimp, slow_count + (B), stream_of(B))
+  int64_t base[WALK_NB];
+  base[0] = 0;
+  for (int b = 1; b < WALK_NB; ++b) base[b] = base[b - 1] + nslow[b - 1];
+#define GC_WALK(DD, B) launch_walk<DD, walk_nw(B)>(ctx, res, mu, fill, nslow[B], lists + base[B], stream_of(B))
   if (D == 2) {
     GC_WALK(2, 0);
     GC_WALK(2, 1);
@@ -1863,56 +2034,67 @@ int gc_cut_cells(gecut_ctx* ctx, gecut_result* res) {
   sz.num_subcells = sz.num_subcell_points = sz.num_subfacets = sz.num_subfacet_points = 0;
   if (nsimp == 0) return GECUT_OK;
   if (L == 1) return gc_cut_cells_l1(ctx, res);
-  // counters: cells, points, fac[L], fpt[L] (fpt unused for L == 1)
-  const int narr = 2 + L + (L > 1 ? L : 0);
-  uint32_t* pool = nullptr;
+  // ---- L > 1: tile totals (k_cutm_count + k_cut_walk<count> for the recorded simplices) -> scan over tiles -> fill
+  GcScratch scratch(ctx);  // every block below is released on every exit path
+  GcMulti mu{};
+  mu.nch = 2 + 2 * L;
+  mu.ntiles = gc_div_up(nsimp, 32);
   uint64_t* totals_dev = nullptr;
-  GC_CHECK(gc_malloc(ctx, (void**)&pool, sizeof(uint32_t) * nsimp * narr));
-  GC_CHECK(gc_malloc(ctx, (void**)&totals_dev, sizeof(uint64_t) * narr));
-  GcCounters cn{};
-  cn.cells = pool;
-  cn.points = pool + nsimp;
-  for (int k = 0; k < L; ++k) {
-    cn.fac[k] = pool + (2 + k) * nsimp;
-    cn.fpt[k] = (L > 1) ? pool + (2 + L + k) * nsimp : nullptr;
-  }
-  // simplices cut by two or more level sets are collected and walked by a second, dense launch
-  uint32_t* slow_list = nullptr;
-  uint32_t* slow_count = nullptr;
-  GC_CHECK(gc_malloc(ctx, (void**)&slow_list, sizeof(uint32_t) * nsimp * WALK_NB));
-  GC_CHECK(gc_malloc(ctx, (void**)&slow_count, sizeof(uint32_t) * 8));
-  GC_CUDA(cudaMemsetAsync(slow_count, 0, sizeof(uint32_t) * 8, ctx->stream));
-  launch_fast(ctx, res, nsimp, cn, false, slow_list, slow_count);
-  int64_t nslow[WALK_NB];
+  GC_CHECK(scratch.alloc(&mu.tile, sizeof(uint32_t) * mu.ntiles * mu.nch));
+  GC_CHECK(scratch.alloc(&mu.sinfo, sizeof(uint32_t) * nsimp));
+  GC_CHECK(scratch.alloc(&mu.slow_simp, sizeof(uint32_t) * nsimp));
+  GC_CHECK(scratch.alloc(&mu.slow_bucket, (size_t)nsimp));
+  GC_CHECK(scratch.alloc(&mu.slow_count, sizeof(uint32_t) * 16));
+  GC_CHECK(scratch.alloc(&totals_dev, sizeof(uint64_t) * mu.nch));
+  GC_CUDA(cudaMemsetAsync(mu.slow_count, 0, sizeof(uint32_t) * 16, ctx->stream));
+  launch_fast_count(ctx, res, nsimp, mu);
+  GC_CHECK(gc_launch_check(ctx, "k_cutm_count"));
+  int64_t nslow[WALK_NB], nslow_total = 0;
   {
     uint32_t* hs = (uint32_t*)ctx->h_pinned;
-    GC_CUDA(cudaMemcpyAsync(hs, slow_count, sizeof(uint32_t) * WALK_NB, cudaMemcpyDeviceToHost, ctx->stream));
+    GC_CUDA(cudaMemcpyAsync(hs, mu.slow_count, sizeof(uint32_t) * (WALK_NB + 1), cudaMemcpyDeviceToHost, ctx->stream));
     GC_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int b = 0; b < WALK_NB; ++b) nslow[b] = (int64_t)hs[b];
+    nslow_total = (int64_t)hs[WALK_NB];
   }
   if (getenv("GECUT_WALK_DEBUG")) fprintf(stderr, "[gecut] tree-walk buckets: %lld %lld %lld %lld %lld of %lld simplices\n", (long long)nslow[0], (long long)nslow[1], (long long)nslow[2], (long long)nslow[3], (long long)nslow[4], (long long)nsimp);
-  GC_CHECK(dispatch_walk(ctx, res, nsimp, cn, false, nslow, slow_list, slow_count));
-  GC_CHECK(gc_launch_check(ctx, "k_cut_walk(count)"));
-  GC_CHECK(gc_exclusive_scan_u32_multi(ctx, pool, pool, nsimp, narr, totals_dev));
+  uint32_t* lists = nullptr;
+  if (nslow_total > 0) {
+    // slot-indexed counters of the recorded simplices, one dense slot list per launch bucket
+    mu.slow_n = nslow_total;
+    uint32_t* cursor = nullptr;
+    GC_CHECK(scratch.alloc(&mu.slow_val, sizeof(uint32_t) * nslow_total * mu.nch));
+    GC_CHECK(scratch.alloc(&lists, sizeof(uint32_t) * nslow_total));
+    GC_CHECK(scratch.alloc(&cursor, sizeof(uint32_t) * 2 * WALK_NB));
+    uint32_t hb[2 * WALK_NB];
+    uint32_t acc = 0;
+    for (int b = 0; b < WALK_NB; ++b) {
+      hb[b] = acc;            // base of bucket b
+      hb[WALK_NB + b] = 0u;   // cursor
+      acc += (uint32_t)nslow[b];
+    }
+    uint32_t* hp = (uint32_t*)ctx->h_pinned + 512;  // the pinned page is reused right away: keep clear of the read-back area
+    memcpy(hp, hb, sizeof(hb));
+    GC_CUDA(cudaMemcpyAsync(cursor, hp, sizeof(hb), cudaMemcpyHostToDevice, ctx->stream));
+    GC_LAUNCH(ctx, "k_cutm_bucketize", k_cutm_bucketize<<<(unsigned)gc_div_up(nslow_total, 256), 256, 0, ctx->stream>>>(
+        mu.slow_bucket, nslow_total, cursor, cursor + WALK_NB, lists));
+    GC_CHECK(dispatch_walk(ctx, res, mu, false, nslow, lists));
+    GC_CHECK(gc_launch_check(ctx, "k_cut_walk(count)"));
+  }
+  GC_CHECK(gc_exclusive_scan_u32_multi(ctx, mu.tile, mu.tile, mu.ntiles, mu.nch, totals_dev));
   uint64_t* h = (uint64_t*)ctx->h_pinned;
-  GC_CUDA(cudaMemcpyAsync(h, totals_dev, sizeof(uint64_t) * narr, cudaMemcpyDeviceToHost, ctx->stream));
+  GC_CUDA(cudaMemcpyAsync(h, totals_dev, sizeof(uint64_t) * mu.nch, cudaMemcpyDeviceToHost, ctx->stream));
   GC_CUDA(cudaStreamSynchronize(ctx->stream));
   uint64_t nsc = h[0], nscp = h[1], nsf = 0, nsfp = 0;
   for (int k = 0; k < L; ++k) {
-    cn.fac_base[k] = (uint32_t)nsf;
-    cn.fpt_base[k] = (uint32_t)nsfp;
+    mu.fac_base[k] = (uint32_t)nsf;
+    mu.fpt_base[k] = (uint32_t)nsfp;
     nsf += h[2 + k];
-    if (L > 1) nsfp += h[2 + L + k];
+    nsfp += h[2 + L + k];
   }
-  if (L == 1) nsfp = nscp;
-  cn.total_points = (uint32_t)nscp;
   const uint64_t lim = 2147483647ull;
   if (nsc * (uint64_t)(D + 1) >= lim || nscp > lim || nsf > lim || nsfp > lim || nsc > lim) {
     ctx->err = "Int32 ids of the SubCellData/SubFacetData layout would overflow";
-    gc_free(ctx, pool);
-    gc_free(ctx, totals_dev);
-    gc_free(ctx, slow_list);
-    gc_free(ctx, slow_count);
     return GECUT_ERR_OVERFLOW;
   }
   sz.num_subcells = (int64_t)nsc;
@@ -1940,14 +2122,8 @@ int gc_cut_cells(gecut_ctx* ctx, gecut_result* res) {
     GC_CHECK(gc_malloc(ctx, (void**)&lay.sf_R, sizeof(double) * nsfp * D));
   }
   GC_CHECK(gc_malloc(ctx, (void**)&res->cut_sc_ptr, sizeof(uint32_t) * 2 * (ncut + 1)));
-  GC_LAUNCH(ctx, "k_extract_sc_ptr", k_extract_sc_ptr<<<(unsigned)gc_div_up(ncut + 1, 256), 256, 0, ctx->stream>>>(
-      cn.cells, cn.points, g.nt0, ncut, (uint32_t)nsc, (uint32_t)nscp, res->cut_sc_ptr));
-  launch_fast(ctx, res, nsimp, cn, true, slow_list, slow_count);
-  GC_CHECK(dispatch_walk(ctx, res, nsimp, cn, true, nslow, slow_list, slow_count));
-  int st = gc_launch_check(ctx, "k_cut_walk(fill)");
-  gc_free(ctx, pool);
-  gc_free(ctx, totals_dev);
-  gc_free(ctx, slow_list);
-  gc_free(ctx, slow_count);
-  return st;
+  launch_fast_fill(ctx, res, nsimp, mu);
+  GC_CHECK(gc_launch_check(ctx, "k_cutm_fill"));
+  if (nslow_total > 0) GC_CHECK(dispatch_walk(ctx, res, mu, true, nslow, lists));
+  return gc_launch_check(ctx, "k_cut_walk(fill)");
 }

@@ -93,17 +93,6 @@ struct GcLayout {
   double* sf_meas;
 };
 
-// Per stage-0-simplex counters (pass 1) / exclusive offsets (pass 2).
-struct GcCounters {
-  uint32_t* cells;
-  uint32_t* points;
-  uint32_t* fac[GC_LMAX];
-  uint32_t* fpt[GC_LMAX];
-  uint32_t fac_base[GC_LMAX];  // global offset of the facets of level set ls (merge_sub_face_data order)
-  uint32_t fpt_base[GC_LMAX];
-  uint32_t total_points;  // subcell points of the whole result (end of the last warp's range in the fill walk)
-};
-
 // ------------------------------------------------------------------------------------------------
 // Context / result / selection objects behind the opaque ABI handles.
 // ------------------------------------------------------------------------------------------------
