@@ -236,6 +236,7 @@ def algorithmic_bytes(s, model, nsel, nfsel, nodal=False, ncellsel=1):
     # L > 1: k_cutm_fill writes the layout of the simplices cut by at most one level set (the bulk), k_cut_walk the rest;
     # the whole layout is attributed to the tile kernel (the walk's share is not subtracted: an upper bound of its GB/s)
     k["k_cutm_fill"] += meas
+    k["k_cut_two_fill"] = None
     k["k_count_bgcells"] = L * Nc * ncellsel
     k["k_select_subcells"] = int(s.num_subcells) * L * 2 * ncellsel + 4 * nsel
     k["k_flag_subcells"] = int(s.num_subcells) * (4 + 2 * L + 4)

@@ -481,16 +481,18 @@ __device__ __forceinline__ void walk_item(const GcGrid& g, const GcLeaves& lv, c
 // their counters live in slot-indexed arrays, are added to the tile totals with atomics (integer sums: order-free) and are
 // replaced by their start offsets by the fill kernel of the tile before the walk writes.
 constexpr uint32_t CM_SLOW = 0x80000000u;  // sinfo: recorded simplex, low bits = slot
+constexpr int CM_NBK = WALK_NB + 1;          // launch buckets of the recorded simplices
 struct GcMulti {
   int nch;                // 2 + 2L
   int64_t ntiles;
   uint32_t* tile;         // [nch][ntiles] totals (count pass) -> exclusive bases (scan)
   uint32_t* sinfo;        // [nsimp] fast: outm | a << 16 | case << 20 | mixed << 24; recorded: CM_SLOW | slot
   uint32_t* slow_simp;    // [slot] -> stage-0 simplex
-  uint8_t* slow_bucket;   // [slot] -> launch bucket of the walk
+  uint8_t* slow_bucket;   // [slot] -> launch bucket: 0 = exactly two mixed level sets (k_cut_two), 1 + b = generic walk
+  uint32_t* slow_mask;    // [slot] -> mixed-sign level sets | all-OUT level sets << 16
   uint32_t* slow_val;     // [nch][slow_n] counters (walk count) -> start offsets (fill of the tile)
   int64_t slow_n;
-  uint32_t* slow_count;   // [WALK_NB] recorded simplices per bucket, [WALK_NB] their total (slot allocator)
+  uint32_t* slow_count;   // [CM_NBK] recorded simplices per bucket, [CM_NBK] their total (slot allocator)
   uint32_t fac_base[GC_LMAX];  // global offset of the facets of level set ls (merge_sub_face_data order)
   uint32_t fpt_base[GC_LMAX];
 };
@@ -582,13 +584,20 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
   }
 }
 
-// recorded simplices -> one dense slot list per launch bucket (any order inside a bucket)
+// recorded simplices -> one dense slot list per launch bucket (any order inside a bucket); one atomic per warp and bucket
 __global__ void k_cutm_bucketize(const uint8_t* __restrict__ slow_bucket, int64_t n, const uint32_t* __restrict__ base,
                                  uint32_t* __restrict__ cursor, uint32_t* __restrict__ lists) {
   const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= n) return;
-  const int b = slow_bucket[slot];
-  lists[base[b] + atomicAdd(cursor + b, 1u)] = (uint32_t)slot;
+  const int lane = threadIdx.x & 31;
+  const int b = slot < n ? (int)slow_bucket[slot] : -1;
+  for (int bk = 0; bk < CM_NBK; ++bk) {
+    const uint32_t bm = __ballot_sync(0xffffffffu, b == bk);
+    if (!bm) continue;
+    uint32_t first = 0u;
+    if (lane == __ffs(bm) - 1) first = atomicAdd(cursor + bk, (uint32_t)__popc(bm));
+    first = __shfl_sync(0xffffffffu, first, __ffs(bm) - 1);
+    if (b == bk) lists[base[bk] + first + (uint32_t)__popc(bm & ((1u << lane) - 1u))] = (uint32_t)slot;
+  }
 }
 
 // ================================================================================================
@@ -740,6 +749,8 @@ k_cutm_count(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict
   const int64_t s = tile * 32 + lane;
   uint32_t ncell = 0, npt = 0, nfac = 0;
   int a = -1;  // cutting stage of a fast simplex with facets
+  int rec_bucket = -1;
+  uint32_t rec_mask = 0u;
   if (s < nsimp) {
     CmLane<D> ln;
     cm_lane_setup<D>(g, vtab, s_swap, cutcells, s, ln);
@@ -773,15 +784,16 @@ k_cutm_count(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict
       }
     }
     if (__popc(mixed) > 1) {
-      // recorded for the tree walk, bucketed by the number of level sets the walk has to track
-      const int nw = __popc((mixed | 3u) & ((1u << L) - 1u));
+      // recorded: exactly two mixed level sets -> the stackless depth-2 kernel; more -> the generic tree walk, bucketed by
+      // the number of level sets it has to track
       int bucket = 0;
-      while (nw > walk_nw(bucket)) bucket++;
-      atomicAdd(&mu.slow_count[bucket], 1u);
-      const uint32_t slot = atomicAdd(&mu.slow_count[WALK_NB], 1u);
-      mu.slow_simp[slot] = (uint32_t)s;
-      mu.slow_bucket[slot] = (uint8_t)bucket;
-      mu.sinfo[s] = CM_SLOW | slot;
+      if (__popc(mixed) > 2) {
+        const int nw = __popc((mixed | 3u) & ((1u << L) - 1u));
+        while (nw > walk_nw(bucket)) bucket++;
+        bucket++;
+      }
+      rec_bucket = bucket;
+      rec_mask = mixed | (outm << 16);
     } else {
       const int aa = mixed ? (31 - __clz(mixed)) : 0;  // the only stage that can cut (stage 0 is visited in any case)
       const uint32_t vl = cm_skip_cell_stages<D>(TC, outm, L, aa);
@@ -794,6 +806,26 @@ k_cutm_count(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict
       npt = aa == 0 ? TC.npts[c] : ncell * (D + 1);
       if (nfac) a = aa;
       mu.sinfo[s] = outm | ((uint32_t)aa << 16) | ((uint32_t)c << 20) | (mixed ? 1u << 24 : 0u);
+    }
+  }
+  // recorded simplices: one slot each; the lanes of a warp share one atomic per counter
+  {
+    const uint32_t recm = __ballot_sync(0xffffffffu, rec_bucket >= 0);
+    if (recm) {
+      uint32_t base = 0u;
+      if (lane == __ffs(recm) - 1) base = atomicAdd(&mu.slow_count[CM_NBK], (uint32_t)__popc(recm));
+      base = __shfl_sync(0xffffffffu, base, __ffs(recm) - 1);
+      if (rec_bucket >= 0) {
+        const uint32_t slot = base + (uint32_t)__popc(recm & ((1u << lane) - 1u));
+        mu.slow_simp[slot] = (uint32_t)s;
+        mu.slow_bucket[slot] = (uint8_t)rec_bucket;
+        mu.slow_mask[slot] = rec_mask;
+        mu.sinfo[s] = CM_SLOW | slot;
+      }
+      for (int bk = 0; bk < CM_NBK; ++bk) {
+        const uint32_t bm = __ballot_sync(0xffffffffu, rec_bucket == bk);
+        if (bm && lane == __ffs(bm) - 1) atomicAdd(&mu.slow_count[bk], (uint32_t)__popc(bm));
+      }
     }
   }
   // tile totals of the fast simplices (the walk adds the recorded ones)
@@ -1197,6 +1229,462 @@ k_cutm_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
     for (int kk = 1; kk < L; ++kk)
       lay.sc_state[(int64_t)kk * lay.sc_pitch + cid] =
           (kk == aa) ? TC.sub_inout[cc][j] : (((om >> kk) & 1u) ? (int8_t)GC_OUT : (int8_t)GC_IN);
+  }
+}
+
+// ================================================================================================
+// Recorded simplices cut by EXACTLY TWO level sets a > b (all but a handful of the recorded ones: two surfaces meet
+// along curves, three only at points).  The refinement tree has a fixed shape, so it is walked without a stack, without
+// a point pool in local memory and with a fraction of the generic walk's code:
+//   stage a cuts the simplex (<= NPC points PA, shared by the 8 lanes of the simplex), its <= 2 facets are re-cut by b;
+//   every child of stage a (one lane each) is cut by b (points PB of the lane), the <= 2 facets of that cut are re-cut
+//   by a -- their vertices carry the ROUNDED values of level set a (zero up to round-off on the cut points of stage a),
+//   exactly like the reference's set_point_data! interpolates every pending level set (CutTriangulations.jl:123-135);
+//   everything below passes through the remaining all-IN / all-OUT stages as vertex permutations.
+// Same work split, counters and offsets as k_cut_walk (lane j < 6: child j; lanes 6, 7: the facets of stage a).
+// ================================================================================================
+constexpr int TWO_T = 64;
+
+template <int D>
+struct TwoSmem {
+  static constexpr int NPC = WalkCfg<D>::NPC, NPF = WalkCfg<D>::NPF;
+  static constexpr int PAS = 2 * D + 2;  // x, r, wa, wb
+  static constexpr int PBS = 2 * D + 1;  // x, r, wa
+  double pa[TWO_T / WALK_ITEMS][NPC * PAS];
+  double pb[TWO_T][NPC * PBS + 1];
+  double fe[TWO_T][NPF * 2 * D + 1];
+};
+
+template <int D, bool FILL>
+__global__ void __launch_bounds__(TWO_T)
+k_cut_two(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
+          const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
+          const int32_t* __restrict__ cutcells, GcMulti mu, GcLayout lay,
+          const uint32_t* __restrict__ slots, int64_t nslots) {
+  using SM = TwoSmem<D>;
+  constexpr int PAS = SM::PAS, PBS = SM::PBS;
+  constexpr uint32_t FULLM = 0xffffffffu;
+  extern __shared__ __align__(16) unsigned char two_smem[];
+  SM& sm = *reinterpret_cast<SM*>(two_smem);
+  __shared__ GcSimplexTable s_tab[2];
+  __shared__ uint8_t s_swap[8];
+  {
+    const uint32_t* src0 = reinterpret_cast<const uint32_t*>(tables + (D - 1));
+    const uint32_t* src1 = reinterpret_cast<const uint32_t*>(tables + (D - 2));
+    uint32_t* dst0 = reinterpret_cast<uint32_t*>(&s_tab[0]);
+    uint32_t* dst1 = reinterpret_cast<uint32_t*>(&s_tab[1]);
+    for (int i = threadIdx.x; i < (int)(sizeof(GcSimplexTable) / 4); i += blockDim.x) {
+      dst0[i] = src0[i];
+      dst1[i] = src1[i];
+    }
+  }
+  const uint8_t* vtab = (g.simplexified ? simp_raw : simp_pos) + (D - 2) * 24;
+  cm_swap_flags<D>(g, vtab, s_swap);
+  __syncthreads();
+  const GcSimplexTable& TC = s_tab[0];
+  const GcSimplexTable& TF = s_tab[1];
+  const int L = lv.L;
+  const int lane = threadIdx.x & 31;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t idx = gtid / WALK_ITEMS;
+  const int item = (int)(gtid % WALK_ITEMS);
+  const bool valid = idx < nslots;  // idle lanes still take part in the shuffles / warp barriers
+  const uint32_t slot = valid ? slots[idx] : 0u;
+  const int64_t s = valid ? (int64_t)mu.slow_simp[slot] : 0;
+  const uint32_t mask = valid ? mu.slow_mask[slot] : 3u;
+  const uint32_t mixed = mask & 0xFFFFu, outm = mask >> 16;
+  const int a = 31 - __clz(mixed), b = __ffs(mixed) - 1;
+  const int c_allout = (1 << (D + 1)) - 1, fc_allout = (1 << D) - 1;
+  double* PA = sm.pa[threadIdx.x / WALK_ITEMS];
+  double* PB = sm.pb[threadIdx.x];
+  double* FE = sm.fe[threadIdx.x];
+  auto cst = [&](int k) -> int8_t { return ((outm >> k) & 1u) ? (int8_t)GC_OUT : (int8_t)GC_IN; };
+
+  // ---- stage-0 simplex in arrival order at stage a: lane i <= D of the group sets up vertex i
+  CmLane<D> ln;
+  cm_lane_setup<D>(g, vtab, s_swap, cutcells, s, ln);
+  const int32_t bgcell1 = ln.bgcell1;
+  const uint32_t vl = cm_skip_cell_stages<D>(TC, outm, L, a);
+  if (item <= D) {
+    const int m = (vl >> (2 * item)) & 3u;
+    const int lvid = (ln.lv4 >> (8 * m)) & 0xFFu;
+    const int nijk[3] = {ln.ijk[0] + (lvid & 1), ln.ijk[1] + ((lvid >> 1) & 1), ln.ijk[2] + ((lvid >> 2) & 1)};
+    const double x[3] = {gc_coord(g, 0, nijk[0]), gc_coord(g, 1, nijk[1]), D == 3 ? gc_coord(g, 2, nijk[2]) : 0.0};
+    const int64_t node = (D == 3) ? ((int64_t)nijk[0] + (int64_t)g.nn[0] * ((int64_t)nijk[1] + (int64_t)g.nn[1] * nijk[2]))
+                                  : ((int64_t)nijk[0] + (int64_t)g.nn[0] * nijk[1]);
+    double* p = PA + item * PAS;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      p[d] = x[d];
+      p[D + d] = (double)((ln.rv4 >> (8 * m + d)) & 1u);
+    }
+    p[2 * D] = lv.leaf[a].kind == GECUT_LEAF_NODAL ? __ldg(lv.nodal[a] + (node - lv.nodal_base)) : gc_eval_leaf(lv.leaf[a], x, D);
+    p[2 * D + 1] = lv.leaf[b].kind == GECUT_LEAF_NODAL ? __ldg(lv.nodal[b] + (node - lv.nodal_base)) : gc_eval_leaf(lv.leaf[b], x, D);
+  }
+  __syncwarp();
+  // ---- stage a: case, cut points (lane D+1+q of the group computes cut point q)
+  int ca = 0;
+#pragma unroll
+  for (int i = 0; i <= D; ++i)
+    if (PA[i * PAS + 2 * D] > 0.0) ca |= 1 << i;
+  if (item > D && TC.inoutcut[ca] == GC_CUT) {
+    int q = D + 1;
+    for (int ed = 0; ed < TC.nedges; ++ed) {
+      const int ia = TC.edges[ed][0], ib = TC.edges[ed][1];
+      if (((ca >> ia) ^ (ca >> ib)) & 1) {
+        if (q == item) {
+          const double* p1 = PA + ia * PAS;
+          const double* p2 = PA + ib * PAS;
+          const double w1 = fabs(p1[2 * D]), w2 = fabs(p2[2 * D]);
+          const double coeff = __ddiv_rn(w1, __dadd_rn(w1, w2));
+          double* po = PA + q * PAS;
+#pragma unroll
+          for (int k = 0; k < PAS; ++k) po[k] = gc_lerp(p1[k], p2[k], coeff);  // x, r and BOTH pending values
+        }
+        q++;
+      }
+    }
+  }
+  __syncwarp();
+
+  uint32_t n_cells = 0, n_pts = 0, n_fa = 0, n_fpa = 0, n_fb = 0, n_fpb = 0;  // counters of this item
+  uint32_t cell_off = 0, pt_off = 0, fa_off = 0, fpa_off = 0, fb_off = 0, fpb_off = 0;
+  // emission helpers (FILL only)
+  auto put_facet = [&](uint32_t fid, uint32_t pb0, const uint8_t* lp, const double* nrm, const double (*pf)[3], int ls,
+                       int k1, int8_t s1, int k2, int8_t s2) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      lay.sf_c2p[(int64_t)fid * D + i] = (int32_t)(pb0 + lp[i] + 1);
+      lay.sf_N[(int64_t)fid * D + i] = nrm[i];
+    }
+    lay.sf_c2bg[fid] = bgcell1;
+    lay.sf_meas[fid] = integrate_one<D - 1>(simplex_meas<D, D - 1>(pf));
+    for (int kk = 0; kk < L; ++kk)
+      lay.sf_state[(int64_t)kk * lay.sf_pitch + fid] =
+          (kk == ls) ? (int8_t)GECUT_INTERFACE : (kk == k1 ? s1 : (kk == k2 ? s2 : cst(kk)));
+  };
+  // Two passes over the same code: pass 0 counts, the 8-lane scan turns the counters into offsets, pass 1 writes.
+  // (!FILL: pass 0 only.)
+  for (int pass = 0; pass < (FILL ? 2 : 1); ++pass) {
+    const bool wr = FILL && pass == 1;
+    if (valid && item < (int)TC.nsub[ca]) {
+      // ================= child `item` of stage a
+      const int j = item;
+      const int8_t sta = TC.sub_inout[ca][j];
+      const uint32_t q1 = cm_skip_cell_stages<D>(TC, outm, a, b);
+      double wbv[D + 1];
+#pragma unroll
+      for (int i = 0; i <= D; ++i) {
+        const double* p = PA + TC.sub_pts[ca][j][(q1 >> (2 * i)) & 3u] * PAS;
+#pragma unroll
+        for (int k = 0; k < PBS; ++k) PB[i * PBS + k] = p[k];
+        wbv[i] = p[2 * D + 1];
+      }
+      int cb = 0;
+#pragma unroll
+      for (int i = 0; i <= D; ++i)
+        if (wbv[i] > 0.0) cb |= 1 << i;
+      int np = D + 1;
+      if (TC.inoutcut[cb] == GC_CUT) {
+        for (int ed = 0; ed < TC.nedges; ++ed) {
+          const int ia = TC.edges[ed][0], ib = TC.edges[ed][1];
+          if (((cb >> ia) ^ (cb >> ib)) & 1) {
+            double wa1 = wbv[0], wb1 = wbv[0];
+#pragma unroll
+            for (int m = 1; m <= D; ++m) {
+              if (ia == m) wa1 = wbv[m];
+              if (ib == m) wb1 = wbv[m];
+            }
+            const double w1 = fabs(wa1), w2 = fabs(wb1);
+            const double coeff = __ddiv_rn(w1, __dadd_rn(w1, w2));
+#pragma unroll
+            for (int k = 0; k < PBS; ++k) PB[np * PBS + k] = gc_lerp(PB[ia * PBS + k], PB[ib * PBS + k], coeff);
+            np++;
+          }
+        }
+      }
+      // ---- facets of stage b, re-cut by a (then constant stages down to klast)
+      const int klast = b == 0 ? 1 : 0;
+      const int nfb = TC.nfac[cb];
+      uint32_t fo = fb_off, fpo = fpb_off;
+      for (int f = 0; f < nfb; ++f) {
+        const uint8_t* fp = TC.fac_pts[cb][f];
+        double nrm[3] = {0.0, 0.0, 0.0};
+        if (wr) unit_normal<D>(PB + fp[0] * PBS, PB + fp[1] * PBS, PB + fp[D - 1] * PBS, (double)TC.fac_orient[cb][f], nrm);
+        const uint32_t qf = cm_skip_facet_stages<D>(TF, outm, L, a, b);
+        int fca = 0;
+        double wav[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          const double* p = PB + fp[(qf >> (2 * i)) & 3u] * PBS;
+#pragma unroll
+          for (int k = 0; k < 2 * D; ++k) FE[i * 2 * D + k] = p[k];
+          wav[i] = p[2 * D];
+          if (wav[i] > 0.0) fca |= 1 << i;
+        }
+        int fn = D;
+        if (TF.inoutcut[fca] == GC_CUT) {
+          for (int ed = 0; ed < TF.nedges; ++ed) {
+            const int ia = TF.edges[ed][0], ib = TF.edges[ed][1];
+            if (((fca >> ia) ^ (fca >> ib)) & 1) {
+              double v1 = wav[0], v2 = wav[0];
+#pragma unroll
+              for (int m = 1; m < D; ++m) {
+                if (ia == m) v1 = wav[m];
+                if (ib == m) v2 = wav[m];
+              }
+              const double w1 = fabs(v1), w2 = fabs(v2);
+              const double coeff = __ddiv_rn(w1, __dadd_rn(w1, w2));
+#pragma unroll
+              for (int k = 0; k < 2 * D; ++k) FE[fn * 2 * D + k] = gc_lerp(FE[ia * 2 * D + k], FE[ib * 2 * D + k], coeff);
+              fn++;
+            }
+          }
+        }
+        const int nsf = TF.nsub[fca];
+        if (a == klast) {
+          // emitted at stage a itself: one point block, nsf children
+          if (wr) {
+            for (int p = 0; p < fn; ++p)
+#pragma unroll
+              for (int d = 0; d < D; ++d) {
+                lay.sf_X[(int64_t)(fpo + p) * D + d] = FE[p * 2 * D + d];
+                lay.sf_R[(int64_t)(fpo + p) * D + d] = FE[p * 2 * D + D + d];
+              }
+            for (int jj = 0; jj < nsf; ++jj) {
+              double pf[D][3];
+#pragma unroll
+              for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int d = 0; d < D; ++d) pf[i][d] = FE[TF.sub_pts[fca][jj][i] * 2 * D + d];
+              put_facet(fo + jj, fpo, TF.sub_pts[fca][jj], nrm, pf, b, a, TF.sub_inout[fca][jj], -1, 0);
+            }
+          }
+          fo += nsf;
+          fpo += fn;
+        } else {
+          const uint32_t q2 = cm_skip_facet_stages<D>(TF, outm, a, klast, b);
+          const int fc0 = ((outm >> klast) & 1u) ? fc_allout : 0;
+          if (wr) {
+            for (int jj = 0; jj < nsf; ++jj) {
+              uint8_t fv[D];
+#pragma unroll
+              for (int i = 0; i < D; ++i) fv[i] = TF.sub_pts[fca][jj][(q2 >> (2 * i)) & 3u];
+              const uint32_t pb0 = fpo + (uint32_t)jj * D;
+              double pf[D][3];
+#pragma unroll
+              for (int i = 0; i < D; ++i) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                  lay.sf_X[(int64_t)(pb0 + i) * D + d] = FE[fv[i] * 2 * D + d];
+                  lay.sf_R[(int64_t)(pb0 + i) * D + d] = FE[fv[i] * 2 * D + D + d];
+                  pf[i][d] = FE[fv[TF.sub_pts[fc0][0][i]] * 2 * D + d];
+                }
+              }
+              put_facet(fo + jj, pb0, TF.sub_pts[fc0][0], nrm, pf, b, a, TF.sub_inout[fca][jj], klast, TF.sub_inout[fc0][0]);
+            }
+          }
+          fo += nsf;
+          fpo += (uint32_t)nsf * D;
+        }
+      }
+      // ---- cells of this child
+      const int nsb = TC.nsub[cb];
+      uint32_t ncell_out, npt_out;
+      if (b == 0) {
+        if (wr) {
+          for (int p = 0; p < np; ++p)
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+              lay.sc_X[(int64_t)(pt_off + p) * D + d] = PB[p * PBS + d];
+              lay.sc_R[(int64_t)(pt_off + p) * D + d] = PB[p * PBS + D + d];
+            }
+          for (int jj = 0; jj < nsb; ++jj) {
+            const uint32_t cid = cell_off + jj;
+            int32_t row[D + 1];
+            double pc[D + 1][3];
+#pragma unroll
+            for (int i = 0; i <= D; ++i) {
+              const int li = TC.sub_pts[cb][jj][i];
+              row[i] = (int32_t)(pt_off + li + 1);
+#pragma unroll
+              for (int d = 0; d < D; ++d) pc[i][d] = PB[li * PBS + d];
+            }
+            store_c2p_row<D>(lay.sc_c2p, cid, row);
+            lay.sc_c2bg[cid] = bgcell1;
+            lay.sc_meas[cid] = integrate_one<D>(simplex_meas<D, D>(pc));
+            lay.sc_state[cid] = TC.sub_inout[cb][jj];
+            for (int kk = 1; kk < L; ++kk) lay.sc_state[(int64_t)kk * lay.sc_pitch + cid] = kk == a ? sta : cst(kk);
+          }
+        }
+        ncell_out = nsb;
+        npt_out = np;
+      } else {
+        const uint32_t qc = cm_skip_cell_stages<D>(TC, outm, b, 0);
+        const int c0 = (outm & 1u) ? c_allout : 0;
+        if (wr) {
+          for (int jj = 0; jj < nsb; ++jj) {
+            uint8_t cv[D + 1];
+#pragma unroll
+            for (int i = 0; i <= D; ++i) cv[i] = TC.sub_pts[cb][jj][(qc >> (2 * i)) & 3u];
+            const uint32_t pb0 = pt_off + (uint32_t)jj * (D + 1), cid = cell_off + jj;
+            int32_t row[D + 1];
+            double pc[D + 1][3];
+#pragma unroll
+            for (int i = 0; i <= D; ++i) {
+#pragma unroll
+              for (int d = 0; d < D; ++d) {
+                lay.sc_X[(int64_t)(pb0 + i) * D + d] = PB[cv[i] * PBS + d];
+                lay.sc_R[(int64_t)(pb0 + i) * D + d] = PB[cv[i] * PBS + D + d];
+              }
+              const int li = TC.sub_pts[c0][0][i];
+              row[i] = (int32_t)(pb0 + li + 1);
+#pragma unroll
+              for (int d = 0; d < D; ++d) pc[i][d] = PB[cv[li] * PBS + d];
+            }
+            store_c2p_row<D>(lay.sc_c2p, cid, row);
+            lay.sc_c2bg[cid] = bgcell1;
+            lay.sc_meas[cid] = integrate_one<D>(simplex_meas<D, D>(pc));
+            lay.sc_state[cid] = TC.sub_inout[c0][0];
+            const int8_t stb = TC.sub_inout[cb][jj];
+            for (int kk = 1; kk < L; ++kk)
+              lay.sc_state[(int64_t)kk * lay.sc_pitch + cid] = kk == a ? sta : (kk == b ? stb : cst(kk));
+          }
+        }
+        ncell_out = nsb;
+        npt_out = (uint32_t)nsb * (D + 1);
+      }
+      if (pass == 0) {
+        n_cells = ncell_out;
+        n_pts = npt_out;
+        n_fb = fo - fb_off;
+        n_fpb = fpo - fpb_off;
+      }
+    } else if (valid && item >= 6 && item - 6 < (int)TC.nfac[ca]) {
+      // ================= facet `item - 6` of stage a, re-cut by b (then constant stages down to stage 0)
+      const int f = item - 6;
+      const uint8_t* fp = TC.fac_pts[ca][f];
+      double nrm[3] = {0.0, 0.0, 0.0};
+      if (wr) unit_normal<D>(PA + fp[0] * PAS, PA + fp[1] * PAS, PA + fp[D - 1] * PAS, (double)TC.fac_orient[ca][f], nrm);
+      const uint32_t qf = cm_skip_facet_stages<D>(TF, outm, L, b, a);
+      int fcb = 0;
+      double wv[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const double* p = PA + fp[(qf >> (2 * i)) & 3u] * PAS;
+#pragma unroll
+        for (int k = 0; k < 2 * D; ++k) FE[i * 2 * D + k] = p[k];
+        wv[i] = p[2 * D + 1];
+        if (wv[i] > 0.0) fcb |= 1 << i;
+      }
+      int fn = D;
+      if (TF.inoutcut[fcb] == GC_CUT) {
+        for (int ed = 0; ed < TF.nedges; ++ed) {
+          const int ia = TF.edges[ed][0], ib = TF.edges[ed][1];
+          if (((fcb >> ia) ^ (fcb >> ib)) & 1) {
+            double v1 = wv[0], v2 = wv[0];
+#pragma unroll
+            for (int m = 1; m < D; ++m) {
+              if (ia == m) v1 = wv[m];
+              if (ib == m) v2 = wv[m];
+            }
+            const double w1 = fabs(v1), w2 = fabs(v2);
+            const double coeff = __ddiv_rn(w1, __dadd_rn(w1, w2));
+#pragma unroll
+            for (int k = 0; k < 2 * D; ++k) FE[fn * 2 * D + k] = gc_lerp(FE[ia * 2 * D + k], FE[ib * 2 * D + k], coeff);
+            fn++;
+          }
+        }
+      }
+      const int nsf = TF.nsub[fcb];
+      uint32_t nfo, npo;
+      if (b == 0) {
+        if (wr) {
+          for (int p = 0; p < fn; ++p)
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+              lay.sf_X[(int64_t)(fpa_off + p) * D + d] = FE[p * 2 * D + d];
+              lay.sf_R[(int64_t)(fpa_off + p) * D + d] = FE[p * 2 * D + D + d];
+            }
+          for (int jj = 0; jj < nsf; ++jj) {
+            double pf[D][3];
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+              for (int d = 0; d < D; ++d) pf[i][d] = FE[TF.sub_pts[fcb][jj][i] * 2 * D + d];
+            put_facet(fa_off + jj, fpa_off, TF.sub_pts[fcb][jj], nrm, pf, a, 0, TF.sub_inout[fcb][jj], -1, 0);
+          }
+        }
+        nfo = nsf;
+        npo = fn;
+      } else {
+        const uint32_t q2 = cm_skip_facet_stages<D>(TF, outm, b, 0, a);
+        const int fc0 = (outm & 1u) ? fc_allout : 0;
+        if (wr) {
+          for (int jj = 0; jj < nsf; ++jj) {
+            uint8_t fv[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) fv[i] = TF.sub_pts[fcb][jj][(q2 >> (2 * i)) & 3u];
+            const uint32_t pb0 = fpa_off + (uint32_t)jj * D;
+            double pf[D][3];
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+#pragma unroll
+              for (int d = 0; d < D; ++d) {
+                lay.sf_X[(int64_t)(pb0 + i) * D + d] = FE[fv[i] * 2 * D + d];
+                lay.sf_R[(int64_t)(pb0 + i) * D + d] = FE[fv[i] * 2 * D + D + d];
+                pf[i][d] = FE[fv[TF.sub_pts[fc0][0][i]] * 2 * D + d];
+              }
+            }
+            put_facet(fa_off + jj, pb0, TF.sub_pts[fc0][0], nrm, pf, a, b, TF.sub_inout[fcb][jj], 0, TF.sub_inout[fc0][0]);
+          }
+        }
+        nfo = nsf;
+        npo = (uint32_t)nsf * D;
+      }
+      if (pass == 0) {
+        n_fa = nfo;
+        n_fpa = npo;
+      }
+    }
+    if (pass == 1) break;
+    // ---- inclusive scans over the WALK_ITEMS lanes of the simplex
+    auto seg_scan = [&](uint32_t v) -> uint32_t {
+#pragma unroll
+      for (int o = 1; o < WALK_ITEMS; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(FULLM, v, o);
+        if ((lane & (WALK_ITEMS - 1)) >= o) v += up;
+      }
+      return v;
+    };
+    const uint32_t ic = seg_scan(n_cells), ip = seg_scan(n_pts), ifa = seg_scan(n_fa), ipa = seg_scan(n_fpa),
+                   ifb = seg_scan(n_fb), ipb = seg_scan(n_fpb);
+    uint32_t* val = mu.slow_val + slot;  // channel ch at val[ch * slow_n]
+    if (!FILL) {
+      if (valid && item == WALK_ITEMS - 1) {
+        const int64_t tile = s / 32;
+        val[0] = ic;
+        val[mu.slow_n] = ip;
+        val[(int64_t)(2 + a) * mu.slow_n] = ifa;
+        val[(int64_t)(2 + L + a) * mu.slow_n] = ipa;
+        val[(int64_t)(2 + b) * mu.slow_n] = ifb;
+        val[(int64_t)(2 + L + b) * mu.slow_n] = ipb;
+        atomicAdd(mu.tile + tile, ic);
+        atomicAdd(mu.tile + mu.ntiles + tile, ip);
+        if (ifa) atomicAdd(mu.tile + (int64_t)(2 + a) * mu.ntiles + tile, ifa);
+        if (ipa) atomicAdd(mu.tile + (int64_t)(2 + L + a) * mu.ntiles + tile, ipa);
+        if (ifb) atomicAdd(mu.tile + (int64_t)(2 + b) * mu.ntiles + tile, ifb);
+        if (ipb) atomicAdd(mu.tile + (int64_t)(2 + L + b) * mu.ntiles + tile, ipb);
+      }
+    } else if (valid) {
+      // start offsets of the simplex, left by the fill kernel of its tile (k_cutm_fill)
+      cell_off = val[0] + ic - n_cells;
+      pt_off = val[mu.slow_n] + ip - n_pts;
+      fa_off = mu.fac_base[a] + val[(int64_t)(2 + a) * mu.slow_n] + ifa - n_fa;
+      fpa_off = mu.fpt_base[a] + val[(int64_t)(2 + L + a) * mu.slow_n] + ipa - n_fpa;
+      fb_off = mu.fac_base[b] + val[(int64_t)(2 + b) * mu.slow_n] + ifb - n_fb;
+      fpb_off = mu.fpt_base[b] + val[(int64_t)(2 + L + b) * mu.slow_n] + ipb - n_fpb;
+    }
   }
 }
 
@@ -1765,18 +2253,42 @@ void launch_fast_fill(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, co
         res->cut_sc_ptr));
 }
 
-// one dense launch per bucket of recorded simplices (nslow[b] slots starting at lists + base[b]).  The buckets are
-// independent and each launch lasts as long as its slowest thread, so they run concurrently on side streams.
+void launch_two(gecut_ctx* ctx, const gecut_result* res, const GcMulti& mu, bool fill, int64_t nslots, const uint32_t* slots,
+                cudaStream_t stream) {
+  const unsigned nb = (unsigned)gc_div_up(nslots * WALK_ITEMS, TWO_T);
+  if (nb == 0) return;
+#define GC_TWO(DD, FF, NAME)                                                                                              \
+  do {                                                                                                                    \
+    static bool attr_done = false;                                                                                        \
+    if (!attr_done) {                                                                                                     \
+      cudaFuncSetAttribute(k_cut_two<DD, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TwoSmem<DD>));       \
+      attr_done = true;                                                                                                   \
+    }                                                                                                                     \
+    GC_LAUNCH(ctx, NAME, k_cut_two<DD, FF><<<nb, TWO_T, sizeof(TwoSmem<DD>), stream>>>(                                      \
+                             res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw, ctx->d_simplexify_pos,           \
+                             res->lay.cutcells, mu, res->lay, slots, nslots));                                              \
+  } while (0)
+  if (res->grid.D == 2) {
+    if (fill) GC_TWO(2, true, "k_cut_two_fill"); else GC_TWO(2, false, "k_cut_two_count");
+  } else {
+    if (fill) GC_TWO(3, true, "k_cut_two_fill"); else GC_TWO(3, false, "k_cut_two_count");
+  }
+#undef GC_TWO
+}
+
+// one dense launch per bucket of recorded simplices (nslow[b] slots starting at lists + base[b]): bucket 0 = the depth-2
+// kernel, 1 + b = the generic walk tracking walk_nw(b) level sets.  The buckets are independent and each launch lasts as
+// long as its slowest thread, so they run concurrently on side streams.
 int dispatch_walk(gecut_ctx* ctx, const gecut_result* res, const GcMulti& mu, bool fill, const int64_t* nslow,
                   const uint32_t* lists) {
   const int D = res->grid.D;
   int nonempty = 0;
-  for (int b = 0; b < WALK_NB; ++b) nonempty += nslow[b] > 0 ? 1 : 0;
+  for (int b = 0; b < CM_NBK; ++b) nonempty += nslow[b] > 0 ? 1 : 0;
   if (nonempty == 0) return GECUT_OK;
   const bool fork = nonempty > 1 && !ctx->prof_on;  // per-kernel profiling times launches on the main stream
   if (fork) {
     if (!ctx->ev_fork) GC_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-    for (int b = 0; b < WALK_NB; ++b) {
+    for (int b = 0; b < CM_NBK; ++b) {
       if (!ctx->side[b]) GC_CUDA(cudaStreamCreateWithFlags(&ctx->side[b], cudaStreamNonBlocking));
       if (!ctx->ev_join[b]) GC_CUDA(cudaEventCreateWithFlags(&ctx->ev_join[b], cudaEventDisableTiming));
     }
@@ -1787,10 +2299,11 @@ int dispatch_walk(gecut_ctx* ctx, const gecut_result* res, const GcMulti& mu, bo
     cudaStreamWaitEvent(ctx->side[b], ctx->ev_fork, 0);
     return ctx->side[b];
   };
-  int64_t base[WALK_NB];
+  int64_t base[CM_NBK];
   base[0] = 0;
-  for (int b = 1; b < WALK_NB; ++b) base[b] = base[b - 1] + nslow[b - 1];
-#define GC_WALK(DD, B) launch_walk<DD, walk_nw(B)>(ctx, res, mu, fill, nslow[B], lists + base[B], stream_of(B))
+  for (int b = 1; b < CM_NBK; ++b) base[b] = base[b - 1] + nslow[b - 1];
+  launch_two(ctx, res, mu, fill, nslow[0], lists + base[0], stream_of(0));
+#define GC_WALK(DD, B) launch_walk<DD, walk_nw(B)>(ctx, res, mu, fill, nslow[1 + B], lists + base[1 + B], stream_of(1 + B))
   if (D == 2) {
     GC_WALK(2, 0);
     GC_WALK(2, 1);
@@ -1806,7 +2319,7 @@ int dispatch_walk(gecut_ctx* ctx, const gecut_result* res, const GcMulti& mu, bo
   }
 #undef GC_WALK
   if (fork) {
-    for (int b = 0; b < WALK_NB; ++b) {
+    for (int b = 0; b < CM_NBK; ++b) {
       if (nslow[b] == 0) continue;
       GC_CUDA(cudaEventRecord(ctx->ev_join[b], ctx->side[b]));
       GC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[b], 0));
@@ -2044,40 +2557,43 @@ int gc_cut_cells(gecut_ctx* ctx, gecut_result* res) {
   GC_CHECK(scratch.alloc(&mu.sinfo, sizeof(uint32_t) * nsimp));
   GC_CHECK(scratch.alloc(&mu.slow_simp, sizeof(uint32_t) * nsimp));
   GC_CHECK(scratch.alloc(&mu.slow_bucket, (size_t)nsimp));
+  GC_CHECK(scratch.alloc(&mu.slow_mask, sizeof(uint32_t) * nsimp));
   GC_CHECK(scratch.alloc(&mu.slow_count, sizeof(uint32_t) * 16));
   GC_CHECK(scratch.alloc(&totals_dev, sizeof(uint64_t) * mu.nch));
   GC_CUDA(cudaMemsetAsync(mu.slow_count, 0, sizeof(uint32_t) * 16, ctx->stream));
   launch_fast_count(ctx, res, nsimp, mu);
   GC_CHECK(gc_launch_check(ctx, "k_cutm_count"));
-  int64_t nslow[WALK_NB], nslow_total = 0;
+  int64_t nslow[CM_NBK], nslow_total = 0;
   {
     uint32_t* hs = (uint32_t*)ctx->h_pinned;
-    GC_CUDA(cudaMemcpyAsync(hs, mu.slow_count, sizeof(uint32_t) * (WALK_NB + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    GC_CUDA(cudaMemcpyAsync(hs, mu.slow_count, sizeof(uint32_t) * (CM_NBK + 1), cudaMemcpyDeviceToHost, ctx->stream));
     GC_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (int b = 0; b < WALK_NB; ++b) nslow[b] = (int64_t)hs[b];
-    nslow_total = (int64_t)hs[WALK_NB];
+    for (int b = 0; b < CM_NBK; ++b) nslow[b] = (int64_t)hs[b];
+    nslow_total = (int64_t)hs[CM_NBK];
   }
-  if (getenv("GECUT_WALK_DEBUG")) fprintf(stderr, "[gecut] tree-walk buckets: %lld %lld %lld %lld %lld of %lld simplices\n", (long long)nslow[0], (long long)nslow[1], (long long)nslow[2], (long long)nslow[3], (long long)nslow[4], (long long)nsimp);
+  if (getenv("GECUT_WALK_DEBUG")) fprintf(stderr, "[gecut] recorded simplices: two level sets %lld, tree walk %lld %lld %lld %lld %lld, of %lld\n", (long long)nslow[0], (long long)nslow[1], (long long)nslow[2], (long long)nslow[3], (long long)nslow[4], (long long)nslow[5], (long long)nsimp);
   uint32_t* lists = nullptr;
   if (nslow_total > 0) {
     // slot-indexed counters of the recorded simplices, one dense slot list per launch bucket
     mu.slow_n = nslow_total;
     uint32_t* cursor = nullptr;
     GC_CHECK(scratch.alloc(&mu.slow_val, sizeof(uint32_t) * nslow_total * mu.nch));
+    // the depth-2 kernel writes only the channels of its two level sets
+    GC_CUDA(cudaMemsetAsync(mu.slow_val, 0, sizeof(uint32_t) * nslow_total * mu.nch, ctx->stream));
     GC_CHECK(scratch.alloc(&lists, sizeof(uint32_t) * nslow_total));
-    GC_CHECK(scratch.alloc(&cursor, sizeof(uint32_t) * 2 * WALK_NB));
-    uint32_t hb[2 * WALK_NB];
+    GC_CHECK(scratch.alloc(&cursor, sizeof(uint32_t) * 2 * CM_NBK));
+    uint32_t hb[2 * CM_NBK];
     uint32_t acc = 0;
-    for (int b = 0; b < WALK_NB; ++b) {
-      hb[b] = acc;            // base of bucket b
-      hb[WALK_NB + b] = 0u;   // cursor
+    for (int b = 0; b < CM_NBK; ++b) {
+      hb[b] = acc;           // base of bucket b
+      hb[CM_NBK + b] = 0u;   // cursor
       acc += (uint32_t)nslow[b];
     }
     uint32_t* hp = (uint32_t*)ctx->h_pinned + 512;  // the pinned page is reused right away: keep clear of the read-back area
     memcpy(hp, hb, sizeof(hb));
     GC_CUDA(cudaMemcpyAsync(cursor, hp, sizeof(hb), cudaMemcpyHostToDevice, ctx->stream));
     GC_LAUNCH(ctx, "k_cutm_bucketize", k_cutm_bucketize<<<(unsigned)gc_div_up(nslow_total, 256), 256, 0, ctx->stream>>>(
-        mu.slow_bucket, nslow_total, cursor, cursor + WALK_NB, lists));
+        mu.slow_bucket, nslow_total, cursor, cursor + CM_NBK, lists));
     GC_CHECK(dispatch_walk(ctx, res, mu, false, nslow, lists));
     GC_CHECK(gc_launch_check(ctx, "k_cut_walk(count)"));
   }
