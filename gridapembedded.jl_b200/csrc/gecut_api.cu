@@ -161,6 +161,10 @@ void free_result_arrays(gecut_result* r) {
   gc_free(ctx, l.sf_meas);
   gc_free(ctx, r->cutmask);
   gc_free(ctx, r->cutcount);
+  gc_free(ctx, r->cut22mask);
+  gc_free(ctx, r->tile_n22);
+  r->cut22mask = nullptr;
+  r->tile_n22 = nullptr;
   for (auto& kv : r->prog_rows) {
     gc_free(ctx, kv.second.first);
     gc_free(ctx, kv.second.second);
@@ -272,6 +276,7 @@ int do_cut(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* leaves, int
     ctx->err = "memset of the bg counters failed";
     return fail(GECUT_ERR_CUDA);
   }
+  r->want_n22 = !classify_only && L == 1 && g.simplexified && g.D == 3;
   st = gc_classify(ctx, r);
   if (st != GECUT_OK) return fail(st);
   st = gc_compact_cutcells(ctx, r);

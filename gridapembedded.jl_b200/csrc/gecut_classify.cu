@@ -178,6 +178,93 @@ namespace {
 // Warp-autonomous marching: every warp owns a tile of WXT x-words (32 cubes each) x TY cell rows and marches through
 // ZS layers of the last direction.  No block barrier in the loop (only __syncwarp); two node planes of sign words per
 // level set live in a warp-private slice of shared memory.
+
+// ---- box culling -----------------------------------------------------------------------------------------------------
+// Conservative sign of a closed-form level set over a whole box of nodes (x in [xlo, xhi], y in [ylo, yhi], a range of the
+// marching coordinate).  SPHERE / CYLINDER:  phi = |w|^2 - (w.v)^2 - R^2 = sum_d w_d^2 (1 - v_d^2) - 2 sum_{d<e} w_d w_e
+// v_d v_e - R^2 (an identity for ANY v; v = 0 for the sphere), PLANE: phi = w.v; every term is bounded by interval
+// arithmetic on the per-direction ranges.  The box is declared one-signed only when the bound clears zero by 1e-9 of the
+// magnitude of the terms -- six orders of magnitude above the rounding error of the reference formula (a few ulp of the
+// same magnitude), so the exact evaluation it replaces would have given the same sign at every node: results stay bit
+// identical, nodes near a surface are always evaluated exactly.
+constexpr int CLS_CBN = 10;
+constexpr int CLS_CZ = 8;  // layers per culling chunk
+
+__device__ __forceinline__ void cls_range_mul(double k, double lo, double hi, double* rlo, double* rhi) {
+  const double a = k * lo, b = k * hi;
+  *rlo = fmin(a, b);
+  *rhi = fmax(a, b);
+}
+
+template <int D>
+__device__ __forceinline__ void cls_tile_bounds(const gecut_leaf& lf, double xlo, double xhi, double ylo, double yhi,
+                                                double* cb) {
+  const double wxl = xlo - lf.x0[0], wxh = xhi - lf.x0[0];
+  const double wyl = (D == 3) ? ylo - lf.x0[1] : 0.0, wyh = (D == 3) ? yhi - lf.x0[1] : 0.0;
+  if (lf.kind == GECUT_LEAF_PLANE) {
+    cls_range_mul(lf.v[0], wxl, wxh, cb + 0, cb + 1);
+    if (D == 3) cls_range_mul(lf.v[1], wyl, wyh, cb + 2, cb + 3);
+    else cb[2] = cb[3] = 0.0;
+    return;
+  }
+  const bool sph = lf.kind == GECUT_LEAF_SPHERE;
+  const double v0 = sph ? 0.0 : lf.v[0], v1 = (sph || D == 2) ? 0.0 : lf.v[1];
+  const double sxl = (wxl <= 0.0 && wxh >= 0.0) ? 0.0 : fmin(wxl * wxl, wxh * wxh), sxh = fmax(wxl * wxl, wxh * wxh);
+  const double syl = (wyl <= 0.0 && wyh >= 0.0) ? 0.0 : fmin(wyl * wyl, wyh * wyh), syh = fmax(wyl * wyl, wyh * wyh);
+  cls_range_mul(1.0 - v0 * v0, sxl, sxh, cb + 0, cb + 1);
+  cls_range_mul(1.0 - v1 * v1, syl, syh, cb + 2, cb + 3);
+  if (D == 2) cb[2] = cb[3] = 0.0;
+  // cross term -2 v0 v1 wx wy: interval product of the two ranges
+  const double k = -2.0 * v0 * v1;
+  const double p1 = k * wxl * wyl, p2 = k * wxl * wyh, p3 = k * wxh * wyl, p4 = k * wxh * wyh;
+  cb[4] = fmin(fmin(p1, p2), fmin(p3, p4));
+  cb[5] = fmax(fmax(p1, p2), fmax(p3, p4));
+  cb[6] = wxl;
+  cb[7] = wxh;
+  cb[8] = wyl;
+  cb[9] = wyh;
+}
+
+// 0: mixed or too close to call, 1: every node of the box has phi <= 0 (IN), 2: every node has phi > 0 (OUT); the box is
+// the tile's node patch x the node planes with marching coordinate in [zlo, zhi]
+template <int D>
+__device__ __forceinline__ uint32_t cls_box_flag(const gecut_leaf& lf, const double* cb, double zlo, double zhi) {
+  const double wzl = zlo - lf.x0[D - 1], wzh = zhi - lf.x0[D - 1];
+  double lo, hi, mag;
+  if (lf.kind == GECUT_LEAF_PLANE) {
+    double tl, th;
+    cls_range_mul(lf.v[D - 1], wzl, wzh, &tl, &th);
+    lo = cb[0] + cb[2] + tl;
+    hi = cb[1] + cb[3] + th;
+    mag = fmax(fabs(cb[0]), fabs(cb[1])) + fmax(fabs(cb[2]), fabs(cb[3])) + fmax(fabs(tl), fabs(th));
+  } else {
+    const bool sph = lf.kind == GECUT_LEAF_SPHERE;
+    const double v0 = sph ? 0.0 : lf.v[0], v1 = (sph || D == 2) ? 0.0 : lf.v[1], vz = sph ? 0.0 : lf.v[D - 1];
+    const double szl = (wzl <= 0.0 && wzh >= 0.0) ? 0.0 : fmin(wzl * wzl, wzh * wzh), szh = fmax(wzl * wzl, wzh * wzh);
+    double ql, qh;
+    cls_range_mul(1.0 - vz * vz, szl, szh, &ql, &qh);
+    lo = cb[0] + cb[2] + ql + cb[4];
+    hi = cb[1] + cb[3] + qh + cb[5];
+    mag = fabs(cb[1]) + fabs(cb[3]) + fabs(qh) + fmax(fabs(cb[4]), fabs(cb[5]));
+    if (!sph) {  // cross terms with the marching direction: -2 v_d v_z w_d w_z, interval products
+      const double kx = -2.0 * v0 * vz, ky = -2.0 * v1 * vz;
+      const double a1 = kx * cb[6] * wzl, a2 = kx * cb[6] * wzh, a3 = kx * cb[7] * wzl, a4 = kx * cb[7] * wzh;
+      const double b1 = ky * cb[8] * wzl, b2 = ky * cb[8] * wzh, b3 = ky * cb[9] * wzl, b4 = ky * cb[9] * wzh;
+      const double xl = fmin(fmin(a1, a2), fmin(a3, a4)), xh = fmax(fmax(a1, a2), fmax(a3, a4));
+      const double yl = fmin(fmin(b1, b2), fmin(b3, b4)), yh = fmax(fmax(b1, b2), fmax(b3, b4));
+      lo += xl + yl;
+      hi += xh + yh;
+      mag += fmax(fabs(xl), fabs(xh)) + fmax(fabs(yl), fabs(yh));
+    }
+    const double c = lf.R * lf.R;
+    lo -= c;
+    hi -= c;
+    mag += c;
+  }
+  const double tol = 1e-9 * mag;
+  return lo > tol ? 2u : (hi < -tol ? 1u : 0u);
+}
+
 template <int D, bool SIMPLEX>
 struct ClsCfg {
   static constexpr int NVC = 1 << D;                             // vertices of the n-cube
@@ -270,9 +357,14 @@ __device__ __forceinline__ void cls_store_any(int8_t* out, const unsigned long l
 template <int D, bool SIMPLEX, int LH, bool SG /* some level set of the launch comes as precomputed sign words */>
 __global__ void __launch_bounds__(ClsCfg<D, SIMPLEX>::WARPS * 32, CLS_MIN_BLOCKS)
 k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64_t pitch,
-           uint32_t* __restrict__ cutmask, uint32_t* __restrict__ cutcount, const uint8_t* __restrict__ simplexify_raw,
+           uint32_t* __restrict__ cutmask, uint32_t* __restrict__ cutcount,
+           uint32_t* __restrict__ cut22count /* TET cells split 2-2 per group (one level set), or nullptr */,
+           uint32_t* __restrict__ cut22mask /* ... and which ones, laid out like cutmask; written for crossed groups only */,
+           const uint8_t* __restrict__ simplexify_raw,
            unsigned long long* __restrict__ bg_counts /* [L][2][6]: IN / OUT cells per level set and cell type */,
-           int ZS, int ntx, int nty, int64_t ntiles, int accumulate /* OR into the cut mask of earlier level-set chunks */) {
+           int ZS, int ntx, int nty, int64_t ntiles, int accumulate /* OR into the cut mask of earlier level-set chunks */,
+           const uint32_t* __restrict__ worklist /* tiles k_classify_cull left to this kernel (+ their number), or nullptr */,
+           const uint32_t* __restrict__ worklist_n) {
   using C = ClsCfg<D, SIMPLEX>;
   constexpr int NVC = C::NVC, CPC = C::CPC, LPW = C::LPW, CPL = C::CPL, WXT = C::WXT, TY = C::TY, RY = C::RY;
   constexpr int PW = C::PW, NQ = C::NQ, WARPS = C::WARPS;
@@ -280,6 +372,10 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
   constexpr int ROWD = 1 + 2 * (LH > 0 ? LH : 0);  // doubles per node row: y, then (wy^2, wy*vy) per hoisted level set
   constexpr uint32_t FULL = 0xffffffffu;
   extern __shared__ __align__(16) unsigned char cls_smem[];
+  if (worklist != nullptr) {  // the grid is sized for every tile; blocks past the end of the list leave at once
+    ntiles = (int64_t)*worklist_n;
+    if ((int64_t)blockIdx.x * C::WARPS >= ntiles) return;
+  }
   __shared__ unsigned long long s_lut[SIMPLEX ? (1 << NVC) : 1];  // sign byte of an n-cube -> states of its CPC simplices
   // per warp and level set: IN[6], OUT[6] per cell type, + IN/OUT of uniform groups (warp-private: no block barrier)
   __shared__ unsigned int s_cnt_all[WARPS][GC_LMAX * 14];
@@ -307,8 +403,9 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
   }
   __syncthreads();
 
-  const int64_t tile = (int64_t)blockIdx.x * WARPS + wid;
-  if (tile < ntiles) {
+  const int64_t slot = (int64_t)blockIdx.x * WARPS + wid;
+  if (slot < ntiles) {
+    const int64_t tile = worklist != nullptr ? (int64_t)worklist[slot] : slot;
     const int nx = g.n[0];
     const int ny = (D == 3) ? g.n[1] : 1;
     const int wxtot = gc_words_per_row(nx);
@@ -542,8 +639,14 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
         const int64_t cube0 = rowid * nx + i0 + c0;
         const int64_t gidx = rowid * wxtot + (w0 + ww_c);
         uint32_t cutacc[CPC];
+        uint32_t n22 = 0u;
+        bool slow_word = false;  // some level set of this launch crosses the lane's 32-cube word
 #pragma unroll
-        for (int t = 0; t < CPC; ++t) cutacc[t] = (accumulate && word_on) ? cutmask[gidx * CPC + t] : 0u;
+        for (int t = 0; t < CPC; ++t) cutacc[t] = 0u;
+        if (accumulate && word_on && cutcount[gidx] != 0u) {  // mask words exist only where the group count is not zero
+#pragma unroll
+          for (int t = 0; t < CPC; ++t) cutacc[t] = cutmask[gidx * CPC + t];
+        }
         for (int ls = 0; ls < L; ++ls) {
           uint32_t V[NVC];
 #pragma unroll
@@ -578,6 +681,7 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
             }
           } else {
             slow_seen = true;
+            slow_word = slow_word || !w_uni;
             if (SIMPLEX) {
               // per cell type: any / all over the simplex' vertices -> cut mask word and tallies
 #pragma unroll
@@ -590,6 +694,14 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
                   all &= a;
                 }
                 cutacc[t] |= any & ~all & livew;
+                if (D == 3 && cut22count != nullptr) {
+                  // a cut TET has 1, 2 or 3 vertices OUT: even parity = the 2-2 split (6 subcells, 8 points, 2 facets)
+                  const uint32_t par = V[gc_simplexify_raw(D - 2, t, 0)] ^ V[gc_simplexify_raw(D - 2, t, 1)] ^
+                                       V[gc_simplexify_raw(D - 2, t, 2)] ^ V[gc_simplexify_raw(D - 2, t, D)];
+                  const uint32_t s22 = any & ~all & livew & ~par;
+                  n22 += __popc(s22);
+                  if (word_on) cut22mask[gidx * CPC + t] = s22;  // read by k_cutmask_emit where the group count is not 0
+                }
                 if (lane_on) {
                   cnt_in[t] += __popc((~any >> c0) & livel);
                   cnt_out[t] += __popc((all >> c0) & livel);
@@ -641,7 +753,9 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
           }
           if (L > 1) flush_counts(ls);
         }
-        if (word_on) {
+        if (word_on && slow_word) {
+          // mask, count (and 2-2 count) were zeroed before the first launch: only the groups a surface crosses -- a few per
+          // cent -- store anything (scattered 4-byte stores of zeros cost partial-sector read-modify-writes in DRAM)
           uint32_t* cm = cutmask + gidx * CPC;
           uint32_t n = 0u;
 #pragma unroll
@@ -650,6 +764,9 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
             n += __popc(cutacc[t]);
           }
           cutcount[gidx] = n;
+          if (SIMPLEX && D == 3 && cut22count != nullptr) {
+            cut22count[gidx] = n22;
+          }
         }
       }
       __syncwarp();  // the next plane overwrites the buffer this step has just read
@@ -666,30 +783,140 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
 }
 
 
+// Kernel 1 of the closed-form classification: one warp per tile of WXT x-words x TY rows x CLS_CZ layers.  When every level
+// set of the launch has one sign on all nodes of the tile's box (interval bounds, ~3/4 of the tiles of a 512^3 sphere) the
+// tile's states are constants and it holds no cut cell: no node is evaluated, the bytes leave at store speed (few
+// registers, full occupancy).  The other tiles go on a work list for the marching kernel, whose latency-bound work then
+// comes in equal pieces and no longer shares its few resident warps with the streaming part.
+template <int D, bool SIMPLEX, int LH>
+__global__ void __launch_bounds__(256)
+k_classify_cull(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64_t pitch,
+                unsigned long long* __restrict__ bg_counts, int ntx, int nty, int64_t ntiles,
+                uint32_t* __restrict__ worklist, uint32_t* __restrict__ worklist_n) {
+  using C = ClsCfg<D, SIMPLEX>;
+  constexpr int CPC = C::CPC, LPW = C::LPW, CPL = C::CPL, WXT = C::WXT, TY = C::TY, NQ = C::NQ;
+  constexpr uint32_t FULL = 0xffffffffu;
+  __shared__ unsigned int s_uni[LH][2];
+  if (threadIdx.x < LH * 2) s_uni[threadIdx.x >> 1][threadIdx.x & 1] = 0u;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (tile < ntiles) {
+    const int nx = g.n[0];
+    const int ny = (D == 3) ? g.n[1] : 1;
+    const int tx = (int)(tile % ntx);
+    const int ty = (int)((tile / ntx) % nty);
+    const int tz = (int)(tile / ((int64_t)ntx * nty));
+    const int w0 = tx * WXT, j0 = ty * TY;
+    const int kz0 = g.k0 + tz * CLS_CZ, kz1 = min(kz0 + CLS_CZ, g.k1);
+    // the box: node columns 32*w0 .. 32*(w0+WXT) (incl. the halo column), node rows j0 .. j0+TY, node planes kz0 .. kz1
+    const double xlo = gc_coord(g, 0, 32 * w0), xhi = gc_coord(g, 0, min(32 * (w0 + WXT), g.nn[0] - 1));
+    const double ylo = (D == 3) ? gc_coord(g, 1, j0) : 0.0;
+    const double yhi = (D == 3) ? gc_coord(g, 1, min(j0 + TY, g.nn[1] - 1)) : 0.0;
+    const double zlo = gc_coord(g, D - 1, kz0), zhi = gc_coord(g, D - 1, kz1);
+    uint32_t uflags = 0u;
+    bool all_uni = true;
+#pragma unroll
+    for (int ls = 0; ls < LH; ++ls) {
+      double cb[CLS_CBN];
+      cls_tile_bounds<D>(lv.leaf[ls], xlo, xhi, ylo, yhi, cb);
+      const uint32_t uf = cls_box_flag<D>(lv.leaf[ls], cb, zlo, zhi);
+      uflags |= uf << (2 * ls);
+      all_uni = all_uni && uf != 0u;
+    }
+    if (!all_uni) {
+      if (lane == 0) worklist[atomicAdd(worklist_n, 1u)] = (uint32_t)tile;
+    } else {
+      const int task = lane / LPW, sub = lane % LPW;
+      const int ww_c = task % WXT, r_c = task / WXT;
+      const int c0 = sub * CPL;
+      const int i0 = 32 * (w0 + ww_c);
+      const int jc = j0 + r_c;
+      const int nl = max(0, min(CPL, min(32, nx - i0) - c0));  // live cubes of this lane
+      const bool lane_on = nl > 0 && jc < ny;
+      const bool vec_ok = (nx & 31) == 0;
+      const int64_t layer_rows = (D == 3) ? ny : 1;
+      const int nlay = kz1 - kz0;
+      const int64_t rowid0 = (int64_t)(kz0 - g.k0) * layer_rows + jc;
+      const int64_t step = layer_rows * nx * CPC;
+#pragma unroll
+      for (int ls = 0; ls < LH; ++ls) {
+        const uint32_t uf = (uflags >> (2 * ls)) & 3u;
+        unsigned int mine = 0u;
+        if (lane_on) {
+          unsigned long long e[NQ];
+          const unsigned long long pat = uf == 1u ? 0xFFFFFFFFFFFFFFFFull : 0x0101010101010101ull;
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) e[q] = pat;
+          int8_t* out = states + (int64_t)ls * pitch + (rowid0 * nx + i0 + c0) * CPC;
+          if (vec_ok) {
+#pragma unroll
+            for (int q = 0; q < CLS_CZ; ++q)
+              if (q < nlay) cls_store<NQ>(out + q * step, e);
+          } else {
+            for (int q = 0; q < nlay; ++q, out += step) cls_store_any<NQ>(out, e, nl * CPC);
+          }
+          mine = (unsigned int)(nl * nlay);
+        }
+        const unsigned int tot = __reduce_add_sync(FULL, mine);
+        if (lane == 0 && tot) atomicAdd(&s_uni[ls][uf == 1u ? 0 : 1], tot);
+      }
+    }
+  }
+  __syncthreads();
+  // one-signed tiles count for every cell type of the n-cube
+  if (threadIdx.x < LH * 2 * CPC) {
+    const int ls = threadIdx.x / (2 * CPC), io = (threadIdx.x / CPC) & 1, t = threadIdx.x % CPC;
+    const unsigned int v = s_uni[ls][io];
+    if (v) atomicAdd(&bg_counts[ls * 12 + io * 6 + t], (unsigned long long)v);
+  }
+}
+
+
 // ---- compaction of the cut mask -------------------------------------------------------------------
-template <int CPC>
-__global__ void k_cutmask_emit(const uint32_t* __restrict__ cutmask, int64_t ngroups, const uint32_t* __restrict__ offs,
-                               int nx, int wxtot, int32_t* __restrict__ cutcells) {
-  int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// One thread per 32-cube group; the exclusive scan of the group counts gives the group's first slot and (from the next
+// prefix) its count -- the mask words of empty groups are never read (k_classify writes only the words of crossed groups).
+// Cells leave in (cube, cell type) order = ascending cell id.
+// T22: one level set on TET cells -- also hand the fill kernel the base of every tile of 32 consecutive cut cells: the
+// number of 2-2 splits before the tile (group prefix from the scan + the 2-2 bits of the cells of this group before it)
+template <int CPC, bool T22>
+__global__ void __launch_bounds__(256)
+k_cutmask_emit(const uint32_t* __restrict__ cutmask, int64_t ngroups, const uint32_t* __restrict__ offs, uint32_t total,
+               int nx, int wxtot, int32_t* __restrict__ cutcells, const uint32_t* __restrict__ cut22mask,
+               const uint32_t* __restrict__ offs22, uint32_t total22, uint32_t* __restrict__ tile_n22) {
+  const int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gidx >= ngroups) return;
-  uint32_t m[CPC];
-  uint32_t any = 0;
+  uint32_t o = offs[gidx];
+  const uint32_t o_next = gidx + 1 < ngroups ? offs[gidx + 1] : total;
+  if (o_next == o) return;
+  uint32_t m[CPC], s[T22 ? CPC : 1];
+  uint32_t any = 0u, b = 0u;
 #pragma unroll
   for (int t = 0; t < CPC; ++t) {
     m[t] = cutmask[gidx * CPC + t];
     any |= m[t];
   }
-  if (!any) return;
-  int64_t rowid = gidx / wxtot;
-  int w = (int)(gidx % wxtot);
-  int64_t cube0 = rowid * nx + 32 * (int64_t)w;
-  uint32_t o = offs[gidx];
+  if (T22) {
+    b = offs22[gidx];
+    const bool has = (gidx + 1 < ngroups ? offs22[gidx + 1] : total22) != b;  // k_classify wrote the bits of such groups only
+#pragma unroll
+    for (int t = 0; t < CPC; ++t) s[t] = has ? cut22mask[gidx * CPC + t] : 0u;
+  }
+  const int64_t rowid = gidx / wxtot;
+  const int w = (int)(gidx - rowid * wxtot);
+  const int64_t cube0 = rowid * nx + 32 * (int64_t)w;
   while (any) {
-    int c = __ffs(any) - 1;
+    const int c = __ffs(any) - 1;
     any &= any - 1;
 #pragma unroll
     for (int t = 0; t < CPC; ++t)
-      if ((m[t] >> c) & 1u) cutcells[o++] = (int32_t)((cube0 + c) * CPC + t + 1);
+      if ((m[t] >> c) & 1u) {
+        if (T22) {
+          if ((o & 31u) == 0u) tile_n22[o >> 5] = b;
+          b += (s[t] >> c) & 1u;
+        }
+        cutcells[o++] = (int32_t)((cube0 + c) * CPC + t + 1);
+      }
   }
 }
 
@@ -770,7 +997,10 @@ int gc_classify(gecut_ctx* ctx, gecut_result* res) {
   const int wxtot = gc_words_per_row(nx);
   const int nlayers = g.k1 - g.k0;
   const int64_t rows = (g.D == 3) ? (int64_t)nlayers * g.n[1] : (int64_t)nlayers;
-  GC_CHECK(gc_malloc(ctx, (void**)&res->cutcount, sizeof(uint32_t) * rows * wxtot));
+  GC_CHECK(gc_malloc(ctx, (void**)&res->cutcount, sizeof(uint32_t) * rows * wxtot * (res->want_n22 ? 2 : 1)));
+  GC_CUDA(cudaMemsetAsync(res->cutcount, 0, sizeof(uint32_t) * rows * wxtot * (res->want_n22 ? 2 : 1), ctx->stream));
+  uint32_t* cut22 = res->want_n22 ? res->cutcount + rows * wxtot : nullptr;
+  if (res->want_n22) GC_CHECK(gc_malloc(ctx, (void**)&res->cut22mask, sizeof(uint32_t) * rows * wxtot * 6));
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
   // More than two level sets, all in closed form: chunks of two go through the hoisted kernel (LH = 2), each chunk
@@ -835,10 +1065,34 @@ int gc_classify(gecut_ctx* ctx, gecut_result* res) {
       const int acc = ls0 > 0 ? 1 : 0;
       bool any_signs = false;
       for (int i = 0; i < nl; ++i) any_signs = any_signs || lv.signs[i] != nullptr;
+      // closed-form leaves in the hoisted kernels: cull first (k_classify_cull writes the one-signed tiles of CLS_CZ layers at
+      // store speed and lists the others), then march only the listed tiles
+      bool cull = !any_signs && LH > 0;
+      for (int i = 0; i < nl; ++i) {
+        const int k = lv.leaf[i].kind;
+        cull = cull && (k == GECUT_LEAF_SPHERE || k == GECUT_LEAF_PLANE || k == GECUT_LEAF_CYLINDER);
+      }
+      uint32_t* wl = nullptr;
+      int zs_l = zs;
+      int64_t ntiles_l = ntiles;
+      unsigned nb_l = nb;
+      if (cull) {
+        zs_l = CLS_CZ;
+        ntiles_l = (int64_t)ntx * nty * gc_div_up(nlayers, CLS_CZ);
+        nb_l = (unsigned)gc_div_up(ntiles_l, C::WARPS);
+        GC_CHECK(gc_malloc(ctx, (void**)&wl, sizeof(uint32_t) * (ntiles_l + 1)));
+        GC_CUDA(cudaMemsetAsync(wl + ntiles_l, 0, sizeof(uint32_t), ctx->stream));
+        const unsigned nbc = (unsigned)gc_div_up(ntiles_l, 256 / 32);
+#define GC_CULL(LHV)                                                                                                  \
+  GC_LAUNCH(ctx, "k_classify_cull", k_classify_cull<D, S, LHV><<<nbc, 256, 0, ctx->stream>>>(                          \
+      g, lv, states, res->lay.bg_pitch, counts, ntx, nty, ntiles_l, wl, wl + ntiles_l))
+        if (nl == 1) GC_CULL(1); else GC_CULL(2);
+#undef GC_CULL
+      }
 #define GC_CLS(LHV, SGV)                                                                                              \
-  GC_LAUNCH(ctx, "k_classify", k_classify<D, S, LHV, SGV><<<nb, C::WARPS * 32, smem, ctx->stream>>>(                   \
-      g, lv, states, res->lay.bg_pitch, res->cutmask, res->cutcount, ctx->d_simplexify_raw, counts, zs, ntx, nty,     \
-      ntiles, acc))
+  GC_LAUNCH(ctx, "k_classify", k_classify<D, S, LHV, SGV><<<nb_l, C::WARPS * 32, smem, ctx->stream>>>(                 \
+      g, lv, states, res->lay.bg_pitch, res->cutmask, res->cutcount, cut22, res->cut22mask, ctx->d_simplexify_raw, counts, zs_l, ntx, nty, \
+      ntiles_l, acc, wl, wl ? wl + ntiles_l : nullptr))
       // the sign-word branch is compiled out of the closed-form instances (it cost the tet kernel 24 bytes of spills)
       if (any_signs) {
         if (nl == 1) GC_CLS(1, true);
@@ -850,20 +1104,24 @@ int gc_classify(gecut_ctx* ctx, gecut_result* res) {
         else GC_CLS(0, false);
       }
 #undef GC_CLS
+      gc_free(ctx, wl);  // stream-ordered cache: not handed out again before the two launches have run
     }
+    return (int)GECUT_OK;
   };
+  int lst;
   if (g.D == 3) {
     if (g.simplexified)
-      launch(std::integral_constant<int, 3>{}, std::true_type{});
+      lst = launch(std::integral_constant<int, 3>{}, std::true_type{});
     else
-      launch(std::integral_constant<int, 3>{}, std::false_type{});
+      lst = launch(std::integral_constant<int, 3>{}, std::false_type{});
   } else {
     if (g.simplexified)
-      launch(std::integral_constant<int, 2>{}, std::true_type{});
+      lst = launch(std::integral_constant<int, 2>{}, std::true_type{});
     else
-      launch(std::integral_constant<int, 2>{}, std::false_type{});
+      lst = launch(std::integral_constant<int, 2>{}, std::false_type{});
   }
   gc_free(ctx, sign_pool);  // stream-ordered cache: the block is not handed out before the launches above have run
+  GC_CHECK(lst);
   return gc_launch_check(ctx, "k_classify");
 }
 
@@ -875,28 +1133,40 @@ int gc_compact_cutcells(gecut_ctx* ctx, gecut_result* res) {
   const int64_t ngroups = rows * wxtot;
   uint32_t* counts = res->cutcount;  // cut cells per 32-cube group, written by k_classify
   uint64_t* total_dev = nullptr;
-  GC_CHECK(gc_malloc(ctx, (void**)&total_dev, sizeof(uint64_t)));
+  GC_CHECK(gc_malloc(ctx, (void**)&total_dev, sizeof(uint64_t) * 2));
   const int T = 256;
   const unsigned nb = (unsigned)gc_div_up(ngroups, T);
-  GC_CHECK(gc_exclusive_scan_u32(ctx, counts, counts, ngroups, total_dev));
+  // channel 0: cut cells per group; channel 1 (want_n22): TET cells split 2-2 per group -- one launch for both
+  GC_CHECK(gc_exclusive_scan_u32_multi(ctx, counts, counts, ngroups, res->want_n22 ? 2 : 1, total_dev));
   uint64_t* h = (uint64_t*)ctx->h_pinned;
-  GC_CUDA(cudaMemcpyAsync(h, total_dev, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  GC_CUDA(cudaMemcpyAsync(h + 1, res->bg_counts_dev, sizeof(uint64_t) * res->L * 12, cudaMemcpyDeviceToHost, ctx->stream));
+  h[1] = 0;
+  GC_CUDA(cudaMemcpyAsync(h, total_dev, sizeof(uint64_t) * (res->want_n22 ? 2 : 1), cudaMemcpyDeviceToHost, ctx->stream));
+  GC_CUDA(cudaMemcpyAsync(h + 2, res->bg_counts_dev, sizeof(uint64_t) * res->L * 12, cudaMemcpyDeviceToHost, ctx->stream));
   GC_CUDA(cudaStreamSynchronize(ctx->stream));
   const int64_t ncut = (int64_t)h[0];
-  for (int i = 0; i < res->L * 12; ++i) res->bg_counts[i] = (int64_t)h[1 + i];
+  res->n22 = (int64_t)h[1];
+  for (int i = 0; i < res->L * 12; ++i) res->bg_counts[i] = (int64_t)h[2 + i];
   res->sizes.num_cutcells = ncut;
   if (ncut > 0) {
     GC_CHECK(gc_malloc(ctx, (void**)&res->lay.cutcells, sizeof(int32_t) * ncut));
     switch (g.cpc) {
-      case 1: GC_LAUNCH(ctx, "k_cutmask_emit", k_cutmask_emit<1><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts, nx, wxtot, res->lay.cutcells)); break;
-      case 2: GC_LAUNCH(ctx, "k_cutmask_emit", k_cutmask_emit<2><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts, nx, wxtot, res->lay.cutcells)); break;
-      default: GC_LAUNCH(ctx, "k_cutmask_emit", k_cutmask_emit<6><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts, nx, wxtot, res->lay.cutcells)); break;
+      case 1: GC_LAUNCH(ctx, "k_cutmask_emit", k_cutmask_emit<1, false><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts, (uint32_t)ncut, nx, wxtot, res->lay.cutcells, nullptr, nullptr, 0u, nullptr)); break;
+      case 2: GC_LAUNCH(ctx, "k_cutmask_emit", k_cutmask_emit<2, false><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts, (uint32_t)ncut, nx, wxtot, res->lay.cutcells, nullptr, nullptr, 0u, nullptr)); break;
+      default:
+        if (res->want_n22) {
+          GC_CHECK(gc_malloc(ctx, (void**)&res->tile_n22, sizeof(uint32_t) * gc_div_up(ncut, 32)));
+          GC_LAUNCH(ctx, "k_cutmask_emit", k_cutmask_emit<6, true><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts, (uint32_t)ncut, nx, wxtot, res->lay.cutcells, res->cut22mask, counts + ngroups, (uint32_t)res->n22, res->tile_n22));
+        } else {
+          GC_LAUNCH(ctx, "k_cutmask_emit", k_cutmask_emit<6, false><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts, (uint32_t)ncut, nx, wxtot, res->lay.cutcells, nullptr, nullptr, 0u, nullptr));
+        }
+        break;
     }
   }
   int st = gc_launch_check(ctx, "cutmask compaction");
   gc_free(ctx, res->cutcount);
   res->cutcount = nullptr;
+  gc_free(ctx, res->cut22mask);
+  res->cut22mask = nullptr;
   gc_free(ctx, total_dev);
   return st;
 }

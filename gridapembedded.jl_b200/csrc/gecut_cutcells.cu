@@ -1803,82 +1803,6 @@ k_cut1_count(const GcGrid g, const GcLeaves lv, const uint8_t* __restrict__ simp
   }
 }
 
-// Tile totals for simplex bg cells (one stage-0 simplex per cut cell, so a tile is 32 consecutive cut cells): one warp
-// per tile, the three counters packed in one word and reduced with a single warp reduction -- no shared-memory atomics,
-// no block barrier; every lane has four independent cells in flight.
-template <int D>
-__global__ void __launch_bounds__(256)
-k_cut1_count_sx(const GcGrid g, const GcLeaves lv, const uint8_t* __restrict__ simp_raw,
-                const int32_t* __restrict__ cutcells, int64_t ncut, uint32_t* __restrict__ tile_cells,
-                uint32_t* __restrict__ tile_points, uint32_t* __restrict__ tile_facets, int64_t ntiles) {
-  constexpr int CPC = (D == 3) ? 6 : 2;
-  constexpr int TPW = 4;  // tiles per warp
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int32_t cell1[TPW];
-#pragma unroll
-  for (int j = 0; j < TPW; ++j) {
-    const int64_t k = (warp * TPW + j) * 32 + lane;
-    cell1[j] = k < ncut ? cutcells[k] : 0;
-  }
-  const double RR = __dmul_rn(lv.leaf[0].R, lv.leaf[0].R);
-#pragma unroll
-  for (int j = 0; j < TPW; ++j) {
-    const int64_t tile = warp * TPW + j;
-    if (tile >= ntiles) break;
-    uint32_t pk = 0u;
-    if (cell1[j] > 0) {
-      const uint32_t cell = (uint32_t)(cell1[j] - 1);
-      const uint32_t cube = cell / (uint32_t)CPC;
-      const int typ = (int)(cell - cube * (uint32_t)CPC);
-      int ijk[3];
-      const uint32_t row = cube / (uint32_t)g.n[0];
-      ijk[0] = (int)(cube - row * (uint32_t)g.n[0]);
-      if (D == 3) {
-        const uint32_t lay3 = row / (uint32_t)g.n[1];
-        ijk[1] = (int)(row - lay3 * (uint32_t)g.n[1]);
-        ijk[2] = (int)lay3 + g.k0;
-      } else {
-        ijk[1] = (int)row + g.k0;
-        ijk[2] = 0;
-      }
-      const uint32_t lv4 = *reinterpret_cast<const uint32_t*>(simp_raw + (D - 2) * 24 + typ * 4);
-      int nout = 0;
-#pragma unroll
-      for (int m = 0; m <= D; ++m) {
-        const int lvid = (lv4 >> (8 * m)) & 0xFFu;
-        const int nijk[3] = {ijk[0] + (lvid & 1), ijk[1] + ((lvid >> 1) & 1), ijk[2] + ((lvid >> 2) & 1)};
-        double v;
-        const int kind = lv.leaf[0].kind;
-        if (kind == GECUT_LEAF_NODAL) {
-          const int64_t node = (D == 3) ? ((int64_t)nijk[0] + (int64_t)g.nn[0] * ((int64_t)nijk[1] + (int64_t)g.nn[1] * nijk[2]))
-                                        : ((int64_t)nijk[0] + (int64_t)g.nn[0] * nijk[1]);
-          v = __ldg(lv.nodal[0] + (node - lv.nodal_base));
-        } else {
-          const double xx[3] = {gc_coord(g, 0, nijk[0]), gc_coord(g, 1, nijk[1]), D == 3 ? gc_coord(g, 2, nijk[2]) : 0.0};
-          if (kind == GECUT_LEAF_SPHERE) {
-            double w[3] = {__dsub_rn(xx[0], lv.leaf[0].x0[0]), __dsub_rn(xx[1], lv.leaf[0].x0[1]),
-                           D == 3 ? __dsub_rn(xx[2], lv.leaf[0].x0[2]) : 0.0};
-            v = __dsub_rn(gc_dot3(w, w, D), RR);
-          } else {
-            v = gc_eval_leaf(lv.leaf[0], xx, D);
-          }
-        }
-        nout += v > 0.0 ? 1 : 0;
-      }
-      const int kk = min(nout, D + 1 - nout);  // 0: uncut, 1: one vertex split off, 2: two-two split (TET only)
-      pk = (D == 3) ? (kk == 0 ? cut1_pack(1, 4, 0) : kk == 1 ? cut1_pack(4, 7, 1) : cut1_pack(6, 8, 2))
-                    : (kk == 0 ? cut1_pack(1, 3, 0) : cut1_pack(3, 5, 1));
-    }
-    const uint32_t total = __reduce_add_sync(0xffffffffu, pk);
-    if (lane == 0) {
-      tile_cells[tile] = total >> 21;
-      tile_points[tile] = (total >> 10) & 0x7FFu;
-      tile_facets[tile] = total & 0x3FFu;
-    }
-  }
-}
-
 // warp copy of n doubles from the staging buffer to global memory: every instruction moves 512 contiguous bytes
 // (16 per lane), which is conflict-free on the shared-memory side and whole sectors on the global side.  The caller
 // staged element k at src[k] with src = stage + (global index of element 0 mod 4), so both sides share the 16-byte phase.
@@ -2051,7 +1975,26 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
   const uint32_t excl = cut1_warp_scan(valid ? cut1_pack(nsub, np, nfac) : 0u, &total);
   const uint32_t lc = excl >> 21, lp = (excl >> 10) & 0x7FFu, lf = excl & 0x3FFu;    // tile-local offsets
   const uint32_t tc = total >> 21, tp = (total >> 10) & 0x7FFu, tf = total & 0x3FFu;  // tile totals
-  const uint32_t gc = tile_cells[tile], gp = tile_points[tile], gf = tile_facets[tile];  // tile bases
+  // tile bases.  n-cube cells: from the count pass + scan.  Simplex cells: every listed cell is cut, so the sizes are linear
+  // in the number of cells (c0 = 32*tile) and of 2-2 TET splits (tile_cells[tile], written by k_cutmask_emit) before the tile
+  uint32_t gc, gp, gf;
+  if (SX) {
+    const uint32_t c0 = (uint32_t)(tile * CUT1_TILE);
+    if (D == 3) {
+      const uint32_t b = tile_cells[tile];
+      gc = 4u * c0 + 2u * b;
+      gp = 7u * c0 + b;
+      gf = c0 + b;
+    } else {
+      gc = 3u * c0;
+      gp = 5u * c0;
+      gf = c0;
+    }
+  } else {
+    gc = tile_cells[tile];
+    gp = tile_points[tile];
+    gf = tile_facets[tile];
+  }
   // staged doubles start at `phase` so that shared and global memory have the same 32-byte phase (vector copy-out)
   const uint32_t phase = (uint32_t)(((uint64_t)gp * D) & 3u);
   double* stage_p = stage + phase;
@@ -2438,35 +2381,48 @@ static int gc_cut_cells_l1(gecut_ctx* ctx, gecut_result* res) {
   GcScratch scratch(ctx);  // tiles, totals, tile statistics: released on every exit path
   uint32_t* tiles = nullptr;
   uint64_t* totals_dev = nullptr;
-  GC_CHECK(scratch.alloc(&tiles, sizeof(uint32_t) * ntiles * 3));
-  GC_CHECK(scratch.alloc(&totals_dev, sizeof(uint64_t) * 3));
-  uint32_t *t_cells = tiles, *t_points = tiles + ntiles, *t_facets = tiles + 2 * ntiles;
-  {
+  uint32_t *t_cells = nullptr, *t_points = nullptr, *t_facets = nullptr;
+  uint64_t nsc = 0, nscp = 0, nsf = 0;
+  if (g.simplexified) {
+    // every listed cell is cut: TRI -> (3, 5, 1); TET -> (4, 7, 1), or (6, 8, 2) for the n22 cells that split 2-2 (counted by
+    // k_classify).  No count pass, no scan, no read-back; the tile bases come from k_cutmask_emit.
+    if (D == 3 && !res->want_n22) {
+      ctx->err = "internal: the 2-2 split count of the classification is missing";
+      return GECUT_ERR_INVALID;
+    }
+    const uint64_t nc = (uint64_t)ncut, b = (uint64_t)res->n22;
+    nsc = D == 3 ? 4 * nc + 2 * b : 3 * nc;
+    nscp = D == 3 ? 7 * nc + b : 5 * nc;
+    nsf = D == 3 ? nc + b : nc;
+    if (D == 3) t_cells = res->tile_n22;  // 2-2 TETs before every tile (k_cutmask_emit)
+  } else {
+    GC_CHECK(scratch.alloc(&tiles, sizeof(uint32_t) * ntiles * 3));
+    GC_CHECK(scratch.alloc(&totals_dev, sizeof(uint64_t) * 3));
+    t_cells = tiles;
+    t_points = tiles + ntiles;
+    t_facets = tiles + 2 * ntiles;
+  }
+  if (!g.simplexified) {
     // 128 cells per block = 128*nt0/32 whole tiles (nt0 in {1, 2, 6})
     const int cpb = 128;
     const unsigned nbc = (unsigned)gc_div_up(ncut, cpb);
-    if (g.simplexified) {
-      // one simplex per cut cell: warp-per-tile counting
-      const unsigned nbs = (unsigned)gc_div_up(ntiles, (int64_t)(256 / 32) * 4);
-      if (D == 2)
-        GC_LAUNCH(ctx, "k_cut1_count", k_cut1_count_sx<2><<<nbs, 256, 0, ctx->stream>>>(
-            g, res->leaves, ctx->d_simplexify_raw, res->lay.cutcells, ncut, t_cells, t_points, t_facets, ntiles));
-      else
-        GC_LAUNCH(ctx, "k_cut1_count", k_cut1_count_sx<3><<<nbs, 256, 0, ctx->stream>>>(
-            g, res->leaves, ctx->d_simplexify_raw, res->lay.cutcells, ncut, t_cells, t_points, t_facets, ntiles));
-    } else if (D == 2)
+    if (D == 2)
       GC_LAUNCH(ctx, "k_cut1_count", k_cut1_count<2><<<nbc, 128, 0, ctx->stream>>>(
           g, res->leaves, ctx->d_simplexify_raw, ctx->d_simplexify_pos, res->lay.cutcells, ncut, cpb, t_cells, t_points, t_facets, ntiles));
     else
       GC_LAUNCH(ctx, "k_cut1_count", k_cut1_count<3><<<nbc, 128, 0, ctx->stream>>>(
           g, res->leaves, ctx->d_simplexify_raw, ctx->d_simplexify_pos, res->lay.cutcells, ncut, cpb, t_cells, t_points, t_facets, ntiles));
   }
-  GC_CHECK(gc_launch_check(ctx, "k_cut1_count"));
-  GC_CHECK(gc_exclusive_scan_u32_multi(ctx, tiles, tiles, ntiles, 3, totals_dev));
-  uint64_t* h = (uint64_t*)ctx->h_pinned;
-  GC_CUDA(cudaMemcpyAsync(h, totals_dev, sizeof(uint64_t) * 3, cudaMemcpyDeviceToHost, ctx->stream));
-  GC_CUDA(cudaStreamSynchronize(ctx->stream));
-  const uint64_t nsc = h[0], nscp = h[1], nsf = h[2];
+  if (!g.simplexified) {
+    GC_CHECK(gc_launch_check(ctx, "k_cut1_count"));
+    GC_CHECK(gc_exclusive_scan_u32_multi(ctx, tiles, tiles, ntiles, 3, totals_dev));
+    uint64_t* h = (uint64_t*)ctx->h_pinned;
+    GC_CUDA(cudaMemcpyAsync(h, totals_dev, sizeof(uint64_t) * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    GC_CUDA(cudaStreamSynchronize(ctx->stream));
+    nsc = h[0];
+    nscp = h[1];
+    nsf = h[2];
+  }
   const uint64_t lim = 2147483647ull;
   if (nsc * (uint64_t)(D + 1) >= lim || nscp > lim || nsf > lim) {
     ctx->err = "Int32 ids of the SubCellData/SubFacetData layout would overflow";
@@ -2525,6 +2481,10 @@ static int gc_cut_cells_l1(gecut_ctx* ctx, gecut_result* res) {
 #undef GC_FILL1
   }
   int st = gc_launch_check(ctx, "k_cut1_fill");
+  if (res->tile_n22) {  // the tile bases have served (stream-ordered cache: not handed out before the fill has run)
+    gc_free(ctx, res->tile_n22);
+    res->tile_n22 = nullptr;
+  }
   if (st == GECUT_OK) {
     GC_LAUNCH(ctx, "k_tile_stats_reduce", k_tile_stats_reduce<<<NBR, 256, 0, ctx->stream>>>(tile_stats, ntiles, st_partial, st_ticket, st_out));
     st = gc_launch_check(ctx, "k_tile_stats_reduce");

@@ -149,6 +149,14 @@ struct gecut_result {
   GcLayout lay{};
   uint32_t* cutmask = nullptr;
   uint32_t* cutcount = nullptr;   // cut cells per 32-cube group (k_classify -> compaction, then freed)
+  // one level set on simplexified 3-D models: k_classify also counts, per group, the cut TETs whose vertices split 2-2
+  // (second channel of `cutcount`) and marks them; the three sizes of the layout are linear in (cut cells, 2-2 cells) and
+  // the compaction hands the fill kernel the number of 2-2 cells before every tile, so the L = 1 path needs no count pass,
+  // no second scan and no second read-back
+  bool want_n22 = false;
+  int64_t n22 = 0;
+  uint32_t* cut22mask = nullptr;  // which cut TETs split 2-2 (layout of cutmask; k_classify -> k_cutmask_emit, then freed)
+  uint32_t* tile_n22 = nullptr;   // 2-2 TETs before every tile of 32 cut cells (k_cutmask_emit -> k_cut1_fill, then freed)
   // memoised program rows (key = program tokens): results of multi-operator boolean programs over the subcell and the
   // bg-cell state rows, evaluated once and shared by every selection / integration that uses the same geometry
   std::map<std::string, std::pair<int8_t*, int8_t*>> prog_rows;

@@ -35,5 +35,5 @@ tot_i = sum(a[0] for a in agg.values()) or 1
 tot_s = sum(a[1] for a in agg.values()) or 1
 print("total warp instructions %.3g, stall samples %.3g" % (tot_i, tot_s))
 print("%6s %6s %8s  %s" % ("inst%", "stall%", "smem wf", "line"))
-for key, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+for key, a in sorted(agg.items(), key=lambda kv: -kv[1][int(sys.argv[4]) if len(sys.argv) > 4 else 1])[:top]:
     print("%6.2f %6.2f %8.3g  %s:%d  %s" % (100 * a[0] / tot_i, 100 * a[1] / tot_s, a[2], key[1], key[2], key[3]))
