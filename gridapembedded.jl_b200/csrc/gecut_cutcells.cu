@@ -2009,6 +2009,71 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
       coeff[e] = __ddiv_rn(w1, __dadd_rn(w1, w2));  // (CutTriangulations.jl:213-215)
     }
   }
+  // Simplex bg cells without per-entity measures (ANALYTIC): the IN / OUT measure of the cut cell in closed form from the
+  // cut fractions -- the crossing points are the zeros of the LINEAR interpolant of the vertex values, so the pieces are a
+  // corner simplex + its complement (1 vertex split off) or two wedges (2-2 split) whose barycentric volumes are products of
+  // the fractions; every term is a product of numbers in [0, 1] and only sums occur (no cancellation), so the result is
+  // within a few ulp of the exact measure of the piece -- the sum of the subcell measures the reference forms differs from
+  // it by the rounding of its own determinants (same order).  Saves the gather of 4 staged points per subcell.
+  constexpr bool ANALYTIC = SX && !WM;
+  double vi = 0.0, vo = 0.0;
+  if (ANALYTIC && valid) {
+    double x3[D + 1][3];
+#pragma unroll
+    for (int i = 0; i <= D; ++i)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) x3[i][d] = d < D ? X[i][d < D ? d : 0] : 0.0;
+    const double m0 = integrate_one<D>(simplex_meas<D, D>(x3));
+    const int nout = __popc((unsigned)c);
+    if (!iscut) {
+      if (nout == 0) vi = m0; else vo = m0;
+    } else if (D == 2 || nout != 2) {
+      // one vertex `iso` on its own side: fractions f_k from iso along its D cut edges; corner = prod f_k,
+      // rest = 1 - prod f_k = (1 - f_1) + f_1 (1 - f_2) + f_1 f_2 (1 - f_3)
+      const bool iso_out = nout == 1;
+      const int iso = __ffs(iso_out ? c : (~c & ((1 << (D + 1)) - 1))) - 1;
+      double prod = 1.0, rest = 0.0;
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        if (coeff[e] >= 0.0) {
+          const double cf = coeff[e], omc = __dsub_rn(1.0, cf);
+          const bool from_a = cut1_edge_a<D>(e) == iso;
+          const double f = from_a ? cf : omc, g1 = from_a ? omc : cf;
+          rest += prod * g1;
+          prod *= f;
+        }
+      }
+      const double corner = m0 * prod, other = m0 * rest;
+      vi = iso_out ? other : corner;
+      vo = iso_out ? corner : other;
+    } else {
+      // 2-2 split: OUT vertices p < q, IN vertices r < s; fractions from the OUT end: a = p->r, b = p->s, c = q->r, d = q->s.
+      // OUT wedge = (p,q,Ppr,Pps) + (q,Ppr,Pps,Pqs) + (q,Ppr,Pqs,Pqr) = ab + ad(1-b) + (1-a)cd, IN wedge by symmetry
+      const int pp = __ffs(c) - 1, rr = __ffs(~c & 15) - 1;
+      double fa = 0.0, fb = 0.0, fc = 0.0, fd = 0.0, ga = 0.0, gb = 0.0, gc_ = 0.0, gd = 0.0;
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        if (coeff[e] >= 0.0) {
+          const int ea = cut1_edge_a<D>(e), eb = cut1_edge_b<D>(e);
+          const bool a_out = (c >> ea) & 1;
+          const int vo_ = a_out ? ea : eb, vi_ = a_out ? eb : ea;
+          const double cf = coeff[e], omc = __dsub_rn(1.0, cf);
+          const double f = a_out ? cf : omc, g1 = a_out ? omc : cf;
+          const int role = (vo_ == pp ? 0 : 2) + (vi_ == rr ? 0 : 1);
+          if (role == 0) { fa = f; ga = g1; }
+          else if (role == 1) { fb = f; gb = g1; }
+          else if (role == 2) { fc = f; gc_ = g1; }
+          else { fd = f; gd = g1; }
+        }
+      }
+      vo = m0 * (fa * fb + fa * fd * gb + ga * fc * fd);
+      vi = m0 * (ga * gc_ + ga * gd * fc + fa * gb * gd);
+    }
+  }
+  if (ANALYTIC) {  // parked in the (otherwise unused) subcell-measure slots until the end of the tile: lane-private
+    vstage[lane] = vi;
+    vstage[CUT1_TILE + lane] = vo;
+  }
   if (valid) {
     if (t0 == 0) {  // first subcell / first point of this cut cell
       sc_ptr[2 * kcut] = gc + lc;
@@ -2056,13 +2121,6 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
     const uint32_t plo = (r.x >> 4) & 0xFFFu;
     const int j = (int)(idx - r.y);
     const uint32_t pts = *reinterpret_cast<const uint32_t*>(TC.sub_pts[cc][j]);  // D+1 local point ids
-    double pc[D + 1][3];
-#pragma unroll
-    for (int v = 0; v <= D; ++v) {
-      const double* pv = stage_p + (plo + ((pts >> (8 * v)) & 0xFFu)) * D;
-#pragma unroll
-      for (int d = 0; d < D; ++d) pc[v][d] = pv[d];
-    }
     const int64_t o = (int64_t)gc + idx;
     if (D == 3) {
       reinterpret_cast<int4*>(lay.sc_c2p)[o] =
@@ -2074,16 +2132,27 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
     }
     lay.sc_c2bg[o] = (int32_t)r.w;
     const int8_t io = TC.sub_inout[cc][j];
-    const double ms = integrate_one<D>(simplex_meas<D, D>(pc));
     lay.sc_state[o] = io;
-    if (WM) lay.sc_meas[o] = ms;
-    if (io == GC_IN) {
-      st_in += ms;
-      st_nin++;
+    if (ANALYTIC) {
+      if (io == GC_IN) st_nin++;
     } else {
-      st_out += ms;
+      double pc[D + 1][3];
+#pragma unroll
+      for (int v = 0; v <= D; ++v) {
+        const double* pv = stage_p + (plo + ((pts >> (8 * v)) & 0xFFu)) * D;
+#pragma unroll
+        for (int d = 0; d < D; ++d) pc[v][d] = pv[d];
+      }
+      const double ms = integrate_one<D>(simplex_meas<D, D>(pc));
+      if (WM) lay.sc_meas[o] = ms;
+      if (io == GC_IN) {
+        st_in += ms;
+        st_nin++;
+      } else {
+        st_out += ms;
+      }
+      if (SX) vstage[idx] = io == GC_IN ? ms : -ms;
     }
-    if (SX) vstage[idx] = io == GC_IN ? ms : -ms;
   }
   // ======================================== phase D: lane = subfacet
   for (uint32_t idx = lane; idx < tf; idx += CUT1_TILE) {
@@ -2111,6 +2180,11 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
     if (WM) lay.sf_meas[o] = mf;
     st_surf += mf;
   }
+  if (ANALYTIC) {  // lane = simplex
+    st_in = vstage[lane];
+    st_out = vstage[CUT1_TILE + lane];
+    if (valid) cell_vio[s] = make_double2(st_in, st_out);
+  }
   // fixed lane assignment + fixed shuffle tree: the tile sums are reproducible
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -2121,7 +2195,7 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
   }
   if (lane == 0) tile_stats[tile] = make_double4(st_in, st_out, st_surf, (double)st_nin);
   __syncwarp();
-  if (SX && valid) {
+  if (SX && !ANALYTIC && valid) {
     // simplex bg cells: a lane is a cut cell; IN / OUT measure of the cell in subcell order (the input of the P1
     // Laplacian and of get_cell_measure, no pass over the subcells later)
     const uint4 rr = rec[lane];  // case and first subcell of this lane's simplex (phase A)
