@@ -1818,6 +1818,33 @@ __device__ __forceinline__ void cut1_copy_doubles(double* __restrict__ dst, cons
   if (((n - head) & 1u) && lane == 0) dst[n - 1] = src[n - 1];
 }
 
+// The same copy handed to the TMA engine: one elected lane issues a bulk shared -> global copy of the 16-byte aligned body
+// (cp.async.bulk, SASS UBLKCP), so the tile's points leave the staging buffer without passing through the LSU data pipe
+// that bounds this kernel (ncu: 84 % of its peak; the LDS.128 + STG.128 pairs of the warp copy were 10 % of its shared-
+// memory wavefronts and half of its global-store sectors).  Every lane fences its own staging writes towards the async
+// proxy first; the caller waits with cut1_bulk_wait_read before the staging buffer is written again (or the warp exits).
+__device__ __forceinline__ void cut1_bulk_copy_doubles(double* __restrict__ dst, const double* __restrict__ src, uint32_t n,
+                                                       uint32_t phase, int lane) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) {
+    const uint32_t head = min(n, phase & 1u);  // element before the first 16-byte boundary
+    if (head) dst[0] = src[0];
+    const uint32_t nvec = (n - head) >> 1;
+    if (nvec) {
+      const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(src + head);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + head), "r"(saddr), "r"(nvec * 16u)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    if ((n - head) & 1u) dst[n - 1] = src[n - 1];
+  }
+}
+__device__ __forceinline__ void cut1_bulk_wait_read(int lane) {
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncwarp();
+}
+
 // edge e of the simplex in Gridap order: TRI [1,2],[1,3],[2,3]; TET [1,2],[1,3],[2,3],[1,4],[2,4],[3,4] (0-based ends)
 template <int D>
 __device__ __forceinline__ constexpr int cut1_edge_a(int e) {
@@ -2107,9 +2134,9 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
     for (int f = 0; f < NFAC; ++f)
       if (f < nfac) own_f[lf + f] = (uint8_t)lane;
   }
-  __syncwarp();
-  // ======================================== phase X: point_to_coords of the tile
-  cut1_copy_doubles(lay.sc_X + (int64_t)gp * D, stage_p, tp * D, phase, lane);
+  // ======================================== phase X: point_to_coords of the tile (asynchronous: the staged points are only
+  // read until phase R)
+  cut1_bulk_copy_doubles(lay.sc_X + (int64_t)gp * D, stage_p, tp * D, phase, lane);
   // ======================================== phase C: lane = subcell
   // tile statistics for the selections of a single-leaf geometry (no pass over the subcells later): measure of the IN and
   // of the OUT subcells, measure of the subfacets, number of IN subcells
@@ -2208,6 +2235,7 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
     cell_vio[s] = make_double2(vi, vo);  // SX: one stage-0 simplex per cut cell
   }
   // ======================================== phase R: reference coordinates (lane = simplex), same staging buffer
+  cut1_bulk_wait_read(lane);  // the physical points have left the staging buffer
   if (valid) {
 #pragma unroll
     for (int i = 0; i <= D; ++i)
@@ -2230,8 +2258,8 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
       }
     }
   }
-  __syncwarp();
-  cut1_copy_doubles(lay.sc_R + (int64_t)gp * D, stage_p, tp * D, phase, lane);
+  cut1_bulk_copy_doubles(lay.sc_R + (int64_t)gp * D, stage_p, tp * D, phase, lane);
+  cut1_bulk_wait_read(lane);  // the block's shared memory must stay until the engine has read it
 }
 
 template <int D, int NW>
