@@ -216,6 +216,12 @@ def lib():
     L.gecut_profile.restype = cint
     L.gecut_profile_report.argtypes = [vp]
     L.gecut_profile_report.restype = C.c_char_p
+    L.gecut_host_alloc.argtypes = [C.c_size_t, P(vp)]
+    L.gecut_host_free.argtypes = [vp]
+    L.gecut_host_register.argtypes = [vp, C.c_size_t]
+    L.gecut_host_unregister.argtypes = [vp]
+    for name in ("gecut_host_alloc", "gecut_host_free", "gecut_host_register", "gecut_host_unregister"):
+        getattr(L, name).restype = cint
     L.gecut_cut.argtypes = [vp, P(Grid), P(LeafRec), cint, P(vp), cint, P(vp)]
     L.gecut_classify.argtypes = [vp, P(Grid), P(LeafRec), cint, P(vp), cint, P(vp)]
     L.gecut_eval_leaf_at_nodes.argtypes = [vp, P(Grid), P(LeafRec), vp, cint]
@@ -281,12 +287,31 @@ COMM_SYMBOLS = ["gecut_comm_unique_id", "gecut_comm_init", "gecut_comm_free", "g
 
 EXPORTED_SYMBOLS = FACET_SYMBOLS + COMM_SYMBOLS + ["gecut_create", "gecut_destroy", "gecut_set_stream", "gecut_last_error", "gecut_launch_count",
                     "gecut_profile", "gecut_profile_report", "gecut_trim",
+                    "gecut_host_alloc", "gecut_host_free", "gecut_host_register", "gecut_host_unregister",
                     "gecut_cut", "gecut_classify", "gecut_eval_leaf_at_nodes", "gecut_result_free",
                     "gecut_result_sizes", "gecut_result_device_ptrs", "gecut_result_copy", "gecut_bgcell_to_inoutcut",
                     "gecut_subcell_to_inout", "gecut_select_cells", "gecut_select_boundary", "gecut_selection_free",
                     "gecut_selection_sizes", "gecut_selection_copy", "gecut_selection_gather",
                     "gecut_integrate_measure", "gecut_integrate_laplacian", "gecut_selection_device_laplacian",
                     "gecut_cell_measure"]
+
+
+def pinned_empty(shape, dtype):
+    """numpy array over page-locked memory from gecut_host_alloc (the zero-copy destination of gecut_result_copy: what the
+    Julia shim wraps with unsafe_wrap); freed with the array."""
+    import weakref
+    import numpy as np
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) if len(tuple(shape)) else 1
+    ptr = C.c_void_p()
+    L = lib()
+    rc = L.gecut_host_alloc(C.c_size_t(max(n, 1) * dt.itemsize), C.byref(ptr))
+    if rc != GECUT_OK:
+        raise GecutError(f"gecut_host_alloc failed with status {rc}")
+    buf = (C.c_char * (max(n, 1) * dt.itemsize)).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
+    weakref.finalize(buf, L.gecut_host_free, ptr)
+    return arr
 
 
 class Context:

@@ -536,6 +536,39 @@ const char* gecut_last_error(const gecut_ctx* ctx) { return ctx ? ctx->err.c_str
 
 int64_t gecut_launch_count(const gecut_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int gecut_host_alloc(size_t bytes, void** ptr) {
+  if (!ptr) return GECUT_ERR_INVALID;
+  *ptr = nullptr;
+  if (bytes == 0) return GECUT_OK;
+  const cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *ptr = nullptr;
+    return e == cudaErrorMemoryAllocation ? GECUT_ERR_OOM : GECUT_ERR_CUDA;
+  }
+  return GECUT_OK;
+}
+
+int gecut_host_free(void* ptr) {
+  if (!ptr) return GECUT_OK;
+  return cudaFreeHost(ptr) == cudaSuccess ? GECUT_OK : GECUT_ERR_CUDA;
+}
+
+int gecut_host_register(void* ptr, size_t bytes) {
+  if (!ptr || bytes == 0) return GECUT_ERR_INVALID;
+  const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? GECUT_ERR_OOM : GECUT_ERR_CUDA;
+  }
+  return GECUT_OK;
+}
+
+int gecut_host_unregister(void* ptr) {
+  if (!ptr) return GECUT_ERR_INVALID;
+  return cudaHostUnregister(ptr) == cudaSuccess ? GECUT_OK : GECUT_ERR_CUDA;
+}
+
 int gecut_trim(gecut_ctx* ctx) {
   if (!ctx) return GECUT_ERR_INVALID;
   DeviceGuard guard(ctx->device);

@@ -19,6 +19,7 @@
 #ifndef GECUT_H
 #define GECUT_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -173,6 +174,16 @@ int gecut_result_free(gecut_result* res);
 int gecut_result_sizes(const gecut_result* res, gecut_sizes* sizes);
 int gecut_result_device_ptrs(const gecut_result* res, gecut_buffers* dev);
 int gecut_result_copy(const gecut_result* res, const gecut_buffers* host);
+
+/* Page-locked host memory for the destinations of gecut_result_copy / gecut_selection_copy / the element matrices: a
+ * binding wraps the pointer in its own array type without a copy (Julia: unsafe_wrap(Vector{Point{D,Float64}}, ptr, n) feeds
+ * SubCellData, src/Interfaces/SubCellTriangulations.jl:2-7, directly) and the device -> host copy runs at the PCIe rate in one
+ * pass (pageable destinations are staged by the driver at a fraction of it).  Portable across contexts; no context needed.
+ * gecut_host_register pins memory the host language allocated itself (e.g. a Julia Vector the GC owns). */
+int gecut_host_alloc(size_t bytes, void** ptr);
+int gecut_host_free(void* ptr);
+int gecut_host_register(void* ptr, size_t bytes);
+int gecut_host_unregister(void* ptr);
 
 /* ---- selectors -------------------------------------------------------------------------------------------------- */
 /* compute_bgcell_to_inoutcut(cut, geo) (src/Interfaces/EmbeddedDiscretizations.jl:91-105) -> Nc Int8 on the host */

@@ -121,32 +121,68 @@ function _run(cutter::B200LevelSetCutter, fname::Symbol, bgmodel, geom, simplexi
   res[], oid_to_ls
 end
 
+# ---- zero-copy host arrays (SURVEY 8f.3) -----------------------------------------------------------------------------------
+# The layout arrays are allocated page-locked by the library (gecut_host_alloc) and wrapped in place: gecut_result_copy's
+# cudaMemcpyAsync lands directly in the memory that becomes `SubCellData.point_to_coords::Vector{Point{D,Float64}}`
+# (`Point{D,Float64}` is isbits, so the wrap is a reinterpretation of the D*n doubles, src/Interfaces/SubCellTriangulations.jl:2-7).
+# One pass over the data, at the PCIe rate; no `collect`, no pageable staging.  The memory returns to the library when the
+# wrapping Array is garbage collected.
+function _pinned(::Type{T}, n::Integer) where {T}
+  n == 0 && return Vector{T}(undef, 0)
+  r = Ref{Ptr{Cvoid}}(C_NULL)
+  st = ccall((:gecut_host_alloc, libgecut), Cint, (Csize_t, Ptr{Ptr{Cvoid}}), n * sizeof(T), r)
+  st == 0 || error("gecut_host_alloc($(n * sizeof(T)) bytes) failed with status $st")
+  p = r[]
+  v = unsafe_wrap(Vector{T}, Ptr{T}(p), n; own = false)
+  finalizer(_ -> ccall((:gecut_host_free, libgecut), Cint, (Ptr{Cvoid},), p), v)
+  v
+end
+
+# L rows of n Int8 in ONE pinned block (gecut_result_copy writes rows at pitch n); every row is its own Vector{Int8}, as the
+# reference's Vector{Vector{Int8}} wants, and the block is released when the last row has been collected
+function _pinned_rows(n::Integer, L::Integer)
+  (n == 0 || L == 0) && return [Vector{Int8}(undef, n) for _ in 1:L], Ptr{Int8}(C_NULL)
+  r = Ref{Ptr{Cvoid}}(C_NULL)
+  st = ccall((:gecut_host_alloc, libgecut), Cint, (Csize_t, Ptr{Ptr{Cvoid}}), n * L, r)
+  st == 0 || error("gecut_host_alloc($(n * L) bytes) failed with status $st")
+  p = r[]
+  alive = Threads.Atomic{Int}(L)
+  rows = [unsafe_wrap(Vector{Int8}, Ptr{Int8}(p) + (l - 1) * n, n; own = false) for l in 1:L]
+  for row in rows
+    finalizer(row) do _
+      Threads.atomic_sub!(alive, 1) == 1 && ccall((:gecut_host_free, libgecut), Cint, (Ptr{Cvoid},), p)
+    end
+  end
+  rows, Ptr{Int8}(p)
+end
+
 function _copy_out(cutter, res)
   sz = Ref{GecutSizes}()
   _check(cutter, ccall((:gecut_result_sizes, libgecut), Cint, (Ptr{Cvoid}, Ref{GecutSizes}), res, sz), "gecut_result_sizes")
   s = sz[]; D = Int(s.D); L = Int(s.num_levelsets)
-  bg  = Matrix{Int8}(undef, s.num_bgcells, L)
-  c2p = Vector{Int32}(undef, s.num_subcells*(D+1)); c2b = Vector{Int32}(undef, s.num_subcells)
-  X = Vector{Float64}(undef, s.num_subcell_points*D); R = similar(X)
-  sci = Matrix{Int8}(undef, s.num_subcells, L)
-  f2p = Vector{Int32}(undef, s.num_subfacets*D); f2b = Vector{Int32}(undef, s.num_subfacets)
-  N = Vector{Float64}(undef, s.num_subfacets*D)
-  # one level set: the subfacet points ARE the subcell points (CutTriangulations.jl:365-378): share the host arrays
+  P = Point{D,Float64}
+  bg, bgp   = _pinned_rows(s.num_bgcells, L)
+  sci, scip = _pinned_rows(s.num_subcells, L)
+  sfi, sfip = _pinned_rows(s.num_subfacets, L)
+  c2p = _pinned(Int32, s.num_subcells*(D+1)); c2b = _pinned(Int32, s.num_subcells)
+  X = _pinned(P, s.num_subcell_points); R = _pinned(P, s.num_subcell_points)
+  f2p = _pinned(Int32, s.num_subfacets*D); f2b = _pinned(Int32, s.num_subfacets)
+  N = _pinned(P, s.num_subfacets)
+  # one level set: the subfacet points ARE the subcell points (CutTriangulations.jl:365-378): the two structs share the arrays
   alias = s.subfacet_points_alias != 0
-  fX = alias ? X : Vector{Float64}(undef, s.num_subfacet_points*D); fR = alias ? R : similar(fX)
-  sfi = Matrix{Int8}(undef, s.num_subfacets, L)
-  b = GecutBuffers(pointer(bg), C_NULL, pointer(c2p), pointer(c2b), pointer(X), pointer(R), pointer(sci),
-                   pointer(f2p), pointer(f2b), pointer(N), alias ? Ptr{Float64}(C_NULL) : pointer(fX),
-                   alias ? Ptr{Float64}(C_NULL) : pointer(fR), pointer(sfi), 0, 0, 0)
+  fX = alias ? X : _pinned(P, s.num_subfacet_points); fR = alias ? R : _pinned(P, s.num_subfacet_points)
+  dp(v) = Ptr{Float64}(pointer(v))
+  b = GecutBuffers(bgp, C_NULL, pointer(c2p), pointer(c2b), dp(X), dp(R), scip,
+                   pointer(f2p), pointer(f2b), dp(N), alias ? Ptr{Float64}(C_NULL) : dp(fX),
+                   alias ? Ptr{Float64}(C_NULL) : dp(fR), sfip, 0, 0, 0)
   GC.@preserve bg c2p c2b X R sci f2p f2b N fX fR sfi begin
     _check(cutter, ccall((:gecut_result_copy, libgecut), Cint, (Ptr{Cvoid}, Ref{GecutBuffers}), res, b), "gecut_result_copy")
   end
-  pts(v) = collect(reinterpret(Point{D,Float64}, v))
+  # Table ptrs are arithmetic (every row has D+1 resp. D entries): 4 bytes per row, filled on the host
   table(data, n, stride) = Table(data, collect(Int32, 1:stride:(n*stride+1)))
-  subcells  = SubCellData(table(c2p, s.num_subcells, D+1), c2b, pts(X), pts(R))
-  subfacets = SubFacetData(table(f2p, s.num_subfacets, D), pts(N), f2b, pts(fX), pts(fR))
-  rows(m) = [m[:, ls] for ls in 1:L]
-  rows(bg), subcells, rows(sci), subfacets, rows(sfi)
+  subcells  = SubCellData(table(c2p, s.num_subcells, D+1), c2b, X, R)
+  subfacets = SubFacetData(table(f2p, s.num_subfacets, D), N, f2b, fX, fR)
+  bg, subcells, sci, subfacets, sfi
 end
 
 _cartesian(m::CartesianDiscreteModel) = (m, false)
@@ -226,19 +262,19 @@ function cut_facets(cutter::B200LevelSetCutter, bgmodel::CartesianDiscreteModel,
   _check(cutter, ccall((:gecut_facet_result_sizes, libgecut), Cint, (Ptr{Cvoid}, Ref{GecutFacetSizes}), res, sz),
          "gecut_facet_result_sizes")
   s = sz[]; D = Int(s.D); L = Int(s.num_levelsets)
-  bg  = Matrix{Int8}(undef, s.num_bgfacets, L)
-  c2p = Vector{Int32}(undef, s.num_subfacets*D); c2b = Vector{Int32}(undef, s.num_subfacets)
-  X = Vector{Float64}(undef, s.num_subfacet_points*D); R = Vector{Float64}(undef, s.num_subfacet_points*(D-1))
-  sfi = Matrix{Int8}(undef, s.num_subfacets, L)
-  b = GecutFacetBuffers(pointer(bg), C_NULL, C_NULL, C_NULL, pointer(c2p), pointer(c2b), pointer(X), pointer(R), pointer(sfi))
+  bg, bgp   = _pinned_rows(s.num_bgfacets, L)
+  sfi, sfip = _pinned_rows(s.num_subfacets, L)
+  c2p = _pinned(Int32, s.num_subfacets*D); c2b = _pinned(Int32, s.num_subfacets)
+  X = _pinned(Point{D,Float64}, s.num_subfacet_points); R = _pinned(Point{D-1,Float64}, s.num_subfacet_points)
+  b = GecutFacetBuffers(bgp, C_NULL, C_NULL, C_NULL, pointer(c2p), pointer(c2b), Ptr{Float64}(pointer(X)),
+                        Ptr{Float64}(pointer(R)), sfip)
   GC.@preserve bg c2p c2b X R sfi begin
     _check(cutter, ccall((:gecut_facet_result_copy, libgecut), Cint, (Ptr{Cvoid}, Ref{GecutFacetBuffers}), res, b),
            "gecut_facet_result_copy")
   end
   ccall((:gecut_facet_result_free, libgecut), Cint, (Ptr{Cvoid},), res)
-  subfacets = SubCellData(Table(c2p, collect(Int32, 1:D:(s.num_subfacets*D+1))), c2b,
-                          collect(reinterpret(Point{D,Float64}, X)), collect(reinterpret(Point{D-1,Float64}, R)))
-  EmbeddedFacetDiscretization(bgmodel, [bg[:, ls] for ls in 1:L], subfacets, [sfi[:, ls] for ls in 1:L], oid_to_ls, geom)
+  subfacets = SubCellData(Table(c2p, collect(Int32, 1:D:(s.num_subfacets*D+1))), c2b, X, R)
+  EmbeddedFacetDiscretization(bgmodel, bg, subfacets, sfi, oid_to_ls, geom)
 end
 
 function compute_bgfacet_to_inoutcut(cutter::B200LevelSetCutter, bgmodel::CartesianDiscreteModel, geom)

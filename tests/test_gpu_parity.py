@@ -701,3 +701,41 @@ def test_baseline_c4_stokes_discrete_geometry_256():
         tb.close()
     t.close()
     gd.close()
+
+
+@pytest.mark.gpu
+def test_zero_copy_pinned_destinations():
+    """gecut_result_copy straight into page-locked memory from gecut_host_alloc (what the Julia shim wraps with
+    unsafe_wrap into SubCellData / SubFacetData) gives the same arrays as the pageable path; gecut_host_register pins memory
+    the host language owns."""
+    import ctypes as C
+    from gecut import _lib
+    model, geo = CASES["sphere_tet_12"]()
+    gd = cut(model, geo)
+    ref = gd.to_host()
+    s = gd.sizes
+    D, L = int(s.D), int(s.num_levelsets)
+    shapes = {"ls_to_bgcell_to_inoutcut": ((L, s.num_bgcells), np.int8), "cutcell_to_cell": ((s.num_cutcells,), np.int32),
+              "sc_cell_to_points": ((s.num_subcells, D + 1), np.int32), "sc_cell_to_bgcell": ((s.num_subcells,), np.int32),
+              "sc_point_to_coords": ((s.num_subcell_points, D), np.float64),
+              "sc_point_to_rcoords": ((s.num_subcell_points, D), np.float64),
+              "ls_to_subcell_to_inout": ((L, s.num_subcells), np.int8),
+              "sf_facet_to_points": ((s.num_subfacets, D), np.int32), "sf_facet_to_bgcell": ((s.num_subfacets,), np.int32),
+              "sf_facet_to_normal": ((s.num_subfacets, D), np.float64),
+              "ls_to_subfacet_to_inout": ((L, s.num_subfacets), np.int8)}
+    bufs = {k: _lib.pinned_empty(tuple(int(x) for x in shp), dt) for k, (shp, dt) in shapes.items()}
+    got = gd.to_host(buffers=bufs)
+    for k in shapes:
+        assert got[k] is bufs[k] or np.shares_memory(got[k], bufs[k]), k
+        assert np.array_equal(bufs[k], ref[k]), k
+    # memory owned by the host language, pinned in place
+    own = np.empty(int(s.num_subcell_points) * D, dtype=np.float64)
+    lib = _lib.lib()
+    assert lib.gecut_host_register(C.c_void_p(own.ctypes.data), C.c_size_t(own.nbytes)) == 0
+    try:
+        got2 = gd.to_host(buffers={"sc_point_to_coords": own.reshape(-1, D)})
+        assert np.array_equal(got2["sc_point_to_coords"], ref["sc_point_to_coords"])
+    finally:
+        assert lib.gecut_host_unregister(C.c_void_p(own.ctypes.data)) == 0
+    assert lib.gecut_host_register(None, 0) != 0
+    gd.close()

@@ -79,3 +79,67 @@ def test_simplexify_positive_orientation():
             assert d > 0
             vol += d
         assert abs(vol - (2 if name == "QUAD" else 6)) < 1e-14  # sum of D! * simplex volumes = D! * 1
+
+
+def _julia_style_dump(doc):
+    """What `JSON3.write(LookupTable(p))` would hold for our tables (field names of LookupTables.jl:2-13; VectorValue as
+    {"data": [...]}, orientations as Float64, plus the normals the struct carries and our JSON does not)."""
+    import gen_lookup_tables as g
+    dump = {}
+    for name, t in doc["tables"].items():
+        jt = {"num_cases": t["num_cases"], "case_to_inoutcut": t["case_to_inoutcut"]}
+        if "case_to_subcell_to_points" in t:
+            jt.update({k: t[k] for k in ("case_to_subcell_to_points", "case_to_subcell_to_inout", "case_to_num_subcells_in",
+                                         "case_to_num_subcells_out", "case_to_subfacet_to_points")})
+            jt["case_to_subfacet_to_orientation"] = [[float(o) for o in case] for case in t["case_to_subfacet_to_orientation"]]
+            jt["case_to_point_to_coordinates"] = [[{"data": list(x)} for x in case] for case in t["case_to_point_to_coordinates"]]
+            jt["case_to_subfacet_to_normal"] = [
+                [{"data": [float(v) for v in g._unit_normal_from_points([coords[q - 1] for q in f])]} for f in facets]
+                for coords, facets in zip(t["case_to_point_to_coordinates"], t["case_to_subfacet_to_points"])]
+        else:  # n-cubes: the reference allocates empty per-case vectors
+            for k in ("case_to_subcell_to_points", "case_to_subcell_to_inout", "case_to_subfacet_to_points",
+                      "case_to_subfacet_to_normal", "case_to_subfacet_to_orientation", "case_to_point_to_coordinates"):
+                jt[k] = [[] for _ in range(t["num_cases"])]
+            jt["case_to_num_subcells_in"] = [0] * t["num_cases"]
+            jt["case_to_num_subcells_out"] = [0] * t["num_cases"]
+        dump[name] = jt
+    return dump
+
+
+def test_julia_dump_loader_round_trip():
+    """A reference-held `LookupTable` dump drops in without code changes: a synthetic dump in the reference's field layout
+    goes through oracle/load_julia_tables.py and yields exactly the document the oracle and the library consume."""
+    import load_julia_tables as lj
+    gold = json.load(open(GOLD))
+    dump = json.loads(json.dumps(_julia_style_dump(gold)))  # through text, as a file would
+    doc = lj.convert(dump)
+    assert doc["tables"] == gold["tables"]
+    assert doc["simplexify"] == gold["simplexify"]
+
+
+def test_julia_dump_loader_takes_the_dump_not_the_generator():
+    """The loader really uses the dump's connectivity (another valid table gives another document) and rejects dumps
+    that violate the table invariants."""
+    import copy
+    import pytest
+    import load_julia_tables as lj
+    gold = json.load(open(GOLD))
+    dump = _julia_style_dump(gold)
+    alt = copy.deepcopy(dump)
+    # another valid ordering of TRI case 2 and of its mirror case: swap the first two subcells (and their states)
+    for c in (1, 6):
+        sc, io = alt["TRI"]["case_to_subcell_to_points"][c], alt["TRI"]["case_to_subcell_to_inout"][c]
+        sc[0], sc[1] = sc[1], sc[0]
+        io[0], io[1] = io[1], io[0]
+    doc = lj.convert(alt)
+    assert doc["tables"]["TRI"]["case_to_subcell_to_points"][1] != gold["tables"]["TRI"]["case_to_subcell_to_points"][1]
+    assert doc["tables"]["TET"] == gold["tables"]["TET"]
+    bad = copy.deepcopy(dump)
+    a = bad["TET"]["case_to_subcell_to_points"][1][0]
+    a[0], a[1] = a[1], a[0]  # negative Jacobian
+    with pytest.raises(AssertionError):
+        lj.convert(bad)
+    bad2 = copy.deepcopy(dump)
+    del bad2["HEX"]
+    with pytest.raises(ValueError):
+        lj.convert(bad2)
