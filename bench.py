@@ -386,7 +386,8 @@ def run_reference(args, n):
 
 
 # --------------------------------------------------------------------------------------------------------------------
-def multi_gpu_legs(args, n, rank, world, local_rank, ctx, model, geo, slab, state, step_bytes, ms_step, peak, barrier, stream):
+def multi_gpu_legs(args, n, rank, world, local_rank, ctx, model, geo, slab, state, step_bytes, ms_step, peak, barrier, stream,
+                   host_barrier):
     """N > 1 only.  (1) Every number the ranks all-reduced through the library's NCCL communicator is recomputed by rank 0
     alone, slab by slab on its own GPU, and must agree (counts exactly, integrals to 1e-12).  (2) iso-work efficiency: the
     mean per-GPU fraction of the HBM roofline at N ranks over the fraction one GPU reaches on the N = 1 model, measured in
@@ -420,20 +421,23 @@ def multi_gpu_legs(args, n, rank, world, local_rank, ctx, model, geo, slab, stat
     # ---- (1) slab-by-slab on one GPU
     slabs = [None] * world
     dist.all_gather_object(slabs, tuple(slab))
+    host_barrier()
     check = None
     if rank == 0:
         tot = [0.0] * 5
         for sl in slabs:
             part = one(LevelSetCutter(ctx, slab=tuple(sl)), model, geo, lap=False)
             tot = [a + b for a, b in zip(tot, part)]
-        glob = [state["vol"], state["surf"], float(state["global_counts"]["cut_cells"]),
-                float(state["global_counts"]["subcells"]), state["vols"][-1]]
+        glob = [state["gvol"], state["gsurf"], float(state["global_counts"]["cut_cells"]),
+                float(state["global_counts"]["subcells"]), state["gvols"][-1]]
         ok = (tot[2] == glob[2] and tot[3] == glob[3] and
               all(abs(a - b) <= 1e-12 * abs(a) for a, b in ((tot[0], glob[0]), (tot[1], glob[1]), (tot[4], glob[4]))))
         check = {"ok": bool(ok), "nccl": glob, "single_gpu_slab_by_slab": tot}
         if not ok:
-            raise SystemExit(f"the {world}-rank NCCL result differs from the single-GPU slab-by-slab result: {check}")
-    barrier()
+            sys.stderr.write(f"the {world}-rank NCCL result differs from the single-GPU slab-by-slab result: {check}\n")
+            sys.stderr.flush()
+            os._exit(3)  # the other ranks wait on a barrier: leave without the interpreter's tear-down
+    host_barrier()
 
     # ---- (2) iso-work efficiency
     bytes_t = torch.tensor([float(step_bytes)], dtype=torch.float64, device=dev)
@@ -441,6 +445,7 @@ def multi_gpu_legs(args, n, rank, world, local_rank, ctx, model, geo, slab, stat
     frac_n = float(bytes_t[0]) / world / (ms_step * 1e-3) / 1e9 / peak
     iso = None
     model1, geo1, _ = make_workload(args.workload, n, 1)
+    host_barrier()
     if rank == 0:
         c1 = LevelSetCutter(ctx)
         for _ in range(3):
@@ -468,7 +473,7 @@ def multi_gpu_legs(args, n, rank, world, local_rank, ctx, model, geo, slab, stat
                "iso_work_efficiency": round(frac_n / frac_1, 4), "single_gpu_ms_per_step": round(ms1, 4),
                "note": "mean per-GPU step_roofline.frac at N ranks / the same fraction of the N = 1 model timed on rank 0 in "
                        "this run (device-resident laplacian, same kernels)"}
-    barrier()
+    host_barrier()
 
     # ---- (3) DiscreteGeometry leg (skipped when the main leg already ran --nodal)
     nodal = None
@@ -510,7 +515,7 @@ def multi_gpu_legs(args, n, rank, world, local_rank, ctx, model, geo, slab, stat
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         g2 = ctx.comm_fetch(red2.data_ptr(), 5)
         same = (g2[2] == float(state["global_counts"]["cut_cells"]) and g2[3] == float(state["global_counts"]["subcells"]) and
-                abs(g2[0] - state["vol"]) <= 1e-12 * abs(state["vol"]) and abs(g2[1] - state["surf"]) <= 1e-12 * abs(state["surf"]))
+                abs(g2[0] - state["gvol"]) <= 1e-12 * abs(state["gvol"]) and abs(g2[1] - state["gsurf"]) <= 1e-12 * abs(state["gsurf"]))
         if not same:
             raise SystemExit(f"DiscreteGeometry leg: global numbers {g2} differ from the closed-form leg")
         msn = float(t[0]) / args.steps
@@ -614,10 +619,24 @@ def run_b200(args, n, rank, world, local_rank):
         from gecut.distributed import init_library_communicator
         init_library_communicator(ctx)
 
+    host_pg = None
+    if world > 1:
+        # host-side (gloo) group for the sections only rank 0 works in: an NCCL barrier would leave a kernel spinning on
+        # every other GPU, and a driver call that synchronises peer devices on rank 0 (cudaMalloc of a new block size with
+        # peer access enabled) then never returns
+        host_pg = dist.new_group(backend="gloo")
+        import faulthandler
+        faulthandler.dump_traceback_later(420, exit=True)  # a hang prints the Python stacks and ends the run
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def host_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=host_pg)
 
     state = {}
 
@@ -712,8 +731,9 @@ def run_b200(args, n, rank, world, local_rank):
     timed_clock_samples = len(sampler.samples) if sampler else 0
     launches = ctx.launch_count - l0
     glob = ctx.comm_fetch(red.data_ptr(), 5) if world > 1 else list(state["local"])
-    state["vol"], state["surf"] = glob[0], glob[1]
-    state["vols"] = [glob[0]] + ([glob[4]] if len(state["vols"]) > 1 else [])
+    # global numbers under their own keys: later steps (profiling, end to end) overwrite the per-rank entries of `state`
+    state["gvol"], state["gsurf"] = glob[0], glob[1]
+    state["gvols"] = [glob[0]] + ([glob[4]] if len(state["vols"]) > 1 else [])
     state["global_counts"] = {"cut_cells": int(glob[2]), "subcells": int(glob[3])}
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
@@ -776,7 +796,7 @@ def run_b200(args, n, rank, world, local_rank):
     multi = None
     if world > 1:
         multi = multi_gpu_legs(args, n, rank, world, local_rank, ctx, model, geo, slab, state, step_bytes, ms_step, peak,
-                               barrier, stream)
+                               barrier, stream, host_barrier)
 
     # ---- end to end through the C ABI with HOST buffers ------------------------------------------------------------
     e2e = None
@@ -861,7 +881,7 @@ def run_b200(args, n, rank, world, local_rank):
                        "per_gpu_counts": {"cut_cells": int(s.num_cutcells), "subcells": int(s.num_subcells),
                                           "subcell_points": int(s.num_subcell_points), "subfacets": int(s.num_subfacets)},
                        "global_counts": state["global_counts"],
-                       "integrals": {"volume": state["vol"], "surface": state["surf"], "volumes": state["vols"]}},
+                       "integrals": {"volume": state["gvol"], "surface": state["gsurf"], "volumes": state["gvols"]}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "multi_gpu": multi,
             "roofline": roofline, "step_roofline": step_roofline, "kernels": kernels[:12], "cpu_baseline": cpu,
             "north_star_csg": csg, "classify_split_ms": state.get("classify_split_ms"),
