@@ -1700,15 +1700,16 @@ k_cut_two(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ 
 constexpr int CUT1_TILE = 32;    // one warp = one tile: warps run their phases independently (no block barriers)
 constexpr int CUT1_BLOCK = 128;  // threads per block of the fill kernel (4 independent tiles)
 #ifndef CUT1_MINB
-#define CUT1_MINB 5
+#define CUT1_MINB 6  // 24 warps per SM (80 registers, 34 KB of shared memory per block): 0.66 -> 0.60 ms on 512^3 tets vs 5
 #endif
 
 // shared memory of one warp of the fill kernel: staged points (+ phase pad), cut-edge coefficients, 16-byte records,
 // subcell measures, owner maps; 32-byte multiple
-template <int D>
+template <int D, bool SX = false>
 __host__ __device__ constexpr int cut1_warp_bytes() {
+  // measure slots: simplex bg cells (closed-form cell measures) only park (IN, OUT) of the lane's cell, n-cube cells none
   return (((CUT1_TILE * ((D == 3) ? 8 : 5) * D + 4) * 8 + CUT1_TILE * ((D == 3) ? 4 : 2) * 8 + CUT1_TILE * 16 +
-           CUT1_TILE * ((D == 3) ? 6 : 3) * 8 +  // signed subcell measures of the tile (per-cell IN / OUT sums)
+           (SX ? CUT1_TILE * 2 : 0) * 8 +
            CUT1_TILE * ((D == 3) ? 6 : 3) + CUT1_TILE * ((D == 3) ? 2 : 1)) + 31) / 32 * 32;
 }
 
@@ -1877,7 +1878,7 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
   constexpr int NPC = WalkCfg<D>::NPC;
   constexpr int NSUB = (D == 3) ? 6 : 3, NFAC = (D == 3) ? 2 : 1, NE = (D == 3) ? 6 : 3;
   constexpr int STG = CUT1_TILE * NPC * D + 4;     // staged doubles per warp (+ phase pad)
-  constexpr int WBYTES = cut1_warp_bytes<D>();
+  constexpr int WBYTES = cut1_warp_bytes<D, SX && !WM>();
   extern __shared__ __align__(32) unsigned char fill_smem[];
   __shared__ GcSimplexTable s_tab;
   __shared__ uint8_t s_swap[8];
@@ -1924,8 +1925,9 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
   constexpr int NCE = (D == 3) ? 4 : 2;  // a cut simplex has at most NCE cut edges
   double* cstash = stage + STG;          // [NCE][32] coefficients of the cut edges, parked here between phases A and R
   uint4* rec = reinterpret_cast<uint4*>(wbase + sizeof(double) * (STG + NCE * CUT1_TILE));
-  double* vstage = reinterpret_cast<double*>(rec + CUT1_TILE);  // [NSUB*32] measure of every subcell, sign bit = OUT
-  uint8_t* own_c = reinterpret_cast<uint8_t*>(vstage + CUT1_TILE * NSUB);
+  double* vstage = reinterpret_cast<double*>(rec + CUT1_TILE);  // simplex bg cells: [2][32] (IN, OUT) measure of the lane's cell
+  static_assert(!SX || !WM, "simplex bg cells use the closed-form cell measures");
+  uint8_t* own_c = reinterpret_cast<uint8_t*>(vstage + CUT1_TILE * (SX ? 2 : 0));
   uint8_t* own_f = own_c + CUT1_TILE * NSUB;
   const int64_t tile = (int64_t)blockIdx.x * (CUT1_BLOCK / CUT1_TILE) + wid;
   if (tile * CUT1_TILE >= nsimp) return;  // whole warp beyond the end (no block barrier below)
@@ -2178,7 +2180,6 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
       } else {
         st_out += ms;
       }
-      if (SX) vstage[idx] = io == GC_IN ? ms : -ms;
     }
   }
   // ======================================== phase D: lane = subfacet
@@ -2222,18 +2223,6 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
   }
   if (lane == 0) tile_stats[tile] = make_double4(st_in, st_out, st_surf, (double)st_nin);
   __syncwarp();
-  if (SX && !ANALYTIC && valid) {
-    // simplex bg cells: a lane is a cut cell; IN / OUT measure of the cell in subcell order (the input of the P1
-    // Laplacian and of get_cell_measure, no pass over the subcells later)
-    const uint4 rr = rec[lane];  // case and first subcell of this lane's simplex (phase A)
-    const int ns = TC.nsub[rr.x & 15u];
-    double vi = 0.0, vo = 0.0;
-    for (int j = 0; j < ns; ++j) {
-      const double v = vstage[rr.y + j];
-      if (signbit(v)) vo += -v; else vi += v;
-    }
-    cell_vio[s] = make_double2(vi, vo);  // SX: one stage-0 simplex per cut cell
-  }
   // ======================================== phase R: reference coordinates (lane = simplex), same staging buffer
   cut1_bulk_wait_read(lane);  // the physical points have left the staging buffer
   if (valid) {
@@ -2570,10 +2559,10 @@ static int gc_cut_cells_l1(gecut_ctx* ctx, gecut_result* res) {
     const unsigned nbf = (unsigned)gc_div_up(ntiles, CUT1_BLOCK / CUT1_TILE);
 #define GC_FILL1(DD, SXV, MB)                                                                                          \
   GC_LAUNCH(ctx, "k_cut1_fill",                                                                                        \
-            k_cut1_fill<DD, SXV, MB, !SXV><<<nbf, CUT1_BLOCK, (size_t)cut1_warp_bytes<DD>() * (CUT1_BLOCK / CUT1_TILE), ctx->stream>>>( \
+            k_cut1_fill<DD, SXV, MB, !SXV><<<nbf, CUT1_BLOCK, (size_t)cut1_warp_bytes<DD, SXV>() * (CUT1_BLOCK / CUT1_TILE), ctx->stream>>>( \
                 g, res->leaves, ctx->d_tables, ctx->d_simplexify_raw, ctx->d_simplexify_pos, lay.cutcells, nsimp, t_cells,   \
                 t_points, t_facets, lay, res->cut_sc_ptr, tile_stats, res->cell_vio))
-#define GC_FILL2(DD, SXV) GC_FILL1(DD, SXV, CUT1_MINB)
+#define GC_FILL2(DD, SXV) GC_FILL1(DD, SXV, (SXV ? CUT1_MINB : 5))  // n-cube cells: 5 blocks (6 spill and lose 4 %)
     if (D == 2) {
       if (g.simplexified) GC_FILL2(2, true); else GC_FILL2(2, false);
     } else {
