@@ -690,7 +690,9 @@ def run_b200(args, n, rank, world, local_rank):
         t.append(time.perf_counter())
         dbg.append([round((b - a) * 1e3, 2) for a, b in zip(t[:-1], t[1:])])
         if e2e:
-            cg.to_host(buffers=host["layout"])
+            t0 = time.perf_counter()
+            cg.to_host(buffers=host["layout"])  # blocking: returns when the last array has landed
+            state.setdefault("d2h_s", []).append(time.perf_counter() - t0)
         vol, surf = vols[0], surfs[0]
         local = [vol, surf, float(cg.num_cutcells), float(cg.sizes.num_subcells), vols[-1]]
         if world > 1:  # global integrals + counts: the only data-path collective, device resident
@@ -841,7 +843,34 @@ def run_b200(args, n, rank, world, local_rank):
         ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local_rank}")
         if world > 1:
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        # where the end-to-end time goes: the blocking copy-out of the layout (max over ranks), and the floor of this box for
+        # it -- one plain cudaMemcpyAsync of the same number of bytes into pinned memory, all ranks at the same time
+        lay_bytes = sum(a.nbytes for a in host["layout"].values())
+        d2h_ms = torch.tensor([1e3 * sum(state["d2h_s"][-e2e_steps:]) / e2e_steps], dtype=torch.float64, device=f"cuda:{local_rank}")
+        src = torch.empty(lay_bytes, dtype=torch.uint8, device=f"cuda:{local_rank}")
+        dst = torch.empty(lay_bytes, dtype=torch.uint8, pin_memory=True)
+        dst.copy_(src, non_blocking=True)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(2):
+            dst.copy_(src, non_blocking=True)
+        f1.record(stream)
+        barrier()
+        floor_ms = torch.tensor([f0.elapsed_time(f1) / 2], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if world > 1:
+            dist.all_reduce(d2h_ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(floor_ms, op=dist.ReduceOp.MAX)
+        del src, dst
+        d2h_detail = {"layout_bytes_per_gpu": int(lay_bytes), "copy_out_ms_per_step": round(float(d2h_ms[0]), 3),
+                      "copy_out_gbs_per_gpu": round(lay_bytes / (float(d2h_ms[0]) * 1e-3) / 1e9, 2),
+                      "floor_ms": round(float(floor_ms[0]), 3),
+                      "floor_gbs_per_gpu": round(lay_bytes / (float(floor_ms[0]) * 1e-3) / 1e9, 2),
+                      "copy_out_over_floor": round(float(floor_ms[0]) / float(d2h_ms[0]), 3),
+                      "note": "floor = one cudaMemcpyAsync of the same bytes device -> pinned host, every rank at the same time "
+                              "(max over ranks); copy_out = gecut_result_copy's 11 per-array copies"}
         e2e = {"value": cubes_total * e2e_steps / (float(ems[0]) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h": d2h_detail,
                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": float(ems[0]) / e2e_steps,
                "what": "gecut_cut + selectors + integrals through the C ABI, whole EmbeddedDiscretization layout and the "
                        "element matrices copied into pinned HOST buffers every step; the input is an AnalyticalGeometry "

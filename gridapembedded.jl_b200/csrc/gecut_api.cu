@@ -162,6 +162,8 @@ void free_result_arrays(gecut_result* r) {
   gc_free(ctx, r->cutmask);
   gc_free(ctx, r->cutcount);
   gc_free(ctx, r->cut22mask);
+  gc_free(ctx, r->rowcount);
+  r->rowcount = nullptr;
   gc_free(ctx, r->tile_n22);
   r->cut22mask = nullptr;
   r->tile_n22 = nullptr;

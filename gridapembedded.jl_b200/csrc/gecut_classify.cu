@@ -360,6 +360,8 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
            uint32_t* __restrict__ cutmask, uint32_t* __restrict__ cutcount,
            uint32_t* __restrict__ cut22count /* TET cells split 2-2 per group (one level set), or nullptr */,
            uint32_t* __restrict__ cut22mask /* ... and which ones, laid out like cutmask; written for crossed groups only */,
+           uint32_t* __restrict__ rowcount /* [2][rows]: cut cells (2-2 TETs) per x-row of cubes, summed with atomics */,
+           int64_t nrows,
            const uint8_t* __restrict__ simplexify_raw,
            unsigned long long* __restrict__ bg_counts /* [L][2][6]: IN / OUT cells per level set and cell type */,
            int ZS, int ntx, int nty, int64_t ntiles, int accumulate /* OR into the cut mask of earlier level-set chunks */,
@@ -643,9 +645,13 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
         bool slow_word = false;  // some level set of this launch crosses the lane's 32-cube word
 #pragma unroll
         for (int t = 0; t < CPC; ++t) cutacc[t] = 0u;
-        if (accumulate && word_on && cutcount[gidx] != 0u) {  // mask words exist only where the group count is not zero
+        uint32_t n_old = 0u;  // the group's count after the earlier level-set chunks
+        if (accumulate && word_on) {
+          n_old = cutcount[gidx];
+          if (n_old != 0u) {  // mask words exist only where the group count is not zero
 #pragma unroll
-          for (int t = 0; t < CPC; ++t) cutacc[t] = cutmask[gidx * CPC + t];
+            for (int t = 0; t < CPC; ++t) cutacc[t] = cutmask[gidx * CPC + t];
+          }
         }
         for (int ls = 0; ls < L; ++ls) {
           uint32_t V[NVC];
@@ -764,8 +770,11 @@ k_classify(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, int64
             n += __popc(cutacc[t]);
           }
           cutcount[gidx] = n;
+          // per-row totals: the compaction scans the rows (16x fewer elements than groups at 512 cubes per row)
+          if (n != n_old) atomicAdd(&rowcount[rowid], n - n_old);
           if (SIMPLEX && D == 3 && cut22count != nullptr) {
             cut22count[gidx] = n22;
+            if (n22) atomicAdd(&rowcount[nrows + rowid], n22);
           }
         }
       }
@@ -874,36 +883,40 @@ k_classify_cull(const GcGrid g, const GcLeaves lv, int8_t* __restrict__ states, 
 
 
 // ---- compaction of the cut mask -------------------------------------------------------------------
-// One thread per 32-cube group; the exclusive scan of the group counts gives the group's first slot and (from the next
-// prefix) its count -- the mask words of empty groups are never read (k_classify writes only the words of crossed groups).
-// Cells leave in (cube, cell type) order = ascending cell id.
+// One thread per 32-cube group.  The scan runs over the per-ROW totals (k_classify adds every crossed group to its row);
+// a group that holds cut cells finds its first slot as row prefix + the counts of the groups before it in the row -- the
+// counts and mask words of empty groups are never read beyond the group's own count.  Cells leave in (cube, cell type)
+// order = ascending cell id.
 // T22: one level set on TET cells -- also hand the fill kernel the base of every tile of 32 consecutive cut cells: the
-// number of 2-2 splits before the tile (group prefix from the scan + the 2-2 bits of the cells of this group before it)
+// number of 2-2 splits before the tile (row prefix + groups before + the 2-2 bits of the cells of this group before it)
 template <int CPC, bool T22>
 __global__ void __launch_bounds__(256)
-k_cutmask_emit(const uint32_t* __restrict__ cutmask, int64_t ngroups, const uint32_t* __restrict__ offs, uint32_t total,
-               int nx, int wxtot, int32_t* __restrict__ cutcells, const uint32_t* __restrict__ cut22mask,
-               const uint32_t* __restrict__ offs22, uint32_t total22, uint32_t* __restrict__ tile_n22) {
+k_cutmask_emit(const uint32_t* __restrict__ cutmask, int64_t ngroups, const uint32_t* __restrict__ cutcount,
+               const uint32_t* __restrict__ rowoffs, int64_t nrows, int nx, int wxtot, int32_t* __restrict__ cutcells,
+               const uint32_t* __restrict__ cut22mask, const uint32_t* __restrict__ cut22count,
+               uint32_t* __restrict__ tile_n22) {
   const int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gidx >= ngroups) return;
-  uint32_t o = offs[gidx];
-  const uint32_t o_next = gidx + 1 < ngroups ? offs[gidx + 1] : total;
-  if (o_next == o) return;
+  if (cutcount[gidx] == 0u) return;
+  const int64_t rowid = gidx / wxtot;
+  const int w = (int)(gidx - rowid * wxtot);
+  uint32_t o = rowoffs[rowid], b = T22 ? rowoffs[nrows + rowid] : 0u;
+  for (int q = 0; q < w; ++q) {  // (16-byte loads of the row were measured slower: 0.095 against 0.085 ms)
+    o += cutcount[rowid * wxtot + q];
+    if (T22) b += cut22count[rowid * wxtot + q];
+  }
   uint32_t m[CPC], s[T22 ? CPC : 1];
-  uint32_t any = 0u, b = 0u;
+  uint32_t any = 0u;
 #pragma unroll
   for (int t = 0; t < CPC; ++t) {
     m[t] = cutmask[gidx * CPC + t];
     any |= m[t];
   }
   if (T22) {
-    b = offs22[gidx];
-    const bool has = (gidx + 1 < ngroups ? offs22[gidx + 1] : total22) != b;  // k_classify wrote the bits of such groups only
+    const bool has = cut22count[gidx] != 0u;  // k_classify wrote the bits of such groups only
 #pragma unroll
     for (int t = 0; t < CPC; ++t) s[t] = has ? cut22mask[gidx * CPC + t] : 0u;
   }
-  const int64_t rowid = gidx / wxtot;
-  const int w = (int)(gidx - rowid * wxtot);
   const int64_t cube0 = rowid * nx + 32 * (int64_t)w;
   while (any) {
     const int c = __ffs(any) - 1;
@@ -1000,6 +1013,8 @@ int gc_classify(gecut_ctx* ctx, gecut_result* res) {
   GC_CHECK(gc_malloc(ctx, (void**)&res->cutcount, sizeof(uint32_t) * rows * wxtot * (res->want_n22 ? 2 : 1)));
   GC_CUDA(cudaMemsetAsync(res->cutcount, 0, sizeof(uint32_t) * rows * wxtot * (res->want_n22 ? 2 : 1), ctx->stream));
   uint32_t* cut22 = res->want_n22 ? res->cutcount + rows * wxtot : nullptr;
+  GC_CHECK(gc_malloc(ctx, (void**)&res->rowcount, sizeof(uint32_t) * rows * 2));
+  GC_CUDA(cudaMemsetAsync(res->rowcount, 0, sizeof(uint32_t) * rows * 2, ctx->stream));
   if (res->want_n22) GC_CHECK(gc_malloc(ctx, (void**)&res->cut22mask, sizeof(uint32_t) * rows * wxtot * 6));
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
@@ -1091,7 +1106,7 @@ int gc_classify(gecut_ctx* ctx, gecut_result* res) {
       }
 #define GC_CLS(LHV, SGV)                                                                                              \
   GC_LAUNCH(ctx, "k_classify", k_classify<D, S, LHV, SGV><<<nb_l, C::WARPS * 32, smem, ctx->stream>>>(                 \
-      g, lv, states, res->lay.bg_pitch, res->cutmask, res->cutcount, cut22, res->cut22mask, ctx->d_simplexify_raw, counts, zs_l, ntx, nty, \
+      g, lv, states, res->lay.bg_pitch, res->cutmask, res->cutcount, cut22, res->cut22mask, res->rowcount, rows, ctx->d_simplexify_raw, counts, zs_l, ntx, nty, \
       ntiles_l, acc, wl, wl ? wl + ntiles_l : nullptr))
       // the sign-word branch is compiled out of the closed-form instances (it cost the tet kernel 24 bytes of spills)
       if (any_signs) {
@@ -1136,11 +1151,12 @@ int gc_compact_cutcells(gecut_ctx* ctx, gecut_result* res) {
   GC_CHECK(gc_malloc(ctx, (void**)&total_dev, sizeof(uint64_t) * 2));
   const int T = 256;
   const unsigned nb = (unsigned)gc_div_up(ngroups, T);
-  // channel 0: cut cells per group; channel 1 (want_n22): TET cells split 2-2 per group -- one launch for both
-  GC_CHECK(gc_exclusive_scan_u32_multi(ctx, counts, counts, ngroups, res->want_n22 ? 2 : 1, total_dev));
+  // channel 0: cut cells per row of cubes; channel 1: TET cells split 2-2 per row -- one launch for both
+  uint32_t* rowoffs = res->rowcount;
+  GC_CHECK(gc_exclusive_scan_u32_multi(ctx, rowoffs, rowoffs, rows, 2, total_dev));
   uint64_t* h = (uint64_t*)ctx->h_pinned;
   h[1] = 0;
-  GC_CUDA(cudaMemcpyAsync(h, total_dev, sizeof(uint64_t) * (res->want_n22 ? 2 : 1), cudaMemcpyDeviceToHost, ctx->stream));
+  GC_CUDA(cudaMemcpyAsync(h, total_dev, sizeof(uint64_t) * 2, cudaMemcpyDeviceToHost, ctx->stream));
   GC_CUDA(cudaMemcpyAsync(h + 2, res->bg_counts_dev, sizeof(uint64_t) * res->L * 12, cudaMemcpyDeviceToHost, ctx->stream));
   GC_CUDA(cudaStreamSynchronize(ctx->stream));
   const int64_t ncut = (int64_t)h[0];
@@ -1150,14 +1166,14 @@ int gc_compact_cutcells(gecut_ctx* ctx, gecut_result* res) {
   if (ncut > 0) {
     GC_CHECK(gc_malloc(ctx, (void**)&res->lay.cutcells, sizeof(int32_t) * ncut));
     switch (g.cpc) {
-      case 1: GC_LAUNCH(ctx, "k_cutmask_emit", k_cutmask_emit<1, false><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts, (uint32_t)ncut, nx, wxtot, res->lay.cutcells, nullptr, nullptr, 0u, nullptr)); break;
-      case 2: GC_LAUNCH(ctx, "k_cutmask_emit", k_cutmask_emit<2, false><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts, (uint32_t)ncut, nx, wxtot, res->lay.cutcells, nullptr, nullptr, 0u, nullptr)); break;
+      case 1: GC_LAUNCH(ctx, "k_cutmask_emit", k_cutmask_emit<1, false><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts, rowoffs, rows, nx, wxtot, res->lay.cutcells, nullptr, nullptr, nullptr)); break;
+      case 2: GC_LAUNCH(ctx, "k_cutmask_emit", k_cutmask_emit<2, false><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts, rowoffs, rows, nx, wxtot, res->lay.cutcells, nullptr, nullptr, nullptr)); break;
       default:
         if (res->want_n22) {
           GC_CHECK(gc_malloc(ctx, (void**)&res->tile_n22, sizeof(uint32_t) * gc_div_up(ncut, 32)));
-          GC_LAUNCH(ctx, "k_cutmask_emit", k_cutmask_emit<6, true><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts, (uint32_t)ncut, nx, wxtot, res->lay.cutcells, res->cut22mask, counts + ngroups, (uint32_t)res->n22, res->tile_n22));
+          GC_LAUNCH(ctx, "k_cutmask_emit", k_cutmask_emit<6, true><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts, rowoffs, rows, nx, wxtot, res->lay.cutcells, res->cut22mask, counts + ngroups, res->tile_n22));
         } else {
-          GC_LAUNCH(ctx, "k_cutmask_emit", k_cutmask_emit<6, false><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts, (uint32_t)ncut, nx, wxtot, res->lay.cutcells, nullptr, nullptr, 0u, nullptr));
+          GC_LAUNCH(ctx, "k_cutmask_emit", k_cutmask_emit<6, false><<<nb, T, 0, ctx->stream>>>(res->cutmask, ngroups, counts, rowoffs, rows, nx, wxtot, res->lay.cutcells, nullptr, nullptr, nullptr));
         }
         break;
     }
@@ -1167,6 +1183,8 @@ int gc_compact_cutcells(gecut_ctx* ctx, gecut_result* res) {
   res->cutcount = nullptr;
   gc_free(ctx, res->cut22mask);
   res->cut22mask = nullptr;
+  gc_free(ctx, res->rowcount);
+  res->rowcount = nullptr;
   gc_free(ctx, total_dev);
   return st;
 }

@@ -155,6 +155,7 @@ struct gecut_result {
   // no second scan and no second read-back
   bool want_n22 = false;
   int64_t n22 = 0;
+  uint32_t* rowcount = nullptr;   // [2][rows]: cut cells / 2-2 TETs per x-row of cubes (k_classify -> scan -> k_cutmask_emit)
   uint32_t* cut22mask = nullptr;  // which cut TETs split 2-2 (layout of cutmask; k_classify -> k_cutmask_emit, then freed)
   uint32_t* tile_n22 = nullptr;   // 2-2 TETs before every tile of 32 cut cells (k_cutmask_emit -> k_cut1_fill, then freed)
   // memoised program rows (key = program tokens): results of multi-operator boolean programs over the subcell and the
