@@ -487,7 +487,22 @@ int gecut_create(int device, void* cuda_stream, gecut_ctx** out) {
     uint64_t thr = UINT64_MAX;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
-  bool ok = cudaMalloc((void**)&ctx->d_tables, sizeof(GC_SIMPLEX_TABLES)) == cudaSuccess &&
+  // behind the three tables: packed vertex order -> packed order after an all-IN / all-OUT stage (cm_skip_*_stages)
+  uint8_t perm_lut[3 * 512];
+  for (int di = 0; di < 3; ++di) {
+    const int n = di + 2;  // vertices of the simplex
+    for (int b = 0; b < 2; ++b) {
+      const uint8_t* pm = GC_SIMPLEX_TABLES[di].sub_pts[b ? (1 << n) - 1 : 0][0];
+      for (int q = 0; q < 256; ++q) {
+        int out = 0;
+        for (int i = 0; i < n; ++i) out |= ((q >> (2 * pm[i])) & 3) << (2 * i);
+        perm_lut[di * 512 + b * 256 + q] = (uint8_t)out;
+      }
+    }
+  }
+  bool ok = cudaMalloc((void**)&ctx->d_tables, sizeof(GC_SIMPLEX_TABLES) + sizeof(perm_lut)) == cudaSuccess &&
+            cudaMemcpy(reinterpret_cast<uint8_t*>(ctx->d_tables) + sizeof(GC_SIMPLEX_TABLES), perm_lut, sizeof(perm_lut),
+                       cudaMemcpyHostToDevice) == cudaSuccess &&
             cudaMalloc((void**)&ctx->d_simplexify_raw, sizeof(GC_SIMPLEXIFY_RAW)) == cudaSuccess &&
             cudaMalloc((void**)&ctx->d_simplexify_pos, sizeof(GC_SIMPLEXIFY_POS)) == cudaSuccess &&
             cudaMemcpy(ctx->d_tables, GC_SIMPLEX_TABLES, sizeof(GC_SIMPLEX_TABLES), cudaMemcpyHostToDevice) == cudaSuccess &&

@@ -684,45 +684,37 @@ __device__ __forceinline__ void cm_lane_setup(const GcGrid& g, const uint8_t* vt
 }
 
 // vertex order in which a simplex arrives at stage `lo` after the all-IN / all-OUT stages hi-1 ... lo+1 (each a vertex
-// permutation = the single child of that table row), as 2-bit entries
+// permutation = the single child of that table row), as 2-bit entries.  One stage = one look-up: the host tabulates, for
+// the all-IN and the all-OUT row of every simplex table, packed order -> packed order after the stage (GC_PERM_LUT_BYTES
+// bytes behind the tables); the kernels keep the two tables they need in shared memory.  (The first version composed byte
+// arrays in local memory: 240 M sectors of local loads in k_cutm_fill on the 512^3 CSG model.)
+constexpr int GC_PERM_LUT_BYTES = 3 * 512;  // [simplex dimension - 1][all-IN, all-OUT][256]
+
 template <int D>
-__device__ __forceinline__ uint32_t cm_skip_cell_stages(const GcSimplexTable& TC, uint32_t outm, int hi, int lo) {
-  const int c_allout = (1 << (D + 1)) - 1;
-  uint8_t vl[D + 1];
-#pragma unroll
-  for (int i = 0; i <= D; ++i) vl[i] = (uint8_t)i;
-  for (int k = hi - 1; k > lo; --k) {
-    const uint8_t* pm = TC.sub_pts[((outm >> k) & 1u) ? c_allout : 0][0];
-    uint8_t tmp[D + 1];
-#pragma unroll
-    for (int i = 0; i <= D; ++i) tmp[i] = vl[pm[i]];
-#pragma unroll
-    for (int i = 0; i <= D; ++i) vl[i] = tmp[i];
-  }
-  uint32_t q = 0;
-#pragma unroll
-  for (int i = 0; i <= D; ++i) q |= (uint32_t)vl[i] << (2 * i);
+__device__ __forceinline__ void cm_load_perm_luts(const GcSimplexTable* __restrict__ tables, uint8_t* s_plut, uint8_t* s_flut) {
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(tables + 3);
+  const uint32_t* pc = base + (D - 1) * 128;
+  const uint32_t* pf = base + (D - 2) * 128;
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) reinterpret_cast<uint32_t*>(s_plut)[i] = pc[i];
+  // facets have at most 3 vertices: 64 packed orders per row
+  for (int i = threadIdx.x; i < 32; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(s_flut)[i] = pf[(i >> 4) * 64 + (i & 15)];
+}
+
+template <int D>
+__device__ __forceinline__ uint32_t cm_skip_cell_stages(const uint8_t* lut, uint32_t outm, int hi, int lo) {
+  uint32_t q = (D == 3) ? 0xE4u : 0x24u;  // identity: entry i = i
+  for (int k = hi - 1; k > lo; --k) q = lut[((outm >> k) & 1u) * 256u + q];
   return q;
 }
 
 template <int D>
-__device__ __forceinline__ uint32_t cm_skip_facet_stages(const GcSimplexTable& TF, uint32_t outm, int hi, int lo, int skip) {
-  const int fc_allout = (1 << D) - 1;
-  uint8_t vl[D];
-#pragma unroll
-  for (int i = 0; i < D; ++i) vl[i] = (uint8_t)i;
+__device__ __forceinline__ uint32_t cm_skip_facet_stages(const uint8_t* lut, uint32_t outm, int hi, int lo, int skip) {
+  uint32_t q = (D == 3) ? 0x24u : 0x04u;
   for (int k = hi - 1; k > lo; --k) {
     if (k == skip) continue;
-    const uint8_t* pm = TF.sub_pts[((outm >> k) & 1u) ? fc_allout : 0][0];
-    uint8_t tmp[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) tmp[i] = vl[pm[i]];
-#pragma unroll
-    for (int i = 0; i < D; ++i) vl[i] = tmp[i];
+    q = lut[((outm >> k) & 1u) * 64u + q];
   }
-  uint32_t q = 0;
-#pragma unroll
-  for (int i = 0; i < D; ++i) q |= (uint32_t)vl[i] << (2 * i);
   return q;
 }
 
@@ -733,6 +725,8 @@ k_cutm_count(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict
              const int32_t* __restrict__ cutcells, int64_t nsimp, GcMulti mu) {
   __shared__ GcSimplexTable s_tab;
   __shared__ uint8_t s_swap[8];
+  __shared__ __align__(4) uint8_t s_plut[512], s_flut[128];
+  cm_load_perm_luts<D>(tables, s_plut, s_flut);
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(tables + (D - 1));
     uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
@@ -796,7 +790,7 @@ k_cutm_count(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict
       rec_mask = mixed | (outm << 16);
     } else {
       const int aa = mixed ? (31 - __clz(mixed)) : 0;  // the only stage that can cut (stage 0 is visited in any case)
-      const uint32_t vl = cm_skip_cell_stages<D>(TC, outm, L, aa);
+      const uint32_t vl = cm_skip_cell_stages<D>(s_plut, outm, L, aa);
       if (!mixed) sa = ((outm >> aa) & 1u) ? (1u << (D + 1)) - 1u : 0u;
       int c = 0;  // case in arrival order
 #pragma unroll
@@ -850,7 +844,8 @@ template <int D>
 struct CmSmem {
   static constexpr int NPC = WalkCfg<D>::NPC;
   static constexpr int SSTR = NPC * 2 * D + 1;  // doubles per lane: x then r of <= NPC points, odd stride
-  static constexpr int PCAP = 1024;             // points of a tile that go through the staged copy-out
+  static constexpr int PCAP = 768;              // points of a tile that go through the staged copy-out (32 simplices x 6 children x 4;
+                                                // more -- tiles with recorded simplices -- fall back to direct stores)
   static constexpr int NSUBMAX = (D == 3) ? 6 : 3;
   double sx[32 * SSTR];
   double fstash[32][8];   // <= 2 facets per lane: unit normal (D) + measure
@@ -874,6 +869,8 @@ k_cutm_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
   extern __shared__ __align__(16) unsigned char cm_smem[];
   __shared__ GcSimplexTable s_tab[2];  // [0]: D-simplex (cells), [1]: (D-1)-simplex (facet pass-through rows)
   __shared__ uint8_t s_swap[8];
+  __shared__ __align__(4) uint8_t s_plut[512], s_flut[128];
+  cm_load_perm_luts<D>(tables, s_plut, s_flut);
   {
     const uint32_t* src0 = reinterpret_cast<const uint32_t*>(tables + (D - 1));
     const uint32_t* src1 = reinterpret_cast<const uint32_t*>(tables + (D - 2));
@@ -992,7 +989,7 @@ k_cutm_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
     CmLane<D> ln;
     cm_lane_setup<D>(g, vtab, s_swap, cutcells, s, ln);
     const bool mixed = (info >> 24) & 1u;
-    const uint32_t vl = cm_skip_cell_stages<D>(TC, outm, L, a);
+    const uint32_t vl = cm_skip_cell_stages<D>(s_plut, outm, L, a);
     // vertices in arrival order into slots 0..D; values of level set a (the only one whose values matter) alongside
     double W[D + 1];
 #pragma unroll
@@ -1041,7 +1038,7 @@ k_cutm_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
       const int klast = a == 0 ? 1 : 0;
       const int fc = ((outm >> klast) & 1u) ? fc_allout : 0;
       w_fc = fc;
-      const uint32_t qf = cm_skip_facet_stages<D>(TF, outm, L, klast, a);  // the same for every facet of the simplex
+      const uint32_t qf = cm_skip_facet_stages<D>(s_flut, outm, L, klast, a);  // the same for every facet of the simplex
       for (int f = 0; f < (int)nfac; ++f) {
         const uint8_t* fp = TC.fac_pts[c][f];
         double q1[3], q2[3], q3[3], nrm[3];
@@ -1086,7 +1083,7 @@ k_cutm_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
     } else {
       // cut at stage a > 0: every child goes down to stage 0 alone (composed permutations of the stages a-1 ... 1, the
       // same for every child) and is emitted there as an uncut simplex with its own copy of its D+1 points
-      qc = cm_skip_cell_stages<D>(TC, outm, a, 0);
+      qc = cm_skip_cell_stages<D>(s_plut, outm, a, 0);
       for (int j = 0; j < (int)ncell; ++j) {
         const uint32_t pb = pt_off + (uint32_t)j * (D + 1);
 #pragma unroll
@@ -1268,6 +1265,8 @@ k_cut_two(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ 
   SM& sm = *reinterpret_cast<SM*>(two_smem);
   __shared__ GcSimplexTable s_tab[2];
   __shared__ uint8_t s_swap[8];
+  __shared__ __align__(4) uint8_t s_plut[512], s_flut[128];
+  cm_load_perm_luts<D>(tables, s_plut, s_flut);
   {
     const uint32_t* src0 = reinterpret_cast<const uint32_t*>(tables + (D - 1));
     const uint32_t* src1 = reinterpret_cast<const uint32_t*>(tables + (D - 2));
@@ -1304,7 +1303,7 @@ k_cut_two(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ 
   CmLane<D> ln;
   cm_lane_setup<D>(g, vtab, s_swap, cutcells, s, ln);
   const int32_t bgcell1 = ln.bgcell1;
-  const uint32_t vl = cm_skip_cell_stages<D>(TC, outm, L, a);
+  const uint32_t vl = cm_skip_cell_stages<D>(s_plut, outm, L, a);
   if (item <= D) {
     const int m = (vl >> (2 * item)) & 3u;
     const int lvid = (ln.lv4 >> (8 * m)) & 0xFFu;
@@ -1371,7 +1370,7 @@ k_cut_two(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ 
       // ================= child `item` of stage a
       const int j = item;
       const int8_t sta = TC.sub_inout[ca][j];
-      const uint32_t q1 = cm_skip_cell_stages<D>(TC, outm, a, b);
+      const uint32_t q1 = cm_skip_cell_stages<D>(s_plut, outm, a, b);
       double wbv[D + 1];
 #pragma unroll
       for (int i = 0; i <= D; ++i) {
@@ -1411,7 +1410,7 @@ k_cut_two(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ 
         const uint8_t* fp = TC.fac_pts[cb][f];
         double nrm[3] = {0.0, 0.0, 0.0};
         if (wr) unit_normal<D>(PB + fp[0] * PBS, PB + fp[1] * PBS, PB + fp[D - 1] * PBS, (double)TC.fac_orient[cb][f], nrm);
-        const uint32_t qf = cm_skip_facet_stages<D>(TF, outm, L, a, b);
+        const uint32_t qf = cm_skip_facet_stages<D>(s_flut, outm, L, a, b);
         int fca = 0;
         double wav[D];
 #pragma unroll
@@ -1463,7 +1462,7 @@ k_cut_two(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ 
           fo += nsf;
           fpo += fn;
         } else {
-          const uint32_t q2 = cm_skip_facet_stages<D>(TF, outm, a, klast, b);
+          const uint32_t q2 = cm_skip_facet_stages<D>(s_flut, outm, a, klast, b);
           const int fc0 = ((outm >> klast) & 1u) ? fc_allout : 0;
           if (wr) {
             for (int jj = 0; jj < nsf; ++jj) {
@@ -1520,7 +1519,7 @@ k_cut_two(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ 
         ncell_out = nsb;
         npt_out = np;
       } else {
-        const uint32_t qc = cm_skip_cell_stages<D>(TC, outm, b, 0);
+        const uint32_t qc = cm_skip_cell_stages<D>(s_plut, outm, b, 0);
         const int c0 = (outm & 1u) ? c_allout : 0;
         if (wr) {
           for (int jj = 0; jj < nsb; ++jj) {
@@ -1566,7 +1565,7 @@ k_cut_two(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ 
       const uint8_t* fp = TC.fac_pts[ca][f];
       double nrm[3] = {0.0, 0.0, 0.0};
       if (wr) unit_normal<D>(PA + fp[0] * PAS, PA + fp[1] * PAS, PA + fp[D - 1] * PAS, (double)TC.fac_orient[ca][f], nrm);
-      const uint32_t qf = cm_skip_facet_stages<D>(TF, outm, L, b, a);
+      const uint32_t qf = cm_skip_facet_stages<D>(s_flut, outm, L, b, a);
       int fcb = 0;
       double wv[D];
 #pragma unroll
@@ -1618,7 +1617,7 @@ k_cut_two(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ 
         nfo = nsf;
         npo = fn;
       } else {
-        const uint32_t q2 = cm_skip_facet_stages<D>(TF, outm, b, 0, a);
+        const uint32_t q2 = cm_skip_facet_stages<D>(s_flut, outm, b, 0, a);
         const int fc0 = (outm & 1u) ? fc_allout : 0;
         if (wr) {
           for (int jj = 0; jj < nsf; ++jj) {
