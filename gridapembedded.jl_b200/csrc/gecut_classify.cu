@@ -265,6 +265,12 @@ __device__ __forceinline__ uint32_t cls_box_flag(const gecut_leaf& lf, const dou
   return lo > tol ? 2u : (hi < -tol ? 1u : 0u);
 }
 
+#ifndef CLS_WXT_TET
+#define CLS_WXT_TET 2
+#endif
+#ifndef CLS_WXT_HEX
+#define CLS_WXT_HEX 2
+#endif
 template <int D, bool SIMPLEX>
 struct ClsCfg {
   static constexpr int NVC = 1 << D;                             // vertices of the n-cube
@@ -272,7 +278,7 @@ struct ClsCfg {
   static constexpr int LPW = (D == 3) ? (SIMPLEX ? 2 : 1) : 4;   // lanes sharing one 32-cube word
   static constexpr int CPL = 32 / LPW;                           // cubes per lane and layer
   static constexpr int NTASK = 32 / LPW;                         // words per warp and layer
-  static constexpr int WXT = (D == 3) ? (SIMPLEX ? 2 : 4) : 8;   // x words of the warp tile
+  static constexpr int WXT = (D == 3) ? (SIMPLEX ? CLS_WXT_TET : CLS_WXT_HEX) : 8;   // x words of the warp tile
   static constexpr int TY = NTASK / WXT;                         // cell rows of the warp tile
   static constexpr int RY = (D == 3) ? TY + 1 : 1;               // node rows per plane
   static constexpr int PW = RY * (WXT + 1);                      // sign words per plane and level set (+ x halo bit)
