@@ -27,6 +27,15 @@
 
 namespace {
 
+// Node coordinate for the facet kernels.  On a z-slab (layers [k0, k1) of the last direction) the facet grid is the LOCAL
+// model of the rank -- partition (.., k1 - k0), local facet numbering, as every rank of the reference's distributed mode
+// cuts its own local model (src/Distributed/DistributedDiscretizations.jl:42-53) -- but its nodes keep the GLOBAL
+// coordinates pmin + (k0 + k) * dx, so a slab's facets are bit-identical to the same facets of the whole model.
+template <int D>
+__device__ __forceinline__ double fc_coord(const GcGrid& g, int d, int i) {
+  return gc_coord(g, d, d == D - 1 ? i + g.k0 : i);
+}
+
 template <int D>
 __device__ __forceinline__ double leaf_at_node(const GcGrid& g, const GcLeaves& lv, int ls, const int* nijk) {
   if (lv.leaf[ls].kind == GECUT_LEAF_NODAL) {
@@ -34,7 +43,7 @@ __device__ __forceinline__ double leaf_at_node(const GcGrid& g, const GcLeaves& 
                                   : ((int64_t)nijk[0] + (int64_t)g.nn[0] * nijk[1]);
     return __ldg(lv.nodal[ls] + node);
   }
-  const double x[3] = {gc_coord(g, 0, nijk[0]), gc_coord(g, 1, nijk[1]), D == 3 ? gc_coord(g, 2, nijk[2]) : 0.0};
+  const double x[3] = {fc_coord<D>(g, 0, nijk[0]), fc_coord<D>(g, 1, nijk[1]), D == 3 ? fc_coord<D>(g, 2, nijk[2]) : 0.0};
   return gc_eval_leaf(lv.leaf[ls], x, D);
 }
 
@@ -66,8 +75,8 @@ k_node_signs(const GcGrid g, const GcLeaves lv, int wxt, uint32_t* __restrict__ 
   const int i = wx * 32 + threadIdx.x;
   const bool valid = i < g.nn[0];
   const int ic = valid ? i : g.nn[0] - 1;
-  const double x = gc_coord(g, 0, ic);
-  const double y = D == 3 ? gc_coord(g, 1, j) : 0.0;
+  const double x = fc_coord<D>(g, 0, ic);
+  const double y = D == 3 ? fc_coord<D>(g, 1, j) : 0.0;
   for (int ls = 0; ls < lv.L; ++ls) {
     const gecut_leaf& lf = lv.leaf[ls];
     const int kind = lf.kind;
@@ -92,7 +101,7 @@ k_node_signs(const GcGrid g, const GcLeaves lv, int wxt, uint32_t* __restrict__ 
     const double tt = kind == GECUT_LEAF_DOUGHNUT ? __dsub_rn(lf.R, __dsqrt_rn(ww)) : 0.0;
     const double t2 = __dmul_rn(tt, tt);
     for (int k = kbeg; k < kend; ++k) {
-      const double wl = __dsub_rn(gc_coord(g, M, k), lf.x0[M]);
+      const double wl = __dsub_rn(fc_coord<D>(g, M, k), lf.x0[M]);
       double val;
       if (kind == GECUT_LEAF_SPHERE) {
         val = __dsub_rn(__dadd_rn(ww, __dmul_rn(wl, wl)), R2);
@@ -411,7 +420,7 @@ k_facet_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict
     const int lvid = DS == 2 ? gc_simplexify_pos(0, t, m) : m;
     int nijk[3];
     facet_node<D>(fi, lvid, nijk);
-    const double x[3] = {gc_coord(g, 0, nijk[0]), gc_coord(g, 1, nijk[1]), D == 3 ? gc_coord(g, 2, nijk[2]) : 0.0};
+    const double x[3] = {fc_coord<D>(g, 0, nijk[0]), fc_coord<D>(g, 1, nijk[1]), D == 3 ? fc_coord<D>(g, 2, nijk[2]) : 0.0};
 #pragma unroll
     for (int d = 0; d < D; ++d) pool[m].x[d] = x[d];
 #pragma unroll
@@ -423,17 +432,17 @@ k_facet_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict
   {
     int n0[3];
     facet_node<D>(fi, 0, n0);
-    q0[0] = gc_coord(g, 0, n0[0]);
-    q0[1] = gc_coord(g, 1, n0[1]);
-    q0[2] = D == 3 ? gc_coord(g, 2, n0[2]) : 0.0;
+    q0[0] = fc_coord<D>(g, 0, n0[0]);
+    q0[1] = fc_coord<D>(g, 1, n0[1]);
+    q0[2] = D == 3 ? fc_coord<D>(g, 2, n0[2]) : 0.0;
     double dot = 0.0;
 #pragma unroll
     for (int a = 0; a < DS; ++a) {
       int na[3];
       facet_node<D>(fi, 1 << a, na);
-      qa[a][0] = gc_coord(g, 0, na[0]);
-      qa[a][1] = gc_coord(g, 1, na[1]);
-      qa[a][2] = D == 3 ? gc_coord(g, 2, na[2]) : 0.0;
+      qa[a][0] = fc_coord<D>(g, 0, na[0]);
+      qa[a][1] = fc_coord<D>(g, 1, na[1]);
+      qa[a][2] = D == 3 ? fc_coord<D>(g, 2, na[2]) : 0.0;
 #pragma unroll
       for (int d = 0; d < D; ++d)
         dot = __dadd_rn(dot, __dmul_rn(__dsub_rn(pool[a + 1].x[d], pool[0].x[d]), __dsub_rn(qa[a][d], q0[d])));
@@ -961,10 +970,6 @@ int gecut_cut_facets(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* l
     ctx->err = "cut_facets is implemented for n-cube Cartesian models only (not simplexified)";
     return GECUT_ERR_NOTIMPLEMENTED;
   }
-  if (!(grid->slab_begin == 0 && grid->slab_end == 0)) {
-    ctx->err = "cut_facets works on the whole model (no slab)";
-    return GECUT_ERR_NOTIMPLEMENTED;
-  }
   DeviceGuard guard(ctx->device);
   gecut_facet_result* r = new (std::nothrow) gecut_facet_result();
   if (!r) return GECUT_ERR_OOM;
@@ -974,6 +979,16 @@ int gecut_cut_facets(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* l
   if (st != GECUT_OK) {
     delete r;
     return st;
+  }
+  {
+    // z-slab: the facet grid of the rank's LOCAL model (layers [k0, k1) of the last direction as a Cartesian model of its own:
+    // local numbering, the slab's lower and upper planes are boundary facets of the local model); k0 stays as the shift of
+    // the node coordinates (fc_coord)
+    GcGrid& gg = r->grid;
+    const int Dg = gg.D, nloc = gg.k1 - gg.k0;
+    gg.n[Dg - 1] = nloc;
+    gg.nn[Dg - 1] = nloc + 1;
+    gg.k1 = gg.k0 + nloc;
   }
   const GcGrid& g = r->grid;
   auto fail = [&](int code) {
@@ -990,7 +1005,9 @@ int gecut_cut_facets(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* l
   }
   r->leaves.L = L;
   r->leaves.nodal_base = 0;
-  const int64_t nn_total = g.layer_nodes * g.nn[D - 1];
+  const int64_t nn_total = g.layer_nodes * g.nn[D - 1];  // nodes of the (local) model
+  // NODAL vectors: of the whole model (skip the planes below the slab) or slab-local (they start at the slab's first plane)
+  const int64_t nodal_skip = grid->nodal_slab_local ? 0 : (int64_t)g.k0 * g.layer_nodes;
   for (int i = 0; i < L; ++i) {
     r->leaves.leaf[i] = leaves[i];
     r->leaves.nodal[i] = nullptr;
@@ -1009,14 +1026,14 @@ int gecut_cut_facets(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* l
         return fail(GECUT_ERR_INVALID);
       }
       if (nodal_on_device) {
-        r->leaves.nodal[i] = nodal_values[i];
+        r->leaves.nodal[i] = nodal_values[i] + nodal_skip;
       } else {
         double* d = nullptr;
         st = gc_malloc(ctx, (void**)&d, sizeof(double) * nn_total);
         if (st != GECUT_OK) return fail(st);
         r->nodal_dev[i] = d;
         r->owns_nodal[i] = true;
-        if (cudaMemcpyAsync(d, nodal_values[i], sizeof(double) * nn_total, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+        if (cudaMemcpyAsync(d, nodal_values[i] + nodal_skip, sizeof(double) * nn_total, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
           ctx->err = "H2D copy of nodal values failed";
           return fail(GECUT_ERR_CUDA);
         }

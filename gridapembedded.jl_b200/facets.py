@@ -110,13 +110,20 @@ class EmbeddedFacetDiscretization:
 
 
 def _call_cut_facets(cutter: LevelSetCutter, background, geom, classify_only: bool) -> EmbeddedFacetDiscretization:
-    if cutter.slab is not None:
-        raise NotImplementedError("cut_facets works on the whole model (no slab)")
+    """With a z-slab cutter (`LevelSetCutter(ctx, slab=(k0, k1))`) the result is the facet discretization of the rank's LOCAL
+    model -- layers [k0, k1) as a Cartesian model of its own, local facet numbering, global node coordinates -- the way every
+    rank of the reference's distributed mode cuts its own local model (`src/Distributed/DistributedDiscretizations.jl:42-53`)."""
     if background.simplexified:
         raise NotImplementedError("cut_facets is implemented for n-cube Cartesian models")
     ctx = cutter.ctx
-    leaves, nodal, oid_to_ls = flatten_geometry(background, geom)
-    grid = make_grid(background)
+    num_nodal, planes = None, None
+    if cutter.nodal_slab_local and cutter.slab is not None:
+        layer_nodes = background.num_nodes // (background.partition[-1] + 1)
+        num_nodal = layer_nodes * (cutter.slab[1] - cutter.slab[0] + 1)
+        planes = (cutter.slab[0], cutter.slab[1])
+    leaves, nodal, oid_to_ls = flatten_geometry(background, geom, num_nodal=num_nodal, nodal_planes=planes)
+    grid = make_grid(background, cutter.slab)
+    grid.nodal_slab_local = 1 if num_nodal is not None else 0
     recs = make_leaf_records(leaves)
     ptrs, on_device, keep = _nodal_pointers(ctx, background, nodal)
     out = C.c_void_p()
@@ -124,7 +131,18 @@ def _call_cut_facets(cutter: LevelSetCutter, background, geom, classify_only: bo
                                    1 if classify_only else 0, C.byref(out))
     ctx.check(rc, "gecut_cut_facets")
     del keep
-    return EmbeddedFacetDiscretization(ctx, out, background, geom, oid_to_ls)
+    local = background
+    if cutter.slab is not None:  # the local model of the rank (facet ids, boundary flags and sizes refer to it)
+        from .cartesian import CartesianDiscreteModel
+        k0, k1 = int(cutter.slab[0]), int(cutter.slab[1])
+        D = background.D
+        dz = background.sizes[D - 1]
+        pmin, pmax, part = list(background.pmin), list(background.pmax), list(background.partition)
+        pmax[D - 1] = pmin[D - 1] + k1 * dz
+        pmin[D - 1] = pmin[D - 1] + k0 * dz
+        part[D - 1] = k1 - k0
+        local = CartesianDiscreteModel(tuple(pmin), tuple(pmax), tuple(part))
+    return EmbeddedFacetDiscretization(ctx, out, local, geom, oid_to_ls)
 
 
 def _cutter_cut_facets(self, background, geom):

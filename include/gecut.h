@@ -235,7 +235,11 @@ int gecut_selection_device_laplacian(const gecut_selection* sel, double** K_cut_
 /* ---- cut_facets ----------------------------------------------------------------------------- */
 /* cut_facets(::LevelSetCutter, bgmodel, geo) (src/LevelSetCutters/LevelSetCutters.jl:107-142): the marching-simplex
  * machinery on Grid(ReferenceFE{D-1}, bgmodel) without boundary -> EmbeddedFacetDiscretization
- * (src/Interfaces/EmbeddedFacetDiscretizations.jl:28-35).  n-cube Cartesian models, whole model (no slab) only.
+ * (src/Interfaces/EmbeddedFacetDiscretizations.jl:28-35).  n-cube Cartesian models.  With grid->slab_begin/end the result is
+ * the facet discretization of the rank's LOCAL model -- layers [slab_begin, slab_end) as a Cartesian model of its own (local
+ * facet numbering; its lower and upper planes are boundary facets of the local model), node coordinates global, so a slab's
+ * facets are bit-identical to the same facets of the whole model (the reference's ranks cut their local models the same way,
+ * src/Distributed/DistributedDiscretizations.jl:42-53).
  * Facet numbering (Gridap `generate_cell_to_faces`, assumption A8 in DESIGN.md): first encounter over (cell ascending,
  * local facet ascending), local facets QUAD [1,2],[3,4],[1,3],[2,4] / HEX [1,2,3,4],[5,6,7,8],[1,2,5,6],[3,4,7,8],
  * [1,3,5,7],[2,4,6,8]; a facet keeps the node order of the local facet of the cell that meets it first. */

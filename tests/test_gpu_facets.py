@@ -142,8 +142,8 @@ def test_facets_unsupported_inputs():
     with pytest.raises(NotImplementedError):
         cut_facets(model, disk(0.3, x0=(0.5, 0.5)))
     m = CartesianDiscreteModel((0, 1, 0, 1), (4, 4))
-    with pytest.raises(NotImplementedError):
-        LevelSetCutter(slab=(0, 2)).cut_facets(m, disk(0.3, x0=(0.5, 0.5)))
+    with pytest.raises(_lib.GecutError):  # slabs are supported; an empty / out-of-range one is an invalid argument
+        LevelSetCutter(slab=(3, 9)).cut_facets(m, disk(0.3, x0=(0.5, 0.5)))
     # raw ABI: simplexified grids are refused with NOTIMPLEMENTED, not silently mis-numbered
     ctx = _lib.default_context()
     import ctypes as C
@@ -202,3 +202,84 @@ def test_facets_properties_at_scale(case):
     anycut = (hh["ls_to_facet_to_inoutcut"] == 0).any(0)
     assert np.array_equal(np.nonzero(anycut)[0] + 1, hh["cutfacet_to_facet"])
     fc.close()
+
+
+@pytest.mark.parametrize("name,nslab", [("disk_odd", 3), ("three_disks", 2), ("sphere_odd", 3), ("csg_10", 2), ("bimaterial", 3)])
+def test_facet_slab_is_the_local_model_of_the_whole_cut(name, nslab):
+    """z-slabs (multi-GPU partition): cut_facets with `slab=(k0, k1)` is the facet discretization of the rank's LOCAL model
+    (local numbering) on GLOBAL node coordinates: every array equals the whole-model result on the facets of the slab, bit
+    for bit, through the facet -> node-tuple map."""
+    model, geo = CASES[name]()
+    D = model.D
+    ctx = _lib.default_context()
+    whole = cut_facets(model, geo)
+    hw = whole.to_host(topology=True)
+    gnodes = {tuple(r): f for f, r in enumerate(hw["facet_to_nodes"])}
+    # sub-facets of every cut facet of the whole model (contiguous, in cut-facet order)
+    wsf = {}
+    for i, f in enumerate(hw["sf_cell_to_bgcell"]):
+        wsf.setdefault(int(f) - 1, []).append(i)
+    nz = model.partition[-1]
+    layer_nodes = model.num_nodes // (nz + 1)
+    cuts = [round(q * nz / nslab) for q in range(nslab + 1)]
+    total_cutf = 0
+    for k0, k1 in zip(cuts[:-1], cuts[1:]):
+        loc = LevelSetCutter(ctx, slab=(k0, k1)).cut_facets(model, geo)
+        hl = loc.to_host(topology=True)
+        assert loc.bgmodel.partition[-1] == k1 - k0
+        # local facet -> global facet through the (ordered) node tuple
+        l2g = np.array([gnodes[tuple(int(v) + k0 * layer_nodes for v in r)] for r in hl["facet_to_nodes"]], dtype=np.int64)
+        assert len(set(l2g.tolist())) == len(l2g)
+        assert np.array_equal(hl["ls_to_facet_to_inoutcut"], hw["ls_to_facet_to_inoutcut"][:, l2g])
+        lcut = hl["cutfacet_to_facet"] - 1
+        assert np.all(np.diff(lcut) > 0)
+        gcut = set((hw["cutfacet_to_facet"] - 1).tolist())
+        assert set(l2g[lcut].tolist()) == {f for f in gcut if f in set(l2g.tolist())}
+        # sub-facets: per cut facet the same simplices, points, reference points and states
+        lsf = {}
+        for i, f in enumerate(hl["sf_cell_to_bgcell"]):
+            lsf.setdefault(int(f) - 1, []).append(i)
+        assert sorted(lsf) == sorted(lcut.tolist())
+        for f, ids in lsf.items():
+            gids = wsf[int(l2g[f])]
+            assert len(ids) == len(gids)
+            a, b = np.asarray(ids), np.asarray(gids)
+            assert np.array_equal(hl["ls_to_subfacet_to_inout"][:, a], hw["ls_to_subfacet_to_inout"][:, b])
+            pa, pb = hl["sf_cell_to_points"][a] - 1, hw["sf_cell_to_points"][b] - 1
+            assert np.array_equal(pa - pa.min(), pb - pb.min())
+            assert np.array_equal(hl["sf_point_to_coords"][pa.ravel()], hw["sf_point_to_coords"][pb.ravel()])
+            assert np.array_equal(hl["sf_point_to_rcoords"][pa.ravel()], hw["sf_point_to_rcoords"][pb.ravel()])
+        total_cutf += len(lcut)
+        # the slab's lower / upper planes are boundary facets of the local model
+        assert int(loc.sizes.num_boundary_facets) == int(hl["facet_is_boundary"].sum())
+        loc.close()
+    # every cut facet of the model shows up in the slabs; those on the planes shared by two slabs in both
+    shared = 0
+    for kk in cuts[1:-1]:
+        on_plane = [f for f in (hw["cutfacet_to_facet"] - 1)
+                    if all((int(v) - 1) // layer_nodes == kk for v in hw["facet_to_nodes"][f])]
+        shared += len(on_plane)
+    assert total_cutf == len(hw["cutfacet_to_facet"]) + shared
+    whole.close()
+
+
+def test_facet_slab_with_slab_local_nodal_values():
+    """DiscreteGeometry given as slab-local nodal vectors (node planes k0..k1 only): same facets as the closed-form slab."""
+    from gecut.cutters import evaluate_leaves_at_nodes
+    from gecut.csg import find_unique_leaves, replace_data
+    model, geo = CASES["sphere_odd"]()
+    ctx = _lib.default_context()
+    k0, k1 = 3, 8
+    ref = LevelSetCutter(ctx, slab=(k0, k1)).cut_facets(model, geo)
+    hr = ref.to_host(topology=True)
+    tree = geo.get_tree()
+    payloads, oid_to_j = find_unique_leaves(tree)
+    bufs = [evaluate_leaves_at_nodes(model, [pl], ctx=ctx, device_output=True, slab=(k0, k1))[0] for pl in payloads]
+    dgeo = DiscreteGeometry(replace_data(lambda d: d, lambda d: (bufs[oid_to_j[id(d[0])]], d[1], d[2]), tree), model)
+    loc = LevelSetCutter(ctx, slab=(k0, k1), nodal_slab_local=True).cut_facets(model, dgeo)
+    hl = loc.to_host(topology=True)
+    for k in ("ls_to_facet_to_inoutcut", "cutfacet_to_facet", "sf_cell_to_points", "sf_cell_to_bgcell", "sf_point_to_coords",
+              "sf_point_to_rcoords", "ls_to_subfacet_to_inout"):
+        assert np.array_equal(hl[k], hr[k]), k
+    ref.close()
+    loc.close()
