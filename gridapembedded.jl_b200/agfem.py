@@ -79,6 +79,56 @@ def aggregate(strategy: AggregateCutCellsByThreshold, cut: EmbeddedDiscretizatio
     return out
 
 
+def aggregate_slabs(strategy: AggregateCutCellsByThreshold, cuts, facets=None, geo=None, in_or_out=IN, comm: bool = False):
+    """Aggregation over z-slabs (`src/Distributed/DistributedAgFEM.jl:52-144`): `cuts` = the slab discretizations of one
+    model in ascending layer order (results of `LevelSetCutter(ctx, slab=(k0, k1)).cut`), `facets` = the matching slab facet
+    discretizations (default: classified here).  Returns one `cell_to_cellin` per slab with GLOBAL 1-based root ids; the
+    concatenation equals `aggregate` on the whole model.  `comm=True`: ONE slab per rank (`cuts` is this rank's cut), ghost
+    layers and termination through the library's NCCL communicator (`gecut_comm_aggregate`, collective)."""
+    if not isinstance(strategy, AggregateCutCellsByThreshold):
+        raise NotImplementedError("abstract method")
+    if in_or_out not in (IN, OUT):
+        raise ValueError("in_or_out must be IN or OUT")
+    single = isinstance(cuts, EmbeddedDiscretization)
+    cuts = [cuts] if single else list(cuts)
+    if comm and len(cuts) != 1:
+        raise ValueError("comm=True takes the one slab this rank owns")
+    ctx = cuts[0].ctx
+    own = []
+    if facets is None:
+        facets = []
+        for c in cuts:
+            slab = c.slab if getattr(c, "slab", None) is not None else None
+            f = _call_cut_facets(LevelSetCutter(ctx, slab=slab), c.bgmodel, c.geo, True)
+            own.append(f)
+            facets.append(f)
+    else:
+        facets = [facets] if isinstance(facets, EmbeddedFacetDiscretization) else list(facets)
+    if len(facets) != len(cuts):
+        raise ValueError("one facet discretization per slab")
+    prog = cuts[0].program(geo)
+    fprog = facets[0].program(geo)
+    outs = [np.empty(c.num_bgcells, np.int32) for c in cuts]
+    try:
+        if comm:
+            ctx.check(ctx._lib.gecut_comm_aggregate(cuts[0].handle, facets[0].handle, prog.ctypes.data, prog.size,
+                                                    fprog.ctypes.data, fprog.size, int(in_or_out),
+                                                    C.c_double(strategy.threshold), C.c_void_p(outs[0].ctypes.data), 0),
+                      "gecut_comm_aggregate")
+        else:
+            n = len(cuts)
+            hc = (C.c_void_p * n)(*[c.handle for c in cuts])
+            hf = (C.c_void_p * n)(*[f.handle for f in facets])
+            ho = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+            ctx.check(ctx._lib.gecut_aggregate_slabs(hc, hf, n, prog.ctypes.data, prog.size, fprog.ctypes.data, fprog.size,
+                                                     int(in_or_out), C.c_double(strategy.threshold), ho, 0),
+                      "gecut_aggregate_slabs")
+    finally:
+        for f in own:
+            f.close()
+    return outs[0] if single else outs
+
+
 def GhostSkeleton(cut: EmbeddedDiscretization, in_or_out=None, geo=None, ids: bool = False):
     """`GhostSkeleton(cut[, in_or_out=ACTIVE_IN][, geo or name])` (`EmbeddedDiscretizations.jl:465-543`): the
     `facet_to_mask` (bool per bg facet, Gridap facet numbering) the reference hands to `SkeletonTriangulation(model, mask)`;

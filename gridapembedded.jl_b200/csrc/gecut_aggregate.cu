@@ -13,6 +13,7 @@
 // sum of its selected subcells in subcell order (move_contributions), divided by the cell measure.
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "gecut_facets.cuh"
 
@@ -20,20 +21,23 @@ namespace {
 
 // cell_to_cellin / touched for every cell: roots are the cells with unit cut measure >= threshold (:141-146); uncut
 // cells have unit measure 1 (state == loc) or 0
+// z-slabs: the arrays hold the slab's own layers behind an optional ghost layer (`shift` = cells of the lower ghost layer);
+// roots are GLOBAL cell ids (`goff` = cells below the slab), as the distributed reference stores them
+// (src/Distributed/DistributedAgFEM.jl:101-105).  Whole model: shift = goff = 0.
 __global__ void k_agg_init(const GcLayout lay, int64_t nc, const GcProgram prog, int loc, double threshold,
-                           int32_t* __restrict__ cellin, uint8_t* __restrict__ touched) {
+                           int64_t shift, int64_t goff, int32_t* __restrict__ cellin, uint8_t* __restrict__ touched) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nc) return;
   const int st = gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, c);
   const double unit = st == loc ? 1.0 : 0.0;  // CUT cells are overwritten by k_agg_init_cut
   const bool root = st != GC_CUT && unit >= threshold;
-  cellin[c] = root ? (int32_t)(c + 1) : 0;
-  touched[c] = root ? 1 : 0;
+  cellin[c + shift] = root ? (int32_t)(c + goff + 1) : 0;
+  touched[c + shift] = root ? 1 : 0;
 }
 
 __global__ void k_agg_init_cut(const GcLayout lay, const uint32_t* __restrict__ sc_ptr, int64_t ncut, const GcProgram prog,
-                               int loc, double threshold, double cell_meas, int32_t* __restrict__ cellin,
-                               uint8_t* __restrict__ touched) {
+                               int loc, double threshold, double cell_meas, int64_t shift, int64_t goff,
+                               int32_t* __restrict__ cellin, uint8_t* __restrict__ touched) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= ncut) return;
   const int64_t c = (int64_t)lay.cutcells[k] - 1;
@@ -43,8 +47,8 @@ __global__ void k_agg_init_cut(const GcLayout lay, const uint32_t* __restrict__ 
   for (uint32_t e = s0; e < s1; ++e)
     if (gc_eval_inoutcut(prog, lay.sc_state, lay.sc_pitch, (int64_t)e) == loc) V += lay.sc_meas[e];
   const bool root = V / cell_meas >= threshold;
-  cellin[c] = root ? (int32_t)(c + 1) : 0;
-  touched[c] = root ? 1 : 0;
+  cellin[c + shift] = root ? (int32_t)(c + goff + 1) : 0;
+  touched[c + shift] = root ? 1 : 0;
 }
 
 // max over the vertex pairs of two cells of |p - q| (_find_best_neighbor :213-218), vertices in Gridap order
@@ -64,20 +68,26 @@ __device__ __forceinline__ double max_vertex_distance(const GcGrid& g, const int
   return d;
 }
 
-// one sweep (:155-176): untouched CUT cells look for the touched face neighbour whose root is closest
+// one sweep (:155-176): untouched CUT cells look for the touched face neighbour whose root is closest.  `g` is the cut's grid
+// (global sizes, slab [k0, k1)), `gf` the facet grid of the rank's local model (local numbering); neighbours across the
+// slab's lower / upper plane live in the ghost layers (`glo`, `ghi`: the layer exists), roots are global cell ids.
 template <int D>
-__global__ void k_agg_sweep(const GcGrid g, const GcLayout lay, int64_t ncut, const GcProgram prog, int loc,
-                            const int8_t* __restrict__ facet_state, int32_t* __restrict__ cellin,
-                            const uint8_t* __restrict__ touched, uint32_t* __restrict__ not_aggregated) {
+__global__ void k_agg_sweep(const GcGrid g, const GcGrid gf, const GcLayout lay, int64_t ncut, const GcProgram prog, int loc,
+                            const int8_t* __restrict__ facet_state, int64_t shift, int glo, int ghi,
+                            int32_t* __restrict__ cellin, const uint8_t* __restrict__ touched,
+                            uint32_t* __restrict__ not_aggregated) {
   const int64_t kk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (kk >= ncut) return;
-  const int64_t cell = (int64_t)lay.cutcells[kk] - 1;
-  if (touched[cell]) return;
+  const int64_t cell = (int64_t)lay.cutcells[kk] - 1;  // slab-local
+  if (touched[cell + shift]) return;
   if (gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, cell) != GC_CUT) return;
-  int c[3];
+  const int nl = g.k1 - g.k0;  // own layers
+  int c[3];                    // local: the last index counts from the slab's first layer
   c[0] = (int)(cell % g.n[0]);
   c[1] = D == 3 ? (int)((cell / g.n[0]) % g.n[1]) : (int)(cell / g.n[0]);
   c[2] = D == 3 ? (int)(cell / ((int64_t)g.n[0] * g.n[1])) : 0;
+  int cg[3] = {c[0], c[1], c[2]};  // global
+  cg[D - 1] += g.k0;
   double dmin = INFINITY;
   int64_t best = -1;
   // faces in Gridap's local order: highest direction first, low then high
@@ -85,20 +95,26 @@ __global__ void k_agg_sweep(const GcGrid g, const GcLayout lay, int64_t ncut, co
   for (int d = D - 1; d >= 0; --d) {
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
-      const int64_t f = facet_id_of<D>(g, c[0], c[1], c[2], d, side);
+      const int64_t f = facet_id_of<D>(gf, c[0], c[1], c[2], d, side);
       const int io = facet_state[f];
       if (io != GC_CUT && io != loc) continue;
       int nb[3] = {c[0], c[1], c[2]};
       nb[d] += side == 0 ? -1 : 1;
-      if (nb[d] < 0 || nb[d] >= g.n[d]) continue;  // boundary facet: the cell itself is the only one around
-      const int64_t neigh = (int64_t)nb[0] + (int64_t)g.n[0] * ((int64_t)nb[1] + (int64_t)g.n[1] * nb[2]);
+      if (d == D - 1) {
+        // boundary facet of the MODEL: the cell itself is the only one around; of the slab: the neighbour is a ghost
+        if ((nb[d] < 0 && !glo) || (nb[d] >= nl && !ghi)) continue;
+      } else if (nb[d] < 0 || nb[d] >= g.n[d]) {
+        continue;
+      }
+      const int64_t neigh = (D == 3 ? (int64_t)nb[0] + (int64_t)g.n[0] * ((int64_t)nb[1] + (int64_t)g.n[1] * nb[2])
+                                    : (int64_t)nb[0] + (int64_t)g.n[0] * nb[1]) + shift;
       if (!touched[neigh]) continue;
-      const int64_t root = (int64_t)cellin[neigh] - 1;
+      const int64_t root = (int64_t)cellin[neigh] - 1;  // global
       int r[3];
       r[0] = (int)(root % g.n[0]);
       r[1] = D == 3 ? (int)((root / g.n[0]) % g.n[1]) : (int)(root / g.n[0]);
       r[2] = D == 3 ? (int)(root / ((int64_t)g.n[0] * g.n[1])) : 0;
-      const double dist = max_vertex_distance<D>(g, c, r);
+      const double dist = max_vertex_distance<D>(g, cg, r);
       if (__dmul_rn(1.0 + 1.0e-9, dist) < dmin) {
         dmin = dist;
         best = neigh;
@@ -106,17 +122,17 @@ __global__ void k_agg_sweep(const GcGrid g, const GcLayout lay, int64_t ncut, co
     }
   }
   if (best >= 0)
-    cellin[cell] = cellin[best];  // `best` is touched: its root is final, no race with other threads of the sweep
+    cellin[cell + shift] = cellin[best];  // `best` is touched: its root is final, no race with other threads of the sweep
   else
     atomicAdd(not_aggregated, 1u);
 }
 
 // _touch_aggregated_cells! (:235-241) restricted to the cells that can change (cut cells)
-__global__ void k_agg_touch(const GcLayout lay, int64_t ncut, const int32_t* __restrict__ cellin,
+__global__ void k_agg_touch(const GcLayout lay, int64_t ncut, int64_t shift, const int32_t* __restrict__ cellin,
                             uint8_t* __restrict__ touched) {
   const int64_t kk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (kk >= ncut) return;
-  const int64_t cell = (int64_t)lay.cutcells[kk] - 1;
+  const int64_t cell = (int64_t)lay.cutcells[kk] - 1 + shift;
   if (cellin[cell] > 0) touched[cell] = 1;
 }
 
@@ -242,15 +258,146 @@ extern "C" int gecut_ghost_skeleton(const gecut_result* cut, const int32_t* prog
   return done(GECUT_OK);
 }
 
-extern "C" int gecut_aggregate(const gecut_result* cut, const gecut_facet_result* facets, const int32_t* program,
-                               int len, const int32_t* facet_program, int facet_len, int side, double threshold,
-                               int32_t* cell_to_cellin, int on_device) {
-  if (!cut || !facets || !cell_to_cellin) return GECUT_ERR_INVALID;
-  gecut_ctx* ctx = cut->ctx;
-  if (facets->ctx != ctx) {
+// ------------------------------------------------------------------------------------------------
+// Aggregation over one or several z-slabs.  A sweep of the reference is a Jacobi step (a cell reads only `touched` flags and
+// roots frozen during the sweep), so the distributed algorithm (src/Distributed/DistributedAgFEM.jl:86-144: own cells
+// swept, then `consistent!` on touched / cellin, `reduction!(&, all_aggregated)`) gives exactly the roots of the serial one
+// when the ghost layers are refreshed after every sweep.  One AggSlab per slab; the transport of the ghost layers is the
+// only difference between the whole model (none), several slabs on one GPU (device copies) and one slab per rank (NCCL).
+// ------------------------------------------------------------------------------------------------
+struct AggSlab {
+  const gecut_result* cut = nullptr;
+  const gecut_facet_result* fac = nullptr;
+  GcProgram p{}, pf{};
+  int32_t* cellin = nullptr;  // [ghost lo][own layers][ghost hi]
+  uint8_t* touched = nullptr;
+  int8_t* frow = nullptr;
+  const int8_t* facet_state = nullptr;
+  uint32_t* flag = nullptr;
+  int64_t layer = 0, nc = 0, ncut = 0, shift = 0, goff = 0, ntot = 0;
+  int glo = 0, ghi = 0;
+  bool owns_cellin = true;
+};
+
+static void agg_release(gecut_ctx* ctx, AggSlab& a) {
+  if (a.owns_cellin) gc_free(ctx, a.cellin);
+  gc_free(ctx, a.touched);
+  gc_free(ctx, a.frow);
+  gc_free(ctx, a.flag);
+  a.cellin = nullptr;
+  a.touched = nullptr;
+  a.frow = nullptr;
+  a.flag = nullptr;
+}
+
+// validation + allocation + the two initialisation passes of one slab
+static int agg_setup(gecut_ctx* ctx, AggSlab& a, const gecut_result* cut, const gecut_facet_result* facets,
+                     const int32_t* program, int len, const int32_t* facet_program, int facet_len, int side,
+                     double threshold, int32_t* dev_out /* whole model only: write straight into the caller's array */) {
+  a.cut = cut;
+  a.fac = facets;
+  if (facets->ctx != ctx || cut->ctx != ctx) {
     ctx->err = "aggregate: the cell and facet discretizations belong to different contexts";
     return GECUT_ERR_INVALID;
   }
+  const GcGrid& g = cut->grid;
+  const GcGrid& gf = facets->grid;
+  const int D = g.D;
+  if (g.simplexified) {
+    ctx->err = "aggregate is implemented for n-cube Cartesian models";
+    return GECUT_ERR_NOTIMPLEMENTED;
+  }
+  bool same = g.D == gf.D && cut->L == facets->L && gf.k0 == g.k0 && gf.n[D - 1] == g.k1 - g.k0;
+  for (int d = 0; d + 1 < D; ++d) same = same && g.n[d] == gf.n[d];
+  if (!same) {
+    ctx->err = "aggregate: cut and cut_facets come from different models / slabs / geometries";
+    return GECUT_ERR_INVALID;
+  }
+  GC_CHECK(gc_make_program(ctx, program, len, cut->L, &a.p));
+  // compute_bgfacet_to_inoutcut(cut_facets, geo) evaluates the geometry over cut_facets' OWN oid_to_ls (CellAggregation.jl:90):
+  // its level-set rows may be numbered differently from the cell discretization's
+  a.pf = a.p;
+  if (facet_program) GC_CHECK(gc_make_program(ctx, facet_program, facet_len, facets->L, &a.pf));
+  a.nc = cut->sizes.num_bgcells;
+  a.ncut = cut->sizes.num_cutcells;
+  a.layer = g.layer_cubes;
+  a.glo = g.k0 > 0 ? 1 : 0;
+  a.ghi = g.k1 < g.n[D - 1] ? 1 : 0;
+  a.shift = a.glo ? a.layer : 0;
+  a.goff = (int64_t)g.k0 * g.layer_cubes;
+  a.ntot = a.nc + (a.glo + a.ghi) * a.layer;
+  if (a.ncut > 0 && !cut->cut_sc_ptr) {
+    ctx->err = "aggregate needs the subcells of cut(), not a classification-only result";
+    return GECUT_ERR_INVALID;
+  }
+  if (dev_out && a.ntot == a.nc) {
+    a.cellin = dev_out;
+    a.owns_cellin = false;
+  } else {
+    GC_CHECK(gc_malloc(ctx, (void**)&a.cellin, sizeof(int32_t) * a.ntot));
+  }
+  GC_CHECK(gc_malloc(ctx, (void**)&a.touched, (size_t)a.ntot));
+  GC_CHECK(gc_malloc(ctx, (void**)&a.flag, sizeof(uint32_t)));
+  if (a.ntot != a.nc) {  // ghost layers start untouched; the first exchange fills them
+    GC_CUDA(cudaMemsetAsync(a.cellin, 0, sizeof(int32_t) * a.ntot, ctx->stream));
+    GC_CUDA(cudaMemsetAsync(a.touched, 0, (size_t)a.ntot, ctx->stream));
+  }
+  const int64_t nf = facets->sizes.num_bgfacets;
+  if (a.pf.len == 1) {  // the level set's own row for a single leaf, else the program's row
+    a.facet_state = facets->lay.bg_state + (int64_t)a.pf.tok[0] * facets->lay.bg_pitch;
+  } else {
+    GC_CHECK(gc_malloc(ctx, (void**)&a.frow, (size_t)pad_pitch(nf)));
+    GC_CHECK(gc_eval_rows(ctx, facets->lay.bg_state, facets->lay.bg_pitch, nf, a.pf, a.frow, true));
+    a.facet_state = a.frow;
+  }
+  const int T = 256;
+  GC_LAUNCH(ctx, "k_agg_init", k_agg_init<<<(unsigned)gc_div_up(a.nc, T), T, 0, ctx->stream>>>(
+      cut->lay, a.nc, a.p, side, threshold, a.shift, a.goff, a.cellin, a.touched));
+  GC_CHECK(gc_launch_check(ctx, "k_agg_init"));
+  if (a.ncut > 0) {
+    // get_cell_measure(bgtrian): tensor Gauss rule of degree 2 on the n-cube, sum_q w_q |det J|
+    const double detJ = g.dx[0] * g.dx[1] * (D == 3 ? g.dx[2] : 1.0);
+    const int nq = 1 << D;
+    const double w = D == 2 ? 0.25 : 0.125;
+    double cell_meas = 0.0;
+    for (int q = 0; q < nq; ++q) cell_meas += w * fabs(detJ);
+    GC_CHECK(gc_ensure_measures(ctx, cut));
+    GC_LAUNCH(ctx, "k_agg_init_cut", k_agg_init_cut<<<(unsigned)gc_div_up(a.ncut, T), T, 0, ctx->stream>>>(
+        cut->lay, cut->cut_sc_ptr, a.ncut, a.p, side, threshold, cell_meas, a.shift, a.goff, a.cellin, a.touched));
+    GC_CHECK(gc_launch_check(ctx, "k_agg_init_cut"));
+  }
+  return GECUT_OK;
+}
+
+static int agg_sweep(gecut_ctx* ctx, AggSlab& a, int side) {
+  GC_CUDA(cudaMemsetAsync(a.flag, 0, sizeof(uint32_t), ctx->stream));
+  if (a.ncut == 0) return GECUT_OK;
+  const int T = 256;
+  const GcGrid& g = a.cut->grid;
+  if (g.D == 2)
+    GC_LAUNCH(ctx, "k_agg_sweep", k_agg_sweep<2><<<(unsigned)gc_div_up(a.ncut, T), T, 0, ctx->stream>>>(
+        g, a.fac->grid, a.cut->lay, a.ncut, a.p, side, a.facet_state, a.shift, a.glo, a.ghi, a.cellin, a.touched, a.flag));
+  else
+    GC_LAUNCH(ctx, "k_agg_sweep", k_agg_sweep<3><<<(unsigned)gc_div_up(a.ncut, T), T, 0, ctx->stream>>>(
+        g, a.fac->grid, a.cut->lay, a.ncut, a.p, side, a.facet_state, a.shift, a.glo, a.ghi, a.cellin, a.touched, a.flag));
+  return gc_launch_check(ctx, "k_agg_sweep");
+}
+
+static int agg_touch(gecut_ctx* ctx, AggSlab& a) {
+  if (a.ncut == 0) return GECUT_OK;
+  const int T = 256;
+  GC_LAUNCH(ctx, "k_agg_touch", k_agg_touch<<<(unsigned)gc_div_up(a.ncut, T), T, 0, ctx->stream>>>(a.cut->lay, a.ncut, a.shift, a.cellin, a.touched));
+  return gc_launch_check(ctx, "k_agg_touch");
+}
+
+static int agg_copy_out(gecut_ctx* ctx, AggSlab& a, int32_t* out, int on_device) {
+  if (!a.owns_cellin) return GECUT_OK;  // written in place
+  GC_CUDA(cudaMemcpyAsync(out, a.cellin + a.shift, sizeof(int32_t) * a.nc, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                          ctx->stream));
+  return GECUT_OK;
+}
+
+static int agg_check_args(gecut_ctx* ctx, int side, double threshold) {
   if (!(threshold >= 0.0 && threshold <= 1.0)) {
     ctx->err = "Agg. threshold must be in [0,1]";  // AggregateCutCellsByThreshold (:64-68)
     return GECUT_ERR_INVALID;
@@ -259,112 +406,159 @@ extern "C" int gecut_aggregate(const gecut_result* cut, const gecut_facet_result
     ctx->err = "aggregate: in_or_out must be IN or OUT";
     return GECUT_ERR_INVALID;
   }
-  const GcGrid& g = cut->grid;
-  const GcGrid& gf = facets->grid;
-  if (g.simplexified || g.k0 != 0 || g.k1 != g.n[g.D - 1]) {
-    ctx->err = "aggregate is implemented for whole n-cube Cartesian models";
-    return GECUT_ERR_NOTIMPLEMENTED;
+  return GECUT_OK;
+}
+
+// slabs of ONE context (one GPU), in ascending layer order, together covering the model; ghost layers by device copies
+static int agg_run_local(gecut_ctx* ctx, std::vector<AggSlab>& S, int side, int32_t* const* outs, int on_device) {
+  const int n = (int)S.size();
+  auto exchange = [&]() -> int {
+    for (int r = 0; r + 1 < n; ++r) {
+      AggSlab &lo = S[r], &hi = S[r + 1];
+      const int64_t L = lo.layer;
+      // last own layer of `lo` -> lower ghost of `hi`; first own layer of `hi` -> upper ghost of `lo`
+      GC_CUDA(cudaMemcpyAsync(hi.cellin, lo.cellin + lo.shift + lo.nc - L, sizeof(int32_t) * L, cudaMemcpyDeviceToDevice, ctx->stream));
+      GC_CUDA(cudaMemcpyAsync(hi.touched, lo.touched + lo.shift + lo.nc - L, (size_t)L, cudaMemcpyDeviceToDevice, ctx->stream));
+      GC_CUDA(cudaMemcpyAsync(lo.cellin + lo.shift + lo.nc, hi.cellin + hi.shift, sizeof(int32_t) * L, cudaMemcpyDeviceToDevice, ctx->stream));
+      GC_CUDA(cudaMemcpyAsync(lo.touched + lo.shift + lo.nc, hi.touched + hi.shift, (size_t)L, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return GECUT_OK;
+  };
+  GC_CHECK(exchange());
+  int64_t ncut_all = 0;
+  for (auto& a : S) ncut_all += a.ncut;
+  bool all_aggregated = ncut_all == 0;
+  for (int iter = 0; iter < 20 && !all_aggregated; ++iter) {  // max_iters (:153)
+    for (auto& a : S) GC_CHECK(agg_sweep(ctx, a, side));
+    uint32_t* h = (uint32_t*)ctx->h_pinned;
+    for (int r = 0; r < n; ++r) GC_CUDA(cudaMemcpyAsync(h + r, S[r].flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GC_CUDA(cudaStreamSynchronize(ctx->stream));
+    all_aggregated = true;
+    for (int r = 0; r < n; ++r) all_aggregated = all_aggregated && h[r] == 0u;
+    if (!all_aggregated) {
+      for (auto& a : S) GC_CHECK(agg_touch(ctx, a));
+      GC_CHECK(exchange());
+    }
   }
-  if (g.D != gf.D || g.n[0] != gf.n[0] || g.n[1] != gf.n[1] || g.n[2] != gf.n[2] || cut->L != facets->L) {
-    ctx->err = "aggregate: cut and cut_facets come from different models / geometries";
+  if (!all_aggregated) {
+    ctx->err = "aggregate: not all cut cells could be aggregated in 20 sweeps (reference: @assert all_aggregated)";
+    return GECUT_ERR_INVALID;
+  }
+  for (int r = 0; r < n; ++r) GC_CHECK(agg_copy_out(ctx, S[r], outs[r], on_device));
+  GC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GECUT_OK;
+}
+
+extern "C" int gecut_aggregate(const gecut_result* cut, const gecut_facet_result* facets, const int32_t* program,
+                               int len, const int32_t* facet_program, int facet_len, int side, double threshold,
+                               int32_t* cell_to_cellin, int on_device) {
+  if (!cut || !facets || !cell_to_cellin) return GECUT_ERR_INVALID;
+  gecut_ctx* ctx = cut->ctx;
+  GC_CHECK(agg_check_args(ctx, side, threshold));
+  const GcGrid& g = cut->grid;
+  if (g.k0 != 0 || g.k1 != g.n[g.D - 1]) {
+    ctx->err = "aggregate: this is a z-slab of the model (gecut_aggregate_slabs / gecut_comm_aggregate)";
     return GECUT_ERR_INVALID;
   }
   DeviceGuard guard(ctx->device);
-  GcProgram p;
-  GC_CHECK(gc_make_program(ctx, program, len, cut->L, &p));
-  // compute_bgfacet_to_inoutcut(cut_facets, geo) evaluates the geometry over cut_facets' OWN oid_to_ls (CellAggregation.jl:90):
-  // its level-set rows may be numbered differently from the cell discretization's
-  GcProgram pf = p;
-  if (facet_program) GC_CHECK(gc_make_program(ctx, facet_program, facet_len, facets->L, &pf));
-  const int64_t nc = cut->sizes.num_bgcells, ncut = cut->sizes.num_cutcells, nf = facets->sizes.num_bgfacets;
-  const int D = g.D;
-  int32_t* cellin = nullptr;
-  uint8_t* touched = nullptr;
-  int8_t* frow = nullptr;
-  uint32_t* flag = nullptr;
+  std::vector<AggSlab> S(1);
+  int st = agg_setup(ctx, S[0], cut, facets, program, len, facet_program, facet_len, side, threshold,
+                     on_device ? cell_to_cellin : nullptr);
+  int32_t* outs[1] = {cell_to_cellin};
+  if (st == GECUT_OK) st = agg_run_local(ctx, S, side, outs, on_device);
+  agg_release(ctx, S[0]);
+  return st;
+}
+
+extern "C" int gecut_aggregate_slabs(const gecut_result* const* cuts, const gecut_facet_result* const* facets, int nslabs,
+                                     const int32_t* program, int len, const int32_t* facet_program, int facet_len, int side,
+                                     double threshold, int32_t* const* cell_to_cellin, int on_device) {
+  if (!cuts || !facets || !cell_to_cellin || nslabs < 1 || nslabs > 256) return GECUT_ERR_INVALID;
+  for (int r = 0; r < nslabs; ++r)
+    if (!cuts[r] || !facets[r] || !cell_to_cellin[r]) return GECUT_ERR_INVALID;
+  gecut_ctx* ctx = cuts[0]->ctx;
+  GC_CHECK(agg_check_args(ctx, side, threshold));
+  // the slabs must tile the layer axis of one model in ascending order
+  const GcGrid& g0 = cuts[0]->grid;
+  bool ok = g0.k0 == 0 && cuts[nslabs - 1]->grid.k1 == g0.n[g0.D - 1];
+  for (int r = 0; r + 1 < nslabs && ok; ++r) {
+    const GcGrid &a = cuts[r]->grid, &b = cuts[r + 1]->grid;
+    ok = a.k1 == b.k0 && a.D == b.D && a.n[0] == b.n[0] && a.n[1] == b.n[1] && a.n[2] == b.n[2];
+  }
+  if (!ok) {
+    ctx->err = "aggregate_slabs: the slabs must cover the layers of one model in ascending order";
+    return GECUT_ERR_INVALID;
+  }
+  DeviceGuard guard(ctx->device);
+  std::vector<AggSlab> S((size_t)nslabs);
   int st = GECUT_OK;
-  auto done = [&](int code) {
-    if (!on_device) gc_free(ctx, cellin);
-    gc_free(ctx, touched);
-    gc_free(ctx, frow);
-    gc_free(ctx, flag);
-    return code;
+  for (int r = 0; r < nslabs && st == GECUT_OK; ++r)
+    st = agg_setup(ctx, S[r], cuts[r], facets[r], program, len, facet_program, facet_len, side, threshold, nullptr);
+  if (st == GECUT_OK) st = agg_run_local(ctx, S, side, cell_to_cellin, on_device);
+  for (auto& a : S) agg_release(ctx, a);
+  return st;
+}
+
+// one slab per rank: ghost layers by ncclSend / ncclRecv with the ranks below and above, termination by all-reduce
+int gc_comm_exchange_layers(gecut_ctx* ctx, const void* send_lo, void* recv_lo, const void* send_hi, void* recv_hi, size_t bytes);
+int gc_comm_allreduce_sum_u32(gecut_ctx* ctx, uint32_t* value_dev);
+
+extern "C" int gecut_comm_aggregate(const gecut_result* cut, const gecut_facet_result* facets, const int32_t* program,
+                                    int len, const int32_t* facet_program, int facet_len, int side, double threshold,
+                                    int32_t* cell_to_cellin, int on_device) {
+  if (!cut || !facets || !cell_to_cellin) return GECUT_ERR_INVALID;
+  gecut_ctx* ctx = cut->ctx;
+  GC_CHECK(agg_check_args(ctx, side, threshold));
+  if (!ctx->comm) {
+    ctx->err = "no communicator on this context (gecut_comm_init)";
+    return GECUT_ERR_INVALID;
+  }
+  const GcGrid& g = cut->grid;
+  // rank r owns a slab above rank r-1's: the first rank starts at layer 0, the last one ends at the top
+  if ((ctx->comm_rank == 0) != (g.k0 == 0) || (ctx->comm_rank == ctx->comm_world - 1) != (g.k1 == g.n[g.D - 1])) {
+    ctx->err = "comm_aggregate: the ranks must own the z-slabs in ascending order";
+    return GECUT_ERR_INVALID;
+  }
+  DeviceGuard guard(ctx->device);
+  AggSlab a;
+  int st = agg_setup(ctx, a, cut, facets, program, len, facet_program, facet_len, side, threshold, nullptr);
+  auto exchange = [&]() -> int {
+    const int64_t L = a.layer;
+    GC_CHECK(gc_comm_exchange_layers(ctx, a.cellin + a.shift, a.cellin, a.cellin + a.shift + a.nc - L, a.cellin + a.shift + a.nc,
+                                     sizeof(int32_t) * L));
+    return gc_comm_exchange_layers(ctx, a.touched + a.shift, a.touched, a.touched + a.shift + a.nc - L,
+                                   a.touched + a.shift + a.nc, (size_t)L);
   };
-  if (on_device) {
-    cellin = cell_to_cellin;
-  } else {
-    st = gc_malloc(ctx, (void**)&cellin, sizeof(int32_t) * nc);
-    if (st != GECUT_OK) return done(st);
-  }
-  st = gc_malloc(ctx, (void**)&touched, (size_t)nc);
-  if (st == GECUT_OK) st = gc_malloc(ctx, (void**)&flag, sizeof(uint32_t));
-  if (st != GECUT_OK) return done(st);
-  // compute_bgfacet_to_inoutcut(cut_facets, geo): the level set's own row for a single leaf, else the program's row
-  const int8_t* facet_state = nullptr;
-  if (pf.len == 1) {
-    facet_state = facets->lay.bg_state + (int64_t)pf.tok[0] * facets->lay.bg_pitch;
-  } else {
-    st = gc_malloc(ctx, (void**)&frow, (size_t)pad_pitch(nf));
-    if (st == GECUT_OK) st = gc_eval_rows(ctx, facets->lay.bg_state, facets->lay.bg_pitch, nf, pf, frow, true);
-    if (st != GECUT_OK) return done(st);
-    facet_state = frow;
-  }
-  const int T = 256;
-  GC_LAUNCH(ctx, "k_agg_init", k_agg_init<<<(unsigned)gc_div_up(nc, T), T, 0, ctx->stream>>>(cut->lay, nc, p, side, threshold, cellin, touched));
-  st = gc_launch_check(ctx, "k_agg_init");
-  if (st != GECUT_OK) return done(st);
-  if (ncut > 0 && !cut->cut_sc_ptr) {
-    ctx->err = "aggregate needs the subcells of cut(), not a classification-only result";
-    return done(GECUT_ERR_INVALID);
-  }
-  if (ncut > 0) {
-    // get_cell_measure(bgtrian): tensor Gauss rule of degree 2 on the n-cube, sum_q w_q |det J|
-    const double detJ = g.dx[0] * g.dx[1] * (D == 3 ? g.dx[2] : 1.0);
-    const int nq = 1 << D;
-    const double w = D == 2 ? 0.25 : 0.125;
-    double cell_meas = 0.0;
-    for (int q = 0; q < nq; ++q) cell_meas += w * fabs(detJ);
-    st = gc_ensure_measures(ctx, cut);
-    if (st != GECUT_OK) return done(st);
-    GC_LAUNCH(ctx, "k_agg_init_cut", k_agg_init_cut<<<(unsigned)gc_div_up(ncut, T), T, 0, ctx->stream>>>(
-        cut->lay, cut->cut_sc_ptr, ncut, p, side, threshold, cell_meas, cellin, touched));
-    st = gc_launch_check(ctx, "k_agg_init_cut");
-    if (st != GECUT_OK) return done(st);
-    bool all_aggregated = false;
-    for (int iter = 0; iter < 20 && !all_aggregated; ++iter) {  // max_iters (:153)
-      if (cudaMemsetAsync(flag, 0, sizeof(uint32_t), ctx->stream) != cudaSuccess) return done(GECUT_ERR_CUDA);
-      if (D == 2)
-        GC_LAUNCH(ctx, "k_agg_sweep", k_agg_sweep<2><<<(unsigned)gc_div_up(ncut, T), T, 0, ctx->stream>>>(g, cut->lay, ncut, p, side, facet_state, cellin, touched, flag));
-      else
-        GC_LAUNCH(ctx, "k_agg_sweep", k_agg_sweep<3><<<(unsigned)gc_div_up(ncut, T), T, 0, ctx->stream>>>(g, cut->lay, ncut, p, side, facet_state, cellin, touched, flag));
-      st = gc_launch_check(ctx, "k_agg_sweep");
-      if (st != GECUT_OK) return done(st);
-      uint32_t* h = (uint32_t*)ctx->h_pinned;
-      if (cudaMemcpyAsync(h, flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-          cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
-        ctx->err = "aggregate: sweep failed";
-        return done(GECUT_ERR_CUDA);
-      }
-      all_aggregated = h[0] == 0u;
-      if (!all_aggregated) {
-        GC_LAUNCH(ctx, "k_agg_touch", k_agg_touch<<<(unsigned)gc_div_up(ncut, T), T, 0, ctx->stream>>>(cut->lay, ncut, cellin, touched));
-        st = gc_launch_check(ctx, "k_agg_touch");
-        if (st != GECUT_OK) return done(st);
-      }
+  // a failure before the collectives would leave the other ranks waiting: every rank goes through the same sequence and
+  // the local status joins the all-reduced flag
+  if (st == GECUT_OK) st = exchange();
+  bool all_aggregated = false;
+  for (int iter = 0; iter < 20 && !all_aggregated && st == GECUT_OK; ++iter) {
+    st = agg_sweep(ctx, a, side);
+    if (st == GECUT_OK) st = gc_comm_allreduce_sum_u32(ctx, a.flag);
+    if (st != GECUT_OK) break;
+    uint32_t* h = (uint32_t*)ctx->h_pinned;
+    if (cudaMemcpyAsync(h, a.flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+      ctx->err = "comm_aggregate: sweep failed";
+      st = GECUT_ERR_CUDA;
+      break;
     }
+    all_aggregated = h[0] == 0u;
     if (!all_aggregated) {
-      ctx->err = "aggregate: not all cut cells could be aggregated in 20 sweeps (reference: @assert all_aggregated)";
-      return done(GECUT_ERR_INVALID);
+      st = agg_touch(ctx, a);
+      if (st == GECUT_OK) st = exchange();
     }
   }
-  if (!on_device &&
-      cudaMemcpyAsync(cell_to_cellin, cellin, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) {
-    ctx->err = "aggregate: D2H copy failed";
-    return done(GECUT_ERR_CUDA);
+  if (st == GECUT_OK && !all_aggregated) {
+    ctx->err = "aggregate: not all cut cells could be aggregated in 20 sweeps (reference: @assert all_aggregated)";
+    st = GECUT_ERR_INVALID;
   }
-  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
-    ctx->err = "aggregate failed";
-    return done(GECUT_ERR_CUDA);
+  if (st == GECUT_OK) st = agg_copy_out(ctx, a, cell_to_cellin, on_device);
+  if (st == GECUT_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    ctx->err = "comm_aggregate failed";
+    st = GECUT_ERR_CUDA;
   }
-  return done(GECUT_OK);
+  agg_release(ctx, a);
+  return st;
 }

@@ -68,6 +68,31 @@ int need_comm(gecut_ctx* ctx) {
 
 }  // namespace
 
+// ghost layers of the slab-wise aggregation (gecut_aggregate.cu): `send_lo` goes to rank-1 and `recv_lo` comes from it,
+// `send_hi` / `recv_hi` likewise with rank+1; one group, stream-ordered
+int gc_comm_exchange_layers(gecut_ctx* ctx, const void* send_lo, void* recv_lo, const void* send_hi, void* recv_hi, size_t bytes) {
+  GC_CHECK(need_comm(ctx));
+  ncclComm_t comm = (ncclComm_t)ctx->comm;
+  const int r = ctx->comm_rank, w = ctx->comm_world;
+  GC_NCCL(ncclGroupStart());
+  if (r > 0) {
+    GC_NCCL(ncclSend(send_lo, bytes, ncclUint8, r - 1, comm, ctx->stream));
+    GC_NCCL(ncclRecv(recv_lo, bytes, ncclUint8, r - 1, comm, ctx->stream));
+  }
+  if (r + 1 < w) {
+    GC_NCCL(ncclSend(send_hi, bytes, ncclUint8, r + 1, comm, ctx->stream));
+    GC_NCCL(ncclRecv(recv_hi, bytes, ncclUint8, r + 1, comm, ctx->stream));
+  }
+  GC_NCCL(ncclGroupEnd());
+  return GECUT_OK;
+}
+
+int gc_comm_allreduce_sum_u32(gecut_ctx* ctx, uint32_t* value_dev) {
+  GC_CHECK(need_comm(ctx));
+  GC_NCCL(ncclAllReduce(value_dev, value_dev, 1, ncclUint32, ncclSum, (ncclComm_t)ctx->comm, ctx->stream));
+  return GECUT_OK;
+}
+
 extern "C" {
 
 int gecut_comm_unique_id(void* id) {

@@ -164,7 +164,9 @@ class LevelSetCutter(Cutter):
         rc = fn(self.ctx.handle, C.byref(grid), recs, len(leaves), ptrs, 1 if on_device else 0, C.byref(out))
         self.ctx.check(rc, fn_name)
         del keep
-        return EmbeddedDiscretization(self.ctx, out, model, geom, oid_to_ls)
+        disc = EmbeddedDiscretization(self.ctx, out, model, geom, oid_to_ls)
+        disc.slab = tuple(self.slab) if self.slab is not None else None  # z-slab of the model this result covers
+        return disc
 
     def cut(self, background, geom):
         """`cut(cutter::LevelSetCutter, background, geom)` (`LevelSetCutters.jl:79-82`)."""

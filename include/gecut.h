@@ -310,6 +310,15 @@ int gecut_facet_selection_measure(const gecut_facet_selection* sel, double* sub_
 int gecut_aggregate(const gecut_result* cut, const gecut_facet_result* facets, const int32_t* program, int len,
                     const int32_t* facet_program, int facet_len, int side, double threshold, int32_t* cell_to_cellin,
                     int on_device);
+/* The same over z-slabs (src/Distributed/DistributedAgFEM.jl:52-144, `_distributed_aggregate_by_threshold_barrier`): every slab
+ * sweeps its own cut cells, the cell layers two slabs share as ghosts (touched flags and roots) are refreshed after every sweep,
+ * the loop ends when no slab has an unaggregated cut cell.  A sweep only reads state frozen during the sweep, so the roots equal
+ * the whole-model aggregation's.  `cell_to_cellin[r]` (num_bgcells of slab r) receives GLOBAL 1-based root cell ids, as the
+ * reference stores them (:101-105).  `cuts[r]` / `facets[r]`: results of gecut_cut / gecut_cut_facets with the same slab, all in
+ * one context, in ascending layer order, together covering the model (a model cut slab by slab on one GPU). */
+int gecut_aggregate_slabs(const gecut_result* const* cuts, const gecut_facet_result* const* facets, int nslabs,
+                          const int32_t* program, int len, const int32_t* facet_program, int facet_len, int side,
+                          double threshold, int32_t* const* cell_to_cellin, int on_device);
 
 /* GhostSkeleton(cut, in_or_out, geo) (src/Interfaces/EmbeddedDiscretizations.jl:504-543): the interior facets with at
  * least one CUT cell around and both cells active (CUT or `side`; side = GECUT_IN / GECUT_OUT for ACTIVE_IN / ACTIVE_OUT,
@@ -353,6 +362,12 @@ int gecut_comm_allreduce_sum(gecut_ctx* ctx, const double* host_values, int n, d
 int gecut_comm_fetch(gecut_ctx* ctx, const double* values_dev, int n, double* host_out);
 /* sizes of every rank's result (all_sizes[world]): offsets of the rank-major global layout = exclusive sums.  Blocking. */
 int gecut_comm_allgather_sizes(gecut_ctx* ctx, const gecut_result* res, gecut_sizes* all_sizes);
+/* gecut_aggregate_slabs with one slab per rank (ranks own the z-slabs in ascending order): ghost cell layers by grouped
+ * ncclSend / ncclRecv with rank-1 / rank+1 after every sweep (`consistent!`, DistributedAgFEM.jl:124-128), termination by
+ * ncclAllReduce (`reduction!(&, all_aggregated)`, :130).  Collective: every rank calls it.  Global root ids. */
+int gecut_comm_aggregate(const gecut_result* cut, const gecut_facet_result* facets, const int32_t* program, int len,
+                         const int32_t* facet_program, int facet_len, int side, double threshold, int32_t* cell_to_cellin,
+                         int on_device);
 
 #ifdef __cplusplus
 }

@@ -113,3 +113,34 @@ def test_ghost_skeleton_parity(name):
     with pytest.raises(NotImplementedError):
         GhostSkeleton(cg, PHYSICAL_IN, nm)
     cg.close()
+
+
+@pytest.mark.parametrize("name,nslab", [("disk_30", 3), ("three_disks", 2), ("sphere", 3), ("csg", 2), ("bimaterial", 4)])
+@pytest.mark.parametrize("threshold", [1.0, 0.4])
+def test_aggregation_over_slabs_equals_the_whole_model(name, nslab, threshold):
+    """Distributed aggregation (`src/Distributed/DistributedAgFEM.jl:52-144`) on z-slabs: every slab sweeps its own cut cells
+    with the ghost cell layers refreshed after every sweep; the global roots equal the whole-model aggregation (and hence the
+    oracle's).  The slabs live on one GPU here (ghost layers by device copies); `gecut_comm_aggregate` runs the same sweeps
+    with NCCL transport (tests/test_gpu_multigpu.py)."""
+    from gecut import aggregate_slabs, LevelSetCutter, _lib
+    model, geo, nm = CASES[name]()
+    ctx = _lib.default_context()
+    strategy = AggregateCutCellsByThreshold(threshold)
+    nz = model.partition[-1]
+    cutsz = [round(q * nz / nslab) for q in range(nslab + 1)]
+    for side in (IN, OUT):
+        whole_cut = cut(model, geo)
+        try:
+            want = aggregate(strategy, whole_cut, nm, side)
+        except _lib.GecutError:
+            whole_cut.close()
+            continue  # the reference's @assert all_aggregated fires for this case: nothing to compare
+        cuts = [LevelSetCutter(ctx, slab=(a, b)).cut(model, geo) for a, b in zip(cutsz[:-1], cutsz[1:])]
+        got = aggregate_slabs(strategy, cuts, None, nm, side)
+        assert np.array_equal(np.concatenate(got), want)
+        # with user-supplied slab facet discretizations (full cut_facets, not only the classification)
+        facets = [LevelSetCutter(ctx, slab=(a, b)).cut_facets(model, geo) for a, b in zip(cutsz[:-1], cutsz[1:])]
+        got2 = aggregate_slabs(strategy, cuts, facets, nm, side)
+        assert np.array_equal(np.concatenate(got2), want)
+        for o in cuts + facets + [whole_cut]:
+            o.close()
