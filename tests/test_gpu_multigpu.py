@@ -134,6 +134,23 @@ def _worker(rank, world, port, q):
                 nod = lcut.cut(model, dgeo).to_host()
                 for k in hp:
                     assert np.array_equal(nod[k], hp[k]), (label, how, k)
+            # ---- distributed AgFEM aggregation (n-cube models): slab facets + ghost cell layers over NCCL == whole model
+            if not model.simplexified:
+                from gecut import aggregate, aggregate_slabs, AggregateCutCellsByThreshold
+                for thr in (1.0, 0.5):
+                    strategy = AggregateCutCellsByThreshold(thr)
+                    for side in (G.IN, G.OUT):
+                        try:
+                            want = aggregate(strategy, whole, name, side)
+                        except _lib.GecutError:
+                            want = None  # the reference's @assert all_aggregated: every rank must see the same failure
+                        try:
+                            got = aggregate_slabs(strategy, part, None, name, side, comm=True)
+                        except _lib.GecutError:
+                            got = None
+                        assert (want is None) == (got is None), (label, thr, side)
+                        if want is not None:
+                            assert np.array_equal(got, want[off:off + nc]), (label, thr, side)
             # a sign flip in ONE rank's copy of the shared plane is seen by every rank
             if rank == 0:
                 i = int(torch.argmax(torch.abs(bufs[0][-layer_nodes:])))
@@ -196,6 +213,9 @@ def test_library_communicator_single_rank():
     assert torch.equal(v, w)
     with pytest.raises(_lib.GecutError):
         ctx.comm_init(ctx.comm_unique_id(), 0, 1)  # already has one
+    # the distributed aggregation on a world of 1 is the whole-model aggregation
+    from gecut import aggregate, aggregate_slabs, AggregateAllCutCells
+    assert np.array_equal(aggregate_slabs(AggregateAllCutCells(), cg, comm=True), aggregate(AggregateAllCutCells(), cg))
     cg.close()
     ctx.comm_free()
     ctx.close()
