@@ -169,17 +169,53 @@ def get_geometry_names(geo: Geometry) -> List[str]:
     return [n.data[1] for n in pre_order_dfs(geo.get_tree()) if n.data[1] != ""]
 
 
+class LevelSetMap(dict):
+    """`oid_to_ls`: id(payload) -> level set, plus the egal keys (`by_key`) so that a geometry built later from equal
+    closed-form leaves (Julia: the same `objectid`) finds its level sets too."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.by_key: Dict[Any, int] = {}
+
+    def level_set_of(self, payload) -> int:
+        ls = self.get(id(payload))
+        if ls is None:
+            ls = self.by_key.get(_egal_key(payload))
+        if ls is None:
+            raise KeyError("this leaf is not one of the level sets of the discretization")
+        return ls
+
+
+def _egal_key(payload):
+    """What Julia's `objectid` sees (`DiscreteGeometries.jl:69`): closures over isbits values (the closed-form leaf functions of
+    `AnalyticalGeometries.jl` capture a radius, a centre, a direction) are immutable, so two of them built from the same
+    numbers are egal and hash alike -- `sphere(1.0)` twice is ONE level set in the reference.  Closed-form payloads compare
+    by kind and parameter bits; everything else (arbitrary callables, value vectors) by identity."""
+    kind = getattr(payload, "kind", None)
+    if kind is None or getattr(payload, "fun", None) is not None or not hasattr(payload, "x0"):
+        return ("id", id(payload))
+    import struct
+    bits = struct.pack("<9d", *payload.x0, *payload.v, payload.R, payload.r, 0.0)
+    return ("leaf", int(kind), int(getattr(payload, "dim", 0)), bits)
+
+
 def find_unique_leaves(tree: Node):
     """`_find_unique_leaves` (`DiscreteGeometries.jl:65-74`): payloads of the unique
-    leaves (first DFS occurrence) and the map `id(payload) -> ls` (0-based here)."""
+    leaves (first DFS occurrence) and the map `id(payload) -> ls` (0-based here); the ids of ALL payload objects that are
+    egal to a unique leaf (see `_egal_key`) map to its level set."""
     j_to_payload: List[Any] = []
-    oid_to_j: Dict[int, int] = {}
+    oid_to_j = LevelSetMap()
+    key_to_j = oid_to_j.by_key
     for leaf in leaves(tree):
         payload = leaf.data[0]
         oid = id(payload)
-        if oid not in oid_to_j:
-            oid_to_j[oid] = len(j_to_payload)
+        if oid in oid_to_j:
+            continue
+        key = _egal_key(payload)
+        if key not in key_to_j:
+            key_to_j[key] = len(j_to_payload)
             j_to_payload.append(payload)
+        oid_to_j[oid] = key_to_j[key]
     return j_to_payload, oid_to_j
 
 
@@ -192,7 +228,7 @@ def compile_postfix(tree: Node, oid_to_ls: Dict[int, int]) -> List[int]:
 
     def rec(n: Node):
         if n.is_leaf:
-            out.append(oid_to_ls[id(n.data[0])])
+            out.append(oid_to_ls.level_set_of(n.data[0]) if isinstance(oid_to_ls, LevelSetMap) else oid_to_ls[id(n.data[0])])
             return
         for c in n.children():
             rec(c)

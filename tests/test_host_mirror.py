@@ -59,9 +59,10 @@ def test_unique_leaves_numbering():
     prog = compile_postfix(g.get_tree(), oid)
     assert prog == [0, 1, OP_INTERSECT, 2, OP_INTERSECT, 3, OP_SETDIFF, 3, 2, OP_COMPLEMENT, OP_UNION, OP_UNION]
     assert compile_postfix(get_geometry(g, "solid").get_tree(), oid) == [3, 2, OP_COMPLEMENT, OP_UNION]
-    # two spheres with equal parameters are still two level sets (distinct closures in the reference)
+    # two spheres with equal parameters are ONE level set: Julia closures over isbits values are egal, `objectid` agrees
+    # (ADVICE round 1); see test_unique_leaves_follow_julia_objectid_for_closed_forms
     p2, _ = find_unique_leaves(union(sphere(1), sphere(1)).get_tree())
-    assert len(p2) == 2
+    assert len(p2) == 1
 
 
 def test_cube_and_square_planes():
@@ -184,3 +185,22 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle_binding" not in txt and "gecut_oracle" not in txt, f
+
+
+def test_unique_leaves_follow_julia_objectid_for_closed_forms():
+    """Julia's `objectid` makes two closures over the same isbits values ONE level set
+    (`DiscreteGeometries.jl:65-74`): `sphere(1.0)` built twice is deduplicated, different parameters or host callables are not."""
+    from gecut import sphere, cylinder, union, intersect, AnalyticalGeometry
+    from gecut.csg import find_unique_leaves, compile_postfix
+    a, b, c = sphere(1.0), sphere(1.0), sphere(1.0, x0=(0.1, 0.0, 0.0))
+    payloads, oid_to_j = find_unique_leaves(union(intersect(a, c), b).get_tree())
+    assert len(payloads) == 2
+    assert oid_to_j[id(a.get_tree().data[0])] == oid_to_j[id(b.get_tree().data[0])] == 0
+    assert oid_to_j[id(c.get_tree().data[0])] == 1
+    # a geometry built LATER from an equal closed form finds the level set too (same objectid in Julia)
+    assert compile_postfix(sphere(1.0).get_tree(), oid_to_j) == [0]
+    f = lambda x: x[:, 0]  # noqa: E731
+    g1, g2 = AnalyticalGeometry(f, dim=3), AnalyticalGeometry(lambda x: x[:, 0], dim=3)
+    payloads, _ = find_unique_leaves(union(g1, g2).get_tree())
+    assert len(payloads) == 2  # arbitrary callables: identity
+    assert len(find_unique_leaves(union(cylinder(0.3), cylinder(0.3, v=(0, 1, 0))).get_tree())[0]) == 2
