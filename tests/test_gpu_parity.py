@@ -97,7 +97,23 @@ CASES = {
     "stokes_hex": lambda: (lambda g: (CartesianDiscreteModel(g[1], g[2], (24, 6, 6)), g[0]))(stokes_geometry()),
     "no_cut": lambda: (CartesianDiscreteModel((2, 2, 2), (3, 3, 3), (6, 5, 4)), sphere(0.7)),
     "all_in": lambda: (CartesianDiscreteModel((-.1, -.1), (.1, .1), (7, 3)), disk(0.7)),
+    # models several classification tiles wide (64 x 8 x 8 / 64 x 16 x 8 cubes) with surfaces ON tile boundaries and node planes:
+    # the interval culling (k_classify_cull) must hand every tile a surface touches to the exact marching kernel
+    "cull_plane_on_tile_boundary": lambda: (CartesianDiscreteModel((0., 0., 0.), (3., 1., 1.), (96, 32, 24)), cull_planes()),
+    "cull_sphere_through_nodes_tet": lambda: (simplexify(CartesianDiscreteModel((0., 0., 0.), (4., 2., 2.), (128, 16, 16))),
+                                              sphere(0.75, x0=(2.0, 1.0, 1.0))),
+    "cull_oblique_cylinders": lambda: (CartesianDiscreteModel((0., 0., 0.), (4., 1., 1.), (128, 24, 20)),
+                                       union(cylinder(0.3, x0=(2.0, 0.5, 0.5), v=(1, 1, 0.5)),
+                                             cylinder(0.2, x0=(1.0, 0.5, 0.5), v=(0, 0, 1)))),
+    "cull_disk_2d": lambda: (CartesianDiscreteModel((0., 0.), (8., 2.), (512, 64)), disk(0.75, x0=(4.0, 1.0))),
 }
+
+
+def cull_planes():
+    # x = 2.0 is node column 64 (the boundary of the first tile), z = 1/3 is node plane 8 (a chunk boundary): values are exactly 0
+    # there (IN); the third plane is oblique
+    return intersect(intersect(plane(x0=(2.0, 0., 0.), v=(1, 0, 0)), plane(x0=(0., 0., 8 * (1.0 / 24)), v=(0, 0, -1))),
+                     plane(x0=(1.0, 0.5, 0.5), v=(-1, 0.3, 0.2)))
 
 
 def assert_float_equal(a, b, what):
