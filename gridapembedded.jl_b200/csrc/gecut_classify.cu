@@ -902,14 +902,33 @@ k_cutmask_emit(const uint32_t* __restrict__ cutmask, int64_t ngroups, const uint
                const uint32_t* __restrict__ cut22mask, const uint32_t* __restrict__ cut22count,
                uint32_t* __restrict__ tile_n22) {
   const int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gidx >= ngroups) return;
-  if (cutcount[gidx] == 0u) return;
-  const int64_t rowid = gidx / wxtot;
+  const bool in_range = gidx < ngroups;
+  const uint32_t mine = in_range ? cutcount[gidx] : 0u;
+  const uint32_t mine22 = (T22 && in_range) ? cut22count[gidx] : 0u;
+  const int64_t rowid = in_range ? gidx / wxtot : 0;
   const int w = (int)(gidx - rowid * wxtot);
-  uint32_t o = rowoffs[rowid], b = T22 ? rowoffs[nrows + rowid] : 0u;
-  for (int q = 0; q < w; ++q) {  // (16-byte loads of the row were measured slower: 0.095 against 0.085 ms)
-    o += cutcount[rowid * wxtot + q];
-    if (T22) b += cut22count[rowid * wxtot + q];
+  uint32_t o = 0u, b = 0u;
+  if (wxtot <= 32 && (32 % wxtot) == 0) {
+    // the groups of a row are wxtot consecutive lanes (ngroups and the block size are multiples of wxtot): the counts before
+    // the group in its row come from a segmented warp scan instead of w loads
+    const int lane = threadIdx.x & 31, pos = lane & (wxtot - 1);
+    uint32_t x = mine | (mine22 << 16);  // <= 192 cells per group, <= 32 groups: both halves stay below 2^16
+    for (int d = 1; d < wxtot; d <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, x, d);
+      if (pos >= d) x += up;
+    }
+    x -= mine | (mine22 << 16);
+    if (!in_range || mine == 0u) return;
+    o = rowoffs[rowid] + (x & 0xFFFFu);
+    if (T22) b = rowoffs[nrows + rowid] + (x >> 16);
+  } else {
+    if (!in_range || mine == 0u) return;
+    o = rowoffs[rowid];
+    b = T22 ? rowoffs[nrows + rowid] : 0u;
+    for (int q = 0; q < w; ++q) {
+      o += cutcount[rowid * wxtot + q];
+      if (T22) b += cut22count[rowid * wxtot + q];
+    }
   }
   uint32_t m[CPC], s[T22 ? CPC : 1];
   uint32_t any = 0u;
@@ -919,7 +938,7 @@ k_cutmask_emit(const uint32_t* __restrict__ cutmask, int64_t ngroups, const uint
     any |= m[t];
   }
   if (T22) {
-    const bool has = cut22count[gidx] != 0u;  // k_classify wrote the bits of such groups only
+    const bool has = mine22 != 0u;  // k_classify wrote the bits of such groups only
 #pragma unroll
     for (int t = 0; t < CPC; ++t) s[t] = has ? cut22mask[gidx * CPC + t] : 0u;
   }
