@@ -19,4 +19,4 @@ from .measures import Measure, integrate_measure, integrate_laplacian, get_cell_
 from .distributed import DistributedLevelSetCutter, slab_range
 from .facets import (EmbeddedFacetDiscretization, cut_facets, compute_bgfacet_to_inoutcut, compute_subfacet_to_inout,
                      BoundaryTriangulation, SkeletonTriangulation)
-from .agfem import AggregateCutCellsByThreshold, AggregateAllCutCells, aggregate, aggregate_slabs, GhostSkeleton
+from .agfem import AggregateCutCellsByThreshold, AggregateAllCutCells, aggregate, aggregate_slabs, GhostSkeleton, GhostSkeleton_slabs

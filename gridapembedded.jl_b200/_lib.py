@@ -256,6 +256,8 @@ def lib():
     L.gecut_aggregate_slabs.argtypes = [P(vp), P(vp), cint, vp, cint, vp, cint, cint, C.c_double, P(vp), cint]
     L.gecut_comm_aggregate.argtypes = [vp, vp, vp, cint, vp, cint, cint, C.c_double, vp, cint]
     L.gecut_ghost_skeleton.argtypes = [vp, vp, cint, cint, P(i64), vp, vp]
+    L.gecut_ghost_skeleton_slabs.argtypes = [P(vp), cint, vp, cint, cint, P(i64), P(vp)]
+    L.gecut_comm_ghost_skeleton.argtypes = [vp, vp, cint, cint, P(i64), vp]
     L.gecut_comm_unique_id.argtypes = [vp]
     L.gecut_comm_init.argtypes = [vp, vp, cint, cint]
     L.gecut_comm_free.argtypes = [vp]
@@ -281,11 +283,13 @@ def lib():
 FACET_SYMBOLS = ["gecut_cut_facets", "gecut_facet_result_free", "gecut_facet_result_sizes", "gecut_facet_result_copy",
                  "gecut_bgfacet_to_inoutcut", "gecut_subfacet_to_inout", "gecut_select_facets",
                  "gecut_facet_selection_free", "gecut_facet_selection_sizes", "gecut_facet_selection_copy",
-                 "gecut_facet_selection_measure", "gecut_aggregate", "gecut_aggregate_slabs", "gecut_ghost_skeleton"]
+                 "gecut_facet_selection_measure", "gecut_aggregate", "gecut_aggregate_slabs", "gecut_ghost_skeleton",
+                 "gecut_ghost_skeleton_slabs"]
 
 COMM_SYMBOLS = ["gecut_comm_unique_id", "gecut_comm_init", "gecut_comm_free", "gecut_comm_rank",
                 "gecut_comm_exchange_ghost_planes", "gecut_comm_check_consistency", "gecut_comm_allreduce_sum",
-                "gecut_comm_fetch", "gecut_comm_allgather_sizes", "gecut_comm_aggregate"]
+                "gecut_comm_fetch", "gecut_comm_allgather_sizes", "gecut_comm_aggregate",
+                "gecut_comm_ghost_skeleton"]
 
 EXPORTED_SYMBOLS = FACET_SYMBOLS + COMM_SYMBOLS + ["gecut_create", "gecut_destroy", "gecut_set_stream", "gecut_last_error", "gecut_launch_count",
                     "gecut_profile", "gecut_profile_report", "gecut_trim",

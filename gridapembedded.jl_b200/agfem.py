@@ -161,3 +161,50 @@ def GhostSkeleton(cut: EmbeddedDiscretization, in_or_out=None, geo=None, ids: bo
     ctx.check(ctx._lib.gecut_ghost_skeleton(cut.handle, prog.ctypes.data, prog.size, int(side), C.byref(n),
                                             C.c_void_p(mask.ctypes.data), None), "gecut_ghost_skeleton")
     return mask.astype(bool)
+
+
+def _local_num_facets(model, slab) -> int:
+    part = list(model.partition)
+    if slab is not None:
+        part[-1] = int(slab[1]) - int(slab[0])
+    D = model.D
+    return sum(int(np.prod([part[e] + (1 if e == d else 0) for e in range(D)])) for d in range(D))
+
+
+def GhostSkeleton_slabs(cuts, in_or_out=None, geo=None, comm: bool = False):
+    """`GhostSkeleton` over z-slabs (the reference's ranks build it on their local models, `src/Distributed`): one
+    `facet_to_mask` per slab in the facet numbering of the slab's local model (`LevelSetCutter(ctx, slab).cut_facets`); the
+    cells across a shared plane are read from the adjacent slab (`comm=True`: ONE slab per rank, boundary cell layers over the
+    library's NCCL communicator)."""
+    from .discretizations import ACTIVE_IN
+    if isinstance(in_or_out, (str, Geometry)) and geo is None:
+        in_or_out, geo = None, in_or_out
+    if in_or_out is None:
+        in_or_out = ACTIVE_IN
+    if isinstance(in_or_out, tuple):
+        raise NotImplementedError("Not implemented but not needed in practice. Ghost stabilization can be integrated in "
+                                  "full facets.")
+    side = in_or_out if isinstance(in_or_out, int) else in_or_out.in_or_out
+    if side not in (IN, OUT, 0):
+        raise ValueError("in_or_out must be ACTIVE_IN, ACTIVE_OUT or IN / OUT / CUT")
+    single = isinstance(cuts, EmbeddedDiscretization)
+    cuts = [cuts] if single else list(cuts)
+    if comm and len(cuts) != 1:
+        raise ValueError("comm=True takes the one slab this rank owns")
+    ctx = cuts[0].ctx
+    prog = cuts[0].program(geo)
+    masks = [np.empty(_local_num_facets(c.bgmodel, getattr(c, "slab", None)), np.int8) for c in cuts]
+    n = len(cuts)
+    counts = (C.c_int64 * n)()
+    if comm:
+        ctx.check(ctx._lib.gecut_comm_ghost_skeleton(cuts[0].handle, prog.ctypes.data, prog.size, int(side), counts,
+                                                     C.c_void_p(masks[0].ctypes.data)), "gecut_comm_ghost_skeleton")
+    else:
+        hc = (C.c_void_p * n)(*[c.handle for c in cuts])
+        hm = (C.c_void_p * n)(*[m.ctypes.data for m in masks])
+        ctx.check(ctx._lib.gecut_ghost_skeleton_slabs(hc, n, prog.ctypes.data, prog.size, int(side), counts, hm),
+                  "gecut_ghost_skeleton_slabs")
+    for m, k in zip(masks, counts):
+        assert int(m.sum()) == int(k)
+    out = [m.astype(bool) for m in masks]
+    return out[0] if single else out

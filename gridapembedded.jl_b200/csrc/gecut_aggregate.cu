@@ -11,6 +11,7 @@
 // topology of the Cartesian model is closed form (gecut_facets.cuh): no cell_to_faces / face_to_cells tables exist.
 // Only the O(n^2) cut cells are visited after the O(n^3) initialisation pass; the unit cut measure of a cut cell is the
 // sum of its selected subcells in subcell order (move_contributions), divided by the cell measure.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -140,12 +141,15 @@ __global__ void k_agg_touch(const GcLayout lay, int64_t ncut, int64_t shift, con
 // with at least one CUT cell around and both cells active (CUT or `side`).  Every such facet touches a CUT cell, so
 // the O(n^2) cut cells drive the pass; a facet between two CUT cells is written by both with the same value.
 template <int D>
-__global__ void k_ghost_mask(const GcGrid g, const GcLayout lay, int64_t ncut, const GcProgram prog, int side,
+__global__ void k_ghost_mask(const GcGrid g, const GcGrid gf, const GcLayout lay, int64_t ncut, const GcProgram prog, int side,
+                             const int8_t* __restrict__ lo_rows, int64_t lo_pitch, int64_t lo_base,
+                             const int8_t* __restrict__ hi_rows, int64_t hi_pitch, int64_t hi_base,
                              int8_t* __restrict__ mask, unsigned long long* __restrict__ count) {
   const int64_t kk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (kk >= ncut) return;
-  const int64_t cell = (int64_t)lay.cutcells[kk] - 1;
+  const int64_t cell = (int64_t)lay.cutcells[kk] - 1;  // slab-local
   if (gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, cell) != GC_CUT) return;
+  const int nl = g.k1 - g.k0;
   int c[3];
   c[0] = (int)(cell % g.n[0]);
   c[1] = D == 3 ? (int)((cell / g.n[0]) % g.n[1]) : (int)(cell / g.n[0]);
@@ -156,15 +160,34 @@ __global__ void k_ghost_mask(const GcGrid g, const GcLayout lay, int64_t ncut, c
     for (int sd = 0; sd < 2; ++sd) {
       int nb[3] = {c[0], c[1], c[2]};
       nb[d] += sd == 0 ? -1 : 1;
-      if (nb[d] < 0 || nb[d] >= g.n[d]) continue;
-      const int64_t neigh = (int64_t)nb[0] + (int64_t)g.n[0] * ((int64_t)nb[1] + (int64_t)g.n[1] * nb[2]);
-      const int st = gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, neigh);
+      int st;
+      if (d == D - 1 && (nb[d] < 0 || nb[d] >= nl)) {
+        // across the slab's lower / upper plane: the neighbour's states come from the adjacent slab (its last / first layer);
+        // no adjacent slab = boundary of the model
+        const int8_t* rows = nb[d] < 0 ? lo_rows : hi_rows;
+        if (!rows) continue;
+        const int64_t in_layer = D == 3 ? (int64_t)nb[0] + (int64_t)g.n[0] * nb[1] : (int64_t)nb[0];
+        st = gc_eval_inoutcut(prog, rows, nb[d] < 0 ? lo_pitch : hi_pitch, (nb[d] < 0 ? lo_base : hi_base) + in_layer);
+      } else {
+        if (nb[d] < 0 || nb[d] >= g.n[d]) continue;
+        const int64_t neigh = D == 3 ? (int64_t)nb[0] + (int64_t)g.n[0] * ((int64_t)nb[1] + (int64_t)g.n[1] * nb[2])
+                                     : (int64_t)nb[0] + (int64_t)g.n[0] * nb[1];
+        st = gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, neigh);
+      }
       if (st != GC_CUT && st != side) continue;
-      mask[facet_id_of<D>(g, c[0], c[1], c[2], d, sd)] = 1;
-      // counted once: by the CUT cell on the low side, or by this cell when the neighbour is not CUT
-      if (st != GC_CUT || sd == 1) atomicAdd(count, 1ull);
+      mask[facet_id_of<D>(gf, c[0], c[1], c[2], d, sd)] = 1;
+      // whole model: counted once -- by the CUT cell on the low side, or by this cell when the neighbour is not CUT
+      if (count && (st != GC_CUT || sd == 1)) atomicAdd(count, 1ull);
     }
   }
+}
+
+// number of marked facets (slab version: a facet on a plane two slabs share is marked -- and counted -- in both local models)
+__global__ void __launch_bounds__(256) k_count_mask(const int8_t* __restrict__ mask, int64_t n, unsigned long long* __restrict__ count) {
+  unsigned int mine = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) mine += mask[i] ? 1u : 0u;
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(count, (unsigned long long)mine);
 }
 
 __global__ void k_mask_to_flags(const int8_t* __restrict__ mask, int64_t n, uint32_t* __restrict__ flags) {
@@ -213,9 +236,9 @@ extern "C" int gecut_ghost_skeleton(const gecut_result* cut, const int32_t* prog
   const int T = 256;
   if (ncut > 0) {
     if (D == 2)
-      GC_LAUNCH(ctx, "k_ghost_mask", k_ghost_mask<2><<<(unsigned)gc_div_up(ncut, T), T, 0, ctx->stream>>>(g, cut->lay, ncut, p, side, mask, cnt));
+      GC_LAUNCH(ctx, "k_ghost_mask", k_ghost_mask<2><<<(unsigned)gc_div_up(ncut, T), T, 0, ctx->stream>>>(g, g, cut->lay, ncut, p, side, nullptr, 0, 0, nullptr, 0, 0, mask, cnt));
     else
-      GC_LAUNCH(ctx, "k_ghost_mask", k_ghost_mask<3><<<(unsigned)gc_div_up(ncut, T), T, 0, ctx->stream>>>(g, cut->lay, ncut, p, side, mask, cnt));
+      GC_LAUNCH(ctx, "k_ghost_mask", k_ghost_mask<3><<<(unsigned)gc_div_up(ncut, T), T, 0, ctx->stream>>>(g, g, cut->lay, ncut, p, side, nullptr, 0, 0, nullptr, 0, 0, mask, cnt));
     st = gc_launch_check(ctx, "k_ghost_mask");
     if (st != GECUT_OK) return done(st);
   }
@@ -561,4 +584,123 @@ extern "C" int gecut_comm_aggregate(const gecut_result* cut, const gecut_facet_r
   }
   agg_release(ctx, a);
   return st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GhostSkeleton over z-slabs: the mask of the rank's LOCAL model (the facet numbering of gecut_cut_facets with the same
+// slab).  Facets on the plane two slabs share are interior facets of the model: the state of the cell on the other side
+// comes from the adjacent slab's boundary cell layer -- read in place when the slabs live in one context, received by
+// ncclSend / ncclRecv otherwise.
+// ------------------------------------------------------------------------------------------------
+static int ghost_slab(gecut_ctx* ctx, const gecut_result* cut, const GcProgram& p, int side, const int8_t* lo_rows,
+                      int64_t lo_pitch, int64_t lo_base, const int8_t* hi_rows, int64_t hi_pitch, int64_t hi_base,
+                      int64_t* n_ghost, int8_t* mask_host) {
+  const GcGrid& g = cut->grid;
+  const int D = g.D;
+  GcGrid gf = g;  // the local model of the slab
+  gf.n[D - 1] = g.k1 - g.k0;
+  gf.nn[D - 1] = gf.n[D - 1] + 1;
+  const int64_t nf = D == 2 ? num_facets<2>(gf) : num_facets<3>(gf);
+  const int64_t ncut = cut->sizes.num_cutcells;
+  GcScratch scratch(ctx);
+  int8_t* mask = nullptr;
+  unsigned long long* cnt = nullptr;
+  GC_CHECK(scratch.alloc(&mask, (size_t)pad_pitch(nf)));
+  GC_CHECK(scratch.alloc(&cnt, sizeof(unsigned long long)));
+  GC_CUDA(cudaMemsetAsync(mask, 0, (size_t)nf, ctx->stream));
+  GC_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), ctx->stream));
+  const int T = 256;
+  if (ncut > 0) {
+    if (D == 2)
+      GC_LAUNCH(ctx, "k_ghost_mask", k_ghost_mask<2><<<(unsigned)gc_div_up(ncut, T), T, 0, ctx->stream>>>(
+          g, gf, cut->lay, ncut, p, side, lo_rows, lo_pitch, lo_base, hi_rows, hi_pitch, hi_base, mask, nullptr));
+    else
+      GC_LAUNCH(ctx, "k_ghost_mask", k_ghost_mask<3><<<(unsigned)gc_div_up(ncut, T), T, 0, ctx->stream>>>(
+          g, gf, cut->lay, ncut, p, side, lo_rows, lo_pitch, lo_base, hi_rows, hi_pitch, hi_base, mask, nullptr));
+    GC_CHECK(gc_launch_check(ctx, "k_ghost_mask"));
+    GC_LAUNCH(ctx, "k_count_mask", k_count_mask<<<(unsigned)std::min<int64_t>(1184, gc_div_up(nf, T)), T, 0, ctx->stream>>>(mask, nf, cnt));
+    GC_CHECK(gc_launch_check(ctx, "k_count_mask"));
+  }
+  uint64_t* h = (uint64_t*)ctx->h_pinned;
+  GC_CUDA(cudaMemcpyAsync(h, cnt, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (mask_host) GC_CUDA(cudaMemcpyAsync(mask_host, mask, (size_t)nf, cudaMemcpyDeviceToHost, ctx->stream));
+  GC_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (n_ghost) *n_ghost = (int64_t)h[0];
+  return GECUT_OK;
+}
+
+static int ghost_check_args(gecut_ctx* ctx, const gecut_result* cut, int side) {
+  if (side != GECUT_IN && side != GECUT_OUT && side != GECUT_CUT) {
+    ctx->err = "ghost skeleton: in_or_out must be IN, OUT or CUT";
+    return GECUT_ERR_INVALID;
+  }
+  if (cut->grid.simplexified) {
+    ctx->err = "GhostSkeleton is implemented for n-cube Cartesian models";
+    return GECUT_ERR_NOTIMPLEMENTED;
+  }
+  return GECUT_OK;
+}
+
+extern "C" int gecut_ghost_skeleton_slabs(const gecut_result* const* cuts, int nslabs, const int32_t* program, int len, int side,
+                                          int64_t* n_ghost, int8_t* const* facet_to_mask) {
+  if (!cuts || nslabs < 1 || nslabs > 256) return GECUT_ERR_INVALID;
+  for (int r = 0; r < nslabs; ++r)
+    if (!cuts[r]) return GECUT_ERR_INVALID;
+  gecut_ctx* ctx = cuts[0]->ctx;
+  const GcGrid& g0 = cuts[0]->grid;
+  bool ok = g0.k0 == 0 && cuts[nslabs - 1]->grid.k1 == g0.n[g0.D - 1];
+  for (int r = 0; r < nslabs && ok; ++r) ok = cuts[r]->ctx == ctx && cuts[r]->L == cuts[0]->L;
+  for (int r = 0; r + 1 < nslabs && ok; ++r) ok = cuts[r]->grid.k1 == cuts[r + 1]->grid.k0;
+  if (!ok) {
+    ctx->err = "ghost_skeleton_slabs: the slabs must cover the layers of one model in ascending order, in one context";
+    return GECUT_ERR_INVALID;
+  }
+  DeviceGuard guard(ctx->device);
+  for (int r = 0; r < nslabs; ++r) {
+    GC_CHECK(ghost_check_args(ctx, cuts[r], side));
+    GcProgram p;
+    GC_CHECK(gc_make_program(ctx, program, len, cuts[r]->L, &p));
+    const gecut_result* lo = r > 0 ? cuts[r - 1] : nullptr;
+    const gecut_result* hi = r + 1 < nslabs ? cuts[r + 1] : nullptr;
+    const int64_t layer = g0.layer_cubes;
+    GC_CHECK(ghost_slab(ctx, cuts[r], p, side, lo ? lo->lay.bg_state : nullptr, lo ? lo->lay.bg_pitch : 0,
+                        lo ? lo->sizes.num_bgcells - layer : 0, hi ? hi->lay.bg_state : nullptr, hi ? hi->lay.bg_pitch : 0, 0,
+                        n_ghost ? n_ghost + r : nullptr, facet_to_mask ? facet_to_mask[r] : nullptr));
+  }
+  return GECUT_OK;
+}
+
+extern "C" int gecut_comm_ghost_skeleton(const gecut_result* cut, const int32_t* program, int len, int side, int64_t* n_ghost,
+                                         int8_t* facet_to_mask) {
+  if (!cut) return GECUT_ERR_INVALID;
+  gecut_ctx* ctx = cut->ctx;
+  GC_CHECK(ghost_check_args(ctx, cut, side));
+  if (!ctx->comm) {
+    ctx->err = "no communicator on this context (gecut_comm_init)";
+    return GECUT_ERR_INVALID;
+  }
+  const GcGrid& g = cut->grid;
+  if ((ctx->comm_rank == 0) != (g.k0 == 0) || (ctx->comm_rank == ctx->comm_world - 1) != (g.k1 == g.n[g.D - 1])) {
+    ctx->err = "comm_ghost_skeleton: the ranks must own the z-slabs in ascending order";
+    return GECUT_ERR_INVALID;
+  }
+  DeviceGuard guard(ctx->device);
+  GcProgram p;
+  GC_CHECK(gc_make_program(ctx, program, len, cut->L, &p));
+  // the L state rows of the slab's first / last cell layer, packed [L][layer], to the ranks below / above
+  const int L = cut->L;
+  const int64_t layer = g.layer_cubes, nc = cut->sizes.num_bgcells;
+  GcScratch scratch(ctx);
+  int8_t* buf = nullptr;  // [send lo][send hi][recv lo][recv hi], L * layer bytes each
+  const size_t blk = (size_t)L * layer;
+  GC_CHECK(scratch.alloc(&buf, 4 * blk));
+  for (int ls = 0; ls < L; ++ls) {
+    const int8_t* row = cut->lay.bg_state + (int64_t)ls * cut->lay.bg_pitch;
+    GC_CUDA(cudaMemcpyAsync(buf + (size_t)ls * layer, row, (size_t)layer, cudaMemcpyDeviceToDevice, ctx->stream));
+    GC_CUDA(cudaMemcpyAsync(buf + blk + (size_t)ls * layer, row + nc - layer, (size_t)layer, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  GC_CHECK(gc_comm_exchange_layers(ctx, buf, buf + 2 * blk, buf + blk, buf + 3 * blk, blk));
+  const bool has_lo = ctx->comm_rank > 0, has_hi = ctx->comm_rank + 1 < ctx->comm_world;
+  return ghost_slab(ctx, cut, p, side, has_lo ? buf + 2 * blk : nullptr, layer, 0, has_hi ? buf + 3 * blk : nullptr, layer, 0,
+                    n_ghost, facet_to_mask);
 }

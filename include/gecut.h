@@ -328,6 +328,12 @@ int gecut_aggregate_slabs(const gecut_result* const* cuts, const gecut_facet_res
  * Whole n-cube Cartesian models. */
 int gecut_ghost_skeleton(const gecut_result* cut, const int32_t* program, int len, int side, int64_t* n_ghost,
                          int8_t* facet_to_mask, int32_t* facet_ids);
+/* The same over z-slabs of one context (in ascending layer order, covering the model): `facet_to_mask[r]` (host, NULL skipped)
+ * is the mask of slab r's LOCAL model -- the facet numbering of gecut_cut_facets with the same slab -- and n_ghost[r] the
+ * number of its marked facets.  A facet on the plane two slabs share is an interior facet of the model: the cell on its other
+ * side is read from the adjacent slab, and the facet is marked (and counted) in both local models. */
+int gecut_ghost_skeleton_slabs(const gecut_result* const* cuts, int nslabs, const int32_t* program, int len, int side,
+                               int64_t* n_ghost, int8_t* const* facet_to_mask);
 
 /* ---- multi-GPU: z-slab partition, one context per GPU / process ------------------------------ */
 /* cut(cutter, bgmodel::DistributedDiscreteModel, geo) (src/Distributed/DistributedDiscretizations.jl:33-40): every rank
@@ -365,6 +371,10 @@ int gecut_comm_allgather_sizes(gecut_ctx* ctx, const gecut_result* res, gecut_si
 /* gecut_aggregate_slabs with one slab per rank (ranks own the z-slabs in ascending order): ghost cell layers by grouped
  * ncclSend / ncclRecv with rank-1 / rank+1 after every sweep (`consistent!`, DistributedAgFEM.jl:124-128), termination by
  * ncclAllReduce (`reduction!(&, all_aggregated)`, :130).  Collective: every rank calls it.  Global root ids. */
+/* gecut_ghost_skeleton_slabs with one slab per rank: the state rows of the boundary cell layers travel by grouped
+ * ncclSend / ncclRecv.  Collective. */
+int gecut_comm_ghost_skeleton(const gecut_result* cut, const int32_t* program, int len, int side, int64_t* n_ghost,
+                              int8_t* facet_to_mask);
 int gecut_comm_aggregate(const gecut_result* cut, const gecut_facet_result* facets, const int32_t* program, int len,
                          const int32_t* facet_program, int facet_len, int side, double threshold, int32_t* cell_to_cellin,
                          int on_device);

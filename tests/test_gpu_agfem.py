@@ -144,3 +144,37 @@ def test_aggregation_over_slabs_equals_the_whole_model(name, nslab, threshold):
         assert np.array_equal(np.concatenate(got2), want)
         for o in cuts + facets + [whole_cut]:
             o.close()
+
+
+@pytest.mark.parametrize("name,nslab", [("disk_30", 3), ("three_disks", 2), ("sphere", 3), ("csg", 2), ("bimaterial", 4)])
+def test_ghost_skeleton_over_slabs_equals_the_whole_model(name, nslab):
+    """GhostSkeleton on z-slabs: the mask of every slab's local model equals the whole-model mask on the slab's facets
+    (through the facet -> node-tuple map), including the facets on the planes two slabs share."""
+    from gecut import GhostSkeleton, GhostSkeleton_slabs, LevelSetCutter, _lib, ACTIVE_IN, ACTIVE_OUT
+    model, geo, nm = CASES[name]()
+    ctx = _lib.default_context()
+    whole_cut = cut(model, geo)
+    wf = cut_facets(model, geo)
+    hw = wf.to_host(topology=True)
+    gnodes = {tuple(r): f for f, r in enumerate(hw["facet_to_nodes"])}
+    nz = model.partition[-1]
+    layer_nodes = model.num_nodes // (nz + 1)
+    cutsz = [round(q * nz / nslab) for q in range(nslab + 1)]
+    slabs = list(zip(cutsz[:-1], cutsz[1:]))
+    cuts = [LevelSetCutter(ctx, slab=s).cut(model, geo) for s in slabs]
+    l2g = []
+    for s in slabs:
+        lf = LevelSetCutter(ctx, slab=s).cut_facets(model, geo)
+        hl = lf.to_host(topology=True)
+        l2g.append(np.array([gnodes[tuple(int(v) + s[0] * layer_nodes for v in r)] for r in hl["facet_to_nodes"]]))
+        lf.close()
+    for sel in (ACTIVE_IN, ACTIVE_OUT):
+        want = GhostSkeleton(whole_cut, sel, nm)
+        got = GhostSkeleton_slabs(cuts, sel, nm)
+        seen = np.zeros(len(want), bool)
+        for m, g in zip(got, l2g):
+            assert np.array_equal(m, want[g])
+            seen[g[m]] = True
+        assert np.array_equal(seen, want)  # every ghost facet of the model is marked in some slab
+    for o in cuts + [whole_cut, wf]:
+        o.close()

@@ -151,6 +151,17 @@ def _worker(rank, world, port, q):
                         assert (want is None) == (got is None), (label, thr, side)
                         if want is not None:
                             assert np.array_equal(got, want[off:off + nc]), (label, thr, side)
+                # GhostSkeleton of the rank's local model: cells across the shared plane come over NCCL
+                from gecut import GhostSkeleton, GhostSkeleton_slabs
+                wf = G.LevelSetCutter(ctx).cut_facets(model, geo)
+                gn = {tuple(r): f for f, r in enumerate(wf.to_host(topology=True)["facet_to_nodes"])}
+                lf = G.LevelSetCutter(ctx, slab=part.slab).cut_facets(model, geo) if part.slab else wf
+                k0s = part.slab[0] if part.slab else 0
+                l2g = np.array([gn[tuple(int(v) + k0s * layer_nodes for v in r)]
+                                for r in lf.to_host(topology=True)["facet_to_nodes"]])
+                want_mask = GhostSkeleton(whole, None, name)
+                got_mask = GhostSkeleton_slabs(part, None, name, comm=True)
+                assert np.array_equal(got_mask, want_mask[l2g]), label
             # a sign flip in ONE rank's copy of the shared plane is seen by every rank
             if rank == 0:
                 i = int(torch.argmax(torch.abs(bufs[0][-layer_nodes:])))
