@@ -182,6 +182,26 @@ __global__ void k_ghost_mask(const GcGrid g, const GcGrid gf, const GcLayout lay
   }
 }
 
+// facets on the plane a slab shares with its lower (which = 0) / upper (which = 1) neighbour: one thread per cell of the slab's
+// boundary layer; the facet is a ghost facet when one of the two cells around it is CUT and both are active -- also when the
+// CUT cell is the neighbour's (the cut-cell driven pass above only sees this slab's own cut cells)
+template <int D>
+__global__ void k_ghost_mask_plane(const GcGrid g, const GcGrid gf, const GcLayout lay, const GcProgram prog, int side, int which,
+                                   const int8_t* __restrict__ nb_rows, int64_t nb_pitch, int64_t nb_base,
+                                   int8_t* __restrict__ mask) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.layer_cubes) return;
+  const int nl = g.k1 - g.k0;
+  const int64_t cell = which == 0 ? e : (int64_t)(nl - 1) * g.layer_cubes + e;
+  const int so = gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, cell);
+  const int sn = gc_eval_inoutcut(prog, nb_rows, nb_pitch, nb_base + e);
+  if (so != GC_CUT && sn != GC_CUT) return;
+  if ((so != GC_CUT && so != side) || (sn != GC_CUT && sn != side)) return;
+  const int i = (int)(e % g.n[0]), j = D == 3 ? (int)(e / g.n[0]) : 0;
+  const int c[3] = {i, D == 3 ? j : (which == 0 ? 0 : nl - 1), D == 3 ? (which == 0 ? 0 : nl - 1) : 0};
+  mask[facet_id_of<D>(gf, c[0], c[1], c[2], D - 1, which)] = 1;
+}
+
 // number of marked facets (slab version: a facet on a plane two slabs share is marked -- and counted -- in both local models)
 __global__ void __launch_bounds__(256) k_count_mask(const int8_t* __restrict__ mask, int64_t n, unsigned long long* __restrict__ count) {
   unsigned int mine = 0;
@@ -618,6 +638,20 @@ static int ghost_slab(gecut_ctx* ctx, const gecut_result* cut, const GcProgram& 
       GC_LAUNCH(ctx, "k_ghost_mask", k_ghost_mask<3><<<(unsigned)gc_div_up(ncut, T), T, 0, ctx->stream>>>(
           g, gf, cut->lay, ncut, p, side, lo_rows, lo_pitch, lo_base, hi_rows, hi_pitch, hi_base, mask, nullptr));
     GC_CHECK(gc_launch_check(ctx, "k_ghost_mask"));
+  }
+  for (int which = 0; which < 2; ++which) {
+    const int8_t* rows = which == 0 ? lo_rows : hi_rows;
+    if (!rows) continue;
+    const unsigned nbp = (unsigned)gc_div_up(g.layer_cubes, T);
+    if (D == 2)
+      GC_LAUNCH(ctx, "k_ghost_mask_plane", k_ghost_mask_plane<2><<<nbp, T, 0, ctx->stream>>>(
+          g, gf, cut->lay, p, side, which, rows, which == 0 ? lo_pitch : hi_pitch, which == 0 ? lo_base : hi_base, mask));
+    else
+      GC_LAUNCH(ctx, "k_ghost_mask_plane", k_ghost_mask_plane<3><<<nbp, T, 0, ctx->stream>>>(
+          g, gf, cut->lay, p, side, which, rows, which == 0 ? lo_pitch : hi_pitch, which == 0 ? lo_base : hi_base, mask));
+    GC_CHECK(gc_launch_check(ctx, "k_ghost_mask_plane"));
+  }
+  {
     GC_LAUNCH(ctx, "k_count_mask", k_count_mask<<<(unsigned)std::min<int64_t>(1184, gc_div_up(nf, T)), T, 0, ctx->stream>>>(mask, nf, cnt));
     GC_CHECK(gc_launch_check(ctx, "k_count_mask"));
   }
