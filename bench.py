@@ -132,7 +132,7 @@ def slab_of(model, rank, world):
 
 class ClockSampler:
     """SM clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe), read through NVML in-process
-    (pynvml / nvidia-ml-py) every 20 ms: the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*`
+    (pynvml / nvidia-ml-py) every 5 ms: the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*`
     prints, without the heavy per-sample cost of the nvidia-smi loop (which was measured to stretch 5.5 ms steps to
     10-16 ms).  Falls back to one `nvidia-smi` query after the timed region if NVML is unavailable."""
 
@@ -170,7 +170,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.005)
 
     def clear(self):
         self.samples.clear()
@@ -189,7 +189,7 @@ class ClockSampler:
         self.thread.join(timeout=1)
         sm = sorted(self.samples)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.smax, "reasons": sorted(self.reasons),
-                "samples": len(sm), "source": "NVML in-process, 20 ms period"}
+                "samples": len(sm), "source": "NVML in-process, 5 ms period"}
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -895,7 +895,7 @@ def run_b200(args, n, rank, world, local_rank):
         clocks = sampler.stop()
         clocks["samples_timed_region"] = timed_clock_samples
         clocks["note"] = ("sampled from the first timed step to the end of the end-to-end leg (the device-resident timed "
-                          "region alone lasts tens of ms = 1-2 samples at the 20 ms period)")
+                          "region alone lasts tens of ms = a handful of samples at the 5 ms period)")
     if rank == 0:
         lb = layout_bytes(s)
         line = {
