@@ -839,6 +839,166 @@ k_cutm_count(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict
   }
 }
 
+// ---- n-cube cells: the count pass in two kernels.  The NT0 stage-0 simplices of a cut cell share the 2^D vertices of the
+// cube, so ONE thread per cut cell evaluates the L level sets at the 2^D vertices (3x fewer leaf evaluations than D+1
+// vertices per simplex: every cube vertex sits in 3 of the 6 TETs) and writes the info words / records of its NT0 simplices;
+// the tile totals are a second, memory-light pass over the info words (lane = simplex).
+template <int D>
+__global__ void __launch_bounds__(128)
+k_cutm_count_cells(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
+                   const uint8_t* __restrict__ simp_pos, const int32_t* __restrict__ cutcells, int64_t ncut, GcMulti mu) {
+  constexpr int NT0 = (D == 3) ? 6 : 2, NVC = 1 << D;
+  __shared__ GcSimplexTable s_tab;
+  __shared__ uint8_t s_swap[8];
+  __shared__ uint32_t s_lv4[8];
+  __shared__ __align__(4) uint8_t s_plut[512], s_flut[128];
+  cm_load_perm_luts<D>(tables, s_plut, s_flut);
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(tables + (D - 1));
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
+    for (int i = threadIdx.x; i < (int)(sizeof(GcSimplexTable) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  const uint8_t* vtab = simp_pos + (D - 2) * 24;
+  cm_swap_flags<D>(g, vtab, s_swap);
+  __syncthreads();
+  if (threadIdx.x < NT0) {  // vertex ids of every stage-0 simplex type, first two swapped when its Jacobian is negative
+    uint32_t l4 = *reinterpret_cast<const uint32_t*>(vtab + threadIdx.x * 4);
+    if (s_swap[threadIdx.x]) l4 = __byte_perm(l4, 0u, 0x3201);
+    s_lv4[threadIdx.x] = l4;
+  }
+  __syncthreads();
+  const GcSimplexTable& TC = s_tab;
+  const int L = lv.L;
+  const int64_t kcut = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (kcut >= ncut) return;
+  const uint32_t cell = (uint32_t)(cutcells[kcut] - 1);
+  int ijk[3];
+  const uint32_t row = cell / (uint32_t)g.n[0];
+  ijk[0] = (int)(cell - row * (uint32_t)g.n[0]);
+  if (D == 3) {
+    const uint32_t lay3 = row / (uint32_t)g.n[1];
+    ijk[1] = (int)(row - lay3 * (uint32_t)g.n[1]);
+    ijk[2] = (int)lay3 + g.k0;
+  } else {
+    ijk[1] = (int)row + g.k0;
+    ijk[2] = 0;
+  }
+  double xc[3][2];  // the two node coordinates of the cube per direction
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    xc[d][0] = d < D ? gc_coord(g, d, ijk[d]) : 0.0;
+    xc[d][1] = d < D ? gc_coord(g, d, ijk[d] + 1) : 0.0;
+  }
+  const int64_t node0 = (D == 3) ? ((int64_t)ijk[0] + (int64_t)g.nn[0] * ((int64_t)ijk[1] + (int64_t)g.nn[1] * ijk[2]))
+                                 : ((int64_t)ijk[0] + (int64_t)g.nn[0] * ijk[1]);
+  uint32_t mixed[NT0], outm[NT0], sa[NT0];
+#pragma unroll
+  for (int t = 0; t < NT0; ++t) mixed[t] = outm[t] = sa[t] = 0u;
+  for (int k = 0; k < L; ++k) {
+    const bool nodal = lv.leaf[k].kind == GECUT_LEAF_NODAL;
+    uint32_t cube = 0u;
+#pragma unroll
+    for (int v = 0; v < NVC; ++v) {
+      double val;
+      if (nodal) {
+        const int64_t node = node0 + (v & 1) + (int64_t)g.nn[0] * (((v >> 1) & 1) + (D == 3 ? (int64_t)g.nn[1] * ((v >> 2) & 1) : 0));
+        val = __ldg(lv.nodal[k] + (node - lv.nodal_base));
+      } else {
+        const double x[3] = {xc[0][v & 1], xc[1][(v >> 1) & 1], D == 3 ? xc[2][(v >> 2) & 1] : 0.0};
+        val = gc_eval_leaf(lv.leaf[k], x, D);
+      }
+      cube |= (val > 0.0 ? 1u : 0u) << v;
+    }
+    const uint32_t full = (1u << (D + 1)) - 1u;
+#pragma unroll
+    for (int t = 0; t < NT0; ++t) {
+      const uint32_t l4 = s_lv4[t];
+      uint32_t sb = 0u;
+#pragma unroll
+      for (int m = 0; m <= D; ++m) sb |= ((cube >> ((l4 >> (8 * m)) & 0xFFu)) & 1u) << m;
+      if (sb == full) outm[t] |= 1u << k;
+      else if (sb != 0u) {
+        mixed[t] |= 1u << k;
+        sa[t] = sb;  // the highest mixed level set stays
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < NT0; ++t) {
+    const int64_t s = kcut * NT0 + t;
+    if (__popc(mixed[t]) > 1) {
+      // recorded: exactly two mixed level sets -> the stackless depth-2 kernel; more -> the generic tree walk, bucketed by
+      // the number of level sets it has to track
+      int bucket = 0;
+      if (__popc(mixed[t]) > 2) {
+        const int nw = __popc((mixed[t] | 3u) & ((1u << L) - 1u));
+        while (nw > walk_nw(bucket)) bucket++;
+        bucket++;
+      }
+      const uint32_t slot = atomicAdd(&mu.slow_count[CM_NBK], 1u);
+      atomicAdd(&mu.slow_count[bucket], 1u);
+      mu.slow_simp[slot] = (uint32_t)s;
+      mu.slow_bucket[slot] = (uint8_t)bucket;
+      mu.slow_mask[slot] = mixed[t] | (outm[t] << 16);
+      mu.sinfo[s] = CM_SLOW | slot;
+    } else {
+      const int aa = mixed[t] ? (31 - __clz(mixed[t])) : 0;  // the only stage that can cut (stage 0 is visited in any case)
+      const uint32_t vl = cm_skip_cell_stages<D>(s_plut, outm[t], L, aa);
+      uint32_t sat = sa[t];
+      if (!mixed[t]) sat = ((outm[t] >> aa) & 1u) ? (1u << (D + 1)) - 1u : 0u;
+      int c = 0;  // case in arrival order
+#pragma unroll
+      for (int i = 0; i <= D; ++i) c |= (int)((sat >> ((vl >> (2 * i)) & 3u)) & 1u) << i;
+      mu.sinfo[s] = outm[t] | ((uint32_t)aa << 16) | ((uint32_t)c << 20) | (mixed[t] ? 1u << 24 : 0u);
+    }
+  }
+  (void)TC;
+}
+
+// tile totals of the fast simplices from their info words (the walk adds the recorded ones)
+template <int D>
+__global__ void __launch_bounds__(256)
+k_cutm_tiles(const GcSimplexTable* __restrict__ tables, int L, int64_t nsimp, GcMulti mu) {
+  __shared__ GcSimplexTable s_tab;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(tables + (D - 1));
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
+    for (int i = threadIdx.x; i < (int)(sizeof(GcSimplexTable) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const GcSimplexTable& TC = s_tab;
+  const int lane = threadIdx.x & 31;
+  const int64_t tile = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  if (tile * 32 >= nsimp) return;
+  const int64_t s = tile * 32 + lane;
+  uint32_t ncell = 0, npt = 0, nfac = 0;
+  int a = -1;
+  if (s < nsimp) {
+    const uint32_t info = mu.sinfo[s];
+    if (!(info & CM_SLOW)) {
+      const int aa = (int)((info >> 16) & 15u), c = (int)((info >> 20) & 15u);
+      ncell = TC.nsub[c];
+      nfac = TC.nfac[c];
+      npt = aa == 0 ? TC.npts[c] : ncell * (D + 1);
+      if (nfac) a = aa;
+    }
+  }
+  const uint32_t tc = __reduce_add_sync(0xffffffffu, ncell), tp = __reduce_add_sync(0xffffffffu, npt);
+  const uint32_t present = __reduce_or_sync(0xffffffffu, a >= 0 ? 1u << a : 0u);
+  // channel ch of the tile goes out through lane ch (ch = 0 subcells, 1 points, 2 + k facets of level set k, 2 + L + k their
+  // points): one store instruction per tile instead of 2 + 2 L by lane 0
+  uint32_t v0 = lane == 0 ? tc : (lane == 1 ? tp : 0u), v1 = 0u;
+  for (int k = 0; k < L; ++k) {
+    uint32_t tf = 0u;
+    if ((present >> k) & 1u) tf = __reduce_add_sync(0xffffffffu, a == k ? nfac : 0u);
+    if (lane == 2 + k) v0 = tf;
+    if (lane == 2 + L + k) v0 = tf * D;  // a passed-through facet keeps its D points
+    if (lane + 32 == 2 + L + k) v1 = tf * D;
+  }
+  if (lane < 2 + 2 * L) mu.tile[(int64_t)lane * mu.ntiles + tile] = v0;
+  if (lane + 32 < 2 + 2 * L) mu.tile[(int64_t)(lane + 32) * mu.ntiles + tile] = v1;
+}
+
 // shared memory of one warp of k_cutm_fill
 template <int D>
 struct CmSmem {
@@ -2293,6 +2453,20 @@ void launch_walk(gecut_ctx* ctx, const gecut_result* res, const GcMulti& mu, boo
 }
 
 void launch_fast_count(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcMulti& mu) {
+  if (!res->grid.simplexified && !getenv("GECUT_COUNT_PER_SIMPLEX")) {  // n-cube cells: thread per cut cell, then the tile totals
+    const int64_t ncut = res->sizes.num_cutcells;
+    const unsigned nbc = (unsigned)gc_div_up(ncut, 128), nbt = (unsigned)gc_div_up(mu.ntiles, 256 / 32);
+    if (res->grid.D == 2) {
+      GC_LAUNCH(ctx, "k_cutm_count", k_cutm_count_cells<2><<<nbc, 128, 0, ctx->stream>>>(res->grid, res->leaves, ctx->d_tables,
+                                                                                        ctx->d_simplexify_pos, res->lay.cutcells, ncut, mu));
+      GC_LAUNCH(ctx, "k_cutm_tiles", k_cutm_tiles<2><<<nbt, 256, 0, ctx->stream>>>(ctx->d_tables, res->L, nsimp, mu));
+    } else {
+      GC_LAUNCH(ctx, "k_cutm_count", k_cutm_count_cells<3><<<nbc, 128, 0, ctx->stream>>>(res->grid, res->leaves, ctx->d_tables,
+                                                                                        ctx->d_simplexify_pos, res->lay.cutcells, ncut, mu));
+      GC_LAUNCH(ctx, "k_cutm_tiles", k_cutm_tiles<3><<<nbt, 256, 0, ctx->stream>>>(ctx->d_tables, res->L, nsimp, mu));
+    }
+    return;
+  }
   const unsigned nb = (unsigned)gc_div_up(mu.ntiles, CM_T / 32);
   if (res->grid.D == 2)
     GC_LAUNCH(ctx, "k_cutm_count", k_cutm_count<2><<<nb, CM_T, 0, ctx->stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
