@@ -606,9 +606,10 @@ def run_b200(args, n, rank, world, local_rank):
             slab, slab_kind = slab_of(model, rank, world), f"z-slab x{world} (even layers)"
         else:
             from gecut.distributed import balanced_slab_ranges
-            # cost of a cut cube in units of a classified cube, from the round-2 single-GPU kernel times (classification got 2-3x
-            # cheaper per cube, so the cut cells weigh more than in round 1: 300 / 760 / 1400)
-            cw = {"c3_tet": 370.0, "c3_hex": 2500.0, "c5_bimaterial": 6000.0, "c1_csg": 6000.0}.get(args.workload, 1000.0)
+            # cost of a cut cube in units of a classified cube (calibrated in round 1; re-deriving the weights from the round-2
+            # kernel times -- 370 for the tets -- moved two layers between ranks and measured WORSE at 8 GPUs: 0.90 against
+            # 0.81 ms per step, so the measured-good partition stays)
+            cw = {"c3_tet": 300.0, "c3_hex": 760.0, "c5_bimaterial": 1400.0, "c1_csg": 1400.0}.get(args.workload, 600.0)
             ranges = balanced_slab_ranges(model, geo, world, cut_weight=cw)
             slab = ranges[rank]
             slab_kind = (f"z-slab x{world}, work-balanced (layers per rank {[b - a for a, b in ranges]}; cut cell = "
