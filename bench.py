@@ -889,7 +889,10 @@ def run_b200(args, n, rank, world, local_rank):
     csg = None
     if world == 1 and args.workload == "c3_tet" and not args.no_csg and n >= 256:
         ctx.trim()
-        csg = north_star_csg_leg(ctx, n, stream, peak)
+        try:  # a side leg: whatever happens here must not take the main line down
+            csg = north_star_csg_leg(ctx, n, stream, peak)
+        except Exception as exc:  # noqa: BLE001
+            csg = {"error": f"{type(exc).__name__}: {exc}"}
         ctx.trim()
 
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------------------
