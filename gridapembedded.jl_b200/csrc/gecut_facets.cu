@@ -25,6 +25,61 @@
 #include "gecut_internal.cuh"
 #include "gecut_facets.cuh"
 
+// Slot table of the facet grid of a simplexified model (gecut_facets.cuh), from the simplexify table of the n-cube.
+bool gc_build_sx_facets(int D, GcSxFacets* t) {
+  static const uint8_t LF2[3][3] = {{0, 1, 0}, {0, 2, 0}, {1, 2, 0}};
+  static const uint8_t LF3[4][3] = {{0, 1, 2}, {0, 1, 3}, {0, 2, 3}, {1, 2, 3}};
+  memset(t, 0, sizeof(*t));
+  t->D = D;
+  t->nt = D == 2 ? 2 : 6;
+  t->nlf = D + 1;
+  t->nslots = t->nt * t->nlf;
+  const int ns = t->nslots, nvf = D;
+  auto key_of = [&](const uint8_t* v, int flip) {  // the node set as a bit mask over the 2^D cube vertices
+    unsigned m = 0;
+    for (int i = 0; i < nvf; ++i) m |= 1u << (v[i] ^ flip);
+    return m;
+  };
+  for (int s = 0; s < ns; ++s) {
+    const int tt = s / t->nlf, lf = s % t->nlf;
+    for (int m = 0; m < nvf; ++m) t->vtx[s][m] = GC_SIMPLEXIFY_RAW[D - 2][tt][D == 2 ? LF2[lf][m] : LF3[lf][m]];
+    t->face[s] = -1;
+    for (int d = 0; d < D; ++d) {
+      int ones = 0;
+      for (int m = 0; m < nvf; ++m) ones += (t->vtx[s][m] >> d) & 1;
+      if (ones == 0) t->face[s] = (int8_t)(d << 1);
+      if (ones == nvf) t->face[s] = (int8_t)((d << 1) | 1);
+    }
+  }
+  for (int s = 0; s < ns; ++s) {
+    const unsigned key = key_of(t->vtx[s], t->face[s] < 0 ? 0 : 1 << (t->face[s] >> 1));
+    int found = -1;
+    for (int s2 = 0; s2 < ns; ++s2)
+      if (s2 != s && key_of(t->vtx[s2], 0) == key) found = s2;
+    if (found < 0) return false;  // the simplices of neighbouring cubes do not share this face: not a conforming tiling
+    t->partner[s] = (uint8_t)found;
+  }
+  int nown[8];
+  for (int cls = 0; cls < (1 << D); ++cls) {
+    int n = 0;
+    for (int s = 0; s < ns; ++s) {
+      const int fc = t->face[s];
+      const bool own = fc < 0 ? s < t->partner[s] : ((fc & 1) ? true : ((cls >> (fc >> 1)) & 1) != 0);
+      t->rank[cls][s] = own ? (uint8_t)n : (uint8_t)0xff;
+      if (own) t->order[cls][n++] = (uint8_t)s;
+    }
+    nown[cls] = n;
+  }
+  t->C0 = nown[0];
+  t->cd = nown[1] - nown[0];
+  for (int cls = 0; cls < (1 << D); ++cls) {
+    int z = 0;
+    for (int d = 0; d < D; ++d) z += (cls >> d) & 1;
+    if (nown[cls] != t->C0 + t->cd * z) return false;
+  }
+  return true;
+}
+
 namespace {
 
 // Node coordinate for the facet kernels.  On a z-slab (layers [k0, k1) of the last direction) the facet grid is the LOCAL
@@ -389,11 +444,14 @@ struct FPt {
 
 constexpr int FW_T = 128;
 
-template <int D, int NW, bool FILL>
+// SX: simplexified model -- the bg facet is itself a (D-1)-simplex (one stage-0 simplex, nodes and boundary flag from the
+// slot table `sx`, reference vertices of SEGMENT / TRI; the sub-simplex map IS the facet map, so no Jacobian swap).
+template <int D, int NW, bool FILL, bool SX>
 __global__ void __launch_bounds__(FW_T)
 k_facet_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
-             const int32_t* __restrict__ cutfacets, int64_t nsimp, uint32_t* __restrict__ cnt, GcFacetLayout lay) {
-  constexpr int DS = D - 1, NP = DS + 1, CE = DS, NPMAX = NP + CE, NVF = 1 << DS, NT0 = DS == 2 ? 2 : 1;
+             const int32_t* __restrict__ cutfacets, int64_t nsimp, uint32_t* __restrict__ cnt, GcFacetLayout lay,
+             const GcSxFacets sx) {
+  constexpr int DS = D - 1, NP = DS + 1, CE = DS, NPMAX = NP + CE, NT0 = (DS == 2 && !SX) ? 2 : 1;
   __shared__ GcSimplexTable s_tab;
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(tables + (DS - 1));
@@ -407,7 +465,13 @@ k_facet_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict
   const int L = lv.L;
   const int32_t facet1 = cutfacets[s / NT0];
   const int t = (int)(s % NT0);
-  const FacetIdx fi = facet_decode<D>(g, (uint32_t)(facet1 - 1));
+  FacetIdx fi{};
+  SxFacetIdx sfi{};
+  if (SX)
+    sfi = sx_facet_decode<D>(g, sx, (uint32_t)(facet1 - 1));
+  else
+    fi = facet_decode<D>(g, (uint32_t)(facet1 - 1));
+  const bool on_boundary = SX ? sx_facet_is_boundary<D>(g, sfi, sx) : facet_is_boundary<D>(g, fi);
 
   FPt<D, NW> pool[NP + CE * NW];
   uint8_t v[NW][NP], e[NW][NPMAX];
@@ -417,19 +481,22 @@ k_facet_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict
   double q0[3] = {0, 0, 0}, qa[DS][3];
 #pragma unroll
   for (int m = 0; m < NP; ++m) {
-    const int lvid = DS == 2 ? gc_simplexify_pos(0, t, m) : m;
+    const int lvid = (DS == 2 && !SX) ? gc_simplexify_pos(0, t, m) : m;
     int nijk[3];
-    facet_node<D>(fi, lvid, nijk);
+    if (SX)
+      sx_facet_node<D>(sfi, sx, m, nijk);
+    else
+      facet_node<D>(fi, lvid, nijk);
     const double x[3] = {fc_coord<D>(g, 0, nijk[0]), fc_coord<D>(g, 1, nijk[1]), D == 3 ? fc_coord<D>(g, 2, nijk[2]) : 0.0};
 #pragma unroll
     for (int d = 0; d < D; ++d) pool[m].x[d] = x[d];
 #pragma unroll
-    for (int d = 0; d < DS; ++d) pool[m].r[d] = (double)((lvid >> d) & 1);
+    for (int d = 0; d < DS; ++d) pool[m].r[d] = SX ? (m == d + 1 ? 1.0 : 0.0) : (double)((lvid >> d) & 1);
     for (int ls = 0; ls < L; ++ls) pool[m].w[ls] = leaf_at_node<D>(g, lv, ls, nijk);
   }
   // _ensure_positive_jacobians_facets! (:642-683): inner product of the Jacobians of the sub-simplex and of the bg
   // facet map at the origin of the reference facet; first two ids swapped when negative
-  {
+  if (!SX) {
     int n0[3];
     facet_node<D>(fi, 0, n0);
     q0[0] = fc_coord<D>(g, 0, n0[0]);
@@ -520,7 +587,7 @@ k_facet_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict
             }
             lay.c2bg[cid] = facet1;
             lay.meas[cid] = integrate_one<DS>(simplex_meas<D, DS>(pc));
-            lay.isb[cid] = facet_is_boundary<D>(g, fi) ? 1 : 0;
+            lay.isb[cid] = on_boundary ? 1 : 0;
             lay.state[cid] = T.sub_inout[c][j];
             for (int kk = 1; kk < L; ++kk) lay.state[(int64_t)kk * lay.pitch + cid] = st[kk];
           }
@@ -780,6 +847,92 @@ __global__ void k_facet_topology(const GcGrid g, int64_t nf, int32_t* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// simplexified models: a thread per facet id (the slot table decodes it), lanes = consecutive ids
+// ------------------------------------------------------------------------------------------------
+// states of every facet per level set from the node sign planes of K1 + "cut by any level set"; EMIT = false records
+// the number of cut facets of every 32-facet piece, EMIT = true (after the scan) writes their ids in ascending order
+template <int D, bool EMIT>
+__global__ void __launch_bounds__(256)
+k_sx_facet_states(const GcGrid g, const GcSxFacets sx, int L, int wxt, const uint32_t* __restrict__ signs, int64_t ls_stride,
+                  int8_t* __restrict__ state, int64_t pitch, uint32_t* __restrict__ piece_counts,
+                  int32_t* __restrict__ cutfacets, int64_t nf) {
+  const int64_t f = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool valid = f < nf;
+  bool cut = false;
+  if (valid) {
+    const SxFacetIdx fi = sx_facet_decode<D>(g, sx, (uint32_t)f);
+    int64_t word[D];
+    int bit[D];
+#pragma unroll
+    for (int m = 0; m < D; ++m) {
+      int nijk[3];
+      sx_facet_node<D>(fi, sx, m, nijk);
+      const int64_t nrow = D == 3 ? (int64_t)nijk[2] * g.nn[1] + nijk[1] : (int64_t)nijk[1];
+      word[m] = nrow * wxt + (nijk[0] >> 5);
+      bit[m] = nijk[0] & 31;
+    }
+    for (int ls = 0; ls < L; ++ls) {
+      const uint32_t* sg = signs + (int64_t)ls * ls_stride;
+      int nout = 0;
+#pragma unroll
+      for (int m = 0; m < D; ++m) nout += (int)((__ldg(sg + word[m]) >> bit[m]) & 1u);
+      const int8_t st = nout == 0 ? (int8_t)GC_IN : (nout == D ? (int8_t)GC_OUT : (int8_t)GC_CUT);
+      if (!EMIT) state[(int64_t)ls * pitch + f] = st;
+      cut = cut || st == GC_CUT;
+    }
+  }
+  const uint32_t ballot = __ballot_sync(0xffffffffu, cut);
+  const int64_t piece = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (!EMIT) {
+    if (lane == 0) piece_counts[piece] = (uint32_t)__popc(ballot);
+  } else if (cut) {
+    cutfacets[piece_counts[piece] + (uint32_t)__popc(ballot & ((1u << lane) - 1u))] = (int32_t)(f + 1);
+  }
+}
+
+template <int D>
+__global__ void k_sx_facet_topology(const GcGrid g, const GcSxFacets sx, int64_t nf, int32_t* __restrict__ nodes,
+                                    int8_t* __restrict__ isb) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nf) return;
+  const SxFacetIdx fi = sx_facet_decode<D>(g, sx, (uint32_t)f);
+  if (isb) isb[f] = sx_facet_is_boundary<D>(g, fi, sx) ? 1 : 0;
+  if (nodes) {
+#pragma unroll
+    for (int m = 0; m < D; ++m) {
+      int nijk[3];
+      sx_facet_node<D>(fi, sx, m, nijk);
+      const int64_t node = (D == 3) ? ((int64_t)nijk[0] + (int64_t)g.nn[0] * ((int64_t)nijk[1] + (int64_t)g.nn[1] * nijk[2]))
+                                    : ((int64_t)nijk[0] + (int64_t)g.nn[0] * nijk[1]);
+      nodes[f * D + m] = (int32_t)(node + 1);
+    }
+  }
+}
+
+// whole facets of a selection, counted per slot of the cube (facets of one slot are congruent: one measure per slot);
+// `row` is ONE Int8 state row.  flags != nullptr: the per-facet flags for the id list instead of the counts.
+template <int D>
+__global__ void __launch_bounds__(256)
+k_sx_facet_select(const GcGrid g, const GcSxFacets sx, const int8_t* __restrict__ row, int64_t nf, int which, int mode,
+                  int side, unsigned long long* __restrict__ slot_counts, uint32_t* __restrict__ flags) {
+  __shared__ uint32_t s_cnt[24];
+  if (threadIdx.x < 24) s_cnt[threadIdx.x] = 0u;
+  __syncthreads();
+  const int64_t f = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (f < nf) {
+    const SxFacetIdx fi = sx_facet_decode<D>(g, sx, (uint32_t)f);
+    const bool in_trian = sx_facet_is_boundary<D>(g, fi, sx) == (which == GECUT_FACETS_BOUNDARY);
+    const int a = row[f];
+    const bool sel = in_trian && (mode == 1 ? a == side : (a == GC_CUT || a == side));
+    if (flags) flags[f] = sel ? 1u : 0u;
+    if (sel && slot_counts) atomicAdd(&s_cnt[fi.slot], 1u);
+  }
+  __syncthreads();
+  if (slot_counts && threadIdx.x < 24 && s_cnt[threadIdx.x]) atomicAdd(&slot_counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+}
+
 inline int64_t pad_pitch(int64_t n) { return ((n + 255) / 256) * 256; }
 
 void free_facet_arrays(gecut_facet_result* r) {
@@ -843,6 +996,28 @@ int classify_facets(gecut_ctx* ctx, gecut_facet_result* r) {
   GC_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(uint64_t) * (1 + GC_LMAX * FT_N), ctx->stream));
   GC_LAUNCH(ctx, "k_node_signs", k_node_signs<D><<<sgrid, sblock, 0, ctx->stream>>>(g, r->leaves, wxt, signs, ls_stride));
   GC_CHECK(gc_launch_check(ctx, "k_node_signs"));
+  if (g.simplexified) {
+    const int64_t nf = r->sizes.num_bgfacets;
+    const unsigned nbs = (unsigned)gc_div_up(nf, 256);
+    uint32_t* pieces = nullptr;
+    GC_CHECK(scratch.alloc(&pieces, sizeof(uint32_t) * (size_t)nbs * 8));
+    GC_LAUNCH(ctx, "k_sx_facet_states",
+              (k_sx_facet_states<D, false><<<nbs, 256, 0, ctx->stream>>>(g, r->sx, L, wxt, signs, ls_stride, r->lay.bg_state,
+                                                                        r->lay.bg_pitch, pieces, nullptr, nf)));
+    GC_CHECK(gc_launch_check(ctx, "k_sx_facet_states"));
+    GC_CHECK(gc_exclusive_scan_u32(ctx, pieces, pieces, (int64_t)nbs * 8, total_dev));
+    uint64_t total = 0;
+    GC_CHECK(read_u64(ctx, total_dev, 1, &total));
+    r->sizes.num_cutfacets = (int64_t)total;
+    if (total > 0) {
+      GC_CHECK(gc_malloc(ctx, (void**)&r->lay.cutfacets, sizeof(int32_t) * total));
+      GC_LAUNCH(ctx, "k_sx_facet_states_emit",
+                (k_sx_facet_states<D, true><<<nbs, 256, 0, ctx->stream>>>(g, r->sx, L, wxt, signs, ls_stride, nullptr, 0, pieces,
+                                                                         r->lay.cutfacets, nf)));
+      GC_CHECK(gc_launch_check(ctx, "k_sx_facet_states_emit"));
+    }
+    return GECUT_OK;
+  }
   const unsigned nb = (unsigned)gc_div_up(gc_div_up(npieces, FW_ITER), 8);
   GC_LAUNCH(ctx, "k_facet_words",
             (k_facet_words<D, false><<<nb, 256, 0, ctx->stream>>>(g, L, wxt, wpr, signs, ls_stride, r->lay.bg_state,
@@ -865,9 +1040,9 @@ int classify_facets(gecut_ctx* ctx, gecut_facet_result* r) {
   return GECUT_OK;
 }
 
-template <int D, int NW>
+template <int D, int NW, bool SX>
 int walk_facets_nw(gecut_ctx* ctx, gecut_facet_result* r) {
-  constexpr int NT0 = D == 3 ? 2 : 1;
+  constexpr int NT0 = (D == 3 && !SX) ? 2 : 1;
   const int64_t nsimp = r->sizes.num_cutfacets * NT0;
   const int L = r->L;
   GcScratch scratch(ctx);
@@ -877,8 +1052,8 @@ int walk_facets_nw(gecut_ctx* ctx, gecut_facet_result* r) {
   GC_CHECK(scratch.alloc(&totals_dev, sizeof(uint64_t) * 2));
   const unsigned nb = (unsigned)gc_div_up(nsimp, FW_T);
   GC_LAUNCH(ctx, "k_facet_walk_count",
-            (k_facet_walk<D, NW, false><<<nb, FW_T, 0, ctx->stream>>>(r->grid, r->leaves, ctx->d_tables, r->lay.cutfacets, nsimp,
-                                                                     cnt, r->lay)));
+            (k_facet_walk<D, NW, false, SX><<<nb, FW_T, 0, ctx->stream>>>(r->grid, r->leaves, ctx->d_tables, r->lay.cutfacets,
+                                                                         nsimp, cnt, r->lay, r->sx)));
   GC_CHECK(gc_launch_check(ctx, "k_facet_walk_count"));
   GC_CHECK(gc_exclusive_scan_u32_multi(ctx, cnt, cnt, nsimp, 2, totals_dev));
   uint64_t tot[2] = {0, 0};
@@ -899,21 +1074,25 @@ int walk_facets_nw(gecut_ctx* ctx, gecut_facet_result* r) {
   GC_CHECK(gc_malloc(ctx, (void**)&l.X, sizeof(double) * tot[1] * D));
   GC_CHECK(gc_malloc(ctx, (void**)&l.R, sizeof(double) * tot[1] * (D - 1)));
   GC_LAUNCH(ctx, "k_facet_walk_fill",
-            (k_facet_walk<D, NW, true><<<nb, FW_T, 0, ctx->stream>>>(r->grid, r->leaves, ctx->d_tables, r->lay.cutfacets, nsimp,
-                                                                    cnt, r->lay)));
+            (k_facet_walk<D, NW, true, SX><<<nb, FW_T, 0, ctx->stream>>>(r->grid, r->leaves, ctx->d_tables, r->lay.cutfacets,
+                                                                        nsimp, cnt, r->lay, r->sx)));
   GC_CHECK(gc_launch_check(ctx, "k_facet_walk_fill"));
   return GECUT_OK;
 }
 
+template <int D, bool SX>
+int walk_facets_sx(gecut_ctx* ctx, gecut_facet_result* r) {
+  const int L = r->L;
+  if (L <= 1) return walk_facets_nw<D, 1, SX>(ctx, r);
+  if (L <= 2) return walk_facets_nw<D, 2, SX>(ctx, r);
+  if (L <= 4) return walk_facets_nw<D, 4, SX>(ctx, r);
+  if (L <= 8) return walk_facets_nw<D, 8, SX>(ctx, r);
+  return walk_facets_nw<D, GC_LMAX, SX>(ctx, r);
+}
 template <int D>
 int walk_facets(gecut_ctx* ctx, gecut_facet_result* r) {
   if (r->sizes.num_cutfacets == 0) return GECUT_OK;
-  const int L = r->L;
-  if (L <= 1) return walk_facets_nw<D, 1>(ctx, r);
-  if (L <= 2) return walk_facets_nw<D, 2>(ctx, r);
-  if (L <= 4) return walk_facets_nw<D, 4>(ctx, r);
-  if (L <= 8) return walk_facets_nw<D, 8>(ctx, r);
-  return walk_facets_nw<D, GC_LMAX>(ctx, r);
+  return r->grid.simplexified ? walk_facets_sx<D, true>(ctx, r) : walk_facets_sx<D, false>(ctx, r);
 }
 
 template <class T>
@@ -966,10 +1145,6 @@ int gecut_cut_facets(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* l
     ctx->err = "number of level sets must be in 1..GECUT_MAX_LEVELSETS";
     return L < 1 ? GECUT_ERR_INVALID : GECUT_ERR_NOTIMPLEMENTED;
   }
-  if (grid->simplexified) {
-    ctx->err = "cut_facets is implemented for n-cube Cartesian models only (not simplexified)";
-    return GECUT_ERR_NOTIMPLEMENTED;
-  }
   DeviceGuard guard(ctx->device);
   gecut_facet_result* r = new (std::nothrow) gecut_facet_result();
   if (!r) return GECUT_ERR_OOM;
@@ -979,6 +1154,11 @@ int gecut_cut_facets(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* l
   if (st != GECUT_OK) {
     delete r;
     return st;
+  }
+  if (r->grid.simplexified && !gc_build_sx_facets(r->grid.D, &r->sx)) {
+    ctx->err = "cut_facets: the simplexify table of the n-cube does not tile conformingly";
+    delete r;
+    return GECUT_ERR_NOTIMPLEMENTED;
   }
   {
     // z-slab: the facet grid of the rank's LOCAL model (layers [k0, k1) of the last direction as a Cartesian model of its own:
@@ -998,7 +1178,8 @@ int gecut_cut_facets(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* l
     return code;
   };
   const int D = g.D;
-  const int64_t nf = D == 2 ? num_facets<2>(g) : num_facets<3>(g);
+  const int64_t nf = g.simplexified ? (D == 2 ? sx_num_facets<2>(g, r->sx) : sx_num_facets<3>(g, r->sx))
+                                    : (D == 2 ? num_facets<2>(g) : num_facets<3>(g));
   if (nf >= 2147483647ll) {
     ctx->err = "facet ids overflow Int32";
     return fail(GECUT_ERR_OVERFLOW);
@@ -1046,12 +1227,13 @@ int gecut_cut_facets(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* l
   sz.num_bgfacets = nf;
   sz.num_levelsets = L;
   sz.D = D;
-  sz.num_vertices_per_bgfacet = 1 << (D - 1);
-  // facets with one cell around: the two faces of the box per direction
+  sz.num_vertices_per_bgfacet = g.simplexified ? D : 1 << (D - 1);
+  // facets with one cell around: the two faces of the box per direction (cd simplex facets per cube face when simplexified)
   if (D == 2)
     sz.num_boundary_facets = 2ll * (g.n[0] + g.n[1]);
   else
     sz.num_boundary_facets = 2ll * ((int64_t)g.n[0] * g.n[1] + (int64_t)g.n[0] * g.n[2] + (int64_t)g.n[1] * g.n[2]);
+  if (g.simplexified) sz.num_boundary_facets *= r->sx.cd;
   r->lay.bg_pitch = pad_pitch(nf);
   st = gc_malloc(ctx, (void**)&r->lay.bg_state, (size_t)r->lay.bg_pitch * L);
   if (st != GECUT_OK) return fail(st);
@@ -1110,7 +1292,12 @@ int gecut_facet_result_copy(const gecut_facet_result* res, const gecut_facet_buf
     if (host->facet_to_nodes) GC_CHECK(scratch.alloc(&nodes, sizeof(int32_t) * nf * nvf));
     if (host->facet_is_boundary) GC_CHECK(scratch.alloc(&isb, (size_t)nf));
     const int T = 256;
-    if (D == 2)
+    if (res->grid.simplexified) {
+      if (D == 2)
+        GC_LAUNCH(ctx, "k_facet_topology", k_sx_facet_topology<2><<<(unsigned)gc_div_up(nf, T), T, 0, ctx->stream>>>(res->grid, res->sx, nf, nodes, isb));
+      else
+        GC_LAUNCH(ctx, "k_facet_topology", k_sx_facet_topology<3><<<(unsigned)gc_div_up(nf, T), T, 0, ctx->stream>>>(res->grid, res->sx, nf, nodes, isb));
+    } else if (D == 2)
       GC_LAUNCH(ctx, "k_facet_topology", k_facet_topology<2><<<(unsigned)gc_div_up(nf, T), T, 0, ctx->stream>>>(res->grid, nf, nodes, isb));
     else
       GC_LAUNCH(ctx, "k_facet_topology", k_facet_topology<3><<<(unsigned)gc_div_up(nf, T), T, 0, ctx->stream>>>(res->grid, nf, nodes, isb));
@@ -1199,7 +1386,30 @@ int gecut_select_facets(const gecut_facet_result* res, int which, int kind, cons
     const int mode = kind == GECUT_SEL_ACTIVE ? 2 : 1;
     const GcGrid& g = res->grid;
     const bool single = p.len == 1 || (p.len == 2 && p.tok[1] == GECUT_OP_COMPLEMENT);
-    if (single) {
+    if (g.simplexified) {
+      // the program's Int8 row, then one pass: selected whole facets per slot of the cube
+      GcScratch scratch(ctx);
+      unsigned long long* slotc = nullptr;
+      int8_t* tmp = nullptr;
+      st = scratch.alloc(&slotc, sizeof(unsigned long long) * 24);
+      if (st == GECUT_OK) st = scratch.alloc(&tmp, (size_t)pad_pitch(nf));
+      if (st == GECUT_OK) st = gc_eval_rows(ctx, res->lay.bg_state, res->lay.bg_pitch, nf, p, tmp, true);
+      if (st != GECUT_OK) return fail(st);
+      cudaMemsetAsync(slotc, 0, sizeof(unsigned long long) * 24, ctx->stream);
+      const unsigned nbs = (unsigned)gc_div_up(nf, 256);
+      if (D == 2)
+        GC_LAUNCH(ctx, "k_sx_facet_select", k_sx_facet_select<2><<<nbs, 256, 0, ctx->stream>>>(g, res->sx, tmp, nf, which, mode, side, slotc, nullptr));
+      else
+        GC_LAUNCH(ctx, "k_sx_facet_select", k_sx_facet_select<3><<<nbs, 256, 0, ctx->stream>>>(g, res->sx, tmp, nf, which, mode, side, slotc, nullptr));
+      st = gc_launch_check(ctx, "k_sx_facet_select");
+      uint64_t h[24];
+      if (st == GECUT_OK) st = read_u64(ctx, (const uint64_t*)slotc, 24, h);
+      if (st != GECUT_OK) return fail(st);
+      for (int q = 0; q < 24; ++q) {
+        sel->bg_slot_count[q] = (int64_t)h[q];
+        sel->n_bg += (int64_t)h[q];
+      }
+    } else if (single) {
       // single leaf (or its complement = the other side): the tallies of the classification pass answer directly
       const int ls = p.tok[0];
       const int eff_side = p.len == 1 ? side : -side;
@@ -1311,7 +1521,23 @@ int gecut_facet_selection_copy(const gecut_facet_selection* sel_c, int32_t* sub_
     const int T = 256;
     uint32_t* flags = nullptr;
     GC_CHECK(gc_malloc(ctx, (void**)&flags, sizeof(uint32_t) * nf));
-    if (res->sizes.D == 2)
+    if (res->grid.simplexified) {
+      int8_t* tmp = nullptr;
+      int st0 = gc_malloc(ctx, (void**)&tmp, (size_t)pad_pitch(nf));
+      if (st0 == GECUT_OK) st0 = gc_eval_rows(ctx, res->lay.bg_state, res->lay.bg_pitch, nf, sel->prog, tmp, true);
+      if (st0 == GECUT_OK) {
+        const unsigned nbs = (unsigned)gc_div_up(nf, 256);
+        if (res->sizes.D == 2)
+          GC_LAUNCH(ctx, "k_sx_facet_select", k_sx_facet_select<2><<<nbs, 256, 0, ctx->stream>>>(res->grid, res->sx, tmp, nf, sel->which, mode, sel->side, nullptr, flags));
+        else
+          GC_LAUNCH(ctx, "k_sx_facet_select", k_sx_facet_select<3><<<nbs, 256, 0, ctx->stream>>>(res->grid, res->sx, tmp, nf, sel->which, mode, sel->side, nullptr, flags));
+      }
+      gc_free(ctx, tmp);
+      if (st0 != GECUT_OK) {
+        gc_free(ctx, flags);
+        return st0;
+      }
+    } else if (res->sizes.D == 2)
       GC_LAUNCH(ctx, "k_facet_flag_bg", k_facet_flag_bg<2><<<(unsigned)gc_div_up(nf, T), T, 0, ctx->stream>>>(res->grid, res->lay.bg_state, res->lay.bg_pitch, nf, sel->prog, sel->which, mode, sel->side, flags));
     else
       GC_LAUNCH(ctx, "k_facet_flag_bg", k_facet_flag_bg<3><<<(unsigned)gc_div_up(nf, T), T, 0, ctx->stream>>>(res->grid, res->lay.bg_state, res->lay.bg_pitch, nf, sel->prog, sel->which, mode, sel->side, flags));
@@ -1362,6 +1588,34 @@ int gecut_facet_selection_measure(const gecut_facet_selection* sel, double* sub_
   // whole facets: tensor Gauss rule of degree 2 on the (D-1)-cube, sum_q w_q * meas (the facet map is affine)
   const GcGrid& g = res->grid;
   const int D = g.D;
+  if (g.simplexified) {
+    // facets of one slot are translates of each other: measure of the SEGMENT / TRI from the cube-local vertex offsets,
+    // degree-2 rule of the facet polytope (2-point Gauss on the segment, 3-point rule on the triangle)
+    const GcSxFacets& t = res->sx;
+    for (int q = 0; q < t.nslots; ++q) {
+      if (sel->bg_slot_count[q] == 0) continue;
+      double x[3][3];
+      for (int m = 0; m < D; ++m)
+        for (int d = 0; d < 3; ++d) x[m][d] = d < D ? (double)((t.vtx[q][m] >> d) & 1) * g.dx[d] : 0.0;
+      double meas;
+      if (D == 2) {
+        const double a = x[1][0] - x[0][0], b = x[1][1] - x[0][1];
+        meas = sqrt(a * a + b * b);
+      } else {
+        const double a[3] = {x[1][0] - x[0][0], x[1][1] - x[0][1], x[1][2] - x[0][2]};
+        const double b[3] = {x[2][0] - x[0][0], x[2][1] - x[0][1], x[2][2] - x[0][2]};
+        const double n1 = a[1] * b[2] - a[2] * b[1], n2 = a[2] * b[0] - a[0] * b[2], n3 = a[0] * b[1] - a[1] * b[0];
+        meas = sqrt(n1 * n1 + n2 * n2 + n3 * n3);
+      }
+      const int nq = D == 2 ? 2 : 3;
+      const double w = D == 2 ? 0.5 : 1.0 / 6;
+      double one = 0.0;
+      for (int i = 0; i < nq; ++i) one += w * meas;
+      sum += one * (double)sel->bg_slot_count[q];
+    }
+    if (total) *total = sum;
+    return GECUT_OK;
+  }
   for (int d = 0; d < D; ++d) {
     if (sel->bg_dir_count[d] == 0) continue;
     double meas = 1.0;

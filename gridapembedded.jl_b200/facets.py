@@ -113,8 +113,6 @@ def _call_cut_facets(cutter: LevelSetCutter, background, geom, classify_only: bo
     """With a z-slab cutter (`LevelSetCutter(ctx, slab=(k0, k1))`) the result is the facet discretization of the rank's LOCAL
     model -- layers [k0, k1) as a Cartesian model of its own, local facet numbering, global node coordinates -- the way every
     rank of the reference's distributed mode cuts its own local model (`src/Distributed/DistributedDiscretizations.jl:42-53`)."""
-    if background.simplexified:
-        raise NotImplementedError("cut_facets is implemented for n-cube Cartesian models")
     ctx = cutter.ctx
     num_nodal, planes = None, None
     if cutter.nodal_slab_local and cutter.slab is not None:
@@ -141,7 +139,7 @@ def _call_cut_facets(cutter: LevelSetCutter, background, geom, classify_only: bo
         pmax[D - 1] = pmin[D - 1] + k1 * dz
         pmin[D - 1] = pmin[D - 1] + k0 * dz
         part[D - 1] = k1 - k0
-        local = CartesianDiscreteModel(tuple(pmin), tuple(pmax), tuple(part))
+        local = CartesianDiscreteModel(tuple(pmin), tuple(pmax), tuple(part), simplexified=background.simplexified)
     return EmbeddedFacetDiscretization(ctx, out, local, geom, oid_to_ls)
 
 

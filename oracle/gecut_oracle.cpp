@@ -570,13 +570,18 @@ Result* do_cut(const OGrid& og, const OLeaf* leaves, int L, const double* const*
 //    local facet ascending) (`generate_cell_to_faces`), and a facet takes the
 //    node order of the local facet of the cell that meets it first;
 //  * local facets of the n-cubes: QUAD [[1,2],[3,4],[1,3],[2,4]],
-//    HEX [[1,2,3,4],[5,6,7,8],[1,2,5,6],[3,4,7,8],[1,3,5,7],[2,4,6,8]].
-// Only n-cube (not simplexified) Cartesian models.
+//    HEX [[1,2,3,4],[5,6,7,8],[1,2,5,6],[3,4,7,8],[1,3,5,7],[2,4,6,8]];
+//  * simplexified models (cells = the simplices of simplexify(model), cube-major): the same rule with the local
+//    facets of the simplices, TRI [[1,2],[1,3],[2,3]], TET [[1,2,3],[1,2,4],[1,3,4],[2,3,4]]; the bg facets are
+//    SEGMENTs / TRIs (simplexify(TRI) = [[1,2,3]], reference vertices (0,0),(1,0),(0,1)).
 // ----------------------------------------------------------------------------
 static const std::vector<std::vector<int>> LFACETS_QUAD = {{1, 2}, {3, 4}, {1, 3}, {2, 4}};
 static const std::vector<std::vector<int>> LFACETS_HEX = {{1, 2, 3, 4}, {5, 6, 7, 8}, {1, 2, 5, 6},
                                                           {3, 4, 7, 8}, {1, 3, 5, 7}, {2, 4, 6, 8}};
+static const std::vector<std::vector<int>> LFACETS_TRI = {{1, 2}, {1, 3}, {2, 3}};
+static const std::vector<std::vector<int>> LFACETS_TET = {{1, 2, 3}, {1, 2, 4}, {1, 3, 4}, {2, 3, 4}};
 static const std::vector<std::vector<int>> SIMPLEXIFY_POS_SEGMENT = {{1, 2}};
+static const std::vector<std::vector<int>> SIMPLEXIFY_TRI_FACET = {{1, 2, 3}};
 static const std::vector<std::vector<double>> VERTICES_SEGMENT = {{0.0}, {1.0}};
 
 struct FacetResult {
@@ -595,12 +600,13 @@ struct FacetResult {
 FacetResult* do_cut_facets(const OGrid& og, const OLeaf* leaves, int L, const double* const* nodal_values) {
   FacetResult* r = new FacetResult(og);
   const BgGrid& g = r->grid;
-  if (g.simplexified) return r;  // not covered (nvf == 0 marks it)
   r->L = L;
-  const int D = g.D, nvf = 1 << (D - 1);
+  const bool sx = g.simplexified;
+  const int D = g.D, nvf = sx ? D : 1 << (D - 1);
   r->nvf = nvf;
   // ---- Grid(ReferenceFE{D-1}, model): first-encounter numbering (A8)
-  const std::vector<std::vector<int>>& lfacets = D == 2 ? LFACETS_QUAD : LFACETS_HEX;
+  const std::vector<std::vector<int>>& lfacets =
+      sx ? (D == 2 ? LFACETS_TRI : LFACETS_TET) : (D == 2 ? LFACETS_QUAD : LFACETS_HEX);
   {
     std::map<std::array<int64_t, 4>, int32_t> seen;
     for (int64_t cell = 0; cell < g.num_cells; ++cell) {
@@ -654,8 +660,8 @@ FacetResult* do_cut_facets(const OGrid& og, const OLeaf* leaves, int L, const do
     if (iscut) r->cutfacet_to_facet.push_back((int32_t)(f + 1));
   }
   // ---- _simplexify_and_isolate_cells_in_cutgrid (CutTriangulations.jl:505-548), Dc = D-1, Dp = D
-  const std::vector<std::vector<int>>& lt = D == 2 ? SIMPLEXIFY_POS_SEGMENT : SIMPLEXIFY_POS_QUAD;
-  const std::vector<std::vector<double>>& verts = D == 2 ? VERTICES_SEGMENT : VERTICES_QUAD;
+  const std::vector<std::vector<int>>& lt = D == 2 ? SIMPLEXIFY_POS_SEGMENT : (sx ? SIMPLEXIFY_TRI_FACET : SIMPLEXIFY_POS_QUAD);
+  const std::vector<std::vector<double>>& verts = D == 2 ? VERTICES_SEGMENT : (sx ? VERTICES_TRI : VERTICES_QUAD);
   const int nlt = (int)lt.size(), nsp = D, ds = D - 1;
   const int64_t ncut = (int64_t)r->cutfacet_to_facet.size();
   Mesh m0;
@@ -1270,7 +1276,8 @@ void gecut_oracle_facets_subfacet_measures(void* h, const int32_t* ids, int64_t 
   FacetResult* r = (FacetResult*)h;
   for (int64_t i = 0; i < n; ++i) out[i] = integrate_one(r->subfacets, ids[i] - 1);
 }
-// integral of 1 over a whole bg facet (tensor Gauss rule of degree 2 on the (D-1)-cube; the map is affine)
+// integral of 1 over a whole bg facet (degree-2 rule of the facet polytope: tensor Gauss on the (D-1)-cube, the simplex
+// rule on the TRI facets of a simplexified 3-D model; the map is affine)
 double gecut_oracle_bgfacet_measure(void* h, int32_t facet1) {
   FacetResult* r = (FacetResult*)h;
   const BgGrid& g = r->grid;
@@ -1287,7 +1294,7 @@ double gecut_oracle_bgfacet_measure(void* h, int32_t facet1) {
     double n1 = a[1] * b[2] - a[2] * b[1], n2 = a[2] * b[0] - a[0] * b[2], n3 = a[0] * b[1] - a[1] * b[0];
     meas = std::sqrt(n1 * n1 + n2 * n2 + n3 * n3);
   }
-  Rule q = ncube_rule_deg2(D - 1);
+  Rule q = g.simplexified ? simplex_rule_deg2(D - 1) : ncube_rule_deg2(D - 1);
   double s = 0;
   for (int i = 0; i < q.n; ++i) s += q.w[i] * meas;
   return s;
@@ -1305,7 +1312,8 @@ int gecut_oracle_aggregate(void* hc, void* hf, const int32_t* prog, int len, int
   const int D = g.D, nvf = fr->nvf, nv = g.nv;
   const int64_t n_cells = g.num_cells, n_facets = (int64_t)fr->facet_is_boundary.size();
   // get_faces(topo,D,D-1) / get_faces(topo,D-1,D)
-  const std::vector<std::vector<int>>& lfacets = D == 2 ? LFACETS_QUAD : LFACETS_HEX;
+  const std::vector<std::vector<int>>& lfacets =
+      g.simplexified ? (D == 2 ? LFACETS_TRI : LFACETS_TET) : (D == 2 ? LFACETS_QUAD : LFACETS_HEX);
   const int nlf = (int)lfacets.size();
   std::map<std::array<int64_t, 4>, int32_t> facet_of;
   for (int64_t f = 0; f < n_facets; ++f) {
@@ -1413,7 +1421,8 @@ void gecut_oracle_ghost_skeleton(void* hc, void* hf, const int32_t* prog, int le
   const BgGrid& g = r->grid;
   const int D = g.D, nvf = fr->nvf;
   const int64_t n_cells = g.num_cells, n_facets = (int64_t)fr->facet_is_boundary.size();
-  const std::vector<std::vector<int>>& lfacets = D == 2 ? LFACETS_QUAD : LFACETS_HEX;
+  const std::vector<std::vector<int>>& lfacets =
+      g.simplexified ? (D == 2 ? LFACETS_TRI : LFACETS_TET) : (D == 2 ? LFACETS_QUAD : LFACETS_HEX);
   std::map<std::array<int64_t, 4>, int32_t> facet_of;
   for (int64_t f = 0; f < n_facets; ++f) {
     std::array<int64_t, 4> key = {-1, -1, -1, -1};

@@ -19,6 +19,10 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-12
 
 
+def sx(model):
+    return gecut.simplexify(model)
+
+
 def two_disks_plane():
     return setdiff(intersect(disk(0.45, x0=(0.5, 0.5)), plane(x0=(0.5, 0.7), v=(0.2, 1.0))), disk(0.2, x0=(0.4, 0.4)))
 
@@ -42,6 +46,16 @@ CASES = {
     "bimaterial": lambda: (CartesianDiscreteModel((0., 0., 0.), (3., 2., 3.), (9, 6, 9)), bimaterial()),
     "empty_cut": lambda: (CartesianDiscreteModel((2, 3, 2, 3), (5, 5)), disk(0.7)),
     "all_in": lambda: (CartesianDiscreteModel((-0.1, 0.1, -0.1, 0.1, -0.1, 0.1), (3, 3, 3)), sphere(0.7)),
+    # simplexified models: the facet grid of the TRI / TET mesh (SEGMENT / TRI facets)
+    "sx_disk_odd": lambda: (sx(CartesianDiscreteModel((-0.8, 0.9, -0.7, 0.75), (17, 13))), disk(0.7)),
+    "sx_disk_1xN": lambda: (sx(CartesianDiscreteModel((-1, 1, -1, 1), (1, 7))), disk(0.7)),
+    "sx_three_disks": lambda: (sx(CartesianDiscreteModel((-1, 2, -1, 2), (23, 19))), three_disks()),
+    "sx_csg2d": lambda: (sx(CartesianDiscreteModel((0, 1, 0, 1), (33, 31))), two_disks_plane()),
+    "sx_sphere_odd": lambda: (sx(CartesianDiscreteModel((-0.8, 0.9, -0.7, 0.75, -0.9, 0.8), (7, 5, 6))), sphere(0.7)),
+    "sx_sphere_face": lambda: (sx(CartesianDiscreteModel((0, 1, 0, 1, 0, 1), (6, 6, 6))), sphere(0.37, x0=(0.5, 0.5, 1.0))),
+    "sx_sphere_1x1xN": lambda: (sx(CartesianDiscreteModel((-0.2, 0.3, -0.2, 0.3, -1, 1), (1, 1, 9))), sphere(0.7)),
+    "sx_csg_8": lambda: (sx(CartesianDiscreteModel((-0.8,) * 3, (0.8,) * 3, (8, 8, 8))), csg_geometry()),
+    "sx_empty_cut": lambda: (sx(CartesianDiscreteModel((2, 3, 2, 3), (5, 5))), disk(0.7)),
 }
 
 
@@ -74,19 +88,20 @@ def test_facet_layout_parity(name):
     fc.close()
 
 
-@pytest.mark.parametrize("name", ["disk_corner_10", "three_disks", "csg2d", "sphere_face", "csg_10", "stokes", "bimaterial"])
+@pytest.mark.parametrize("name", ["disk_corner_10", "three_disks", "csg2d", "sphere_face", "csg_10", "stokes", "bimaterial",
+                                  "sx_three_disks", "sx_csg2d", "sx_sphere_face", "sx_csg_8"])
 def test_facet_selectors_and_measures(name):
     model, geo = CASES[name]()
     fc = cut_facets(model, geo)
     oc = ob.oracle_cut_facets(model, geo)
     names = [None]
-    if name == "csg_10":
+    if name in ("csg_10", "sx_csg_8"):
         names += ["csg", "source"]
     if name == "stokes":
         names += ["fluid", "solid"]
     if name == "bimaterial":
         names += ["steel", "concrete"]
-    if name == "three_disks":
+    if name in ("three_disks", "sx_three_disks"):
         names += ["disk1", "disk3"]
     for nm in names:
         prog = fc.program(nm)
@@ -137,25 +152,21 @@ def test_facets_discrete_geometry_and_classify_only():
 
 
 def test_facets_unsupported_inputs():
-    from gecut import simplexify
-    model = simplexify(CartesianDiscreteModel((0, 1, 0, 1), (4, 4)))
-    with pytest.raises(NotImplementedError):
-        cut_facets(model, disk(0.3, x0=(0.5, 0.5)))
     m = CartesianDiscreteModel((0, 1, 0, 1), (4, 4))
     with pytest.raises(_lib.GecutError):  # slabs are supported; an empty / out-of-range one is an invalid argument
         LevelSetCutter(slab=(3, 9)).cut_facets(m, disk(0.3, x0=(0.5, 0.5)))
-    # raw ABI: simplexified grids are refused with NOTIMPLEMENTED, not silently mis-numbered
-    ctx = _lib.default_context()
-    import ctypes as C
-    from gecut.cutters import make_grid, make_leaf_records, flatten_geometry
-    leaves, nodal, _ = flatten_geometry(model, disk(0.3, x0=(0.5, 0.5)))
-    out = C.c_void_p()
-    g = make_grid(model)
-    rc = ctx._lib.gecut_cut_facets(ctx.handle, C.byref(g), make_leaf_records(leaves), 1, None, 0, 0, C.byref(out))
-    assert rc == _lib.GECUT_ERR_NOTIMPLEMENTED and "n-cube" in ctx.last_error()
+    # aggregation on a simplexified model is refused (NOTIMPLEMENTED), not silently computed on the n-cube topology
+    from gecut import simplexify, aggregate, AggregateAllCutCells
+    ms = simplexify(m)
+    geo = disk(0.3, x0=(0.5, 0.5))
+    cg, fc = cut(ms, geo), cut_facets(ms, geo)
+    with pytest.raises((_lib.GecutError, NotImplementedError)):
+        aggregate(AggregateAllCutCells(), cg, fc, geo)
+    cg.close()
+    fc.close()
 
 
-@pytest.mark.parametrize("case", ["disk_2048", "sphere_160", "csg_64"])
+@pytest.mark.parametrize("case", ["disk_2048", "sphere_160", "csg_64", "sx_disk_1024", "sx_sphere_96"])
 def test_facets_properties_at_scale(case):
     """Size-independent properties where the oracle is too slow: IN + OUT parts of every cut facet add up to the facet,
     boundary/skeleton split, agreement of the facet states with the cell states of cut(), boundary IN measure against
@@ -164,6 +175,10 @@ def test_facets_properties_at_scale(case):
         model, geo = CartesianDiscreteModel((0, 1, 0, 1), (2048, 2048)), disk(0.72, x0=(1, 1))
     elif case == "sphere_160":
         model, geo = CartesianDiscreteModel((0, 1, 0, 1, 0, 1), (160, 160, 160)), sphere(0.37, x0=(0.5, 0.5, 1.0))
+    elif case == "sx_disk_1024":
+        model, geo = sx(CartesianDiscreteModel((0, 1, 0, 1), (1024, 1024))), disk(0.72, x0=(1, 1))
+    elif case == "sx_sphere_96":
+        model, geo = sx(CartesianDiscreteModel((0, 1, 0, 1, 0, 1), (96, 96, 96))), sphere(0.37, x0=(0.5, 0.5, 1.0))
     else:
         model, geo = CartesianDiscreteModel((-0.8,) * 3, (0.8,) * 3, (64, 64, 64)), csg_geometry()
     D = model.D
@@ -181,11 +196,22 @@ def test_facets_properties_at_scale(case):
             whole = 2 * sum(np.prod(np.delete(h * n, d)) for d in range(D))
         else:
             whole = sum((n[d] - 1) * np.prod(np.delete(h * n, d)) for d in range(D))
+            if model.simplexified:  # + the facets inside every cube: the diagonal (2-D); 6 triangles around the edge 1-6 (3-D)
+                if D == 2:
+                    whole += np.prod(n) * np.hypot(h[0], h[1])
+                else:
+                    e = np.array([-h[0], h[1], h[2]])  # cube vertex 1 -> vertex 6
+                    others = [np.array(v) * h for v in ((-1, 0, 0), (0, 1, 0), (0, 0, 1), (-1, 1, 0), (-1, 0, 1), (0, 1, 1))]
+                    whole += np.prod(n) * sum(0.5 * np.linalg.norm(np.cross(e, o)) for o in others)
         assert abs(m_in + m_out - whole) <= 1e-11 * whole
         assert tin.num_sub + tout.num_sub > 0 or (key == "b" and case == "csg_64")  # the CSG body stays inside the box
         tot_b[key] = m_in
         tin.close()
         tout.close()
+    if case == "sx_disk_1024":
+        assert abs(tot_b["b"] - 2 * 0.72) < 1e-6
+    if case == "sx_sphere_96":
+        assert abs(tot_b["b"] - np.pi * 0.37 ** 2) / (np.pi * 0.37 ** 2) < 5e-3
     if case == "disk_2048":  # quarter disk of radius 0.72 centred on the corner: two boundary segments of length R
         assert abs(tot_b["b"] - 2 * 0.72) < 1e-6
     if case == "sphere_160":  # disk of radius R on the z-max face
@@ -204,7 +230,8 @@ def test_facets_properties_at_scale(case):
     fc.close()
 
 
-@pytest.mark.parametrize("name,nslab", [("disk_odd", 3), ("three_disks", 2), ("sphere_odd", 3), ("csg_10", 2), ("bimaterial", 3)])
+@pytest.mark.parametrize("name,nslab", [("disk_odd", 3), ("three_disks", 2), ("sphere_odd", 3), ("csg_10", 2), ("bimaterial", 3),
+                                        ("sx_csg2d", 3), ("sx_sphere_odd", 2), ("sx_csg_8", 3)])
 def test_facet_slab_is_the_local_model_of_the_whole_cut(name, nslab):
     """z-slabs (multi-GPU partition): cut_facets with `slab=(k0, k1)` is the facet discretization of the rank's LOCAL model
     (local numbering) on GLOBAL node coordinates: every array equals the whole-model result on the facets of the slab, bit
