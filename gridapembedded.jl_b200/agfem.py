@@ -155,9 +155,7 @@ def GhostSkeleton(cut: EmbeddedDiscretization, in_or_out=None, geo=None, ids: bo
             ctx.check(ctx._lib.gecut_ghost_skeleton(cut.handle, prog.ctypes.data, prog.size, int(side), C.byref(n), None,
                                                     C.c_void_p(out.ctypes.data)), "gecut_ghost_skeleton")
         return out
-    m = cut.bgmodel
-    nf = sum(int(np.prod([m.partition[e] + (1 if e == d else 0) for e in range(m.D)])) for d in range(m.D))
-    mask = np.empty(nf, np.int8)
+    mask = np.empty(_local_num_facets(cut.bgmodel, None), np.int8)
     ctx.check(ctx._lib.gecut_ghost_skeleton(cut.handle, prog.ctypes.data, prog.size, int(side), C.byref(n),
                                             C.c_void_p(mask.ctypes.data), None), "gecut_ghost_skeleton")
     return mask.astype(bool)
@@ -168,7 +166,11 @@ def _local_num_facets(model, slab) -> int:
     if slab is not None:
         part[-1] = int(slab[1]) - int(slab[0])
     D = model.D
-    return sum(int(np.prod([part[e] + (1 if e == d else 0) for e in range(D)])) for d in range(D))
+    nf = sum(int(np.prod([part[e] + (1 if e == d else 0) for e in range(D)])) for d in range(D))
+    if model.simplexified:
+        # facets of the TRI / TET mesh: the n-cube faces split into 1 / 2 simplices + 1 / 6 facets inside every cube
+        nf = (1 if D == 2 else 2) * nf + (1 if D == 2 else 6) * int(np.prod(part))
+    return nf
 
 
 def GhostSkeleton_slabs(cuts, in_or_out=None, geo=None, comm: bool = False):

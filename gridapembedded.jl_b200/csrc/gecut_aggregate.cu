@@ -202,6 +202,206 @@ __global__ void k_ghost_mask_plane(const GcGrid g, const GcGrid gf, const GcLayo
   mask[facet_id_of<D>(gf, c[0], c[1], c[2], D - 1, which)] = 1;
 }
 
+// ------------------------------------------------------------------------------------------------
+// simplexified models: cell = nt * cube + simplex; the neighbour across local facet lf is the slot table's partner --
+// another simplex of the same cube, or a simplex of the cube across the face (gecut_facets.cuh)
+// ------------------------------------------------------------------------------------------------
+struct SxNeighbour {
+  int cube[3];  // slab-local cube of the neighbour (the last index may be -1 / nl: ghost layer)
+  int t;        // its simplex
+  bool exists;  // false: boundary facet of the model in a direction without slabs
+};
+
+template <int D>
+__device__ __forceinline__ SxNeighbour sx_neighbour(const GcGrid& g, const GcSxFacets& sx, const int* c, int slot) {
+  SxNeighbour r;
+  r.cube[0] = c[0];
+  r.cube[1] = c[1];
+  r.cube[2] = c[2];
+  r.t = sx.partner[slot] / sx.nlf;
+  r.exists = true;
+  const int fc = sx.face[slot];
+  if (fc >= 0) {
+    const int d = fc >> 1;
+    r.cube[d] += (fc & 1) ? 1 : -1;
+    if (d != D - 1 && (r.cube[d] < 0 || r.cube[d] >= g.n[d])) r.exists = false;
+  }
+  return r;
+}
+
+template <int D>
+__device__ __forceinline__ double max_vertex_distance_sx(const GcGrid& g, const uint8_t* __restrict__ simp_raw, const int* a,
+                                                         int ta, const int* b, int tb) {
+  double d = 0.0;
+  for (int p = 0; p <= D; ++p) {
+    const int lp = simp_raw[(D - 2) * 24 + ta * 4 + p];
+    for (int q = 0; q <= D; ++q) {
+      const int lq = simp_raw[(D - 2) * 24 + tb * 4 + q];
+      double s2 = 0.0;
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const double w = __dsub_rn(gc_coord(g, c, a[c] + ((lp >> c) & 1)), gc_coord(g, c, b[c] + ((lq >> c) & 1)));
+        s2 = __dadd_rn(s2, __dmul_rn(w, w));
+      }
+      d = fmax(d, __dsqrt_rn(s2));
+    }
+  }
+  return d;
+}
+
+template <int D>
+__global__ void k_agg_sweep_sx(const GcGrid g, const GcGrid gf, const GcSxFacets sx, const uint8_t* __restrict__ simp_raw,
+                               const GcLayout lay, int64_t ncut, const GcProgram prog, int loc,
+                               const int8_t* __restrict__ facet_state, int64_t shift, int glo, int ghi,
+                               int32_t* __restrict__ cellin, const uint8_t* __restrict__ touched,
+                               uint32_t* __restrict__ not_aggregated) {
+  const int64_t kk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (kk >= ncut) return;
+  const int64_t cell = (int64_t)lay.cutcells[kk] - 1;  // slab-local
+  if (touched[cell + shift]) return;
+  if (gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, cell) != GC_CUT) return;
+  const int nl = g.k1 - g.k0, nt = sx.nt;
+  const int64_t cube = cell / nt;
+  const int t = (int)(cell % nt);
+  int c[3];
+  c[0] = (int)(cube % g.n[0]);
+  c[1] = D == 3 ? (int)((cube / g.n[0]) % g.n[1]) : (int)(cube / g.n[0]);
+  c[2] = D == 3 ? (int)(cube / ((int64_t)g.n[0] * g.n[1])) : 0;
+  int cg[3] = {c[0], c[1], c[2]};
+  cg[D - 1] += g.k0;
+  double dmin = INFINITY;
+  int64_t best = -1;
+  for (int lf = 0; lf <= D; ++lf) {  // local facets in Gridap's order
+    const int slot = t * sx.nlf + lf;
+    const int64_t f = sx_facet_id_of<D>(gf, sx, c[0], c[1], c[2], slot);
+    const int io = facet_state[f];
+    if (io != GC_CUT && io != loc) continue;
+    const SxNeighbour nb = sx_neighbour<D>(g, sx, c, slot);
+    if (!nb.exists) continue;
+    if ((nb.cube[D - 1] < 0 && !glo) || (nb.cube[D - 1] >= nl && !ghi)) continue;
+    const int64_t ncube = D == 3 ? (int64_t)nb.cube[0] + (int64_t)g.n[0] * ((int64_t)nb.cube[1] + (int64_t)g.n[1] * nb.cube[2])
+                                 : (int64_t)nb.cube[0] + (int64_t)g.n[0] * nb.cube[1];
+    const int64_t neigh = ncube * nt + nb.t + shift;
+    if (!touched[neigh]) continue;
+    const int64_t root = (int64_t)cellin[neigh] - 1;  // global
+    const int64_t rcube = root / nt;
+    const int rt = (int)(root % nt);
+    int r[3];
+    r[0] = (int)(rcube % g.n[0]);
+    r[1] = D == 3 ? (int)((rcube / g.n[0]) % g.n[1]) : (int)(rcube / g.n[0]);
+    r[2] = D == 3 ? (int)(rcube / ((int64_t)g.n[0] * g.n[1])) : 0;
+    const double dist = max_vertex_distance_sx<D>(g, simp_raw, cg, t, r, rt);
+    if (__dmul_rn(1.0 + 1.0e-9, dist) < dmin) {
+      dmin = dist;
+      best = neigh;
+    }
+  }
+  if (best >= 0)
+    cellin[cell + shift] = cellin[best];
+  else
+    atomicAdd(not_aggregated, 1u);
+}
+
+// unit cut measure of the cut simplices.  get_cell_measure of a simplexified model integrates over every cell's OWN node
+// coordinates (an UnstructuredGrid: |det J| from pmin + i * dx differences, not from dx), so the measure of a cell varies
+// in the last bits from cube to cube -- and a cut cell whose `loc` part is the whole cell (surface through its vertices)
+// sits exactly on the threshold.  Evaluated per cell with the operation order of the oracle / Gridap.
+template <int D>
+__global__ void k_agg_init_cut_sx(const GcGrid g, const uint8_t* __restrict__ simp_raw, const GcLayout lay,
+                                  const uint32_t* __restrict__ sc_ptr, int64_t ncut, const GcProgram prog, int loc,
+                                  double threshold, int nt, int64_t shift, int64_t goff, int32_t* __restrict__ cellin,
+                                  uint8_t* __restrict__ touched) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= ncut) return;
+  const int64_t c = (int64_t)lay.cutcells[k] - 1;
+  if (gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, c) != GC_CUT) return;
+  double V = 0.0;
+  const uint32_t s0 = sc_ptr[2 * k], s1 = sc_ptr[2 * k + 2];
+  for (uint32_t e = s0; e < s1; ++e)
+    if (gc_eval_inoutcut(prog, lay.sc_state, lay.sc_pitch, (int64_t)e) == loc) V += lay.sc_meas[e];
+  const int64_t cube = c / nt;
+  const int t = (int)(c % nt);
+  int ijk[3];
+  ijk[0] = (int)(cube % g.n[0]);
+  ijk[1] = D == 3 ? (int)((cube / g.n[0]) % g.n[1]) : (int)(cube / g.n[0]);
+  ijk[2] = D == 3 ? (int)(cube / ((int64_t)g.n[0] * g.n[1])) : 0;
+  ijk[D - 1] += g.k0;
+  double x[D + 1][3];
+#pragma unroll
+  for (int m = 0; m <= D; ++m) {
+    const int lv = simp_raw[(D - 2) * 24 + t * 4 + m];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) x[m][d] = d < D ? gc_coord(g, d, ijk[d] + ((lv >> d) & 1)) : 0.0;
+  }
+  const double cell_meas = integrate_one<D>(simplex_meas<D, D>(x));
+  const bool root = V / cell_meas >= threshold;
+  cellin[c + shift] = root ? (int32_t)(c + goff + 1) : 0;
+  touched[c + shift] = root ? 1 : 0;
+}
+
+template <int D>
+__global__ void k_ghost_mask_sx(const GcGrid g, const GcGrid gf, const GcSxFacets sx, const GcLayout lay, int64_t ncut,
+                                const GcProgram prog, int side, const int8_t* __restrict__ lo_rows, int64_t lo_pitch,
+                                int64_t lo_base, const int8_t* __restrict__ hi_rows, int64_t hi_pitch, int64_t hi_base,
+                                int8_t* __restrict__ mask, unsigned long long* __restrict__ count) {
+  const int64_t kk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (kk >= ncut) return;
+  const int64_t cell = (int64_t)lay.cutcells[kk] - 1;  // slab-local
+  if (gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, cell) != GC_CUT) return;
+  const int nl = g.k1 - g.k0, nt = sx.nt;
+  const int64_t cube = cell / nt;
+  const int t = (int)(cell % nt);
+  int c[3];
+  c[0] = (int)(cube % g.n[0]);
+  c[1] = D == 3 ? (int)((cube / g.n[0]) % g.n[1]) : (int)(cube / g.n[0]);
+  c[2] = D == 3 ? (int)(cube / ((int64_t)g.n[0] * g.n[1])) : 0;
+  for (int lf = 0; lf <= D; ++lf) {
+    const int slot = t * sx.nlf + lf;
+    const SxNeighbour nb = sx_neighbour<D>(g, sx, c, slot);
+    if (!nb.exists) continue;
+    int st;
+    int64_t neigh = -1;
+    if (nb.cube[D - 1] < 0 || nb.cube[D - 1] >= nl) {
+      const int8_t* rows = nb.cube[D - 1] < 0 ? lo_rows : hi_rows;
+      if (!rows) continue;  // boundary of the model
+      const int64_t in_layer = D == 3 ? (int64_t)nb.cube[0] + (int64_t)g.n[0] * nb.cube[1] : (int64_t)nb.cube[0];
+      st = gc_eval_inoutcut(prog, rows, nb.cube[D - 1] < 0 ? lo_pitch : hi_pitch,
+                            (nb.cube[D - 1] < 0 ? lo_base : hi_base) + in_layer * nt + nb.t);
+    } else {
+      const int64_t ncube = D == 3 ? (int64_t)nb.cube[0] + (int64_t)g.n[0] * ((int64_t)nb.cube[1] + (int64_t)g.n[1] * nb.cube[2])
+                                   : (int64_t)nb.cube[0] + (int64_t)g.n[0] * nb.cube[1];
+      neigh = ncube * nt + nb.t;
+      st = gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, neigh);
+    }
+    if (st != GC_CUT && st != side) continue;
+    mask[sx_facet_id_of<D>(gf, sx, c[0], c[1], c[2], slot)] = 1;
+    // whole model: a facet between two CUT cells is counted by the one with the lower id
+    if (count && (st != GC_CUT || neigh > cell)) atomicAdd(count, 1ull);
+  }
+}
+
+// facets on the plane a slab shares with its lower (which = 0) / upper (which = 1) neighbour, a thread per cube of the
+// slab's boundary layer (see k_ghost_mask_plane)
+template <int D>
+__global__ void k_ghost_mask_plane_sx(const GcGrid g, const GcGrid gf, const GcSxFacets sx, const GcLayout lay,
+                                      const GcProgram prog, int side, int which, const int8_t* __restrict__ nb_rows,
+                                      int64_t nb_pitch, int64_t nb_base, int8_t* __restrict__ mask) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.layer_cubes) return;
+  const int nl = g.k1 - g.k0, nt = sx.nt;
+  const int64_t cube = which == 0 ? e : (int64_t)(nl - 1) * g.layer_cubes + e;
+  const int i = (int)(e % g.n[0]), j = D == 3 ? (int)(e / g.n[0]) : 0;
+  const int c[3] = {i, D == 3 ? j : (which == 0 ? 0 : nl - 1), D == 3 ? (which == 0 ? 0 : nl - 1) : 0};
+  for (int slot = 0; slot < sx.nslots; ++slot) {
+    if (sx.face[slot] != (((D - 1) << 1) | which)) continue;
+    const int so = gc_eval_inoutcut(prog, lay.bg_state, lay.bg_pitch, cube * nt + slot / sx.nlf);
+    const int sn = gc_eval_inoutcut(prog, nb_rows, nb_pitch, nb_base + e * nt + sx.partner[slot] / sx.nlf);
+    if (so != GC_CUT && sn != GC_CUT) continue;
+    if ((so != GC_CUT && so != side) || (sn != GC_CUT && sn != side)) continue;
+    mask[sx_facet_id_of<D>(gf, sx, c[0], c[1], c[2], slot)] = 1;
+  }
+}
+
 // number of marked facets (slab version: a facet on a plane two slabs share is marked -- and counted -- in both local models)
 __global__ void __launch_bounds__(256) k_count_mask(const int8_t* __restrict__ mask, int64_t n, unsigned long long* __restrict__ count) {
   unsigned int mine = 0;
@@ -216,6 +416,8 @@ __global__ void k_mask_to_flags(const int8_t* __restrict__ mask, int64_t n, uint
 }
 
 inline int64_t pad_pitch(int64_t n) { return ((n + 255) / 256) * 256; }
+// bg cells of one layer of the last direction (a layer of cubes holds nt simplices per cube when simplexified)
+inline int64_t layer_cells(const GcGrid& g) { return g.layer_cubes * (g.simplexified ? g.nt : 1); }
 
 }  // namespace
 
@@ -228,15 +430,21 @@ extern "C" int gecut_ghost_skeleton(const gecut_result* cut, const int32_t* prog
     ctx->err = "ghost skeleton: in_or_out must be IN, OUT or CUT";
     return GECUT_ERR_INVALID;
   }
-  if (g.simplexified || g.k0 != 0 || g.k1 != g.n[g.D - 1]) {
-    ctx->err = "GhostSkeleton is implemented for whole n-cube Cartesian models";
+  if (g.k0 != 0 || g.k1 != g.n[g.D - 1]) {
+    ctx->err = "GhostSkeleton of a z-slab: use gecut_ghost_skeleton_slabs / gecut_comm_ghost_skeleton";
     return GECUT_ERR_NOTIMPLEMENTED;
   }
   DeviceGuard guard(ctx->device);
   GcProgram p;
   GC_CHECK(gc_make_program(ctx, program, len, cut->L, &p));
   const int D = g.D;
-  const int64_t nf = D == 2 ? num_facets<2>(g) : num_facets<3>(g);
+  GcSxFacets sx{};
+  if (g.simplexified && !gc_build_sx_facets(D, &sx)) {
+    ctx->err = "ghost skeleton: the simplexify table of the n-cube does not tile conformingly";
+    return GECUT_ERR_NOTIMPLEMENTED;
+  }
+  const int64_t nf = g.simplexified ? (D == 2 ? sx_num_facets<2>(g, sx) : sx_num_facets<3>(g, sx))
+                                    : (D == 2 ? num_facets<2>(g) : num_facets<3>(g));
   const int64_t ncut = cut->sizes.num_cutcells;
   int8_t* mask = nullptr;
   unsigned long long* cnt = nullptr;
@@ -255,7 +463,11 @@ extern "C" int gecut_ghost_skeleton(const gecut_result* cut, const int32_t* prog
   }
   const int T = 256;
   if (ncut > 0) {
-    if (D == 2)
+    if (g.simplexified && D == 2)
+      GC_LAUNCH(ctx, "k_ghost_mask", k_ghost_mask_sx<2><<<(unsigned)gc_div_up(ncut, T), T, 0, ctx->stream>>>(g, g, sx, cut->lay, ncut, p, side, nullptr, 0, 0, nullptr, 0, 0, mask, cnt));
+    else if (g.simplexified)
+      GC_LAUNCH(ctx, "k_ghost_mask", k_ghost_mask_sx<3><<<(unsigned)gc_div_up(ncut, T), T, 0, ctx->stream>>>(g, g, sx, cut->lay, ncut, p, side, nullptr, 0, 0, nullptr, 0, 0, mask, cnt));
+    else if (D == 2)
       GC_LAUNCH(ctx, "k_ghost_mask", k_ghost_mask<2><<<(unsigned)gc_div_up(ncut, T), T, 0, ctx->stream>>>(g, g, cut->lay, ncut, p, side, nullptr, 0, 0, nullptr, 0, 0, mask, cnt));
     else
       GC_LAUNCH(ctx, "k_ghost_mask", k_ghost_mask<3><<<(unsigned)gc_div_up(ncut, T), T, 0, ctx->stream>>>(g, g, cut->lay, ncut, p, side, nullptr, 0, 0, nullptr, 0, 0, mask, cnt));
@@ -320,6 +532,7 @@ struct AggSlab {
   int64_t layer = 0, nc = 0, ncut = 0, shift = 0, goff = 0, ntot = 0;
   int glo = 0, ghi = 0;
   bool owns_cellin = true;
+  GcSxFacets sx{};  // simplexified models
 };
 
 static void agg_release(gecut_ctx* ctx, AggSlab& a) {
@@ -346,11 +559,12 @@ static int agg_setup(gecut_ctx* ctx, AggSlab& a, const gecut_result* cut, const 
   const GcGrid& g = cut->grid;
   const GcGrid& gf = facets->grid;
   const int D = g.D;
-  if (g.simplexified) {
-    ctx->err = "aggregate is implemented for n-cube Cartesian models";
+  if (g.simplexified && !gc_build_sx_facets(D, &a.sx)) {
+    ctx->err = "aggregate: the simplexify table of the n-cube does not tile conformingly";
     return GECUT_ERR_NOTIMPLEMENTED;
   }
-  bool same = g.D == gf.D && cut->L == facets->L && gf.k0 == g.k0 && gf.n[D - 1] == g.k1 - g.k0;
+  bool same = g.D == gf.D && cut->L == facets->L && gf.k0 == g.k0 && gf.n[D - 1] == g.k1 - g.k0 &&
+              g.simplexified == gf.simplexified;
   for (int d = 0; d + 1 < D; ++d) same = same && g.n[d] == gf.n[d];
   if (!same) {
     ctx->err = "aggregate: cut and cut_facets come from different models / slabs / geometries";
@@ -363,11 +577,11 @@ static int agg_setup(gecut_ctx* ctx, AggSlab& a, const gecut_result* cut, const 
   if (facet_program) GC_CHECK(gc_make_program(ctx, facet_program, facet_len, facets->L, &a.pf));
   a.nc = cut->sizes.num_bgcells;
   a.ncut = cut->sizes.num_cutcells;
-  a.layer = g.layer_cubes;
+  a.layer = layer_cells(g);
   a.glo = g.k0 > 0 ? 1 : 0;
   a.ghi = g.k1 < g.n[D - 1] ? 1 : 0;
   a.shift = a.glo ? a.layer : 0;
-  a.goff = (int64_t)g.k0 * g.layer_cubes;
+  a.goff = (int64_t)g.k0 * a.layer;
   a.ntot = a.nc + (a.glo + a.ghi) * a.layer;
   if (a.ncut > 0 && !cut->cut_sc_ptr) {
     ctx->err = "aggregate needs the subcells of cut(), not a classification-only result";
@@ -405,6 +619,16 @@ static int agg_setup(gecut_ctx* ctx, AggSlab& a, const gecut_result* cut, const 
     double cell_meas = 0.0;
     for (int q = 0; q < nq; ++q) cell_meas += w * fabs(detJ);
     GC_CHECK(gc_ensure_measures(ctx, cut));
+    if (g.simplexified) {
+      if (D == 2)
+        GC_LAUNCH(ctx, "k_agg_init_cut", k_agg_init_cut_sx<2><<<(unsigned)gc_div_up(a.ncut, T), T, 0, ctx->stream>>>(
+            g, ctx->d_simplexify_raw, cut->lay, cut->cut_sc_ptr, a.ncut, a.p, side, threshold, g.nt, a.shift, a.goff, a.cellin,
+            a.touched));
+      else
+        GC_LAUNCH(ctx, "k_agg_init_cut", k_agg_init_cut_sx<3><<<(unsigned)gc_div_up(a.ncut, T), T, 0, ctx->stream>>>(
+            g, ctx->d_simplexify_raw, cut->lay, cut->cut_sc_ptr, a.ncut, a.p, side, threshold, g.nt, a.shift, a.goff, a.cellin,
+            a.touched));
+    } else
     GC_LAUNCH(ctx, "k_agg_init_cut", k_agg_init_cut<<<(unsigned)gc_div_up(a.ncut, T), T, 0, ctx->stream>>>(
         cut->lay, cut->cut_sc_ptr, a.ncut, a.p, side, threshold, cell_meas, a.shift, a.goff, a.cellin, a.touched));
     GC_CHECK(gc_launch_check(ctx, "k_agg_init_cut"));
@@ -417,6 +641,17 @@ static int agg_sweep(gecut_ctx* ctx, AggSlab& a, int side) {
   if (a.ncut == 0) return GECUT_OK;
   const int T = 256;
   const GcGrid& g = a.cut->grid;
+  if (g.simplexified) {
+    if (g.D == 2)
+      GC_LAUNCH(ctx, "k_agg_sweep", k_agg_sweep_sx<2><<<(unsigned)gc_div_up(a.ncut, T), T, 0, ctx->stream>>>(
+          g, a.fac->grid, a.sx, ctx->d_simplexify_raw, a.cut->lay, a.ncut, a.p, side, a.facet_state, a.shift, a.glo, a.ghi,
+          a.cellin, a.touched, a.flag));
+    else
+      GC_LAUNCH(ctx, "k_agg_sweep", k_agg_sweep_sx<3><<<(unsigned)gc_div_up(a.ncut, T), T, 0, ctx->stream>>>(
+          g, a.fac->grid, a.sx, ctx->d_simplexify_raw, a.cut->lay, a.ncut, a.p, side, a.facet_state, a.shift, a.glo, a.ghi,
+          a.cellin, a.touched, a.flag));
+    return gc_launch_check(ctx, "k_agg_sweep");
+  }
   if (g.D == 2)
     GC_LAUNCH(ctx, "k_agg_sweep", k_agg_sweep<2><<<(unsigned)gc_div_up(a.ncut, T), T, 0, ctx->stream>>>(
         g, a.fac->grid, a.cut->lay, a.ncut, a.p, side, a.facet_state, a.shift, a.glo, a.ghi, a.cellin, a.touched, a.flag));
@@ -620,7 +855,13 @@ static int ghost_slab(gecut_ctx* ctx, const gecut_result* cut, const GcProgram& 
   GcGrid gf = g;  // the local model of the slab
   gf.n[D - 1] = g.k1 - g.k0;
   gf.nn[D - 1] = gf.n[D - 1] + 1;
-  const int64_t nf = D == 2 ? num_facets<2>(gf) : num_facets<3>(gf);
+  GcSxFacets sx{};
+  if (g.simplexified && !gc_build_sx_facets(D, &sx)) {
+    ctx->err = "ghost skeleton: the simplexify table of the n-cube does not tile conformingly";
+    return GECUT_ERR_NOTIMPLEMENTED;
+  }
+  const int64_t nf = g.simplexified ? (D == 2 ? sx_num_facets<2>(gf, sx) : sx_num_facets<3>(gf, sx))
+                                    : (D == 2 ? num_facets<2>(gf) : num_facets<3>(gf));
   const int64_t ncut = cut->sizes.num_cutcells;
   GcScratch scratch(ctx);
   int8_t* mask = nullptr;
@@ -631,7 +872,13 @@ static int ghost_slab(gecut_ctx* ctx, const gecut_result* cut, const GcProgram& 
   GC_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), ctx->stream));
   const int T = 256;
   if (ncut > 0) {
-    if (D == 2)
+    if (g.simplexified && D == 2)
+      GC_LAUNCH(ctx, "k_ghost_mask", k_ghost_mask_sx<2><<<(unsigned)gc_div_up(ncut, T), T, 0, ctx->stream>>>(
+          g, gf, sx, cut->lay, ncut, p, side, lo_rows, lo_pitch, lo_base, hi_rows, hi_pitch, hi_base, mask, nullptr));
+    else if (g.simplexified)
+      GC_LAUNCH(ctx, "k_ghost_mask", k_ghost_mask_sx<3><<<(unsigned)gc_div_up(ncut, T), T, 0, ctx->stream>>>(
+          g, gf, sx, cut->lay, ncut, p, side, lo_rows, lo_pitch, lo_base, hi_rows, hi_pitch, hi_base, mask, nullptr));
+    else if (D == 2)
       GC_LAUNCH(ctx, "k_ghost_mask", k_ghost_mask<2><<<(unsigned)gc_div_up(ncut, T), T, 0, ctx->stream>>>(
           g, gf, cut->lay, ncut, p, side, lo_rows, lo_pitch, lo_base, hi_rows, hi_pitch, hi_base, mask, nullptr));
     else
@@ -643,7 +890,13 @@ static int ghost_slab(gecut_ctx* ctx, const gecut_result* cut, const GcProgram& 
     const int8_t* rows = which == 0 ? lo_rows : hi_rows;
     if (!rows) continue;
     const unsigned nbp = (unsigned)gc_div_up(g.layer_cubes, T);
-    if (D == 2)
+    if (g.simplexified && D == 2)
+      GC_LAUNCH(ctx, "k_ghost_mask_plane", k_ghost_mask_plane_sx<2><<<nbp, T, 0, ctx->stream>>>(
+          g, gf, sx, cut->lay, p, side, which, rows, which == 0 ? lo_pitch : hi_pitch, which == 0 ? lo_base : hi_base, mask));
+    else if (g.simplexified)
+      GC_LAUNCH(ctx, "k_ghost_mask_plane", k_ghost_mask_plane_sx<3><<<nbp, T, 0, ctx->stream>>>(
+          g, gf, sx, cut->lay, p, side, which, rows, which == 0 ? lo_pitch : hi_pitch, which == 0 ? lo_base : hi_base, mask));
+    else if (D == 2)
       GC_LAUNCH(ctx, "k_ghost_mask_plane", k_ghost_mask_plane<2><<<nbp, T, 0, ctx->stream>>>(
           g, gf, cut->lay, p, side, which, rows, which == 0 ? lo_pitch : hi_pitch, which == 0 ? lo_base : hi_base, mask));
     else
@@ -668,10 +921,7 @@ static int ghost_check_args(gecut_ctx* ctx, const gecut_result* cut, int side) {
     ctx->err = "ghost skeleton: in_or_out must be IN, OUT or CUT";
     return GECUT_ERR_INVALID;
   }
-  if (cut->grid.simplexified) {
-    ctx->err = "GhostSkeleton is implemented for n-cube Cartesian models";
-    return GECUT_ERR_NOTIMPLEMENTED;
-  }
+  (void)cut;
   return GECUT_OK;
 }
 
@@ -696,7 +946,7 @@ extern "C" int gecut_ghost_skeleton_slabs(const gecut_result* const* cuts, int n
     GC_CHECK(gc_make_program(ctx, program, len, cuts[r]->L, &p));
     const gecut_result* lo = r > 0 ? cuts[r - 1] : nullptr;
     const gecut_result* hi = r + 1 < nslabs ? cuts[r + 1] : nullptr;
-    const int64_t layer = g0.layer_cubes;
+    const int64_t layer = layer_cells(g0);
     GC_CHECK(ghost_slab(ctx, cuts[r], p, side, lo ? lo->lay.bg_state : nullptr, lo ? lo->lay.bg_pitch : 0,
                         lo ? lo->sizes.num_bgcells - layer : 0, hi ? hi->lay.bg_state : nullptr, hi ? hi->lay.bg_pitch : 0, 0,
                         n_ghost ? n_ghost + r : nullptr, facet_to_mask ? facet_to_mask[r] : nullptr));
@@ -723,7 +973,7 @@ extern "C" int gecut_comm_ghost_skeleton(const gecut_result* cut, const int32_t*
   GC_CHECK(gc_make_program(ctx, program, len, cut->L, &p));
   // the L state rows of the slab's first / last cell layer, packed [L][layer], to the ranks below / above
   const int L = cut->L;
-  const int64_t layer = g.layer_cubes, nc = cut->sizes.num_bgcells;
+  const int64_t layer = layer_cells(g), nc = cut->sizes.num_bgcells;
   GcScratch scratch(ctx);
   int8_t* buf = nullptr;  // [send lo][send hi][recv lo][recv hi], L * layer bytes each
   const size_t blk = (size_t)L * layer;

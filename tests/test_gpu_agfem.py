@@ -20,6 +20,12 @@ CASES = {
     "bimaterial": lambda: (CartesianDiscreteModel((0., 0., 0.), (3., 2., 3.), (18, 12, 18)), bimaterial(), "steel"),
     # too coarse for an IN root inside the cylinders: the reference's @assert all_aggregated fires
     "bimaterial_coarse": lambda: (CartesianDiscreteModel((0., 0., 0.), (3., 2., 3.), (9, 6, 9)), bimaterial(), "steel"),
+    # simplexified models (cells = the TRI / TET of simplexify(model), topology through the facet grid of the simplices)
+    "sx_disk_30": lambda: (simplexify(CartesianDiscreteModel((0, 1, 0, 1), (30, 30))), disk(0.4, x0=(0.5, 0.5)), None),
+    "sx_disk_corner": lambda: (simplexify(CartesianDiscreteModel((0, 1, 0, 1), (17, 23))), disk(0.72, x0=(1, 1)), None),
+    "sx_three_disks": lambda: (simplexify(CartesianDiscreteModel((-1, 2, -1, 2), (23, 19))), three_disks(), None),
+    "sx_sphere": lambda: (simplexify(CartesianDiscreteModel((-1, 1, -1, 1, -1, 1), (9, 8, 7))), sphere(0.7), None),
+    "sx_csg": lambda: (simplexify(CartesianDiscreteModel((-0.8,) * 3, (0.8,) * 3, (10, 10, 10))), csg_geometry(), "csg"),
 }
 
 
@@ -60,12 +66,15 @@ def test_aggregate_defaults_and_errors():
     assert np.array_equal(a, aggregate(AggregateAllCutCells(), cg, geo, IN))
     with pytest.raises(ValueError):
         AggregateCutCellsByThreshold(1.5)
-    # simplexified models: not implemented (needs the facet grid of the simplexified model)
+    # simplexified models go through the same entry points (facet grid of the simplices)
     ms = simplexify(model)
     cs = cut(ms, geo)
-    with pytest.raises((NotImplementedError, gecut._lib.GecutError)):
-        aggregate(AggregateAllCutCells(), cs)
-    for x in (cg, fc, cs):
+    fs = cut_facets(ms, geo)
+    a = aggregate(AggregateAllCutCells(), cs)
+    assert a.shape == (ms.num_cells,) and np.array_equal(a, aggregate(AggregateAllCutCells(), cs, fs))
+    with pytest.raises(gecut._lib.GecutError):  # a facet discretization of another model
+        aggregate(AggregateAllCutCells(), cs, fc)
+    for x in (cg, fc, cs, fs):
         x.close()
 
 
@@ -95,7 +104,8 @@ def test_aggregate_at_scale():
     fc.close()
 
 
-@pytest.mark.parametrize("name", ["disk_30", "disk_corner", "three_disks", "sphere", "csg", "bimaterial"])
+@pytest.mark.parametrize("name", ["disk_30", "disk_corner", "three_disks", "sphere", "csg", "bimaterial",
+                                  "sx_disk_30", "sx_disk_corner", "sx_three_disks", "sx_sphere", "sx_csg"])
 def test_ghost_skeleton_parity(name):
     from gecut import GhostSkeleton, ACTIVE_IN, ACTIVE_OUT, PHYSICAL_IN
     model, geo, nm = CASES[name]()
@@ -115,7 +125,8 @@ def test_ghost_skeleton_parity(name):
     cg.close()
 
 
-@pytest.mark.parametrize("name,nslab", [("disk_30", 3), ("three_disks", 2), ("sphere", 3), ("csg", 2), ("bimaterial", 4)])
+@pytest.mark.parametrize("name,nslab", [("disk_30", 3), ("three_disks", 2), ("sphere", 3), ("csg", 2), ("bimaterial", 4),
+                                        ("sx_three_disks", 3), ("sx_sphere", 2), ("sx_csg", 3)])
 @pytest.mark.parametrize("threshold", [1.0, 0.4])
 def test_aggregation_over_slabs_equals_the_whole_model(name, nslab, threshold):
     """Distributed aggregation (`src/Distributed/DistributedAgFEM.jl:52-144`) on z-slabs: every slab sweeps its own cut cells
@@ -146,7 +157,8 @@ def test_aggregation_over_slabs_equals_the_whole_model(name, nslab, threshold):
             o.close()
 
 
-@pytest.mark.parametrize("name,nslab", [("disk_30", 3), ("three_disks", 2), ("sphere", 3), ("csg", 2), ("bimaterial", 4)])
+@pytest.mark.parametrize("name,nslab", [("disk_30", 3), ("three_disks", 2), ("sphere", 3), ("csg", 2), ("bimaterial", 4),
+                                        ("sx_three_disks", 3), ("sx_sphere", 2), ("sx_csg", 3)])
 def test_ghost_skeleton_over_slabs_equals_the_whole_model(name, nslab):
     """GhostSkeleton on z-slabs: the mask of every slab's local model equals the whole-model mask on the slab's facets
     (through the facet -> node-tuple map), including the facets on the planes two slabs share."""

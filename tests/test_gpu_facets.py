@@ -155,15 +155,6 @@ def test_facets_unsupported_inputs():
     m = CartesianDiscreteModel((0, 1, 0, 1), (4, 4))
     with pytest.raises(_lib.GecutError):  # slabs are supported; an empty / out-of-range one is an invalid argument
         LevelSetCutter(slab=(3, 9)).cut_facets(m, disk(0.3, x0=(0.5, 0.5)))
-    # aggregation on a simplexified model is refused (NOTIMPLEMENTED), not silently computed on the n-cube topology
-    from gecut import simplexify, aggregate, AggregateAllCutCells
-    ms = simplexify(m)
-    geo = disk(0.3, x0=(0.5, 0.5))
-    cg, fc = cut(ms, geo), cut_facets(ms, geo)
-    with pytest.raises((_lib.GecutError, NotImplementedError)):
-        aggregate(AggregateAllCutCells(), cg, fc, geo)
-    cg.close()
-    fc.close()
 
 
 @pytest.mark.parametrize("case", ["disk_2048", "sphere_160", "csg_64", "sx_disk_1024", "sx_sphere_96"])
