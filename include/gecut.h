@@ -235,14 +235,16 @@ int gecut_selection_device_laplacian(const gecut_selection* sel, double** K_cut_
 /* ---- cut_facets ----------------------------------------------------------------------------- */
 /* cut_facets(::LevelSetCutter, bgmodel, geo) (src/LevelSetCutters/LevelSetCutters.jl:107-142): the marching-simplex
  * machinery on Grid(ReferenceFE{D-1}, bgmodel) without boundary -> EmbeddedFacetDiscretization
- * (src/Interfaces/EmbeddedFacetDiscretizations.jl:28-35).  n-cube Cartesian models.  With grid->slab_begin/end the result is
+ * (src/Interfaces/EmbeddedFacetDiscretizations.jl:28-35).  Cartesian models, n-cube or simplexified (the facet grid of the
+ * TRI / TET mesh: SEGMENT / TRI bg facets, cut without a stage-0 simplexification).  With grid->slab_begin/end the result is
  * the facet discretization of the rank's LOCAL model -- layers [slab_begin, slab_end) as a Cartesian model of its own (local
  * facet numbering; its lower and upper planes are boundary facets of the local model), node coordinates global, so a slab's
  * facets are bit-identical to the same facets of the whole model (the reference's ranks cut their local models the same way,
  * src/Distributed/DistributedDiscretizations.jl:42-53).
  * Facet numbering (Gridap `generate_cell_to_faces`, assumption A8 in DESIGN.md): first encounter over (cell ascending,
  * local facet ascending), local facets QUAD [1,2],[3,4],[1,3],[2,4] / HEX [1,2,3,4],[5,6,7,8],[1,2,5,6],[3,4,7,8],
- * [1,3,5,7],[2,4,6,8]; a facet keeps the node order of the local facet of the cell that meets it first. */
+ * [1,3,5,7],[2,4,6,8], TRI [1,2],[1,3],[2,3] / TET [1,2,3],[1,2,4],[1,3,4],[2,3,4]; a facet keeps the node order of the local
+ * facet of the cell that meets it first.  Both numberings are closed-form on a Cartesian model (no topology tables). */
 typedef struct gecut_facet_result gecut_facet_result;       /* device-resident EmbeddedFacetDiscretization          */
 typedef struct gecut_facet_selection gecut_facet_selection; /* BoundaryTriangulation / SkeletonTriangulation(cut_facets,...) */
 
@@ -254,7 +256,7 @@ typedef struct {
   int64_t num_subfacet_points;  /* Nsfp                                                                            */
   int32_t num_levelsets;
   int32_t D;
-  int32_t num_vertices_per_bgfacet; /* 2 (SEGMENT) or 4 (QUAD)                                                     */
+  int32_t num_vertices_per_bgfacet; /* 2 (SEGMENT), 4 (QUAD) or 3 (TRI, simplexified 3-D models)                    */
   int32_t pad;
 } gecut_facet_sizes;
 
@@ -306,7 +308,8 @@ int gecut_facet_selection_measure(const gecut_facet_selection* sel, double* sub_
  * compiled over the FACET discretization's own level-set numbering (its oid_to_ls, CellAggregation.jl:90); NULL = the
  * two discretizations number their level sets alike and `program` serves both.  threshold = 1 is
  * AggregateAllCutCells().  Fails with GECUT_ERR_INVALID when 20 sweeps do not aggregate every cut cell (the reference's
- * @assert all_aggregated).  Whole n-cube Cartesian models. */
+ * @assert all_aggregated).  Whole Cartesian models, n-cube or simplexified (cells = the simplices, neighbours through the
+ * facet grid of the simplices; `cut` and `facets` must come from the same model). */
 int gecut_aggregate(const gecut_result* cut, const gecut_facet_result* facets, const int32_t* program, int len,
                     const int32_t* facet_program, int facet_len, int side, double threshold, int32_t* cell_to_cellin,
                     int on_device);
@@ -325,7 +328,7 @@ int gecut_aggregate_slabs(const gecut_result* const* cuts, const gecut_facet_res
  * GECUT_CUT for the cut cells alone).  *n_ghost = number of such facets; `facet_to_mask` (host, num_bgfacets Int8, NULL
  * skipped) is the mask handed to SkeletonTriangulation(model, facet_to_mask); `facet_ids` (host, *n_ghost Int32 from a
  * previous call, NULL skipped) the same facets as an ascending 1-based list.  Facet numbering as in gecut_cut_facets.
- * Whole n-cube Cartesian models. */
+ * Whole Cartesian models, n-cube or simplexified. */
 int gecut_ghost_skeleton(const gecut_result* cut, const int32_t* program, int len, int side, int64_t* n_ghost,
                          int8_t* facet_to_mask, int32_t* facet_ids);
 /* The same over z-slabs of one context (in ascending layer order, covering the model): `facet_to_mask[r]` (host, NULL skipped)
