@@ -234,7 +234,8 @@ struct GecutFacetBuffers
   sf_point_to_coords::Ptr{Float64}; sf_point_to_rcoords::Ptr{Float64}; ls_to_subfacet_to_inout::Ptr{Int8}
 end
 
-function _run_facets(cutter::B200LevelSetCutter, bgmodel::CartesianDiscreteModel, geom, classify_only::Bool)
+function _run_facets(cutter::B200LevelSetCutter, bgmodel, geom, classify_only::Bool;
+                     simplexified::Bool=false, cartesian=bgmodel)
   ctx = _ctx(cutter)
   j_to_fun, oid_to_ls = _find_unique_leaves(get_tree(geom))
   coords = collect1d(get_node_coordinates(get_grid(bgmodel)))
@@ -242,7 +243,8 @@ function _run_facets(cutter::B200LevelSetCutter, bgmodel::CartesianDiscreteModel
   for f in j_to_fun
     r, v = _leaf_record(f, coords); push!(recs, r); push!(nodal, v)
   end
-  g = _grid(bgmodel)
+  g = _grid(cartesian)
+  g = GecutGrid(g.D, simplexified ? 1 : 0, g.pmin, g.pmax, g.partition, 0, 0, 0)
   ptrs = Ptr{Float64}[v === nothing ? C_NULL : pointer(v) for v in nodal]
   res = Ref{Ptr{Cvoid}}(C_NULL)
   GC.@preserve nodal begin
@@ -256,8 +258,12 @@ end
 
 # The facet ids of the library follow Gridap's own numbering of Grid(ReferenceFE{D-1}, model) (first encounter over
 # (cell, local facet), DESIGN.md assumption A8), so `cell_to_bgcell` indexes get_face_nodes(model, D-1) directly.
-function cut_facets(cutter::B200LevelSetCutter, bgmodel::CartesianDiscreteModel, geom)
-  res, oid_to_ls = _run_facets(cutter, bgmodel, geom, false)
+cut_facets(cutter::B200LevelSetCutter, bgmodel::CartesianDiscreteModel, geom) = _cut_facets(cutter, bgmodel, geom, false, bgmodel)
+# simplexified model: the facet grid of the TRI / TET mesh (SEGMENT / TRI bg facets), same first-encounter numbering
+cut_facets(cutter::B200LevelSetCutter, bg::SimplexifiedCartesian, geom) = _cut_facets(cutter, bg.model, geom, true, bg.cartesian)
+
+function _cut_facets(cutter::B200LevelSetCutter, bgmodel, geom, simplexified::Bool, cartesian)
+  res, oid_to_ls = _run_facets(cutter, bgmodel, geom, false; simplexified=simplexified, cartesian=cartesian)
   sz = Ref{GecutFacetSizes}()
   _check(cutter, ccall((:gecut_facet_result_sizes, libgecut), Cint, (Ptr{Cvoid}, Ref{GecutFacetSizes}), res, sz),
          "gecut_facet_result_sizes")
@@ -277,8 +283,13 @@ function cut_facets(cutter::B200LevelSetCutter, bgmodel::CartesianDiscreteModel,
   EmbeddedFacetDiscretization(bgmodel, bg, subfacets, sfi, oid_to_ls, geom)
 end
 
-function compute_bgfacet_to_inoutcut(cutter::B200LevelSetCutter, bgmodel::CartesianDiscreteModel, geom)
-  res, oid_to_ls = _run_facets(cutter, bgmodel, geom, true)
+compute_bgfacet_to_inoutcut(cutter::B200LevelSetCutter, bgmodel::CartesianDiscreteModel, geom) =
+  _bgfacet_to_inoutcut(cutter, bgmodel, geom, false, bgmodel)
+compute_bgfacet_to_inoutcut(cutter::B200LevelSetCutter, bg::SimplexifiedCartesian, geom) =
+  _bgfacet_to_inoutcut(cutter, bg.model, geom, true, bg.cartesian)
+
+function _bgfacet_to_inoutcut(cutter::B200LevelSetCutter, bgmodel, geom, simplexified::Bool, cartesian)
+  res, oid_to_ls = _run_facets(cutter, bgmodel, geom, true; simplexified=simplexified, cartesian=cartesian)
   prog = _postfix(get_tree(geom), oid_to_ls)
   out = Vector{Int8}(undef, num_facets(bgmodel))
   _check(cutter, ccall((:gecut_bgfacet_to_inoutcut, libgecut), Cint, (Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Int8}),
