@@ -493,6 +493,7 @@ struct GcMulti {
   uint32_t* slow_val;     // [nch][slow_n] counters (walk count) -> start offsets (fill of the tile)
   int64_t slow_n;
   uint32_t* slow_count;   // [CM_NBK] recorded simplices per bucket, [CM_NBK] their total (slot allocator)
+  unsigned long long* two_items;  // [bucket-0 slots x WALK_ITEMS] per-item counters of k_cut_two (count -> fill)
   uint32_t fac_base[GC_LMAX];  // global offset of the facets of level set ls (merge_sub_face_data order)
   uint32_t fpt_base[GC_LMAX];
 };
@@ -1550,10 +1551,41 @@ k_cut_two(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ 
       lay.sf_state[(int64_t)kk * lay.sf_pitch + fid] =
           (kk == ls) ? (int8_t)GECUT_INTERFACE : (kk == k1 ? s1 : (kk == k2 ? s2 : cst(kk)));
   };
-  // Two passes over the same code: pass 0 counts, the 8-lane scan turns the counters into offsets, pass 1 writes.
-  // (!FILL: pass 0 only.)
-  for (int pass = 0; pass < (FILL ? 2 : 1); ++pass) {
-    const bool wr = FILL && pass == 1;
+  // inclusive scan over the WALK_ITEMS lanes of the simplex
+  auto seg_scan = [&](uint32_t v) -> uint32_t {
+#pragma unroll
+    for (int o = 1; o < WALK_ITEMS; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(FULLM, v, o);
+      if ((lane & (WALK_ITEMS - 1)) >= o) v += up;
+    }
+    return v;
+  };
+  // The count launch leaves the six counters of every item (one byte each) in mu.two_items; the fill launch turns them
+  // into offsets with the 8-lane scans and runs the body once, writing.  (The launches of one cut use the same slot
+  // list, so gtid addresses the same item in both.)
+  if (FILL) {
+    const unsigned long long pk = mu.two_items[gtid];
+    n_cells = (uint32_t)(pk & 0xFFu);
+    n_pts = (uint32_t)((pk >> 8) & 0xFFu);
+    n_fa = (uint32_t)((pk >> 16) & 0xFFu);
+    n_fpa = (uint32_t)((pk >> 24) & 0xFFu);
+    n_fb = (uint32_t)((pk >> 32) & 0xFFu);
+    n_fpb = (uint32_t)((pk >> 40) & 0xFFu);
+    const uint32_t ic = seg_scan(n_cells), ip = seg_scan(n_pts), ifa = seg_scan(n_fa), ipa = seg_scan(n_fpa),
+                   ifb = seg_scan(n_fb), ipb = seg_scan(n_fpb);
+    if (valid) {
+      // start offsets of the simplex, left by the fill kernel of its tile (k_cutm_fill)
+      const uint32_t* val = mu.slow_val + slot;  // channel ch at val[ch * slow_n]
+      cell_off = val[0] + ic - n_cells;
+      pt_off = val[mu.slow_n] + ip - n_pts;
+      fa_off = mu.fac_base[a] + val[(int64_t)(2 + a) * mu.slow_n] + ifa - n_fa;
+      fpa_off = mu.fpt_base[a] + val[(int64_t)(2 + L + a) * mu.slow_n] + ipa - n_fpa;
+      fb_off = mu.fac_base[b] + val[(int64_t)(2 + b) * mu.slow_n] + ifb - n_fb;
+      fpb_off = mu.fpt_base[b] + val[(int64_t)(2 + L + b) * mu.slow_n] + ipb - n_fpb;
+    }
+  }
+  {
+    constexpr bool wr = FILL;
     if (valid && item < (int)TC.nsub[ca]) {
       // ================= child `item` of stage a
       const int j = item;
@@ -1741,7 +1773,7 @@ k_cut_two(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ 
         ncell_out = nsb;
         npt_out = (uint32_t)nsb * (D + 1);
       }
-      if (pass == 0) {
+      if (!FILL) {
         n_cells = ncell_out;
         n_pts = npt_out;
         n_fb = fo - fb_off;
@@ -1829,48 +1861,33 @@ k_cut_two(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ 
         nfo = nsf;
         npo = (uint32_t)nsf * D;
       }
-      if (pass == 0) {
+      if (!FILL) {
         n_fa = nfo;
         n_fpa = npo;
       }
     }
-    if (pass == 1) break;
-    // ---- inclusive scans over the WALK_ITEMS lanes of the simplex
-    auto seg_scan = [&](uint32_t v) -> uint32_t {
-#pragma unroll
-      for (int o = 1; o < WALK_ITEMS; o <<= 1) {
-        const uint32_t up = __shfl_up_sync(FULLM, v, o);
-        if ((lane & (WALK_ITEMS - 1)) >= o) v += up;
-      }
-      return v;
-    };
+  }
+  if (!FILL) {
+    mu.two_items[gtid] = (unsigned long long)n_cells | ((unsigned long long)n_pts << 8) | ((unsigned long long)n_fa << 16) |
+                         ((unsigned long long)n_fpa << 24) | ((unsigned long long)n_fb << 32) |
+                         ((unsigned long long)n_fpb << 40);
     const uint32_t ic = seg_scan(n_cells), ip = seg_scan(n_pts), ifa = seg_scan(n_fa), ipa = seg_scan(n_fpa),
                    ifb = seg_scan(n_fb), ipb = seg_scan(n_fpb);
-    uint32_t* val = mu.slow_val + slot;  // channel ch at val[ch * slow_n]
-    if (!FILL) {
-      if (valid && item == WALK_ITEMS - 1) {
-        const int64_t tile = s / 32;
-        val[0] = ic;
-        val[mu.slow_n] = ip;
-        val[(int64_t)(2 + a) * mu.slow_n] = ifa;
-        val[(int64_t)(2 + L + a) * mu.slow_n] = ipa;
-        val[(int64_t)(2 + b) * mu.slow_n] = ifb;
-        val[(int64_t)(2 + L + b) * mu.slow_n] = ipb;
-        atomicAdd(mu.tile + tile, ic);
-        atomicAdd(mu.tile + mu.ntiles + tile, ip);
-        if (ifa) atomicAdd(mu.tile + (int64_t)(2 + a) * mu.ntiles + tile, ifa);
-        if (ipa) atomicAdd(mu.tile + (int64_t)(2 + L + a) * mu.ntiles + tile, ipa);
-        if (ifb) atomicAdd(mu.tile + (int64_t)(2 + b) * mu.ntiles + tile, ifb);
-        if (ipb) atomicAdd(mu.tile + (int64_t)(2 + L + b) * mu.ntiles + tile, ipb);
-      }
-    } else if (valid) {
-      // start offsets of the simplex, left by the fill kernel of its tile (k_cutm_fill)
-      cell_off = val[0] + ic - n_cells;
-      pt_off = val[mu.slow_n] + ip - n_pts;
-      fa_off = mu.fac_base[a] + val[(int64_t)(2 + a) * mu.slow_n] + ifa - n_fa;
-      fpa_off = mu.fpt_base[a] + val[(int64_t)(2 + L + a) * mu.slow_n] + ipa - n_fpa;
-      fb_off = mu.fac_base[b] + val[(int64_t)(2 + b) * mu.slow_n] + ifb - n_fb;
-      fpb_off = mu.fpt_base[b] + val[(int64_t)(2 + L + b) * mu.slow_n] + ipb - n_fpb;
+    if (valid && item == WALK_ITEMS - 1) {
+      uint32_t* val = mu.slow_val + slot;  // channel ch at val[ch * slow_n]
+      const int64_t tile = s / 32;
+      val[0] = ic;
+      val[mu.slow_n] = ip;
+      val[(int64_t)(2 + a) * mu.slow_n] = ifa;
+      val[(int64_t)(2 + L + a) * mu.slow_n] = ipa;
+      val[(int64_t)(2 + b) * mu.slow_n] = ifb;
+      val[(int64_t)(2 + L + b) * mu.slow_n] = ipb;
+      atomicAdd(mu.tile + tile, ic);
+      atomicAdd(mu.tile + mu.ntiles + tile, ip);
+      if (ifa) atomicAdd(mu.tile + (int64_t)(2 + a) * mu.ntiles + tile, ifa);
+      if (ipa) atomicAdd(mu.tile + (int64_t)(2 + L + a) * mu.ntiles + tile, ipa);
+      if (ifb) atomicAdd(mu.tile + (int64_t)(2 + b) * mu.ntiles + tile, ifb);
+      if (ipb) atomicAdd(mu.tile + (int64_t)(2 + L + b) * mu.ntiles + tile, ipb);
     }
   }
 }
@@ -2833,6 +2850,8 @@ int gc_cut_cells(gecut_ctx* ctx, gecut_result* res) {
     // the depth-2 kernel writes only the channels of its two level sets
     GC_CUDA(cudaMemsetAsync(mu.slow_val, 0, sizeof(uint32_t) * nslow_total * mu.nch, ctx->stream));
     GC_CHECK(scratch.alloc(&lists, sizeof(uint32_t) * nslow_total));
+    if (nslow[0] > 0)  // rounded up to whole blocks: every thread of the launches stores / loads its word
+      GC_CHECK(scratch.alloc(&mu.two_items, sizeof(unsigned long long) * (size_t)gc_div_up(nslow[0] * WALK_ITEMS, TWO_T) * TWO_T));
     GC_CHECK(scratch.alloc(&cursor, sizeof(uint32_t) * 2 * CM_NBK));
     uint32_t hb[2 * CM_NBK];
     uint32_t acc = 0;
