@@ -1437,7 +1437,9 @@ struct TwoSmem {
   static constexpr int PAS = 2 * D + 2;  // x, r, wa, wb
   static constexpr int PBS = 2 * D + 1;  // x, r, wa
   double pa[TWO_T / WALK_ITEMS][NPC * PAS];
-  double pb[TWO_T][NPC * PBS + 1];
+  // cut points of stage b of the child items (6 of the 8 lanes of a simplex); a child's vertices stay in PA
+  static constexpr int NEWB = NPC - (D + 1);
+  double pb[TWO_T / WALK_ITEMS * 6][NEWB * PBS + 1];
   double fe[TWO_T][NPF * 2 * D + 1];
 };
 
@@ -1484,7 +1486,7 @@ k_cut_two(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ 
   const int a = 31 - __clz(mixed), b = __ffs(mixed) - 1;
   const int c_allout = (1 << (D + 1)) - 1, fc_allout = (1 << D) - 1;
   double* PA = sm.pa[threadIdx.x / WALK_ITEMS];
-  double* PB = sm.pb[threadIdx.x];
+  double* PBN = sm.pb[(threadIdx.x / WALK_ITEMS) * 6 + (threadIdx.x % WALK_ITEMS < 6 ? threadIdx.x % WALK_ITEMS : 0)];
   double* FE = sm.fe[threadIdx.x];
   auto cst = [&](int k) -> int8_t { return ((outm >> k) & 1u) ? (int8_t)GC_OUT : (int8_t)GC_IN; };
 
@@ -1591,14 +1593,19 @@ k_cut_two(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ 
       const int j = item;
       const int8_t sta = TC.sub_inout[ca][j];
       const uint32_t q1 = cm_skip_cell_stages<D>(s_plut, outm, a, b);
+      // points of the child: its D+1 vertices are points of stage a (slots of PA, 4 bits each in vmap: the layouts of a PA
+      // and a PBN row agree on x, r, wa), the cut points of stage b go to the lane's PBN rows
       double wbv[D + 1];
+      uint32_t vmap = 0u;
 #pragma unroll
       for (int i = 0; i <= D; ++i) {
-        const double* p = PA + TC.sub_pts[ca][j][(q1 >> (2 * i)) & 3u] * PAS;
-#pragma unroll
-        for (int k = 0; k < PBS; ++k) PB[i * PBS + k] = p[k];
-        wbv[i] = p[2 * D + 1];
+        const uint32_t sl = TC.sub_pts[ca][j][(q1 >> (2 * i)) & 3u];
+        vmap |= sl << (4 * i);
+        wbv[i] = PA[sl * PAS + 2 * D + 1];
       }
+      auto pbp = [&](int li) -> const double* {
+        return li <= D ? PA + ((vmap >> (4 * li)) & 15u) * PAS : PBN + (li - (D + 1)) * PBS;
+      };
       int cb = 0;
 #pragma unroll
       for (int i = 0; i <= D; ++i)
@@ -1617,7 +1624,7 @@ k_cut_two(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ 
             const double w1 = fabs(wa1), w2 = fabs(wb1);
             const double coeff = __ddiv_rn(w1, __dadd_rn(w1, w2));
 #pragma unroll
-            for (int k = 0; k < PBS; ++k) PB[np * PBS + k] = gc_lerp(PB[ia * PBS + k], PB[ib * PBS + k], coeff);
+            for (int k = 0; k < PBS; ++k) PBN[(np - (D + 1)) * PBS + k] = gc_lerp(pbp(ia)[k], pbp(ib)[k], coeff);
             np++;
           }
         }
@@ -1629,13 +1636,13 @@ k_cut_two(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ 
       for (int f = 0; f < nfb; ++f) {
         const uint8_t* fp = TC.fac_pts[cb][f];
         double nrm[3] = {0.0, 0.0, 0.0};
-        if (wr) unit_normal<D>(PB + fp[0] * PBS, PB + fp[1] * PBS, PB + fp[D - 1] * PBS, (double)TC.fac_orient[cb][f], nrm);
+        if (wr) unit_normal<D>(pbp(fp[0]), pbp(fp[1]), pbp(fp[D - 1]), (double)TC.fac_orient[cb][f], nrm);
         const uint32_t qf = cm_skip_facet_stages<D>(s_flut, outm, L, a, b);
         int fca = 0;
         double wav[D];
 #pragma unroll
         for (int i = 0; i < D; ++i) {
-          const double* p = PB + fp[(qf >> (2 * i)) & 3u] * PBS;
+          const double* p = pbp(fp[(qf >> (2 * i)) & 3u]);
 #pragma unroll
           for (int k = 0; k < 2 * D; ++k) FE[i * 2 * D + k] = p[k];
           wav[i] = p[2 * D];
@@ -1712,12 +1719,14 @@ k_cut_two(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ 
       uint32_t ncell_out, npt_out;
       if (b == 0) {
         if (wr) {
-          for (int p = 0; p < np; ++p)
+          for (int p = 0; p < np; ++p) {
+            const double* src = pbp(p);
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-              lay.sc_X[(int64_t)(pt_off + p) * D + d] = PB[p * PBS + d];
-              lay.sc_R[(int64_t)(pt_off + p) * D + d] = PB[p * PBS + D + d];
+              lay.sc_X[(int64_t)(pt_off + p) * D + d] = src[d];
+              lay.sc_R[(int64_t)(pt_off + p) * D + d] = src[D + d];
             }
+          }
           for (int jj = 0; jj < nsb; ++jj) {
             const uint32_t cid = cell_off + jj;
             int32_t row[D + 1];
@@ -1727,7 +1736,7 @@ k_cut_two(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ 
               const int li = TC.sub_pts[cb][jj][i];
               row[i] = (int32_t)(pt_off + li + 1);
 #pragma unroll
-              for (int d = 0; d < D; ++d) pc[i][d] = PB[li * PBS + d];
+              for (int d = 0; d < D; ++d) pc[i][d] = pbp(li)[d];
             }
             store_c2p_row<D>(lay.sc_c2p, cid, row);
             lay.sc_c2bg[cid] = bgcell1;
@@ -1753,13 +1762,13 @@ k_cut_two(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ 
             for (int i = 0; i <= D; ++i) {
 #pragma unroll
               for (int d = 0; d < D; ++d) {
-                lay.sc_X[(int64_t)(pb0 + i) * D + d] = PB[cv[i] * PBS + d];
-                lay.sc_R[(int64_t)(pb0 + i) * D + d] = PB[cv[i] * PBS + D + d];
+                lay.sc_X[(int64_t)(pb0 + i) * D + d] = pbp(cv[i])[d];
+                lay.sc_R[(int64_t)(pb0 + i) * D + d] = pbp(cv[i])[D + d];
               }
               const int li = TC.sub_pts[c0][0][i];
               row[i] = (int32_t)(pb0 + li + 1);
 #pragma unroll
-              for (int d = 0; d < D; ++d) pc[i][d] = PB[cv[li] * PBS + d];
+              for (int d = 0; d < D; ++d) pc[i][d] = pbp(cv[li])[d];
             }
             store_c2p_row<D>(lay.sc_c2p, cid, row);
             lay.sc_c2bg[cid] = bgcell1;
