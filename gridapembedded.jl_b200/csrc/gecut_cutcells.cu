@@ -494,6 +494,8 @@ struct GcMulti {
   int64_t slow_n;
   uint32_t* slow_count;   // [CM_NBK] recorded simplices per bucket, [CM_NBK] their total (slot allocator)
   unsigned long long* two_items;  // [bucket-0 slots x WALK_ITEMS] per-item counters of k_cut_two (count -> fill)
+  uint32_t* walk_items;   // [nch][walk_items_n] per-item counters of k_cut_walk (count -> fill), items of all walk buckets
+  int64_t walk_items_n;
   uint32_t fac_base[GC_LMAX];  // global offset of the facets of level set ls (merge_sub_face_data order)
   uint32_t fpt_base[GC_LMAX];
 };
@@ -503,7 +505,7 @@ __global__ void __launch_bounds__(WALK_T)
 k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
            const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
            const int32_t* __restrict__ cutcells, GcMulti mu, GcLayout lay,
-           const uint32_t* __restrict__ slots, int64_t nslots) {
+           const uint32_t* __restrict__ slots, int64_t nslots, int64_t items_base) {
   // WALK_ITEMS lanes per RECORDED simplex (those cut by two or more level sets, listed by k_cutm_count): the tree walk is
   // an order of magnitude longer than the no-tree path, so it runs in its own dense launches.
   constexpr int LM = GC_LMAX;
@@ -532,7 +534,25 @@ k_cut_walk(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__
   uint32_t n_cells = 0, n_pts = 0, n_fac[LM], n_fpt[LM];
 #pragma unroll
   for (int k = 0; k < LM; ++k) n_fac[k] = n_fpt[k] = 0;
-  if (valid) walk_item<D, NW, false>(g, lv, s_tab[0], s_tab[1], simp_raw, simp_pos, lay, s, bgcell1, item, n_cells, n_pts, n_fac, n_fpt);
+  // the count launch walks and leaves the item's counters in mu.walk_items; the fill launch (same slot list, same gtid)
+  // reads them back instead of walking twice
+  uint32_t* wi = mu.walk_items + items_base + gtid;  // channel ch at wi[ch * walk_items_n]
+  if (valid && !FILL) {
+    walk_item<D, NW, false>(g, lv, s_tab[0], s_tab[1], simp_raw, simp_pos, lay, s, bgcell1, item, n_cells, n_pts, n_fac, n_fpt);
+    wi[0] = n_cells;
+    wi[mu.walk_items_n] = n_pts;
+    for (int k = 0; k < L; ++k) {
+      wi[(int64_t)(2 + k) * mu.walk_items_n] = n_fac[k];
+      wi[(int64_t)(2 + L + k) * mu.walk_items_n] = n_fpt[k];
+    }
+  } else if (valid) {
+    n_cells = wi[0];
+    n_pts = wi[mu.walk_items_n];
+    for (int k = 0; k < L; ++k) {
+      n_fac[k] = wi[(int64_t)(2 + k) * mu.walk_items_n];
+      n_fpt[k] = wi[(int64_t)(2 + L + k) * mu.walk_items_n];
+    }
+  }
   // inclusive scan over the WALK_ITEMS lanes of the simplex
   const int lane = threadIdx.x & 31;
   auto seg_scan = [&](uint32_t v) -> uint32_t {
@@ -2466,16 +2486,16 @@ k_cut1_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
 
 template <int D, int NW>
 void launch_walk(gecut_ctx* ctx, const gecut_result* res, const GcMulti& mu, bool fill, int64_t nslots,
-                 const uint32_t* slots, cudaStream_t stream) {
+                 const uint32_t* slots, int64_t items_base, cudaStream_t stream) {
   const int T = WALK_T;
   const unsigned nb = (unsigned)gc_div_up(nslots * WALK_ITEMS, T);
   if (nb == 0) return;
   if (fill)
     GC_LAUNCH(ctx, "k_cut_walk_fill", k_cut_walk<D, NW, true><<<nb, T, 0, stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
-                                                       ctx->d_simplexify_pos, res->lay.cutcells, mu, res->lay, slots, nslots));
+                                                       ctx->d_simplexify_pos, res->lay.cutcells, mu, res->lay, slots, nslots, items_base));
   else
     GC_LAUNCH(ctx, "k_cut_walk_count", k_cut_walk<D, NW, false><<<nb, T, 0, stream>>>(res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw,
-                                                        ctx->d_simplexify_pos, res->lay.cutcells, mu, res->lay, slots, nslots));
+                                                        ctx->d_simplexify_pos, res->lay.cutcells, mu, res->lay, slots, nslots, items_base));
 }
 
 void launch_fast_count(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcMulti& mu) {
@@ -2564,7 +2584,8 @@ int dispatch_walk(gecut_ctx* ctx, const gecut_result* res, const GcMulti& mu, bo
   base[0] = 0;
   for (int b = 1; b < CM_NBK; ++b) base[b] = base[b - 1] + nslow[b - 1];
   launch_two(ctx, res, mu, fill, nslow[0], lists + base[0], stream_of(0));
-#define GC_WALK(DD, B) launch_walk<DD, walk_nw(B)>(ctx, res, mu, fill, nslow[1 + B], lists + base[1 + B], stream_of(1 + B))
+#define GC_WALK(DD, B) \
+  launch_walk<DD, walk_nw(B)>(ctx, res, mu, fill, nslow[1 + B], lists + base[1 + B], (base[1 + B] - base[1]) * WALK_ITEMS, stream_of(1 + B))
   if (D == 2) {
     GC_WALK(2, 0);
     GC_WALK(2, 1);
@@ -2859,6 +2880,10 @@ int gc_cut_cells(gecut_ctx* ctx, gecut_result* res) {
     // the depth-2 kernel writes only the channels of its two level sets
     GC_CUDA(cudaMemsetAsync(mu.slow_val, 0, sizeof(uint32_t) * nslow_total * mu.nch, ctx->stream));
     GC_CHECK(scratch.alloc(&lists, sizeof(uint32_t) * nslow_total));
+    if (nslow_total > nslow[0]) {
+      mu.walk_items_n = (nslow_total - nslow[0]) * WALK_ITEMS;
+      GC_CHECK(scratch.alloc(&mu.walk_items, sizeof(uint32_t) * (size_t)mu.walk_items_n * mu.nch));
+    }
     if (nslow[0] > 0)  // rounded up to whole blocks: every thread of the launches stores / loads its word
       GC_CHECK(scratch.alloc(&mu.two_items, sizeof(unsigned long long) * (size_t)gc_div_up(nslow[0] * WALK_ITEMS, TWO_T) * TWO_T));
     GC_CHECK(scratch.alloc(&cursor, sizeof(uint32_t) * 2 * CM_NBK));
