@@ -635,7 +635,13 @@ __global__ void k_cutm_bucketize(const uint8_t* __restrict__ slow_bucket, int64_
 //                  subcell points through a point map, C lane = subcell (connectivity row, bg cell, measure, L state
 //                  bytes: neighbouring lanes write neighbouring addresses).
 // ================================================================================================
-constexpr int CM_T = 64;  // threads per block: 2 independent warp tiles
+constexpr int CM_T = 64;  // threads per block of the count kernel: 2 independent warp tiles
+// fill kernel: 8 independent warp tiles per block.  The warps of a block start together and run the same phases at about
+// the same time, so they share the instruction lines they fetch (the kernel is ~64 KB of code; with 2-warp blocks the 16
+// warps of an SM were spread all over it and instruction fetch was the largest stall, ncu r2_c1_final)
+#ifndef CMF_T
+#define CMF_T 256
+#endif
 
 template <int D>
 struct CmLane {
@@ -1058,7 +1064,7 @@ __device__ __forceinline__ double cm_rcoord(const double* SXo, int p, int d) {
 }
 
 template <int D>
-__global__ void __launch_bounds__(CM_T)
+__global__ void __launch_bounds__(CMF_T)
 k_cutm_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict__ tables,
             const uint8_t* __restrict__ simp_raw, const uint8_t* __restrict__ simp_pos,
             const int32_t* __restrict__ cutcells, int64_t nsimp, GcMulti mu, GcLayout lay,
@@ -1089,7 +1095,7 @@ k_cutm_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
   const int L = lv.L;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   SM& sm = *reinterpret_cast<SM*>(cm_smem + (size_t)wid * sizeof(SM));
-  const int64_t tile = (int64_t)blockIdx.x * (CM_T / 32) + wid;
+  const int64_t tile = (int64_t)blockIdx.x * (CMF_T / 32) + wid;
   if (tile * 32 >= nsimp) return;  // whole warp beyond the end (no block barrier below)
   const int64_t s = tile * 32 + lane;
   const bool valid = s < nsimp;
@@ -1449,7 +1455,7 @@ k_cutm_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
 //   everything below passes through the remaining all-IN / all-OUT stages as vertex permutations.
 // Same work split, counters and offsets as k_cut_walk (lane j < 6: child j; lanes 6, 7: the facets of stage a).
 // ================================================================================================
-constexpr int TWO_T = 64;
+constexpr int TWO_T = 128;  // 16 simplices per block (4 warps that start together share their instruction fetches)
 
 template <int D>
 struct TwoSmem {
@@ -2523,13 +2529,18 @@ void launch_fast_count(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, c
 }
 
 void launch_fast_fill(gecut_ctx* ctx, const gecut_result* res, int64_t nsimp, const GcMulti& mu) {
-  const unsigned nb = (unsigned)gc_div_up(mu.ntiles, CM_T / 32);
+  const unsigned nb = (unsigned)gc_div_up(mu.ntiles, CMF_T / 32);
+  // per device (a process may drive several): set on every launch, it is a host-side table write
   if (res->grid.D == 2)
-    GC_LAUNCH(ctx, "k_cutm_fill", k_cutm_fill<2><<<nb, CM_T, sizeof(CmSmem<2>) * (CM_T / 32), ctx->stream>>>(
+    cudaFuncSetAttribute(k_cutm_fill<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(CmSmem<2>) * (CMF_T / 32)));
+  else
+    cudaFuncSetAttribute(k_cutm_fill<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(CmSmem<3>) * (CMF_T / 32)));
+  if (res->grid.D == 2)
+    GC_LAUNCH(ctx, "k_cutm_fill", k_cutm_fill<2><<<nb, CMF_T, sizeof(CmSmem<2>) * (CMF_T / 32), ctx->stream>>>(
         res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw, ctx->d_simplexify_pos, res->lay.cutcells, nsimp, mu, res->lay,
         res->cut_sc_ptr));
   else
-    GC_LAUNCH(ctx, "k_cutm_fill", k_cutm_fill<3><<<nb, CM_T, sizeof(CmSmem<3>) * (CM_T / 32), ctx->stream>>>(
+    GC_LAUNCH(ctx, "k_cutm_fill", k_cutm_fill<3><<<nb, CMF_T, sizeof(CmSmem<3>) * (CMF_T / 32), ctx->stream>>>(
         res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw, ctx->d_simplexify_pos, res->lay.cutcells, nsimp, mu, res->lay,
         res->cut_sc_ptr));
 }
