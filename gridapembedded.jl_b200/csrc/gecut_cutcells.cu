@@ -636,11 +636,13 @@ __global__ void k_cutm_bucketize(const uint8_t* __restrict__ slow_bucket, int64_
 //                  bytes: neighbouring lanes write neighbouring addresses).
 // ================================================================================================
 constexpr int CM_T = 64;  // threads per block of the count kernel: 2 independent warp tiles
-// fill kernel: 8 independent warp tiles per block.  The warps of a block start together and run the same phases at about
-// the same time, so they share the instruction lines they fetch (the kernel is ~64 KB of code; with 2-warp blocks the 16
-// warps of an SM were spread all over it and instruction fetch was the largest stall, ncu r2_c1_final)
+// fill kernel: 9 independent warp tiles per block, 2 blocks = 18 warps per SM (2 x (9 x 12.2 + 3) KB of shared memory).  The
+// warps of a block start together and run the same phases at about the same time, so they share the instruction lines they
+// fetch: the kernel is ~64 KB of code, with 2-warp blocks the 16 warps of an SM were spread all over it and instruction
+// fetch was the largest stall (ncu r2_c1_final: no_instruction 2.1 per issue).  512^3 CSG: 11.9 ms with 64 threads,
+// 10.3 with 256, 9.8 with 288, 11.3 with 512 (one block per SM: the SM idles while the block's last warps finish).
 #ifndef CMF_T
-#define CMF_T 256
+#define CMF_T 288
 #endif
 
 template <int D>
@@ -1455,7 +1457,7 @@ k_cutm_fill(const GcGrid g, const GcLeaves lv, const GcSimplexTable* __restrict_
 //   everything below passes through the remaining all-IN / all-OUT stages as vertex permutations.
 // Same work split, counters and offsets as k_cut_walk (lane j < 6: child j; lanes 6, 7: the facets of stage a).
 // ================================================================================================
-constexpr int TWO_T = 128;  // 16 simplices per block (4 warps that start together share their instruction fetches)
+constexpr int TWO_T = 192;  // 24 simplices per block (6 warps that start together share their instruction fetches; 2 blocks per SM)
 
 template <int D>
 struct TwoSmem {
