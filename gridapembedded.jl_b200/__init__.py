@@ -18,5 +18,5 @@ from .discretizations import (IN, OUT, CUT, INTERFACE, CUT_IN, CUT_OUT, PHYSICAL
 from .measures import Measure, integrate_measure, integrate_laplacian, get_cell_measure
 from .distributed import DistributedLevelSetCutter, slab_range
 from .facets import (EmbeddedFacetDiscretization, cut_facets, compute_bgfacet_to_inoutcut, compute_subfacet_to_inout,
-                     BoundaryTriangulation, SkeletonTriangulation)
+                     BoundaryTriangulation, SkeletonTriangulation, facet_topology)
 from .agfem import AggregateCutCellsByThreshold, AggregateAllCutCells, aggregate, aggregate_slabs, GhostSkeleton, GhostSkeleton_slabs

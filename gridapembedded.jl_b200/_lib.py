@@ -245,6 +245,7 @@ def lib():
     L.gecut_facet_result_free.argtypes = [vp]
     L.gecut_facet_result_sizes.argtypes = [vp, P(FacetSizes)]
     L.gecut_facet_result_copy.argtypes = [vp, P(FacetBuffers)]
+    L.gecut_facet_topology_host.argtypes = [P(Grid), i64, i64, vp, vp, P(i64), P(C.c_int32)]
     L.gecut_bgfacet_to_inoutcut.argtypes = [vp, vp, cint, vp]
     L.gecut_subfacet_to_inout.argtypes = [vp, vp, cint, vp]
     L.gecut_select_facets.argtypes = [vp, cint, cint, vp, cint, cint, P(vp)]
@@ -281,6 +282,7 @@ def lib():
 
 
 FACET_SYMBOLS = ["gecut_cut_facets", "gecut_facet_result_free", "gecut_facet_result_sizes", "gecut_facet_result_copy",
+                 "gecut_facet_topology_host",
                  "gecut_bgfacet_to_inoutcut", "gecut_subfacet_to_inout", "gecut_select_facets",
                  "gecut_facet_selection_free", "gecut_facet_selection_sizes", "gecut_facet_selection_copy",
                  "gecut_facet_selection_measure", "gecut_aggregate", "gecut_aggregate_slabs", "gecut_ghost_skeleton",

@@ -1251,6 +1251,61 @@ int gecut_cut_facets(gecut_ctx* ctx, const gecut_grid* grid, const gecut_leaf* l
   return GECUT_OK;
 }
 
+// Facet numbering on the host: the index arithmetic of the kernels (facet_decode / sx_facet_decode are __host__ __device__),
+// no device work.  For host programs that need the nodes of a few facets, and for the CPU tests that pin the closed forms
+// to the oracle's first-encounter numbering.
+int gecut_facet_topology_host(const gecut_grid* grid, int64_t first, int64_t count, int32_t* facet_to_nodes,
+                              int8_t* is_boundary_out, int64_t* num_facets_out, int32_t* nodes_per_facet) {
+  if (!grid || (grid->D != 2 && grid->D != 3)) return GECUT_ERR_INVALID;
+  const int D = grid->D;
+  GcGrid g{};
+  g.D = D;
+  g.simplexified = grid->simplexified ? 1 : 0;
+  for (int d = 0; d < 3; ++d) {
+    g.n[d] = d < D ? grid->partition[d] : 1;
+    if (g.n[d] < 1) return GECUT_ERR_INVALID;
+  }
+  if (grid->slab_begin != 0 || grid->slab_end != 0) {  // the local model of the slab
+    if (grid->slab_begin < 0 || grid->slab_end <= grid->slab_begin || grid->slab_end > grid->partition[D - 1]) return GECUT_ERR_INVALID;
+    g.n[D - 1] = grid->slab_end - grid->slab_begin;
+  }
+  for (int d = 0; d < 3; ++d) g.nn[d] = d < D ? g.n[d] + 1 : 1;
+  GcSxFacets sx{};
+  if (g.simplexified && !gc_build_sx_facets(D, &sx)) return GECUT_ERR_NOTIMPLEMENTED;
+  const int64_t nf = g.simplexified ? (D == 2 ? sx_num_facets<2>(g, sx) : sx_num_facets<3>(g, sx))
+                                    : (D == 2 ? num_facets<2>(g) : num_facets<3>(g));
+  const int nvf = g.simplexified ? D : 1 << (D - 1);
+  if (num_facets_out) *num_facets_out = nf;
+  if (nodes_per_facet) *nodes_per_facet = nvf;
+  if (count == 0) return GECUT_OK;
+  if (first < 0 || count < 0 || first + count > nf || nf >= 2147483647ll) return GECUT_ERR_INVALID;
+  for (int64_t q = 0; q < count; ++q) {
+    const uint32_t f = (uint32_t)(first + q);
+    bool isb;
+    int nijk[4][3];
+    if (g.simplexified) {
+      const SxFacetIdx fi = D == 2 ? sx_facet_decode<2>(g, sx, f) : sx_facet_decode<3>(g, sx, f);
+      isb = D == 2 ? sx_facet_is_boundary<2>(g, fi, sx) : sx_facet_is_boundary<3>(g, fi, sx);
+      for (int m = 0; m < nvf; ++m) {
+        if (D == 2) sx_facet_node<2>(fi, sx, m, nijk[m]); else sx_facet_node<3>(fi, sx, m, nijk[m]);
+      }
+    } else {
+      const FacetIdx fi = D == 2 ? facet_decode<2>(g, f) : facet_decode<3>(g, f);
+      isb = D == 2 ? facet_is_boundary<2>(g, fi) : facet_is_boundary<3>(g, fi);
+      for (int m = 0; m < nvf; ++m) {
+        if (D == 2) facet_node<2>(fi, m, nijk[m]); else facet_node<3>(fi, m, nijk[m]);
+      }
+    }
+    if (is_boundary_out) is_boundary_out[q] = isb ? 1 : 0;
+    if (facet_to_nodes)
+      for (int m = 0; m < nvf; ++m) {
+        const int64_t node = (int64_t)nijk[m][0] + (int64_t)g.nn[0] * ((int64_t)nijk[m][1] + (D == 3 ? (int64_t)g.nn[1] * nijk[m][2] : 0));
+        facet_to_nodes[q * nvf + m] = (int32_t)(node + 1);
+      }
+  }
+  return GECUT_OK;
+}
+
 int gecut_facet_result_free(gecut_facet_result* res) {
   if (!res) return GECUT_OK;
   if (res->live_selections > 0) {  // deferred: the last selection of this result releases it

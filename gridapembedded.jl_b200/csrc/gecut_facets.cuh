@@ -85,7 +85,7 @@ __host__ __device__ inline int64_t num_facets(const GcGrid& g) {
 }
 
 template <int D>
-__device__ __forceinline__ FacetIdx facet_decode(const GcGrid& g, uint32_t f) {
+__host__ __device__ inline FacetIdx facet_decode(const GcGrid& g, uint32_t f) {
   FacetIdx r;
   uint32_t rem = f;
   int k = 0;
@@ -143,7 +143,7 @@ __device__ __forceinline__ FacetIdx facet_decode(const GcGrid& g, uint32_t f) {
 
 // multi-index of local node m (0 .. 2^(D-1)-1) of the facet: the free directions ascending, lower one fastest
 template <int D>
-__device__ __forceinline__ void facet_node(const FacetIdx& fi, int m, int* nijk) {
+__host__ __device__ inline void facet_node(const FacetIdx& fi, int m, int* nijk) {
   nijk[0] = fi.ijk[0];
   nijk[1] = fi.ijk[1];
   nijk[2] = D == 3 ? fi.ijk[2] : 0;
@@ -158,7 +158,7 @@ __device__ __forceinline__ void facet_node(const FacetIdx& fi, int m, int* nijk)
 }
 
 template <int D>
-__device__ __forceinline__ bool facet_is_boundary(const GcGrid& g, const FacetIdx& fi) {
+__host__ __device__ inline bool facet_is_boundary(const GcGrid& g, const FacetIdx& fi) {
   return fi.side == 0 || fi.ijk[fi.d] == g.n[fi.d] - 1;
 }
 

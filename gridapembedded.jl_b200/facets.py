@@ -292,3 +292,24 @@ def SkeletonTriangulation(cut: EmbeddedFacetDiscretization, in_or_out=PHYSICAL_I
     """`SkeletonTriangulation(cut::EmbeddedFacetDiscretization[, in_or_out][, geo or name])` (`:54-103`): the plus and
     the minus side select the same facets, so one selection stands for both."""
     return _select(cut, _lib.FACETS_SKELETON, in_or_out, geo)
+
+
+def facet_topology(model, slab=None):
+    """`(facet_to_nodes, facet_is_boundary)` of `Grid(ReferenceFE{D-1}, model)` in Gridap's numbering, from the closed
+    forms of the library on the HOST (`gecut_facet_topology_host`: index arithmetic only, no device) -- what
+    `get_face_nodes(model, D-1)` and the one-cell-around mask give in the reference.  `slab=(k0, k1)`: the local model of
+    the slab."""
+    from .cutters import make_grid
+    L = _lib.lib()
+    grid = make_grid(model, slab)
+    nf, nvf = C.c_int64(0), C.c_int32(0)
+    rc = L.gecut_facet_topology_host(C.byref(grid), 0, 0, None, None, C.byref(nf), C.byref(nvf))
+    if rc != _lib.GECUT_OK:
+        raise _lib.GecutError(f"gecut_facet_topology_host failed with status {rc}")
+    nodes = np.empty((nf.value, nvf.value), np.int32)
+    isb = np.empty(nf.value, np.int8)
+    rc = L.gecut_facet_topology_host(C.byref(grid), 0, nf.value, C.c_void_p(nodes.ctypes.data), C.c_void_p(isb.ctypes.data),
+                                     C.byref(nf), C.byref(nvf))
+    if rc != _lib.GECUT_OK:
+        raise _lib.GecutError(f"gecut_facet_topology_host failed with status {rc}")
+    return nodes, isb

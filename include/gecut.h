@@ -260,6 +260,14 @@ typedef struct {
   int32_t pad;
 } gecut_facet_sizes;
 
+/* The closed-form facet numbering on the HOST (index arithmetic only, no device, no context): 1-based nodes
+ * (`*nodes_per_facet` per facet, facet node order) and boundary flags of the bg facets [first, first + count) (0-based ids) of
+ * the model -- of the slab's local model when grid->slab_begin/end are set.  NULL outputs are skipped; count = 0 just returns
+ * the sizes.  The same functions the kernels decode facet ids with (csrc/gecut_facets.cuh); tests/test_facet_numbering.py pins
+ * them to the oracle's first-encounter numbering (Gridap `generate_cell_to_faces`) without a GPU. */
+int gecut_facet_topology_host(const gecut_grid* grid, int64_t first, int64_t count, int32_t* facet_to_nodes,
+                              int8_t* facet_is_boundary, int64_t* num_facets, int32_t* nodes_per_facet);
+
 /* host destinations (NULL entries skipped) of gecut_facet_result_copy */
 typedef struct {
   int8_t* ls_to_facet_to_inoutcut;  /* L x Nf                                                                      */
