@@ -324,11 +324,20 @@ mutable struct B200DeviceCut
   oid_to_ls::Dict{UInt,Int}
   geom
   bgmodel
+  simplexified::Bool
+  cartesian
 end
 
 function device_cut(cutter::B200LevelSetCutter, bgmodel::CartesianDiscreteModel, geom)
   res, oid_to_ls = _run(cutter, :gecut_cut, bgmodel, geom, false, bgmodel)
-  d = B200DeviceCut(cutter, res, oid_to_ls, geom, bgmodel)
+  d = B200DeviceCut(cutter, res, oid_to_ls, geom, bgmodel, false, bgmodel)
+  finalizer(x -> ccall((:gecut_result_free, libgecut), Cint, (Ptr{Cvoid},), x.res), d)
+  d
+end
+
+function device_cut(cutter::B200LevelSetCutter, bg::SimplexifiedCartesian, geom)
+  res, oid_to_ls = _run(cutter, :gecut_cut, bg.model, geom, true, bg.cartesian)
+  d = B200DeviceCut(cutter, res, oid_to_ls, geom, bg.model, true, bg.cartesian)
   finalizer(x -> ccall((:gecut_result_free, libgecut), Cint, (Ptr{Cvoid},), x.res), d)
   d
 end
@@ -404,7 +413,8 @@ end
 
 "aggregate(AggregateCutCellsByThreshold(threshold), cutgeo, cutgeo_facets, geo, in_or_out) on the device"
 function device_aggregate(d::B200DeviceCut, geo=d.geom; side::Integer=IN, threshold::Real=1.0)
-  fres, _ = _run_facets(d.cutter, d.bgmodel, d.geom, true)   # classification of the facets is all the aggregation needs
+  # classification of the facets is all the aggregation needs (simplexified models: the facet grid of the TRI / TET mesh)
+  fres, _ = _run_facets(d.cutter, d.bgmodel, d.geom, true; simplexified=d.simplexified, cartesian=d.cartesian)
   prog = _program(d, geo)
   out = Vector{Int32}(undef, num_cells(d.bgmodel))
   # the facet result was cut from the same geometry object, so both discretizations share oid_to_ls: no second program
