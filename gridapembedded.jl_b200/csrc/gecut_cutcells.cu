@@ -2553,11 +2553,8 @@ void launch_two(gecut_ctx* ctx, const gecut_result* res, const GcMulti& mu, bool
   if (nb == 0) return;
 #define GC_TWO(DD, FF, NAME)                                                                                              \
   do {                                                                                                                    \
-    static bool attr_done = false;                                                                                        \
-    if (!attr_done) {                                                                                                     \
-      cudaFuncSetAttribute(k_cut_two<DD, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TwoSmem<DD>));       \
-      attr_done = true;                                                                                                   \
-    }                                                                                                                     \
+    /* per device (a process may drive several): set on every launch, it is a host-side table write */                   \
+    cudaFuncSetAttribute(k_cut_two<DD, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TwoSmem<DD>));         \
     GC_LAUNCH(ctx, NAME, k_cut_two<DD, FF><<<nb, TWO_T, sizeof(TwoSmem<DD>), stream>>>(                                      \
                              res->grid, res->leaves, ctx->d_tables, ctx->d_simplexify_raw, ctx->d_simplexify_pos,           \
                              res->lay.cutcells, mu, res->lay, slots, nslots));                                              \
