@@ -163,3 +163,88 @@ def test_facet_states_match_cell_states():
         r = R[c2p[:, v] - 1]
         x = Xn[:, 0] + r[:, :1] * (Xn[:, 1] - Xn[:, 0]) + r[:, 1:] * (Xn[:, 2] - Xn[:, 0])
         assert np.abs(x - X[c2p[:, v] - 1]).max() < 1e-13
+
+
+# ---- simplexified models: the facet grid of the TRI / TET mesh ---------------------------------------------------------
+def _simplex_cellwise_defect(model, oc, fc, p):
+    """Per bg SIMPLEX K: D |K ∩ Ω| - [ Σ_{facets F of K} (x_F · n_F) |F ∩ Ω| + ∫_{Γ ∩ K} x · n ] (divergence theorem for
+    F(x) = x on K ∩ Ω): ties the IN part of every bg facet of cut_facets -- boundary and interior, axis-aligned and
+    diagonal -- to the subcells and the embedded boundary of cut().  A level set is linear on a simplex, so the trace of
+    the cell's cut on a facet IS the facet's own cut: the defect is round-off for every cell."""
+    D = model.D
+    X = model.node_coordinates()
+    cells = model.cell_node_ids() - 1
+    Nc = cells.shape[0]
+    vol = np.zeros(Nc)
+    ids = oc.select_subcells(p, IN)
+    c2bg = oc.array("subcells.cell_to_bgcell")
+    np.add.at(vol, c2bg[ids - 1] - 1, oc.subcell_measures(ids))
+    for c in oc.select_bgcells(p, IN):
+        vol[c - 1] += oc.bgcell_measure(int(c))
+    flux = np.zeros(Nc)
+    fids, ori = oc.select_boundary(p)
+    fX = oc.array("subfacets.point_to_coords").reshape(-1, D)
+    f2p = oc.array("subfacets.facet_to_points").reshape(-1, D)
+    f2bg = oc.array("subfacets.facet_to_bgcell")
+    f2n = oc.array("subfacets.facet_to_normal").reshape(-1, D)
+    nrm = f2n[fids - 1] * ori[:, None]
+    x0 = fX[f2p[fids - 1][:, 0] - 1]
+    np.add.at(flux, f2bg[fids - 1] - 1, (x0 * nrm).sum(1) * oc.subfacet_measures(fids))
+    # IN measure of every bg facet
+    fn = fc.array("facet_nodes").reshape(-1, fc.nvf)
+    area = np.zeros(fc.Nf)
+    for which in (ob.BOUNDARY_FACETS, ob.SKELETON_FACETS):
+        sub = fc.select(p, which, ob.SEL_CUT, IN)
+        np.add.at(area, fc.array("subfacets.cell_to_bgcell")[sub - 1] - 1, fc.subfacet_measures(sub))
+        for f in fc.select(p, which, ob.SEL_BG, IN):
+            area[f - 1] += fc.bgfacet_measure(int(f))
+    facet_of = {tuple(sorted(r)): f for f, r in enumerate(fn.tolist())}
+    lfacets = [(0, 1), (0, 2), (1, 2)] if D == 2 else [(0, 1, 2), (0, 1, 3), (0, 2, 3), (1, 2, 3)]
+    for c in range(Nc):
+        nodes = cells[c]
+        for lf in lfacets:
+            f = facet_of[tuple(sorted(int(nodes[i]) for i in lf))]
+            if area[f] == 0.0:
+                continue
+            P = X[nodes[list(lf)]]
+            opp = X[nodes[[i for i in range(D + 1) if i not in lf][0]]]
+            if D == 2:
+                e = P[1] - P[0]
+                n = np.array([e[1], -e[0]])
+            else:
+                n = np.cross(P[1] - P[0], P[2] - P[0])
+            n = n / np.linalg.norm(n)
+            if np.dot(n, opp - P[0]) > 0:
+                n = -n
+            flux[c] += np.dot(P[0], n) * area[f]
+    return D * vol - flux
+
+
+@pytest.mark.parametrize("case", ["disk", "csg2d", "sphere", "csg3d"])
+def test_cellwise_divergence_theorem_simplexified(case):
+    from gecut import simplexify
+    if case == "disk":
+        model, geo, nm = simplexify(CartesianDiscreteModel((0, 1, 0, 1), (12, 9))), disk(0.72, x0=(1, 1)), None
+    elif case == "csg2d":
+        geo = setdiff(intersect(disk(0.45, x0=(0.5, 0.5)), plane(x0=(0.5, 0.7), v=(0.2, 1.0))), disk(0.2, x0=(0.4, 0.4)))
+        model, nm = simplexify(CartesianDiscreteModel((0, 1, 0, 1), (12, 9))), None
+    elif case == "sphere":
+        model, geo, nm = simplexify(CartesianDiscreteModel((0, 1, 0, 1, 0, 1), (6, 5, 4))), sphere(0.45, x0=(0.5, 0.55, 0.8)), None
+    else:
+        model, geo, nm = simplexify(CartesianDiscreteModel((-0.8,) * 3, (0.8,) * 3, (6, 6, 6))), csg_geometry(), "csg"
+    oc, fc = both(model, geo)
+    p = prog(oc, nm)
+    assert fc.nvf == model.D and fc.Ncutf > 0 and fc.Nsf >= fc.Ncutf
+    defect = _simplex_cellwise_defect(model, oc, fc, p)
+    assert np.abs(defect).max() < 1e-12
+    # boundary / skeleton split of the facet grid: IN + OUT parts add up to every facet
+    for which in (ob.BOUNDARY_FACETS, ob.SKELETON_FACETS):
+        tot = 0.0
+        for side in (IN, OUT):
+            sub = fc.select(p, which, ob.SEL_CUT, side)
+            whole = fc.select(p, which, ob.SEL_BG, side)
+            tot += fc.subfacet_measures(sub).sum() + sum(fc.bgfacet_measure(int(f)) for f in whole)
+        isb = fc.array("facet_is_boundary").astype(bool)
+        sel = np.nonzero(isb if which == ob.BOUNDARY_FACETS else ~isb)[0]
+        ref = sum(fc.bgfacet_measure(int(f) + 1) for f in sel)
+        assert abs(tot - ref) < 1e-11 * ref
