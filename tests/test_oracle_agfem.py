@@ -112,3 +112,70 @@ def test_ghost_skeleton_mask():
         assert mask.sum() > 0
     # ACTIVE_IN ghosts contain the CUT-only ghosts
     assert np.all(ob.oracle_ghost_skeleton(oc, fc, p, IN)[ob.oracle_ghost_skeleton(oc, fc, p, CUT)])
+
+
+# ---- simplexified models: cells = the TRI / TET of simplexify(model), topology through the facet grid of the simplices ----
+def _simplex_adjacency(model, fc):
+    D = model.D
+    cells = model.cell_node_ids() - 1
+    fn = fc.array("facet_nodes").reshape(-1, fc.nvf)
+    facet_of = {tuple(sorted(r)): f for f, r in enumerate(fn.tolist())}
+    lfacets = [(0, 1), (0, 2), (1, 2)] if D == 2 else [(0, 1, 2), (0, 1, 3), (0, 2, 3), (1, 2, 3)]
+    f2c = [[] for _ in range(fc.Nf)]
+    for c, nodes in enumerate(cells.tolist()):
+        for lf in lfacets:
+            f2c[facet_of[tuple(sorted(nodes[i] for i in lf))]].append(c)
+    return f2c
+
+
+@pytest.mark.parametrize("case", ["disk", "sphere", "csg"])
+@pytest.mark.parametrize("thr", [0.4, 1.0])
+def test_cell_aggregation_simplexified(case, thr):
+    from gecut import simplexify
+    if case == "disk":
+        model, geo, nm = simplexify(CartesianDiscreteModel((0, 1, 0, 1), (30, 30))), disk(0.4, x0=(0.5, 0.5)), None
+    elif case == "sphere":
+        model, geo, nm = simplexify(CartesianDiscreteModel((-1, 1, -1, 1, -1, 1), (9, 8, 7))), sphere(0.7), None
+    else:
+        model, geo, nm = simplexify(CartesianDiscreteModel((-0.8,) * 3, (0.8,) * 3, (8, 8, 8))), csg_geometry(), "csg"
+    oc, fc = setup(model, geo)
+    g = geo if nm is None else get_geometry(geo, nm)
+    p = compile_postfix(g.get_tree(), oc.oid_to_ls)
+    f2c = _simplex_adjacency(model, fc)
+    assert all(len(c) in (1, 2) for c in f2c)
+    assert sum(len(c) == 1 for c in f2c) == fc.Nboundary
+    st = oc.bgcell_to_inoutcut(p)
+    n = model.num_cells
+    cells = np.arange(1, n + 1)
+    nbr = {}
+    for c in f2c:
+        if len(c) == 2:
+            nbr.setdefault(c[0], []).append(c[1])
+            nbr.setdefault(c[1], []).append(c[0])
+    for loc in (IN, OUT):
+        agg, ok = ob.oracle_aggregate(oc, fc, p, loc, thr)
+        assert ok
+        assert np.all(agg[st == -loc] == 0)
+        assert np.all(agg[st == loc] == cells[st == loc])
+        assert np.all(agg[st == CUT] > 0)
+        roots = np.unique(agg[agg > 0])
+        assert np.all(agg[roots - 1] == roots)
+        ids = oc.select_subcells(p, loc)
+        vol = np.zeros(n)
+        np.add.at(vol, oc.array("subcells.cell_to_bgcell")[ids - 1] - 1, oc.subcell_measures(ids))
+        meas = np.array([oc.bgcell_measure(int(c)) for c in cells[st == CUT]])
+        unit = np.zeros(n)
+        unit[st == CUT] = vol[st == CUT] / meas
+        cut_roots = roots[st[roots - 1] == CUT]
+        assert np.all(unit[cut_roots - 1] >= thr - 1e-12)
+        slaves = cells[(st == CUT) & (agg != cells)]
+        assert np.all(unit[slaves - 1] < thr + 1e-12)
+        for c in slaves:  # connected to the root through face neighbours with the same root
+            assert any(agg[x] == agg[c - 1] for x in nbr[c - 1])
+    # ghost skeleton: interior facets next to a CUT cell whose two cells are active
+    for side in (IN, OUT, CUT):
+        mask = ob.oracle_ghost_skeleton(oc, fc, p, side)
+        act = lambda s: s == CUT or s == side
+        expect = np.array([len(c) == 2 and (st[c[0]] == CUT or st[c[1]] == CUT) and act(st[c[0]]) and act(st[c[1]])
+                           for c in f2c])
+        assert np.array_equal(mask, expect)
